@@ -1,0 +1,260 @@
+"""fermat_b200 — B200-native drop-in for the `-pt` wavefront path tracer of NVlabs/fermat.
+
+This module is a thin ctypes binding over the C ABI in include/fermat_b200.h (built as
+fermat_b200/libfermat_b200.so by `make` / `__graft_entry__.build()`), mirroring the reference's host
+objects for the path: `Scene` ~ the host half of RenderingContext::init, `RenderingContext` ~
+RenderingContextImpl + PathTracer (src/renderer.h:52-228, src/renderers/pathtracer.h:265-305).
+
+There is no CPU fallback: every compute entry point raises if the CUDA library or a device is missing.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfermat_b200.so")
+
+FB_CHANNELS = {"DIFFUSE_C": 0, "DIFFUSE_A": 1, "SPECULAR_C": 2, "SPECULAR_A": 3,
+               "DIRECT_C": 4, "COMPOSITED_C": 5, "FILTERED_C": 6, "LUMINANCE": 7}
+
+
+class PTOptions(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in (
+        "max_path_length", "direct_lighting", "direct_lighting_nee", "direct_lighting_bsdf",
+        "indirect_lighting_nee", "indirect_lighting_bsdf", "visible_lights", "diffuse_scattering",
+        "glossy_scattering", "indirect_glossy", "rr", "nee_type")]
+
+
+class TextureView(C.Structure):
+    _fields_ = [("texels", C.POINTER(C.c_float)), ("res_x", C.c_uint32), ("res_y", C.c_uint32)]
+
+
+class SceneView(C.Structure):
+    _fields_ = [
+        ("num_triangles", C.c_uint32), ("num_vertices", C.c_uint32), ("num_materials", C.c_uint32), ("num_textures", C.c_uint32),
+        ("vertex_indices", C.POINTER(C.c_int32)), ("vertex_data", C.POINTER(C.c_float)),
+        ("texture_indices_comp", C.POINTER(C.c_int32)), ("material_indices", C.POINTER(C.c_int32)),
+        ("materials", C.c_void_p), ("tex_bias", C.c_float * 2), ("tex_scale", C.c_float * 2),
+        ("textures", C.POINTER(TextureView)),
+        ("eye", C.c_float * 3), ("aim", C.c_float * 3), ("up", C.c_float * 3), ("fov", C.c_float), ("aspect", C.c_float),
+        ("res_x", C.c_uint32), ("res_y", C.c_uint32),
+        ("n_vpls", C.c_uint32), ("vpls", C.c_void_p), ("vpl_norm", C.c_float),
+        ("n_prims", C.c_uint32), ("mesh_cdf", C.POINTER(C.c_float)), ("mesh_inv_area", C.POINTER(C.c_float)),
+        ("n_dir_lights", C.c_uint32), ("dir_lights", C.POINTER(C.c_float)),
+        ("glossy_reflectance", C.POINTER(C.c_float)),
+        ("n_dimensions", C.c_uint32), ("tile_size", C.c_uint32), ("shifts", C.POINTER(C.c_float)),
+        ("n_bvh_nodes", C.c_uint32), ("bvh_nodes", C.c_void_p), ("bvh_index", C.POINTER(C.c_uint32)),
+        ("bbox_min", C.c_float * 3), ("bbox_max", C.c_float * 3),
+        ("options", PTOptions),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [("shade_events", C.c_uint64), ("shadow_events", C.c_uint64), ("passes", C.c_uint64),
+                ("kernel_launches", C.c_uint64), ("device_ms", C.c_double)]
+
+
+_lib = None
+
+
+def lib():
+    """Load libfermat_b200.so (raises if it has not been built — there is no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("%s is missing: run `make` (or __graft_entry__.build()) first" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, u32, u64, i32, f32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.c_float
+    pf = C.POINTER(C.c_float)
+    sig = {
+        "fb200_last_error": (C.c_char_p, []),
+        "fb200_scene_create": (vp, [i32, C.POINTER(C.c_char_p)]),
+        "fb200_scene_destroy": (None, [vp]),
+        "fb200_scene_get_view": (i32, [vp, C.POINTER(SceneView)]),
+        "fb200_scene_save_snapshot": (i32, [vp, C.c_char_p]),
+        "fb200_scene_bvh_stats": (i32, [vp, C.POINTER(u64 * 4), C.POINTER(f32)]),
+        "fb200_scene_sample_2d": (f32, [vp, u32, u32, u32, u32]),
+        "fb200_context_create": (vp, [vp, i32]),
+        "fb200_context_destroy": (None, [vp]),
+        "fb200_context_clear": (i32, [vp]),
+        "fb200_context_render": (i32, [vp, u32, i32]),
+        "fb200_context_synchronize": (i32, [vp]),
+        "fb200_context_res": (i32, [vp, C.POINTER(u32), C.POINTER(u32)]),
+        "fb200_context_fb_device_ptr": (vp, [vp, i32]),
+        "fb200_context_fb_download": (i32, [vp, i32, pf]),
+        "fb200_context_fb_upload": (i32, [vp, i32, pf]),
+        "fb200_context_get_stats": (i32, [vp, C.POINTER(Stats)]),
+        "fb200_context_stream": (vp, [vp]),
+        "fb200_context_owned_pixels": (u64, [vp]),
+        "fb200_trace": (i32, [vp, pf, pf, u32]),
+        "fb200_trace_shadow": (i32, [vp, pf, C.POINTER(C.c_uint8), u32]),
+        "fb200_trace_device": (i32, [vp, vp, vp, u32]),
+        "fb200_trace_shadow_device": (i32, [vp, vp, vp, u32]),
+        "fb200_bsdf_eval": (i32, [vp, pf, pf, u32]),
+        "register_plugin": (u32, [vp]),
+    }
+    missing = []
+    for name, (res, args) in sig.items():
+        try:
+            fn = getattr(L, name)
+        except AttributeError:
+            missing.append(name)
+            continue
+        fn.restype, fn.argtypes = res, args
+    L._missing = missing
+    _lib = L
+    return L
+
+
+def exported_symbols():
+    """Names include/fermat_b200.h declares, and the subset missing from the loaded library."""
+    L = lib()
+    return L._missing
+
+
+def _err():
+    return lib().fb200_last_error().decode("utf-8", "replace")
+
+
+def _fptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+class Scene:
+    """Host-only scene: mesh + materials + textures, sampler tables, VPLs, BVH (no GPU needed)."""
+
+    def __init__(self, args):
+        self.args = [str(a) for a in args]
+        argv = (C.c_char_p * len(self.args))(*[a.encode() for a in self.args])
+        self._h = lib().fb200_scene_create(len(self.args), argv)
+        if not self._h:
+            raise RuntimeError("fb200_scene_create failed: " + _err())
+        self.view = SceneView()
+        if lib().fb200_scene_get_view(self._h, C.byref(self.view)) != 0:
+            raise RuntimeError(_err())
+
+    @property
+    def res(self):
+        return int(self.view.res_x), int(self.view.res_y)
+
+    def bvh_stats(self):
+        out = (C.c_uint64 * 4)()
+        sah = C.c_float()
+        lib().fb200_scene_bvh_stats(self._h, C.byref(out), C.byref(sah))
+        return {"wide_nodes": out[0], "triangles": out[1], "max_depth": out[2], "bvh2_nodes": out[3], "sah_cost": sah.value}
+
+    def save_snapshot(self, filename):
+        if lib().fb200_scene_save_snapshot(self._h, str(filename).encode()) != 0:
+            raise RuntimeError(_err())
+
+    def sample_2d(self, instance, px, py, dim):
+        return lib().fb200_scene_sample_2d(self._h, instance, px, py, dim)
+
+    def close(self):
+        if self._h:
+            lib().fb200_scene_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _CudaArray:
+    """Exposes a raw device pointer through __cuda_array_interface__ (zero-copy torch.as_tensor)."""
+
+    def __init__(self, ptr, shape, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+class RenderingContext:
+    """RenderingContext + PathTracer on one CUDA device (reference src/renderer.h:52-228)."""
+
+    def __init__(self, scene, device=0):
+        self.scene = scene
+        self._h = lib().fb200_context_create(scene._h, int(device))
+        if not self._h:
+            raise RuntimeError("fb200_context_create failed: " + _err())
+        self.device = int(device)
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise RuntimeError(_err())
+
+    def res(self):
+        x, y = C.c_uint32(), C.c_uint32()
+        self._chk(lib().fb200_context_res(self._h, C.byref(x), C.byref(y)))
+        return x.value, y.value
+
+    def clear(self):
+        self._chk(lib().fb200_context_clear(self._h))
+
+    def render(self, instance, sync=True):
+        self._chk(lib().fb200_context_render(self._h, int(instance), 1 if sync else 0))
+
+    def synchronize(self):
+        self._chk(lib().fb200_context_synchronize(self._h))
+
+    def download(self, channel="COMPOSITED_C"):
+        w, h = self.res()
+        out = np.empty((h, w, 4), dtype=np.float32)
+        self._chk(lib().fb200_context_fb_download(self._h, FB_CHANNELS.get(channel, channel), _fptr(out)))
+        return out
+
+    def upload(self, channel, image):
+        img = np.ascontiguousarray(image, dtype=np.float32)
+        self._chk(lib().fb200_context_fb_upload(self._h, FB_CHANNELS.get(channel, channel), _fptr(img)))
+
+    def fb_tensor(self, channel="COMPOSITED_C"):
+        """torch view (no copy) of a frame-buffer channel living in device memory."""
+        import torch
+        w, h = self.res()
+        ptr = lib().fb200_context_fb_device_ptr(self._h, FB_CHANNELS.get(channel, channel))
+        if not ptr:
+            raise RuntimeError(_err())
+        return torch.as_tensor(_CudaArray(ptr, (h, w, 4)), device="cuda:%d" % self.device)
+
+    def stats(self):
+        s = Stats()
+        self._chk(lib().fb200_context_get_stats(self._h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in Stats._fields_}
+
+    def stream(self):
+        return lib().fb200_context_stream(self._h)
+
+    def owned_pixels(self):
+        return int(lib().fb200_context_owned_pixels(self._h))
+
+    # --- hot-path entry points (host buffers) ---
+    def trace(self, rays):
+        rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)
+        hits = np.empty((rays.shape[0], 4), dtype=np.float32)
+        self._chk(lib().fb200_trace(self._h, _fptr(rays), _fptr(hits), rays.shape[0]))
+        return hits
+
+    def trace_shadow(self, rays):
+        rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)
+        occ = np.empty(rays.shape[0], dtype=np.uint8)
+        self._chk(lib().fb200_trace_shadow(self._h, _fptr(rays), occ.ctypes.data_as(C.POINTER(C.c_uint8)), rays.shape[0]))
+        return occ
+
+    def bsdf_eval(self, rec):
+        rec = np.ascontiguousarray(rec, dtype=np.float32).reshape(-1, 12)
+        out = np.empty((rec.shape[0], 25), dtype=np.float32)
+        self._chk(lib().fb200_bsdf_eval(self._h, _fptr(rec), _fptr(out), rec.shape[0]))
+        return out
+
+    def close(self):
+        if self._h:
+            lib().fb200_context_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,298 @@
+// bvh.cpp — see bvh.h
+#include "bvh.h"
+#include <algorithm>
+#include <deque>
+#include <stdio.h>
+
+namespace fb {
+
+namespace {
+
+struct PrimRef { Bbox3 box; V3 centroid; };
+
+inline float axis(const V3& v, int a) { return a == 0 ? v.x : (a == 1 ? v.y : v.z); }
+
+const int N_BINS = 16;
+
+struct BuildTask { uint32 node, begin, end; };
+
+} // anonymous namespace
+
+void build_bvh2(const Mesh& mesh, Bvh2& bvh, uint32 max_leaf_size)
+{
+	const uint32 n = (uint32)mesh.num_triangles();
+	std::vector<PrimRef> prims(n);
+	bvh.index.resize(n);
+	for (uint32 i = 0; i < n; ++i)
+	{
+		const int4 t = mesh.vertex_indices[i];
+		Bbox3 b;
+		b.insert(V3(mesh.vertex_data[t.x])); b.insert(V3(mesh.vertex_data[t.y])); b.insert(V3(mesh.vertex_data[t.z]));
+		prims[i].box = b;
+		prims[i].centroid = (b.lo + b.hi) * 0.5f;
+		bvh.index[i] = i;
+	}
+	bvh.nodes.clear();
+	bvh.nodes.reserve(2 * (size_t)n + 2);
+	bvh.nodes.push_back(Bvh2Node());
+
+	std::vector<BuildTask> stack;
+	stack.push_back(BuildTask{ 0u, 0u, n });
+	std::vector<uint32>& idx = bvh.index;
+
+	while (!stack.empty())
+	{
+		const BuildTask task = stack.back(); stack.pop_back();
+		const uint32 count = task.end - task.begin;
+		Bbox3 box, cbox;
+		for (uint32 i = task.begin; i < task.end; ++i) { box.insert(prims[idx[i]].box); cbox.insert(prims[idx[i]].centroid); }
+
+		Bvh2Node& node = bvh.nodes[task.node];
+		node.bmin[0] = box.lo.x; node.bmin[1] = box.lo.y; node.bmin[2] = box.lo.z;
+		node.bmax[0] = box.hi.x; node.bmax[1] = box.hi.y; node.bmax[2] = box.hi.z;
+
+		auto make_leaf = [&]() {
+			Bvh2Node& nd = bvh.nodes[task.node];
+			nd.packed_info = task.begin << 2;
+			nd.range_size = count;
+		};
+		if (count <= 1) { make_leaf(); continue; }
+
+		// binned SAH over the three axes
+		float best_cost = 1.0e30f; int best_axis = -1; int best_bin = -1;
+		const V3 cext = cbox.hi - cbox.lo;
+		for (int a = 0; a < 3; ++a)
+		{
+			const float ext = axis(cext, a);
+			if (!(ext > 0.0f)) continue;
+			Bbox3 bin_box[N_BINS]; uint32 bin_cnt[N_BINS] = { 0 };
+			const float k = float(N_BINS) / ext, lo = axis(cbox.lo, a);
+			for (uint32 i = task.begin; i < task.end; ++i)
+			{
+				int b = (int)((axis(prims[idx[i]].centroid, a) - lo) * k);
+				b = b < 0 ? 0 : (b >= N_BINS ? N_BINS - 1 : b);
+				bin_box[b].insert(prims[idx[i]].box); bin_cnt[b]++;
+			}
+			float right_area[N_BINS]; uint32 right_cnt[N_BINS];
+			Bbox3 acc; uint32 c = 0;
+			for (int b = N_BINS - 1; b > 0; --b)
+			{
+				acc.insert(bin_box[b]); c += bin_cnt[b];
+				right_area[b] = c ? acc.half_area() : 0.0f; right_cnt[b] = c;
+			}
+			acc = Bbox3(); c = 0;
+			for (int b = 0; b < N_BINS - 1; ++b)
+			{
+				acc.insert(bin_box[b]); c += bin_cnt[b];
+				if (c == 0 || right_cnt[b + 1] == 0) continue;
+				const float cost = acc.half_area() * c + right_area[b + 1] * right_cnt[b + 1];
+				if (cost < best_cost) { best_cost = cost; best_axis = a; best_bin = b; }
+			}
+		}
+
+		const float parent_area = box.half_area();
+		const float leaf_cost = float(count) * parent_area;              // c_isect = 1
+		const float split_cost = best_axis >= 0 ? 1.0f * parent_area + best_cost : 1.0e30f;   // c_trav = 1
+		if (count <= max_leaf_size && leaf_cost <= split_cost) { make_leaf(); continue; }
+
+		uint32 mid;
+		if (best_axis >= 0)
+		{
+			const float ext = axis(cext, best_axis), lo = axis(cbox.lo, best_axis), k = float(N_BINS) / ext;
+			uint32* first = &idx[task.begin]; uint32* last = &idx[0] + task.end;
+			uint32* m = std::partition(first, last, [&](uint32 p) {
+				int b = (int)((axis(prims[p].centroid, best_axis) - lo) * k);
+				b = b < 0 ? 0 : (b >= N_BINS ? N_BINS - 1 : b);
+				return b <= best_bin; });
+			mid = (uint32)(m - &idx[0]);
+		}
+		else mid = task.begin;
+		if (mid == task.begin || mid == task.end)
+		{
+			// all centroids coincide: split the range in half
+			mid = task.begin + count / 2;
+		}
+
+		const uint32 child = (uint32)bvh.nodes.size();
+		bvh.nodes.push_back(Bvh2Node()); bvh.nodes.push_back(Bvh2Node());
+		Bvh2Node& nd = bvh.nodes[task.node];
+		nd.packed_info = 3u | (child << 2);
+		nd.range_size = count;
+		stack.push_back(BuildTask{ child + 1, mid, task.end });
+		stack.push_back(BuildTask{ child, task.begin, mid });
+	}
+	bvh.sah_cost = compute_sah_cost(bvh);
+}
+
+float compute_sah_cost(const Bvh2& bvh, float c_trav, float c_isect)
+{
+	if (bvh.nodes.empty()) return 0.0f;
+	auto area = [](const Bvh2Node& n) {
+		const float dx = n.bmax[0] - n.bmin[0], dy = n.bmax[1] - n.bmin[1], dz = n.bmax[2] - n.bmin[2];
+		return dx * dy + dy * dz + dz * dx; };
+	const double root = area(bvh.nodes[0]);
+	if (!(root > 0.0)) return 0.0f;
+	double cost = 0.0;
+	for (size_t i = 0; i < bvh.nodes.size(); ++i)
+	{
+		const Bvh2Node& n = bvh.nodes[i];
+		cost += n.is_leaf() ? double(area(n)) * n.range_size * c_isect : double(area(n)) * c_trav;
+	}
+	return float(cost / root);
+}
+
+// ------------------------------------------------------------------------------------------
+// 8-wide collapse
+// ------------------------------------------------------------------------------------------
+namespace {
+struct WideTask { uint32 bvh2_node; uint32 wide_node; };
+inline Bbox3 node_box(const Bvh2Node& n) { Bbox3 b; b.lo = V3(n.bmin[0], n.bmin[1], n.bmin[2]); b.hi = V3(n.bmax[0], n.bmax[1], n.bmax[2]); return b; }
+}
+
+void collapse_to_wide(const Mesh& mesh, const Bvh2& bvh, WideBvh& wide)
+{
+	wide.nodes.clear(); wide.tris.clear(); wide.max_depth = 0;
+	if (bvh.nodes.empty()) return;
+	wide.nodes.reserve(bvh.nodes.size() / 4 + 16);
+	wide.tris.reserve(bvh.index.size());
+
+	std::deque<WideTask> queue;
+	std::vector<uint32> depth;
+	wide.nodes.push_back(WideNode());
+	depth.push_back(1);
+	queue.push_back(WideTask{ 0u, 0u });
+
+	while (!queue.empty())
+	{
+		const WideTask task = queue.front(); queue.pop_front();
+		const Bvh2Node& root = bvh.nodes[task.bvh2_node];
+
+		// gather up to 8 children: repeatedly open the internal child with the largest area
+		uint32 children[8]; uint32 nc = 0;
+		if (root.is_leaf()) children[nc++] = task.bvh2_node;
+		else { children[nc++] = root.child(0); children[nc++] = root.child(1); }
+		while (nc < 8)
+		{
+			int best = -1; float best_area = -1.0f;
+			for (uint32 i = 0; i < nc; ++i)
+			{
+				const Bvh2Node& c = bvh.nodes[children[i]];
+				if (c.is_leaf()) continue;
+				const float a = node_box(c).half_area();
+				if (a > best_area) { best_area = a; best = (int)i; }
+			}
+			if (best < 0) break;
+			const Bvh2Node& c = bvh.nodes[children[best]];
+			children[best] = c.child(0);
+			children[nc++] = c.child(1);
+		}
+
+		// assign children to slots: slot s "looks" along d_s = (s&4 ? + : -, s&2 ? + : -, s&1 ? + : -);
+		// greedy on the largest projection of the child centroid offset (Ylitie et al. 2017, sec. 4.2)
+		const Bbox3 pbox = node_box(root);
+		const V3 pc = (pbox.lo + pbox.hi) * 0.5f;
+		int slot_of[8]; bool slot_used[8] = { false }; bool child_done[8] = { false };
+		for (uint32 i = 0; i < nc; ++i) slot_of[i] = -1;
+		for (uint32 round = 0; round < nc; ++round)
+		{
+			float best = -1.0e30f; int bc = -1, bs = -1;
+			for (uint32 c = 0; c < nc; ++c)
+			{
+				if (child_done[c]) continue;
+				const Bbox3 cb = node_box(bvh.nodes[children[c]]);
+				const V3 off = (cb.lo + cb.hi) * 0.5f - pc;
+				for (int s = 0; s < 8; ++s)
+				{
+					if (slot_used[s]) continue;
+					const float v = ((s & 4) ? off.x : -off.x) + ((s & 2) ? off.y : -off.y) + ((s & 1) ? off.z : -off.z);
+					if (v > best) { best = v; bc = (int)c; bs = s; }
+				}
+			}
+			slot_of[bc] = bs; slot_used[bs] = true; child_done[bc] = true;
+		}
+		int child_in_slot[8];
+		for (int s = 0; s < 8; ++s) child_in_slot[s] = -1;
+		for (uint32 c = 0; c < nc; ++c) child_in_slot[slot_of[c]] = (int)children[c];
+
+		// quantisation frame
+		WideNode node;
+		memset(&node, 0, sizeof(node));
+		node.px = pbox.lo.x; node.py = pbox.lo.y; node.pz = pbox.lo.z;
+		int e[3];
+		for (int a = 0; a < 3; ++a)
+		{
+			const float ext = axis(pbox.hi, a) - axis(pbox.lo, a);
+			// smallest power of two with ext / 2^e <= 255 (strictly conservative under fp32 rounding)
+			int ex = ext > 0.0f ? (int)ceilf(log2f(ext / 255.0f)) : -126;
+			while (ext > 0.0f && ext / exp2f((float)ex) > 255.0f) ex++;
+			if (ex < -126) ex = -126;
+			if (ex > 127) ex = 127;
+			e[a] = ex;
+		}
+		node.ex = (uint8_t)(e[0] + 127); node.ey = (uint8_t)(e[1] + 127); node.ez = (uint8_t)(e[2] + 127);
+		const float inv_scale[3] = { exp2f((float)-e[0]), exp2f((float)-e[1]), exp2f((float)-e[2]) };
+
+		node.child_base = (uint32)wide.nodes.size();
+		node.tri_base = (uint32)wide.tris.size();
+		uint32 n_internal = 0, tri_offset = 0;
+		for (int s = 0; s < 8; ++s)
+		{
+			if (child_in_slot[s] < 0) { node.meta[s] = 0; continue; }
+			const Bvh2Node& c = bvh.nodes[child_in_slot[s]];
+			const Bbox3 cb = node_box(c);
+			auto qlo = [&](float v, float p, float is) { float q = floorf((v - p) * is); q = q < 0.0f ? 0.0f : (q > 255.0f ? 255.0f : q); return (uint8_t)q; };
+			auto qhi = [&](float v, float p, float is) { float q = ceilf((v - p) * is); q = q < 0.0f ? 0.0f : (q > 255.0f ? 255.0f : q); return (uint8_t)q; };
+			node.qlox[s] = qlo(cb.lo.x, pbox.lo.x, inv_scale[0]); node.qhix[s] = qhi(cb.hi.x, pbox.lo.x, inv_scale[0]);
+			node.qloy[s] = qlo(cb.lo.y, pbox.lo.y, inv_scale[1]); node.qhiy[s] = qhi(cb.hi.y, pbox.lo.y, inv_scale[1]);
+			node.qloz[s] = qlo(cb.lo.z, pbox.lo.z, inv_scale[2]); node.qhiz[s] = qhi(cb.hi.z, pbox.lo.z, inv_scale[2]);
+			// make the de-quantised box strictly contain the fp32 box even after rounding of p + q*scale
+			auto fix = [&](uint8_t& lo, uint8_t& hi, float blo, float bhi, float p, int ex) {
+				const float sc = exp2f((float)ex);
+				while (lo > 0 && p + lo * sc > blo) lo--;
+				while (hi < 255 && p + hi * sc < bhi) hi++;
+			};
+			fix(node.qlox[s], node.qhix[s], cb.lo.x, cb.hi.x, pbox.lo.x, e[0]);
+			fix(node.qloy[s], node.qhiy[s], cb.lo.y, cb.hi.y, pbox.lo.y, e[1]);
+			fix(node.qloz[s], node.qhiz[s], cb.lo.z, cb.hi.z, pbox.lo.z, e[2]);
+
+			if (c.is_leaf())
+			{
+				const uint32 cnt = c.range_size;                 // 1..3
+				const uint32 unary = cnt == 1 ? 1u : (cnt == 2 ? 3u : 7u);
+				node.meta[s] = (uint8_t)((unary << 5) | tri_offset);
+				for (uint32 k = 0; k < cnt; ++k)
+				{
+					const uint32 tri_id = bvh.index[c.leaf_begin() + k];
+					const int4 t = mesh.vertex_indices[tri_id];
+					WideTri wt;
+					const float4 a = mesh.vertex_data[t.x], b = mesh.vertex_data[t.y], d = mesh.vertex_data[t.z];
+					wt.v0 = float4{ a.x, a.y, a.z, uint_as_float(tri_id) };
+					wt.v1 = float4{ b.x, b.y, b.z, uint_as_float((uint32)t.w) };
+					wt.v2 = float4{ d.x, d.y, d.z, 0.0f };
+					wide.tris.push_back(wt);
+				}
+				tri_offset += cnt;
+			}
+			else
+			{
+				node.meta[s] = (uint8_t)((1u << 5) | (24u + (uint32)s));
+				node.imask |= (uint8_t)(1u << s);
+				n_internal++;
+			}
+		}
+		// allocate the internal children contiguously, in slot order
+		const uint32 d = depth[task.wide_node];
+		if (d > wide.max_depth) wide.max_depth = d;
+		for (int s = 0; s < 8; ++s)
+			if (node.imask & (1u << s))
+			{
+				const uint32 wi = (uint32)wide.nodes.size();
+				wide.nodes.push_back(WideNode());
+				depth.push_back(d + 1);
+				queue.push_back(WideTask{ (uint32)child_in_slot[s], wi });
+			}
+		wide.nodes[task.wide_node] = node;
+	}
+}
+
+} // namespace fb

@@ -1,0 +1,183 @@
+// pt_scene.cpp — see pt_scene.h
+#include "pt_scene.h"
+#include <stdexcept>
+#include <string.h>
+#include <stdlib.h>
+#include <stdio.h>
+#include <dlfcn.h>
+
+namespace fb {
+
+void pt_options_defaults(PTOptions& o)
+{
+	// reference src/renderers/pathtracer.h:186-199
+	o.max_path_length = 6;
+	o.direct_lighting = 1; o.direct_lighting_nee = 1; o.direct_lighting_bsdf = 1;
+	o.indirect_lighting_nee = 1; o.indirect_lighting_bsdf = 1;
+	o.visible_lights = 1; o.diffuse_scattering = 1; o.glossy_scattering = 1; o.indirect_glossy = 0; o.rr = 1;
+	o.nee_type = 1;
+}
+
+void pt_options_parse(PTOptions& o, int argc, const char* const* argv)
+{
+	auto is = [&](int i, const char* s) { return strcmp(argv[i], s) == 0; };
+	for (int i = 0; i < argc; ++i)
+	{
+		if ((is(i, "-pl") || is(i, "-path-length") || is(i, "-max-path-length")) && i + 1 < argc) o.max_path_length = (uint32)atoi(argv[++i]);
+		else if (is(i, "-bounces") && i + 1 < argc) o.max_path_length = (uint32)atoi(argv[++i]) + 1;
+		else if (is(i, "-nee") && i + 1 < argc) o.direct_lighting_nee = o.indirect_lighting_nee = atoi(argv[++i]) > 0;
+		else if (is(i, "-bsdf") && i + 1 < argc) o.direct_lighting_bsdf = o.indirect_lighting_bsdf = atoi(argv[++i]) > 0;
+		else if (is(i, "-direct-nee") && i + 1 < argc) o.direct_lighting_nee = atoi(argv[++i]) > 0;
+		else if (is(i, "-direct-bsdf") && i + 1 < argc) o.direct_lighting_bsdf = atoi(argv[++i]) > 0;
+		else if (is(i, "-indirect-nee") && i + 1 < argc) o.indirect_lighting_nee = atoi(argv[++i]) > 0;
+		else if (is(i, "-indirect-bsdf") && i + 1 < argc) o.indirect_lighting_bsdf = atoi(argv[++i]) > 0;
+		else if (is(i, "-visible-lights") && i + 1 < argc) o.visible_lights = atoi(argv[++i]) > 0;
+		else if (is(i, "-direct-lighting") && i + 1 < argc) o.direct_lighting = atoi(argv[++i]) > 0;
+		else if (is(i, "-indirect-glossy") && i + 1 < argc) o.indirect_glossy = atoi(argv[++i]) > 0;
+		else if (is(i, "-diffuse") && i + 1 < argc) o.diffuse_scattering = atoi(argv[++i]) > 0;
+		else if (is(i, "-glossy") && i + 1 < argc) o.glossy_scattering = atoi(argv[++i]) > 0;
+		else if (is(i, "-rr") && i + 1 < argc) o.rr = atoi(argv[++i]) > 0;
+		else if ((is(i, "-nee-algorithm") || is(i, "-nee-alg")) && i + 1 < argc)
+		{
+			if (strcmp(argv[i + 1], "mesh") == 0) o.nee_type = 0;
+			else if (strcmp(argv[i + 1], "vpl") == 0) o.nee_type = 1;
+			else if (strcmp(argv[i + 1], "rl") == 0) o.nee_type = 2;
+			++i;
+		}
+	}
+}
+
+std::string default_tables_path()
+{
+	// <dir of this shared object>/data/pt_tables.bin
+	Dl_info info;
+	if (dladdr((void*)&default_tables_path, &info) && info.dli_fname)
+	{
+		std::string p = info.dli_fname;
+		const size_t k = p.find_last_of('/');
+		p = (k == std::string::npos) ? std::string(".") : p.substr(0, k);
+		return p + "/data/pt_tables.bin";
+	}
+	return "fermat_b200/data/pt_tables.bin";
+}
+
+// packed tables: {u32 magic 'FBT1', u32 n_glossy, u32 n_slices, u32 tile} glossy[n_glossy] slices[n_slices*tile*tile*3]
+static void load_tables(const std::string& file, std::vector<float>& glossy, std::vector<float>& blue_noise)
+{
+	FILE* f = fopen(file.c_str(), "rb");
+	if (!f) throw std::runtime_error("unable to open the sampler/BSDF tables: " + file + " (run tools/pack_tables.py)");
+	uint32 hd[4];
+	if (fread(hd, 4, 4, f) != 4 || hd[0] != 0x31544246u) { fclose(f); throw std::runtime_error("bad tables file: " + file); }
+	glossy.resize(hd[1]);
+	blue_noise.resize((size_t)hd[2] * hd[3] * hd[3] * 3);
+	const bool ok = fread(glossy.data(), 4, glossy.size(), f) == glossy.size() &&
+					fread(blue_noise.data(), 4, blue_noise.size(), f) == blue_noise.size();
+	fclose(f);
+	if (!ok || hd[1] != 32u * 32u * 32u * 32u || hd[3] != 256u) throw std::runtime_error("truncated tables file: " + file);
+}
+
+void scene_init(fb200_scene& s, int argc, const char* const* argv)
+{
+	const char* filename = NULL;
+	bool overwrite_camera = false;
+	pt_options_defaults(s.options);
+	// Camera defaults, reference src/camera.h:54-61
+	s.scene.camera.eye = float3{ 0, -1, 0 }; s.scene.camera.aim = float3{ 0, 0, 0 }; s.scene.camera.up = float3{ 0, 0, 1 };
+	s.scene.camera.dx = float3{ 1, 0, 0 };
+	s.scene.camera.fov = 60.0f * 3.14159265358979323846f / 180.0f;
+
+	// RenderingContextImpl::init argument scan, reference src/renderer.cu:493-539
+	for (int i = 0; i < argc; ++i)
+	{
+		if (strcmp(argv[i], "-i") == 0 && i + 1 < argc) filename = argv[++i];
+		else if ((strcmp(argv[i], "-r") == 0 || strcmp(argv[i], "-res") == 0) && i + 2 < argc) { s.res_x = (uint32)atoi(argv[++i]); s.res_y = (uint32)atoi(argv[++i]); }
+		else if ((strcmp(argv[i], "-a") == 0 || strcmp(argv[i], "-aspect") == 0) && i + 1 < argc) s.aspect = (float)atof(argv[++i]);
+		else if (strcmp(argv[i], "-c") == 0 && i + 1 < argc)
+		{
+			if (!read_camera_file(argv[++i], s.scene.camera)) throw std::runtime_error(std::string("failed opening camera file ") + argv[i]);
+			overwrite_camera = true;
+		}
+		else if (strcmp(argv[i], "-tables") == 0 && i + 1 < argc) s.tables_file = argv[++i];
+		else if (strcmp(argv[i], "-shard") == 0 && i + 2 < argc) { s.shard_rank = (uint32)atoi(argv[++i]); s.shard_count = (uint32)atoi(argv[++i]); }
+		else if (strcmp(argv[i], "-passes") == 0 && i + 1 < argc) s.n_passes = atoi(argv[++i]);
+		else if (strcmp(argv[i], "-o") == 0 && i + 1 < argc) s.output_name = argv[++i];
+	}
+	if (s.aspect == 0.0f) s.aspect = float(s.res_x) / float(s.res_y);
+	if (!filename) throw std::runtime_error("no input scene: pass -i scene.{fa,obj,fbs}");
+	if (s.res_x == 0 || s.res_y == 0 || (uint64)s.res_x * s.res_y >= (1u << 27)) throw std::runtime_error("unsupported resolution (PixelInfo holds 27 pixel bits)");
+	if (s.shard_count == 0 || s.shard_rank >= s.shard_count) throw std::runtime_error("bad -shard rank/count");
+	pt_options_parse(s.options, argc, argv);
+	if (s.options.max_path_length == 0 || s.options.max_path_length > 62) throw std::runtime_error("unsupported path length");
+	if (s.options.nee_type == 2) throw std::runtime_error("-nee-alg rl is not part of the -pt hot path implemented here");
+
+	load_scene(filename, s.scene, overwrite_camera);
+
+	if (s.tables_file.empty()) s.tables_file = default_tables_path();
+	std::vector<float> blue_noise;
+	load_tables(s.tables_file, s.glossy_reflectance, blue_noise);
+
+	// the context's own sampler is built first and consumes the head of the rand() stream
+	// (reference src/renderer.cu:949-953), then the path tracer's (pathtracer_impl.h:147-150)
+	s.rng = MsvcRand(1u);
+	s.context_sequence.setup(6 * 12, 256, s.rng, blue_noise);
+	s.sequence.setup(6 * (s.options.max_path_length + 1), 256, s.rng, blue_noise);
+	// the context sequence is not read by the path tracer: release it
+	std::vector<float>().swap(s.context_sequence.shifts);
+	std::vector<float>().swap(s.context_sequence.shifts_t);
+
+	s.mesh_lights.init(s.res_x * s.res_y, s.scene, 0u);
+	if (s.mesh_lights.vpls.empty()) s.options.nee_type = 0;     // pathtracer_impl.h:165-166
+
+	build_bvh2(s.scene.mesh, s.bvh2, 3);
+	collapse_to_wide(s.scene.mesh, s.bvh2, s.wide);
+
+	s.texture_views.resize(s.scene.textures.size());
+	for (size_t i = 0; i < s.scene.textures.size(); ++i)
+	{
+		const TextureImage& t = s.scene.textures[i];
+		fb200_texture_view v;
+		v.texels = t.levels.empty() ? NULL : reinterpret_cast<const float*>(t.levels[0].data());
+		v.res_x = t.levels.empty() ? 0 : t.res_x[0];
+		v.res_y = t.levels.empty() ? 0 : t.res_y[0];
+		s.texture_views[i] = v;
+	}
+	s.dir_light_floats.clear();
+	for (size_t i = 0; i < s.scene.dir_lights.size(); ++i)
+	{
+		const DirectionalLight& l = s.scene.dir_lights[i];
+		const float f[6] = { l.dir.x, l.dir.y, l.dir.z, l.color.x, l.color.y, l.color.z };
+		s.dir_light_floats.insert(s.dir_light_floats.end(), f, f + 6);
+	}
+}
+
+void scene_fill_view(const fb200_scene& s, fb200_scene_view& v)
+{
+	memset(&v, 0, sizeof(v));
+	const Mesh& m = s.scene.mesh;
+	v.num_triangles = (uint32)m.num_triangles(); v.num_vertices = (uint32)m.num_vertices();
+	v.num_materials = (uint32)m.materials.size(); v.num_textures = (uint32)s.texture_views.size();
+	v.vertex_indices = reinterpret_cast<const int32_t*>(m.vertex_indices.data());
+	v.vertex_data = reinterpret_cast<const float*>(m.vertex_data.data());
+	v.texture_indices_comp = m.texture_indices_comp.empty() ? NULL : reinterpret_cast<const int32_t*>(m.texture_indices_comp.data());
+	v.material_indices = m.material_indices.data();
+	v.materials = m.materials.data();
+	v.tex_bias[0] = m.tex_bias.x; v.tex_bias[1] = m.tex_bias.y; v.tex_scale[0] = m.tex_scale.x; v.tex_scale[1] = m.tex_scale.y;
+	v.textures = s.texture_views.empty() ? NULL : s.texture_views.data();
+	const Camera& c = s.scene.camera;
+	v.eye[0] = c.eye.x; v.eye[1] = c.eye.y; v.eye[2] = c.eye.z;
+	v.aim[0] = c.aim.x; v.aim[1] = c.aim.y; v.aim[2] = c.aim.z;
+	v.up[0] = c.up.x; v.up[1] = c.up.y; v.up[2] = c.up.z;
+	v.fov = c.fov; v.aspect = s.aspect; v.res_x = s.res_x; v.res_y = s.res_y;
+	v.n_vpls = (uint32)s.mesh_lights.vpls.size(); v.vpls = s.mesh_lights.vpls.data(); v.vpl_norm = s.mesh_lights.normalization_coeff;
+	v.n_prims = (uint32)s.mesh_lights.mesh_cdf.size(); v.mesh_cdf = s.mesh_lights.mesh_cdf.data(); v.mesh_inv_area = s.mesh_lights.mesh_inv_area.data();
+	v.n_dir_lights = (uint32)s.scene.dir_lights.size(); v.dir_lights = s.dir_light_floats.empty() ? NULL : s.dir_light_floats.data();
+	v.glossy_reflectance = s.glossy_reflectance.data();
+	v.n_dimensions = s.sequence.n_dimensions; v.tile_size = s.sequence.tile_size; v.shifts = s.sequence.shifts.data();
+	v.n_bvh_nodes = (uint32)s.bvh2.nodes.size(); v.bvh_nodes = s.bvh2.nodes.data(); v.bvh_index = s.bvh2.index.data();
+	v.bbox_min[0] = s.scene.bbox.lo.x; v.bbox_min[1] = s.scene.bbox.lo.y; v.bbox_min[2] = s.scene.bbox.lo.z;
+	v.bbox_max[0] = s.scene.bbox.hi.x; v.bbox_max[1] = s.scene.bbox.hi.y; v.bbox_max[2] = s.scene.bbox.hi.z;
+	static_assert(sizeof(fb200_pt_options) == sizeof(PTOptions), "options layout");
+	memcpy(&v.options, &s.options, sizeof(PTOptions));
+}
+
+} // namespace fb

@@ -1,0 +1,49 @@
+// pt_scene.h — everything the `-pt` renderer needs on the host before a device is involved:
+// command line, scene, sampler tables, VPLs, BVH. It is the host-only half of
+// RenderingContextImpl::init + PathTracer::init (reference src/renderer.cu:467-991,
+// src/renderers/pathtracer_impl.h:99-178).
+#pragma once
+#include "scene.h"
+#include "sampler.h"
+#include "mesh_lights.h"
+#include "bvh.h"
+#include "../../../include/fermat_b200.h"
+
+struct fb200_scene
+{
+	fb::Scene          scene;
+	fb::PTOptions      options;
+	uint32_t           res_x, res_y;
+	float              aspect;
+	uint32_t           shard_rank, shard_count;
+	int                n_passes;               // -passes (CLI only)
+	std::string        output_name;            // -o (CLI only)
+	std::string        tables_file;
+
+	std::vector<float> glossy_reflectance;     // 32^4
+	fb::MsvcRand       rng;                    // process-wide rand() stream of the reference
+	fb::TiledSequence  context_sequence;       // RenderingContext's own 72-dim sequence (consumes rand() first)
+	fb::TiledSequence  sequence;               // the path tracer's 6*(L+1)-dim sequence
+	uint32_t           sequence_instance;
+	fb::MeshLights     mesh_lights;
+	fb::Bvh2           bvh2;
+	fb::WideBvh        wide;
+
+	std::vector<fb200_texture_view> texture_views;   // backing store of the view
+	std::vector<float> dir_light_floats;
+
+	fb200_scene() : res_x(1600), res_y(900), aspect(0.0f), shard_rank(0), shard_count(1), n_passes(1), sequence_instance(0xFFFFFFFFu) {}
+};
+
+namespace fb {
+
+void pt_options_defaults(PTOptions& o);
+void pt_options_parse(PTOptions& o, int argc, const char* const* argv);   // reference src/renderers/pathtracer.h:202-249
+
+// throws std::runtime_error
+void scene_init(fb200_scene& s, int argc, const char* const* argv);
+void scene_fill_view(const fb200_scene& s, fb200_scene_view& v);
+
+std::string default_tables_path();
+
+} // namespace fb

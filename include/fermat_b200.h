@@ -1,0 +1,168 @@
+/* fermat_b200.h — C ABI of the B200-native `-pt` renderer for NVlabs/fermat.
+ *
+ * Every entry point uses plain pointers and sizes (no C++ or torch types) so that it can be bound
+ * from the reference's C++ (dlopen), from Python (ctypes) or any other FFI. Each declaration cites
+ * the reference interface it stands in for (paths relative to the Fermat repository root).
+ *
+ * Two layers:
+ *   1. the drop-in plugin boundary  — `register_plugin`, exactly the symbol Fermat's plugin loader
+ *      resolves (src/renderer.cu:441-460, example src/renderers/hellopt_plugin.cpp:35-39);
+ *   2. a flat C restatement of the RenderingContext / RendererInterface / RTContext calls made on
+ *      the `-pt` path, for hosts that cannot pass C++ objects.
+ */
+#ifndef FERMAT_B200_H
+#define FERMAT_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------------------------------------
+ * 1. plugin boundary
+ * ------------------------------------------------------------------------------------------- */
+
+/* `extern "C" uint32 register_plugin(RenderingContext& renderer)`
+ * replaces: the DLL entry point loaded by RenderingContextImpl::load_plugin (src/renderer.cu:441-460;
+ * src/renderers/hellopt_plugin.cpp:35-39). The argument is a pointer to a RenderingContext exposing
+ * `register_renderer(const char*, RendererFactoryFunction)` (src/renderer.h:220); the return value
+ * is the renderer id. Our own C++ host (fermat_b200/csrc/host/rendering_context.h) provides that
+ * class with the reference's method names. */
+uint32_t register_plugin(void* rendering_context);
+
+/* ---------------------------------------------------------------------------------------------
+ * 2. flat API
+ * ------------------------------------------------------------------------------------------- */
+
+typedef struct fb200_scene   fb200_scene;     /* host-side scene + sampler + VPLs + BVH (no GPU needed) */
+typedef struct fb200_context fb200_context;   /* RenderingContext + PathTracer bound to one CUDA device */
+
+/* PTOptions, src/renderers/pathtracer.h:169-250 (same fields, one uint32 each) */
+typedef struct fb200_pt_options
+{
+	uint32_t max_path_length;
+	uint32_t direct_lighting, direct_lighting_nee, direct_lighting_bsdf;
+	uint32_t indirect_lighting_nee, indirect_lighting_bsdf;
+	uint32_t visible_lights, diffuse_scattering, glossy_scattering, indirect_glossy, rr;
+	uint32_t nee_type;
+} fb200_pt_options;
+
+typedef struct fb200_texture_view { const float* texels; uint32_t res_x, res_y; } fb200_texture_view;
+
+/* A read-only view of everything the path tracer consumes, as host pointers.
+ * It is the host twin of RenderingContextView (src/renderer_view.h:80-131) restricted to the `-pt`
+ * path, and it is what the CPU oracle under oracle/ takes as input. */
+typedef struct fb200_scene_view
+{
+	/* MeshView, src/mesh/MeshView.h:96-145 */
+	uint32_t num_triangles, num_vertices, num_materials, num_textures;
+	const int32_t* vertex_indices;         /* int4 / triangle, .w = visibility flags          */
+	const float*   vertex_data;            /* float4 / vertex, .w = 10-10-10 packed normal    */
+	const int32_t* texture_indices_comp;   /* int4 / triangle (half2 uv bits, -1 none) or NULL */
+	const int32_t* material_indices;       /* int / triangle                                  */
+	const void*    materials;              /* MeshMaterial[num_materials], 208 B each         */
+	float          tex_bias[2], tex_scale[2];
+	const fb200_texture_view* textures;    /* LOD 0 of MipMapView[num_textures]               */
+	/* camera, src/camera.h:46-62, and frame size */
+	float    eye[3], aim[3], up[3], fov, aspect;
+	uint32_t res_x, res_y;
+	/* MeshLight, src/lights.h:299-515 */
+	uint32_t n_vpls;      const void*  vpls;        /* VPL[n_vpls], 16 B each {prim_id, u, v, E} */
+	float    vpl_norm;
+	uint32_t n_prims;     const float* mesh_cdf;    const float* mesh_inv_area;
+	uint32_t n_dir_lights; const float* dir_lights; /* {dir.xyz, color.xyz} each                 */
+	/* Bsdf albedo table, vs/fermat/glossy_reflectance.dat, src/bsdf.h:1253-1268 */
+	const float* glossy_reflectance;       /* 32^4 floats */
+	/* TiledSequenceView, src/tiled_sequence.h:53-111 */
+	uint32_t n_dimensions, tile_size;
+	const float* shifts;                   /* [dim][tile_size^2] */
+	/* scene BVH in CUGAR builder-output format, contrib/cugar/bvh/bvh_node.h:79-137 */
+	uint32_t n_bvh_nodes; const void* bvh_nodes; const uint32_t* bvh_index;
+	float    bbox_min[3], bbox_max[3];
+	fb200_pt_options options;
+} fb200_scene_view;
+
+typedef struct fb200_stats
+{
+	uint64_t shade_events;     /* sum of in-queue sizes, src/pathtracer_kernels.h:360 ("samples") */
+	uint64_t shadow_events;    /* shadow rays traced                                             */
+	uint64_t passes;
+	uint64_t kernel_launches;  /* launches of our kernels since the context was created          */
+	double   device_ms;        /* device time of all render() calls (CUDA events)                */
+} fb200_stats;
+
+/* last error message of the calling thread ("" if none). Errors never fall back to a CPU path. */
+const char* fb200_last_error(void);
+
+/* --- scene (host only) ---------------------------------------------------------------------- */
+
+/* Parses the same command line as RenderingContextImpl::init (src/renderer.cu:493-539: -i -r -a -c)
+ * and PTOptions::parse (src/renderers/pathtracer.h:202-249), plus:
+ *   -tables <file>   packed sampler/BSDF tables (default: fermat_b200/data/pt_tables.bin)
+ *   -shard r n       this process renders tile shard r of n (default 0 1)
+ * then loads the scene, builds sampler tables, VPLs (n_vpls = res_x*res_y) and the BVH.
+ * Returns NULL on failure (see fb200_last_error). */
+fb200_scene* fb200_scene_create(int argc, const char* const* argv);
+void         fb200_scene_destroy(fb200_scene*);
+int          fb200_scene_get_view(const fb200_scene*, fb200_scene_view* out);
+/* write / the pre-processed scene as a binary snapshot (.fbs) that fb200_scene_create can load with -i */
+int          fb200_scene_save_snapshot(const fb200_scene*, const char* filename);
+/* wide-BVH statistics: out[0]=#wide nodes, out[1]=#triangles, out[2]=max depth, out[3]=#bvh2 nodes */
+int          fb200_scene_bvh_stats(const fb200_scene*, uint64_t out[4], float* sah_cost);
+/* TiledSequenceView::sample_2d for pass `instance` (src/tiled_sequence.h:93-105) */
+float        fb200_scene_sample_2d(fb200_scene*, uint32_t instance, uint32_t px, uint32_t py, uint32_t dim);
+
+/* --- rendering context (needs a CUDA device; fails loudly without one) ------------------------ */
+
+/* RenderingContext::init + PathTracer::init (src/renderer.cu:467-991, src/renderers/pathtracer_impl.h:99-178)
+ * on CUDA device `device`. The scene stays owned by the caller and must outlive the context. */
+fb200_context* fb200_context_create(fb200_scene*, int device);
+void           fb200_context_destroy(fb200_context*);
+/* RenderingContext::clear (src/renderer.cu) — zero all frame-buffer channels */
+int fb200_context_clear(fb200_context*);
+/* RenderingContext::render(instance) -> RendererInterface::render (src/renderer.cu:1029-1056,
+ * src/renderers/pathtracer_impl.h:197-324): one progressive pass. Asynchronous on the context's
+ * stream unless `sync` is non-zero. */
+int fb200_context_render(fb200_context*, uint32_t instance, int sync);
+int fb200_context_synchronize(fb200_context*);
+/* res() (src/renderer.h) */
+int fb200_context_res(const fb200_context*, uint32_t* res_x, uint32_t* res_y);
+/* device pointer of frame-buffer channel `channel` (float4 per pixel, FBufferDesc order,
+ * src/renderer_view.h:133-145); the image a multi-GPU host reduces with NCCL */
+void* fb200_context_fb_device_ptr(fb200_context*, int channel);
+/* copy a channel to host memory: dst holds 4*res_x*res_y floats */
+int fb200_context_fb_download(fb200_context*, int channel, float* dst);
+/* copy a host image into a channel (used to seed accumulation tests) */
+int fb200_context_fb_upload(fb200_context*, int channel, const float* src);
+int fb200_context_get_stats(fb200_context*, fb200_stats* out);
+/* CUDA stream handle (cudaStream_t) the context launches on */
+void* fb200_context_stream(fb200_context*);
+/* number of pixels this shard owns */
+uint64_t fb200_context_owned_pixels(const fb200_context*);
+
+/* --- hot-path entry points on caller-provided HOST buffers (copies included) ------------------ */
+
+/* RTContext::trace (src/rt.cpp:558-583): closest hit. rays: n x {origin.xyz, tmin, dir.xyz, tmax};
+ * hits: n x {t, as_float(triId), u, v}; miss = {-1, -1, 0, 0}. u,v are rounded through fp16 as the
+ * reference's payload does (src/kernels/optix_payload.h:75-78). */
+int fb200_trace(fb200_context*, const float* rays, float* hits, uint32_t n);
+/* RTContext::trace_shadow (src/rt.cpp:610-635): any hit with triangle-flag masking.
+ * rays: n x {origin.xyz, as_float(mask), dir.xyz, tmax}; occluded[i] = 1 / 0 */
+int fb200_trace_shadow(fb200_context*, const float* rays, uint8_t* occluded, uint32_t n);
+/* same on device pointers, asynchronous on the context stream (kernel-only timing) */
+int fb200_trace_device(fb200_context*, const void* d_rays, void* d_hits, uint32_t n);
+int fb200_trace_shadow_device(fb200_context*, const void* d_rays, void* d_occluded, uint32_t n);
+
+/* Bsdf evaluation harness (device): for n records {tri_id, u, v, in.xyz, out.xyz, z[3]} builds the
+ * EyeVertex exactly like shade_vertex does (src/bpt_utils.h:585-642) and returns
+ *   f_and_p : 4 x rgb + 4 pdfs  (Bsdf::f_and_p, src/bsdf.h:366-412)           -> 16 floats
+ *   sample  : out.xyz, g.rgb, p, p_proj, component (Bsdf::sample, :921-1199)   ->  9 floats
+ * rec: n x 12 floats, out: n x 25 floats. Host buffers. */
+int fb200_bsdf_eval(fb200_context*, const float* rec, float* out, uint32_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FERMAT_B200_H */

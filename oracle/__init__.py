@@ -1,0 +1,126 @@
+"""CPU oracle of the `-pt` hot path — TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this package. It is the checker (and the reported CPU baseline), never the product: nothing under
+fermat_b200/ imports, links or executes anything from here.
+
+liboracle.so is built by `make -C oracle` from pt_oracle.cpp (our scalar restatement of the reference
+algorithm, each function citing the Fermat file:line it follows). oracle/_ref/libref_bsdf.so, when
+present, is the reference's own Bsdf compiled from /root/reference and pins the restatement.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liboracle.so")
+REF_LIB_PATH = os.path.join(_HERE, "_ref", "libref_bsdf.so")
+
+
+class OracleStats(C.Structure):
+    _fields_ = [("shade_events", C.c_uint64), ("shadow_events", C.c_uint64), ("nodes_visited", C.c_uint64),
+                ("tris_tested", C.c_uint64), ("per_bounce", C.c_uint64 * 64)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("%s missing: run `make -C oracle`" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        pf = C.POINTER(C.c_float)
+        L.oracle_render_pass.restype = C.c_int
+        L.oracle_render_pass.argtypes = [C.c_void_p, C.c_uint32, pf, C.POINTER(C.c_uint32), C.c_uint64, C.c_int, C.c_int, C.POINTER(OracleStats)]
+        L.oracle_trace.restype = C.c_int
+        L.oracle_trace.argtypes = [C.c_void_p, pf, pf, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.oracle_trace_shadow.restype = C.c_int
+        L.oracle_trace_shadow.argtypes = [C.c_void_p, pf, C.POINTER(C.c_uint8), C.c_uint32]
+        L.oracle_bsdf_eval.restype = C.c_int
+        L.oracle_bsdf_eval.argtypes = [C.c_void_p, pf, pf, C.c_uint32]
+        L.oracle_bsdf_raw.restype = C.c_int
+        L.oracle_bsdf_raw.argtypes = [pf, pf, pf, C.c_uint32]
+        L.oracle_num_threads.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _fptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def new_framebuffer(view):
+    """8 channels x H x W x float4, zero (RenderingContext::clear)."""
+    return np.zeros((8, int(view.res_y), int(view.res_x), 4), dtype=np.float32)
+
+
+def render_pass(view, instance, fb, pixels=None, threads=0, count_traversal=False):
+    """One progressive pass of the oracle into `fb` (in place). Returns an OracleStats."""
+    st = OracleStats()
+    if pixels is not None:
+        pixels = np.ascontiguousarray(pixels, dtype=np.uint32)
+        pp, n = pixels.ctypes.data_as(C.POINTER(C.c_uint32)), pixels.size
+    else:
+        pp, n = None, 0
+    rc = lib().oracle_render_pass(C.addressof(view), int(instance), _fptr(fb), pp, n, int(threads), 1 if count_traversal else 0, C.byref(st))
+    assert rc == 0
+    return st
+
+
+def trace(view, rays):
+    rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)
+    hits = np.empty((rays.shape[0], 4), dtype=np.float32)
+    nodes, tris = C.c_uint64(), C.c_uint64()
+    lib().oracle_trace(C.addressof(view), _fptr(rays), _fptr(hits), rays.shape[0], C.byref(nodes), C.byref(tris))
+    return hits, nodes.value, tris.value
+
+
+def trace_shadow(view, rays):
+    rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)
+    occ = np.empty(rays.shape[0], dtype=np.uint8)
+    lib().oracle_trace_shadow(C.addressof(view), _fptr(rays), occ.ctypes.data_as(C.POINTER(C.c_uint8)), rays.shape[0])
+    return occ
+
+
+def bsdf_eval(view, rec):
+    rec = np.ascontiguousarray(rec, dtype=np.float32).reshape(-1, 12)
+    out = np.empty((rec.shape[0], 25), dtype=np.float32)
+    lib().oracle_bsdf_eval(C.addressof(view), _fptr(rec), _fptr(out), rec.shape[0])
+    return out
+
+
+def bsdf_raw(table, rec):
+    table = np.ascontiguousarray(table, dtype=np.float32)
+    rec = np.ascontiguousarray(rec, dtype=np.float32).reshape(-1, 33)
+    out = np.empty((rec.shape[0], 25), dtype=np.float32)
+    lib().oracle_bsdf_raw(_fptr(table), _fptr(rec), _fptr(out), rec.shape[0])
+    return out
+
+
+def num_threads():
+    return lib().oracle_num_threads()
+
+
+def ref_lib():
+    """The reference's own Bsdf compiled verbatim (oracle/_ref), or None if it was not built."""
+    if not os.path.exists(REF_LIB_PATH):
+        return None
+    L = C.CDLL(REF_LIB_PATH)
+    pf = C.POINTER(C.c_float)
+    L.ref_bsdf_raw.restype = C.c_int
+    L.ref_bsdf_raw.argtypes = [pf, pf, pf, C.c_uint32]
+    return L
+
+
+def ref_bsdf_raw(table, rec):
+    L = ref_lib()
+    if L is None:
+        raise RuntimeError("oracle/_ref/libref_bsdf.so not built")
+    table = np.ascontiguousarray(table, dtype=np.float32)
+    rec = np.ascontiguousarray(rec, dtype=np.float32).reshape(-1, 33)
+    out = np.empty((rec.shape[0], 25), dtype=np.float32)
+    L.ref_bsdf_raw(_fptr(table), _fptr(rec), _fptr(out), rec.shape[0])
+    return out

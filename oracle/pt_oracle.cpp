@@ -1,0 +1,718 @@
+// pt_oracle.cpp — TEST INFRASTRUCTURE ONLY.
+//
+// Scalar CPU restatement of Fermat's `-pt` hot path: closest-hit / any-hit ray queries against the
+// scene BVH, vertex set-up, VPL next-event estimation, emissive hits with MIS, BSDF sampling with
+// implicit Russian roulette and frame-buffer accumulation. It is the checker for the CUDA path under
+// fermat_b200/ and the CPU baseline of bench.py; only tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / --impl reference legs may load it. The product never links or calls it.
+//
+// Follows (paths relative to the Fermat repository):
+//   src/pathtracer_kernels.h:309-391   path_trace_loop (wave order; here depth-first per pixel, which
+//                                      leaves every pixel's accumulation order unchanged)
+//   src/pathtracer_core.h:594-620      compute_per_bounce_options
+//   src/pathtracer_core.h:633-656      generate_primary_ray;  src/camera.h:142-163, 232-252
+//   src/pathtracer_core.h:771-1254     shade_vertex
+//   src/pathtracer_core.h:705-738      solve_occlusion -> src/pathtracer_vertex_processor.h:204-239
+//   src/pathtracer_vertex_processor.h:89-188   NEE / scattering weights, emissive accumulation
+//   src/bpt_utils.h:585-642            EyeVertex::setup;  src/mesh_utils.h:184-310 setup_differential_geometry
+//   src/mesh/MeshCompression.h:52-68   decompress_tex_coord;  contrib/cugar/linalg/vector_inl.h:389-421, 748-798
+//   src/texture_view.h:171-202         bilinear_texture_lookup
+//   src/lights.h:276-431               DirectionalLight / MeshLight sample + map
+//   src/tiled_sequence.h:93-105, src/tiled_sequence.cu:36-52,100-110   sampler
+//   src/framebuffer.h:425-444          add_in;  src/renderer.cu:292-362 multiply_frame / update_variances
+//   src/kernels/optix_rt.cu:46-82,134-164, optix_base_shaders.h:43-91, optix_base_shadow_shaders.h:43-72,
+//   optix_payload.h:75-78              ray query semantics (closest hit, masked any hit, fp16 barycentrics)
+// Ray/triangle and ray/box arithmetic itself lives in closed-source OptiX 6 in the reference; parity at
+// that boundary is geometric (see DESIGN.md "Oracle").
+#include "../include/fermat_b200.h"
+#include "oracle_bsdf.h"
+#include <vector>
+#include <algorithm>
+#include <stdio.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace oracle {
+
+struct MeshMaterialPOD      // 208 B, src/mesh/MeshView.h:55-91
+{
+	float diffuse[4], diffuse_trans[4], ambient[4], specular[4], emissive[4], reflectivity[4];
+	float roughness, ior, opacity; int flags;
+	struct TexRef { uint32_t texture, pad; float scaling[2]; } ambient_map, diffuse_map, diffuse_trans_map, specular_map, emissive_map, bump_map;
+};
+static_assert(sizeof(MeshMaterialPOD) == 208, "layout");
+struct VPLPOD { uint32_t prim_id; float u, v, E; };
+struct NodePOD { uint32_t packed, range; float lo[3], hi[3]; };
+
+struct Ray { vec3 o; float tmin; vec3 d; float tmax; uint32_t mask; };
+struct Hit { float t; int tri; float u, v; };
+
+struct TravStats { uint64_t nodes, tris; };
+
+// ---------------------------------------------------------------------------------------------
+// ray queries over the Bvh_node_3d tree
+// ---------------------------------------------------------------------------------------------
+static inline bool slab(const NodePOD& n, vec3 o, vec3 inv, float tmin, float tmax, float& tnear)
+{
+	float t0 = tmin, t1 = tmax;
+	for (int a = 0; a < 3; ++a)
+	{
+		float ta = (n.lo[a] - o[a]) * inv[a], tb = (n.hi[a] - o[a]) * inv[a];
+		if (ta > tb) std::swap(ta, tb);
+		// conservative: widen the far plane by 2 ulp-ish so that flat boxes and fp rounding never cull a true hit
+		tb *= 1.0000004f;
+		if (!(ta <= t1 && tb >= t0)) { if (ta == ta && tb == tb) return false; }   // NaN (0*inf) -> keep
+		if (ta > t0) t0 = ta;
+		if (tb < t1) t1 = tb;
+	}
+	tnear = t0;
+	return true;
+}
+
+// Moller-Trumbore without culling, plain (unfused) fp32 operations in this exact order — the CUDA
+// kernel performs the same sequence so that hits agree bit for bit.
+static inline bool intersect_tri(vec3 o, vec3 d, vec3 v0, vec3 v1, vec3 v2, float& t, float& bu, float& bv)
+{
+	const vec3 e1 = v1 - v0, e2 = v2 - v0;
+	const vec3 p = cross(d, e2);
+	const float det = dot(e1, p);
+	if (det == 0.0f) return false;
+	const float inv = 1.0f / det;
+	const vec3 tv = o - v0;
+	bu = dot(tv, p) * inv;
+	if (!(bu >= 0.0f && bu <= 1.0f)) return false;
+	const vec3 q = cross(tv, e1);
+	bv = dot(d, q) * inv;
+	if (!(bv >= 0.0f && bu + bv <= 1.0f)) return false;
+	t = dot(e2, q) * inv;
+	return true;
+}
+
+struct SceneRef
+{
+	const fb200_scene_view* s;
+	const int32_t* vi; const float* vd; const NodePOD* nodes;
+	vec3 vertex(int i) const { return vec3(vd[4 * i], vd[4 * i + 1], vd[4 * i + 2]); }
+};
+
+static Hit trace_closest(const SceneRef& sc, const Ray& ray, TravStats* st)
+{
+	Hit best = { -1.0f, -1, 0.0f, 0.0f };
+	if (sc.s->n_bvh_nodes == 0) return best;
+	float tmax = ray.tmax;
+	const vec3 inv(1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z);
+	uint32_t stack[128]; int sp = 0;
+	stack[sp++] = 0;
+	float bbu = 0, bbv = 0;
+	while (sp)
+	{
+		const uint32_t ni = stack[--sp];
+		const NodePOD& n = sc.nodes[ni];
+		float tn;
+		if (st) st->nodes++;
+		if (!slab(n, ray.o, inv, ray.tmin, tmax, tn)) continue;
+		if ((n.packed & 3u) == 0u)
+		{
+			const uint32_t begin = n.packed >> 2;
+			for (uint32_t k = 0; k < n.range; ++k)
+			{
+				const uint32_t tri = sc.s->bvh_index[begin + k];
+				if (st) st->tris++;
+				float t, bu, bv;
+				if (!intersect_tri(ray.o, ray.d, sc.vertex(sc.vi[4 * tri]), sc.vertex(sc.vi[4 * tri + 1]), sc.vertex(sc.vi[4 * tri + 2]), t, bu, bv)) continue;
+				// accept t in (tmin, tmax); ties on t go to the smaller triangle id, so the result is the
+				// lexicographic minimum of (t, triId) and does not depend on traversal order
+				if (t > ray.tmin && (t < tmax || (t == tmax && best.tri >= 0 && (int)tri < best.tri)))
+				{
+					tmax = t; best.t = t; best.tri = (int)tri; bbu = bu; bbv = bv;
+				}
+			}
+		}
+		else
+		{
+			const uint32_t c0 = n.packed >> 2, c1 = c0 + 1;
+			float t0, t1;
+			const bool h0 = slab(sc.nodes[c0], ray.o, inv, ray.tmin, tmax, t0);
+			const bool h1 = slab(sc.nodes[c1], ray.o, inv, ray.tmin, tmax, t1);
+			if (st) st->nodes += 0;   // child boxes are counted when popped
+			if (h0 && h1) { if (t0 <= t1) { stack[sp++] = c1; stack[sp++] = c0; } else { stack[sp++] = c0; stack[sp++] = c1; } }
+			else if (h0) stack[sp++] = c0;
+			else if (h1) stack[sp++] = c1;
+		}
+	}
+	if (best.tri >= 0)
+	{
+		// reference convention: u = weight of v0, v = weight of v1, both rounded through fp16
+		// (optix_base_shaders.h:50-57, optix_payload.h:75-78)
+		best.u = h2f(f2h(1.0f - bbu - bbv));
+		best.v = h2f(f2h(bbu));
+	}
+	return best;
+}
+
+static bool trace_any(const SceneRef& sc, const Ray& ray, TravStats* st)
+{
+	if (sc.s->n_bvh_nodes == 0) return false;
+	const vec3 inv(1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z);
+	uint32_t stack[128]; int sp = 0;
+	stack[sp++] = 0;
+	while (sp)
+	{
+		const NodePOD& n = sc.nodes[stack[--sp]];
+		float tn;
+		if (st) st->nodes++;
+		if (!slab(n, ray.o, inv, 0.0f, ray.tmax, tn)) continue;
+		if ((n.packed & 3u) == 0u)
+		{
+			const uint32_t begin = n.packed >> 2;
+			for (uint32_t k = 0; k < n.range; ++k)
+			{
+				const uint32_t tri = sc.s->bvh_index[begin + k];
+				if (st) st->tris++;
+				if (ray.mask & (uint32_t)sc.vi[4 * tri + 3]) continue;    // masked any-hit: ignore (optix_base_shadow_shaders.h:52-63)
+				float t, bu, bv;
+				if (intersect_tri(ray.o, ray.d, sc.vertex(sc.vi[4 * tri]), sc.vertex(sc.vi[4 * tri + 1]), sc.vertex(sc.vi[4 * tri + 2]), t, bu, bv) && t > 0.0f && t < ray.tmax)
+					return true;
+			}
+		}
+		else { const uint32_t c0 = n.packed >> 2; stack[sp++] = c0 + 1; stack[sp++] = c0; }
+	}
+	return false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// vertex set-up
+// ---------------------------------------------------------------------------------------------
+static inline vec3 orthogonal(vec3 v)
+{
+	if (v.x * v.x < v.y * v.y)
+	{
+		if (v.x * v.x < v.z * v.z) return vec3(0.0f, -v.z, v.y);
+		return vec3(-v.y, v.x, 0.0f);
+	}
+	if (v.y * v.y < v.z * v.z) return vec3(v.z, 0.0f, -v.x);
+	return vec3(-v.y, v.x, 0.0f);
+}
+static inline vec3 unpack_normal(uint32_t b)
+{
+	const vec3 u((float)(b & 0x3FFu) / 1023, (float)((b >> 10) & 0x3FFu) / 1023, (float)((b >> 20) & 0x3FFu) / 1023);
+	return u * 2.0f - vec3(1.0f);
+}
+
+static void setup_differential_geometry(const SceneRef& sc, uint32_t tri, float u, float v, Geom* g)
+{
+	const int i0 = sc.vi[4 * tri], i1 = sc.vi[4 * tri + 1], i2 = sc.vi[4 * tri + 2];
+	const vec3 p0 = sc.vertex(i0), p1 = sc.vertex(i1), p2 = sc.vertex(i2);
+	g->position = p2 * (1.0f - u - v) + p0 * u + p1 * v;
+	g->normal_g = normalize(cross(p0 - p2, p1 - p2));
+	const vec3 n0 = unpack_normal(f2u(sc.vd[4 * i0 + 3])), n1 = unpack_normal(f2u(sc.vd[4 * i1 + 3])), n2 = unpack_normal(f2u(sc.vd[4 * i2 + 3]));
+	const vec3 N = normalize(n2 * (1.0f - u - v) + n0 * u + n1 * v);
+	g->normal_s = N;
+	g->tangent = orthogonal(N);
+	g->binormal = cross(N, g->tangent);
+	if (sc.s->texture_indices_comp)
+	{
+		const int32_t* t = sc.s->texture_indices_comp + 4 * tri;
+		auto dec = [&](int32_t packed) {
+			const float tx = h2f((uint16_t)((uint32_t)packed & 0xFFFFu)), ty = h2f((uint16_t)((uint32_t)packed >> 16));
+			return vec2(tx * sc.s->tex_scale[0] + sc.s->tex_bias[0], ty * sc.s->tex_scale[1] + sc.s->tex_bias[1]); };
+		const vec2 t0 = t[0] >= 0 ? dec(t[0]) : vec2(1.0f, 0.0f);
+		const vec2 t1 = t[1] >= 0 ? dec(t[1]) : vec2(0.0f, 1.0f);
+		const vec2 t2 = t[2] >= 0 ? dec(t[2]) : vec2(0.0f, 0.0f);
+		const float w = 1.0f - u - v;
+		g->st[0] = t2.x * w + t0.x * u + t1.x * v;
+		g->st[1] = t2.y * w + t0.y * u + t1.y * v;
+	}
+	else { g->st[0] = u; g->st[1] = v; }
+}
+
+struct Tex4 { float x, y, z, w; };
+static Tex4 bilinear_texture_lookup(const fb200_scene_view* s, float sx, float sy, const MeshMaterialPOD::TexRef& ref)
+{
+	const Tex4 def = { 1.0f, 1.0f, 1.0f, 1.0f };
+	if (ref.texture == 0xFFFFFFFFu || ref.texture >= s->num_textures || s->textures[ref.texture].texels == NULL) return def;
+	const fb200_texture_view& tex = s->textures[ref.texture];
+	sx *= ref.scaling[0]; sy *= ref.scaling[1];
+	sx = mod1(sx, 1.0f); sy = mod1(sy, 1.0f);
+	const uint32_t x = std::min((uint32_t)(sx * tex.res_x), tex.res_x - 1), y = std::min((uint32_t)(sy * tex.res_y), tex.res_y - 1);
+	const uint32_t xx = (x + 1) % tex.res_x, yy = (y + 1) % tex.res_y;
+	const float* q0 = tex.texels + 4 * ((size_t)y * tex.res_x + x), *q1 = tex.texels + 4 * ((size_t)y * tex.res_x + xx);
+	const float* q2 = tex.texels + 4 * ((size_t)yy * tex.res_x + x), *q3 = tex.texels + 4 * ((size_t)yy * tex.res_x + xx);
+	const float u = mod1(sx * tex.res_x, 1.0f), v = mod1(sy * tex.res_y, 1.0f);
+	float r[4];
+	for (int c = 0; c < 4; ++c) r[c] = (q0[c] * (1 - u) + q1[c] * u) * (1 - v) + (q2[c] * (1 - u) + q3[c] * u) * v;
+	return Tex4{ r[0], r[1], r[2], r[3] };
+}
+
+static Material fetch_material(const SceneRef& sc, uint32_t tri, const Geom& g, bool all_maps)
+{
+	const MeshMaterialPOD& m = reinterpret_cast<const MeshMaterialPOD*>(sc.s->materials)[sc.s->material_indices[tri]];
+	Material r;
+	r.diffuse = vec3(m.diffuse[0], m.diffuse[1], m.diffuse[2]);
+	r.diffuse_trans = vec3(m.diffuse_trans[0], m.diffuse_trans[1], m.diffuse_trans[2]);
+	r.specular = vec3(m.specular[0], m.specular[1], m.specular[2]);
+	r.emissive = vec3(m.emissive[0], m.emissive[1], m.emissive[2]);
+	r.reflectivity = vec3(m.reflectivity[0], m.reflectivity[1], m.reflectivity[2]);
+	r.roughness = m.roughness; r.ior = m.ior; r.opacity = m.opacity;
+	if (all_maps)
+	{
+		const Tex4 d = bilinear_texture_lookup(sc.s, g.st[0], g.st[1], m.diffuse_map);        r.diffuse *= vec3(d.x, d.y, d.z);
+		const Tex4 s = bilinear_texture_lookup(sc.s, g.st[0], g.st[1], m.specular_map);       r.specular *= vec3(s.x, s.y, s.z);
+		const Tex4 e = bilinear_texture_lookup(sc.s, g.st[0], g.st[1], m.emissive_map);       r.emissive *= vec3(e.x, e.y, e.z);
+		const Tex4 t = bilinear_texture_lookup(sc.s, g.st[0], g.st[1], m.diffuse_trans_map);  r.diffuse_trans *= vec3(t.x, t.y, t.z);
+	}
+	else
+	{
+		const Tex4 e = bilinear_texture_lookup(sc.s, g.st[0], g.st[1], m.emissive_map);       r.emissive *= vec3(e.x, e.y, e.z);
+	}
+	return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sampler
+// ---------------------------------------------------------------------------------------------
+static inline float randfloat(uint32_t i, uint32_t p)
+{
+	i ^= p; i ^= i >> 17; i ^= i >> 10; i *= 0xb36534e5u; i ^= i >> 12; i ^= i >> 21; i *= 0x93fc4795u;
+	i ^= 0xdf6e307fu; i ^= i >> 17; i *= 1 | p >> 18;
+	return i * (1.0f / 4294967808.0f);
+}
+struct Sampler
+{
+	const fb200_scene_view* s; std::vector<float> seq;
+	Sampler(const fb200_scene_view* v, uint32_t instance) : s(v), seq(v->n_dimensions)
+	{
+		for (uint32_t d = 0; d < v->n_dimensions; ++d) seq[d] = randfloat(d, instance + 1);
+	}
+	float sample_2d(uint32_t px, uint32_t py, uint32_t dim) const
+	{
+		const uint32_t T = s->tile_size; const size_t S = (size_t)T * T;
+		const uint32_t shift = (px & (T - 1)) + (py & (T - 1)) * T;
+		const uint32_t tile = ((px / T) & (T - 1)) + ((py / T) & (T - 1)) * T;
+		const float sample = fmodf(seq[dim] + s->shifts[dim * S + shift], 1.0f);
+		return fmodf(sample + s->shifts[dim * S + tile], 1.0f);
+	}
+};
+
+// ---------------------------------------------------------------------------------------------
+// frame buffer
+// ---------------------------------------------------------------------------------------------
+enum { DIFFUSE_C = 0, DIFFUSE_A = 1, SPECULAR_C = 2, SPECULAR_A = 3, DIRECT_C = 4, COMPOSITED_C = 5, FILTERED_C = 6, LUMINANCE = 7 };
+
+struct FB
+{
+	float* data; size_t n_pixels;
+	float* px(int ch, uint32_t p) { return data + ((size_t)ch * n_pixels + p) * 4; }
+	// add_in<ALPHA_AS_VARIANCE> (src/framebuffer.h:425-444)
+	void add_in(bool var, int ch, uint32_t p, vec3 f, float inv_n)
+	{
+		float* m = px(ch, p);
+		const vec3 delta = f - vec3(m[0], m[1], m[2]);
+		m[0] += f.x * inv_n; m[1] += f.y * inv_n; m[2] += f.z * inv_n;
+		if (var) { const float ld = max_comp(delta); m[3] += ld * ld * inv_n; }
+	}
+};
+
+static inline float power_heuristic(float p1, float p2)
+{
+	const bool i1 = !std::isfinite(p1), i2 = !std::isfinite(p2);
+	return i1 ? 1.0f : i2 ? 0.0f : (p1 * p1) / (p1 * p1 + p2 * p2);
+}
+static inline float pdf_product(float p1, float p2) { return std::isfinite(p1) && std::isfinite(p2) ? p1 * p2 : INFINITY; }
+
+struct PassStats { uint64_t shade_events, shadow_events; TravStats trav; uint64_t per_bounce[64]; };
+
+// MeshLight::map_impl on a freshly set-up light vertex (src/lights.h:374-404)
+static void light_map(const SceneRef& sc, bool use_vpls, uint32_t prim, const Geom& lg, float* pdf, vec3* edf)
+{
+	const fb200_scene_view* s = sc.s;
+	const Material m = fetch_material(sc, prim, lg, false);
+	if (use_vpls) *pdf = fmaxf(fabsf(m.emissive.x), fmaxf(fabsf(m.emissive.y), fabsf(m.emissive.z))) / s->vpl_norm;
+	else *pdf = (s->mesh_cdf[prim] - (prim ? s->mesh_cdf[prim - 1] : 0)) * s->mesh_inv_area[prim];
+	*edf = m.emissive;
+}
+
+// one path, all bounces
+static void trace_path(const SceneRef& sc, const Sampler& smp, FB& fb, uint32_t px, uint32_t py, float frame_weight, vec3 U, vec3 V, vec3 W, PassStats& st, bool count_trav)
+{
+	const fb200_scene_view* s = sc.s;
+	const fb200_pt_options& o = s->options;
+	const uint32_t pixel = px + py * s->res_x;
+	// PathTracer::init falls back to the plain mesh sampler when there are no VPLs (pathtracer_impl.h:165-166);
+	// do_nee is gated on the VPL count whichever sampler is active (pathtracer_core.h:601-602)
+	const bool have_vpls = s->n_vpls > 0;
+	const bool use_vpls = o.nee_type == 1 && have_vpls;
+	const uint32_t n_vpls = use_vpls ? s->n_vpls : 0;
+
+	// primary ray (pathtracer_core.h:633-656)
+	Ray ray;
+	{
+		const float u = smp.sample_2d(px, py, 0), v = smp.sample_2d(px, py, 1);
+		const float dx = (px + u) / float(s->res_x) * 2.f - 1.f, dy = (py + v) / float(s->res_y) * 2.f - 1.f;
+		ray.o = vec3(s->eye[0], s->eye[1], s->eye[2]);
+		ray.d = dx * U + dy * V + W;
+		ray.tmin = 0.0f; ray.tmax = 1e34f; ray.mask = 0;
+	}
+	vec3 w(1.0f); float p_prev = 1.0f;
+	uint32_t comp = 0; bool diffuse_flag = false;
+	TravStats* ts = count_trav ? &st.trav : NULL;
+
+	for (uint32_t bounce = 0; bounce < o.max_path_length; ++bounce)
+	{
+		// compute_per_bounce_options
+		const bool do_nee = have_vpls && (bounce + 2 <= o.max_path_length) &&
+			((bounce == 0 && o.direct_lighting_nee && o.direct_lighting) || (bounce > 0 && o.indirect_lighting_nee));
+		const bool do_emissive = (bounce == 0 && o.visible_lights) || (bounce == 1 && o.direct_lighting_bsdf && o.direct_lighting) || (bounce > 1 && o.indirect_lighting_bsdf);
+		const uint32_t max_path_vertices = o.max_path_length + (((o.max_path_length == 2 && o.direct_lighting_bsdf) || (o.max_path_length > 2 && o.indirect_lighting_bsdf)) ? 1 : 0);
+		const bool do_scatter = bounce + 2 < max_path_vertices;
+
+		st.shade_events++; st.per_bounce[bounce < 64 ? bounce : 63]++;
+		const Hit hit = trace_closest(sc, ray, ts);
+		if (!(hit.t > 0.0f && hit.tri >= 0)) return;       // environment: nothing (pathtracer_core.h:1249-1252)
+
+		// EyeVertex::setup
+		Geom g;
+		setup_differential_geometry(sc, (uint32_t)hit.tri, hit.u, hit.v, &g);
+		g.position = ray.o + hit.t * ray.d;
+		const Material mat = fetch_material(sc, (uint32_t)hit.tri, g, true);
+		const vec3 in = -normalize(ray.d);
+		const Bsdf bsdf(mat, s->glossy_reflectance);
+
+		if (bounce == 0)
+		{
+			// albedo channels (G-buffer writes are not part of the radiance oracle)
+			float* da = fb.px(DIFFUSE_A, pixel); float* sa = fb.px(SPECULAR_A, pixel);
+			da[0] += mat.diffuse.x * frame_weight; da[1] += mat.diffuse.y * frame_weight; da[2] += mat.diffuse.z * frame_weight; da[3] += 0.0f * frame_weight;
+			sa[0] += (mat.specular.x + 1.0f) * 0.5f * frame_weight; sa[1] += (mat.specular.y + 1.0f) * 0.5f * frame_weight;
+			sa[2] += (mat.specular.z + 1.0f) * 0.5f * frame_weight; sa[3] += (0.0f + 1.0f) * 0.5f * frame_weight;
+		}
+
+		float z[6];
+		for (uint32_t i = 0; i < 6; ++i) z[i] = smp.sample_2d(px, py, (bounce + 1) * 6 + i);
+
+		struct Pending { bool on; Ray r; vec3 w_d, w_g; } pend[2];
+		pend[0].on = pend[1].on = false;
+
+		// directional lights (pathtracer_core.h:870-988)
+		if ((bounce + 2 <= o.max_path_length) && (bounce > 0 || o.direct_lighting) && s->n_dir_lights)
+		{
+			const uint32_t li = (uint32_t)std::max(std::min((int32_t)(z[2] * float(s->n_dir_lights)), (int32_t)(s->n_dir_lights - 1)), 0);
+			const vec3 ldir(s->dir_lights[6 * li], s->dir_lights[6 * li + 1], s->dir_lights[6 * li + 2]);
+			const vec3 lcol(s->dir_lights[6 * li + 3], s->dir_lights[6 * li + 4], s->dir_lights[6 * li + 5]);
+			const float FAR = 1.0e8f;
+			const vec3 lpos = g.position - ldir * FAR;
+			float light_pdf = 1.0f;
+			light_pdf /= s->n_dir_lights;
+			vec3 out = lpos - g.position;
+			const float d2 = fmaxf(1.0e-8f, square_length(out));
+			out *= 1.0f / sqrtf(d2);
+			vec3 f[4]; float p[4];
+			bsdf.f_and_p(g, in, out, f, p);
+			const vec3 edf = FAR * FAR * lcol;
+			const vec3 f_L = (dot(ldir, -out) > 0.0f ? edf : vec3(0.0f)) / light_pdf;
+			const float G = fabsf(dot(out, g.normal_s) * dot(out, ldir)) / d2;
+			const vec3 fd = o.diffuse_scattering ? f[kDR] + f[kDT] : vec3(0.0f), fg = o.glossy_scattering ? f[kGR] + f[kGT] : vec3(0.0f);
+			const vec3 fl = f_L * G * 1.0f;
+			const vec3 w_d = (bounce == 0 ? fd : fd + fg) * w * fl, w_g = (bounce == 0 ? fg : fd + fg) * w * fl;
+			const vec3 ow = w_d + w_g;
+			if (max_comp(ow) > 0.0f && finite3(ow))
+			{
+				pend[0].on = true;
+				pend[0].r.o = g.position - ray.d * 1.0e-3f;
+				pend[0].r.d = lpos - pend[0].r.o;
+				pend[0].r.mask = 0x1u; pend[0].r.tmax = 0.9999f; pend[0].r.tmin = 0.0f;
+				pend[0].w_d = w_d; pend[0].w_g = w_g;
+			}
+		}
+
+		// next-event estimation (pathtracer_core.h:991-1106)
+		if (do_nee)
+		{
+			uint32_t prim; float lu, lv;
+			if (n_vpls)
+			{
+				const uint32_t l = std::min((uint32_t)(z[2] * float(n_vpls)), n_vpls - 1);
+				const VPLPOD& vpl = reinterpret_cast<const VPLPOD*>(s->vpls)[l];
+				prim = vpl.prim_id; lu = vpl.u; lv = vpl.v;
+			}
+			else
+			{
+				const float one = u2f(0x3F7FFFFFu);
+				prim = (uint32_t)(std::upper_bound(s->mesh_cdf, s->mesh_cdf + s->n_prims, std::min(z[2], one)) - s->mesh_cdf);
+				lu = z[0]; lv = z[1];
+				if (lu + lv > 1.0f) { lu = 1.0f - lu; lv = 1.0f - lv; }
+			}
+			Geom lg;
+			setup_differential_geometry(sc, prim, lu, lv, &lg);
+			float light_pdf; vec3 edf;
+			light_map(sc, use_vpls, prim, lg, &light_pdf, &edf);
+
+			vec3 out = lg.position - g.position;
+			const float d2 = fmaxf(1.0e-8f, square_length(out));
+			out *= 1.0f / sqrtf(d2);
+			vec3 f[4]; float p[4];
+			bsdf.f_and_p(g, in, out, f, p);
+			vec3 f_s(0.0f); float p_s = 0.0f;
+			if (o.diffuse_scattering) { f_s += f[kDR] + f[kDT]; p_s += p[kDR] + p[kDT]; }
+			if (o.glossy_scattering) { f_s += f[kGR] + f[kGT]; p_s += p[kGR] + p[kGT]; }
+			const vec3 f_L = (dot(lg.normal_s, -out) > 0.0f ? edf : vec3(0.0f)) / light_pdf;
+			const float G = fabsf(dot(out, g.normal_s) * dot(out, lg.normal_s)) / d2;
+			const float p1 = light_pdf, p2 = p_s * G;
+			const float mis_w = ((bounce == 0 && o.direct_lighting_bsdf) || (bounce > 0 && o.indirect_lighting_bsdf)) ? power_heuristic(p1, p2) : 1.0f;
+			const vec3 fd = o.diffuse_scattering ? f[kDR] + f[kDT] : vec3(0.0f), fg = o.glossy_scattering ? f[kGR] + f[kGT] : vec3(0.0f);
+			const vec3 fl = f_L * G * mis_w;
+			const vec3 w_d = (bounce == 0 ? fd : fd + fg) * w * fl, w_g = (bounce == 0 ? fg : fd + fg) * w * fl;
+			const vec3 ow = w_d + w_g;
+			if (max_comp(ow) > 0.0f && finite3(ow))
+			{
+				pend[1].on = true;
+				pend[1].r.o = g.position - ray.d * 1.0e-4f;
+				pend[1].r.d = lg.position - pend[1].r.o;
+				pend[1].r.mask = 0x2u; pend[1].r.tmax = 0.9999f; pend[1].r.tmin = 0.0f;
+				pend[1].w_d = w_d; pend[1].w_g = w_g;
+			}
+		}
+
+		// emissive hit (pathtracer_core.h:1109-1154)
+		if (do_emissive)
+		{
+			float light_pdf; vec3 edf;
+			light_map(sc, use_vpls, (uint32_t)hit.tri, g, &light_pdf, &edf);
+			const vec3 f_L = dot(g.normal_s, in) > 0.0f ? edf : vec3(0.0f);
+			const float d2 = fmaxf(1.0e-10f, hit.t * hit.t);
+			const float G_partial = fabsf(dot(in, g.normal_s)) / d2;
+			const float p1 = pdf_product(G_partial, p_prev), p2 = light_pdf;
+			const float mis_w = ((bounce == 1 && o.direct_lighting_nee) || (bounce > 1 && o.indirect_lighting_nee)) ? power_heuristic(p1, p2) : 1.0f;
+			const vec3 ow = w * f_L * mis_w;
+			if (max_comp(ow) > 0.0f && finite3(ow))
+			{
+				fb.add_in(false, COMPOSITED_C, pixel, ow, frame_weight);
+				if (bounce == 0) fb.add_in(false, DIRECT_C, pixel, ow, frame_weight);
+				else
+				{
+					if (comp & cDiffuseMask) fb.add_in(true, DIFFUSE_C, pixel, ow, frame_weight);
+					if (comp & cGlossyMask)  fb.add_in(true, SPECULAR_C, pixel, ow, frame_weight);
+				}
+			}
+		}
+
+		// scattering (pathtracer_core.h:1157-1247)
+		bool cont = false;
+		Ray next; vec3 next_w(0.0f); float next_p = 0.0f; uint32_t next_comp = 0;
+		if (do_scatter)
+		{
+			// NOTE: component masks other than "all" are out of scope of the oracle
+			uint32_t out_comp; vec3 out, gg; float p, p_proj;
+			bsdf.sample(g, z + 3, in, out_comp, out, p, p_proj, gg);
+			const vec3 ow = gg * w;
+			if (out_comp != cAbsorption && p != 0.0f && max_comp(ow) > 0.0f && finite3(ow))
+			{
+				cont = true;
+				next.o = g.position; next.d = out; next.tmin = 1.0e-3f; next.tmax = 1.0e8f; next.mask = 0;
+				next_w = ow; next_p = p; next_comp = out_comp;
+			}
+		}
+
+		// solve_occlusion for this wave's shadow rays (dir-light first, then NEE: queue order)
+		for (int k = 0; k < 2; ++k)
+			if (pend[k].on)
+			{
+				st.shadow_events++;
+				const bool occluded = trace_any(sc, pend[k].r, ts);
+				if (!occluded)
+				{
+					fb.add_in(false, COMPOSITED_C, pixel, pend[k].w_d + pend[k].w_g, frame_weight);
+					if (bounce == 0)
+					{
+						fb.add_in(true, DIFFUSE_C, pixel, pend[k].w_d, frame_weight);
+						fb.add_in(true, SPECULAR_C, pixel, pend[k].w_g, frame_weight);
+					}
+					else
+					{
+						if (comp & cDiffuseMask) fb.add_in(true, DIFFUSE_C, pixel, pend[k].w_d, frame_weight);
+						if (comp & cGlossyMask)  fb.add_in(true, SPECULAR_C, pixel, pend[k].w_g, frame_weight);
+					}
+				}
+			}
+
+		if (!cont) return;
+		ray = next; w = next_w; p_prev = next_p;
+		diffuse_flag = diffuse_flag || (next_comp & cDiffuseMask);
+		comp = next_comp & 0xFu;      // PixelInfo::comp is a 4-bit field (pathtracer_core.h:527-542)
+		(void)diffuse_flag;
+	}
+}
+
+static void camera_frame(const fb200_scene_view* s, vec3& U, vec3& V, vec3& W)
+{
+	const vec3 eye(s->eye[0], s->eye[1], s->eye[2]), aim(s->aim[0], s->aim[1], s->aim[2]), up(s->up[0], s->up[1], s->up[2]);
+	W = aim - eye;
+	const float wlen = sqrtf(dot(W, W));
+	U = normalize(cross(W, up));
+	V = normalize(cross(U, W));
+	const float ulen = wlen * tanf(s->fov / 2.0f);
+	U = vec3(U.x * ulen, U.y * ulen, U.z * ulen);
+	const float vlen = ulen / s->aspect;
+	V = vec3(V.x * vlen, V.y * vlen, V.z * vlen);
+}
+
+} // namespace oracle
+
+using namespace oracle;
+
+extern "C" {
+
+struct oracle_stats { uint64_t shade_events, shadow_events, nodes_visited, tris_tested; uint64_t per_bounce[64]; };
+
+// One progressive pass over the pixels [pixel_begin, pixel_end) of the frame (row-major), or over the
+// explicit list `pixels` (n_pixels entries) when it is not NULL. fb: 8 channels x res_x*res_y x float4.
+// Runs rescale_frame (multiply_frame, src/renderer.cu:292-311,413-416) on the touched pixels first and
+// update_variances (:333-362) afterwards, as RenderingContext::render / PathTracer::render do.
+int oracle_render_pass(const fb200_scene_view* s, uint32_t instance, float* fbdata, const uint32_t* pixels, uint64_t n_pixels,
+					   int n_threads, int count_traversal, oracle_stats* out)
+{
+	SceneRef sc = { s, s->vertex_indices, s->vertex_data, reinterpret_cast<const NodePOD*>(s->bvh_nodes) };
+	const size_t P = (size_t)s->res_x * s->res_y;
+	if (!pixels) n_pixels = P;
+	FB fb = { fbdata, P };
+	Sampler smp(s, instance);
+	vec3 U, V, W; camera_frame(s, U, V, W);
+	const float scale = float(instance) / float(instance + 1), frame_weight = 1.0f / float(instance + 1);
+	const uint32_t n = instance + 1;
+#ifdef _OPENMP
+	if (n_threads > 0) omp_set_num_threads(n_threads);
+#endif
+	oracle_stats total; memset(&total, 0, sizeof(total));
+	#pragma omp parallel
+	{
+		PassStats st; memset(&st, 0, sizeof(st));
+		#pragma omp for schedule(dynamic, 256)
+		for (long long k = 0; k < (long long)n_pixels; ++k)
+		{
+			const uint32_t p = pixels ? pixels[k] : (uint32_t)k;
+			// multiply_frame_kernel
+			float* lum = fb.px(LUMINANCE, p);
+			lum[0] = max_comp(vec3(fb.px(DIRECT_C, p)[0], fb.px(DIRECT_C, p)[1], fb.px(DIRECT_C, p)[2]));
+			lum[1] = max_comp(vec3(fb.px(DIFFUSE_C, p)[0], fb.px(DIFFUSE_C, p)[1], fb.px(DIFFUSE_C, p)[2]));
+			lum[2] = max_comp(vec3(fb.px(SPECULAR_C, p)[0], fb.px(SPECULAR_C, p)[1], fb.px(SPECULAR_C, p)[2]));
+			lum[3] = max_comp(vec3(fb.px(COMPOSITED_C, p)[0], fb.px(COMPOSITED_C, p)[1], fb.px(COMPOSITED_C, p)[2]));
+			const int scaled[6] = { DIFFUSE_C, DIFFUSE_A, SPECULAR_C, SPECULAR_A, DIRECT_C, COMPOSITED_C };
+			for (int c = 0; c < 6; ++c) for (int i = 0; i < 4; ++i) fb.px(scaled[c], p)[i] *= scale;
+
+			trace_path(sc, smp, fb, p % s->res_x, p / s->res_x, frame_weight, U, V, W, st, count_traversal != 0);
+
+			// update_variances_kernel
+			const float nl[4] = {
+				max_comp(vec3(fb.px(DIRECT_C, p)[0], fb.px(DIRECT_C, p)[1], fb.px(DIRECT_C, p)[2])),
+				max_comp(vec3(fb.px(DIFFUSE_C, p)[0], fb.px(DIFFUSE_C, p)[1], fb.px(DIFFUSE_C, p)[2])),
+				max_comp(vec3(fb.px(SPECULAR_C, p)[0], fb.px(SPECULAR_C, p)[1], fb.px(SPECULAR_C, p)[2])),
+				max_comp(vec3(fb.px(COMPOSITED_C, p)[0], fb.px(COMPOSITED_C, p)[1], fb.px(COMPOSITED_C, p)[2])) };
+			const int vch[4] = { DIRECT_C, DIFFUSE_C, SPECULAR_C, COMPOSITED_C };
+			for (int c = 0; c < 4; ++c)
+			{
+				const float d1 = n * (nl[c] - lum[c]), d2 = (n - 1) * (nl[c] - lum[c]);
+				fb.px(vch[c], p)[3] += (d1 * d2) / (n * n);
+			}
+		}
+		#pragma omp critical
+		{
+			total.shade_events += st.shade_events; total.shadow_events += st.shadow_events;
+			total.nodes_visited += st.trav.nodes; total.tris_tested += st.trav.tris;
+			for (int b = 0; b < 64; ++b) total.per_bounce[b] += st.per_bounce[b];
+		}
+	}
+	if (out) *out = total;
+	return 0;
+}
+
+// closest hit for n rays {o.xyz, tmin, d.xyz, tmax} -> hits {t, as_float(tri), u, v}
+int oracle_trace(const fb200_scene_view* s, const float* rays, float* hits, uint32_t n, uint64_t* nodes, uint64_t* tris)
+{
+	SceneRef sc = { s, s->vertex_indices, s->vertex_data, reinterpret_cast<const NodePOD*>(s->bvh_nodes) };
+	uint64_t tn = 0, tt = 0;
+	#pragma omp parallel for schedule(dynamic, 1024) reduction(+:tn,tt)
+	for (long long i = 0; i < (long long)n; ++i)
+	{
+		Ray r; r.o = vec3(rays[8 * i], rays[8 * i + 1], rays[8 * i + 2]); r.tmin = rays[8 * i + 3];
+		r.d = vec3(rays[8 * i + 4], rays[8 * i + 5], rays[8 * i + 6]); r.tmax = rays[8 * i + 7]; r.mask = 0;
+		TravStats st = { 0, 0 };
+		const Hit h = trace_closest(sc, r, &st);
+		hits[4 * i] = h.t; hits[4 * i + 1] = u2f((uint32_t)h.tri); hits[4 * i + 2] = h.u; hits[4 * i + 3] = h.v;
+		tn += st.nodes; tt += st.tris;
+	}
+	if (nodes) *nodes = tn;
+	if (tris) *tris = tt;
+	return 0;
+}
+
+// any hit for n rays {o.xyz, as_float(mask), d.xyz, tmax} -> 1 occluded / 0
+int oracle_trace_shadow(const fb200_scene_view* s, const float* rays, uint8_t* occluded, uint32_t n)
+{
+	SceneRef sc = { s, s->vertex_indices, s->vertex_data, reinterpret_cast<const NodePOD*>(s->bvh_nodes) };
+	#pragma omp parallel for schedule(dynamic, 1024)
+	for (long long i = 0; i < (long long)n; ++i)
+	{
+		Ray r; r.o = vec3(rays[8 * i], rays[8 * i + 1], rays[8 * i + 2]); r.mask = f2u(rays[8 * i + 3]); r.tmin = 0.0f;
+		r.d = vec3(rays[8 * i + 4], rays[8 * i + 5], rays[8 * i + 6]); r.tmax = rays[8 * i + 7];
+		occluded[i] = trace_any(sc, r, NULL) ? 1 : 0;
+	}
+	return 0;
+}
+
+// Bsdf harness, same record layout as fb200_bsdf_eval: rec = {tri_id(as float bits), u, v, in.xyz, out.xyz, z0,z1,z2}
+// out = f[4] rgb (12), p[4], sample: out.xyz, g.rgb, p, p_proj, comp(as float value)
+int oracle_bsdf_eval(const fb200_scene_view* s, const float* rec, float* out, uint32_t n)
+{
+	SceneRef sc = { s, s->vertex_indices, s->vertex_data, reinterpret_cast<const NodePOD*>(s->bvh_nodes) };
+	for (uint32_t i = 0; i < n; ++i)
+	{
+		const float* r = rec + 12 * i; float* o = out + 25 * i;
+		const uint32_t tri = f2u(r[0]);
+		Geom g; setup_differential_geometry(sc, tri, r[1], r[2], &g);
+		const Material mat = fetch_material(sc, tri, g, true);
+		const Bsdf bsdf(mat, s->glossy_reflectance);
+		const vec3 in(r[3], r[4], r[5]), outd(r[6], r[7], r[8]);
+		vec3 f[4]; float p[4];
+		bsdf.f_and_p(g, in, outd, f, p);
+		for (int c = 0; c < 4; ++c) { o[3 * c] = f[c].x; o[3 * c + 1] = f[c].y; o[3 * c + 2] = f[c].z; o[12 + c] = p[c]; }
+		uint32_t comp; vec3 so, sg; float sp, spp;
+		bsdf.sample(g, r + 9, in, comp, so, sp, spp, sg);
+		o[16] = so.x; o[17] = so.y; o[18] = so.z; o[19] = sg.x; o[20] = sg.y; o[21] = sg.z; o[22] = sp; o[23] = spp; o[24] = (float)comp;
+	}
+	return 0;
+}
+
+// raw Bsdf harness on explicit geometry + material (used to pin this restatement against oracle/_ref):
+// rec = {N.xyz, T.xyz, B.xyz, in.xyz, out.xyz, z0..2, Kd.rgb, Td.rgb, Ks.rgb, Kr.rgb, roughness, ior, opacity} = 33 floats
+int oracle_bsdf_raw(const float* table, const float* rec, float* out, uint32_t n)
+{
+	for (uint32_t i = 0; i < n; ++i)
+	{
+		const float* r = rec + 33 * i; float* o = out + 25 * i;
+		Geom g; g.normal_s = g.normal_g = vec3(r[0], r[1], r[2]); g.tangent = vec3(r[3], r[4], r[5]); g.binormal = vec3(r[6], r[7], r[8]);
+		g.position = vec3(0.0f); g.st[0] = g.st[1] = 0.0f;
+		Material m; m.diffuse = vec3(r[18], r[19], r[20]); m.diffuse_trans = vec3(r[21], r[22], r[23]); m.specular = vec3(r[24], r[25], r[26]);
+		m.reflectivity = vec3(r[27], r[28], r[29]); m.emissive = vec3(0.0f); m.roughness = r[30]; m.ior = r[31]; m.opacity = r[32];
+		const Bsdf bsdf(m, table);
+		const vec3 in(r[9], r[10], r[11]), outd(r[12], r[13], r[14]);
+		vec3 f[4]; float p[4];
+		bsdf.f_and_p(g, in, outd, f, p);
+		for (int c = 0; c < 4; ++c) { o[3 * c] = f[c].x; o[3 * c + 1] = f[c].y; o[3 * c + 2] = f[c].z; o[12 + c] = p[c]; }
+		uint32_t comp; vec3 so, sg; float sp, spp;
+		bsdf.sample(g, r + 15, in, comp, so, sp, spp, sg);
+		o[16] = so.x; o[17] = so.y; o[18] = so.z; o[19] = sg.x; o[20] = sg.y; o[21] = sg.z; o[22] = sp; o[23] = spp; o[24] = (float)comp;
+	}
+	return 0;
+}
+
+int oracle_num_threads(void)
+{
+#ifdef _OPENMP
+	return omp_get_max_threads();
+#else
+	return 1;
+#endif
+}
+
+} // extern "C"
