@@ -1,0 +1,167 @@
+// capi_context.cpp — device half of the C ABI declared in include/fermat_b200.h
+#include "rendering_context.h"
+#include <string.h>
+
+namespace fb { void set_last_error(const std::string& e); }
+
+struct fb200_context
+{
+	RenderingContext rc;
+	fb::DeviceBuffer cursor;      // work cursor of the stand-alone ray queries
+};
+
+namespace {
+PathTracer* pt_of(fb200_context* c) { return static_cast<PathTracer*>(c->rc.renderer()); }
+
+template <typename F> int guarded(F f)
+{
+	try { f(); fb::set_last_error(""); return 0; }
+	catch (const std::exception& e) { fb::set_last_error(e.what()); return -1; }
+}
+}
+
+extern "C" {
+
+fb200_context* fb200_context_create(fb200_scene* scene, int device)
+{
+	if (!scene) { fb::set_last_error("null scene"); return NULL; }
+	fb200_context* c = NULL;
+	try
+	{
+		c = new fb200_context();
+		char arg0[] = "-pt";
+		char* argv[] = { arg0 };
+		c->rc.init_with_scene(scene, device, 1, argv);
+		c->cursor.alloc(sizeof(uint32_t));
+		fb::set_last_error("");
+		return c;
+	}
+	catch (const std::exception& e)
+	{
+		fb::set_last_error(e.what());
+		delete c;
+		return NULL;
+	}
+}
+
+void fb200_context_destroy(fb200_context* c) { delete c; }
+
+int fb200_context_clear(fb200_context* c) { return guarded([&] { c->rc.clear(); }); }
+
+int fb200_context_render(fb200_context* c, uint32_t instance, int sync)
+{
+	return guarded([&] { c->rc.render(instance); if (sync) c->rc.synchronize(); });
+}
+
+int fb200_context_synchronize(fb200_context* c) { return guarded([&] { c->rc.synchronize(); }); }
+
+int fb200_context_res(const fb200_context* c, uint32_t* rx, uint32_t* ry)
+{
+	const uint2 r = c->rc.res();
+	if (rx) *rx = r.x;
+	if (ry) *ry = r.y;
+	return 0;
+}
+
+void* fb200_context_fb_device_ptr(fb200_context* c, int channel)
+{
+	if (channel < 0 || channel >= fb::FB_NUM_CHANNELS) { fb::set_last_error("bad channel"); return NULL; }
+	return c->rc.get_frame_buffer().channels[channel].ptr;
+}
+
+int fb200_context_fb_download(fb200_context* c, int channel, float* dst)
+{
+	return guarded([&] {
+		if (channel < 0 || channel >= fb::FB_NUM_CHANNELS) throw std::runtime_error("bad channel");
+		fb::DeviceBuffer& b = c->rc.get_frame_buffer().channels[channel];
+		fb::cuda_check(cudaMemcpyAsync(dst, b.ptr, b.bytes, cudaMemcpyDeviceToHost, c->rc.stream()), "fb download");
+		c->rc.synchronize();
+	});
+}
+
+int fb200_context_fb_upload(fb200_context* c, int channel, const float* src)
+{
+	return guarded([&] {
+		if (channel < 0 || channel >= fb::FB_NUM_CHANNELS) throw std::runtime_error("bad channel");
+		fb::DeviceBuffer& b = c->rc.get_frame_buffer().channels[channel];
+		fb::cuda_check(cudaMemcpyAsync(b.ptr, src, b.bytes, cudaMemcpyHostToDevice, c->rc.stream()), "fb upload");
+		c->rc.synchronize();
+	});
+}
+
+int fb200_context_get_stats(fb200_context* c, fb200_stats* out)
+{
+	return guarded([&] {
+		const fb::PassTotals t = pt_of(c)->totals(c->rc);
+		out->shade_events = t.shade_events; out->shadow_events = t.shadow_events;
+		out->passes = pt_of(c)->passes(); out->kernel_launches = c->rc.kernel_launches; out->device_ms = pt_of(c)->device_ms();
+	});
+}
+
+void* fb200_context_stream(fb200_context* c) { return (void*)c->rc.stream(); }
+uint64_t fb200_context_owned_pixels(const fb200_context* c) { return static_cast<PathTracer*>(const_cast<fb200_context*>(c)->rc.renderer())->owned_pixels(); }
+
+int fb200_trace_device(fb200_context* c, const void* d_rays, void* d_hits, uint32_t n)
+{
+	return guarded([&] {
+		fb::cuda_check(cudaMemsetAsync(c->cursor.ptr, 0, sizeof(uint32_t), c->rc.stream()), "memset");
+		fb::cuda_check(fb::launch_trace_rays(c->rc.device_scene(), c->rc.launch_config(), (const float4*)d_rays, (float4*)d_hits, n, c->cursor.as<uint32_t>(), c->rc.stream()), "trace");
+		c->rc.kernel_launches++;
+	});
+}
+
+int fb200_trace_shadow_device(fb200_context* c, const void* d_rays, void* d_occ, uint32_t n)
+{
+	return guarded([&] {
+		fb::cuda_check(cudaMemsetAsync(c->cursor.ptr, 0, sizeof(uint32_t), c->rc.stream()), "memset");
+		fb::cuda_check(fb::launch_trace_shadow_rays(c->rc.device_scene(), c->rc.launch_config(), (const float4*)d_rays, (unsigned char*)d_occ, n, c->cursor.as<uint32_t>(), c->rc.stream()), "trace_shadow");
+		c->rc.kernel_launches++;
+	});
+}
+
+int fb200_trace(fb200_context* c, const float* rays, float* hits, uint32_t n)
+{
+	return guarded([&] {
+		fb::DeviceBuffer dr, dh;
+		dr.upload(rays, (size_t)n * 32, c->rc.stream());
+		dh.alloc((size_t)n * 16);
+		if (fb200_trace_device(c, dr.ptr, dh.ptr, n) != 0) throw std::runtime_error(fb200_last_error());
+		fb::cuda_check(cudaMemcpyAsync(hits, dh.ptr, (size_t)n * 16, cudaMemcpyDeviceToHost, c->rc.stream()), "D2H");
+		c->rc.synchronize();
+	});
+}
+
+int fb200_trace_shadow(fb200_context* c, const float* rays, uint8_t* occluded, uint32_t n)
+{
+	return guarded([&] {
+		fb::DeviceBuffer dr, dh;
+		dr.upload(rays, (size_t)n * 32, c->rc.stream());
+		dh.alloc((size_t)n);
+		if (fb200_trace_shadow_device(c, dr.ptr, dh.ptr, n) != 0) throw std::runtime_error(fb200_last_error());
+		fb::cuda_check(cudaMemcpyAsync(occluded, dh.ptr, (size_t)n, cudaMemcpyDeviceToHost, c->rc.stream()), "D2H");
+		c->rc.synchronize();
+	});
+}
+
+int fb200_bsdf_eval(fb200_context* c, const float* rec, float* out, uint32_t n)
+{
+	return guarded([&] {
+		fb::DeviceBuffer dr, dout;
+		dr.upload(rec, (size_t)n * 12 * 4, c->rc.stream());
+		dout.alloc((size_t)n * 25 * 4);
+		fb::cuda_check(fb::launch_bsdf_eval(c->rc.device_scene(), dr.as<float>(), dout.as<float>(), n, c->rc.stream()), "bsdf_eval");
+		c->rc.kernel_launches++;
+		fb::cuda_check(cudaMemcpyAsync(out, dout.ptr, (size_t)n * 25 * 4, cudaMemcpyDeviceToHost, c->rc.stream()), "D2H");
+		c->rc.synchronize();
+	});
+}
+
+// the plugin entry point Fermat's loader resolves (src/renderer.cu:441-460): registers the renderer under
+// the name "pt" and returns its id. `rendering_context` points to a RenderingContext.
+uint32_t register_plugin(void* rendering_context)
+{
+	RenderingContext* rc = static_cast<RenderingContext*>(rendering_context);
+	return rc->register_renderer("pt", &PathTracer::factory);
+}
+
+} // extern "C"

@@ -1,0 +1,173 @@
+// pathtracer.cpp — host driver of the `-pt` renderer: PathTracer::init / PathTracer::render
+// (reference src/renderers/pathtracer_impl.h:99-178, 197-324) and the wavefront loop path_trace_loop
+// (src/pathtracer_kernels.h:309-391), restated for a device-resident schedule: the whole pass is enqueued
+// on one stream, queue sizes stay on the device, nothing is read back.
+#include "rendering_context.h"
+#include <string.h>
+
+using namespace fb;
+
+PathTracer::PathTracer() : m_n_tiles(0), m_tiles_x(0), m_owned_pixels(0), m_capacity(0), m_passes(0), m_device_ms(0.0), m_events(false)
+{
+	pt_options_defaults(m_options);
+	memset(m_queue, 0, sizeof(m_queue));
+	memset(&m_shadow, 0, sizeof(m_shadow));
+}
+
+namespace {
+// bump allocator over the queue arena, every array aligned to 256 B (cf. cugar::memory_arena,
+// contrib/cugar/basic/memory_arena.h:44-76)
+struct Arena
+{
+	char* base; size_t size;
+	Arena(void* b) : base((char*)b), size(0) {}
+	template <typename T> T* alloc(size_t n)
+	{
+		size = (size + 255) & ~size_t(255);
+		T* p = base ? reinterpret_cast<T*>(base + size) : NULL;
+		size += n * sizeof(T);
+		return p;
+	}
+};
+void carve(Arena& a, size_t cap, size_t shadow_cap, PathQueue q[2], ShadowQueue& sq)
+{
+	for (int i = 0; i < 2; ++i)
+	{
+		q[i].ray_o = a.alloc<float4>(cap); q[i].ray_d = a.alloc<float4>(cap); q[i].hit = a.alloc<float4>(cap);
+		q[i].weight = a.alloc<float4>(cap); q[i].pixel = a.alloc<uint32>(cap);
+	}
+	sq.ray_o = a.alloc<float4>(shadow_cap); sq.ray_d = a.alloc<float4>(shadow_cap);
+	sq.w_d = a.alloc<float4>(shadow_cap); sq.w_g = a.alloc<float4>(shadow_cap);
+}
+}
+
+void PathTracer::init(int argc, char** argv, RenderingContext& renderer)
+{
+	fb200_scene& s = *renderer.scene();
+	// the options were parsed together with the scene (they size the sampler); parse again here as the
+	// reference does (pathtracer_impl.h:105) so that a renderer created on its own behaves the same
+	m_options = s.options;
+	const uint2 res = renderer.res();
+
+	fprintf(stderr, "  PT settings:\n    path-length     : %u\n    nee algorithm   : %s\n", m_options.max_path_length, m_options.nee_type == 1 ? "vpl" : "mesh");
+
+	// tile shard of this process: tile T = ty*tiles_x + tx belongs to rank (T + ty) % shard_count
+	const uint32 TILE = 32;
+	m_tiles_x = (res.x + TILE - 1) / TILE;
+	const uint32 tiles_y = (res.y + TILE - 1) / TILE;
+	std::vector<uint32> tiles;
+	m_owned_pixels = 0;
+	for (uint32 ty = 0; ty < tiles_y; ++ty)
+		for (uint32 tx = 0; tx < m_tiles_x; ++tx)
+		{
+			const uint32 T = ty * m_tiles_x + tx;
+			if ((T + ty) % s.shard_count != s.shard_rank) continue;
+			tiles.push_back(T);
+			const uint32 w = (tx + 1) * TILE <= res.x ? TILE : res.x - tx * TILE, h = (ty + 1) * TILE <= res.y ? TILE : res.y - ty * TILE;
+			m_owned_pixels += (uint64_t)w * h;
+		}
+	m_n_tiles = (uint32)tiles.size();
+	m_tile_list.upload(tiles.data(), tiles.size() * sizeof(uint32), renderer.stream());
+
+	// queue arena: dry run for the size, then one allocation (pathtracer_impl.h:124-145)
+	m_capacity = m_owned_pixels;
+	const size_t shadow_cap = s.scene.dir_lights.empty() ? m_capacity : 2 * m_capacity;
+	{
+		Arena dry(NULL);
+		PathQueue q[2]; ShadowQueue sq;
+		carve(dry, m_capacity, shadow_cap, q, sq);
+		fprintf(stderr, "  allocating queue storage: %.1f MB\n", float(dry.size) / (1024 * 1024));
+		m_memory_pool.alloc(dry.size + 256);
+	}
+	Arena arena(m_memory_pool.ptr);
+	carve(arena, m_capacity, shadow_cap, m_queue, m_shadow);
+
+	m_counters.alloc(sizeof(PassCounters));
+	m_totals.alloc(sizeof(PassTotals));
+	cuda_check(cudaMemsetAsync(m_totals.ptr, 0, sizeof(PassTotals), renderer.stream()), "memset totals");
+	cuda_check(cudaEventCreate(&m_ev0), "event"); cuda_check(cudaEventCreate(&m_ev1), "event");
+}
+
+void PathTracer::render(const uint32_t instance, RenderingContext& renderer)
+{
+	fb200_scene& s = *renderer.scene();
+	const DeviceScene& sc = renderer.device_scene();
+	const LaunchConfig& lc = renderer.launch_config();
+	cudaStream_t stream = renderer.stream();
+
+	if (!m_events) { cuda_check(cudaEventRecord(m_ev0, stream), "event record"); m_events = true; }
+
+	// pre-multiply the previous frame for blending (pathtracer_impl.h:201)
+	renderer.rescale_frame(instance);
+
+	// per-pass sampler offsets (TiledSequence::set_instance, src/tiled_sequence.cu:100-110)
+	s.sequence.set_instance(instance);
+	s.sequence_instance = instance;
+	const std::vector<float>& seq = s.sequence.sequence;
+
+	PassParams pp;
+	memset(&pp, 0, sizeof(pp));
+	pp.instance = instance;
+	pp.frame_weight = 1.0f / float(instance + 1);
+	{
+		// camera_frame (src/camera.h:142-163)
+		const Camera& c = renderer.get_camera();
+		V3 W = V3(c.aim) - V3(c.eye);
+		const float wlen = sqrtf(dot(W, W));
+		V3 U = normalize(cross(W, V3(c.up)));
+		V3 V = normalize(cross(U, W));
+		const float ulen = wlen * tanf(c.fov / 2.0f);
+		U = V3(U.x * ulen, U.y * ulen, U.z * ulen);
+		const float vlen = ulen / renderer.get_aspect_ratio();
+		V = V3(V.x * vlen, V.y * vlen, V.z * vlen);
+		pp.U[0] = U.x; pp.U[1] = U.y; pp.U[2] = U.z; pp.V[0] = V.x; pp.V[1] = V.y; pp.V[2] = V.z; pp.W[0] = W.x; pp.W[1] = W.y; pp.W[2] = W.z;
+		pp.eye[0] = c.eye.x; pp.eye[1] = c.eye.y; pp.eye[2] = c.eye.z;
+	}
+	pp.tile_list = m_tile_list.as<uint32>(); pp.n_tiles = m_n_tiles; pp.tiles_x = m_tiles_x;
+
+	PassCounters* ctr = m_counters.as<PassCounters>();
+	PassTotals* tot = m_totals.as<PassTotals>();
+	cuda_check(cudaMemsetAsync(ctr, 0, sizeof(PassCounters), stream), "memset counters");
+
+	const FrameBufferView fbv = renderer.get_frame_buffer().view();
+	const float seq2[2] = { seq[0], seq[1] };
+	cuda_check(launch_generate_primary(sc, pp, m_queue[0], ctr, seq2, stream), "generate_primary");
+	renderer.kernel_launches++;
+
+	// path_trace_loop: trace -> shade -> shadow trace + solve_occlusion, per bounce; no host round trips
+	for (uint32 bounce = 0; bounce < m_options.max_path_length; ++bounce)
+	{
+		const PathQueue& in = m_queue[bounce & 1];
+		const PathQueue& out = m_queue[(bounce + 1) & 1];
+		cuda_check(launch_trace_closest(sc, lc, in, ctr, bounce, stream), "trace");
+		float seq6[6];
+		for (int i = 0; i < 6; ++i) seq6[i] = seq[(bounce + 1) * 6 + i];
+		cuda_check(launch_shade(sc, lc, pp, in, out, m_shadow, fbv, ctr, tot, bounce, seq6, (uint32)m_capacity, stream), "shade");
+		cuda_check(launch_trace_shadow(sc, lc, m_shadow, fbv, ctr, tot, bounce, pp.frame_weight, stream), "trace_shadow");
+		renderer.kernel_launches += 3;
+	}
+
+	renderer.update_variances(instance);
+	cuda_check(cudaEventRecord(m_ev1, stream), "event record");
+	m_passes++;
+}
+
+PassTotals PathTracer::totals(RenderingContext& renderer)
+{
+	PassTotals t;
+	cuda_check(cudaMemcpyAsync(&t, m_totals.ptr, sizeof(t), cudaMemcpyDeviceToHost, renderer.stream()), "read totals");
+	renderer.synchronize();
+	if (m_events)
+	{
+		float ms = 0.0f;
+		if (cudaEventElapsedTime(&ms, m_ev0, m_ev1) == cudaSuccess) m_device_ms += ms;
+		m_events = false;
+	}
+	return t;
+}
+
+void PathTracer::dump_speed_stats(FILE* stats)
+{
+	// the reference writes per-stage running means (pathtracer_impl.h:342-350); we report pass totals
+	fprintf(stats, "%f, %llu\n", m_device_ms, (unsigned long long)m_passes);
+}

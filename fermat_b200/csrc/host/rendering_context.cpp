@@ -1,0 +1,192 @@
+// rendering_context.cpp — see rendering_context.h
+#include "rendering_context.h"
+#include <string.h>
+
+namespace fb {
+
+void cuda_check(cudaError_t e, const char* what)
+{
+	if (e != cudaSuccess)
+		throw cuda_error(std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+void DeviceBuffer::alloc(size_t n)
+{
+	release();
+	if (n == 0) return;
+	cuda_check(cudaMalloc(&ptr, n), "cudaMalloc");
+	bytes = n;
+}
+void DeviceBuffer::release()
+{
+	if (ptr) cudaFree(ptr);
+	ptr = NULL; bytes = 0;
+}
+void DeviceBuffer::upload(const void* src, size_t n, cudaStream_t s)
+{
+	alloc(n);
+	if (n) cuda_check(cudaMemcpyAsync(ptr, src, n, cudaMemcpyHostToDevice, s), "cudaMemcpy H2D");
+}
+
+} // namespace fb
+
+using namespace fb;
+
+void FBufferStorage::resize(uint32_t rx, uint32_t ry)
+{
+	res_x = rx; res_y = ry;
+	for (int c = 0; c < FB_NUM_CHANNELS; ++c) channels[c].alloc((size_t)rx * ry * sizeof(float4));
+}
+void FBufferStorage::clear(cudaStream_t s)
+{
+	for (int c = 0; c < FB_NUM_CHANNELS; ++c)
+		cuda_check(cudaMemsetAsync(channels[c].ptr, 0, channels[c].bytes, s), "cudaMemset fb");
+}
+FrameBufferView FBufferStorage::view() const
+{
+	FrameBufferView v;
+	for (int c = 0; c < FB_NUM_CHANNELS; ++c) v.channels[c] = channels[c].as<float4>();
+	v.n_pixels = res_x * res_y;
+	return v;
+}
+
+RenderingContext::RenderingContext() : kernel_launches(0), m_scene(NULL), m_owns_scene(false), m_device(0), m_stream(0), m_renderer(NULL)
+{
+	memset(&m_dscene, 0, sizeof(m_dscene));
+	memset(&m_lc, 0, sizeof(m_lc));
+	// built-in renderers (the reference registers its own list here, src/renderer.cu:471-477)
+	register_renderer("pt", &PathTracer::factory);
+}
+
+RenderingContext::~RenderingContext()
+{
+	if (m_renderer) m_renderer->destroy();
+	for (size_t i = 0; i < d_textures.size(); ++i) delete d_textures[i];
+	if (m_stream) cudaStreamDestroy(m_stream);
+	if (m_owns_scene) delete m_scene;
+}
+
+uint32_t RenderingContext::register_renderer(const char* name, RendererFactoryFunction factory)
+{
+	m_renderer_names.push_back(name);
+	m_renderer_factories.push_back(factory);
+	return uint32_t(m_renderer_factories.size() - 1);
+}
+
+void RenderingContext::init(int argc, char** argv)
+{
+	fb200_scene* s = new fb200_scene();
+	try { scene_init(*s, argc, argv); }
+	catch (...) { delete s; throw; }
+	int device = 0;
+	for (int i = 0; i + 1 < argc; ++i) if (strcmp(argv[i], "-device") == 0) device = atoi(argv[i + 1]);
+	m_owns_scene = true;
+	init_with_scene(s, device, argc, argv);
+}
+
+void RenderingContext::init_with_scene(fb200_scene* scene, int device, int argc, char** argv)
+{
+	m_scene = scene;
+	m_device = device;
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count == 0)
+		throw cuda_error(std::string("no CUDA device available (") + cudaGetErrorString(e) + "): the -pt renderer has no CPU fallback");
+	if (device < 0 || device >= count) throw cuda_error("invalid CUDA device index");
+	cuda_check(cudaSetDevice(device), "cudaSetDevice");
+	cuda_check(cudaStreamCreateWithFlags(&m_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+	cuda_check(configure_kernels(m_lc, device), "configure_kernels");
+
+	m_fb.resize(scene->res_x, scene->res_y);
+	m_fb.clear(m_stream);
+	upload_scene();
+
+	// pick the renderer: the last `-<name>` matching a registered renderer wins (src/renderer.cu:528-538); default pt
+	uint32_t type = 0;
+	for (int i = 0; i < argc; ++i)
+		if (argv[i][0] == '-')
+			for (size_t r = 0; r < m_renderer_names.size(); ++r)
+				if (m_renderer_names[r] == argv[i] + 1) type = (uint32_t)r;
+	m_renderer = m_renderer_factories[type]();
+	m_renderer->init(argc, argv, *this);
+	synchronize();
+}
+
+void RenderingContext::upload_scene()
+{
+	fb200_scene& s = *m_scene;
+	const Mesh& m = s.scene.mesh;
+	DeviceScene& d = m_dscene;
+	memset(&d, 0, sizeof(d));
+	d_vertex_indices.upload(m.vertex_indices.data(), m.vertex_indices.size() * sizeof(int4), m_stream);
+	d_vertex_data.upload(m.vertex_data.data(), m.vertex_data.size() * sizeof(float4), m_stream);
+	d_texture_indices_comp.upload(m.texture_indices_comp.data(), m.texture_indices_comp.size() * sizeof(int4), m_stream);
+	d_material_indices.upload(m.material_indices.data(), m.material_indices.size() * sizeof(int), m_stream);
+	d_materials.upload(m.materials.data(), m.materials.size() * sizeof(MeshMaterial), m_stream);
+	std::vector<TextureView> views(s.scene.textures.size());
+	for (size_t i = 0; i < s.scene.textures.size(); ++i)
+	{
+		const TextureImage& t = s.scene.textures[i];
+		DeviceBuffer* b = new DeviceBuffer();
+		d_textures.push_back(b);
+		if (!t.levels.empty())
+		{
+			b->upload(t.levels[0].data(), t.levels[0].size() * sizeof(float4), m_stream);
+			views[i].texels = b->as<float4>(); views[i].res_x = t.res_x[0]; views[i].res_y = t.res_y[0];
+		}
+		else { views[i].texels = NULL; views[i].res_x = views[i].res_y = 0; }
+	}
+	d_texture_views.upload(views.data(), views.size() * sizeof(TextureView), m_stream);
+	d_nodes.upload(s.wide.nodes.data(), s.wide.nodes.size() * sizeof(WideNode), m_stream);
+	d_tris.upload(s.wide.tris.data(), s.wide.tris.size() * sizeof(WideTri), m_stream);
+	d_vpls.upload(s.mesh_lights.vpls.data(), s.mesh_lights.vpls.size() * sizeof(VPL), m_stream);
+	d_mesh_cdf.upload(s.mesh_lights.mesh_cdf.data(), s.mesh_lights.mesh_cdf.size() * sizeof(float), m_stream);
+	d_mesh_inv_area.upload(s.mesh_lights.mesh_inv_area.data(), s.mesh_lights.mesh_inv_area.size() * sizeof(float), m_stream);
+	d_dir_lights.upload(s.scene.dir_lights.data(), s.scene.dir_lights.size() * sizeof(DirectionalLight), m_stream);
+	d_glossy.upload(s.glossy_reflectance.data(), s.glossy_reflectance.size() * sizeof(float), m_stream);
+	d_shifts_t.upload(s.sequence.shifts_t.data(), s.sequence.shifts_t.size() * sizeof(float), m_stream);
+
+	d.vertex_indices = d_vertex_indices.as<int4>(); d.vertex_data = d_vertex_data.as<float4>();
+	d.texture_indices_comp = d_texture_indices_comp.as<int4>(); d.material_indices = d_material_indices.as<int>();
+	d.materials = d_materials.as<MeshMaterial>(); d.tex_bias = m.tex_bias; d.tex_scale = m.tex_scale;
+	d.textures = d_texture_views.as<TextureView>(); d.num_textures = (uint32)views.size(); d.num_triangles = (uint32)m.num_triangles();
+	d.nodes = d_nodes.as<WideNode>(); d.tris = d_tris.as<WideTri>(); d.num_nodes = (uint32)s.wide.nodes.size();
+	const uint32 max_staged = m_lc.staged_bytes / (uint32)sizeof(WideNode);
+	d.staged_nodes = d.num_nodes < max_staged ? d.num_nodes : max_staged;
+	d.vpls = d_vpls.as<VPL>(); d.n_vpls = (uint32)s.mesh_lights.vpls.size();
+	d.use_vpls = (s.options.nee_type == 1 && d.n_vpls > 0) ? 1u : 0u;
+	d.vpl_norm = s.mesh_lights.normalization_coeff;
+	d.mesh_cdf = d_mesh_cdf.as<float>(); d.mesh_inv_area = d_mesh_inv_area.as<float>(); d.n_prims = (uint32)s.mesh_lights.mesh_cdf.size();
+	d.dir_lights = d_dir_lights.as<DirectionalLight>(); d.n_dir_lights = (uint32)s.scene.dir_lights.size();
+	d.glossy_reflectance = d_glossy.as<float>(); d.shifts_t = d_shifts_t.as<float>(); d.n_dims = s.sequence.n_dimensions;
+	d.res_x = s.res_x; d.res_y = s.res_y; d.options = s.options;
+	cuda_check(cudaStreamSynchronize(m_stream), "scene upload");
+}
+
+void RenderingContext::clear() { m_fb.clear(m_stream); }
+
+void RenderingContext::render(const uint32_t instance)
+{
+	// the reference also binds the view, clears the G-buffer and tone-maps to RGBA around this call
+	// (src/renderer.cu:1029-1056); those are outside the `-pt` hot path
+	m_renderer->render(instance, *this);
+}
+
+void RenderingContext::rescale_frame(const uint32_t instance)
+{
+	cuda_check(launch_rescale_frame(m_fb.view(), float(instance) / float(instance + 1), m_stream), "rescale_frame");
+	kernel_launches++;
+}
+void RenderingContext::update_variances(const uint32_t instance)
+{
+	cuda_check(launch_update_variances(m_fb.view(), instance + 1, m_stream), "update_variances");
+	kernel_launches++;
+}
+void RenderingContext::synchronize() { cuda_check(cudaStreamSynchronize(m_stream), "stream synchronize"); }
+void RenderingContext::download_channel(int channel, float* dst)
+{
+	if (channel < 0 || channel >= FB_NUM_CHANNELS) throw std::runtime_error("bad channel");
+	DeviceBuffer& b = m_fb.channels[channel];
+	cuda_check(cudaMemcpyAsync(dst, b.ptr, b.bytes, cudaMemcpyDeviceToHost, m_stream), "fb download");
+	synchronize();
+}

@@ -1,0 +1,131 @@
+// rendering_context.h — host mirror of Fermat's RenderingContext for the `-pt` path
+// (reference src/renderer.h:52-228, src/renderer_impl.h, src/renderer.cu). Same method names and
+// meaning for everything a renderer plugin calls back; ownership as in the reference: the context owns
+// the scene, textures, frame buffer and sampler tables, the renderer owns its queues and options.
+#pragma once
+#include "renderer_interface.h"
+#include "pt_scene.h"
+#include "../kernels/device_scene.h"
+#include "../kernels/pt_kernels.h"
+#include <cuda_runtime.h>
+#include <vector>
+#include <string>
+#include <stdexcept>
+
+namespace fb {
+
+struct cuda_error : public std::runtime_error
+{
+	cuda_error(const std::string& what) : std::runtime_error(what) {}
+};
+void cuda_check(cudaError_t e, const char* what);      // throws cuda_error (the reference throws cugar::cuda_error)
+
+// owning device allocation
+struct DeviceBuffer
+{
+	void* ptr; size_t bytes;
+	DeviceBuffer() : ptr(NULL), bytes(0) {}
+	~DeviceBuffer() { release(); }
+	DeviceBuffer(const DeviceBuffer&) = delete;
+	DeviceBuffer& operator=(const DeviceBuffer&) = delete;
+	void alloc(size_t n);
+	void release();
+	void upload(const void* src, size_t n, cudaStream_t s = 0);
+	template <typename T> T* as() const { return reinterpret_cast<T*>(ptr); }
+};
+
+} // namespace fb
+
+// FBufferStorage: 8 float4 channels (reference src/framebuffer.h:295-372, src/renderer_view.h:133-145)
+struct FBufferStorage
+{
+	fb::DeviceBuffer channels[fb::FB_NUM_CHANNELS];
+	uint32_t res_x, res_y;
+	void resize(uint32_t rx, uint32_t ry);
+	void clear(cudaStream_t s);
+	fb::FrameBufferView view() const;
+};
+
+struct RenderingContext
+{
+	RenderingContext();
+	~RenderingContext();
+
+	// RenderingContext::init (src/renderer.cu:467-991): parses the command line, loads the scene and builds
+	// everything, selects the renderer named by `-<name>` (default "pt") and calls its init()
+	void init(int argc, char** argv);
+	// variant used by the C ABI: scene already built by the caller
+	void init_with_scene(fb200_scene* scene, int device, int argc, char** argv);
+
+	uint32_t register_renderer(const char* name, RendererFactoryFunction factory);   // src/renderer.cu:1020-1025
+	void     clear();                                                                 // zero the frame buffer
+	void     render(const uint32_t instance);                                         // src/renderer.cu:1029-1056
+	void     rescale_frame(const uint32_t instance);                                  // src/renderer.cu:413-416
+	void     update_variances(const uint32_t instance);                               // src/renderer.cu:431-437
+	uint2    res() const { uint2 r; r.x = m_scene->res_x; r.y = m_scene->res_y; return r; }
+	const fb::Camera& get_camera() const { return m_scene->scene.camera; }
+	FBufferStorage& get_frame_buffer() { return m_fb; }
+	float    get_aspect_ratio() const { return m_scene->aspect; }
+	fb::Bbox3 compute_bbox() const { return m_scene->scene.bbox; }
+
+	// our additions (not in the reference interface)
+	fb200_scene*            scene() { return m_scene; }
+	const fb::DeviceScene&  device_scene() const { return m_dscene; }
+	fb::DeviceScene&        device_scene() { return m_dscene; }
+	const fb::LaunchConfig& launch_config() const { return m_lc; }
+	cudaStream_t            stream() const { return m_stream; }
+	int                     device() const { return m_device; }
+	void                    synchronize();
+	void                    download_channel(int channel, float* dst);   // blocking copy of one float4 channel to the host
+	RendererInterface*      renderer() { return m_renderer; }
+	uint64_t                kernel_launches;
+
+private:
+	void upload_scene();
+
+	fb200_scene*       m_scene;
+	bool               m_owns_scene;
+	int                m_device;
+	cudaStream_t       m_stream;
+	FBufferStorage     m_fb;
+	fb::DeviceScene    m_dscene;
+	fb::LaunchConfig   m_lc;
+	RendererInterface* m_renderer;
+	std::vector<std::string>             m_renderer_names;
+	std::vector<RendererFactoryFunction> m_renderer_factories;
+	// device copies
+	fb::DeviceBuffer d_vertex_indices, d_vertex_data, d_texture_indices_comp, d_material_indices, d_materials,
+					 d_texture_views, d_nodes, d_tris, d_vpls, d_mesh_cdf, d_mesh_inv_area, d_dir_lights,
+					 d_glossy, d_shifts_t;
+	std::vector<fb::DeviceBuffer*> d_textures;
+};
+
+// the `-pt` renderer (reference src/renderers/pathtracer.h:265-305)
+struct PathTracer final : RendererInterface
+{
+	PathTracer();
+	static RendererInterface* factory() { return new PathTracer(); }
+
+	void init(int argc, char** argv, RenderingContext& renderer);
+	void render(const uint32_t instance, RenderingContext& renderer);
+	void destroy() { delete this; }
+	void dump_speed_stats(FILE* stats);
+
+	// stand-alone queries / stats used by the C ABI
+	fb::PassTotals totals(RenderingContext& renderer);
+	uint64_t owned_pixels() const { return m_owned_pixels; }
+	uint64_t passes() const { return m_passes; }
+	double   device_ms() const { return m_device_ms; }
+
+private:
+	fb::PTOptions    m_options;
+	fb::DeviceBuffer m_memory_pool;          // queue arena (reference: m_memory_pool, pathtracer.h:288)
+	fb::PathQueue    m_queue[2];
+	fb::ShadowQueue  m_shadow;
+	fb::DeviceBuffer m_counters, m_totals, m_tile_list;
+	uint32_t         m_n_tiles, m_tiles_x;
+	uint64_t         m_owned_pixels, m_capacity, m_passes;
+	double           m_device_ms;
+	cudaEvent_t      m_ev0, m_ev1;
+	bool             m_events;
+};

@@ -1,0 +1,88 @@
+// device_scene.h — device-side views shared by the kernels and their host launchers.
+#pragma once
+#include "../host/fb_types.h"
+#include "../host/fb_math.h"
+
+namespace fb {
+
+// everything read-only that a pass needs; lives in HBM, replicated per GPU
+struct DeviceScene
+{
+	// MeshView (reference src/mesh/MeshView.h:96-145)
+	const int4*         vertex_indices;
+	const float4*       vertex_data;
+	const int4*         texture_indices_comp;   // may be NULL
+	const int*          material_indices;
+	const MeshMaterial* materials;
+	float2              tex_bias, tex_scale;
+	const TextureView*  textures;
+	uint32              num_textures;
+	uint32              num_triangles;
+	// wide BVH
+	const WideNode*     nodes;
+	const WideTri*      tris;
+	uint32              num_nodes;
+	uint32              staged_nodes;           // nodes [0, staged_nodes) are staged into shared memory by the trace kernels
+	// lights
+	const VPL*          vpls;
+	uint32              n_vpls;                 // VPL count of the scene (gates NEE, pathtracer_core.h:601)
+	uint32              use_vpls;               // 1: sample/map through VPLs, 0: through the triangle CDF
+	float               vpl_norm;
+	const float*        mesh_cdf;
+	const float*        mesh_inv_area;
+	uint32              n_prims;
+	const DirectionalLight* dir_lights;
+	uint32              n_dir_lights;
+	// tables
+	const float*        glossy_reflectance;     // 32^4
+	const float*        shifts_t;               // [tile*tile][n_dims] transposed sampler shifts
+	uint32              n_dims;
+	// frame
+	uint32              res_x, res_y;
+	PTOptions           options;
+};
+
+// SoA path queue: one entry per live path of the current wave (B200 layout: every array is read and
+// written with 128-bit accesses; the reference's `cones` array is dropped because the PT vertex processor
+// never reads it — src/pathtracer_vertex_processor.h:58)
+struct PathQueue
+{
+	float4* ray_o;      // origin.xyz, tmin
+	float4* ray_d;      // dir.xyz, tmax
+	float4* hit;        // t, as_float(triId), u, v   (written by the closest-hit kernel)
+	float4* weight;     // path weight rgb, p_prev
+	uint32* pixel;      // PixelInfo bits: pixel:27 comp:4 diffuse:1 (src/pathtracer_core.h:527-542)
+};
+
+struct ShadowQueue
+{
+	float4* ray_o;      // origin.xyz, as_float(mask)
+	float4* ray_d;      // dir.xyz, tmax
+	float4* w_d;        // diffuse NEE weight rgb, .w = as_float(PixelInfo bits)
+	float4* w_g;        // glossy NEE weight rgb
+};
+
+struct FrameBufferView
+{
+	float4* channels[FB_NUM_CHANNELS];
+	uint32  n_pixels;
+};
+
+// device counters of one pass; all zeroed by one memset at pass start
+struct PassCounters
+{
+	uint32 in_size[64];        // entries in the path queue consumed at bounce b
+	uint32 shadow_size[64];    // entries in the shadow queue produced at bounce b
+	uint32 trace_next[64];     // work-fetch cursors of the persistent kernels
+	uint32 shadow_next[64];
+	uint32 shade_next[64];
+	uint32 pad[64];
+};
+
+struct PassTotals              // accumulated across passes (never reset by render())
+{
+	unsigned long long shade_events;
+	unsigned long long shadow_events;
+};
+
+} // namespace fb

@@ -1,0 +1,531 @@
+// pt_kernels.cu — the wavefront kernels of the B200-native `-pt` renderer.
+//
+//   k_rescale_frame      RenderingContext::rescale_frame   (reference src/renderer.cu:292-311, 413-416)
+//   k_generate_primary   generate_primary_rays_kernel      (src/pathtracer_kernels.h:133-163, pathtracer_core.h:633-656)
+//   k_trace<false>       RTContext::trace, closest hit     (src/rt.cpp:558-583 -> OptiX; here: our own traversal)
+//   k_shade              shade_hits_kernel / shade_vertex  (src/pathtracer_kernels.h:189-227, pathtracer_core.h:771-1254)
+//   k_trace<true>        RTContext::trace_shadow + solve_occlusion_kernel fused
+//                                                          (src/rt.cpp:610-635, pathtracer_kernels.h:248-267, pathtracer_core.h:705-738)
+//   k_update_variances   RenderingContext::update_variances (src/renderer.cu:333-362)
+//
+// Wave scheduling differs from the reference on purpose: queue sizes never leave the device. Every kernel
+// reads its element count from PassCounters, the trace kernels are persistent (one resident grid, warps pull
+// batches of rays from a global cursor), and the host enqueues the whole pass without a single sync
+// (reference: 2 blocking read-backs + 5 device syncs per bounce, src/pathtracer_kernels.h:318-385).
+#include "pt_kernels.h"
+#include "traversal.cuh"
+#include "shading.cuh"
+
+namespace fb {
+
+// ------------------------------------------------------------------------------------------------
+// frame-buffer element-wise kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_rescale_frame(FrameBufferView fb, float scale)
+{
+	const uint32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= fb.n_pixels) return;
+	const float4 d = fb.channels[FB_DIRECT_C][i], df = fb.channels[FB_DIFFUSE_C][i], sp = fb.channels[FB_SPECULAR_C][i], co = fb.channels[FB_COMPOSITED_C][i];
+	fb.channels[FB_LUMINANCE][i] = make_float4(fmaxf(d.x, fmaxf(d.y, d.z)), fmaxf(df.x, fmaxf(df.y, df.z)), fmaxf(sp.x, fmaxf(sp.y, sp.z)), fmaxf(co.x, fmaxf(co.y, co.z)));
+	auto mul = [scale](float4 v) { return make_float4(v.x * scale, v.y * scale, v.z * scale, v.w * scale); };
+	fb.channels[FB_DIFFUSE_C][i] = mul(df);
+	fb.channels[FB_DIFFUSE_A][i] = mul(fb.channels[FB_DIFFUSE_A][i]);
+	fb.channels[FB_SPECULAR_C][i] = mul(sp);
+	fb.channels[FB_SPECULAR_A][i] = mul(fb.channels[FB_SPECULAR_A][i]);
+	fb.channels[FB_DIRECT_C][i] = mul(d);
+	fb.channels[FB_COMPOSITED_C][i] = mul(co);
+}
+
+__global__ void __launch_bounds__(256) k_update_variances(FrameBufferView fb, uint32 n)
+{
+	const uint32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= fb.n_pixels) return;
+	const float4 old_lum = fb.channels[FB_LUMINANCE][i];
+	float4 d = fb.channels[FB_DIRECT_C][i], df = fb.channels[FB_DIFFUSE_C][i], sp = fb.channels[FB_SPECULAR_C][i], co = fb.channels[FB_COMPOSITED_C][i];
+	const float nl[4] = { fmaxf(d.x, fmaxf(d.y, d.z)), fmaxf(df.x, fmaxf(df.y, df.z)), fmaxf(sp.x, fmaxf(sp.y, sp.z)), fmaxf(co.x, fmaxf(co.y, co.z)) };
+	const float ol[4] = { old_lum.x, old_lum.y, old_lum.z, old_lum.w };
+	float dv[4];
+	#pragma unroll
+	for (int c = 0; c < 4; ++c)
+	{
+		const float d1 = n * (nl[c] - ol[c]), d2 = (n - 1) * (nl[c] - ol[c]);
+		dv[c] = (d1 * d2) / (n * n);
+	}
+	d.w += dv[0]; df.w += dv[1]; sp.w += dv[2]; co.w += dv[3];
+	fb.channels[FB_DIRECT_C][i] = d; fb.channels[FB_DIFFUSE_C][i] = df; fb.channels[FB_SPECULAR_C][i] = sp; fb.channels[FB_COMPOSITED_C][i] = co;
+}
+
+// ------------------------------------------------------------------------------------------------
+// primary rays
+// ------------------------------------------------------------------------------------------------
+#define FB_TILE 32u
+
+__global__ void __launch_bounds__(256) k_generate_primary(DeviceScene sc, PassParams pp, PathQueue q, PassCounters* ctr, float seq0, float seq1)
+{
+	const uint32 j = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32 tile_slot = j / (FB_TILE * FB_TILE);
+	bool valid = tile_slot < pp.n_tiles;
+	uint32 px = 0, py = 0;
+	if (valid)
+	{
+		const uint32 tile = __ldg(pp.tile_list + tile_slot);
+		px = (tile % pp.tiles_x) * FB_TILE + (j & (FB_TILE - 1));
+		py = (tile / pp.tiles_x) * FB_TILE + ((j / FB_TILE) & (FB_TILE - 1));
+		valid = px < sc.res_x && py < sc.res_y;
+	}
+	const uint32 slot = warp_append_slot(&ctr->in_size[0], valid);
+	if (!valid) return;
+
+	// dims 0,1 of the sampler jitter the pixel (pathtracer_core.h:642-649)
+	const uint32 T = 256u;
+	const uint32 shift = (px & (T - 1)) + (py & (T - 1)) * T;
+	const uint32 tile = ((px / T) & (T - 1)) + ((py / T) & (T - 1)) * T;
+	const float2 sa = __ldg(reinterpret_cast<const float2*>(sc.shifts_t + (size_t)shift * sc.n_dims));
+	const float2 sb = __ldg(reinterpret_cast<const float2*>(sc.shifts_t + (size_t)tile * sc.n_dims));
+	const float u = fmodf(fmodf(seq0 + sa.x, 1.0f) + sb.x, 1.0f);
+	const float v = fmodf(fmodf(seq1 + sa.y, 1.0f) + sb.y, 1.0f);
+	const float dx = (px + u) / float(sc.res_x) * 2.f - 1.f;
+	const float dy = (py + v) / float(sc.res_y) * 2.f - 1.f;
+	const V3 U(pp.U[0], pp.U[1], pp.U[2]), Vv(pp.V[0], pp.V[1], pp.V[2]), W(pp.W[0], pp.W[1], pp.W[2]);
+	const V3 d = dx * U + dy * Vv + W;
+	q.ray_o[slot] = make_float4(pp.eye[0], pp.eye[1], pp.eye[2], 0.0f);
+	q.ray_d[slot] = make_float4(d.x, d.y, d.z, 1e34f);
+	q.weight[slot] = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+	q.pixel[slot] = px + py * sc.res_x;          // PixelInfo(pixel, comp = 0, diffuse = 0)
+}
+
+// ------------------------------------------------------------------------------------------------
+// persistent traversal kernels
+// ------------------------------------------------------------------------------------------------
+enum TraceMode { TRACE_QUEUE_CLOSEST = 0, TRACE_QUEUE_SHADOW = 1, TRACE_RAYS_CLOSEST = 2, TRACE_RAYS_SHADOW = 3 };
+
+struct TraceArgs
+{
+	const float4* ray_o; const float4* ray_d; uint32 stride;   // ray i = {ray_o[i*stride], ray_d[i*stride]}
+	const uint32* n_ptr; uint32 n_value;
+	uint32* cursor;
+	float4* hits;                  // closest modes
+	unsigned char* occluded;       // TRACE_RAYS_SHADOW
+	// TRACE_QUEUE_SHADOW epilogue = solve_occlusion
+	const float4* w_d; const float4* w_g;
+	FrameBufferView fb; float frame_weight; uint32 bounce;
+	unsigned long long* event_counter;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256, 4) k_trace(DeviceScene sc, TraceArgs a)
+{
+	constexpr bool ANY = (MODE == TRACE_QUEUE_SHADOW || MODE == TRACE_RAYS_SHADOW);
+	extern __shared__ float4 smem[];
+	// [0,16): mbarrier; staged nodes follow
+	unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem);
+	const float4* smem_nodes = smem + 1;
+	stage_nodes_tma(smem + 1, sc.nodes, sc.staged_nodes * (uint32)sizeof(WideNode), bar);
+
+	const uint32 n = a.n_ptr ? *a.n_ptr : a.n_value;
+	if (MODE == TRACE_QUEUE_SHADOW && blockIdx.x == 0 && threadIdx.x == 0 && a.event_counter) atomicAdd(a.event_counter, (unsigned long long)n);
+	const int lane = threadIdx.x & 31;
+
+	Traversal<ANY> trav;
+	bool active = false;
+	uint32 ray_idx = 0;
+
+	for (;;)
+	{
+		// refill idle lanes: one atomic per warp
+		const unsigned need = __ballot_sync(0xFFFFFFFFu, !active);
+		if (need)
+		{
+			const int leader = __ffs(need) - 1;
+			uint32 base = 0;
+			if (lane == leader) base = atomicAdd(a.cursor, (uint32)__popc(need));
+			base = __shfl_sync(0xFFFFFFFFu, base, leader);
+			if (!active)
+			{
+				ray_idx = base + __popc(need & ((1u << lane) - 1u));
+				if (ray_idx < n)
+				{
+					const float4 o = __ldg(a.ray_o + (size_t)ray_idx * a.stride), d = __ldg(a.ray_d + (size_t)ray_idx * a.stride);
+					trav.init(o, d, ANY ? __float_as_uint(o.w) : 0u);
+					active = true;
+				}
+			}
+		}
+		if (!__any_sync(0xFFFFFFFFu, active)) break;
+
+		for (int it = 0; it < 24 && active; ++it)
+		{
+			if (!trav.step(sc, smem_nodes))
+			{
+				active = false;
+				if (MODE == TRACE_QUEUE_CLOSEST || MODE == TRACE_RAYS_CLOSEST) a.hits[ray_idx] = trav.hit_record();
+				else if (MODE == TRACE_RAYS_SHADOW) a.occluded[ray_idx] = trav.occluded ? 1 : 0;
+				else if (!trav.occluded)
+				{
+					// solve_occlusion -> PTVertexProcessor::accumulate_nee (pathtracer_vertex_processor.h:204-239)
+					const float4 wd4 = __ldg(a.w_d + ray_idx), wg4 = __ldg(a.w_g + ray_idx);
+					const V3 w_d(wd4), w_g(wg4);
+					const uint32 info = __float_as_uint(wd4.w);
+					const uint32 pixel = info & 0x07FFFFFFu, comp = (info >> 27) & 0xFu;
+					add_in<false>(a.fb.channels[FB_COMPOSITED_C], pixel, w_d + w_g, a.frame_weight);
+					if (a.bounce == 0)
+					{
+						add_in<true>(a.fb.channels[FB_DIFFUSE_C], pixel, w_d, a.frame_weight);
+						add_in<true>(a.fb.channels[FB_SPECULAR_C], pixel, w_g, a.frame_weight);
+					}
+					else
+					{
+						if (comp & kDiffuseMask) add_in<true>(a.fb.channels[FB_DIFFUSE_C], pixel, w_d, a.frame_weight);
+						if (comp & kGlossyMask)  add_in<true>(a.fb.channels[FB_SPECULAR_C], pixel, w_g, a.frame_weight);
+					}
+				}
+			}
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// shade
+// ------------------------------------------------------------------------------------------------
+struct ShadeArgs
+{
+	PathQueue in, out; ShadowQueue sq; FrameBufferView fb;
+	PassCounters* ctr; PassTotals* tot;
+	uint32 bounce; float frame_weight; float seq[6];
+	uint32 do_nee, do_emissive, do_scatter, do_dirlight;
+};
+
+__global__ void __launch_bounds__(128, 4) k_shade(DeviceScene sc, ShadeArgs a)
+{
+	const uint32 n = a.ctr->in_size[a.bounce];
+	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&a.tot->shade_events, (unsigned long long)n);
+	const PTOptions& o = sc.options;
+	const uint32 bounce = a.bounce;
+	uint32* shadow_counter = &a.ctr->shadow_size[bounce];
+	uint32* scatter_counter = &a.ctr->in_size[bounce + 1];
+
+	const uint32 n_round = (n + 31u) & ~31u;
+	for (uint32 idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_round; idx += gridDim.x * blockDim.x)
+	{
+		bool valid = idx < n;
+		// outputs of this lane
+		bool dl_on = false, nee_on = false, scat_on = false;
+		float4 dl_o, dl_d, dl_wd, dl_wg, nee_o, nee_d, nee_wd, nee_wg, sc_o, sc_d, sc_w;
+		uint32 sc_info = 0, info = 0;
+
+		float4 hit = make_float4(-1.0f, 0.0f, 0.0f, 0.0f);
+		if (valid) { hit = a.in.hit[idx]; valid = (hit.x > 0.0f) && (__float_as_int(hit.y) >= 0); }
+		if (valid)
+		{
+			const uint32 tri = __float_as_uint(hit.y);
+			const float4 ro = a.in.ray_o[idx], rd = a.in.ray_d[idx], w4 = a.in.weight[idx];
+			info = a.in.pixel[idx];
+			const uint32 pixel = info & 0x07FFFFFFu, comp = (info >> 27) & 0xFu;
+			const V3 ray_o(ro), ray_d(rd), w(w4);
+			const float p_prev = w4.w;
+
+			// ---- EyeVertex::setup (src/bpt_utils.h:585-642) ----
+			Frame g; V3 unused; float s, t;
+			setup_geometry<false>(sc, tri, hit.z, hit.w, g, unused, s, t);
+			const V3 position = ray_o + hit.x * ray_d;
+			const MeshMaterial* m = sc.materials + __ldg(sc.material_indices + tri);
+			const float4* m4 = reinterpret_cast<const float4*>(m);
+			const float4 mp = __ldg(m4 + 6);                      // roughness, ior, opacity, flags
+			const V3 kd = V3(__ldg(m4 + 0)) * texture_rgb(sc, s, t, load_texref(m, 8));
+			const V3 ks = V3(__ldg(m4 + 3)) * texture_rgb(sc, s, t, load_texref(m, 10));
+			const V3 ke = V3(__ldg(m4 + 4)) * texture_rgb(sc, s, t, load_texref(m, 11));
+			const V3 td = V3(__ldg(m4 + 1)) * texture_rgb(sc, s, t, load_texref(m, 9));
+			const V3 kr = V3(__ldg(m4 + 5));
+			const V3 in = -normalize(ray_d);
+			BsdfParams b;
+			bsdf_init(b, kd, td, ks, kr, mp.x, mp.y, mp.z);
+
+			if (bounce == 0)
+			{
+				// surface albedos (pathtracer_core.h:809-811)
+				float4 da = a.fb.channels[FB_DIFFUSE_A][pixel], sa = a.fb.channels[FB_SPECULAR_A][pixel];
+				da.x += kd.x * a.frame_weight; da.y += kd.y * a.frame_weight; da.z += kd.z * a.frame_weight; da.w += 0.0f * a.frame_weight;
+				sa.x += (ks.x + 1.0f) * 0.5f * a.frame_weight; sa.y += (ks.y + 1.0f) * 0.5f * a.frame_weight;
+				sa.z += (ks.z + 1.0f) * 0.5f * a.frame_weight; sa.w += (0.0f + 1.0f) * 0.5f * a.frame_weight;
+				a.fb.channels[FB_DIFFUSE_A][pixel] = da; a.fb.channels[FB_SPECULAR_A][pixel] = sa;
+			}
+
+			float z[6];
+			vertex_samples(sc, pixel % sc.res_x, pixel / sc.res_x, (bounce + 1) * 6, a.seq, z);
+
+			// ---- directional lights (pathtracer_core.h:870-988) ----
+			if (a.do_dirlight)
+			{
+				const uint32 li = (uint32)max(min((int)(z[2] * float(sc.n_dir_lights)), (int)(sc.n_dir_lights - 1)), 0);
+				const DirectionalLight L = sc.dir_lights[li];
+				const V3 ldir(L.dir), lcol(L.color);
+				const float FAR = 1.0e8f;
+				const V3 lpos = position - ldir * FAR;
+				float light_pdf = 1.0f;
+				light_pdf /= sc.n_dir_lights;
+				V3 out = lpos - position;
+				const float d2 = fmaxf(1.0e-8f, square_length(out));
+				out *= 1.0f / sqrtf(d2);
+				V3 fd, fg; float pd, pg;
+				bsdf_f_and_p(b, sc.glossy_reflectance, g, in, out, fd, fg, pd, pg);
+				if (!o.diffuse_scattering) fd = V3(0.0f);
+				if (!o.glossy_scattering) fg = V3(0.0f);
+				const V3 edf = FAR * FAR * lcol;
+				const V3 f_L = (dot(ldir, -out) > 0.0f ? edf : V3(0.0f)) / light_pdf;
+				const float G = fabsf(dot(out, g.normal_s) * dot(out, ldir)) / d2;
+				const V3 fl = f_L * G * 1.0f;
+				const V3 w_d = (bounce == 0 ? fd : fd + fg) * w * fl, w_g = (bounce == 0 ? fg : fd + fg) * w * fl;
+				const V3 ow = w_d + w_g;
+				if (max_comp(ow) > 0.0f && is_finite(ow))
+				{
+					dl_on = true;
+					const V3 org = position - ray_d * 1.0e-3f;
+					const V3 dir = lpos - org;
+					dl_o = make_float4(org.x, org.y, org.z, __uint_as_float(0x1u));
+					dl_d = make_float4(dir.x, dir.y, dir.z, 0.9999f);
+					dl_wd = make_float4(w_d.x, w_d.y, w_d.z, __uint_as_float(info));
+					dl_wg = make_float4(w_g.x, w_g.y, w_g.z, 0.0f);
+				}
+			}
+
+			// ---- next-event estimation (pathtracer_core.h:991-1106) ----
+			if (a.do_nee)
+			{
+				uint32 prim; float lu, lv;
+				if (sc.use_vpls)
+				{
+					const uint32 l = min((uint32)(z[2] * float(sc.n_vpls)), sc.n_vpls - 1);
+					const float4 vpl = __ldg(reinterpret_cast<const float4*>(sc.vpls) + l);
+					prim = __float_as_uint(vpl.x); lu = vpl.y; lv = vpl.z;
+				}
+				else
+				{
+					// upper_bound over the triangle CDF (lights.h:335-352)
+					const float x = fminf(z[2], __uint_as_float(0x3F7FFFFFu));
+					uint32 lo = 0, cnt = sc.n_prims;
+					while (cnt > 0) { const uint32 step = cnt / 2; if (!(x < __ldg(sc.mesh_cdf + lo + step))) { lo += step + 1; cnt -= step + 1; } else cnt = step; }
+					prim = lo; lu = z[0]; lv = z[1];
+					if (lu + lv > 1.0f) { lu = 1.0f - lu; lv = 1.0f - lv; }
+				}
+				Frame lg; V3 lpos; float ls, lt;
+				setup_geometry<true>(sc, prim, lu, lv, lg, lpos, ls, lt);
+				float light_pdf; V3 edf;
+				light_map(sc, prim, ls, lt, light_pdf, edf);
+
+				V3 out = lpos - position;
+				const float d2 = fmaxf(1.0e-8f, square_length(out));
+				out *= 1.0f / sqrtf(d2);
+				V3 fd, fg; float pd, pg;
+				bsdf_f_and_p(b, sc.glossy_reflectance, g, in, out, fd, fg, pd, pg);
+				float p_s = 0.0f;
+				if (o.diffuse_scattering) p_s += pd; else fd = V3(0.0f);
+				if (o.glossy_scattering) p_s += pg; else fg = V3(0.0f);
+				const V3 f_L = (dot(lg.normal_s, -out) > 0.0f ? edf : V3(0.0f)) / light_pdf;
+				const float G = fabsf(dot(out, g.normal_s) * dot(out, lg.normal_s)) / d2;
+				const float p1 = light_pdf, p2 = p_s * G;
+				const float mis_w = ((bounce == 0 && o.direct_lighting_bsdf) || (bounce > 0 && o.indirect_lighting_bsdf)) ? power_heuristic(p1, p2) : 1.0f;
+				const V3 fl = f_L * G * mis_w;
+				const V3 w_d = (bounce == 0 ? fd : fd + fg) * w * fl, w_g = (bounce == 0 ? fg : fd + fg) * w * fl;
+				const V3 ow = w_d + w_g;
+				if (max_comp(ow) > 0.0f && is_finite(ow))
+				{
+					nee_on = true;
+					const V3 org = position - ray_d * 1.0e-4f;
+					const V3 dir = lpos - org;
+					nee_o = make_float4(org.x, org.y, org.z, __uint_as_float(0x2u));
+					nee_d = make_float4(dir.x, dir.y, dir.z, 0.9999f);
+					nee_wd = make_float4(w_d.x, w_d.y, w_d.z, __uint_as_float(info));
+					nee_wg = make_float4(w_g.x, w_g.y, w_g.z, 0.0f);
+				}
+			}
+
+			// ---- emissive hit with MIS against NEE at the previous vertex (pathtracer_core.h:1109-1154) ----
+			if (a.do_emissive)
+			{
+				float light_pdf;
+				if (sc.use_vpls) light_pdf = fmaxf(fabsf(ke.x), fmaxf(fabsf(ke.y), fabsf(ke.z))) / sc.vpl_norm;
+				else light_pdf = (__ldg(sc.mesh_cdf + tri) - (tri ? __ldg(sc.mesh_cdf + tri - 1) : 0.0f)) * __ldg(sc.mesh_inv_area + tri);
+				const V3 f_L = dot(g.normal_s, in) > 0.0f ? ke : V3(0.0f);
+				const float d2 = fmaxf(1.0e-10f, hit.x * hit.x);
+				const float G_partial = fabsf(dot(in, g.normal_s)) / d2;
+				const float p1 = pdf_product(G_partial, p_prev), p2 = light_pdf;
+				const float mis_w = ((bounce == 1 && o.direct_lighting_nee) || (bounce > 1 && o.indirect_lighting_nee)) ? power_heuristic(p1, p2) : 1.0f;
+				const V3 ow = w * f_L * mis_w;
+				if (max_comp(ow) > 0.0f && is_finite(ow))
+				{
+					add_in<false>(a.fb.channels[FB_COMPOSITED_C], pixel, ow, a.frame_weight);
+					if (bounce == 0) add_in<false>(a.fb.channels[FB_DIRECT_C], pixel, ow, a.frame_weight);
+					else
+					{
+						if (comp & kDiffuseMask) add_in<true>(a.fb.channels[FB_DIFFUSE_C], pixel, ow, a.frame_weight);
+						if (comp & kGlossyMask)  add_in<true>(a.fb.channels[FB_SPECULAR_C], pixel, ow, a.frame_weight);
+					}
+				}
+			}
+
+			// ---- scattering with implicit Russian roulette (pathtracer_core.h:1157-1247) ----
+			if (a.do_scatter)
+			{
+				uint32 out_comp; V3 out, gg; float p, p_proj;
+				bsdf_sample(b, sc.glossy_reflectance, g, z[3], z[4], z[5], in, out_comp, out, p, p_proj, gg);
+				const V3 ow = gg * w;
+				if (out_comp != kAbsorption && p != 0.0f && max_comp(ow) > 0.0f && is_finite(ow))
+				{
+					scat_on = true;
+					sc_o = make_float4(position.x, position.y, position.z, 1.0e-3f);
+					sc_d = make_float4(out.x, out.y, out.z, 1.0e8f);
+					sc_w = make_float4(ow.x, ow.y, ow.z, p);
+					const uint32 diffuse_flag = (info >> 31) | ((out_comp & kDiffuseMask) ? 1u : 0u);
+					sc_info = pixel | ((out_comp & 0xFu) << 27) | (diffuse_flag << 31);
+				}
+			}
+		}
+
+		// ---- queue appends: whole warp, one atomic per queue (warp-ballot compaction) ----
+		if (a.do_dirlight)
+		{
+			const uint32 slot = warp_append_slot(shadow_counter, dl_on);
+			if (dl_on) { a.sq.ray_o[slot] = dl_o; a.sq.ray_d[slot] = dl_d; a.sq.w_d[slot] = dl_wd; a.sq.w_g[slot] = dl_wg; }
+		}
+		if (a.do_nee)
+		{
+			const uint32 slot = warp_append_slot(shadow_counter, nee_on);
+			if (nee_on) { a.sq.ray_o[slot] = nee_o; a.sq.ray_d[slot] = nee_d; a.sq.w_d[slot] = nee_wd; a.sq.w_g[slot] = nee_wg; }
+		}
+		if (a.do_scatter)
+		{
+			const uint32 slot = warp_append_slot(scatter_counter, scat_on);
+			if (scat_on) { a.out.ray_o[slot] = sc_o; a.out.ray_d[slot] = sc_d; a.out.weight[slot] = sc_w; a.out.pixel[slot] = sc_info; }
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// Bsdf parity harness (same record layout as oracle_bsdf_eval)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_bsdf_eval(DeviceScene sc, const float* __restrict__ rec, float* __restrict__ out, uint32 n)
+{
+	const uint32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const float* r = rec + 12 * i; float* o = out + 25 * i;
+	const uint32 tri = __float_as_uint(r[0]);
+	Frame g; V3 unused; float s, t;
+	setup_geometry<false>(sc, tri, r[1], r[2], g, unused, s, t);
+	const MeshMaterial* m = sc.materials + sc.material_indices[tri];
+	const float4* m4 = reinterpret_cast<const float4*>(m);
+	const float4 mp = m4[6];
+	const V3 kd = V3(m4[0]) * texture_rgb(sc, s, t, load_texref(m, 8));
+	const V3 ks = V3(m4[3]) * texture_rgb(sc, s, t, load_texref(m, 10));
+	const V3 td = V3(m4[1]) * texture_rgb(sc, s, t, load_texref(m, 9));
+	BsdfParams b;
+	bsdf_init(b, kd, td, ks, V3(m4[5]), mp.x, mp.y, mp.z);
+	const V3 in(r[3], r[4], r[5]), outd(r[6], r[7], r[8]);
+	V3 f[4]; float p[4];
+	bsdf_f_and_p_components(b, sc.glossy_reflectance, g, in, outd, f, p);
+	for (int c = 0; c < 4; ++c) { o[3 * c] = f[c].x; o[3 * c + 1] = f[c].y; o[3 * c + 2] = f[c].z; o[12 + c] = p[c]; }
+	uint32 comp; V3 so, sg; float sp, spp;
+	bsdf_sample(b, sc.glossy_reflectance, g, r[9], r[10], r[11], in, comp, so, sp, spp, sg);
+	o[16] = so.x; o[17] = so.y; o[18] = so.z; o[19] = sg.x; o[20] = sg.y; o[21] = sg.z; o[22] = sp; o[23] = spp; o[24] = (float)comp;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+cudaError_t configure_kernels(LaunchConfig& lc, int device)
+{
+	cudaDeviceProp prop;
+	cudaError_t e = cudaGetDeviceProperties(&prop, device);
+	if (e != cudaSuccess) return e;
+	lc.sm_count = prop.multiProcessorCount;
+	lc.trace_threads = 256;
+	lc.trace_ctas_per_sm = 4;
+	const int max_smem = 48 * 1024;   // per CTA: 4 CTAs x 48 KB fit the 227 KB of an SM
+	e = cudaFuncSetAttribute(k_trace<TRACE_QUEUE_CLOSEST>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); if (e) return e;
+	e = cudaFuncSetAttribute(k_trace<TRACE_QUEUE_SHADOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); if (e) return e;
+	e = cudaFuncSetAttribute(k_trace<TRACE_RAYS_CLOSEST>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); if (e) return e;
+	e = cudaFuncSetAttribute(k_trace<TRACE_RAYS_SHADOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); if (e) return e;
+	lc.staged_bytes = (uint32)max_smem - 16u;
+	return cudaSuccess;
+}
+
+static inline uint32 staged_smem(const DeviceScene& sc) { return 16u + sc.staged_nodes * (uint32)sizeof(WideNode); }
+
+cudaError_t launch_rescale_frame(const FrameBufferView& fb, float scale, cudaStream_t s)
+{
+	k_rescale_frame<<<(fb.n_pixels + 255) / 256, 256, 0, s>>>(fb, scale);
+	return cudaGetLastError();
+}
+cudaError_t launch_update_variances(const FrameBufferView& fb, uint32 n, cudaStream_t s)
+{
+	k_update_variances<<<(fb.n_pixels + 255) / 256, 256, 0, s>>>(fb, n);
+	return cudaGetLastError();
+}
+cudaError_t launch_generate_primary(const DeviceScene& sc, const PassParams& pp, const PathQueue& q, PassCounters* ctr, const float seq2[2], cudaStream_t s)
+{
+	const uint32 total = pp.n_tiles * FB_TILE * FB_TILE;
+	if (total == 0) return cudaSuccess;
+	k_generate_primary<<<(total + 255) / 256, 256, 0, s>>>(sc, pp, q, ctr, seq2[0], seq2[1]);
+	return cudaGetLastError();
+}
+cudaError_t launch_trace_closest(const DeviceScene& sc, const LaunchConfig& lc, const PathQueue& q, PassCounters* ctr, uint32 bounce, cudaStream_t s)
+{
+	TraceArgs a; memset(&a, 0, sizeof(a));
+	a.ray_o = q.ray_o; a.ray_d = q.ray_d; a.stride = 1; a.n_ptr = &ctr->in_size[bounce]; a.cursor = &ctr->trace_next[bounce]; a.hits = q.hit;
+	k_trace<TRACE_QUEUE_CLOSEST><<<lc.sm_count * lc.trace_ctas_per_sm, lc.trace_threads, staged_smem(sc), s>>>(sc, a);
+	return cudaGetLastError();
+}
+cudaError_t launch_trace_shadow(const DeviceScene& sc, const LaunchConfig& lc, const ShadowQueue& sq, const FrameBufferView& fb, PassCounters* ctr, PassTotals* tot,
+								uint32 bounce, float frame_weight, cudaStream_t s)
+{
+	TraceArgs a; memset(&a, 0, sizeof(a));
+	a.ray_o = sq.ray_o; a.ray_d = sq.ray_d; a.stride = 1; a.n_ptr = &ctr->shadow_size[bounce]; a.cursor = &ctr->shadow_next[bounce];
+	a.w_d = sq.w_d; a.w_g = sq.w_g; a.fb = fb; a.frame_weight = frame_weight; a.bounce = bounce; a.event_counter = &tot->shadow_events;
+	k_trace<TRACE_QUEUE_SHADOW><<<lc.sm_count * lc.trace_ctas_per_sm, lc.trace_threads, staged_smem(sc), s>>>(sc, a);
+	return cudaGetLastError();
+}
+cudaError_t launch_trace_rays(const DeviceScene& sc, const LaunchConfig& lc, const float4* rays, float4* hits, uint32 n, uint32* cursor, cudaStream_t s)
+{
+	TraceArgs a; memset(&a, 0, sizeof(a));
+	a.ray_o = rays; a.ray_d = rays + 1; a.stride = 2; a.n_value = n; a.cursor = cursor; a.hits = hits;
+	k_trace<TRACE_RAYS_CLOSEST><<<lc.sm_count * lc.trace_ctas_per_sm, lc.trace_threads, staged_smem(sc), s>>>(sc, a);
+	return cudaGetLastError();
+}
+cudaError_t launch_trace_shadow_rays(const DeviceScene& sc, const LaunchConfig& lc, const float4* rays, unsigned char* occluded, uint32 n, uint32* cursor, cudaStream_t s)
+{
+	TraceArgs a; memset(&a, 0, sizeof(a));
+	a.ray_o = rays; a.ray_d = rays + 1; a.stride = 2; a.n_value = n; a.cursor = cursor; a.occluded = occluded;
+	k_trace<TRACE_RAYS_SHADOW><<<lc.sm_count * lc.trace_ctas_per_sm, lc.trace_threads, staged_smem(sc), s>>>(sc, a);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_shade(const DeviceScene& sc, const LaunchConfig& lc, const PassParams& pp, const PathQueue& in, const PathQueue& out, const ShadowQueue& sq,
+						 const FrameBufferView& fb, PassCounters* ctr, PassTotals* tot, uint32 bounce, const float seq6[6], uint32 capacity, cudaStream_t s)
+{
+	ShadeArgs a;
+	a.in = in; a.out = out; a.sq = sq; a.fb = fb; a.ctr = ctr; a.tot = tot; a.bounce = bounce; a.frame_weight = pp.frame_weight;
+	for (int i = 0; i < 6; ++i) a.seq[i] = seq6[i];
+	// compute_per_bounce_options (pathtracer_core.h:594-620)
+	const PTOptions& o = sc.options;
+	a.do_nee = sc.n_vpls && (bounce + 2 <= o.max_path_length) &&
+		((bounce == 0 && o.direct_lighting_nee && o.direct_lighting) || (bounce > 0 && o.indirect_lighting_nee));
+	a.do_emissive = (bounce == 0 && o.visible_lights) || (bounce == 1 && o.direct_lighting_bsdf && o.direct_lighting) || (bounce > 1 && o.indirect_lighting_bsdf);
+	const uint32 max_path_vertices = o.max_path_length + (((o.max_path_length == 2 && o.direct_lighting_bsdf) || (o.max_path_length > 2 && o.indirect_lighting_bsdf)) ? 1 : 0);
+	a.do_scatter = bounce + 2 < max_path_vertices;
+	a.do_dirlight = (bounce + 2 <= o.max_path_length) && (bounce > 0 || o.direct_lighting) && sc.n_dir_lights;
+	const uint32 threads = 128;
+	uint32 blocks = (capacity + threads - 1) / threads;
+	const uint32 max_blocks = (uint32)lc.sm_count * 16u;
+	if (blocks > max_blocks) blocks = max_blocks;
+	if (blocks == 0) blocks = 1;
+	k_shade<<<blocks, threads, 0, s>>>(sc, a);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_bsdf_eval(const DeviceScene& sc, const float* rec, float* out, uint32 n, cudaStream_t s)
+{
+	if (n == 0) return cudaSuccess;
+	k_bsdf_eval<<<(n + 127) / 128, 128, 0, s>>>(sc, rec, out, n);
+	return cudaGetLastError();
+}
+
+} // namespace fb

@@ -1,0 +1,46 @@
+// pt_kernels.h — host-callable launchers of the wavefront path-tracing kernels (pt_kernels.cu).
+// All launches are asynchronous on the given stream; none synchronises or reads anything back.
+#pragma once
+#include "device_scene.h"
+#include <cuda_runtime.h>
+
+namespace fb {
+
+struct PassParams
+{
+	uint32 instance;
+	float  frame_weight;            // 1 / (instance + 1)
+	float  U[3], V[3], W[3];        // camera frame (reference src/camera.h:142-163)
+	float  eye[3];
+	const uint32* tile_list;        // tiles owned by this shard
+	uint32 n_tiles;                 // number of owned tiles
+	uint32 tiles_x;                 // tiles per row of the full frame
+};
+
+struct LaunchConfig
+{
+	int sm_count;
+	int trace_ctas_per_sm;
+	int trace_threads;
+	uint32 staged_bytes;            // shared memory used for staged nodes
+};
+
+// error code (cudaError_t) of the launch is returned; kernels count their own launches in `launches`
+cudaError_t launch_rescale_frame(const FrameBufferView& fb, float scale, cudaStream_t s);
+cudaError_t launch_update_variances(const FrameBufferView& fb, uint32 n, cudaStream_t s);
+cudaError_t launch_generate_primary(const DeviceScene& sc, const PassParams& pp, const PathQueue& q, PassCounters* ctr, const float seq2[2], cudaStream_t s);
+cudaError_t launch_trace_closest(const DeviceScene& sc, const LaunchConfig& lc, const PathQueue& q, PassCounters* ctr, uint32 bounce, cudaStream_t s);
+cudaError_t launch_shade(const DeviceScene& sc, const LaunchConfig& lc, const PassParams& pp, const PathQueue& in, const PathQueue& out, const ShadowQueue& sq,
+						 const FrameBufferView& fb, PassCounters* ctr, PassTotals* tot, uint32 bounce, const float seq6[6], uint32 capacity, cudaStream_t s);
+cudaError_t launch_trace_shadow(const DeviceScene& sc, const LaunchConfig& lc, const ShadowQueue& sq, const FrameBufferView& fb, PassCounters* ctr, PassTotals* tot,
+								uint32 bounce, float frame_weight, cudaStream_t s);
+
+// stand-alone ray queries on caller-provided device buffers (RTContext::trace / trace_shadow twins)
+cudaError_t launch_trace_rays(const DeviceScene& sc, const LaunchConfig& lc, const float4* rays, float4* hits, uint32 n, uint32* cursor, cudaStream_t s);
+cudaError_t launch_trace_shadow_rays(const DeviceScene& sc, const LaunchConfig& lc, const float4* rays, unsigned char* occluded, uint32 n, uint32* cursor, cudaStream_t s);
+// Bsdf parity harness
+cudaError_t launch_bsdf_eval(const DeviceScene& sc, const float* rec, float* out, uint32 n, cudaStream_t s);
+
+cudaError_t configure_kernels(LaunchConfig& lc, int device);
+
+} // namespace fb

@@ -1,0 +1,152 @@
+// shading.cuh — vertex set-up, texture taps, light mapping, sampler and frame-buffer helpers used by
+// the shade kernel. Each routine cites the reference code whose result it reproduces.
+#pragma once
+#include "device_scene.h"
+#include "bsdf.cuh"
+#include <cuda_fp16.h>
+
+namespace fb {
+
+// cugar::orthogonal (contrib/cugar/linalg/vector_inl.h:389-421) — NOT normalised
+FB_D V3 orthogonal(V3 v)
+{
+	if (v.x * v.x < v.y * v.y)
+	{
+		if (v.x * v.x < v.z * v.z) return V3(0.0f, -v.z, v.y);
+		return V3(-v.y, v.x, 0.0f);
+	}
+	if (v.y * v.y < v.z * v.z) return V3(v.z, 0.0f, -v.x);
+	return V3(-v.y, v.x, 0.0f);
+}
+// 10-10-10 normal decode (vector_inl.h:776-798)
+FB_D V3 unpack_normal(uint32 b)
+{
+	const V3 u((float)(b & 0x3FFu) / 1023, (float)((b >> 10) & 0x3FFu) / 1023, (float)((b >> 20) & 0x3FFu) / 1023);
+	return u * 2.0f - V3(1.0f);
+}
+// decompress_tex_coord (src/mesh/MeshCompression.h:52-68)
+FB_D V2 decompress_tex(const DeviceScene& sc, int packed)
+{
+	const __half2_raw hr = { (unsigned short)((uint32)packed & 0xFFFFu), (unsigned short)((uint32)packed >> 16) };
+	const float2 tn = __half22float2(__half2(hr));
+	return V2(tn.x * sc.tex_scale.x + sc.tex_bias.x, tn.y * sc.tex_scale.y + sc.tex_bias.y);
+}
+FB_D float mod1(float x, float m) { return x > 0.0f ? fmodf(x, m) : m - fmodf(-x, m); }   // cugar::mod
+
+// interpolated shading frame + texture coordinates (src/mesh_utils.h:184-288). `position` is produced
+// only when asked for (the eye vertex re-derives it from the ray, src/bpt_utils.h:608).
+template <bool WITH_POSITION>
+FB_D void setup_geometry(const DeviceScene& sc, uint32 tri, float u, float v, Frame& g, V3& position, float& s, float& t)
+{
+	const int4 idx = __ldg(sc.vertex_indices + tri);
+	const float4 a = __ldg(sc.vertex_data + idx.x), b = __ldg(sc.vertex_data + idx.y), c = __ldg(sc.vertex_data + idx.z);
+	const float w = 1.0f - u - v;
+	if (WITH_POSITION) position = V3(c) * w + V3(a) * u + V3(b) * v;
+	const V3 n0 = unpack_normal(__float_as_uint(a.w)), n1 = unpack_normal(__float_as_uint(b.w)), n2 = unpack_normal(__float_as_uint(c.w));
+	const V3 N = normalize(n2 * w + n0 * u + n1 * v);
+	g.normal_s = N;
+	g.tangent = orthogonal(N);
+	g.binormal = cross(N, g.tangent);
+	if (sc.texture_indices_comp)
+	{
+		const int4 ti = __ldg(sc.texture_indices_comp + tri);
+		const V2 t0 = ti.x >= 0 ? decompress_tex(sc, ti.x) : V2(1.0f, 0.0f);
+		const V2 t1 = ti.y >= 0 ? decompress_tex(sc, ti.y) : V2(0.0f, 1.0f);
+		const V2 t2 = ti.z >= 0 ? decompress_tex(sc, ti.z) : V2(0.0f, 0.0f);
+		s = t2.x * w + t0.x * u + t1.x * v;
+		t = t2.y * w + t0.y * u + t1.y * v;
+	}
+	else { s = u; t = v; }
+}
+
+// bilinear_texture_lookup at LOD 0 with wrap (src/texture_view.h:171-202); default value (1,1,1,1)
+FB_D V3 texture_rgb(const DeviceScene& sc, float s, float t, const TextureReference ref)
+{
+	if (ref.texture == 0xFFFFFFFFu || ref.texture >= sc.num_textures) return V3(1.0f);
+	const TextureView tex = sc.textures[ref.texture];
+	if (tex.texels == NULL) return V3(1.0f);
+	s *= ref.scaling.x; t *= ref.scaling.y;
+	s = mod1(s, 1.0f); t = mod1(t, 1.0f);
+	const uint32 x = min((uint32)(s * tex.res_x), tex.res_x - 1), y = min((uint32)(t * tex.res_y), tex.res_y - 1);
+	const uint32 xx = (x + 1) % tex.res_x, yy = (y + 1) % tex.res_y;
+	const float4 q0 = __ldg(tex.texels + (size_t)y * tex.res_x + x), q1 = __ldg(tex.texels + (size_t)y * tex.res_x + xx);
+	const float4 q2 = __ldg(tex.texels + (size_t)yy * tex.res_x + x), q3 = __ldg(tex.texels + (size_t)yy * tex.res_x + xx);
+	const float u = mod1(s * tex.res_x, 1.0f), v = mod1(t * tex.res_y, 1.0f);
+	return V3((q0.x * (1 - u) + q1.x * u) * (1 - v) + (q2.x * (1 - u) + q3.x * u) * v,
+			  (q0.y * (1 - u) + q1.y * u) * (1 - v) + (q2.y * (1 - u) + q3.y * u) * v,
+			  (q0.z * (1 - u) + q1.z * u) * (1 - v) + (q2.z * (1 - u) + q3.z * u) * v);
+}
+
+FB_D TextureReference load_texref(const MeshMaterial* m, int which)   // which: byte offset / 16 of the reference inside MeshMaterial
+{
+	const float4 r = __ldg(reinterpret_cast<const float4*>(m) + which);
+	TextureReference t;
+	t.texture = __float_as_uint(r.x); t.pad_ = 0; t.scaling.x = r.z; t.scaling.y = r.w;
+	return t;
+}
+
+// textured emission + light pdf of a point on triangle `prim` (MeshLight::map_impl, src/lights.h:374-431)
+FB_D void light_map(const DeviceScene& sc, uint32 prim, float s, float t, float& pdf, V3& emissive)
+{
+	const MeshMaterial* m = sc.materials + __ldg(sc.material_indices + prim);
+	const float4 e = __ldg(reinterpret_cast<const float4*>(m) + 4);
+	emissive = V3(e) * texture_rgb(sc, s, t, load_texref(m, 11));
+	if (sc.use_vpls) pdf = fmaxf(fabsf(emissive.x), fmaxf(fabsf(emissive.y), fabsf(emissive.z))) / sc.vpl_norm;
+	else pdf = (__ldg(sc.mesh_cdf + prim) - (prim ? __ldg(sc.mesh_cdf + prim - 1) : 0.0f)) * __ldg(sc.mesh_inv_area + prim);
+}
+
+// TiledSequenceView::sample_2d over the transposed shift table: the six dimensions of one vertex are
+// 24 contiguous bytes per table row (src/tiled_sequence.h:62-105, src/tiled_sequence.cu:36-52)
+FB_D void vertex_samples(const DeviceScene& sc, uint32 px, uint32 py, uint32 first_dim, const float seq[6], float z[6])
+{
+	const uint32 T = 256u;
+	const uint32 shift = (px & (T - 1)) + (py & (T - 1)) * T;
+	const uint32 tile = ((px / T) & (T - 1)) + ((py / T) & (T - 1)) * T;
+	const float2* a = reinterpret_cast<const float2*>(sc.shifts_t + (size_t)shift * sc.n_dims + first_dim);
+	const float2* b = reinterpret_cast<const float2*>(sc.shifts_t + (size_t)tile * sc.n_dims + first_dim);
+	#pragma unroll
+	for (int i = 0; i < 3; ++i)
+	{
+		const float2 sa = __ldg(a + i), sb = __ldg(b + i);
+		z[2 * i]     = fmodf(fmodf(seq[2 * i] + sa.x, 1.0f) + sb.x, 1.0f);
+		z[2 * i + 1] = fmodf(fmodf(seq[2 * i + 1] + sa.y, 1.0f) + sb.y, 1.0f);
+	}
+}
+
+// add_in<ALPHA_AS_VARIANCE> (src/framebuffer.h:425-444); non-atomic like the reference: one writer per
+// pixel per kernel by construction
+template <bool VAR>
+FB_D void add_in(float4* channel, uint32 pixel, V3 f, float inv_n)
+{
+	float4 m = channel[pixel];
+	if (VAR)
+	{
+		const float ld = fmaxf(f.x - m.x, fmaxf(f.y - m.y, f.z - m.z));
+		m.w += ld * ld * inv_n;
+	}
+	m.x += f.x * inv_n; m.y += f.y * inv_n; m.z += f.z * inv_n;
+	channel[pixel] = m;
+}
+
+FB_D float power_heuristic(float p1, float p2)   // src/mis_utils.h:43-52
+{
+	const bool i1 = !isfinite(p1), i2 = !isfinite(p2);
+	return i1 ? 1.0f : i2 ? 0.0f : (p1 * p1) / (p1 * p1 + p2 * p2);
+}
+FB_D float pdf_product(float p1, float p2) { return isfinite(p1) && isfinite(p2) ? p1 * p2 : __int_as_float(0x7f800000); }  // src/bpt_utils.h:84-90
+
+// warp-aggregated queue slot allocation (replaces PTRayQueue::warp_append, src/pathtracer_queues.h:66-92):
+// one atomic per warp, lanes take consecutive slots in lane order. All 32 lanes must call it.
+FB_D uint32 warp_append_slot(uint32* counter, bool pred)
+{
+	const unsigned m = __ballot_sync(0xFFFFFFFFu, pred);
+	if (m == 0u) return 0xFFFFFFFFu;
+	const int lane = threadIdx.x & 31;
+	const int leader = __ffs(m) - 1;
+	uint32 base = 0;
+	if (lane == leader) base = atomicAdd(counter, (uint32)__popc(m));
+	base = __shfl_sync(0xFFFFFFFFu, base, leader);
+	return base + __popc(m & ((1u << lane) - 1u));
+}
+
+} // namespace fb

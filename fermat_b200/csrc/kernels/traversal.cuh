@@ -1,0 +1,252 @@
+// traversal.cuh — ray queries against the 8-wide compressed BVH (fb_types.h WideNode / WideTri).
+//
+// Replaces the reference's OptiX launches: closest hit `RTContext::trace` (src/rt.cpp:558-583,
+// src/kernels/optix_rt.cu:46-82, optix_base_shaders.h:43-91) and masked any hit `RTContext::trace_shadow`
+// (src/rt.cpp:610-635, optix_rt.cu:134-164, optix_base_shadow_shaders.h:43-72). Semantics kept:
+//   * parametric interval on the UN-NORMALISED direction, closest hit accepts t in (tmin, tmax);
+//   * hit = {t, triId, u, v}, u = weight of vertex 0, v = weight of vertex 1, both rounded through fp16
+//     (optix_payload.h:75-78); miss = {-1, -1};
+//   * any-hit ignores a triangle iff (ray.mask & triangle flags) != 0 and stops at the first accepted hit.
+// The traversal order / node format is ours: Ylitie-Karras-Laine compressed wide BVH, one ray per lane,
+// node hits kept as bit groups on a short per-lane stack, top of the tree read from shared memory.
+//
+// The triangle test is Moller-Trumbore in plain unfused fp32 (-fmad=false), operation for operation the
+// one in oracle/pt_oracle.cpp, so accepted hits carry identical bits on both sides; ties on t resolve to the
+// smaller triangle id, which makes the result independent of traversal order.
+#pragma once
+#include "device_scene.h"
+#include <cuda_fp16.h>
+
+namespace fb {
+
+#define FB_TRAV_STACK 28
+
+FB_D uint32 sign_extend_s8x4(uint32 x)
+{
+	uint32 r;
+	asm("prmt.b32 %0, %1, 0x0, 0x0000BA98;" : "=r"(r) : "r"(x));
+	return r;
+}
+FB_D uint32 bfind(uint32 x) { return 31u - (uint32)__clz((int)x); }
+
+struct TravRay
+{
+	float ox, oy, oz, tmin;
+	float dx, dy, dz, tmax;
+};
+
+struct TravHit { float t; int tri; float bu, bv; };
+
+// load the 5 x 16 B of node `idx` from the staged shared-memory copy or from global memory
+FB_D void load_node(const WideNode* __restrict__ nodes, const float4* __restrict__ smem_nodes, uint32 staged, uint32 idx,
+					float4& n0, float4& n1, float4& n2, float4& n3, float4& n4)
+{
+	if (idx < staged)
+	{
+		const float4* p = smem_nodes + idx * 5u;
+		n0 = p[0]; n1 = p[1]; n2 = p[2]; n3 = p[3]; n4 = p[4];
+	}
+	else
+	{
+		const float4* p = reinterpret_cast<const float4*>(nodes) + (size_t)idx * 5u;
+		n0 = __ldg(p); n1 = __ldg(p + 1); n2 = __ldg(p + 2); n3 = __ldg(p + 3); n4 = __ldg(p + 4);
+	}
+}
+
+// Per-lane traversal state machine. `ANY_HIT` = masked occlusion query.
+template <bool ANY_HIT>
+struct Traversal
+{
+	TravRay ray;
+	float idx_, idy_, idz_;          // 1 / dir
+	uint32 octinv4;
+	uint2 ngroup, tgroup;
+	uint2 stack[FB_TRAV_STACK];
+	int   sp;
+	TravHit hit;
+	uint32 mask;                     // any-hit: ray visibility mask
+	bool  occluded;
+
+	FB_D void init(float4 o, float4 d, uint32 ray_mask)
+	{
+		ray.ox = o.x; ray.oy = o.y; ray.oz = o.z; ray.dx = d.x; ray.dy = d.y; ray.dz = d.z;
+		ray.tmin = ANY_HIT ? 0.0f : o.w;
+		ray.tmax = d.w;
+		mask = ray_mask;
+		idx_ = 1.0f / d.x; idy_ = 1.0f / d.y; idz_ = 1.0f / d.z;
+		const uint32 octinv = (d.x < 0.0f ? 0u : 4u) | (d.y < 0.0f ? 0u : 2u) | (d.z < 0.0f ? 0u : 1u);
+		octinv4 = octinv * 0x01010101u;
+		ngroup = make_uint2(0u, 0x80000000u);
+		tgroup = make_uint2(0u, 0u);
+		sp = 0;
+		hit.t = -1.0f; hit.tri = -1; hit.bu = 0.0f; hit.bv = 0.0f;
+		occluded = false;
+	}
+
+	// one traversal step; returns false when the query is finished
+	FB_D bool step(const DeviceScene& sc, const float4* __restrict__ smem_nodes)
+	{
+		if (ngroup.y > 0x00FFFFFFu)
+		{
+			const uint32 hits = ngroup.y;
+			const uint32 child_bit = bfind(hits);
+			const uint32 base = ngroup.x;
+			ngroup.y &= ~(1u << child_bit);
+			if (ngroup.y > 0x00FFFFFFu) { stack[sp++] = ngroup; }
+			const uint32 slot = (child_bit - 24u) ^ (octinv4 & 0xFFu);
+			const uint32 rel = __popc(hits & ~(0xFFFFFFFFu << slot) & 0xFFu);
+			const uint32 node_idx = base + rel;
+
+			float4 n0, n1, n2, n3, n4;
+			load_node(sc.nodes, smem_nodes, sc.staged_nodes, node_idx, n0, n1, n2, n3, n4);
+
+			const uint32 e_imask = __float_as_uint(n0.w);
+			ngroup.x = __float_as_uint(n1.x);
+			tgroup.x = __float_as_uint(n1.y);
+			tgroup.y = 0u;
+			uint32 hitmask = 0u;
+
+			const float sx = __uint_as_float((e_imask & 0xFFu) << 23);
+			const float sy = __uint_as_float(((e_imask >> 8) & 0xFFu) << 23);
+			const float sz = __uint_as_float(((e_imask >> 16) & 0xFFu) << 23);
+			const float aix = sx * idx_, aiy = sy * idy_, aiz = sz * idz_;
+			const float aox = (n0.x - ray.ox) * idx_, aoy = (n0.y - ray.oy) * idy_, aoz = (n0.z - ray.oz) * idz_;
+			const bool nx = ray.dx < 0.0f, ny = ray.dy < 0.0f, nz = ray.dz < 0.0f;
+
+			#pragma unroll
+			for (int half_ = 0; half_ < 2; ++half_)
+			{
+				const uint32 meta4 = __float_as_uint(half_ == 0 ? n1.z : n1.w);
+				const uint32 is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+				const uint32 inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
+				const uint32 bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1F1F1F1Fu;
+				const uint32 child_bits4 = (meta4 >> 5) & 0x07070707u;
+
+				const uint32 qlox = __float_as_uint(half_ == 0 ? n2.x : n2.y), qloy = __float_as_uint(half_ == 0 ? n2.z : n2.w);
+				const uint32 qloz = __float_as_uint(half_ == 0 ? n3.x : n3.y), qhix = __float_as_uint(half_ == 0 ? n3.z : n3.w);
+				const uint32 qhiy = __float_as_uint(half_ == 0 ? n4.x : n4.y), qhiz = __float_as_uint(half_ == 0 ? n4.z : n4.w);
+				const uint32 xmin = nx ? qhix : qlox, xmax = nx ? qlox : qhix;
+				const uint32 ymin = ny ? qhiy : qloy, ymax = ny ? qloy : qhiy;
+				const uint32 zmin = nz ? qhiz : qloz, zmax = nz ? qloz : qhiz;
+
+				#pragma unroll
+				for (int j = 0; j < 4; ++j)
+				{
+					const int sh = j * 8;
+					const float t0x = fmaf((float)((xmin >> sh) & 0xFFu), aix, aox), t1x = fmaf((float)((xmax >> sh) & 0xFFu), aix, aox);
+					const float t0y = fmaf((float)((ymin >> sh) & 0xFFu), aiy, aoy), t1y = fmaf((float)((ymax >> sh) & 0xFFu), aiy, aoy);
+					const float t0z = fmaf((float)((zmin >> sh) & 0xFFu), aiz, aoz), t1z = fmaf((float)((zmax >> sh) & 0xFFu), aiz, aoz);
+					const float cmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, ray.tmin));
+					// far side widened by 4e-7 relative so that fp rounding never culls a box whose geometry is hit
+					const float cmax = fminf(fminf(t1x, t1y), fminf(t1z, ray.tmax)) * 1.0000004f;
+					if (cmin <= cmax)
+						hitmask |= ((child_bits4 >> sh) & 0xFFu) << ((bit_index4 >> sh) & 0xFFu);
+				}
+			}
+			ngroup.y = (hitmask & 0xFF000000u) | (e_imask >> 24);
+			tgroup.y = hitmask & 0x00FFFFFFu;
+		}
+		else
+		{
+			tgroup = ngroup;
+			ngroup = make_uint2(0u, 0u);
+		}
+
+		while (tgroup.y != 0u)
+		{
+			const uint32 k = bfind(tgroup.y);
+			tgroup.y &= ~(1u << k);
+			const float4* tp = reinterpret_cast<const float4*>(sc.tris) + (size_t)(tgroup.x + k) * 3u;
+			const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+			if (ANY_HIT && (mask & __float_as_uint(b.w))) continue;
+
+			// Moller-Trumbore, unfused, same operation order as oracle/pt_oracle.cpp intersect_tri()
+			const float e1x = b.x - a.x, e1y = b.y - a.y, e1z = b.z - a.z;
+			const float e2x = c.x - a.x, e2y = c.y - a.y, e2z = c.z - a.z;
+			const float px = ray.dy * e2z - ray.dz * e2y, py = ray.dz * e2x - ray.dx * e2z, pz = ray.dx * e2y - ray.dy * e2x;
+			const float det = e1x * px + e1y * py + e1z * pz;
+			if (det == 0.0f) continue;
+			const float inv = 1.0f / det;
+			const float tx = ray.ox - a.x, ty = ray.oy - a.y, tz = ray.oz - a.z;
+			const float bu = (tx * px + ty * py + tz * pz) * inv;
+			if (!(bu >= 0.0f && bu <= 1.0f)) continue;
+			const float qx = ty * e1z - tz * e1y, qy = tz * e1x - tx * e1z, qz = tx * e1y - ty * e1x;
+			const float bv = (ray.dx * qx + ray.dy * qy + ray.dz * qz) * inv;
+			if (!(bv >= 0.0f && bu + bv <= 1.0f)) continue;
+			const float t = (e2x * qx + e2y * qy + e2z * qz) * inv;
+			if (ANY_HIT)
+			{
+				if (t > 0.0f && t < ray.tmax) { occluded = true; return false; }
+			}
+			else
+			{
+				const int tri = (int)__float_as_uint(a.w);
+				if (t > ray.tmin && (t < ray.tmax || (t == ray.tmax && hit.tri >= 0 && tri < hit.tri)))
+				{
+					ray.tmax = t; hit.t = t; hit.tri = tri; hit.bu = bu; hit.bv = bv;
+				}
+			}
+		}
+
+		if (ngroup.y <= 0x00FFFFFFu)
+		{
+			if (sp == 0) return false;
+			ngroup = stack[--sp];
+		}
+		return true;
+	}
+
+	// reference hit record: u = weight of v0, v = weight of v1, through fp16
+	FB_D float4 hit_record() const
+	{
+		if (hit.tri < 0) return make_float4(-1.0f, __int_as_float(-1), 0.0f, 0.0f);
+		const float u = __half2float(__float2half_rn(1.0f - hit.bu - hit.bv));
+		const float v = __half2float(__float2half_rn(hit.bu));
+		return make_float4(hit.t, __int_as_float(hit.tri), u, v);
+	}
+};
+
+// ---- shared-memory staging of the top of the tree with one bulk asynchronous copy (TMA, 1-D) --------
+// Copies `bytes` (multiple of 16) from global to shared memory and waits for completion. Must be called by
+// all threads of the CTA; thread 0 issues the copy.
+FB_D void stage_nodes_tma(void* smem_dst, const void* gmem_src, uint32 bytes, unsigned long long* bar)
+{
+#if __CUDA_ARCH__ >= 900
+	const uint32 bar_addr = (uint32)__cvta_generic_to_shared(bar);
+	const uint32 dst_addr = (uint32)__cvta_generic_to_shared(smem_dst);
+	if (threadIdx.x == 0)
+	{
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_addr));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	if (threadIdx.x == 0 && bytes)
+	{
+		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar_addr), "r"(bytes) : "memory");
+		// the bulk copy engine takes up to 2^20-16 bytes per instruction; issue in 32 KB chunks
+		uint32 off = 0;
+		while (off < bytes)
+		{
+			const uint32 chunk = min(bytes - off, 32768u);
+			asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+				:: "r"(dst_addr + off), "l"(reinterpret_cast<const char*>(gmem_src) + off), "r"(chunk), "r"(bar_addr) : "memory");
+			off += chunk;
+		}
+	}
+	if (bytes)
+	{
+		uint32 done = 0;
+		while (!done)
+		{
+			asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+				: "=r"(done) : "r"(bar_addr), "r"(0u) : "memory");
+		}
+	}
+#else
+	for (uint32 i = threadIdx.x; i < bytes / 16u; i += blockDim.x)
+		reinterpret_cast<float4*>(smem_dst)[i] = reinterpret_cast<const float4*>(gmem_src)[i];
+	__syncthreads();
+#endif
+}
+
+} // namespace fb
