@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py — Msamples/s of the `-pt` hot path (sample = one (path, bounce) shade event, the reference's own
+counter `stats.shade_events`, src/pathtracer_kernels.h:360).
+
+  python bench.py --gpus N --steps K --warmup W          our CUDA path (one process per GPU under torchrun for N > 1)
+  python bench.py --impl reference ...                   the CPU restatement of the reference's algorithm (oracle/),
+                                                         timed on the box's host cores (the reference itself cannot run:
+                                                         OptiX 6 + Win32)
+
+A step is one progressive pass (render(instance)) over the frame. Workload at N = 1: BASELINE.json configs[1],
+bathroom2 1600x900, 8 bounces. For N > 1 the frame grows with N at constant pixels per GPU (weak scaling, same camera),
+tile-sharded over the ranks with ONE NCCL reduce of the accumulated image per pass.
+Prints one JSON line (rank 0).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Msamples/sec (paths x bounces)"
+BOUNCES = 8
+
+
+def workload(args):
+    scene = args.scene or os.path.join(ROOT, "scenes", "_cache", "bathroom2.fbs")
+    name = "bathroom2"
+    if not os.path.exists(scene):
+        # the named scene could not be shipped: say so in the output instead of silently measuring something else
+        scene = os.path.join(ROOT, "tests", "golden", "cornellbox_jp.fbs")
+        name = "cornellbox_jp (FALLBACK: scenes/_cache/bathroom2.fbs missing)"
+    elif args.scene:
+        name = os.path.splitext(os.path.basename(scene))[0]
+    return scene, name
+
+
+def frame_size(args, n_gpus):
+    if args.res:
+        return args.res[0], args.res[1]
+    s = math.sqrt(n_gpus)
+    return int(round(1600 * s)), int(round(900 * s))
+
+
+class ClockSampler(threading.Thread):
+    """samples nvidia-smi clocks / throttle reasons while the timed region runs"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        reasons = []
+        for i, nm in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")):
+            if any(len(r) >= 6 and r[2 + i].lower().startswith("active") for r in self.rows):
+                reasons.append(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_baseline(scene, res, threads=0, target_s=12.0, count_traversal=True):
+    """the oracle (kind "port") on a bounded, strided sample of the workload's pixels; ~target_s of CPU work"""
+    import fermat_b200 as fb
+    import oracle
+    sc = fb.Scene(["-i", scene, "-r", str(res[0]), str(res[1]), "-bounces", str(BOUNCES)])
+    P = res[0] * res[1]
+    fbuf = oracle.new_framebuffer(sc.view)
+    probe = np.arange(0, P, 101, dtype=np.uint32)
+    oracle.render_pass(sc.view, 0, fbuf, pixels=probe, threads=threads)       # warm caches / thread pool
+    t = time.perf_counter()
+    st = oracle.render_pass(sc.view, 0, fbuf, pixels=probe, threads=threads)
+    dt = max(time.perf_counter() - t, 1e-3)
+    rate = st.shade_events / dt
+    per_pixel = st.shade_events / probe.size
+    n_pix = int(min(P, max(probe.size, target_s * rate / per_pixel)))
+    stride = max(1, P // n_pix)
+    pixels = np.arange(0, P, stride, dtype=np.uint32)
+    t = time.perf_counter()
+    st = oracle.render_pass(sc.view, 1, fbuf, pixels=pixels, threads=threads, count_traversal=count_traversal)
+    dt = time.perf_counter() - t
+    cores = threads if threads > 0 else oracle.num_threads()
+    out = {"value": st.shade_events / dt * 1e-6, "unit": "Msamples/s", "cores": cores, "kind": "port",
+           "sample": "oracle (scalar C++ restatement, OpenMP over pixels), 1 pass over every %d-th pixel of %dx%d (%d pixels, %d samples, %.1f s)" % (
+               stride, res[0], res[1], pixels.size, st.shade_events, dt)}
+    trav = None
+    if count_traversal and st.shade_events:
+        trav = {"closest_nodes_per_ray": st.nodes_visited / st.shade_events, "closest_tris_per_ray": st.tris_tested / st.shade_events,
+                "shadow_nodes_per_ray": st.shadow_nodes_visited / max(st.shadow_events, 1), "shadow_tris_per_ray": st.shadow_tris_tested / max(st.shadow_events, 1),
+                "shadow_rays_per_sample": st.shadow_events / st.shade_events}
+    sc.close()
+    return out, trav
+
+
+def run_reference(args):
+    """--impl reference: the CPU restatement of the reference's algorithm on all host cores, same config/metric"""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import fermat_b200 as fb
+    import oracle
+    scene, name = workload(args)
+    res = frame_size(args, 1)
+    sc = fb.Scene(["-i", scene, "-r", str(res[0]), str(res[1]), "-bounces", str(BOUNCES)])
+    P = res[0] * res[1]
+    fbuf = oracle.new_framebuffer(sc.view)
+    probe = np.arange(0, P, 101, dtype=np.uint32)
+    oracle.render_pass(sc.view, 0, fbuf, pixels=probe)                        # warm caches / thread pool
+    t = time.perf_counter()
+    st = oracle.render_pass(sc.view, 0, fbuf, pixels=probe)
+    rate = st.shade_events / max(time.perf_counter() - t, 1e-3)
+    per_pixel = st.shade_events / probe.size
+    budget = 90.0 / max(args.steps + args.warmup, 1)                 # whole run within a few minutes
+    stride = max(1, int(P / max(probe.size, min(5.0, budget) * rate / per_pixel)))
+    pixels = np.arange(0, P, stride, dtype=np.uint32)
+    for i in range(args.warmup):
+        oracle.render_pass(sc.view, i, fbuf, pixels=pixels)
+    ev = 0
+    t = time.perf_counter()
+    for i in range(args.warmup, args.warmup + args.steps):
+        ev += oracle.render_pass(sc.view, i, fbuf, pixels=pixels).shade_events
+    dt = time.perf_counter() - t
+    v = ev / dt * 1e-6
+    cores = oracle.num_threads()
+    sample = "each step = one oracle pass over every %d-th pixel of %dx%d (%d pixels)" % (stride, res[0], res[1], pixels.size)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "Msamples/s", "n_gpus": 0, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s -pt %dx%d, %d bounces" % (name, res[0], res[1], BOUNCES), "note": "CPU restatement of the reference algorithm (the reference needs OptiX 6 / Win32 and cannot run)"},
+        "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import fermat_b200 as fb
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the -pt renderer has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    scene, name = workload(args)
+    res = frame_size(args, world)
+    sc = fb.Scene(["-i", scene, "-r", str(res[0]), str(res[1]), "-bounces", str(BOUNCES), "-shard", str(rank), str(world)])
+    rc = fb.RenderingContext(sc, local)
+    stream = torch.cuda.ExternalStream(rc.stream(), device=torch.device("cuda", local))
+    comp = rc.fb_tensor("COMPOSITED_C")
+    send = torch.empty_like(comp)
+    host = torch.empty(comp.shape, dtype=torch.float32, pin_memory=True)
+    host_np = host.numpy()
+    import ctypes as C
+    host_ptr = C.cast(host.data_ptr(), C.POINTER(C.c_float))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        rc.synchronize()
+
+    def step(i, reduce_image):
+        rc.render(i, sync=False)
+        if world > 1 and reduce_image:
+            with torch.cuda.stream(stream):
+                send.copy_(comp, non_blocking=True)
+                dist.reduce(send, dst=0, op=dist.ReduceOp.SUM)      # the single image reduce per frame (NVLink)
+
+    rc.clear()
+    for i in range(args.warmup):
+        step(i, True)
+    barrier()
+
+    # ---------------- device-timed region: K passes, inputs resident in HBM ----------------
+    rc.set_profiling(True)
+    k0 = rc.kernel_times()
+    s0 = rc.stats()
+    clocks = ClockSampler(local) if rank == 0 else None
+    if clocks:
+        clocks.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    wall0 = time.perf_counter()
+    for i in range(args.warmup, args.warmup + args.steps):
+        step(i, True)
+    ev1.record(stream)
+    barrier()
+    wall = time.perf_counter() - wall0
+    ms = ev0.elapsed_time(ev1)
+    clk = clocks.stop() if clocks else None
+    s1 = rc.stats()
+    k1 = rc.kernel_times()
+    rc.set_profiling(False)
+    samples = s1["shade_events"] - s0["shade_events"]
+    shadow = s1["shadow_events"] - s0["shadow_events"]
+    launches = s1["kernel_launches"] - s0["kernel_launches"]
+    t = torch.tensor([ms, float(samples), float(shadow), float(launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, samples, shadow, launches = float(tmax[0]), float(tsum[1]), float(tsum[2]), float(tsum[3])
+    value = samples / (ms * 1e-3) * 1e-6
+
+    # ---------------- end-to-end region: render() through the C ABI + device->host read of the frame ----------------
+    barrier()
+    e0 = rc.stats()["shade_events"]
+    w0 = time.perf_counter()
+    for i in range(args.warmup + args.steps, args.warmup + 2 * args.steps):
+        step(i, True)
+        if rank == 0:
+            if world > 1:
+                with torch.cuda.stream(stream):
+                    host.copy_(send, non_blocking=False)
+            else:
+                fb.lib().fb200_context_fb_download(rc._h, fb.FB_CHANNELS["COMPOSITED_C"], host_ptr)
+    barrier()
+    e2e_s = time.perf_counter() - w0
+    e_samples = rc.stats()["shade_events"] - e0
+    te = torch.tensor([e2e_s, float(e_samples)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        a = te.clone(); dist.all_reduce(a, op=dist.ReduceOp.MAX)
+        b = te.clone(); dist.all_reduce(b, op=dist.ReduceOp.SUM)
+        e2e_s, e_samples = float(a[0]), float(b[1])
+    e2e_value = e_samples / e2e_s * 1e-6
+    finite = bool(np.isfinite(host_np).all()) if rank == 0 else True
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- CPU baseline (rank 0, N = 1 only) and roofline ----------------
+    base, trav = (None, None)
+    trav_file = os.path.join(ROOT, "profiles", "trav_counts_%s.json" % name.split()[0])
+    if world == 1 and not args.no_cpu_baseline:
+        base, trav = cpu_baseline(scene, res)
+    if trav is None and os.path.exists(trav_file):
+        trav = json.load(open(trav_file))
+    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_file):
+        peak, peak_src = float(json.load(open(peaks_file))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+
+    kt = {k: {"ms": k1[k]["ms"] - k0[k]["ms"], "launches": k1[k]["launches"] - k0[k]["launches"]} for k in k1}
+    rank_samples = s1["shade_events"] - s0["shade_events"]
+    rank_shadow = s1["shadow_events"] - s0["shadow_events"]
+    # algorithmic bytes: queue/attribute/frame-buffer bytes from the reference's layouts plus
+    # 32 B per BVH2 node visited + 64 B per triangle tested by the oracle's scalar traversal of the same tree
+    tb = trav or {"closest_nodes_per_ray": 0, "closest_tris_per_ray": 0, "shadow_nodes_per_ray": 0, "shadow_tris_per_ray": 0}
+    alg = {
+        "trace": rank_samples * (48 + 32 * tb["closest_nodes_per_ray"] + 64 * tb["closest_tris_per_ray"]),
+        "shade": rank_samples * (88 + 84 + 72 + 96),
+        "shadow": rank_shadow * (48 + 80 + 64 + 32 * tb["shadow_nodes_per_ray"] + 64 * tb["shadow_tris_per_ray"]),
+    }
+    kernels = {}
+    for k in ("trace", "shade", "shadow"):
+        sec = kt[k]["ms"] * 1e-3
+        kernels[k] = {"ms_per_launch": kt[k]["ms"] / max(kt[k]["launches"], 1), "launches": kt[k]["launches"],
+                      "share_of_step": kt[k]["ms"] / max(sum(v["ms"] for v in kt.values()), 1e-9),
+                      "algorithmic_GBps": alg[k] / max(sec, 1e-12) * 1e-9}
+    dom = max(("trace", "shade", "shadow"), key=lambda k: kt[k]["ms"])
+    ncu_file = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    traffic = None
+    if os.path.exists(ncu_file):
+        traffic = json.load(open(ncu_file)).get(dom)
+    roofline = {"bound": "hbm", "kernel": {"trace": "k_trace<closest>", "shade": "k_shade", "shadow": "k_trace<shadow>+accumulate"}[dom],
+                "achieved": kernels[dom]["algorithmic_GBps"], "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                "frac": kernels[dom]["algorithmic_GBps"] / peak, "traffic": traffic,
+                "bytes_note": "algorithmic bytes = SURVEY 8d: reference queue/attribute/FB layouts + 32 B/node + 64 B/tri of the oracle's BVH2 traversal%s" % ("" if trav else " (traversal counts unavailable: queue bytes only)")}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s -pt %dx%d, %d bounces, default seeds, passes %d..%d" % (name, res[0], res[1], BOUNCES, args.warmup, args.warmup + args.steps - 1),
+                   "parallelism": "tile-sharded x%d, one NCCL reduce of COMPOSITED per pass" % world if world > 1 else "single GPU",
+                   "l2": "working set per pass (queues + 8-channel frame buffer, > 400 MB) exceeds the 126 MB L2",
+                   "target": ">= 200 Msamples/s (BASELINE.json)"},
+        "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": 4 * sc.view.n_dimensions + 96, "d2h_bytes_per_step": int(comp.numel() * 4),
+                "note": "render(instance) through the C ABI + frame read back to pinned host memory every pass; the scene is resident like model weights"},
+        "gpu_launches": int(launches), "wall_s": wall, "samples": samples, "shadow_rays": shadow, "finite": finite,
+        "clocks": clk, "roofline": roofline, "kernels": kernels,
+    }
+    if base:
+        out["cpu_baseline"] = base
+    if trav:
+        out["traversal_counts"] = trav
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    rc.close()
+    sc.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=24)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scene", default=None)
+    ap.add_argument("--res", type=int, nargs=2, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if args.gpus != world and world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py: --gpus %d needs torchrun --nproc-per-node %d" % (args.gpus, args.gpus))
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -76,6 +76,13 @@ def lib():
         "fb200_scene_save_snapshot": (i32, [vp, C.c_char_p]),
         "fb200_scene_bvh_stats": (i32, [vp, C.POINTER(u64 * 4), C.POINTER(f32)]),
         "fb200_scene_sample_2d": (f32, [vp, u32, u32, u32, u32]),
+        "fb200_scene_owned_pixels": (u64, [vp, C.POINTER(u32), u64]),
+        "fb200_diag_lfsr": (i32, [u32, pf, u32]),
+        "fb200_diag_randfloat": (f32, [u32, u32]),
+        "fb200_diag_float_to_half": (u32, [f32]),
+        "fb200_diag_half_to_float": (f32, [u32]),
+        "fb200_diag_pack_normal": (u32, [f32, f32, f32]),
+        "fb200_diag_msvc_rand": (i32, [u32, C.POINTER(C.c_int32), u32]),
         "fb200_context_create": (vp, [vp, i32]),
         "fb200_context_destroy": (None, [vp]),
         "fb200_context_clear": (i32, [vp]),
@@ -87,6 +94,8 @@ def lib():
         "fb200_context_fb_upload": (i32, [vp, i32, pf]),
         "fb200_context_get_stats": (i32, [vp, C.POINTER(Stats)]),
         "fb200_context_stream": (vp, [vp]),
+        "fb200_context_set_profiling": (i32, [vp, i32]),
+        "fb200_context_get_kernel_times": (i32, [vp, C.POINTER(C.c_double * 4), C.POINTER(u64 * 4)]),
         "fb200_context_owned_pixels": (u64, [vp]),
         "fb200_trace": (i32, [vp, pf, pf, u32]),
         "fb200_trace_shadow": (i32, [vp, pf, C.POINTER(C.c_uint8), u32]),
@@ -148,6 +157,13 @@ class Scene:
     def save_snapshot(self, filename):
         if lib().fb200_scene_save_snapshot(self._h, str(filename).encode()) != 0:
             raise RuntimeError(_err())
+
+    def owned_pixels(self):
+        """Global pixel indices of this scene's tile shard (-shard r n)."""
+        n = lib().fb200_scene_owned_pixels(self._h, None, 0)
+        out = np.empty(n, dtype=np.uint32)
+        lib().fb200_scene_owned_pixels(self._h, out.ctypes.data_as(C.POINTER(C.c_uint32)), n)
+        return out
 
     def sample_2d(self, instance, px, py, dim):
         return lib().fb200_scene_sample_2d(self._h, instance, px, py, dim)
@@ -225,6 +241,16 @@ class RenderingContext:
 
     def stream(self):
         return lib().fb200_context_stream(self._h)
+
+    def set_profiling(self, on=True):
+        self._chk(lib().fb200_context_set_profiling(self._h, 1 if on else 0))
+
+    def kernel_times(self):
+        """Accumulated device ms and launch counts per kernel class (see include/fermat_b200.h)."""
+        ms, n = (C.c_double * 4)(), (C.c_uint64 * 4)()
+        self._chk(lib().fb200_context_get_kernel_times(self._h, C.byref(ms), C.byref(n)))
+        names = ("frame", "trace", "shade", "shadow")
+        return {k: {"ms": ms[i], "launches": int(n[i])} for i, k in enumerate(names)}
 
     def owned_pixels(self):
         return int(lib().fb200_context_owned_pixels(self._h))

@@ -98,6 +98,13 @@ int fb200_context_get_stats(fb200_context* c, fb200_stats* out)
 	});
 }
 
+int fb200_context_set_profiling(fb200_context* c, int on) { pt_of(c)->set_profiling(on != 0); return 0; }
+
+int fb200_context_get_kernel_times(fb200_context* c, double out_ms[4], uint64_t out_launches[4])
+{
+	return guarded([&] { pt_of(c)->kernel_times(c->rc, out_ms, out_launches); });
+}
+
 void* fb200_context_stream(fb200_context* c) { return (void*)c->rc.stream(); }
 uint64_t fb200_context_owned_pixels(const fb200_context* c) { return static_cast<PathTracer*>(const_cast<fb200_context*>(c)->rc.renderer())->owned_pixels(); }
 

@@ -54,6 +54,42 @@ int fb200_scene_bvh_stats(const fb200_scene* s, uint64_t out[4], float* sah_cost
 	return 0;
 }
 
+uint64_t fb200_scene_owned_pixels(const fb200_scene* s, uint32_t* out, uint64_t capacity)
+{
+	if (!s) return 0;
+	std::vector<uint32_t> tiles; uint32_t tiles_x = 0;
+	const uint64_t owned = fb::shard_tiles(s->res_x, s->res_y, s->shard_rank, s->shard_count, tiles, tiles_x);
+	if (out)
+	{
+		uint64_t k = 0;
+		for (size_t t = 0; t < tiles.size(); ++t)
+			for (uint32_t j = 0; j < 32 * 32; ++j)
+			{
+				const uint32_t px = (tiles[t] % tiles_x) * 32 + (j & 31), py = (tiles[t] / tiles_x) * 32 + (j >> 5);
+				if (px < s->res_x && py < s->res_y && k < capacity) out[k++] = px + py * s->res_x;
+			}
+	}
+	return owned;
+}
+
+// diagnostics: host codecs / streams the parity tests pin against the reference's own code
+int fb200_diag_lfsr(uint32_t seed_arg, float* out, uint32_t n)
+{
+	fb::LFSRStream r(1u, fb::hash_u32(seed_arg));
+	for (uint32_t i = 0; i < n; ++i) out[i] = r.next();
+	return 0;
+}
+float    fb200_diag_randfloat(uint32_t i, uint32_t p) { return fb::randfloat(i, p); }
+uint32_t fb200_diag_float_to_half(float f) { return fb::float_to_half_rn(f); }
+float    fb200_diag_half_to_float(uint32_t h) { return fb::half_to_float((uint16_t)h); }
+uint32_t fb200_diag_pack_normal(float x, float y, float z) { return fb::pack_normal_10_10_10(fb::V3(x, y, z)); }
+int      fb200_diag_msvc_rand(uint32_t seed, int32_t* out, uint32_t n)
+{
+	fb::MsvcRand r(seed);
+	for (uint32_t i = 0; i < n; ++i) out[i] = r.next();
+	return 0;
+}
+
 float fb200_scene_sample_2d(fb200_scene* s, uint32_t instance, uint32_t px, uint32_t py, uint32_t dim)
 {
 	if (!s || dim >= s->sequence.n_dimensions) return -1.0f;

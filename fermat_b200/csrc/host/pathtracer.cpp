@@ -7,8 +7,9 @@
 
 using namespace fb;
 
-PathTracer::PathTracer() : m_n_tiles(0), m_tiles_x(0), m_owned_pixels(0), m_capacity(0), m_passes(0), m_device_ms(0.0), m_events(false)
+PathTracer::PathTracer() : m_n_tiles(0), m_tiles_x(0), m_owned_pixels(0), m_capacity(0), m_passes(0), m_device_ms(0.0), m_events(false), m_profiling(false)
 {
+	for (int i = 0; i < 4; ++i) { m_class_ms[i] = 0.0; m_class_launches[i] = 0; }
 	pt_options_defaults(m_options);
 	memset(m_queue, 0, sizeof(m_queue));
 	memset(&m_shadow, 0, sizeof(m_shadow));
@@ -52,20 +53,8 @@ void PathTracer::init(int argc, char** argv, RenderingContext& renderer)
 	fprintf(stderr, "  PT settings:\n    path-length     : %u\n    nee algorithm   : %s\n", m_options.max_path_length, m_options.nee_type == 1 ? "vpl" : "mesh");
 
 	// tile shard of this process: tile T = ty*tiles_x + tx belongs to rank (T + ty) % shard_count
-	const uint32 TILE = 32;
-	m_tiles_x = (res.x + TILE - 1) / TILE;
-	const uint32 tiles_y = (res.y + TILE - 1) / TILE;
 	std::vector<uint32> tiles;
-	m_owned_pixels = 0;
-	for (uint32 ty = 0; ty < tiles_y; ++ty)
-		for (uint32 tx = 0; tx < m_tiles_x; ++tx)
-		{
-			const uint32 T = ty * m_tiles_x + tx;
-			if ((T + ty) % s.shard_count != s.shard_rank) continue;
-			tiles.push_back(T);
-			const uint32 w = (tx + 1) * TILE <= res.x ? TILE : res.x - tx * TILE, h = (ty + 1) * TILE <= res.y ? TILE : res.y - ty * TILE;
-			m_owned_pixels += (uint64_t)w * h;
-		}
+	m_owned_pixels = shard_tiles(res.x, res.y, s.shard_rank, s.shard_count, tiles, m_tiles_x);
 	m_n_tiles = (uint32)tiles.size();
 	m_tile_list.upload(tiles.data(), tiles.size() * sizeof(uint32), renderer.stream());
 
@@ -88,6 +77,27 @@ void PathTracer::init(int argc, char** argv, RenderingContext& renderer)
 	cuda_check(cudaEventCreate(&m_ev0), "event"); cuda_check(cudaEventCreate(&m_ev1), "event");
 }
 
+cudaEvent_t PathTracer::take_event()
+{
+	if (!m_event_pool.empty()) { cudaEvent_t e = m_event_pool.back(); m_event_pool.pop_back(); return e; }
+	cudaEvent_t e;
+	cuda_check(cudaEventCreate(&e), "event");
+	return e;
+}
+
+void PathTracer::kernel_times(RenderingContext& renderer, double out_ms[4], uint64_t out_launches[4])
+{
+	renderer.synchronize();
+	for (size_t i = 0; i < m_spans.size(); ++i)
+	{
+		float ms = 0.0f;
+		if (cudaEventElapsedTime(&ms, m_spans[i].a, m_spans[i].b) == cudaSuccess) { m_class_ms[m_spans[i].cls] += ms; m_class_launches[m_spans[i].cls]++; }
+		m_event_pool.push_back(m_spans[i].a); m_event_pool.push_back(m_spans[i].b);
+	}
+	m_spans.clear();
+	for (int i = 0; i < 4; ++i) { out_ms[i] = m_class_ms[i]; out_launches[i] = m_class_launches[i]; }
+}
+
 void PathTracer::render(const uint32_t instance, RenderingContext& renderer)
 {
 	fb200_scene& s = *renderer.scene();
@@ -96,9 +106,15 @@ void PathTracer::render(const uint32_t instance, RenderingContext& renderer)
 	cudaStream_t stream = renderer.stream();
 
 	if (!m_events) { cuda_check(cudaEventRecord(m_ev0, stream), "event record"); m_events = true; }
+	// optional per-kernel timing: an event pair around each launch (no synchronisation; resolved in kernel_times)
+	Span span; span.cls = -1;
+	auto begin = [&](int cls) { if (m_profiling) { span.cls = cls; span.a = take_event(); span.b = take_event(); cuda_check(cudaEventRecord(span.a, stream), "event record"); } };
+	auto end = [&]() { if (m_profiling) { cuda_check(cudaEventRecord(span.b, stream), "event record"); m_spans.push_back(span); } };
 
 	// pre-multiply the previous frame for blending (pathtracer_impl.h:201)
+	begin(0);
 	renderer.rescale_frame(instance);
+	end();
 
 	// per-pass sampler offsets (TiledSequence::set_instance, src/tiled_sequence.cu:100-110)
 	s.sequence.set_instance(instance);
@@ -131,7 +147,9 @@ void PathTracer::render(const uint32_t instance, RenderingContext& renderer)
 
 	const FrameBufferView fbv = renderer.get_frame_buffer().view();
 	const float seq2[2] = { seq[0], seq[1] };
+	begin(0);
 	cuda_check(launch_generate_primary(sc, pp, m_queue[0], ctr, seq2, stream), "generate_primary");
+	end();
 	renderer.kernel_launches++;
 
 	// path_trace_loop: trace -> shade -> shadow trace + solve_occlusion, per bounce; no host round trips
@@ -139,15 +157,23 @@ void PathTracer::render(const uint32_t instance, RenderingContext& renderer)
 	{
 		const PathQueue& in = m_queue[bounce & 1];
 		const PathQueue& out = m_queue[(bounce + 1) & 1];
+		begin(1);
 		cuda_check(launch_trace_closest(sc, lc, in, ctr, bounce, stream), "trace");
+		end();
 		float seq6[6];
 		for (int i = 0; i < 6; ++i) seq6[i] = seq[(bounce + 1) * 6 + i];
+		begin(2);
 		cuda_check(launch_shade(sc, lc, pp, in, out, m_shadow, fbv, ctr, tot, bounce, seq6, (uint32)m_capacity, stream), "shade");
+		end();
+		begin(3);
 		cuda_check(launch_trace_shadow(sc, lc, m_shadow, fbv, ctr, tot, bounce, pp.frame_weight, stream), "trace_shadow");
+		end();
 		renderer.kernel_launches += 3;
 	}
 
+	begin(0);
 	renderer.update_variances(instance);
+	end();
 	cuda_check(cudaEventRecord(m_ev1, stream), "event record");
 	m_passes++;
 }

@@ -150,6 +150,25 @@ void scene_init(fb200_scene& s, int argc, const char* const* argv)
 	}
 }
 
+uint64_t shard_tiles(uint32_t res_x, uint32_t res_y, uint32_t rank, uint32_t count, std::vector<uint32_t>& tiles, uint32_t& tiles_x)
+{
+	const uint32 TILE = 32;
+	tiles_x = (res_x + TILE - 1) / TILE;
+	const uint32 tiles_y = (res_y + TILE - 1) / TILE;
+	tiles.clear();
+	uint64_t owned = 0;
+	for (uint32 ty = 0; ty < tiles_y; ++ty)
+		for (uint32 tx = 0; tx < tiles_x; ++tx)
+		{
+			const uint32 T = ty * tiles_x + tx;
+			if ((T + ty) % count != rank) continue;
+			tiles.push_back(T);
+			const uint32 w = (tx + 1) * TILE <= res_x ? TILE : res_x - tx * TILE, h = (ty + 1) * TILE <= res_y ? TILE : res_y - ty * TILE;
+			owned += (uint64_t)w * h;
+		}
+	return owned;
+}
+
 void scene_fill_view(const fb200_scene& s, fb200_scene_view& v)
 {
 	memset(&v, 0, sizeof(v));

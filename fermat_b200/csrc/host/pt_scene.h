@@ -46,4 +46,9 @@ void scene_fill_view(const fb200_scene& s, fb200_scene_view& v);
 
 std::string default_tables_path();
 
+// Tile sharding of the frame over `count` processes: 32x32 tiles, tile T = ty*tiles_x + tx
+// belongs to rank (T + ty) % count (diagonal stripes, so that neither rows nor columns of tiles map to one
+// rank). Fills `tiles` with the tile ids owned by `rank`, returns the number of in-frame pixels they cover.
+uint64_t shard_tiles(uint32_t res_x, uint32_t res_y, uint32_t rank, uint32_t count, std::vector<uint32_t>& tiles, uint32_t& tiles_x);
+
 } // namespace fb

@@ -116,6 +116,10 @@ struct PathTracer final : RendererInterface
 	uint64_t owned_pixels() const { return m_owned_pixels; }
 	uint64_t passes() const { return m_passes; }
 	double   device_ms() const { return m_device_ms; }
+	// per-kernel-class device time (CUDA events on the launching stream). Classes: 0 frame-buffer element-wise
+	// + primary rays, 1 closest-hit trace, 2 shade, 3 shadow trace + accumulate. out_ms / out_launches: 4 entries.
+	void     set_profiling(bool on) { m_profiling = on; }
+	void     kernel_times(RenderingContext& renderer, double out_ms[4], uint64_t out_launches[4]);
 
 private:
 	fb::PTOptions    m_options;
@@ -128,4 +132,11 @@ private:
 	double           m_device_ms;
 	cudaEvent_t      m_ev0, m_ev1;
 	bool             m_events;
+	bool             m_profiling;
+	struct Span { int cls; cudaEvent_t a, b; };
+	std::vector<Span>        m_spans;         // recorded, not yet resolved
+	std::vector<cudaEvent_t> m_event_pool;
+	double           m_class_ms[4];
+	uint64_t         m_class_launches[4];
+	cudaEvent_t      take_event();
 };

@@ -114,6 +114,21 @@ int          fb200_scene_bvh_stats(const fb200_scene*, uint64_t out[4], float* s
 /* TiledSequenceView::sample_2d for pass `instance` (src/tiled_sequence.h:93-105) */
 float        fb200_scene_sample_2d(fb200_scene*, uint32_t instance, uint32_t px, uint32_t py, uint32_t dim);
 
+/* global pixel indices (x + y*res_x) of the tile shard this scene was created for (-shard r n): writes up
+ * to `capacity` entries to `out` (may be NULL) and returns the owned-pixel count */
+uint64_t     fb200_scene_owned_pixels(const fb200_scene*, uint32_t* out, uint64_t capacity);
+
+/* diagnostics: host codecs and random streams, pinned by tests against the reference's own code
+ * (contrib/cugar/sampling/lfsr.h with seed hash(seed_arg) as src/mesh_lights.cu:171-172 uses it;
+ * cugar::randfloat, contrib/cugar/basic/numbers.h:752-763; __floats2half2_rn as in src/mesh/MeshCompression.h:36-50;
+ * cugar::pack_normal, contrib/cugar/linalg/vector_inl.h:786-790; MSVC rand() as consumed by src/tiled_sampling.h:44-47) */
+int      fb200_diag_lfsr(uint32_t seed_arg, float* out, uint32_t n);
+float    fb200_diag_randfloat(uint32_t i, uint32_t p);
+uint32_t fb200_diag_float_to_half(float f);
+float    fb200_diag_half_to_float(uint32_t h);
+uint32_t fb200_diag_pack_normal(float x, float y, float z);
+int      fb200_diag_msvc_rand(uint32_t seed, int32_t* out, uint32_t n);
+
 /* --- rendering context (needs a CUDA device; fails loudly without one) ------------------------ */
 
 /* RenderingContext::init + PathTracer::init (src/renderer.cu:467-991, src/renderers/pathtracer_impl.h:99-178)
@@ -137,6 +152,11 @@ int fb200_context_fb_download(fb200_context*, int channel, float* dst);
 /* copy a host image into a channel (used to seed accumulation tests) */
 int fb200_context_fb_upload(fb200_context*, int channel, const float* src);
 int fb200_context_get_stats(fb200_context*, fb200_stats* out);
+/* per-kernel-class device time, measured with CUDA event pairs on the launching stream (the reference's
+ * FERMAT_CUDA_TIME scoped timers, src/pathtracer_kernels.h:341-382, without their device syncs).
+ * classes: 0 frame-buffer element-wise + primary rays, 1 closest-hit trace, 2 shade, 3 shadow trace + accumulate */
+int fb200_context_set_profiling(fb200_context*, int on);
+int fb200_context_get_kernel_times(fb200_context*, double out_ms[4], uint64_t out_launches[4]);
 /* CUDA stream handle (cudaStream_t) the context launches on */
 void* fb200_context_stream(fb200_context*);
 /* number of pixels this shard owns */

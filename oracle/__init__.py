@@ -20,7 +20,8 @@ REF_LIB_PATH = os.path.join(_HERE, "_ref", "libref_bsdf.so")
 
 class OracleStats(C.Structure):
     _fields_ = [("shade_events", C.c_uint64), ("shadow_events", C.c_uint64), ("nodes_visited", C.c_uint64),
-                ("tris_tested", C.c_uint64), ("per_bounce", C.c_uint64 * 64)]
+                ("tris_tested", C.c_uint64), ("per_bounce", C.c_uint64 * 64),
+                ("shadow_nodes_visited", C.c_uint64), ("shadow_tris_tested", C.c_uint64)]
 
 
 _lib = None

@@ -321,7 +321,7 @@ static inline float power_heuristic(float p1, float p2)
 }
 static inline float pdf_product(float p1, float p2) { return std::isfinite(p1) && std::isfinite(p2) ? p1 * p2 : INFINITY; }
 
-struct PassStats { uint64_t shade_events, shadow_events; TravStats trav; uint64_t per_bounce[64]; };
+struct PassStats { uint64_t shade_events, shadow_events; TravStats trav, trav_shadow; uint64_t per_bounce[64]; };
 
 // MeshLight::map_impl on a freshly set-up light vertex (src/lights.h:374-404)
 static void light_map(const SceneRef& sc, bool use_vpls, uint32_t prim, const Geom& lg, float* pdf, vec3* edf)
@@ -519,7 +519,7 @@ static void trace_path(const SceneRef& sc, const Sampler& smp, FB& fb, uint32_t 
 			if (pend[k].on)
 			{
 				st.shadow_events++;
-				const bool occluded = trace_any(sc, pend[k].r, ts);
+				const bool occluded = trace_any(sc, pend[k].r, count_trav ? &st.trav_shadow : NULL);
 				if (!occluded)
 				{
 					fb.add_in(false, COMPOSITED_C, pixel, pend[k].w_d + pend[k].w_g, frame_weight);
@@ -563,7 +563,7 @@ using namespace oracle;
 
 extern "C" {
 
-struct oracle_stats { uint64_t shade_events, shadow_events, nodes_visited, tris_tested; uint64_t per_bounce[64]; };
+struct oracle_stats { uint64_t shade_events, shadow_events, nodes_visited, tris_tested; uint64_t per_bounce[64]; uint64_t shadow_nodes_visited, shadow_tris_tested; };
 
 // One progressive pass over the pixels [pixel_begin, pixel_end) of the frame (row-major), or over the
 // explicit list `pixels` (n_pixels entries) when it is not NULL. fb: 8 channels x res_x*res_y x float4.
@@ -618,7 +618,7 @@ int oracle_render_pass(const fb200_scene_view* s, uint32_t instance, float* fbda
 		#pragma omp critical
 		{
 			total.shade_events += st.shade_events; total.shadow_events += st.shadow_events;
-			total.nodes_visited += st.trav.nodes; total.tris_tested += st.trav.tris;
+			total.nodes_visited += st.trav.nodes; total.tris_tested += st.trav.tris; total.shadow_nodes_visited += st.trav_shadow.nodes; total.shadow_tris_tested += st.trav_shadow.tris;
 			for (int b = 0; b < 64; ++b) total.per_bounce[b] += st.per_bounce[b];
 		}
 	}

@@ -1,0 +1,158 @@
+"""Host logic of the path (no GPU): C ABI surface, scene model, sampler tables, VPLs, BVH."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, CORNELL, cornell_args, have_gpu
+
+
+def test_library_exports_every_declared_symbol(fb):
+    header = open(os.path.join(ROOT, "include", "fermat_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    names = set(re.findall(r"\b((?:fb200_|register_plugin)\w*)\s*\(", header))
+    assert len(names) >= 30
+    L = C.CDLL(fb.LIB_PATH)
+    missing = [n for n in sorted(names) if not hasattr(L, n)]
+    assert not missing, missing
+    assert fb.exported_symbols() == []          # and the Python binding knows no symbol the library lacks
+
+
+def test_scene_view_of_cornellbox(cornell_scene):
+    v = cornell_scene.view
+    assert v.num_triangles == 36 and v.num_materials == 10
+    assert (v.res_x, v.res_y) == (64, 64)
+    assert v.options.max_path_length == 5            # -bounces 4 => 5 (src/renderers/pathtracer.h:210-211)
+    assert v.n_dimensions == 6 * (5 + 1) and v.tile_size == 256
+    assert v.n_vpls == 64 * 64                       # n_vpls = res_x*res_y (pathtracer_impl.h:152-157)
+    # camera-frontal.txt
+    assert np.allclose(v.eye[:], [0, 1.3, 1.5]) and abs(v.fov - 1.81) < 1e-6
+    tri = np.ctypeslib.as_array(v.vertex_indices, shape=(36, 4))
+    assert tri[:, :3].min() >= 0 and tri[:, :3].max() < v.num_vertices
+    # flat-shaded mesh: unified vertices carry the packed geometric normal of their triangle
+    vd = np.ctypeslib.as_array(v.vertex_data, shape=(v.num_vertices, 4))
+    bits = vd[:, 3].view(np.uint32)
+    n = np.stack([(bits & 1023), (bits >> 10) & 1023, (bits >> 20) & 1023], 1).astype(np.float32) / 1023 * 2 - 1
+    assert np.allclose(np.linalg.norm(n, axis=1), 1.0, atol=5e-3)
+
+
+def test_vpls_lie_on_emitters(cornell_scene):
+    v = cornell_scene.view
+    vpl = np.ctypeslib.as_array(C.cast(v.vpls, C.POINTER(C.c_float)), shape=(v.n_vpls, 4))
+    prim = vpl[:, 0].view(np.uint32)
+    mats = np.ctypeslib.as_array(C.cast(v.materials, C.POINTER(C.c_float)), shape=(v.num_materials, 52))
+    mi = np.ctypeslib.as_array(v.material_indices, shape=(v.num_triangles,))
+    emissive = mats[mi[prim], 16:19]
+    assert (emissive.max(axis=1) > 0).all()
+    assert (vpl[:, 1] >= 0).all() and (vpl[:, 2] >= 0).all() and (vpl[:, 1] + vpl[:, 2] <= 1.0 + 1e-6).all()
+    cdf = np.ctypeslib.as_array(v.mesh_cdf, shape=(v.n_prims,))
+    assert cdf[-1] == 1.0 and (np.diff(cdf) >= 0).all()
+    assert v.vpl_norm > 0
+
+
+def test_sampler_tables(fb, cornell_scene, tables):
+    v = cornell_scene.view
+    S = 256 * 256
+    shifts = np.ctypeslib.as_array(v.shifts, shape=(v.n_dimensions, S))
+    assert shifts.min() >= 0.0 and shifts.max() <= 1.0
+    # slices 0..6 (dims 0..20) are the blue-noise files, AoS float3 -> SoA (src/tiled_sampling.h:312-337)
+    bn = tables["blue_noise"].reshape(7, S, 3)
+    for z in range(7):
+        for c in range(3):
+            assert np.array_equal(shifts[3 * z + c], bn[z, :, c])
+    # later slices come from the multi-jittered stack: x and y stay perfectly stratified (one point per 1/256
+    # stratum per row/column). The z components are exchanged among slices with the MSVC LCG, whose outputs
+    # 65536 calls apart are strongly correlated, so their per-slice histogram is not flat — faithful, not a bug.
+    for d in range(21, v.n_dimensions):
+        if d % 3 != 2:
+            h, _ = np.histogram(shifts[d], bins=256, range=(0, 1))
+            assert (np.abs(h - 256) <= 2).all()      # (bin edges in fp32 can move a boundary point by one bin)
+    # sample_2d = fmod(fmod(seq + shift[pixel in tile]) + shift[tile]) (src/tiled_sequence.h:62-105)
+    L = fb.lib()
+    for (px, py, dim, inst) in [(3, 5, 0, 0), (300, 17, 7, 3), (63, 63, 35, 9)]:
+        seq = np.float32(L.fb200_diag_randfloat(dim, inst + 1))
+        a = np.fmod(seq + shifts[dim, (px & 255) + (py & 255) * 256], np.float32(1.0)).astype(np.float32)
+        want = np.fmod(a + shifts[dim, ((px >> 8) & 255) + ((py >> 8) & 255) * 256], np.float32(1.0))
+        assert cornell_scene.sample_2d(inst, px, py, dim) == pytest.approx(float(want), abs=0)
+
+
+def test_bvh2_is_a_valid_cugar_tree(cornell_scene):
+    v = cornell_scene.view
+    nodes = np.ctypeslib.as_array(C.cast(v.bvh_nodes, C.POINTER(C.c_uint32)), shape=(v.n_bvh_nodes, 8))
+    boxes = nodes[:, 2:8].view(np.float32)
+    index = np.ctypeslib.as_array(v.bvh_index, shape=(v.num_triangles,))
+    assert sorted(index.tolist()) == list(range(v.num_triangles))
+    tri = np.ctypeslib.as_array(v.vertex_indices, shape=(v.num_triangles, 4))
+    vd = np.ctypeslib.as_array(v.vertex_data, shape=(v.num_vertices, 4))[:, :3]
+    seen = np.zeros(v.num_triangles, bool)
+    stack = [0]
+    while stack:
+        i = stack.pop()
+        packed, rng = int(nodes[i, 0]), int(nodes[i, 1])
+        if packed & 3 == 0:
+            begin = packed >> 2
+            assert 1 <= rng <= 3
+            for k in range(begin, begin + rng):
+                t = index[k]
+                assert not seen[t]
+                seen[t] = True
+                p = vd[tri[t, :3]]
+                assert (p >= boxes[i, :3] - 1e-6).all() and (p <= boxes[i, 3:] + 1e-6).all()
+        else:
+            assert packed & 3 == 3
+            c = packed >> 2
+            for ch in (c, c + 1):
+                assert (boxes[ch, :3] >= boxes[i, :3]).all() and (boxes[ch, 3:] <= boxes[i, 3:]).all()
+                stack.append(ch)
+    assert seen.all()
+    st = cornell_scene.bvh_stats()
+    assert st["triangles"] == 36 and st["bvh2_nodes"] == v.n_bvh_nodes and st["wide_nodes"] >= 1
+
+
+def test_shards_partition_the_frame(fb):
+    full = None
+    for n in (1, 2, 3, 8):
+        seen = []
+        for r in range(n):
+            sc = fb.Scene(cornell_args(80, 1, ["-shard", str(r), str(n)]))     # 80 is not a multiple of the 32-pixel tile
+            seen.append(sc.owned_pixels())
+            sc.close()
+        allp = np.concatenate(seen)
+        assert allp.size == 80 * 80 and np.unique(allp).size == 80 * 80
+        if n > 1:
+            sizes = [s.size for s in seen]
+            assert max(sizes) - min(sizes) <= 2 * 32 * 32
+
+
+def test_bad_arguments_fail_loudly(fb):
+    with pytest.raises(RuntimeError):
+        fb.Scene(["-r", "8", "8"])                       # no -i
+    with pytest.raises(RuntimeError):
+        fb.Scene(["-i", "/nonexistent/scene.obj"])
+    with pytest.raises(RuntimeError):
+        fb.Scene(cornell_args(8, 1, ["-shard", "2", "2"]))
+    with pytest.raises(RuntimeError):
+        fb.Scene(cornell_args(8, 1, ["-nee-alg", "rl"]))
+
+
+def test_no_cpu_fallback_without_gpu(fb, cornell_scene):
+    if have_gpu():
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        fb.RenderingContext(cornell_scene)
+
+
+def test_obj_loader_on_reference_model_if_present(fb):
+    ref = "/root/reference/models/CornellBox"
+    if not os.path.isdir(ref):
+        pytest.skip("reference models not available")
+    a = fb.Scene(["-i", os.path.join(ref, "CornellBox-JP.obj"), "-c", os.path.join(ref, "camera-frontal.txt"), "-r", "64", "64", "-bounces", "4"])
+    b = fb.Scene(cornell_args(64, 4))
+    va, vb = a.view, b.view
+    assert va.num_triangles == vb.num_triangles and va.num_vertices == vb.num_vertices
+    assert np.array_equal(np.ctypeslib.as_array(va.vertex_data, shape=(va.num_vertices, 4)).view(np.uint32),
+                          np.ctypeslib.as_array(vb.vertex_data, shape=(vb.num_vertices, 4)).view(np.uint32))
+    assert np.array_equal(np.ctypeslib.as_array(va.vertex_indices, shape=(36, 4)), np.ctypeslib.as_array(vb.vertex_indices, shape=(36, 4)))
+    a.close(); b.close()

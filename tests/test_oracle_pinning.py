@@ -1,0 +1,82 @@
+"""The oracle is only as good as its pinning: check it against outputs of the REFERENCE'S OWN CODE.
+
+tests/golden/bsdf_golden.npz and streams.npz were produced by tools/make_golden.py running the reference's
+Bsdf (src/bsdf.h + contrib/cugar/bsdf/*.h), LFSR stream and randfloat compiled verbatim from /root/reference
+(oracle/_ref, recipe oracle/build_ref.sh). The reference publishes no golden vectors of its own for this
+path, so these are the reference-generated fixtures the rules ask for.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+
+def _golden():
+    g = np.load(os.path.join(GOLDEN, "bsdf_golden.npz"))
+    return g["rec"], g["out"]
+
+
+def test_oracle_bsdf_is_bit_exact_on_reference_vectors(oracle, tables):
+    rec, ref = _golden()
+    mine = oracle.bsdf_raw(tables["glossy"], rec)
+    assert not np.isnan(mine).any()
+    eq = mine.view(np.uint32) == ref.view(np.uint32)
+    has_ior = rec[:, 31] != 0
+    assert has_ior.sum() > 3000
+    # every output (4 f rgb, 4 pdfs, sampled dir, weight, pdfs, component) identical to the last bit
+    assert eq[has_ior].all(), "restated Bsdf diverges from the reference's own code"
+    # ior == 0: the reference converts eta/2 = +inf to uint32, which is undefined in the host build the golden
+    # vectors come from (x86 gives 0) and saturating on the device the reference really runs on (gives 31);
+    # the oracle follows the device. Everything that does not read the albedo table must still agree exactly.
+    z = ~has_ior
+    assert (mine[z, 24] == ref[z, 24]).mean() > 0.95          # chosen component
+    same_comp = z & (mine[:, 24] == ref[:, 24])
+    assert eq[same_comp][:, 16:19].all()                        # sampled direction
+    assert eq[z][:, 6:12].all() and eq[z][:, 14:16].all()      # glossy lobes f and p
+
+
+def test_oracle_bsdf_components_cover_all_lobes():
+    rec, ref = _golden()
+    comps = set(int(c) for c in np.unique(ref[:, 24]))
+    assert comps == {0, 1, 2, 4, 8, 16}                         # absorption, DR, DT, GR, GT, clearcoat
+
+
+def test_live_reference_matches_golden_if_built(oracle, tables):
+    if oracle.ref_lib() is None:
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    rec, ref = _golden()
+    live = oracle.ref_bsdf_raw(tables["glossy"], rec)
+    assert (live.view(np.uint32) == ref.view(np.uint32)).all()
+
+
+def test_host_streams_match_reference(fb):
+    s = np.load(os.path.join(GOLDEN, "streams.npz"))
+    L = fb.lib()
+    out = np.zeros(64, np.float32)
+    L.fb200_diag_lfsr(1351, out.ctypes.data_as(C.POINTER(C.c_float)), 64)
+    assert (out.view(np.uint32) == s["lfsr_1351"].view(np.uint32)).all()
+    # SURVEY.md §8c known answers of LFSRRandomStream(&gen, 1, hash(1351)).next()
+    assert abs(out[0] - 0.854813814) < 1e-7 and abs(out[1] - 0.573444545) < 1e-7
+    rf = np.array([[L.fb200_diag_randfloat(d, p) for p in range(1, 9)] for d in range(60)], np.float32)
+    assert (rf.view(np.uint32) == s["randfloat"].view(np.uint32)).all()
+
+
+def test_msvc_rand_known_answers(fb):
+    # MSVC CRT: srand(1); rand() -> 41, 18467, 6334, 26500, 19169 (documented sequence of the LCG 214013/2531011)
+    out = np.zeros(5, np.int32)
+    fb.lib().fb200_diag_msvc_rand(1, out.ctypes.data_as(C.POINTER(C.c_int32)), 5)
+    assert out.tolist() == [41, 18467, 6334, 26500, 19169]
+
+
+def test_half_codec_matches_numpy(fb):
+    L = fb.lib()
+    rng = np.random.default_rng(3)
+    vals = np.concatenate([rng.random(2000, dtype=np.float32), rng.normal(size=2000).astype(np.float32) * 100,
+                           np.array([0.0, 1.0, 65504.0, 65519.9, 65520.0, 1e-8, 6e-8, 6.1e-5, 2.0 ** -24, 2.0 ** -25, 3 * 2.0 ** -25], np.float32)])
+    for v in vals:
+        h = L.fb200_diag_float_to_half(float(v))
+        assert h == int(np.float16(v).view(np.uint16)), v
+        assert L.fb200_diag_half_to_float(h) == float(np.float16(v)) or np.isinf(np.float16(v))
