@@ -131,11 +131,44 @@ def _fptr(a):
     return a.ctypes.data_as(C.POINTER(C.c_float))
 
 
+def resolve_scene(path):
+    """Return a loadable scene file for `path`: `<path>` itself if it exists, else `<path>.xz` unpacked once into a
+    per-user temp directory (scene snapshots travel to the GPU boxes xz-compressed, tools/make_snapshots.py)."""
+    path = str(path)
+    if os.path.exists(path):
+        return path
+    xz = path + ".xz"
+    if not os.path.exists(xz):
+        return path
+    import lzma
+    import tempfile
+    out_dir = os.path.join(tempfile.gettempdir(), "fermat_b200_scenes")
+    os.makedirs(out_dir, exist_ok=True)
+    out = os.path.join(out_dir, "%d_%s" % (int(os.path.getmtime(xz)), os.path.basename(path)))
+    if not os.path.exists(out):
+        tmp = out + ".%d.tmp" % os.getpid()
+        with lzma.open(xz, "rb") as f, open(tmp, "wb") as g:
+            while True:
+                b = f.read(1 << 24)
+                if not b:
+                    break
+                g.write(b)
+        os.replace(tmp, out)
+    return out
+
+
+def scene_available(path):
+    return os.path.exists(str(path)) or os.path.exists(str(path) + ".xz")
+
+
 class Scene:
     """Host-only scene: mesh + materials + textures, sampler tables, VPLs, BVH (no GPU needed)."""
 
     def __init__(self, args):
         self.args = [str(a) for a in args]
+        for i, a in enumerate(self.args[:-1]):
+            if a == "-i":
+                self.args[i + 1] = resolve_scene(self.args[i + 1])
         argv = (C.c_char_p * len(self.args))(*[a.encode() for a in self.args])
         self._h = lib().fb200_scene_create(len(self.args), argv)
         if not self._h:
