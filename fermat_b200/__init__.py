@@ -13,7 +13,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfermat_b200.so")
+# FERMAT_B200_LIB selects an alternative build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("FERMAT_B200_LIB") or os.path.join(_HERE, "libfermat_b200.so")
 
 FB_CHANNELS = {"DIFFUSE_C": 0, "DIFFUSE_A": 1, "SPECULAR_C": 2, "SPECULAR_A": 3,
                "DIRECT_C": 4, "COMPOSITED_C": 5, "FILTERED_C": 6, "LUMINANCE": 7}

@@ -97,6 +97,19 @@ __global__ void __launch_bounds__(256) k_generate_primary(DeviceScene sc, PassPa
 // ------------------------------------------------------------------------------------------------
 // persistent traversal kernels
 // ------------------------------------------------------------------------------------------------
+#ifndef FB_TRACE_THREADS
+#define FB_TRACE_THREADS 256
+#endif
+#ifndef FB_TRACE_MIN_BLOCKS
+#define FB_TRACE_MIN_BLOCKS 4
+#endif
+#ifndef FB_SHADE_MIN_BLOCKS
+#define FB_SHADE_MIN_BLOCKS 4
+#endif
+#ifndef FB_REFILL_LANES
+#define FB_REFILL_LANES 8          // idle lanes of a warp that trigger a refill from the ray queue
+#endif
+
 enum TraceMode { TRACE_QUEUE_CLOSEST = 0, TRACE_QUEUE_SHADOW = 1, TRACE_RAYS_CLOSEST = 2, TRACE_RAYS_SHADOW = 3 };
 
 struct TraceArgs
@@ -113,7 +126,7 @@ struct TraceArgs
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(256, 4) k_trace(DeviceScene sc, TraceArgs a)
+__global__ void __launch_bounds__(FB_TRACE_THREADS, FB_TRACE_MIN_BLOCKS) k_trace(DeviceScene sc, TraceArgs a)
 {
 	constexpr bool ANY = (MODE == TRACE_QUEUE_SHADOW || MODE == TRACE_RAYS_SHADOW);
 	extern __shared__ float4 smem[];
@@ -130,16 +143,18 @@ __global__ void __launch_bounds__(256, 4) k_trace(DeviceScene sc, TraceArgs a)
 	bool active = false;
 	uint32 ray_idx = 0;
 
+	bool exhausted = false;          // warp-uniform: the cursor ran past the end of the queue
 	for (;;)
 	{
-		// refill idle lanes: one atomic per warp
+		// refill idle lanes as soon as a few of them are free: one atomic per warp
 		const unsigned need = __ballot_sync(0xFFFFFFFFu, !active);
-		if (need)
+		if (need && !exhausted && (__popc(need) >= FB_REFILL_LANES || need == 0xFFFFFFFFu))
 		{
 			const int leader = __ffs(need) - 1;
 			uint32 base = 0;
 			if (lane == leader) base = atomicAdd(a.cursor, (uint32)__popc(need));
 			base = __shfl_sync(0xFFFFFFFFu, base, leader);
+			if (base + (uint32)__popc(need) > n) exhausted = true;
 			if (!active)
 			{
 				ray_idx = base + __popc(need & ((1u << lane) - 1u));
@@ -151,11 +166,18 @@ __global__ void __launch_bounds__(256, 4) k_trace(DeviceScene sc, TraceArgs a)
 				}
 			}
 		}
-		if (!__any_sync(0xFFFFFFFFu, active)) break;
+		if (!__any_sync(0xFFFFFFFFu, active)) { if (exhausted) break; else continue; }
 
-		for (int it = 0; it < 24 && active; ++it)
+		// one iteration = [acquire] [one node visit] [one triangle test], each executed by every lane that has such work
+		bool done = false;
+		if (active)
 		{
-			if (!trav.step(sc, smem_nodes))
+			done = !trav.acquire();
+			if (!done && !trav.has_tri()) trav.node_step(sc, smem_nodes);
+		}
+		if (active && !done && trav.has_tri()) done = trav.tri_step(sc);
+		{
+			if (active && done)
 			{
 				active = false;
 				if (MODE == TRACE_QUEUE_CLOSEST || MODE == TRACE_RAYS_CLOSEST) a.hits[ray_idx] = trav.hit_record();
@@ -195,7 +217,7 @@ struct ShadeArgs
 	uint32 do_nee, do_emissive, do_scatter, do_dirlight;
 };
 
-__global__ void __launch_bounds__(128, 4) k_shade(DeviceScene sc, ShadeArgs a)
+__global__ void __launch_bounds__(128, FB_SHADE_MIN_BLOCKS) k_shade(DeviceScene sc, ShadeArgs a)
 {
 	const uint32 n = a.ctr->in_size[a.bounce];
 	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&a.tot->shade_events, (unsigned long long)n);
@@ -438,8 +460,10 @@ cudaError_t configure_kernels(LaunchConfig& lc, int device)
 	if (e != cudaSuccess) return e;
 	lc.sm_count = prop.multiProcessorCount;
 	lc.trace_threads = 256;
-	lc.trace_ctas_per_sm = 4;
-	const int max_smem = 48 * 1024;   // per CTA: 4 CTAs x 48 KB fit the 227 KB of an SM
+	lc.trace_threads = FB_TRACE_THREADS;
+	lc.trace_ctas_per_sm = FB_TRACE_MIN_BLOCKS;
+	// per CTA: all resident CTAs of an SM share its 227 KB (1 KB reserved per CTA)
+	const int max_smem = ((220 * 1024 / FB_TRACE_MIN_BLOCKS) / 1024) * 1024 > 48 * 1024 ? 48 * 1024 : ((220 * 1024 / FB_TRACE_MIN_BLOCKS) / 1024) * 1024;
 	e = cudaFuncSetAttribute(k_trace<TRACE_QUEUE_CLOSEST>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); if (e) return e;
 	e = cudaFuncSetAttribute(k_trace<TRACE_QUEUE_SHADOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); if (e) return e;
 	e = cudaFuncSetAttribute(k_trace<TRACE_RAYS_CLOSEST>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); if (e) return e;

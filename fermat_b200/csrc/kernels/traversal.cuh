@@ -83,10 +83,29 @@ struct Traversal
 		occluded = false;
 	}
 
-	// one traversal step; returns false when the query is finished
-	FB_D bool step(const DeviceScene& sc, const float4* __restrict__ smem_nodes)
+	// The traversal is split into three uniform pieces so that the warp executes, per iteration of the
+	// kernel loop, ONE node block and ONE triangle block with every lane that has such work taking part
+	// (instead of each lane running its own node-then-all-triangles sequence and serialising the warp):
+	//   acquire()   : make sure the lane holds a node group or a triangle group, popping the stack if needed
+	//   node_step() : visit one wide node (lanes with a pending node and no pending triangle)
+	//   tri_step()  : test one triangle (lanes with a pending triangle)
+	FB_D bool has_node() const { return ngroup.y > 0x00FFFFFFu; }
+	FB_D bool has_tri() const { return tgroup.y != 0u; }
+
+	// returns false when the query is finished (nothing pending, stack empty)
+	FB_D bool acquire()
 	{
-		if (ngroup.y > 0x00FFFFFFu)
+		if (!has_node() && !has_tri())
+		{
+			if (sp == 0) return false;
+			const uint2 e = stack[--sp];
+			if (e.y > 0x00FFFFFFu) ngroup = e; else tgroup = e;
+		}
+		return true;
+	}
+
+	FB_D void node_step(const DeviceScene& sc, const float4* __restrict__ smem_nodes)
+	{
 		{
 			const uint32 hits = ngroup.y;
 			const uint32 child_bit = bfind(hits);
@@ -146,54 +165,44 @@ struct Traversal
 			ngroup.y = (hitmask & 0xFF000000u) | (e_imask >> 24);
 			tgroup.y = hitmask & 0x00FFFFFFu;
 		}
+	}
+
+	// test ONE pending triangle; returns true when an any-hit query found its occluder
+	FB_D bool tri_step(const DeviceScene& sc)
+	{
+		const uint32 k = bfind(tgroup.y);
+		tgroup.y &= ~(1u << k);
+		const float4* tp = reinterpret_cast<const float4*>(sc.tris) + (size_t)(tgroup.x + k) * 3u;
+		const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+		if (ANY_HIT && (mask & __float_as_uint(b.w))) return false;
+
+		// Moller-Trumbore, unfused, same operation order as oracle/pt_oracle.cpp intersect_tri()
+		const float e1x = b.x - a.x, e1y = b.y - a.y, e1z = b.z - a.z;
+		const float e2x = c.x - a.x, e2y = c.y - a.y, e2z = c.z - a.z;
+		const float px = ray.dy * e2z - ray.dz * e2y, py = ray.dz * e2x - ray.dx * e2z, pz = ray.dx * e2y - ray.dy * e2x;
+		const float det = e1x * px + e1y * py + e1z * pz;
+		if (det == 0.0f) return false;
+		const float inv = 1.0f / det;
+		const float tx = ray.ox - a.x, ty = ray.oy - a.y, tz = ray.oz - a.z;
+		const float bu = (tx * px + ty * py + tz * pz) * inv;
+		if (!(bu >= 0.0f && bu <= 1.0f)) return false;
+		const float qx = ty * e1z - tz * e1y, qy = tz * e1x - tx * e1z, qz = tx * e1y - ty * e1x;
+		const float bv = (ray.dx * qx + ray.dy * qy + ray.dz * qz) * inv;
+		if (!(bv >= 0.0f && bu + bv <= 1.0f)) return false;
+		const float t = (e2x * qx + e2y * qy + e2z * qz) * inv;
+		if (ANY_HIT)
+		{
+			if (t > 0.0f && t < ray.tmax) { occluded = true; return true; }
+		}
 		else
 		{
-			tgroup = ngroup;
-			ngroup = make_uint2(0u, 0u);
-		}
-
-		while (tgroup.y != 0u)
-		{
-			const uint32 k = bfind(tgroup.y);
-			tgroup.y &= ~(1u << k);
-			const float4* tp = reinterpret_cast<const float4*>(sc.tris) + (size_t)(tgroup.x + k) * 3u;
-			const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
-			if (ANY_HIT && (mask & __float_as_uint(b.w))) continue;
-
-			// Moller-Trumbore, unfused, same operation order as oracle/pt_oracle.cpp intersect_tri()
-			const float e1x = b.x - a.x, e1y = b.y - a.y, e1z = b.z - a.z;
-			const float e2x = c.x - a.x, e2y = c.y - a.y, e2z = c.z - a.z;
-			const float px = ray.dy * e2z - ray.dz * e2y, py = ray.dz * e2x - ray.dx * e2z, pz = ray.dx * e2y - ray.dy * e2x;
-			const float det = e1x * px + e1y * py + e1z * pz;
-			if (det == 0.0f) continue;
-			const float inv = 1.0f / det;
-			const float tx = ray.ox - a.x, ty = ray.oy - a.y, tz = ray.oz - a.z;
-			const float bu = (tx * px + ty * py + tz * pz) * inv;
-			if (!(bu >= 0.0f && bu <= 1.0f)) continue;
-			const float qx = ty * e1z - tz * e1y, qy = tz * e1x - tx * e1z, qz = tx * e1y - ty * e1x;
-			const float bv = (ray.dx * qx + ray.dy * qy + ray.dz * qz) * inv;
-			if (!(bv >= 0.0f && bu + bv <= 1.0f)) continue;
-			const float t = (e2x * qx + e2y * qy + e2z * qz) * inv;
-			if (ANY_HIT)
+			const int tri = (int)__float_as_uint(a.w);
+			if (t > ray.tmin && (t < ray.tmax || (t == ray.tmax && hit.tri >= 0 && tri < hit.tri)))
 			{
-				if (t > 0.0f && t < ray.tmax) { occluded = true; return false; }
-			}
-			else
-			{
-				const int tri = (int)__float_as_uint(a.w);
-				if (t > ray.tmin && (t < ray.tmax || (t == ray.tmax && hit.tri >= 0 && tri < hit.tri)))
-				{
-					ray.tmax = t; hit.t = t; hit.tri = tri; hit.bu = bu; hit.bv = bv;
-				}
+				ray.tmax = t; hit.t = t; hit.tri = tri; hit.bu = bu; hit.bv = bv;
 			}
 		}
-
-		if (ngroup.y <= 0x00FFFFFFu)
-		{
-			if (sp == 0) return false;
-			ngroup = stack[--sp];
-		}
-		return true;
+		return false;
 	}
 
 	// reference hit record: u = weight of v0, v = weight of v1, through fp16

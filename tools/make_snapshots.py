@@ -20,12 +20,16 @@ CACHE = os.path.join(ROOT, "scenes", "_cache")
 
 def snapshot(args, out):
     import fermat_b200 as fb
-    if os.path.exists(out):
-        return out
-    sc = fb.Scene(args + ["-r", "64", "64"])      # resolution only sizes the VPL set, which is not stored
-    sc.save_snapshot(out)
-    print("wrote", out, sc.bvh_stats())
-    sc.close()
+    if not os.path.exists(out):
+        sc = fb.Scene(args + ["-r", "64", "64"])      # resolution only sizes the VPL set, which is not stored
+        sc.save_snapshot(out)
+        print("wrote", out, sc.bvh_stats())
+        sc.close()
+    # the GPU boxes receive the xz twin (.gpurunignore drops the raw file); fermat_b200.resolve_scene unpacks it
+    if out.startswith(CACHE) and not os.path.exists(out + ".xz"):
+        import lzma
+        with open(out, "rb") as f, lzma.open(out + ".xz", "wb", preset=1) as g:
+            g.write(f.read())
     return out
 
 
