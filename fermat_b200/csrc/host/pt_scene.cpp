@@ -56,7 +56,12 @@ std::string default_tables_path()
 		std::string p = info.dli_fname;
 		const size_t k = p.find_last_of('/');
 		p = (k == std::string::npos) ? std::string(".") : p.substr(0, k);
-		return p + "/data/pt_tables.bin";
+		const std::string a = p + "/data/pt_tables.bin", b = p + "/../data/pt_tables.bin";   // (tuning variants live one level down)
+		FILE* f = fopen(a.c_str(), "rb");
+		if (f) { fclose(f); return a; }
+		f = fopen(b.c_str(), "rb");
+		if (f) { fclose(f); return b; }
+		return a;
 	}
 	return "fermat_b200/data/pt_tables.bin";
 }

@@ -79,6 +79,18 @@ struct PassCounters
 	uint32 pad[64];
 };
 
+// Queue traffic is touched once per wave: mark it evict-first ("streaming") so that it does not push the
+// L2-resident BVH and attribute arrays out (the reference's queues are plain loads/stores).
+#ifndef FB_STREAM_HINTS
+#define FB_STREAM_HINTS 1
+#endif
+#if defined(__CUDACC__)
+FB_D float4 ld_stream(const float4* p) { return FB_STREAM_HINTS ? __ldcs(p) : *p; }
+FB_D uint32 ld_stream(const uint32* p) { return FB_STREAM_HINTS ? __ldcs(p) : *p; }
+FB_D void   st_stream(float4* p, float4 v) { if (FB_STREAM_HINTS) __stcs(p, v); else *p = v; }
+FB_D void   st_stream(uint32* p, uint32 v) { if (FB_STREAM_HINTS) __stcs(p, v); else *p = v; }
+#endif
+
 struct PassTotals              // accumulated across passes (never reset by render())
 {
 	unsigned long long shade_events;

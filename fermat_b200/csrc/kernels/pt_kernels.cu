@@ -88,10 +88,10 @@ __global__ void __launch_bounds__(256) k_generate_primary(DeviceScene sc, PassPa
 	const float dy = (py + v) / float(sc.res_y) * 2.f - 1.f;
 	const V3 U(pp.U[0], pp.U[1], pp.U[2]), Vv(pp.V[0], pp.V[1], pp.V[2]), W(pp.W[0], pp.W[1], pp.W[2]);
 	const V3 d = dx * U + dy * Vv + W;
-	q.ray_o[slot] = make_float4(pp.eye[0], pp.eye[1], pp.eye[2], 0.0f);
-	q.ray_d[slot] = make_float4(d.x, d.y, d.z, 1e34f);
-	q.weight[slot] = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
-	q.pixel[slot] = px + py * sc.res_x;          // PixelInfo(pixel, comp = 0, diffuse = 0)
+	st_stream(q.ray_o + slot, make_float4(pp.eye[0], pp.eye[1], pp.eye[2], 0.0f));
+	st_stream(q.ray_d + slot, make_float4(d.x, d.y, d.z, 1e34f));
+	st_stream(q.weight + slot, make_float4(1.0f, 1.0f, 1.0f, 1.0f));
+	st_stream(q.pixel + slot, px + py * sc.res_x);          // PixelInfo(pixel, comp = 0, diffuse = 0)
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(FB_TRACE_THREADS, FB_TRACE_MIN_BLOCKS) k_trace
 				ray_idx = base + __popc(need & ((1u << lane) - 1u));
 				if (ray_idx < n)
 				{
-					const float4 o = __ldg(a.ray_o + (size_t)ray_idx * a.stride), d = __ldg(a.ray_d + (size_t)ray_idx * a.stride);
+					const float4 o = ld_stream(a.ray_o + (size_t)ray_idx * a.stride), d = ld_stream(a.ray_d + (size_t)ray_idx * a.stride);
 					trav.init(o, d, ANY ? __float_as_uint(o.w) : 0u);
 					active = true;
 				}
@@ -180,12 +180,12 @@ __global__ void __launch_bounds__(FB_TRACE_THREADS, FB_TRACE_MIN_BLOCKS) k_trace
 			if (active && done)
 			{
 				active = false;
-				if (MODE == TRACE_QUEUE_CLOSEST || MODE == TRACE_RAYS_CLOSEST) a.hits[ray_idx] = trav.hit_record();
+				if (MODE == TRACE_QUEUE_CLOSEST || MODE == TRACE_RAYS_CLOSEST) st_stream(a.hits + ray_idx, trav.hit_record());
 				else if (MODE == TRACE_RAYS_SHADOW) a.occluded[ray_idx] = trav.occluded ? 1 : 0;
 				else if (!trav.occluded)
 				{
 					// solve_occlusion -> PTVertexProcessor::accumulate_nee (pathtracer_vertex_processor.h:204-239)
-					const float4 wd4 = __ldg(a.w_d + ray_idx), wg4 = __ldg(a.w_g + ray_idx);
+					const float4 wd4 = ld_stream(a.w_d + ray_idx), wg4 = ld_stream(a.w_g + ray_idx);
 					const V3 w_d(wd4), w_g(wg4);
 					const uint32 info = __float_as_uint(wd4.w);
 					const uint32 pixel = info & 0x07FFFFFFu, comp = (info >> 27) & 0xFu;
@@ -236,12 +236,12 @@ __global__ void __launch_bounds__(128, FB_SHADE_MIN_BLOCKS) k_shade(DeviceScene 
 		uint32 sc_info = 0, info = 0;
 
 		float4 hit = make_float4(-1.0f, 0.0f, 0.0f, 0.0f);
-		if (valid) { hit = a.in.hit[idx]; valid = (hit.x > 0.0f) && (__float_as_int(hit.y) >= 0); }
+		if (valid) { hit = ld_stream(a.in.hit + idx); valid = (hit.x > 0.0f) && (__float_as_int(hit.y) >= 0); }
 		if (valid)
 		{
 			const uint32 tri = __float_as_uint(hit.y);
-			const float4 ro = a.in.ray_o[idx], rd = a.in.ray_d[idx], w4 = a.in.weight[idx];
-			info = a.in.pixel[idx];
+			const float4 ro = ld_stream(a.in.ray_o + idx), rd = ld_stream(a.in.ray_d + idx), w4 = ld_stream(a.in.weight + idx);
+			info = ld_stream(a.in.pixel + idx);
 			const uint32 pixel = info & 0x07FFFFFFu, comp = (info >> 27) & 0xFu;
 			const V3 ray_o(ro), ray_d(rd), w(w4);
 			const float p_prev = w4.w;
@@ -407,17 +407,17 @@ __global__ void __launch_bounds__(128, FB_SHADE_MIN_BLOCKS) k_shade(DeviceScene 
 		if (a.do_dirlight)
 		{
 			const uint32 slot = warp_append_slot(shadow_counter, dl_on);
-			if (dl_on) { a.sq.ray_o[slot] = dl_o; a.sq.ray_d[slot] = dl_d; a.sq.w_d[slot] = dl_wd; a.sq.w_g[slot] = dl_wg; }
+			if (dl_on) { st_stream(a.sq.ray_o + slot, dl_o); st_stream(a.sq.ray_d + slot, dl_d); st_stream(a.sq.w_d + slot, dl_wd); st_stream(a.sq.w_g + slot, dl_wg); }
 		}
 		if (a.do_nee)
 		{
 			const uint32 slot = warp_append_slot(shadow_counter, nee_on);
-			if (nee_on) { a.sq.ray_o[slot] = nee_o; a.sq.ray_d[slot] = nee_d; a.sq.w_d[slot] = nee_wd; a.sq.w_g[slot] = nee_wg; }
+			if (nee_on) { st_stream(a.sq.ray_o + slot, nee_o); st_stream(a.sq.ray_d + slot, nee_d); st_stream(a.sq.w_d + slot, nee_wd); st_stream(a.sq.w_g + slot, nee_wg); }
 		}
 		if (a.do_scatter)
 		{
 			const uint32 slot = warp_append_slot(scatter_counter, scat_on);
-			if (scat_on) { a.out.ray_o[slot] = sc_o; a.out.ray_d[slot] = sc_d; a.out.weight[slot] = sc_w; a.out.pixel[slot] = sc_info; }
+			if (scat_on) { st_stream(a.out.ray_o + slot, sc_o); st_stream(a.out.ray_d + slot, sc_d); st_stream(a.out.weight + slot, sc_w); st_stream(a.out.pixel + slot, sc_info); }
 		}
 	}
 }
