@@ -19,7 +19,10 @@
 
 namespace fb {
 
-#define FB_TRAV_STACK 28
+#define FB_TRAV_STACK 32
+#ifndef FB_PREFETCH
+#define FB_PREFETCH 0              // bit 0: prefetch the next node, bit 1: prefetch the hit triangles (into L1)
+#endif
 
 FB_D uint32 sign_extend_s8x4(uint32 x)
 {
@@ -164,6 +167,30 @@ struct Traversal
 			}
 			ngroup.y = (hitmask & 0xFF000000u) | (e_imask >> 24);
 			tgroup.y = hitmask & 0x00FFFFFFu;
+#if FB_PREFETCH & 1
+			// start pulling the node this lane will visit next into L1 while the triangles of this one are tested
+			if (ngroup.y > 0x00FFFFFFu)
+			{
+				const uint32 cb = bfind(ngroup.y);
+				const uint32 sl = (cb - 24u) ^ (octinv4 & 0xFFu);
+				const uint32 nidx = ngroup.x + __popc(ngroup.y & ~(0xFFFFFFFFu << sl) & 0xFFu);
+				if (nidx >= sc.staged_nodes)
+				{
+					const char* p = reinterpret_cast<const char*>(sc.nodes) + (size_t)nidx * 80u;
+					asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+					asm volatile("prefetch.global.L1 [%0];" :: "l"(p + 64));
+				}
+			}
+#endif
+#if FB_PREFETCH & 2
+			// and every triangle that is going to be tested
+			for (uint32 tb = tgroup.y; tb; tb &= tb - 1u)
+			{
+				const char* p = reinterpret_cast<const char*>(sc.tris) + (size_t)(tgroup.x + (uint32)__ffs((int)tb) - 1u) * 48u;
+				asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+				asm volatile("prefetch.global.L1 [%0];" :: "l"(p + 32));
+			}
+#endif
 		}
 	}
 
