@@ -8,7 +8,7 @@ HOST_DIR  := fermat_b200/csrc/host
 KERN_DIR  := fermat_b200/csrc/kernels
 BUILD     := build
 
-CXXFLAGS  := -O2 -g -std=c++17 -fPIC -Wall -Wno-unused-function -Wno-sign-compare -I$(CUDA_HOME)/include -Iinclude
+CXXFLAGS  := -O2 -g -std=c++17 -fPIC -fopenmp -Wall -Wno-unused-function -Wno-sign-compare -I$(CUDA_HOME)/include -Iinclude
 # -fmad=false: the kernels state their fused operations explicitly (fmaf) so that the arithmetic the
 # parity tests pin is the arithmetic that runs (DESIGN.md "Numerics").
 NVFLAGS   := -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false \
@@ -34,7 +34,7 @@ $(BUILD)/%.cu.o: $(KERN_DIR)/%.cu $(wildcard $(KERN_DIR)/*.cuh) $(wildcard $(KER
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(BUILD)/$*.ptxas.log || (cat $(BUILD)/$*.ptxas.log; false)
 
 $(LIB): $(HOST_OBJ) $(KERN_OBJ)
-	$(NVCC) -shared -o $@ $^ -cudart static -Xlinker --no-undefined -ldl -lpthread
+	$(NVCC) -shared -o $@ $^ -cudart static -Xlinker --no-undefined -ldl -lpthread -lgomp
 
 $(CLI): $(BUILD)/main.o $(LIB)
 	$(CXX) -o $@ $(BUILD)/main.o -Lfermat_b200 -lfermat_b200 -Wl,-rpath,'$$ORIGIN' -ldl

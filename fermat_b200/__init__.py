@@ -84,6 +84,7 @@ def lib():
         "fb200_diag_half_to_float": (f32, [u32]),
         "fb200_diag_pack_normal": (u32, [f32, f32, f32]),
         "fb200_diag_msvc_rand": (i32, [u32, C.POINTER(C.c_int32), u32]),
+        "fb200_diag_wide_trace": (i32, [vp, pf, pf, u32, C.POINTER(u64), C.POINTER(u64)]),
         "fb200_context_create": (vp, [vp, i32]),
         "fb200_context_destroy": (None, [vp]),
         "fb200_context_clear": (i32, [vp]),
@@ -198,6 +199,14 @@ class Scene:
         out = np.empty(n, dtype=np.uint32)
         lib().fb200_scene_owned_pixels(self._h, out.ctypes.data_as(C.POINTER(C.c_uint32)), n)
         return out
+
+    def wide_trace(self, rays):
+        """Host emulation of the device's wide-BVH closest-hit traversal: (hits, wide nodes visited, triangles tested)."""
+        rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)
+        hits = np.empty((rays.shape[0], 4), dtype=np.float32)
+        nodes, tris = C.c_uint64(), C.c_uint64()
+        lib().fb200_diag_wide_trace(self._h, _fptr(rays), _fptr(hits), rays.shape[0], C.byref(nodes), C.byref(tris))
+        return hits, nodes.value, tris.value
 
     def sample_2d(self, instance, px, py, dim):
         return lib().fb200_scene_sample_2d(self._h, instance, px, py, dim)

@@ -109,6 +109,9 @@ __global__ void __launch_bounds__(256) k_generate_primary(DeviceScene sc, PassPa
 #ifndef FB_REFILL_LANES
 #define FB_REFILL_LANES 1          // idle lanes of a warp that trigger a refill from the ray queue
 #endif
+#ifndef FB_TRI_LOOP
+#define FB_TRI_LOOP 1
+#endif
 #ifndef FB_TRAV_BATCH
 #define FB_TRAV_BATCH 24           // traversal iterations a lane runs between two warp-wide refill votes
 #endif
@@ -179,7 +182,11 @@ __global__ void __launch_bounds__(FB_TRACE_THREADS, FB_TRACE_MIN_BLOCKS) k_trace
 		{
 			bool done = !trav.acquire();
 			if (!done && !trav.has_tri()) trav.node_step(sc, smem_nodes);
+#if FB_TRI_LOOP
+			while (!done && trav.has_tri()) done = trav.tri_step(sc);      // all triangles of the node before the next node
+#else
 			if (!done && trav.has_tri()) done = trav.tri_step(sc);
+#endif
 			if (active && done)
 			{
 				active = false;
@@ -466,7 +473,7 @@ cudaError_t configure_kernels(LaunchConfig& lc, int device)
 	lc.trace_threads = FB_TRACE_THREADS;
 	lc.trace_ctas_per_sm = FB_TRACE_MIN_BLOCKS;
 	// per CTA: all resident CTAs of an SM share its 227 KB (1 KB reserved per CTA)
-	const int max_smem = ((220 * 1024 / FB_TRACE_MIN_BLOCKS) / 1024) * 1024 > 48 * 1024 ? 48 * 1024 : ((220 * 1024 / FB_TRACE_MIN_BLOCKS) / 1024) * 1024;
+	const int max_smem = ((225 * 1024 / FB_TRACE_MIN_BLOCKS) - 1024) & ~1023;
 	e = cudaFuncSetAttribute(k_trace<TRACE_QUEUE_CLOSEST>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); if (e) return e;
 	e = cudaFuncSetAttribute(k_trace<TRACE_QUEUE_SHADOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); if (e) return e;
 	e = cudaFuncSetAttribute(k_trace<TRACE_RAYS_CLOSEST>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); if (e) return e;

@@ -128,6 +128,9 @@ uint32_t fb200_diag_float_to_half(float f);
 float    fb200_diag_half_to_float(uint32_t h);
 uint32_t fb200_diag_pack_normal(float x, float y, float z);
 int      fb200_diag_msvc_rand(uint32_t seed, int32_t* out, uint32_t n);
+/* scalar HOST emulation of the device traversal of the 8-wide BVH (closest hit, same record format as
+ * fb200_trace): validates the BVH collapse and measures tree quality without a GPU. Never used for rendering. */
+int      fb200_diag_wide_trace(const fb200_scene*, const float* rays, float* hits, uint32_t n, uint64_t* nodes_visited, uint64_t* tris_tested);
 
 /* --- rendering context (needs a CUDA device; fails loudly without one) ------------------------ */
 

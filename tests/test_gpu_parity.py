@@ -204,7 +204,11 @@ def test_big_scenes_against_oracle(fb, oracle, scene, res, bounces):
     rays = _random_rays(sc.view, 100000, 21, inside=False)
     hg, (ho, _, _) = rc.trace(rays), oracle.trace(sc.view, rays)
     same = (hg.view(np.uint32) == ho.view(np.uint32)).all(axis=1)
-    assert same.mean() > 0.9999, "mismatching hits: %d" % (~same).sum()
+    # coplanar overlapping triangles are hit at parameters one or two ulps apart; which of them survives then
+    # depends on box-test rounding in two different trees: such near-ties are the one allowed difference
+    tie = (hg[:, 0] > 0) & (ho[:, 0] > 0) & (np.abs(hg[:, 0] - ho[:, 0]) <= 4e-7 * np.abs(ho[:, 0]))
+    assert (same | tie).mean() > 0.99999, "mismatching hits: %d" % (~(same | tie)).sum()
+    assert same.mean() > 0.999
     # 2. one full pass: per-pixel parity at equal spp with the same seeds
     fbuf = oracle.new_framebuffer(sc.view)
     rc.clear()

@@ -111,6 +111,30 @@ def test_bvh2_is_a_valid_cugar_tree(cornell_scene):
     assert st["triangles"] == 36 and st["bvh2_nodes"] == v.n_bvh_nodes and st["wide_nodes"] >= 1
 
 
+def test_wide_bvh_collapse_agrees_with_binary_tree(fb, oracle, cornell_scene):
+    """The 8-wide compressed BVH (quantised boxes, slot ordering) must return the same hits as the oracle's scalar
+    traversal of the CUGAR-format binary tree it was collapsed from (host emulation of the device traversal)."""
+    scenes = [cornell_scene]
+    extra = os.path.join(ROOT, "scenes", "_cache", "cornellbox_glossy.fbs")
+    if fb.scene_available(extra):
+        scenes.append(fb.Scene(["-i", extra, "-r", "32", "32", "-bounces", "1"]))
+    for sc in scenes:
+        v = sc.view
+        rng = np.random.default_rng(2)
+        n = 50000
+        lo, hi = np.array(v.bbox_min[:]), np.array(v.bbox_max[:])
+        rays = np.zeros((n, 8), np.float32)
+        rays[:, 0:3] = lo - 0.2 * (hi - lo) + 1.4 * (hi - lo) * rng.random((n, 3))
+        d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+        rays[:, 4:7] = d * rng.uniform(0.3, 3.0, (n, 1))
+        rays[::5, 5] = 0.0                                  # axis-parallel components
+        rays[:, 3] = 1e-3; rays[:, 7] = 1e8
+        hw, wn, wt = sc.wide_trace(rays)
+        ho, on, ot = oracle.trace(v, rays)
+        assert np.array_equal(hw.view(np.uint32), ho.view(np.uint32))
+        assert wn < on                                       # the wide tree visits fewer nodes than the binary one
+
+
 def test_shards_partition_the_frame(fb):
     full = None
     for n in (1, 2, 3, 8):
