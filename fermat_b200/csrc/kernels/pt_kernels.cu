@@ -109,11 +109,14 @@ __global__ void __launch_bounds__(256) k_generate_primary(DeviceScene sc, PassPa
 #ifndef FB_REFILL_LANES
 #define FB_REFILL_LANES 1          // idle lanes of a warp that trigger a refill from the ray queue
 #endif
+#ifndef FB_STAGE_KB
+#define FB_STAGE_KB 16             // KB of top-of-tree nodes each trace CTA stages in shared memory
+#endif
 #ifndef FB_TRI_LOOP
 #define FB_TRI_LOOP 1
 #endif
 #ifndef FB_TRAV_BATCH
-#define FB_TRAV_BATCH 24           // traversal iterations a lane runs between two warp-wide refill votes
+#define FB_TRAV_BATCH 4            // traversal iterations a lane runs between two warp-wide refill votes
 #endif
 
 enum TraceMode { TRACE_QUEUE_CLOSEST = 0, TRACE_QUEUE_SHADOW = 1, TRACE_RAYS_CLOSEST = 2, TRACE_RAYS_SHADOW = 3 };
@@ -473,7 +476,10 @@ cudaError_t configure_kernels(LaunchConfig& lc, int device)
 	lc.trace_threads = FB_TRACE_THREADS;
 	lc.trace_ctas_per_sm = FB_TRACE_MIN_BLOCKS;
 	// per CTA: all resident CTAs of an SM share its 227 KB (1 KB reserved per CTA)
-	const int max_smem = ((225 * 1024 / FB_TRACE_MIN_BLOCKS) - 1024) & ~1023;
+	// shared memory per CTA for the staged top of the tree. Shared memory and L1 share the SM's 228 KB, and the
+	// traversal lives on L1 hits (per-lane stacks, hot nodes and triangles), so staging is deliberately small.
+	const int cap_smem = ((225 * 1024 / FB_TRACE_MIN_BLOCKS) - 1024) & ~1023;
+	const int max_smem = (FB_STAGE_KB * 1024 + 16) < cap_smem ? (FB_STAGE_KB * 1024 + 16) : cap_smem;
 	e = cudaFuncSetAttribute(k_trace<TRACE_QUEUE_CLOSEST>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); if (e) return e;
 	e = cudaFuncSetAttribute(k_trace<TRACE_QUEUE_SHADOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); if (e) return e;
 	e = cudaFuncSetAttribute(k_trace<TRACE_RAYS_CLOSEST>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); if (e) return e;
