@@ -275,6 +275,26 @@ FB_D void bsdf_f_and_p_components(const BsdfParams& b, const float* __restrict__
 	p[B_GT] = p_gt * (w_p[B_GT] * coat_t);
 }
 
+// sin and cos as a fixed sequence of IEEE fp32 operations (Cody-Waite reduction by pi/2 in three parts, minimax
+// polynomials on [-pi/4, pi/4], ~1 ulp): with -fmad=false the host executes exactly the same sequence, which
+// makes sampled directions reproducible to the bit between the device and the CPU checker. (The reference calls
+// sinf/cosf, whose last-place rounding differs between CUDA and any libm and is not part of its specification.)
+FB_D void fb_sincosf(float x, float* s, float* c)
+{
+	const float kf = rintf(x * 0.636619772f);
+	const int k = (int)kf;
+	float r = x - kf * 1.5703125f;
+	r = r - kf * 4.837512969970703125e-4f;
+	r = r - kf * 7.54978995489188216e-8f;
+	const float z = r * r;
+	const float ps = ((-1.9515295891e-4f * z + 8.3321608736e-3f) * z - 1.6666654611e-1f) * z * r + r;
+	const float pc = ((2.443315711809948e-5f * z - 1.388731625493765e-3f) * z + 4.166664568298827e-2f) * z * z - 0.5f * z + 1.0f;
+	const bool swap = k & 1;
+	const float ss = swap ? pc : ps, cc = swap ? ps : pc;
+	*s = (k & 2) ? -ss : ss;
+	*c = ((k + 1) & 2) ? -cc : cc;
+}
+
 FB_D V2 square_to_unit_disk(float sx, float sy)
 {
 	float phi, r;
@@ -289,7 +309,9 @@ FB_D V2 square_to_unit_disk(float sx, float sy)
 		if (a < bb) { r = -a; phi = (FB_PI / 4) * (4 + (bb / a)); }
 		else        { r = -bb; phi = bb != 0 ? (FB_PI / 4) * (6 - (a / bb)) : 0; }
 	}
-	return V2(r * cosf(phi), r * sinf(phi));
+	float sp, cp;
+	fb_sincosf(phi, &sp, &cp);
+	return V2(r * cp, r * sp);
 }
 
 // vndf_ggx_smith_sample (ggx_common.h:264-290) wrapped by GGXSmithMicrofacetDistribution::sample (ggx_smith.h:114-134)
@@ -302,8 +324,10 @@ FB_D V3 ggx_sample_h_local(float alpha, float u0, float u1, V3 Vl)
 	const float a = 1.0f / (1.0f + V.z);
 	const float r = sqrtf(u0);
 	const float phi = (u1 < a) ? u1 / a * FB_PI : FB_PI + (u1 - a) / (1.0f - a) * FB_PI;
-	const float P1 = r * cosf(phi);
-	const float P2 = r * sinf(phi) * ((u1 < a) ? 1.0f : V.z);
+	float sp, cp;
+	fb_sincosf(phi, &sp, &cp);
+	const float P1 = r * cp;
+	const float P2 = r * sp * ((u1 < a) ? 1.0f : V.z);
 	V3 N = P1 * T1 + P2 * T2 + sqrtf(fmaxf(0.0f, 1.0f - P1 * P1 - P2 * P2)) * V;
 	N = normalize(V3(alpha * N.x, alpha * N.y, fmaxf(0.0f, N.z)));
 	N.z *= sgn;

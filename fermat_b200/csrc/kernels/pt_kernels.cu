@@ -104,19 +104,19 @@ __global__ void __launch_bounds__(256) k_generate_primary(DeviceScene sc, PassPa
 #define FB_TRACE_MIN_BLOCKS 4
 #endif
 #ifndef FB_SHADE_MIN_BLOCKS
-#define FB_SHADE_MIN_BLOCKS 4
+#define FB_SHADE_MIN_BLOCKS 5
 #endif
 #ifndef FB_REFILL_LANES
 #define FB_REFILL_LANES 1          // idle lanes of a warp that trigger a refill from the ray queue
 #endif
 #ifndef FB_STAGE_KB
-#define FB_STAGE_KB 16             // KB of top-of-tree nodes each trace CTA stages in shared memory
+#define FB_STAGE_KB 8              // KB of top-of-tree nodes each trace CTA stages in shared memory (sweep: 0 638, 8 630, 16 626, 55 599 Msamples/s)
 #endif
 #ifndef FB_TRI_LOOP
 #define FB_TRI_LOOP 1
 #endif
 #ifndef FB_TRAV_BATCH
-#define FB_TRAV_BATCH 4            // traversal iterations a lane runs between two warp-wide refill votes
+#define FB_TRAV_BATCH 3            // traversal iterations a lane runs between two warp-wide refill votes (sweep: 2-3 best)
 #endif
 
 enum TraceMode { TRACE_QUEUE_CLOSEST = 0, TRACE_QUEUE_SHADOW = 1, TRACE_RAYS_CLOSEST = 2, TRACE_RAYS_SHADOW = 3 };

@@ -45,6 +45,8 @@ def lib():
         L.oracle_bsdf_raw.restype = C.c_int
         L.oracle_bsdf_raw.argtypes = [pf, pf, pf, C.c_uint32]
         L.oracle_num_threads.restype = C.c_int
+        L.oracle_set_trig_mode.argtypes = [C.c_int]
+        L.oracle_det_sincos.argtypes = [pf, pf, pf, C.c_uint32]
         _lib = L
     return _lib
 
@@ -99,6 +101,18 @@ def bsdf_raw(table, rec):
     out = np.empty((rec.shape[0], 25), dtype=np.float32)
     lib().oracle_bsdf_raw(_fptr(table), _fptr(rec), _fptr(out), rec.shape[0])
     return out
+
+
+def set_trig_mode(mode):
+    """0 = libm sinf/cosf (for pinning against oracle/_ref), 1 = fixed-sequence sincos shared with the kernels (default)."""
+    lib().oracle_set_trig_mode(int(mode))
+
+
+def det_sincos(x):
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    s, c = np.empty_like(x), np.empty_like(x)
+    lib().oracle_det_sincos(_fptr(x), _fptr(s), _fptr(c), x.size)
+    return s, c
 
 
 def num_threads():

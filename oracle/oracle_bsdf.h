@@ -50,7 +50,9 @@ inline vec2 square_to_unit_disk(vec2 seed)
 		if (a < b) { r = -a; phi = (PI_F / 4) * (4 + (b / a)); }
 		else       { r = -b; phi = b != 0 ? (PI_F / 4) * (6 - (a / b)) : 0; }
 	}
-	return vec2(r * cosf(phi), r * sinf(phi));
+	float sp, cp;
+	o_sincosf(phi, &sp, &cp);
+	return vec2(r * cp, r * sp);
 }
 inline vec3 square_to_cosine_hemisphere(vec2 uv)
 {
@@ -107,8 +109,10 @@ inline vec3 vndf_ggx_smith_sample(vec2 s, float alpha, vec3 _V)
 	const float a = 1.0f / (1.0f + V.z);
 	const float r = sqrtf(s.x);
 	const float phi = (s.y < a) ? s.y / a * PI_F : PI_F + (s.y - a) / (1.0f - a) * PI_F;
-	const float P1 = r * cosf(phi);
-	const float P2 = r * sinf(phi) * ((s.y < a) ? 1.0f : V.z);
+	float sp, cp;
+	o_sincosf(phi, &sp, &cp);
+	const float P1 = r * cp;
+	const float P2 = r * sp * ((s.y < a) ? 1.0f : V.z);
 	vec3 N = P1 * T1 + P2 * T2 + sqrtf(fmaxf(0.0f, 1.0f - P1 * P1 - P2 * P2)) * V;
 	N = normalize(vec3(alpha * N.x, alpha * N.y, fmaxf(0.0f, N.z)));
 	return N;

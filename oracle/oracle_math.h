@@ -44,6 +44,36 @@ inline float saturate(float x) { return fmaxf(fminf(x, 1.0f), 0.0f); }
 inline float sqr(float x) { return x * x; }
 inline float mod1(float x, float m) { return x > 0.0f ? fmodf(x, m) : m - fmodf(-x, m); }  // cugar::mod, numbers.h:606
 
+// sin/cos. The reference calls the platform's sinf/cosf (CUDA's on the device), whose last-place rounding is not
+// part of its specification. Mode 0 = this host's libm (used when the oracle is pinned against the reference's own
+// code compiled on this host); mode 1 (default) = a fixed sequence of IEEE fp32 operations (Cody-Waite reduction by
+// pi/2 in three parts + the classic degree-7/8 minimax polynomials on [-pi/4, pi/4], ~1 ulp) that the CUDA kernels
+// execute identically, so that sampled directions — and with them whole paths — agree bit for bit between the two.
+inline int& trig_mode() { static int m = 1; return m; }
+inline void det_sincosf(float x, float* s, float* c)
+{
+	const float kf = rintf(x * 0.636619772f);
+	const int k = (int)kf;
+	float r = x - kf * 1.5703125f;
+	r = r - kf * 4.837512969970703125e-4f;
+	r = r - kf * 7.54978995489188216e-8f;
+	const float z = r * r;
+	const float ps = ((-1.9515295891e-4f * z + 8.3321608736e-3f) * z - 1.6666654611e-1f) * z * r + r;
+	const float pc = ((2.443315711809948e-5f * z - 1.388731625493765e-3f) * z + 4.166664568298827e-2f) * z * z - 0.5f * z + 1.0f;
+	switch (k & 3)
+	{
+	case 0: *s = ps; *c = pc; break;
+	case 1: *s = pc; *c = -ps; break;
+	case 2: *s = -ps; *c = -pc; break;
+	default: *s = -pc; *c = ps; break;
+	}
+}
+inline void o_sincosf(float x, float* s, float* c)
+{
+	if (trig_mode() == 0) { *s = sinf(x); *c = cosf(x); }
+	else det_sincosf(x, s, c);
+}
+
 inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 inline float    u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 

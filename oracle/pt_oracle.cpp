@@ -706,6 +706,15 @@ int oracle_bsdf_raw(const float* table, const float* rec, float* out, uint32_t n
 	return 0;
 }
 
+// 0: libm sinf/cosf (pinning against the reference's host-compiled Bsdf), 1: the fixed-sequence sincos shared with the kernels
+void oracle_set_trig_mode(int mode) { trig_mode() = mode; }
+
+// the fixed-sequence sincos itself, for accuracy tests
+void oracle_det_sincos(const float* x, float* s, float* c, uint32_t n)
+{
+	for (uint32_t i = 0; i < n; ++i) det_sincosf(x[i], s + i, c + i);
+}
+
 int oracle_num_threads(void)
 {
 #ifdef _OPENMP

@@ -21,7 +21,11 @@ def _golden():
 
 def test_oracle_bsdf_is_bit_exact_on_reference_vectors(oracle, tables):
     rec, ref = _golden()
-    mine = oracle.bsdf_raw(tables["glossy"], rec)
+    oracle.set_trig_mode(0)              # the reference vectors were produced on this host's libm sinf/cosf
+    try:
+        mine = oracle.bsdf_raw(tables["glossy"], rec)
+    finally:
+        oracle.set_trig_mode(1)
     assert not np.isnan(mine).any()
     eq = mine.view(np.uint32) == ref.view(np.uint32)
     has_ior = rec[:, 31] != 0
@@ -36,6 +40,22 @@ def test_oracle_bsdf_is_bit_exact_on_reference_vectors(oracle, tables):
     same_comp = z & (mine[:, 24] == ref[:, 24])
     assert eq[same_comp][:, 16:19].all()                        # sampled direction
     assert eq[z][:, 6:12].all() and eq[z][:, 14:16].all()      # glossy lobes f and p
+
+
+def test_fixed_sequence_sincos_is_accurate_and_close_to_the_pinned_mode(oracle, tables):
+    """Mode 1 (shared with the kernels) replaces libm's sinf/cosf by a fixed fp32 sequence: it must stay within
+    ~1 ulp of the true values, and the Bsdf it feeds within fp32 noise of the reference-pinned mode 0."""
+    x = np.concatenate([np.linspace(0, 2 * np.pi, 200001), np.linspace(-1, 8, 50001)]).astype(np.float32)
+    s, c = oracle.det_sincos(x)
+    xs = x.astype(np.float64)
+    ulp = np.spacing(np.float32(1.0))
+    assert np.abs(s - np.sin(xs)).max() < 1.5 * ulp and np.abs(c - np.cos(xs)).max() < 1.5 * ulp
+    rec, ref = _golden()
+    mine = oracle.bsdf_raw(tables["glossy"], rec)               # default mode 1
+    ok = (rec[:, 31] != 0) & (mine[:, 24] == ref[:, 24])
+    assert ok.sum() > 3400
+    assert np.abs(mine[ok, 16:19] - ref[ok, 16:19]).max() < 2e-6   # sampled directions
+    assert np.array_equal(mine[:, :16].view(np.uint32)[rec[:, 31] != 0], ref[:, :16].view(np.uint32)[rec[:, 31] != 0])  # f_and_p has no trig
 
 
 def test_oracle_bsdf_components_cover_all_lobes():
