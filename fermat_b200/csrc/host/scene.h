@@ -70,6 +70,10 @@ void load_materials(const std::string& filename, Mesh& mesh);
 void load_fa(const std::string& filename, Mesh& mesh, std::vector<Camera>& cameras,
 			 std::vector<DirectionalLight>& dir_lights, std::vector<std::string>& dirs);
 bool read_camera_file(const std::string& filename, Camera& camera);
+// PLY meshes and the pbrt-v3 subset Fermat imports (reference src/mesh/pbrt_importer.cpp; pbrt_loader.cpp)
+void load_ply(const std::string& filename, Mesh& mesh);
+void load_pbrt(const std::string& filename, Mesh& mesh, Camera& camera, std::vector<DirectionalLight>& dir_lights,
+			   std::vector<std::string>& dirs, float& exposure, float& gamma);
 
 void merge(Mesh& mesh, const Mesh& other);
 void transform(Mesh& mesh, const float M[16]);
