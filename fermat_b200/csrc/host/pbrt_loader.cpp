@@ -296,6 +296,12 @@ V3 fresnel_conductor(float ci, V3 etai, V3 etat, V3 k)
 
 TextureReference no_texture() { TextureReference r; r.texture = 0xFFFFFFFFu; r.pad_ = 0; r.scaling = float2{ 1.0f, 1.0f }; return r; }
 float4 f4(V3 v) { return float4{ v.x, v.y, v.z, 0.0f }; }
+MeshMaterial zero_material()          // MeshMaterial::zero_material(): everything 0, no textures
+{
+	MeshMaterial m; memset(&m, 0, sizeof(m));
+	m.ambient_map = m.diffuse_map = m.diffuse_trans_map = m.specular_map = m.emissive_map = m.bump_map = no_texture();
+	return m;
+}
 
 struct Importer
 {
@@ -424,7 +430,7 @@ struct Importer
 				o.texture_data[t] = float2{ float(u) / float(US), 1.0f - float(v) / float(VS) };
 			}
 		o.group_names.push_back("sphere"); o.group_offsets.push_back(0); o.group_offsets.push_back(o.num_triangles());
-		MeshMaterial dm; memset(&dm, 0, sizeof(dm)); o.materials.push_back(dm); o.material_names.push_back("");
+		o.materials.push_back(zero_material()); o.material_names.push_back("");
 	}
 
 	void shape(const std::string& type, const Params& ps)
@@ -458,7 +464,7 @@ struct Importer
 				if (puv) other.texture_data.push_back(float2{ puv->floats[2 * i], puv->floats[2 * i + 1] });
 			}
 			other.group_names.push_back("trianglemesh"); other.group_offsets.push_back(0); other.group_offsets.push_back((int)nt);
-			MeshMaterial dm; memset(&dm, 0, sizeof(dm)); other.materials.push_back(dm); other.material_names.push_back("");
+			other.materials.push_back(zero_material()); other.material_names.push_back("");
 			merge_with_material(other, default_material);
 		}
 		else if (type == "disk")
@@ -471,7 +477,7 @@ struct Importer
 			for (uint32 i = 0; i < N; ++i) other.vertex_data.push_back(float4{ sinf(angle * i) * radius, 0.0f, cosf(angle * i) * radius, 0.0f });
 			other.vertex_data.push_back(float4{ 0, 0, 0, 0 });
 			other.group_names.push_back("disk"); other.group_offsets.push_back(0); other.group_offsets.push_back((int)N);
-			MeshMaterial dm; memset(&dm, 0, sizeof(dm)); other.materials.push_back(dm); other.material_names.push_back("");
+			other.materials.push_back(zero_material()); other.material_names.push_back("");
 			merge_with_material(other, default_material);
 		}
 	}

@@ -613,7 +613,8 @@ void load_fa(const std::string& filename_in, Mesh& mesh, std::vector<Camera>& ca
 	if (!ends_with(filename, ".fa"))
 	{
 		if (ends_with(filename, ".fbs")) throw std::runtime_error("snapshots cannot be nested in .fa scenes");
-		load_obj(filename, mesh);                    // "let's try with the other loader" (:345-349)
+		if (ends_with(filename, ".ply")) load_ply(filename, mesh);
+		else load_obj(filename, mesh);               // "let's try with the other loader" (:345-349)
 		return;
 	}
 
@@ -990,6 +991,17 @@ void load_scene(const std::string& filename, Scene& scene, bool camera_overridde
 	}
 	else if (ends_with(filename, ".obj"))
 		load_obj(filename, scene.mesh);
+	else if (ends_with(filename, ".ply"))
+		load_ply(filename, scene.mesh);
+	else if (ends_with(filename, ".pbrt"))
+	{
+		// the pbrt importer always sets the camera and the film options (reference src/renderer.cu:709-718)
+		Camera cam = scene.camera;
+		std::vector<std::string> dirs = scene.search_dirs;
+		load_pbrt(filename, scene.mesh, cam, scene.dir_lights, dirs, scene.exposure, scene.gamma);
+		scene.search_dirs = dirs;
+		if (!camera_overridden) scene.camera = cam;
+	}
 	else
 		throw std::runtime_error("unsupported scene format: " + filename);
 

@@ -183,7 +183,8 @@ def test_energy_partition_between_nee_and_bsdf_sampling(fb):
     assert abs(means["bsdf"] - means["mis"]) / means["mis"] < 0.06
 
 
-@pytest.mark.parametrize("scene,res,bounces", [("bathroom2", (400, 225), 8), ("water_caustic", (320, 180), 16), ("cornellbox_glossy", (128, 128), 4)])
+@pytest.mark.parametrize("scene,res,bounces", [("bathroom2", (400, 225), 8), ("material_testball", (256, 256), 12), ("water_caustic", (320, 180), 16),
+                                               ("cornellbox_glossy", (128, 128), 4)])
 def test_big_scenes_against_oracle(fb, oracle, scene, res, bounces):
     path = os.path.join(CACHE, scene + ".fbs")
     if not fb.scene_available(path):

@@ -51,6 +51,9 @@ def main(which=None):
     # C4: water_caustic
     wc = os.path.join(models, "water_caustic")
     done["water_caustic"] = snapshot(["-i", os.path.join(wc, "water_caustic.fa")], os.path.join(CACHE, "water_caustic.fbs"))
+    # C3: material-testball (pbrt scene: PLY meshes, substrate/glass/metal/matte materials, env-map light)
+    mt = os.path.join(models, "material-testball")
+    done["material_testball"] = snapshot(["-i", os.path.join(mt, "scene.pbrt")], os.path.join(CACHE, "material_testball.fbs"))
     # C2 / C5: bathroom2 (the .obj ships zipped)
     out = os.path.join(CACHE, "bathroom2.fbs")
     if not os.path.exists(out):
