@@ -90,6 +90,8 @@ def cpu_baseline(scene, res, threads=0, target_s=12.0, count_traversal=True):
     """the oracle (kind "port") on a bounded, strided sample of the workload's pixels; ~target_s of CPU work"""
     import fermat_b200 as fb
     import oracle
+    if threads <= 0:
+        threads = len(os.sched_getaffinity(0))       # all host cores we may use (torchrun exports OMP_NUM_THREADS=1)
     sc = fb.Scene(["-i", scene, "-r", str(res[0]), str(res[1]), "-bounces", str(BOUNCES)])
     P = res[0] * res[1]
     fbuf = oracle.new_framebuffer(sc.view)
@@ -137,25 +139,25 @@ def run_reference(args):
     P = res[0] * res[1]
     fbuf = oracle.new_framebuffer(sc.view)
     probe = np.arange(0, P, 101, dtype=np.uint32)
-    oracle.render_pass(sc.view, 0, fbuf, pixels=probe)                        # warm caches / thread pool
+    cores = len(os.sched_getaffinity(0))                                      # torchrun exports OMP_NUM_THREADS=1: ask for all cores explicitly
+    oracle.render_pass(sc.view, 0, fbuf, pixels=probe, threads=cores)         # warm caches / thread pool
     t = time.perf_counter()
-    st = oracle.render_pass(sc.view, 0, fbuf, pixels=probe)
+    st = oracle.render_pass(sc.view, 0, fbuf, pixels=probe, threads=cores)
     rate = st.shade_events / max(time.perf_counter() - t, 1e-3)
     per_pixel = st.shade_events / probe.size
     budget = 90.0 / max(args.steps + args.warmup, 1)                 # whole run within a few minutes
     stride = max(1, int(P / max(probe.size, min(5.0, budget) * rate / per_pixel)))
     pixels = np.arange(0, P, stride, dtype=np.uint32)
     for i in range(args.warmup):
-        oracle.render_pass(sc.view, i, fbuf, pixels=pixels)
+        oracle.render_pass(sc.view, i, fbuf, pixels=pixels, threads=cores)
     ev = 0
     t = time.perf_counter()
     for i in range(args.warmup, args.warmup + args.steps):
-        ev += oracle.render_pass(sc.view, i, fbuf, pixels=pixels).shade_events
+        ev += oracle.render_pass(sc.view, i, fbuf, pixels=pixels, threads=cores).shade_events
     dt = time.perf_counter() - t
     v = ev / dt * 1e-6
-    cores = oracle.num_threads()
     sample = "each step = one oracle pass over every %d-th pixel of %dx%d (%d pixels)" % (stride, res[0], res[1], pixels.size)
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "Msamples/s", "n_gpus": 0, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%s -pt %dx%d, %d bounces" % (name, res[0], res[1], BOUNCES), "note": "CPU restatement of the reference algorithm (the reference needs OptiX 6 / Win32 and cannot run)"},
@@ -175,6 +177,8 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device — the -pt renderer has no CPU path (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local)
     if world > 1:
+        # keep stdout to the single JSON line: NCCL's version/debug banner goes to a file
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_debug.%h.%p.log")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     scene, name = workload(args)
@@ -322,14 +326,29 @@ def run_ours(args):
         out["cpu_baseline"] = base
     if trav:
         out["traversal_counts"] = trav
-    print(json.dumps(out))
+    emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
     rc.close()
     sc.close()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the ONE line of stdout (everything else any library prints is routed to stderr, see main)"""
+    f = _REAL_STDOUT or sys.__stdout__
+    f.write(line + "\n")
+    f.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    # keep stdout clean for the JSON line: C libraries (NCCL banner, our own fprintf) and Python prints go to stderr
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=24)

@@ -94,6 +94,7 @@ def lib():
         "fb200_context_fb_device_ptr": (vp, [vp, i32]),
         "fb200_context_fb_download": (i32, [vp, i32, pf]),
         "fb200_context_fb_upload": (i32, [vp, i32, pf]),
+        "fb200_context_gbuffer_download": (i32, [vp, pf, pf, C.POINTER(u32), pf]),
         "fb200_context_get_stats": (i32, [vp, C.POINTER(Stats)]),
         "fb200_context_stream": (vp, [vp]),
         "fb200_context_set_profiling": (i32, [vp, i32]),
@@ -263,6 +264,14 @@ class RenderingContext:
         out = np.empty((h, w, 4), dtype=np.float32)
         self._chk(lib().fb200_context_fb_download(self._h, FB_CHANNELS.get(channel, channel), _fptr(out)))
         return out
+
+    def download_gbuffer(self):
+        """G-buffer of the last pass: dict(geo (H,W,4) f32, uv (H,W,4) f32, tri (H,W) u32, depth (H,W) f32)."""
+        w, h = self.res()
+        geo, uv = np.empty((h, w, 4), np.float32), np.empty((h, w, 4), np.float32)
+        tri, depth = np.empty((h, w), np.uint32), np.empty((h, w), np.float32)
+        self._chk(lib().fb200_context_gbuffer_download(self._h, _fptr(geo), _fptr(uv), tri.ctypes.data_as(C.POINTER(C.c_uint32)), _fptr(depth)))
+        return {"geo": geo, "uv": uv, "tri": tri, "depth": depth}
 
     def upload(self, channel, image):
         img = np.ascontiguousarray(image, dtype=np.float32)

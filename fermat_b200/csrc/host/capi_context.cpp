@@ -79,6 +79,19 @@ int fb200_context_fb_download(fb200_context* c, int channel, float* dst)
 	});
 }
 
+int fb200_context_gbuffer_download(fb200_context* c, float* geo, float* uv, uint32_t* tri, float* depth)
+{
+	return guarded([&] {
+		const fb::FrameBufferView v = c->rc.get_frame_buffer().view();
+		const size_t P = v.n_pixels;
+		if (geo) fb::cuda_check(cudaMemcpyAsync(geo, v.gb_geo, P * 16, cudaMemcpyDeviceToHost, c->rc.stream()), "gbuffer download");
+		if (uv) fb::cuda_check(cudaMemcpyAsync(uv, v.gb_uv, P * 16, cudaMemcpyDeviceToHost, c->rc.stream()), "gbuffer download");
+		if (tri) fb::cuda_check(cudaMemcpyAsync(tri, v.gb_tri, P * 4, cudaMemcpyDeviceToHost, c->rc.stream()), "gbuffer download");
+		if (depth) fb::cuda_check(cudaMemcpyAsync(depth, v.gb_depth, P * 4, cudaMemcpyDeviceToHost, c->rc.stream()), "gbuffer download");
+		c->rc.synchronize();
+	});
+}
+
 int fb200_context_fb_upload(fb200_context* c, int channel, const float* src)
 {
 	return guarded([&] {

@@ -37,6 +37,11 @@ void FBufferStorage::resize(uint32_t rx, uint32_t ry)
 {
 	res_x = rx; res_y = ry;
 	for (int c = 0; c < FB_NUM_CHANNELS; ++c) channels[c].alloc((size_t)rx * ry * sizeof(float4));
+	gbuffer.alloc((size_t)rx * ry * (16 + 16 + 4 + 4));
+}
+void FBufferStorage::clear_gbuffer(cudaStream_t s)
+{
+	cuda_check(cudaMemsetAsync(gbuffer.ptr, 0xFF, gbuffer.bytes, s), "cudaMemset gbuffer");
 }
 void FBufferStorage::clear(cudaStream_t s)
 {
@@ -48,6 +53,12 @@ FrameBufferView FBufferStorage::view() const
 	FrameBufferView v;
 	for (int c = 0; c < FB_NUM_CHANNELS; ++c) v.channels[c] = channels[c].as<float4>();
 	v.n_pixels = res_x * res_y;
+	const size_t P = (size_t)res_x * res_y;
+	char* g = gbuffer.as<char>();
+	v.gb_geo = reinterpret_cast<float4*>(g);
+	v.gb_uv = reinterpret_cast<float4*>(g + P * 16);
+	v.gb_tri = reinterpret_cast<uint32*>(g + P * 32);
+	v.gb_depth = reinterpret_cast<float*>(g + P * 36);
 	return v;
 }
 
@@ -196,8 +207,8 @@ void RenderingContext::clear() { m_fb.clear(m_stream); }
 
 void RenderingContext::render(const uint32_t instance)
 {
-	// the reference also binds the view, clears the G-buffer and tone-maps to RGBA around this call
-	// (src/renderer.cu:1029-1056); those are outside the `-pt` hot path
+	// src/renderer.cu:1029-1056: clear the G-buffer, run the renderer (tone-mapping to RGBA is left to the caller)
+	m_fb.clear_gbuffer(m_stream);
 	m_renderer->render(instance, *this);
 }
 

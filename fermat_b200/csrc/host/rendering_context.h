@@ -40,9 +40,11 @@ struct DeviceBuffer
 struct FBufferStorage
 {
 	fb::DeviceBuffer channels[fb::FB_NUM_CHANNELS];
+	fb::DeviceBuffer gbuffer;          // geo (float4) | uv (float4) | tri (u32) | depth (f32), one allocation
 	uint32_t res_x, res_y;
 	void resize(uint32_t rx, uint32_t ry);
 	void clear(cudaStream_t s);
+	void clear_gbuffer(cudaStream_t s);   // GBufferStorage::clear (src/framebuffer.h:178-185): 0xFF bytes
 	fb::FrameBufferView view() const;
 };
 

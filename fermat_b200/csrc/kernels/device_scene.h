@@ -66,6 +66,11 @@ struct FrameBufferView
 {
 	float4* channels[FB_NUM_CHANNELS];
 	uint32  n_pixels;
+	// G-buffer (reference src/framebuffer.h:49-143): written at bounce 0, cleared to 0xFF bytes every pass
+	float4* gb_geo;     // position.xyz, 2x15-bit packed shading normal
+	float4* gb_uv;      // hit u, v, texture s, t
+	uint32* gb_tri;     // triangle id
+	float*  gb_depth;   // hit t
 };
 
 // device counters of one pass; all zeroed by one memset at pass start

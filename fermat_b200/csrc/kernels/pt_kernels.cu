@@ -149,6 +149,12 @@ __global__ void __launch_bounds__(FB_TRACE_THREADS, FB_TRACE_MIN_BLOCKS) k_trace
 	const int lane = threadIdx.x & 31;
 
 	Traversal<ANY> trav;
+#if FB_SMEM_STACK > 0
+	// shared-memory part of the per-lane stacks sits behind the staged nodes
+	trav.sstack = reinterpret_cast<uint2*>(smem + 1 + sc.staged_nodes * 5u) + threadIdx.x;
+#else
+	trav.sstack = NULL;
+#endif
 	bool active = false;
 	uint32 ray_idx = 0;
 
@@ -277,6 +283,20 @@ __global__ void __launch_bounds__(128, FB_SHADE_MIN_BLOCKS) k_shade(DeviceScene 
 
 			if (bounce == 0)
 			{
+				// G-buffer (pathtracer_core.h:802-806; GBufferView::pack_geometry, src/framebuffer.h:84-90)
+				if (a.fb.gb_geo)
+				{
+					const V3 N = g.normal_s;
+					float phi;
+					if (fabsf(N.z) >= 1.0f - 1.0e-5f) phi = 0.0f;
+					else { phi = atan2f(N.y, N.x); phi = phi < 0.0f ? phi + 2.0f * FB_PI : phi; }
+					const float sqx = phi / (2.0f * FB_PI), sqy = (N.z + 1.0f) * 0.5f;
+					const uint32 qx = (uint32)max(min((int)(sqx * 32767.0f), 32766), 0), qy = (uint32)max(min((int)(sqy * 32767.0f), 32766), 0);
+					st_stream(a.fb.gb_geo + pixel, make_float4(position.x, position.y, position.z, __uint_as_float(qx | (qy << 15))));
+					st_stream(a.fb.gb_uv + pixel, make_float4(hit.z, hit.w, s, t));
+					st_stream(a.fb.gb_tri + pixel, tri);
+					a.fb.gb_depth[pixel] = hit.x;
+				}
 				// surface albedos (pathtracer_core.h:809-811)
 				float4 da = a.fb.channels[FB_DIFFUSE_A][pixel], sa = a.fb.channels[FB_SPECULAR_A][pixel];
 				da.x += kd.x * a.frame_weight; da.y += kd.y * a.frame_weight; da.z += kd.z * a.frame_weight; da.w += 0.0f * a.frame_weight;
@@ -479,16 +499,17 @@ cudaError_t configure_kernels(LaunchConfig& lc, int device)
 	// shared memory per CTA for the staged top of the tree. Shared memory and L1 share the SM's 228 KB, and the
 	// traversal lives on L1 hits (per-lane stacks, hot nodes and triangles), so staging is deliberately small.
 	const int cap_smem = ((225 * 1024 / FB_TRACE_MIN_BLOCKS) - 1024) & ~1023;
-	const int max_smem = (FB_STAGE_KB * 1024 + 16) < cap_smem ? (FB_STAGE_KB * 1024 + 16) : cap_smem;
-	e = cudaFuncSetAttribute(k_trace<TRACE_QUEUE_CLOSEST>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); if (e) return e;
-	e = cudaFuncSetAttribute(k_trace<TRACE_QUEUE_SHADOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); if (e) return e;
-	e = cudaFuncSetAttribute(k_trace<TRACE_RAYS_CLOSEST>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); if (e) return e;
-	e = cudaFuncSetAttribute(k_trace<TRACE_RAYS_SHADOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem); if (e) return e;
+	const int stack_smem = FB_SMEM_STACK * 8 * FB_TRACE_THREADS;
+	const int max_smem = ((FB_STAGE_KB * 1024 + 16) < cap_smem - stack_smem ? (FB_STAGE_KB * 1024 + 16) : cap_smem - stack_smem);
+	e = cudaFuncSetAttribute(k_trace<TRACE_QUEUE_CLOSEST>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem + stack_smem); if (e) return e;
+	e = cudaFuncSetAttribute(k_trace<TRACE_QUEUE_SHADOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem + stack_smem); if (e) return e;
+	e = cudaFuncSetAttribute(k_trace<TRACE_RAYS_CLOSEST>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem + stack_smem); if (e) return e;
+	e = cudaFuncSetAttribute(k_trace<TRACE_RAYS_SHADOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem + stack_smem); if (e) return e;
 	lc.staged_bytes = (uint32)max_smem - 16u;
 	return cudaSuccess;
 }
 
-static inline uint32 staged_smem(const DeviceScene& sc) { return 16u + sc.staged_nodes * (uint32)sizeof(WideNode); }
+static inline uint32 staged_smem(const DeviceScene& sc) { return 16u + sc.staged_nodes * (uint32)sizeof(WideNode) + FB_SMEM_STACK * 8u * FB_TRACE_THREADS; }
 
 cudaError_t launch_rescale_frame(const FrameBufferView& fb, float scale, cudaStream_t s)
 {

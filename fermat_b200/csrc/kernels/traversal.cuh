@@ -20,6 +20,9 @@
 namespace fb {
 
 #define FB_TRAV_STACK 32
+#ifndef FB_SMEM_STACK
+#define FB_SMEM_STACK 0            // per-lane stack entries kept in shared memory (0 = all in local memory)
+#endif
 #ifndef FB_PREFETCH
 #define FB_PREFETCH 0              // bit 0: prefetch the next node, bit 1: prefetch the hit triangles (into L1)
 #endif
@@ -64,7 +67,8 @@ struct Traversal
 	float idx_, idy_, idz_;          // 1 / dir
 	uint32 octinv4;
 	uint2 ngroup, tgroup;
-	uint2 stack[FB_TRAV_STACK];
+	uint2 stack[FB_TRAV_STACK - FB_SMEM_STACK];   // entries beyond the shared-memory part (local memory)
+	uint2* sstack;                                // this lane's column of the CTA's shared-memory stack (stride = blockDim.x)
 	int   sp;
 	TravHit hit;
 	uint32 mask;                     // any-hit: ray visibility mask
@@ -92,6 +96,26 @@ struct Traversal
 	//   acquire()   : make sure the lane holds a node group or a triangle group, popping the stack if needed
 	//   node_step() : visit one wide node (lanes with a pending node and no pending triangle)
 	//   tri_step()  : test one triangle (lanes with a pending triangle)
+	// the first FB_SMEM_STACK entries of every lane's stack live in shared memory (conflict-free column layout),
+	// deeper entries in local memory: most rays never go deeper than a handful of entries
+	FB_D void push(uint2 e)
+	{
+#if FB_SMEM_STACK > 0
+		if (sp < FB_SMEM_STACK) sstack[sp * blockDim.x] = e; else stack[sp - FB_SMEM_STACK] = e;
+#else
+		stack[sp] = e;
+#endif
+		sp++;
+	}
+	FB_D uint2 pop()
+	{
+		--sp;
+#if FB_SMEM_STACK > 0
+		return sp < FB_SMEM_STACK ? sstack[sp * blockDim.x] : stack[sp - FB_SMEM_STACK];
+#else
+		return stack[sp];
+#endif
+	}
 	FB_D bool has_node() const { return ngroup.y > 0x00FFFFFFu; }
 	FB_D bool has_tri() const { return tgroup.y != 0u; }
 
@@ -101,7 +125,7 @@ struct Traversal
 		if (!has_node() && !has_tri())
 		{
 			if (sp == 0) return false;
-			const uint2 e = stack[--sp];
+			const uint2 e = pop();
 			if (e.y > 0x00FFFFFFu) ngroup = e; else tgroup = e;
 		}
 		return true;
@@ -114,7 +138,7 @@ struct Traversal
 			const uint32 child_bit = bfind(hits);
 			const uint32 base = ngroup.x;
 			ngroup.y &= ~(1u << child_bit);
-			if (ngroup.y > 0x00FFFFFFu) { stack[sp++] = ngroup; }
+			if (ngroup.y > 0x00FFFFFFu) push(ngroup);
 			const uint32 slot = (child_bit - 24u) ^ (octinv4 & 0xFFu);
 			const uint32 rel = __popc(hits & ~(0xFFFFFFFFu << slot) & 0xFFu);
 			const uint32 node_idx = base + rel;

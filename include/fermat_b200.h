@@ -152,6 +152,10 @@ int fb200_context_res(const fb200_context*, uint32_t* res_x, uint32_t* res_y);
 void* fb200_context_fb_device_ptr(fb200_context*, int channel);
 /* copy a channel to host memory: dst holds 4*res_x*res_y floats */
 int fb200_context_fb_download(fb200_context*, int channel, float* dst);
+/* copy the G-buffer of the last pass to host memory (GBufferView, src/framebuffer.h:49-143): geo and uv hold 4 floats
+ * per pixel (position + 2x15-bit packed normal bits; hit u, v, texture s, t), tri and depth one value per pixel;
+ * pixels whose primary ray missed keep the 0xFF clear pattern. Any pointer may be NULL. */
+int fb200_context_gbuffer_download(fb200_context*, float* geo, float* uv, uint32_t* tri, float* depth);
 /* copy a host image into a channel (used to seed accumulation tests) */
 int fb200_context_fb_upload(fb200_context*, int channel, const float* src);
 int fb200_context_get_stats(fb200_context*, fb200_stats* out);

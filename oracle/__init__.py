@@ -103,6 +103,23 @@ def bsdf_raw(table, rec):
     return out
 
 
+def render_pass_with_gbuffer(view, instance, fb, threads=0):
+    """render_pass that also returns the G-buffer the reference writes at bounce 0 (0xFF-cleared first)."""
+    h, w = int(view.res_y), int(view.res_x)
+    geo = np.full((h, w, 4), np.frombuffer(b"\xff" * 4, np.float32)[0], np.float32)
+    uv = geo.copy()
+    tri = np.full((h, w), 0xFFFFFFFF, np.uint32)
+    depth = np.full((h, w), np.frombuffer(b"\xff" * 4, np.float32)[0], np.float32)
+    L = lib()
+    L.oracle_set_gbuffer.argtypes = [C.c_void_p] * 4
+    L.oracle_set_gbuffer(geo.ctypes.data, uv.ctypes.data, tri.ctypes.data, depth.ctypes.data)
+    try:
+        st = render_pass(view, instance, fb, threads=threads)
+    finally:
+        L.oracle_set_gbuffer(None, None, None, None)
+    return st, {"geo": geo, "uv": uv, "tri": tri, "depth": depth}
+
+
 def set_trig_mode(mode):
     """0 = libm sinf/cosf (for pinning against oracle/_ref), 1 = fixed-sequence sincos shared with the kernels (default)."""
     lib().oracle_set_trig_mode(int(mode))

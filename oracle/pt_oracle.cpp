@@ -321,6 +321,9 @@ static inline float power_heuristic(float p1, float p2)
 }
 static inline float pdf_product(float p1, float p2) { return std::isfinite(p1) && std::isfinite(p2) ? p1 * p2 : INFINITY; }
 
+struct GBufferOut { float* geo; float* uv; uint32_t* tri; float* depth; };
+static GBufferOut g_gbuffer = { NULL, NULL, NULL, NULL };     // optional outputs, set by oracle_set_gbuffer
+
 struct PassStats { uint64_t shade_events, shadow_events; TravStats trav, trav_shadow; uint64_t per_bounce[64]; };
 
 // MeshLight::map_impl on a freshly set-up light vertex (src/lights.h:374-404)
@@ -379,9 +382,25 @@ static void trace_path(const SceneRef& sc, const Sampler& smp, FB& fb, uint32_t 
 		const vec3 in = -normalize(ray.d);
 		const Bsdf bsdf(mat, s->glossy_reflectance);
 
+		if (bounce == 0 && g_gbuffer.geo)
+		{
+			// G-buffer (pathtracer_core.h:802-806; pack_geometry src/framebuffer.h:84-90; uniform_sphere_to_square
+			// contrib/cugar/spherical/mappings_inline.h:174-185; pack_vector contrib/cugar/linalg/vector_inl.h:454-462)
+			const vec3 N = g.normal_s;
+			float phi;
+			if (fabsf(N.z) >= 1.0f - 1.0e-5f) phi = 0.0f;
+			else { phi = atan2f(N.y, N.x); phi = phi < 0.0f ? phi + 2.0f * PI_F : phi; }
+			const float sqx = phi / (2.0f * PI_F), sqy = (N.z + 1.0f) * 0.5f;
+			const uint32_t qx = (uint32_t)std::max(std::min((int32_t)(sqx * 32767.0f), 32766), 0), qy = (uint32_t)std::max(std::min((int32_t)(sqy * 32767.0f), 32766), 0);
+			float* geo = g_gbuffer.geo + 4 * (size_t)pixel; float* uv = g_gbuffer.uv + 4 * (size_t)pixel;
+			geo[0] = g.position.x; geo[1] = g.position.y; geo[2] = g.position.z; geo[3] = u2f(qx | (qy << 15));
+			uv[0] = hit.u; uv[1] = hit.v; uv[2] = g.st[0]; uv[3] = g.st[1];
+			g_gbuffer.tri[pixel] = (uint32_t)hit.tri;
+			g_gbuffer.depth[pixel] = hit.t;
+		}
 		if (bounce == 0)
 		{
-			// albedo channels (G-buffer writes are not part of the radiance oracle)
+			// albedo channels
 			float* da = fb.px(DIFFUSE_A, pixel); float* sa = fb.px(SPECULAR_A, pixel);
 			da[0] += mat.diffuse.x * frame_weight; da[1] += mat.diffuse.y * frame_weight; da[2] += mat.diffuse.z * frame_weight; da[3] += 0.0f * frame_weight;
 			sa[0] += (mat.specular.x + 1.0f) * 0.5f * frame_weight; sa[1] += (mat.specular.y + 1.0f) * 0.5f * frame_weight;
@@ -705,6 +724,9 @@ int oracle_bsdf_raw(const float* table, const float* rec, float* out, uint32_t n
 	}
 	return 0;
 }
+
+// optional G-buffer outputs of oracle_render_pass (geo, uv: 4 floats per pixel; tri, depth: 1 per pixel); NULLs disable
+void oracle_set_gbuffer(float* geo, float* uv, uint32_t* tri, float* depth) { g_gbuffer.geo = geo; g_gbuffer.uv = uv; g_gbuffer.tri = tri; g_gbuffer.depth = depth; }
 
 // 0: libm sinf/cosf (pinning against the reference's host-compiled Bsdf), 1: the fixed-sequence sincos shared with the kernels
 void oracle_set_trig_mode(int mode) { trig_mode() = mode; }

@@ -105,6 +105,26 @@ def test_render_matches_oracle_per_pixel(cornell, oracle, fb):
     assert s["kernel_launches"] > 0
 
 
+def test_gbuffer_matches_oracle(cornell, oracle):
+    sc, rc = cornell
+    fbuf = oracle.new_framebuffer(sc.view)
+    rc.clear()
+    rc.render(0)
+    _, want = oracle.render_pass_with_gbuffer(sc.view, 0, fbuf)
+    got = rc.download_gbuffer()
+    assert np.array_equal(got["tri"], want["tri"])
+    assert np.array_equal(got["depth"].view(np.uint32), want["depth"].view(np.uint32))
+    assert np.array_equal(got["uv"].view(np.uint32), want["uv"].view(np.uint32))
+    assert np.array_equal(got["geo"][..., :3].view(np.uint32), want["geo"][..., :3].view(np.uint32))
+    # packed normal: atan2f is a library call on both sides, allow one 15-bit quantum
+    gn, wn = got["geo"][..., 3].view(np.uint32), want["geo"][..., 3].view(np.uint32)
+    hit = want["tri"] != 0xFFFFFFFF
+    dx = np.abs((gn & 32767).astype(np.int64) - (wn & 32767).astype(np.int64))[hit]
+    dy = np.abs((gn >> 15).astype(np.int64) - (wn >> 15).astype(np.int64))[hit]
+    assert dx.max() <= 1 and dy.max() <= 1 and (dx == 0).mean() > 0.99
+    assert (gn[~hit] == 0xFFFFFFFF).all()            # misses keep the clear pattern
+
+
 def test_committed_golden_image(fb):
     """64x64, 4 bounces, 8 spp CornellBox rendered by the oracle and committed (tools/make_golden_image.py)."""
     p = os.path.join(GOLDEN, "cornell_64_8spp.npz")
