@@ -60,11 +60,21 @@ FB_D void setup_geometry(const DeviceScene& sc, uint32 tri, float u, float v, Fr
 }
 
 // bilinear_texture_lookup at LOD 0 with wrap (src/texture_view.h:171-202); default value (1,1,1,1)
+// (the filtered fetch is kept out of line: it is called from five places and inlining five copies of its
+// fmodf/bilinear code bloats the shade kernel past the instruction cache)
+static __device__ __noinline__ V3 texture_fetch_bilinear(const TextureView tex, float s, float t, float2 scaling);
+
 FB_D V3 texture_rgb(const DeviceScene& sc, float s, float t, const TextureReference ref)
 {
 	if (ref.texture == 0xFFFFFFFFu || ref.texture >= sc.num_textures) return V3(1.0f);
 	const TextureView tex = sc.textures[ref.texture];
 	if (tex.texels == NULL) return V3(1.0f);
+	return texture_fetch_bilinear(tex, s, t, ref.scaling);
+}
+
+static __device__ __noinline__ V3 texture_fetch_bilinear(const TextureView tex, float s, float t, float2 scaling)
+{
+	TextureReference ref; ref.scaling = scaling;
 	s *= ref.scaling.x; t *= ref.scaling.y;
 	s = mod1(s, 1.0f); t = mod1(t, 1.0f);
 	const uint32 x = min((uint32)(s * tex.res_x), tex.res_x - 1), y = min((uint32)(t * tex.res_y), tex.res_y - 1);
@@ -95,6 +105,10 @@ FB_D void light_map(const DeviceScene& sc, uint32 prim, float s, float t, float&
 	else pdf = (__ldg(sc.mesh_cdf + prim) - (prim ? __ldg(sc.mesh_cdf + prim - 1) : 0.0f)) * __ldg(sc.mesh_inv_area + prim);
 }
 
+// fmodf(x, 1) for x in [0, 2): exact on both branches (x - 1 is representable for x in [1, 2)), so this is
+// bit-identical to the reference's fmodf on the sums of two values from [0, 1] that the sampler forms
+FB_D float wrap1(float x) { return x >= 1.0f ? x - 1.0f : x; }
+
 // TiledSequenceView::sample_2d over the transposed shift table: the six dimensions of one vertex are
 // 24 contiguous bytes per table row (src/tiled_sequence.h:62-105, src/tiled_sequence.cu:36-52)
 FB_D void vertex_samples(const DeviceScene& sc, uint32 px, uint32 py, uint32 first_dim, const float seq[6], float z[6])
@@ -108,8 +122,8 @@ FB_D void vertex_samples(const DeviceScene& sc, uint32 px, uint32 py, uint32 fir
 	for (int i = 0; i < 3; ++i)
 	{
 		const float2 sa = __ldg(a + i), sb = __ldg(b + i);
-		z[2 * i]     = fmodf(fmodf(seq[2 * i] + sa.x, 1.0f) + sb.x, 1.0f);
-		z[2 * i + 1] = fmodf(fmodf(seq[2 * i + 1] + sa.y, 1.0f) + sb.y, 1.0f);
+		z[2 * i]     = wrap1(wrap1(seq[2 * i] + sa.x) + sb.x);
+		z[2 * i + 1] = wrap1(wrap1(seq[2 * i + 1] + sa.y) + sb.y);
 	}
 }
 
