@@ -27,7 +27,7 @@ all: $(LIB) $(CLI) oracle
 $(BUILD):
 	mkdir -p $(BUILD)
 
-$(BUILD)/%.o: $(HOST_DIR)/%.cpp $(wildcard $(HOST_DIR)/*.h) include/fermat_b200.h | $(BUILD)
+$(BUILD)/%.o: $(HOST_DIR)/%.cpp $(wildcard $(HOST_DIR)/*.h) $(wildcard $(KERN_DIR)/*.h) include/fermat_b200.h | $(BUILD)
 	$(CXX) $(CXXFLAGS) -c $< -o $@
 
 $(BUILD)/%.cu.o: $(KERN_DIR)/%.cu $(wildcard $(KERN_DIR)/*.cuh) $(wildcard $(KERN_DIR)/*.h) $(wildcard $(HOST_DIR)/*.h) include/fermat_b200.h | $(BUILD)

@@ -188,7 +188,7 @@ class Scene:
         out = (C.c_uint64 * 4)()
         sah = C.c_float()
         lib().fb200_scene_bvh_stats(self._h, C.byref(out), C.byref(sah))
-        return {"wide_nodes": out[0], "triangles": out[1], "max_depth": out[2], "bvh2_nodes": out[3], "sah_cost": sah.value}
+        return {"wide_nodes": out[0], "triangles": out[1], "max_depth": out[2] & 0xFFFFFFFF, "max_stack": out[2] >> 32, "bvh2_nodes": out[3], "sah_cost": sah.value}
 
     def save_snapshot(self, filename):
         if lib().fb200_scene_save_snapshot(self._h, str(filename).encode()) != 0:

@@ -3,6 +3,10 @@
 #include <algorithm>
 #include <deque>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdexcept>
+#include <string>
 
 namespace fb {
 
@@ -12,7 +16,9 @@ struct PrimRef { Bbox3 box; V3 centroid; };
 
 inline float axis(const V3& v, int a) { return a == 0 ? v.x : (a == 1 ? v.y : v.z); }
 
-const int N_BINS = 16;
+const int MAX_BINS = 64;
+int   N_BINS = 16;          // FB200_BVH_BINS
+float C_ISECT = 1.0f;       // FB200_BVH_CI: triangle cost relative to a node visit in the binary build
 
 struct BuildTask { uint32 node, begin, end; };
 
@@ -21,6 +27,8 @@ struct BuildTask { uint32 node, begin, end; };
 void build_bvh2(const Mesh& mesh, Bvh2& bvh, uint32 max_leaf_size)
 {
 	const uint32 n = (uint32)mesh.num_triangles();
+	if (const char* s = getenv("FB200_BVH_BINS")) { N_BINS = atoi(s); N_BINS = N_BINS < 2 ? 2 : (N_BINS > MAX_BINS ? MAX_BINS : N_BINS); }
+	if (const char* s = getenv("FB200_BVH_CI")) C_ISECT = (float)atof(s);
 	std::vector<PrimRef> prims(n);
 	bvh.index.resize(n);
 	for (uint32 i = 0; i < n; ++i)
@@ -65,7 +73,7 @@ void build_bvh2(const Mesh& mesh, Bvh2& bvh, uint32 max_leaf_size)
 		{
 			const float ext = axis(cext, a);
 			if (!(ext > 0.0f)) continue;
-			Bbox3 bin_box[N_BINS]; uint32 bin_cnt[N_BINS] = { 0 };
+			Bbox3 bin_box[MAX_BINS]; uint32 bin_cnt[MAX_BINS] = { 0 };
 			const float k = float(N_BINS) / ext, lo = axis(cbox.lo, a);
 			for (uint32 i = task.begin; i < task.end; ++i)
 			{
@@ -73,7 +81,7 @@ void build_bvh2(const Mesh& mesh, Bvh2& bvh, uint32 max_leaf_size)
 				b = b < 0 ? 0 : (b >= N_BINS ? N_BINS - 1 : b);
 				bin_box[b].insert(prims[idx[i]].box); bin_cnt[b]++;
 			}
-			float right_area[N_BINS]; uint32 right_cnt[N_BINS];
+			float right_area[MAX_BINS]; uint32 right_cnt[MAX_BINS];
 			Bbox3 acc; uint32 c = 0;
 			for (int b = N_BINS - 1; b > 0; --b)
 			{
@@ -91,8 +99,8 @@ void build_bvh2(const Mesh& mesh, Bvh2& bvh, uint32 max_leaf_size)
 		}
 
 		const float parent_area = box.half_area();
-		const float leaf_cost = float(count) * parent_area;              // c_isect = 1
-		const float split_cost = best_axis >= 0 ? 1.0f * parent_area + best_cost : 1.0e30f;   // c_trav = 1
+		const float leaf_cost = C_ISECT * float(count) * parent_area;
+		const float split_cost = best_axis >= 0 ? 1.0f * parent_area + C_ISECT * best_cost : 1.0e30f;   // c_trav = 1
 		if (count <= max_leaf_size && leaf_cost <= split_cost) { make_leaf(); continue; }
 
 		uint32 mid;
@@ -147,19 +155,119 @@ float compute_sah_cost(const Bvh2& bvh, float c_trav, float c_isect)
 namespace {
 struct WideTask { uint32 bvh2_node; uint32 wide_node; };
 inline Bbox3 node_box(const Bvh2Node& n) { Bbox3 b; b.lo = V3(n.bmin[0], n.bmin[1], n.bmin[2]); b.hi = V3(n.bmax[0], n.bmax[1], n.bmax[2]); return b; }
+
+float env_float(const char* name, float def) { const char* s = getenv(name); return s ? (float)atof(s) : def; }
+
+// SAH-optimal choice of which Bvh2 nodes become the children of each wide node (Ylitie, Karras, Laine 2017,
+// sec. 4.1): cost[n][i-1] = cheapest way to represent the subtree of n as a forest of at most i wide-node
+// children, i = 1..7; a subtree with <= 3 triangles may also become one leaf slot.
+struct CollapsePlan
+{
+	static const int W = 8;
+	std::vector<float>   cost;       // [n * 7 + (i-1)]
+	std::vector<uint8_t> split;      // [n * 8 + (i-1)]: i = 1: 1 = leaf / 0 = internal; i = 2..7: 0 = take i-1, else roots given to the left child;
+	                                 // [n * 8 + 7]: roots given to the left child when n is opened as a wide node (8 children)
+	std::vector<uint32>  first_prim; // first slot of n's range in Bvh2::index
+
+	void build(const Bvh2& bvh, float c_node, float c_prim)
+	{
+		const size_t N = bvh.nodes.size();
+		cost.assign(N * 7, 0.0f); split.assign(N * 8, 0); first_prim.assign(N, 0);
+		for (size_t ii = N; ii-- > 0;)      // children are stored after their parent
+		{
+			const Bvh2Node& n = bvh.nodes[ii];
+			const float A = node_box(n).half_area();
+			float* c = &cost[ii * 7]; uint8_t* s = &split[ii * 8];
+			if (n.is_leaf())
+			{
+				first_prim[ii] = n.leaf_begin();
+				for (int i = 0; i < 7; ++i) c[i] = A * n.range_size * c_prim;
+				s[0] = 1;
+				continue;
+			}
+			const uint32 l = n.child(0), r = n.child(1);
+			first_prim[ii] = first_prim[l];
+			const float* cl = &cost[(size_t)l * 7]; const float* cr = &cost[(size_t)r * 7];
+			auto distribute = [&](int j, uint8_t& best_k) {
+				float best = 1.0e38f;
+				for (int k = 1; k < j; ++k)
+				{
+					if (k > 7 || j - k > 7) continue;
+					const float v = cl[k - 1] + cr[j - k - 1];
+					if (v < best) { best = v; best_k = (uint8_t)k; }
+				}
+				return best; };
+			const float c_internal = distribute(W, s[7]) + A * c_node;
+			const float c_leaf = n.range_size <= 3 ? A * n.range_size * c_prim : 1.0e38f;
+			s[0] = c_leaf <= c_internal ? 1 : 0;
+			c[0] = s[0] ? c_leaf : c_internal;
+			for (int i = 2; i <= 7; ++i)
+			{
+				uint8_t k = 0;
+				const float d = distribute(i, k);
+				if (d < c[i - 2]) { c[i - 1] = d; s[i - 1] = k; }
+				else { c[i - 1] = c[i - 2]; s[i - 1] = 0; }
+			}
+		}
+	}
+	bool is_leaf(uint32 n) const { return split[(size_t)n * 8] != 0; }
+
+	// children of wide node opened at Bvh2 node n
+	uint32 gather(const Bvh2& bvh, uint32 n, uint32* out) const
+	{
+		uint32 nc = 0;
+		const Bvh2Node& nd = bvh.nodes[n];
+		const int k = split[(size_t)n * 8 + 7];
+		expand(bvh, nd.child(0), k, out, nc);
+		expand(bvh, nd.child(1), W - k, out, nc);
+		return nc;
+	}
+	void expand(const Bvh2& bvh, uint32 m, int budget, uint32* out, uint32& nc) const
+	{
+		while (budget > 1 && split[(size_t)m * 8 + budget - 1] == 0) budget--;
+		if (budget > 7) budget = 7;
+		if (budget <= 1 || bvh.nodes[m].is_leaf()) { out[nc++] = m; return; }
+		const int k = split[(size_t)m * 8 + budget - 1];
+		expand(bvh, bvh.nodes[m].child(0), k, out, nc);
+		expand(bvh, bvh.nodes[m].child(1), budget - k, out, nc);
+	}
+};
 }
+
+static void collapse_impl(const Mesh& mesh, const Bvh2& bvh, WideBvh& wide, const bool use_plan);
 
 void collapse_to_wide(const Mesh& mesh, const Bvh2& bvh, WideBvh& wide)
 {
-	wide.nodes.clear(); wide.tris.clear(); wide.max_depth = 0;
+	const char* mode = getenv("FB200_BVH_COLLAPSE");
+	const bool greedy = mode && strcmp(mode, "greedy") == 0;
+	if (!greedy)
+	{
+		collapse_impl(mesh, bvh, wide, true);
+		if (getenv("FB200_BVH_VERBOSE")) fprintf(stderr, "collapse_to_wide: SAH plan: %zu nodes, depth %u, stack %u\n", wide.nodes.size(), wide.max_depth, wide.max_stack);
+		if (wide.max_stack <= WIDE_STACK_ENTRIES) return;
+	}
+	// the area-greedy collapse produces shallower, bushier trees
+	collapse_impl(mesh, bvh, wide, false);
+	if (wide.max_stack > WIDE_STACK_ENTRIES)
+		throw std::runtime_error("collapse_to_wide: the scene BVH needs " + std::to_string(wide.max_stack) + " traversal stack entries, more than the kernels hold");
+}
+
+static void collapse_impl(const Mesh& mesh, const Bvh2& bvh, WideBvh& wide, const bool use_plan)
+{
+	wide.nodes.clear(); wide.tris.clear(); wide.max_depth = 0; wide.max_stack = 0;
 	if (bvh.nodes.empty()) return;
 	wide.nodes.reserve(bvh.nodes.size() / 4 + 16);
 	wide.tris.reserve(bvh.index.size());
 
+	CollapsePlan plan;
+	if (use_plan) plan.build(bvh, env_float("FB200_BVH_CNODE", 1.0f), env_float("FB200_BVH_CPRIM", 0.3f));
+	auto leaf_child = [&](uint32 n) { return use_plan ? plan.is_leaf(n) : bvh.nodes[n].is_leaf(); };
+	auto leaf_first = [&](uint32 n) { return use_plan ? plan.first_prim[n] : bvh.nodes[n].leaf_begin(); };
+
 	std::deque<WideTask> queue;
-	std::vector<uint32> depth;
+	std::vector<uint32> depth, need;
 	wide.nodes.push_back(WideNode());
-	depth.push_back(1);
+	depth.push_back(1); need.push_back(0);
 	queue.push_back(WideTask{ 0u, 0u });
 
 	while (!queue.empty())
@@ -167,11 +275,13 @@ void collapse_to_wide(const Mesh& mesh, const Bvh2& bvh, WideBvh& wide)
 		const WideTask task = queue.front(); queue.pop_front();
 		const Bvh2Node& root = bvh.nodes[task.bvh2_node];
 
-		// gather up to 8 children: repeatedly open the internal child with the largest area
+		// gather up to 8 children: by the SAH-optimal plan, or (FB200_BVH_COLLAPSE=greedy) by repeatedly
+		// opening the internal child with the largest area
 		uint32 children[8]; uint32 nc = 0;
 		if (root.is_leaf()) children[nc++] = task.bvh2_node;
+		else if (use_plan) nc = plan.gather(bvh, task.bvh2_node, children);
 		else { children[nc++] = root.child(0); children[nc++] = root.child(1); }
-		while (nc < 8)
+		while (!use_plan && nc < 8)
 		{
 			int best = -1; float best_area = -1.0f;
 			for (uint32 i = 0; i < nc; ++i)
@@ -255,14 +365,14 @@ void collapse_to_wide(const Mesh& mesh, const Bvh2& bvh, WideBvh& wide)
 			fix(node.qloy[s], node.qhiy[s], cb.lo.y, cb.hi.y, pbox.lo.y, e[1]);
 			fix(node.qloz[s], node.qhiz[s], cb.lo.z, cb.hi.z, pbox.lo.z, e[2]);
 
-			if (c.is_leaf())
+			if (leaf_child((uint32)child_in_slot[s]))
 			{
 				const uint32 cnt = c.range_size;                 // 1..3
 				const uint32 unary = cnt == 1 ? 1u : (cnt == 2 ? 3u : 7u);
 				node.meta[s] = (uint8_t)((unary << 5) | tri_offset);
 				for (uint32 k = 0; k < cnt; ++k)
 				{
-					const uint32 tri_id = bvh.index[c.leaf_begin() + k];
+					const uint32 tri_id = bvh.index[leaf_first((uint32)child_in_slot[s]) + k];
 					const int4 t = mesh.vertex_indices[tri_id];
 					WideTri wt;
 					const float4 a = mesh.vertex_data[t.x], b = mesh.vertex_data[t.y], d = mesh.vertex_data[t.z];
@@ -283,12 +393,17 @@ void collapse_to_wide(const Mesh& mesh, const Bvh2& bvh, WideBvh& wide)
 		// allocate the internal children contiguously, in slot order
 		const uint32 d = depth[task.wide_node];
 		if (d > wide.max_depth) wide.max_depth = d;
+		// a ray leaves one stack entry behind at every node where it hits two or more internal children
+		// (Traversal::node_step), so the entries it can hold below this node grow by one iff n_internal >= 2
+		const uint32 held = need[task.wide_node] + (n_internal >= 2 ? 1u : 0u);
+		if (held > wide.max_stack) wide.max_stack = held;
 		for (int s = 0; s < 8; ++s)
 			if (node.imask & (1u << s))
 			{
 				const uint32 wi = (uint32)wide.nodes.size();
 				wide.nodes.push_back(WideNode());
 				depth.push_back(d + 1);
+				need.push_back(held);
 				queue.push_back(WideTask{ (uint32)child_in_slot[s], wi });
 			}
 		wide.nodes[task.wide_node] = node;

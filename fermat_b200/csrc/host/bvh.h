@@ -25,6 +25,7 @@ struct WideBvh
 	std::vector<WideNode> nodes;     // breadth-first
 	std::vector<WideTri>  tris;      // leaf order
 	uint32 max_depth;
+	uint32 max_stack;                // exact worst-case number of traversal stack entries any ray can need
 };
 
 // binned-SAH top-down build; leaves hold at most `max_leaf_size` triangles (<= 3 so that a leaf fits

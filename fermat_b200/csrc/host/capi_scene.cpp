@@ -49,7 +49,7 @@ int fb200_scene_save_snapshot(const fb200_scene* s, const char* filename)
 int fb200_scene_bvh_stats(const fb200_scene* s, uint64_t out[4], float* sah_cost)
 {
 	if (!s || !out) { fb::set_last_error("null argument"); return -1; }
-	out[0] = s->wide.nodes.size(); out[1] = s->wide.tris.size(); out[2] = s->wide.max_depth; out[3] = s->bvh2.nodes.size();
+	out[0] = s->wide.nodes.size(); out[1] = s->wide.tris.size(); out[2] = s->wide.max_depth | ((uint64_t)s->wide.max_stack << 32); out[3] = s->bvh2.nodes.size();
 	if (sah_cost) *sah_cost = s->bvh2.sah_cost;
 	return 0;
 }

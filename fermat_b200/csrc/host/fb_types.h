@@ -146,6 +146,13 @@ struct WideNode
 };
 static_assert(sizeof(WideNode) == 80, "WideNode must be 80 B");
 
+// traversal stack entries per ray in the kernels (kernels/traversal.cuh); the builder guarantees that no
+// ray can need more (bvh.h WideBvh::max_stack) or refuses the scene
+#ifndef FB_WIDE_STACK_ENTRIES
+#define FB_WIDE_STACK_ENTRIES 64
+#endif
+const uint32 WIDE_STACK_ENTRIES = FB_WIDE_STACK_ENTRIES;
+
 // triangle record used by traversal: 3 vertices + original triangle id + visibility flags
 struct WideTri
 {

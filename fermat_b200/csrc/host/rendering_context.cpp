@@ -193,6 +193,7 @@ void RenderingContext::upload_scene()
 	d.nodes = d_nodes.as<WideNode>(); d.tris = reinterpret_cast<const WideTri*>((const char*)d_nodes.ptr + node_bytes); d.num_nodes = (uint32)s.wide.nodes.size();
 	const uint32 max_staged = m_lc.staged_bytes / (uint32)sizeof(WideNode);
 	d.staged_nodes = d.num_nodes < max_staged ? d.num_nodes : max_staged;
+	d.f32_2p23_bits = 0x4B000000u;
 	d.vpls = d_vpls.as<VPL>(); d.n_vpls = (uint32)s.mesh_lights.vpls.size();
 	d.use_vpls = (s.options.nee_type == 1 && d.n_vpls > 0) ? 1u : 0u;
 	d.vpl_norm = s.mesh_lights.normalization_coeff;

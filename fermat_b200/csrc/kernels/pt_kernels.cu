@@ -149,6 +149,8 @@ __global__ void __launch_bounds__(FB_TRACE_THREADS, FB_TRACE_MIN_BLOCKS) k_trace
 	const int lane = threadIdx.x & 31;
 
 	Traversal<ANY> trav;
+	uint2 local_stack[FB_TRAV_STACK - FB_SMEM_STACK];
+	trav.stack = local_stack;
 #if FB_SMEM_STACK > 0
 	// shared-memory part of the per-lane stacks sits behind the staged nodes
 	trav.sstack = reinterpret_cast<uint2*>(smem + 1 + sc.staged_nodes * 5u) + threadIdx.x;

@@ -19,9 +19,12 @@
 
 namespace fb {
 
-#define FB_TRAV_STACK 32
+#define FB_TRAV_STACK WIDE_STACK_ENTRIES   // the builder refuses trees that could need more (bvh.h WideBvh::max_stack)
 #ifndef FB_SMEM_STACK
 #define FB_SMEM_STACK 0            // per-lane stack entries kept in shared memory (0 = all in local memory)
+#endif
+#ifndef FB_USE_I2F
+#define FB_USE_I2F 0               // 1: convert the quantised box bytes with I2F.U8 (XU pipe) instead of PRMT + FADD
 #endif
 #ifndef FB_PREFETCH
 #define FB_PREFETCH 0              // bit 0: prefetch the next node, bit 1: prefetch the hit triangles (into L1)
@@ -34,6 +37,21 @@ FB_D uint32 sign_extend_s8x4(uint32 x)
 	return r;
 }
 FB_D uint32 bfind(uint32 x) { return 31u - (uint32)__clz((int)x); }
+
+// byte J of w as a float, without the conversion unit: I2F.U8 issues at a quarter of the FP32 rate and the
+// 48 conversions of a node visit made the XU pipe the busiest one of the traversal kernels (r01 profile: 49 %).
+// PRMT builds the float 2^23 + byte, the subtraction is exact, so the value is identical to (float)byte.
+// `magic` = 0x4B000000 comes from the kernel's constant bank (DeviceScene::f32_2p23_bits) rather than from a
+// literal: PRMT encodes one immediate only, and with a literal ptxas keeps the four selectors in registers and
+// re-materialises them over and over; this way the selector is the immediate and the constant costs no register.
+FB_D float byte_to_float(uint32 w, int j, uint32 magic)   // j: compile-time constant after unrolling
+{
+#if FB_USE_I2F
+	return (float)((w >> (8 * j)) & 0xFFu);
+#else
+	return __uint_as_float(__byte_perm(w, magic, 0x7540u | (uint32)j)) - 8388608.0f;
+#endif
+}
 
 struct TravRay
 {
@@ -67,7 +85,9 @@ struct Traversal
 	float idx_, idy_, idz_;          // 1 / dir
 	uint32 octinv4;
 	uint2 ngroup, tgroup;
-	uint2 stack[FB_TRAV_STACK - FB_SMEM_STACK];   // entries beyond the shared-memory part (local memory)
+	uint2* stack;                                 // entries beyond the shared-memory part: a local-memory array of the kernel,
+	                                              // FB_TRAV_STACK - FB_SMEM_STACK long (kept OUT of this struct so that the rest
+	                                              // of the state is promoted to registers)
 	uint2* sstack;                                // this lane's column of the CTA's shared-memory stack (stride = blockDim.x)
 	int   sp;
 	TravHit hit;
@@ -179,9 +199,10 @@ struct Traversal
 				for (int j = 0; j < 4; ++j)
 				{
 					const int sh = j * 8;
-					const float t0x = fmaf((float)((xmin >> sh) & 0xFFu), aix, aox), t1x = fmaf((float)((xmax >> sh) & 0xFFu), aix, aox);
-					const float t0y = fmaf((float)((ymin >> sh) & 0xFFu), aiy, aoy), t1y = fmaf((float)((ymax >> sh) & 0xFFu), aiy, aoy);
-					const float t0z = fmaf((float)((zmin >> sh) & 0xFFu), aiz, aoz), t1z = fmaf((float)((zmax >> sh) & 0xFFu), aiz, aoz);
+					const uint32 mg = sc.f32_2p23_bits;
+					const float t0x = fmaf(byte_to_float(xmin, j, mg), aix, aox), t1x = fmaf(byte_to_float(xmax, j, mg), aix, aox);
+					const float t0y = fmaf(byte_to_float(ymin, j, mg), aiy, aoy), t1y = fmaf(byte_to_float(ymax, j, mg), aiy, aoy);
+					const float t0z = fmaf(byte_to_float(zmin, j, mg), aiz, aoz), t1z = fmaf(byte_to_float(zmax, j, mg), aiz, aoz);
 					const float cmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, ray.tmin));
 					// far side widened by 4e-7 relative so that fp rounding never culls a box whose geometry is hit
 					const float cmax = fminf(fminf(t1x, t1y), fminf(t1z, ray.tmax)) * 1.0000004f;

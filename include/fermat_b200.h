@@ -109,7 +109,8 @@ void         fb200_scene_destroy(fb200_scene*);
 int          fb200_scene_get_view(const fb200_scene*, fb200_scene_view* out);
 /* write / the pre-processed scene as a binary snapshot (.fbs) that fb200_scene_create can load with -i */
 int          fb200_scene_save_snapshot(const fb200_scene*, const char* filename);
-/* wide-BVH statistics: out[0]=#wide nodes, out[1]=#triangles, out[2]=max depth, out[3]=#bvh2 nodes */
+/* wide-BVH statistics: out[0]=#wide nodes, out[1]=#triangles, out[2]=max depth | (worst-case traversal stack entries << 32),
+ * out[3]=#bvh2 nodes */
 int          fb200_scene_bvh_stats(const fb200_scene*, uint64_t out[4], float* sah_cost);
 /* TiledSequenceView::sample_2d for pass `instance` (src/tiled_sequence.h:93-105) */
 float        fb200_scene_sample_2d(fb200_scene*, uint32_t instance, uint32_t px, uint32_t py, uint32_t dim);

@@ -600,7 +600,9 @@ int oracle_render_pass(const fb200_scene_view* s, uint32_t instance, float* fbda
 	const float scale = float(instance) / float(instance + 1), frame_weight = 1.0f / float(instance + 1);
 	const uint32_t n = instance + 1;
 #ifdef _OPENMP
-	if (n_threads > 0) omp_set_num_threads(n_threads);
+	// n_threads <= 0: the process default (omp_set_num_threads is sticky, so remember what the default was)
+	static const int default_threads = omp_get_max_threads();
+	omp_set_num_threads(n_threads > 0 ? n_threads : default_threads);
 #endif
 	oracle_stats total; memset(&total, 0, sizeof(total));
 	#pragma omp parallel
