@@ -238,6 +238,8 @@ static void collapse_impl(const Mesh& mesh, const Bvh2& bvh, WideBvh& wide, cons
 
 void collapse_to_wide(const Mesh& mesh, const Bvh2& bvh, WideBvh& wide)
 {
+	// the kernels pack (triangle slot << 5 | lane) into 32 bits (Traversal::coop_tri_phase)
+	if (bvh.index.size() >= (size_t(1) << 27)) throw std::runtime_error("collapse_to_wide: more than 2^27 triangles");
 	const char* mode = getenv("FB200_BVH_COLLAPSE");
 	const bool greedy = mode && strcmp(mode, "greedy") == 0;
 	if (!greedy)

@@ -115,6 +115,12 @@ __global__ void __launch_bounds__(256) k_generate_primary(DeviceScene sc, PassPa
 #ifndef FB_TRI_LOOP
 #define FB_TRI_LOOP 1
 #endif
+#ifndef FB_COOP_TRI
+#define FB_COOP_TRI 1              // 1: warp-shared triangle tests (Traversal::coop_tri_phase); 0: every lane loops over its own
+#endif
+#ifndef FB_RAYS_PER_LANE
+#define FB_RAYS_PER_LANE 0         // > 0: trace CTAs beyond queue_length / (threads x this) exit immediately
+#endif
 #ifndef FB_TRAV_BATCH
 #define FB_TRAV_BATCH 3            // traversal iterations a lane runs between two warp-wide refill votes (sweep: 2-3 best)
 #endif
@@ -138,13 +144,23 @@ template <int MODE>
 __global__ void __launch_bounds__(FB_TRACE_THREADS, FB_TRACE_MIN_BLOCKS) k_trace(DeviceScene sc, TraceArgs a)
 {
 	constexpr bool ANY = (MODE == TRACE_QUEUE_SHADOW || MODE == TRACE_RAYS_SHADOW);
+	const uint32 n = a.n_ptr ? *a.n_ptr : a.n_value;
+#if FB_RAYS_PER_LANE > 0
+	// size the persistent grid to the queue (its length is only known on the device): a lane that gets just one or two
+	// rays cannot even out their different lengths against its warp mates', so CTAs beyond n / (threads x R) leave at once;
+	// one CTA per SM always stays
+	{
+		const uint32 want = (n + FB_TRACE_THREADS * FB_RAYS_PER_LANE - 1u) / (FB_TRACE_THREADS * FB_RAYS_PER_LANE);
+		const uint32 keep = gridDim.x / FB_TRACE_MIN_BLOCKS;
+		if (blockIdx.x >= (want > keep ? want : keep)) return;
+	}
+#endif
 	extern __shared__ float4 smem[];
 	// [0,16): mbarrier; staged nodes follow
 	unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem);
 	const float4* smem_nodes = smem + 1;
 	stage_nodes_tma(smem + 1, sc.nodes, sc.staged_nodes * (uint32)sizeof(WideNode), bar);
 
-	const uint32 n = a.n_ptr ? *a.n_ptr : a.n_value;
 	if (MODE == TRACE_QUEUE_SHADOW && blockIdx.x == 0 && threadIdx.x == 0 && a.event_counter) atomicAdd(a.event_counter, (unsigned long long)n);
 	const int lane = threadIdx.x & 31;
 
@@ -156,6 +172,10 @@ __global__ void __launch_bounds__(FB_TRACE_THREADS, FB_TRACE_MIN_BLOCKS) k_trace
 	trav.sstack = reinterpret_cast<uint2*>(smem + 1 + sc.staged_nodes * 5u) + threadIdx.x;
 #else
 	trav.sstack = NULL;
+#endif
+#if FB_COOP_TRI
+	// this warp's 32-entry (ray, triangle) pair list, behind the staged nodes and the shared-memory stacks
+	uint32* pair_buf = reinterpret_cast<uint32*>(smem + 1 + sc.staged_nodes * 5u) + FB_SMEM_STACK * 2u * FB_TRACE_THREADS + (threadIdx.x >> 5) * 32u;
 #endif
 	bool active = false;
 	uint32 ray_idx = 0;
@@ -189,6 +209,19 @@ __global__ void __launch_bounds__(FB_TRACE_THREADS, FB_TRACE_MIN_BLOCKS) k_trace
 		// own before the warp reconverges at the refill vote: the traversal is bound by L2 latency, not by issue
 		// slots, and diverged lanes of a warp overlap each other's outstanding loads (measured: batch 24 beats a
 		// fully converged loop by 12 % although the latter executes 29 % fewer instructions).
+#if FB_COOP_TRI
+		// warp-converged iteration: every lane with a pending node visits it, then the triangles all lanes found are
+		// pooled and tested by the whole warp (Traversal::coop_tri_phase); idle lanes of a thin warp test their mates' triangles
+		{
+			bool done = false;
+			if (active)
+			{
+				done = !trav.acquire();
+				if (!done) trav.node_step(sc, smem_nodes);
+			}
+			trav.coop_tri_phase(sc, active && !done, pair_buf, lane);
+			if (active && !done) done = (ANY && trav.occluded) || (!trav.has_node() && trav.sp == 0);
+#else
 		for (int it = 0; it < FB_TRAV_BATCH && active; ++it)
 		{
 			bool done = !trav.acquire();
@@ -198,6 +231,7 @@ __global__ void __launch_bounds__(FB_TRACE_THREADS, FB_TRACE_MIN_BLOCKS) k_trace
 #else
 			if (!done && trav.has_tri()) done = trav.tri_step(sc);
 #endif
+#endif // FB_COOP_TRI
 			if (active && done)
 			{
 				active = false;
@@ -505,7 +539,7 @@ cudaError_t configure_kernels(LaunchConfig& lc, int device)
 	// shared memory per CTA for the staged top of the tree. Shared memory and L1 share the SM's 228 KB, and the
 	// traversal lives on L1 hits (per-lane stacks, hot nodes and triangles), so staging is deliberately small.
 	const int cap_smem = ((225 * 1024 / FB_TRACE_MIN_BLOCKS) - 1024) & ~1023;
-	const int stack_smem = FB_SMEM_STACK * 8 * FB_TRACE_THREADS;
+	const int stack_smem = FB_SMEM_STACK * 8 * FB_TRACE_THREADS + FB_COOP_TRI * 4 * FB_TRACE_THREADS;   // per-lane stacks + pair lists
 	const int max_smem = ((FB_STAGE_KB * 1024 + 16) < cap_smem - stack_smem ? (FB_STAGE_KB * 1024 + 16) : cap_smem - stack_smem);
 	e = cudaFuncSetAttribute(k_trace<TRACE_QUEUE_CLOSEST>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem + stack_smem); if (e) return e;
 	e = cudaFuncSetAttribute(k_trace<TRACE_QUEUE_SHADOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem + stack_smem); if (e) return e;
@@ -515,7 +549,7 @@ cudaError_t configure_kernels(LaunchConfig& lc, int device)
 	return cudaSuccess;
 }
 
-static inline uint32 staged_smem(const DeviceScene& sc) { return 16u + sc.staged_nodes * (uint32)sizeof(WideNode) + FB_SMEM_STACK * 8u * FB_TRACE_THREADS; }
+static inline uint32 staged_smem(const DeviceScene& sc) { return 16u + sc.staged_nodes * (uint32)sizeof(WideNode) + FB_SMEM_STACK * 8u * FB_TRACE_THREADS + FB_COOP_TRI * 4u * FB_TRACE_THREADS; }
 
 cudaError_t launch_rescale_frame(const FrameBufferView& fb, float scale, cudaStream_t s)
 {
