@@ -4,6 +4,7 @@
 // on one stream, queue sizes stay on the device, nothing is read back.
 #include "rendering_context.h"
 #include <string.h>
+#include <stdlib.h>
 
 using namespace fb;
 
@@ -75,6 +76,11 @@ void PathTracer::init(int argc, char** argv, RenderingContext& renderer)
 	m_totals.alloc(sizeof(PassTotals));
 	cuda_check(cudaMemsetAsync(m_totals.ptr, 0, sizeof(PassTotals), renderer.stream()), "memset totals");
 	cuda_check(cudaEventCreate(&m_ev0), "event"); cuda_check(cudaEventCreate(&m_ev1), "event");
+	cuda_check(cudaStreamCreateWithFlags(&m_side_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+	cuda_check(cudaEventCreateWithFlags(&m_ev_shaded, cudaEventDisableTiming), "event");
+	cuda_check(cudaEventCreateWithFlags(&m_ev_shadowed, cudaEventDisableTiming), "event");
+	const char* ov = getenv("FB200_OVERLAP");
+	m_overlap = ov ? atoi(ov) : 1;
 }
 
 cudaEvent_t PathTracer::take_event()
@@ -153,23 +159,49 @@ void PathTracer::render(const uint32_t instance, RenderingContext& renderer)
 	renderer.kernel_launches++;
 
 	// path_trace_loop: trace -> shade -> shadow trace + solve_occlusion, per bounce; no host round trips
-	for (uint32 bounce = 0; bounce < m_options.max_path_length; ++bounce)
+	//
+	// The shadow trace of bounce b and the closest-hit trace of bounce b+1 are independent (the first reads the shadow
+	// queue and adds to the frame buffer, the second reads the scatter queue and writes hits), and both are persistent
+	// kernels whose last long rays leave most lanes idle: they are launched on two streams so that the CTAs of the one
+	// fill the SM slots the other frees while it drains. shade(b+1) waits for both, which keeps every pixel's
+	// accumulation order (and so the image, bit for bit) unchanged. With per-kernel profiling on, everything stays on
+	// one stream so that the event spans do not overlap.
+	const bool overlap = m_overlap != 0 && !m_profiling;
+	const uint32 L = m_options.max_path_length;
+	for (uint32 bounce = 0; bounce < L; ++bounce)
 	{
 		const PathQueue& in = m_queue[bounce & 1];
 		const PathQueue& out = m_queue[(bounce + 1) & 1];
-		begin(1);
-		cuda_check(launch_trace_closest(sc, lc, in, ctr, bounce, stream), "trace");
-		end();
+		if (bounce == 0 || !overlap)
+		{
+			begin(1);
+			cuda_check(launch_trace_closest(sc, lc, in, ctr, bounce, stream), "trace");
+			end();
+		}
 		float seq6[6];
 		for (int i = 0; i < 6; ++i) seq6[i] = seq[(bounce + 1) * 6 + i];
+		if (overlap && bounce > 0) cuda_check(cudaStreamWaitEvent(stream, m_ev_shadowed, 0), "wait");   // shadow(b-1) before shade(b)
 		begin(2);
 		cuda_check(launch_shade(sc, lc, pp, in, out, m_shadow, fbv, ctr, tot, bounce, seq6, (uint32)m_capacity, stream), "shade");
 		end();
-		begin(3);
-		cuda_check(launch_trace_shadow(sc, lc, m_shadow, fbv, ctr, tot, bounce, pp.frame_weight, stream), "trace_shadow");
-		end();
+		if (!overlap)
+		{
+			begin(3);
+			cuda_check(launch_trace_shadow(sc, lc, m_shadow, fbv, ctr, tot, bounce, pp.frame_weight, stream), "trace_shadow");
+			end();
+		}
+		else
+		{
+			cuda_check(cudaEventRecord(m_ev_shaded, stream), "event record");
+			cuda_check(cudaStreamWaitEvent(m_side_stream, m_ev_shaded, 0), "wait");
+			if (m_overlap == 2 && bounce + 1 < L) cuda_check(launch_trace_closest(sc, lc, out, ctr, bounce + 1, stream), "trace");
+			cuda_check(launch_trace_shadow(sc, lc, m_shadow, fbv, ctr, tot, bounce, pp.frame_weight, m_side_stream), "trace_shadow");
+			cuda_check(cudaEventRecord(m_ev_shadowed, m_side_stream), "event record");
+			if (m_overlap != 2 && bounce + 1 < L) cuda_check(launch_trace_closest(sc, lc, out, ctr, bounce + 1, stream), "trace");
+		}
 		renderer.kernel_launches += 3;
 	}
+	if (overlap) cuda_check(cudaStreamWaitEvent(stream, m_ev_shadowed, 0), "wait");
 
 	begin(0);
 	renderer.update_variances(instance);

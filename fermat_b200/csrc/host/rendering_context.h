@@ -133,6 +133,9 @@ private:
 	uint64_t         m_owned_pixels, m_capacity, m_passes;
 	double           m_device_ms;
 	cudaEvent_t      m_ev0, m_ev1;
+	cudaStream_t     m_side_stream;           // shadow trace of bounce b runs here, beside the closest-hit trace of bounce b+1
+	cudaEvent_t      m_ev_shaded, m_ev_shadowed;
+	int              m_overlap;               // 0: one stream; 1: overlap, shadow launched first; 2: overlap, trace launched first
 	bool             m_events;
 	bool             m_profiling;
 	struct Span { int cls; cudaEvent_t a, b; };
