@@ -8,12 +8,24 @@
 
 using namespace fb;
 
-PathTracer::PathTracer() : m_n_tiles(0), m_tiles_x(0), m_owned_pixels(0), m_capacity(0), m_passes(0), m_device_ms(0.0), m_events(false), m_profiling(false)
+PathTracer::PathTracer() : m_tiles_x(0), m_owned_pixels(0), m_passes(0), m_device_ms(0.0), m_overlap(1), m_trace_ctas(0), m_events(false), m_profiling(false)
 {
 	for (int i = 0; i < 4; ++i) { m_class_ms[i] = 0.0; m_class_launches[i] = 0; }
 	pt_options_defaults(m_options);
-	memset(m_queue, 0, sizeof(m_queue));
-	memset(&m_shadow, 0, sizeof(m_shadow));
+}
+
+PathTracer::~PathTracer()
+{
+	for (size_t k = 0; k < m_sub.size(); ++k)
+	{
+		SubFrame* f = m_sub[k];
+		if (!f) continue;
+		if (f->stream) cudaStreamDestroy(f->stream);
+		cudaStreamDestroy(f->side_stream);
+		cudaEventDestroy(f->ev_shaded); cudaEventDestroy(f->ev_shadowed); cudaEventDestroy(f->ev_done);
+		delete f;
+	}
+	for (size_t i = 0; i < m_event_pool.size(); ++i) cudaEventDestroy(m_event_pool[i]);
 }
 
 namespace {
@@ -56,31 +68,60 @@ void PathTracer::init(int argc, char** argv, RenderingContext& renderer)
 	// tile shard of this process: tile T = ty*tiles_x + tx belongs to rank (T + ty) % shard_count
 	std::vector<uint32> tiles;
 	m_owned_pixels = shard_tiles(res.x, res.y, s.shard_rank, s.shard_count, tiles, m_tiles_x);
-	m_n_tiles = (uint32)tiles.size();
-	m_tile_list.upload(tiles.data(), tiles.size() * sizeof(uint32), renderer.stream());
+
+	// sub-frames: the owned tiles dealt round-robin (FB200_SUBFRAMES, default 2; at least 64 tiles each)
+	const char* env = getenv("FB200_SUBFRAMES");
+	uint32 n_sub = env ? (uint32)atoi(env) : 2u;
+	while (n_sub > 1 && tiles.size() / n_sub < 64) n_sub--;
+	if (n_sub < 1) n_sub = 1;
+	env = getenv("FB200_OVERLAP");
+	m_overlap = env ? atoi(env) : 1;
+	env = getenv("FB200_TRACE_CTAS");
+	// each persistent trace launch takes this many CTA slots per SM, so that the kernels of two streams are co-resident
+	// (sweep on bathroom2, Msamples/s: 1 sub-frame 1040; 2 sub-frames x 4 CTAs 1045, x 2 CTAs 1110; 4 x 1 1129; 6 x 2 878)
+	m_trace_ctas = env ? atoi(env) : (n_sub > 1 ? 2 : 0);
+
+	std::vector<std::vector<uint32> > sub_tiles(n_sub);
+	for (size_t j = 0; j < tiles.size(); ++j) sub_tiles[j % n_sub].push_back(tiles[j]);
 
 	// queue arena: dry run for the size, then one allocation (pathtracer_impl.h:124-145)
-	m_capacity = m_owned_pixels;
-	const size_t shadow_cap = s.scene.dir_lights.empty() ? m_capacity : 2 * m_capacity;
+	const bool dirlights = !s.scene.dir_lights.empty();
+	m_sub.resize(n_sub);
+	for (int dry_run = 1; dry_run >= 0; --dry_run)
 	{
-		Arena dry(NULL);
-		PathQueue q[2]; ShadowQueue sq;
-		carve(dry, m_capacity, shadow_cap, q, sq);
-		fprintf(stderr, "  allocating queue storage: %.1f MB\n", float(dry.size) / (1024 * 1024));
-		m_memory_pool.alloc(dry.size + 256);
+		Arena arena(dry_run ? NULL : m_memory_pool.ptr);
+		for (uint32 k = 0; k < n_sub; ++k)
+		{
+			if (dry_run) { m_sub[k] = new SubFrame(); memset(m_sub[k]->queue, 0, sizeof(m_sub[k]->queue)); memset(&m_sub[k]->shadow, 0, sizeof(m_sub[k]->shadow)); }
+			SubFrame& f = *m_sub[k];
+			f.n_tiles = (uint32)sub_tiles[k].size();
+			f.capacity = (uint64_t)f.n_tiles * 32u * 32u;
+			carve(arena, f.capacity, dirlights ? 2 * f.capacity : f.capacity, f.queue, f.shadow);
+		}
+		if (dry_run)
+		{
+			fprintf(stderr, "  allocating queue storage: %.1f MB (%u sub-frame%s)\n", float(arena.size) / (1024 * 1024), n_sub, n_sub > 1 ? "s" : "");
+			m_memory_pool.alloc(arena.size + 256);
+		}
 	}
-	Arena arena(m_memory_pool.ptr);
-	carve(arena, m_capacity, shadow_cap, m_queue, m_shadow);
+	for (uint32 k = 0; k < n_sub; ++k)
+	{
+		SubFrame& f = *m_sub[k];
+		f.tile_list.upload(sub_tiles[k].data(), sub_tiles[k].size() * sizeof(uint32), renderer.stream());
+		f.counters.alloc(sizeof(PassCounters));
+		f.stream = NULL;
+		if (n_sub > 1) cuda_check(cudaStreamCreateWithFlags(&f.stream, cudaStreamNonBlocking), "cudaStreamCreate");
+		cuda_check(cudaStreamCreateWithFlags(&f.side_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+		cuda_check(cudaEventCreateWithFlags(&f.ev_shaded, cudaEventDisableTiming), "event");
+		cuda_check(cudaEventCreateWithFlags(&f.ev_shadowed, cudaEventDisableTiming), "event");
+		cuda_check(cudaEventCreateWithFlags(&f.ev_done, cudaEventDisableTiming), "event");
+	}
 
-	m_counters.alloc(sizeof(PassCounters));
 	m_totals.alloc(sizeof(PassTotals));
 	cuda_check(cudaMemsetAsync(m_totals.ptr, 0, sizeof(PassTotals), renderer.stream()), "memset totals");
 	cuda_check(cudaEventCreate(&m_ev0), "event"); cuda_check(cudaEventCreate(&m_ev1), "event");
-	cuda_check(cudaStreamCreateWithFlags(&m_side_stream, cudaStreamNonBlocking), "cudaStreamCreate");
-	cuda_check(cudaEventCreateWithFlags(&m_ev_shaded, cudaEventDisableTiming), "event");
-	cuda_check(cudaEventCreateWithFlags(&m_ev_shadowed, cudaEventDisableTiming), "event");
-	const char* ov = getenv("FB200_OVERLAP");
-	m_overlap = ov ? atoi(ov) : 1;
+	cuda_check(cudaEventCreateWithFlags(&m_ev_start, cudaEventDisableTiming), "event");
+	renderer.synchronize();      // the uploads above read host vectors that go out of scope here
 }
 
 cudaEvent_t PathTracer::take_event()
@@ -107,12 +148,9 @@ void PathTracer::kernel_times(RenderingContext& renderer, double out_ms[4], uint
 void PathTracer::render(const uint32_t instance, RenderingContext& renderer)
 {
 	fb200_scene& s = *renderer.scene();
-	const DeviceScene& sc = renderer.device_scene();
-	const LaunchConfig& lc = renderer.launch_config();
 	cudaStream_t stream = renderer.stream();
 
 	if (!m_events) { cuda_check(cudaEventRecord(m_ev0, stream), "event record"); m_events = true; }
-	// optional per-kernel timing: an event pair around each launch (no synchronisation; resolved in kernel_times)
 	Span span; span.cls = -1;
 	auto begin = [&](int cls) { if (m_profiling) { span.cls = cls; span.a = take_event(); span.b = take_event(); cuda_check(cudaEventRecord(span.a, stream), "event record"); } };
 	auto end = [&]() { if (m_profiling) { cuda_check(cudaEventRecord(span.b, stream), "event record"); m_spans.push_back(span); } };
@@ -145,33 +183,67 @@ void PathTracer::render(const uint32_t instance, RenderingContext& renderer)
 		pp.U[0] = U.x; pp.U[1] = U.y; pp.U[2] = U.z; pp.V[0] = V.x; pp.V[1] = V.y; pp.V[2] = V.z; pp.W[0] = W.x; pp.W[1] = W.y; pp.W[2] = W.z;
 		pp.eye[0] = c.eye.x; pp.eye[1] = c.eye.y; pp.eye[2] = c.eye.z;
 	}
-	pp.tile_list = m_tile_list.as<uint32>(); pp.n_tiles = m_n_tiles; pp.tiles_x = m_tiles_x;
+	pp.tiles_x = m_tiles_x;
 
-	PassCounters* ctr = m_counters.as<PassCounters>();
+	// With per-kernel profiling on, every kernel of every sub-frame runs on the context's stream, one after the
+	// other, so that the event spans do not overlap; otherwise each sub-frame runs on its own pair of streams.
+	const bool concurrent = !m_profiling;
+	if (concurrent && m_sub.size() > 1) cuda_check(cudaEventRecord(m_ev_start, stream), "event record");
+	for (size_t k = 0; k < m_sub.size(); ++k)
+	{
+		SubFrame& f = *m_sub[k];
+		cudaStream_t fs = (concurrent && f.stream) ? f.stream : stream;
+		if (fs != stream) cuda_check(cudaStreamWaitEvent(fs, m_ev_start, 0), "wait");
+		render_subframe(f, pp, seq, renderer, fs, concurrent && m_overlap != 0);
+		if (fs != stream)
+		{
+			cuda_check(cudaEventRecord(f.ev_done, fs), "event record");
+			cuda_check(cudaStreamWaitEvent(stream, f.ev_done, 0), "wait");
+		}
+	}
+
+	begin(0);
+	renderer.update_variances(instance);
+	end();
+	cuda_check(cudaEventRecord(m_ev1, stream), "event record");
+	m_passes++;
+}
+
+// path_trace_loop over the pixels of one sub-frame: trace -> shade -> shadow trace + solve_occlusion, per bounce;
+// queue sizes stay on the device, nothing is read back.
+//
+// The shadow trace of bounce b and the closest-hit trace of bounce b+1 are independent (the first reads the shadow
+// queue and adds to the frame buffer, the second reads the scatter queue and writes hits), and both are persistent
+// kernels whose last long rays leave most lanes idle: with `overlap` they are launched on two streams so that the CTAs
+// of the one fill the SM slots the other frees while it drains. shade(b+1) waits for both, which keeps every pixel's
+// accumulation order (and so the image, bit for bit) unchanged.
+void PathTracer::render_subframe(SubFrame& f, const PassParams& pass, const std::vector<float>& seq, RenderingContext& renderer, cudaStream_t stream, bool overlap)
+{
+	const DeviceScene& sc = renderer.device_scene();
+	LaunchConfig lc = renderer.launch_config();
+	if (m_trace_ctas > 0 && m_trace_ctas < lc.trace_ctas_per_sm) lc.trace_ctas_per_sm = m_trace_ctas;
+	Span span; span.cls = -1;
+	auto begin = [&](int cls) { if (m_profiling) { span.cls = cls; span.a = take_event(); span.b = take_event(); cuda_check(cudaEventRecord(span.a, stream), "event record"); } };
+	auto end = [&]() { if (m_profiling) { cuda_check(cudaEventRecord(span.b, stream), "event record"); m_spans.push_back(span); } };
+
+	PassParams pp = pass;
+	pp.tile_list = f.tile_list.as<uint32>(); pp.n_tiles = f.n_tiles;
+	PassCounters* ctr = f.counters.as<PassCounters>();
 	PassTotals* tot = m_totals.as<PassTotals>();
 	cuda_check(cudaMemsetAsync(ctr, 0, sizeof(PassCounters), stream), "memset counters");
 
 	const FrameBufferView fbv = renderer.get_frame_buffer().view();
 	const float seq2[2] = { seq[0], seq[1] };
 	begin(0);
-	cuda_check(launch_generate_primary(sc, pp, m_queue[0], ctr, seq2, stream), "generate_primary");
+	cuda_check(launch_generate_primary(sc, pp, f.queue[0], ctr, seq2, stream), "generate_primary");
 	end();
 	renderer.kernel_launches++;
 
-	// path_trace_loop: trace -> shade -> shadow trace + solve_occlusion, per bounce; no host round trips
-	//
-	// The shadow trace of bounce b and the closest-hit trace of bounce b+1 are independent (the first reads the shadow
-	// queue and adds to the frame buffer, the second reads the scatter queue and writes hits), and both are persistent
-	// kernels whose last long rays leave most lanes idle: they are launched on two streams so that the CTAs of the one
-	// fill the SM slots the other frees while it drains. shade(b+1) waits for both, which keeps every pixel's
-	// accumulation order (and so the image, bit for bit) unchanged. With per-kernel profiling on, everything stays on
-	// one stream so that the event spans do not overlap.
-	const bool overlap = m_overlap != 0 && !m_profiling;
 	const uint32 L = m_options.max_path_length;
 	for (uint32 bounce = 0; bounce < L; ++bounce)
 	{
-		const PathQueue& in = m_queue[bounce & 1];
-		const PathQueue& out = m_queue[(bounce + 1) & 1];
+		const PathQueue& in = f.queue[bounce & 1];
+		const PathQueue& out = f.queue[(bounce + 1) & 1];
 		if (bounce == 0 || !overlap)
 		{
 			begin(1);
@@ -180,34 +252,27 @@ void PathTracer::render(const uint32_t instance, RenderingContext& renderer)
 		}
 		float seq6[6];
 		for (int i = 0; i < 6; ++i) seq6[i] = seq[(bounce + 1) * 6 + i];
-		if (overlap && bounce > 0) cuda_check(cudaStreamWaitEvent(stream, m_ev_shadowed, 0), "wait");   // shadow(b-1) before shade(b)
+		if (overlap && bounce > 0) cuda_check(cudaStreamWaitEvent(stream, f.ev_shadowed, 0), "wait");   // shadow(b-1) before shade(b)
 		begin(2);
-		cuda_check(launch_shade(sc, lc, pp, in, out, m_shadow, fbv, ctr, tot, bounce, seq6, (uint32)m_capacity, stream), "shade");
+		cuda_check(launch_shade(sc, lc, pp, in, out, f.shadow, fbv, ctr, tot, bounce, seq6, (uint32)f.capacity, stream), "shade");
 		end();
 		if (!overlap)
 		{
 			begin(3);
-			cuda_check(launch_trace_shadow(sc, lc, m_shadow, fbv, ctr, tot, bounce, pp.frame_weight, stream), "trace_shadow");
+			cuda_check(launch_trace_shadow(sc, lc, f.shadow, fbv, ctr, tot, bounce, pp.frame_weight, stream), "trace_shadow");
 			end();
 		}
 		else
 		{
-			cuda_check(cudaEventRecord(m_ev_shaded, stream), "event record");
-			cuda_check(cudaStreamWaitEvent(m_side_stream, m_ev_shaded, 0), "wait");
-			if (m_overlap == 2 && bounce + 1 < L) cuda_check(launch_trace_closest(sc, lc, out, ctr, bounce + 1, stream), "trace");
-			cuda_check(launch_trace_shadow(sc, lc, m_shadow, fbv, ctr, tot, bounce, pp.frame_weight, m_side_stream), "trace_shadow");
-			cuda_check(cudaEventRecord(m_ev_shadowed, m_side_stream), "event record");
-			if (m_overlap != 2 && bounce + 1 < L) cuda_check(launch_trace_closest(sc, lc, out, ctr, bounce + 1, stream), "trace");
+			cuda_check(cudaEventRecord(f.ev_shaded, stream), "event record");
+			cuda_check(cudaStreamWaitEvent(f.side_stream, f.ev_shaded, 0), "wait");
+			cuda_check(launch_trace_shadow(sc, lc, f.shadow, fbv, ctr, tot, bounce, pp.frame_weight, f.side_stream), "trace_shadow");
+			cuda_check(cudaEventRecord(f.ev_shadowed, f.side_stream), "event record");
+			if (bounce + 1 < L) cuda_check(launch_trace_closest(sc, lc, out, ctr, bounce + 1, stream), "trace");
 		}
 		renderer.kernel_launches += 3;
 	}
-	if (overlap) cuda_check(cudaStreamWaitEvent(stream, m_ev_shadowed, 0), "wait");
-
-	begin(0);
-	renderer.update_variances(instance);
-	end();
-	cuda_check(cudaEventRecord(m_ev1, stream), "event record");
-	m_passes++;
+	if (overlap) cuda_check(cudaStreamWaitEvent(stream, f.ev_shadowed, 0), "wait");
 }
 
 PassTotals PathTracer::totals(RenderingContext& renderer)

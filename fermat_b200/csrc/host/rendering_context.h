@@ -106,6 +106,7 @@ private:
 struct PathTracer final : RendererInterface
 {
 	PathTracer();
+	~PathTracer();
 	static RendererInterface* factory() { return new PathTracer(); }
 
 	void init(int argc, char** argv, RenderingContext& renderer);
@@ -126,16 +127,27 @@ struct PathTracer final : RendererInterface
 private:
 	fb::PTOptions    m_options;
 	fb::DeviceBuffer m_memory_pool;          // queue arena (reference: m_memory_pool, pathtracer.h:288)
-	fb::PathQueue    m_queue[2];
-	fb::ShadowQueue  m_shadow;
-	fb::DeviceBuffer m_counters, m_totals, m_tile_list;
-	uint32_t         m_n_tiles, m_tiles_x;
-	uint64_t         m_owned_pixels, m_capacity, m_passes;
+	// the owned tiles are dealt round-robin to a few sub-frames, each with its own queues, counters and pair of
+	// streams: independent wavefronts over disjoint pixels whose kernels fill each other's drained SM slots
+	struct SubFrame
+	{
+		fb::DeviceBuffer tile_list, counters;
+		uint32_t         n_tiles;
+		uint64_t         capacity;
+		fb::PathQueue    queue[2];
+		fb::ShadowQueue  shadow;
+		cudaStream_t     stream, side_stream;     // stream == NULL: the context's stream
+		cudaEvent_t      ev_shaded, ev_shadowed, ev_done;
+	};
+	std::vector<SubFrame*> m_sub;
+	fb::DeviceBuffer m_totals;
+	uint32_t         m_tiles_x;
+	uint64_t         m_owned_pixels, m_passes;
 	double           m_device_ms;
-	cudaEvent_t      m_ev0, m_ev1;
-	cudaStream_t     m_side_stream;           // shadow trace of bounce b runs here, beside the closest-hit trace of bounce b+1
-	cudaEvent_t      m_ev_shaded, m_ev_shadowed;
-	int              m_overlap;               // 0: one stream; 1: overlap, shadow launched first; 2: overlap, trace launched first
+	cudaEvent_t      m_ev0, m_ev1, m_ev_start;
+	int              m_overlap;               // 0: one stream per sub-frame; else the shadow trace of bounce b runs beside the closest-hit trace of bounce b+1
+	int              m_trace_ctas;            // CTAs per SM of each persistent trace launch
+	void             render_subframe(SubFrame& f, const fb::PassParams& pp, const std::vector<float>& seq, RenderingContext& renderer, cudaStream_t stream, bool overlap);
 	bool             m_events;
 	bool             m_profiling;
 	struct Span { int cls; cudaEvent_t a, b; };

@@ -1,7 +1,8 @@
 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
-for ov in 0 1 2; do
-echo "overlap $ov" | tee -a gpurun_out/sweep.txt
-FB200_OVERLAP=$ov python bench.py --steps 16 --warmup 3 --no-cpu-baseline 2>gpurun_out/ov$ov.err | python -c "
+for cfg in "1 0" "2 0" "2 2" "3 0" "3 2" "4 0" "4 2" "4 1" "6 2"; do
+set -- $cfg
+echo "subframes $1 ctas $2" | tee -a gpurun_out/sweep.txt
+FB200_SUBFRAMES=$1 FB200_TRACE_CTAS=$2 python bench.py --steps 16 --warmup 3 --no-cpu-baseline 2>gpurun_out/sf.err | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
 print('   %7.1f Msamples/s  %6.3f ms/pass e2e %7.1f | trace %.3f shade %.3f shadow %.3f' % (d['value'], d['ms_per_step'], d['e2e']['value'], d['kernels']['trace']['ms_per_launch'], d['kernels']['shade']['ms_per_launch'], d['kernels']['shadow']['ms_per_launch']))" | tee -a gpurun_out/sweep.txt
