@@ -118,6 +118,9 @@ __global__ void __launch_bounds__(256) k_generate_primary(DeviceScene sc, PassPa
 #ifndef FB_COOP_TRI
 #define FB_COOP_TRI 1              // 1: warp-shared triangle tests (Traversal::coop_tri_phase); 0: every lane loops over its own
 #endif
+#ifndef FB_SPLIT_RAYS
+#define FB_SPLIT_RAYS 1            // 1: once the queue is empty, idle lanes take over stack entries of their warp mates' rays
+#endif
 #ifndef FB_RAYS_PER_LANE
 #define FB_RAYS_PER_LANE 0         // > 0: trace CTAs beyond queue_length / (threads x this) exit immediately
 #endif
@@ -175,8 +178,13 @@ __global__ void __launch_bounds__(FB_TRACE_THREADS, FB_TRACE_MIN_BLOCKS) k_trace
 #endif
 #if FB_COOP_TRI
 	// this warp's 32-entry (ray, triangle) pair list, behind the staged nodes and the shared-memory stacks
-	uint32* pair_buf = reinterpret_cast<uint32*>(smem + 1 + sc.staged_nodes * 5u) + FB_SMEM_STACK * 2u * FB_TRACE_THREADS + (threadIdx.x >> 5) * 32u;
+	uint32* pair_buf = reinterpret_cast<uint32*>(smem + 1 + sc.staged_nodes * 5u) + FB_SMEM_STACK * 2u * FB_TRACE_THREADS + (threadIdx.x >> 5) * 64u;
+	// helpers still at work on the ray owned by each lane of this warp (ray splitting, below)
+	uint32* pending = pair_buf + 32;
+	pending[lane] = 0u;
+	__syncwarp();
 #endif
+	int root = lane;                 // owner of the ray this lane works on
 	bool active = false;
 	uint32 ray_idx = 0;
 
@@ -205,6 +213,53 @@ __global__ void __launch_bounds__(FB_TRACE_THREADS, FB_TRACE_MIN_BLOCKS) k_trace
 		}
 		if (!__any_sync(0xFFFFFFFFu, active)) { if (exhausted) break; else continue; }
 
+#if FB_COOP_TRI && FB_SPLIT_RAYS
+		// Ray splitting. A few rays (grazing a tessellated floor, say) visit twenty times more nodes than the average one,
+		// and once the queue is empty the kernel only waits for them with nearly every lane idle. From then on an idle
+		// lane takes the top stack entry - a group of sibling subtrees - of a busy lane of its warp, together with a copy
+		// of the ray, and traverses it on its own; its triangle hits are delivered to the owner lane by coop_tri_phase,
+		// which keeps the closest (t, triangle id), so the result does not depend on who traversed what. Helpers refresh
+		// their far bound from the owner every iteration; the owner retires its ray when its own traversal is finished
+		// and no helper is left (pending[]).
+		if (exhausted)
+		{
+			unsigned idle = __ballot_sync(0xFFFFFFFFu, !active);
+			unsigned donors = __ballot_sync(0xFFFFFFFFu, active && trav.has_node() && trav.sp > 0);
+			while (idle && donors)
+			{
+				const int h = __ffs((int)idle) - 1, d = __ffs((int)donors) - 1;
+				idle &= idle - 1u; donors &= donors - 1u;
+				uint2 e = make_uint2(0u, 0u);
+				if (lane == d) e = trav.pop();
+				e.x = __shfl_sync(0xFFFFFFFFu, e.x, d); e.y = __shfl_sync(0xFFFFFFFFu, e.y, d);
+				const float ox = __shfl_sync(0xFFFFFFFFu, trav.ray.ox, d), oy = __shfl_sync(0xFFFFFFFFu, trav.ray.oy, d), oz = __shfl_sync(0xFFFFFFFFu, trav.ray.oz, d);
+				const float dx = __shfl_sync(0xFFFFFFFFu, trav.ray.dx, d), dy = __shfl_sync(0xFFFFFFFFu, trav.ray.dy, d), dz = __shfl_sync(0xFFFFFFFFu, trav.ray.dz, d);
+				const float t0 = __shfl_sync(0xFFFFFFFFu, trav.ray.tmin, d), t1 = __shfl_sync(0xFFFFFFFFu, trav.ray.tmax, d);
+				const float ix = __shfl_sync(0xFFFFFFFFu, trav.idx_, d), iy = __shfl_sync(0xFFFFFFFFu, trav.idy_, d), iz = __shfl_sync(0xFFFFFFFFu, trav.idz_, d);
+				const uint32 oct = __shfl_sync(0xFFFFFFFFu, trav.octinv4, d), msk = __shfl_sync(0xFFFFFFFFu, trav.mask, d);
+				const int rt = __shfl_sync(0xFFFFFFFFu, root, d);
+				if (lane == h)
+				{
+					trav.ray.ox = ox; trav.ray.oy = oy; trav.ray.oz = oz; trav.ray.dx = dx; trav.ray.dy = dy; trav.ray.dz = dz;
+					trav.ray.tmin = t0; trav.ray.tmax = t1; trav.idx_ = ix; trav.idy_ = iy; trav.idz_ = iz;
+					trav.octinv4 = oct; trav.mask = msk;
+					trav.ngroup = e; trav.tgroup = make_uint2(0u, 0u); trav.sp = 0;
+					trav.hit.t = -1.0f; trav.hit.tri = -1; trav.occluded = false;
+					root = rt; active = true;
+					atomicAdd(&pending[rt], 1u);
+				}
+			}
+			__syncwarp();
+			const float root_tmax = __shfl_sync(0xFFFFFFFFu, trav.ray.tmax, root);
+			const bool root_occluded = ANY && __shfl_sync(0xFFFFFFFFu, trav.occluded ? 1 : 0, root) != 0;
+			if (active && root != lane)
+			{
+				trav.ray.tmax = fminf(trav.ray.tmax, root_tmax);
+				if (root_occluded) trav.occluded = true;
+			}
+		}
+#endif
+
 		// one iteration = [acquire] [one node visit] [one triangle test]. Lanes run FB_TRAV_BATCH iterations on their
 		// own before the warp reconverges at the refill vote: the traversal is bound by L2 latency, not by issue
 		// slots, and diverged lanes of a warp overlap each other's outstanding loads (measured: batch 24 beats a
@@ -219,8 +274,15 @@ __global__ void __launch_bounds__(FB_TRACE_THREADS, FB_TRACE_MIN_BLOCKS) k_trace
 				done = !trav.acquire();
 				if (!done) trav.node_step(sc, smem_nodes);
 			}
-			trav.coop_tri_phase(sc, active && !done, pair_buf, lane);
+			trav.coop_tri_phase(sc, active && !done, pair_buf, lane, root);
 			if (active && !done) done = (ANY && trav.occluded) || (!trav.has_node() && trav.sp == 0);
+#if FB_SPLIT_RAYS
+			if (active && done)
+			{
+				if (root != lane) { atomicSub(&pending[root], 1u); root = lane; active = false; done = false; }   // a helper is through with its share
+				else if (pending[lane] != 0u) done = false;                                                  // the owner waits for its helpers
+			}
+#endif
 #else
 		for (int it = 0; it < FB_TRAV_BATCH && active; ++it)
 		{
@@ -539,7 +601,7 @@ cudaError_t configure_kernels(LaunchConfig& lc, int device)
 	// shared memory per CTA for the staged top of the tree. Shared memory and L1 share the SM's 228 KB, and the
 	// traversal lives on L1 hits (per-lane stacks, hot nodes and triangles), so staging is deliberately small.
 	const int cap_smem = ((225 * 1024 / FB_TRACE_MIN_BLOCKS) - 1024) & ~1023;
-	const int stack_smem = FB_SMEM_STACK * 8 * FB_TRACE_THREADS + FB_COOP_TRI * 4 * FB_TRACE_THREADS;   // per-lane stacks + pair lists
+	const int stack_smem = FB_SMEM_STACK * 8 * FB_TRACE_THREADS + FB_COOP_TRI * 8 * FB_TRACE_THREADS;   // per-lane stacks + pair lists and helper counts
 	const int max_smem = ((FB_STAGE_KB * 1024 + 16) < cap_smem - stack_smem ? (FB_STAGE_KB * 1024 + 16) : cap_smem - stack_smem);
 	e = cudaFuncSetAttribute(k_trace<TRACE_QUEUE_CLOSEST>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem + stack_smem); if (e) return e;
 	e = cudaFuncSetAttribute(k_trace<TRACE_QUEUE_SHADOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem + stack_smem); if (e) return e;
@@ -549,7 +611,7 @@ cudaError_t configure_kernels(LaunchConfig& lc, int device)
 	return cudaSuccess;
 }
 
-static inline uint32 staged_smem(const DeviceScene& sc) { return 16u + sc.staged_nodes * (uint32)sizeof(WideNode) + FB_SMEM_STACK * 8u * FB_TRACE_THREADS + FB_COOP_TRI * 4u * FB_TRACE_THREADS; }
+static inline uint32 staged_smem(const DeviceScene& sc) { return 16u + sc.staged_nodes * (uint32)sizeof(WideNode) + FB_SMEM_STACK * 8u * FB_TRACE_THREADS + FB_COOP_TRI * 8u * FB_TRACE_THREADS; }
 
 cudaError_t launch_rescale_frame(const FrameBufferView& fb, float scale, cudaStream_t s)
 {

@@ -284,7 +284,9 @@ struct Traversal
 	// owner's ray by shuffles, runs the same Moller-Trumbore sequence as tri_step, and hits travel back to the
 	// owner, which applies the same acceptance rule (smallest t, then smallest triangle id): the result is
 	// independent of which lane tested what. Must be called by all 32 lanes; `mine` = this lane takes part.
-	FB_D void coop_tri_phase(const DeviceScene& sc, const bool mine, uint32* __restrict__ pairs, const int lane)
+	// `root` = lane that owns the ray this lane works on (itself, unless the lane is helping with a split ray, see
+	// k_trace): hits are delivered there.
+	FB_D void coop_tri_phase(const DeviceScene& sc, const bool mine, uint32* __restrict__ pairs, const int lane, const int root)
 	{
 		const uint32 FULL = 0xFFFFFFFFu;
 		uint32 m = mine ? tgroup.y : 0u;
@@ -319,6 +321,7 @@ struct Traversal
 			const float rdx = __shfl_sync(FULL, ray.dx, owner), rdy = __shfl_sync(FULL, ray.dy, owner), rdz = __shfl_sync(FULL, ray.dz, owner);
 			const float rtmin = __shfl_sync(FULL, ray.tmin, owner), rtmax = __shfl_sync(FULL, ray.tmax, owner);
 			const uint32 rmask = ANY_HIT ? __shfl_sync(FULL, mask, owner) : 0u;
+			const int dest = __shfl_sync(FULL, root, owner);
 
 			bool found = false;
 			float ht = 0.0f, hbu = 0.0f, hbv = 0.0f; int htri = -1;
@@ -355,7 +358,7 @@ struct Traversal
 			}
 			if (ANY_HIT)
 			{
-				const uint32 occ = __reduce_or_sync(FULL, found ? (1u << owner) : 0u);
+				const uint32 occ = __reduce_or_sync(FULL, found ? (1u << dest) : 0u);
 				if ((occ >> lane) & 1u) occluded = true;
 			}
 			else
@@ -365,7 +368,7 @@ struct Traversal
 				{
 					const int src = __ffs((int)hm) - 1;
 					hm &= hm - 1u;
-					const int o = __shfl_sync(FULL, owner, src);
+					const int o = __shfl_sync(FULL, dest, src);
 					const float t = __shfl_sync(FULL, ht, src), bu = __shfl_sync(FULL, hbu, src), bv = __shfl_sync(FULL, hbv, src);
 					const int tri = __shfl_sync(FULL, htri, src);
 					if (lane == o && (t < ray.tmax || (t == ray.tmax && hit.tri >= 0 && tri < hit.tri)))

@@ -1,7 +1,8 @@
 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
-for cfg in "1 0" "2 0" "2 2" "3 0" "3 2" "4 0" "4 2" "4 1" "6 2"; do
+sh tools/sweep.sh
+for cfg in "1 0" "2 1" "4 1"; do
 set -- $cfg
-echo "subframes $1 ctas $2" | tee -a gpurun_out/sweep.txt
+echo "split, subframes $1 ctas $2" | tee -a gpurun_out/sweep.txt
 FB200_SUBFRAMES=$1 FB200_TRACE_CTAS=$2 python bench.py --steps 16 --warmup 3 --no-cpu-baseline 2>gpurun_out/sf.err | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
