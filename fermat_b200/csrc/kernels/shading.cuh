@@ -19,9 +19,18 @@ FB_D V3 orthogonal(V3 v)
 	return V3(-v.y, v.x, 0.0f);
 }
 // 10-10-10 normal decode (vector_inl.h:776-798)
+// x / 1023 for the integers x = 0..1023, correctly rounded without the division sequence: one Newton step on
+// q = x * RN(1/1023) with exact residual. Equal to the IEEE quotient for all 1024 inputs
+// (tests/test_host_scene.py::test_div1023_sequence_is_exact checks every one).
+FB_D float div1023(float x)
+{
+	const float r = 1.0f / 1023.0f;
+	const float q = x * r;
+	return fmaf(fmaf(-q, 1023.0f, x), r, q);
+}
 FB_D V3 unpack_normal(uint32 b)
 {
-	const V3 u((float)(b & 0x3FFu) / 1023, (float)((b >> 10) & 0x3FFu) / 1023, (float)((b >> 20) & 0x3FFu) / 1023);
+	const V3 u(div1023((float)(b & 0x3FFu)), div1023((float)((b >> 10) & 0x3FFu)), div1023((float)((b >> 20) & 0x3FFu)));
 	return u * 2.0f - V3(1.0f);
 }
 // decompress_tex_coord (src/mesh/MeshCompression.h:52-68)
@@ -31,7 +40,11 @@ FB_D V2 decompress_tex(const DeviceScene& sc, int packed)
 	const float2 tn = __half22float2(__half2(hr));
 	return V2(tn.x * sc.tex_scale.x + sc.tex_bias.x, tn.y * sc.tex_scale.y + sc.tex_bias.y);
 }
-FB_D float mod1(float x, float m) { return x > 0.0f ? fmodf(x, m) : m - fmodf(-x, m); }   // cugar::mod
+// cugar::mod(x, 1) = x > 0 ? fmodf(x, 1) : 1 - fmodf(-x, 1). fmodf(a, 1) for a >= 0 is the fractional part a - trunc(a),
+// which is exactly representable, so the subtraction below returns the same bits as fmodf without its reduction loop
+// (inf -> NaN and NaN -> NaN on both routes)
+FB_D float frac_exact(float a) { return a - truncf(a); }
+FB_D float mod1(float x, float m) { return x > 0.0f ? frac_exact(x) : m - frac_exact(-x); }   // only ever called with m = 1
 
 // interpolated shading frame + texture coordinates (src/mesh_utils.h:184-288). `position` is produced
 // only when asked for (the eye vertex re-derives it from the ray, src/bpt_utils.h:608).

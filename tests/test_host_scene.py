@@ -180,3 +180,27 @@ def test_obj_loader_on_reference_model_if_present(fb):
                           np.ctypeslib.as_array(vb.vertex_data, shape=(vb.num_vertices, 4)).view(np.uint32))
     assert np.array_equal(np.ctypeslib.as_array(va.vertex_indices, shape=(36, 4)), np.ctypeslib.as_array(vb.vertex_indices, shape=(36, 4)))
     a.close(); b.close()
+
+
+def test_div1023_sequence_is_exact():
+    """shading.cuh div1023(): x * RN(1/1023) refined by one exact-residual Newton step equals the IEEE quotient x / 1023
+    for every 10-bit integer (the packed-normal decode relies on it to stay bit-identical to the oracle's division)."""
+    libm = C.CDLL("libm.so.6")
+    libm.fmaf.restype = C.c_float
+    libm.fmaf.argtypes = [C.c_float, C.c_float, C.c_float]
+    f32 = np.float32
+    r = f32(1.0) / f32(1023.0)
+    for i in range(1024):
+        x = f32(i)
+        q = f32(x * r)
+        e = f32(libm.fmaf(-q, f32(1023.0), x))
+        q2 = f32(libm.fmaf(e, r, q))
+        assert q2 == f32(x / f32(1023.0)), i
+
+
+def test_fractional_part_equals_fmodf():
+    """shading.cuh frac_exact(): a - trunc(a) carries the same bits as fmodf(a, 1) for a >= 0 (texture wrap)."""
+    rng = np.random.default_rng(3)
+    a = np.concatenate([rng.random(20000, dtype=np.float32) * np.float32(10.0) ** rng.integers(-6, 8, 20000).astype(np.float32),
+                        np.array([0.0, 1.0, 0.5, 1e-30, 3.0e38, 16777216.0, 8388607.5], np.float32)])
+    assert np.array_equal((a - np.trunc(a)).view(np.uint32), np.fmod(a, np.float32(1.0)).view(np.uint32))

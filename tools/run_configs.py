@@ -81,6 +81,7 @@ def main():
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--only", default="")
     ap.add_argument("--spp-parity", type=int, default=128)
+    ap.add_argument("--spp-parity-small", type=int, default=32, help="parity spp of C3 / C4")
     a = ap.parse_args()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     q = a.quick
@@ -88,8 +89,8 @@ def main():
         ("C1", "tests/golden/cornellbox_jp.fbs", (512, 512), 4, 64, 64, 0, 1),
         ("C1_1024spp", "tests/golden/cornellbox_jp.fbs", (512, 512), 4, 1024, 32 if q else 1024, 0, None),
         ("C2", "scenes/_cache/bathroom2.fbs", (1600, 900), 8, 1024, 8 if q else a.spp_parity, 0, None),
-        ("C3", "scenes/_cache/material_testball.fbs", (1024, 1024), 12, 256, 8 if q else 32, 0, None),
-        ("C4", "scenes/_cache/water_caustic.fbs", (1600, 900), 16, 256, 8 if q else 32, 0, None),
+        ("C3", "scenes/_cache/material_testball.fbs", (1024, 1024), 12, 256, 8 if q else a.spp_parity_small, 0, None),
+        ("C4", "scenes/_cache/water_caustic.fbs", (1600, 900), 16, 256, 8 if q else a.spp_parity_small, 0, None),
     ]
     only = set(x for x in a.only.split(",") if x)
     results = []
