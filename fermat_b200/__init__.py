@@ -93,6 +93,7 @@ def lib():
         "fb200_context_res": (i32, [vp, C.POINTER(u32), C.POINTER(u32)]),
         "fb200_context_fb_device_ptr": (vp, [vp, i32]),
         "fb200_context_fb_download": (i32, [vp, i32, pf]),
+        "fb200_context_fb_download_async": (i32, [vp, i32, vp]),
         "fb200_context_fb_upload": (i32, [vp, i32, pf]),
         "fb200_context_gbuffer_download": (i32, [vp, pf, pf, C.POINTER(u32), pf]),
         "fb200_context_get_stats": (i32, [vp, C.POINTER(Stats)]),
@@ -264,6 +265,11 @@ class RenderingContext:
         out = np.empty((h, w, 4), dtype=np.float32)
         self._chk(lib().fb200_context_fb_download(self._h, FB_CHANNELS.get(channel, channel), _fptr(out)))
         return out
+
+    def download_async(self, pinned_host_ptr, channel="COMPOSITED_C"):
+        """Start an asynchronous copy of a channel into PINNED host memory (address as int); the next pass may be
+        enqueued right away, `synchronize()` completes the copy."""
+        self._chk(lib().fb200_context_fb_download_async(self._h, FB_CHANNELS.get(channel, channel), C.c_void_p(int(pinned_host_ptr))))
 
     def download_gbuffer(self):
         """G-buffer of the last pass: dict(geo (H,W,4) f32, uv (H,W,4) f32, tri (H,W) u32, depth (H,W) f32)."""

@@ -79,6 +79,11 @@ int fb200_context_fb_download(fb200_context* c, int channel, float* dst)
 	});
 }
 
+int fb200_context_fb_download_async(fb200_context* c, int channel, float* pinned_dst)
+{
+	return guarded([&] { c->rc.download_channel_async(channel, pinned_dst); });
+}
+
 int fb200_context_gbuffer_download(fb200_context* c, float* geo, float* uv, uint32_t* tri, float* depth)
 {
 	return guarded([&] {

@@ -117,8 +117,19 @@ void PathTracer::init(int argc, char** argv, RenderingContext& renderer)
 		cuda_check(cudaEventCreateWithFlags(&f.ev_done, cudaEventDisableTiming), "event");
 	}
 
+	{
+		std::vector<RenderingContext::Partition> parts(n_sub);
+		for (uint32 k = 0; k < n_sub; ++k)
+		{
+			parts[k].stream = m_sub[k]->stream ? m_sub[k]->stream : renderer.raw_stream();
+			PixelSet ps; ps.tile_list = m_sub[k]->tile_list.as<uint32>(); ps.n_tiles = m_sub[k]->n_tiles; ps.tiles_x = m_tiles_x; ps.res_x = res.x; ps.res_y = res.y;
+			parts[k].pixels = ps;
+		}
+		renderer.set_partitions(parts);
+		renderer.set_renderer_clears_gbuffer(true);
+	}
 	m_totals.alloc(sizeof(PassTotals));
-	cuda_check(cudaMemsetAsync(m_totals.ptr, 0, sizeof(PassTotals), renderer.stream()), "memset totals");
+	cuda_check(cudaMemsetAsync(m_totals.ptr, 0, sizeof(PassTotals), renderer.raw_stream()), "memset totals");
 	cuda_check(cudaEventCreate(&m_ev0), "event"); cuda_check(cudaEventCreate(&m_ev1), "event");
 	cuda_check(cudaEventCreateWithFlags(&m_ev_start, cudaEventDisableTiming), "event");
 	renderer.synchronize();      // the uploads above read host vectors that go out of scope here
@@ -148,17 +159,6 @@ void PathTracer::kernel_times(RenderingContext& renderer, double out_ms[4], uint
 void PathTracer::render(const uint32_t instance, RenderingContext& renderer)
 {
 	fb200_scene& s = *renderer.scene();
-	cudaStream_t stream = renderer.stream();
-
-	if (!m_events) { cuda_check(cudaEventRecord(m_ev0, stream), "event record"); m_events = true; }
-	Span span; span.cls = -1;
-	auto begin = [&](int cls) { if (m_profiling) { span.cls = cls; span.a = take_event(); span.b = take_event(); cuda_check(cudaEventRecord(span.a, stream), "event record"); } };
-	auto end = [&]() { if (m_profiling) { cuda_check(cudaEventRecord(span.b, stream), "event record"); m_spans.push_back(span); } };
-
-	// pre-multiply the previous frame for blending (pathtracer_impl.h:201)
-	begin(0);
-	renderer.rescale_frame(instance);
-	end();
 
 	// per-pass sampler offsets (TiledSequence::set_instance, src/tiled_sequence.cu:100-110)
 	s.sequence.set_instance(instance);
@@ -185,27 +185,28 @@ void PathTracer::render(const uint32_t instance, RenderingContext& renderer)
 	}
 	pp.tiles_x = m_tiles_x;
 
-	// With per-kernel profiling on, every kernel of every sub-frame runs on the context's stream, one after the
-	// other, so that the event spans do not overlap; otherwise each sub-frame runs on its own pair of streams.
+	// Every sub-frame is a pipeline of its own: rescale its pixels, trace the pass, update its variances, all on its
+	// own stream, and pass i+1 of one sub-frame may start while pass i of another is still in its last bounces. The
+	// context's stream gets involved only when somebody uses it (RenderingContext::stream() joins the sub-frames and
+	// flags the use; the next pass is then ordered behind whatever was enqueued there). With per-kernel profiling on,
+	// every kernel of every sub-frame runs on the context's stream, one after the other, so that the spans do not overlap.
 	const bool concurrent = !m_profiling;
-	if (concurrent && m_sub.size() > 1) cuda_check(cudaEventRecord(m_ev_start, stream), "event record");
+	cudaStream_t main_stream = concurrent ? renderer.raw_stream() : renderer.stream();
+	if (!m_events) { cuda_check(cudaEventRecord(m_ev0, renderer.stream()), "event record"); m_events = true; }
+	const bool fence = renderer.take_touched();
+	if (concurrent && fence) cuda_check(cudaEventRecord(m_ev_start, main_stream), "event record");
 	for (size_t k = 0; k < m_sub.size(); ++k)
 	{
 		SubFrame& f = *m_sub[k];
-		cudaStream_t fs = (concurrent && f.stream) ? f.stream : stream;
-		if (fs != stream) cuda_check(cudaStreamWaitEvent(fs, m_ev_start, 0), "wait");
+		cudaStream_t fs = (concurrent && f.stream) ? f.stream : main_stream;
+		if (fs != main_stream && fence) cuda_check(cudaStreamWaitEvent(fs, m_ev_start, 0), "wait");
 		render_subframe(f, pp, seq, renderer, fs, concurrent && m_overlap != 0);
-		if (fs != stream)
+		if (fs != main_stream)
 		{
 			cuda_check(cudaEventRecord(f.ev_done, fs), "event record");
-			cuda_check(cudaStreamWaitEvent(stream, f.ev_done, 0), "wait");
+			renderer.add_pending(f.ev_done);
 		}
 	}
-
-	begin(0);
-	renderer.update_variances(instance);
-	end();
-	cuda_check(cudaEventRecord(m_ev1, stream), "event record");
 	m_passes++;
 }
 
@@ -221,7 +222,7 @@ void PathTracer::render_subframe(SubFrame& f, const PassParams& pass, const std:
 {
 	const DeviceScene& sc = renderer.device_scene();
 	LaunchConfig lc = renderer.launch_config();
-	if (m_trace_ctas > 0 && m_trace_ctas < lc.trace_ctas_per_sm) lc.trace_ctas_per_sm = m_trace_ctas;
+	if (!m_profiling && m_trace_ctas > 0 && m_trace_ctas < lc.trace_ctas_per_sm) lc.trace_ctas_per_sm = m_trace_ctas;   // alone on the GPU (profiling) a launch takes every slot
 	Span span; span.cls = -1;
 	auto begin = [&](int cls) { if (m_profiling) { span.cls = cls; span.a = take_event(); span.b = take_event(); cuda_check(cudaEventRecord(span.a, stream), "event record"); } };
 	auto end = [&]() { if (m_profiling) { cuda_check(cudaEventRecord(span.b, stream), "event record"); m_spans.push_back(span); } };
@@ -233,11 +234,16 @@ void PathTracer::render_subframe(SubFrame& f, const PassParams& pass, const std:
 	cuda_check(cudaMemsetAsync(ctr, 0, sizeof(PassCounters), stream), "memset counters");
 
 	const FrameBufferView fbv = renderer.get_frame_buffer().view();
+	PixelSet pixels; pixels.tile_list = pp.tile_list; pixels.n_tiles = pp.n_tiles; pixels.tiles_x = pp.tiles_x; pixels.res_x = sc.res_x; pixels.res_y = sc.res_y;
+	// pre-multiply the previous frame for blending (pathtracer_impl.h:201 -> RenderingContext::rescale_frame), this sub-frame's pixels
+	begin(0);
+	cuda_check(launch_rescale_frame(fbv, pixels, float(pp.instance) / float(pp.instance + 1), stream), "rescale_frame");
+	end();
 	const float seq2[2] = { seq[0], seq[1] };
 	begin(0);
-	cuda_check(launch_generate_primary(sc, pp, f.queue[0], ctr, seq2, stream), "generate_primary");
+	cuda_check(launch_generate_primary(sc, pp, f.queue[0], ctr, seq2, fbv, stream), "generate_primary");
 	end();
-	renderer.kernel_launches++;
+	renderer.kernel_launches += 2;
 
 	const uint32 L = m_options.max_path_length;
 	for (uint32 bounce = 0; bounce < L; ++bounce)
@@ -273,12 +279,19 @@ void PathTracer::render_subframe(SubFrame& f, const PassParams& pass, const std:
 		renderer.kernel_launches += 3;
 	}
 	if (overlap) cuda_check(cudaStreamWaitEvent(stream, f.ev_shadowed, 0), "wait");
+	// RenderingContext::update_variances (pathtracer_impl.h:322), this sub-frame's pixels
+	begin(0);
+	cuda_check(launch_update_variances(fbv, pixels, pp.instance + 1, stream), "update_variances");
+	end();
+	renderer.kernel_launches++;
 }
 
 PassTotals PathTracer::totals(RenderingContext& renderer)
 {
 	PassTotals t;
-	cuda_check(cudaMemcpyAsync(&t, m_totals.ptr, sizeof(t), cudaMemcpyDeviceToHost, renderer.stream()), "read totals");
+	cudaStream_t stream = renderer.stream();      // joins the sub-frame streams
+	if (m_events) cuda_check(cudaEventRecord(m_ev1, stream), "event record");
+	cuda_check(cudaMemcpyAsync(&t, m_totals.ptr, sizeof(t), cudaMemcpyDeviceToHost, stream), "read totals");
 	renderer.synchronize();
 	if (m_events)
 	{

@@ -62,7 +62,8 @@ FrameBufferView FBufferStorage::view() const
 	return v;
 }
 
-RenderingContext::RenderingContext() : kernel_launches(0), m_scene(NULL), m_owns_scene(false), m_device(0), m_stream(0), m_renderer(NULL)
+RenderingContext::RenderingContext() : kernel_launches(0), m_scene(NULL), m_owns_scene(false), m_device(0), m_stream(0), m_renderer(NULL),
+	m_touched(true), m_renderer_clears_gbuffer(false), m_copy_stream(0), m_ev_copied(0), m_ev_main(0), m_copy_in_flight(false)
 {
 	memset(&m_dscene, 0, sizeof(m_dscene));
 	memset(&m_lc, 0, sizeof(m_lc));
@@ -74,6 +75,10 @@ RenderingContext::~RenderingContext()
 {
 	if (m_renderer) m_renderer->destroy();
 	for (size_t i = 0; i < d_textures.size(); ++i) delete d_textures[i];
+	if (m_copy_stream) cudaStreamDestroy(m_copy_stream);
+	if (m_ev_copied) cudaEventDestroy(m_ev_copied);
+	if (m_ev_main) cudaEventDestroy(m_ev_main);
+	for (size_t i = 0; i < m_ev_snap.size(); ++i) cudaEventDestroy(m_ev_snap[i]);
 	if (m_stream) cudaStreamDestroy(m_stream);
 	if (m_owns_scene) delete m_scene;
 }
@@ -204,30 +209,80 @@ void RenderingContext::upload_scene()
 	cuda_check(cudaStreamSynchronize(m_stream), "scene upload");
 }
 
-void RenderingContext::clear() { m_fb.clear(m_stream); }
+void RenderingContext::clear() { m_fb.clear(stream()); }
 
 void RenderingContext::render(const uint32_t instance)
 {
 	// src/renderer.cu:1029-1056: clear the G-buffer, run the renderer (tone-mapping to RGBA is left to the caller)
-	m_fb.clear_gbuffer(m_stream);
+	if (!m_renderer_clears_gbuffer) m_fb.clear_gbuffer(stream());     // PathTracer resets it pixel by pixel as it starts the paths
 	m_renderer->render(instance, *this);
 }
 
 void RenderingContext::rescale_frame(const uint32_t instance)
 {
-	cuda_check(launch_rescale_frame(m_fb.view(), float(instance) / float(instance + 1), m_stream), "rescale_frame");
+	cuda_check(launch_rescale_frame(m_fb.view(), whole_frame(), float(instance) / float(instance + 1), stream()), "rescale_frame");
 	kernel_launches++;
 }
 void RenderingContext::update_variances(const uint32_t instance)
 {
-	cuda_check(launch_update_variances(m_fb.view(), instance + 1, m_stream), "update_variances");
+	cuda_check(launch_update_variances(m_fb.view(), whole_frame(), instance + 1, stream()), "update_variances");
 	kernel_launches++;
 }
-void RenderingContext::synchronize() { cuda_check(cudaStreamSynchronize(m_stream), "stream synchronize"); }
+void RenderingContext::add_pending(cudaEvent_t done)
+{
+	for (size_t i = 0; i < m_pending.size(); ++i) if (m_pending[i] == done) return;
+	m_pending.push_back(done);
+}
+void RenderingContext::join()
+{
+	for (size_t i = 0; i < m_pending.size(); ++i) cuda_check(cudaStreamWaitEvent(m_stream, m_pending[i], 0), "join");
+	m_pending.clear();
+	m_touched = true;
+}
+void RenderingContext::synchronize()
+{
+	join();
+	cuda_check(cudaStreamSynchronize(m_stream), "stream synchronize");
+	if (m_copy_in_flight) { cuda_check(cudaStreamSynchronize(m_copy_stream), "copy stream synchronize"); m_copy_in_flight = false; }
+}
 void RenderingContext::download_channel(int channel, float* dst)
 {
 	if (channel < 0 || channel >= FB_NUM_CHANNELS) throw std::runtime_error("bad channel");
 	DeviceBuffer& b = m_fb.channels[channel];
-	cuda_check(cudaMemcpyAsync(dst, b.ptr, b.bytes, cudaMemcpyDeviceToHost, m_stream), "fb download");
+	cuda_check(cudaMemcpyAsync(dst, b.ptr, b.bytes, cudaMemcpyDeviceToHost, stream()), "fb download");
 	synchronize();
+}
+void RenderingContext::download_channel_async(int channel, float* pinned_dst)
+{
+	if (channel < 0 || channel >= FB_NUM_CHANNELS) throw std::runtime_error("bad channel");
+	const FrameBufferView fbv = m_fb.view();
+	const size_t bytes = (size_t)fbv.n_pixels * sizeof(float4);
+	if (!m_copy_stream)
+	{
+		cuda_check(cudaStreamCreateWithFlags(&m_copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+		cuda_check(cudaEventCreateWithFlags(&m_ev_copied, cudaEventDisableTiming), "event");
+		cuda_check(cudaEventCreateWithFlags(&m_ev_main, cudaEventDisableTiming), "event");
+		m_snapshot.alloc(bytes);
+		cuda_check(cudaMemsetAsync(m_snapshot.ptr, 0, bytes, m_copy_stream), "memset snapshot");   // pixels of other ranks stay zero, like the frame buffer's
+		cuda_check(cudaEventRecord(m_ev_copied, m_copy_stream), "event record");
+		m_copy_in_flight = true;
+	}
+	std::vector<Partition> parts = m_parts;
+	if (parts.empty()) { Partition p; p.stream = stream(); p.pixels = whole_frame(); parts.push_back(p); }
+	while (m_ev_snap.size() < parts.size()) { cudaEvent_t e; cuda_check(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event"); m_ev_snap.push_back(e); }
+	// whatever sits on the context's own stream (a pass rendered there, a consumer) comes first
+	cuda_check(cudaEventRecord(m_ev_main, m_stream), "event record");
+	for (size_t i = 0; i < parts.size(); ++i)
+	{
+		cudaStream_t ps = parts[i].stream;
+		if (ps != m_stream) cuda_check(cudaStreamWaitEvent(ps, m_ev_main, 0), "wait");
+		if (m_copy_in_flight) cuda_check(cudaStreamWaitEvent(ps, m_ev_copied, 0), "wait");      // the previous snapshot has left the device buffer
+		cuda_check(launch_copy_channel(fbv, channel, reinterpret_cast<float4*>(m_snapshot.ptr), parts[i].pixels, ps), "copy_channel");
+		cuda_check(cudaEventRecord(m_ev_snap[i], ps), "event record");
+		cuda_check(cudaStreamWaitEvent(m_copy_stream, m_ev_snap[i], 0), "wait");
+		kernel_launches++;
+	}
+	cuda_check(cudaMemcpyAsync(pinned_dst, m_snapshot.ptr, bytes, cudaMemcpyDeviceToHost, m_copy_stream), "fb download");
+	cuda_check(cudaEventRecord(m_ev_copied, m_copy_stream), "event record");
+	m_copy_in_flight = true;
 }

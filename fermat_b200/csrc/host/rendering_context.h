@@ -75,10 +75,25 @@ struct RenderingContext
 	const fb::DeviceScene&  device_scene() const { return m_dscene; }
 	fb::DeviceScene&        device_scene() { return m_dscene; }
 	const fb::LaunchConfig& launch_config() const { return m_lc; }
-	cudaStream_t            stream() const { return m_stream; }
+	// The context's stream, for consumers and producers of the frame buffer. A renderer may run a pass on private
+	// streams and leave it un-joined on return (PathTracer does): stream() first makes the context's stream wait
+	// for that work (join) and notes that somebody is using it, so that the next pass is ordered after whatever
+	// the caller enqueues. raw_stream() is the renderer's own access, without either effect.
+	cudaStream_t            stream() { join(); return m_stream; }
+	cudaStream_t            raw_stream() const { return m_stream; }
+	void                    join();
+	void                    add_pending(cudaEvent_t done);                // renderer: the context's stream must wait for `done` before its next use
+	bool                    take_touched() { const bool t = m_touched; m_touched = false; return t; }
 	int                     device() const { return m_device; }
 	void                    synchronize();
 	void                    download_channel(int channel, float* dst);   // blocking copy of one float4 channel to the host
+	// Asynchronous read-back of one channel into PINNED host memory: each partition of the frame (the renderer's
+	// sub-frames) is copied into a device snapshot on its own stream as soon as its pass is complete, the snapshot goes
+	// to the host on a copy stream, and the next pass starts without waiting for either. synchronize() completes it.
+	struct Partition { cudaStream_t stream; fb::PixelSet pixels; };
+	void                    set_partitions(const std::vector<Partition>& parts) { m_parts = parts; }
+	void                    set_renderer_clears_gbuffer(bool b) { m_renderer_clears_gbuffer = b; }
+	void                    download_channel_async(int channel, float* pinned_dst);
 	RendererInterface*      renderer() { return m_renderer; }
 	uint64_t                kernel_launches;
 
@@ -93,6 +108,15 @@ private:
 	fb::DeviceScene    m_dscene;
 	fb::LaunchConfig   m_lc;
 	RendererInterface* m_renderer;
+	std::vector<cudaEvent_t> m_pending;
+	bool                     m_touched;
+	bool                     m_renderer_clears_gbuffer;
+	std::vector<Partition>   m_parts;
+	cudaStream_t             m_copy_stream;
+	fb::DeviceBuffer         m_snapshot;
+	cudaEvent_t              m_ev_copied, m_ev_main;
+	std::vector<cudaEvent_t> m_ev_snap;
+	bool                     m_copy_in_flight;
 	std::vector<std::string>             m_renderer_names;
 	std::vector<RendererFactoryFunction> m_renderer_factories;
 	// device copies

@@ -21,10 +21,25 @@ namespace fb {
 // ------------------------------------------------------------------------------------------------
 // frame-buffer element-wise kernels
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_rescale_frame(FrameBufferView fb, float scale)
+#define FB_TILE 32u
+
+// thread j -> pixel of the set: the whole frame (tile_list == NULL) or the j-th pixel of a list of 32x32 tiles
+FB_D bool pixel_of_set(const PixelSet& ps, const uint32 j, const uint32 n_pixels, uint32& pixel)
 {
-	const uint32 i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= fb.n_pixels) return;
+	if (ps.tile_list == NULL) { pixel = j; return j < n_pixels; }
+	const uint32 tile_slot = j / (FB_TILE * FB_TILE);
+	if (tile_slot >= ps.n_tiles) return false;
+	const uint32 tile = __ldg(ps.tile_list + tile_slot);
+	const uint32 px = (tile % ps.tiles_x) * FB_TILE + (j & (FB_TILE - 1));
+	const uint32 py = (tile / ps.tiles_x) * FB_TILE + ((j / FB_TILE) & (FB_TILE - 1));
+	pixel = px + py * ps.res_x;
+	return px < ps.res_x && py < ps.res_y;
+}
+
+__global__ void __launch_bounds__(256) k_rescale_frame(FrameBufferView fb, PixelSet ps, float scale)
+{
+	uint32 i;
+	if (!pixel_of_set(ps, blockIdx.x * blockDim.x + threadIdx.x, fb.n_pixels, i)) return;
 	const float4 d = fb.channels[FB_DIRECT_C][i], df = fb.channels[FB_DIFFUSE_C][i], sp = fb.channels[FB_SPECULAR_C][i], co = fb.channels[FB_COMPOSITED_C][i];
 	fb.channels[FB_LUMINANCE][i] = make_float4(fmaxf(d.x, fmaxf(d.y, d.z)), fmaxf(df.x, fmaxf(df.y, df.z)), fmaxf(sp.x, fmaxf(sp.y, sp.z)), fmaxf(co.x, fmaxf(co.y, co.z)));
 	auto mul = [scale](float4 v) { return make_float4(v.x * scale, v.y * scale, v.z * scale, v.w * scale); };
@@ -36,10 +51,10 @@ __global__ void __launch_bounds__(256) k_rescale_frame(FrameBufferView fb, float
 	fb.channels[FB_COMPOSITED_C][i] = mul(co);
 }
 
-__global__ void __launch_bounds__(256) k_update_variances(FrameBufferView fb, uint32 n)
+__global__ void __launch_bounds__(256) k_update_variances(FrameBufferView fb, PixelSet ps, uint32 n)
 {
-	const uint32 i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= fb.n_pixels) return;
+	uint32 i;
+	if (!pixel_of_set(ps, blockIdx.x * blockDim.x + threadIdx.x, fb.n_pixels, i)) return;
 	const float4 old_lum = fb.channels[FB_LUMINANCE][i];
 	float4 d = fb.channels[FB_DIRECT_C][i], df = fb.channels[FB_DIFFUSE_C][i], sp = fb.channels[FB_SPECULAR_C][i], co = fb.channels[FB_COMPOSITED_C][i];
 	const float nl[4] = { fmaxf(d.x, fmaxf(d.y, d.z)), fmaxf(df.x, fmaxf(df.y, df.z)), fmaxf(sp.x, fmaxf(sp.y, sp.z)), fmaxf(co.x, fmaxf(co.y, co.z)) };
@@ -58,9 +73,7 @@ __global__ void __launch_bounds__(256) k_update_variances(FrameBufferView fb, ui
 // ------------------------------------------------------------------------------------------------
 // primary rays
 // ------------------------------------------------------------------------------------------------
-#define FB_TILE 32u
-
-__global__ void __launch_bounds__(256) k_generate_primary(DeviceScene sc, PassParams pp, PathQueue q, PassCounters* ctr, float seq0, float seq1)
+__global__ void __launch_bounds__(256) k_generate_primary(DeviceScene sc, PassParams pp, PathQueue q, PassCounters* ctr, float seq0, float seq1, FrameBufferView fb)
 {
 	const uint32 j = blockIdx.x * blockDim.x + threadIdx.x;
 	const uint32 tile_slot = j / (FB_TILE * FB_TILE);
@@ -75,6 +88,16 @@ __global__ void __launch_bounds__(256) k_generate_primary(DeviceScene sc, PassPa
 	}
 	const uint32 slot = warp_append_slot(&ctr->in_size[0], valid);
 	if (!valid) return;
+	if (fb.gb_geo)
+	{
+		// GBufferStorage::clear (0xFF bytes, src/renderer.cu:1040) for this pixel: a miss leaves it like that
+		const uint32 pixel = px + py * sc.res_x;
+		const float nan_bits = __uint_as_float(0xFFFFFFFFu);
+		st_stream(fb.gb_geo + pixel, make_float4(nan_bits, nan_bits, nan_bits, nan_bits));
+		st_stream(fb.gb_uv + pixel, make_float4(nan_bits, nan_bits, nan_bits, nan_bits));
+		st_stream(fb.gb_tri + pixel, 0xFFFFFFFFu);
+		fb.gb_depth[pixel] = nan_bits;
+	}
 
 	// dims 0,1 of the sampler jitter the pixel (pathtracer_core.h:642-649)
 	const uint32 T = 256u;
@@ -613,21 +636,40 @@ cudaError_t configure_kernels(LaunchConfig& lc, int device)
 
 static inline uint32 staged_smem(const DeviceScene& sc) { return 16u + sc.staged_nodes * (uint32)sizeof(WideNode) + FB_SMEM_STACK * 8u * FB_TRACE_THREADS + FB_COOP_TRI * 8u * FB_TRACE_THREADS; }
 
-cudaError_t launch_rescale_frame(const FrameBufferView& fb, float scale, cudaStream_t s)
+static inline uint32 set_threads(const FrameBufferView& fb, const PixelSet& ps) { return ps.tile_list ? ps.n_tiles * FB_TILE * FB_TILE : fb.n_pixels; }
+cudaError_t launch_rescale_frame(const FrameBufferView& fb, const PixelSet& ps, float scale, cudaStream_t s)
 {
-	k_rescale_frame<<<(fb.n_pixels + 255) / 256, 256, 0, s>>>(fb, scale);
+	const uint32 n = set_threads(fb, ps);
+	if (n == 0) return cudaSuccess;
+	k_rescale_frame<<<(n + 255) / 256, 256, 0, s>>>(fb, ps, scale);
 	return cudaGetLastError();
 }
-cudaError_t launch_update_variances(const FrameBufferView& fb, uint32 n, cudaStream_t s)
+cudaError_t launch_update_variances(const FrameBufferView& fb, const PixelSet& ps, uint32 n_passes, cudaStream_t s)
 {
-	k_update_variances<<<(fb.n_pixels + 255) / 256, 256, 0, s>>>(fb, n);
+	const uint32 n = set_threads(fb, ps);
+	if (n == 0) return cudaSuccess;
+	k_update_variances<<<(n + 255) / 256, 256, 0, s>>>(fb, ps, n_passes);
 	return cudaGetLastError();
 }
-cudaError_t launch_generate_primary(const DeviceScene& sc, const PassParams& pp, const PathQueue& q, PassCounters* ctr, const float seq2[2], cudaStream_t s)
+// copy one frame-buffer channel's pixels of the set into `dst` (same indexing)
+__global__ void __launch_bounds__(256) k_copy_channel(const float4* __restrict__ src, float4* __restrict__ dst, PixelSet ps, uint32 n_pixels)
+{
+	uint32 i;
+	if (!pixel_of_set(ps, blockIdx.x * blockDim.x + threadIdx.x, n_pixels, i)) return;
+	dst[i] = src[i];
+}
+cudaError_t launch_copy_channel(const FrameBufferView& fb, int channel, float4* dst, const PixelSet& ps, cudaStream_t s)
+{
+	const uint32 n = set_threads(fb, ps);
+	if (n == 0) return cudaSuccess;
+	k_copy_channel<<<(n + 255) / 256, 256, 0, s>>>(fb.channels[channel], dst, ps, fb.n_pixels);
+	return cudaGetLastError();
+}
+cudaError_t launch_generate_primary(const DeviceScene& sc, const PassParams& pp, const PathQueue& q, PassCounters* ctr, const float seq2[2], const FrameBufferView& fb, cudaStream_t s)
 {
 	const uint32 total = pp.n_tiles * FB_TILE * FB_TILE;
 	if (total == 0) return cudaSuccess;
-	k_generate_primary<<<(total + 255) / 256, 256, 0, s>>>(sc, pp, q, ctr, seq2[0], seq2[1]);
+	k_generate_primary<<<(total + 255) / 256, 256, 0, s>>>(sc, pp, q, ctr, seq2[0], seq2[1], fb);
 	return cudaGetLastError();
 }
 cudaError_t launch_trace_closest(const DeviceScene& sc, const LaunchConfig& lc, const PathQueue& q, PassCounters* ctr, uint32 bounce, cudaStream_t s)

@@ -26,9 +26,17 @@ struct LaunchConfig
 };
 
 // error code (cudaError_t) of the launch is returned; kernels count their own launches in `launches`
-cudaError_t launch_rescale_frame(const FrameBufferView& fb, float scale, cudaStream_t s);
-cudaError_t launch_update_variances(const FrameBufferView& fb, uint32 n, cudaStream_t s);
-cudaError_t launch_generate_primary(const DeviceScene& sc, const PassParams& pp, const PathQueue& q, PassCounters* ctr, const float seq2[2], cudaStream_t s);
+// pixels an element-wise frame-buffer kernel covers: the whole frame (tile_list == NULL) or a list of 32x32 tiles
+struct PixelSet
+{
+	const uint32* tile_list; uint32 n_tiles, tiles_x, res_x, res_y;
+};
+inline PixelSet whole_frame() { PixelSet p; p.tile_list = NULL; p.n_tiles = 0; p.tiles_x = 0; p.res_x = 0; p.res_y = 0; return p; }
+cudaError_t launch_rescale_frame(const FrameBufferView& fb, const PixelSet& ps, float scale, cudaStream_t s);
+cudaError_t launch_update_variances(const FrameBufferView& fb, const PixelSet& ps, uint32 n_passes, cudaStream_t s);
+cudaError_t launch_copy_channel(const FrameBufferView& fb, int channel, float4* dst, const PixelSet& ps, cudaStream_t s);
+// also resets the G-buffer of every pixel it starts a path for (pass `fb` with gb_geo == NULL to skip)
+cudaError_t launch_generate_primary(const DeviceScene& sc, const PassParams& pp, const PathQueue& q, PassCounters* ctr, const float seq2[2], const FrameBufferView& fb, cudaStream_t s);
 cudaError_t launch_trace_closest(const DeviceScene& sc, const LaunchConfig& lc, const PathQueue& q, PassCounters* ctr, uint32 bounce, cudaStream_t s);
 cudaError_t launch_shade(const DeviceScene& sc, const LaunchConfig& lc, const PassParams& pp, const PathQueue& in, const PathQueue& out, const ShadowQueue& sq,
 						 const FrameBufferView& fb, PassCounters* ctr, PassTotals* tot, uint32 bounce, const float seq6[6], uint32 capacity, cudaStream_t s);

@@ -142,8 +142,10 @@ void           fb200_context_destroy(fb200_context*);
 /* RenderingContext::clear (src/renderer.cu) — zero all frame-buffer channels */
 int fb200_context_clear(fb200_context*);
 /* RenderingContext::render(instance) -> RendererInterface::render (src/renderer.cu:1029-1056,
- * src/renderers/pathtracer_impl.h:197-324): one progressive pass. Asynchronous on the context's
- * stream unless `sync` is non-zero. */
+ * src/renderers/pathtracer_impl.h:197-324): one progressive pass. Asynchronous unless `sync` is non-zero: the pass is
+ * enqueued on the renderer's private streams and becomes visible to the context's stream when fb200_context_stream /
+ * _synchronize / _fb_download / _get_stats is called (the reference's contract - complete on return - is what
+ * sync = 1 or any of those calls gives). */
 int fb200_context_render(fb200_context*, uint32_t instance, int sync);
 int fb200_context_synchronize(fb200_context*);
 /* res() (src/renderer.h) */
@@ -153,6 +155,10 @@ int fb200_context_res(const fb200_context*, uint32_t* res_x, uint32_t* res_y);
 void* fb200_context_fb_device_ptr(fb200_context*, int channel);
 /* copy a channel to host memory: dst holds 4*res_x*res_y floats */
 int fb200_context_fb_download(fb200_context*, int channel, float* dst);
+/* asynchronous read-back of a channel into PINNED host memory (4*res_x*res_y floats): the finished pass is snapshot
+ * on the device and copied out on a copy stream while the next pass renders; the data is complete after
+ * fb200_context_synchronize. Successive calls are ordered; the host buffer must stay valid until then. */
+int fb200_context_fb_download_async(fb200_context*, int channel, float* pinned_dst);
 /* copy the G-buffer of the last pass to host memory (GBufferView, src/framebuffer.h:49-143): geo and uv hold 4 floats
  * per pixel (position + 2x15-bit packed normal bits; hit u, v, texture s, t), tri and depth one value per pixel;
  * pixels whose primary ray missed keep the 0xFF clear pattern. Any pointer may be NULL. */
@@ -165,7 +171,9 @@ int fb200_context_get_stats(fb200_context*, fb200_stats* out);
  * classes: 0 frame-buffer element-wise + primary rays, 1 closest-hit trace, 2 shade, 3 shadow trace + accumulate */
 int fb200_context_set_profiling(fb200_context*, int on);
 int fb200_context_get_kernel_times(fb200_context*, double out_ms[4], uint64_t out_launches[4]);
-/* CUDA stream handle (cudaStream_t) the context launches on */
+/* CUDA stream handle (cudaStream_t) of the context. Every call first orders the stream behind the passes rendered
+ * so far (they run on the renderer's private streams) and makes the next pass wait for what the caller enqueues on it:
+ * call it again before each use rather than caching the handle. */
 void* fb200_context_stream(fb200_context*);
 /* number of pixels this shard owns */
 uint64_t fb200_context_owned_pixels(const fb200_context*);
