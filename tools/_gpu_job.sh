@@ -1,10 +1,11 @@
-python -m pytest tests -m gpu -q -x 2>&1 | tail -3
-for cfg in "2 2" "3 1" "4 1" "1 0"; do
-set -- $cfg
-echo "subframes $1 ctas $2" | tee -a gpurun_out/sweep.txt
-FB200_SUBFRAMES=$1 FB200_TRACE_CTAS=$2 python bench.py --steps 16 --warmup 3 --no-cpu-baseline 2>gpurun_out/sf.err | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1])
-print('   %7.1f Msamples/s  %6.3f ms/pass e2e %7.1f | trace %.3f shade %.3f shadow %.3f finite %s' % (d['value'], d['ms_per_step'], d['e2e']['value'], d['kernels']['trace']['ms_per_launch'], d['kernels']['shade']['ms_per_launch'], d['kernels']['shadow']['ms_per_launch'], d['finite']))" | tee -a gpurun_out/sweep.txt
-tail -3 gpurun_out/sf.err | cut -c1-300
-done
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 2 --steps 16 --warmup 3 > gpurun_out/r01g_bench_n2.json 2> gpurun_out/r01g_bench_n2.err
+python -c "
+import json
+d=json.loads(open('gpurun_out/r01g_bench_n2.json').read().strip().splitlines()[-1]); print('N=2', d['value'], d['e2e']['value'], d['finite'])"
+tail -2 gpurun_out/r01g_bench_n2.err | cut -c1-200
+python bench.py --res 3840 2160 --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/r01g_bench_4k_n1.json 2> gpurun_out/r01g_bench_4k_n1.err
+python -c "
+import json
+d=json.loads(open('gpurun_out/r01g_bench_4k_n1.json').read().strip().splitlines()[-1]); print('4K N=1', d['value'], d['e2e']['value'], d['ms_per_step'], d['finite'])"
+timeout 200 python tools/run_configs.py --only C1_gpu > gpurun_out/configs_r01_c1gpu.json 2> gpurun_out/configs_r01_c1gpu.err
+grep -o '"Msamples_per_s_device": [0-9.]*\|"rel_l2_composited": [0-9.e-]*' gpurun_out/configs_r01_c1gpu.err

@@ -88,6 +88,7 @@ def main():
     cfgs = [
         ("C1", "tests/golden/cornellbox_jp.fbs", (512, 512), 4, 64, 64, 0, 1),
         ("C1_1024spp", "tests/golden/cornellbox_jp.fbs", (512, 512), 4, 1024, 32 if q else 1024, 0, None),
+        ("C1_gpu", "tests/golden/cornellbox_jp.fbs", (512, 512), 4, 1032, 8, 0, None),          # GPU throughput over 1024 passes
         ("C2", "scenes/_cache/bathroom2.fbs", (1600, 900), 8, 1024, 8 if q else a.spp_parity, 0, None),
         ("C3", "scenes/_cache/material_testball.fbs", (1024, 1024), 12, 256, 8 if q else a.spp_parity_small, 0, None),
         ("C4", "scenes/_cache/water_caustic.fbs", (1600, 900), 16, 256, 8 if q else a.spp_parity_small, 0, None),
