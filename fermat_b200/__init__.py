@@ -101,6 +101,7 @@ def lib():
         "fb200_context_set_profiling": (i32, [vp, i32]),
         "fb200_context_get_kernel_times": (i32, [vp, C.POINTER(C.c_double * 4), C.POINTER(u64 * 4)]),
         "fb200_context_owned_pixels": (u64, [vp]),
+        "fb200_context_build_lbvh": (C.c_int64, [vp, u32, i32, vp, u64, C.POINTER(u32), C.POINTER(u64), pf]),
         "fb200_trace": (i32, [vp, pf, pf, u32]),
         "fb200_trace_shadow": (i32, [vp, pf, C.POINTER(C.c_uint8), u32]),
         "fb200_trace_device": (i32, [vp, vp, vp, u32]),
@@ -241,6 +242,8 @@ class RenderingContext:
         if not self._h:
             raise RuntimeError("fb200_context_create failed: " + _err())
         self.device = int(device)
+        # `-bvh lbvh` builds the tree while the context is created: refresh the view's pointers to the host copy
+        lib().fb200_scene_get_view(scene._h, C.byref(scene.view))
 
     def _chk(self, rc):
         if rc != 0:
@@ -312,6 +315,27 @@ class RenderingContext:
 
     def owned_pixels(self):
         return int(lib().fb200_context_owned_pixels(self._h))
+
+    def build_lbvh(self, max_leaf_size=1, adopt=False, want_codes=False):
+        """Build the scene BVH on the device with CUGAR's LBVH (include/fermat_b200.h). Returns dict(nodes = structured
+        array of Bvh_node_3d records, index, codes (if asked), device_ms). adopt=True also makes it the traversal tree."""
+        n = int(self.scene.view.num_triangles)
+        node_dt = np.dtype([("packed_info", "<u4"), ("range_size", "<u4"), ("bmin", "<f4", 3), ("bmax", "<f4", 3)])
+        nodes = np.zeros(2 * max(n, 1), dtype=node_dt)
+        index = np.zeros(max(n, 1), dtype=np.uint32)
+        codes = np.zeros(max(n, 1), dtype=np.uint64) if want_codes else None
+        ms = C.c_float()
+        cnt = lib().fb200_context_build_lbvh(self._h, int(max_leaf_size), 1 if adopt else 0, nodes.ctypes.data_as(C.c_void_p), nodes.shape[0],
+                                             index.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                             codes.ctypes.data_as(C.POINTER(C.c_uint64)) if want_codes else None, C.byref(ms))
+        if cnt < 0:
+            raise RuntimeError(_err())
+        if adopt:   # the scene's host copy of the tree was replaced: refresh the view's pointers
+            lib().fb200_scene_get_view(self.scene._h, C.byref(self.scene.view))
+        out = {"nodes": nodes[:cnt], "index": index[:n], "device_ms": ms.value}
+        if want_codes:
+            out["codes"] = codes[:n]
+        return out
 
     # --- hot-path entry points (host buffers) ---
     def trace(self, rays):

@@ -126,6 +126,24 @@ int fb200_context_get_kernel_times(fb200_context* c, double out_ms[4], uint64_t 
 void* fb200_context_stream(fb200_context* c) { return (void*)c->rc.stream(); }
 uint64_t fb200_context_owned_pixels(const fb200_context* c) { return static_cast<PathTracer*>(const_cast<fb200_context*>(c)->rc.renderer())->owned_pixels(); }
 
+int64_t fb200_context_build_lbvh(fb200_context* c, uint32_t max_leaf_size, int adopt, void* nodes, uint64_t node_capacity, uint32_t* index, uint64_t* codes, float* device_ms)
+{
+	int64_t count = -1;
+	const int rc = guarded([&] {
+		std::vector<fb::Bvh2Node> nv; std::vector<uint32_t> iv; std::vector<uint64_t> cv;
+		const uint32_t n = c->rc.build_lbvh(max_leaf_size, adopt != 0, nodes ? &nv : NULL, index ? &iv : NULL, codes ? &cv : NULL, device_ms);
+		if (nodes)
+		{
+			if (node_capacity < n) throw std::runtime_error("fb200_context_build_lbvh: node_capacity too small");
+			memcpy(nodes, nv.data(), (size_t)n * sizeof(fb::Bvh2Node));
+		}
+		if (index && !iv.empty()) memcpy(index, iv.data(), iv.size() * sizeof(uint32_t));
+		if (codes && !cv.empty()) memcpy(codes, cv.data(), cv.size() * sizeof(uint64_t));
+		count = n;
+	});
+	return rc == 0 ? count : -1;
+}
+
 int fb200_trace_device(fb200_context* c, const void* d_rays, void* d_hits, uint32_t n)
 {
 	return guarded([&] {

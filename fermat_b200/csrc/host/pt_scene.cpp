@@ -106,6 +106,13 @@ void scene_init(fb200_scene& s, int argc, const char* const* argv)
 		else if (strcmp(argv[i], "-shard") == 0 && i + 2 < argc) { s.shard_rank = (uint32)atoi(argv[++i]); s.shard_count = (uint32)atoi(argv[++i]); }
 		else if (strcmp(argv[i], "-passes") == 0 && i + 1 < argc) s.n_passes = atoi(argv[++i]);
 		else if (strcmp(argv[i], "-o") == 0 && i + 1 < argc) s.output_name = argv[++i];
+		else if (strcmp(argv[i], "-bvh") == 0 && i + 1 < argc)
+		{
+			++i;
+			if (strcmp(argv[i], "sah") == 0) s.bvh_builder = 0;
+			else if (strcmp(argv[i], "lbvh") == 0) s.bvh_builder = 1;
+			else throw std::runtime_error(std::string("unknown -bvh builder: ") + argv[i] + " (sah | lbvh)");
+		}
 	}
 	if (s.aspect == 0.0f) s.aspect = float(s.res_x) / float(s.res_y);
 	if (!filename) throw std::runtime_error("no input scene: pass -i scene.{fa,obj,fbs}");
@@ -133,8 +140,12 @@ void scene_init(fb200_scene& s, int argc, const char* const* argv)
 	s.mesh_lights.init(s.res_x * s.res_y, s.scene, 0u);
 	if (s.mesh_lights.vpls.empty()) s.options.nee_type = 0;     // pathtracer_impl.h:165-166
 
-	build_bvh2(s.scene.mesh, s.bvh2, 3);
-	collapse_to_wide(s.scene.mesh, s.bvh2, s.wide);
+	// -bvh lbvh: the tree is built on the device when a context is created (RenderingContext::build_lbvh)
+	if (s.bvh_builder == 0)
+	{
+		build_bvh2(s.scene.mesh, s.bvh2, 3);
+		collapse_to_wide(s.scene.mesh, s.bvh2, s.wide);
+	}
 
 	s.texture_views.resize(s.scene.textures.size());
 	for (size_t i = 0; i < s.scene.textures.size(); ++i)

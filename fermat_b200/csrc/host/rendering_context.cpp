@@ -117,6 +117,7 @@ void RenderingContext::init_with_scene(fb200_scene* scene, int device, int argc,
 	m_fb.resize(scene->res_x, scene->res_y);
 	m_fb.clear(m_stream);
 	upload_scene();
+	if (scene->bvh_builder == 1) build_lbvh(3, true, NULL, NULL, NULL, NULL);
 
 	// pick the renderer: the last `-<name>` matching a registered renderer wins (src/renderer.cu:528-538); default pt
 	uint32_t type = 0;
@@ -129,31 +130,20 @@ void RenderingContext::init_with_scene(fb200_scene* scene, int device, int argc,
 	synchronize();
 }
 
-void RenderingContext::upload_scene()
+void RenderingContext::set_wide_pointers()
 {
 	fb200_scene& s = *m_scene;
-	const Mesh& m = s.scene.mesh;
 	DeviceScene& d = m_dscene;
-	memset(&d, 0, sizeof(d));
-	d_vertex_indices.upload(m.vertex_indices.data(), m.vertex_indices.size() * sizeof(int4), m_stream);
-	d_vertex_data.upload(m.vertex_data.data(), m.vertex_data.size() * sizeof(float4), m_stream);
-	d_texture_indices_comp.upload(m.texture_indices_comp.data(), m.texture_indices_comp.size() * sizeof(int4), m_stream);
-	d_material_indices.upload(m.material_indices.data(), m.material_indices.size() * sizeof(int), m_stream);
-	d_materials.upload(m.materials.data(), m.materials.size() * sizeof(MeshMaterial), m_stream);
-	std::vector<TextureView> views(s.scene.textures.size());
-	for (size_t i = 0; i < s.scene.textures.size(); ++i)
-	{
-		const TextureImage& t = s.scene.textures[i];
-		DeviceBuffer* b = new DeviceBuffer();
-		d_textures.push_back(b);
-		if (!t.levels.empty())
-		{
-			b->upload(t.levels[0].data(), t.levels[0].size() * sizeof(float4), m_stream);
-			views[i].texels = b->as<float4>(); views[i].res_x = t.res_x[0]; views[i].res_y = t.res_y[0];
-		}
-		else { views[i].texels = NULL; views[i].res_x = views[i].res_y = 0; }
-	}
-	d_texture_views.upload(views.data(), views.size() * sizeof(TextureView), m_stream);
+	const size_t node_bytes = (s.wide.nodes.size() * sizeof(WideNode) + 255) & ~size_t(255);
+	d.nodes = d_nodes.as<WideNode>(); d.tris = reinterpret_cast<const WideTri*>((const char*)d_nodes.ptr + node_bytes); d.num_nodes = (uint32)s.wide.nodes.size();
+	const uint32 max_staged = m_lc.staged_bytes / (uint32)sizeof(WideNode);
+	d.staged_nodes = d.num_nodes < max_staged ? d.num_nodes : max_staged;
+	d.f32_2p23_bits = 0x4B000000u;
+}
+
+void RenderingContext::upload_wide_bvh()
+{
+	fb200_scene& s = *m_scene;
 	// the wide BVH lives in ONE allocation (nodes, then triangles) so that a single L2 access-policy window can
 	// pin it: the tree (bathroom2: 75 MB) fits the 126 MB L2, the streaming queues that would evict it do not
 	const size_t node_bytes = (s.wide.nodes.size() * sizeof(WideNode) + 255) & ~size_t(255);
@@ -184,6 +174,34 @@ void RenderingContext::upload_scene()
 			if (cudaStreamSetAttribute(m_stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
 		}
 	}
+}
+
+void RenderingContext::upload_scene()
+{
+	fb200_scene& s = *m_scene;
+	const Mesh& m = s.scene.mesh;
+	DeviceScene& d = m_dscene;
+	memset(&d, 0, sizeof(d));
+	d_vertex_indices.upload(m.vertex_indices.data(), m.vertex_indices.size() * sizeof(int4), m_stream);
+	d_vertex_data.upload(m.vertex_data.data(), m.vertex_data.size() * sizeof(float4), m_stream);
+	d_texture_indices_comp.upload(m.texture_indices_comp.data(), m.texture_indices_comp.size() * sizeof(int4), m_stream);
+	d_material_indices.upload(m.material_indices.data(), m.material_indices.size() * sizeof(int), m_stream);
+	d_materials.upload(m.materials.data(), m.materials.size() * sizeof(MeshMaterial), m_stream);
+	std::vector<TextureView> views(s.scene.textures.size());
+	for (size_t i = 0; i < s.scene.textures.size(); ++i)
+	{
+		const TextureImage& t = s.scene.textures[i];
+		DeviceBuffer* b = new DeviceBuffer();
+		d_textures.push_back(b);
+		if (!t.levels.empty())
+		{
+			b->upload(t.levels[0].data(), t.levels[0].size() * sizeof(float4), m_stream);
+			views[i].texels = b->as<float4>(); views[i].res_x = t.res_x[0]; views[i].res_y = t.res_y[0];
+		}
+		else { views[i].texels = NULL; views[i].res_x = views[i].res_y = 0; }
+	}
+	d_texture_views.upload(views.data(), views.size() * sizeof(TextureView), m_stream);
+	upload_wide_bvh();
 	d_vpls.upload(s.mesh_lights.vpls.data(), s.mesh_lights.vpls.size() * sizeof(VPL), m_stream);
 	d_mesh_cdf.upload(s.mesh_lights.mesh_cdf.data(), s.mesh_lights.mesh_cdf.size() * sizeof(float), m_stream);
 	d_mesh_inv_area.upload(s.mesh_lights.mesh_inv_area.data(), s.mesh_lights.mesh_inv_area.size() * sizeof(float), m_stream);
@@ -195,10 +213,7 @@ void RenderingContext::upload_scene()
 	d.texture_indices_comp = d_texture_indices_comp.as<int4>(); d.material_indices = d_material_indices.as<int>();
 	d.materials = d_materials.as<MeshMaterial>(); d.tex_bias = m.tex_bias; d.tex_scale = m.tex_scale;
 	d.textures = d_texture_views.as<TextureView>(); d.num_textures = (uint32)views.size(); d.num_triangles = (uint32)m.num_triangles();
-	d.nodes = d_nodes.as<WideNode>(); d.tris = reinterpret_cast<const WideTri*>((const char*)d_nodes.ptr + node_bytes); d.num_nodes = (uint32)s.wide.nodes.size();
-	const uint32 max_staged = m_lc.staged_bytes / (uint32)sizeof(WideNode);
-	d.staged_nodes = d.num_nodes < max_staged ? d.num_nodes : max_staged;
-	d.f32_2p23_bits = 0x4B000000u;
+	set_wide_pointers();
 	d.vpls = d_vpls.as<VPL>(); d.n_vpls = (uint32)s.mesh_lights.vpls.size();
 	d.use_vpls = (s.options.nee_type == 1 && d.n_vpls > 0) ? 1u : 0u;
 	d.vpl_norm = s.mesh_lights.normalization_coeff;
@@ -285,4 +300,60 @@ void RenderingContext::download_channel_async(int channel, float* pinned_dst)
 	cuda_check(cudaMemcpyAsync(pinned_dst, m_snapshot.ptr, bytes, cudaMemcpyDeviceToHost, m_copy_stream), "fb download");
 	cuda_check(cudaEventRecord(m_ev_copied, m_copy_stream), "event record");
 	m_copy_in_flight = true;
+}
+
+uint32_t RenderingContext::build_lbvh(uint32_t max_leaf_size, bool adopt, std::vector<Bvh2Node>* nodes_out, std::vector<uint32_t>* index_out,
+									  std::vector<uint64_t>* codes_out, float* device_ms)
+{
+	fb200_scene& s = *m_scene;
+	const uint32 n = (uint32)s.scene.mesh.num_triangles();
+	if (max_leaf_size == 0) max_leaf_size = 1;
+	if (adopt && max_leaf_size > 3) throw std::runtime_error("build_lbvh: a tree the traversal kernels adopt needs max_leaf_size <= 3");
+	if (n >= (1u << 27)) throw std::runtime_error("build_lbvh: more than 2^27 triangles");
+	synchronize();                       // nothing may still be tracing the tree we are about to replace
+
+	const size_t N = n ? n : 1;
+	DeviceBuffer work, d_bvh2, d_index, d_count;
+	work.alloc(lbvh_workspace_bytes(n));
+	d_bvh2.alloc(2 * N * sizeof(Bvh2Node));
+	d_index.alloc(N * sizeof(uint32));
+	d_count.alloc(8);
+	const Bbox3& bb = s.scene.bbox;
+	const float bbox[6] = { bb.lo.x, bb.lo.y, bb.lo.z, bb.hi.x, bb.hi.y, bb.hi.z };
+	cudaEvent_t e0, e1;
+	cuda_check(cudaEventCreate(&e0), "event"); cuda_check(cudaEventCreate(&e1), "event");
+	unsigned long long* d_codes = NULL;
+	cuda_check(cudaEventRecord(e0, m_stream), "event record");
+	cuda_check(launch_lbvh_build(m_dscene.vertex_indices, m_dscene.vertex_data, n, bbox, max_leaf_size, work.ptr, work.bytes,
+		d_bvh2.as<Bvh2Node>(), d_index.as<uint32>(), &d_codes, d_count.as<uint32>(), m_lc.sm_count, m_stream), "lbvh build");
+	cuda_check(cudaEventRecord(e1, m_stream), "event record");
+	kernel_launches += 4 + 2 * LBVH_MAX_LEVELS + (n ? 8 : 0);
+	uint32 count[2] = { 0, 0 };
+	cuda_check(cudaMemcpyAsync(count, d_count.ptr, 8, cudaMemcpyDeviceToHost, m_stream), "D2H");
+	cuda_check(cudaStreamSynchronize(m_stream), "lbvh build");
+	float ms = 0.0f;
+	cudaEventElapsedTime(&ms, e0, e1);
+	cudaEventDestroy(e0); cudaEventDestroy(e1);
+	if (device_ms) *device_ms = ms;
+	if (count[0] != count[1]) throw std::runtime_error("build_lbvh: the radix tree is deeper than LBVH_MAX_LEVELS");
+	const uint32 n_nodes = count[1];
+
+	Bvh2 bvh;
+	if (adopt || nodes_out) { bvh.nodes.resize(n_nodes); cuda_check(cudaMemcpy(bvh.nodes.data(), d_bvh2.ptr, (size_t)n_nodes * sizeof(Bvh2Node), cudaMemcpyDeviceToHost), "D2H"); }
+	if (adopt || index_out) { bvh.index.resize(n); if (n) cuda_check(cudaMemcpy(bvh.index.data(), d_index.ptr, (size_t)n * sizeof(uint32), cudaMemcpyDeviceToHost), "D2H"); }
+	if (codes_out) { codes_out->resize(n); if (n) cuda_check(cudaMemcpy(codes_out->data(), d_codes, (size_t)n * 8, cudaMemcpyDeviceToHost), "D2H"); }
+	if (nodes_out) *nodes_out = bvh.nodes;
+	if (index_out) *index_out = bvh.index;
+	if (adopt)
+	{
+		bvh.sah_cost = compute_sah_cost(bvh);
+		WideBvh wide;
+		if (n) collapse_to_wide(s.scene.mesh, bvh, wide);        // throws if the tree would overflow the traversal stack
+		s.bvh2.nodes.swap(bvh.nodes); s.bvh2.index.swap(bvh.index); s.bvh2.sah_cost = bvh.sah_cost;
+		s.wide.nodes.swap(wide.nodes); s.wide.tris.swap(wide.tris); s.wide.max_depth = wide.max_depth; s.wide.max_stack = wide.max_stack;
+		upload_wide_bvh();
+		set_wide_pointers();
+		cuda_check(cudaStreamSynchronize(m_stream), "wide BVH upload");
+	}
+	return n_nodes;
 }

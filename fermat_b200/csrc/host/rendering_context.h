@@ -7,6 +7,7 @@
 #include "pt_scene.h"
 #include "../kernels/device_scene.h"
 #include "../kernels/pt_kernels.h"
+#include "../kernels/lbvh_kernels.h"
 #include <cuda_runtime.h>
 #include <vector>
 #include <string>
@@ -95,10 +96,20 @@ struct RenderingContext
 	void                    set_renderer_clears_gbuffer(bool b) { m_renderer_clears_gbuffer = b; }
 	void                    download_channel_async(int channel, float* pinned_dst);
 	RendererInterface*      renderer() { return m_renderer; }
+	// Scene BVH built ON THE DEVICE with CUGAR's LBVH (kernels/lbvh_kernels.cu) from the mesh arrays resident there —
+	// the role of RTContext::create_geometry's Trbvh build (src/rt.cpp:307-324) and of RendererInterface::update_scene
+	// re-builds. Returns the node count. `adopt`: collapse the tree to the 8-wide layout and make it the one the
+	// traversal kernels read (needs max_leaf_size <= 3: a leaf must fit one child slot). nodes/index/codes: optional
+	// copies of the Bvh_node_3d array, the triangle permutation and the sorted Morton codes. Throws on failure and
+	// then leaves the current tree in place.
+	uint32_t                build_lbvh(uint32_t max_leaf_size, bool adopt, std::vector<fb::Bvh2Node>* nodes, std::vector<uint32_t>* index,
+									   std::vector<uint64_t>* codes, float* device_ms);
 	uint64_t                kernel_launches;
 
 private:
 	void upload_scene();
+	void upload_wide_bvh();
+	void set_wide_pointers();
 
 	fb200_scene*       m_scene;
 	bool               m_owns_scene;

@@ -178,6 +178,24 @@ void* fb200_context_stream(fb200_context*);
 /* number of pixels this shard owns */
 uint64_t fb200_context_owned_pixels(const fb200_context*);
 
+/* Scene BVH built ON THE DEVICE by CUGAR's LBVH algorithm: 60-bit Morton codes of the triangle-box centres in the
+ * scene's bounding box, radix sort, radix tree with middle splits for runs of equal codes, Bvh_node_3d output
+ * (contrib/cugar/bvh/cuda/lbvh_builder_inline.h:57-149, contrib/cugar/radixtree/cuda/radixtree_inline.h:93-262,
+ * contrib/cugar/bits/morton.h:260-287, contrib/cugar/bvh/bvh_node.h:79-137), nodes in the breadth-first order of the
+ * reference's host generate_radix_tree (contrib/cugar/radixtree/radixtree_inline.h:74-176), boxes refitted bottom-up.
+ * Stands in for RTContext::create_geometry's acceleration-structure build (src/rt.cpp:307-324) and for the re-build a
+ * RendererInterface::update_scene implies (src/renderer.cu:1013).
+ *   max_leaf_size   triangles per leaf (>= 1)
+ *   adopt           non-zero: collapse the tree to the 8-wide layout and make it the one the traversal kernels use
+ *                   from now on (needs max_leaf_size <= 3); zero: build only
+ *   nodes           NULL or room for node_capacity 32-byte Bvh_node_3d records (2*num_triangles is always enough)
+ *   index           NULL or num_triangles triangle ids (the sorted permutation leaf ranges index into)
+ *   codes           NULL or num_triangles sorted Morton codes
+ *   device_ms       NULL or device time of the build (CUDA events), without the collapse / upload of `adopt`
+ * Returns the node count, or -1 (fb200_last_error says why; the tree in use is then unchanged). */
+int64_t fb200_context_build_lbvh(fb200_context*, uint32_t max_leaf_size, int adopt, void* nodes, uint64_t node_capacity,
+                                 uint32_t* index, uint64_t* codes, float* device_ms);
+
 /* --- hot-path entry points on caller-provided HOST buffers (copies included) ------------------ */
 
 /* RTContext::trace (src/rt.cpp:558-583): closest hit. rays: n x {origin.xyz, tmin, dir.xyz, tmax};

@@ -120,6 +120,52 @@ def render_pass_with_gbuffer(view, instance, fb, threads=0):
     return st, {"geo": geo, "uv": uv, "tri": tri, "depth": depth}
 
 
+NODE_DTYPE = np.dtype([("packed_info", "<u4"), ("range_size", "<u4"), ("bmin", "<f4", 3), ("bmax", "<f4", 3)])
+
+
+def morton60(points, bbox):
+    """60-bit Morton codes of (n,3) float32 points in the frame bbox = (min xyz, max xyz) (cugar::morton_functor<uint64,3>)."""
+    pts = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 3)
+    bb = np.ascontiguousarray(bbox, dtype=np.float32).reshape(6)
+    codes = np.zeros(pts.shape[0], dtype=np.uint64)
+    lib().oracle_morton60(pts.ctypes.data_as(C.c_void_p), C.c_uint32(pts.shape[0]), bb.ctypes.data_as(C.c_void_p), codes.ctypes.data_as(C.c_void_p))
+    return codes
+
+
+def radix_tree(sorted_codes, max_leaf_size):
+    """CUGAR's radix tree over sorted codes: (nodes (k,2) u32 = packed_info/range_size, ranges (k,2) u32, parents (k,) u32)."""
+    codes = np.ascontiguousarray(sorted_codes, dtype=np.uint64)
+    n = codes.shape[0]
+    nodes = np.zeros((2 * max(n, 1), 2), np.uint32); ranges = np.zeros_like(nodes); parents = np.zeros(2 * max(n, 1), np.uint32)
+    L = lib()
+    L.oracle_radix_tree.restype = C.c_int64
+    k = L.oracle_radix_tree(codes.ctypes.data_as(C.c_void_p), C.c_uint32(n), C.c_uint32(max_leaf_size), nodes.ctypes.data_as(C.c_void_p),
+                            ranges.ctypes.data_as(C.c_void_p), parents.ctypes.data_as(C.c_void_p))
+    return nodes[:k], ranges[:k], parents[:k]
+
+
+def lbvh_build(view, max_leaf_size):
+    """CPU restatement of CUGAR's LBVH over the scene's triangles: dict(nodes (Bvh_node_3d records), index, codes)."""
+    n = int(view.num_triangles)
+    nodes = np.zeros(2 * max(n, 1), dtype=NODE_DTYPE)
+    index = np.zeros(max(n, 1), np.uint32); codes = np.zeros(max(n, 1), np.uint64)
+    L = lib()
+    L.oracle_lbvh_build.restype = C.c_int64
+    k = L.oracle_lbvh_build(C.c_void_p(C.addressof(view)), C.c_uint32(max_leaf_size), codes.ctypes.data_as(C.c_void_p), index.ctypes.data_as(C.c_void_p),
+                            nodes.ctypes.data_as(C.c_void_p))
+    return {"nodes": nodes[:k], "index": index[:n], "codes": codes[:n]}
+
+
+def ref_lbvh_lib():
+    """The reference's own Morton functor + host generate_radix_tree (oracle/_ref/libref_lbvh.so), or None."""
+    p = os.path.join(_HERE, "_ref", "libref_lbvh.so")
+    if not os.path.exists(p):
+        return None
+    L = C.CDLL(p)
+    L.ref_radix_tree.restype = C.c_longlong
+    return L
+
+
 def set_trig_mode(mode):
     """0 = libm sinf/cosf (for pinning against oracle/_ref), 1 = fixed-sequence sincos shared with the kernels (default)."""
     lib().oracle_set_trig_mode(int(mode))

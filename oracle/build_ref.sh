@@ -104,3 +104,68 @@ $CXX -O2 -std=c++14 -fPIC -shared -w -ffp-contract=off \
     -I$OV -I$REF/src -I$REF/src/mesh -I$REF/contrib -I/usr/local/cuda/include \
     -o $OUT/libref_bsdf.so $OUT/ref_shim.cpp
 echo "built $OUT/libref_bsdf.so"
+
+# ---- the reference's own LBVH pieces that compile on the host: morton_functor<uint64,3> (contrib/cugar/bits/morton.h)
+# and the host generate_radix_tree (contrib/cugar/radixtree/radixtree_inline.h), writing Bvh_node_3d through the
+# leaf_range_tag writer rule (bintree/bintree_writer.h:129-145). One more overlay patch: linalg/bbox.h:62 says
+# `typedef typename Vector_t vector_type;` (accepted by MSVC only). Pins oracle/lbvh_oracle.cpp.
+sed -E 's/typedef typename Vector_t([[:space:]]+)vector_type;/typedef Vector_t\1vector_type;/' $REF/contrib/cugar/linalg/bbox.h > $OV/cugar/linalg/bbox.h
+cat > $OUT/ref_lbvh_shim.cpp <<'EOF'
+#include <vector>
+#include <algorithm>
+#include <cugar/basic/types.h>
+#include <cugar/basic/numbers.h>
+#include <cugar/linalg/vector.h>
+#include <cugar/linalg/bbox.h>
+#include <cugar/bits/morton.h>
+#include <cugar/bintree/bintree_node.h>
+#include <cugar/bvh/bvh_node.h>
+#include <cugar/radixtree/radixtree.h>
+struct Ctx
+{
+	std::vector<cugar::Bvh_node_3d>* nodes; std::vector<uint2>* ranges;
+	void write_node(const cugar::uint32 node, const cugar::uint32 parent, bool p1, bool p2, const cugar::uint32 offset, const cugar::uint32 skip_node, const cugar::uint32 level, const cugar::uint32 begin, const cugar::uint32 end, const cugar::uint32 split_index)
+	{
+		if (p1 || p2) (*nodes)[node] = cugar::Bintree_node<cugar::leaf_range_tag>(p1, p2, offset, end - begin);
+		else (*nodes)[node] = cugar::Bintree_node<cugar::leaf_range_tag>(begin, end);
+		(*ranges)[node] = make_uint2(begin, end);
+	}
+	void write_leaf(const cugar::uint32, const cugar::uint32 node_index, const cugar::uint32 begin, const cugar::uint32 end) { (*ranges)[node_index] = make_uint2(begin, end); }
+};
+struct Tree
+{
+	typedef Ctx context_type;
+	std::vector<cugar::Bvh_node_3d> nodes; std::vector<uint2> ranges;
+	void reserve_nodes(cugar::uint32 n) { nodes.resize(n); ranges.resize(n); }
+	void reserve_leaves(cugar::uint32) {}
+	Ctx get_context() { Ctx c; c.nodes = &nodes; c.ranges = &ranges; return c; }
+};
+extern "C" void ref_morton60(const float* pts, unsigned n, const float* bb, unsigned long long* codes)
+{
+	const cugar::Bbox3f bbox(cugar::Vector3f(bb[0], bb[1], bb[2]), cugar::Vector3f(bb[3], bb[4], bb[5]));
+	const cugar::morton_functor<cugar::uint64, 3u, cugar::Bbox3f> mf(bbox);
+	for (unsigned i = 0; i < n; ++i) codes[i] = mf(cugar::Vector3f(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]));
+}
+// radix tree over sorted codes: nodes_out 2 u32 per node, ranges_out (begin, end) per node; returns the node count
+extern "C" long long ref_radix_tree(const unsigned long long* codes_in, unsigned n, unsigned max_leaf, unsigned* nodes_out, unsigned* ranges_out)
+{
+	std::vector<cugar::uint64> codes(codes_in, codes_in + n);
+	Tree tree;
+	cugar::generate_radix_tree(n, &codes[0], 60u, max_leaf, false, true, tree);
+	unsigned count = 1;
+	for (unsigned i = 0; i < count; ++i)
+	{
+		const cugar::Bvh_node_3d nd = tree.nodes[i];
+		if (!nd.is_leaf()) count = std::max(count, nd.get_child_index() + 2u);
+		nodes_out[2 * i] = ((const unsigned*)&nd)[0]; nodes_out[2 * i + 1] = ((const unsigned*)&nd)[1];
+		ranges_out[2 * i] = tree.ranges[i].x; ranges_out[2 * i + 1] = tree.ranges[i].y;
+	}
+	return count;
+}
+EOF
+$CXX -O2 -std=c++14 -fPIC -shared -w -fpermissive -ffp-contract=off \
+    -include $OV/ref_prefix.h \
+    -DFERMAT_API_EXTERN= -DTHRUST_DEVICE_SYSTEM=THRUST_DEVICE_SYSTEM_CPP \
+    -I$OV -I$REF/src -I$REF/contrib -I/usr/local/cuda/include \
+    -o $OUT/libref_lbvh.so $OUT/ref_lbvh_shim.cpp
+echo "built $OUT/libref_lbvh.so"

@@ -1,0 +1,194 @@
+"""CUGAR-format LBVH: the oracle against vectors produced by the REFERENCE'S OWN Morton functor and
+host generate_radix_tree (tools/make_golden_lbvh.py -> tests/golden/lbvh_golden.npz), then the device builder against the
+oracle, bit for bit, and the property the traversal rests on: hits do not depend on which tree is traversed."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import CACHE, GOLDEN, cornell_args
+
+
+def _cases():
+    g = np.load(os.path.join(GOLDEN, "lbvh_golden.npz"))
+    for k in range(int(g["n_cases"])):
+        yield k, {n: g["%s_%d" % (n, k)] for n in ("pts", "bbox", "leaf", "codes", "nodes", "ranges")}
+
+
+def test_oracle_morton_and_radix_tree_match_the_reference_vectors(oracle):
+    seen = 0
+    for k, c in _cases():
+        codes = oracle.morton60(c["pts"], c["bbox"])
+        assert (codes == c["codes"]).all(), "Morton codes of case %d differ from the reference's functor" % k
+        nodes, ranges, parents = oracle.radix_tree(np.sort(codes, kind="stable"), int(c["leaf"]))
+        assert nodes.shape == c["nodes"].shape, "case %d: node count" % k
+        assert (nodes == c["nodes"]).all() and (ranges == c["ranges"]).all(), "case %d: tree differs from the reference's" % k
+        seen += 1
+    assert seen >= 9
+
+
+def test_live_reference_radix_tree_if_built(oracle):
+    R = oracle.ref_lbvh_lib()
+    if R is None:
+        pytest.skip("oracle/_ref/libref_lbvh.so not built (no /root/reference on this machine)")
+    rng = np.random.default_rng(5)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    for n, leaf in [(5000, 1), (20000, 3), (777, 4)]:
+        pts = (rng.normal(size=(n, 3)) * 0.1 + 0.5).astype(np.float32)
+        bb = np.concatenate([pts.min(0), pts.max(0)]).astype(np.float32)
+        ref_codes = np.zeros(n, np.uint64)
+        R.ref_morton60(vp(pts), C.c_uint32(n), vp(bb), vp(ref_codes))
+        assert (oracle.morton60(pts, bb) == ref_codes).all()
+        s = np.sort(ref_codes, kind="stable")
+        if np.unique(s, return_counts=True)[1].max() > leaf:
+            continue
+        rn = np.zeros((2 * n, 2), np.uint32); rr = np.zeros_like(rn)
+        m = R.ref_radix_tree(vp(s), C.c_uint32(n), C.c_uint32(leaf), vp(rn), vp(rr))
+        nodes, ranges, _ = oracle.radix_tree(s, leaf)
+        assert m == nodes.shape[0] and (nodes == rn[:m]).all() and (ranges == rr[:m]).all()
+
+
+def _check_tree(nodes, ranges, n, leaf):
+    """children adjacent and after their parent, ranges partition, leaves small enough"""
+    assert tuple(ranges[0]) == (0, n)
+    leaves = 0
+    for i in range(nodes.shape[0]):
+        info, size = int(nodes[i, 0]), int(nodes[i, 1])
+        b, e = int(ranges[i, 0]), int(ranges[i, 1])
+        assert size == e - b
+        if info & 3:
+            assert info & 3 == 3
+            c = info >> 2
+            assert c > i and c + 1 < nodes.shape[0]
+            assert ranges[c, 0] == b and ranges[c, 1] == ranges[c + 1, 0] and ranges[c + 1, 1] == e
+            assert ranges[c, 1] > b and ranges[c, 1] < e
+        else:
+            assert info >> 2 == b and size <= max(leaf, 1)
+            leaves += size
+    assert leaves == n
+
+
+def test_runs_of_equal_codes_are_split_in_the_middle(oracle):
+    # the device kernel's rule (radixtree/cuda/radixtree_inline.h:175,199-203), which the host twin lacks
+    codes = np.sort(np.repeat(np.array([5, 9, 9 << 30, (9 << 30) + 1], np.uint64), [1, 37, 64, 3]))
+    for leaf in (1, 2, 3):
+        nodes, ranges, parents = oracle.radix_tree(codes, leaf)
+        _check_tree(nodes, ranges, codes.size, leaf)
+        # the node holding exactly the run of 64 equal codes splits into 32 + 32
+        i = [k for k in range(nodes.shape[0]) if tuple(ranges[k]) == (38, 102)][0]
+        c = int(nodes[i, 0]) >> 2
+        assert tuple(ranges[c]) == (38, 70) and tuple(ranges[c + 1]) == (70, 102)
+    nodes, ranges, _ = oracle.radix_tree(np.zeros(0, np.uint64), 1)         # empty input: one empty leaf
+    assert nodes.shape[0] == 1 and tuple(nodes[0]) == (0, 0)
+
+
+def test_oracle_lbvh_on_the_cornell_box(oracle, cornell_scene):
+    v = cornell_scene.view
+    n = int(v.num_triangles)
+    for leaf in (1, 3):
+        t = oracle.lbvh_build(v, leaf)
+        nodes = t["nodes"]
+        assert sorted(t["index"].tolist()) == list(range(n))
+        assert (np.diff(t["codes"].astype(np.int64)) >= 0).all()
+        raw = np.stack([nodes["packed_info"], nodes["range_size"]], 1)
+        _, ranges, _ = oracle.radix_tree(t["codes"], leaf)
+        _check_tree(raw, ranges, n, leaf)
+        # boxes: every triangle inside its leaf's box, children inside their parent
+        vi = np.ctypeslib.as_array(v.vertex_indices, (n, 4)); vd = np.ctypeslib.as_array(v.vertex_data, (int(v.num_vertices), 4))
+        for i, nd in enumerate(nodes):
+            if nd["packed_info"] & 3:
+                c = int(nd["packed_info"]) >> 2
+                for cc in (c, c + 1):
+                    assert (nodes[cc]["bmin"] >= nd["bmin"]).all() and (nodes[cc]["bmax"] <= nd["bmax"]).all()
+            else:
+                for j in range(int(ranges[i, 0]), int(ranges[i, 1])):
+                    p = vd[vi[t["index"][j], :3], :3]
+                    assert (p >= nd["bmin"]).all() and (p <= nd["bmax"]).all()
+        root = nodes[0]
+        assert np.allclose(root["bmin"], list(v.bbox_min)) and np.allclose(root["bmax"], list(v.bbox_max))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# device builder
+# ---------------------------------------------------------------------------------------------------------
+def _same_tree(dev, ora):
+    assert dev["nodes"].shape == ora["nodes"].shape
+    assert (dev["codes"] == ora["codes"]).all()
+    assert (dev["index"] == ora["index"]).all()
+    assert dev["nodes"].tobytes() == ora["nodes"].tobytes(), "device LBVH differs from the oracle's"
+
+
+@pytest.mark.gpu
+def test_device_lbvh_is_bit_identical_to_the_oracle(fb, oracle):
+    sc = fb.Scene(cornell_args(64, 4))
+    rc = fb.RenderingContext(sc, 0)
+    for leaf in (1, 2, 3, 8):
+        _same_tree(rc.build_lbvh(leaf, want_codes=True), oracle.lbvh_build(sc.view, leaf))
+    rc.close(); sc.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scene", ["cornellbox_glossy", "water_caustic", "bathroom2"])
+def test_device_lbvh_on_big_scenes(fb, oracle, scene):
+    path = os.path.join(CACHE, scene + ".fbs")
+    if not fb.scene_available(path):
+        pytest.skip("scene snapshot %s not present" % scene)
+    sc = fb.Scene(["-i", path, "-r", "64", "64", "-bounces", "2"])
+    rc = fb.RenderingContext(sc, 0)
+    dev = rc.build_lbvh(3, want_codes=True)
+    _same_tree(dev, oracle.lbvh_build(sc.view, 3))
+    again = rc.build_lbvh(3, want_codes=True)                  # bit-reproducible from run to run
+    assert again["nodes"].tobytes() == dev["nodes"].tobytes() and (again["index"] == dev["index"]).all()
+    rc.close(); sc.close()
+
+
+@pytest.mark.gpu
+def test_adopted_lbvh_gives_the_same_hits_and_the_same_image(fb, oracle):
+    """Closest hits are defined by the triangles alone (ties go to the smaller triangle id), so swapping the SAH tree
+    built on the host for the LBVH built on the device must not change a single bit of the hits or of a rendered frame."""
+    path = os.path.join(CACHE, "cornellbox_glossy.fbs")
+    args = ["-i", path, "-r", "96", "96", "-bounces", "4"] if fb.scene_available(path) else cornell_args(96, 4)
+    sc = fb.Scene(args)
+    rc = fb.RenderingContext(sc, 0)
+    rng = np.random.default_rng(3)
+    n = 20000
+    lo, hi = np.array(list(sc.view.bbox_min)), np.array(list(sc.view.bbox_max))
+    rays = np.zeros((n, 8), np.float32)
+    rays[:, 0:3] = lo + rng.random((n, 3)) * (hi - lo)
+    rays[:, 4:7] = rng.normal(size=(n, 3))
+    rays[:, 3] = 1e-4; rays[:, 7] = 1e30
+    hits_sah = rc.trace(rays)
+    rc.clear()
+    for i in range(3):
+        rc.render(i)
+    img_sah = rc.download()
+    sah_stats = sc.bvh_stats()
+
+    t = rc.build_lbvh(3, adopt=True)
+    lbvh_stats = sc.bvh_stats()
+    assert lbvh_stats["bvh2_nodes"] == t["nodes"].shape[0] and sah_stats["bvh2_nodes"] > 0
+    hits_lbvh = rc.trace(rays)
+    assert hits_lbvh.tobytes() == hits_sah.tobytes()
+    ohits, _, _ = oracle.trace(sc.view, rays)                   # the oracle now walks the adopted LBVH too
+    assert ohits.tobytes() == hits_lbvh.tobytes()
+    rc.clear()
+    for i in range(3):
+        rc.render(i)
+    assert rc.download().tobytes() == img_sah.tobytes()
+    rc.close(); sc.close()
+
+
+@pytest.mark.gpu
+def test_bvh_lbvh_command_line_option(fb, oracle):
+    sc = fb.Scene(cornell_args(64, 4, ["-bvh", "lbvh"]))
+    assert sc.bvh_stats()["bvh2_nodes"] == 0                    # nothing is built on the host
+    rc = fb.RenderingContext(sc, 0)
+    assert sc.bvh_stats()["bvh2_nodes"] > 0
+    ref = fb.Scene(cornell_args(64, 4))
+    rr = fb.RenderingContext(ref, 0)
+    for c in (rc, rr):
+        c.clear(); c.render(0)
+    assert rc.download().tobytes() == rr.download().tobytes()
+    for o in (rc, rr, sc, ref):
+        o.close()
