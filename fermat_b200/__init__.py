@@ -101,6 +101,11 @@ def lib():
         "fb200_context_set_profiling": (i32, [vp, i32]),
         "fb200_context_get_kernel_times": (i32, [vp, C.POINTER(C.c_double * 4), C.POINTER(u64 * 4)]),
         "fb200_context_owned_pixels": (u64, [vp]),
+        "fb200_context_filter": (i32, [vp, u32]),
+        "fb200_context_to_rgba": (i32, [vp, u32, vp]),
+        "fb200_context_rgba_device_ptr": (vp, [vp]),
+        "fb200_scene_get_tonemap": (i32, [vp, pf, pf]),
+        "fb200_write_tga": (i32, [C.c_char_p, u32, u32, vp]),
         "fb200_context_build_lbvh": (C.c_int64, [vp, u32, i32, vp, u64, C.POINTER(u32), C.POINTER(u64), pf]),
         "fb200_trace": (i32, [vp, pf, pf, u32]),
         "fb200_trace_shadow": (i32, [vp, pf, C.POINTER(C.c_uint8), u32]),
@@ -162,6 +167,13 @@ def resolve_scene(path):
     return out
 
 
+def write_tga(filename, rgba):
+    """cugar::write_tga(..., TGAPixels::RGBA): 24-bit BGR file from an (H, W, 4) uint8 image."""
+    img = np.ascontiguousarray(rgba, dtype=np.uint8)
+    if lib().fb200_write_tga(str(filename).encode(), img.shape[1], img.shape[0], img.ctypes.data_as(C.c_void_p)) != 0:
+        raise RuntimeError(_err())
+
+
 def scene_available(path):
     return os.path.exists(str(path)) or os.path.exists(str(path) + ".xz")
 
@@ -191,6 +203,12 @@ class Scene:
         sah = C.c_float()
         lib().fb200_scene_bvh_stats(self._h, C.byref(out), C.byref(sah))
         return {"wide_nodes": out[0], "triangles": out[1], "max_depth": out[2] & 0xFFFFFFFF, "max_stack": out[2] >> 32, "bvh2_nodes": out[3], "sah_cost": sah.value}
+
+    def tonemap(self):
+        """(exposure, gamma) of the scene's film."""
+        e, g = C.c_float(), C.c_float()
+        lib().fb200_scene_get_tonemap(self._h, C.byref(e), C.byref(g))
+        return e.value, g.value
 
     def save_snapshot(self, filename):
         if lib().fb200_scene_save_snapshot(self._h, str(filename).encode()) != 0:
@@ -315,6 +333,17 @@ class RenderingContext:
 
     def owned_pixels(self):
         return int(lib().fb200_context_owned_pixels(self._h))
+
+    def filter(self, instance):
+        """RenderingContext::filter: EAW-denoise DIFFUSE_C / SPECULAR_C of the pass just rendered into FILTERED_C."""
+        self._chk(lib().fb200_context_filter(self._h, int(instance)))
+
+    def to_rgba(self, mode=0):
+        """to_rgba into an (H, W, 4) uint8 array; mode = the reference's ShadingMode value (0 shaded, 10 filtered, ...)."""
+        w, h = self.res()
+        out = np.zeros((h, w, 4), dtype=np.uint8)
+        self._chk(lib().fb200_context_to_rgba(self._h, int(mode), out.ctypes.data_as(C.c_void_p)))
+        return out
 
     def build_lbvh(self, max_leaf_size=1, adopt=False, want_codes=False):
         """Build the scene BVH on the device with CUGAR's LBVH (include/fermat_b200.h). Returns dict(nodes = structured

@@ -126,6 +126,15 @@ int fb200_context_get_kernel_times(fb200_context* c, double out_ms[4], uint64_t 
 void* fb200_context_stream(fb200_context* c) { return (void*)c->rc.stream(); }
 uint64_t fb200_context_owned_pixels(const fb200_context* c) { return static_cast<PathTracer*>(const_cast<fb200_context*>(c)->rc.renderer())->owned_pixels(); }
 
+int fb200_context_filter(fb200_context* c, uint32_t instance) { return guarded([&] { c->rc.filter(instance); }); }
+int fb200_context_to_rgba(fb200_context* c, uint32_t mode, uint8_t* host_rgba) { return guarded([&] { c->rc.to_rgba(mode, host_rgba); }); }
+void* fb200_context_rgba_device_ptr(fb200_context* c)
+{
+	void* p = NULL;
+	guarded([&] { p = c->rc.get_device_rgba_buffer(); });
+	return p;
+}
+
 int64_t fb200_context_build_lbvh(fb200_context* c, uint32_t max_leaf_size, int adopt, void* nodes, uint64_t node_capacity, uint32_t* index, uint64_t* codes, float* device_ms)
 {
 	int64_t count = -1;

@@ -2,6 +2,8 @@
 #include "pt_scene.h"
 #include <stdexcept>
 #include <string>
+#include <vector>
+#include <stdio.h>
 
 namespace fb {
 static thread_local std::string g_last_error;
@@ -51,6 +53,35 @@ int fb200_scene_bvh_stats(const fb200_scene* s, uint64_t out[4], float* sah_cost
 	if (!s || !out) { fb::set_last_error("null argument"); return -1; }
 	out[0] = s->wide.nodes.size(); out[1] = s->wide.tris.size(); out[2] = s->wide.max_depth | ((uint64_t)s->wide.max_stack << 32); out[3] = s->bvh2.nodes.size();
 	if (sah_cost) *sah_cost = s->bvh2.sah_cost;
+	return 0;
+}
+
+int fb200_scene_get_tonemap(const fb200_scene* s, float* exposure, float* gamma)
+{
+	if (!s) { fb::set_last_error("null argument"); return -1; }
+	if (exposure) *exposure = s->scene.exposure;
+	if (gamma) *gamma = s->scene.gamma;
+	return 0;
+}
+
+int fb200_write_tga(const char* filename, uint32_t width, uint32_t height, const uint8_t* rgba)
+{
+	if (!filename || !rgba || width > 65535u || height > 65535u) { fb::set_last_error("fb200_write_tga: bad argument"); return -1; }
+	FILE* f = fopen(filename, "wb");
+	if (!f) { fb::set_last_error(std::string("fb200_write_tga: cannot open ") + filename); return -1; }
+	// 18-byte header: uncompressed true colour (type 2), 24 bits, origin bottom-left (descriptor 0)
+	unsigned char hd[18] = { 0 };
+	hd[2] = 2; hd[12] = width & 0xFF; hd[13] = (width >> 8) & 0xFF; hd[14] = height & 0xFF; hd[15] = (height >> 8) & 0xFF; hd[16] = 24;
+	bool ok = fwrite(hd, 1, 18, f) == 18;
+	std::vector<unsigned char> row((size_t)width * 3);
+	for (uint32_t y = 0; y < height && ok; ++y)
+	{
+		const uint8_t* src = rgba + (size_t)y * width * 4;
+		for (uint32_t x = 0; x < width; ++x) { row[3 * x] = src[4 * x + 2]; row[3 * x + 1] = src[4 * x + 1]; row[3 * x + 2] = src[4 * x]; }   // RGBA -> BGR
+		ok = fwrite(row.data(), 1, row.size(), f) == row.size();
+	}
+	fclose(f);
+	if (!ok) { fb::set_last_error(std::string("fb200_write_tga: short write to ") + filename); return -1; }
 	return 0;
 }
 

@@ -1,7 +1,8 @@
 // main.cpp — headless batch front end with the reference's command line (reference src/main.cu:100-218):
 //   fermat_pt -pt -i scene.{fa,obj,fbs} [-r W H] [-c camera.txt] [-bounces N] [-passes P] [-o out] [-device D]
 // Renders passes 0..P inclusive (the reference's loop is inclusive: `-passes 1023` = 1024 spp, main.cu:167),
-// writes <out>.tga (tone-mapped, exposure*c/(1+c), gamma 2.2 — to_rgba_kernel, src/renderer.cu:83-282) and
+// writes <out>.tga (to_rgba on the device: exposure, c/(1+c), gamma — src/renderer.cu:83-282; `-filtered` runs the EAW
+// denoiser first and saves FILTERED_C, src/renderer.cu:1099-1160) and
 // <out>.pfm (linear COMPOSITED_C), prints Msamples/s.
 #include "rendering_context.h"
 #include <stdio.h>
@@ -44,27 +45,13 @@ int main(int argc, char** argv)
 			}
 		}
 		{
-			FILE* f = fopen((out + ".tga").c_str(), "wb");
-			if (f)
-			{
-				unsigned char hd[18] = { 0 };
-				hd[2] = 2; hd[12] = res.x & 0xFF; hd[13] = (res.x >> 8) & 0xFF; hd[14] = res.y & 0xFF; hd[15] = (res.y >> 8) & 0xFF; hd[16] = 24;
-				fwrite(hd, 1, 18, f);
-				std::vector<unsigned char> row(res.x * 3);
-				for (uint32_t y = 0; y < res.y; ++y)
-				{
-					for (uint32_t x = 0; x < res.x; ++x)
-						for (int c = 0; c < 3; ++c)
-						{
-							float v = img[((size_t)y * res.x + x) * 4 + c] * s.scene.exposure;
-							v = v / (1.0f + v);
-							v = powf(v < 0.0f ? 0.0f : v, 1.0f / s.scene.gamma);
-							row[x * 3 + (2 - c)] = (unsigned char)(v >= 1.0f ? 255 : v * 255.0f);
-						}
-					fwrite(row.data(), 1, row.size(), f);
-				}
-				fclose(f);
-			}
+			// RenderingContext::render's tail (src/renderer.cu:1045-1049): optional EAW filter, then to_rgba; main.cu:171-183 saves it
+			bool filtered = false;
+			for (int i = 0; i < argc; ++i) if (strcmp(argv[i], "-filtered") == 0) filtered = true;
+			if (filtered) rc.filter((uint32_t)n_passes);
+			std::vector<uint8_t> rgba((size_t)res.x * res.y * 4);
+			rc.to_rgba(filtered ? fb::SHADING_FILTERED : fb::SHADING_SHADED, rgba.data());
+			if (fb200_write_tga((out + ".tga").c_str(), res.x, res.y, rgba.data()) != 0) fprintf(stderr, "warning: %s\n", fb200_last_error());
 		}
 		for (int i = 0; i + 1 < argc; ++i)
 			if (strcmp(argv[i], "-benchmark") == 0)

@@ -357,3 +357,87 @@ uint32_t RenderingContext::build_lbvh(uint32_t max_leaf_size, bool adopt, std::v
 	}
 	return n_nodes;
 }
+
+// camera_frame (reference src/camera.h:142-163)
+static void camera_frame(const Camera& c, const float aspect, V3& U, V3& V, V3& W)
+{
+	W = V3(c.aim) - V3(c.eye);
+	const float wlen = sqrtf(dot(W, W));
+	U = normalize(cross(W, V3(c.up)));
+	V = normalize(cross(U, W));
+	const float ulen = wlen * tanf(c.fov / 2.0f);
+	U = V3(U.x * ulen, U.y * ulen, U.z * ulen);
+	const float vlen = ulen / aspect;
+	V = V3(V.x * vlen, V.y * vlen, V.z * vlen);
+}
+
+void RenderingContext::filter(const uint32_t instance)
+{
+	const FrameBufferView fbv = m_fb.view();
+	const uint32 rx = m_scene->res_x, ry = m_scene->res_y;
+	const size_t P = (size_t)rx * ry;
+	if (!m_normals.ptr)
+	{
+		for (int i = 0; i < 4; ++i) m_fb_temp[i].alloc(P * sizeof(float4));
+		for (int i = 0; i < 2; ++i) m_var[i].alloc(P * sizeof(float));
+		m_normals.alloc(P * sizeof(float4));
+	}
+	cudaStream_t s = stream();
+	// "clear the output filter": FILTERED_C = DIRECT_C (src/renderer.cu:1101-1102)
+	cuda_check(cudaMemcpyAsync(fbv.channels[FB_FILTERED_C], fbv.channels[FB_DIRECT_C], P * sizeof(float4), cudaMemcpyDeviceToDevice, s), "filter: copy");
+	cuda_check(launch_unpack_gbuffer(fbv, m_normals.as<float4>(), s), "unpack_gbuffer");
+
+	EawParams p;
+	p.phi_normal = 2.0f; p.phi_position = 1.0f;
+	p.phi_color = float(instance * instance + 1) / 10000.0f;      // (uint32 arithmetic, as in the reference :1118)
+	p.w_min = 1.0e-4f;
+	V3 U, V, W;
+	camera_frame(m_scene->scene.camera, m_scene->aspect, U, V, W);
+	const Camera& cam = m_scene->scene.camera;
+	p.E[0] = cam.eye.x; p.E[1] = cam.eye.y; p.E[2] = cam.eye.z;
+	p.U[0] = U.x; p.U[1] = U.y; p.U[2] = U.z; p.V[0] = V.x; p.V[1] = V.y; p.V[2] = V.z; p.W[0] = W.x; p.W[1] = W.y; p.W[2] = W.z;
+
+	EawChannels<2> ch;
+	const int input[2] = { FB_DIFFUSE_C, FB_SPECULAR_C }, weight[2] = { FB_DIFFUSE_A, FB_SPECULAR_A };
+	for (int c = 0; c < 2; ++c) { ch.img[c] = fbv.channels[input[c]]; ch.w_img[c] = fbv.channels[weight[c]]; ch.var[c] = m_var[c].as<float>(); ch.src[c] = NULL; ch.dst[c] = NULL; }
+	cuda_check(launch_filter_variance2(ch, rx, ry, 2, s), "filter_variance");
+	kernel_launches += 2;
+
+	// iteration schedule of EAW(n_iterations, dst, w_img, img, ...) (src/eaw.cu:320-368), both channels per launch
+	const uint32 n_iterations = 7;
+	uint32 in_buffer = 0;
+	for (uint32 i = 0; i < n_iterations; ++i)
+	{
+		const uint32 out_buffer = in_buffer ? 0 : 1;
+		for (int c = 0; c < 2; ++c)
+		{
+			ch.src[c] = i == 0 ? fbv.channels[input[c]] : m_fb_temp[2 * c + in_buffer].as<float4>();
+			ch.dst[c] = i == n_iterations - 1 ? fbv.channels[FB_FILTERED_C] : m_fb_temp[2 * c + out_buffer].as<float4>();
+		}
+		const int mode = i == n_iterations - 1 ? 2 : (i == 0 ? 1 : 0);
+		cuda_check(launch_eaw2(mode, ch, fbv.gb_geo, m_normals.as<float4>(), p, rx, ry, 1u << i, s), "EAW");
+		kernel_launches++;
+		in_buffer = out_buffer;
+	}
+}
+
+uint8_t* RenderingContext::get_device_rgba_buffer()
+{
+	if (!m_rgba.ptr) m_rgba.alloc((size_t)m_scene->res_x * m_scene->res_y * 4);
+	return m_rgba.as<uint8_t>();
+}
+
+void RenderingContext::to_rgba(uint32_t mode, uint8_t* host_rgba)
+{
+	uint8_t* d = get_device_rgba_buffer();
+	cudaStream_t s = stream();
+	// pixels of modes the kernel does not write stay zero
+	cuda_check(cudaMemsetAsync(d, 0, m_rgba.bytes, s), "memset rgba");
+	cuda_check(launch_to_rgba(m_fb.view(), mode, m_scene->scene.exposure, m_scene->scene.gamma, reinterpret_cast<uchar4*>(d), s), "to_rgba");
+	kernel_launches++;
+	if (host_rgba)
+	{
+		cuda_check(cudaMemcpyAsync(host_rgba, d, m_rgba.bytes, cudaMemcpyDeviceToHost, s), "rgba download");
+		synchronize();
+	}
+}

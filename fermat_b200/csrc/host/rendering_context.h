@@ -8,6 +8,7 @@
 #include "../kernels/device_scene.h"
 #include "../kernels/pt_kernels.h"
 #include "../kernels/lbvh_kernels.h"
+#include "../kernels/post_kernels.h"
 #include <cuda_runtime.h>
 #include <vector>
 #include <string>
@@ -104,6 +105,13 @@ struct RenderingContext
 	// then leaves the current tree in place.
 	uint32_t                build_lbvh(uint32_t max_leaf_size, bool adopt, std::vector<fb::Bvh2Node>* nodes, std::vector<uint32_t>* index,
 									   std::vector<uint64_t>* codes, float* device_ms);
+	// RenderingContext::filter (src/renderer.cu:1099-1160): FILTERED_C = DIRECT_C + albedo-modulated EAW-filtered
+	// DIFFUSE_C and SPECULAR_C (7 a-trous iterations, variance-guided). Needs the G-buffer of the pass just rendered.
+	void                    filter(const uint32_t instance);
+	// to_rgba (src/renderer.cu:83-282): tone-map / visualise into the context's 8-bit RGBA buffer (get_device_rgba_buffer),
+	// optionally copying it to the host (4 bytes per pixel). `mode`: fb::ShadingMode = the reference's ShadingMode values.
+	void                    to_rgba(uint32_t mode, uint8_t* host_rgba);
+	uint8_t*                get_device_rgba_buffer();
 	uint64_t                kernel_launches;
 
 private:
@@ -135,6 +143,9 @@ private:
 					 d_texture_views, d_nodes, d_tris, d_vpls, d_mesh_cdf, d_mesh_inv_area, d_dir_lights,
 					 d_glossy, d_shifts_t;
 	std::vector<fb::DeviceBuffer*> d_textures;
+	// post-processing scratch (allocated on first use): 2 ping-pong images per filtered channel, filtered variances,
+	// unpacked normals, 8-bit output
+	fb::DeviceBuffer m_fb_temp[4], m_var[2], m_normals, m_rgba;
 };
 
 // the `-pt` renderer (reference src/renderers/pathtracer.h:265-305)

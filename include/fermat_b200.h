@@ -133,6 +133,13 @@ int      fb200_diag_msvc_rand(uint32_t seed, int32_t* out, uint32_t n);
  * fb200_trace): validates the BVH collapse and measures tree quality without a GPU. Never used for rendering. */
 int      fb200_diag_wide_trace(const fb200_scene*, const float* rays, float* hits, uint32_t n, uint64_t* nodes_visited, uint64_t* tris_tested);
 
+/* film exposure and gamma of the scene (RenderingContext's m_exposure / m_gamma, src/renderer.cu:715-717; 1 and 2.2
+ * unless a pbrt film sets them) */
+int fb200_scene_get_tonemap(const fb200_scene*, float* exposure, float* gamma);
+/* cugar::write_tga with TGAPixels::RGBA (contrib/cugar/image/tga.cpp:133-185): 24-bit uncompressed BGR, rows in buffer
+ * order. Returns 0 on success. */
+int fb200_write_tga(const char* filename, uint32_t width, uint32_t height, const uint8_t* rgba);
+
 /* --- rendering context (needs a CUDA device; fails loudly without one) ------------------------ */
 
 /* RenderingContext::init + PathTracer::init (src/renderer.cu:467-991, src/renderers/pathtracer_impl.h:99-178)
@@ -177,6 +184,21 @@ int fb200_context_get_kernel_times(fb200_context*, double out_ms[4], uint64_t ou
 void* fb200_context_stream(fb200_context*);
 /* number of pixels this shard owns */
 uint64_t fb200_context_owned_pixels(const fb200_context*);
+
+/* RenderingContext::filter (src/renderer.cu:1099-1160): the Edge-Avoiding A-trous Wavelet denoiser (src/eaw.cu:36-368,
+ * filter_variance src/renderer.cu:366-399). FILTERED_C = DIRECT_C + DIFFUSE_A * eaw(DIFFUSE_C / DIFFUSE_A) +
+ * SPECULAR_A * eaw(SPECULAR_C / SPECULAR_A), 7 iterations, guided by the G-buffer of the pass just rendered and by the
+ * running variance estimates in the channels' .w. `instance` sets phi_color = (instance^2 + 1) / 10000. Asynchronous on
+ * the context's stream. */
+int fb200_context_filter(fb200_context*, uint32_t instance);
+/* to_rgba (src/renderer.cu:83-282) into the context's 8-bit RGBA buffer: exposure, c/(1+c), gamma, min(c*256, 255) for
+ * the colour modes; albedo / variance / uv / normal visualisations as in the reference. `shading_mode` takes the
+ * reference's ShadingMode values (src/renderer_view.h:62-77: 0 shaded, 1 uv, 4 albedo, 5 diffuse albedo, 6 specular
+ * albedo, 7 diffuse colour, 8 specular colour, 9 direct lighting, 10 filtered, 11 variance, 12 normal); modes the
+ * reference's kernel ignores leave the buffer zero. host_rgba: NULL, or room for 4*res_x*res_y bytes (blocking copy). */
+int fb200_context_to_rgba(fb200_context*, uint32_t shading_mode, uint8_t* host_rgba);
+/* device pointer of that RGBA buffer (RenderingContext::get_device_rgba_buffer, src/renderer.h) */
+void* fb200_context_rgba_device_ptr(fb200_context*);
 
 /* Scene BVH built ON THE DEVICE by CUGAR's LBVH algorithm: 60-bit Morton codes of the triangle-box centres in the
  * scene's bounding box, radix sort, radix tree with middle splits for runs of equal codes, Bvh_node_3d output

@@ -166,6 +166,49 @@ def ref_lbvh_lib():
     return L
 
 
+def filter_variance(img, fw):
+    """filter_variance_kernel: box mean (radius fw, clamped at the borders) of img[..., 3]."""
+    img = np.ascontiguousarray(img, dtype=np.float32)
+    h, w = img.shape[:2]
+    var = np.zeros((h, w), np.float32)
+    lib().oracle_filter_variance(img.ctypes.data_as(C.c_void_p), C.c_int(w), C.c_int(h), C.c_uint32(fw), var.ctypes.data_as(C.c_void_p))
+    return var
+
+
+def camera_frame(view):
+    """camera_frame (src/camera.h:142-163) of the scene view, in float32 like the host code: (E, U, V, W) as 12 floats."""
+    f = np.float32
+    eye, aim, up = (np.array(list(x), f) for x in (view.eye, view.aim, view.up))
+    W = aim - eye
+    wlen = np.sqrt(f(np.dot(W, W)))
+    U = np.cross(W, up).astype(f); U = (U / np.sqrt(f(np.dot(U, U)))).astype(f)
+    V = np.cross(U, W).astype(f); V = (V / np.sqrt(f(np.dot(V, V)))).astype(f)
+    ulen = f(wlen * f(np.tan(f(view.fov) / f(2))))
+    vlen = f(ulen / f(view.aspect))
+    return np.concatenate([eye, U * ulen, V * vlen, W]).astype(f)
+
+
+def eaw_filter(fb, geo, cam, instance):
+    """RenderingContext::filter on an (8, H, W, 4) frame buffer (in place: writes channel 6 = FILTERED_C)."""
+    assert fb.dtype == np.float32 and fb.flags["C_CONTIGUOUS"] and fb.shape[0] == 8
+    geo = np.ascontiguousarray(geo, dtype=np.float32)
+    cam = np.ascontiguousarray(cam, dtype=np.float32)
+    h, w = fb.shape[1:3]
+    lib().oracle_filter(fb.ctypes.data_as(C.c_void_p), geo.ctypes.data_as(C.c_void_p), C.c_int(w), C.c_int(h), cam.ctypes.data_as(C.c_void_p), C.c_uint32(instance))
+    return fb[6]
+
+
+def to_rgba(fb, geo, uv, mode, exposure, gamma):
+    """to_rgba_kernel on an (8, H, W, 4) frame buffer + G-buffer planes -> (H, W, 4) uint8."""
+    fb = np.ascontiguousarray(fb, dtype=np.float32)
+    geo = np.ascontiguousarray(geo, dtype=np.float32); uv = np.ascontiguousarray(uv, dtype=np.float32)
+    h, w = fb.shape[1:3]
+    out = np.zeros((h, w, 4), np.uint8)
+    lib().oracle_to_rgba(fb.ctypes.data_as(C.c_void_p), geo.ctypes.data_as(C.c_void_p), uv.ctypes.data_as(C.c_void_p), C.c_uint64(h * w),
+                         C.c_uint32(mode), C.c_float(exposure), C.c_float(gamma), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
 def set_trig_mode(mode):
     """0 = libm sinf/cosf (for pinning against oracle/_ref), 1 = fixed-sequence sincos shared with the kernels (default)."""
     lib().oracle_set_trig_mode(int(mode))

@@ -1,0 +1,171 @@
+"""Post pipeline: EAW denoiser, variance filter, to_rgba, TGA writer. The reference has no vectors for
+these kernels and they are device-only (parity unpinned): the CPU restatement (oracle/post_oracle.cpp, launch by launch in
+the reference's order) is checked by properties here, and the device kernels — which filter both channels per launch and
+unpack normals once — are checked against it within a floating-point tolerance."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import CACHE, cornell_args
+
+MISS = np.frombuffer(b"\xff" * 4, np.float32)[0]
+
+
+def _pack_geo(pos, normal):
+    """GBufferView::pack_geometry (src/framebuffer.h:84-90) in numpy."""
+    n = normal / np.linalg.norm(normal, axis=-1, keepdims=True)
+    phi = np.where(np.abs(n[..., 2]) >= 1.0 - 1e-5, 0.0, np.arctan2(n[..., 1], n[..., 0]))
+    phi = np.where(phi < 0, phi + 2 * np.pi, phi)
+    qx = np.clip((phi / (2 * np.pi) * 32767).astype(np.int64), 0, 32766).astype(np.uint32)
+    qy = np.clip(((n[..., 2] + 1) * 0.5 * 32767).astype(np.int64), 0, 32766).astype(np.uint32)
+    geo = np.zeros(pos.shape[:-1] + (4,), np.float32)
+    geo[..., :3] = pos
+    geo[..., 3] = (qx | (qy << 15)).astype(np.uint32).view(np.float32)
+    return geo
+
+
+def _synthetic(h=24, w=40, seed=0):
+    rng = np.random.default_rng(seed)
+    fb = np.zeros((8, h, w, 4), np.float32)
+    fb[0, ..., :3] = 0.5 + 0.1 * rng.random((h, w, 3)); fb[0, ..., 3] = 0.01 * rng.random((h, w))     # DIFFUSE_C (+ variance in .w)
+    fb[1, ..., :3] = 0.3 + 0.6 * rng.random((h, w, 3))                                                 # DIFFUSE_A
+    fb[2, ..., :3] = 0.2 * rng.random((h, w, 3)); fb[2, ..., 3] = 0.02 * rng.random((h, w))            # SPECULAR_C
+    fb[3, ..., :3] = 0.5 + 0.5 * rng.random((h, w, 3))                                                 # SPECULAR_A
+    fb[4, ..., :3] = rng.random((h, w, 3))                                                             # DIRECT_C
+    ys, xs = np.mgrid[0:h, 0:w]
+    pos = np.stack([xs * 0.05, ys * 0.05, np.full((h, w), -3.0)], -1).astype(np.float32)
+    nrm = np.zeros((h, w, 3), np.float32); nrm[..., 2] = 1.0
+    nrm[:, w // 2:, :] = (1.0, 0.0, 0.0)                                                              # a crease down the middle
+    geo = _pack_geo(pos, nrm)
+    cam = np.array([0, 0, 0, 1.2, 0, 0, 0, 0.8, 0, 0, 0, -1], np.float32)                              # E, U, V, W
+    return fb, geo, cam
+
+
+def test_filter_variance_is_a_clamped_box_mean(oracle):
+    rng = np.random.default_rng(1)
+    img = rng.random((9, 13, 4)).astype(np.float32)
+    var = oracle.filter_variance(img, 2)
+    for (y, x) in [(0, 0), (4, 6), (8, 12), (1, 11)]:
+        win = img[max(y - 2, 0):min(y + 2, 8) + 1, max(x - 2, 0):min(x + 2, 12) + 1, 3]
+        assert abs(var[y, x] - win.astype(np.float64).mean()) < 1e-6
+    assert np.allclose(oracle.filter_variance(np.full((5, 5, 4), 0.25, np.float32), 1), 0.25)
+
+
+def test_eaw_on_misses_is_the_identity(oracle):
+    fb, geo, cam = _synthetic()
+    geo[..., 3] = MISS                     # every primary ray missed: nothing is filtered, demodulate * modulate = input
+    out = oracle.eaw_filter(fb.copy(), geo, cam, 3)
+    want = fb[4] + fb[0] + fb[2]
+    assert np.allclose(out[..., :3], want[..., :3], rtol=2e-6, atol=1e-7)
+
+
+def test_eaw_smooths_within_surfaces_and_stops_at_the_crease(oracle):
+    fb, geo, cam = _synthetic(seed=2)
+    h, w = fb.shape[1:3]
+    fb[1, ..., :3] = 1.0; fb[3, ..., :3] = 1.0                          # unit albedos: FILTERED = DIRECT + eaw(D) + eaw(S)
+    fb[2] = 0.0; fb[4] = 0.0
+    fb[0, :, : w // 2, :3] = 0.2 + 0.02 * np.random.default_rng(3).random((h, w // 2, 3))   # dark left face
+    fb[0, :, w // 2:, :3] = 0.8 + 0.02 * np.random.default_rng(4).random((h, w - w // 2, 3))  # bright right face
+    fb[0, ..., 3] = 1.0                                                 # large variance: colour differences do not stop the filter
+    out = oracle.eaw_filter(fb.copy(), geo, cam, 0)[..., :3]
+    left, right = out[:, : w // 2], out[:, w // 2:]
+    assert left.std() < 0.3 * fb[0, :, : w // 2, :3].std() and right.std() < 0.3 * fb[0, :, w // 2:, :3].std()
+    assert abs(left.mean() - 0.21) < 0.01 and abs(right.mean() - 0.81) < 0.01    # no bleeding across the normal discontinuity
+    # a flat image is a fixed point
+    fb[0, ..., :3] = 0.5
+    assert np.allclose(oracle.eaw_filter(fb.copy(), geo, cam, 5)[..., :3], 0.5, atol=1e-6)
+
+
+def test_to_rgba_modes(oracle):
+    fb, geo, cam = _synthetic(seed=5)
+    uv = np.random.default_rng(6).random(geo.shape).astype(np.float32)
+    fb[5, ..., :3] = fb[4, ..., :3] * 3.0
+    img = oracle.to_rgba(fb, geo, uv, 0, 1.5, 2.2)
+    c = fb[5].astype(np.float64) * 1.5
+    want = np.minimum(((c / (c + 1)) ** (1 / 2.2)) * 256, 255).astype(np.uint8)
+    assert np.abs(img.astype(int) - want.astype(int)).max() <= 1
+    assert (oracle.to_rgba(fb, geo, uv, 5, 1.0, 2.2) == np.minimum(fb[1] * 256, 255).astype(np.uint8)).all()     # diffuse albedo
+    assert (oracle.to_rgba(fb, geo, uv, 2, 1.0, 2.2) == 0).all()                # kUVStretch: the reference's kernel has no branch
+    n = oracle.to_rgba(fb, geo, uv, 12, 1.0, 2.2)                               # normals: +z on the left, +x on the right
+    h, w = n.shape[:2]
+    # (the 2x15-bit packing clamps to 32766/32767: +z comes back tilted by about 0.6 degrees)
+    assert np.abs(n[0, 0, :3].astype(int) - (128, 128, 255)).max() <= 2 and np.abs(n[0, w - 1, :3].astype(int) - (255, 128, 128)).max() <= 2
+    u = oracle.to_rgba(fb, geo, uv, 1, 1.0, 2.2)
+    assert (u[..., 0] == np.minimum(uv[..., 2] * 256, 255).astype(np.uint8)).all() and (u[..., 2] == 128).all()
+
+
+def test_write_tga_layout(fb, tmp_path):
+    img = np.zeros((3, 5, 4), np.uint8)
+    img[..., 0] = 10; img[..., 1] = 20; img[..., 2] = 30; img[..., 3] = 40
+    img[2, 4, :3] = (1, 2, 3)
+    f = tmp_path / "t.tga"
+    fb.write_tga(f, img)
+    raw = f.read_bytes()
+    assert len(raw) == 18 + 3 * 5 * 3
+    assert raw[2] == 2 and raw[12] == 5 and raw[14] == 3 and raw[16] == 24 and raw[17] == 0
+    assert raw[18:21] == bytes([30, 20, 10]) and raw[-3:] == bytes([3, 2, 1])      # BGR, rows in buffer order
+    with pytest.raises(RuntimeError):
+        fb.write_tga(tmp_path / "no_such_dir" / "x.tga", img)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# device
+# ---------------------------------------------------------------------------------------------------------
+def _render(fb, args, passes):
+    sc = fb.Scene(args)
+    rc = fb.RenderingContext(sc, 0)
+    rc.clear()
+    for i in range(passes):
+        rc.render(i)
+    return sc, rc
+
+
+def _download_all(fb, rc):
+    chans = np.stack([rc.download(c) for c in range(8)], 0)
+    return np.ascontiguousarray(chans), rc.download_gbuffer()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scene,res", [("cornell", 96), ("cornellbox_glossy", 128)])
+def test_device_eaw_matches_the_restatement(fb, oracle, scene, res):
+    if scene == "cornell":
+        args = cornell_args(res, 4)
+    else:
+        path = os.path.join(CACHE, scene + ".fbs")
+        if not fb.scene_available(path):
+            pytest.skip("scene snapshot %s not present" % scene)
+        args = ["-i", path, "-r", str(res), str(res - 32), "-bounces", "4"]       # non-square, not a multiple of the tile
+    passes = 4
+    sc, rc = _render(fb, args, passes)
+    chans, gb = _download_all(fb, rc)
+    rc.filter(passes - 1)
+    got = rc.download("FILTERED_C")
+    want = oracle.eaw_filter(chans.copy(), gb["geo"], oracle.camera_frame(sc.view), passes - 1)
+    assert np.isfinite(got[..., :3]).all()
+    err = np.abs(got[..., :3] - want[..., :3]) / (np.abs(want[..., :3]) + 1e-3)
+    assert err.max() < 2e-3 and err.mean() < 1e-5, (err.max(), err.mean())
+    # the other channels are untouched
+    for c in (0, 1, 2, 3, 4, 5):
+        assert rc.download(c).tobytes() == chans[c].tobytes()
+    # the denoised image is smoother than the noisy one and keeps its energy
+    noisy = chans[5][..., :3]
+    assert abs(got[..., :3].mean() - noisy.mean()) < 0.05 * noisy.mean()
+    rc.close(); sc.close()
+
+
+@pytest.mark.gpu
+def test_device_to_rgba_matches_the_restatement(fb, oracle, tmp_path):
+    sc, rc = _render(fb, cornell_args(80, 4), 3)
+    rc.filter(2)
+    chans, gb = _download_all(fb, rc)
+    exposure, gamma = sc.tonemap()
+    assert (exposure, round(gamma, 4)) == (1.0, 2.2)
+    for mode in (0, 1, 2, 4, 5, 6, 7, 8, 9, 10, 11, 12):
+        got = rc.to_rgba(mode)
+        want = oracle.to_rgba(chans, gb["geo"], gb["uv"], mode, exposure, gamma)
+        d = np.abs(got.astype(int) - want.astype(int))
+        assert d.max() <= 1 and (d != 0).mean() < 2e-3, (mode, d.max(), (d != 0).mean())       # powf / sinf differ by ulps
+    fb.write_tga(tmp_path / "cornell.tga", rc.to_rgba(0))
+    assert os.path.getsize(tmp_path / "cornell.tga") == 18 + 80 * 80 * 3
+    rc.close(); sc.close()
