@@ -48,6 +48,7 @@ class SceneView(C.Structure):
         ("n_bvh_nodes", C.c_uint32), ("bvh_nodes", C.c_void_p), ("bvh_index", C.POINTER(C.c_uint32)),
         ("bbox_min", C.c_float * 3), ("bbox_max", C.c_float * 3),
         ("options", PTOptions),
+        ("n_bvh_index", C.c_uint32),
     ]
 
 

@@ -104,7 +104,23 @@ void build_bvh2(const Mesh& mesh, Bvh2& bvh, uint32 max_leaf_size)
 		if (count <= max_leaf_size && leaf_cost <= split_cost) { make_leaf(); continue; }
 
 		uint32 mid;
-		if (best_axis >= 0)
+		if (best_axis >= 0 && !(parent_area > 0.0f))
+		{
+			// A node whose box has no area (degenerate triangles strung along a line or collapsed to a point: bathroom2 has
+			// 1319 of them in a row) makes every candidate cost 0, the first bin boundary wins, and the node peels off one
+			// bin per level: a 50-level chain that sets the traversal-stack bound for the whole scene. Split such nodes at
+			// the median along their longest axis instead.
+			int a = 0;
+			if (cext.y > axis(cext, a)) a = 1;
+			if (cext.z > axis(cext, a)) a = 2;
+			uint32* first = &idx[task.begin]; uint32* last = &idx[0] + task.end;
+			uint32* m = first + count / 2;
+			std::nth_element(first, m, last, [&](uint32 p, uint32 q) {
+				const float cp = axis(prims[p].centroid, a), cq = axis(prims[q].centroid, a);
+				return cp < cq || (cp == cq && p < q); });
+			mid = (uint32)(m - &idx[0]);
+		}
+		else if (best_axis >= 0)
 		{
 			const float ext = axis(cext, best_axis), lo = axis(cbox.lo, best_axis), k = float(N_BINS) / ext;
 			uint32* first = &idx[task.begin]; uint32* last = &idx[0] + task.end;

@@ -111,7 +111,8 @@ void scene_init(fb200_scene& s, int argc, const char* const* argv)
 			++i;
 			if (strcmp(argv[i], "sah") == 0) s.bvh_builder = 0;
 			else if (strcmp(argv[i], "lbvh") == 0) s.bvh_builder = 1;
-			else throw std::runtime_error(std::string("unknown -bvh builder: ") + argv[i] + " (sah | lbvh)");
+			else if (strcmp(argv[i], "sbvh") == 0) s.bvh_builder = 2;
+			else throw std::runtime_error(std::string("unknown -bvh builder: ") + argv[i] + " (sah | sbvh | lbvh)");
 		}
 	}
 	if (s.aspect == 0.0f) s.aspect = float(s.res_x) / float(s.res_y);
@@ -141,9 +142,13 @@ void scene_init(fb200_scene& s, int argc, const char* const* argv)
 	if (s.mesh_lights.vpls.empty()) s.options.nee_type = 0;     // pathtracer_impl.h:165-166
 
 	// -bvh lbvh: the tree is built on the device when a context is created (RenderingContext::build_lbvh)
-	if (s.bvh_builder == 0)
+	if (const char* e = getenv("FB200_BVH_BUILDER"))      // experiments: override the builder without touching the command line
 	{
-		build_bvh2(s.scene.mesh, s.bvh2, 3);
+		if (strcmp(e, "sah") == 0) s.bvh_builder = 0; else if (strcmp(e, "lbvh") == 0) s.bvh_builder = 1; else if (strcmp(e, "sbvh") == 0) s.bvh_builder = 2;
+	}
+	if (s.bvh_builder != 1)
+	{
+		if (s.bvh_builder == 2) build_sbvh2(s.scene.mesh, s.bvh2, 3); else build_bvh2(s.scene.mesh, s.bvh2, 3);
 		collapse_to_wide(s.scene.mesh, s.bvh2, s.wide);
 	}
 
@@ -208,7 +213,7 @@ void scene_fill_view(const fb200_scene& s, fb200_scene_view& v)
 	v.n_dir_lights = (uint32)s.scene.dir_lights.size(); v.dir_lights = s.dir_light_floats.empty() ? NULL : s.dir_light_floats.data();
 	v.glossy_reflectance = s.glossy_reflectance.data();
 	v.n_dimensions = s.sequence.n_dimensions; v.tile_size = s.sequence.tile_size; v.shifts = s.sequence.shifts.data();
-	v.n_bvh_nodes = (uint32)s.bvh2.nodes.size(); v.bvh_nodes = s.bvh2.nodes.data(); v.bvh_index = s.bvh2.index.data();
+	v.n_bvh_nodes = (uint32)s.bvh2.nodes.size(); v.bvh_nodes = s.bvh2.nodes.data(); v.bvh_index = s.bvh2.index.data(); v.n_bvh_index = (uint32)s.bvh2.index.size();
 	v.bbox_min[0] = s.scene.bbox.lo.x; v.bbox_min[1] = s.scene.bbox.lo.y; v.bbox_min[2] = s.scene.bbox.lo.z;
 	v.bbox_max[0] = s.scene.bbox.hi.x; v.bbox_max[1] = s.scene.bbox.hi.y; v.bbox_max[2] = s.scene.bbox.hi.z;
 	static_assert(sizeof(fb200_pt_options) == sizeof(PTOptions), "options layout");

@@ -95,6 +95,7 @@ FB_D float4 ld_stream(const float4* p) { return FB_STREAM_HINTS ? __ldcs(p) : *p
 FB_D uint32 ld_stream(const uint32* p) { return FB_STREAM_HINTS ? __ldcs(p) : *p; }
 FB_D void   st_stream(float4* p, float4 v) { if (FB_STREAM_HINTS) __stcs(p, v); else *p = v; }
 FB_D void   st_stream(uint32* p, uint32 v) { if (FB_STREAM_HINTS) __stcs(p, v); else *p = v; }
+FB_D void   prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 #endif
 
 struct PassTotals              // accumulated across passes (never reset by render())

@@ -147,6 +147,13 @@ __global__ void __launch_bounds__(256) k_generate_primary(DeviceScene sc, PassPa
 #ifndef FB_RAYS_PER_LANE
 #define FB_RAYS_PER_LANE 0         // > 0: trace CTAs beyond queue_length / (threads x this) exit immediately
 #endif
+#ifndef FB_SHADE_PREFETCH
+#define FB_SHADE_PREFETCH 0        // 1: fetch the VPL and pull the light triangle's index records towards L1 before the hit vertex is set up;
+                                   // 2: also pull its vertices and material once the hit's own gathers are in flight
+#endif
+#ifndef FB_MATCH_PENDING
+#define FB_MATCH_PENDING 0         // 1: an owner finds out whether helpers still work on its ray with one warp match instead of shared-memory counters
+#endif
 #ifndef FB_TRAV_BATCH
 #define FB_TRAV_BATCH 3            // traversal iterations a lane runs between two warp-wide refill votes (sweep: 2-3 best)
 #endif
@@ -269,7 +276,9 @@ __global__ void __launch_bounds__(FB_TRACE_THREADS, FB_TRACE_MIN_BLOCKS) k_trace
 					trav.ngroup = e; trav.tgroup = make_uint2(0u, 0u); trav.sp = 0;
 					trav.hit.t = -1.0f; trav.hit.tri = -1; trav.occluded = false;
 					root = rt; active = true;
+#if !FB_MATCH_PENDING
 					atomicAdd(&pending[rt], 1u);
+#endif
 				}
 			}
 			__syncwarp();
@@ -299,7 +308,14 @@ __global__ void __launch_bounds__(FB_TRACE_THREADS, FB_TRACE_MIN_BLOCKS) k_trace
 			}
 			trav.coop_tri_phase(sc, active && !done, pair_buf, lane, root);
 			if (active && !done) done = (ANY && trav.occluded) || (!trav.has_node() && trav.sp == 0);
-#if FB_SPLIT_RAYS
+#if FB_SPLIT_RAYS && FB_MATCH_PENDING
+			if (exhausted)       // (warp-uniform; helpers exist only from then on)
+			{
+				if (active && done && root != lane) { root = lane; active = false; done = false; }                // a helper is through with its share
+				const uint32 team = __match_any_sync(0xFFFFFFFFu, active ? (uint32)root : 32u + (uint32)lane);     // lanes at work on the same ray
+				if (active && done && __popc(team) > 1) done = false;                                             // the owner waits for its helpers
+			}
+#elif FB_SPLIT_RAYS
 			if (active && done)
 			{
 				if (root != lane) { atomicSub(&pending[root], 1u); root = lane; active = false; done = false; }   // a helper is through with its share
@@ -390,6 +406,24 @@ __global__ void __launch_bounds__(128, FB_SHADE_MIN_BLOCKS) k_shade(DeviceScene 
 			const V3 ray_o(ro), ray_d(rd), w(w4);
 			const float p_prev = w4.w;
 
+			// the samples of this vertex depend on the pixel only: fetch them before the geometry gathers start
+			float z[6];
+			vertex_samples(sc, pixel % sc.res_x, pixel / sc.res_x, (bounce + 1) * 6, a.seq, z);
+#if FB_SHADE_PREFETCH
+			// The light vertex of next-event estimation is a second gather chain (VPL -> triangle indices -> vertices ->
+			// material -> emission texture) that depends on z[2] alone. Start it now, so that it runs beside the hit
+			// vertex's own chain instead of after it: the kernel is bound by the latency of these dependent gathers.
+			uint32 pf_prim = 0xFFFFFFFFu;
+			if (a.do_nee && sc.use_vpls)
+			{
+				const uint32 l = min((uint32)(z[2] * float(sc.n_vpls)), sc.n_vpls - 1);
+				pf_prim = __float_as_uint(__ldg(reinterpret_cast<const float4*>(sc.vpls) + l).x);
+				prefetch_l1(sc.vertex_indices + pf_prim);
+				prefetch_l1(sc.material_indices + pf_prim);
+				if (sc.texture_indices_comp) prefetch_l1(sc.texture_indices_comp + pf_prim);
+			}
+#endif
+
 			// ---- EyeVertex::setup (src/bpt_utils.h:585-642) ----
 			Frame g; V3 unused; float s, t;
 			setup_geometry<false>(sc, tri, hit.z, hit.w, g, unused, s, t);
@@ -430,8 +464,15 @@ __global__ void __launch_bounds__(128, FB_SHADE_MIN_BLOCKS) k_shade(DeviceScene 
 				a.fb.channels[FB_DIFFUSE_A][pixel] = da; a.fb.channels[FB_SPECULAR_A][pixel] = sa;
 			}
 
-			float z[6];
-			vertex_samples(sc, pixel % sc.res_x, pixel / sc.res_x, (bounce + 1) * 6, a.seq, z);
+#if FB_SHADE_PREFETCH >= 2
+			if (pf_prim != 0xFFFFFFFFu)
+			{
+				const int4 lt = __ldg(sc.vertex_indices + pf_prim);
+				prefetch_l1(sc.vertex_data + lt.x); prefetch_l1(sc.vertex_data + lt.y); prefetch_l1(sc.vertex_data + lt.z);
+				const char* lm = reinterpret_cast<const char*>(sc.materials + __ldg(sc.material_indices + pf_prim));
+				prefetch_l1(lm + 64); prefetch_l1(lm + 176);      // emissive colour, emissive map reference
+			}
+#endif
 
 			// ---- directional lights (pathtracer_core.h:870-988) ----
 			if (DIRLIGHT && a.do_dirlight)

@@ -26,6 +26,10 @@ namespace fb {
 #ifndef FB_USE_I2F
 #define FB_USE_I2F 0               // 1: convert the quantised box bytes with I2F.U8 (XU pipe) instead of PRMT + FADD
 #endif
+#ifndef FB_FOLD_MAGIC
+#define FB_FOLD_MAGIC 0            // 1: leave the 2^15 offset of the PRMT-built plane coordinate in place and fold it into the slab
+                                   // constants (one FADD less per plane, 48 per node visit), with a proven-conservative widening
+#endif
 #ifndef FB_PREFETCH
 #define FB_PREFETCH 0              // bit 0: prefetch the next node, bit 1: prefetch the hit triangles (into L1)
 #endif
@@ -51,6 +55,12 @@ FB_D float byte_to_float(uint32 w, int j, uint32 magic)   // j: compile-time con
 #else
 	return __uint_as_float(__byte_perm(w, magic, 0x7540u | (uint32)j)) - 8388608.0f;
 #endif
+}
+
+// FB_FOLD_MAGIC: float 2^15 + byte, the byte placed in mantissa bits 8..15 of 0x47000000 by one PRMT (exact)
+FB_D float byte_plus_2p15(uint32 w, int j, uint32 magic15)   // magic15 = 0x47000000
+{
+	return __uint_as_float(__byte_perm(w, magic15, 0x7604u | ((uint32)j << 4)));
 }
 
 struct TravRay
@@ -178,6 +188,18 @@ struct Traversal
 			const float aix = sx * idx_, aiy = sy * idy_, aiz = sz * idz_;
 			const float aox = (n0.x - ray.ox) * idx_, aoy = (n0.y - ray.oy) * idy_, aoz = (n0.z - ray.oz) * idz_;
 			const bool nx = ray.dx < 0.0f, ny = ray.dy < 0.0f, nz = ray.dz < 0.0f;
+#if FB_FOLD_MAGIC
+			// plane parameter t = q * ai + ao with q = byte. With q' = 2^15 + q this is q' * ai + (ao - 2^15 ai): the offset moves
+			// into the constant. Rounding (ao - 2^15 ai) costs at most half an ulp of it, i.e. <= 2^-24 (|ao| + 2^15 |ai|); the
+			// near planes use the constant lowered and the far planes the constant raised by 2^-8 |ai| + 2^-22 |ao'| (> 2x that
+			// bound, and 1/256 of a quantisation step), so no box that the unfolded test accepts in exact arithmetic is rejected.
+			// A NaN constant (axis-parallel ray through the node's origin plane) drops out of fmaxf/fminf: conservative as well.
+			const float bx2 = aox - 32768.0f * aix, by2 = aoy - 32768.0f * aiy, bz2 = aoz - 32768.0f * aiz;
+			const float slx = fabsf(aix) * 0.00390625f + fabsf(bx2) * 2.3841858e-7f;
+			const float sly = fabsf(aiy) * 0.00390625f + fabsf(by2) * 2.3841858e-7f;
+			const float slz = fabsf(aiz) * 0.00390625f + fabsf(bz2) * 2.3841858e-7f;
+			const float lox_ = bx2 - slx, hix_ = bx2 + slx, loy_ = by2 - sly, hiy_ = by2 + sly, loz_ = bz2 - slz, hiz_ = bz2 + slz;
+#endif
 
 			#pragma unroll
 			for (int half_ = 0; half_ < 2; ++half_)
@@ -199,10 +221,17 @@ struct Traversal
 				for (int j = 0; j < 4; ++j)
 				{
 					const int sh = j * 8;
+#if FB_FOLD_MAGIC
+					const uint32 mg = sc.f32_2p23_bits ^ 0x0C000000u;      // 0x4B000000 -> 0x47000000 = 2^15
+					const float t0x = fmaf(byte_plus_2p15(xmin, j, mg), aix, lox_), t1x = fmaf(byte_plus_2p15(xmax, j, mg), aix, hix_);
+					const float t0y = fmaf(byte_plus_2p15(ymin, j, mg), aiy, loy_), t1y = fmaf(byte_plus_2p15(ymax, j, mg), aiy, hiy_);
+					const float t0z = fmaf(byte_plus_2p15(zmin, j, mg), aiz, loz_), t1z = fmaf(byte_plus_2p15(zmax, j, mg), aiz, hiz_);
+#else
 					const uint32 mg = sc.f32_2p23_bits;
 					const float t0x = fmaf(byte_to_float(xmin, j, mg), aix, aox), t1x = fmaf(byte_to_float(xmax, j, mg), aix, aox);
 					const float t0y = fmaf(byte_to_float(ymin, j, mg), aiy, aoy), t1y = fmaf(byte_to_float(ymax, j, mg), aiy, aoy);
 					const float t0z = fmaf(byte_to_float(zmin, j, mg), aiz, aoz), t1z = fmaf(byte_to_float(zmax, j, mg), aiz, aoz);
+#endif
 					const float cmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, ray.tmin));
 					// far side widened by 4e-7 relative so that fp rounding never culls a box whose geometry is hit
 					const float cmax = fminf(fminf(t1x, t1y), fminf(t1z, ray.tmax)) * 1.0000004f;

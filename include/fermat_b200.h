@@ -82,6 +82,9 @@ typedef struct fb200_scene_view
 	uint32_t n_bvh_nodes; const void* bvh_nodes; const uint32_t* bvh_index;
 	float    bbox_min[3], bbox_max[3];
 	fb200_pt_options options;
+	/* entries of bvh_index: num_triangles, or more when the tree was built with spatial splits (`-bvh sbvh`: a triangle
+	 * may be referenced from several leaves) */
+	uint32_t n_bvh_index;
 } fb200_scene_view;
 
 typedef struct fb200_stats

@@ -7,7 +7,7 @@ cd "$(dirname "$0")/.."
 make -s -j8 fermat_b200/libfermat_b200.so > /dev/null
 mkdir -p fermat_b200/variants build/variants
 NVCC=/usr/local/cuda/bin/nvcc
-HOSTOBJ=$(ls build/*.o | grep -v -e 'build/main.o' -e '\.cu\.o$')
+HOSTOBJ=$(ls build/*.o | grep -v -e 'build/main.o' -e 'build/pt_kernels.cu.o')
 for spec in "$@"; do
   name=${spec%%:*}; flags=${spec#*:}
   $NVCC -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -Xcompiler -fPIC -Iinclude -Ifermat_b200/csrc/host \
