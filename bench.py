@@ -269,10 +269,35 @@ def run_ours(args):
     value = samples / (ms * 1e-3) * 1e-6
 
     # ---------------- end-to-end region: render() through the C ABI + device->host read of the frame ----------------
+    # W untimed end-to-end warm-up steps first: the read-back path has its own cold start (snapshot buffer and copy stream
+    # are created on first use, the copy engine and the PCIe link of a GPU that has sat idle through the reference arm
+    # come up from a low-power state: on a fresh box the first bench of a session measured 400-550 Msamples/s end to end
+    # where every later one measured ~1290). Then copies of the frame until their rate has settled (bounded at 2 s).
+    barrier()
+    e2e_first = args.warmup + 2 * args.steps
+    for i in range(e2e_first, e2e_first + args.warmup):
+        step(i, True, read_back=True)
+        if rank == 0 and world == 1:
+            rc.download_async(hosts[i & 1].data_ptr())
+    if copy_stream is not None:
+        copy_stream.synchronize()
+    barrier()
+    pcie_gbs = None
+    if rank == 0:
+        rates, t_end = [], time.perf_counter() + 2.0
+        while time.perf_counter() < t_end:
+            t0 = time.perf_counter()
+            host.copy_(comp, non_blocking=True)
+            torch.cuda.synchronize()
+            rates.append(comp.numel() * 4 / (time.perf_counter() - t0) * 1e-9)
+            if len(rates) >= 8 and max(rates[-4:]) < 1.05 * min(rates[-4:]):
+                break
+        pcie_gbs = rates[-1]
+    e2e_first += args.warmup
     barrier()
     e0 = rc.stats()["shade_events"]
     w0 = time.perf_counter()
-    for i in range(args.warmup + 2 * args.steps, args.warmup + 3 * args.steps):
+    for i in range(e2e_first, e2e_first + args.steps):
         step(i, True, read_back=True)
         if rank == 0 and world == 1:
             # every pass's frame goes to pinned host memory; the copy of pass i overlaps the rendering of pass i+1
@@ -343,6 +368,7 @@ def run_ours(args):
                    "l2": "working set per pass (queues + 8-channel frame buffer, > 400 MB) exceeds the 126 MB L2",
                    "target": ">= 200 Msamples/s (BASELINE.json)"},
         "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": 4 * sc.view.n_dimensions + 96, "d2h_bytes_per_step": int(comp.numel() * 4),
+                "warmup_steps": args.warmup, "d2h_GBps_after_warmup": pcie_gbs,
                 "note": ("render(instance) through the C ABI + the frame of EVERY pass read back to pinned host memory (fb200_context_fb_download_async: device snapshot, "
                          "then a copy that overlaps the next pass; two host buffers); the scene is resident like model weights") if world == 1 else
                         "render(instance) through the C ABI on every rank + NCCL reduce + rank 0 copies the reduced frame of EVERY pass to pinned host memory on a copy stream (two reduce / host buffers, the copy of frame i overlaps pass i+1); the scene is resident like model weights"},

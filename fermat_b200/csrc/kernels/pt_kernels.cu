@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(256) k_generate_primary(DeviceScene sc, PassPa
 #define FB_TRACE_MIN_BLOCKS 4
 #endif
 #ifndef FB_SHADE_MIN_BLOCKS
-#define FB_SHADE_MIN_BLOCKS 5
+#define FB_SHADE_MIN_BLOCKS 6          // 80 registers (r02 sweep, Msamples/s: 5 blocks 1334, 6 blocks 1355, 8 blocks 1351)
 #endif
 #ifndef FB_REFILL_LANES
 #define FB_REFILL_LANES 1          // idle lanes of a warp that trigger a refill from the ray queue
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(256) k_generate_primary(DeviceScene sc, PassPa
                                    // 2: also pull its vertices and material once the hit's own gathers are in flight
 #endif
 #ifndef FB_MATCH_PENDING
-#define FB_MATCH_PENDING 0         // 1: an owner finds out whether helpers still work on its ray with one warp match instead of shared-memory counters
+#define FB_MATCH_PENDING 1         // 1 (r02 sweep: +0.9 %): an owner finds out whether helpers still work on its ray with one warp match instead of shared-memory counters
 #endif
 #ifndef FB_TRAV_BATCH
 #define FB_TRAV_BATCH 3            // traversal iterations a lane runs between two warp-wide refill votes (sweep: 2-3 best)

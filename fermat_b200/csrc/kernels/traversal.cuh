@@ -27,7 +27,7 @@ namespace fb {
 #define FB_USE_I2F 0               // 1: convert the quantised box bytes with I2F.U8 (XU pipe) instead of PRMT + FADD
 #endif
 #ifndef FB_FOLD_MAGIC
-#define FB_FOLD_MAGIC 0            // 1: leave the 2^15 offset of the PRMT-built plane coordinate in place and fold it into the slab
+#define FB_FOLD_MAGIC 1            // 1 (r02 sweep: +0.4 %): leave the 2^15 offset of the PRMT-built plane coordinate in place and fold it into the slab
                                    // constants (one FADD less per plane, 48 per node visit), with a proven-conservative widening
 #endif
 #ifndef FB_PREFETCH

