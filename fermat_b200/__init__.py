@@ -98,6 +98,9 @@ def lib():
         "fb200_context_fb_upload": (i32, [vp, i32, pf]),
         "fb200_context_gbuffer_download": (i32, [vp, pf, pf, C.POINTER(u32), pf]),
         "fb200_context_get_stats": (i32, [vp, C.POINTER(Stats)]),
+        "fb200_context_get_bounce_times": (i32, [vp, C.POINTER(C.c_double * 256)]),
+        "fb200_diag_pass_counters": (i32, [vp, u32, vp, u64]),
+        "fb200_context_get_suspension_stats": (i32, [vp, C.POINTER(u64 * 2)]),
         "fb200_context_stream": (vp, [vp]),
         "fb200_context_set_profiling": (i32, [vp, i32]),
         "fb200_context_get_kernel_times": (i32, [vp, C.POINTER(C.c_double * 4), C.POINTER(u64 * 4)]),
@@ -126,6 +129,12 @@ def lib():
     L._missing = missing
     _lib = L
     return L
+
+
+# struct PassCounters (fermat_b200/csrc/kernels/device_scene.h)
+PASS_COUNTERS_DTYPE = np.dtype([("in_size", "<u4", 64), ("shadow_size", "<u4", 64), ("trace_next", "<u4", 64), ("shadow_next", "<u4", 64),
+                                ("shade_next", "<u4", 64), ("pad", "<u4", 64), ("cont_tasks", "<u4", (2, 64)), ("cont_next", "<u4", (2, 64)),
+                                ("cont_rays", "<u4", (2, 64)), ("stat_max", "<u4", (2, 64, 4)), ("stat_sum", "<u8", (2, 64, 16))])
 
 
 def exported_symbols():
@@ -319,6 +328,12 @@ class RenderingContext:
         self._chk(lib().fb200_context_get_stats(self._h, C.byref(s)))
         return {k: getattr(s, k) for k, _ in Stats._fields_}
 
+    def suspension_stats(self):
+        """(rays suspended, continuation tasks) since the context was created; zeros unless FB200_SUSPEND is set."""
+        out = (C.c_uint64 * 2)()
+        self._chk(lib().fb200_context_get_suspension_stats(self._h, C.byref(out)))
+        return int(out[0]), int(out[1])
+
     def stream(self):
         return lib().fb200_context_stream(self._h)
 
@@ -331,6 +346,21 @@ class RenderingContext:
         self._chk(lib().fb200_context_get_kernel_times(self._h, C.byref(ms), C.byref(n)))
         names = ("frame", "trace", "shade", "shadow")
         return {k: {"ms": ms[i], "launches": int(n[i])} for i, k in enumerate(names)}
+
+    def bounce_times(self):
+        """Accumulated device ms per kernel class and bounce: dict(class -> list of 64); needs set_profiling()."""
+        ms = (C.c_double * 256)()
+        self._chk(lib().fb200_context_get_bounce_times(self._h, C.byref(ms)))
+        names = ("frame", "trace", "shade", "shadow")
+        return {k: [ms[i * 64 + b] for b in range(64)] for i, k in enumerate(names)}
+
+    def pass_counters(self, subframe=0):
+        """Device-side counters of one sub-frame after the last pass (struct PassCounters, device_scene.h), or None if
+        there is no such sub-frame: queue sizes per bounce and, with a -DFB_TRACE_STATS=1 build, traversal statistics."""
+        buf = np.zeros(PASS_COUNTERS_DTYPE.itemsize, np.uint8)
+        if lib().fb200_diag_pass_counters(self._h, subframe, buf.ctypes.data_as(C.c_void_p), buf.nbytes) != 0:
+            return None
+        return buf.view(PASS_COUNTERS_DTYPE)[0]
 
     def owned_pixels(self):
         return int(lib().fb200_context_owned_pixels(self._h))

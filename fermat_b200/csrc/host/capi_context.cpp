@@ -116,6 +116,24 @@ int fb200_context_get_stats(fb200_context* c, fb200_stats* out)
 	});
 }
 
+int fb200_context_get_suspension_stats(fb200_context* c, uint64_t out[2])
+{
+	return guarded([&] {
+		const fb::PassTotals t = pt_of(c)->totals(c->rc);
+		out[0] = t.suspended_rays; out[1] = t.continuation_tasks;
+	});
+}
+
+int fb200_context_get_bounce_times(fb200_context* c, double out_ms[4 * 64])
+{
+	return guarded([&] { pt_of(c)->bounce_times(c->rc, out_ms); });
+}
+
+int fb200_diag_pass_counters(fb200_context* c, uint32_t subframe, void* out, uint64_t bytes)
+{
+	return guarded([&] { if (!pt_of(c)->read_pass_counters(c->rc, subframe, out, (size_t)bytes)) throw std::runtime_error("no such sub-frame"); });
+}
+
 int fb200_context_set_profiling(fb200_context* c, int on) { pt_of(c)->set_profiling(on != 0); return 0; }
 
 int fb200_context_get_kernel_times(fb200_context* c, double out_ms[4], uint64_t out_launches[4])

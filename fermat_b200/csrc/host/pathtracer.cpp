@@ -8,9 +8,10 @@
 
 using namespace fb;
 
-PathTracer::PathTracer() : m_tiles_x(0), m_owned_pixels(0), m_passes(0), m_device_ms(0.0), m_overlap(1), m_trace_ctas(0), m_events(false), m_profiling(false)
+PathTracer::PathTracer() : m_tiles_x(0), m_owned_pixels(0), m_passes(0), m_device_ms(0.0), m_overlap(1), m_trace_ctas(0), m_suspend_after(-1), m_events(false), m_profiling(false)
 {
 	for (int i = 0; i < 4; ++i) { m_class_ms[i] = 0.0; m_class_launches[i] = 0; }
+	memset(m_bounce_ms, 0, sizeof(m_bounce_ms));
 	pt_options_defaults(m_options);
 }
 
@@ -52,6 +53,7 @@ void carve(Arena& a, size_t cap, size_t shadow_cap, PathQueue q[2], ShadowQueue&
 	}
 	sq.ray_o = a.alloc<float4>(shadow_cap); sq.ray_d = a.alloc<float4>(shadow_cap);
 	sq.w_d = a.alloc<float4>(shadow_cap); sq.w_g = a.alloc<float4>(shadow_cap);
+	sq.occluded = a.alloc<unsigned char>(shadow_cap);
 }
 }
 
@@ -81,6 +83,15 @@ void PathTracer::init(int argc, char** argv, RenderingContext& renderer)
 	// (sweep on bathroom2, Msamples/s: 1 sub-frame 1040; 2 sub-frames x 4 CTAs 1045, x 2 CTAs 1110; 4 x 1 1129; 6 x 2 878)
 	m_trace_ctas = env ? atoi(env) : (n_sub > 1 ? 2 : 0);
 
+	// ray suspension (ContQueue, device_scene.h): a trace warp whose queue ran dry hands what is left of its rays to a
+	// second launch after this many further iterations (FB200_SUSPEND, < 0 = off)
+	env = getenv("FB200_SUSPEND");
+	m_suspend_after = env ? atoi(env) : -1;
+	// a lane suspends at most one ray and a launch has at most sm_count x CTAs x threads lanes
+	const LaunchConfig lc0 = renderer.launch_config();
+	const uint32 cont_rays = m_suspend_after >= 0 ? (uint32)(lc0.sm_count * lc0.trace_ctas_per_sm * lc0.trace_threads) : 0u;
+	const uint32 cont_tasks = cont_rays * 6u;
+
 	std::vector<std::vector<uint32> > sub_tiles(n_sub);
 	for (size_t j = 0; j < tiles.size(); ++j) sub_tiles[j % n_sub].push_back(tiles[j]);
 
@@ -92,11 +103,16 @@ void PathTracer::init(int argc, char** argv, RenderingContext& renderer)
 		Arena arena(dry_run ? NULL : m_memory_pool.ptr);
 		for (uint32 k = 0; k < n_sub; ++k)
 		{
-			if (dry_run) { m_sub[k] = new SubFrame(); memset(m_sub[k]->queue, 0, sizeof(m_sub[k]->queue)); memset(&m_sub[k]->shadow, 0, sizeof(m_sub[k]->shadow)); }
+			if (dry_run) { m_sub[k] = new SubFrame(); memset(m_sub[k]->queue, 0, sizeof(m_sub[k]->queue)); memset(&m_sub[k]->shadow, 0, sizeof(m_sub[k]->shadow)); memset(m_sub[k]->cont, 0, sizeof(m_sub[k]->cont)); }
 			SubFrame& f = *m_sub[k];
 			f.n_tiles = (uint32)sub_tiles[k].size();
 			f.capacity = (uint64_t)f.n_tiles * 32u * 32u;
 			carve(arena, f.capacity, dirlights ? 2 * f.capacity : f.capacity, f.queue, f.shadow);
+			for (int c = 0; c < 2 && cont_rays; ++c)
+			{
+				f.cont[c].tasks = arena.alloc<uint4>(cont_tasks); f.cont[c].ray_of_slot = arena.alloc<uint32>(cont_rays); f.cont[c].keys = arena.alloc<unsigned long long>(cont_rays);
+				f.cont[c].task_capacity = cont_tasks; f.cont[c].ray_capacity = cont_rays;
+			}
 		}
 		if (dry_run)
 		{
@@ -129,6 +145,8 @@ void PathTracer::init(int argc, char** argv, RenderingContext& renderer)
 		renderer.set_renderer_clears_gbuffer(true);
 	}
 	m_totals.alloc(sizeof(PassTotals));
+	for (uint32 k = 0; k < n_sub; ++k)
+		for (int c = 0; c < 2; ++c) m_sub[k]->cont[c].totals = &m_totals.as<PassTotals>()->suspended_rays;
 	cuda_check(cudaMemsetAsync(m_totals.ptr, 0, sizeof(PassTotals), renderer.raw_stream()), "memset totals");
 	cuda_check(cudaEventCreate(&m_ev0), "event"); cuda_check(cudaEventCreate(&m_ev1), "event");
 	cuda_check(cudaEventCreateWithFlags(&m_ev_start, cudaEventDisableTiming), "event");
@@ -149,7 +167,11 @@ void PathTracer::kernel_times(RenderingContext& renderer, double out_ms[4], uint
 	for (size_t i = 0; i < m_spans.size(); ++i)
 	{
 		float ms = 0.0f;
-		if (cudaEventElapsedTime(&ms, m_spans[i].a, m_spans[i].b) == cudaSuccess) { m_class_ms[m_spans[i].cls] += ms; m_class_launches[m_spans[i].cls]++; }
+		if (cudaEventElapsedTime(&ms, m_spans[i].a, m_spans[i].b) == cudaSuccess)
+		{
+			m_class_ms[m_spans[i].cls] += ms; m_class_launches[m_spans[i].cls]++;
+			m_bounce_ms[m_spans[i].cls][m_spans[i].bounce & 63u] += ms;
+		}
 		m_event_pool.push_back(m_spans[i].a); m_event_pool.push_back(m_spans[i].b);
 	}
 	m_spans.clear();
@@ -223,7 +245,7 @@ void PathTracer::render_subframe(SubFrame& f, const PassParams& pass, const std:
 	const DeviceScene& sc = renderer.device_scene();
 	LaunchConfig lc = renderer.launch_config();
 	if (!m_profiling && m_trace_ctas > 0 && m_trace_ctas < lc.trace_ctas_per_sm) lc.trace_ctas_per_sm = m_trace_ctas;   // alone on the GPU (profiling) a launch takes every slot
-	Span span; span.cls = -1;
+	Span span; span.cls = -1; span.bounce = 0;
 	auto begin = [&](int cls) { if (m_profiling) { span.cls = cls; span.a = take_event(); span.b = take_event(); cuda_check(cudaEventRecord(span.a, stream), "event record"); } };
 	auto end = [&]() { if (m_profiling) { cuda_check(cudaEventRecord(span.b, stream), "event record"); m_spans.push_back(span); } };
 
@@ -246,15 +268,18 @@ void PathTracer::render_subframe(SubFrame& f, const PassParams& pass, const std:
 	renderer.kernel_launches += 2;
 
 	const uint32 L = m_options.max_path_length;
+	uint32 n_launches = 0;
 	for (uint32 bounce = 0; bounce < L; ++bounce)
 	{
+		span.bounce = bounce;
 		const PathQueue& in = f.queue[bounce & 1];
 		const PathQueue& out = f.queue[(bounce + 1) & 1];
 		if (bounce == 0 || !overlap)
 		{
 			begin(1);
-			cuda_check(launch_trace_closest(sc, lc, in, ctr, bounce, stream), "trace");
+			cuda_check(launch_trace_closest(sc, lc, in, ctr, bounce, stream, &f.cont[0], m_suspend_after, &n_launches), "trace");
 			end();
+			renderer.kernel_launches += n_launches;
 		}
 		float seq6[6];
 		for (int i = 0; i < 6; ++i) seq6[i] = seq[(bounce + 1) * 6 + i];
@@ -265,25 +290,48 @@ void PathTracer::render_subframe(SubFrame& f, const PassParams& pass, const std:
 		if (!overlap)
 		{
 			begin(3);
-			cuda_check(launch_trace_shadow(sc, lc, f.shadow, fbv, ctr, tot, bounce, pp.frame_weight, stream), "trace_shadow");
+			cuda_check(launch_trace_shadow(sc, lc, f.shadow, fbv, ctr, tot, bounce, pp.frame_weight, stream, &f.cont[1], m_suspend_after, &n_launches), "trace_shadow");
 			end();
+			renderer.kernel_launches += n_launches;
 		}
 		else
 		{
 			cuda_check(cudaEventRecord(f.ev_shaded, stream), "event record");
 			cuda_check(cudaStreamWaitEvent(f.side_stream, f.ev_shaded, 0), "wait");
-			cuda_check(launch_trace_shadow(sc, lc, f.shadow, fbv, ctr, tot, bounce, pp.frame_weight, f.side_stream), "trace_shadow");
+			cuda_check(launch_trace_shadow(sc, lc, f.shadow, fbv, ctr, tot, bounce, pp.frame_weight, f.side_stream, &f.cont[1], m_suspend_after, &n_launches), "trace_shadow");
+			renderer.kernel_launches += n_launches;
 			cuda_check(cudaEventRecord(f.ev_shadowed, f.side_stream), "event record");
-			if (bounce + 1 < L) cuda_check(launch_trace_closest(sc, lc, out, ctr, bounce + 1, stream), "trace");
+			if (bounce + 1 < L)
+			{
+				cuda_check(launch_trace_closest(sc, lc, out, ctr, bounce + 1, stream, &f.cont[0], m_suspend_after, &n_launches), "trace");
+				renderer.kernel_launches += n_launches;
+			}
 		}
-		renderer.kernel_launches += 3;
+		renderer.kernel_launches += 1;
 	}
 	if (overlap) cuda_check(cudaStreamWaitEvent(stream, f.ev_shadowed, 0), "wait");
+	span.bounce = 0;
 	// RenderingContext::update_variances (pathtracer_impl.h:322), this sub-frame's pixels
 	begin(0);
 	cuda_check(launch_update_variances(fbv, pixels, pp.instance + 1, stream), "update_variances");
 	end();
 	renderer.kernel_launches++;
+}
+
+void PathTracer::bounce_times(RenderingContext& renderer, double out_ms[4 * 64])
+{
+	double ms[4]; uint64_t launches[4];
+	kernel_times(renderer, ms, launches);          // resolves the pending spans
+	memcpy(out_ms, m_bounce_ms, sizeof(m_bounce_ms));
+}
+
+bool PathTracer::read_pass_counters(RenderingContext& renderer, uint32_t k, void* out, size_t bytes)
+{
+	if (k >= m_sub.size()) return false;
+	cudaStream_t stream = renderer.stream();       // joins the sub-frame streams
+	cuda_check(cudaMemcpyAsync(out, m_sub[k]->counters.ptr, bytes < sizeof(PassCounters) ? bytes : sizeof(PassCounters), cudaMemcpyDeviceToHost, stream), "read counters");
+	renderer.synchronize();
+	return true;
 }
 
 PassTotals PathTracer::totals(RenderingContext& renderer)

@@ -169,6 +169,9 @@ struct PathTracer final : RendererInterface
 	// + primary rays, 1 closest-hit trace, 2 shade, 3 shadow trace + accumulate. out_ms / out_launches: 4 entries.
 	void     set_profiling(bool on) { m_profiling = on; }
 	void     kernel_times(RenderingContext& renderer, double out_ms[4], uint64_t out_launches[4]);
+	void     bounce_times(RenderingContext& renderer, double out_ms[4 * 64]);       // [class][bounce], summed over launches like kernel_times
+	// raw PassCounters of sub-frame k as the last pass left them (queue sizes per bounce, diagnostic statistics); false: no such sub-frame
+	bool     read_pass_counters(RenderingContext& renderer, uint32_t k, void* out, size_t bytes);
 
 private:
 	fb::PTOptions    m_options;
@@ -182,6 +185,7 @@ private:
 		uint64_t         capacity;
 		fb::PathQueue    queue[2];
 		fb::ShadowQueue  shadow;
+		fb::ContQueue    cont[2];                 // continuation queues of the closest-hit / the shadow trace launches (ray suspension)
 		cudaStream_t     stream, side_stream;     // stream == NULL: the context's stream
 		cudaEvent_t      ev_shaded, ev_shadowed, ev_done;
 	};
@@ -193,13 +197,15 @@ private:
 	cudaEvent_t      m_ev0, m_ev1, m_ev_start;
 	int              m_overlap;               // 0: one stream per sub-frame; else the shadow trace of bounce b runs beside the closest-hit trace of bounce b+1
 	int              m_trace_ctas;            // CTAs per SM of each persistent trace launch
+	int              m_suspend_after;         // ray suspension: tail iterations before a trace warp hands its rays over (< 0: off)
 	void             render_subframe(SubFrame& f, const fb::PassParams& pp, const std::vector<float>& seq, RenderingContext& renderer, cudaStream_t stream, bool overlap);
 	bool             m_events;
 	bool             m_profiling;
-	struct Span { int cls; cudaEvent_t a, b; };
+	struct Span { int cls; uint32_t bounce; cudaEvent_t a, b; };
 	std::vector<Span>        m_spans;         // recorded, not yet resolved
 	std::vector<cudaEvent_t> m_event_pool;
 	double           m_class_ms[4];
+	double           m_bounce_ms[4][64];      // the same per bounce (class 0: [0] only)
 	uint64_t         m_class_launches[4];
 	cudaEvent_t      take_event();
 };

@@ -152,7 +152,27 @@ __global__ void __launch_bounds__(256) k_generate_primary(DeviceScene sc, PassPa
                                    // 2: also pull its vertices and material once the hit's own gathers are in flight
 #endif
 #ifndef FB_MATCH_PENDING
-#define FB_MATCH_PENDING 1         // 1 (r02 sweep: +0.9 %): an owner finds out whether helpers still work on its ray with one warp match instead of shared-memory counters
+#define FB_MATCH_PENDING 1         // 1 (r02 sweep: +0.9 %): an owner finds out whether helpers still work on its ray with one warp match instead of shared-memory counters;
+                                   // 2 (r03: +0.2 %, noise): with one warp-wide OR of the helpers' root bits
+#endif
+#ifndef FB_SPLIT_BOTTOM
+#define FB_SPLIT_BOTTOM 0          // 1 (r03: -0.9 % alone, +0.7 % with the rest): a donor hands over the BOTTOM entry of its stack (the siblings nearest the root: the largest part of what is
+                                   // left of the ray) instead of the top one, and keeps its own entries in front-to-back order
+#endif
+#ifndef FB_THIN_QUOTA
+#define FB_THIN_QUOTA 0            // > 0 (r03, 8 / 16 / 32: +0.4 % / +0.5 % / +0.4 %, within noise): when the queue holds fewer rays than this many per warp, every warp of the launch takes its even share of
+                                   // rays only and its other lanes help from the first iteration on (short queues of the late bounces)
+#endif
+#ifndef FB_SPLIT_ACCUMULATE
+#define FB_SPLIT_ACCUMULATE 1      // 1 (r03: +3.8 %): the shadow trace only records which rays are occluded and a streaming kernel behind it adds the
+                                   // unoccluded samples to the frame buffer (0: a lane does that itself when its ray retires, two dependent HBM
+                                   // round trips - weights, then the pixel - during which its whole warp waits: 3800 of 9400 cycles per iteration)
+#endif
+#ifndef FB_PAR_SPLIT
+#define FB_PAR_SPLIT 1             // 1 (r03: +2.9 %): ray splitting pairs all idle lanes with all donors in one step (per-lane shuffle sources) instead of pair by pair
+#endif
+#ifndef FB_TRACE_STATS
+#define FB_TRACE_STATS 0           // 1: the queue trace launches fill PassCounters::stat_max / stat_sum (diagnostic build, tools/trace_stats.py)
 #endif
 #ifndef FB_TRAV_BATCH
 #define FB_TRAV_BATCH 3            // traversal iterations a lane runs between two warp-wide refill votes (sweep: 2-3 best)
@@ -171,13 +191,51 @@ struct TraceArgs
 	const float4* w_d; const float4* w_g;
 	FrameBufferView fb; float frame_weight; uint32 bounce;
 	unsigned long long* event_counter;
+	// ray suspension (ContQueue, device_scene.h). phase 0: rays from the queue, lanes suspend what is left `suspend_after`
+	// iterations after the queue ran dry (< 0: never); phase 1: the tasks of that launch
+	ContQueue cont; uint32* cont_tasks; uint32* cont_next; uint32* cont_rays;
+	int suspend_after;
+	uint32* stat_max; unsigned long long* stat_sum;   // FB_TRACE_STATS: this launch's rows of PassCounters::stat_max / stat_sum
 };
 
-template <int MODE>
+// PHASE of a queue trace launch: the plain kernel, the one whose warps suspend their last rays, the one that runs the tasks
+enum TracePhase { TRACE_PLAIN = 0, TRACE_SUSPENDING = 1, TRACE_TASKS = 2 };
+
+FB_D unsigned long long pack_hit_key(float t, int tri) { return ((unsigned long long)__float_as_uint(t) << 32) | (unsigned long long)(uint32)tri; }
+
+// solve_occlusion -> PTVertexProcessor::accumulate_nee (pathtracer_vertex_processor.h:204-239) for one unoccluded shadow ray
+FB_D void accumulate_unoccluded(const TraceArgs& a, const uint32 ray_idx)
+{
+	const float4 wd4 = ld_stream(a.w_d + ray_idx), wg4 = ld_stream(a.w_g + ray_idx);
+	const V3 w_d(wd4), w_g(wg4);
+	const uint32 info = __float_as_uint(wd4.w);
+	const uint32 pixel = info & 0x07FFFFFFu, comp = (info >> 27) & 0xFu;
+	add_in<false>(a.fb.channels[FB_COMPOSITED_C], pixel, w_d + w_g, a.frame_weight);
+	if (a.bounce == 0)
+	{
+		add_in<true>(a.fb.channels[FB_DIFFUSE_C], pixel, w_d, a.frame_weight);
+		add_in<true>(a.fb.channels[FB_SPECULAR_C], pixel, w_g, a.frame_weight);
+	}
+	else
+	{
+		if (comp & kDiffuseMask) add_in<true>(a.fb.channels[FB_DIFFUSE_C], pixel, w_d, a.frame_weight);
+		if (comp & kGlossyMask)  add_in<true>(a.fb.channels[FB_SPECULAR_C], pixel, w_g, a.frame_weight);
+	}
+}
+
+template <int MODE, int PHASE = TRACE_PLAIN>
 __global__ void __launch_bounds__(FB_TRACE_THREADS, FB_TRACE_MIN_BLOCKS) k_trace(DeviceScene sc, TraceArgs a)
 {
 	constexpr bool ANY = (MODE == TRACE_QUEUE_SHADOW || MODE == TRACE_RAYS_SHADOW);
-	const uint32 n = a.n_ptr ? *a.n_ptr : a.n_value;
+	constexpr bool tasks_phase = PHASE == TRACE_TASKS;       // this launch works on the continuation tasks of the previous one
+	constexpr bool may_suspend = PHASE == TRACE_SUSPENDING;
+	static_assert(PHASE == TRACE_PLAIN || MODE == TRACE_QUEUE_CLOSEST || MODE == TRACE_QUEUE_SHADOW, "only queue launches suspend rays");
+	uint32 n = a.n_ptr ? *a.n_ptr : a.n_value;
+	if (tasks_phase)
+	{
+		n = min(*a.cont_tasks, a.cont.task_capacity);
+		if (n == 0) return;                                    // (nothing was suspended)
+	}
 #if FB_RAYS_PER_LANE > 0
 	// size the persistent grid to the queue (its length is only known on the device): a lane that gets just one or two
 	// rays cannot even out their different lengths against its warp mates', so CTAs beyond n / (threads x R) leave at once;
@@ -194,7 +252,7 @@ __global__ void __launch_bounds__(FB_TRACE_THREADS, FB_TRACE_MIN_BLOCKS) k_trace
 	const float4* smem_nodes = smem + 1;
 	stage_nodes_tma(smem + 1, sc.nodes, sc.staged_nodes * (uint32)sizeof(WideNode), bar);
 
-	if (MODE == TRACE_QUEUE_SHADOW && blockIdx.x == 0 && threadIdx.x == 0 && a.event_counter) atomicAdd(a.event_counter, (unsigned long long)n);
+	if (MODE == TRACE_QUEUE_SHADOW && !tasks_phase && blockIdx.x == 0 && threadIdx.x == 0 && a.event_counter) atomicAdd(a.event_counter, (unsigned long long)n);
 	const int lane = threadIdx.x & 31;
 
 	Traversal<ANY> trav;
@@ -219,29 +277,125 @@ __global__ void __launch_bounds__(FB_TRACE_THREADS, FB_TRACE_MIN_BLOCKS) k_trace
 	uint32 ray_idx = 0;
 
 	bool exhausted = false;          // warp-uniform: the cursor ran past the end of the queue
+#if FB_THIN_QUOTA > 0 && FB_COOP_TRI && FB_SPLIT_RAYS
+	// Short queue (late bounces: fewer rays than lanes). Warps that grab 32 rays each leave most warps of the launch - most
+	// of the machine - without work, and the launch lasts as long as the longest ray of the few busy warps. Instead every
+	// warp keeps at most its even share of rays in flight and its other lanes split those rays from the first iteration on.
+	const uint32 n_warps = gridDim.x * (blockDim.x >> 5);
+	const uint32 share = (n + n_warps - 1u) / n_warps;
+	const bool thin = share < (uint32)FB_THIN_QUOTA;                           // launch-uniform
+	const uint32 quota = thin ? (share > 0u ? share : 1u) : 32u;
+#else
+	constexpr bool thin = false;
+#endif
+	int  tail_iters = 0;             // warp-uniform: iterations since then
+	bool can_suspend = may_suspend;
+	uint32* const cursor = tasks_phase ? a.cont_next : a.cursor;
+#if FB_TRACE_STATS
+	uint32 st_iters = 0, st_tail = 0, st_lanes = 0, st_helpers = 0, st_ray = 0, st_longest_ray = 0; bool st_busy = false;
+	const long long st_t0 = clock64();
+	long long st_c[4] = { 0, 0, 0, 0 }, st_tri[6] = { 0, 0, 0, 0, 0, 0 }, st_mark = st_t0;
+	#define FB_STAT_MARK(k) { const long long t_ = clock64(); st_c[k] += t_ - st_mark; st_mark = t_; }
+#else
+	#define FB_STAT_MARK(k)
+#endif
 	for (;;)
 	{
 		// refill idle lanes as soon as a few of them are free: one atomic per warp
-		const unsigned need = __ballot_sync(0xFFFFFFFFu, !active);
+		unsigned need = __ballot_sync(0xFFFFFFFFu, !active);
+#if FB_THIN_QUOTA > 0 && FB_COOP_TRI && FB_SPLIT_RAYS
+		if (thin && need && !exhausted)
+		{
+			// rays in flight in this warp = lanes that own one; take what is missing to the quota, for the first idle lanes
+			const uint32 owners = (uint32)__popc(__ballot_sync(0xFFFFFFFFu, active && root == lane));
+			uint32 want = owners < quota ? quota - owners : 0u;
+			if (want > (uint32)__popc(need)) want = (uint32)__popc(need);
+			unsigned pick = 0u;
+			for (unsigned m = need; want; --want) { pick |= m & (0u - m); m &= m - 1u; }
+			need = pick;
+		}
+#endif
 		if (need && !exhausted && (__popc(need) >= FB_REFILL_LANES || need == 0xFFFFFFFFu))
 		{
 			const int leader = __ffs(need) - 1;
 			uint32 base = 0;
-			if (lane == leader) base = atomicAdd(a.cursor, (uint32)__popc(need));
+			if (lane == leader) base = atomicAdd(cursor, (uint32)__popc(need));
 			base = __shfl_sync(0xFFFFFFFFu, base, leader);
 			if (base + (uint32)__popc(need) > n) exhausted = true;
+#if FB_THIN_QUOTA > 0 && FB_COOP_TRI && FB_SPLIT_RAYS
+			if (!active && ((need >> lane) & 1u))
+#else
 			if (!active)
+#endif
 			{
 				ray_idx = base + __popc(need & ((1u << lane) - 1u));
-				if (ray_idx < n)
+				if (ray_idx < n && !tasks_phase)
 				{
 					const float4 o = ld_stream(a.ray_o + (size_t)ray_idx * a.stride), d = ld_stream(a.ray_d + (size_t)ray_idx * a.stride);
 					trav.init(o, d, ANY ? __float_as_uint(o.w) : 0u);
 					active = true;
 				}
+				else if (ray_idx < n)
+				{
+					// a continuation task: one pending entry of a suspended ray, traversed as a query of its own
+					const uint4 task = __ldcs(a.cont.tasks + ray_idx);
+					ray_idx = task.x;                                         // from here on: the slot of the suspended ray
+					const unsigned long long key = ray_idx != 0xFFFFFFFFu ? __ldcg(a.cont.keys + ray_idx) : 0ull;
+					if (ray_idx != 0xFFFFFFFFu && !(ANY && key != 0ull))         // (void task / the ray is known to be occluded already)
+					{
+						const uint32 r = __ldg(a.cont.ray_of_slot + ray_idx);
+						const float4 o = ld_stream(a.ray_o + (size_t)r * a.stride), d = ld_stream(a.ray_d + (size_t)r * a.stride);
+						trav.init(o, d, ANY ? __float_as_uint(o.w) : 0u);
+						trav.ngroup = make_uint2(0u, 0u);
+						if (task.z > 0x00FFFFFFu) trav.ngroup = make_uint2(task.y, task.z); else trav.tgroup = make_uint2(task.y, task.z);
+						if (!ANY) trav.adopt_key(key);
+						active = true;
+					}
+				}
 			}
 		}
+		if (exhausted) tail_iters++;
 		if (!__any_sync(0xFFFFFFFFu, active)) { if (exhausted) break; else continue; }
+#if FB_TRACE_STATS
+		if (st_busy) FB_STAT_MARK(3) else st_mark = clock64();
+		st_iters++; st_busy = true; if (exhausted) st_tail++;
+		st_lanes += (uint32)__popc(__ballot_sync(0xFFFFFFFFu, active)); st_helpers += (uint32)__popc(__ballot_sync(0xFFFFFFFFu, active && root != lane));
+		if (active && root == lane) { st_ray++; st_longest_ray = max(st_longest_ray, st_ray); } else st_ray = 0;     // iterations the lane's own ray has been in flight
+#endif
+
+		// ---- suspension: hand what is left of this warp's rays to the continuation launch (ContQueue, device_scene.h) ----
+		if (can_suspend && tail_iters > a.suspend_after)
+		{
+			const uint32 FULL = 0xFFFFFFFFu;
+			const bool owner = active && root == lane;
+			const uint32 cnt = active ? ((trav.has_node() ? 1u : 0u) + (trav.has_tri() ? 1u : 0u) + (uint32)trav.sp) : 0u;
+			uint32 incl = cnt;
+			#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) { const uint32 v = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += v; }
+			const uint32 total = __shfl_sync(FULL, incl, 31);
+			const unsigned owners = __ballot_sync(FULL, owner);
+			uint32 tbase = 0, sbase = 0;
+			if (lane == 0) { tbase = atomicAdd(a.cont_tasks, total); sbase = atomicAdd(a.cont_rays, (uint32)__popc(owners)); }
+			tbase = __shfl_sync(FULL, tbase, 0); sbase = __shfl_sync(FULL, sbase, 0);
+			const bool fits = tbase + total <= a.cont.task_capacity && sbase + (uint32)__popc(owners) <= a.cont.ray_capacity;
+			const uint32 my_slot = sbase + (uint32)__popc(owners & ((1u << lane) - 1u));
+			const uint32 slot = __shfl_sync(FULL, my_slot, root);            // helpers: the slot of the ray they work on
+			if (owner && my_slot < a.cont.ray_capacity)
+			{
+				a.cont.ray_of_slot[my_slot] = fits ? ray_idx : 0xFFFFFFFFu;
+				if (fits) a.cont.keys[my_slot] = ANY ? 0ull : (trav.hit.tri >= 0 ? pack_hit_key(trav.hit.t, trav.hit.tri) : ~0ull);
+			}
+			if (active)
+			{
+				uint32 k = tbase + incl - cnt;
+				const uint32 tslot = fits ? slot : 0xFFFFFFFFu;            // queue full: the claimed entries are voided and the rays stay here
+				if (trav.has_node()) { if (k < a.cont.task_capacity) a.cont.tasks[k] = make_uint4(tslot, trav.ngroup.x, trav.ngroup.y, 0u); ++k; }
+				if (trav.has_tri())  { if (k < a.cont.task_capacity) a.cont.tasks[k] = make_uint4(tslot, trav.tgroup.x, trav.tgroup.y, 0u); ++k; }
+				for (int i = 0; i < trav.sp; ++i, ++k) if (k < a.cont.task_capacity) a.cont.tasks[k] = make_uint4(tslot, trav.stack[i].x, trav.stack[i].y, 0u);
+			}
+			if (fits) { active = false; root = lane; }                       // the resolve kernel completes these rays
+			can_suspend = false;
+		}
 
 #if FB_COOP_TRI && FB_SPLIT_RAYS
 		// Ray splitting. A few rays (grazing a tessellated floor, say) visit twenty times more nodes than the average one,
@@ -251,16 +405,71 @@ __global__ void __launch_bounds__(FB_TRACE_THREADS, FB_TRACE_MIN_BLOCKS) k_trace
 		// which keeps the closest (t, triangle id), so the result does not depend on who traversed what. Helpers refresh
 		// their far bound from the owner every iteration; the owner retires its ray when its own traversal is finished
 		// and no helper is left (pending[]).
-		if (exhausted)
+		if (exhausted || thin)
 		{
 			unsigned idle = __ballot_sync(0xFFFFFFFFu, !active);
 			unsigned donors = __ballot_sync(0xFFFFFFFFu, active && trav.has_node() && trav.sp > 0);
+#if FB_PAR_SPLIT
+			// the k-th idle lane takes an entry of the k-th donor, all pairs at once: every lane shuffles from its own source
+			const int n_pairs = min(__popc(idle), __popc(donors));
+			if (n_pairs > 0)
+			{
+				const unsigned lt = (1u << lane) - 1u;
+				const bool is_helper = !active && __popc(idle & lt) < n_pairs;
+				const bool is_donor = ((donors >> lane) & 1u) && __popc(donors & lt) < n_pairs;
+				// (donor ranks -> lanes through the warp's pair list, which is free between two triangle phases)
+				if (is_donor) pair_buf[__popc(donors & lt)] = (uint32)lane;
+				__syncwarp();
+				const int src = is_helper ? (int)pair_buf[__popc(idle & lt)] : lane;
+				__syncwarp();
+				uint2 e = make_uint2(0u, 0u);
+				if (is_donor)
+				{
+#if FB_SPLIT_BOTTOM && FB_SMEM_STACK == 0
+					e = local_stack[0];
+					--trav.sp;
+					for (int i = 0; i < trav.sp; ++i) local_stack[i] = local_stack[i + 1];
+#else
+					e = trav.pop();
+#endif
+				}
+				e.x = __shfl_sync(0xFFFFFFFFu, e.x, src); e.y = __shfl_sync(0xFFFFFFFFu, e.y, src);
+				const float ox = __shfl_sync(0xFFFFFFFFu, trav.ray.ox, src), oy = __shfl_sync(0xFFFFFFFFu, trav.ray.oy, src), oz = __shfl_sync(0xFFFFFFFFu, trav.ray.oz, src);
+				const float dx = __shfl_sync(0xFFFFFFFFu, trav.ray.dx, src), dy = __shfl_sync(0xFFFFFFFFu, trav.ray.dy, src), dz = __shfl_sync(0xFFFFFFFFu, trav.ray.dz, src);
+				const float t0 = __shfl_sync(0xFFFFFFFFu, trav.ray.tmin, src), t1 = __shfl_sync(0xFFFFFFFFu, trav.ray.tmax, src);
+				const float ix = __shfl_sync(0xFFFFFFFFu, trav.idx_, src), iy = __shfl_sync(0xFFFFFFFFu, trav.idy_, src), iz = __shfl_sync(0xFFFFFFFFu, trav.idz_, src);
+				const uint32 oct = __shfl_sync(0xFFFFFFFFu, trav.octinv4, src), msk = __shfl_sync(0xFFFFFFFFu, trav.mask, src);
+				const int rt = __shfl_sync(0xFFFFFFFFu, root, src);
+				if (is_helper)
+				{
+					trav.ray.ox = ox; trav.ray.oy = oy; trav.ray.oz = oz; trav.ray.dx = dx; trav.ray.dy = dy; trav.ray.dz = dz;
+					trav.ray.tmin = t0; trav.ray.tmax = t1; trav.idx_ = ix; trav.idy_ = iy; trav.idz_ = iz;
+					trav.octinv4 = oct; trav.mask = msk;
+					trav.ngroup = e; trav.tgroup = make_uint2(0u, 0u); trav.sp = 0;
+					trav.hit.t = -1.0f; trav.hit.tri = -1; trav.occluded = false;
+					root = rt; active = true;
+#if !FB_MATCH_PENDING
+					atomicAdd(&pending[rt], 1u);
+#endif
+				}
+			}
+			idle = 0u;       // (the pair-by-pair loop below is skipped)
+#endif
 			while (idle && donors)
 			{
 				const int h = __ffs((int)idle) - 1, d = __ffs((int)donors) - 1;
 				idle &= idle - 1u; donors &= donors - 1u;
 				uint2 e = make_uint2(0u, 0u);
+#if FB_SPLIT_BOTTOM && FB_SMEM_STACK == 0
+				if (lane == d)
+				{
+					e = local_stack[0];
+					--trav.sp;
+					for (int i = 0; i < trav.sp; ++i) local_stack[i] = local_stack[i + 1];
+				}
+#else
 				if (lane == d) e = trav.pop();
+#endif
 				e.x = __shfl_sync(0xFFFFFFFFu, e.x, d); e.y = __shfl_sync(0xFFFFFFFFu, e.y, d);
 				const float ox = __shfl_sync(0xFFFFFFFFu, trav.ray.ox, d), oy = __shfl_sync(0xFFFFFFFFu, trav.ray.oy, d), oz = __shfl_sync(0xFFFFFFFFu, trav.ray.oz, d);
 				const float dx = __shfl_sync(0xFFFFFFFFu, trav.ray.dx, d), dy = __shfl_sync(0xFFFFFFFFu, trav.ray.dy, d), dz = __shfl_sync(0xFFFFFFFFu, trav.ray.dz, d);
@@ -301,15 +510,58 @@ __global__ void __launch_bounds__(FB_TRACE_THREADS, FB_TRACE_MIN_BLOCKS) k_trace
 		// pooled and tested by the whole warp (Traversal::coop_tri_phase); idle lanes of a thin warp test their mates' triangles
 		{
 			bool done = false;
+			FB_STAT_MARK(0)
+			// a task refreshes its far bound from the ray's key, where the other tasks of the same ray publish their hits
+			// (issued before the node visit, consumed after it: the load rides along with the node fetch)
+			unsigned long long fresh = ANY ? 0ull : ~0ull;
+			if (tasks_phase && active && root == lane) fresh = __ldcg(a.cont.keys + ray_idx);
 			if (active)
 			{
 				done = !trav.acquire();
 				if (!done) trav.node_step(sc, smem_nodes);
+#if FB_PREFETCH & 4
+				// pull the node this lane visits next - the next child of the group at hand or of the group on top of the stack -
+				// towards L1 while the triangle phase runs: the two L2 round trips of an iteration overlap
+				if (!done)
+				{
+					uint2 g = trav.ngroup;
+					if (!(g.y > 0x00FFFFFFu) && trav.sp > 0) g = local_stack[trav.sp - 1];
+					if (g.y > 0x00FFFFFFu)
+					{
+						const uint32 sl = (bfind(g.y) - 24u) ^ (trav.octinv4 & 0xFFu);
+						const uint32 nidx = g.x + __popc(g.y & ~(0xFFFFFFFFu << sl) & 0xFFu);
+						if (nidx >= sc.staged_nodes)
+						{
+							const char* p = reinterpret_cast<const char*>(sc.nodes) + (size_t)nidx * 80u;
+							asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+							asm volatile("prefetch.global.L1 [%0];" :: "l"(p + 64));
+						}
+					}
+				}
+#endif
 			}
+			if (tasks_phase && active && root == lane)
+			{
+				if (ANY) { if (fresh != 0ull) trav.occluded = true; }
+				else trav.adopt_key(fresh);
+			}
+			FB_STAT_MARK(1)
+#if FB_TRACE_STATS
+			trav.coop_tri_phase(sc, active && !done, pair_buf, lane, root, st_tri);
+#else
 			trav.coop_tri_phase(sc, active && !done, pair_buf, lane, root);
+#endif
+			FB_STAT_MARK(2)
 			if (active && !done) done = (ANY && trav.occluded) || (!trav.has_node() && trav.sp == 0);
-#if FB_SPLIT_RAYS && FB_MATCH_PENDING
-			if (exhausted)       // (warp-uniform; helpers exist only from then on)
+#if FB_SPLIT_RAYS && FB_MATCH_PENDING == 2
+			if (exhausted || thin)       // (warp-uniform; helpers exist only then)
+			{
+				if (active && done && root != lane) { root = lane; active = false; done = false; }                // a helper is through with its share
+				const uint32 helped = __reduce_or_sync(0xFFFFFFFFu, (active && root != lane) ? (1u << root) : 0u);   // rays that still have helpers at work
+				if (active && done && ((helped >> lane) & 1u)) done = false;                                      // the owner waits for its helpers
+			}
+#elif FB_SPLIT_RAYS && FB_MATCH_PENDING
+			if (exhausted || thin)       // (warp-uniform; helpers exist only then)
 			{
 				if (active && done && root != lane) { root = lane; active = false; done = false; }                // a helper is through with its share
 				const uint32 team = __match_any_sync(0xFFFFFFFFu, active ? (uint32)root : 32u + (uint32)lane);     // lanes at work on the same ray
@@ -336,30 +588,80 @@ __global__ void __launch_bounds__(FB_TRACE_THREADS, FB_TRACE_MIN_BLOCKS) k_trace
 			if (active && done)
 			{
 				active = false;
-				if (MODE == TRACE_QUEUE_CLOSEST || MODE == TRACE_RAYS_CLOSEST) st_stream(a.hits + ray_idx, trav.hit_record());
-				else if (MODE == TRACE_RAYS_SHADOW) a.occluded[ray_idx] = trav.occluded ? 1 : 0;
-				else if (!trav.occluded)
+				if (tasks_phase)
 				{
-					// solve_occlusion -> PTVertexProcessor::accumulate_nee (pathtracer_vertex_processor.h:204-239)
-					const float4 wd4 = ld_stream(a.w_d + ray_idx), wg4 = ld_stream(a.w_g + ray_idx);
-					const V3 w_d(wd4), w_g(wg4);
-					const uint32 info = __float_as_uint(wd4.w);
-					const uint32 pixel = info & 0x07FFFFFFu, comp = (info >> 27) & 0xFu;
-					add_in<false>(a.fb.channels[FB_COMPOSITED_C], pixel, w_d + w_g, a.frame_weight);
-					if (a.bounce == 0)
-					{
-						add_in<true>(a.fb.channels[FB_DIFFUSE_C], pixel, w_d, a.frame_weight);
-						add_in<true>(a.fb.channels[FB_SPECULAR_C], pixel, w_g, a.frame_weight);
-					}
-					else
-					{
-						if (comp & kDiffuseMask) add_in<true>(a.fb.channels[FB_DIFFUSE_C], pixel, w_d, a.frame_weight);
-						if (comp & kGlossyMask)  add_in<true>(a.fb.channels[FB_SPECULAR_C], pixel, w_g, a.frame_weight);
-					}
+					// merge this subtree's result into the suspended ray's key
+					if (ANY) { if (trav.occluded) a.cont.keys[ray_idx] = 1ull; }
+					else if (trav.hit.tri >= 0) atomicMin(a.cont.keys + ray_idx, pack_hit_key(trav.hit.t, trav.hit.tri));
 				}
+				else if (MODE == TRACE_QUEUE_CLOSEST || MODE == TRACE_RAYS_CLOSEST) st_stream(a.hits + ray_idx, trav.hit_record());
+				else if (MODE == TRACE_RAYS_SHADOW || FB_SPLIT_ACCUMULATE) a.occluded[ray_idx] = trav.occluded ? 1 : 0;
+				else if (!trav.occluded) accumulate_unoccluded(a, ray_idx);
 			}
 		}
 	}
+#if FB_TRACE_STATS
+	if (a.stat_max && st_longest_ray) atomicMax(a.stat_max + 3, st_longest_ray);
+	if (lane == 0 && a.stat_max && st_busy)
+	{
+		atomicMax(a.stat_max + 0, st_iters); atomicAdd(a.stat_max + 1, 1u); atomicMax(a.stat_max + 2, (uint32)(clock64() - st_t0));
+		atomicAdd(a.stat_sum + 0, (unsigned long long)st_iters); atomicAdd(a.stat_sum + 1, (unsigned long long)st_lanes);
+		atomicAdd(a.stat_sum + 2, (unsigned long long)st_helpers); atomicAdd(a.stat_sum + 3, (unsigned long long)st_tail);
+		for (int k = 0; k < 4; ++k) atomicAdd(a.stat_sum + 4 + k, (unsigned long long)st_c[k]);
+		for (int k = 0; k < 6; ++k) atomicAdd(a.stat_sum + 8 + k, (unsigned long long)st_tri[k]);
+	}
+#endif
+}
+
+// completes the rays a trace launch suspended, once their continuation tasks have run (ContQueue, device_scene.h)
+template <bool ANY>
+__global__ void __launch_bounds__(128) k_resolve_suspended(DeviceScene sc, TraceArgs a)
+{
+	const uint32 n = min(*a.cont_rays, a.cont.ray_capacity);
+	if (blockIdx.x == 0 && threadIdx.x == 0 && n && a.cont.totals)
+	{
+		atomicAdd(a.cont.totals, (unsigned long long)n);                                                         // PassTotals::suspended_rays
+		atomicAdd(a.cont.totals + 1, (unsigned long long)min(*a.cont_tasks, a.cont.task_capacity));             // PassTotals::continuation_tasks
+	}
+	for (uint32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+	{
+		const uint32 ray_idx = a.cont.ray_of_slot[i];
+		if (ray_idx == 0xFFFFFFFFu) continue;
+		const unsigned long long key = a.cont.keys[i];
+#if FB_SPLIT_ACCUMULATE
+		if (ANY) { a.occluded[ray_idx] = key != 0ull ? 1 : 0; continue; }
+#else
+		if (ANY) { if (key == 0ull) accumulate_unoccluded(a, ray_idx); continue; }
+#endif
+		if (key == ~0ull) { st_stream(a.hits + ray_idx, make_float4(-1.0f, __int_as_float(-1), 0.0f, 0.0f)); continue; }
+		const float t = __uint_as_float((uint32)(key >> 32));
+		const int tri = (int)(uint32)(key & 0xFFFFFFFFull);
+		// barycentrics of the winning triangle: the Moller-Trumbore sequence of Traversal::coop_tri_phase on the same vertex
+		// floats (WideTri copies them from the mesh arrays), so the record carries the bits a local hit would have carried
+		const float4 o = ld_stream(a.ray_o + (size_t)ray_idx * a.stride), d = ld_stream(a.ray_d + (size_t)ray_idx * a.stride);
+		const int4 vi = __ldg(sc.vertex_indices + tri);
+		const float4 va = __ldg(sc.vertex_data + vi.x), vb = __ldg(sc.vertex_data + vi.y), vc = __ldg(sc.vertex_data + vi.z);
+		const float e1x = vb.x - va.x, e1y = vb.y - va.y, e1z = vb.z - va.z;
+		const float e2x = vc.x - va.x, e2y = vc.y - va.y, e2z = vc.z - va.z;
+		const float px = d.y * e2z - d.z * e2y, py = d.z * e2x - d.x * e2z, pz = d.x * e2y - d.y * e2x;
+		const float det = e1x * px + e1y * py + e1z * pz;
+		const float inv = 1.0f / det;
+		const float tx = o.x - va.x, ty = o.y - va.y, tz = o.z - va.z;
+		const float bu = (tx * px + ty * py + tz * pz) * inv;
+		const float qx = ty * e1z - tz * e1y, qy = tz * e1x - tx * e1z, qz = tx * e1y - ty * e1x;
+		const float bv = (d.x * qx + d.y * qy + d.z * qz) * inv;
+		const float u = __half2float(__float2half_rn(1.0f - bu - bv)), v = __half2float(__float2half_rn(bu));
+		st_stream(a.hits + ray_idx, make_float4(t, __int_as_float(tri), u, v));
+	}
+}
+
+// solve_occlusion_kernel (pathtracer_kernels.h:248-267) as a pass of its own over the shadow queue (FB_SPLIT_ACCUMULATE): consecutive
+// threads read consecutive weights, and nobody waits for the frame buffer but the thread that adds to it
+__global__ void __launch_bounds__(256) k_accumulate_unoccluded(TraceArgs a)
+{
+	const uint32 n = *a.n_ptr;
+	for (uint32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+		if (a.occluded[i] == 0) accumulate_unoccluded(a, i);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -713,20 +1015,53 @@ cudaError_t launch_generate_primary(const DeviceScene& sc, const PassParams& pp,
 	k_generate_primary<<<(total + 255) / 256, 256, 0, s>>>(sc, pp, q, ctr, seq2[0], seq2[1], fb);
 	return cudaGetLastError();
 }
-cudaError_t launch_trace_closest(const DeviceScene& sc, const LaunchConfig& lc, const PathQueue& q, PassCounters* ctr, uint32 bounce, cudaStream_t s)
+static void set_cont(TraceArgs& a, const ContQueue* cont, PassCounters* ctr, int which, uint32 bounce, int suspend_after)
+{
+	a.suspend_after = -1;
+	if (cont == NULL || cont->tasks == NULL || suspend_after < 0) return;
+	a.cont = *cont; a.cont_tasks = &ctr->cont_tasks[which][bounce]; a.cont_next = &ctr->cont_next[which][bounce]; a.cont_rays = &ctr->cont_rays[which][bounce];
+	a.suspend_after = suspend_after;
+}
+cudaError_t launch_trace_closest(const DeviceScene& sc, const LaunchConfig& lc, const PathQueue& q, PassCounters* ctr, uint32 bounce, cudaStream_t s,
+								 const ContQueue* cont, int suspend_after, uint32* launches)
 {
 	TraceArgs a; memset(&a, 0, sizeof(a));
 	a.ray_o = q.ray_o; a.ray_d = q.ray_d; a.stride = 1; a.n_ptr = &ctr->in_size[bounce]; a.cursor = &ctr->trace_next[bounce]; a.hits = q.hit;
-	k_trace<TRACE_QUEUE_CLOSEST><<<lc.sm_count * lc.trace_ctas_per_sm, lc.trace_threads, staged_smem(sc), s>>>(sc, a);
+	set_cont(a, cont, ctr, 0, bounce, suspend_after);
+	a.stat_max = ctr->stat_max[0][bounce]; a.stat_sum = ctr->stat_sum[0][bounce];
+	if (launches) *launches = a.suspend_after >= 0 ? 3 : 1;
+	if (a.suspend_after < 0)
+		k_trace<TRACE_QUEUE_CLOSEST><<<lc.sm_count * lc.trace_ctas_per_sm, lc.trace_threads, staged_smem(sc), s>>>(sc, a);
+	else
+	{
+		k_trace<TRACE_QUEUE_CLOSEST, TRACE_SUSPENDING><<<lc.sm_count * lc.trace_ctas_per_sm, lc.trace_threads, staged_smem(sc), s>>>(sc, a);
+		k_trace<TRACE_QUEUE_CLOSEST, TRACE_TASKS><<<lc.sm_count * lc.trace_ctas_per_sm, lc.trace_threads, staged_smem(sc), s>>>(sc, a);
+		k_resolve_suspended<false><<<lc.sm_count, 128, 0, s>>>(sc, a);
+	}
 	return cudaGetLastError();
 }
 cudaError_t launch_trace_shadow(const DeviceScene& sc, const LaunchConfig& lc, const ShadowQueue& sq, const FrameBufferView& fb, PassCounters* ctr, PassTotals* tot,
-								uint32 bounce, float frame_weight, cudaStream_t s)
+								uint32 bounce, float frame_weight, cudaStream_t s, const ContQueue* cont, int suspend_after, uint32* launches)
 {
 	TraceArgs a; memset(&a, 0, sizeof(a));
 	a.ray_o = sq.ray_o; a.ray_d = sq.ray_d; a.stride = 1; a.n_ptr = &ctr->shadow_size[bounce]; a.cursor = &ctr->shadow_next[bounce];
 	a.w_d = sq.w_d; a.w_g = sq.w_g; a.fb = fb; a.frame_weight = frame_weight; a.bounce = bounce; a.event_counter = &tot->shadow_events;
-	k_trace<TRACE_QUEUE_SHADOW><<<lc.sm_count * lc.trace_ctas_per_sm, lc.trace_threads, staged_smem(sc), s>>>(sc, a);
+	a.occluded = sq.occluded;
+	set_cont(a, cont, ctr, 1, bounce, suspend_after);
+	a.stat_max = ctr->stat_max[1][bounce]; a.stat_sum = ctr->stat_sum[1][bounce];
+	if (launches) *launches = a.suspend_after >= 0 ? 3 : 1;
+	if (a.suspend_after < 0)
+		k_trace<TRACE_QUEUE_SHADOW><<<lc.sm_count * lc.trace_ctas_per_sm, lc.trace_threads, staged_smem(sc), s>>>(sc, a);
+	else
+	{
+		k_trace<TRACE_QUEUE_SHADOW, TRACE_SUSPENDING><<<lc.sm_count * lc.trace_ctas_per_sm, lc.trace_threads, staged_smem(sc), s>>>(sc, a);
+		k_trace<TRACE_QUEUE_SHADOW, TRACE_TASKS><<<lc.sm_count * lc.trace_ctas_per_sm, lc.trace_threads, staged_smem(sc), s>>>(sc, a);
+		k_resolve_suspended<true><<<lc.sm_count, 128, 0, s>>>(sc, a);
+	}
+#if FB_SPLIT_ACCUMULATE
+	k_accumulate_unoccluded<<<lc.sm_count * 4, 256, 0, s>>>(a);
+	if (launches) *launches += 1;
+#endif
 	return cudaGetLastError();
 }
 cudaError_t launch_trace_rays(const DeviceScene& sc, const LaunchConfig& lc, const float4* rays, float4* hits, uint32 n, uint32* cursor, cudaStream_t s)

@@ -37,11 +37,14 @@ cudaError_t launch_update_variances(const FrameBufferView& fb, const PixelSet& p
 cudaError_t launch_copy_channel(const FrameBufferView& fb, int channel, float4* dst, const PixelSet& ps, cudaStream_t s);
 // also resets the G-buffer of every pixel it starts a path for (pass `fb` with gb_geo == NULL to skip)
 cudaError_t launch_generate_primary(const DeviceScene& sc, const PassParams& pp, const PathQueue& q, PassCounters* ctr, const float seq2[2], const FrameBufferView& fb, cudaStream_t s);
-cudaError_t launch_trace_closest(const DeviceScene& sc, const LaunchConfig& lc, const PathQueue& q, PassCounters* ctr, uint32 bounce, cudaStream_t s);
+// cont / suspend_after: ray suspension (ContQueue, device_scene.h); NULL or a negative count turns it off. With it on, a
+// trace is three launches: the rays, the continuation tasks of the suspended ones, the resolve kernel (`launches` says how many)
+cudaError_t launch_trace_closest(const DeviceScene& sc, const LaunchConfig& lc, const PathQueue& q, PassCounters* ctr, uint32 bounce, cudaStream_t s,
+								 const ContQueue* cont = NULL, int suspend_after = -1, uint32* launches = NULL);
 cudaError_t launch_shade(const DeviceScene& sc, const LaunchConfig& lc, const PassParams& pp, const PathQueue& in, const PathQueue& out, const ShadowQueue& sq,
 						 const FrameBufferView& fb, PassCounters* ctr, PassTotals* tot, uint32 bounce, const float seq6[6], uint32 capacity, cudaStream_t s);
 cudaError_t launch_trace_shadow(const DeviceScene& sc, const LaunchConfig& lc, const ShadowQueue& sq, const FrameBufferView& fb, PassCounters* ctr, PassTotals* tot,
-								uint32 bounce, float frame_weight, cudaStream_t s);
+								uint32 bounce, float frame_weight, cudaStream_t s, const ContQueue* cont = NULL, int suspend_after = -1, uint32* launches = NULL);
 
 // stand-alone ray queries on caller-provided device buffers (RTContext::trace / trace_shadow twins)
 cudaError_t launch_trace_rays(const DeviceScene& sc, const LaunchConfig& lc, const float4* rays, float4* hits, uint32 n, uint32* cursor, cudaStream_t s);

@@ -181,10 +181,19 @@ int fb200_context_get_stats(fb200_context*, fb200_stats* out);
  * classes: 0 frame-buffer element-wise + primary rays, 1 closest-hit trace, 2 shade, 3 shadow trace + accumulate */
 int fb200_context_set_profiling(fb200_context*, int on);
 int fb200_context_get_kernel_times(fb200_context*, double out_ms[4], uint64_t out_launches[4]);
+/* the same spans per bounce: out_ms[class * 64 + bounce], summed over passes and sub-frames (class 0 under bounce 0) */
+int fb200_context_get_bounce_times(fb200_context*, double out_ms[4 * 64]);
+/* diagnostic: the renderer's device-side counters of sub-frame `subframe` (struct PassCounters, fermat_b200/csrc/kernels/
+ * device_scene.h: queue sizes per bounce, the FB_TRACE_STATS statistics) as the last pass left them; copies min(bytes,
+ * sizeof(PassCounters)) bytes. Fails when there is no such sub-frame. */
+int fb200_diag_pass_counters(fb200_context*, uint32_t subframe, void* out, uint64_t bytes);
 /* CUDA stream handle (cudaStream_t) of the context. Every call first orders the stream behind the passes rendered
  * so far (they run on the renderer's private streams) and makes the next pass wait for what the caller enqueues on it:
  * call it again before each use rather than caching the handle. */
 void* fb200_context_stream(fb200_context*);
+/* ray suspension (FB200_SUSPEND=<iterations>, off by default): out[0] = rays the persistent trace launches handed to
+ * their continuation launches since the context was created, out[1] = the subtree tasks those rays were cut into */
+int fb200_context_get_suspension_stats(fb200_context*, uint64_t out[2]);
 /* number of pixels this shard owns */
 uint64_t fb200_context_owned_pixels(const fb200_context*);
 

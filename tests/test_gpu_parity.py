@@ -235,6 +235,38 @@ def test_big_scenes_against_oracle(fb, oracle, scene, res, bounces):
     rc.close(); sc.close()
 
 
+def test_ray_suspension_leaves_every_result_unchanged(fb, oracle, monkeypatch, after="0"):
+    """FB200_SUSPEND: trace warps hand the rays they still hold, a few iterations after the queue ran dry, to a second
+    launch as independent subtree tasks (ContQueue, device_scene.h). Closest hit = min over (t, triangle id) and
+    occlusion = any: cutting a ray up must not change a single bit of the frame."""
+    def frames(args, passes):
+        sc = fb.Scene(args)
+        rc = fb.RenderingContext(sc)
+        rc.clear()
+        for i in range(passes):
+            rc.render(i, sync=False)
+        out = [rc.download(n) for n in ("COMPOSITED_C", "DIRECT_C", "DIFFUSE_C", "SPECULAR_C")], rc.stats(), rc.suspension_stats(), rc.download_gbuffer()
+        rc.close(); sc.close()
+        return out
+    cases = [(cornell_args(96, 4), 4)]
+    path = os.path.join(CACHE, "bathroom2.fbs")
+    if fb.scene_available(path):
+        cases.append((["-i", path, "-r", "800", "450", "-bounces", "8"], 2))
+    for args, passes in cases:
+        monkeypatch.delenv("FB200_SUSPEND", raising=False)
+        want, st0, susp0, gb0 = frames(args, passes)
+        assert susp0 == (0, 0)
+        monkeypatch.setenv("FB200_SUSPEND", after)
+        got, st1, susp1, gb1 = frames(args, passes)
+        assert susp1[0] > 0 and susp1[1] >= susp1[0] // 2, susp1       # rays were suspended, and cut into tasks
+        for a, b in zip(got, want):
+            assert np.array_equal(a, b)
+        assert np.array_equal(gb0["tri"], gb1["tri"]) and np.array_equal(gb0["uv"].view(np.uint32), gb1["uv"].view(np.uint32))
+        assert st0["shade_events"] == st1["shade_events"] and st0["shadow_events"] == st1["shadow_events"]
+        assert st1["kernel_launches"] > st0["kernel_launches"]
+    monkeypatch.delenv("FB200_SUSPEND", raising=False)
+
+
 def test_full_size_workload_properties(fb):
     """BASELINE.json configs[1] at full size (1600x900, 8 bounces): size-independent properties."""
     path = os.path.join(CACHE, "bathroom2.fbs")
