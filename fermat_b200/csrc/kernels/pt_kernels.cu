@@ -290,6 +290,7 @@ __global__ void __launch_bounds__(FB_TRACE_THREADS, FB_TRACE_MIN_BLOCKS) k_trace
 #endif
 	int  tail_iters = 0;             // warp-uniform: iterations since then
 	bool can_suspend = may_suspend;
+	bool flip = false;               // warp-uniform: pool order of the triangle phase (FB_LAZY_TRI)
 	uint32* const cursor = tasks_phase ? a.cont_next : a.cursor;
 #if FB_TRACE_STATS
 	uint32 st_iters = 0, st_tail = 0, st_lanes = 0, st_helpers = 0, st_ray = 0, st_longest_ray = 0; bool st_busy = false;
@@ -518,7 +519,11 @@ __global__ void __launch_bounds__(FB_TRACE_THREADS, FB_TRACE_MIN_BLOCKS) k_trace
 			if (active)
 			{
 				done = !trav.acquire();
+#if FB_LAZY_TRI
+				if (!done && !trav.has_tri()) trav.node_step(sc, smem_nodes);      // (a ray with triangles left over from the last round waits for them)
+#else
 				if (!done) trav.node_step(sc, smem_nodes);
+#endif
 #if FB_PREFETCH & 4
 				// pull the node this lane visits next - the next child of the group at hand or of the group on top of the stack -
 				// towards L1 while the triangle phase runs: the two L2 round trips of an iteration overlap
@@ -547,12 +552,15 @@ __global__ void __launch_bounds__(FB_TRACE_THREADS, FB_TRACE_MIN_BLOCKS) k_trace
 			}
 			FB_STAT_MARK(1)
 #if FB_TRACE_STATS
-			trav.coop_tri_phase(sc, active && !done, pair_buf, lane, root, st_tri);
+			trav.coop_tri_phase(sc, active && !done, pair_buf, lane, root, st_tri, flip);
+#elif FB_LAZY_TRI
+			trav.coop_tri_phase(sc, active && !done, pair_buf, lane, root, NULL, flip);
 #else
 			trav.coop_tri_phase(sc, active && !done, pair_buf, lane, root);
 #endif
+			flip = !flip;
 			FB_STAT_MARK(2)
-			if (active && !done) done = (ANY && trav.occluded) || (!trav.has_node() && trav.sp == 0);
+			if (active && !done) done = (ANY && trav.occluded) || (!trav.has_node() && trav.sp == 0 && !(FB_LAZY_TRI && trav.has_tri()));
 #if FB_SPLIT_RAYS && FB_MATCH_PENDING == 2
 			if (exhausted || thin)       // (warp-uniform; helpers exist only then)
 			{

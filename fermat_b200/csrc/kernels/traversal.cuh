@@ -30,6 +30,14 @@ namespace fb {
 #define FB_FOLD_MAGIC 1            // 1 (r02 sweep: +0.4 %): leave the 2^15 offset of the PRMT-built plane coordinate in place and fold it into the slab
                                    // constants (one FADD less per plane, 48 per node visit), with a proven-conservative widening
 #endif
+#ifndef FB_LAZY_TRI
+#define FB_LAZY_TRI 0              // 1: the triangle phase tests the pooled pairs 32 at a time but does not run a round for a remainder: after the first
+                                   // round, pairs that do not fill a whole round stay with their rays (which sit out the next node visit) and are pooled
+                                   // with the next iteration's, the pool order flipping every iteration so that nobody is left behind twice
+#endif
+#if FB_LAZY_TRI && (FB_PAR_LIST || FB_SEG_DELIVER)
+#error "FB_LAZY_TRI keeps the list-based triangle phase"
+#endif
 #ifndef FB_PAR_LIST
 #define FB_PAR_LIST 0              // 1 (r03: -2.7 % device-timed, +0.5 % end to end: noise): triangle phase: lane j finds the j-th pooled (ray, triangle) pair by a search over the lanes' prefix sums
                                    // (shuffles only) instead of reading a list the owners wrote to shared memory one triangle at a time
@@ -336,7 +344,7 @@ struct Traversal
 	// k_trace): hits are delivered there.
 	// (TRI_MARK: cycle counters of the diagnostic build, k_trace FB_TRACE_STATS; st = NULL otherwise)
 	#define FB_TRI_MARK(k) if (st) { const long long t_ = clock64(); st[k] += t_ - st_mark; st_mark = t_; }
-	FB_D void coop_tri_phase(const DeviceScene& sc, const bool mine, uint32* __restrict__ pairs, const int lane, const int root, long long* st = NULL)
+	FB_D void coop_tri_phase(const DeviceScene& sc, const bool mine, uint32* __restrict__ pairs, const int lane, const int root, long long* st = NULL, const bool flip = false)
 	{
 		const uint32 FULL = 0xFFFFFFFFu;
 		long long st_mark = st ? clock64() : 0;
@@ -353,10 +361,16 @@ struct Traversal
 			if (lane >= d) incl += v;
 		}
 		const uint32 total = __shfl_sync(FULL, incl, 31);
+#if FB_LAZY_TRI
+		uint32 next = flip ? total - incl : incl - k;   // pool index of this lane's next unlisted triangle (lanes in descending order every other iteration)
+		const uint32 limit = total < 32u ? total : (total & ~31u);
+#else
 		uint32 next = incl - k;                    // pool index of this lane's next unlisted triangle
+		const uint32 limit = total;
+#endif
 		FB_TRI_MARK(0)
 
-		for (uint32 base = 0; base < total; base += 32u)
+		for (uint32 base = 0; base < limit; base += 32u)
 		{
 			const bool valid = base + (uint32)lane < total;
 #if FB_PAR_LIST
@@ -500,6 +514,9 @@ struct Traversal
 			__syncwarp();
 			FB_TRI_MARK(5)
 		}
+#if FB_LAZY_TRI
+		if (mine) tgroup.y = m;                    // pairs beyond the last whole round stay pending
+#endif
 	}
 
 	// reference hit record: u = weight of v0, v = weight of v1, through fp16

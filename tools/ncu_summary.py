@@ -81,10 +81,11 @@ def main():
         for d in out:
             w.writerow([("%.6g" % d[n]) if isinstance(d.get(n), float) else d.get(n, "") for n in names])
     if a.traffic:
-        cls = {"trace": [], "shadow": [], "shade": []}
+        cls = {"trace": [], "shadow": [], "shade": [], "accumulate": []}
         for d in out:
             k = d["kernel"]
-            c = "shade" if "k_shade" in k else ("trace" if "k_trace<0>" in k or "k_trace<(int)0>" in k else ("shadow" if "k_trace" in k else None))
+            closest = any(s in k for s in ("k_trace<0>", "k_trace<(int)0>", "k_trace<0,", "k_trace<(int)0,"))
+            c = "shade" if "k_shade" in k else ("accumulate" if "k_accumulate" in k else ("trace" if closest else ("shadow" if "k_trace" in k else None)))
             if c:
                 cls[c].append(d["dram_read"] + d["dram_write"])
         t = {c: (sum(v) / len(v) if v else None) for c, v in cls.items()}
