@@ -27,6 +27,11 @@ class PTOptions(C.Structure):
         "glossy_scattering", "indirect_glossy", "rr", "nee_type")]
 
 
+class PSFOptions(C.Structure):
+    _fields_ = [("enabled", C.c_uint32), ("psf_depth", C.c_uint32), ("psf_width", C.c_float), ("psf_min_dist", C.c_float),
+                ("psf_max_prob", C.c_float), ("psf_temporal_reuse", C.c_uint32), ("firefly_filter", C.c_float), ("log_hash_size", C.c_uint32)]
+
+
 class TextureView(C.Structure):
     _fields_ = [("texels", C.POINTER(C.c_float)), ("res_x", C.c_uint32), ("res_y", C.c_uint32)]
 
@@ -49,6 +54,7 @@ class SceneView(C.Structure):
         ("bbox_min", C.c_float * 3), ("bbox_max", C.c_float * 3),
         ("options", PTOptions),
         ("n_bvh_index", C.c_uint32),
+        ("psf", PSFOptions),
     ]
 
 
@@ -133,7 +139,7 @@ def lib():
 
 # struct PassCounters (fermat_b200/csrc/kernels/device_scene.h)
 PASS_COUNTERS_DTYPE = np.dtype([("in_size", "<u4", 64), ("shadow_size", "<u4", 64), ("trace_next", "<u4", 64), ("shadow_next", "<u4", 64),
-                                ("shade_next", "<u4", 64), ("pad", "<u4", 64), ("cont_tasks", "<u4", (2, 64)), ("cont_next", "<u4", (2, 64)),
+                                ("shade_next", "<u4", 64), ("ref_size", "<u4", 64), ("cont_tasks", "<u4", (2, 64)), ("cont_next", "<u4", (2, 64)),
                                 ("cont_rays", "<u4", (2, 64)), ("stat_max", "<u4", (2, 64, 4)), ("stat_sum", "<u8", (2, 64, 16))])
 
 

@@ -29,8 +29,8 @@ fb200_context* fb200_context_create(fb200_scene* scene, int device)
 	try
 	{
 		c = new fb200_context();
-		char arg0[] = "-pt";
-		char* argv[] = { arg0 };
+		char arg_pt[] = "-pt", arg_psfpt[] = "-psfpt";
+		char* argv[] = { scene->psf.enabled ? arg_psfpt : arg_pt };      // the renderer the scene's command line asked for
 		c->rc.init_with_scene(scene, device, 1, argv);
 		c->cursor.alloc(sizeof(uint32_t));
 		fb::set_last_error("");
@@ -231,6 +231,7 @@ int fb200_bsdf_eval(fb200_context* c, const float* rec, float* out, uint32_t n)
 uint32_t register_plugin(void* rendering_context)
 {
 	RenderingContext* rc = static_cast<RenderingContext*>(rendering_context);
+	rc->register_renderer("psfpt", &PathTracer::factory_psf);      // the filtered variant rides along (src/renderer.cu:471-477 lists both)
 	return rc->register_renderer("pt", &PathTracer::factory);
 }
 

@@ -8,8 +8,9 @@
 
 using namespace fb;
 
-PathTracer::PathTracer() : m_tiles_x(0), m_owned_pixels(0), m_passes(0), m_device_ms(0.0), m_overlap(1), m_trace_ctas(0), m_suspend_after(-1), m_events(false), m_profiling(false)
+PathTracer::PathTracer() : m_tiles_x(0), m_owned_pixels(0), m_passes(0), m_device_ms(0.0), m_overlap(1), m_trace_ctas(0), m_suspend_after(-1), m_psf(false), m_events(false), m_profiling(false)
 {
+	memset(&m_psf_view, 0, sizeof(m_psf_view));
 	for (int i = 0; i < 4; ++i) { m_class_ms[i] = 0.0; m_class_launches[i] = 0; }
 	memset(m_bounce_ms, 0, sizeof(m_bounce_ms));
 	pt_options_defaults(m_options);
@@ -44,13 +45,15 @@ struct Arena
 		return p;
 	}
 };
-void carve(Arena& a, size_t cap, size_t shadow_cap, PathQueue q[2], ShadowQueue& sq)
+void carve(Arena& a, size_t cap, size_t shadow_cap, PathQueue q[2], ShadowQueue& sq, bool psf)
 {
 	for (int i = 0; i < 2; ++i)
 	{
 		q[i].ray_o = a.alloc<float4>(cap); q[i].ray_d = a.alloc<float4>(cap); q[i].hit = a.alloc<float4>(cap);
 		q[i].weight = a.alloc<float4>(cap); q[i].pixel = a.alloc<uint32>(cap);
+		if (psf) { q[i].cone = a.alloc<float2>(cap); q[i].vinfo = a.alloc<uint32>(cap); }
 	}
+	if (psf) sq.vinfo = a.alloc<uint32>(shadow_cap);
 	sq.ray_o = a.alloc<float4>(shadow_cap); sq.ray_d = a.alloc<float4>(shadow_cap);
 	sq.w_d = a.alloc<float4>(shadow_cap); sq.w_g = a.alloc<float4>(shadow_cap);
 	sq.occluded = a.alloc<unsigned char>(shadow_cap);
@@ -65,15 +68,23 @@ void PathTracer::init(int argc, char** argv, RenderingContext& renderer)
 	m_options = s.options;
 	const uint2 res = renderer.res();
 
-	fprintf(stderr, "  PT settings:\n    path-length     : %u\n    nee algorithm   : %s\n", m_options.max_path_length, m_options.nee_type == 1 ? "vpl" : "mesh");
+	fprintf(stderr, "  %s settings:\n    path-length     : %u\n    nee algorithm   : %s\n", m_psf ? "PSFPT" : "PT", m_options.max_path_length, m_options.nee_type == 1 ? "vpl" : "mesh");
+	if (m_psf)
+	{
+		const fb200_psf_options& po = s.psf;
+		fprintf(stderr, "    filter width    : %f\n    filter depth    : %u\n    filter min-dist : %f\n    firefly filter  : %f\n", po.psf_width, po.psf_depth, po.psf_min_dist, po.firefly_filter);
+		if (!kernels_split_accumulate()) throw std::runtime_error("-psfpt needs kernels built with FB_SPLIT_ACCUMULATE");
+		if (!s.scene.dir_lights.empty()) throw std::runtime_error("-psfpt: directional lights are not supported");
+	}
 
 	// tile shard of this process: tile T = ty*tiles_x + tx belongs to rank (T + ty) % shard_count
 	std::vector<uint32> tiles;
 	m_owned_pixels = shard_tiles(res.x, res.y, s.shard_rank, s.shard_count, tiles, m_tiles_x);
 
 	// sub-frames: the owned tiles dealt round-robin (FB200_SUBFRAMES, default 2; at least 64 tiles each)
+	// (`-psfpt`: one sub-frame - the references are splat once every path of the pass has fed its cell)
 	const char* env = getenv("FB200_SUBFRAMES");
-	uint32 n_sub = env ? (uint32)atoi(env) : 2u;
+	uint32 n_sub = m_psf ? 1u : (env ? (uint32)atoi(env) : 2u);
 	while (n_sub > 1 && tiles.size() / n_sub < 64) n_sub--;
 	if (n_sub < 1) n_sub = 1;
 	env = getenv("FB200_OVERLAP");
@@ -107,7 +118,14 @@ void PathTracer::init(int argc, char** argv, RenderingContext& renderer)
 			SubFrame& f = *m_sub[k];
 			f.n_tiles = (uint32)sub_tiles[k].size();
 			f.capacity = (uint64_t)f.n_tiles * 32u * 32u;
-			carve(arena, f.capacity, dirlights ? 2 * f.capacity : f.capacity, f.queue, f.shadow);
+			carve(arena, f.capacity, dirlights ? 2 * f.capacity : f.capacity, f.queue, f.shadow, m_psf);
+			if (m_psf)
+			{
+				// reference queue: one segment per bounce (src/renderers/psfpt_impl.h:145-160 sizes it n_pixels x (path length + 1))
+				const size_t n_refs = f.capacity * m_options.max_path_length;
+				m_psf_view.ref_w_d = arena.alloc<float4>(n_refs); m_psf_view.ref_w_g = arena.alloc<float4>(n_refs); m_psf_view.ref_pixels = arena.alloc<uint2>(n_refs);
+				m_psf_view.ref_capacity = (uint32)f.capacity;
+			}
 			for (int c = 0; c < 2 && cont_rays; ++c)
 			{
 				f.cont[c].tasks = arena.alloc<uint4>(cont_tasks); f.cont[c].ray_of_slot = arena.alloc<uint32>(cont_rays); f.cont[c].keys = arena.alloc<unsigned long long>(cont_rays);
@@ -143,6 +161,18 @@ void PathTracer::init(int argc, char** argv, RenderingContext& renderer)
 		}
 		renderer.set_partitions(parts);
 		renderer.set_renderer_clears_gbuffer(true);
+	}
+	if (m_psf)
+	{
+		const fb200_psf_options& po = s.psf;
+		const size_t n = size_t(1) << po.log_hash_size;
+		m_psf_keys.alloc(n * sizeof(unsigned long long)); m_psf_values.alloc(n * sizeof(float4));
+		m_psf_view.keys = m_psf_keys.as<unsigned long long>(); m_psf_view.values = m_psf_values.as<float4>(); m_psf_view.mask = (uint32)(n - 1);
+		m_psf_view.psf_depth = po.psf_depth; m_psf_view.psf_width = po.psf_width; m_psf_view.psf_max_prob = po.psf_max_prob; m_psf_view.firefly_filter = po.firefly_filter;
+		const Bbox3& bb = s.scene.bbox;
+		m_psf_view.bbox_lo[0] = bb.lo.x; m_psf_view.bbox_lo[1] = bb.lo.y; m_psf_view.bbox_lo[2] = bb.lo.z;
+		m_psf_view.bbox_hi[0] = bb.hi.x; m_psf_view.bbox_hi[1] = bb.hi.y; m_psf_view.bbox_hi[2] = bb.hi.z;
+		fprintf(stderr, "  allocating filter cache: %.1f MB (%llu cells)\n", float(n * 24) / (1024 * 1024), (unsigned long long)n);
 	}
 	m_totals.alloc(sizeof(PassTotals));
 	for (uint32 k = 0; k < n_sub; ++k)
@@ -206,6 +236,23 @@ void PathTracer::render(const uint32_t instance, RenderingContext& renderer)
 		pp.eye[0] = c.eye.x; pp.eye[1] = c.eye.y; pp.eye[2] = c.eye.z;
 	}
 	pp.tiles_x = m_tiles_x;
+	{
+		const Camera& c = renderer.get_camera();
+		const float tn = tanf(c.fov / 2);
+		pp.cam_w_len = sqrtf(pp.W[0] * pp.W[0] + pp.W[1] * pp.W[1] + pp.W[2] * pp.W[2]);
+		pp.cam_sq_pixel_focal = (float(renderer.res().x * renderer.res().y) / 4.0f) / (tn * tn);
+	}
+	if (m_psf)
+	{
+		m_psf_view.instance = instance;
+		if ((instance % s.psf.psf_temporal_reuse) == 0)
+		{
+			// DeviceHashTable::clear (src/hashmap.h:52-58); the values are zeroed here rather than by whoever inserts a key first
+			cudaStream_t st = renderer.stream();
+			cuda_check(cudaMemsetAsync(m_psf_keys.ptr, 0xFF, m_psf_keys.bytes, st), "clear filter cache");
+			cuda_check(cudaMemsetAsync(m_psf_values.ptr, 0, m_psf_values.bytes, st), "clear filter cache");
+		}
+	}
 
 	// Every sub-frame is a pipeline of its own: rescale its pixels, trace the pass, update its variances, all on its
 	// own stream, and pass i+1 of one sub-frame may start while pass i of another is still in its last bounces. The
@@ -269,6 +316,7 @@ void PathTracer::render_subframe(SubFrame& f, const PassParams& pass, const std:
 
 	const uint32 L = m_options.max_path_length;
 	uint32 n_launches = 0;
+	const PsfView* psf = m_psf ? &m_psf_view : NULL;
 	for (uint32 bounce = 0; bounce < L; ++bounce)
 	{
 		span.bounce = bounce;
@@ -285,12 +333,12 @@ void PathTracer::render_subframe(SubFrame& f, const PassParams& pass, const std:
 		for (int i = 0; i < 6; ++i) seq6[i] = seq[(bounce + 1) * 6 + i];
 		if (overlap && bounce > 0) cuda_check(cudaStreamWaitEvent(stream, f.ev_shadowed, 0), "wait");   // shadow(b-1) before shade(b)
 		begin(2);
-		cuda_check(launch_shade(sc, lc, pp, in, out, f.shadow, fbv, ctr, tot, bounce, seq6, (uint32)f.capacity, stream), "shade");
+		cuda_check(launch_shade(sc, lc, pp, in, out, f.shadow, fbv, ctr, tot, bounce, seq6, (uint32)f.capacity, stream, psf), "shade");
 		end();
 		if (!overlap)
 		{
 			begin(3);
-			cuda_check(launch_trace_shadow(sc, lc, f.shadow, fbv, ctr, tot, bounce, pp.frame_weight, stream, &f.cont[1], m_suspend_after, &n_launches), "trace_shadow");
+			cuda_check(launch_trace_shadow(sc, lc, f.shadow, fbv, ctr, tot, bounce, pp.frame_weight, stream, &f.cont[1], m_suspend_after, &n_launches, psf), "trace_shadow");
 			end();
 			renderer.kernel_launches += n_launches;
 		}
@@ -298,7 +346,7 @@ void PathTracer::render_subframe(SubFrame& f, const PassParams& pass, const std:
 		{
 			cuda_check(cudaEventRecord(f.ev_shaded, stream), "event record");
 			cuda_check(cudaStreamWaitEvent(f.side_stream, f.ev_shaded, 0), "wait");
-			cuda_check(launch_trace_shadow(sc, lc, f.shadow, fbv, ctr, tot, bounce, pp.frame_weight, f.side_stream, &f.cont[1], m_suspend_after, &n_launches), "trace_shadow");
+			cuda_check(launch_trace_shadow(sc, lc, f.shadow, fbv, ctr, tot, bounce, pp.frame_weight, f.side_stream, &f.cont[1], m_suspend_after, &n_launches, psf), "trace_shadow");
 			renderer.kernel_launches += n_launches;
 			cuda_check(cudaEventRecord(f.ev_shadowed, f.side_stream), "event record");
 			if (bounce + 1 < L)
@@ -311,11 +359,27 @@ void PathTracer::render_subframe(SubFrame& f, const PassParams& pass, const std:
 	}
 	if (overlap) cuda_check(cudaStreamWaitEvent(stream, f.ev_shadowed, 0), "wait");
 	span.bounce = 0;
+	if (m_psf)
+	{
+		// psf_blending (src/renderers/psfpt_impl.h:133-143), one bounce's references after the other
+		begin(0);
+		for (uint32 bounce = 0; bounce < L; ++bounce) cuda_check(launch_psf_blend(lc, m_psf_view, fbv, ctr, bounce, pp.frame_weight, stream), "psf_blend");
+		end();
+		renderer.kernel_launches += L;
+	}
 	// RenderingContext::update_variances (pathtracer_impl.h:322), this sub-frame's pixels
 	begin(0);
 	cuda_check(launch_update_variances(fbv, pixels, pp.instance + 1, stream), "update_variances");
 	end();
 	renderer.kernel_launches++;
+	if (m_psf)
+	{
+		// PSFPT::render (src/renderers/psfpt_impl.h:264): renderer.clamp_frame( 100.0f )
+		begin(0);
+		cuda_check(launch_clamp_frame(fbv, pixels, 100.0f, stream), "clamp_frame");
+		end();
+		renderer.kernel_launches++;
+	}
 }
 
 void PathTracer::bounce_times(RenderingContext& renderer, double out_ms[4 * 64])

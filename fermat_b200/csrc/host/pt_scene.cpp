@@ -47,6 +47,29 @@ void pt_options_parse(PTOptions& o, int argc, const char* const* argv)
 	}
 }
 
+void psf_options_defaults(fb200_psf_options& o)
+{
+	o.enabled = 0; o.psf_depth = 1; o.psf_width = 3.0f; o.psf_min_dist = 0.1f; o.psf_max_prob = 32.0f; o.psf_temporal_reuse = 64; o.firefly_filter = 100.0f;
+	o.log_hash_size = 26;      // HASH_SIZE = 64 M entries, src/renderers/psfpt_impl.h:46
+}
+
+void psf_options_parse(fb200_psf_options& o, int argc, const char* const* argv)
+{
+	auto is = [&](int i, const char* s) { return strcmp(argv[i], s) == 0; };
+	for (int i = 0; i < argc; ++i)
+	{
+		if (is(i, "-psfpt")) o.enabled = 1;
+		else if (is(i, "-pt")) o.enabled = 0;
+		else if (is(i, "-filter-depth") && i + 1 < argc) o.psf_depth = (uint32)atoi(argv[++i]);
+		else if (is(i, "-filter-width") && i + 1 < argc) o.psf_width = (float)atof(argv[++i]);
+		else if (is(i, "-filter-min-dist") && i + 1 < argc) o.psf_min_dist = (float)atof(argv[++i]);
+		else if (is(i, "-filter-max-prob") && i + 1 < argc) o.psf_max_prob = (float)atof(argv[++i]);
+		else if (is(i, "-temporal-reuse") && i + 1 < argc) o.psf_temporal_reuse = (uint32)atoi(argv[++i]);
+		else if ((is(i, "-firefly-filter") || is(i, "-ff")) && i + 1 < argc) o.firefly_filter = (float)atof(argv[++i]);
+		else if (is(i, "-psf-hash-bits") && i + 1 < argc) o.log_hash_size = (uint32)atoi(argv[++i]);
+	}
+}
+
 std::string default_tables_path()
 {
 	// <dir of this shared object>/data/pt_tables.bin
@@ -86,6 +109,7 @@ void scene_init(fb200_scene& s, int argc, const char* const* argv)
 	const char* filename = NULL;
 	bool overwrite_camera = false;
 	pt_options_defaults(s.options);
+	psf_options_defaults(s.psf);
 	// Camera defaults, reference src/camera.h:54-61
 	s.scene.camera.eye = float3{ 0, -1, 0 }; s.scene.camera.aim = float3{ 0, 0, 0 }; s.scene.camera.up = float3{ 0, 0, 1 };
 	s.scene.camera.dx = float3{ 1, 0, 0 };
@@ -120,6 +144,9 @@ void scene_init(fb200_scene& s, int argc, const char* const* argv)
 	if (s.res_x == 0 || s.res_y == 0 || (uint64)s.res_x * s.res_y >= (1u << 27)) throw std::runtime_error("unsupported resolution (PixelInfo holds 27 pixel bits)");
 	if (s.shard_count == 0 || s.shard_rank >= s.shard_count) throw std::runtime_error("bad -shard rank/count");
 	pt_options_parse(s.options, argc, argv);
+	psf_options_parse(s.psf, argc, argv);
+	if (s.psf.psf_temporal_reuse == 0) s.psf.psf_temporal_reuse = 1;
+	if (s.psf.log_hash_size < 10 || s.psf.log_hash_size > 28) throw std::runtime_error("-psf-hash-bits out of range (10..28)");
 	if (s.options.max_path_length == 0 || s.options.max_path_length > 62) throw std::runtime_error("unsupported path length");
 	if (s.options.nee_type == 2) throw std::runtime_error("-nee-alg rl is not part of the -pt hot path implemented here");
 
@@ -218,6 +245,7 @@ void scene_fill_view(const fb200_scene& s, fb200_scene_view& v)
 	v.bbox_max[0] = s.scene.bbox.hi.x; v.bbox_max[1] = s.scene.bbox.hi.y; v.bbox_max[2] = s.scene.bbox.hi.z;
 	static_assert(sizeof(fb200_pt_options) == sizeof(PTOptions), "options layout");
 	memcpy(&v.options, &s.options, sizeof(PTOptions));
+	v.psf = s.psf;
 }
 
 } // namespace fb

@@ -13,6 +13,7 @@ struct fb200_scene
 {
 	fb::Scene          scene;
 	fb::PTOptions      options;
+	fb200_psf_options  psf;                    // -psfpt and its options (src/renderers/psfpt.h:350-388)
 	uint32_t           res_x, res_y;
 	float              aspect;
 	uint32_t           shard_rank, shard_count;
@@ -40,6 +41,8 @@ namespace fb {
 
 void pt_options_defaults(PTOptions& o);
 void pt_options_parse(PTOptions& o, int argc, const char* const* argv);   // reference src/renderers/pathtracer.h:202-249
+void psf_options_defaults(fb200_psf_options& o);                           // src/renderers/psfpt.h:359-365
+void psf_options_parse(fb200_psf_options& o, int argc, const char* const* argv);   // src/renderers/psfpt.h:367-387
 
 // throws std::runtime_error
 void scene_init(fb200_scene& s, int argc, const char* const* argv);

@@ -69,6 +69,7 @@ RenderingContext::RenderingContext() : kernel_launches(0), m_scene(NULL), m_owns
 	memset(&m_lc, 0, sizeof(m_lc));
 	// built-in renderers (the reference registers its own list here, src/renderer.cu:471-477)
 	register_renderer("pt", &PathTracer::factory);
+	register_renderer("psfpt", &PathTracer::factory_psf);
 }
 
 RenderingContext::~RenderingContext()

@@ -154,6 +154,7 @@ struct PathTracer final : RendererInterface
 	PathTracer();
 	~PathTracer();
 	static RendererInterface* factory() { return new PathTracer(); }
+	static RendererInterface* factory_psf() { PathTracer* p = new PathTracer(); p->m_psf = true; return p; }   // the `-psfpt` renderer
 
 	void init(int argc, char** argv, RenderingContext& renderer);
 	void render(const uint32_t instance, RenderingContext& renderer);
@@ -198,6 +199,11 @@ private:
 	int              m_overlap;               // 0: one stream per sub-frame; else the shadow trace of bounce b runs beside the closest-hit trace of bounce b+1
 	int              m_trace_ctas;            // CTAs per SM of each persistent trace launch
 	int              m_suspend_after;         // ray suspension: tail iterations before a trace warp hands its rays over (< 0: off)
+	// `-psfpt` (path-space filtering, src/renderers/psfpt_impl.h): the same loop with PSFPTVertexProcessor's policies, a hash of cache
+	// cells that lives across passes, and a splat of the references at the end of the pass
+	bool             m_psf;
+	fb::DeviceBuffer m_psf_keys, m_psf_values;
+	fb::PsfView      m_psf_view;
 	void             render_subframe(SubFrame& f, const fb::PassParams& pp, const std::vector<float>& seq, RenderingContext& renderer, cudaStream_t stream, bool overlap);
 	bool             m_events;
 	bool             m_profiling;

@@ -53,6 +53,10 @@ struct PathQueue
 	float4* hit;        // t, as_float(triId), u, v   (written by the closest-hit kernel)
 	float4* weight;     // path weight rgb, p_prev
 	uint32* pixel;      // PixelInfo bits: pixel:27 comp:4 diffuse:1 (src/pathtracer_core.h:527-542)
+	// `-psfpt` only (NULL otherwise): the ray cone {radius so far, solid-angle pdf of the direction} and the vertex processor's
+	// per-path word (PTRayQueue::cones, pixels.y: src/pathtracer_queues.h:44-53)
+	float2* cone;
+	uint32* vinfo;
 };
 
 struct ShadowQueue
@@ -62,6 +66,23 @@ struct ShadowQueue
 	float4* w_d;        // diffuse NEE weight rgb, .w = as_float(PixelInfo bits)
 	float4* w_g;        // glossy NEE weight rgb
 	unsigned char* occluded;   // outcome of the shadow trace, read by the accumulation kernel (FB_SPLIT_ACCUMULATE)
+	uint32* vinfo;             // `-psfpt` only: the vertex_info of the vertex the shadow ray leaves (src/pathtracer_core.h:1098)
+};
+
+// State of the path-space filter (`-psfpt`, src/renderers/psfpt_impl.h:101-113): the hash of cache cells, their values, and the queue
+// of references (paths that ended in a cell), kept as one segment per bounce so that a pixel owns at most one entry per segment.
+// The reference stores cell values behind a second table of unique slots; here the slot IS the position in the open-addressing
+// table (29 bits of CacheInfo hold it), which is equivalent as far as the vertex processor can tell.
+struct PsfView
+{
+	unsigned long long* keys;      // ~0 = empty
+	float4* values;                // rgb sum, sample count
+	uint32  mask;                  // table entries - 1
+	float4* ref_w_d; float4* ref_w_g; uint2* ref_pixels;   // [bounce * ref_capacity + i]
+	uint32  ref_capacity;
+	uint32  psf_depth; float psf_width, psf_max_prob, firefly_filter;
+	float   bbox_lo[3], bbox_hi[3];
+	uint32  instance;
 };
 
 struct FrameBufferView
@@ -83,7 +104,7 @@ struct PassCounters
 	uint32 trace_next[64];     // work-fetch cursors of the persistent kernels
 	uint32 shadow_next[64];
 	uint32 shade_next[64];
-	uint32 pad[64];
+	uint32 ref_size[64];       // `-psfpt`: entries in the reference queue segment of bounce b (was padding)
 	// continuation queues of the trace launches (ContQueue below): tasks written / fetched, rays suspended, per bounce;
 	// [0] closest-hit trace, [1] shadow trace
 	uint32 cont_tasks[2][64];

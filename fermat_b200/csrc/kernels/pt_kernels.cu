@@ -115,6 +115,24 @@ __global__ void __launch_bounds__(256) k_generate_primary(DeviceScene sc, PassPa
 	st_stream(q.ray_d + slot, make_float4(d.x, d.y, d.z, 1e34f));
 	st_stream(q.weight + slot, make_float4(1.0f, 1.0f, 1.0f, 1.0f));
 	st_stream(q.pixel + slot, px + py * sc.res_x);          // PixelInfo(pixel, comp = 0, diffuse = 0)
+	if (q.cone)
+	{
+		// `-psfpt`: the primary ray cone {0, camera_direction_pdf} (src/pathtracer_kernels.h:153-159, src/camera.h:232-252)
+		float out_p = 0.0f;
+		const float t = dot(d, W) / (pp.cam_w_len * pp.cam_w_len);
+		if (t >= 0.0f)
+		{
+			const V3 I = d / t - W;
+			const float Ix = dot(I, U) / square_length(U), Iy = dot(I, Vv) / square_length(Vv);
+			if (Ix >= -1.0f && Ix <= 1.0f && Iy >= -1.0f && Iy <= 1.0f)
+			{
+				const float cos_theta = dot(d, W) / pp.cam_w_len;
+				out_p = pp.cam_sq_pixel_focal / (cos_theta * cos_theta * cos_theta);
+			}
+		}
+		q.cone[slot] = make_float2(0.0f, out_p);
+		q.vinfo[slot] = FB_PSF_INVALID;
+	}
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -204,7 +222,8 @@ enum TracePhase { TRACE_PLAIN = 0, TRACE_SUSPENDING = 1, TRACE_TASKS = 2 };
 FB_D unsigned long long pack_hit_key(float t, int tri) { return ((unsigned long long)__float_as_uint(t) << 32) | (unsigned long long)(uint32)tri; }
 
 // solve_occlusion -> PTVertexProcessor::accumulate_nee (pathtracer_vertex_processor.h:204-239) for one unoccluded shadow ray
-FB_D void accumulate_unoccluded(const TraceArgs& a, const uint32 ray_idx)
+template <typename Args>
+FB_D void accumulate_unoccluded(const Args& a, const uint32 ray_idx)
 {
 	const float4 wd4 = ld_stream(a.w_d + ray_idx), wg4 = ld_stream(a.w_g + ray_idx);
 	const V3 w_d(wd4), w_g(wg4);
@@ -665,11 +684,91 @@ __global__ void __launch_bounds__(128) k_resolve_suspended(DeviceScene sc, Trace
 
 // solve_occlusion_kernel (pathtracer_kernels.h:248-267) as a pass of its own over the shadow queue (FB_SPLIT_ACCUMULATE): consecutive
 // threads read consecutive weights, and nobody waits for the frame buffer but the thread that adds to it
-__global__ void __launch_bounds__(256) k_accumulate_unoccluded(TraceArgs a)
+struct AccumArgs
+{
+	const uint32* n_ptr; const unsigned char* occluded;
+	const float4* w_d; const float4* w_g; const uint32* vinfo;
+	FrameBufferView fb; float frame_weight; uint32 bounce;
+	PsfView psf;
+};
+
+// PSFPTVertexProcessor::accumulate_nee (src/psfpt_vertex_processor.h:374-438) for one unoccluded shadow ray. The queue carries the
+// vertex_info preprocess_vertex returned (comp = 0: src/pathtracer_core.h:1098 passes vertex_info, not out_vertex_info), so the
+// DIFFUSE_COMP branch is never taken in the reference either; it is restated for completeness.
+FB_D void accumulate_unoccluded_psf(const AccumArgs& a, const uint32 ray_idx)
+{
+	const float4 wd4 = ld_stream(a.w_d + ray_idx), wg4 = ld_stream(a.w_g + ray_idx);
+	const V3 w_d(wd4), w_g(wg4);
+	const uint32 info = __float_as_uint(wd4.w), vinfo = a.vinfo[ray_idx];
+	const uint32 pixel = info & 0x07FFFFFFu, comp = (info >> 27) & 0xFu;
+	const float ff = a.psf.firefly_filter;
+	if (psf_slot(vinfo) != FB_PSF_INVALID_SLOT)
+	{
+		const bool diffuse_only = psf_comp(vinfo) == FB_PSF_DIFFUSE_COMP;
+		psf_add(a.psf, psf_slot(vinfo), diffuse_only ? w_d : w_d + w_g);
+		if (diffuse_only)
+		{
+			add_in<false>(a.fb.channels[FB_COMPOSITED_C], pixel, psf_clamp_sample(w_g, ff), a.frame_weight);
+			add_in<true>(a.fb.channels[(a.bounce == 0 || (comp & kGlossyMask)) ? FB_SPECULAR_C : FB_DIFFUSE_C], pixel, psf_clamp_sample(w_g, ff), a.frame_weight);
+		}
+	}
+	else
+	{
+		add_in<false>(a.fb.channels[FB_COMPOSITED_C], pixel, psf_clamp_sample(w_d + w_g, ff), a.frame_weight);
+		if (a.bounce == 0)
+		{
+			add_in<true>(a.fb.channels[FB_DIFFUSE_C], pixel, psf_clamp_sample(w_d, ff), a.frame_weight);
+			add_in<true>(a.fb.channels[FB_SPECULAR_C], pixel, psf_clamp_sample(w_g, ff), a.frame_weight);
+		}
+		else
+		{
+			if (comp & kDiffuseMask) add_in<true>(a.fb.channels[FB_DIFFUSE_C], pixel, psf_clamp_sample(w_d + w_g, ff), a.frame_weight);
+			if (comp & kGlossyMask)  add_in<true>(a.fb.channels[FB_SPECULAR_C], pixel, psf_clamp_sample(w_d + w_g, ff), a.frame_weight);
+		}
+	}
+}
+
+template <bool PSF>
+__global__ void __launch_bounds__(256) k_accumulate_unoccluded(AccumArgs a)
 {
 	const uint32 n = *a.n_ptr;
 	for (uint32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-		if (a.occluded[i] == 0) accumulate_unoccluded(a, i);
+		if (a.occluded[i] == 0) { if (PSF) accumulate_unoccluded_psf(a, i); else accumulate_unoccluded(a, i); }
+}
+
+// psf_blending_kernel (src/renderers/psfpt_impl.h:101-131) over the reference-queue segment of one bounce: a pixel owns at most one
+// entry per segment, so the non-atomic add_in of the reference is race-free here
+__global__ void __launch_bounds__(256) k_psf_blend(PsfView psf, FrameBufferView fb, const PassCounters* ctr, uint32 bounce, float frame_weight)
+{
+	const uint32 n = min(ctr->ref_size[bounce], psf.ref_capacity);
+	for (uint32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+	{
+		const size_t k = (size_t)bounce * psf.ref_capacity + i;
+		const uint2 px = psf.ref_pixels[k];
+		const uint32 slot = psf_slot(px.y);
+		if (slot == FB_PSF_INVALID_SLOT) continue;
+		const uint32 pixel = px.x & 0x07FFFFFFu, comp = (px.x >> 27) & 0xFu;
+		const V3 w_d(psf.ref_w_d[k]), w_g(psf.ref_w_g[k]);
+		const float4 cv = psf.values[slot];
+		const V3 c(cv.x / cv.w, cv.y / cv.w, cv.z / cv.w);
+		const V3 w = ((comp & kDiffuseMask) ? w_d : V3(0.0f)) + ((comp & kGlossyMask) ? w_g : V3(0.0f));
+		const V3 cw = c * w;
+		add_in<false>(fb.channels[FB_COMPOSITED_C], pixel, V3(fminf(cw.x, psf.firefly_filter), fminf(cw.y, psf.firefly_filter), fminf(cw.z, psf.firefly_filter)), frame_weight);
+		if (comp & kDiffuseMask) add_in<true>(fb.channels[FB_DIFFUSE_C], pixel, c * w_d, frame_weight);
+		if (comp & kGlossyMask)  add_in<true>(fb.channels[FB_SPECULAR_C], pixel, c * w_g, frame_weight);
+	}
+}
+
+// clamp_frame_kernel (src/renderer.cu:314-331)
+__global__ void __launch_bounds__(256) k_clamp_frame(FrameBufferView fb, PixelSet ps, float max_value)
+{
+	uint32 i;
+	if (!pixel_of_set(ps, blockIdx.x * blockDim.x + threadIdx.x, fb.n_pixels, i)) return;
+	auto cl = [max_value](float4 v) { return make_float4(fminf(v.x, max_value), fminf(v.y, max_value), fminf(v.z, max_value), fminf(v.w, max_value)); };
+	fb.channels[FB_DIFFUSE_C][i] = cl(fb.channels[FB_DIFFUSE_C][i]);
+	fb.channels[FB_SPECULAR_C][i] = cl(fb.channels[FB_SPECULAR_C][i]);
+	fb.channels[FB_DIRECT_C][i] = cl(fb.channels[FB_DIRECT_C][i]);
+	fb.channels[FB_COMPOSITED_C][i] = cl(fb.channels[FB_COMPOSITED_C][i]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -681,12 +780,15 @@ struct ShadeArgs
 	PassCounters* ctr; PassTotals* tot;
 	uint32 bounce; float frame_weight; float seq[6];
 	uint32 do_nee, do_emissive, do_scatter, do_dirlight;
+	PsfView psf;                     // PSF instantiation only
 };
 
 // DIRLIGHT: scenes with DirectionalLights (rare) get their own instantiation; keeping that block — a second inlined
 // Bsdf evaluation — out of the common kernel shortens it by a fifth, and the kernel is instruction-fetch sensitive
 // (r01 profile: 22 % of the stall samples were "no instruction" with the 157 KB monolith).
-template <bool DIRLIGHT>
+// PSF: PSFPTVertexProcessor's policies (src/psfpt_vertex_processor.h) instead of PTVertexProcessor's - the `-psfpt` renderer on the same
+// loop; every difference is behind `if (PSF)`, so the `-pt` instantiations are the kernels they were.
+template <bool DIRLIGHT, bool PSF = false>
 __global__ void __launch_bounds__(128, FB_SHADE_MIN_BLOCKS) k_shade(DeviceScene sc, ShadeArgs a)
 {
 	const uint32 n = a.ctr->in_size[a.bounce];
@@ -704,6 +806,9 @@ __global__ void __launch_bounds__(128, FB_SHADE_MIN_BLOCKS) k_shade(DeviceScene 
 		bool dl_on = false, nee_on = false, scat_on = false;
 		float4 dl_o, dl_d, dl_wd, dl_wg, nee_o, nee_d, nee_wd, nee_wg, sc_o, sc_d, sc_w;
 		uint32 sc_info = 0, info = 0;
+		// PSF: this vertex's / the scattered path's CacheInfo, the scattered ray's cone, the reference this vertex appends
+		uint32 vinfo = FB_PSF_INVALID, sc_vinfo = FB_PSF_INVALID; float2 sc_cone = make_float2(0.0f, 0.0f);
+		bool ref_on = false; float4 ref_wd, ref_wg; uint32 ref_cache = FB_PSF_INVALID;
 
 		float4 hit = make_float4(-1.0f, 0.0f, 0.0f, 0.0f);
 		if (valid) { hit = ld_stream(a.in.hit + idx); valid = (hit.x > 0.0f) && (__float_as_int(hit.y) >= 0); }
@@ -749,6 +854,40 @@ __global__ void __launch_bounds__(128, FB_SHADE_MIN_BLOCKS) k_shade(DeviceScene 
 			const V3 in = -normalize(ray_d);
 			BsdfParams b;
 			bsdf_init(b, kd, td, ks, kr, mp.x, mp.y, mp.z);
+
+			// ---- PSFPTVertexProcessor::preprocess_vertex (src/psfpt_vertex_processor.h:123-199); cone radius: src/pathtracer_core.h:816-819 ----
+			uint32 prev_vinfo = FB_PSF_INVALID; bool new_entry = false; float cone_radius = 0.0f;
+			if (PSF)
+			{
+				const float2 cone = a.in.cone[idx];
+				prev_vinfo = a.in.vinfo[idx];
+				const float prev_G_prime = fabsf(dot(in, g.normal_s)) / (hit.x * hit.x);
+				const float area_prob = 1.0f / sqrtf(cone.y * prev_G_prime);      // cugar::rsqrtf; an exact division here and in the oracle
+				cone_radius = cone.x + area_prob;
+				uint32 slot = psf_slot(prev_vinfo);
+				if (slot == FB_PSF_INVALID_SLOT && bounce >= a.psf.psf_depth && p_prev < a.psf.psf_max_prob)
+				{
+					const uint32 pixel_hash = pixel + a.psf.instance * sc.res_x * sc.res_y;
+					float jitter[6];
+					#pragma unroll
+					for (uint32 i = 0; i < 6; ++i) jitter[i] = randfloat_d(i, pixel_hash);
+					const V3 Ns = dot(in, g.normal_s) > 0.0f ? g.normal_s : -g.normal_s;
+					const unsigned long long key = spatial_hash(position, Ns, g.tangent, g.binormal, V3(a.psf.bbox_lo[0], a.psf.bbox_lo[1], a.psf.bbox_lo[2]),
+															   V3(a.psf.bbox_hi[0], a.psf.bbox_hi[1], a.psf.bbox_hi[2]), jitter, cone_radius * a.psf.psf_width, bounce == 0 ? 2.0f : 1.0f);
+					slot = psf_insert(a.psf, key);
+					if (slot != FB_PSF_INVALID_SLOT)
+					{
+						atomicAdd(&a.psf.values[slot].w, 1.0f);
+						const V3 w_mod = w * psf_floor4(kd);
+						const V3 rd_ = (comp & kDiffuseMask) ? w_mod : V3(0.0f), rg_ = ((comp & kGlossyMask) && bounce) ? w_mod : V3(0.0f);
+						ref_on = true;
+						ref_wd = make_float4(rd_.x, rd_.y, rd_.z, 0.0f); ref_wg = make_float4(rg_.x, rg_.y, rg_.z, 0.0f);
+						ref_cache = psf_pack(slot, FB_PSF_ALL_COMPS, 0u);
+						new_entry = true;
+					}
+				}
+				vinfo = psf_pack(slot, 0u, new_entry ? 1u : 0u);
+			}
 
 			if (bounce == 0)
 			{
@@ -856,7 +995,13 @@ __global__ void __launch_bounds__(128, FB_SHADE_MIN_BLOCKS) k_shade(DeviceScene 
 				const float p1 = light_pdf, p2 = p_s * G;
 				const float mis_w = ((bounce == 0 && o.direct_lighting_bsdf) || (bounce > 0 && o.indirect_lighting_bsdf)) ? power_heuristic(p1, p2) : 1.0f;
 				const V3 fl = f_L * G * mis_w;
-				const V3 w_d = (bounce == 0 ? fd : fd + fg) * w * fl, w_g = (bounce == 0 ? fg : fd + fg) * w * fl;
+				V3 w_d = (bounce == 0 ? fd : fd + fg) * w * fl, w_g = (bounce == 0 ? fg : fd + fg) * w * fl;
+				if (PSF)
+				{
+					// PSFPTVertexProcessor::compute_nee_weights (src/psfpt_vertex_processor.h:204-268)
+					if (new_entry) { w_d = (fd / psf_floor4(kd)) * fl; w_g = fg * w * fl; }
+					else { w_d = fd * w * fl; w_g = fg * w * fl; }
+				}
 				const V3 ow = w_d + w_g;
 				if (max_comp(ow) > 0.0f && is_finite(ow))
 				{
@@ -884,13 +1029,20 @@ __global__ void __launch_bounds__(128, FB_SHADE_MIN_BLOCKS) k_shade(DeviceScene 
 				const V3 ow = w * f_L * mis_w;
 				if (max_comp(ow) > 0.0f && is_finite(ow))
 				{
-					add_in<false>(a.fb.channels[FB_COMPOSITED_C], pixel, ow, a.frame_weight);
-					if (bounce == 0) add_in<false>(a.fb.channels[FB_DIRECT_C], pixel, ow, a.frame_weight);
-					else
+					// PTVertexProcessor::accumulate_emissive, or PSFPTVertexProcessor's (src/psfpt_vertex_processor.h:326-369): clamped, and
+					// into the cache cell once the path feeds one
+					const V3 cw = PSF ? psf_clamp_sample(ow, a.psf.firefly_filter) : ow;
+					if (!PSF || psf_slot(prev_vinfo) == FB_PSF_INVALID_SLOT)
 					{
-						if (comp & kDiffuseMask) add_in<true>(a.fb.channels[FB_DIFFUSE_C], pixel, ow, a.frame_weight);
-						if (comp & kGlossyMask)  add_in<true>(a.fb.channels[FB_SPECULAR_C], pixel, ow, a.frame_weight);
+						add_in<false>(a.fb.channels[FB_COMPOSITED_C], pixel, cw, a.frame_weight);
+						if (bounce == 0) add_in<false>(a.fb.channels[FB_DIRECT_C], pixel, cw, a.frame_weight);
+						else
+						{
+							if (comp & kDiffuseMask) add_in<true>(a.fb.channels[FB_DIFFUSE_C], pixel, cw, a.frame_weight);
+							if (comp & kGlossyMask)  add_in<true>(a.fb.channels[FB_SPECULAR_C], pixel, cw, a.frame_weight);
+						}
 					}
+					else psf_add(a.psf, psf_slot(prev_vinfo), cw);
 				}
 			}
 
@@ -899,7 +1051,14 @@ __global__ void __launch_bounds__(128, FB_SHADE_MIN_BLOCKS) k_shade(DeviceScene 
 			{
 				uint32 out_comp; V3 out, gg; float p, p_proj;
 				bsdf_sample(b, sc.glossy_reflectance, g, z[3], z[4], z[5], in, out_comp, out, p, p_proj, gg);
-				const V3 ow = gg * w;
+				V3 ow = gg * w;
+				if (PSF)
+				{
+					// PSFPTVertexProcessor::compute_scattering_weights (src/psfpt_vertex_processor.h:273-321); cone: src/pathtracer_core.h:1222-1227
+					sc_vinfo = (psf_slot(prev_vinfo) == FB_PSF_INVALID_SLOT && (out_comp & kGlossyMask)) ? prev_vinfo : psf_pack(psf_slot(vinfo), FB_PSF_ALL_COMPS, 0u);
+					if (new_entry && (out_comp & kDiffuseMask)) ow = gg / psf_floor4(kd);
+					sc_cone = make_float2(cone_radius, fmaxf(p, 32.0f));
+				}
 				if (out_comp != kAbsorption && p != 0.0f && max_comp(ow) > 0.0f && is_finite(ow))
 				{
 					scat_on = true;
@@ -922,11 +1081,23 @@ __global__ void __launch_bounds__(128, FB_SHADE_MIN_BLOCKS) k_shade(DeviceScene 
 		{
 			const uint32 slot = warp_append_slot(shadow_counter, nee_on);
 			if (nee_on) { st_stream(a.sq.ray_o + slot, nee_o); st_stream(a.sq.ray_d + slot, nee_d); st_stream(a.sq.w_d + slot, nee_wd); st_stream(a.sq.w_g + slot, nee_wg); }
+			if (PSF && nee_on) a.sq.vinfo[slot] = vinfo;
 		}
 		if (a.do_scatter)
 		{
 			const uint32 slot = warp_append_slot(scatter_counter, scat_on);
 			if (scat_on) { st_stream(a.out.ray_o + slot, sc_o); st_stream(a.out.ray_d + slot, sc_d); st_stream(a.out.weight + slot, sc_w); st_stream(a.out.pixel + slot, sc_info); }
+			if (PSF && scat_on) { a.out.cone[slot] = sc_cone; a.out.vinfo[slot] = sc_vinfo; }
+		}
+		if (PSF)
+		{
+			// PSFRefQueue::warp_append (src/renderers/psfpt_impl.h:61-71), into this bounce's segment
+			const uint32 slot = warp_append_slot(&a.ctr->ref_size[bounce], ref_on);
+			if (ref_on && slot < a.psf.ref_capacity)
+			{
+				const size_t k = (size_t)bounce * a.psf.ref_capacity + slot;
+				a.psf.ref_w_d[k] = ref_wd; a.psf.ref_w_g[k] = ref_wg; a.psf.ref_pixels[k] = make_uint2(info, ref_cache);
+			}
 		}
 	}
 }
@@ -1048,8 +1219,10 @@ cudaError_t launch_trace_closest(const DeviceScene& sc, const LaunchConfig& lc, 
 	}
 	return cudaGetLastError();
 }
+bool kernels_split_accumulate() { return FB_SPLIT_ACCUMULATE != 0; }
+
 cudaError_t launch_trace_shadow(const DeviceScene& sc, const LaunchConfig& lc, const ShadowQueue& sq, const FrameBufferView& fb, PassCounters* ctr, PassTotals* tot,
-								uint32 bounce, float frame_weight, cudaStream_t s, const ContQueue* cont, int suspend_after, uint32* launches)
+								uint32 bounce, float frame_weight, cudaStream_t s, const ContQueue* cont, int suspend_after, uint32* launches, const PsfView* psf)
 {
 	TraceArgs a; memset(&a, 0, sizeof(a));
 	a.ray_o = sq.ray_o; a.ray_d = sq.ray_d; a.stride = 1; a.n_ptr = &ctr->shadow_size[bounce]; a.cursor = &ctr->shadow_next[bounce];
@@ -1067,8 +1240,15 @@ cudaError_t launch_trace_shadow(const DeviceScene& sc, const LaunchConfig& lc, c
 		k_resolve_suspended<true><<<lc.sm_count, 128, 0, s>>>(sc, a);
 	}
 #if FB_SPLIT_ACCUMULATE
-	k_accumulate_unoccluded<<<lc.sm_count * 4, 256, 0, s>>>(a);
-	if (launches) *launches += 1;
+	{
+		AccumArgs ac; memset(&ac, 0, sizeof(ac));
+		ac.n_ptr = a.n_ptr; ac.occluded = sq.occluded; ac.w_d = sq.w_d; ac.w_g = sq.w_g; ac.vinfo = sq.vinfo; ac.fb = fb; ac.frame_weight = frame_weight; ac.bounce = bounce;
+		if (psf) { ac.psf = *psf; k_accumulate_unoccluded<true><<<lc.sm_count * 4, 256, 0, s>>>(ac); }
+		else k_accumulate_unoccluded<false><<<lc.sm_count * 4, 256, 0, s>>>(ac);
+		if (launches) *launches += 1;
+	}
+#else
+	if (psf) return cudaErrorNotSupported;       // (the filtered renderer needs the accumulation pass)
 #endif
 	return cudaGetLastError();
 }
@@ -1087,10 +1267,24 @@ cudaError_t launch_trace_shadow_rays(const DeviceScene& sc, const LaunchConfig& 
 	return cudaGetLastError();
 }
 
+cudaError_t launch_psf_blend(const LaunchConfig& lc, const PsfView& psf, const FrameBufferView& fb, const PassCounters* ctr, uint32 bounce, float frame_weight, cudaStream_t s)
+{
+	k_psf_blend<<<lc.sm_count * 4, 256, 0, s>>>(psf, fb, ctr, bounce, frame_weight);
+	return cudaGetLastError();
+}
+cudaError_t launch_clamp_frame(const FrameBufferView& fb, const PixelSet& ps, float max_value, cudaStream_t s)
+{
+	const uint32 n = ps.tile_list ? ps.n_tiles * FB_TILE * FB_TILE : fb.n_pixels;
+	if (n == 0) return cudaSuccess;
+	k_clamp_frame<<<(n + 255) / 256, 256, 0, s>>>(fb, ps, max_value);
+	return cudaGetLastError();
+}
+
 cudaError_t launch_shade(const DeviceScene& sc, const LaunchConfig& lc, const PassParams& pp, const PathQueue& in, const PathQueue& out, const ShadowQueue& sq,
-						 const FrameBufferView& fb, PassCounters* ctr, PassTotals* tot, uint32 bounce, const float seq6[6], uint32 capacity, cudaStream_t s)
+						 const FrameBufferView& fb, PassCounters* ctr, PassTotals* tot, uint32 bounce, const float seq6[6], uint32 capacity, cudaStream_t s, const PsfView* psf)
 {
 	ShadeArgs a;
+	memset(&a.psf, 0, sizeof(a.psf));
 	a.in = in; a.out = out; a.sq = sq; a.fb = fb; a.ctr = ctr; a.tot = tot; a.bounce = bounce; a.frame_weight = pp.frame_weight;
 	for (int i = 0; i < 6; ++i) a.seq[i] = seq6[i];
 	// compute_per_bounce_options (pathtracer_core.h:594-620)
@@ -1106,7 +1300,13 @@ cudaError_t launch_shade(const DeviceScene& sc, const LaunchConfig& lc, const Pa
 	const uint32 max_blocks = (uint32)lc.sm_count * 16u;
 	if (blocks > max_blocks) blocks = max_blocks;
 	if (blocks == 0) blocks = 1;
-	if (sc.n_dir_lights) k_shade<true><<<blocks, threads, 0, s>>>(sc, a);
+	if (psf)
+	{
+		if (sc.n_dir_lights) return cudaErrorNotSupported;
+		a.psf = *psf;
+		k_shade<false, true><<<blocks, threads, 0, s>>>(sc, a);
+	}
+	else if (sc.n_dir_lights) k_shade<true><<<blocks, threads, 0, s>>>(sc, a);
 	else k_shade<false><<<blocks, threads, 0, s>>>(sc, a);
 	return cudaGetLastError();
 }

@@ -12,6 +12,7 @@ struct PassParams
 	float  frame_weight;            // 1 / (instance + 1)
 	float  U[3], V[3], W[3];        // camera frame (reference src/camera.h:142-163)
 	float  eye[3];
+	float  cam_w_len, cam_sq_pixel_focal;   // |W| and Camera::square_pixel_focal_length (src/camera.h:122-128): the primary cone of `-psfpt`
 	const uint32* tile_list;        // tiles owned by this shard
 	uint32 n_tiles;                 // number of owned tiles
 	uint32 tiles_x;                 // tiles per row of the full frame
@@ -42,9 +43,15 @@ cudaError_t launch_generate_primary(const DeviceScene& sc, const PassParams& pp,
 cudaError_t launch_trace_closest(const DeviceScene& sc, const LaunchConfig& lc, const PathQueue& q, PassCounters* ctr, uint32 bounce, cudaStream_t s,
 								 const ContQueue* cont = NULL, int suspend_after = -1, uint32* launches = NULL);
 cudaError_t launch_shade(const DeviceScene& sc, const LaunchConfig& lc, const PassParams& pp, const PathQueue& in, const PathQueue& out, const ShadowQueue& sq,
-						 const FrameBufferView& fb, PassCounters* ctr, PassTotals* tot, uint32 bounce, const float seq6[6], uint32 capacity, cudaStream_t s);
+						 const FrameBufferView& fb, PassCounters* ctr, PassTotals* tot, uint32 bounce, const float seq6[6], uint32 capacity, cudaStream_t s,
+						 const PsfView* psf = NULL);      // psf != NULL: the `-psfpt` vertex processor
 cudaError_t launch_trace_shadow(const DeviceScene& sc, const LaunchConfig& lc, const ShadowQueue& sq, const FrameBufferView& fb, PassCounters* ctr, PassTotals* tot,
-								uint32 bounce, float frame_weight, cudaStream_t s, const ContQueue* cont = NULL, int suspend_after = -1, uint32* launches = NULL);
+								uint32 bounce, float frame_weight, cudaStream_t s, const ContQueue* cont = NULL, int suspend_after = -1, uint32* launches = NULL,
+								const PsfView* psf = NULL);
+// `-psfpt`: splat the references of one bounce (psf_blending, src/renderers/psfpt_impl.h:101-143); RenderingContext::clamp_frame (src/renderer.cu:421-427)
+cudaError_t launch_psf_blend(const LaunchConfig& lc, const PsfView& psf, const FrameBufferView& fb, const PassCounters* ctr, uint32 bounce, float frame_weight, cudaStream_t s);
+cudaError_t launch_clamp_frame(const FrameBufferView& fb, const PixelSet& ps, float max_value, cudaStream_t s);
+bool kernels_split_accumulate();      // built with FB_SPLIT_ACCUMULATE (the filtered renderer needs it)
 
 // stand-alone ray queries on caller-provided device buffers (RTContext::trace / trace_shadow twins)
 cudaError_t launch_trace_rays(const DeviceScene& sc, const LaunchConfig& lc, const float4* rays, float4* hits, uint32 n, uint32* cursor, cudaStream_t s);

@@ -176,4 +176,82 @@ FB_D uint32 warp_append_slot(uint32* counter, bool pred)
 	return base + __popc(m & ((1u << lane) - 1u));
 }
 
+// ------------------------------------------------------------------------------------------------
+// path-space filtering (`-psfpt`): PSFPTVertexProcessor's helpers (src/psfpt_vertex_processor.h, src/spatial_hash.h)
+// ------------------------------------------------------------------------------------------------
+// CacheInfo (src/psfpt_vertex_processor.h:48-72): slot:29, comp:2, new_entry:1
+#define FB_PSF_INVALID      0xFFFFFFFFu
+#define FB_PSF_INVALID_SLOT 0x1FFFFFFFu
+#define FB_PSF_DIFFUSE_COMP 1u
+#define FB_PSF_ALL_COMPS    3u
+FB_D uint32 psf_pack(uint32 slot, uint32 comp, uint32 new_entry) { return (slot & FB_PSF_INVALID_SLOT) | (comp << 29) | (new_entry << 31); }
+FB_D uint32 psf_slot(uint32 info) { return info & FB_PSF_INVALID_SLOT; }
+FB_D uint32 psf_comp(uint32 info) { return (info >> 29) & 3u; }
+
+// cugar::randfloat (contrib/cugar/basic/numbers.h:752-763)
+FB_D float randfloat_d(uint32 i, uint32 p)
+{
+	i ^= p; i ^= i >> 17; i ^= i >> 10; i *= 0xb36534e5u; i ^= i >> 12; i ^= i >> 21; i *= 0x93fc4795u;
+	i ^= 0xdf6e307fu; i ^= i >> 17; i *= 1 | p >> 18;
+	return i * (1.0f / 4294967808.0f);
+}
+// cugar::round (numbers.h:512-516), cugar::quantize (:600-603)
+FB_D float cg_round(float x) { const int y = x > 0.0f ? int(x) : int(x) - 1; return (x - float(y) > 0.5f) ? float(y) + 1.0f : float(y); }
+FB_D uint32 cg_quantize(float x, uint32 n) { return (uint32)max(min(int(x * float(n)), int(n - 1)), 0); }
+// cugar::square_to_unit_disk (contrib/cugar/spherical/mappings_inline.h:56-87), with the shared fixed-sequence sincos
+FB_D void square_to_unit_disk(float sx, float sy, float& dx, float& dy)
+{
+	float phi, r;
+	const float a = 2 * sx - 1, b = 2 * sy - 1;
+	if (a > -b) { if (a > b) { r = a; phi = (FB_PI / 4) * (b / a); } else { r = b; phi = (FB_PI / 4) * (2 - (a / b)); } }
+	else { if (a < b) { r = -a; phi = (FB_PI / 4) * (4 + (b / a)); } else { r = -b; phi = b != 0 ? (FB_PI / 4) * (6 - (a / b)) : 0; } }
+	float s, c; fb_sincosf(phi, &s, &c);
+	dx = r * c; dy = r * s;
+}
+// spatial_hash (src/spatial_hash.h:74-149), the overload preprocess_vertex calls
+FB_D unsigned long long spatial_hash(V3 P, V3 N, V3 T, V3 B, V3 bbox_lo, V3 bbox_hi, const float samples[6], float cone_radius, float filter_radius)
+{
+	const uint32 normal_bits = 4;
+	const float world_extent = max_comp(bbox_hi - bbox_lo);
+	const float float_grid_size = fmaxf(world_extent / (2.0f * cone_radius), 1.0f);
+	const float flog_grid_size = log2f(float_grid_size);
+	const uint32 log_grid_size = uint32(flog_grid_size);
+	const float rlog_grid_size = flog_grid_size - log_grid_size;
+	const uint32 log_grid_size_i = log_grid_size + (samples[5] < rlog_grid_size ? 1u : 0u);
+	const uint32 grid_size = 1u << log_grid_size_i;
+	float rx, ry; square_to_unit_disk(samples[0], samples[1], rx, ry);
+	rx = (filter_radius * cone_radius) * rx; ry = (filter_radius * cone_radius) * ry;
+	const V3 shading_loc = float(grid_size) * (P + T * rx + B * ry - bbox_lo) / world_extent;
+	const uint32 lx = uint32(fmaxf(cg_round(shading_loc.x), 0.0f)), ly = uint32(fmaxf(cg_round(shading_loc.y), 0.0f)), lz = uint32(fmaxf(cg_round(shading_loc.z), 0.0f));
+	const float jx = samples[3] / float(1u << (normal_bits / 2)), jy = samples[4] / float(1u << (normal_bits / 2));
+	float phi;
+	if (fabsf(N.z) >= 1.0f - 1.0e-5f) phi = 0.0f;
+	else { phi = atan2f(N.y, N.x); phi = phi < 0.0f ? phi + 2.0f * FB_PI : phi; }
+	float ux = phi / (2.0f * FB_PI), uy = (N.z + 1.0f) * 0.5f;
+	ux = mod1(ux + jx, 1.0f);
+	uy = fminf(uy + jy, 1.0f);
+	const uint32 MAXQ = (1u << (normal_bits / 2)) - 1u;
+	const uint32 shading_normal_i = cg_quantize(ux, MAXQ) | (cg_quantize(uy, MAXQ) << (normal_bits / 2));
+	const uint32 comp_mask = (1u << 17) - 1u;
+	return ((unsigned long long)(lx & comp_mask) << 0) | ((unsigned long long)(ly & comp_mask) << 17) | ((unsigned long long)(lz & comp_mask) << 34) |
+		   ((unsigned long long)log_grid_size_i << 51) | ((unsigned long long)shading_normal_i << 56);
+}
+// SyncFreeHashMap::insert stand-in: open addressing with linear probing on a 64-bit CAS; returns the table position of `key`
+// (its slot), FB_PSF_INVALID_SLOT when the table is full
+FB_D uint32 psf_insert(const PsfView& v, unsigned long long key)
+{
+	unsigned long long h64 = key * 0x9E3779B97F4A7C15ull; h64 ^= h64 >> 29; h64 *= 0xBF58476D1CE4E5B9ull; h64 ^= h64 >> 32;
+	uint32 h = (uint32)h64 & v.mask;
+	for (uint32 probe = 0; probe < 4096u; ++probe)
+	{
+		const unsigned long long old = atomicCAS(v.keys + h, ~0ull, key);
+		if (old == ~0ull || old == key) return h;
+		h = (h + 1u) & v.mask;
+	}
+	return FB_PSF_INVALID_SLOT;
+}
+FB_D V3 psf_clamp_sample(V3 v, float ff) { return is_finite(v) ? V3(fminf(v.x, ff), fminf(v.y, ff), fminf(v.z, ff)) : V3(0.0f); }   // PSFPTVertexProcessor::clamp_sample
+FB_D V3 psf_floor4(V3 c) { return V3(fmaxf(c.x, 1.0e-4f), fmaxf(c.y, 1.0e-4f), fmaxf(c.z, 1.0e-4f)); }                             // modulate / demodulate, src/filters.h:57-72
+FB_D void psf_add(const PsfView& v, uint32 slot, V3 w) { float* p = reinterpret_cast<float*>(v.values + slot); atomicAdd(p, w.x); atomicAdd(p + 1, w.y); atomicAdd(p + 2, w.z); }
+
 } // namespace fb

@@ -49,6 +49,19 @@ typedef struct fb200_pt_options
 	uint32_t nee_type;
 } fb200_pt_options;
 
+/* PSFPTOptions beyond PTOptions, src/renderers/psfpt.h:350-388 (`-psfpt` renderer, path-space filtering) */
+typedef struct fb200_psf_options
+{
+	uint32_t enabled;              /* the scene was created with -psfpt                         */
+	uint32_t psf_depth;            /* -filter-depth    (1)                                      */
+	float    psf_width;            /* -filter-width    (3)                                      */
+	float    psf_min_dist;         /* -filter-min-dist (0.1, parsed and unused like the reference) */
+	float    psf_max_prob;         /* -filter-max-prob (32)                                     */
+	uint32_t psf_temporal_reuse;   /* -temporal-reuse  (64): the cache is cleared every so many passes */
+	float    firefly_filter;       /* -firefly-filter / -ff (100)                               */
+	uint32_t log_hash_size;        /* -psf-hash-bits   (26: the reference's 64 M entries)       */
+} fb200_psf_options;
+
 typedef struct fb200_texture_view { const float* texels; uint32_t res_x, res_y; } fb200_texture_view;
 
 /* A read-only view of everything the path tracer consumes, as host pointers.
@@ -85,6 +98,7 @@ typedef struct fb200_scene_view
 	/* entries of bvh_index: num_triangles, or more when the tree was built with spatial splits (`-bvh sbvh`: a triangle
 	 * may be referenced from several leaves) */
 	uint32_t n_bvh_index;
+	fb200_psf_options psf;
 } fb200_scene_view;
 
 typedef struct fb200_stats

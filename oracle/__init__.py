@@ -36,6 +36,12 @@ def lib():
         pf = C.POINTER(C.c_float)
         L.oracle_render_pass.restype = C.c_int
         L.oracle_render_pass.argtypes = [C.c_void_p, C.c_uint32, pf, C.POINTER(C.c_uint32), C.c_uint64, C.c_int, C.c_int, C.POINTER(OracleStats)]
+        L.oracle_psf_create.restype = C.c_void_p
+        L.oracle_psf_destroy.argtypes = [C.c_void_p]
+        L.oracle_psf_cells.restype = C.c_uint64
+        L.oracle_psf_cells.argtypes = [C.c_void_p]
+        L.oracle_render_pass_psf.restype = C.c_int
+        L.oracle_render_pass_psf.argtypes = [C.c_void_p, C.c_uint32, pf, C.c_void_p, C.c_int, C.POINTER(OracleStats)]
         L.oracle_trace.restype = C.c_int
         L.oracle_trace.argtypes = [C.c_void_p, pf, pf, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.oracle_trace_shadow.restype = C.c_int
@@ -70,6 +76,31 @@ def render_pass(view, instance, fb, pixels=None, threads=0, count_traversal=Fals
         pp, n = None, 0
     rc = lib().oracle_render_pass(C.addressof(view), int(instance), _fptr(fb), pp, n, int(threads), 1 if count_traversal else 0, C.byref(st))
     assert rc == 0
+    return st
+
+
+class PsfState:
+    """The `-psfpt` filter's state across passes: the hash of cache cells and their values (src/renderers/psfpt_impl.h:110-113)."""
+
+    def __init__(self):
+        self._h = lib().oracle_psf_create()
+
+    def cells(self):
+        return int(lib().oracle_psf_cells(self._h))
+
+    def close(self):
+        if self._h:
+            lib().oracle_psf_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+
+def render_pass_psf(view, instance, fb, state, threads=0):
+    """One progressive pass of the path-space filtering path tracer (PSFPT::render) into `fb` (in place), whole frame."""
+    st = OracleStats()
+    rc = lib().oracle_render_pass_psf(C.addressof(view), int(instance), _fptr(fb), state._h, int(threads), C.byref(st))
+    assert rc == 0, "oracle_render_pass_psf failed (directional lights are not supported by the filtered renderer)"
     return st
 
 

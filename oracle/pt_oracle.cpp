@@ -22,11 +22,17 @@
 //   src/framebuffer.h:425-444          add_in;  src/renderer.cu:292-362 multiply_frame / update_variances
 //   src/kernels/optix_rt.cu:46-82,134-164, optix_base_shaders.h:43-91, optix_base_shadow_shaders.h:43-72,
 //   optix_payload.h:75-78              ray query semantics (closest hit, masked any hit, fp16 barycentrics)
+// and, for the `-psfpt` renderer (path-space filtering on the same path tracing loop):
+//   src/psfpt_vertex_processor.h:40-476   PSFPTVertexProcessor (cache slots, weights, accumulation)
+//   src/spatial_hash.h:74-149             jittered spatial hash of a vertex
+//   src/renderers/psfpt_impl.h:101-143, 256-265, 300-416   reference queue, psf_blending, PSFPT::render / render_pass
+//   src/filters.h:57-72                   modulate / demodulate;  src/renderer.cu:314-331 clamp_frame
 // Ray/triangle and ray/box arithmetic itself lives in closed-source OptiX 6 in the reference; parity at
 // that boundary is geometric (see DESIGN.md "Oracle").
 #include "../include/fermat_b200.h"
 #include "oracle_bsdf.h"
 #include <vector>
+#include <unordered_map>
 #include <algorithm>
 #include <stdio.h>
 #ifdef _OPENMP
@@ -336,8 +342,96 @@ static void light_map(const SceneRef& sc, bool use_vpls, uint32_t prim, const Ge
 	*edf = m.emissive;
 }
 
-// one path, all bounces
-static void trace_path(const SceneRef& sc, const Sampler& smp, FB& fb, uint32_t px, uint32_t py, float frame_weight, vec3 U, vec3 V, vec3 W, PassStats& st, bool count_trav)
+// ---------------------------------------------------------------------------------------------
+// path-space filtering (`-psfpt`)
+// ---------------------------------------------------------------------------------------------
+// PSFPTVertexProcessor::CacheInfo (src/psfpt_vertex_processor.h:48-72): slot:29, comp:2, new_entry:1
+static const uint32_t PSF_INVALID = 0xFFFFFFFFu, PSF_INVALID_SLOT = (1u << 29) - 1u;
+static const uint32_t PSF_DIFFUSE_COMP = 1u, PSF_ALL_COMPS = 3u;
+static inline uint32_t psf_pack(uint32_t slot, uint32_t comp, uint32_t new_entry) { return (slot & PSF_INVALID_SLOT) | (comp << 29) | (new_entry << 31); }
+static inline uint32_t psf_slot(uint32_t info) { return info & PSF_INVALID_SLOT; }
+static inline uint32_t psf_comp(uint32_t info) { return (info >> 29) & 3u; }
+
+struct PsfRef { uint32_t pixel_info, cache; vec3 w_d, w_g; };
+
+struct PsfState
+{
+	std::unordered_map<uint64_t, uint32_t> cells;     // key -> slot (psf_hashmap, src/renderers/psfpt_impl.h:110)
+	std::vector<float> values;                         // float4 per slot: rgb sum, sample count (psf_values)
+	std::vector<PsfRef> refs[64];                      // the reference queue, kept per bounce (a pixel has at most one per bounce)
+#ifdef _OPENMP
+	omp_lock_t lock;
+	PsfState() { omp_init_lock(&lock); }
+	~PsfState() { omp_destroy_lock(&lock); }
+	void acquire() { omp_set_lock(&lock); }
+	void release() { omp_unset_lock(&lock); }
+#else
+	void acquire() {}
+	void release() {}
+#endif
+	void clear() { cells.clear(); values.clear(); }
+	uint32_t insert(uint64_t key)
+	{
+		auto it = cells.find(key);
+		if (it != cells.end()) return it->second;
+		const uint32_t slot = (uint32_t)cells.size();
+		cells.emplace(key, slot);
+		values.resize(values.size() + 4, 0.0f);
+		return slot;
+	}
+};
+
+// cugar::round (contrib/cugar/basic/numbers.h:512-516), cugar::quantize (:600-603)
+static inline float cg_round(float x) { const int y = x > 0.0f ? int(x) : int(x) - 1; return (x - float(y) > 0.5f) ? float(y) + 1.0f : float(y); }
+static inline uint32_t cg_quantize(float x, uint32_t n) { return (uint32_t)std::max(std::min(int32_t(x * float(n)), int32_t(n - 1)), int32_t(0)); }
+
+// cugar::square_to_unit_disk (contrib/cugar/spherical/mappings_inline.h:56-87)
+static inline void square_to_unit_disk(float sx, float sy, float* dx, float* dy)
+{
+	float phi, r;
+	const float a = 2 * sx - 1, b = 2 * sy - 1;
+	if (a > -b) { if (a > b) { r = a; phi = (PI_F / 4) * (b / a); } else { r = b; phi = (PI_F / 4) * (2 - (a / b)); } }
+	else { if (a < b) { r = -a; phi = (PI_F / 4) * (4 + (b / a)); } else { r = -b; phi = b != 0 ? (PI_F / 4) * (6 - (a / b)) : 0; } }
+	float s, c; o_sincosf(phi, &s, &c);
+	*dx = r * c; *dy = r * s;
+}
+
+// spatial_hash (src/spatial_hash.h:74-149), the overload PSFPTVertexProcessor::preprocess_vertex calls
+static uint64_t spatial_hash(vec3 P, vec3 N, vec3 T, vec3 B, vec3 bbox_lo, vec3 bbox_hi, const float samples[6], float cone_radius, float filter_radius)
+{
+	const uint32_t normal_bits = 4;
+	const float world_extent = max_comp(bbox_hi - bbox_lo);
+	const float float_grid_size = fmaxf(world_extent / (2.0f * cone_radius), 1.0f);
+	const float flog_grid_size = log2f(float_grid_size);
+	const uint32_t log_grid_size = uint32_t(flog_grid_size);
+	const float rlog_grid_size = flog_grid_size - log_grid_size;
+	const uint32_t log_grid_size_i = log_grid_size + (samples[5] < rlog_grid_size ? 1u : 0u);
+	const uint32_t grid_size = 1u << log_grid_size_i;
+	float rx, ry; square_to_unit_disk(samples[0], samples[1], &rx, &ry);
+	rx = (filter_radius * cone_radius) * rx; ry = (filter_radius * cone_radius) * ry;
+	const vec3 shading_loc = float(grid_size) * (P + T * rx + B * ry - bbox_lo) / world_extent;
+	const uint32_t lx = uint32_t(fmaxf(cg_round(shading_loc.x), 0.0f)), ly = uint32_t(fmaxf(cg_round(shading_loc.y), 0.0f)), lz = uint32_t(fmaxf(cg_round(shading_loc.z), 0.0f));
+	const float jx = samples[3] / float(1u << (normal_bits / 2)), jy = samples[4] / float(1u << (normal_bits / 2));
+	// uniform_sphere_to_square (contrib/cugar/spherical/mappings_inline.h:174-185)
+	float phi;
+	if (fabsf(N.z) >= 1.0f - 1.0e-5f) phi = 0.0f;
+	else { phi = atan2f(N.y, N.x); phi = phi < 0.0f ? phi + 2.0f * PI_F : phi; }
+	float ux = phi / (2.0f * PI_F), uy = (N.z + 1.0f) * 0.5f;
+	ux = mod1(ux + jx, 1.0f);
+	uy = fminf(uy + jy, 1.0f);
+	// pack_vector (contrib/cugar/linalg/vector_inl.h:454-462)
+	const uint32_t MAXQ = (1u << (normal_bits / 2)) - 1u;
+	const uint32_t shading_normal_i = cg_quantize(ux, MAXQ) | (cg_quantize(uy, MAXQ) << (normal_bits / 2));
+	const uint32_t comp_mask = (1u << 17) - 1u;
+	return (uint64_t(lx & comp_mask) << 0) | (uint64_t(ly & comp_mask) << 17) | (uint64_t(lz & comp_mask) << 34) | (uint64_t(log_grid_size_i) << 51) | (uint64_t(shading_normal_i) << 56);
+}
+
+static inline vec3 psf_clamp_sample(vec3 v, float ff) { return finite3(v) ? vec3(fminf(v.x, ff), fminf(v.y, ff), fminf(v.z, ff)) : vec3(0.0f); }
+static inline vec3 psf_floor4(vec3 c) { return vec3(fmaxf(c.x, 1.0e-4f), fmaxf(c.y, 1.0e-4f), fmaxf(c.z, 1.0e-4f)); }   // modulate / demodulate, src/filters.h:57-72
+
+// one path, all bounces; psf != NULL: the PSFPTVertexProcessor policies instead of PTVertexProcessor's
+static void trace_path(const SceneRef& sc, const Sampler& smp, FB& fb, uint32_t px, uint32_t py, float frame_weight, vec3 U, vec3 V, vec3 W, PassStats& st, bool count_trav,
+					   PsfState* psf = NULL, uint32_t instance = 0)
 {
 	const fb200_scene_view* s = sc.s;
 	const fb200_pt_options& o = s->options;
@@ -360,6 +454,28 @@ static void trace_path(const SceneRef& sc, const Sampler& smp, FB& fb, uint32_t 
 	vec3 w(1.0f); float p_prev = 1.0f;
 	uint32_t comp = 0; bool diffuse_flag = false;
 	TravStats* ts = count_trav ? &st.trav : NULL;
+	// PSFPT: ray cone {radius so far, solid-angle pdf of the last direction} and the cache slot the path feeds (src/pathtracer_kernels.h:153-159)
+	const fb200_psf_options& po = s->psf;
+	float cone_x = 0.0f, cone_y = 0.0f;
+	uint32_t prev_vinfo = PSF_INVALID;
+	if (psf)
+	{
+		// camera_direction_pdf (src/camera.h:232-252) with square_pixel_focal_length (:122-128)
+		const float W_len = sqrtf(dot(W, W));
+		const float tn = tanf(s->fov / 2);
+		const float sq_focal = (float(s->res_x * s->res_y) / 4.0f) / (tn * tn);
+		const float t = dot(ray.d, W) / (W_len * W_len);
+		if (t >= 0.0f)
+		{
+			const vec3 I = ray.d / t - W;
+			const float Ix = dot(I, U) / square_length(U), Iy = dot(I, V) / square_length(V);
+			if (Ix >= -1.0f && Ix <= 1.0f && Iy >= -1.0f && Iy <= 1.0f)
+			{
+				const float cos_theta = dot(ray.d, W) / W_len;
+				cone_y = sq_focal / (cos_theta * cos_theta * cos_theta);
+			}
+		}
+	}
 
 	for (uint32_t bounce = 0; bounce < o.max_path_length; ++bounce)
 	{
@@ -405,6 +521,40 @@ static void trace_path(const SceneRef& sc, const Sampler& smp, FB& fb, uint32_t 
 			da[0] += mat.diffuse.x * frame_weight; da[1] += mat.diffuse.y * frame_weight; da[2] += mat.diffuse.z * frame_weight; da[3] += 0.0f * frame_weight;
 			sa[0] += (mat.specular.x + 1.0f) * 0.5f * frame_weight; sa[1] += (mat.specular.y + 1.0f) * 0.5f * frame_weight;
 			sa[2] += (mat.specular.z + 1.0f) * 0.5f * frame_weight; sa[3] += (0.0f + 1.0f) * 0.5f * frame_weight;
+		}
+
+		// PSFPTVertexProcessor::preprocess_vertex (src/psfpt_vertex_processor.h:123-199), cone radius as in shade_vertex (src/pathtracer_core.h:816-819)
+		const uint32_t info = pixel | (comp << 27) | ((diffuse_flag ? 1u : 0u) << 31);      // PixelInfo of the incoming path
+		uint32_t vinfo = PSF_INVALID; bool new_entry = false; float cone_radius = 0.0f;
+		if (psf)
+		{
+			const float prev_G_prime = fabsf(dot(in, g.normal_s)) / (hit.t * hit.t);
+			const float area_prob = 1.0f / sqrtf(cone_y * prev_G_prime);      // cugar::rsqrtf; stated as an exact division on both sides
+			cone_radius = cone_x + area_prob;
+			uint32_t slot = psf_slot(prev_vinfo);
+			if (slot == PSF_INVALID_SLOT && bounce >= po.psf_depth && p_prev < po.psf_max_prob)
+			{
+				const uint32_t pixel_hash = pixel + instance * s->res_x * s->res_y;
+				float jitter[6];
+				for (uint32_t i = 0; i < 6; ++i) jitter[i] = randfloat(i, pixel_hash);
+				const float filter_scale = bounce == 0 ? 2.0f : 1.0f;
+				const vec3 Ns = dot(in, g.normal_s) > 0.0f ? g.normal_s : -g.normal_s;
+				const uint64_t key = spatial_hash(g.position, Ns, g.tangent, g.binormal, vec3(s->bbox_min[0], s->bbox_min[1], s->bbox_min[2]),
+												  vec3(s->bbox_max[0], s->bbox_max[1], s->bbox_max[2]), jitter, cone_radius * po.psf_width, filter_scale);
+				const vec3 w_mod = w * psf_floor4(mat.diffuse);
+				PsfRef ref;
+				ref.pixel_info = info;
+				ref.w_d = (comp & cDiffuseMask) ? w_mod : vec3(0.0f);
+				ref.w_g = ((comp & cGlossyMask) && bounce) ? w_mod : vec3(0.0f);
+				psf->acquire();
+				slot = psf->insert(key);
+				psf->values[4 * (size_t)slot + 3] += 1.0f;
+				ref.cache = psf_pack(slot, PSF_ALL_COMPS, 0);
+				psf->refs[bounce < 64 ? bounce : 63].push_back(ref);
+				psf->release();
+				new_entry = true;
+			}
+			vinfo = psf_pack(slot, 0, new_entry ? 1u : 0u);
 		}
 
 		float z[6];
@@ -481,7 +631,13 @@ static void trace_path(const SceneRef& sc, const Sampler& smp, FB& fb, uint32_t 
 			const float mis_w = ((bounce == 0 && o.direct_lighting_bsdf) || (bounce > 0 && o.indirect_lighting_bsdf)) ? power_heuristic(p1, p2) : 1.0f;
 			const vec3 fd = o.diffuse_scattering ? f[kDR] + f[kDT] : vec3(0.0f), fg = o.glossy_scattering ? f[kGR] + f[kGT] : vec3(0.0f);
 			const vec3 fl = f_L * G * mis_w;
-			const vec3 w_d = (bounce == 0 ? fd : fd + fg) * w * fl, w_g = (bounce == 0 ? fg : fd + fg) * w * fl;
+			vec3 w_d = (bounce == 0 ? fd : fd + fg) * w * fl, w_g = (bounce == 0 ? fg : fd + fg) * w * fl;
+			if (psf)
+			{
+				// PSFPTVertexProcessor::compute_nee_weights (src/psfpt_vertex_processor.h:204-268)
+				if (new_entry) { w_d = (fd / psf_floor4(mat.diffuse)) * fl; w_g = fg * w * fl; }
+				else { w_d = fd * w * fl; w_g = fg * w * fl; }
+			}
 			const vec3 ow = w_d + w_g;
 			if (max_comp(ow) > 0.0f && finite3(ow))
 			{
@@ -506,25 +662,44 @@ static void trace_path(const SceneRef& sc, const Sampler& smp, FB& fb, uint32_t 
 			const vec3 ow = w * f_L * mis_w;
 			if (max_comp(ow) > 0.0f && finite3(ow))
 			{
-				fb.add_in(false, COMPOSITED_C, pixel, ow, frame_weight);
-				if (bounce == 0) fb.add_in(false, DIRECT_C, pixel, ow, frame_weight);
+				// PTVertexProcessor::accumulate_emissive, or PSFPTVertexProcessor's (src/psfpt_vertex_processor.h:326-369): clamped, and into
+				// the cache cell once the path feeds one
+				const vec3 cw = psf ? psf_clamp_sample(ow, po.firefly_filter) : ow;
+				if (!psf || psf_slot(prev_vinfo) == PSF_INVALID_SLOT)
+				{
+					fb.add_in(false, COMPOSITED_C, pixel, cw, frame_weight);
+					if (bounce == 0) fb.add_in(false, DIRECT_C, pixel, cw, frame_weight);
+					else
+					{
+						if (comp & cDiffuseMask) fb.add_in(true, DIFFUSE_C, pixel, cw, frame_weight);
+						if (comp & cGlossyMask)  fb.add_in(true, SPECULAR_C, pixel, cw, frame_weight);
+					}
+				}
 				else
 				{
-					if (comp & cDiffuseMask) fb.add_in(true, DIFFUSE_C, pixel, ow, frame_weight);
-					if (comp & cGlossyMask)  fb.add_in(true, SPECULAR_C, pixel, ow, frame_weight);
+					psf->acquire();
+					float* v = &psf->values[4 * (size_t)psf_slot(prev_vinfo)];
+					v[0] += cw.x; v[1] += cw.y; v[2] += cw.z;
+					psf->release();
 				}
 			}
 		}
 
 		// scattering (pathtracer_core.h:1157-1247)
 		bool cont = false;
-		Ray next; vec3 next_w(0.0f); float next_p = 0.0f; uint32_t next_comp = 0;
+		Ray next; vec3 next_w(0.0f); float next_p = 0.0f; uint32_t next_comp = 0, next_vinfo = PSF_INVALID;
 		if (do_scatter)
 		{
 			// NOTE: component masks other than "all" are out of scope of the oracle
 			uint32_t out_comp; vec3 out, gg; float p, p_proj;
 			bsdf.sample(g, z + 3, in, out_comp, out, p, p_proj, gg);
-			const vec3 ow = gg * w;
+			vec3 ow = gg * w;
+			if (psf)
+			{
+				// PSFPTVertexProcessor::compute_scattering_weights (src/psfpt_vertex_processor.h:273-321)
+				next_vinfo = (psf_slot(prev_vinfo) == PSF_INVALID_SLOT && (out_comp & cGlossyMask)) ? prev_vinfo : psf_pack(psf_slot(vinfo), PSF_ALL_COMPS, 0);
+				if (new_entry && (out_comp & cDiffuseMask)) ow = gg / psf_floor4(mat.diffuse);
+			}
 			if (out_comp != cAbsorption && p != 0.0f && max_comp(ow) > 0.0f && finite3(ow))
 			{
 				cont = true;
@@ -539,7 +714,43 @@ static void trace_path(const SceneRef& sc, const Sampler& smp, FB& fb, uint32_t 
 			{
 				st.shadow_events++;
 				const bool occluded = trace_any(sc, pend[k].r, count_trav ? &st.trav_shadow : NULL);
-				if (!occluded)
+				if (!occluded && psf)
+				{
+					// PSFPTVertexProcessor::accumulate_nee (src/psfpt_vertex_processor.h:374-438). The shadow queue carries the vertex_info
+					// preprocess_vertex returned (comp = 0: src/pathtracer_core.h:1098 passes vertex_info, not out_vertex_info), so the
+					// DIFFUSE_COMP branch below is never taken in the reference either; it is restated for completeness.
+					const float ff = po.firefly_filter;
+					const vec3 wd = pend[k].w_d, wg = pend[k].w_g;
+					if (psf_slot(vinfo) != PSF_INVALID_SLOT)
+					{
+						const bool diffuse_only = psf_comp(vinfo) == PSF_DIFFUSE_COMP;
+						const vec3 cw = diffuse_only ? wd : wd + wg;
+						psf->acquire();
+						float* v = &psf->values[4 * (size_t)psf_slot(vinfo)];
+						v[0] += cw.x; v[1] += cw.y; v[2] += cw.z;
+						psf->release();
+						if (diffuse_only)
+						{
+							fb.add_in(false, COMPOSITED_C, pixel, psf_clamp_sample(wg, ff), frame_weight);
+							fb.add_in(true, (bounce == 0 || (comp & cGlossyMask)) ? SPECULAR_C : DIFFUSE_C, pixel, psf_clamp_sample(wg, ff), frame_weight);
+						}
+					}
+					else
+					{
+						fb.add_in(false, COMPOSITED_C, pixel, psf_clamp_sample(wd + wg, ff), frame_weight);
+						if (bounce == 0)
+						{
+							fb.add_in(true, DIFFUSE_C, pixel, psf_clamp_sample(wd, ff), frame_weight);
+							fb.add_in(true, SPECULAR_C, pixel, psf_clamp_sample(wg, ff), frame_weight);
+						}
+						else
+						{
+							if (comp & cDiffuseMask) fb.add_in(true, DIFFUSE_C, pixel, psf_clamp_sample(wd + wg, ff), frame_weight);
+							if (comp & cGlossyMask)  fb.add_in(true, SPECULAR_C, pixel, psf_clamp_sample(wd + wg, ff), frame_weight);
+						}
+					}
+				}
+				else if (!occluded)
 				{
 					fb.add_in(false, COMPOSITED_C, pixel, pend[k].w_d + pend[k].w_g, frame_weight);
 					if (bounce == 0)
@@ -557,6 +768,8 @@ static void trace_path(const SceneRef& sc, const Sampler& smp, FB& fb, uint32_t 
 
 		if (!cont) return;
 		ray = next; w = next_w; p_prev = next_p;
+		cone_x = cone_radius; cone_y = fmaxf(next_p, 32.0f);      // Bekaert's footprint, src/pathtracer_core.h:1222-1227
+		prev_vinfo = next_vinfo;
 		diffuse_flag = diffuse_flag || (next_comp & cDiffuseMask);
 		comp = next_comp & 0xFu;      // PixelInfo::comp is a 4-bit field (pathtracer_core.h:527-542)
 		(void)diffuse_flag;
@@ -642,6 +855,93 @@ int oracle_render_pass(const fb200_scene_view* s, uint32_t instance, float* fbda
 			total.nodes_visited += st.trav.nodes; total.tris_tested += st.trav.tris; total.shadow_nodes_visited += st.trav_shadow.nodes; total.shadow_tris_tested += st.trav_shadow.tris;
 			for (int b = 0; b < 64; ++b) total.per_bounce[b] += st.per_bounce[b];
 		}
+	}
+	if (out) *out = total;
+	return 0;
+}
+
+// ---- `-psfpt` ------------------------------------------------------------------------------------
+// state of the filter across passes: the hash of cache cells and their values (cleared every psf_temporal_reuse passes)
+void* oracle_psf_create(void) { return new PsfState(); }
+void  oracle_psf_destroy(void* st) { delete static_cast<PsfState*>(st); }
+uint64_t oracle_psf_cells(const void* st) { return static_cast<const PsfState*>(st)->cells.size(); }
+
+// PSFPT::render (src/renderers/psfpt_impl.h:256-265): rescale_frame, the path tracing loop with PSFPTVertexProcessor, psf_blending of
+// the references (:101-143), update_variances, clamp_frame(100). Whole frame only.
+int oracle_render_pass_psf(const fb200_scene_view* s, uint32_t instance, float* fbdata, void* state, int n_threads, oracle_stats* out)
+{
+	if (s->n_dir_lights) return -1;              // (directional lights are not carried into the filtered renderer)
+	PsfState* psf = static_cast<PsfState*>(state);
+	SceneRef sc = { s, s->vertex_indices, s->vertex_data, reinterpret_cast<const NodePOD*>(s->bvh_nodes) };
+	const size_t P = (size_t)s->res_x * s->res_y;
+	FB fb = { fbdata, P };
+	Sampler smp(s, instance);
+	vec3 U, V, W; camera_frame(s, U, V, W);
+	const float scale = float(instance) / float(instance + 1), frame_weight = 1.0f / float(instance + 1);
+	const uint32_t n = instance + 1;
+#ifdef _OPENMP
+	static const int default_threads = omp_get_max_threads();
+	omp_set_num_threads(n_threads > 0 ? n_threads : default_threads);
+#endif
+	if ((instance % s->psf.psf_temporal_reuse) == 0) psf->clear();
+	for (int b = 0; b < 64; ++b) psf->refs[b].clear();
+	oracle_stats total; memset(&total, 0, sizeof(total));
+	#pragma omp parallel
+	{
+		PassStats st; memset(&st, 0, sizeof(st));
+		#pragma omp for schedule(dynamic, 256)
+		for (long long k = 0; k < (long long)P; ++k)
+		{
+			const uint32_t p = (uint32_t)k;
+			float* lum = fb.px(LUMINANCE, p);
+			lum[0] = max_comp(vec3(fb.px(DIRECT_C, p)[0], fb.px(DIRECT_C, p)[1], fb.px(DIRECT_C, p)[2]));
+			lum[1] = max_comp(vec3(fb.px(DIFFUSE_C, p)[0], fb.px(DIFFUSE_C, p)[1], fb.px(DIFFUSE_C, p)[2]));
+			lum[2] = max_comp(vec3(fb.px(SPECULAR_C, p)[0], fb.px(SPECULAR_C, p)[1], fb.px(SPECULAR_C, p)[2]));
+			lum[3] = max_comp(vec3(fb.px(COMPOSITED_C, p)[0], fb.px(COMPOSITED_C, p)[1], fb.px(COMPOSITED_C, p)[2]));
+			const int scaled[6] = { DIFFUSE_C, DIFFUSE_A, SPECULAR_C, SPECULAR_A, DIRECT_C, COMPOSITED_C };
+			for (int c = 0; c < 6; ++c) for (int i = 0; i < 4; ++i) fb.px(scaled[c], p)[i] *= scale;
+			trace_path(sc, smp, fb, p % s->res_x, p / s->res_x, frame_weight, U, V, W, st, false, psf, instance);
+		}
+		#pragma omp critical
+		{
+			total.shade_events += st.shade_events; total.shadow_events += st.shadow_events;
+			for (int b = 0; b < 64; ++b) total.per_bounce[b] += st.per_bounce[b];
+		}
+	}
+	// psf_blending_kernel (src/renderers/psfpt_impl.h:101-131), bounce by bounce: one reference per pixel and bounce at most
+	for (int b = 0; b < 64; ++b)
+		for (size_t i = 0; i < psf->refs[b].size(); ++i)
+		{
+			const PsfRef& r = psf->refs[b][i];
+			const uint32_t slot = psf_slot(r.cache);
+			if (slot == PSF_INVALID_SLOT) continue;
+			const uint32_t pixel = r.pixel_info & 0x07FFFFFFu, rcomp = (r.pixel_info >> 27) & 0xFu;
+			const float* cv = &psf->values[4 * (size_t)slot];
+			const vec3 c(cv[0] / cv[3], cv[1] / cv[3], cv[2] / cv[3]);
+			const vec3 w = ((rcomp & cDiffuseMask) ? r.w_d : vec3(0.0f)) + ((rcomp & cGlossyMask) ? r.w_g : vec3(0.0f));
+			const vec3 cw = c * w, ff(s->psf.firefly_filter);
+			fb.add_in(false, COMPOSITED_C, pixel, vec3(fminf(cw.x, ff.x), fminf(cw.y, ff.y), fminf(cw.z, ff.z)), frame_weight);
+			if (rcomp & cDiffuseMask) fb.add_in(true, DIFFUSE_C, pixel, c * r.w_d, frame_weight);
+			if (rcomp & cGlossyMask)  fb.add_in(true, SPECULAR_C, pixel, c * r.w_g, frame_weight);
+		}
+	#pragma omp parallel for schedule(static)
+	for (long long k = 0; k < (long long)P; ++k)
+	{
+		const uint32_t p = (uint32_t)k;
+		const float* lum = fb.px(LUMINANCE, p);
+		const float nl[4] = {
+			max_comp(vec3(fb.px(DIRECT_C, p)[0], fb.px(DIRECT_C, p)[1], fb.px(DIRECT_C, p)[2])),
+			max_comp(vec3(fb.px(DIFFUSE_C, p)[0], fb.px(DIFFUSE_C, p)[1], fb.px(DIFFUSE_C, p)[2])),
+			max_comp(vec3(fb.px(SPECULAR_C, p)[0], fb.px(SPECULAR_C, p)[1], fb.px(SPECULAR_C, p)[2])),
+			max_comp(vec3(fb.px(COMPOSITED_C, p)[0], fb.px(COMPOSITED_C, p)[1], fb.px(COMPOSITED_C, p)[2])) };
+		const int vch[4] = { DIRECT_C, DIFFUSE_C, SPECULAR_C, COMPOSITED_C };
+		for (int c = 0; c < 4; ++c)
+		{
+			const float d1 = n * (nl[c] - lum[c]), d2 = (n - 1) * (nl[c] - lum[c]);
+			fb.px(vch[c], p)[3] += (d1 * d2) / (n * n);
+		}
+		// clamp_frame_kernel (src/renderer.cu:314-331): all four components of the four colour channels
+		for (int c = 0; c < 4; ++c) for (int i = 0; i < 4; ++i) fb.px(vch[c], p)[i] = fminf(fb.px(vch[c], p)[i], 100.0f);
 	}
 	if (out) *out = total;
 	return 0;
