@@ -183,7 +183,8 @@ def run_ours(args):
 
     scene, name = workload(args)
     res = frame_size(args, world)
-    sc = fb.Scene(["-i", scene, "-r", str(res[0]), str(res[1]), "-bounces", str(BOUNCES), "-shard", str(rank), str(world)])
+    # --psfpt: the path-space filtering renderer on the same workload (not the headline metric: BASELINE.json names -pt)
+    sc = fb.Scene(["-i", scene, "-r", str(res[0]), str(res[1]), "-bounces", str(BOUNCES), "-shard", str(rank), str(world)] + (["-psfpt"] if args.psfpt else []))
     rc = fb.RenderingContext(sc, local)
     stream = torch.cuda.ExternalStream(rc.stream(), device=torch.device("cuda", local))
     comp = rc.fb_tensor("COMPOSITED_C")
@@ -323,7 +324,7 @@ def run_ours(args):
     # ---------------- CPU baseline (rank 0, N = 1 only) and roofline ----------------
     base, trav = (None, None)
     trav_file = os.path.join(ROOT, "profiles", "trav_counts_%s.json" % name.split()[0])
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not args.psfpt:
         base, trav = cpu_baseline(scene, res)
     if trav is None and os.path.exists(trav_file):
         trav = json.load(open(trav_file))
@@ -363,7 +364,7 @@ def run_ours(args):
     out = {
         "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s -pt %dx%d, %d bounces, default seeds, passes %d..%d" % (name, res[0], res[1], BOUNCES, args.warmup, args.warmup + args.steps - 1),
+        "config": {"workload": "%s %s %dx%d, %d bounces, default seeds, passes %d..%d" % (name, "-psfpt" if args.psfpt else "-pt", res[0], res[1], BOUNCES, args.warmup, args.warmup + args.steps - 1),
                    "parallelism": "tile-sharded x%d, one NCCL reduce of COMPOSITED per pass" % world if world > 1 else "single GPU",
                    "l2": "working set per pass (queues + 8-channel frame buffer, > 400 MB) exceeds the 126 MB L2",
                    "target": ">= 200 Msamples/s (BASELINE.json)"},
@@ -411,6 +412,7 @@ def main():
     ap.add_argument("--scene", default=None)
     ap.add_argument("--res", type=int, nargs=2, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--psfpt", action="store_true", help="measure the -psfpt renderer instead of -pt (GPU arm only; implies --no-cpu-baseline)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

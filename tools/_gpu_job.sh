@@ -1,6 +1,7 @@
 #!/bin/sh
 mkdir -p gpurun_out
-timeout 400 python -m pytest tests/test_psfpt.py -x -q -m gpu > gpurun_out/r03_pytest_psfpt.log 2>&1; echo "pytest exit $?" | tee -a gpurun_out/r03_pytest_psfpt.log
-grep -v "^  \|allocating\|settings" gpurun_out/r03_pytest_psfpt.log | tail -30
-FB200_TRACE_CTAS=4 timeout 300 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:"k_trace|k_shade|k_accumulate" --launch-skip 144 -c 72 --csv --log-file gpurun_out/r03_traffic_pass.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r03_ncu_traffic.log 2>&1
-wc -l gpurun_out/r03_traffic_pass.csv
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 4 --steps 16 --warmup 4 > gpurun_out/r03_bench_n4.json 2> gpurun_out/r03_bench_n4.err
+python -c "
+import json
+d=json.loads(open('gpurun_out/r03_bench_n4.json').read().strip().splitlines()[-1]); print('N=4', d['value'], d['e2e']['value'], d['ms_per_step'], d['finite'], d['config']['workload'])"
+tail -2 gpurun_out/r03_bench_n4.err | cut -c1-200
