@@ -170,12 +170,8 @@ __global__ void __launch_bounds__(256) k_generate_primary(DeviceScene sc, PassPa
                                    // 2: also pull its vertices and material once the hit's own gathers are in flight
 #endif
 #ifndef FB_MATCH_PENDING
-#define FB_MATCH_PENDING 1         // 1 (r02 sweep: +0.9 %): an owner finds out whether helpers still work on its ray with one warp match instead of shared-memory counters;
-                                   // 2 (r03: +0.2 %, noise): with one warp-wide OR of the helpers' root bits
-#endif
-#ifndef FB_SPLIT_BOTTOM
-#define FB_SPLIT_BOTTOM 0          // 1 (r03: -0.9 % alone, +0.7 % with the rest): a donor hands over the BOTTOM entry of its stack (the siblings nearest the root: the largest part of what is
-                                   // left of the ray) instead of the top one, and keeps its own entries in front-to-back order
+#define FB_MATCH_PENDING 1         // 1 (r02 sweep: +0.9 %): an owner finds out whether helpers still work on its ray with one warp match instead of shared-memory counters
+                                   // (r03: a warp-wide OR of the helpers' root bits instead of the match: +0.2 %, noise; donating the bottom stack entry: -0.9 %)
 #endif
 #ifndef FB_THIN_QUOTA
 #define FB_THIN_QUOTA 0            // > 0 (r03, 8 / 16 / 32: +0.4 % / +0.5 % / +0.4 %, within noise): when the queue holds fewer rays than this many per warp, every warp of the launch takes its even share of
@@ -309,7 +305,6 @@ __global__ void __launch_bounds__(FB_TRACE_THREADS, FB_TRACE_MIN_BLOCKS) k_trace
 #endif
 	int  tail_iters = 0;             // warp-uniform: iterations since then
 	bool can_suspend = may_suspend;
-	bool flip = false;               // warp-uniform: pool order of the triangle phase (FB_LAZY_TRI)
 	uint32* const cursor = tasks_phase ? a.cont_next : a.cursor;
 #if FB_TRACE_STATS
 	uint32 st_iters = 0, st_tail = 0, st_lanes = 0, st_helpers = 0, st_ray = 0, st_longest_ray = 0; bool st_busy = false;
@@ -445,13 +440,7 @@ __global__ void __launch_bounds__(FB_TRACE_THREADS, FB_TRACE_MIN_BLOCKS) k_trace
 				uint2 e = make_uint2(0u, 0u);
 				if (is_donor)
 				{
-#if FB_SPLIT_BOTTOM && FB_SMEM_STACK == 0
-					e = local_stack[0];
-					--trav.sp;
-					for (int i = 0; i < trav.sp; ++i) local_stack[i] = local_stack[i + 1];
-#else
 					e = trav.pop();
-#endif
 				}
 				e.x = __shfl_sync(0xFFFFFFFFu, e.x, src); e.y = __shfl_sync(0xFFFFFFFFu, e.y, src);
 				const float ox = __shfl_sync(0xFFFFFFFFu, trav.ray.ox, src), oy = __shfl_sync(0xFFFFFFFFu, trav.ray.oy, src), oz = __shfl_sync(0xFFFFFFFFu, trav.ray.oz, src);
@@ -480,16 +469,7 @@ __global__ void __launch_bounds__(FB_TRACE_THREADS, FB_TRACE_MIN_BLOCKS) k_trace
 				const int h = __ffs((int)idle) - 1, d = __ffs((int)donors) - 1;
 				idle &= idle - 1u; donors &= donors - 1u;
 				uint2 e = make_uint2(0u, 0u);
-#if FB_SPLIT_BOTTOM && FB_SMEM_STACK == 0
-				if (lane == d)
-				{
-					e = local_stack[0];
-					--trav.sp;
-					for (int i = 0; i < trav.sp; ++i) local_stack[i] = local_stack[i + 1];
-				}
-#else
 				if (lane == d) e = trav.pop();
-#endif
 				e.x = __shfl_sync(0xFFFFFFFFu, e.x, d); e.y = __shfl_sync(0xFFFFFFFFu, e.y, d);
 				const float ox = __shfl_sync(0xFFFFFFFFu, trav.ray.ox, d), oy = __shfl_sync(0xFFFFFFFFu, trav.ray.oy, d), oz = __shfl_sync(0xFFFFFFFFu, trav.ray.oz, d);
 				const float dx = __shfl_sync(0xFFFFFFFFu, trav.ray.dx, d), dy = __shfl_sync(0xFFFFFFFFu, trav.ray.dy, d), dz = __shfl_sync(0xFFFFFFFFu, trav.ray.dz, d);
@@ -538,31 +518,7 @@ __global__ void __launch_bounds__(FB_TRACE_THREADS, FB_TRACE_MIN_BLOCKS) k_trace
 			if (active)
 			{
 				done = !trav.acquire();
-#if FB_LAZY_TRI
-				if (!done && !trav.has_tri()) trav.node_step(sc, smem_nodes);      // (a ray with triangles left over from the last round waits for them)
-#else
 				if (!done) trav.node_step(sc, smem_nodes);
-#endif
-#if FB_PREFETCH & 4
-				// pull the node this lane visits next - the next child of the group at hand or of the group on top of the stack -
-				// towards L1 while the triangle phase runs: the two L2 round trips of an iteration overlap
-				if (!done)
-				{
-					uint2 g = trav.ngroup;
-					if (!(g.y > 0x00FFFFFFu) && trav.sp > 0) g = local_stack[trav.sp - 1];
-					if (g.y > 0x00FFFFFFu)
-					{
-						const uint32 sl = (bfind(g.y) - 24u) ^ (trav.octinv4 & 0xFFu);
-						const uint32 nidx = g.x + __popc(g.y & ~(0xFFFFFFFFu << sl) & 0xFFu);
-						if (nidx >= sc.staged_nodes)
-						{
-							const char* p = reinterpret_cast<const char*>(sc.nodes) + (size_t)nidx * 80u;
-							asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
-							asm volatile("prefetch.global.L1 [%0];" :: "l"(p + 64));
-						}
-					}
-				}
-#endif
 			}
 			if (tasks_phase && active && root == lane)
 			{
@@ -571,23 +527,13 @@ __global__ void __launch_bounds__(FB_TRACE_THREADS, FB_TRACE_MIN_BLOCKS) k_trace
 			}
 			FB_STAT_MARK(1)
 #if FB_TRACE_STATS
-			trav.coop_tri_phase(sc, active && !done, pair_buf, lane, root, st_tri, flip);
-#elif FB_LAZY_TRI
-			trav.coop_tri_phase(sc, active && !done, pair_buf, lane, root, NULL, flip);
+			trav.coop_tri_phase(sc, active && !done, pair_buf, lane, root, st_tri);
 #else
 			trav.coop_tri_phase(sc, active && !done, pair_buf, lane, root);
 #endif
-			flip = !flip;
 			FB_STAT_MARK(2)
-			if (active && !done) done = (ANY && trav.occluded) || (!trav.has_node() && trav.sp == 0 && !(FB_LAZY_TRI && trav.has_tri()));
-#if FB_SPLIT_RAYS && FB_MATCH_PENDING == 2
-			if (exhausted || thin)       // (warp-uniform; helpers exist only then)
-			{
-				if (active && done && root != lane) { root = lane; active = false; done = false; }                // a helper is through with its share
-				const uint32 helped = __reduce_or_sync(0xFFFFFFFFu, (active && root != lane) ? (1u << root) : 0u);   // rays that still have helpers at work
-				if (active && done && ((helped >> lane) & 1u)) done = false;                                      // the owner waits for its helpers
-			}
-#elif FB_SPLIT_RAYS && FB_MATCH_PENDING
+			if (active && !done) done = (ANY && trav.occluded) || (!trav.has_node() && trav.sp == 0);
+#if FB_SPLIT_RAYS && FB_MATCH_PENDING
 			if (exhausted || thin)       // (warp-uniform; helpers exist only then)
 			{
 				if (active && done && root != lane) { root = lane; active = false; done = false; }                // a helper is through with its share

@@ -30,25 +30,10 @@ namespace fb {
 #define FB_FOLD_MAGIC 1            // 1 (r02 sweep: +0.4 %): leave the 2^15 offset of the PRMT-built plane coordinate in place and fold it into the slab
                                    // constants (one FADD less per plane, 48 per node visit), with a proven-conservative widening
 #endif
-#ifndef FB_LAZY_TRI
-#define FB_LAZY_TRI 0              // 1: the triangle phase tests the pooled pairs 32 at a time but does not run a round for a remainder: after the first
-                                   // round, pairs that do not fill a whole round stay with their rays (which sit out the next node visit) and are pooled
-                                   // with the next iteration's, the pool order flipping every iteration so that nobody is left behind twice
-#endif
-#if FB_LAZY_TRI && (FB_PAR_LIST || FB_SEG_DELIVER)
-#error "FB_LAZY_TRI keeps the list-based triangle phase"
-#endif
-#ifndef FB_PAR_LIST
-#define FB_PAR_LIST 0              // 1 (r03: -2.7 % device-timed, +0.5 % end to end: noise): triangle phase: lane j finds the j-th pooled (ray, triangle) pair by a search over the lanes' prefix sums
-                                   // (shuffles only) instead of reading a list the owners wrote to shared memory one triangle at a time
-#endif
-#ifndef FB_SEG_DELIVER
-#define FB_SEG_DELIVER 0           // 1 (r03: -1.0 %): triangle phase, closest hit: the pairs of one ray are neighbours in the pool, so its best hit is found by a
-                                   // segmented min-reduction (5 shuffle steps) instead of handing the hits to their rays one after the other
-#endif
+// (r03 variants of the triangle phase that were measured and removed again - shuffle-only pair listing, segmented-min hit delivery, no
+// round for a remainder - are in the history: commit 12819dc, numbers in profiles/README.md)
 #ifndef FB_PREFETCH
-#define FB_PREFETCH 0              // bit 0: prefetch the next node, bit 1: prefetch the hit triangles (into L1), bit 2: the next node also when it
-                                   // comes from the stack top (r03: 4 -> -2.7 %, 6 -> -30 %)
+#define FB_PREFETCH 0              // bit 0: prefetch the next node, bit 1: prefetch the hit triangles (into L1) (r03: next node also from the stack top: -2.7 %)
 #endif
 
 FB_D uint32 sign_extend_s8x4(uint32 x)
@@ -344,7 +329,7 @@ struct Traversal
 	// k_trace): hits are delivered there.
 	// (TRI_MARK: cycle counters of the diagnostic build, k_trace FB_TRACE_STATS; st = NULL otherwise)
 	#define FB_TRI_MARK(k) if (st) { const long long t_ = clock64(); st[k] += t_ - st_mark; st_mark = t_; }
-	FB_D void coop_tri_phase(const DeviceScene& sc, const bool mine, uint32* __restrict__ pairs, const int lane, const int root, long long* st = NULL, const bool flip = false)
+	FB_D void coop_tri_phase(const DeviceScene& sc, const bool mine, uint32* __restrict__ pairs, const int lane, const int root, long long* st = NULL)
 	{
 		const uint32 FULL = 0xFFFFFFFFu;
 		long long st_mark = st ? clock64() : 0;
@@ -361,40 +346,12 @@ struct Traversal
 			if (lane >= d) incl += v;
 		}
 		const uint32 total = __shfl_sync(FULL, incl, 31);
-#if FB_LAZY_TRI
-		uint32 next = flip ? total - incl : incl - k;   // pool index of this lane's next unlisted triangle (lanes in descending order every other iteration)
-		const uint32 limit = total < 32u ? total : (total & ~31u);
-#else
 		uint32 next = incl - k;                    // pool index of this lane's next unlisted triangle
-		const uint32 limit = total;
-#endif
 		FB_TRI_MARK(0)
 
-		for (uint32 base = 0; base < limit; base += 32u)
+		for (uint32 base = 0; base < total; base += 32u)
 		{
 			const bool valid = base + (uint32)lane < total;
-#if FB_PAR_LIST
-			// pool index p = base + lane belongs to the first lane whose inclusive prefix sum exceeds p
-			const uint32 p = base + (uint32)lane;
-			int lo = 0, hi = 31;
-			#pragma unroll
-			for (int s = 0; s < 5; ++s)
-			{
-				const int mid = (lo + hi) >> 1;
-				const uint32 v = __shfl_sync(FULL, incl, mid);
-				if (v > p) hi = mid; else lo = mid + 1;
-			}
-			const int owner = valid ? lo : lane;
-			const uint32 o_excl = __shfl_sync(FULL, incl - k, owner), o_m = __shfl_sync(FULL, m, owner), o_base = __shfl_sync(FULL, tgroup.x, owner);
-			// the r-th set bit of the owner's triangle mask (24 bits), r = p - (pairs of the lanes before the owner)
-			uint32 r = p - o_excl, mm = o_m, pos = 0u, c;
-			c = (uint32)__popc(mm & 0xFFFFu); if (r >= c) { r -= c; pos += 16u; mm >>= 16; }
-			c = (uint32)__popc(mm & 0xFFu);   if (r >= c) { r -= c; pos += 8u;  mm >>= 8; }
-			c = (uint32)__popc(mm & 0xFu);    if (r >= c) { r -= c; pos += 4u;  mm >>= 4; }
-			c = (uint32)__popc(mm & 0x3u);    if (r >= c) { r -= c; pos += 2u;  mm >>= 2; }
-			c = mm & 1u;                      if (r >= c) { pos += 1u; }
-			const uint32 e = valid ? (((o_base + pos) << 5) | (uint32)owner) : (uint32)lane;
-#else
 			while (m && next < base + 32u)
 			{
 				const uint32 b = bfind(m);
@@ -405,7 +362,6 @@ struct Traversal
 			__syncwarp();
 			const uint32 e = valid ? pairs[lane] : (uint32)lane;
 			const int owner = (int)(e & 31u);
-#endif
 			FB_TRI_MARK(1)
 			const float rox = __shfl_sync(FULL, ray.ox, owner), roy = __shfl_sync(FULL, ray.oy, owner), roz = __shfl_sync(FULL, ray.oz, owner);
 			const float rdx = __shfl_sync(FULL, ray.dx, owner), rdy = __shfl_sync(FULL, ray.dy, owner), rdz = __shfl_sync(FULL, ray.dz, owner);
@@ -457,45 +413,6 @@ struct Traversal
 			}
 			else
 			{
-#if FB_SEG_DELIVER
-				// segmented min over (t, triangle id): after 5 steps the first pair of every ray holds the ray's best hit of this round
-				// and the lane that found it (t > tmin >= 0: the float bits order like the floats)
-				uint32 kt = found ? __float_as_uint(ht) : 0xFFFFFFFFu, ktri = (uint32)htri, ksrc = (uint32)lane;
-				#pragma unroll
-				for (int d = 1; d < 32; d <<= 1)
-				{
-					const uint32 ot = __shfl_down_sync(FULL, kt, d), otri = __shfl_down_sync(FULL, ktri, d);
-					const uint32 om = __shfl_down_sync(FULL, ((uint32)owner << 5) | ksrc, d);
-					if (lane + d < 32 && (int)(om >> 5) == owner && (ot < kt || (ot == kt && ot != 0xFFFFFFFFu && otri < ktri))) { kt = ot; ktri = otri; ksrc = om & 31u; }
-				}
-				// every lane that listed pairs in this round reads the head of its segment
-				const uint32 excl = incl - k;
-				const bool in_round = k != 0u && excl < base + 32u && incl > base;
-				const int head = in_round ? (excl > base ? (int)(excl - base) : 0) : lane;
-				const uint32 best_t = __shfl_sync(FULL, kt, head), stri = __shfl_sync(FULL, ktri, head);
-				const int ssrc = (int)__shfl_sync(FULL, ksrc, head);
-				const float sbu = __shfl_sync(FULL, hbu, ssrc), sbv = __shfl_sync(FULL, hbv, ssrc);
-				const bool cand = in_round && best_t != 0xFFFFFFFFu;
-				if (cand && root == lane)
-				{
-					const float t = __uint_as_float(best_t);
-					if (t < ray.tmax || (t == ray.tmax && hit.tri >= 0 && (int)stri < hit.tri)) { ray.tmax = t; hit.t = t; hit.tri = (int)stri; hit.bu = sbu; hit.bv = sbv; }
-				}
-				// helpers hand their best hit to the lane that owns the ray (few, and only in the tail)
-				uint32 hm = __ballot_sync(FULL, cand && root != lane);
-				while (hm)
-				{
-					const int src = __ffs((int)hm) - 1;
-					hm &= hm - 1u;
-					const int o = __shfl_sync(FULL, root, src);
-					const float t = __uint_as_float(__shfl_sync(FULL, best_t, src)), bu = __shfl_sync(FULL, sbu, src), bv = __shfl_sync(FULL, sbv, src);
-					const int tri = (int)__shfl_sync(FULL, stri, src);
-					if (lane == o && (t < ray.tmax || (t == ray.tmax && hit.tri >= 0 && tri < hit.tri)))
-					{
-						ray.tmax = t; hit.t = t; hit.tri = tri; hit.bu = bu; hit.bv = bv;
-					}
-				}
-#else
 				uint32 hm = __ballot_sync(FULL, found);
 				while (hm)
 				{
@@ -509,14 +426,10 @@ struct Traversal
 						ray.tmax = t; hit.t = t; hit.tri = tri; hit.bu = bu; hit.bv = bv;
 					}
 				}
-#endif
 			}
 			__syncwarp();
 			FB_TRI_MARK(5)
 		}
-#if FB_LAZY_TRI
-		if (mine) tgroup.y = m;                    // pairs beyond the last whole round stay pending
-#endif
 	}
 
 	// reference hit record: u = weight of v0, v = weight of v1, through fp16
