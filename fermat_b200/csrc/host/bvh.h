@@ -38,6 +38,11 @@ void build_sbvh2(const Mesh& mesh, Bvh2& bvh, uint32 max_leaf_size = 3);
 // SAH cost of a Bvh2 (node cost 1.2? no: plain  sum_area(inner)/area(root) * c_t + sum_area(leaf)*n/area(root) * c_i )
 float compute_sah_cost(const Bvh2& bvh, float c_trav = 1.0f, float c_isect = 1.0f);
 
+// insertion-based optimisation of a built tree (bvh_opt.cpp): up to `max_passes` rounds, each taking the `batch_fraction` of the inner
+// nodes that waste the most surface area out of the tree and reinserting their subtrees where they cost least. Returns the number of
+// subtrees moved; the tree stays in CUGAR's layout.
+uint32 optimize_bvh2(Bvh2& bvh, int max_passes, float batch_fraction = 0.01f, bool verbose = false);
+
 void collapse_to_wide(const Mesh& mesh, const Bvh2& bvh, WideBvh& wide);
 
 } // namespace fb

@@ -119,6 +119,8 @@ const char* fb200_last_error(void);
  * and PTOptions::parse (src/renderers/pathtracer.h:202-249), plus:
  *   -tables <file>   packed sampler/BSDF tables (default: fermat_b200/data/pt_tables.bin)
  *   -shard r n       this process renders tile shard r of n (default 0 1)
+ *   -bvh sah|sbvh|lbvh   scene BVH builder (binned SAH on the host, with spatial splits, or CUGAR's LBVH on the device)
+ *   -bvh-opt N       rounds of insertion-based optimisation of the host-built tree (default 8, 0 = off)
  * then loads the scene, builds sampler tables, VPLs (n_vpls = res_x*res_y) and the BVH.
  * Returns NULL on failure (see fb200_last_error). */
 fb200_scene* fb200_scene_create(int argc, const char* const* argv);

@@ -1,0 +1,98 @@
+"""Insertion-based optimisation of the host-built scene BVH (fermat_b200/csrc/host/bvh_opt.cpp): the tree stays a valid Bvh2 in
+CUGAR's layout, queries return the same hits, and the SAH cost / the nodes a ray visits go down. All on the CPU."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import CACHE, cornell_args
+
+NODE = np.dtype([("packed", "<u4"), ("range", "<u4"), ("lo", "<f4", 3), ("hi", "<f4", 3)])      # Bvh_node_3d, contrib/cugar/bvh/bvh_node.h:79-137
+
+
+def _tree(view):
+    nodes = np.ctypeslib.as_array(np.ctypeslib.ctypes.cast(view.bvh_nodes, np.ctypeslib.ctypes.POINTER(np.ctypeslib.ctypes.c_uint8)), (int(view.n_bvh_nodes) * 32,)).view(NODE)
+    index = np.ctypeslib.as_array(view.bvh_index, (int(view.n_bvh_index),))
+    return nodes, index
+
+
+def _check_layout(view):
+    nodes, index = _tree(view)
+    n_tri = int(view.num_triangles)
+    vi = np.ctypeslib.as_array(view.vertex_indices, (n_tri, 4))
+    vd = np.ctypeslib.as_array(view.vertex_data, (int(view.num_vertices), 4))
+    assert sorted(index.tolist()) == list(range(n_tri))                       # a permutation: every triangle in exactly one leaf
+    leaf = (nodes["packed"] & 3) == 0
+    first = nodes["packed"] >> 2
+    inner = np.where(~leaf)[0]
+    assert ((nodes["packed"][inner] & 3) == 3).all()
+    assert (first[inner] > inner).all()                                       # children adjacent and behind their parent
+    # bottom-up: boxes enclose, counts add up, ranges are contiguous with the left child first
+    begin = np.zeros(len(nodes), np.int64); count = np.zeros(len(nodes), np.int64)
+    for i in range(len(nodes) - 1, -1, -1):
+        if leaf[i]:
+            begin[i], count[i] = first[i], nodes["range"][i]
+            tri = index[begin[i]:begin[i] + count[i]]
+            p = vd[vi[tri, :3].reshape(-1), :3]
+            assert (p >= nodes["lo"][i] - 0).all() and (p <= nodes["hi"][i] + 0).all()
+            assert 1 <= count[i] <= 3
+        else:
+            l, r = first[i], first[i] + 1
+            assert (nodes["lo"][i] <= np.minimum(nodes["lo"][l], nodes["lo"][r])).all() and (nodes["hi"][i] >= np.maximum(nodes["hi"][l], nodes["hi"][r])).all()
+            begin[i], count[i] = begin[l], count[l] + count[r]
+            assert begin[r] == begin[l] + count[l]
+            assert nodes["range"][i] == count[i]
+    assert begin[0] == 0 and count[0] == n_tri
+    # every node but the root is somebody's child exactly once
+    refs = np.concatenate([first[inner], first[inner] + 1])
+    assert sorted(refs.tolist()) == list(range(1, len(nodes)))
+
+
+def _rays(view, n, seed):
+    rng = np.random.default_rng(seed)
+    lo, hi = np.array(view.bbox_min[:]), np.array(view.bbox_max[:])
+    rays = np.zeros((n, 8), np.float32)
+    rays[:, 0:3] = lo + (hi - lo) * rng.random((n, 3))
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays[:, 4:7] = d
+    rays[:, 3] = 1e-3; rays[:, 7] = 1e8
+    return rays
+
+
+def test_optimised_tree_keeps_the_cugar_layout(fb):
+    for passes in ("0", "8"):
+        sc = fb.Scene(cornell_args(32, 2, ["-bvh-opt", passes]))
+        _check_layout(sc.view)
+        sc.close()
+    path = os.path.join(CACHE, "cornellbox_glossy.fbs")
+    if fb.scene_available(path):
+        sc = fb.Scene(["-i", fb.resolve_scene(path), "-r", "32", "32", "-bvh-opt", "8"])
+        _check_layout(sc.view)
+        sc.close()
+
+
+@pytest.mark.parametrize("scene", ["cornellbox_glossy", "water_caustic"])
+def test_optimisation_changes_the_cost_not_the_hits(fb, oracle, scene):
+    path = os.path.join(CACHE, scene + ".fbs")
+    if not fb.scene_available(path):
+        pytest.skip("scene snapshot %s not present" % scene)
+    out = {}
+    for passes in ("0", "8"):
+        sc = fb.Scene(["-i", fb.resolve_scene(path), "-r", "64", "64", "-bvh-opt", passes])
+        rays = _rays(sc.view, 30000, 5)
+        hw, nodes, tris = sc.wide_trace(rays)                 # the device traversal, emulated on the host, on the collapsed tree
+        ho, _, _ = oracle.trace(sc.view, rays)                # the oracle's scalar traversal of the binary tree
+        out[passes] = (hw.copy(), ho.copy(), nodes, sc.bvh_stats())
+        sc.close()
+    same = (out["0"][1].view(np.uint32) == out["8"][1].view(np.uint32)).all(axis=1)
+    # coplanar overlapping triangles hit one or two ulps apart may swap (box-test rounding differs between two trees)
+    tie = np.abs(out["0"][1][:, 0] - out["8"][1][:, 0]) <= 4e-7 * np.abs(out["0"][1][:, 0])
+    assert (same | tie).all() and same.mean() > 0.999
+    for p in ("0", "8"):
+        hw, ho = out[p][0], out[p][1]
+        s2 = (hw.view(np.uint32) == ho.view(np.uint32)).all(axis=1)
+        t2 = np.abs(hw[:, 0] - ho[:, 0]) <= 4e-7 * np.abs(ho[:, 0])
+        assert (s2 | t2).all() and s2.mean() > 0.999
+    assert out["8"][3]["sah_cost"] < out["0"][3]["sah_cost"]
+    assert out["8"][2] <= out["0"][2] * 1.01                  # wide nodes visited by the same rays
+    assert out["8"][3]["max_stack"] <= 64
