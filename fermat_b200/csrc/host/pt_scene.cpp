@@ -182,14 +182,20 @@ void scene_init(fb200_scene& s, int argc, const char* const* argv)
 		// material-testball 18.7 / 15.2, water_caustic 5.03 / 5.00, CornellBox-Glossy 2.03 / 1.61; more passes or batches add < 0.5 %
 		int opt_passes = s.bvh_opt_passes;
 		if (const char* e = getenv("FB200_BVH_OPT")) opt_passes = atoi(e);
+		bool collapsed = false;
 		if (opt_passes > 0)
 		{
 			const float frac = getenv("FB200_BVH_OPT_BATCH") ? (float)atof(getenv("FB200_BVH_OPT_BATCH")) : 0.01f;
-			const float before = s.bvh2.sah_cost;
+			const Bvh2 built = s.bvh2;                  // (kept until the optimised tree has been collapsed: see below)
 			const uint32 moved = optimize_bvh2(s.bvh2, opt_passes, frac, getenv("FB200_BVH_VERBOSE") != NULL);
-			if (getenv("FB200_BVH_VERBOSE")) fprintf(stderr, "  bvh optimisation: %u subtrees moved, SAH cost %.3f -> %.3f\n", moved, before, s.bvh2.sah_cost);
+			if (getenv("FB200_BVH_VERBOSE")) fprintf(stderr, "  bvh optimisation: %u subtrees moved, SAH cost %.3f -> %.3f\n", moved, built.sah_cost, s.bvh2.sah_cost);
+			// the optimisation never makes the tree worse by its own measure, but it may deepen it: if the collapsed tree would need
+			// more traversal-stack entries than the kernels hold, the tree as built is used
+			try { collapse_to_wide(s.scene.mesh, s.bvh2, s.wide); collapsed = true; }
+			catch (const std::exception&) { s.bvh2 = built; }
+			if (collapsed && !(s.bvh2.sah_cost <= built.sah_cost)) { s.bvh2 = built; collapsed = false; }
 		}
-		collapse_to_wide(s.scene.mesh, s.bvh2, s.wide);
+		if (!collapsed) collapse_to_wide(s.scene.mesh, s.bvh2, s.wide);
 	}
 
 	s.texture_views.resize(s.scene.textures.size());
