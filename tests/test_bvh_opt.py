@@ -96,3 +96,41 @@ def test_optimisation_changes_the_cost_not_the_hits(fb, oracle, scene):
     assert out["8"][3]["sah_cost"] < out["0"][3]["sah_cost"]
     assert out["8"][2] <= out["0"][2] * 1.01                  # wide nodes visited by the same rays
     assert out["8"][3]["max_stack"] <= 64
+
+
+def test_triangle_soup_with_degenerate_triangles(fb, oracle, tmp_path):
+    """A random soup with zero-area triangles, duplicates and a line of collinear points (the chain that set bathroom2's stack bound):
+    the optimiser must leave a valid tree and the queries unchanged."""
+    rng = np.random.default_rng(3)
+    n = 3000
+    centers = rng.random((n, 3)) * 10
+    tris = centers[:, None, :] + rng.normal(scale=0.15, size=(n, 3, 3))
+    tris[:50, 2] = tris[:50, 1]                                   # zero-area: two equal vertices
+    tris[50:80] = tris[0]                                         # 30 copies of one triangle
+    line = np.linspace(0, 10, 400)
+    tris[100:500] = np.stack([np.stack([line, line * 0, line * 0], 1)] * 3, 1) + np.array([0, 0, 0])[None, None, :]   # points on a line
+    obj = tmp_path / "soup.obj"
+    with open(obj, "w") as f:
+        f.write("mtllib soup.mtl\nusemtl m\n")
+        for t in tris:
+            for v in t:
+                f.write("v %.6f %.6f %.6f\n" % tuple(v))
+        for i in range(n):
+            f.write("f %d %d %d\n" % (3 * i + 1, 3 * i + 2, 3 * i + 3))
+    with open(tmp_path / "soup.mtl", "w") as f:
+        f.write("newmtl m\nKd 0.5 0.5 0.5\nKe 1 1 1\n")
+    res = {}
+    for passes in ("0", "8"):
+        sc = fb.Scene(["-i", str(obj), "-r", "32", "32", "-bounces", "2", "-bvh-opt", passes])
+        _check_layout(sc.view)
+        rays = _rays(sc.view, 20000, 11)
+        hw, _, _ = sc.wide_trace(rays)
+        ho, _, _ = oracle.trace(sc.view, rays)
+        res[passes] = (hw.copy(), ho.copy(), sc.bvh_stats())
+        sc.close()
+    for p in ("0", "8"):
+        assert np.array_equal(res[p][0].view(np.uint32), res[p][1].view(np.uint32))      # collapsed tree == binary tree, to the bit
+        assert res[p][2]["max_stack"] <= 64
+    assert np.array_equal(res["0"][1].view(np.uint32), res["8"][1].view(np.uint32))       # and the optimisation changed no hit
+    assert res["8"][2]["sah_cost"] <= res["0"][2]["sah_cost"]
+
