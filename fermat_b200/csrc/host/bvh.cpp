@@ -12,7 +12,7 @@ namespace fb {
 
 namespace {
 
-struct PrimRef { Bbox3 box; V3 centroid; };
+struct PrimRef { Bbox3 box; V3 centroid; uint32 id; };
 
 inline float axis(const V3& v, int a) { return a == 0 ? v.x : (a == 1 ? v.y : v.z); }
 
@@ -22,15 +22,144 @@ float C_ISECT = 1.0f;       // FB200_BVH_CI: triangle cost relative to a node vi
 
 struct BuildTask { uint32 node, begin, end; };
 
+struct Bins { Bbox3 box[3][MAX_BINS]; uint32 cnt[3][MAX_BINS]; };
+
+// One node of the binned-SAH build over prims[begin, end): computes the node's box and either decides for a leaf (returns `begin`) or
+// partitions the range and returns the split position. The references themselves are moved (not an index array over them), so
+// every level reads memory front to back. `parallel`: OpenMP over the range - boxes are min/max and bin counts integers, so the
+// decisions do not depend on the number of threads.
+uint32 split_range(PrimRef* prims, const uint32 begin, const uint32 end, const uint32 max_leaf_size, Bbox3& box, const bool parallel)
+{
+	const uint32 count = end - begin;
+	Bbox3 cbox;
+	box = Bbox3();
+	if (parallel)
+	{
+		#pragma omp parallel
+		{
+			Bbox3 b, c;
+			#pragma omp for nowait schedule(static)
+			for (long long i = begin; i < (long long)end; ++i) { b.insert(prims[i].box); c.insert(prims[i].centroid); }
+			#pragma omp critical
+			{ box.insert(b); cbox.insert(c); }
+		}
+	}
+	else for (uint32 i = begin; i < end; ++i) { box.insert(prims[i].box); cbox.insert(prims[i].centroid); }
+	if (count <= 1) return begin;
+
+	// binned SAH over the three axes, one pass over the range
+	const V3 cext = cbox.hi - cbox.lo;
+	float k[3], lo[3]; bool live[3];
+	for (int a = 0; a < 3; ++a) { const float ext = axis(cext, a); live[a] = ext > 0.0f; k[a] = live[a] ? float(N_BINS) / ext : 0.0f; lo[a] = axis(cbox.lo, a); }
+	auto bin_of = [&](const PrimRef& p, int a) { int b = (int)((axis(p.centroid, a) - lo[a]) * k[a]); return b < 0 ? 0 : (b >= N_BINS ? N_BINS - 1 : b); };
+	Bins bins;
+	for (int a = 0; a < 3; ++a) for (int b = 0; b < N_BINS; ++b) { bins.box[a][b] = Bbox3(); bins.cnt[a][b] = 0; }
+	auto accumulate = [&](Bins& t, const PrimRef& p) { for (int a = 0; a < 3; ++a) if (live[a]) { const int b = bin_of(p, a); t.box[a][b].insert(p.box); t.cnt[a][b]++; } };
+	if (parallel)
+	{
+		#pragma omp parallel
+		{
+			Bins t;
+			for (int a = 0; a < 3; ++a) for (int b = 0; b < N_BINS; ++b) { t.box[a][b] = Bbox3(); t.cnt[a][b] = 0; }
+			#pragma omp for nowait schedule(static)
+			for (long long i = begin; i < (long long)end; ++i) accumulate(t, prims[i]);
+			#pragma omp critical
+			for (int a = 0; a < 3; ++a) for (int b = 0; b < N_BINS; ++b) { bins.box[a][b].insert(t.box[a][b]); bins.cnt[a][b] += t.cnt[a][b]; }
+		}
+	}
+	else for (uint32 i = begin; i < end; ++i) accumulate(bins, prims[i]);
+
+	float best_cost = 1.0e30f; int best_axis = -1; int best_bin = -1;
+	for (int a = 0; a < 3; ++a)
+	{
+		if (!live[a]) continue;
+		float right_area[MAX_BINS]; uint32 right_cnt[MAX_BINS];
+		Bbox3 acc; uint32 c = 0;
+		for (int b = N_BINS - 1; b > 0; --b)
+		{
+			acc.insert(bins.box[a][b]); c += bins.cnt[a][b];
+			right_area[b] = c ? acc.half_area() : 0.0f; right_cnt[b] = c;
+		}
+		acc = Bbox3(); c = 0;
+		for (int b = 0; b < N_BINS - 1; ++b)
+		{
+			acc.insert(bins.box[a][b]); c += bins.cnt[a][b];
+			if (c == 0 || right_cnt[b + 1] == 0) continue;
+			const float cost = acc.half_area() * c + right_area[b + 1] * right_cnt[b + 1];
+			if (cost < best_cost) { best_cost = cost; best_axis = a; best_bin = b; }
+		}
+	}
+
+	const float parent_area = box.half_area();
+	const float leaf_cost = C_ISECT * float(count) * parent_area;
+	const float split_cost = best_axis >= 0 ? 1.0f * parent_area + C_ISECT * best_cost : 1.0e30f;   // c_trav = 1
+	if (count <= max_leaf_size && leaf_cost <= split_cost) return begin;
+
+	uint32 mid;
+	PrimRef* first = prims + begin; PrimRef* last = prims + end;
+	if (best_axis >= 0 && !(parent_area > 0.0f))
+	{
+		// A node whose box has no area (degenerate triangles strung along a line or collapsed to a point: bathroom2 has
+		// 1319 of them in a row) makes every candidate cost 0, the first bin boundary wins, and the node peels off one
+		// bin per level: a 50-level chain that sets the traversal-stack bound for the whole scene. Split such nodes at
+		// the median along their longest axis instead.
+		int a = 0;
+		if (cext.y > axis(cext, a)) a = 1;
+		if (cext.z > axis(cext, a)) a = 2;
+		PrimRef* m = first + count / 2;
+		std::nth_element(first, m, last, [&](const PrimRef& p, const PrimRef& q) {
+			const float cp = axis(p.centroid, a), cq = axis(q.centroid, a);
+			return cp < cq || (cp == cq && p.id < q.id); });
+		mid = (uint32)(m - prims);
+	}
+	else if (best_axis >= 0)
+	{
+		PrimRef* m = std::partition(first, last, [&](const PrimRef& p) { return bin_of(p, best_axis) <= best_bin; });
+		mid = (uint32)(m - prims);
+	}
+	else mid = begin;
+	if (mid == begin || mid == end) mid = begin + count / 2;      // all centroids coincide: split the range in half
+	return mid;
+}
+
+void set_box(Bvh2Node& node, const Bbox3& box)
+{
+	node.bmin[0] = box.lo.x; node.bmin[1] = box.lo.y; node.bmin[2] = box.lo.z;
+	node.bmax[0] = box.hi.x; node.bmax[1] = box.hi.y; node.bmax[2] = box.hi.z;
+}
+
+// depth-first build of the subtree over prims[task.begin, task.end) into `nodes`; nodes[task.node] is its root
+void build_subtree(PrimRef* prims, const BuildTask root, const uint32 max_leaf_size, std::vector<Bvh2Node>& nodes)
+{
+	std::vector<BuildTask> stack;
+	stack.push_back(root);
+	while (!stack.empty())
+	{
+		const BuildTask task = stack.back(); stack.pop_back();
+		Bbox3 box;
+		const uint32 mid = split_range(prims, task.begin, task.end, max_leaf_size, box, false);
+		set_box(nodes[task.node], box);
+		nodes[task.node].range_size = task.end - task.begin;
+		if (mid == task.begin) { nodes[task.node].packed_info = task.begin << 2; continue; }
+		const uint32 child = (uint32)nodes.size();
+		nodes.push_back(Bvh2Node()); nodes.push_back(Bvh2Node());
+		nodes[task.node].packed_info = 3u | (child << 2);
+		stack.push_back(BuildTask{ child + 1, mid, task.end });
+		stack.push_back(BuildTask{ child, task.begin, mid });
+	}
+}
+
 } // anonymous namespace
 
+// Top-down binned-SAH build. The top of the tree (ranges above 32 K triangles) is built node by node with the loops over a node's
+// triangles spread over the host threads; the subtrees below are independent and are built one per thread into private arrays,
+// then appended in a fixed order: the tree and its numbering do not depend on the number of threads.
 void build_bvh2(const Mesh& mesh, Bvh2& bvh, uint32 max_leaf_size)
 {
 	const uint32 n = (uint32)mesh.num_triangles();
 	if (const char* s = getenv("FB200_BVH_BINS")) { N_BINS = atoi(s); N_BINS = N_BINS < 2 ? 2 : (N_BINS > MAX_BINS ? MAX_BINS : N_BINS); }
 	if (const char* s = getenv("FB200_BVH_CI")) C_ISECT = (float)atof(s);
 	std::vector<PrimRef> prims(n);
-	bvh.index.resize(n);
 	for (uint32 i = 0; i < n; ++i)
 	{
 		const int4 t = mesh.vertex_indices[i];
@@ -38,113 +167,52 @@ void build_bvh2(const Mesh& mesh, Bvh2& bvh, uint32 max_leaf_size)
 		b.insert(V3(mesh.vertex_data[t.x])); b.insert(V3(mesh.vertex_data[t.y])); b.insert(V3(mesh.vertex_data[t.z]));
 		prims[i].box = b;
 		prims[i].centroid = (b.lo + b.hi) * 0.5f;
-		bvh.index[i] = i;
+		prims[i].id = i;
 	}
 	bvh.nodes.clear();
 	bvh.nodes.reserve(2 * (size_t)n + 2);
 	bvh.nodes.push_back(Bvh2Node());
 
-	std::vector<BuildTask> stack;
+	const uint32 PARALLEL_ABOVE = 32768u;
+	std::vector<BuildTask> stack, subtrees;
 	stack.push_back(BuildTask{ 0u, 0u, n });
-	std::vector<uint32>& idx = bvh.index;
-
 	while (!stack.empty())
 	{
 		const BuildTask task = stack.back(); stack.pop_back();
-		const uint32 count = task.end - task.begin;
-		Bbox3 box, cbox;
-		for (uint32 i = task.begin; i < task.end; ++i) { box.insert(prims[idx[i]].box); cbox.insert(prims[idx[i]].centroid); }
-
-		Bvh2Node& node = bvh.nodes[task.node];
-		node.bmin[0] = box.lo.x; node.bmin[1] = box.lo.y; node.bmin[2] = box.lo.z;
-		node.bmax[0] = box.hi.x; node.bmax[1] = box.hi.y; node.bmax[2] = box.hi.z;
-
-		auto make_leaf = [&]() {
-			Bvh2Node& nd = bvh.nodes[task.node];
-			nd.packed_info = task.begin << 2;
-			nd.range_size = count;
-		};
-		if (count <= 1) { make_leaf(); continue; }
-
-		// binned SAH over the three axes
-		float best_cost = 1.0e30f; int best_axis = -1; int best_bin = -1;
-		const V3 cext = cbox.hi - cbox.lo;
-		for (int a = 0; a < 3; ++a)
-		{
-			const float ext = axis(cext, a);
-			if (!(ext > 0.0f)) continue;
-			Bbox3 bin_box[MAX_BINS]; uint32 bin_cnt[MAX_BINS] = { 0 };
-			const float k = float(N_BINS) / ext, lo = axis(cbox.lo, a);
-			for (uint32 i = task.begin; i < task.end; ++i)
-			{
-				int b = (int)((axis(prims[idx[i]].centroid, a) - lo) * k);
-				b = b < 0 ? 0 : (b >= N_BINS ? N_BINS - 1 : b);
-				bin_box[b].insert(prims[idx[i]].box); bin_cnt[b]++;
-			}
-			float right_area[MAX_BINS]; uint32 right_cnt[MAX_BINS];
-			Bbox3 acc; uint32 c = 0;
-			for (int b = N_BINS - 1; b > 0; --b)
-			{
-				acc.insert(bin_box[b]); c += bin_cnt[b];
-				right_area[b] = c ? acc.half_area() : 0.0f; right_cnt[b] = c;
-			}
-			acc = Bbox3(); c = 0;
-			for (int b = 0; b < N_BINS - 1; ++b)
-			{
-				acc.insert(bin_box[b]); c += bin_cnt[b];
-				if (c == 0 || right_cnt[b + 1] == 0) continue;
-				const float cost = acc.half_area() * c + right_area[b + 1] * right_cnt[b + 1];
-				if (cost < best_cost) { best_cost = cost; best_axis = a; best_bin = b; }
-			}
-		}
-
-		const float parent_area = box.half_area();
-		const float leaf_cost = C_ISECT * float(count) * parent_area;
-		const float split_cost = best_axis >= 0 ? 1.0f * parent_area + C_ISECT * best_cost : 1.0e30f;   // c_trav = 1
-		if (count <= max_leaf_size && leaf_cost <= split_cost) { make_leaf(); continue; }
-
-		uint32 mid;
-		if (best_axis >= 0 && !(parent_area > 0.0f))
-		{
-			// A node whose box has no area (degenerate triangles strung along a line or collapsed to a point: bathroom2 has
-			// 1319 of them in a row) makes every candidate cost 0, the first bin boundary wins, and the node peels off one
-			// bin per level: a 50-level chain that sets the traversal-stack bound for the whole scene. Split such nodes at
-			// the median along their longest axis instead.
-			int a = 0;
-			if (cext.y > axis(cext, a)) a = 1;
-			if (cext.z > axis(cext, a)) a = 2;
-			uint32* first = &idx[task.begin]; uint32* last = &idx[0] + task.end;
-			uint32* m = first + count / 2;
-			std::nth_element(first, m, last, [&](uint32 p, uint32 q) {
-				const float cp = axis(prims[p].centroid, a), cq = axis(prims[q].centroid, a);
-				return cp < cq || (cp == cq && p < q); });
-			mid = (uint32)(m - &idx[0]);
-		}
-		else if (best_axis >= 0)
-		{
-			const float ext = axis(cext, best_axis), lo = axis(cbox.lo, best_axis), k = float(N_BINS) / ext;
-			uint32* first = &idx[task.begin]; uint32* last = &idx[0] + task.end;
-			uint32* m = std::partition(first, last, [&](uint32 p) {
-				int b = (int)((axis(prims[p].centroid, best_axis) - lo) * k);
-				b = b < 0 ? 0 : (b >= N_BINS ? N_BINS - 1 : b);
-				return b <= best_bin; });
-			mid = (uint32)(m - &idx[0]);
-		}
-		else mid = task.begin;
-		if (mid == task.begin || mid == task.end)
-		{
-			// all centroids coincide: split the range in half
-			mid = task.begin + count / 2;
-		}
-
+		if (task.end - task.begin <= PARALLEL_ABOVE) { subtrees.push_back(task); continue; }
+		Bbox3 box;
+		const uint32 mid = split_range(prims.data(), task.begin, task.end, max_leaf_size, box, true);
+		set_box(bvh.nodes[task.node], box);
+		bvh.nodes[task.node].range_size = task.end - task.begin;
+		if (mid == task.begin) { bvh.nodes[task.node].packed_info = task.begin << 2; continue; }
 		const uint32 child = (uint32)bvh.nodes.size();
 		bvh.nodes.push_back(Bvh2Node()); bvh.nodes.push_back(Bvh2Node());
-		Bvh2Node& nd = bvh.nodes[task.node];
-		nd.packed_info = 3u | (child << 2);
-		nd.range_size = count;
+		bvh.nodes[task.node].packed_info = 3u | (child << 2);
 		stack.push_back(BuildTask{ child + 1, mid, task.end });
 		stack.push_back(BuildTask{ child, task.begin, mid });
 	}
+	// independent subtrees: private node arrays (local node 0 = the subtree's root), appended in task order
+	std::vector<std::vector<Bvh2Node> > local(subtrees.size());
+	#pragma omp parallel for schedule(dynamic, 1)
+	for (long long k = 0; k < (long long)subtrees.size(); ++k)
+	{
+		local[k].reserve(2 * (size_t)(subtrees[k].end - subtrees[k].begin) + 2);
+		local[k].push_back(Bvh2Node());
+		build_subtree(prims.data(), BuildTask{ 0u, subtrees[k].begin, subtrees[k].end }, max_leaf_size, local[k]);
+	}
+	for (size_t k = 0; k < subtrees.size(); ++k)
+	{
+		const uint32 base = (uint32)bvh.nodes.size();          // local node j >= 1 becomes node base + j - 1
+		for (size_t j = 0; j < local[k].size(); ++j)
+		{
+			Bvh2Node nd = local[k][j];
+			if (!nd.is_leaf()) nd.packed_info = 3u | ((base + (nd.packed_info >> 2) - 1u) << 2);
+			if (j == 0) bvh.nodes[subtrees[k].node] = nd; else bvh.nodes.push_back(nd);
+		}
+		std::vector<Bvh2Node>().swap(local[k]);
+	}
+	bvh.index.resize(n);
+	for (uint32 i = 0; i < n; ++i) bvh.index[i] = prims[i].id;
 	bvh.sah_cost = compute_sah_cost(bvh);
 }
 

@@ -1,5 +1,6 @@
 // pt_scene.cpp — see pt_scene.h
 #include "pt_scene.h"
+#include <chrono>
 #include <stdexcept>
 #include <string.h>
 #include <stdlib.h>
@@ -176,7 +177,11 @@ void scene_init(fb200_scene& s, int argc, const char* const* argv)
 	}
 	if (s.bvh_builder != 1)
 	{
+		const bool verbose = getenv("FB200_BVH_VERBOSE") != NULL;
+		auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+		const double t_start = now();
 		if (s.bvh_builder == 2) build_sbvh2(s.scene.mesh, s.bvh2, 3); else build_bvh2(s.scene.mesh, s.bvh2, 3);
+		const double t_built = now();
 		// insertion-based optimisation of the finished tree (bvh_opt.cpp): -bvh-opt / FB200_BVH_OPT = passes (0: off). Host probe
 		// (tools/bvh_quality.py, wide nodes visited per ray with 0 / 8 passes): bathroom2 5.65 / 5.11 (SAH cost 32.3 / 28.7, +0.3 s),
 		// material-testball 18.7 / 15.2, water_caustic 5.03 / 5.00, CornellBox-Glossy 2.03 / 1.61; more passes or batches add < 0.5 %
@@ -196,6 +201,7 @@ void scene_init(fb200_scene& s, int argc, const char* const* argv)
 			if (collapsed && !(s.bvh2.sah_cost <= built.sah_cost)) { s.bvh2 = built; collapsed = false; }
 		}
 		if (!collapsed) collapse_to_wide(s.scene.mesh, s.bvh2, s.wide);
+		if (verbose) fprintf(stderr, "  bvh: build %.2f s, optimisation + collapse %.2f s\n", t_built - t_start, now() - t_built);
 	}
 
 	s.texture_views.resize(s.scene.textures.size());
