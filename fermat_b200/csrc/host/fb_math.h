@@ -39,8 +39,15 @@ FB_HD float length(V3 a) { return sqrtf(dot(a, a)); }
 FB_HD V3 normalize(V3 a) { const float l = sqrtf(dot(a, a)); return l > 0.0f ? V3(a.x / l, a.y / l, a.z / l) : a; }
 FB_HD float max_comp(V3 a) { return fmaxf(a.x, fmaxf(a.y, a.z)); }
 FB_HD float min_comp(V3 a) { return fminf(a.x, fminf(a.y, a.z)); }
+// (comparisons rather than fminf / fmaxf on the host: without -ffast-math gcc calls libm for those, and the BVH builders spend their
+// time here; boxes never hold NaNs)
+#ifdef __CUDA_ARCH__
 FB_HD V3 vmin(V3 a, V3 b) { return V3(fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z)); }
 FB_HD V3 vmax(V3 a, V3 b) { return V3(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z)); }
+#else
+FB_HD V3 vmin(V3 a, V3 b) { return V3(b.x < a.x ? b.x : a.x, b.y < a.y ? b.y : a.y, b.z < a.z ? b.z : a.z); }
+FB_HD V3 vmax(V3 a, V3 b) { return V3(b.x > a.x ? b.x : a.x, b.y > a.y ? b.y : a.y, b.z > a.z ? b.z : a.z); }
+#endif
 FB_HD bool  is_finite(float a) { return isfinite(a); }
 FB_HD bool  is_finite(V3 a) { return isfinite(a.x) && isfinite(a.y) && isfinite(a.z); }
 FB_HD float average(V3 a) { return (a.x + a.y + a.z) / 3.0f; }
