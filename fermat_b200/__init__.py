@@ -143,6 +143,9 @@ PASS_COUNTERS_DTYPE = np.dtype([("in_size", "<u4", 64), ("shadow_size", "<u4", 6
                                 ("cont_rays", "<u4", (2, 64)), ("stat_max", "<u4", (2, 64, 4)), ("stat_sum", "<u8", (2, 64, 16))])
 
 
+assert PASS_COUNTERS_DTYPE.itemsize == 21504      # sizeof(PassCounters), static_assert'ed in csrc/host/pathtracer.cpp
+
+
 def exported_symbols():
     """Names include/fermat_b200.h declares, and the subset missing from the loaded library."""
     L = lib()

@@ -8,6 +8,9 @@
 
 using namespace fb;
 
+// fermat_b200/__init__.py mirrors this struct (PASS_COUNTERS_DTYPE) for fb200_diag_pass_counters
+static_assert(sizeof(PassCounters) == 21504, "PassCounters layout changed: update PASS_COUNTERS_DTYPE in fermat_b200/__init__.py");
+
 PathTracer::PathTracer() : m_tiles_x(0), m_owned_pixels(0), m_passes(0), m_device_ms(0.0), m_overlap(1), m_trace_ctas(0), m_suspend_after(-1), m_psf(false), m_events(false), m_profiling(false)
 {
 	memset(&m_psf_view, 0, sizeof(m_psf_view));
