@@ -91,7 +91,9 @@ def lib():
         "fb200_diag_half_to_float": (f32, [u32]),
         "fb200_diag_pack_normal": (u32, [f32, f32, f32]),
         "fb200_diag_msvc_rand": (i32, [u32, C.POINTER(C.c_int32), u32]),
+        "fb200_scene_shadow_order": (i32, [vp, C.POINTER(f32 * 2)]),
         "fb200_diag_wide_trace": (i32, [vp, pf, pf, u32, C.POINTER(u64), C.POINTER(u64)]),
+        "fb200_diag_wide_trace_shadow": (i32, [vp, pf, C.POINTER(C.c_uint8), u32, i32, C.POINTER(u64), C.POINTER(u64)]),
         "fb200_context_create": (vp, [vp, i32]),
         "fb200_context_destroy": (None, [vp]),
         "fb200_context_clear": (i32, [vp]),
@@ -247,6 +249,21 @@ class Scene:
         nodes, tris = C.c_uint64(), C.c_uint64()
         lib().fb200_diag_wide_trace(self._h, _fptr(rays), _fptr(hits), rays.shape[0], C.byref(nodes), C.byref(tris))
         return hits, nodes.value, tris.value
+
+    def shadow_order(self):
+        """(1 if any-hit queries visit the farthest child first else 0, (nodes per sample shadow ray nearest-first, farthest-first))"""
+        probe = (C.c_float * 2)()
+        o = lib().fb200_scene_shadow_order(self._h, C.byref(probe))
+        return int(o), (float(probe[0]), float(probe[1]))
+
+    def wide_trace_shadow(self, rays, order=0):
+        """Host emulation of the device's masked any-hit traversal: (occluded u8[n], wide nodes visited, triangles tested).
+        order: 0 nearest child first (the device), 1 farthest first, 2 slot order."""
+        rays = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)
+        occ = np.empty(rays.shape[0], dtype=np.uint8)
+        nodes, tris = C.c_uint64(), C.c_uint64()
+        lib().fb200_diag_wide_trace_shadow(self._h, _fptr(rays), occ.ctypes.data_as(C.POINTER(C.c_uint8)), rays.shape[0], int(order), C.byref(nodes), C.byref(tris))
+        return occ, nodes.value, tris.value
 
     def sample_2d(self, instance, px, py, dim):
         return lib().fb200_scene_sample_2d(self._h, instance, px, py, dim)

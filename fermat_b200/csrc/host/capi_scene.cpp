@@ -110,6 +110,12 @@ int fb200_diag_lfsr(uint32_t seed_arg, float* out, uint32_t n)
 	for (uint32_t i = 0; i < n; ++i) out[i] = r.next();
 	return 0;
 }
+int      fb200_scene_shadow_order(const fb200_scene* s, float probe[2])
+{
+	if (!s) return -1;
+	if (probe) { probe[0] = s->shadow_probe[0]; probe[1] = s->shadow_probe[1]; }
+	return s->shadow_far_first ? 1 : 0;
+}
 float    fb200_diag_randfloat(uint32_t i, uint32_t p) { return fb::randfloat(i, p); }
 uint32_t fb200_diag_float_to_half(float f) { return fb::float_to_half_rn(f); }
 float    fb200_diag_half_to_float(uint32_t h) { return fb::half_to_float((uint16_t)h); }

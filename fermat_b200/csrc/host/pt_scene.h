@@ -21,6 +21,8 @@ struct fb200_scene
 	std::string        output_name;            // -o (CLI only)
 	std::string        tables_file;
 	int                bvh_opt_passes;         // -bvh-opt N: rounds of insertion-based optimisation after the host build (default 8, 0 = off)
+	bool               shadow_far_first;       // any-hit traversal order (probe_shadow_order, FB200_SHADOW_ORDER)
+	float              shadow_probe[2];        // wide nodes per sample shadow ray, nearest-first / farthest-first (0 if not probed)
 	int                bvh_builder;            // -bvh sah (0, default: binned SAH on the host at scene load) | lbvh (1: CUGAR's LBVH on the device at context creation)
 
 	std::vector<float> glossy_reflectance;     // 32^4
@@ -35,7 +37,7 @@ struct fb200_scene
 	std::vector<fb200_texture_view> texture_views;   // backing store of the view
 	std::vector<float> dir_light_floats;
 
-	fb200_scene() : res_x(1600), res_y(900), aspect(0.0f), shard_rank(0), shard_count(1), n_passes(1), bvh_opt_passes(8), bvh_builder(0), sequence_instance(0xFFFFFFFFu) {}
+	fb200_scene() : res_x(1600), res_y(900), aspect(0.0f), shard_rank(0), shard_count(1), n_passes(1), bvh_opt_passes(8), shadow_far_first(false), bvh_builder(0), sequence_instance(0xFFFFFFFFu) {}
 };
 
 namespace fb {

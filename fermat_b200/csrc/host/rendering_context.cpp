@@ -140,6 +140,7 @@ void RenderingContext::set_wide_pointers()
 	const uint32 max_staged = m_lc.staged_bytes / (uint32)sizeof(WideNode);
 	d.staged_nodes = d.num_nodes < max_staged ? d.num_nodes : max_staged;
 	d.f32_2p23_bits = 0x4B000000u;
+	d.shadow_far_first = s.shadow_far_first ? 1u : 0u;
 }
 
 void RenderingContext::upload_wide_bvh()

@@ -24,6 +24,7 @@ struct DeviceScene
 	uint32              num_nodes;
 	uint32              staged_nodes;           // nodes [0, staged_nodes) are staged into shared memory by the trace kernels
 	uint32              f32_2p23_bits;          // 0x4B000000, read from the constant bank by Traversal::node_step (byte_to_float)
+	uint32              shadow_far_first;       // any-hit queries visit the FARTHEST hit child of a node first (0: the nearest, like closest-hit queries)
 	// lights
 	const VPL*          vpls;
 	uint32              n_vpls;                 // VPL count of the scene (gates NEE, pathtracer_core.h:601)

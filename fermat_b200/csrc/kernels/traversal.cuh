@@ -177,7 +177,12 @@ struct Traversal
 	{
 		{
 			const uint32 hits = ngroup.y;
-			const uint32 child_bit = bfind(hits);
+			// Which hit child next: the nearest (highest bit: slots are numbered against the ray's octant). An occlusion query does not
+			// care about order, only about meeting an occluder soon, and for next-event rays that start ON a surface the nearest nodes
+			// are the clutter around the origin: DeviceScene::shadow_far_first (chosen per scene on the host, pt_scene.cpp
+			// probe_shadow_order) makes any-hit queries take the farthest child first. Same answers either way.
+			uint32 child_bit = bfind(hits);
+			if (ANY_HIT && sc.shadow_far_first) child_bit = 23u + (uint32)__ffs((int)(hits >> 24));
 			const uint32 base = ngroup.x;
 			ngroup.y &= ~(1u << child_bit);
 			if (ngroup.y > 0x00FFFFFFu) push(ngroup);

@@ -150,7 +150,14 @@ uint32_t fb200_diag_pack_normal(float x, float y, float z);
 int      fb200_diag_msvc_rand(uint32_t seed, int32_t* out, uint32_t n);
 /* scalar HOST emulation of the device traversal of the 8-wide BVH (closest hit, same record format as
  * fb200_trace): validates the BVH collapse and measures tree quality without a GPU. Never used for rendering. */
+/* child order of the any-hit (shadow ray) traversal chosen for this scene: 0 nearest hit child first, 1 farthest first; probe[0 / 1] =
+ * wide nodes visited per sample next-event shadow ray either way, measured on the host when the scene was created (0 if not probed).
+ * FB200_SHADOW_ORDER = near (default) | far | auto. */
+int      fb200_scene_shadow_order(const fb200_scene*, float probe[2]);
 int      fb200_diag_wide_trace(const fb200_scene*, const float* rays, float* hits, uint32_t n, uint64_t* nodes_visited, uint64_t* tris_tested);
+/* the any-hit twin: rays {o.xyz, as_float(mask), d.xyz, tmax} -> occluded[n]; order 0 = the device's (nearest child first), 1 = farthest
+ * first, 2 = slot order (same answers, different visit counts: tools/bvh_quality.py --shadow) */
+int      fb200_diag_wide_trace_shadow(const fb200_scene*, const float* rays, uint8_t* occluded, uint32_t n, int order, uint64_t* nodes_visited, uint64_t* tris_tested);
 
 /* film exposure and gamma of the scene (RenderingContext's m_exposure / m_gamma, src/renderer.cu:715-717; 1 and 2.2
  * unless a pbrt film sets them) */

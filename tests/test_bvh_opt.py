@@ -134,3 +134,44 @@ def test_triangle_soup_with_degenerate_triangles(fb, oracle, tmp_path):
     assert np.array_equal(res["0"][1].view(np.uint32), res["8"][1].view(np.uint32))       # and the optimisation changed no hit
     assert res["8"][2]["sah_cost"] <= res["0"][2]["sah_cost"]
 
+
+
+def test_any_hit_order_changes_counts_not_answers(fb, oracle, monkeypatch):
+    """The shadow-ray (masked any-hit) traversal may take a node's hit children nearest-first, farthest-first or in slot order: the host
+    emulation of the device traversal must give the oracle's answers in every order (DeviceScene::shadow_far_first relies on it)."""
+    scenes = [cornell_args(32, 2)]
+    for name in ("cornellbox_glossy", "water_caustic"):
+        path = os.path.join(CACHE, name + ".fbs")
+        if fb.scene_available(path):
+            scenes.append(["-i", fb.resolve_scene(path), "-r", "64", "64"])
+    for args in scenes:
+        sc = fb.Scene(args)
+        rays = _rays(sc.view, 20000, 17)
+        rays[:, 3] = np.uint32(2).view(np.float32)               # NEE mask bit
+        rays[:, 4:7] *= np.random.default_rng(1).uniform(0.5, 6.0, (len(rays), 1)).astype(np.float32)
+        rays[:, 7] = 0.9999
+        want = oracle.trace_shadow(sc.view, rays)
+        counts = []
+        for order in (0, 1, 2):
+            occ, nodes, tris = sc.wide_trace_shadow(rays, order)
+            assert np.array_equal(occ.astype(bool), np.asarray(want).astype(bool))
+            counts.append(nodes)
+        assert 0.02 < np.asarray(want).mean() < 0.98 and len(set(counts)) > 1
+        sc.close()
+
+
+def test_shadow_order_is_near_unless_asked(fb, monkeypatch):
+    monkeypatch.delenv("FB200_SHADOW_ORDER", raising=False)
+    sc = fb.Scene(cornell_args(32, 2))
+    order, probe = sc.shadow_order()
+    assert order == 0 and probe[0] > 0 and probe[1] > 0          # probed, default stays nearest-first
+    sc.close()
+    monkeypatch.setenv("FB200_SHADOW_ORDER", "far")
+    sc = fb.Scene(cornell_args(32, 2))
+    assert sc.shadow_order()[0] == 1
+    sc.close()
+    monkeypatch.setenv("FB200_SHADOW_ORDER", "auto")
+    sc = fb.Scene(cornell_args(32, 2))
+    order, probe = sc.shadow_order()
+    assert order == (1 if probe[1] < 0.95 * probe[0] else 0)
+    sc.close()
