@@ -240,6 +240,29 @@ def to_rgba(fb, geo, uv, mode, exposure, gamma):
     return out
 
 
+def spatial_hash(rec):
+    """The restated spatial hash (src/spatial_hash.h:74-149) on n x 26 records {P, N, T, B, bbox_lo, bbox_hi, samples[6], cone_radius, filter_radius}."""
+    rec = np.ascontiguousarray(rec, dtype=np.float32).reshape(-1, 26)
+    keys = np.empty(rec.shape[0], dtype=np.uint64)
+    L = lib()
+    L.oracle_spatial_hash.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_uint64), C.c_uint32]
+    L.oracle_spatial_hash(_fptr(rec), keys.ctypes.data_as(C.POINTER(C.c_uint64)), rec.shape[0])
+    return keys
+
+
+def ref_spatial_hash(rec):
+    """The REFERENCE's own spatial_hash compiled on this host (oracle/_ref/libref_psf.so); None where /root/reference was not available."""
+    path = os.path.join(_HERE, "_ref", "libref_psf.so")
+    if not os.path.exists(path):
+        return None
+    L = C.CDLL(path)
+    rec = np.ascontiguousarray(rec, dtype=np.float32).reshape(-1, 26)
+    keys = np.empty(rec.shape[0], dtype=np.uint64)
+    L.ref_spatial_hash.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_uint64), C.c_uint32]
+    L.ref_spatial_hash(_fptr(rec), keys.ctypes.data_as(C.POINTER(C.c_uint64)), rec.shape[0])
+    return keys
+
+
 def set_trig_mode(mode):
     """0 = libm sinf/cosf (for pinning against oracle/_ref), 1 = fixed-sequence sincos shared with the kernels (default)."""
     lib().oracle_set_trig_mode(int(mode))

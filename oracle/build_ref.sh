@@ -169,3 +169,33 @@ $CXX -O2 -std=c++14 -fPIC -shared -w -fpermissive -ffp-contract=off \
     -I$OV -I$REF/src -I$REF/contrib -I/usr/local/cuda/include \
     -o $OUT/libref_lbvh.so $OUT/ref_lbvh_shim.cpp
 echo "built $OUT/libref_lbvh.so"
+
+# ---- the reference's own jittered spatial hash (src/spatial_hash.h:74-149, the overload PSFPTVertexProcessor::preprocess_vertex
+# calls) with the cugar mappings it uses. Pins the `-psfpt` restatement (pt_oracle.cpp spatial_hash, tests/test_psfpt.py).
+cat > $OUT/ref_psf_shim.cpp <<'EOF'
+#include <cugar/basic/types.h>
+#include <cugar/basic/numbers.h>
+#include <cugar/linalg/vector.h>
+#include <cugar/linalg/bbox.h>
+#include <cugar/spherical/mappings.h>
+#include <spatial_hash.h>
+// the reference's own spatial_hash (src/spatial_hash.h:74-149), the overload PSFPTVertexProcessor::preprocess_vertex calls.
+// rec: P(3) N(3) T(3) B(3) bbox_lo(3) bbox_hi(3) samples(6) cone_radius filter_radius = 26 floats
+extern "C" int ref_spatial_hash(const float* rec, unsigned long long* keys, unsigned n)
+{
+	for (unsigned i = 0; i < n; ++i)
+	{
+		const float* r = rec + 26 * i;
+		const cugar::Bbox3f bbox(cugar::Vector3f(r[12], r[13], r[14]), cugar::Vector3f(r[15], r[16], r[17]));
+		keys[i] = spatial_hash(0u, cugar::Vector3f(r[0], r[1], r[2]), cugar::Vector3f(r[3], r[4], r[5]), cugar::Vector3f(r[6], r[7], r[8]), cugar::Vector3f(r[9], r[10], r[11]),
+							   bbox, r + 18, r[24], r[25]);
+	}
+	return 0;
+}
+EOF
+$CXX -O2 -std=c++14 -fPIC -shared -w -fpermissive -ffp-contract=off \
+    -include $OV/ref_prefix.h \
+    -DFERMAT_API_EXTERN= -DTHRUST_DEVICE_SYSTEM=THRUST_DEVICE_SYSTEM_CPP \
+    -I$OV -I$REF/src -I$REF/contrib -I/usr/local/cuda/include \
+    -o $OUT/libref_psf.so $OUT/ref_psf_shim.cpp
+echo "built $OUT/libref_psf.so"

@@ -860,6 +860,19 @@ int oracle_render_pass(const fb200_scene_view* s, uint32_t instance, float* fbda
 	return 0;
 }
 
+// the restated spatial hash on records {P, N, T, B, bbox_lo, bbox_hi (3 floats each), samples[6], cone_radius, filter_radius} = 26 floats
+// (same layout as oracle/_ref's ref_spatial_hash, which wraps the reference's own function)
+int oracle_spatial_hash(const float* rec, uint64_t* keys, uint32_t n)
+{
+	for (uint32_t i = 0; i < n; ++i)
+	{
+		const float* r = rec + 26 * i;
+		keys[i] = spatial_hash(vec3(r[0], r[1], r[2]), vec3(r[3], r[4], r[5]), vec3(r[6], r[7], r[8]), vec3(r[9], r[10], r[11]),
+							   vec3(r[12], r[13], r[14]), vec3(r[15], r[16], r[17]), r + 18, r[24], r[25]);
+	}
+	return 0;
+}
+
 // ---- `-psfpt` ------------------------------------------------------------------------------------
 // state of the filter across passes: the hash of cache cells and their values (cleared every psf_temporal_reuse passes)
 void* oracle_psf_create(void) { return new PsfState(); }

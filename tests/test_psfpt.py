@@ -35,6 +35,28 @@ def test_psf_options_follow_the_reference_command_line(fb):
         fb.Scene(cornell_args(32, 2, ["-psfpt", "-psf-hash-bits", "40"]))
 
 
+def test_spatial_hash_is_the_references(oracle):
+    """The restated jittered spatial hash against the reference's own function: committed golden keys (tools/make_golden_psf.py) and,
+    where oracle/_ref was built from /root/reference, the live function on fresh records; in both sincos modes (the hash goes through
+    square_to_unit_disk) the 64-bit keys must be identical."""
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "psf_hash_golden.npz"))
+    for mode in (0, 1):
+        oracle.set_trig_mode(mode)
+        assert np.array_equal(oracle.spatial_hash(g["rec"]), g["keys"])
+    oracle.set_trig_mode(1)
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from make_golden_psf import records
+    rec = records(50000, 99)
+    ref = oracle.ref_spatial_hash(rec)
+    if ref is not None:
+        assert np.array_equal(oracle.spatial_hash(rec), ref)
+    # the key's fields (src/spatial_hash.h:139-145): 3 x 17 bits of grid position, 5 bits of grid level, 4 bits of normal
+    k = g["keys"]
+    assert ((k >> np.uint64(60)) == 0).all() and len(np.unique(k)) > 0.9 * len(k)
+
+
 def test_filtered_and_unfiltered_estimates_agree(fb, oracle):
     """With -filter-depth beyond the path length nothing is cached and PSFPT is a plain (firefly-clamped) path tracer; the filtered
     render must converge to nearly the same image - the filter trades variance for a small bias, it does not move energy."""
