@@ -373,6 +373,9 @@ def run_ours(args):
                 "note": ("render(instance) through the C ABI + the frame of EVERY pass read back to pinned host memory (fb200_context_fb_download_async: device snapshot, "
                          "then a copy that overlaps the next pass; two host buffers); the scene is resident like model weights") if world == 1 else
                         "render(instance) through the C ABI on every rank + NCCL reduce + rank 0 copies the reduced frame of EVERY pass to pinned host memory on a copy stream (two reduce / host buffers, the copy of frame i overlaps pass i+1); the scene is resident like model weights"},
+        # every pixel charged the full path length, whether or not its path survived that long
+        "nominal": {"value": float(res[0]) * res[1] * (BOUNCES + 1) * args.steps / (ms * 1e-3) * 1e-6, "unit": "Msamples/s",
+                    "note": "W x H x (bounces + 1) per pass / device time; `value` counts the shade events that actually happened (%.2f per pixel and pass)" % (samples / (float(res[0]) * res[1] * args.steps))},
         "gpu_launches": int(launches), "wall_s": wall, "samples": samples, "shadow_rays": shadow, "finite": finite,
         "clocks": clk, "roofline": roofline, "kernels": kernels,
         "kernels_note": "CUDA-event spans around every launch over K further passes run on ONE stream; in the timed region the shadow trace of bounce b runs beside the closest-hit trace of bounce b+1 on a second stream",
