@@ -108,7 +108,6 @@ def lib():
         "fb200_context_get_stats": (i32, [vp, C.POINTER(Stats)]),
         "fb200_context_get_bounce_times": (i32, [vp, C.POINTER(C.c_double * 256)]),
         "fb200_diag_pass_counters": (i32, [vp, u32, vp, u64]),
-        "fb200_context_get_suspension_stats": (i32, [vp, C.POINTER(u64 * 2)]),
         "fb200_context_stream": (vp, [vp]),
         "fb200_context_set_profiling": (i32, [vp, i32]),
         "fb200_context_get_kernel_times": (i32, [vp, C.POINTER(C.c_double * 4), C.POINTER(u64 * 4)]),
@@ -141,11 +140,11 @@ def lib():
 
 # struct PassCounters (fermat_b200/csrc/kernels/device_scene.h)
 PASS_COUNTERS_DTYPE = np.dtype([("in_size", "<u4", 64), ("shadow_size", "<u4", 64), ("trace_next", "<u4", 64), ("shadow_next", "<u4", 64),
-                                ("shade_next", "<u4", 64), ("ref_size", "<u4", 64), ("cont_tasks", "<u4", (2, 64)), ("cont_next", "<u4", (2, 64)),
-                                ("cont_rays", "<u4", (2, 64)), ("stat_max", "<u4", (2, 64, 4)), ("stat_sum", "<u8", (2, 64, 16))])
+                                ("shade_next", "<u4", 64), ("ref_size", "<u4", 64), ("dl_size", "<u4", 64), ("dl_next", "<u4", 64),
+                                ("stat_max", "<u4", (2, 64, 4)), ("stat_sum", "<u8", (2, 64, 16))])
 
 
-assert PASS_COUNTERS_DTYPE.itemsize == 21504      # sizeof(PassCounters), static_assert'ed in csrc/host/pathtracer.cpp
+assert PASS_COUNTERS_DTYPE.itemsize == 20480      # sizeof(PassCounters), static_assert'ed in csrc/host/pathtracer.cpp
 
 
 def exported_symbols():
@@ -353,12 +352,6 @@ class RenderingContext:
         s = Stats()
         self._chk(lib().fb200_context_get_stats(self._h, C.byref(s)))
         return {k: getattr(s, k) for k, _ in Stats._fields_}
-
-    def suspension_stats(self):
-        """(rays suspended, continuation tasks) since the context was created; zeros unless FB200_SUSPEND is set."""
-        out = (C.c_uint64 * 2)()
-        self._chk(lib().fb200_context_get_suspension_stats(self._h, C.byref(out)))
-        return int(out[0]), int(out[1])
 
     def stream(self):
         return lib().fb200_context_stream(self._h)

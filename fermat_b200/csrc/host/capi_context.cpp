@@ -116,14 +116,6 @@ int fb200_context_get_stats(fb200_context* c, fb200_stats* out)
 	});
 }
 
-int fb200_context_get_suspension_stats(fb200_context* c, uint64_t out[2])
-{
-	return guarded([&] {
-		const fb::PassTotals t = pt_of(c)->totals(c->rc);
-		out[0] = t.suspended_rays; out[1] = t.continuation_tasks;
-	});
-}
-
 int fb200_context_get_bounce_times(fb200_context* c, double out_ms[4 * 64])
 {
 	return guarded([&] { pt_of(c)->bounce_times(c->rc, out_ms); });

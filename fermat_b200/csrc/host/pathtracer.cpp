@@ -9,9 +9,9 @@
 using namespace fb;
 
 // fermat_b200/__init__.py mirrors this struct (PASS_COUNTERS_DTYPE) for fb200_diag_pass_counters
-static_assert(sizeof(PassCounters) == 21504, "PassCounters layout changed: update PASS_COUNTERS_DTYPE in fermat_b200/__init__.py");
+static_assert(sizeof(PassCounters) == 20480, "PassCounters layout changed: update PASS_COUNTERS_DTYPE in fermat_b200/__init__.py");
 
-PathTracer::PathTracer() : m_tiles_x(0), m_owned_pixels(0), m_passes(0), m_device_ms(0.0), m_overlap(1), m_trace_ctas(0), m_suspend_after(-1), m_psf(false), m_events(false), m_profiling(false)
+PathTracer::PathTracer() : m_tiles_x(0), m_owned_pixels(0), m_passes(0), m_device_ms(0.0), m_ev0(NULL), m_ev1(NULL), m_ev_start(NULL), m_overlap(1), m_trace_ctas(0), m_psf(false), m_events(false), m_profiling(false)
 {
 	memset(&m_psf_view, 0, sizeof(m_psf_view));
 	for (int i = 0; i < 4; ++i) { m_class_ms[i] = 0.0; m_class_launches[i] = 0; }
@@ -25,12 +25,19 @@ PathTracer::~PathTracer()
 	{
 		SubFrame* f = m_sub[k];
 		if (!f) continue;
+		// (init() may have thrown part-way: only what was created is destroyed)
 		if (f->stream) cudaStreamDestroy(f->stream);
-		cudaStreamDestroy(f->side_stream);
-		cudaEventDestroy(f->ev_shaded); cudaEventDestroy(f->ev_shadowed); cudaEventDestroy(f->ev_done);
+		if (f->side_stream) cudaStreamDestroy(f->side_stream);
+		if (f->ev_shaded) cudaEventDestroy(f->ev_shaded);
+		if (f->ev_shadowed) cudaEventDestroy(f->ev_shadowed);
+		if (f->ev_done) cudaEventDestroy(f->ev_done);
 		delete f;
 	}
+	for (size_t i = 0; i < m_spans.size(); ++i) { cudaEventDestroy(m_spans[i].a); cudaEventDestroy(m_spans[i].b); }
 	for (size_t i = 0; i < m_event_pool.size(); ++i) cudaEventDestroy(m_event_pool[i]);
+	if (m_ev0) cudaEventDestroy(m_ev0);
+	if (m_ev1) cudaEventDestroy(m_ev1);
+	if (m_ev_start) cudaEventDestroy(m_ev_start);
 }
 
 namespace {
@@ -97,15 +104,6 @@ void PathTracer::init(int argc, char** argv, RenderingContext& renderer)
 	// (sweep on bathroom2, Msamples/s: 1 sub-frame 1040; 2 sub-frames x 4 CTAs 1045, x 2 CTAs 1110; 4 x 1 1129; 6 x 2 878)
 	m_trace_ctas = env ? atoi(env) : (n_sub > 1 ? 2 : 0);
 
-	// ray suspension (ContQueue, device_scene.h): a trace warp whose queue ran dry hands what is left of its rays to a
-	// second launch after this many further iterations (FB200_SUSPEND, < 0 = off)
-	env = getenv("FB200_SUSPEND");
-	m_suspend_after = env ? atoi(env) : -1;
-	// a lane suspends at most one ray and a launch has at most sm_count x CTAs x threads lanes
-	const LaunchConfig lc0 = renderer.launch_config();
-	const uint32 cont_rays = m_suspend_after >= 0 ? (uint32)(lc0.sm_count * lc0.trace_ctas_per_sm * lc0.trace_threads) : 0u;
-	const uint32 cont_tasks = cont_rays * 6u;
-
 	std::vector<std::vector<uint32> > sub_tiles(n_sub);
 	for (size_t j = 0; j < tiles.size(); ++j) sub_tiles[j % n_sub].push_back(tiles[j]);
 
@@ -117,22 +115,23 @@ void PathTracer::init(int argc, char** argv, RenderingContext& renderer)
 		Arena arena(dry_run ? NULL : m_memory_pool.ptr);
 		for (uint32 k = 0; k < n_sub; ++k)
 		{
-			if (dry_run) { m_sub[k] = new SubFrame(); memset(m_sub[k]->queue, 0, sizeof(m_sub[k]->queue)); memset(&m_sub[k]->shadow, 0, sizeof(m_sub[k]->shadow)); memset(m_sub[k]->cont, 0, sizeof(m_sub[k]->cont)); }
+			if (dry_run) { m_sub[k] = new SubFrame(); m_sub[k]->stream = m_sub[k]->side_stream = NULL; m_sub[k]->ev_shaded = m_sub[k]->ev_shadowed = m_sub[k]->ev_done = NULL; memset(m_sub[k]->queue, 0, sizeof(m_sub[k]->queue)); memset(&m_sub[k]->shadow, 0, sizeof(m_sub[k]->shadow)); memset(&m_sub[k]->shadow_dl, 0, sizeof(m_sub[k]->shadow_dl)); }
 			SubFrame& f = *m_sub[k];
 			f.n_tiles = (uint32)sub_tiles[k].size();
 			f.capacity = (uint64_t)f.n_tiles * 32u * 32u;
-			carve(arena, f.capacity, dirlights ? 2 * f.capacity : f.capacity, f.queue, f.shadow, m_psf);
+			carve(arena, f.capacity, f.capacity, f.queue, f.shadow, m_psf);
+			if (dirlights)
+			{
+				ShadowQueue& d = f.shadow_dl;
+				d.ray_o = arena.alloc<float4>(f.capacity); d.ray_d = arena.alloc<float4>(f.capacity); d.w_d = arena.alloc<float4>(f.capacity); d.w_g = arena.alloc<float4>(f.capacity);
+				d.occluded = arena.alloc<unsigned char>(f.capacity);
+			}
 			if (m_psf)
 			{
 				// reference queue: one segment per bounce (src/renderers/psfpt_impl.h:145-160 sizes it n_pixels x (path length + 1))
 				const size_t n_refs = f.capacity * m_options.max_path_length;
 				m_psf_view.ref_w_d = arena.alloc<float4>(n_refs); m_psf_view.ref_w_g = arena.alloc<float4>(n_refs); m_psf_view.ref_pixels = arena.alloc<uint2>(n_refs);
 				m_psf_view.ref_capacity = (uint32)f.capacity;
-			}
-			for (int c = 0; c < 2 && cont_rays; ++c)
-			{
-				f.cont[c].tasks = arena.alloc<uint4>(cont_tasks); f.cont[c].ray_of_slot = arena.alloc<uint32>(cont_rays); f.cont[c].keys = arena.alloc<unsigned long long>(cont_rays);
-				f.cont[c].task_capacity = cont_tasks; f.cont[c].ray_capacity = cont_rays;
 			}
 		}
 		if (dry_run)
@@ -159,8 +158,7 @@ void PathTracer::init(int argc, char** argv, RenderingContext& renderer)
 		for (uint32 k = 0; k < n_sub; ++k)
 		{
 			parts[k].stream = m_sub[k]->stream ? m_sub[k]->stream : renderer.raw_stream();
-			PixelSet ps; ps.tile_list = m_sub[k]->tile_list.as<uint32>(); ps.n_tiles = m_sub[k]->n_tiles; ps.tiles_x = m_tiles_x; ps.res_x = res.x; ps.res_y = res.y;
-			parts[k].pixels = ps;
+			parts[k].pixels = tile_set(m_sub[k]->tile_list.as<uint32>(), m_sub[k]->n_tiles, m_tiles_x, res.x, res.y);
 		}
 		renderer.set_partitions(parts);
 		renderer.set_renderer_clears_gbuffer(true);
@@ -178,8 +176,6 @@ void PathTracer::init(int argc, char** argv, RenderingContext& renderer)
 		fprintf(stderr, "  allocating filter cache: %.1f MB (%llu cells)\n", float(n * 24) / (1024 * 1024), (unsigned long long)n);
 	}
 	m_totals.alloc(sizeof(PassTotals));
-	for (uint32 k = 0; k < n_sub; ++k)
-		for (int c = 0; c < 2; ++c) m_sub[k]->cont[c].totals = &m_totals.as<PassTotals>()->suspended_rays;
 	cuda_check(cudaMemsetAsync(m_totals.ptr, 0, sizeof(PassTotals), renderer.raw_stream()), "memset totals");
 	cuda_check(cudaEventCreate(&m_ev0), "event"); cuda_check(cudaEventCreate(&m_ev1), "event");
 	cuda_check(cudaEventCreateWithFlags(&m_ev_start, cudaEventDisableTiming), "event");
@@ -306,7 +302,7 @@ void PathTracer::render_subframe(SubFrame& f, const PassParams& pass, const std:
 	cuda_check(cudaMemsetAsync(ctr, 0, sizeof(PassCounters), stream), "memset counters");
 
 	const FrameBufferView fbv = renderer.get_frame_buffer().view();
-	PixelSet pixels; pixels.tile_list = pp.tile_list; pixels.n_tiles = pp.n_tiles; pixels.tiles_x = pp.tiles_x; pixels.res_x = sc.res_x; pixels.res_y = sc.res_y;
+	const PixelSet pixels = tile_set(pp.tile_list, pp.n_tiles, pp.tiles_x, sc.res_x, sc.res_y);
 	// pre-multiply the previous frame for blending (pathtracer_impl.h:201 -> RenderingContext::rescale_frame), this sub-frame's pixels
 	begin(0);
 	cuda_check(launch_rescale_frame(fbv, pixels, float(pp.instance) / float(pp.instance + 1), stream), "rescale_frame");
@@ -320,6 +316,7 @@ void PathTracer::render_subframe(SubFrame& f, const PassParams& pass, const std:
 	const uint32 L = m_options.max_path_length;
 	uint32 n_launches = 0;
 	const PsfView* psf = m_psf ? &m_psf_view : NULL;
+	const bool dirlights = sc.n_dir_lights != 0;
 	for (uint32 bounce = 0; bounce < L; ++bounce)
 	{
 		span.bounce = bounce;
@@ -328,20 +325,21 @@ void PathTracer::render_subframe(SubFrame& f, const PassParams& pass, const std:
 		if (bounce == 0 || !overlap)
 		{
 			begin(1);
-			cuda_check(launch_trace_closest(sc, lc, in, ctr, bounce, stream, &f.cont[0], m_suspend_after, &n_launches), "trace");
+			cuda_check(launch_trace_closest(sc, lc, in, ctr, bounce, stream), "trace");
 			end();
-			renderer.kernel_launches += n_launches;
+			renderer.kernel_launches += 1;
 		}
 		float seq6[6];
 		for (int i = 0; i < 6; ++i) seq6[i] = seq[(bounce + 1) * 6 + i];
 		if (overlap && bounce > 0) cuda_check(cudaStreamWaitEvent(stream, f.ev_shadowed, 0), "wait");   // shadow(b-1) before shade(b)
 		begin(2);
-		cuda_check(launch_shade(sc, lc, pp, in, out, f.shadow, fbv, ctr, tot, bounce, seq6, (uint32)f.capacity, stream, psf), "shade");
+		cuda_check(launch_shade(sc, lc, pp, in, out, f.shadow, f.shadow_dl, fbv, ctr, tot, bounce, seq6, (uint32)f.capacity, stream, psf), "shade");
 		end();
 		if (!overlap)
 		{
 			begin(3);
-			cuda_check(launch_trace_shadow(sc, lc, f.shadow, fbv, ctr, tot, bounce, pp.frame_weight, stream, &f.cont[1], m_suspend_after, &n_launches, psf), "trace_shadow");
+			if (dirlights) { cuda_check(launch_trace_shadow(sc, lc, f.shadow_dl, fbv, ctr, tot, bounce, pp.frame_weight, stream, 1, &n_launches, psf), "trace_shadow"); renderer.kernel_launches += n_launches; }
+			cuda_check(launch_trace_shadow(sc, lc, f.shadow, fbv, ctr, tot, bounce, pp.frame_weight, stream, 0, &n_launches, psf), "trace_shadow");
 			end();
 			renderer.kernel_launches += n_launches;
 		}
@@ -349,13 +347,14 @@ void PathTracer::render_subframe(SubFrame& f, const PassParams& pass, const std:
 		{
 			cuda_check(cudaEventRecord(f.ev_shaded, stream), "event record");
 			cuda_check(cudaStreamWaitEvent(f.side_stream, f.ev_shaded, 0), "wait");
-			cuda_check(launch_trace_shadow(sc, lc, f.shadow, fbv, ctr, tot, bounce, pp.frame_weight, f.side_stream, &f.cont[1], m_suspend_after, &n_launches, psf), "trace_shadow");
+			if (dirlights) { cuda_check(launch_trace_shadow(sc, lc, f.shadow_dl, fbv, ctr, tot, bounce, pp.frame_weight, f.side_stream, 1, &n_launches, psf), "trace_shadow"); renderer.kernel_launches += n_launches; }
+			cuda_check(launch_trace_shadow(sc, lc, f.shadow, fbv, ctr, tot, bounce, pp.frame_weight, f.side_stream, 0, &n_launches, psf), "trace_shadow");
 			renderer.kernel_launches += n_launches;
 			cuda_check(cudaEventRecord(f.ev_shadowed, f.side_stream), "event record");
 			if (bounce + 1 < L)
 			{
-				cuda_check(launch_trace_closest(sc, lc, out, ctr, bounce + 1, stream, &f.cont[0], m_suspend_after, &n_launches), "trace");
-				renderer.kernel_launches += n_launches;
+				cuda_check(launch_trace_closest(sc, lc, out, ctr, bounce + 1, stream), "trace");
+				renderer.kernel_launches += 1;
 			}
 		}
 		renderer.kernel_launches += 1;

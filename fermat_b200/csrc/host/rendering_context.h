@@ -186,7 +186,7 @@ private:
 		uint64_t         capacity;
 		fb::PathQueue    queue[2];
 		fb::ShadowQueue  shadow;
-		fb::ContQueue    cont[2];                 // continuation queues of the closest-hit / the shadow trace launches (ray suspension)
+		fb::ShadowQueue  shadow_dl;               // scenes with DirectionalLights: the queue of their shadow rays (traced and accumulated before the next-event queue)
 		cudaStream_t     stream, side_stream;     // stream == NULL: the context's stream
 		cudaEvent_t      ev_shaded, ev_shadowed, ev_done;
 	};
@@ -198,7 +198,6 @@ private:
 	cudaEvent_t      m_ev0, m_ev1, m_ev_start;
 	int              m_overlap;               // 0: one stream per sub-frame; else the shadow trace of bounce b runs beside the closest-hit trace of bounce b+1
 	int              m_trace_ctas;            // CTAs per SM of each persistent trace launch
-	int              m_suspend_after;         // ray suspension: tail iterations before a trace warp hands its rays over (< 0: off)
 	// `-psfpt` (path-space filtering, src/renderers/psfpt_impl.h): the same loop with PSFPTVertexProcessor's policies, a hash of cache
 	// cells that lives across passes, and a splat of the references at the end of the pass
 	bool             m_psf;

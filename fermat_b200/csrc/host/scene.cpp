@@ -379,9 +379,17 @@ void load_obj(const std::string& filename, Mesh& mesh)
 			} while (ss >> tok);
 			if (corners.size() < 3) break;
 			const int nv = (int)vertices.size(), nn = (int)normals.size(), nt = (int)texcoords.size();
-			auto vi = [&](int i) { return i >= 0 ? i - 1 : nv + i; };
-			auto ni = [&](int i) { return i >= 0 ? i - 1 : nn + i; };
-			auto ti = [&](int i) { return i >= 0 ? i - 1 : nt + i; };
+			// 1-based, negative = relative to the elements read so far; 0 is not an index (it would alias NOT_PROVIDED), and the
+			// resolved value must address an element: a truncated or malformed file fails here instead of in the mesh pre-processing
+			auto resolve = [&](int i, int count, const char* what) -> int
+			{
+				const int r = i > 0 ? i - 1 : count + i;
+				if (i == 0 || r < 0) throw std::runtime_error(std::string("OBJ face: invalid ") + what + " index " + std::to_string(i) + " in " + filename);
+				return r;
+			};
+			auto vi = [&](int i) { return resolve(i, nv, "vertex"); };
+			auto ni = [&](int i) { return resolve(i, nn, "normal"); };
+			auto ti = [&](int i) { return resolve(i, nt, "texture-coordinate"); };
 			// triangle fan (v0, previous v2, new) — reference MeshBase.cpp:1158-1190
 			for (size_t k = 2; k < corners.size(); ++k)
 			{
@@ -965,6 +973,29 @@ static void load_textures(Scene& scene)
 	}
 }
 
+// every index a loader produced (.obj forward references, .ply / pbrt index lists) must address an element of its attribute array
+// before the pre-processing dereferences it (NOT_PROVIDED = -1 is allowed for normals and texture coordinates)
+static void validate_mesh_indices(const Mesh& mesh, const std::string& filename)
+{
+	auto check = [&](const std::vector<int4>& idx, size_t count, bool optional, const char* what)
+	{
+		for (size_t t = 0; t < idx.size(); ++t)
+		{
+			const int v[3] = { idx[t].x, idx[t].y, idx[t].z };
+			for (int k = 0; k < 3; ++k)
+				if (!((v[k] >= 0 && (size_t)v[k] < count) || (optional && v[k] == -1)))
+					throw std::runtime_error(std::string(what) + " index " + std::to_string(v[k]) + " of triangle " + std::to_string(t) + " is out of range [0, " +
+											 std::to_string(count) + ") in " + filename);
+		}
+	};
+	check(mesh.vertex_indices, mesh.vertex_data.size(), false, "vertex");
+	check(mesh.normal_indices, mesh.normal_data.size(), true, "normal");
+	check(mesh.texture_indices, mesh.texture_data.size(), true, "texture-coordinate");
+	for (size_t t = 0; t < mesh.material_indices.size(); ++t)
+		if (mesh.material_indices[t] < 0 || (size_t)mesh.material_indices[t] >= mesh.materials.size())
+			throw std::runtime_error("material index " + std::to_string(mesh.material_indices[t]) + " of triangle " + std::to_string(t) + " is out of range in " + filename);
+}
+
 // ------------------------------------------------------------------------------------------
 // scene entry point
 // ------------------------------------------------------------------------------------------
@@ -1007,6 +1038,7 @@ void load_scene(const std::string& filename, Scene& scene, bool camera_overridde
 
 	if (!cameras.empty() && !camera_overridden) scene.camera = cameras[0];
 
+	validate_mesh_indices(scene.mesh, filename);
 	compress_normals(scene.mesh);
 	compress_tex(scene.mesh);
 	unify_vertex_attributes(scene.mesh);

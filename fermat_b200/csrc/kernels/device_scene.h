@@ -106,11 +106,8 @@ struct PassCounters
 	uint32 shadow_next[64];
 	uint32 shade_next[64];
 	uint32 ref_size[64];       // `-psfpt`: entries in the reference queue segment of bounce b (was padding)
-	// continuation queues of the trace launches (ContQueue below): tasks written / fetched, rays suspended, per bounce;
-	// [0] closest-hit trace, [1] shadow trace
-	uint32 cont_tasks[2][64];
-	uint32 cont_next[2][64];
-	uint32 cont_rays[2][64];
+	uint32 dl_size[64];        // entries in the directional-light shadow queue produced at bounce b (scenes with DirectionalLights)
+	uint32 dl_next[64];        // its work-fetch cursor
 	// traversal statistics of the trace launches, written by the -DFB_TRACE_STATS=1 build only (tools/trace_stats.py):
 	// per [closest / shadow][bounce]: {longest warp: loop iterations, warps that traversed a ray, longest warp: clock cycles,
 	// longest ray: iterations in flight}
@@ -119,25 +116,6 @@ struct PassCounters
 	// [4..7] clock cycles summed over warps: refill + ray splitting, node visit, triangle phase, retirement
 	// [8..13] inside the triangle phase: scan, pair list, ray shuffles, triangle fetch, test + vote, hit delivery
 	unsigned long long stat_sum[2][64][16];
-};
-
-// Continuation queue of a persistent trace launch. A few rays of every wave visit ten or twenty times more nodes than
-// the average one, and one lane walks one ray: once the ray queue is empty the launch lasts as long as its longest
-// ray while nearly every lane idles (late bounces: ~50 of ~90 us per launch). After a few such tail iterations the
-// lanes still at work SUSPEND their rays instead: every pending node group / triangle group / stack entry becomes an
-// independent task {suspended-ray slot, entry} in this queue and the launch ends. A second launch of the same kernel
-// (phase 1) spreads the tasks over the whole machine, each task a closest-hit (or any-hit) query of one subtree that
-// merges its result into the ray's 64-bit key with one atomic: key = (t bits << 32 | triangle id), atomicMin = closest
-// hit with ties to the smaller triangle id — the same rule the lanes apply locally, so the outcome does not depend on how
-// a ray was cut up. A small resolve kernel then writes the hit records (barycentrics recomputed from the winning
-// triangle by the same Moller-Trumbore sequence) or, for shadow rays, runs the accumulation of the unoccluded ones.
-struct ContQueue
-{
-	uint4*  tasks;            // {slot of the suspended ray (0xFFFFFFFF = void), entry.x, entry.y, -}
-	uint32* ray_of_slot;      // queue index of the suspended ray (0xFFFFFFFF = void slot)
-	unsigned long long* keys; // closest: (t bits << 32 | tri) or ~0 = no hit yet; shadow: != 0 = occluded
-	uint32  task_capacity, ray_capacity;
-	unsigned long long* totals; // {rays suspended, tasks written} since the context was created (PassTotals), or NULL
 };
 
 // Queue traffic is touched once per wave: mark it evict-first ("streaming") so that it does not push the
@@ -157,8 +135,6 @@ struct PassTotals              // accumulated across passes (never reset by rend
 {
 	unsigned long long shade_events;
 	unsigned long long shadow_events;
-	unsigned long long suspended_rays;       // rays handed to continuation launches (ContQueue) and the tasks they became
-	unsigned long long continuation_tasks;
 };
 
 } // namespace fb

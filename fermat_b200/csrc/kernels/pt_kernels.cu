@@ -23,10 +23,10 @@ namespace fb {
 // ------------------------------------------------------------------------------------------------
 #define FB_TILE 32u
 
-// thread j -> pixel of the set: the whole frame (tile_list == NULL) or the j-th pixel of a list of 32x32 tiles
+// thread j -> pixel of the set: the whole frame (ps.whole) or the j-th pixel of a (possibly empty) list of 32x32 tiles
 FB_D bool pixel_of_set(const PixelSet& ps, const uint32 j, const uint32 n_pixels, uint32& pixel)
 {
-	if (ps.tile_list == NULL) { pixel = j; return j < n_pixels; }
+	if (ps.whole) { pixel = j; return j < n_pixels; }
 	const uint32 tile_slot = j / (FB_TILE * FB_TILE);
 	if (tile_slot >= ps.n_tiles) return false;
 	const uint32 tile = __ldg(ps.tile_list + tile_slot);
@@ -205,17 +205,8 @@ struct TraceArgs
 	const float4* w_d; const float4* w_g;
 	FrameBufferView fb; float frame_weight; uint32 bounce;
 	unsigned long long* event_counter;
-	// ray suspension (ContQueue, device_scene.h). phase 0: rays from the queue, lanes suspend what is left `suspend_after`
-	// iterations after the queue ran dry (< 0: never); phase 1: the tasks of that launch
-	ContQueue cont; uint32* cont_tasks; uint32* cont_next; uint32* cont_rays;
-	int suspend_after;
 	uint32* stat_max; unsigned long long* stat_sum;   // FB_TRACE_STATS: this launch's rows of PassCounters::stat_max / stat_sum
 };
-
-// PHASE of a queue trace launch: the plain kernel, the one whose warps suspend their last rays, the one that runs the tasks
-enum TracePhase { TRACE_PLAIN = 0, TRACE_SUSPENDING = 1, TRACE_TASKS = 2 };
-
-FB_D unsigned long long pack_hit_key(float t, int tri) { return ((unsigned long long)__float_as_uint(t) << 32) | (unsigned long long)(uint32)tri; }
 
 // solve_occlusion -> PTVertexProcessor::accumulate_nee (pathtracer_vertex_processor.h:204-239) for one unoccluded shadow ray
 template <typename Args>
@@ -238,19 +229,11 @@ FB_D void accumulate_unoccluded(const Args& a, const uint32 ray_idx)
 	}
 }
 
-template <int MODE, int PHASE = TRACE_PLAIN>
+template <int MODE>
 __global__ void __launch_bounds__(FB_TRACE_THREADS, FB_TRACE_MIN_BLOCKS) k_trace(DeviceScene sc, TraceArgs a)
 {
 	constexpr bool ANY = (MODE == TRACE_QUEUE_SHADOW || MODE == TRACE_RAYS_SHADOW);
-	constexpr bool tasks_phase = PHASE == TRACE_TASKS;       // this launch works on the continuation tasks of the previous one
-	constexpr bool may_suspend = PHASE == TRACE_SUSPENDING;
-	static_assert(PHASE == TRACE_PLAIN || MODE == TRACE_QUEUE_CLOSEST || MODE == TRACE_QUEUE_SHADOW, "only queue launches suspend rays");
-	uint32 n = a.n_ptr ? *a.n_ptr : a.n_value;
-	if (tasks_phase)
-	{
-		n = min(*a.cont_tasks, a.cont.task_capacity);
-		if (n == 0) return;                                    // (nothing was suspended)
-	}
+	const uint32 n = a.n_ptr ? *a.n_ptr : a.n_value;
 #if FB_RAYS_PER_LANE > 0
 	// size the persistent grid to the queue (its length is only known on the device): a lane that gets just one or two
 	// rays cannot even out their different lengths against its warp mates', so CTAs beyond n / (threads x R) leave at once;
@@ -267,7 +250,7 @@ __global__ void __launch_bounds__(FB_TRACE_THREADS, FB_TRACE_MIN_BLOCKS) k_trace
 	const float4* smem_nodes = smem + 1;
 	stage_nodes_tma(smem + 1, sc.nodes, sc.staged_nodes * (uint32)sizeof(WideNode), bar);
 
-	if (MODE == TRACE_QUEUE_SHADOW && !tasks_phase && blockIdx.x == 0 && threadIdx.x == 0 && a.event_counter) atomicAdd(a.event_counter, (unsigned long long)n);
+	if (MODE == TRACE_QUEUE_SHADOW && blockIdx.x == 0 && threadIdx.x == 0 && a.event_counter) atomicAdd(a.event_counter, (unsigned long long)n);
 	const int lane = threadIdx.x & 31;
 
 	Traversal<ANY> trav;
@@ -303,9 +286,7 @@ __global__ void __launch_bounds__(FB_TRACE_THREADS, FB_TRACE_MIN_BLOCKS) k_trace
 #else
 	constexpr bool thin = false;
 #endif
-	int  tail_iters = 0;             // warp-uniform: iterations since then
-	bool can_suspend = may_suspend;
-	uint32* const cursor = tasks_phase ? a.cont_next : a.cursor;
+	uint32* const cursor = a.cursor;
 #if FB_TRACE_STATS
 	uint32 st_iters = 0, st_tail = 0, st_lanes = 0, st_helpers = 0, st_ray = 0, st_longest_ray = 0; bool st_busy = false;
 	const long long st_t0 = clock64();
@@ -344,32 +325,14 @@ __global__ void __launch_bounds__(FB_TRACE_THREADS, FB_TRACE_MIN_BLOCKS) k_trace
 #endif
 			{
 				ray_idx = base + __popc(need & ((1u << lane) - 1u));
-				if (ray_idx < n && !tasks_phase)
+				if (ray_idx < n)
 				{
 					const float4 o = ld_stream(a.ray_o + (size_t)ray_idx * a.stride), d = ld_stream(a.ray_d + (size_t)ray_idx * a.stride);
 					trav.init(o, d, ANY ? __float_as_uint(o.w) : 0u);
 					active = true;
 				}
-				else if (ray_idx < n)
-				{
-					// a continuation task: one pending entry of a suspended ray, traversed as a query of its own
-					const uint4 task = __ldcs(a.cont.tasks + ray_idx);
-					ray_idx = task.x;                                         // from here on: the slot of the suspended ray
-					const unsigned long long key = ray_idx != 0xFFFFFFFFu ? __ldcg(a.cont.keys + ray_idx) : 0ull;
-					if (ray_idx != 0xFFFFFFFFu && !(ANY && key != 0ull))         // (void task / the ray is known to be occluded already)
-					{
-						const uint32 r = __ldg(a.cont.ray_of_slot + ray_idx);
-						const float4 o = ld_stream(a.ray_o + (size_t)r * a.stride), d = ld_stream(a.ray_d + (size_t)r * a.stride);
-						trav.init(o, d, ANY ? __float_as_uint(o.w) : 0u);
-						trav.ngroup = make_uint2(0u, 0u);
-						if (task.z > 0x00FFFFFFu) trav.ngroup = make_uint2(task.y, task.z); else trav.tgroup = make_uint2(task.y, task.z);
-						if (!ANY) trav.adopt_key(key);
-						active = true;
-					}
-				}
 			}
 		}
-		if (exhausted) tail_iters++;
 		if (!__any_sync(0xFFFFFFFFu, active)) { if (exhausted) break; else continue; }
 #if FB_TRACE_STATS
 		if (st_busy) FB_STAT_MARK(3) else st_mark = clock64();
@@ -377,40 +340,6 @@ __global__ void __launch_bounds__(FB_TRACE_THREADS, FB_TRACE_MIN_BLOCKS) k_trace
 		st_lanes += (uint32)__popc(__ballot_sync(0xFFFFFFFFu, active)); st_helpers += (uint32)__popc(__ballot_sync(0xFFFFFFFFu, active && root != lane));
 		if (active && root == lane) { st_ray++; st_longest_ray = max(st_longest_ray, st_ray); } else st_ray = 0;     // iterations the lane's own ray has been in flight
 #endif
-
-		// ---- suspension: hand what is left of this warp's rays to the continuation launch (ContQueue, device_scene.h) ----
-		if (can_suspend && tail_iters > a.suspend_after)
-		{
-			const uint32 FULL = 0xFFFFFFFFu;
-			const bool owner = active && root == lane;
-			const uint32 cnt = active ? ((trav.has_node() ? 1u : 0u) + (trav.has_tri() ? 1u : 0u) + (uint32)trav.sp) : 0u;
-			uint32 incl = cnt;
-			#pragma unroll
-			for (int d = 1; d < 32; d <<= 1) { const uint32 v = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += v; }
-			const uint32 total = __shfl_sync(FULL, incl, 31);
-			const unsigned owners = __ballot_sync(FULL, owner);
-			uint32 tbase = 0, sbase = 0;
-			if (lane == 0) { tbase = atomicAdd(a.cont_tasks, total); sbase = atomicAdd(a.cont_rays, (uint32)__popc(owners)); }
-			tbase = __shfl_sync(FULL, tbase, 0); sbase = __shfl_sync(FULL, sbase, 0);
-			const bool fits = tbase + total <= a.cont.task_capacity && sbase + (uint32)__popc(owners) <= a.cont.ray_capacity;
-			const uint32 my_slot = sbase + (uint32)__popc(owners & ((1u << lane) - 1u));
-			const uint32 slot = __shfl_sync(FULL, my_slot, root);            // helpers: the slot of the ray they work on
-			if (owner && my_slot < a.cont.ray_capacity)
-			{
-				a.cont.ray_of_slot[my_slot] = fits ? ray_idx : 0xFFFFFFFFu;
-				if (fits) a.cont.keys[my_slot] = ANY ? 0ull : (trav.hit.tri >= 0 ? pack_hit_key(trav.hit.t, trav.hit.tri) : ~0ull);
-			}
-			if (active)
-			{
-				uint32 k = tbase + incl - cnt;
-				const uint32 tslot = fits ? slot : 0xFFFFFFFFu;            // queue full: the claimed entries are voided and the rays stay here
-				if (trav.has_node()) { if (k < a.cont.task_capacity) a.cont.tasks[k] = make_uint4(tslot, trav.ngroup.x, trav.ngroup.y, 0u); ++k; }
-				if (trav.has_tri())  { if (k < a.cont.task_capacity) a.cont.tasks[k] = make_uint4(tslot, trav.tgroup.x, trav.tgroup.y, 0u); ++k; }
-				for (int i = 0; i < trav.sp; ++i, ++k) if (k < a.cont.task_capacity) a.cont.tasks[k] = make_uint4(tslot, trav.stack[i].x, trav.stack[i].y, 0u);
-			}
-			if (fits) { active = false; root = lane; }                       // the resolve kernel completes these rays
-			can_suspend = false;
-		}
 
 #if FB_COOP_TRI && FB_SPLIT_RAYS
 		// Ray splitting. A few rays (grazing a tessellated floor, say) visit twenty times more nodes than the average one,
@@ -511,19 +440,10 @@ __global__ void __launch_bounds__(FB_TRACE_THREADS, FB_TRACE_MIN_BLOCKS) k_trace
 		{
 			bool done = false;
 			FB_STAT_MARK(0)
-			// a task refreshes its far bound from the ray's key, where the other tasks of the same ray publish their hits
-			// (issued before the node visit, consumed after it: the load rides along with the node fetch)
-			unsigned long long fresh = ANY ? 0ull : ~0ull;
-			if (tasks_phase && active && root == lane) fresh = __ldcg(a.cont.keys + ray_idx);
 			if (active)
 			{
 				done = !trav.acquire();
 				if (!done) trav.node_step(sc, smem_nodes);
-			}
-			if (tasks_phase && active && root == lane)
-			{
-				if (ANY) { if (fresh != 0ull) trav.occluded = true; }
-				else trav.adopt_key(fresh);
 			}
 			FB_STAT_MARK(1)
 #if FB_TRACE_STATS
@@ -561,13 +481,7 @@ __global__ void __launch_bounds__(FB_TRACE_THREADS, FB_TRACE_MIN_BLOCKS) k_trace
 			if (active && done)
 			{
 				active = false;
-				if (tasks_phase)
-				{
-					// merge this subtree's result into the suspended ray's key
-					if (ANY) { if (trav.occluded) a.cont.keys[ray_idx] = 1ull; }
-					else if (trav.hit.tri >= 0) atomicMin(a.cont.keys + ray_idx, pack_hit_key(trav.hit.t, trav.hit.tri));
-				}
-				else if (MODE == TRACE_QUEUE_CLOSEST || MODE == TRACE_RAYS_CLOSEST) st_stream(a.hits + ray_idx, trav.hit_record());
+				if (MODE == TRACE_QUEUE_CLOSEST || MODE == TRACE_RAYS_CLOSEST) st_stream(a.hits + ray_idx, trav.hit_record());
 				else if (MODE == TRACE_RAYS_SHADOW || FB_SPLIT_ACCUMULATE) a.occluded[ray_idx] = trav.occluded ? 1 : 0;
 				else if (!trav.occluded) accumulate_unoccluded(a, ray_idx);
 			}
@@ -584,48 +498,6 @@ __global__ void __launch_bounds__(FB_TRACE_THREADS, FB_TRACE_MIN_BLOCKS) k_trace
 		for (int k = 0; k < 6; ++k) atomicAdd(a.stat_sum + 8 + k, (unsigned long long)st_tri[k]);
 	}
 #endif
-}
-
-// completes the rays a trace launch suspended, once their continuation tasks have run (ContQueue, device_scene.h)
-template <bool ANY>
-__global__ void __launch_bounds__(128) k_resolve_suspended(DeviceScene sc, TraceArgs a)
-{
-	const uint32 n = min(*a.cont_rays, a.cont.ray_capacity);
-	if (blockIdx.x == 0 && threadIdx.x == 0 && n && a.cont.totals)
-	{
-		atomicAdd(a.cont.totals, (unsigned long long)n);                                                         // PassTotals::suspended_rays
-		atomicAdd(a.cont.totals + 1, (unsigned long long)min(*a.cont_tasks, a.cont.task_capacity));             // PassTotals::continuation_tasks
-	}
-	for (uint32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-	{
-		const uint32 ray_idx = a.cont.ray_of_slot[i];
-		if (ray_idx == 0xFFFFFFFFu) continue;
-		const unsigned long long key = a.cont.keys[i];
-#if FB_SPLIT_ACCUMULATE
-		if (ANY) { a.occluded[ray_idx] = key != 0ull ? 1 : 0; continue; }
-#else
-		if (ANY) { if (key == 0ull) accumulate_unoccluded(a, ray_idx); continue; }
-#endif
-		if (key == ~0ull) { st_stream(a.hits + ray_idx, make_float4(-1.0f, __int_as_float(-1), 0.0f, 0.0f)); continue; }
-		const float t = __uint_as_float((uint32)(key >> 32));
-		const int tri = (int)(uint32)(key & 0xFFFFFFFFull);
-		// barycentrics of the winning triangle: the Moller-Trumbore sequence of Traversal::coop_tri_phase on the same vertex
-		// floats (WideTri copies them from the mesh arrays), so the record carries the bits a local hit would have carried
-		const float4 o = ld_stream(a.ray_o + (size_t)ray_idx * a.stride), d = ld_stream(a.ray_d + (size_t)ray_idx * a.stride);
-		const int4 vi = __ldg(sc.vertex_indices + tri);
-		const float4 va = __ldg(sc.vertex_data + vi.x), vb = __ldg(sc.vertex_data + vi.y), vc = __ldg(sc.vertex_data + vi.z);
-		const float e1x = vb.x - va.x, e1y = vb.y - va.y, e1z = vb.z - va.z;
-		const float e2x = vc.x - va.x, e2y = vc.y - va.y, e2z = vc.z - va.z;
-		const float px = d.y * e2z - d.z * e2y, py = d.z * e2x - d.x * e2z, pz = d.x * e2y - d.y * e2x;
-		const float det = e1x * px + e1y * py + e1z * pz;
-		const float inv = 1.0f / det;
-		const float tx = o.x - va.x, ty = o.y - va.y, tz = o.z - va.z;
-		const float bu = (tx * px + ty * py + tz * pz) * inv;
-		const float qx = ty * e1z - tz * e1y, qy = tz * e1x - tx * e1z, qz = tx * e1y - ty * e1x;
-		const float bv = (d.x * qx + d.y * qy + d.z * qz) * inv;
-		const float u = __half2float(__float2half_rn(1.0f - bu - bv)), v = __half2float(__float2half_rn(bu));
-		st_stream(a.hits + ray_idx, make_float4(t, __int_as_float(tri), u, v));
-	}
 }
 
 // solve_occlusion_kernel (pathtracer_kernels.h:248-267) as a pass of its own over the shadow queue (FB_SPLIT_ACCUMULATE): consecutive
@@ -723,6 +595,7 @@ __global__ void __launch_bounds__(256) k_clamp_frame(FrameBufferView fb, PixelSe
 struct ShadeArgs
 {
 	PathQueue in, out; ShadowQueue sq; FrameBufferView fb;
+	ShadowQueue sq_dl;               // DIRLIGHT instantiation: the directional-light samples' own shadow queue (counter PassCounters::dl_size)
 	PassCounters* ctr; PassTotals* tot;
 	uint32 bounce; float frame_weight; float seq[6];
 	uint32 do_nee, do_emissive, do_scatter, do_dirlight;
@@ -1104,7 +977,7 @@ cudaError_t configure_kernels(LaunchConfig& lc, int device)
 
 static inline uint32 staged_smem(const DeviceScene& sc) { return 16u + sc.staged_nodes * (uint32)sizeof(WideNode) + FB_SMEM_STACK * 8u * FB_TRACE_THREADS + FB_COOP_TRI * 8u * FB_TRACE_THREADS; }
 
-static inline uint32 set_threads(const FrameBufferView& fb, const PixelSet& ps) { return ps.tile_list ? ps.n_tiles * FB_TILE * FB_TILE : fb.n_pixels; }
+static inline uint32 set_threads(const FrameBufferView& fb, const PixelSet& ps) { return ps.whole ? fb.n_pixels : ps.n_tiles * FB_TILE * FB_TILE; }
 cudaError_t launch_rescale_frame(const FrameBufferView& fb, const PixelSet& ps, float scale, cudaStream_t s)
 {
 	const uint32 n = set_threads(fb, ps);
@@ -1140,51 +1013,28 @@ cudaError_t launch_generate_primary(const DeviceScene& sc, const PassParams& pp,
 	k_generate_primary<<<(total + 255) / 256, 256, 0, s>>>(sc, pp, q, ctr, seq2[0], seq2[1], fb);
 	return cudaGetLastError();
 }
-static void set_cont(TraceArgs& a, const ContQueue* cont, PassCounters* ctr, int which, uint32 bounce, int suspend_after)
-{
-	a.suspend_after = -1;
-	if (cont == NULL || cont->tasks == NULL || suspend_after < 0) return;
-	a.cont = *cont; a.cont_tasks = &ctr->cont_tasks[which][bounce]; a.cont_next = &ctr->cont_next[which][bounce]; a.cont_rays = &ctr->cont_rays[which][bounce];
-	a.suspend_after = suspend_after;
-}
-cudaError_t launch_trace_closest(const DeviceScene& sc, const LaunchConfig& lc, const PathQueue& q, PassCounters* ctr, uint32 bounce, cudaStream_t s,
-								 const ContQueue* cont, int suspend_after, uint32* launches)
+cudaError_t launch_trace_closest(const DeviceScene& sc, const LaunchConfig& lc, const PathQueue& q, PassCounters* ctr, uint32 bounce, cudaStream_t s)
 {
 	TraceArgs a; memset(&a, 0, sizeof(a));
 	a.ray_o = q.ray_o; a.ray_d = q.ray_d; a.stride = 1; a.n_ptr = &ctr->in_size[bounce]; a.cursor = &ctr->trace_next[bounce]; a.hits = q.hit;
-	set_cont(a, cont, ctr, 0, bounce, suspend_after);
 	a.stat_max = ctr->stat_max[0][bounce]; a.stat_sum = ctr->stat_sum[0][bounce];
-	if (launches) *launches = a.suspend_after >= 0 ? 3 : 1;
-	if (a.suspend_after < 0)
-		k_trace<TRACE_QUEUE_CLOSEST><<<lc.sm_count * lc.trace_ctas_per_sm, lc.trace_threads, staged_smem(sc), s>>>(sc, a);
-	else
-	{
-		k_trace<TRACE_QUEUE_CLOSEST, TRACE_SUSPENDING><<<lc.sm_count * lc.trace_ctas_per_sm, lc.trace_threads, staged_smem(sc), s>>>(sc, a);
-		k_trace<TRACE_QUEUE_CLOSEST, TRACE_TASKS><<<lc.sm_count * lc.trace_ctas_per_sm, lc.trace_threads, staged_smem(sc), s>>>(sc, a);
-		k_resolve_suspended<false><<<lc.sm_count, 128, 0, s>>>(sc, a);
-	}
+	k_trace<TRACE_QUEUE_CLOSEST><<<lc.sm_count * lc.trace_ctas_per_sm, lc.trace_threads, staged_smem(sc), s>>>(sc, a);
 	return cudaGetLastError();
 }
 bool kernels_split_accumulate() { return FB_SPLIT_ACCUMULATE != 0; }
 
 cudaError_t launch_trace_shadow(const DeviceScene& sc, const LaunchConfig& lc, const ShadowQueue& sq, const FrameBufferView& fb, PassCounters* ctr, PassTotals* tot,
-								uint32 bounce, float frame_weight, cudaStream_t s, const ContQueue* cont, int suspend_after, uint32* launches, const PsfView* psf)
+								uint32 bounce, float frame_weight, cudaStream_t s, int which, uint32* launches, const PsfView* psf)
 {
+	// which = 0: the next-event queue; 1: the directional-light queue (its own counters: the two are accumulated one after the other)
 	TraceArgs a; memset(&a, 0, sizeof(a));
-	a.ray_o = sq.ray_o; a.ray_d = sq.ray_d; a.stride = 1; a.n_ptr = &ctr->shadow_size[bounce]; a.cursor = &ctr->shadow_next[bounce];
+	a.ray_o = sq.ray_o; a.ray_d = sq.ray_d; a.stride = 1;
+	a.n_ptr = which ? &ctr->dl_size[bounce] : &ctr->shadow_size[bounce]; a.cursor = which ? &ctr->dl_next[bounce] : &ctr->shadow_next[bounce];
 	a.w_d = sq.w_d; a.w_g = sq.w_g; a.fb = fb; a.frame_weight = frame_weight; a.bounce = bounce; a.event_counter = &tot->shadow_events;
 	a.occluded = sq.occluded;
-	set_cont(a, cont, ctr, 1, bounce, suspend_after);
 	a.stat_max = ctr->stat_max[1][bounce]; a.stat_sum = ctr->stat_sum[1][bounce];
-	if (launches) *launches = a.suspend_after >= 0 ? 3 : 1;
-	if (a.suspend_after < 0)
-		k_trace<TRACE_QUEUE_SHADOW><<<lc.sm_count * lc.trace_ctas_per_sm, lc.trace_threads, staged_smem(sc), s>>>(sc, a);
-	else
-	{
-		k_trace<TRACE_QUEUE_SHADOW, TRACE_SUSPENDING><<<lc.sm_count * lc.trace_ctas_per_sm, lc.trace_threads, staged_smem(sc), s>>>(sc, a);
-		k_trace<TRACE_QUEUE_SHADOW, TRACE_TASKS><<<lc.sm_count * lc.trace_ctas_per_sm, lc.trace_threads, staged_smem(sc), s>>>(sc, a);
-		k_resolve_suspended<true><<<lc.sm_count, 128, 0, s>>>(sc, a);
-	}
+	if (launches) *launches = 1;
+	k_trace<TRACE_QUEUE_SHADOW><<<lc.sm_count * lc.trace_ctas_per_sm, lc.trace_threads, staged_smem(sc), s>>>(sc, a);
 #if FB_SPLIT_ACCUMULATE
 	{
 		AccumArgs ac; memset(&ac, 0, sizeof(ac));
@@ -1220,18 +1070,18 @@ cudaError_t launch_psf_blend(const LaunchConfig& lc, const PsfView& psf, const F
 }
 cudaError_t launch_clamp_frame(const FrameBufferView& fb, const PixelSet& ps, float max_value, cudaStream_t s)
 {
-	const uint32 n = ps.tile_list ? ps.n_tiles * FB_TILE * FB_TILE : fb.n_pixels;
+	const uint32 n = set_threads(fb, ps);
 	if (n == 0) return cudaSuccess;
 	k_clamp_frame<<<(n + 255) / 256, 256, 0, s>>>(fb, ps, max_value);
 	return cudaGetLastError();
 }
 
-cudaError_t launch_shade(const DeviceScene& sc, const LaunchConfig& lc, const PassParams& pp, const PathQueue& in, const PathQueue& out, const ShadowQueue& sq,
+cudaError_t launch_shade(const DeviceScene& sc, const LaunchConfig& lc, const PassParams& pp, const PathQueue& in, const PathQueue& out, const ShadowQueue& sq, const ShadowQueue& sq_dl,
 						 const FrameBufferView& fb, PassCounters* ctr, PassTotals* tot, uint32 bounce, const float seq6[6], uint32 capacity, cudaStream_t s, const PsfView* psf)
 {
 	ShadeArgs a;
 	memset(&a.psf, 0, sizeof(a.psf));
-	a.in = in; a.out = out; a.sq = sq; a.fb = fb; a.ctr = ctr; a.tot = tot; a.bounce = bounce; a.frame_weight = pp.frame_weight;
+	a.in = in; a.out = out; a.sq = sq; a.sq_dl = sq_dl; a.fb = fb; a.ctr = ctr; a.tot = tot; a.bounce = bounce; a.frame_weight = pp.frame_weight;
 	for (int i = 0; i < 6; ++i) a.seq[i] = seq6[i];
 	// compute_per_bounce_options (pathtracer_core.h:594-620)
 	const PTOptions& o = sc.options;

@@ -31,23 +31,26 @@ struct LaunchConfig
 struct PixelSet
 {
 	const uint32* tile_list; uint32 n_tiles, tiles_x, res_x, res_y;
+	uint32 whole;                   // 1: every pixel of the frame (tile_list unused). A tile set may be EMPTY (a shard that owns no tile): it then covers nothing
 };
-inline PixelSet whole_frame() { PixelSet p; p.tile_list = NULL; p.n_tiles = 0; p.tiles_x = 0; p.res_x = 0; p.res_y = 0; return p; }
+inline PixelSet whole_frame() { PixelSet p; p.tile_list = NULL; p.n_tiles = 0; p.tiles_x = 0; p.res_x = 0; p.res_y = 0; p.whole = 1; return p; }
+inline PixelSet tile_set(const uint32* tile_list, uint32 n_tiles, uint32 tiles_x, uint32 res_x, uint32 res_y)
+{
+	PixelSet p; p.tile_list = tile_list; p.n_tiles = n_tiles; p.tiles_x = tiles_x; p.res_x = res_x; p.res_y = res_y; p.whole = 0; return p;
+}
 cudaError_t launch_rescale_frame(const FrameBufferView& fb, const PixelSet& ps, float scale, cudaStream_t s);
 cudaError_t launch_update_variances(const FrameBufferView& fb, const PixelSet& ps, uint32 n_passes, cudaStream_t s);
 cudaError_t launch_copy_channel(const FrameBufferView& fb, int channel, float4* dst, const PixelSet& ps, cudaStream_t s);
 // also resets the G-buffer of every pixel it starts a path for (pass `fb` with gb_geo == NULL to skip)
 cudaError_t launch_generate_primary(const DeviceScene& sc, const PassParams& pp, const PathQueue& q, PassCounters* ctr, const float seq2[2], const FrameBufferView& fb, cudaStream_t s);
-// cont / suspend_after: ray suspension (ContQueue, device_scene.h); NULL or a negative count turns it off. With it on, a
-// trace is three launches: the rays, the continuation tasks of the suspended ones, the resolve kernel (`launches` says how many)
-cudaError_t launch_trace_closest(const DeviceScene& sc, const LaunchConfig& lc, const PathQueue& q, PassCounters* ctr, uint32 bounce, cudaStream_t s,
-								 const ContQueue* cont = NULL, int suspend_after = -1, uint32* launches = NULL);
-cudaError_t launch_shade(const DeviceScene& sc, const LaunchConfig& lc, const PassParams& pp, const PathQueue& in, const PathQueue& out, const ShadowQueue& sq,
+cudaError_t launch_trace_closest(const DeviceScene& sc, const LaunchConfig& lc, const PathQueue& q, PassCounters* ctr, uint32 bounce, cudaStream_t s);
+// sq_dl: the directional-light samples' own shadow queue (only written when the scene has DirectionalLights)
+cudaError_t launch_shade(const DeviceScene& sc, const LaunchConfig& lc, const PassParams& pp, const PathQueue& in, const PathQueue& out, const ShadowQueue& sq, const ShadowQueue& sq_dl,
 						 const FrameBufferView& fb, PassCounters* ctr, PassTotals* tot, uint32 bounce, const float seq6[6], uint32 capacity, cudaStream_t s,
 						 const PsfView* psf = NULL);      // psf != NULL: the `-psfpt` vertex processor
+// shadow trace + solve_occlusion of one shadow queue of bounce `bounce`: which = 0 the next-event queue (`sq`), 1 the directional-light queue
 cudaError_t launch_trace_shadow(const DeviceScene& sc, const LaunchConfig& lc, const ShadowQueue& sq, const FrameBufferView& fb, PassCounters* ctr, PassTotals* tot,
-								uint32 bounce, float frame_weight, cudaStream_t s, const ContQueue* cont = NULL, int suspend_after = -1, uint32* launches = NULL,
-								const PsfView* psf = NULL);
+								uint32 bounce, float frame_weight, cudaStream_t s, int which = 0, uint32* launches = NULL, const PsfView* psf = NULL);
 // `-psfpt`: splat the references of one bounce (psf_blending, src/renderers/psfpt_impl.h:101-143); RenderingContext::clamp_frame (src/renderer.cu:421-427)
 cudaError_t launch_psf_blend(const LaunchConfig& lc, const PsfView& psf, const FrameBufferView& fb, const PassCounters* ctr, uint32 bounce, float frame_weight, cudaStream_t s);
 cudaError_t launch_clamp_frame(const FrameBufferView& fb, const PixelSet& ps, float max_value, cudaStream_t s);

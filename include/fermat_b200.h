@@ -214,9 +214,6 @@ int fb200_diag_pass_counters(fb200_context*, uint32_t subframe, void* out, uint6
  * so far (they run on the renderer's private streams) and makes the next pass wait for what the caller enqueues on it:
  * call it again before each use rather than caching the handle. */
 void* fb200_context_stream(fb200_context*);
-/* ray suspension (FB200_SUSPEND=<iterations>, off by default): out[0] = rays the persistent trace launches handed to
- * their continuation launches since the context was created, out[1] = the subtree tasks those rays were cut into */
-int fb200_context_get_suspension_stats(fb200_context*, uint64_t out[2]);
 /* number of pixels this shard owns */
 uint64_t fb200_context_owned_pixels(const fb200_context*);
 

@@ -4,7 +4,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import CACHE, GOLDEN, cornell_args, rel_l2
+from conftest import CACHE, GOLDEN, ROOT, cornell_args, rel_l2
 
 pytestmark = pytest.mark.gpu
 
@@ -218,6 +218,7 @@ def test_big_scenes_against_oracle(fb, oracle, scene, res, bounces):
     # coplanar overlapping triangles are hit at parameters one or two ulps apart; which of them survives then
     # depends on box-test rounding in two different trees: such near-ties are the one allowed difference
     tie = (hg[:, 0] > 0) & (ho[:, 0] > 0) & (np.abs(hg[:, 0] - ho[:, 0]) <= 4e-7 * np.abs(ho[:, 0]))
+    print("%s: %d of %d hits differ, %d of them near-ties (|dt| <= 4e-7 t)" % (scene, (~same).sum(), same.size, (tie & ~same).sum()))
     assert (same | tie).mean() > 0.99999, "mismatching hits: %d" % (~(same | tie)).sum()
     assert same.mean() > 0.999
     # 2. one full pass: per-pixel parity at equal spp with the same seeds
@@ -235,36 +236,119 @@ def test_big_scenes_against_oracle(fb, oracle, scene, res, bounces):
     rc.close(); sc.close()
 
 
-def test_ray_suspension_leaves_every_result_unchanged(fb, oracle, monkeypatch, after="0"):
-    """FB200_SUSPEND: trace warps hand the rays they still hold, a few iterations after the queue ran dry, to a second
-    launch as independent subtree tasks (ContQueue, device_scene.h). Closest hit = min over (t, triangle id) and
-    occlusion = any: cutting a ray up must not change a single bit of the frame."""
-    def frames(args, passes):
-        sc = fb.Scene(args)
-        rc = fb.RenderingContext(sc)
-        rc.clear()
-        for i in range(passes):
-            rc.render(i, sync=False)
-        out = [rc.download(n) for n in ("COMPOSITED_C", "DIRECT_C", "DIFFUSE_C", "SPECULAR_C")], rc.stats(), rc.suspension_stats(), rc.download_gbuffer()
-        rc.close(); sc.close()
-        return out
-    cases = [(cornell_args(96, 4), 4)]
+ALL_CHANNELS = ("COMPOSITED_C", "DIRECT_C", "DIFFUSE_C", "SPECULAR_C", "DIFFUSE_A", "SPECULAR_A")
+
+
+def _render_both(fb, oracle, args, passes, threads=0):
+    """render `passes` passes with the CUDA path and with the oracle: ({channel: gpu image}, oracle frame buffer, gpu stats, oracle events)"""
+    sc = fb.Scene(args)
+    rc = fb.RenderingContext(sc)
+    fbuf = oracle.new_framebuffer(sc.view)
+    rc.clear()
+    events = shadow = 0
+    for i in range(passes):
+        rc.render(i, sync=False)
+        st = oracle.render_pass(sc.view, i, fbuf, threads=threads)
+        events += st.shade_events; shadow += st.shadow_events
+    got = {n: rc.download(n) for n in ALL_CHANNELS}
+    stats = rc.stats()
+    rc.close(); sc.close()
+    return got, fbuf, stats, (events, shadow)
+
+
+def test_directional_lights_match_oracle(fb, oracle):
+    """SURVEY 8a row a12 (src/pathtracer_core.h:870-988, src/lights.h:276-294): k_shade<DIRLIGHT> on a CornellBox lit by two
+    DirectionalLights (tests/golden/cornellbox_dirlight.fbs, tools/make_snapshots.py) against the oracle on all six channels.
+    A pixel then owns TWO shadow-queue entries per bounce (light sample + next-event sample); they live in separate queues that are
+    accumulated one after the other, so the image is reproducible bit for bit (the reference's solve_occlusion races on them)."""
+    args = ["-i", os.path.join(GOLDEN, "cornellbox_dirlight.fbs"), "-r", "96", "96", "-bounces", "4"]
+    got, fbuf, st, (events, shadow) = _render_both(fb, oracle, args, 8)
+    assert st["shade_events"] == events and st["shadow_events"] == shadow          # integer-exact sample counts, both shadow queues
+    for name in ALL_CHANNELS:
+        g, o = got[name], fbuf[fb.FB_CHANNELS[name]]
+        assert np.isfinite(g).all()
+        assert rel_l2(g, o) < 1e-3, name
+    assert rel_l2(got["COMPOSITED_C"], fbuf[5]) < 1e-5
+    # the directional lights actually contribute: brighter than the same box without them, direct emission unchanged
+    plain, pbuf, _, _ = _render_both(fb, oracle, cornell_args(96, 4), 8)
+    assert got["COMPOSITED_C"][..., :3].mean() > 1.2 * plain["COMPOSITED_C"][..., :3].mean()
+    assert np.array_equal(got["DIRECT_C"], plain["DIRECT_C"])
+    # run-to-run determinism of the two-queue accumulation
+    again, _, _, _ = _render_both(fb, oracle, args, 8)
+    for name in ALL_CHANNELS:
+        assert np.array_equal(again[name], got[name]), name
+
+
+def test_nee_over_the_triangle_cdf_matches_oracle(fb, oracle):
+    """`-nee-alg mesh` (src/lights.h:335-352): next-event samples drawn from the CDF over emissive triangles (device upper_bound
+    loop in k_shade) instead of the pre-sampled VPLs, against the oracle on all six channels; same estimator as the VPL one."""
+    got, fbuf, st, (events, shadow) = _render_both(fb, oracle, cornell_args(96, 4, ["-nee-alg", "mesh"]), 16)
+    assert st["shade_events"] == events and st["shadow_events"] == shadow
+    for name in ALL_CHANNELS:
+        assert rel_l2(got[name], fbuf[fb.FB_CHANNELS[name]]) < 1e-3, name
+    assert rel_l2(got["COMPOSITED_C"], fbuf[5]) < 1e-5
+    vpl, _, _, _ = _render_both(fb, oracle, cornell_args(96, 4), 16)
+    assert not np.array_equal(vpl["COMPOSITED_C"], got["COMPOSITED_C"])            # a different sampler ...
+    m0, m1 = vpl["COMPOSITED_C"][..., :3].mean(), got["COMPOSITED_C"][..., :3].mean()
+    assert abs(m0 - m1) / m0 < 0.03                                                # ... of the same integral
+    glossy = os.path.join(CACHE, "cornellbox_glossy.fbs")
+    if fb.scene_available(glossy):
+        got, fbuf, st, (events, shadow) = _render_both(fb, oracle, ["-i", glossy, "-r", "128", "128", "-bounces", "4", "-nee-alg", "mesh"], 4)
+        assert st["shade_events"] == events
+        assert rel_l2(got["COMPOSITED_C"], fbuf[5]) < 1e-3
+
+
+def test_bathroom2_full_size_against_oracle(fb, oracle):
+    """BASELINE.json configs[1] at its NAMED size, 1600x900 x 8 bounces, 8 spp, CUDA path vs oracle at equal spp with the same seeds,
+    all six channels (the oracle needs a few seconds per pass on the box's host cores)."""
     path = os.path.join(CACHE, "bathroom2.fbs")
-    if fb.scene_available(path):
-        cases.append((["-i", path, "-r", "800", "450", "-bounces", "8"], 2))
-    for args, passes in cases:
-        monkeypatch.delenv("FB200_SUSPEND", raising=False)
-        want, st0, susp0, gb0 = frames(args, passes)
-        assert susp0 == (0, 0)
-        monkeypatch.setenv("FB200_SUSPEND", after)
-        got, st1, susp1, gb1 = frames(args, passes)
-        assert susp1[0] > 0 and susp1[1] >= susp1[0] // 2, susp1       # rays were suspended, and cut into tasks
-        for a, b in zip(got, want):
-            assert np.array_equal(a, b)
-        assert np.array_equal(gb0["tri"], gb1["tri"]) and np.array_equal(gb0["uv"].view(np.uint32), gb1["uv"].view(np.uint32))
-        assert st0["shade_events"] == st1["shade_events"] and st0["shadow_events"] == st1["shadow_events"]
-        assert st1["kernel_launches"] > st0["kernel_launches"]
-    monkeypatch.delenv("FB200_SUSPEND", raising=False)
+    if not fb.scene_available(path):
+        pytest.skip("bathroom2 snapshot not present")
+    spp = 8
+    got, fbuf, st, (events, shadow) = _render_both(fb, oracle, ["-i", path, "-r", "1600", "900", "-bounces", "8"], spp, threads=len(os.sched_getaffinity(0)))
+    for name in ALL_CHANNELS:
+        g, o = got[name], fbuf[fb.FB_CHANNELS[name]]
+        assert np.isfinite(g).all()
+        assert rel_l2(g, o) < 1e-3, (name, rel_l2(g, o))
+    g, o = got["COMPOSITED_C"], fbuf[5]
+    bad = (np.abs(g[..., :3] - o[..., :3]).max(axis=2) > 1e-3 * (1 + o[..., :3].max(axis=2)))
+    print("bathroom2 1600x900 %d spp: rel L2 %.3e, %d of %d pixels took a different path, samples gpu %d / oracle %d" % (
+        spp, rel_l2(g, o), bad.sum(), bad.size, st["shade_events"], events))
+    assert bad.mean() < 1e-3
+    assert abs(st["shade_events"] - events) <= 1e-4 * events and abs(st["shadow_events"] - shadow) <= 1e-4 * shadow
+
+
+def test_bathroom2_1024spp_against_converged_oracle(fb):
+    """The north-star gate as written: per-pixel L2 vs the reference arm < 1e-3 at 1024 spp on bathroom2 1600x900 x 8 bounces. The
+    oracle's 1024-spp render takes ~50 min of host time, so it is a fixture made once by tools/oracle_converged.py
+    (scenes/_cache/, travels with gpurun); the CUDA path renders its 1024 passes here (~4 s)."""
+    path = os.path.join(CACHE, "bathroom2.fbs")
+    fixture = os.path.join(CACHE, "bathroom2_oracle_1600x900_1024spp.npz")
+    if not fb.scene_available(path) or not os.path.exists(fixture):
+        pytest.skip("bathroom2 snapshot or the converged oracle fixture (tools/oracle_converged.py) not present")
+    z = np.load(fixture)
+    spp = int(z["spp"])
+    sc = fb.Scene(["-i", path, "-r", "1600", "900", "-bounces", str(int(z["bounces"]))])
+    rc = fb.RenderingContext(sc)
+    rc.clear()
+    for i in range(spp):
+        rc.render(i, sync=False)
+    ids = [int(c) for c in z["channel_ids"]]
+    names = {v: k for k, v in fb.FB_CHANNELS.items()}
+    report = {}
+    for j, c in enumerate(ids):
+        g = rc.download(names[c])
+        report[names[c]] = rel_l2(g, z["channels"][j])
+    st = rc.stats()
+    rc.close(); sc.close()
+    print("bathroom2 1600x900 %d spp vs converged oracle: %s, samples gpu %d / oracle %d" % (spp, report, st["shade_events"], int(z["events"])))
+    out = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out):
+        import json
+        json.dump({"scene": "bathroom2", "res": [1600, 900], "bounces": int(z["bounces"]), "spp": spp, "rel_l2": report, "gate": 1e-3,
+                   "gpu_samples": st["shade_events"], "oracle_samples": int(z["events"])}, open(os.path.join(out, "parity_bathroom2_1024spp.json"), "w"))
+    assert report["COMPOSITED_C"] < 1e-3, report
+    assert abs(st["shade_events"] - int(z["events"])) <= 1e-4 * int(z["events"])
 
 
 def test_full_size_workload_properties(fb):

@@ -204,3 +204,19 @@ def test_fractional_part_equals_fmodf():
     a = np.concatenate([rng.random(20000, dtype=np.float32) * np.float32(10.0) ** rng.integers(-6, 8, 20000).astype(np.float32),
                         np.array([0.0, 1.0, 0.5, 1e-30, 3.0e38, 16777216.0, 8388607.5], np.float32)])
     assert np.array_equal((a - np.trunc(a)).view(np.uint32), np.fmod(a, np.float32(1.0)).view(np.uint32))
+
+
+def test_malformed_obj_indices_are_rejected(fb, tmp_path):
+    """face indices are range-checked (index 0 aliases NOT_PROVIDED, indices past the element count reach the mesh arrays)."""
+    p = tmp_path / "bad.obj"
+    p.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 7\n")
+    with pytest.raises(RuntimeError, match="out of range"):
+        fb.Scene(["-i", str(p), "-r", "16", "16"])
+    p.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nvn 0 0 1\nf 1//0 2//1 3//1\n")
+    with pytest.raises(RuntimeError, match="invalid normal index 0"):
+        fb.Scene(["-i", str(p), "-r", "16", "16"])
+    p.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nf -1 -2 -9\n")
+    with pytest.raises(RuntimeError, match="invalid vertex index -9"):
+        fb.Scene(["-i", str(p), "-r", "16", "16"])
+    p.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nf -1 -2 -3\n")          # relative indices that do resolve are fine
+    fb.Scene(["-i", str(p), "-r", "16", "16"]).close()

@@ -18,6 +18,14 @@ REF = os.environ.get("FERMAT_REFERENCE", "/root/reference")
 CACHE = os.path.join(ROOT, "scenes", "_cache")
 
 
+DIRLIGHT_FA = """# CornellBox-JP lit by its area light and two directional lights (test fixture for pathtracer_core.h:870-988)
+Camera persp eye 0 1.3 1.5 aim -0.01 0.945 -0.025 up 0 1 0 fov 1.81
+LoadScene %s
+DirectionalLight direction 0.3 -0.4 -1.0 color 2.0 1.9 1.6
+DirectionalLight dir -0.5 -0.3 -1.0 color 0.4 0.5 0.9
+"""
+
+
 def snapshot(args, out):
     import fermat_b200 as fb
     if not os.path.exists(out):
@@ -46,6 +54,13 @@ def main(which=None):
                                   os.path.join(ROOT, "tests", "golden", "cornellbox_jp.fbs"))
     done["cornellbox_glossy"] = snapshot(["-i", os.path.join(cb, "CornellBox-Glossy.obj"), "-c", os.path.join(cb, "camera-frontal.txt")],
                                          os.path.join(CACHE, "cornellbox_glossy.fbs"))
+    # a12 fixture: CornellBox with two DirectionalLights shining in through the open front (grammar: src/mesh/fermat_loader.cpp:294-349;
+    # the reference's own example is models/bathroom2/bathroom_cornell.fa). Written next to the .obj's directory on the search path.
+    fa = os.path.join(CACHE, "_cornellbox_dirlight.fa")
+    with open(fa, "w") as f:
+        f.write(DIRLIGHT_FA % os.path.join(cb, "CornellBox-JP.obj"))
+    done["cornellbox_dirlight"] = snapshot(["-i", fa], os.path.join(ROOT, "tests", "golden", "cornellbox_dirlight.fbs"))
+    os.remove(fa)
     if which == "small":
         return done
     # C4: water_caustic
