@@ -32,8 +32,6 @@ struct WideBvh
 // one child slot of a WideNode)
 void build_bvh2(const Mesh& mesh, Bvh2& bvh, uint32 max_leaf_size = 3);
 
-// the same with spatial splits (sbvh.cpp): a triangle may be referenced from several leaves (index.size() >= #triangles)
-void build_sbvh2(const Mesh& mesh, Bvh2& bvh, uint32 max_leaf_size = 3);
 
 // SAH cost of a Bvh2 (node cost 1.2? no: plain  sum_area(inner)/area(root) * c_t + sum_area(leaf)*n/area(root) * c_i )
 float compute_sah_cost(const Bvh2& bvh, float c_trav = 1.0f, float c_isect = 1.0f);

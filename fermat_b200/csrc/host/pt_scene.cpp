@@ -207,8 +207,7 @@ void scene_init(fb200_scene& s, int argc, const char* const* argv)
 			++i;
 			if (strcmp(argv[i], "sah") == 0) s.bvh_builder = 0;
 			else if (strcmp(argv[i], "lbvh") == 0) s.bvh_builder = 1;
-			else if (strcmp(argv[i], "sbvh") == 0) s.bvh_builder = 2;
-			else throw std::runtime_error(std::string("unknown -bvh builder: ") + argv[i] + " (sah | sbvh | lbvh)");
+			else throw std::runtime_error(std::string("unknown -bvh builder: ") + argv[i] + " (sah | lbvh)");
 		}
 	}
 	if (s.aspect == 0.0f) s.aspect = float(s.res_x) / float(s.res_y);
@@ -243,14 +242,14 @@ void scene_init(fb200_scene& s, int argc, const char* const* argv)
 	// -bvh lbvh: the tree is built on the device when a context is created (RenderingContext::build_lbvh)
 	if (const char* e = getenv("FB200_BVH_BUILDER"))      // experiments: override the builder without touching the command line
 	{
-		if (strcmp(e, "sah") == 0) s.bvh_builder = 0; else if (strcmp(e, "lbvh") == 0) s.bvh_builder = 1; else if (strcmp(e, "sbvh") == 0) s.bvh_builder = 2;
+		if (strcmp(e, "sah") == 0) s.bvh_builder = 0; else if (strcmp(e, "lbvh") == 0) s.bvh_builder = 1;
 	}
 	if (s.bvh_builder != 1)
 	{
 		const bool verbose = getenv("FB200_BVH_VERBOSE") != NULL;
 		auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
 		const double t_start = now();
-		if (s.bvh_builder == 2) build_sbvh2(s.scene.mesh, s.bvh2, 3); else build_bvh2(s.scene.mesh, s.bvh2, 3);
+		build_bvh2(s.scene.mesh, s.bvh2, 3);
 		const double t_built = now();
 		// insertion-based optimisation of the finished tree (bvh_opt.cpp): -bvh-opt / FB200_BVH_OPT = passes (0: off). Host probe
 		// (tools/bvh_quality.py, wide nodes visited per ray with 0 / 8 passes): bathroom2 5.65 / 5.11 (SAH cost 32.3 / 28.7, +0.3 s),
@@ -272,12 +271,13 @@ void scene_init(fb200_scene& s, int argc, const char* const* argv)
 		}
 		if (!collapsed) collapse_to_wide(s.scene.mesh, s.bvh2, s.wide);
 		if (verbose) fprintf(stderr, "  bvh: build %.2f s, optimisation + collapse %.2f s\n", t_built - t_start, now() - t_built);
-		// any-hit child order. FB200_SHADOW_ORDER = near (default: what every GPU measurement so far used) | far | auto (farthest first
-		// when the host probe sees at least 5 % fewer node visits that way)
+		// any-hit child order. FB200_SHADOW_ORDER = auto (default: farthest first when the host probe sees at least 5 % fewer node
+		// visits that way) | near | far. Measured on the B200 (profiles/README.md, r2a sweep, bathroom2 headline workload):
+		// near 1471, far 1527, auto 1516 Msamples/s; every round-1 number was measured with `near`.
 		const char* so = getenv("FB200_SHADOW_ORDER");
 		probe_shadow_order(s);
 		const bool better = s.shadow_probe[0] > 0.0f && s.shadow_probe[1] < 0.95f * s.shadow_probe[0];
-		s.shadow_far_first = so && (strcmp(so, "far") == 0 || (strcmp(so, "auto") == 0 && better));
+		s.shadow_far_first = so ? (strcmp(so, "far") == 0 || (strcmp(so, "auto") == 0 && better)) : better;
 		if (verbose) fprintf(stderr, "  shadow rays: %.2f wide nodes per ray nearest-first, %.2f farthest-first -> %s\n", s.shadow_probe[0], s.shadow_probe[1], s.shadow_far_first ? "far" : "near");
 	}
 

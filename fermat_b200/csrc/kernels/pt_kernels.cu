@@ -621,27 +621,31 @@ __global__ void __launch_bounds__(128, FB_SHADE_MIN_BLOCKS) k_shade(DeviceScene 
 	for (uint32 idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_round; idx += gridDim.x * blockDim.x)
 	{
 		bool valid = idx < n;
-		// outputs of this lane
-		bool dl_on = false, nee_on = false, scat_on = false;
-		float4 dl_o, dl_d, dl_wd, dl_wg, nee_o, nee_d, nee_wd, nee_wg, sc_o, sc_d, sc_w;
-		uint32 sc_info = 0, info = 0;
+		// Every phase below (directional light, next-event estimation, scattering) appends its queue entry right behind its own
+		// arithmetic, with the whole warp taking part in the ballot: an entry is 12-16 registers, and holding all of them to the end
+		// of the iteration (as r01 did) is what pushed the kernel into spills. State that outlives a phase is declared here.
+		uint32 info = 0, pixel = 0, comp = 0, tri = 0;
+		float hit_t = 0.0f, p_prev = 0.0f;
+		float z[6] = { 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f };
+		V3 position, ray_d, in, w, kd, ke;
+		Frame g; BsdfParams b;
 		// PSF: this vertex's / the scattered path's CacheInfo, the scattered ray's cone, the reference this vertex appends
-		uint32 vinfo = FB_PSF_INVALID, sc_vinfo = FB_PSF_INVALID; float2 sc_cone = make_float2(0.0f, 0.0f);
+		uint32 vinfo = FB_PSF_INVALID, prev_vinfo = FB_PSF_INVALID; bool new_entry = false; float cone_radius = 0.0f;
 		bool ref_on = false; float4 ref_wd, ref_wg; uint32 ref_cache = FB_PSF_INVALID;
 
 		float4 hit = make_float4(-1.0f, 0.0f, 0.0f, 0.0f);
 		if (valid) { hit = ld_stream(a.in.hit + idx); valid = (hit.x > 0.0f) && (__float_as_int(hit.y) >= 0); }
 		if (valid)
 		{
-			const uint32 tri = __float_as_uint(hit.y);
+			tri = __float_as_uint(hit.y); hit_t = hit.x;
 			const float4 ro = ld_stream(a.in.ray_o + idx), rd = ld_stream(a.in.ray_d + idx), w4 = ld_stream(a.in.weight + idx);
 			info = ld_stream(a.in.pixel + idx);
-			const uint32 pixel = info & 0x07FFFFFFu, comp = (info >> 27) & 0xFu;
-			const V3 ray_o(ro), ray_d(rd), w(w4);
-			const float p_prev = w4.w;
+			pixel = info & 0x07FFFFFFu; comp = (info >> 27) & 0xFu;
+			const V3 ray_o(ro);
+			ray_d = V3(rd); w = V3(w4);
+			p_prev = w4.w;
 
 			// the samples of this vertex depend on the pixel only: fetch them before the geometry gathers start
-			float z[6];
 			vertex_samples(sc, pixel % sc.res_x, pixel / sc.res_x, (bounce + 1) * 6, a.seq, z);
 #if FB_SHADE_PREFETCH
 			// The light vertex of next-event estimation is a second gather chain (VPL -> triangle indices -> vertices ->
@@ -659,23 +663,21 @@ __global__ void __launch_bounds__(128, FB_SHADE_MIN_BLOCKS) k_shade(DeviceScene 
 #endif
 
 			// ---- EyeVertex::setup (src/bpt_utils.h:585-642) ----
-			Frame g; V3 unused; float s, t;
+			V3 unused; float s, t;
 			setup_geometry<false>(sc, tri, hit.z, hit.w, g, unused, s, t);
-			const V3 position = ray_o + hit.x * ray_d;
+			position = ray_o + hit.x * ray_d;
 			const MeshMaterial* m = sc.materials + __ldg(sc.material_indices + tri);
 			const float4* m4 = reinterpret_cast<const float4*>(m);
 			const float4 mp = __ldg(m4 + 6);                      // roughness, ior, opacity, flags
-			const V3 kd = V3(__ldg(m4 + 0)) * texture_rgb(sc, s, t, load_texref(m, 8));
+			kd = V3(__ldg(m4 + 0)) * texture_rgb(sc, s, t, load_texref(m, 8));
 			const V3 ks = V3(__ldg(m4 + 3)) * texture_rgb(sc, s, t, load_texref(m, 10));
-			const V3 ke = V3(__ldg(m4 + 4)) * texture_rgb(sc, s, t, load_texref(m, 11));
+			ke = V3(__ldg(m4 + 4)) * texture_rgb(sc, s, t, load_texref(m, 11));
 			const V3 td = V3(__ldg(m4 + 1)) * texture_rgb(sc, s, t, load_texref(m, 9));
 			const V3 kr = V3(__ldg(m4 + 5));
-			const V3 in = -normalize(ray_d);
-			BsdfParams b;
+			in = -normalize(ray_d);
 			bsdf_init(b, kd, td, ks, kr, mp.x, mp.y, mp.z);
 
 			// ---- PSFPTVertexProcessor::preprocess_vertex (src/psfpt_vertex_processor.h:123-199); cone radius: src/pathtracer_core.h:816-819 ----
-			uint32 prev_vinfo = FB_PSF_INVALID; bool new_entry = false; float cone_radius = 0.0f;
 			if (PSF)
 			{
 				const float2 cone = a.in.cone[idx];
@@ -741,9 +743,14 @@ __global__ void __launch_bounds__(128, FB_SHADE_MIN_BLOCKS) k_shade(DeviceScene 
 				prefetch_l1(lm + 64); prefetch_l1(lm + 176);      // emissive colour, emissive map reference
 			}
 #endif
+		}
 
-			// ---- directional lights (pathtracer_core.h:870-988) ----
-			if (DIRLIGHT && a.do_dirlight)
+		// ---- directional lights (pathtracer_core.h:870-988) ----
+		if (DIRLIGHT && a.do_dirlight)
+		{
+			bool dl_on = false;
+			float4 dl_o, dl_d, dl_wd, dl_wg;
+			if (valid)
 			{
 				const uint32 li = (uint32)max(min((int)(z[2] * float(sc.n_dir_lights)), (int)(sc.n_dir_lights - 1)), 0);
 				const DirectionalLight L = sc.dir_lights[li];
@@ -776,9 +783,20 @@ __global__ void __launch_bounds__(128, FB_SHADE_MIN_BLOCKS) k_shade(DeviceScene 
 					dl_wg = make_float4(w_g.x, w_g.y, w_g.z, 0.0f);
 				}
 			}
+			// Not into the next-event queue: a pixel would then own two entries of one queue, and the accumulation pass adds to the frame
+			// buffer without atomics, one thread per entry (the reference's solve_occlusion has exactly that race,
+			// src/pathtracer_core.h:705-738). The two queues are traced and accumulated one after the other: directional light first, then
+			// next-event estimation, the order of the queue entries in the reference.
+			const uint32 slot = warp_append_slot(&a.ctr->dl_size[bounce], dl_on);
+			if (dl_on) { st_stream(a.sq_dl.ray_o + slot, dl_o); st_stream(a.sq_dl.ray_d + slot, dl_d); st_stream(a.sq_dl.w_d + slot, dl_wd); st_stream(a.sq_dl.w_g + slot, dl_wg); }
+		}
 
-			// ---- next-event estimation (pathtracer_core.h:991-1106) ----
-			if (a.do_nee)
+		// ---- next-event estimation (pathtracer_core.h:991-1106) ----
+		if (a.do_nee)
+		{
+			bool nee_on = false;
+			float4 nee_o, nee_d, nee_wd, nee_wg;
+			if (valid)
 			{
 				uint32 prim; float lu, lv;
 				if (sc.use_vpls)
@@ -833,40 +851,50 @@ __global__ void __launch_bounds__(128, FB_SHADE_MIN_BLOCKS) k_shade(DeviceScene 
 					nee_wg = make_float4(w_g.x, w_g.y, w_g.z, 0.0f);
 				}
 			}
+			// queue append: whole warp, one atomic (warp-ballot compaction)
+			const uint32 slot = warp_append_slot(shadow_counter, nee_on);
+			if (nee_on) { st_stream(a.sq.ray_o + slot, nee_o); st_stream(a.sq.ray_d + slot, nee_d); st_stream(a.sq.w_d + slot, nee_wd); st_stream(a.sq.w_g + slot, nee_wg); }
+			if (PSF && nee_on) a.sq.vinfo[slot] = vinfo;
+		}
 
-			// ---- emissive hit with MIS against NEE at the previous vertex (pathtracer_core.h:1109-1154) ----
-			if (a.do_emissive)
+		// ---- emissive hit with MIS against NEE at the previous vertex (pathtracer_core.h:1109-1154) ----
+		if (a.do_emissive && valid)
+		{
+			float light_pdf;
+			if (sc.use_vpls) light_pdf = fmaxf(fabsf(ke.x), fmaxf(fabsf(ke.y), fabsf(ke.z))) / sc.vpl_norm;
+			else light_pdf = (__ldg(sc.mesh_cdf + tri) - (tri ? __ldg(sc.mesh_cdf + tri - 1) : 0.0f)) * __ldg(sc.mesh_inv_area + tri);
+			const V3 f_L = dot(g.normal_s, in) > 0.0f ? ke : V3(0.0f);
+			const float d2 = fmaxf(1.0e-10f, hit_t * hit_t);
+			const float G_partial = fabsf(dot(in, g.normal_s)) / d2;
+			const float p1 = pdf_product(G_partial, p_prev), p2 = light_pdf;
+			const float mis_w = ((bounce == 1 && o.direct_lighting_nee) || (bounce > 1 && o.indirect_lighting_nee)) ? power_heuristic(p1, p2) : 1.0f;
+			const V3 ow = w * f_L * mis_w;
+			if (max_comp(ow) > 0.0f && is_finite(ow))
 			{
-				float light_pdf;
-				if (sc.use_vpls) light_pdf = fmaxf(fabsf(ke.x), fmaxf(fabsf(ke.y), fabsf(ke.z))) / sc.vpl_norm;
-				else light_pdf = (__ldg(sc.mesh_cdf + tri) - (tri ? __ldg(sc.mesh_cdf + tri - 1) : 0.0f)) * __ldg(sc.mesh_inv_area + tri);
-				const V3 f_L = dot(g.normal_s, in) > 0.0f ? ke : V3(0.0f);
-				const float d2 = fmaxf(1.0e-10f, hit.x * hit.x);
-				const float G_partial = fabsf(dot(in, g.normal_s)) / d2;
-				const float p1 = pdf_product(G_partial, p_prev), p2 = light_pdf;
-				const float mis_w = ((bounce == 1 && o.direct_lighting_nee) || (bounce > 1 && o.indirect_lighting_nee)) ? power_heuristic(p1, p2) : 1.0f;
-				const V3 ow = w * f_L * mis_w;
-				if (max_comp(ow) > 0.0f && is_finite(ow))
+				// PTVertexProcessor::accumulate_emissive, or PSFPTVertexProcessor's (src/psfpt_vertex_processor.h:326-369): clamped, and
+				// into the cache cell once the path feeds one
+				const V3 cw = PSF ? psf_clamp_sample(ow, a.psf.firefly_filter) : ow;
+				if (!PSF || psf_slot(prev_vinfo) == FB_PSF_INVALID_SLOT)
 				{
-					// PTVertexProcessor::accumulate_emissive, or PSFPTVertexProcessor's (src/psfpt_vertex_processor.h:326-369): clamped, and
-					// into the cache cell once the path feeds one
-					const V3 cw = PSF ? psf_clamp_sample(ow, a.psf.firefly_filter) : ow;
-					if (!PSF || psf_slot(prev_vinfo) == FB_PSF_INVALID_SLOT)
+					add_in<false>(a.fb.channels[FB_COMPOSITED_C], pixel, cw, a.frame_weight);
+					if (bounce == 0) add_in<false>(a.fb.channels[FB_DIRECT_C], pixel, cw, a.frame_weight);
+					else
 					{
-						add_in<false>(a.fb.channels[FB_COMPOSITED_C], pixel, cw, a.frame_weight);
-						if (bounce == 0) add_in<false>(a.fb.channels[FB_DIRECT_C], pixel, cw, a.frame_weight);
-						else
-						{
-							if (comp & kDiffuseMask) add_in<true>(a.fb.channels[FB_DIFFUSE_C], pixel, cw, a.frame_weight);
-							if (comp & kGlossyMask)  add_in<true>(a.fb.channels[FB_SPECULAR_C], pixel, cw, a.frame_weight);
-						}
+						if (comp & kDiffuseMask) add_in<true>(a.fb.channels[FB_DIFFUSE_C], pixel, cw, a.frame_weight);
+						if (comp & kGlossyMask)  add_in<true>(a.fb.channels[FB_SPECULAR_C], pixel, cw, a.frame_weight);
 					}
-					else psf_add(a.psf, psf_slot(prev_vinfo), cw);
 				}
+				else psf_add(a.psf, psf_slot(prev_vinfo), cw);
 			}
+		}
 
-			// ---- scattering with implicit Russian roulette (pathtracer_core.h:1157-1247) ----
-			if (a.do_scatter)
+		// ---- scattering with implicit Russian roulette (pathtracer_core.h:1157-1247) ----
+		if (a.do_scatter)
+		{
+			bool scat_on = false;
+			float4 sc_o, sc_d, sc_w; uint32 sc_info = 0;
+			uint32 sc_vinfo = FB_PSF_INVALID; float2 sc_cone = make_float2(0.0f, 0.0f);
+			if (valid)
 			{
 				uint32 out_comp; V3 out, gg; float p, p_proj;
 				bsdf_sample(b, sc.glossy_reflectance, g, z[3], z[4], z[5], in, out_comp, out, p, p_proj, gg);
@@ -888,22 +916,6 @@ __global__ void __launch_bounds__(128, FB_SHADE_MIN_BLOCKS) k_shade(DeviceScene 
 					sc_info = pixel | ((out_comp & 0xFu) << 27) | (diffuse_flag << 31);
 				}
 			}
-		}
-
-		// ---- queue appends: whole warp, one atomic per queue (warp-ballot compaction) ----
-		if (DIRLIGHT && a.do_dirlight)
-		{
-			const uint32 slot = warp_append_slot(shadow_counter, dl_on);
-			if (dl_on) { st_stream(a.sq.ray_o + slot, dl_o); st_stream(a.sq.ray_d + slot, dl_d); st_stream(a.sq.w_d + slot, dl_wd); st_stream(a.sq.w_g + slot, dl_wg); }
-		}
-		if (a.do_nee)
-		{
-			const uint32 slot = warp_append_slot(shadow_counter, nee_on);
-			if (nee_on) { st_stream(a.sq.ray_o + slot, nee_o); st_stream(a.sq.ray_d + slot, nee_d); st_stream(a.sq.w_d + slot, nee_wd); st_stream(a.sq.w_g + slot, nee_wg); }
-			if (PSF && nee_on) a.sq.vinfo[slot] = vinfo;
-		}
-		if (a.do_scatter)
-		{
 			const uint32 slot = warp_append_slot(scatter_counter, scat_on);
 			if (scat_on) { st_stream(a.out.ray_o + slot, sc_o); st_stream(a.out.ray_d + slot, sc_d); st_stream(a.out.weight + slot, sc_w); st_stream(a.out.pixel + slot, sc_info); }
 			if (PSF && scat_on) { a.out.cone[slot] = sc_cone; a.out.vinfo[slot] = sc_vinfo; }

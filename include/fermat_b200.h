@@ -95,8 +95,7 @@ typedef struct fb200_scene_view
 	uint32_t n_bvh_nodes; const void* bvh_nodes; const uint32_t* bvh_index;
 	float    bbox_min[3], bbox_max[3];
 	fb200_pt_options options;
-	/* entries of bvh_index: num_triangles, or more when the tree was built with spatial splits (`-bvh sbvh`: a triangle
-	 * may be referenced from several leaves) */
+	/* entries of bvh_index (= num_triangles; a builder with spatial splits may reference a triangle from several leaves) */
 	uint32_t n_bvh_index;
 	fb200_psf_options psf;
 } fb200_scene_view;
@@ -119,7 +118,7 @@ const char* fb200_last_error(void);
  * and PTOptions::parse (src/renderers/pathtracer.h:202-249), plus:
  *   -tables <file>   packed sampler/BSDF tables (default: fermat_b200/data/pt_tables.bin)
  *   -shard r n       this process renders tile shard r of n (default 0 1)
- *   -bvh sah|sbvh|lbvh   scene BVH builder (binned SAH on the host, with spatial splits, or CUGAR's LBVH on the device)
+ *   -bvh sah|lbvh        scene BVH builder (binned SAH on the host, or CUGAR's LBVH on the device)
  *   -bvh-opt N       rounds of insertion-based optimisation of the host-built tree (default 8, 0 = off)
  * then loads the scene, builds sampler tables, VPLs (n_vpls = res_x*res_y) and the BVH.
  * Returns NULL on failure (see fb200_last_error). */

@@ -306,15 +306,22 @@ def test_bathroom2_full_size_against_oracle(fb, oracle):
         pytest.skip("bathroom2 snapshot not present")
     spp = 8
     got, fbuf, st, (events, shadow) = _render_both(fb, oracle, ["-i", path, "-r", "1600", "900", "-bounces", "8"], spp, threads=len(os.sched_getaffinity(0)))
-    for name in ALL_CHANNELS:
-        g, o = got[name], fbuf[fb.FB_CHANNELS[name]]
-        assert np.isfinite(g).all()
-        assert rel_l2(g, o) < 1e-3, (name, rel_l2(g, o))
+    # At a coplanar near-tie (two overlapping triangles hit one or two ulps apart) the two sides' different trees may keep a
+    # different one of the pair, and that pixel's path is then a different sample of the same estimator. Equal-spp L2 is
+    # dominated by those few pixels (each weighs 1/spp: 1.08e-3 at 8 spp, 4e-4 at 32 spp, and the 1024-spp gate is the test
+    # below), so the statement here is per pixel: all but a handful of the 1.44 M pixels agree, and the rest of the image to 1e-5.
     g, o = got["COMPOSITED_C"], fbuf[5]
     bad = (np.abs(g[..., :3] - o[..., :3]).max(axis=2) > 1e-3 * (1 + o[..., :3].max(axis=2)))
     print("bathroom2 1600x900 %d spp: rel L2 %.3e, %d of %d pixels took a different path, samples gpu %d / oracle %d" % (
         spp, rel_l2(g, o), bad.sum(), bad.size, st["shade_events"], events))
-    assert bad.mean() < 1e-3
+    assert bad.mean() < 1e-4, bad.sum()
+    for name in ALL_CHANNELS:
+        g, o = got[name], fbuf[fb.FB_CHANNELS[name]]
+        assert np.isfinite(g).all()
+        assert rel_l2(g, o) < 3e-3, (name, rel_l2(g, o))
+        gm, om = g.copy(), o.copy()
+        gm[bad] = 0; om[bad] = 0
+        assert rel_l2(gm, om) < 1e-5, (name, rel_l2(gm, om))
     assert abs(st["shade_events"] - events) <= 1e-4 * events and abs(st["shadow_events"] - shadow) <= 1e-4 * shadow
 
 
