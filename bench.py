@@ -9,7 +9,9 @@ counter `stats.shade_events`, src/pathtracer_kernels.h:360).
 
 A step is one progressive pass (render(instance)) over the frame. Workload at N = 1: BASELINE.json configs[1],
 bathroom2 1600x900, 8 bounces. For N > 1 the frame grows with N at constant pixels per GPU (weak scaling, same camera),
-tile-sharded over the ranks with ONE NCCL reduce of the accumulated image per pass.
+tile-sharded over the ranks with ONE NCCL collective per pass: the product's own frame gather (fb200_context_gather_image: every rank
+sends its packed tiles to rank 0 over NVLink). Every run also reports BASELINE.json configs[4] as named - bathroom2 3840x2160 FIXED,
+tile-sharded over the N GPUs (strong scaling) - in the `strong_c5` block of the same line.
 Prints one JSON line (rank 0).
 """
 import argparse
@@ -165,6 +167,56 @@ def run_reference(args):
         "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+def strong_c5(args, make_context, make_step, sync_all, rank, world, local):
+    """BASELINE.json configs[4]: bathroom2 -pt 3840x2160, 8 bounces, the FIXED frame tile-sharded over the N GPUs (strong scaling) with the
+    frame gather per pass. Device-timed (max over ranks) and end to end (rank 0 reads every assembled frame back); N = 1 is the base."""
+    import torch
+    import torch.distributed as dist
+    res = (3840, 2160)
+    sc, rc = make_context(res)
+    hosts = [torch.empty((res[1], res[0], 4), dtype=torch.float32, pin_memory=True) for _ in range(2)] if rank == 0 else [None, None]
+    step = make_step(rc, hosts)
+    stream = torch.cuda.ExternalStream(rc.stream(), device=torch.device("cuda", local))
+    steps = max(8, args.steps // 2)
+    rc.clear()
+    for i in range(args.warmup):
+        step(i)
+    sync_all(rc)
+    s0 = rc.stats()["shade_events"]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for i in range(args.warmup, args.warmup + steps):
+        step(i)
+    rc.stream()
+    ev1.record(stream)
+    sync_all(rc)
+    ms = ev0.elapsed_time(ev1)
+    s1 = rc.stats()["shade_events"]
+    for i in range(args.warmup + steps, 2 * args.warmup + steps):
+        step(i, read_back=True)
+    sync_all(rc)
+    w0 = time.perf_counter()
+    for i in range(2 * args.warmup + steps, 2 * args.warmup + 2 * steps):
+        step(i, read_back=True)
+    sync_all(rc)
+    e2e_s = time.perf_counter() - w0
+    s2 = rc.stats()["shade_events"]
+    t = torch.tensor([ms, e2e_s, float(s1 - s0), float(s2 - s1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        t = torch.stack([tmax[0], tmax[1], tsum[2], tsum[3]])
+    ms, e2e_s, samples, e_samples = (float(x) for x in t)
+    owned = rc.owned_pixels()
+    rc.close(); sc.close()
+    # (the e2e window renders warmup + steps passes; only the last `steps` are inside the wall-clock span)
+    e_samples *= steps / float(args.warmup + steps)
+    return {"workload": "bathroom2 -pt 3840x2160, %d bounces, frame FIXED, tile-sharded x%d (BASELINE.json configs[4])" % (BOUNCES, world), "scaling": "strong",
+            "n_gpus": world, "steps": steps, "value": samples / (ms * 1e-3) * 1e-6, "unit": "Msamples/s", "ms_per_step": ms / steps,
+            "e2e": {"value": e_samples / e2e_s * 1e-6, "unit": "Msamples/s", "d2h_bytes_per_step": res[0] * res[1] * 16},
+            "pixels_this_rank": owned, "note": "speed-up at N GPUs = this value / the strong_c5 value of the N = 1 run"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -183,66 +235,68 @@ def run_ours(args):
 
     scene, name = workload(args)
     res = frame_size(args, world)
-    # --psfpt: the path-space filtering renderer on the same workload (not the headline metric: BASELINE.json names -pt)
-    sc = fb.Scene(["-i", scene, "-r", str(res[0]), str(res[1]), "-bounces", str(BOUNCES), "-shard", str(rank), str(world)] + (["-psfpt"] if args.psfpt else []))
-    rc = fb.RenderingContext(sc, local)
-    stream = torch.cuda.ExternalStream(rc.stream(), device=torch.device("cuda", local))
-    comp = rc.fb_tensor("COMPOSITED_C")
-    send = torch.empty_like(comp)
-    host = torch.empty(comp.shape, dtype=torch.float32, pin_memory=True)
-    host_b = torch.empty(comp.shape, dtype=torch.float32, pin_memory=True)     # read-backs alternate between two pinned buffers
-    host_np = host.numpy()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        rc.synchronize()
 
-    # N > 1: reduce buffers and host buffers alternate, so that rank 0's copy of frame i to the host (copy stream) overlaps pass i+1
-    sends = [send, torch.empty_like(comp)] if world > 1 else [send]
-    hosts = [host, host_b]
-    copy_stream = torch.cuda.Stream() if world > 1 else None
-    copied = [None, None]
+    def make_context(res):
+        """scene (replicated) + context of this rank's tile shard; for N > 1 the ranks join the product's NCCL communicator"""
+        # --psfpt: the path-space filtering renderer on the same workload (not the headline metric: BASELINE.json names -pt)
+        sc = fb.Scene(["-i", scene, "-r", str(res[0]), str(res[1]), "-bounces", str(BOUNCES), "-shard", str(rank), str(world)] + (["-psfpt"] if args.psfpt else []))
+        rc = fb.RenderingContext(sc, local)
+        if world > 1:
+            ids = [fb.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0, device=torch.device("cuda", local))
+            rc.comm_init(ids[0], rank, world)
+        return sc, rc
 
-    def step(i, reduce_image, read_back=False):
-        rc.render(i, sync=False)
-        if world > 1 and reduce_image:
-            rc.stream()          # orders the context's stream behind the pass just enqueued (and the next pass behind the reduce)
-            sb = sends[i & 1]
-            with torch.cuda.stream(stream):
-                if copied[i & 1] is not None:
-                    stream.wait_event(copied[i & 1])                # the host copy of frame i-2 has left this buffer
-                sb.copy_(comp, non_blocking=True)
-                dist.reduce(sb, dst=0, op=dist.ReduceOp.SUM)        # the single image reduce per frame (NVLink)
-            if read_back and rank == 0:
-                done = torch.cuda.Event()
-                done.record(stream)
-                copy_stream.wait_event(done)
-                with torch.cuda.stream(copy_stream):
-                    hosts[i & 1].copy_(sb, non_blocking=True)
-                    copied[i & 1] = torch.cuda.Event()
-                    copied[i & 1].record(copy_stream)
+    sc, rc = make_context(res)
+    stream = torch.cuda.ExternalStream(rc.stream(), device=torch.device("cuda", local))
+    comp = rc.fb_tensor("COMPOSITED_C")
+    # read-backs alternate between two pinned host buffers
+    hosts = [torch.empty(comp.shape, dtype=torch.float32, pin_memory=True) for _ in range(2)] if rank == 0 else [None, None]
+    host_np = hosts[0].numpy() if rank == 0 else None
+
+    def make_step(rc, hosts):
+        def step(i, read_back=False):
+            """one progressive pass; N > 1: + the frame gather (every rank packs and sends its tiles, rank 0 assembles the frame), the
+            one collective of the path. With read_back, rank 0 also copies the (assembled) frame of THIS pass to pinned host memory.
+            Everything is asynchronous: the copy / the gather of pass i overlap the rendering of pass i+1."""
+            rc.render(i, sync=False)
+            dst = hosts[i & 1].data_ptr() if (read_back and rank == 0) else None
+            if world > 1:
+                rc.gather_image(0, dst)
+            elif dst is not None:
+                rc.download_async(dst)
+        return step
+
+    step = make_step(rc, hosts)
+
+    def sync_all(ctx=None):
+        (ctx or rc).synchronize()
+        barrier()
 
     rc.clear()
     for i in range(args.warmup):
-        step(i, True)
-    barrier()
+        step(i)
+    sync_all()
 
-    # ---------------- device-timed region: K passes, inputs resident in HBM ----------------
+    # ---------------- device-timed region: K passes (+ K frame gathers for N > 1), inputs resident in HBM ----------------
     s0 = rc.stats()
     clocks = ClockSampler(local) if rank == 0 else None
     if clocks:
         clocks.start()
-    barrier()
+    sync_all()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     wall0 = time.perf_counter()
     for i in range(args.warmup, args.warmup + args.steps):
-        step(i, True)
-    rc.stream()                  # join: the passes run on the renderer's private streams
+        step(i)
+    rc.stream()                  # join: the passes run on the renderer's private streams, the gather on its copy stream
     ev1.record(stream)
-    barrier()
+    sync_all()
     wall = time.perf_counter() - wall0
     ms = ev0.elapsed_time(ev1)
     clk = clocks.stop() if clocks else None
@@ -274,38 +328,29 @@ def run_ours(args):
     # are created on first use, the copy engine and the PCIe link of a GPU that has sat idle through the reference arm
     # come up from a low-power state: on a fresh box the first bench of a session measured 400-550 Msamples/s end to end
     # where every later one measured ~1290). Then copies of the frame until their rate has settled (bounded at 2 s).
-    barrier()
+    sync_all()
     e2e_first = args.warmup + 2 * args.steps
     for i in range(e2e_first, e2e_first + args.warmup):
-        step(i, True, read_back=True)
-        if rank == 0 and world == 1:
-            rc.download_async(hosts[i & 1].data_ptr())
-    if copy_stream is not None:
-        copy_stream.synchronize()
-    barrier()
+        step(i, read_back=True)
+    sync_all()
     pcie_gbs = None
     if rank == 0:
         rates, t_end = [], time.perf_counter() + 2.0
         while time.perf_counter() < t_end:
             t0 = time.perf_counter()
-            host.copy_(comp, non_blocking=True)
+            hosts[0].copy_(comp, non_blocking=True)
             torch.cuda.synchronize()
             rates.append(comp.numel() * 4 / (time.perf_counter() - t0) * 1e-9)
             if len(rates) >= 8 and max(rates[-4:]) < 1.05 * min(rates[-4:]):
                 break
         pcie_gbs = rates[-1]
     e2e_first += args.warmup
-    barrier()
+    sync_all()
     e0 = rc.stats()["shade_events"]
     w0 = time.perf_counter()
     for i in range(e2e_first, e2e_first + args.steps):
-        step(i, True, read_back=True)
-        if rank == 0 and world == 1:
-            # every pass's frame goes to pinned host memory; the copy of pass i overlaps the rendering of pass i+1
-            rc.download_async(hosts[i & 1].data_ptr())
-    if copy_stream is not None:
-        copy_stream.synchronize()
-    barrier()
+        step(i, read_back=True)      # every pass's frame goes to pinned host memory; the copy of pass i overlaps the rendering of pass i+1
+    sync_all()
     e2e_s = time.perf_counter() - w0
     e_samples = rc.stats()["shade_events"] - e0
     te = torch.tensor([e2e_s, float(e_samples)], dtype=torch.float64, device="cuda")
@@ -315,6 +360,15 @@ def run_ours(args):
         e2e_s, e_samples = float(a[0]), float(b[1])
     e2e_value = e_samples / e2e_s * 1e-6
     finite = bool(np.isfinite(host_np).all()) if rank == 0 else True
+    h2d_bytes = 4 * sc.view.n_dimensions + 96
+    d2h_bytes = int(comp.numel() * 4)
+    del comp
+    rc.close(); sc.close()
+
+    # ---------------- BASELINE.json configs[4] as named: bathroom2 3840x2160 FIXED, tile-sharded over the N GPUs ----------------
+    strong = None
+    if not args.no_strong and not args.psfpt and not args.res and name == "bathroom2":
+        strong = strong_c5(args, make_context, make_step, sync_all, rank, world, local)
 
     if rank != 0:
         if world > 1:
@@ -359,20 +413,23 @@ def run_ours(args):
     roofline = {"bound": "hbm", "kernel": {"trace": "k_trace<closest>", "shade": "k_shade", "shadow": "k_trace<shadow>+accumulate"}[dom],
                 "achieved": kernels[dom]["algorithmic_GBps"], "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": kernels[dom]["algorithmic_GBps"] / peak, "traffic": traffic,
+                "traffic_source": "profiles/ncu_traffic.json: mean dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel from the committed ncu capture named there (not measured by this run: a bench under ncu is not a bench)",
                 "bytes_note": "algorithmic bytes = SURVEY 8d: reference queue/attribute/FB layouts + 32 B/node + 64 B/tri of the oracle's BVH2 traversal%s" % ("" if trav else " (traversal counts unavailable: queue bytes only)")}
 
     out = {
         "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s %s %dx%d, %d bounces, default seeds, passes %d..%d" % (name, "-psfpt" if args.psfpt else "-pt", res[0], res[1], BOUNCES, args.warmup, args.warmup + args.steps - 1),
-                   "parallelism": "tile-sharded x%d, one NCCL reduce of COMPOSITED per pass" % world if world > 1 else "single GPU",
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "scene bathroom2 of the reference's models/ (snapshot scenes/_cache/bathroom2.fbs), the reference's default sampler seeds; no synthetic rays",
+        "config": {"workload": "%s %s %dx%d, %d bounces" % (name, "-psfpt" if args.psfpt else "-pt", res[0], res[1], BOUNCES),
+                   "passes": "default seeds, instances %d..%d" % (args.warmup, args.warmup + args.steps - 1),
+                   "parallelism": "tile-sharded x%d, one NCCL collective per pass: gather of every rank's packed COMPOSITED tiles on rank 0 (fb200_context_gather_image)" % world if world > 1 else "single GPU",
                    "l2": "working set per pass (queues + 8-channel frame buffer, > 400 MB) exceeds the 126 MB L2",
                    "target": ">= 200 Msamples/s (BASELINE.json)"},
-        "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": 4 * sc.view.n_dimensions + 96, "d2h_bytes_per_step": int(comp.numel() * 4),
+        "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "warmup_steps": args.warmup, "d2h_GBps_after_warmup": pcie_gbs,
                 "note": ("render(instance) through the C ABI + the frame of EVERY pass read back to pinned host memory (fb200_context_fb_download_async: device snapshot, "
                          "then a copy that overlaps the next pass; two host buffers); the scene is resident like model weights") if world == 1 else
-                        "render(instance) through the C ABI on every rank + NCCL reduce + rank 0 copies the reduced frame of EVERY pass to pinned host memory on a copy stream (two reduce / host buffers, the copy of frame i overlaps pass i+1); the scene is resident like model weights"},
+                        "render(instance) through the C ABI on every rank + the frame gather over NCCL + rank 0 copies the assembled frame of EVERY pass to pinned host memory on its copy stream (the gather and copy of frame i overlap pass i+1); the scene is resident like model weights"},
         # every pixel charged the full path length, whether or not its path survived that long
         "nominal": {"value": float(res[0]) * res[1] * (BOUNCES + 1) * args.steps / (ms * 1e-3) * 1e-6, "unit": "Msamples/s",
                     "note": "W x H x (bounces + 1) per pass / device time; `value` counts the shade events that actually happened (%.2f per pixel and pass)" % (samples / (float(res[0]) * res[1] * args.steps))},
@@ -380,6 +437,8 @@ def run_ours(args):
         "clocks": clk, "roofline": roofline, "kernels": kernels,
         "kernels_note": "CUDA-event spans around every launch over K further passes run on ONE stream; in the timed region the shadow trace of bounce b runs beside the closest-hit trace of bounce b+1 on a second stream",
     }
+    if strong:
+        out["strong_c5"] = strong
     if base:
         out["cpu_baseline"] = base
     if trav:
@@ -387,8 +446,6 @@ def run_ours(args):
     emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
-    rc.close()
-    sc.close()
 
 
 _REAL_STDOUT = None
@@ -415,6 +472,7 @@ def main():
     ap.add_argument("--scene", default=None)
     ap.add_argument("--res", type=int, nargs=2, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong_c5 block (bathroom2 3840x2160 fixed, tile-sharded over the N GPUs)")
     ap.add_argument("--psfpt", action="store_true", help="measure the -psfpt renderer instead of -pt (GPU arm only; implies --no-cpu-baseline)")
     args = ap.parse_args()
     if args.warmup < 3:

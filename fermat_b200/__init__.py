@@ -112,6 +112,12 @@ def lib():
         "fb200_context_set_profiling": (i32, [vp, i32]),
         "fb200_context_get_kernel_times": (i32, [vp, C.POINTER(C.c_double * 4), C.POINTER(u64 * 4)]),
         "fb200_context_owned_pixels": (u64, [vp]),
+        "fb200_comm_unique_id": (i32, [vp]),
+        "fb200_context_comm_init": (i32, [vp, vp, i32, i32]),
+        "fb200_context_gather_image": (i32, [vp, i32, i32, vp]),
+        "fb200_context_gathered_device_ptr": (vp, [vp]),
+        "fb200_diag_pack_tiles": (i32, [vp, i32, pf, u64]),
+        "fb200_diag_unpack_tiles": (i32, [vp, u32, u32, pf, u64, pf]),
         "fb200_context_filter": (i32, [vp, u32]),
         "fb200_context_to_rgba": (i32, [vp, u32, vp]),
         "fb200_context_rgba_device_ptr": (vp, [vp]),
@@ -145,6 +151,14 @@ PASS_COUNTERS_DTYPE = np.dtype([("in_size", "<u4", 64), ("shadow_size", "<u4", 6
 
 
 assert PASS_COUNTERS_DTYPE.itemsize == 20480      # sizeof(PassCounters), static_assert'ed in csrc/host/pathtracer.cpp
+
+
+def comm_unique_id():
+    """128 bytes identifying a new NCCL communicator (one rank creates it, every rank passes it to RenderingContext.comm_init)"""
+    buf = (C.c_char * 128)()
+    if lib().fb200_comm_unique_id(C.addressof(buf)) != 0:
+        raise RuntimeError(_err())
+    return bytes(buf)
 
 
 def exported_symbols():
@@ -198,7 +212,22 @@ def scene_available(path):
     return os.path.exists(str(path)) or os.path.exists(str(path) + ".xz")
 
 
-class Scene:
+class _Handle:
+    """`_h` = the C-ABI handle; using a closed object raises instead of handing NULL to the library"""
+    _handle = None
+
+    @property
+    def _h(self):
+        if self._handle is None:
+            raise RuntimeError("%s is closed" % type(self).__name__)
+        return self._handle
+
+    @_h.setter
+    def _h(self, v):
+        self._handle = v
+
+
+class Scene(_Handle):
     """Host-only scene: mesh + materials + textures, sampler tables, VPLs, BVH (no GPU needed)."""
 
     def __init__(self, args):
@@ -207,9 +236,10 @@ class Scene:
             if a == "-i":
                 self.args[i + 1] = resolve_scene(self.args[i + 1])
         argv = (C.c_char_p * len(self.args))(*[a.encode() for a in self.args])
-        self._h = lib().fb200_scene_create(len(self.args), argv)
-        if not self._h:
+        h = lib().fb200_scene_create(len(self.args), argv)
+        if not h:
             raise RuntimeError("fb200_scene_create failed: " + _err())
+        self._h = h
         self.view = SceneView()
         if lib().fb200_scene_get_view(self._h, C.byref(self.view)) != 0:
             raise RuntimeError(_err())
@@ -268,9 +298,9 @@ class Scene:
         return lib().fb200_scene_sample_2d(self._h, instance, px, py, dim)
 
     def close(self):
-        if self._h:
-            lib().fb200_scene_destroy(self._h)
-            self._h = None
+        if self._handle:
+            lib().fb200_scene_destroy(self._handle)
+            self._handle = None
 
     def __del__(self):
         try:
@@ -286,14 +316,15 @@ class _CudaArray:
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
 
 
-class RenderingContext:
+class RenderingContext(_Handle):
     """RenderingContext + PathTracer on one CUDA device (reference src/renderer.h:52-228)."""
 
     def __init__(self, scene, device=0):
         self.scene = scene
-        self._h = lib().fb200_context_create(scene._h, int(device))
-        if not self._h:
+        h = lib().fb200_context_create(scene._h, int(device))
+        if not h:
             raise RuntimeError("fb200_context_create failed: " + _err())
+        self._h = h
         self.device = int(device)
         # `-bvh lbvh` builds the tree while the context is created: refresh the view's pointers to the host copy
         lib().fb200_scene_get_view(scene._h, C.byref(scene.view))
@@ -384,6 +415,37 @@ class RenderingContext:
     def owned_pixels(self):
         return int(lib().fb200_context_owned_pixels(self._h))
 
+    # ---- multi-GPU frame gather (include/fermat_b200.h "multi-GPU") ----
+    def comm_init(self, unique_id, rank, nranks):
+        """join the NCCL communicator of the ranks that shard this frame; `unique_id`: the 128 bytes comm_unique_id() returned on one rank"""
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
+        self._chk(lib().fb200_context_comm_init(self._h, C.addressof(buf), int(rank), int(nranks)))
+
+    def gather_image(self, root=0, pinned_host_ptr=None, channel="COMPOSITED_C"):
+        """every rank, once per frame: this rank's tiles go to `root`, which assembles the frame (asynchronous; synchronize() completes it)"""
+        self._chk(lib().fb200_context_gather_image(self._h, FB_CHANNELS.get(channel, channel), int(root), pinned_host_ptr))
+
+    def gathered_tensor(self):
+        """root: the assembled frame as a CUDA tensor view (H, W, 4)"""
+        import torch
+        w, h = self.res()
+        ptr = lib().fb200_context_gathered_device_ptr(self._h)
+        if not ptr:
+            raise RuntimeError("no frame has been gathered yet")
+        return torch.as_tensor(_CudaArray(ptr, (h, w, 4)), device="cuda:%d" % self.device)
+
+    def pack_tiles(self, n_tiles, channel="COMPOSITED_C"):
+        out = np.zeros(n_tiles * 4096, np.float32)
+        self._chk(lib().fb200_diag_pack_tiles(self._h, FB_CHANNELS.get(channel, channel), _fptr(out), out.size))
+        return out
+
+    def unpack_tiles(self, rank, count, packed):
+        w, h = self.res()
+        packed = np.ascontiguousarray(packed, np.float32)
+        frame = np.zeros((h, w, 4), np.float32)
+        self._chk(lib().fb200_diag_unpack_tiles(self._h, int(rank), int(count), _fptr(packed), packed.size, _fptr(frame)))
+        return frame
+
     def filter(self, instance):
         """RenderingContext::filter: EAW-denoise DIFFUSE_C / SPECULAR_C of the pass just rendered into FILTERED_C."""
         self._chk(lib().fb200_context_filter(self._h, int(instance)))
@@ -436,9 +498,9 @@ class RenderingContext:
         return out
 
     def close(self):
-        if self._h:
-            lib().fb200_context_destroy(self._h)
-            self._h = None
+        if self._handle:
+            lib().fb200_context_destroy(self._handle)
+            self._handle = None
 
     def __del__(self):
         try:

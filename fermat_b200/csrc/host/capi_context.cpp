@@ -84,6 +84,37 @@ int fb200_context_fb_download_async(fb200_context* c, int channel, float* pinned
 	return guarded([&] { c->rc.download_channel_async(channel, pinned_dst); });
 }
 
+// ---- multi-GPU frame gather (RenderingContext::gather_channel_async, host/comm.h) ----
+int fb200_comm_unique_id(void* id128)
+{
+	return guarded([&] { fb::Communicator::unique_id(id128); });
+}
+int fb200_context_comm_init(fb200_context* c, const void* id128, int rank, int nranks)
+{
+	return guarded([&] { c->rc.comm_init(id128, rank, nranks); });
+}
+int fb200_context_gather_image(fb200_context* c, int channel, int root, float* pinned_dst)
+{
+	return guarded([&] { c->rc.gather_channel_async(channel, root, pinned_dst); });
+}
+const float* fb200_context_gathered_device_ptr(fb200_context* c) { return c->rc.gathered_frame(); }
+int fb200_diag_pack_tiles(fb200_context* c, int channel, float* out, uint64_t n_floats)
+{
+	return guarded([&] {
+		std::vector<float> p; c->rc.diag_pack(channel, p);
+		if (p.size() != n_floats) throw std::runtime_error("fb200_diag_pack_tiles: this shard packs " + std::to_string(p.size()) + " floats");
+		if (n_floats) memcpy(out, p.data(), n_floats * sizeof(float));
+	});
+}
+int fb200_diag_unpack_tiles(fb200_context* c, uint32_t rank, uint32_t count, const float* packed, uint64_t n_floats, float* frame)
+{
+	return guarded([&] {
+		std::vector<float> p(packed, packed + n_floats), f;
+		c->rc.diag_unpack(rank, count, p, f);
+		memcpy(frame, f.data(), f.size() * sizeof(float));
+	});
+}
+
 int fb200_context_gbuffer_download(fb200_context* c, float* geo, float* uv, uint32_t* tri, float* depth)
 {
 	return guarded([&] {

@@ -159,6 +159,7 @@ void PathTracer::init(int argc, char** argv, RenderingContext& renderer)
 		{
 			parts[k].stream = m_sub[k]->stream ? m_sub[k]->stream : renderer.raw_stream();
 			parts[k].pixels = tile_set(m_sub[k]->tile_list.as<uint32>(), m_sub[k]->n_tiles, m_tiles_x, res.x, res.y);
+			parts[k].slot0 = k; parts[k].slot_stride = n_sub;            // sub_tiles[j % n_sub]: the packed layout of the frame gather
 		}
 		renderer.set_partitions(parts);
 		renderer.set_renderer_clears_gbuffer(true);

@@ -63,7 +63,7 @@ FrameBufferView FBufferStorage::view() const
 }
 
 RenderingContext::RenderingContext() : kernel_launches(0), m_scene(NULL), m_owns_scene(false), m_device(0), m_stream(0), m_renderer(NULL),
-	m_touched(true), m_renderer_clears_gbuffer(false), m_copy_stream(0), m_ev_copied(0), m_ev_main(0), m_copy_in_flight(false)
+	m_touched(true), m_renderer_clears_gbuffer(false), m_copy_stream(0), m_ev_copied(0), m_ev_main(0), m_copy_in_flight(false), m_tiles_x_all(0), m_gather_root(-1)
 {
 	memset(&m_dscene, 0, sizeof(m_dscene));
 	memset(&m_lc, 0, sizeof(m_lc));
@@ -80,6 +80,7 @@ RenderingContext::~RenderingContext()
 	if (m_ev_copied) cudaEventDestroy(m_ev_copied);
 	if (m_ev_main) cudaEventDestroy(m_ev_main);
 	for (size_t i = 0; i < m_ev_snap.size(); ++i) cudaEventDestroy(m_ev_snap[i]);
+	for (size_t i = 0; i < m_peer_tiles.size(); ++i) delete m_peer_tiles[i];
 	if (m_stream) cudaStreamDestroy(m_stream);
 	if (m_owns_scene) delete m_scene;
 }
@@ -254,6 +255,8 @@ void RenderingContext::join()
 {
 	for (size_t i = 0; i < m_pending.size(); ++i) cuda_check(cudaStreamWaitEvent(m_stream, m_pending[i], 0), "join");
 	m_pending.clear();
+	// an asynchronous read-back / frame gather in flight on the copy stream belongs to "everything rendered so far" as well
+	if (m_copy_in_flight) cuda_check(cudaStreamWaitEvent(m_stream, m_ev_copied, 0), "join");
 	m_touched = true;
 }
 void RenderingContext::synchronize()
@@ -269,23 +272,31 @@ void RenderingContext::download_channel(int channel, float* dst)
 	cuda_check(cudaMemcpyAsync(dst, b.ptr, b.bytes, cudaMemcpyDeviceToHost, stream()), "fb download");
 	synchronize();
 }
-void RenderingContext::download_channel_async(int channel, float* pinned_dst)
+void RenderingContext::ensure_copy_stream()
 {
-	if (channel < 0 || channel >= FB_NUM_CHANNELS) throw std::runtime_error("bad channel");
+	if (m_copy_stream) return;
+	const size_t bytes = (size_t)m_fb.view().n_pixels * sizeof(float4);
+	cuda_check(cudaStreamCreateWithFlags(&m_copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+	cuda_check(cudaEventCreateWithFlags(&m_ev_copied, cudaEventDisableTiming), "event");
+	cuda_check(cudaEventCreateWithFlags(&m_ev_main, cudaEventDisableTiming), "event");
+	m_snapshot.alloc(bytes);
+	cuda_check(cudaMemsetAsync(m_snapshot.ptr, 0, bytes, m_copy_stream), "memset snapshot");   // pixels of other ranks stay zero, like the frame buffer's
+	cuda_check(cudaEventRecord(m_ev_copied, m_copy_stream), "event record");
+	m_copy_in_flight = true;
+}
+
+// Every partition of the frame (the renderer's sub-frames) copies its pixels of `channel` out of the frame buffer on its own stream,
+// behind its pass and ahead of its next one: into the full-frame snapshot, or (packed) into this rank's send buffer of the frame
+// gather. The copy stream is ordered behind all of them.
+void RenderingContext::snapshot_partitions(int channel, bool packed)
+{
 	const FrameBufferView fbv = m_fb.view();
-	const size_t bytes = (size_t)fbv.n_pixels * sizeof(float4);
-	if (!m_copy_stream)
-	{
-		cuda_check(cudaStreamCreateWithFlags(&m_copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
-		cuda_check(cudaEventCreateWithFlags(&m_ev_copied, cudaEventDisableTiming), "event");
-		cuda_check(cudaEventCreateWithFlags(&m_ev_main, cudaEventDisableTiming), "event");
-		m_snapshot.alloc(bytes);
-		cuda_check(cudaMemsetAsync(m_snapshot.ptr, 0, bytes, m_copy_stream), "memset snapshot");   // pixels of other ranks stay zero, like the frame buffer's
-		cuda_check(cudaEventRecord(m_ev_copied, m_copy_stream), "event record");
-		m_copy_in_flight = true;
-	}
 	std::vector<Partition> parts = m_parts;
-	if (parts.empty()) { Partition p; p.stream = stream(); p.pixels = whole_frame(); parts.push_back(p); }
+	if (parts.empty())
+	{
+		if (packed) throw std::runtime_error("frame gather: the renderer registered no tile partitions");
+		Partition p; p.stream = stream(); p.pixels = whole_frame(); p.slot0 = 0; p.slot_stride = 1; parts.push_back(p);
+	}
 	while (m_ev_snap.size() < parts.size()) { cudaEvent_t e; cuda_check(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event"); m_ev_snap.push_back(e); }
 	// whatever sits on the context's own stream (a pass rendered there, a consumer) comes first
 	cuda_check(cudaEventRecord(m_ev_main, m_stream), "event record");
@@ -294,14 +305,156 @@ void RenderingContext::download_channel_async(int channel, float* pinned_dst)
 		cudaStream_t ps = parts[i].stream;
 		if (ps != m_stream) cuda_check(cudaStreamWaitEvent(ps, m_ev_main, 0), "wait");
 		if (m_copy_in_flight) cuda_check(cudaStreamWaitEvent(ps, m_ev_copied, 0), "wait");      // the previous snapshot has left the device buffer
-		cuda_check(launch_copy_channel(fbv, channel, reinterpret_cast<float4*>(m_snapshot.ptr), parts[i].pixels, ps), "copy_channel");
+		if (packed) cuda_check(launch_pack_tiles(fbv.channels[channel], m_sendbuf.as<float4>(), parts[i].pixels, parts[i].slot0, parts[i].slot_stride, fbv.n_pixels, ps), "pack_tiles");
+		else cuda_check(launch_copy_channel(fbv, channel, reinterpret_cast<float4*>(m_snapshot.ptr), parts[i].pixels, ps), "copy_channel");
 		cuda_check(cudaEventRecord(m_ev_snap[i], ps), "event record");
 		cuda_check(cudaStreamWaitEvent(m_copy_stream, m_ev_snap[i], 0), "wait");
 		kernel_launches++;
 	}
-	cuda_check(cudaMemcpyAsync(pinned_dst, m_snapshot.ptr, bytes, cudaMemcpyDeviceToHost, m_copy_stream), "fb download");
+}
+
+void RenderingContext::download_channel_async(int channel, float* pinned_dst)
+{
+	if (channel < 0 || channel >= FB_NUM_CHANNELS) throw std::runtime_error("bad channel");
+	ensure_copy_stream();
+	snapshot_partitions(channel, false);
+	cuda_check(cudaMemcpyAsync(pinned_dst, m_snapshot.ptr, (size_t)m_fb.view().n_pixels * sizeof(float4), cudaMemcpyDeviceToHost, m_copy_stream), "fb download");
 	cuda_check(cudaEventRecord(m_ev_copied, m_copy_stream), "event record");
 	m_copy_in_flight = true;
+}
+
+// ------------------------------------------------------------------------------------------
+// multi-GPU frame gather (host/comm.h)
+// ------------------------------------------------------------------------------------------
+void RenderingContext::comm_init(const void* id128, int rank, int nranks)
+{
+	if ((uint32_t)rank != m_scene->shard_rank || (uint32_t)nranks != m_scene->shard_count)
+		throw std::runtime_error("comm_init: rank / rank count differ from the scene's -shard rank count");
+	cuda_check(cudaSetDevice(m_device), "cudaSetDevice");
+	m_comm.init(id128, rank, nranks);
+}
+
+void RenderingContext::setup_gather(int root)
+{
+	const uint32 N = m_scene->shard_count, me = m_scene->shard_rank;
+	if (m_gather_root != root)
+	{
+		synchronize();
+		for (size_t i = 0; i < m_peer_tiles.size(); ++i) delete m_peer_tiles[i];
+		m_sendbuf.release(); m_recvbuf.release();
+		m_gather_root = root;
+		std::vector<uint32> tiles;
+		m_peer_ntiles.assign(N, 0); m_peer_offset.assign(N, 0); m_peer_count.assign(N, 0);
+		m_peer_tiles.assign(N, NULL);
+		size_t total = 0;
+		for (uint32 r = 0; r < N; ++r)
+		{
+			shard_tiles(m_scene->res_x, m_scene->res_y, r, N, tiles, m_tiles_x_all);
+			m_peer_ntiles[r] = (uint32)tiles.size();
+			m_peer_count[r] = tiles.size() * 1024u * 4u;                 // floats
+			if ((int)r != root) { m_peer_offset[r] = total; total += m_peer_count[r]; }
+			if ((int)me == root && (int)r != root)
+			{
+				m_peer_tiles[r] = new DeviceBuffer();
+				m_peer_tiles[r]->upload(tiles.data(), tiles.size() * sizeof(uint32), m_stream);
+			}
+		}
+		cuda_check(cudaStreamSynchronize(m_stream), "tile lists upload");      // `tiles` is a local
+		if ((int)me == root) m_recvbuf.alloc((total ? total : 4) * sizeof(float));
+		else m_sendbuf.alloc((m_peer_count[me] ? m_peer_count[me] : 4) * sizeof(float));
+	}
+}
+
+void RenderingContext::gather_channel_async(int channel, int root, float* pinned_dst)
+{
+	if (channel < 0 || channel >= FB_NUM_CHANNELS) throw std::runtime_error("bad channel");
+	const uint32 N = m_scene->shard_count, me = m_scene->shard_rank;
+	if (root < 0 || (uint32)root >= N) throw std::runtime_error("bad root rank");
+	if (N > 1 && !m_comm.ready()) throw std::runtime_error("gather_channel_async: call comm_init first");
+	ensure_copy_stream();
+	if (N > 1) setup_gather(root);
+	const FrameBufferView fbv = m_fb.view();
+	if ((int)me != root)
+	{
+		snapshot_partitions(channel, true);
+		m_comm.gather_to_root(m_sendbuf.as<float>(), m_peer_count[me], NULL, NULL, NULL, root, m_copy_stream);
+	}
+	else
+	{
+		snapshot_partitions(channel, false);                             // the root's own tiles
+		if (N > 1)
+		{
+			m_comm.gather_to_root(NULL, 0, m_recvbuf.as<float>(), m_peer_offset.data(), m_peer_count.data(), root, m_copy_stream);
+			for (uint32 r = 0; r < N; ++r)
+			{
+				if ((int)r == root || m_peer_ntiles[r] == 0) continue;
+				const PixelSet ps = tile_set(m_peer_tiles[r]->as<uint32>(), m_peer_ntiles[r], m_tiles_x_all, m_scene->res_x, m_scene->res_y);
+				cuda_check(launch_unpack_tiles(reinterpret_cast<const float4*>(m_recvbuf.as<float>() + m_peer_offset[r]), reinterpret_cast<float4*>(m_snapshot.ptr), ps, fbv.n_pixels, m_copy_stream), "unpack_tiles");
+				kernel_launches++;
+			}
+		}
+		if (pinned_dst) cuda_check(cudaMemcpyAsync(pinned_dst, m_snapshot.ptr, (size_t)fbv.n_pixels * sizeof(float4), cudaMemcpyDeviceToHost, m_copy_stream), "fb download");
+	}
+	cuda_check(cudaEventRecord(m_ev_copied, m_copy_stream), "event record");
+	m_copy_in_flight = true;
+}
+
+void RenderingContext::adopt_gathered_frame(int channel)
+{
+	if (channel < 0 || channel >= FB_NUM_CHANNELS || m_snapshot.ptr == NULL) throw std::runtime_error("adopt_gathered_frame: nothing gathered");
+	synchronize();
+	cuda_check(cudaMemcpyAsync(m_fb.channels[channel].ptr, m_snapshot.ptr, m_fb.channels[channel].bytes, cudaMemcpyDeviceToDevice, stream()), "D2D");
+}
+void RenderingContext::sum_over_ranks(double* values, size_t n)
+{
+	if (!m_comm.ready() || n == 0) return;
+	DeviceBuffer d;
+	d.upload(values, n * sizeof(double), stream());
+	m_comm.all_reduce_sum_f64(d.as<double>(), n, m_stream);
+	cuda_check(cudaMemcpyAsync(values, d.ptr, n * sizeof(double), cudaMemcpyDeviceToHost, m_stream), "D2H");
+	synchronize();
+}
+float* RenderingContext::alloc_pinned(size_t bytes)
+{
+	void* p = NULL;
+	cuda_check(cudaMallocHost(&p, bytes), "cudaMallocHost");
+	return reinterpret_cast<float*>(p);
+}
+void RenderingContext::free_pinned(float* p) { if (p) cudaFreeHost(p); }
+
+void RenderingContext::diag_pack(int channel, std::vector<float>& packed)
+{
+	if (channel < 0 || channel >= FB_NUM_CHANNELS) throw std::runtime_error("bad channel");
+	std::vector<uint32> tiles; uint32 tx;
+	shard_tiles(m_scene->res_x, m_scene->res_y, m_scene->shard_rank, m_scene->shard_count, tiles, tx);
+	ensure_copy_stream();
+	const size_t floats = tiles.size() * 4096u;
+	if (m_sendbuf.bytes < floats * sizeof(float)) { synchronize(); m_sendbuf.release(); m_sendbuf.alloc((floats ? floats : 4) * sizeof(float)); }
+	cuda_check(cudaMemsetAsync(m_sendbuf.ptr, 0, m_sendbuf.bytes, stream()), "memset");
+	synchronize();
+	snapshot_partitions(channel, true);
+	packed.assign(floats, 0.0f);
+	if (floats) cuda_check(cudaMemcpyAsync(packed.data(), m_sendbuf.ptr, floats * sizeof(float), cudaMemcpyDeviceToHost, m_copy_stream), "D2H");
+	cuda_check(cudaEventRecord(m_ev_copied, m_copy_stream), "event record");
+	m_copy_in_flight = true;
+	synchronize();
+}
+
+void RenderingContext::diag_unpack(uint32_t rank, uint32_t count, const std::vector<float>& packed, std::vector<float>& frame)
+{
+	std::vector<uint32> tiles; uint32 tx;
+	shard_tiles(m_scene->res_x, m_scene->res_y, rank, count, tiles, tx);
+	if (packed.size() != tiles.size() * 4096u) throw std::runtime_error("diag_unpack: packed array has the wrong size for that shard");
+	ensure_copy_stream();
+	synchronize();
+	DeviceBuffer d_tiles, d_packed;
+	d_tiles.upload(tiles.data(), tiles.size() * sizeof(uint32), m_copy_stream);
+	d_packed.upload(packed.data(), packed.size() * sizeof(float), m_copy_stream);
+	const FrameBufferView fbv = m_fb.view();
+	cuda_check(launch_unpack_tiles(d_packed.as<float4>(), reinterpret_cast<float4*>(m_snapshot.ptr), tile_set(d_tiles.as<uint32>(), (uint32)tiles.size(), tx, m_scene->res_x, m_scene->res_y), fbv.n_pixels, m_copy_stream), "unpack_tiles");
+	frame.assign((size_t)fbv.n_pixels * 4, 0.0f);
+	cuda_check(cudaMemcpyAsync(frame.data(), m_snapshot.ptr, frame.size() * sizeof(float), cudaMemcpyDeviceToHost, m_copy_stream), "D2H");
+	cuda_check(cudaStreamSynchronize(m_copy_stream), "diag_unpack");
 }
 
 uint32_t RenderingContext::build_lbvh(uint32_t max_leaf_size, bool adopt, std::vector<Bvh2Node>* nodes_out, std::vector<uint32_t>* index_out,

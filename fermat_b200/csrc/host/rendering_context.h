@@ -4,6 +4,7 @@
 // the scene, textures, frame buffer and sampler tables, the renderer owns its queues and options.
 #pragma once
 #include "renderer_interface.h"
+#include "comm.h"
 #include "pt_scene.h"
 #include "../kernels/device_scene.h"
 #include "../kernels/pt_kernels.h"
@@ -92,10 +93,26 @@ struct RenderingContext
 	// Asynchronous read-back of one channel into PINNED host memory: each partition of the frame (the renderer's
 	// sub-frames) is copied into a device snapshot on its own stream as soon as its pass is complete, the snapshot goes
 	// to the host on a copy stream, and the next pass starts without waiting for either. synchronize() completes it.
-	struct Partition { cudaStream_t stream; fb::PixelSet pixels; };
+	// (slot0, slot_stride: the partition holds tiles slot0, slot0 + slot_stride, ... of this rank's tile list: the packed layout of the frame gather)
+	struct Partition { cudaStream_t stream; fb::PixelSet pixels; uint32_t slot0, slot_stride; };
 	void                    set_partitions(const std::vector<Partition>& parts) { m_parts = parts; }
 	void                    set_renderer_clears_gbuffer(bool b) { m_renderer_clears_gbuffer = b; }
 	void                    download_channel_async(int channel, float* pinned_dst);
+	// Multi-GPU (host/comm.h): the ranks that shard one frame (scene created with `-shard rank count` on each) join one NCCL
+	// communicator; gather_channel_async then assembles the frame on `root` once per frame: every rank packs its tiles (on the
+	// sub-frame streams, as soon as each sub-frame's pass is complete), sends them on the copy stream, the root scatters them into its
+	// full-frame snapshot and, if `pinned_dst` is given, copies the assembled frame to the host. The next pass does not wait for any of it.
+	void                    comm_init(const void* id128, int rank, int nranks);
+	fb::Communicator&       comm() { return m_comm; }
+	void                    gather_channel_async(int channel, int root, float* pinned_dst);
+	const float*            gathered_frame() const { return reinterpret_cast<const float*>(m_snapshot.ptr); }   // root: the assembled frame (device), valid after synchronize()
+	void                    adopt_gathered_frame(int channel);            // root: the assembled frame replaces the frame buffer's `channel` (for to_rgba / filters on the whole image)
+	void                    sum_over_ranks(double* values, size_t n);     // bookkeeping (sample counts): in-place sum over the communicator's ranks; no-op without one
+	static float*           alloc_pinned(size_t bytes);
+	static void             free_pinned(float* p);
+	// diagnostics for single-GPU tests of the packed layout: this rank's tiles of `channel`, packed, to the host / a packed array of rank `rank` (of `count`) into the snapshot
+	void                    diag_pack(int channel, std::vector<float>& packed);
+	void                    diag_unpack(uint32_t rank, uint32_t count, const std::vector<float>& packed, std::vector<float>& frame);
 	RendererInterface*      renderer() { return m_renderer; }
 	// Scene BVH built ON THE DEVICE with CUGAR's LBVH (kernels/lbvh_kernels.cu) from the mesh arrays resident there —
 	// the role of RTContext::create_geometry's Trbvh build (src/rt.cpp:307-324) and of RendererInterface::update_scene
@@ -136,6 +153,17 @@ private:
 	cudaEvent_t              m_ev_copied, m_ev_main;
 	std::vector<cudaEvent_t> m_ev_snap;
 	bool                     m_copy_in_flight;
+	void                     ensure_copy_stream();
+	void                     snapshot_partitions(int channel, bool packed);
+	// frame gather
+	fb::Communicator         m_comm;
+	fb::DeviceBuffer         m_sendbuf, m_recvbuf;
+	std::vector<fb::DeviceBuffer*> m_peer_tiles;      // root: every rank's tile list on the device
+	std::vector<uint32_t>    m_peer_ntiles;
+	std::vector<size_t>      m_peer_offset, m_peer_count;   // in floats, into m_recvbuf
+	uint32_t                 m_tiles_x_all;
+	int                      m_gather_root;            // root the gather buffers were set up for (-1: not yet)
+	void                     setup_gather(int root);
 	std::vector<std::string>             m_renderer_names;
 	std::vector<RendererFactoryFunction> m_renderer_factories;
 	// device copies

@@ -1018,6 +1018,40 @@ cudaError_t launch_copy_channel(const FrameBufferView& fb, int channel, float4* 
 	k_copy_channel<<<(n + 255) / 256, 256, 0, s>>>(fb.channels[channel], dst, ps, fb.n_pixels);
 	return cudaGetLastError();
 }
+// Multi-GPU frame gather (host/comm.h): a rank's tiles leave as a PACKED array, 32x32 float4 per tile in the order of the rank's
+// tile list. A sub-frame holds every `slot_stride`-th tile of that list starting at `slot0` (PathTracer deals them round-robin),
+// so each sub-frame packs its own tiles on its own stream as soon as its pass is complete.
+__global__ void __launch_bounds__(256) k_pack_tiles(const float4* __restrict__ src, float4* __restrict__ packed, PixelSet ps, uint32 slot0, uint32 slot_stride, uint32 n_pixels)
+{
+	const uint32 j = blockIdx.x * blockDim.x + threadIdx.x;
+	uint32 i;
+	if (!pixel_of_set(ps, j, n_pixels, i)) return;
+	packed[(size_t)(slot0 + (j / (FB_TILE * FB_TILE)) * slot_stride) * (FB_TILE * FB_TILE) + (j & (FB_TILE * FB_TILE - 1u))] = src[i];
+}
+// the root's side: tile k of the packed array belongs at tile ps.tile_list[k] of the full frame
+__global__ void __launch_bounds__(256) k_unpack_tiles(const float4* __restrict__ packed, float4* __restrict__ dst, PixelSet ps, uint32 n_pixels)
+{
+	const uint32 j = blockIdx.x * blockDim.x + threadIdx.x;
+	uint32 i;
+	if (!pixel_of_set(ps, j, n_pixels, i)) return;
+	dst[i] = packed[j];
+}
+cudaError_t launch_pack_tiles(const float4* src, float4* packed, const PixelSet& ps, uint32 slot0, uint32 slot_stride, uint32 n_pixels, cudaStream_t s)
+{
+	if (ps.whole) return cudaErrorInvalidValue;
+	const uint32 n = ps.n_tiles * FB_TILE * FB_TILE;
+	if (n == 0) return cudaSuccess;
+	k_pack_tiles<<<(n + 255) / 256, 256, 0, s>>>(src, packed, ps, slot0, slot_stride, n_pixels);
+	return cudaGetLastError();
+}
+cudaError_t launch_unpack_tiles(const float4* packed, float4* dst, const PixelSet& ps, uint32 n_pixels, cudaStream_t s)
+{
+	if (ps.whole) return cudaErrorInvalidValue;
+	const uint32 n = ps.n_tiles * FB_TILE * FB_TILE;
+	if (n == 0) return cudaSuccess;
+	k_unpack_tiles<<<(n + 255) / 256, 256, 0, s>>>(packed, dst, ps, n_pixels);
+	return cudaGetLastError();
+}
 cudaError_t launch_generate_primary(const DeviceScene& sc, const PassParams& pp, const PathQueue& q, PassCounters* ctr, const float seq2[2], const FrameBufferView& fb, cudaStream_t s)
 {
 	const uint32 total = pp.n_tiles * FB_TILE * FB_TILE;

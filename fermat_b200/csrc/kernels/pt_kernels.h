@@ -41,6 +41,10 @@ inline PixelSet tile_set(const uint32* tile_list, uint32 n_tiles, uint32 tiles_x
 cudaError_t launch_rescale_frame(const FrameBufferView& fb, const PixelSet& ps, float scale, cudaStream_t s);
 cudaError_t launch_update_variances(const FrameBufferView& fb, const PixelSet& ps, uint32 n_passes, cudaStream_t s);
 cudaError_t launch_copy_channel(const FrameBufferView& fb, int channel, float4* dst, const PixelSet& ps, cudaStream_t s);
+// multi-GPU frame gather: pack the tiles of `ps` into slots slot0, slot0 + slot_stride, ... of a packed array (32x32 float4 per slot) /
+// scatter a packed array back to the tiles of `ps` (host/comm.h)
+cudaError_t launch_pack_tiles(const float4* src, float4* packed, const PixelSet& ps, uint32 slot0, uint32 slot_stride, uint32 n_pixels, cudaStream_t s);
+cudaError_t launch_unpack_tiles(const float4* packed, float4* dst, const PixelSet& ps, uint32 n_pixels, cudaStream_t s);
 // also resets the G-buffer of every pixel it starts a path for (pass `fb` with gb_geo == NULL to skip)
 cudaError_t launch_generate_primary(const DeviceScene& sc, const PassParams& pp, const PathQueue& q, PassCounters* ctr, const float seq2[2], const FrameBufferView& fb, cudaStream_t s);
 cudaError_t launch_trace_closest(const DeviceScene& sc, const LaunchConfig& lc, const PathQueue& q, PassCounters* ctr, uint32 bounce, cudaStream_t s);

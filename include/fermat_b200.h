@@ -213,6 +213,25 @@ int fb200_diag_pass_counters(fb200_context*, uint32_t subframe, void* out, uint6
  * so far (they run on the renderer's private streams) and makes the next pass wait for what the caller enqueues on it:
  * call it again before each use rather than caching the handle. */
 void* fb200_context_stream(fb200_context*);
+/* ---- multi-GPU: the frame gather (the reference is single-GPU, src/renderer.cu has no counterpart) -------------------
+ * One process (or thread) per GPU, each with a context over a scene created with `-shard <rank> <count>`: the frame is split into 32x32
+ * tiles, tile T = ty * tiles_x + tx belongs to rank (T + ty) % count, scene and tables are replicated. The ranks join ONE NCCL
+ * communicator: fb200_comm_unique_id fills 128 bytes (ncclUniqueId) on one rank, the host application hands them to every rank by any
+ * means (a pipe, a file, MPI, torch.distributed), each rank calls fb200_context_comm_init. NCCL is bound at run time (libnccl.so.2).
+ * fb200_context_gather_image, called by EVERY rank once per frame, assembles the frame on `root`: each rank packs its tiles of `channel`
+ * (1/count of the frame) and sends them over NVLink, the root scatters them into a full-frame device buffer
+ * (fb200_context_gathered_device_ptr, float4 per pixel) and, when `pinned_dst` is not NULL, copies that to pinned host memory. All of it
+ * is asynchronous: packing runs behind the pass on the renderer's streams, transfer and host copy on a side stream while the next
+ * pass renders; fb200_context_synchronize completes it. The assembled image equals the unsharded render bit for bit. */
+int fb200_comm_unique_id(void* id128);
+int fb200_context_comm_init(fb200_context*, const void* id128, int rank, int nranks);
+int fb200_context_gather_image(fb200_context*, int channel, int root, float* pinned_dst);
+const float* fb200_context_gathered_device_ptr(fb200_context*);
+/* diagnostics (single-GPU tests of the packed tile layout): this shard's tiles of `channel` packed into `out` (owned tiles x 4096 floats);
+ * a packed array of shard `rank` of `count` scattered into the context's full-frame buffer, which is then copied to `frame`
+ * (res_x * res_y * 4 floats; other pixels keep what earlier calls put there) */
+int fb200_diag_pack_tiles(fb200_context*, int channel, float* out, uint64_t n_floats);
+int fb200_diag_unpack_tiles(fb200_context*, uint32_t rank, uint32_t count, const float* packed, uint64_t n_floats, float* frame);
 /* number of pixels this shard owns */
 uint64_t fb200_context_owned_pixels(const fb200_context*);
 

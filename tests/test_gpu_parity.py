@@ -186,6 +186,42 @@ def test_tile_shards_sum_to_the_full_frame(fb):
     full.close(); full_sc.close()
 
 
+def _shard_tile_count(w, h, rank, count):
+    tx, ty = (w + 31) // 32, (h + 31) // 32
+    return sum(1 for y in range(ty) for x in range(tx) if (y * tx + x + y) % count == rank)
+
+
+@pytest.mark.parametrize("res,shards,subframes", [((200, 136), 3, None), ((2304, 1440), 5, "2"), ((96, 96), 12, None)])
+def test_packed_tiles_reassemble_the_frame(fb, monkeypatch, res, shards, subframes):
+    """The multi-GPU frame gather's data path on ONE GPU (the NCCL hop itself needs several: tools/multigpu_check.py): every shard packs
+    its tiles (fb200_diag_pack_tiles: the kernels and the sub-frame slot layout fb200_context_gather_image uses), the root scatters the
+    packed arrays (fb200_diag_unpack_tiles): the assembled frame equals the unsharded render bit for bit. Ragged edge tiles, several
+    sub-frames per shard, and more shards than tiles (a rank that owns nothing) included."""
+    if subframes:
+        monkeypatch.setenv("FB200_SUBFRAMES", subframes)
+    args = ["-i", os.path.join(GOLDEN, "cornellbox_jp.fbs"), "-r", str(res[0]), str(res[1]), "-bounces", "2"]
+    full_sc = fb.Scene(args)
+    full = fb.RenderingContext(full_sc)
+    full.clear()
+    for i in range(2):
+        full.render(i, sync=False)
+    want = full.download()
+    frame = None
+    for r in range(shards):
+        sc = fb.Scene(args + ["-shard", str(r), str(shards)])
+        rc = fb.RenderingContext(sc)
+        rc.clear()
+        for i in range(2):
+            rc.render(i, sync=False)
+        n = _shard_tile_count(res[0], res[1], r, shards)
+        packed = rc.pack_tiles(n)
+        assert packed.size == n * 4096
+        frame = full.unpack_tiles(r, shards, packed)
+        rc.close(); sc.close()
+    assert np.array_equal(frame, want)
+    full.close(); full_sc.close()
+
+
 def test_energy_partition_between_nee_and_bsdf_sampling(fb):
     """NEE-only, BSDF-only and MIS estimate the same direct lighting (reference CLI toggles, pathtracer.h:206-247).
     Direct lighting only (-bounces 1): at deeper bounces the reference adds the NEE sample to COMPOSITED twice
