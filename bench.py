@@ -53,39 +53,59 @@ def frame_size(args, n_gpus):
 
 
 class ClockSampler(threading.Thread):
-    """samples nvidia-smi clocks / throttle reasons while the timed region runs"""
+    """samples SM clocks / throttle reasons while the timed region runs: NVML every 5 ms (the timed region of the default run lasts
+    ~80 ms, nvidia-smi's own loop cannot go below 100 ms), `nvidia-smi` as the fallback where NVML cannot be loaded"""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
-        self.rows = []
+        self.rows = []                     # (sm MHz, max MHz, reasons bitmask)
         self.stop_flag = False
-        self.proc = None
+        self.source = None
 
     def run(self):
-        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                if self.stop_flag:
-                    break
-                self.rows.append([c.strip() for c in line.split(",")])
+            import pynvml as nv
+            nv.nvmlInit()
+            # torchrun / CUDA_VISIBLE_DEVICES renumber devices: find the NVML handle of the CUDA device by its UUID-free PCI order
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            self.source = "nvml"
+            while not self.stop_flag:
+                self.rows.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), float(mx), int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))))
+                time.sleep(0.005)
+            return
+        except Exception:
+            pass
+        try:
+            q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+                "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+            self.source = "nvidia-smi"
+            while not self.stop_flag:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"], stdout=subprocess.PIPE,
+                                     stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip().split(",")
+                bits = 0
+                for i, b in enumerate((0x8, 0x40, 0x20, 0x4)):
+                    if out[2 + i].strip().lower().startswith("active"):
+                        bits |= b
+                self.rows.append((float(out[0]), float(out[1]), bits))
         except Exception:
             pass
 
     def stop(self):
         self.stop_flag = True
-        if self.proc:
-            self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
-        reasons = []
-        for i, nm in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")):
-            if any(len(r) >= 6 and r[2 + i].lower().startswith("active") for r in self.rows):
-                reasons.append(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+        self.join(timeout=2.0)
+        sm = [r[0] for r in self.rows]
+        mx = [r[1] for r in self.rows]
+        bits = 0
+        for r in self.rows:
+            bits |= r[2]
+        # nvmlClocksEventReason*: 0x4 sw power cap, 0x8 hw slowdown, 0x20 sw thermal slowdown, 0x40 hw thermal slowdown
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        reasons = [n for b, n in names.items() if bits & b]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm), "source": self.source}
 
 
 def cpu_baseline(scene, res, threads=0, target_s=12.0, count_traversal=True):
