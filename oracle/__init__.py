@@ -299,3 +299,119 @@ def ref_bsdf_raw(table, rec):
     out = np.empty((rec.shape[0], 25), dtype=np.float32)
     L.ref_bsdf_raw(_fptr(table), _fptr(rec), _fptr(out), rec.shape[0])
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# probes of single routines + the reference's own code they are pinned against (oracle/build_ref.sh, round 2)
+# ---------------------------------------------------------------------------------------------
+def probe_geometry(view, rec):
+    """setup_differential_geometry on n x (tri, u, v) -> n x 20 (normal_s, normal_g, tangent, binormal, position, s, t, 0 0 0)"""
+    rec = np.ascontiguousarray(rec, dtype=np.float32).reshape(-1, 3)
+    out = np.empty((rec.shape[0], 20), np.float32)
+    L = lib()
+    L.oracle_probe_geometry.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_uint32]
+    L.oracle_probe_geometry(C.addressof(view), _fptr(rec), _fptr(out), rec.shape[0])
+    return out
+
+
+def probe_light(view, Z, use_vpls):
+    """MeshLight::sample_impl on n x 3 random numbers -> n x 16 (prim, u, v, pdf, position, normal_s, emission, 0 0 0)"""
+    Z = np.ascontiguousarray(Z, dtype=np.float32).reshape(-1, 3)
+    out = np.empty((Z.shape[0], 16), np.float32)
+    L = lib()
+    L.oracle_probe_light.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_float), C.c_uint32]
+    L.oracle_probe_light(C.addressof(view), _fptr(Z), 1 if use_vpls else 0, _fptr(out), Z.shape[0])
+    return out
+
+
+def probe_power_heuristic(p1, p2):
+    L = lib()
+    L.oracle_probe_power_heuristic.restype = C.c_float
+    L.oracle_probe_power_heuristic.argtypes = [C.c_float, C.c_float]
+    return np.float32(L.oracle_probe_power_heuristic(float(p1), float(p2)))
+
+
+def probe_vertex_processor(rec):
+    """PTVertexProcessor::accumulate_emissive / accumulate_nee / compute_nee_weights on n x 26 records -> n x 16"""
+    rec = np.ascontiguousarray(rec, dtype=np.float32).reshape(-1, 26)
+    out = np.empty((rec.shape[0], 16), np.float32)
+    L = lib()
+    L.oracle_probe_vertex_processor.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_uint32]
+    L.oracle_probe_vertex_processor(_fptr(rec), _fptr(out), rec.shape[0])
+    return out
+
+
+class _RefScene(C.Structure):       # struct RefScene of oracle/_ref/ref_pt_shim.cpp
+    _fields_ = [("num_vertices", C.c_int), ("num_triangles", C.c_int), ("num_materials", C.c_int), ("num_textures", C.c_int),
+                ("vertex_indices", C.c_void_p), ("vertex_data", C.c_void_p), ("texture_indices_comp", C.c_void_p), ("material_indices", C.c_void_p),
+                ("materials", C.c_void_p), ("tex_bias", C.c_float * 2), ("tex_scale", C.c_float * 2),
+                ("texels", C.POINTER(C.c_void_p)), ("tex_res", C.POINTER(C.c_uint32)),
+                ("n_prims", C.c_uint32), ("mesh_cdf", C.c_void_p), ("mesh_inv_area", C.c_void_p), ("n_vpls", C.c_uint32), ("vpls", C.c_void_p), ("vpl_norm", C.c_float)]
+
+
+def _ref_so(name):
+    p = os.path.join(_HERE, "_ref", name)
+    return C.CDLL(p) if os.path.exists(p) else None
+
+
+class RefPt:
+    """The REFERENCE's own tiled_sampling.h / mis_utils.h / mesh_utils.h / lights.h / edf.h compiled on this host (oracle/_ref/libref_pt.so)
+    and its PTVertexProcessor + add_in (libref_vp.so). `RefPt.load()` returns None where /root/reference was not available at build time."""
+
+    @staticmethod
+    def load():
+        a, b = _ref_so("libref_pt.so"), _ref_so("libref_vp.so")
+        return RefPt(a, b) if a is not None and b is not None else None
+
+    def __init__(self, pt, vp):
+        self.pt, self.vp = pt, vp
+        self.pt.ref_power_heuristic.restype = C.c_float
+        self.pt.ref_power_heuristic.argtypes = [C.c_float, C.c_float]
+
+    def _scene(self, view):
+        n = int(view.num_textures)
+        texels = (C.c_void_p * max(n, 1))()
+        res = (C.c_uint32 * max(2 * n, 2))()
+        for t in range(n):
+            texels[t] = C.cast(view.textures[t].texels, C.c_void_p)
+            res[2 * t], res[2 * t + 1] = view.textures[t].res_x, view.textures[t].res_y
+        # the reference's VPL is {uv, prim_id, E} (src/lights.h:59-76 over VertexGeometryId, src/vertex.h:105-118); our table stores {prim_id, u, v, E}
+        nv = int(view.n_vpls)
+        vpls = np.zeros((max(nv, 1), 4), np.float32)
+        if nv:
+            ours = np.ctypeslib.as_array(C.cast(view.vpls, C.POINTER(C.c_float)), shape=(nv, 4))
+            vpls[:, 0], vpls[:, 1], vpls[:, 2], vpls[:, 3] = ours[:, 1], ours[:, 2], ours[:, 0], ours[:, 3]
+        s = _RefScene(int(view.num_vertices), int(view.num_triangles), int(view.num_materials), n,
+                      C.cast(view.vertex_indices, C.c_void_p), C.cast(view.vertex_data, C.c_void_p), C.cast(view.texture_indices_comp, C.c_void_p),
+                      C.cast(view.material_indices, C.c_void_p), view.materials, view.tex_bias, view.tex_scale, texels, res,
+                      view.n_prims, C.cast(view.mesh_cdf, C.c_void_p), C.cast(view.mesh_inv_area, C.c_void_p), view.n_vpls, vpls.ctypes.data, view.vpl_norm)
+        s._keep = (texels, res, vpls)
+        return s
+
+    def tiled_samples(self, n_dims, tile=256, context_dims=72, seed=1):
+        out = np.empty((n_dims, tile * tile), np.float32)
+        self.pt.ref_tiled_samples(C.c_uint(seed), C.c_uint(context_dims), C.c_uint(n_dims), C.c_uint(tile), _fptr(out))
+        return out
+
+    def power_heuristic(self, p1, p2):
+        return np.float32(self.pt.ref_power_heuristic(float(p1), float(p2)))
+
+    def setup_geometry(self, view, rec):
+        rec = np.ascontiguousarray(rec, dtype=np.float32).reshape(-1, 3)
+        out = np.empty((rec.shape[0], 20), np.float32)
+        s = self._scene(view)
+        self.pt.ref_setup_geometry(C.byref(s), _fptr(rec), _fptr(out), C.c_uint(rec.shape[0]))
+        return out
+
+    def light_sample(self, view, Z, use_vpls):
+        Z = np.ascontiguousarray(Z, dtype=np.float32).reshape(-1, 3)
+        out = np.empty((Z.shape[0], 16), np.float32)
+        s = self._scene(view)
+        self.pt.ref_light_sample(C.byref(s), _fptr(Z), C.c_int(1 if use_vpls else 0), _fptr(out), C.c_uint(Z.shape[0]))
+        return out
+
+    def vertex_processor(self, rec):
+        rec = np.ascontiguousarray(rec, dtype=np.float32).reshape(-1, 26)
+        out = np.empty((rec.shape[0], 16), np.float32)
+        self.vp.ref_vertex_processor(_fptr(rec), _fptr(out), C.c_uint(rec.shape[0]))
+        return out

@@ -199,3 +199,211 @@ $CXX -O2 -std=c++14 -fPIC -shared -w -fpermissive -ffp-contract=off \
     -I$OV -I$REF/src -I$REF/contrib -I/usr/local/cuda/include \
     -o $OUT/libref_psf.so $OUT/ref_psf_shim.cpp
 echo "built $OUT/libref_psf.so"
+
+# ---- more of the `-pt` path pinned to the reference's own code (round 2): the multi-jittered sampler tables (src/tiled_sampling.h),
+# MIS (src/mis_utils.h), vertex set-up (src/mesh_utils.h setup_differential_geometry), the mesh light (src/lights.h MeshLight::
+# sample_impl / map_impl, src/edf.h) and the PT vertex processor's channel routing + add_in (src/pathtracer_vertex_processor.h,
+# src/framebuffer.h:425-444). Overlay additions, all generated here from the sources where they lie:
+#   * cugar/linalg/matrix.h without its MSVC-only friend declarations (the members are public) + the two Matrix * Vector overloads
+#     g++ cannot deduce (int vs uint32 non-type parameters) spelled out;
+#   * buffers.h with the base-class initialiser written `Buffer<T>(...)`; texture.h / framebuffer.h including THAT copy;
+#   * stub <optix_prime/optix_prime.h> (the buffer-format tags src/ray.h names; OptiX is closed source and absent);
+#   * stub <pathtracer_core.h> for the vertex processor ONLY: its real includes (renderer.h -> camera.h -> optixu math, rt.h -> optix)
+#     do not compile without the OptiX SDK; the stub holds `union PixelInfo` cut out of the real file by line pattern and the few
+#     declarations the processor names. shade_vertex itself (device intrinsics, OptiX types) stays unpinned: DESIGN.md section 6.
+sed '/^friend CUGAR_HOST_DEVICE/d' $REF/contrib/cugar/linalg/matrix.h | awk '
+/#include <cugar\/linalg\/matrix_inline.h>/ {
+  print "namespace cugar {";
+  print "inline Vector<float,4> operator*(const Matrix<float,4,4>& m, const Vector<float,4>& v) { Vector<float,4> r; for (int i = 0; i < 4; ++i) { float s = 0.0f; for (int j = 0; j < 4; ++j) s += m(i,j) * v[j]; r[i] = s; } return r; }";
+  print "inline Vector<float,3> operator*(const Matrix<float,3,3>& m, const Vector<float,3>& v) { Vector<float,3> r; for (int i = 0; i < 3; ++i) { float s = 0.0f; for (int j = 0; j < 3; ++j) s += m(i,j) * v[j]; r[i] = s; } return r; }";
+  print "}";
+}
+{ print }' > $OV/cugar/linalg/matrix.h
+sed -e 's/: Buffer(count, TYPE, pageLockedState)/: Buffer<T>(count, TYPE, pageLockedState)/' -e 's/: Buffer(0, TYPE)/: Buffer<T>(0, TYPE)/' $REF/src/buffers.h > $OV/buffers.h
+sed 's/"buffers.h"/<buffers.h>/' $REF/src/texture.h > $OV/texture.h
+# texture_view.h: the const texel accessors return `const float4&` to the VALUE texture_load() returns - a dangling reference that
+# only the device compiler's inlining hides; on the host they return by value
+sed -E 's/FERMAT_HOST_DEVICE const float4& operator\(\)/FERMAT_HOST_DEVICE const float4 operator()/' $REF/src/texture_view.h > $OV/texture_view.h
+# mesh/MeshCompression.h: the host branch of decompress_tex_coord is `assert(0)`; take the __CUDACC__ body (cuda_fp16.h's conversions are host-callable)
+mkdir -p $OV/mesh
+sed 's/^#if defined(__CUDACC__)$/#if 1 \/\/ (overlay: the device body on the host)/' $REF/src/mesh/MeshCompression.h > $OV/mesh/MeshCompression.h
+sed 's/"buffers.h"/<buffers.h>/' $REF/src/framebuffer.h > $OV/framebuffer.h
+mkdir -p $OV/optix_prime $OV/vp
+cat > $OV/optix_prime/optix_prime.h <<'EOF'
+#pragma once
+// stub: the buffer-format tags src/ray.h names
+enum RTPbufferformat { RTP_BUFFER_FORMAT_RAY_ORIGIN_TMIN_DIRECTION_TMAX = 0x200, RTP_BUFFER_FORMAT_RAY_ORIGIN_MASK_DIRECTION_TMAX = 0x201,
+                       RTP_BUFFER_FORMAT_HIT_T_TRIID_U_V = 0x100, RTP_BUFFER_FORMAT_HIT_T_TRIID_INSTID_U_V = 0x101 };
+EOF
+{
+  echo '#pragma once'
+  echo '// stub of src/pathtracer_core.h for compiling src/pathtracer_vertex_processor.h alone (see oracle/build_ref.sh)'
+  echo '#include <framebuffer.h>'
+  echo '#include <cugar/linalg/bbox.h>'
+  echo '#include <bsdf.h>'
+  echo 'struct EyeVertex;'
+  sed -n '/^union PixelInfo/,/^};/p' $REF/src/pathtracer_core.h
+} > $OV/vp/pathtracer_core.h
+{
+  cat <<'EOF'
+#pragma once
+// stub of Fermat's RenderingContextView for the vertex processor: the frame buffer view + what Bsdf::Bsdf reads;
+// `struct FBufferDesc` (the channel numbering) is cut out of the real src/renderer_view.h by line pattern
+#include <mesh/MeshView.h>
+#include <framebuffer.h>
+struct RenderingContextView
+{
+	const float* glossy_reflectance;
+	const float4* ltc_M; const float4* ltc_Minv; const float* ltc_A; unsigned ltc_size;
+	FBufferView fb;
+};
+EOF
+  sed -n '/^struct FBufferDesc/,/^};/p' $REF/src/renderer_view.h
+} > $OV/vp/renderer_view.h
+
+cat > $OUT/ref_pt_shim.cpp <<'EOF'
+// C entry points around more of the reference's own `-pt` code (see oracle/build_ref.sh); record layouts = oracle_probe_* (pt_oracle.cpp)
+#include <cstdlib>
+#include <cstdio>
+#include <vector>
+#include <algorithm>
+#include <cugar/linalg/vector.h>
+namespace cugar { inline Vector3f operator-(const float a, const Vector3f b) { return Vector3f(a - b.x, a - b.y, a - b.z); } }
+// everything tiled_sampling.h includes comes first, so that the two macros below rename nothing but its own calls
+#include <types.h>
+#include <cugar/basic/numbers.h>
+#include <mis_utils.h>
+#include <mesh_utils.h>
+#include <edf.h>
+#include <lights.h>
+// ---- src/tiled_sampling.h driven by MSVC's rand() (LCG 214013 / 2531011, 15 bits), the stream the Windows reference consumes
+static unsigned g_msvc_state = 1u;
+static int msvc_rand() { g_msvc_state = g_msvc_state * 214013u + 2531011u; return (int)((g_msvc_state >> 16) & 0x7fffu); }
+#define rand msvc_rand
+#undef RAND_MAX
+#define RAND_MAX 0x7fff
+#define random fermat_random
+#include <tiled_sampling.h>
+#undef random
+#undef rand
+// the two sets the reference builds from one stream: the context's own 72 dimensions first (src/renderer.cu:953), then the
+// path tracer's n_dims (src/renderers/pathtracer_impl.h:148-150); `out` receives the second one, [n_dims][tile * tile]
+extern "C" int ref_tiled_samples(unsigned seed, unsigned context_dims, unsigned n_dims, unsigned tile, float* out)
+{
+	g_msvc_state = seed;
+	if (context_dims) { std::vector<float> ctx((size_t)tile * tile * context_dims); build_tiled_samples_3d(tile, tile, context_dims / 3, ctx.data()); }
+	build_tiled_samples_3d(tile, tile, n_dims / 3, out);
+	return 0;
+}
+// ---- src/mis_utils.h
+#include <mis_utils.h>
+extern "C" float ref_power_heuristic(float p1, float p2) { return mis_heuristic<POWER_HEURISTIC>(p1, p2); }
+// ---- src/mesh_utils.h, src/lights.h, src/edf.h
+#include <mesh_utils.h>
+#include <edf.h>
+#include <lights.h>
+struct RefScene     // filled by tests/test_oracle_pinning2.py from fb200_scene_view (same binary layouts as MeshView's arrays)
+{
+	int num_vertices, num_triangles, num_materials, num_textures;
+	int* vertex_indices; float* vertex_data; int* texture_indices_comp; int* material_indices; MeshMaterial* materials;
+	float tex_bias[2], tex_scale[2];
+	float** texels; unsigned* tex_res;        // per texture: LOD-0 texels (float4) or NULL, (res_x, res_y)
+	unsigned n_prims; float* mesh_cdf; float* mesh_inv_area; unsigned n_vpls; VPL* vpls; float vpl_norm;
+};
+static MeshView mesh_view(const RefScene& s)
+{
+	MeshView m; memset(&m, 0, sizeof(m));
+	m.num_vertices = s.num_vertices; m.num_triangles = s.num_triangles; m.num_materials = s.num_materials;
+	m.vertex_stride = 4; m.normal_stride = 3; m.texture_stride = 2;
+	m.tex_bias = make_float2(s.tex_bias[0], s.tex_bias[1]); m.tex_scale = make_float2(s.tex_scale[0], s.tex_scale[1]);
+	m.vertex_indices = s.vertex_indices; m.vertex_data = s.vertex_data; m.texture_indices_comp = s.texture_indices_comp;
+	m.material_indices = s.material_indices; m.materials = s.materials;
+	return m;
+}
+extern "C" int ref_setup_geometry(const RefScene* s, const float* rec, float* out, unsigned n)
+{
+	const MeshView mesh = mesh_view(*s);
+	for (unsigned i = 0; i < n; ++i)
+	{
+		VertexGeometry g;
+		setup_differential_geometry(mesh, (uint32)rec[3 * i], rec[3 * i + 1], rec[3 * i + 2], &g);
+		float* o = out + 20 * i;
+		o[0] = g.normal_s.x; o[1] = g.normal_s.y; o[2] = g.normal_s.z; o[3] = g.normal_g.x; o[4] = g.normal_g.y; o[5] = g.normal_g.z;
+		o[6] = g.tangent.x; o[7] = g.tangent.y; o[8] = g.tangent.z; o[9] = g.binormal.x; o[10] = g.binormal.y; o[11] = g.binormal.z;
+		o[12] = g.position.x; o[13] = g.position.y; o[14] = g.position.z; o[15] = g.texture_coords.x; o[16] = g.texture_coords.y; o[17] = o[18] = o[19] = 0.0f;
+	}
+	return 0;
+}
+extern "C" int ref_light_sample(const RefScene* s, const float* Z, int use_vpls, float* out, unsigned n)
+{
+	std::vector<TextureView> levels(s->num_textures); std::vector<MipMapView> maps(s->num_textures);
+	for (int t = 0; t < s->num_textures; ++t)
+	{
+		levels[t].c = reinterpret_cast<float4*>(s->texels[t]); levels[t].res_x = s->tex_res[2 * t]; levels[t].res_y = s->tex_res[2 * t + 1];
+		maps[t].levels = &levels[t]; maps[t].n_levels = s->texels[t] ? 1u : 0u; maps[t].res_x = levels[t].res_x; maps[t].res_y = levels[t].res_y;
+	}
+	const MeshLight light(s->n_prims, s->mesh_cdf, s->mesh_inv_area, mesh_view(*s), maps.data(), use_vpls ? s->n_vpls : 0u, NULL, s->vpls, s->vpl_norm);
+	for (unsigned i = 0; i < n; ++i)
+	{
+		uint32_t prim; cugar::Vector2f uv; VertexGeometry g; float pdf; Edf edf;
+		light.sample_impl(Z + 3 * i, &prim, &uv, &g, &pdf, &edf);
+		float* o = out + 16 * i;
+		o[0] = (float)prim; o[1] = uv.x; o[2] = uv.y; o[3] = pdf; o[4] = g.position.x; o[5] = g.position.y; o[6] = g.position.z;
+		o[7] = g.normal_s.x; o[8] = g.normal_s.y; o[9] = g.normal_s.z; o[10] = edf.color.x; o[11] = edf.color.y; o[12] = edf.color.z; o[13] = o[14] = o[15] = 0.0f;
+	}
+	return 0;
+}
+EOF
+$CXX -O2 -std=c++14 -fPIC -shared -w -fpermissive -ffp-contract=off \
+    -include $OV/ref_prefix.h \
+    -DFERMAT_API_EXTERN= -DFERMAT_API= -DTHRUST_DEVICE_SYSTEM=THRUST_DEVICE_SYSTEM_CPP \
+    -I$OV -I$REF/src -I$REF/src/mesh -I$REF/contrib -I/usr/local/cuda/include \
+    -o $OUT/libref_pt.so $OUT/ref_pt_shim.cpp -L/usr/local/cuda/lib64 -lcudart_static -ldl -lrt -lpthread
+echo "built $OUT/libref_pt.so"
+
+cat > $OUT/ref_vp_shim.cpp <<'EOF'
+// the reference's own PTVertexProcessor (src/pathtracer_vertex_processor.h) + add_in (src/framebuffer.h:425-444) on one-pixel frame buffers.
+// rec (26 floats): kind (0 accumulate_emissive, 1 accumulate_nee, 2 compute_nee_weights), in_bounce, frame_weight, comp, a(3), b(3),
+//                  COMPOSITED(4) DIRECT(4) DIFFUSE(4) SPECULAR(4);  out (16 floats): the four channels afterwards (kind 2: w_d, w_g in [0..5])
+#include <cugar/linalg/vector.h>
+namespace cugar { inline Vector3f operator-(const float a, const Vector3f b) { return Vector3f(a - b.x, a - b.y, a - b.z); } }
+#include <pathtracer_vertex_processor.h>
+struct Ctx { uint32 in_bounce; float frame_weight; };
+extern "C" int ref_vertex_processor(const float* rec, float* out, unsigned n)
+{
+	for (unsigned i = 0; i < n; ++i)
+	{
+		const float* r = rec + 26 * i; float* o = out + 16 * i;
+		float4 px[FBufferDesc::NUM_CHANNELS]; memset(px, 0, sizeof(px));
+		const int ch[4] = { FBufferDesc::COMPOSITED_C, FBufferDesc::DIRECT_C, FBufferDesc::DIFFUSE_C, FBufferDesc::SPECULAR_C };
+		for (int c = 0; c < 4; ++c) px[ch[c]] = make_float4(r[10 + 4 * c], r[11 + 4 * c], r[12 + 4 * c], r[13 + 4 * c]);
+		FBufferChannelView views[FBufferDesc::NUM_CHANNELS];
+		for (int c = 0; c < FBufferDesc::NUM_CHANNELS; ++c) { views[c].res_x = 1; views[c].res_y = 1; views[c].c_ptr = &px[c]; }
+		RenderingContextView rv; memset(&rv, 0, sizeof(rv));
+		rv.fb.n_channels = FBufferDesc::NUM_CHANNELS; rv.fb.channels = views;
+		Ctx ctx; ctx.in_bounce = (uint32)r[1]; ctx.frame_weight = r[2];
+		const PixelInfo info(0u, (uint32)r[3], 0u);
+		const cugar::Vector3f a(r[4], r[5], r[6]), b(r[7], r[8], r[9]);
+		PTVertexProcessor vp;
+		const int kind = (int)r[0];
+		if (kind == 0) vp.accumulate_emissive(ctx, rv, info, 0xFFFFFFFFu, 0xFFFFFFFFu, *(const EyeVertex*)NULL, a);
+		else if (kind == 1) vp.accumulate_nee(ctx, rv, info, 0xFFFFFFFFu, false, a, b);
+		if (kind == 2)
+		{
+			// a = f_d, b = f_g; path weight and light sample ride in the COMPOSITED / DIRECT slots
+			cugar::Vector3f w_d, w_g; uint32 vi;
+			vp.compute_nee_weights(ctx, rv, info, 0xFFFFFFFFu, 0xFFFFFFFFu, *(const EyeVertex*)NULL, a, b, cugar::Vector3f(r[10], r[11], r[12]), cugar::Vector3f(r[14], r[15], r[16]), w_d, w_g, vi);
+			o[0] = w_d.x; o[1] = w_d.y; o[2] = w_d.z; o[3] = w_g.x; o[4] = w_g.y; o[5] = w_g.z;
+			for (int k = 6; k < 16; ++k) o[k] = 0.0f;
+		}
+		else for (int c = 0; c < 4; ++c) { o[4 * c] = px[ch[c]].x; o[4 * c + 1] = px[ch[c]].y; o[4 * c + 2] = px[ch[c]].z; o[4 * c + 3] = px[ch[c]].w; }
+	}
+	return 0;
+}
+EOF
+$CXX -O2 -std=c++14 -fPIC -shared -w -fpermissive -ffp-contract=off \
+    -include $OV/ref_prefix.h \
+    -DFERMAT_API_EXTERN= -DFERMAT_API= -DTHRUST_DEVICE_SYSTEM=THRUST_DEVICE_SYSTEM_CPP \
+    -I$OV/vp -I$OV -I$REF/src -I$REF/src/mesh -I$REF/contrib -I/usr/local/cuda/include \
+    -o $OUT/libref_vp.so $OUT/ref_vp_shim.cpp -L/usr/local/cuda/lib64 -lcudart_static -ldl -lrt -lpthread
+echo "built $OUT/libref_vp.so"

@@ -342,6 +342,57 @@ static void light_map(const SceneRef& sc, bool use_vpls, uint32_t prim, const Ge
 	*edf = m.emissive;
 }
 
+// MeshLight::sample_impl's choice of the light vertex (src/lights.h:313-352): one of the pre-sampled VPLs, or a triangle from the
+// CDF with the folded (z0, z1) as barycentrics
+static void sample_light_vertex(const fb200_scene_view* s, uint32_t n_vpls, const float z[3], uint32_t* prim, float* lu, float* lv)
+{
+	if (n_vpls)
+	{
+		const uint32_t l = std::min((uint32_t)(z[2] * float(n_vpls)), n_vpls - 1);
+		const VPLPOD& vpl = reinterpret_cast<const VPLPOD*>(s->vpls)[l];
+		*prim = vpl.prim_id; *lu = vpl.u; *lv = vpl.v;
+	}
+	else
+	{
+		const float one = u2f(0x3F7FFFFFu);
+		*prim = (uint32_t)(std::upper_bound(s->mesh_cdf, s->mesh_cdf + s->n_prims, std::min(z[2], one)) - s->mesh_cdf);
+		*lu = z[0]; *lv = z[1];
+		if (*lu + *lv > 1.0f) { *lu = 1.0f - *lu; *lv = 1.0f - *lv; }
+	}
+}
+// PTVertexProcessor::compute_nee_weights (src/pathtracer_vertex_processor.h:89-109)
+static inline void pt_compute_nee_weights(uint32_t bounce, vec3 fd, vec3 fg, vec3 w, vec3 fl, vec3* w_d, vec3* w_g)
+{
+	*w_d = (bounce == 0 ? fd : fd + fg) * w * fl;
+	*w_g = (bounce == 0 ? fg : fd + fg) * w * fl;
+}
+// PTVertexProcessor::accumulate_emissive (src/pathtracer_vertex_processor.h:158-188)
+static inline void pt_accumulate_emissive(FB& fb, uint32_t bounce, uint32_t comp, uint32_t pixel, vec3 w, float frame_weight)
+{
+	fb.add_in(false, COMPOSITED_C, pixel, w, frame_weight);
+	if (bounce == 0) fb.add_in(false, DIRECT_C, pixel, w, frame_weight);
+	else
+	{
+		if (comp & cDiffuseMask) fb.add_in(true, DIFFUSE_C, pixel, w, frame_weight);
+		if (comp & cGlossyMask)  fb.add_in(true, SPECULAR_C, pixel, w, frame_weight);
+	}
+}
+// PTVertexProcessor::accumulate_nee for an unoccluded sample (src/pathtracer_vertex_processor.h:204-239)
+static inline void pt_accumulate_nee(FB& fb, uint32_t bounce, uint32_t comp, uint32_t pixel, vec3 w_d, vec3 w_g, float frame_weight)
+{
+	fb.add_in(false, COMPOSITED_C, pixel, w_d + w_g, frame_weight);
+	if (bounce == 0)
+	{
+		fb.add_in(true, DIFFUSE_C, pixel, w_d, frame_weight);
+		fb.add_in(true, SPECULAR_C, pixel, w_g, frame_weight);
+	}
+	else
+	{
+		if (comp & cDiffuseMask) fb.add_in(true, DIFFUSE_C, pixel, w_d, frame_weight);
+		if (comp & cGlossyMask)  fb.add_in(true, SPECULAR_C, pixel, w_g, frame_weight);
+	}
+}
+
 // ---------------------------------------------------------------------------------------------
 // path-space filtering (`-psfpt`)
 // ---------------------------------------------------------------------------------------------
@@ -599,19 +650,7 @@ static void trace_path(const SceneRef& sc, const Sampler& smp, FB& fb, uint32_t 
 		if (do_nee)
 		{
 			uint32_t prim; float lu, lv;
-			if (n_vpls)
-			{
-				const uint32_t l = std::min((uint32_t)(z[2] * float(n_vpls)), n_vpls - 1);
-				const VPLPOD& vpl = reinterpret_cast<const VPLPOD*>(s->vpls)[l];
-				prim = vpl.prim_id; lu = vpl.u; lv = vpl.v;
-			}
-			else
-			{
-				const float one = u2f(0x3F7FFFFFu);
-				prim = (uint32_t)(std::upper_bound(s->mesh_cdf, s->mesh_cdf + s->n_prims, std::min(z[2], one)) - s->mesh_cdf);
-				lu = z[0]; lv = z[1];
-				if (lu + lv > 1.0f) { lu = 1.0f - lu; lv = 1.0f - lv; }
-			}
+			sample_light_vertex(s, n_vpls, z, &prim, &lu, &lv);
 			Geom lg;
 			setup_differential_geometry(sc, prim, lu, lv, &lg);
 			float light_pdf; vec3 edf;
@@ -631,7 +670,8 @@ static void trace_path(const SceneRef& sc, const Sampler& smp, FB& fb, uint32_t 
 			const float mis_w = ((bounce == 0 && o.direct_lighting_bsdf) || (bounce > 0 && o.indirect_lighting_bsdf)) ? power_heuristic(p1, p2) : 1.0f;
 			const vec3 fd = o.diffuse_scattering ? f[kDR] + f[kDT] : vec3(0.0f), fg = o.glossy_scattering ? f[kGR] + f[kGT] : vec3(0.0f);
 			const vec3 fl = f_L * G * mis_w;
-			vec3 w_d = (bounce == 0 ? fd : fd + fg) * w * fl, w_g = (bounce == 0 ? fg : fd + fg) * w * fl;
+			vec3 w_d, w_g;
+			pt_compute_nee_weights(bounce, fd, fg, w, fl, &w_d, &w_g);
 			if (psf)
 			{
 				// PSFPTVertexProcessor::compute_nee_weights (src/psfpt_vertex_processor.h:204-268)
@@ -665,16 +705,7 @@ static void trace_path(const SceneRef& sc, const Sampler& smp, FB& fb, uint32_t 
 				// PTVertexProcessor::accumulate_emissive, or PSFPTVertexProcessor's (src/psfpt_vertex_processor.h:326-369): clamped, and into
 				// the cache cell once the path feeds one
 				const vec3 cw = psf ? psf_clamp_sample(ow, po.firefly_filter) : ow;
-				if (!psf || psf_slot(prev_vinfo) == PSF_INVALID_SLOT)
-				{
-					fb.add_in(false, COMPOSITED_C, pixel, cw, frame_weight);
-					if (bounce == 0) fb.add_in(false, DIRECT_C, pixel, cw, frame_weight);
-					else
-					{
-						if (comp & cDiffuseMask) fb.add_in(true, DIFFUSE_C, pixel, cw, frame_weight);
-						if (comp & cGlossyMask)  fb.add_in(true, SPECULAR_C, pixel, cw, frame_weight);
-					}
-				}
+				if (!psf || psf_slot(prev_vinfo) == PSF_INVALID_SLOT) pt_accumulate_emissive(fb, bounce, comp, pixel, cw, frame_weight);
 				else
 				{
 					psf->acquire();
@@ -750,20 +781,7 @@ static void trace_path(const SceneRef& sc, const Sampler& smp, FB& fb, uint32_t 
 						}
 					}
 				}
-				else if (!occluded)
-				{
-					fb.add_in(false, COMPOSITED_C, pixel, pend[k].w_d + pend[k].w_g, frame_weight);
-					if (bounce == 0)
-					{
-						fb.add_in(true, DIFFUSE_C, pixel, pend[k].w_d, frame_weight);
-						fb.add_in(true, SPECULAR_C, pixel, pend[k].w_g, frame_weight);
-					}
-					else
-					{
-						if (comp & cDiffuseMask) fb.add_in(true, DIFFUSE_C, pixel, pend[k].w_d, frame_weight);
-						if (comp & cGlossyMask)  fb.add_in(true, SPECULAR_C, pixel, pend[k].w_g, frame_weight);
-					}
-				}
+				else if (!occluded) pt_accumulate_nee(fb, bounce, comp, pixel, pend[k].w_d, pend[k].w_g, frame_weight);
 			}
 
 		if (!cont) return;
@@ -1041,6 +1059,70 @@ int oracle_bsdf_raw(const float* table, const float* rec, float* out, uint32_t n
 }
 
 // optional G-buffer outputs of oracle_render_pass (geo, uv: 4 floats per pixel; tri, depth: 1 per pixel); NULLs disable
+// ---- probes: single routines of the path on caller-provided records, for pinning them against the reference's OWN code compiled on
+// the host (oracle/build_ref.sh -> oracle/_ref/libref_pt.so, libref_vp.so; tests/test_oracle_pinning2.py). trace_path calls the same functions.
+// rec: tri, u, v  ->  out (20 floats): normal_s, normal_g, tangent, binormal, position, s, t, 0, 0, 0
+int oracle_probe_geometry(const fb200_scene_view* s, const float* rec, float* out, uint32_t n)
+{
+	SceneRef sc; sc.s = s; sc.vi = s->vertex_indices; sc.vd = s->vertex_data; sc.nodes = NULL;
+	for (uint32_t i = 0; i < n; ++i)
+	{
+		Geom g;
+		setup_differential_geometry(sc, (uint32_t)rec[3 * i], rec[3 * i + 1], rec[3 * i + 2], &g);
+		float* o = out + 20 * i;
+		o[0] = g.normal_s.x; o[1] = g.normal_s.y; o[2] = g.normal_s.z; o[3] = g.normal_g.x; o[4] = g.normal_g.y; o[5] = g.normal_g.z;
+		o[6] = g.tangent.x; o[7] = g.tangent.y; o[8] = g.tangent.z; o[9] = g.binormal.x; o[10] = g.binormal.y; o[11] = g.binormal.z;
+		o[12] = g.position.x; o[13] = g.position.y; o[14] = g.position.z; o[15] = g.st[0]; o[16] = g.st[1]; o[17] = o[18] = o[19] = 0.0f;
+	}
+	return 0;
+}
+// Z (3 floats per record) -> out (16 floats): prim, u, v, pdf, position, normal_s, emission rgb, 0, 0, 0   (MeshLight::sample_impl)
+int oracle_probe_light(const fb200_scene_view* s, const float* Z, int use_vpls, float* out, uint32_t n)
+{
+	SceneRef sc; sc.s = s; sc.vi = s->vertex_indices; sc.vd = s->vertex_data; sc.nodes = NULL;
+	for (uint32_t i = 0; i < n; ++i)
+	{
+		uint32_t prim; float lu, lv;
+		sample_light_vertex(s, use_vpls ? s->n_vpls : 0u, Z + 3 * i, &prim, &lu, &lv);
+		Geom lg;
+		setup_differential_geometry(sc, prim, lu, lv, &lg);
+		float pdf; vec3 edf;
+		light_map(sc, use_vpls != 0, prim, lg, &pdf, &edf);
+		float* o = out + 16 * i;
+		o[0] = (float)prim; o[1] = lu; o[2] = lv; o[3] = pdf; o[4] = lg.position.x; o[5] = lg.position.y; o[6] = lg.position.z;
+		o[7] = lg.normal_s.x; o[8] = lg.normal_s.y; o[9] = lg.normal_s.z; o[10] = edf.x; o[11] = edf.y; o[12] = edf.z; o[13] = o[14] = o[15] = 0.0f;
+	}
+	return 0;
+}
+float oracle_probe_power_heuristic(float p1, float p2) { return power_heuristic(p1, p2); }
+// rec (26 floats): kind (0 accumulate_emissive, 1 accumulate_nee, 2 compute_nee_weights), in_bounce, frame_weight, comp, a(3), b(3),
+// COMPOSITED(4) DIRECT(4) DIFFUSE(4) SPECULAR(4) of one pixel -> out (16 floats): the four channels afterwards (kind 2: w_d, w_g)
+int oracle_probe_vertex_processor(const float* rec, float* out, uint32_t n)
+{
+	for (uint32_t i = 0; i < n; ++i)
+	{
+		const float* r = rec + 26 * i; float* o = out + 16 * i;
+		float px[8 * 4]; memset(px, 0, sizeof(px));
+		const int ch[4] = { COMPOSITED_C, DIRECT_C, DIFFUSE_C, SPECULAR_C };
+		for (int c = 0; c < 4; ++c) for (int k = 0; k < 4; ++k) px[4 * ch[c] + k] = r[10 + 4 * c + k];
+		FB fb; fb.data = px; fb.n_pixels = 1;
+		const uint32_t bounce = (uint32_t)r[1], comp = (uint32_t)r[3];
+		const vec3 a(r[4], r[5], r[6]), b(r[7], r[8], r[9]);
+		const int kind = (int)r[0];
+		if (kind == 0) pt_accumulate_emissive(fb, bounce, comp, 0u, a, r[2]);
+		else if (kind == 1) pt_accumulate_nee(fb, bounce, comp, 0u, a, b, r[2]);
+		if (kind == 2)
+		{
+			vec3 w_d, w_g;
+			pt_compute_nee_weights(bounce, a, b, vec3(r[10], r[11], r[12]), vec3(r[14], r[15], r[16]), &w_d, &w_g);
+			o[0] = w_d.x; o[1] = w_d.y; o[2] = w_d.z; o[3] = w_g.x; o[4] = w_g.y; o[5] = w_g.z;
+			for (int k = 6; k < 16; ++k) o[k] = 0.0f;
+		}
+		else for (int c = 0; c < 4; ++c) for (int k = 0; k < 4; ++k) o[4 * c + k] = px[4 * ch[c] + k];
+	}
+	return 0;
+}
+
 void oracle_set_gbuffer(float* geo, float* uv, uint32_t* tri, float* depth) { g_gbuffer.geo = geo; g_gbuffer.uv = uv; g_gbuffer.tri = tri; g_gbuffer.depth = depth; }
 
 // 0: libm sinf/cosf (pinning against the reference's host-compiled Bsdf), 1: the fixed-sequence sincos shared with the kernels

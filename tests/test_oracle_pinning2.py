@@ -1,0 +1,132 @@
+"""More of the `-pt` path pinned to the reference's OWN code: src/tiled_sampling.h (the multi-jittered sampler
+slices the blue-noise files do not cover), src/mis_utils.h, src/mesh_utils.h setup_differential_geometry, src/lights.h MeshLight
+(sample_impl / map_impl incl. textured emission), src/edf.h, and src/pathtracer_vertex_processor.h + add_in (src/framebuffer.h:425-444).
+Two arms: golden vectors those sources produced here (tools/make_golden_pt.py -> tests/golden/pt_pinning_golden.npz, checked
+everywhere), and the sources themselves compiled by oracle/build_ref.sh (oracle/_ref/libref_pt.so, libref_vp.so; checked live where
+present, on every scene snapshot). All comparisons are bit for bit. CPU only."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from conftest import CACHE, GOLDEN, cornell_args
+
+G = np.load(os.path.join(GOLDEN, "pt_pinning_golden.npz"))
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def same(a, b):
+    a, b = np.asarray(a, np.float32), np.asarray(b, np.float32)
+    return np.array_equal(bits(a)[~(np.isnan(a) & np.isnan(b))], bits(b)[~(np.isnan(a) & np.isnan(b))])
+
+
+@pytest.fixture(scope="module")
+def ref(oracle):
+    return oracle.RefPt.load()
+
+
+def shifts(view):
+    return np.ctypeslib.as_array(view.shifts, shape=(int(view.n_dimensions), int(view.tile_size) ** 2))
+
+
+@pytest.mark.parametrize("bounces", [4, 8])
+def test_sampler_tables_equal_the_references_own(fb, ref, bounces):
+    """dims >= 21 of the PRODUCT's shift table = build_tiled_samples_3d (src/tiled_sampling.h:92-308) driven by MSVC's
+    rand() with the context's 72-dimension set drawn first (src/renderer.cu:953); dims 0..20 are the blue-noise files (pinned elsewhere)."""
+    sc = fb.Scene(cornell_args(32, bounces))
+    t = shifts(sc.view)
+    n = int(sc.view.n_dimensions)
+    assert n == 6 * (bounces + 2)
+    assert hashlib.sha256(t[21:].tobytes()).digest() == G["sampler_sha256_%d" % n].tobytes()
+    stride = t.reshape(-1)[::9973]
+    want = G["sampler_stride_%d" % n]
+    keep = (np.arange(stride.size) * 9973) >= 21 * t.shape[1]
+    assert same(stride[keep], want[keep])
+    if ref is not None:
+        live = ref.tiled_samples(n)
+        assert same(t[21:], live[21:])
+        assert not same(t[:21], live[:21])          # (the leading slices really are replaced by the files)
+    sc.close()
+
+
+def test_mis_weight(oracle, ref):
+    got = np.array([oracle.probe_power_heuristic(a, b) for a, b in G["mis_rec"]], np.float32)
+    assert same(got, G["mis_out"])
+    if ref is not None:
+        assert same(got, np.array([ref.power_heuristic(a, b) for a, b in G["mis_rec"]], np.float32))
+
+
+def test_vertex_setup_and_light_sampling_golden(fb, oracle):
+    sc = fb.Scene(cornell_args(64, 4))
+    assert same(oracle.probe_geometry(sc.view, G["geo_rec"]), G["geo_out"])
+    assert same(oracle.probe_light(sc.view, G["light_Z"], True), G["light_vpl"])
+    assert same(oracle.probe_light(sc.view, G["light_Z"], False), G["light_mesh"])
+    sc.close()
+
+
+def test_vertex_processor_channel_routing_and_add_in(oracle, ref):
+    """accumulate_emissive / accumulate_nee (which channel, variance in alpha: add_in<true>) and compute_nee_weights"""
+    got = oracle.probe_vertex_processor(G["vp_rec"])
+    assert same(got, G["vp_out"])
+    assert len(np.unique(G["vp_rec"][:, 0])) == 3 and len(np.unique(G["vp_rec"][:, 3])) == 16      # all three routines, every lobe mask
+    if ref is not None:
+        assert same(got, ref.vertex_processor(G["vp_rec"]))
+
+
+@pytest.mark.parametrize("scene", ["cornellbox_jp", "cornellbox_dirlight", "cornellbox_glossy", "bathroom2", "material_testball", "water_caustic"])
+def test_live_against_the_reference_on_every_scene(fb, oracle, ref, scene):
+    """setup_differential_geometry (normals through the 10-10-10 packing, fp16 texture coordinates) and MeshLight::sample_impl / map_impl
+    (VPL and CDF samplers, textured emission on material-testball's environment sphere) against the reference's own code, 20 000
+    seeded records per scene."""
+    if ref is None:
+        pytest.skip("oracle/_ref/libref_pt.so not built (needs /root/reference at build time)")
+    path = os.path.join(GOLDEN, scene + ".fbs") if scene.startswith("cornellbox_jp") or scene == "cornellbox_dirlight" else os.path.join(CACHE, scene + ".fbs")
+    if not fb.scene_available(path):
+        pytest.skip("scene snapshot %s not present" % scene)
+    sc = fb.Scene(["-i", path, "-r", "96", "64", "-bounces", "4"])
+    v = sc.view
+    rng = np.random.default_rng(7)
+    n = 20000
+    u = rng.random(n).astype(np.float32); w = (rng.random(n) * (1 - u)).astype(np.float32)
+    rec = np.stack([rng.integers(0, v.num_triangles, n).astype(np.float32), u, w], 1)
+    rec[:8, 1:] = [[0, 0], [1, 0], [0, 1], [0.5, 0.5], [1 / 3, 1 / 3], [1e-7, 1e-7], [0.999, 0.001], [0, 0.5]]     # corners and edges
+    assert same(oracle.probe_geometry(v, rec), ref.setup_geometry(v, rec))
+    Z = rng.random((n, 3)).astype(np.float32)
+    Z[:4] = [[0, 0, 0], [0.999999, 0.999999, 0.99999994], [1, 1, 1], [0.5, 0.5, 0]]
+    if v.n_vpls:
+        assert same(oracle.probe_light(v, Z, True), ref.light_sample(v, Z, True))
+    assert same(oracle.probe_light(v, Z, False), ref.light_sample(v, Z, False))
+    sc.close()
+
+
+@pytest.mark.parametrize("scene,res", [("cornellbox_jp", (64, 64)), ("cornellbox_jp", (200, 120)), ("cornellbox_glossy", (96, 96)), ("bathroom2", (160, 90)), ("water_caustic", (128, 72))])
+def test_vpl_table_against_an_independent_restatement(fb, scene, res):
+    """the product's VPL generator (host/mesh_lights.cpp) against oracle/vpl_numpy.py, a numpy restatement of
+    MeshLightsStorageImpl::init (src/mesh_lights.cu:164-388) that shares no code with it: triangle CDF, 1/area, every VPL
+    {triangle, u, v, E} and the normalisation coefficient, bit for bit. The LFSR stream both read is pinned against the reference's own
+    generator in tests/test_oracle_pinning.py."""
+    import ctypes as C
+    from oracle import vpl_numpy
+    path = os.path.join(GOLDEN, scene + ".fbs") if scene == "cornellbox_jp" else os.path.join(CACHE, scene + ".fbs")
+    if not fb.scene_available(path):
+        pytest.skip("scene snapshot %s not present" % scene)
+    sc = fb.Scene(["-i", path, "-r", str(res[0]), str(res[1]), "-bounces", "2"])
+    v = sc.view
+    n = res[0] * res[1]
+    assert v.n_vpls == n
+    rnd = np.zeros(4 * n, np.float32)
+    assert fb.lib().fb200_diag_lfsr(1351, rnd.ctypes.data_as(C.POINTER(C.c_float)), rnd.size) == 0
+    want = vpl_numpy.restate(v, rnd, n)
+    nt = int(v.num_triangles)
+    assert same(np.ctypeslib.as_array(v.mesh_cdf, shape=(nt,)), want["mesh_cdf"])
+    assert same(np.ctypeslib.as_array(v.mesh_inv_area, shape=(nt,)), want["mesh_inv_area"])
+    got = np.ctypeslib.as_array(C.cast(v.vpls, C.POINTER(C.c_float)), shape=(n, 4))
+    assert np.array_equal(bits(got[:, 0]), bits(want["vpls"][:, 0]))            # triangle ids
+    assert same(got[:, 1:], want["vpls"][:, 1:])                                  # u, v, E
+    assert np.float32(v.vpl_norm).view(np.uint32) == want["norm"].view(np.uint32)
+    assert len(np.unique(bits(got[:, 0]))) >= 2                                   # (several emitting triangles were drawn)
+    sc.close()
