@@ -58,6 +58,16 @@ class SceneView(C.Structure):
     ]
 
 
+class MeshDesc(C.Structure):          # fb200_mesh_desc (include/fermat_b200.h)
+    _fields_ = [("num_triangles", C.c_uint32), ("num_vertices", C.c_uint32), ("num_materials", C.c_uint32), ("num_textures", C.c_uint32),
+                ("num_texture_coordinates", C.c_uint32),
+                ("vertex_indices", C.POINTER(C.c_int32)), ("vertex_data", C.POINTER(C.c_float)), ("texture_indices_comp", C.POINTER(C.c_int32)),
+                ("material_indices", C.POINTER(C.c_int32)), ("texture_indices", C.POINTER(C.c_int32)), ("texture_data", C.POINTER(C.c_float)),
+                ("materials", C.c_void_p), ("tex_bias", C.c_float * 2), ("tex_scale", C.c_float * 2), ("textures", C.POINTER(TextureView)),
+                ("eye", C.c_float * 3), ("aim", C.c_float * 3), ("up", C.c_float * 3), ("dx", C.c_float * 3), ("fov", C.c_float),
+                ("n_dir_lights", C.c_uint32), ("dir_lights", C.POINTER(C.c_float)), ("exposure", C.c_float), ("gamma", C.c_float)]
+
+
 class Stats(C.Structure):
     _fields_ = [("shade_events", C.c_uint64), ("shadow_events", C.c_uint64), ("passes", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("device_ms", C.c_double)]
@@ -79,6 +89,8 @@ def lib():
     sig = {
         "fb200_last_error": (C.c_char_p, []),
         "fb200_scene_create": (vp, [i32, C.POINTER(C.c_char_p)]),
+        "fb200_scene_create_from_mesh": (vp, [C.POINTER(MeshDesc), i32, C.POINTER(C.c_char_p)]),
+        "fb200_context_publish": (i32, [vp, C.POINTER(vp * 8)]),
         "fb200_scene_destroy": (None, [vp]),
         "fb200_scene_get_view": (i32, [vp, C.POINTER(SceneView)]),
         "fb200_scene_save_snapshot": (i32, [vp, C.c_char_p]),
@@ -130,6 +142,8 @@ def lib():
         "fb200_trace_shadow_device": (i32, [vp, vp, vp, u32]),
         "fb200_bsdf_eval": (i32, [vp, pf, pf, u32]),
         "register_plugin": (u32, [vp]),
+        "fb200_context_rendering_context": (vp, [vp]),
+        "fb200_context_select_renderer": (i32, [vp, u32]),
     }
     missing = []
     for name, (res, args) in sig.items():
@@ -230,13 +244,17 @@ class _Handle:
 class Scene(_Handle):
     """Host-only scene: mesh + materials + textures, sampler tables, VPLs, BVH (no GPU needed)."""
 
-    def __init__(self, args):
+    def __init__(self, args, mesh=None):
+        """`mesh`: a MeshDesc (arrays in memory, fb200_scene_create_from_mesh) instead of `-i file` in `args`"""
         self.args = [str(a) for a in args]
         for i, a in enumerate(self.args[:-1]):
             if a == "-i":
                 self.args[i + 1] = resolve_scene(self.args[i + 1])
         argv = (C.c_char_p * len(self.args))(*[a.encode() for a in self.args])
-        h = lib().fb200_scene_create(len(self.args), argv)
+        if mesh is not None:
+            h = lib().fb200_scene_create_from_mesh(C.byref(mesh), len(self.args), argv)
+        else:
+            h = lib().fb200_scene_create(len(self.args), argv)
         if not h:
             raise RuntimeError("fb200_scene_create failed: " + _err())
         self._h = h
@@ -259,6 +277,27 @@ class Scene(_Handle):
         e, g = C.c_float(), C.c_float()
         lib().fb200_scene_get_tonemap(self._h, C.byref(e), C.byref(g))
         return e.value, g.value
+
+    def mesh_desc(self):
+        """this scene's pre-processed arrays as a MeshDesc (pointers into this scene's memory: keep it alive while the descriptor is used)"""
+        v = self.view
+        d = MeshDesc()
+        d.num_triangles, d.num_vertices, d.num_materials, d.num_textures = v.num_triangles, v.num_vertices, v.num_materials, v.num_textures
+        d.vertex_indices, d.vertex_data, d.texture_indices_comp, d.material_indices = v.vertex_indices, v.vertex_data, v.texture_indices_comp, v.material_indices
+        d.materials, d.textures = v.materials, v.textures
+        for i in range(2):
+            d.tex_bias[i], d.tex_scale[i] = v.tex_bias[i], v.tex_scale[i]
+        for i in range(3):
+            d.eye[i], d.aim[i], d.up[i] = v.eye[i], v.aim[i], v.up[i]
+        w = np.array(v.aim[:], np.float32) - np.array(v.eye[:], np.float32)
+        dx = np.cross(w, np.array(v.up[:], np.float32)).astype(np.float32)
+        dx = (dx / np.sqrt(np.float32(np.dot(dx, dx)))).astype(np.float32)
+        for i in range(3):
+            d.dx[i] = dx[i]
+        d.fov = v.fov
+        d.n_dir_lights, d.dir_lights = v.n_dir_lights, v.dir_lights
+        d.exposure, d.gamma = self.tonemap()
+        return d
 
     def save_snapshot(self, filename):
         if lib().fb200_scene_save_snapshot(self._h, str(filename).encode()) != 0:
@@ -414,6 +453,21 @@ class RenderingContext(_Handle):
 
     def owned_pixels(self):
         return int(lib().fb200_context_owned_pixels(self._h))
+
+    def publish(self, tensors):
+        """copy frame-buffer channels into caller-owned device buffers: {channel name or index: CUDA tensor (H, W, 4) float32}"""
+        arr = (C.c_void_p * 8)()
+        for k, t in tensors.items():
+            arr[FB_CHANNELS.get(k, k)] = t.data_ptr()
+        self._chk(lib().fb200_context_publish(self._h, C.byref(arr)))
+
+    # ---- the plugin boundary (src/renderer.cu:441-460)
+    def register_plugin(self):
+        """call the library's exported `register_plugin` on this context's RenderingContext, like Fermat's plugin loader: returns the renderer id"""
+        return int(lib().register_plugin(lib().fb200_context_rendering_context(self._h)))
+
+    def select_renderer(self, renderer_id):
+        self._chk(lib().fb200_context_select_renderer(self._h, int(renderer_id)))
 
     # ---- multi-GPU frame gather (include/fermat_b200.h "multi-GPU") ----
     def comm_init(self, unique_id, rank, nranks):

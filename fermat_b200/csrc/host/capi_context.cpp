@@ -249,6 +249,27 @@ int fb200_bsdf_eval(fb200_context* c, const float* rec, float* out, uint32_t n)
 	});
 }
 
+int fb200_context_publish(fb200_context* c, float* const device_channels[8])
+{
+	return guarded([&] {
+		cudaStream_t st = c->rc.stream();           // joins the passes rendered so far
+		for (int i = 0; i < fb::FB_NUM_CHANNELS && i < 8; ++i)
+			if (device_channels[i])
+			{
+				fb::DeviceBuffer& b = c->rc.get_frame_buffer().channels[i];
+				fb::cuda_check(cudaMemcpyAsync(device_channels[i], b.ptr, b.bytes, cudaMemcpyDeviceToDevice, st), "publish");
+			}
+	});
+}
+
+// the RenderingContext behind a C-ABI context: what a C++ host hands to register_plugin
+void* fb200_context_rendering_context(fb200_context* c) { return c ? static_cast<void*>(&c->rc) : NULL; }
+// RenderingContextImpl::load_plugin's second half (src/renderer.cu:456-460, :957): make renderer `id` the context's renderer
+int fb200_context_select_renderer(fb200_context* c, uint32_t id)
+{
+	return guarded([&] { char arg[] = "-plugin"; char* argv[] = { arg }; c->rc.select_renderer(id, 1, argv); });
+}
+
 // the plugin entry point Fermat's loader resolves (src/renderer.cu:441-460): registers the renderer under
 // the name "pt" and returns its id. `rendering_context` points to a RenderingContext.
 uint32_t register_plugin(void* rendering_context)

@@ -32,6 +32,25 @@ fb200_scene* fb200_scene_create(int argc, const char* const* argv)
 	}
 }
 
+fb200_scene* fb200_scene_create_from_mesh(const fb200_mesh_desc* mesh, int argc, const char* const* argv)
+{
+	if (!mesh) { fb::set_last_error("null mesh"); return NULL; }
+	fb200_scene* s = NULL;
+	try
+	{
+		s = new fb200_scene();
+		fb::scene_init(*s, argc, argv, mesh);
+		fb::set_last_error("");
+		return s;
+	}
+	catch (const std::exception& e)
+	{
+		fb::set_last_error(e.what());
+		delete s;
+		return NULL;
+	}
+}
+
 void fb200_scene_destroy(fb200_scene* s) { delete s; }
 
 int fb200_scene_get_view(const fb200_scene* s, fb200_scene_view* out)

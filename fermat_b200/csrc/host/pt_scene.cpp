@@ -175,7 +175,7 @@ static void load_tables(const std::string& file, std::vector<float>& glossy, std
 	if (!ok || hd[1] != 32u * 32u * 32u * 32u || hd[3] != 256u) throw std::runtime_error("truncated tables file: " + file);
 }
 
-void scene_init(fb200_scene& s, int argc, const char* const* argv)
+void scene_init(fb200_scene& s, int argc, const char* const* argv, const fb200_mesh_desc* mesh)
 {
 	const char* filename = NULL;
 	bool overwrite_camera = false;
@@ -211,7 +211,7 @@ void scene_init(fb200_scene& s, int argc, const char* const* argv)
 		}
 	}
 	if (s.aspect == 0.0f) s.aspect = float(s.res_x) / float(s.res_y);
-	if (!filename) throw std::runtime_error("no input scene: pass -i scene.{fa,obj,fbs}");
+	if (!filename && !mesh) throw std::runtime_error("no input scene: pass -i scene.{fa,obj,fbs}");
 	if (s.res_x == 0 || s.res_y == 0 || (uint64)s.res_x * s.res_y >= (1u << 27)) throw std::runtime_error("unsupported resolution (PixelInfo holds 27 pixel bits)");
 	if (s.shard_count == 0 || s.shard_rank >= s.shard_count) throw std::runtime_error("bad -shard rank/count");
 	pt_options_parse(s.options, argc, argv);
@@ -221,7 +221,8 @@ void scene_init(fb200_scene& s, int argc, const char* const* argv)
 	if (s.options.max_path_length == 0 || s.options.max_path_length > 62) throw std::runtime_error("unsupported path length");
 	if (s.options.nee_type == 2) throw std::runtime_error("-nee-alg rl is not part of the -pt hot path implemented here");
 
-	load_scene(filename, s.scene, overwrite_camera);
+	if (mesh) scene_from_mesh_desc(*mesh, s.scene, overwrite_camera);
+	else load_scene(filename, s.scene, overwrite_camera);
 
 	if (s.tables_file.empty()) s.tables_file = default_tables_path();
 	std::vector<float> blue_noise;

@@ -48,7 +48,8 @@ void psf_options_defaults(fb200_psf_options& o);                           // sr
 void psf_options_parse(fb200_psf_options& o, int argc, const char* const* argv);   // src/renderers/psfpt.h:367-387
 
 // throws std::runtime_error
-void scene_init(fb200_scene& s, int argc, const char* const* argv);
+// `mesh` != NULL: the scene comes from arrays in memory (fb200_scene_create_from_mesh) instead of `-i file`
+void scene_init(fb200_scene& s, int argc, const char* const* argv, const fb200_mesh_desc* mesh = NULL);
 void scene_fill_view(const fb200_scene& s, fb200_scene_view& v);
 
 std::string default_tables_path();

@@ -92,6 +92,18 @@ uint32_t RenderingContext::register_renderer(const char* name, RendererFactoryFu
 	return uint32_t(m_renderer_factories.size() - 1);
 }
 
+void RenderingContext::select_renderer(uint32_t id, int argc, char** argv)
+{
+	if (id >= m_renderer_factories.size()) throw std::runtime_error("select_renderer: no renderer with that id");
+	synchronize();
+	if (m_renderer) { m_renderer->destroy(); m_renderer = NULL; }
+	m_parts.clear();
+	m_renderer_clears_gbuffer = false;
+	m_renderer = m_renderer_factories[id]();
+	m_renderer->init(argc, argv, *this);
+	synchronize();
+}
+
 void RenderingContext::init(int argc, char** argv)
 {
 	fb200_scene* s = new fb200_scene();

@@ -63,6 +63,9 @@ struct RenderingContext
 	void init_with_scene(fb200_scene* scene, int device, int argc, char** argv);
 
 	uint32_t register_renderer(const char* name, RendererFactoryFunction factory);   // src/renderer.cu:1020-1025
+	// instantiate renderer `id` (what load_plugin does with the id register_plugin returns, src/renderer.cu:441-460 -> :957): the current
+	// renderer is destroy()ed, the new one created through its factory and init()ialised
+	void     select_renderer(uint32_t id, int argc, char** argv);
 	void     clear();                                                                 // zero the frame buffer
 	void     render(const uint32_t instance);                                         // src/renderer.cu:1029-1056
 	void     rescale_frame(const uint32_t instance);                                  // src/renderer.cu:413-416

@@ -1055,6 +1055,63 @@ void load_scene(const std::string& filename, Scene& scene, bool camera_overridde
 	load_textures(scene);
 }
 
+void scene_from_mesh_desc(const fb200_mesh_desc& d, Scene& scene, bool camera_overridden)
+{
+	if (!d.vertex_indices || !d.vertex_data || !d.material_indices || !d.materials || d.num_triangles == 0 || d.num_vertices == 0 || d.num_materials == 0)
+		throw std::runtime_error("fb200_mesh_desc: vertex_indices, vertex_data, material_indices and materials are required");
+	Mesh& m = scene.mesh;
+	m = Mesh();
+	const int4* vi = reinterpret_cast<const int4*>(d.vertex_indices);
+	m.vertex_indices.assign(vi, vi + d.num_triangles);
+	const float4* vd = reinterpret_cast<const float4*>(d.vertex_data);
+	m.vertex_data.assign(vd, vd + d.num_vertices);
+	if (d.texture_indices_comp) { const int4* t = reinterpret_cast<const int4*>(d.texture_indices_comp); m.texture_indices_comp.assign(t, t + d.num_triangles); }
+	if (d.texture_indices && d.texture_data)
+	{
+		const int4* t = reinterpret_cast<const int4*>(d.texture_indices); m.texture_indices.assign(t, t + d.num_triangles);
+		const float2* td = reinterpret_cast<const float2*>(d.texture_data); m.texture_data.assign(td, td + d.num_texture_coordinates);
+	}
+	m.material_indices.assign(d.material_indices, d.material_indices + d.num_triangles);
+	const MeshMaterial* mats = reinterpret_cast<const MeshMaterial*>(d.materials);
+	m.materials.assign(mats, mats + d.num_materials);
+	m.material_names.resize(d.num_materials);
+	m.tex_bias = float2{ d.tex_bias[0], d.tex_bias[1] }; m.tex_scale = float2{ d.tex_scale[0], d.tex_scale[1] };
+	validate_mesh_indices(m, "fb200_mesh_desc");
+	for (uint32 i = 0; i < d.num_triangles; ++i)
+		if (!m.texture_indices.empty())
+			for (int k = 0; k < 3; ++k) { const int t = (&m.texture_indices[i].x)[k]; if (t >= (int)d.num_texture_coordinates) throw std::runtime_error("fb200_mesh_desc: texture index out of range"); }
+	scene.textures.assign(d.num_textures, TextureImage());
+	m.textures.resize(d.num_textures);
+	for (uint32 i = 0; i < d.num_textures; ++i)
+	{
+		TextureImage& t = scene.textures[i];
+		t.name = "texture" + std::to_string(i); m.textures[i] = t.name; m.textures_map[t.name] = i;
+		if (d.textures && d.textures[i].texels && d.textures[i].res_x && d.textures[i].res_y)
+		{
+			const float4* tx = reinterpret_cast<const float4*>(d.textures[i].texels);
+			t.levels.push_back(std::vector<float4>(tx, tx + (size_t)d.textures[i].res_x * d.textures[i].res_y));
+			t.res_x.push_back(d.textures[i].res_x); t.res_y.push_back(d.textures[i].res_y);
+			build_mip_chain(t);
+		}
+	}
+	if (!camera_overridden)
+	{
+		Camera& c = scene.camera;
+		c.eye = float3{ d.eye[0], d.eye[1], d.eye[2] }; c.aim = float3{ d.aim[0], d.aim[1], d.aim[2] }; c.up = float3{ d.up[0], d.up[1], d.up[2] };
+		c.dx = float3{ d.dx[0], d.dx[1], d.dx[2] }; c.fov = d.fov;
+	}
+	scene.dir_lights.clear();
+	for (uint32 i = 0; i < d.n_dir_lights; ++i)
+	{
+		DirectionalLight l; const float* f = d.dir_lights + 6 * i;
+		l.dir = float3{ f[0], f[1], f[2] }; l.color = float3{ f[3], f[4], f[5] };
+		scene.dir_lights.push_back(l);
+	}
+	scene.exposure = d.exposure > 0.0f ? d.exposure : 1.0f; scene.gamma = d.gamma > 0.0f ? d.gamma : 2.2f;
+	scene.bbox = Bbox3();
+	for (size_t i = 0; i < m.vertex_data.size(); ++i) scene.bbox.insert(V3(m.vertex_data[i]));
+}
+
 // ------------------------------------------------------------------------------------------
 // binary snapshot ("FBS1"): the pre-processed arrays exactly as the renderer consumes them
 // ------------------------------------------------------------------------------------------

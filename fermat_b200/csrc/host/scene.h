@@ -9,6 +9,7 @@
 //                      reference src/mesh/MeshStorage.cpp:246-331, 430-445, 651-840 and src/renderer.cu:735-744
 //   texture loading    reference src/renderer.cu:785-882 (.tga / .pfm -> float4, w = 0)
 #pragma once
+#include "../../../include/fermat_b200.h"
 #include "fb_types.h"
 #include "fb_math.h"
 #include <string>
@@ -104,5 +105,7 @@ float    half_to_float(uint16_t h);
 bool load_tga(const std::string& filename, uint32& w, uint32& h, std::vector<float4>& texels);
 bool load_pfm(const std::string& filename, uint32& w, uint32& h, std::vector<float4>& texels);
 void build_mip_chain(TextureImage& tex);
+// a scene from pre-processed arrays in memory (include/fermat_b200.h fb200_mesh_desc): the in-memory twin of load_scene_snapshot
+void scene_from_mesh_desc(const fb200_mesh_desc& d, Scene& scene, bool camera_overridden);
 
 } // namespace fb

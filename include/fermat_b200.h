@@ -30,7 +30,9 @@ extern "C" {
  * `register_renderer(const char*, RendererFactoryFunction)` (src/renderer.h:220); the return value
  * is the renderer id. Our own C++ host (fermat_b200/csrc/host/rendering_context.h) provides that
  * class with the reference's method names. */
+#ifndef FB200_NO_PLUGIN_DECLARATION   /* (a translation unit that defines its own register_plugin against Fermat's C++ RenderingContext&: adapter/fermat_adapter.cpp) */
 uint32_t register_plugin(void* rendering_context);
+#endif
 
 /* ---------------------------------------------------------------------------------------------
  * 2. flat API
@@ -123,6 +125,25 @@ const char* fb200_last_error(void);
  * then loads the scene, builds sampler tables, VPLs (n_vpls = res_x*res_y) and the BVH.
  * Returns NULL on failure (see fb200_last_error). */
 fb200_scene* fb200_scene_create(int argc, const char* const* argv);
+/* The same from arrays already in memory instead of `-i file`: what a host that owns a loaded scene passes - Fermat's own
+ * RenderingContext after its mesh pre-processing (compress_normals, compress_tex, unify_vertex_attributes, apply_material_flags:
+ * src/renderer.cu:735-744), see adapter/fermat_adapter.cpp. HOST arrays in MeshView's layouts (src/mesh/MeshView.h:96-145):
+ * int4 per triangle (vertex_indices: .w = material flags; texture_indices_comp: 3 x packed fp16 uv, -1 = none, or NULL), float4 per
+ * vertex (.w = 10-10-10 packed normal), 208-B MeshMaterial records, float4 LOD-0 texel arrays (NULL = missing texture).
+ * texture_indices / texture_data (the uncompressed coordinates, src/mesh/MeshView.h:131-137) are read only to estimate the
+ * emission of TEXTURED emitters (src/mesh_lights.cu:190-246) and may be NULL. Everything is copied. */
+typedef struct fb200_mesh_desc {
+	uint32_t num_triangles, num_vertices, num_materials, num_textures, num_texture_coordinates;
+	const int32_t* vertex_indices; const float* vertex_data; const int32_t* texture_indices_comp; const int32_t* material_indices;
+	const int32_t* texture_indices; const float* texture_data;
+	const void* materials;
+	float tex_bias[2], tex_scale[2];
+	const fb200_texture_view* textures;
+	float eye[3], aim[3], up[3], dx[3], fov;                /* Camera (src/camera.h:46-52) */
+	uint32_t n_dir_lights; const float* dir_lights;          /* direction xyz, colour rgb per light (src/lights.h:256-295) */
+	float exposure, gamma;
+} fb200_mesh_desc;
+fb200_scene* fb200_scene_create_from_mesh(const fb200_mesh_desc* mesh, int argc, const char* const* argv);
 void         fb200_scene_destroy(fb200_scene*);
 int          fb200_scene_get_view(const fb200_scene*, fb200_scene_view* out);
 /* write / the pre-processed scene as a binary snapshot (.fbs) that fb200_scene_create can load with -i */
@@ -232,6 +253,17 @@ const float* fb200_context_gathered_device_ptr(fb200_context*);
  * (res_x * res_y * 4 floats; other pixels keep what earlier calls put there) */
 int fb200_diag_pack_tiles(fb200_context*, int channel, float* out, uint64_t n_floats);
 int fb200_diag_unpack_tiles(fb200_context*, uint32_t rank, uint32_t count, const float* packed, uint64_t n_floats, float* frame);
+/* The C++ RenderingContext behind a C-ABI context (the object a C++ host passes to register_plugin), and the second half of
+ * RenderingContextImpl::load_plugin (src/renderer.cu:456-460 -> m_renderer->init, :957): renderer `id` - an id register_plugin or
+ * RenderingContext::register_renderer returned - replaces the context's current renderer (which is destroy()ed). */
+void* fb200_context_rendering_context(fb200_context*);
+int fb200_context_select_renderer(fb200_context*, uint32_t id);
+
+/* copy the frame-buffer channels (float4 per pixel, res_x * res_y) into caller-owned DEVICE buffers on the context's stream, behind the
+ * passes rendered so far: channels[i] = destination of channel i (fb200 channel numbering = FBufferDesc, src/renderer_view.h:133-145)
+ * or NULL to skip it. This is how a host that owns its frame buffer (Fermat's RenderingContext: adapter/fermat_adapter.cpp) receives
+ * the running mean the renderer keeps. Asynchronous; fb200_context_synchronize or work on fb200_context_stream orders behind it. */
+int fb200_context_publish(fb200_context*, float* const device_channels[8]);
 /* number of pixels this shard owns */
 uint64_t fb200_context_owned_pixels(const fb200_context*);
 

@@ -407,3 +407,58 @@ $CXX -O2 -std=c++14 -fPIC -shared -w -fpermissive -ffp-contract=off \
     -I$OV/vp -I$OV -I$REF/src -I$REF/src/mesh -I$REF/contrib -I/usr/local/cuda/include \
     -o $OUT/libref_vp.so $OUT/ref_vp_shim.cpp -L/usr/local/cuda/lib64 -lcudart_static -ldl -lrt -lpthread
 echo "built $OUT/libref_vp.so"
+
+# ---- overlay_full: the same overlay WITHOUT the renderer_view.h / pathtracer_core.h stubs, plus a stub of the OptiX SDK math headers
+# src/camera.h includes, so that `#include <renderer.h>` - the reference's real RenderingContext - passes a host syntax check.
+# Used by tests/test_boundary.py to check adapter/fermat_adapter.cpp against the real API (never linked, never run).
+OVF=$OUT/overlay_full
+rm -rf $OVF; mkdir -p $OVF/optixu
+for f in cugar mesh optix_prime buffers.h texture.h framebuffer.h texture_view.h ref_prefix.h; do cp -r $OV/$f $OVF/; done
+cat > $OVF/optixu/optixu_matrix.h <<'EOF'
+#pragma once
+// stub of the OptiX SDK math headers (optixu_math_namespace.h / optixu_matrix.h), for SYNTAX CHECKS of code written against Fermat's
+// renderer.h only: the float3 / float4 operators src/camera.h uses and optix::Matrix<4,4>::rotate. The SDK is closed source and absent.
+#include <cuda_runtime.h>
+#include <math.h>
+inline float3 operator+(const float3 a, const float3 b) { return make_float3(a.x + b.x, a.y + b.y, a.z + b.z); }
+inline float3 operator-(const float3 a, const float3 b) { return make_float3(a.x - b.x, a.y - b.y, a.z - b.z); }
+inline float3 operator-(const float3 a) { return make_float3(-a.x, -a.y, -a.z); }
+inline float3 operator*(const float3 a, const float s) { return make_float3(a.x * s, a.y * s, a.z * s); }
+inline float3 operator*(const float s, const float3 a) { return make_float3(a.x * s, a.y * s, a.z * s); }
+inline float3 operator/(const float3 a, const float s) { return make_float3(a.x / s, a.y / s, a.z / s); }
+inline float4 operator+(const float4 a, const float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+inline float4 operator-(const float4 a, const float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+inline float  dot(const float3 a, const float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline float  length(const float3 a) { return sqrtf(dot(a, a)); }
+inline float3 normalize(const float3 a) { return a / length(a); }
+inline float3 cross(const float3 a, const float3 b) { return make_float3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+inline float3 make_float3(const float4 a) { return make_float3(a.x, a.y, a.z); }
+inline float4 make_float4(const float3 a, const float w) { return make_float4(a.x, a.y, a.z, w); }
+namespace optix {
+template <unsigned M, unsigned N> struct Matrix
+{
+	float m[M * N];
+	static Matrix rotate(const float, const float3&) { Matrix r; for (unsigned i = 0; i < M * N; ++i) r.m[i] = (i % (N + 1)) ? 0.0f : 1.0f; return r; }
+	Matrix operator*(const Matrix&) const { return *this; }
+	float4 operator*(const float4& v) const { return v; }
+};
+}
+EOF
+cat > $OVF/adapter_prefix.h <<'EOF'
+#pragma once
+// force-included ahead of Fermat's headers for host-side syntax checks of code written against src/renderer.h: the MSVC-permissive
+// spots g++ rejects, spelled out; nothing here changes what the checked code does
+#include "ref_prefix.h"
+#include <cstdlib>
+#include <cstddef>
+#include <thrust/device_allocator.h>
+namespace thrust { template <typename T> using device_malloc_allocator = device_allocator<T>; }   // (pre-CUDA-11 name, contrib/cugar/basic/vector.h:111)
+namespace cugar { inline size_t min(const size_t a, const size_t b) { return a < b ? a : b; } }     // ambiguous between the uint32 / uint64 overloads on LP64
+#include <cugar/linalg/vector.h>
+namespace cugar {
+inline Vector2f operator-(const Vector2f a, const float b) { return Vector2f(a.x - b, a.y - b); }   // src/camera.h:182
+inline Vector3f operator-(const float a, const Vector3f b) { return Vector3f(a - b.x, a - b.y, a - b.z); }
+}
+#define random fermat_random                                                                       // src/tiled_sampling.h:44 vs glibc's random()
+EOF
+echo "built $OVF (syntax-check overlay for code written against the reference's renderer.h)"

@@ -220,3 +220,26 @@ def test_malformed_obj_indices_are_rejected(fb, tmp_path):
         fb.Scene(["-i", str(p), "-r", "16", "16"])
     p.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nf -1 -2 -3\n")          # relative indices that do resolve are fine
     fb.Scene(["-i", str(p), "-r", "16", "16"]).close()
+
+
+def test_scene_from_arrays_equals_scene_from_file(fb, oracle):
+    """fb200_scene_create_from_mesh (what adapter/fermat_adapter.cpp hands over: arrays a host already holds, in MeshView's layouts)
+    builds the same scene as `-i file`: identical BVH, VPL table, sampler tables, and therefore the same oracle image."""
+    args = ["-r", "48", "40", "-bounces", "3"]
+    a = fb.Scene(cornell_args(48, 3)[:2] + args)
+    b = fb.Scene(args, mesh=a.mesh_desc())
+    va, vb = a.view, b.view
+    for name, n in (("vertex_indices", 4 * va.num_triangles), ("vertex_data", 4 * va.num_vertices), ("material_indices", va.num_triangles),
+                    ("mesh_cdf", va.n_prims), ("mesh_inv_area", va.n_prims), ("shifts", va.n_dimensions * va.tile_size ** 2)):
+        assert np.array_equal(np.ctypeslib.as_array(getattr(va, name), shape=(int(n),)), np.ctypeslib.as_array(getattr(vb, name), shape=(int(n),))), name
+    import ctypes as C
+    assert va.n_vpls == vb.n_vpls and va.vpl_norm == vb.vpl_norm and va.n_bvh_nodes == vb.n_bvh_nodes
+    assert C.string_at(va.vpls, 16 * va.n_vpls) == C.string_at(vb.vpls, 16 * vb.n_vpls)
+    assert C.string_at(va.bvh_nodes, 32 * va.n_bvh_nodes) == C.string_at(vb.bvh_nodes, 32 * vb.n_bvh_nodes)
+    assert list(va.eye) == list(vb.eye) and list(va.aim) == list(vb.aim) and va.fov == vb.fov
+    fa, fbuf = oracle.new_framebuffer(va), oracle.new_framebuffer(vb)
+    oracle.render_pass(va, 0, fa); oracle.render_pass(vb, 0, fbuf)
+    assert np.array_equal(fa, fbuf)
+    with pytest.raises(RuntimeError, match="required"):
+        fb.Scene(args, mesh=fb.MeshDesc())
+    a.close(); b.close()
