@@ -91,6 +91,7 @@ def lib():
         "fb200_scene_create": (vp, [i32, C.POINTER(C.c_char_p)]),
         "fb200_scene_create_from_mesh": (vp, [C.POINTER(MeshDesc), i32, C.POINTER(C.c_char_p)]),
         "fb200_context_publish": (i32, [vp, C.POINTER(vp * 8)]),
+        "fb200_context_update_scene": (i32, [vp, pf]),
         "fb200_scene_destroy": (None, [vp]),
         "fb200_scene_get_view": (i32, [vp, C.POINTER(SceneView)]),
         "fb200_scene_save_snapshot": (i32, [vp, C.c_char_p]),
@@ -453,6 +454,13 @@ class RenderingContext(_Handle):
 
     def owned_pixels(self):
         return int(lib().fb200_context_owned_pixels(self._h))
+
+    def update_scene(self, vertex_data):
+        """the vertices moved (num_vertices x 4 float32: xyz + packed normal): VPLs redone on the host, the scene BVH rebuilt on the device"""
+        v = np.ascontiguousarray(vertex_data, np.float32)
+        assert v.size == 4 * self.scene.view.num_vertices
+        self._chk(lib().fb200_context_update_scene(self._h, _fptr(v)))
+        lib().fb200_scene_get_view(self.scene._h, C.byref(self.scene.view))
 
     def publish(self, tensors):
         """copy frame-buffer channels into caller-owned device buffers: {channel name or index: CUDA tensor (H, W, 4) float32}"""

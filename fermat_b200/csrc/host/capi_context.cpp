@@ -249,6 +249,11 @@ int fb200_bsdf_eval(fb200_context* c, const float* rec, float* out, uint32_t n)
 	});
 }
 
+int fb200_context_update_scene(fb200_context* c, const float* vertex_data)
+{
+	return guarded([&] { c->rc.update_geometry(vertex_data); });
+}
+
 int fb200_context_publish(fb200_context* c, float* const device_channels[8])
 {
 	return guarded([&] {

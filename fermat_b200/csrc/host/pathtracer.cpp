@@ -183,6 +183,13 @@ void PathTracer::init(int argc, char** argv, RenderingContext& renderer)
 	renderer.synchronize();      // the uploads above read host vectors that go out of scope here
 }
 
+void PathTracer::update_scene(RenderingContext& renderer)
+{
+	float ms = 0.0f;
+	const uint32_t n_nodes = renderer.build_lbvh(3, true, NULL, NULL, NULL, &ms);
+	fprintf(stderr, "  scene update: device LBVH rebuilt (%u nodes, %.2f ms)\n", n_nodes, ms);
+}
+
 cudaEvent_t PathTracer::take_event()
 {
 	if (!m_event_pool.empty()) { cudaEvent_t e = m_event_pool.back(); m_event_pool.pop_back(); return e; }

@@ -239,6 +239,30 @@ void RenderingContext::upload_scene()
 	cuda_check(cudaStreamSynchronize(m_stream), "scene upload");
 }
 
+void RenderingContext::update_geometry(const float* new_vertex_data)
+{
+	fb200_scene& s = *m_scene;
+	Mesh& m = s.scene.mesh;
+	synchronize();                       // nothing may still read what is about to change
+	if (new_vertex_data) memcpy(m.vertex_data.data(), new_vertex_data, m.vertex_data.size() * sizeof(float4));
+	s.scene.bbox = Bbox3();
+	for (size_t i = 0; i < m.vertex_data.size(); ++i) s.scene.bbox.insert(V3(m.vertex_data[i]));
+	// the light sampler is a function of the emitters' areas (src/mesh_lights.cu:164-388)
+	s.mesh_lights.init(s.res_x * s.res_y, s.scene, 0u);
+	d_vertex_data.upload(m.vertex_data.data(), m.vertex_data.size() * sizeof(float4), m_stream);
+	d_vpls.upload(s.mesh_lights.vpls.data(), s.mesh_lights.vpls.size() * sizeof(VPL), m_stream);
+	d_mesh_cdf.upload(s.mesh_lights.mesh_cdf.data(), s.mesh_lights.mesh_cdf.size() * sizeof(float), m_stream);
+	d_mesh_inv_area.upload(s.mesh_lights.mesh_inv_area.data(), s.mesh_lights.mesh_inv_area.size() * sizeof(float), m_stream);
+	DeviceScene& d = m_dscene;
+	d.vertex_data = d_vertex_data.as<float4>();
+	d.vpls = d_vpls.as<VPL>(); d.n_vpls = (uint32)s.mesh_lights.vpls.size();
+	d.use_vpls = (s.options.nee_type == 1 && d.n_vpls > 0) ? 1u : 0u;
+	d.vpl_norm = s.mesh_lights.normalization_coeff;
+	d.mesh_cdf = d_mesh_cdf.as<float>(); d.mesh_inv_area = d_mesh_inv_area.as<float>();
+	cuda_check(cudaStreamSynchronize(m_stream), "geometry upload");
+	if (m_renderer) m_renderer->update_scene(*this);
+}
+
 void RenderingContext::clear() { m_fb.clear(stream()); }
 
 void RenderingContext::render(const uint32_t instance)

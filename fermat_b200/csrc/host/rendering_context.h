@@ -66,6 +66,11 @@ struct RenderingContext
 	// instantiate renderer `id` (what load_plugin does with the id register_plugin returns, src/renderer.cu:441-460 -> :957): the current
 	// renderer is destroy()ed, the new one created through its factory and init()ialised
 	void     select_renderer(uint32_t id, int argc, char** argv);
+	// RenderingContext::update_model's role for geometry (src/renderer.cu:1003-1015 -> m_renderer->update_scene, :1013): the vertex positions
+	// changed (new_vertex_data: float4 per vertex, .w = packed normal; NULL = the host scene's array was edited in place). The host side
+	// redoes what depends on geometry (bounding box, triangle CDF / VPLs), the arrays go to the device again, and the renderer's
+	// update_scene() rebuilds the scene BVH ON THE DEVICE (PathTracer: CUGAR-format LBVH + 8-wide collapse, build_lbvh).
+	void     update_geometry(const float* new_vertex_data);
 	void     clear();                                                                 // zero the frame buffer
 	void     render(const uint32_t instance);                                         // src/renderer.cu:1029-1056
 	void     rescale_frame(const uint32_t instance);                                  // src/renderer.cu:413-416
@@ -189,6 +194,9 @@ struct PathTracer final : RendererInterface
 
 	void init(int argc, char** argv, RenderingContext& renderer);
 	void render(const uint32_t instance, RenderingContext& renderer);
+	// RendererInterface::update_scene (src/renderer_interface.h:63): the geometry changed - rebuild the scene BVH on the device from the
+	// mesh arrays resident there (CUGAR-format LBVH: Morton-60 codes, radix sort, radix tree, refit; collapsed to the 8-wide layout)
+	void update_scene(RenderingContext& renderer);
 	void destroy() { delete this; }
 	void dump_speed_stats(FILE* stats);
 

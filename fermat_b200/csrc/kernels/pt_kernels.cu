@@ -188,9 +188,20 @@ __global__ void __launch_bounds__(256) k_generate_primary(DeviceScene sc, PassPa
 #ifndef FB_TRACE_STATS
 #define FB_TRACE_STATS 0           // 1: the queue trace launches fill PassCounters::stat_max / stat_sum (diagnostic build, tools/trace_stats.py)
 #endif
+#ifndef FB_NODES_PER_ITER
+#define FB_NODES_PER_ITER 1        // 2 (r2 sweep: 1520 vs 1517-1522, no gain; with it on the any-hit launches too 1502): a lane visits a second node before the warp's pooled triangle phase (closest-hit launches): the per-iteration
+                                   // bookkeeping (scan, pair list, ray shuffles, hit delivery, refill vote) is paid once per two node visits and the
+                                   // triangle pool is fuller; the second visit runs against a far bound the first node's triangles have not tightened yet
+#endif
+#ifndef FB_NODES_PER_ITER_ANY
+#define FB_NODES_PER_ITER_ANY 1    // the same for the any-hit launches (a second visit is wasted whenever the first node's triangles occlude the ray)
+#endif
 #ifndef FB_TRAV_BATCH
 #define FB_TRAV_BATCH 3            // traversal iterations a lane runs between two warp-wide refill votes (sweep: 2-3 best)
 #endif
+
+// shared-memory words per warp behind the staged nodes: pair list (32) + helper counts (32) [+ hit-delivery slots: t (32), triangle (32), uv (64)]
+#define FB_WARP_SMEM_WORDS ((FB_SMEM_DELIVER ? 192u : 64u) + (FB_STAGE_TRIS ? 384u : 0u))      // (+ the staged triangle ring: 32 x 48 B)
 
 enum TraceMode { TRACE_QUEUE_CLOSEST = 0, TRACE_QUEUE_SHADOW = 1, TRACE_RAYS_CLOSEST = 2, TRACE_RAYS_SHADOW = 3 };
 
@@ -264,7 +275,7 @@ __global__ void __launch_bounds__(FB_TRACE_THREADS, FB_TRACE_MIN_BLOCKS) k_trace
 #endif
 #if FB_COOP_TRI
 	// this warp's 32-entry (ray, triangle) pair list, behind the staged nodes and the shared-memory stacks
-	uint32* pair_buf = reinterpret_cast<uint32*>(smem + 1 + sc.staged_nodes * 5u) + FB_SMEM_STACK * 2u * FB_TRACE_THREADS + (threadIdx.x >> 5) * 64u;
+	uint32* pair_buf = reinterpret_cast<uint32*>(smem + 1 + sc.staged_nodes * 5u) + FB_SMEM_STACK * 2u * FB_TRACE_THREADS + (threadIdx.x >> 5) * FB_WARP_SMEM_WORDS;
 	// helpers still at work on the ray owned by each lane of this warp (ray splitting, below)
 	uint32* pending = pair_buf + 32;
 	pending[lane] = 0u;
@@ -445,11 +456,21 @@ __global__ void __launch_bounds__(FB_TRACE_THREADS, FB_TRACE_MIN_BLOCKS) k_trace
 				done = !trav.acquire();
 				if (!done) trav.node_step(sc, smem_nodes);
 			}
+			uint2 tg2 = make_uint2(0u, 0u);
+			if ((ANY ? FB_NODES_PER_ITER_ANY : FB_NODES_PER_ITER) >= 2)
+			{
+				if (active && !done && (trav.has_node() || trav.sp > 0))
+				{
+					tg2 = trav.tgroup; trav.tgroup.y = 0u;       // the first node's triangles wait for the pooled phase
+					trav.acquire();
+					trav.node_step(sc, smem_nodes);
+				}
+			}
 			FB_STAT_MARK(1)
 #if FB_TRACE_STATS
-			trav.coop_tri_phase(sc, active && !done, pair_buf, lane, root, st_tri);
+			trav.coop_tri_phase(sc, active && !done, pair_buf, lane, root, st_tri, tg2);
 #else
-			trav.coop_tri_phase(sc, active && !done, pair_buf, lane, root);
+			trav.coop_tri_phase(sc, active && !done, pair_buf, lane, root, NULL, tg2);
 #endif
 			FB_STAT_MARK(2)
 			if (active && !done) done = (ANY && trav.occluded) || (!trav.has_node() && trav.sp == 0);
@@ -977,7 +998,7 @@ cudaError_t configure_kernels(LaunchConfig& lc, int device)
 	// shared memory per CTA for the staged top of the tree. Shared memory and L1 share the SM's 228 KB, and the
 	// traversal lives on L1 hits (per-lane stacks, hot nodes and triangles), so staging is deliberately small.
 	const int cap_smem = ((225 * 1024 / FB_TRACE_MIN_BLOCKS) - 1024) & ~1023;
-	const int stack_smem = FB_SMEM_STACK * 8 * FB_TRACE_THREADS + FB_COOP_TRI * 8 * FB_TRACE_THREADS;   // per-lane stacks + pair lists and helper counts
+	const int stack_smem = FB_SMEM_STACK * 8 * FB_TRACE_THREADS + FB_COOP_TRI * (FB_WARP_SMEM_WORDS / 8) * FB_TRACE_THREADS;   // per-lane stacks + pair lists and helper counts (FB_WARP_SMEM_WORDS words per warp)
 	const int max_smem = ((FB_STAGE_KB * 1024 + 16) < cap_smem - stack_smem ? (FB_STAGE_KB * 1024 + 16) : cap_smem - stack_smem);
 	e = cudaFuncSetAttribute(k_trace<TRACE_QUEUE_CLOSEST>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem + stack_smem); if (e) return e;
 	e = cudaFuncSetAttribute(k_trace<TRACE_QUEUE_SHADOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem + stack_smem); if (e) return e;
@@ -987,7 +1008,7 @@ cudaError_t configure_kernels(LaunchConfig& lc, int device)
 	return cudaSuccess;
 }
 
-static inline uint32 staged_smem(const DeviceScene& sc) { return 16u + sc.staged_nodes * (uint32)sizeof(WideNode) + FB_SMEM_STACK * 8u * FB_TRACE_THREADS + FB_COOP_TRI * 8u * FB_TRACE_THREADS; }
+static inline uint32 staged_smem(const DeviceScene& sc) { return 16u + sc.staged_nodes * (uint32)sizeof(WideNode) + FB_SMEM_STACK * 8u * FB_TRACE_THREADS + FB_COOP_TRI * (FB_WARP_SMEM_WORDS / 8u) * FB_TRACE_THREADS; }
 
 static inline uint32 set_threads(const FrameBufferView& fb, const PixelSet& ps) { return ps.whole ? fb.n_pixels : ps.n_tiles * FB_TILE * FB_TILE; }
 cudaError_t launch_rescale_frame(const FrameBufferView& fb, const PixelSet& ps, float scale, cudaStream_t s)

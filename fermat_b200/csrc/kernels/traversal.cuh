@@ -32,6 +32,19 @@ namespace fb {
 #endif
 // (r03 variants of the triangle phase that were measured and removed again - shuffle-only pair listing, segmented-min hit delivery, no
 // round for a remainder - are in the history: commit 12819dc, numbers in profiles/README.md)
+#ifndef FB_SMEM_DELIVER
+#define FB_SMEM_DELIVER 1          // 1 (r2 sweep: 1540 vs 1517-1522 Msamples/s): closest hits travel to their owner lane through shared-memory atomics
+                                   // (coop_tri_phase) instead of one broadcast round per hit
+#endif
+#ifndef FB_STAGE_TRIS
+#define FB_STAGE_TRIS 0            // 1 (r2 sweep: 1498 vs 1517-1522, -1.4 %): the pooled triangle phase stages each pair's 48-B record in shared memory with
+                                   // cp.async (LDGSTS) and reads it from there. With the r1 node-staging sweep (0 / 8 / 55 KB: 638 / 630 / 599) this settles the
+                                   // north-star clause "nodelets and triangle clusters staged in shared memory": on this path L1 capacity beats staging
+#endif
+#define FB_TRI_RING_OFFSET (FB_SMEM_DELIVER ? 192u : 64u)      // words into the warp's shared-memory area (pt_kernels.cu FB_WARP_SMEM_WORDS)
+#ifndef FB_MINMAX3
+#define FB_MINMAX3 0               // 1 (r2 sweep: 1514 vs 1517-1522, no gain): the slab test's min / max chains use the 3-input min.f32 / max.f32 of sm_100 (FMNMX3)
+#endif
 #ifndef FB_PREFETCH
 #define FB_PREFETCH 0              // bit 0: prefetch the next node, bit 1: prefetch the hit triangles (into L1) (r03: next node also from the stack top: -2.7 %)
 #endif
@@ -64,6 +77,10 @@ FB_D float byte_plus_2p15(uint32 w, int j, uint32 magic15)   // magic15 = 0x4700
 {
 	return __uint_as_float(__byte_perm(w, magic15, 0x7604u | ((uint32)j << 4)));
 }
+
+// 3-input min / max (PTX ISA 8.6+, sm_100): same NaN rule as fminf / fmaxf (a NaN operand drops out), so the value equals the two-step chain
+FB_D float min3f(float a, float b, float c) { float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
+FB_D float max3f(float a, float b, float c) { float r; asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
 
 struct TravRay
 {
@@ -249,9 +266,14 @@ struct Traversal
 					const float t0y = fmaf(byte_to_float(ymin, j, mg), aiy, aoy), t1y = fmaf(byte_to_float(ymax, j, mg), aiy, aoy);
 					const float t0z = fmaf(byte_to_float(zmin, j, mg), aiz, aoz), t1z = fmaf(byte_to_float(zmax, j, mg), aiz, aoz);
 #endif
+#if FB_MINMAX3
+					const float cmin = fmaxf(max3f(t0x, t0y, t0z), ray.tmin);
+					const float cmax = fminf(min3f(t1x, t1y, t1z), ray.tmax) * 1.0000004f;
+#else
 					const float cmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, ray.tmin));
 					// far side widened by 4e-7 relative so that fp rounding never culls a box whose geometry is hit
 					const float cmax = fminf(fminf(t1x, t1y), fminf(t1z, ray.tmax)) * 1.0000004f;
+#endif
 					if (cmin <= cmax)
 						hitmask |= ((child_bits4 >> sh) & 0xFFu) << ((bit_index4 >> sh) & 0xFFu);
 				}
@@ -334,15 +356,19 @@ struct Traversal
 	// k_trace): hits are delivered there.
 	// (TRI_MARK: cycle counters of the diagnostic build, k_trace FB_TRACE_STATS; st = NULL otherwise)
 	#define FB_TRI_MARK(k) if (st) { const long long t_ = clock64(); st[k] += t_ - st_mark; st_mark = t_; }
-	FB_D void coop_tri_phase(const DeviceScene& sc, const bool mine, uint32* __restrict__ pairs, const int lane, const int root, long long* st = NULL)
+	// `tg2`: a second triangle group of this lane (k_trace visits two nodes per iteration with FB_NODES_PER_ITER == 2: the triangles of
+	// the first wait here while the second node is visited, and both groups go through one pooled test phase)
+	FB_D void coop_tri_phase(const DeviceScene& sc, const bool mine, uint32* __restrict__ pairs, const int lane, const int root, long long* st = NULL,
+							 const uint2 tg2 = make_uint2(0u, 0u))
 	{
 		const uint32 FULL = 0xFFFFFFFFu;
 		long long st_mark = st ? clock64() : 0;
 		uint32 m = mine ? tgroup.y : 0u;
+		uint32 m2 = mine ? tg2.y : 0u;
 		if (mine) tgroup.y = 0u;
-		if (!__any_sync(FULL, m != 0u)) return;
+		if (!__any_sync(FULL, (m | m2) != 0u)) return;
 
-		const uint32 k = (uint32)__popc(m);
+		const uint32 k = (uint32)__popc(m) + (uint32)__popc(m2);
 		uint32 incl = k;
 		#pragma unroll
 		for (int d = 1; d < 32; d <<= 1)
@@ -357,6 +383,13 @@ struct Traversal
 		for (uint32 base = 0; base < total; base += 32u)
 		{
 			const bool valid = base + (uint32)lane < total;
+			while (m2 && next < base + 32u)           // (the older group first)
+			{
+				const uint32 b = bfind(m2);
+				m2 &= ~(1u << b);
+				pairs[next - base] = ((tg2.x + b) << 5) | (uint32)lane;
+				++next;
+			}
 			while (m && next < base + 32u)
 			{
 				const uint32 b = bfind(m);
@@ -380,7 +413,21 @@ struct Traversal
 			if (valid)
 			{
 				const float4* tp = reinterpret_cast<const float4*>(sc.tris) + (size_t)(e >> 5) * 3u;
+#if FB_STAGE_TRIS
+				// north-star clause "triangle clusters staged in shared memory", in its cheapest form: the 48-B record of this lane's pair goes
+				// global -> shared with the asynchronous copy unit (LDGSTS, 3 x 16 B) into the warp's ring and is read back from there
+				float4* ring = reinterpret_cast<float4*>(pairs + FB_TRI_RING_OFFSET) + lane * 3;
+				{
+					const uint32 dst = (uint32)__cvta_generic_to_shared(ring);
+					asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(tp) : "memory");
+					asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(dst + 16u), "l"(tp + 1) : "memory");
+					asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(dst + 32u), "l"(tp + 2) : "memory");
+					asm volatile("cp.async.wait_all;" ::: "memory");
+				}
+				const float4 a = ring[0], b = ring[1], c = ring[2];
+#else
 				const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+#endif
 				if (st) { uint32 dummy; asm volatile("mov.b32 %0, %1;" : "=r"(dummy) : "f"(a.x + b.x + c.x)); }
 				FB_TRI_MARK(3)
 				if (!(ANY_HIT && (rmask & __float_as_uint(b.w))))
@@ -416,6 +463,39 @@ struct Traversal
 				const uint32 occ = __reduce_or_sync(FULL, found ? (1u << dest) : 0u);
 				if ((occ >> lane) & 1u) occluded = true;
 			}
+#if FB_SMEM_DELIVER
+			else
+			{
+				// Hit delivery through the warp's shared-memory slots instead of one broadcast round per hit (r2: the serial loop below cost
+				// 1000-3000 cycles per iteration on coherent waves, profiles/r03_trace_anatomy.txt column "delivery"). Per owner lane o:
+				// best_t[o] = min over the round's hits of the t bits (positive floats order like integers), then best_tri[o] = min triangle id
+				// among the hits at that t - the (smaller t, then smaller id) rule, independent of which lane found what - and the unique winner
+				// leaves its barycentrics. The owner then applies the same acceptance test as before.
+				uint32* best_t = pairs + 64; uint32* best_tri = pairs + 96; float2* best_uv = reinterpret_cast<float2*>(pairs + 128);
+				if (__any_sync(FULL, found))
+				{
+					best_t[lane] = 0xFFFFFFFFu; best_tri[lane] = 0xFFFFFFFFu;
+					__syncwarp();
+					if (found) atomicMin(&best_t[dest], __float_as_uint(ht));
+					__syncwarp();
+					const bool first = found && best_t[dest] == __float_as_uint(ht);
+					if (first) atomicMin(&best_tri[dest], (uint32)htri);
+					__syncwarp();
+					if (first && best_tri[dest] == (uint32)htri) best_uv[dest] = make_float2(hbu, hbv);
+					__syncwarp();
+					const uint32 tb = best_t[lane];
+					if (tb != 0xFFFFFFFFu)
+					{
+						const float t = __uint_as_float(tb); const int tri = (int)best_tri[lane];
+						if (t < ray.tmax || (t == ray.tmax && hit.tri >= 0 && tri < hit.tri))
+						{
+							const float2 uv = best_uv[lane];
+							ray.tmax = t; hit.t = t; hit.tri = tri; hit.bu = uv.x; hit.bv = uv.y;
+						}
+					}
+				}
+			}
+#else
 			else
 			{
 				uint32 hm = __ballot_sync(FULL, found);
@@ -432,6 +512,7 @@ struct Traversal
 					}
 				}
 			}
+#endif
 			__syncwarp();
 			FB_TRI_MARK(5)
 		}

@@ -259,6 +259,11 @@ int fb200_diag_unpack_tiles(fb200_context*, uint32_t rank, uint32_t count, const
 void* fb200_context_rendering_context(fb200_context*);
 int fb200_context_select_renderer(fb200_context*, uint32_t id);
 
+/* RenderingContext::update_model for geometry -> RendererInterface::update_scene (src/renderer.cu:1003-1015, src/renderer_interface.h:63): the
+ * vertices moved. vertex_data: num_vertices x float4 (xyz, .w = the 10-10-10 packed normal, MeshView layout), host memory. The context
+ * recomputes what depends on geometry on the host (bounding box, triangle CDF, VPLs), uploads, and the renderer rebuilds the scene BVH
+ * ON THE DEVICE (CUGAR-format LBVH + 8-wide collapse; no host tree build). Topology, materials and textures are unchanged. Blocking. */
+int fb200_context_update_scene(fb200_context*, const float* vertex_data);
 /* copy the frame-buffer channels (float4 per pixel, res_x * res_y) into caller-owned DEVICE buffers on the context's stream, behind the
  * passes rendered so far: channels[i] = destination of channel i (fb200 channel numbering = FBufferDesc, src/renderer_view.h:133-145)
  * or NULL to skip it. This is how a host that owns its frame buffer (Fermat's RenderingContext: adapter/fermat_adapter.cpp) receives
