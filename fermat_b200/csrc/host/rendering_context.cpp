@@ -191,6 +191,25 @@ void RenderingContext::upload_wide_bvh()
 	}
 }
 
+// DeviceScene::tri_shade: the 7 words a hit vertex needs, gathered per triangle from the MeshView arrays (device_scene.h)
+void RenderingContext::upload_tri_shade()
+{
+	const Mesh& m = m_scene->scene.mesh;
+	const size_t nt = (size_t)m.num_triangles();
+	std::vector<uint4> rec(2 * nt);
+	for (size_t i = 0; i < nt; ++i)
+	{
+		const int4 tri = m.vertex_indices[i];
+		auto nbits = [&](int v) { uint32 b; memcpy(&b, &m.vertex_data[v].w, 4); return b; };
+		const int4 tt = m.texture_indices_comp.empty() ? int4{ -1, -1, -1, 0 } : m.texture_indices_comp[i];
+		rec[2 * i] = uint4{ nbits(tri.x), nbits(tri.y), nbits(tri.z), (uint32)tt.x };
+		rec[2 * i + 1] = uint4{ (uint32)tt.y, (uint32)tt.z, (uint32)m.material_indices[i], 0u };
+	}
+	d_tri_shade.upload(rec.data(), rec.size() * sizeof(uint4), m_stream);
+	cuda_check(cudaStreamSynchronize(m_stream), "shading records upload");      // `rec` is a local
+	m_dscene.tri_shade = d_tri_shade.as<uint4>();
+}
+
 void RenderingContext::upload_scene()
 {
 	fb200_scene& s = *m_scene;
@@ -237,6 +256,7 @@ void RenderingContext::upload_scene()
 	d.glossy_reflectance = d_glossy.as<float>(); d.shifts_t = d_shifts_t.as<float>(); d.n_dims = s.sequence.n_dimensions;
 	d.res_x = s.res_x; d.res_y = s.res_y; d.options = s.options;
 	cuda_check(cudaStreamSynchronize(m_stream), "scene upload");
+	upload_tri_shade();
 }
 
 void RenderingContext::update_geometry(const float* new_vertex_data)
@@ -260,6 +280,7 @@ void RenderingContext::update_geometry(const float* new_vertex_data)
 	d.vpl_norm = s.mesh_lights.normalization_coeff;
 	d.mesh_cdf = d_mesh_cdf.as<float>(); d.mesh_inv_area = d_mesh_inv_area.as<float>();
 	cuda_check(cudaStreamSynchronize(m_stream), "geometry upload");
+	upload_tri_shade();                  // (the packed normals ride in the vertices' .w)
 	if (m_renderer) m_renderer->update_scene(*this);
 }
 

@@ -177,7 +177,8 @@ private:
 	// device copies
 	fb::DeviceBuffer d_vertex_indices, d_vertex_data, d_texture_indices_comp, d_material_indices, d_materials,
 					 d_texture_views, d_nodes, d_tris, d_vpls, d_mesh_cdf, d_mesh_inv_area, d_dir_lights,
-					 d_glossy, d_shifts_t;
+					 d_glossy, d_shifts_t, d_tri_shade;
+	void upload_tri_shade();
 	std::vector<fb::DeviceBuffer*> d_textures;
 	// post-processing scratch (allocated on first use): 2 ping-pong images per filtered channel, filtered variances,
 	// unpacked normals, 8-bit output

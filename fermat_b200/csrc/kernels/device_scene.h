@@ -14,6 +14,10 @@ struct DeviceScene
 	const int4*         texture_indices_comp;   // may be NULL
 	const int*          material_indices;
 	const MeshMaterial* materials;
+	// Per-triangle shading record (ours, built on upload from the arrays above; 32 B = one sector): {packed normal of the 3 corners,
+	// packed fp16 uv of the 3 corners (-1 = none), material id, 0}. The hit vertex of k_shade needs exactly these 7 words; through the
+	// MeshView arrays they are a chain index -> 3 vertices (+ texture triangle + material id): two dependent gathers over 6 sectors.
+	const uint4*        tri_shade;              // [2 * triangle]
 	float2              tex_bias, tex_scale;
 	const TextureView*  textures;
 	uint32              num_textures;

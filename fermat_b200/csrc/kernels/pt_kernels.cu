@@ -188,6 +188,9 @@ __global__ void __launch_bounds__(256) k_generate_primary(DeviceScene sc, PassPa
 #ifndef FB_TRACE_STATS
 #define FB_TRACE_STATS 0           // 1: the queue trace launches fill PassCounters::stat_max / stat_sum (diagnostic build, tools/trace_stats.py)
 #endif
+#ifndef FB_TRI_SHADE_RECORD
+#define FB_TRI_SHADE_RECORD 1      // 1: k_shade reads the hit triangle's normals / uvs / material id from the 32-B per-triangle record (DeviceScene::tri_shade)
+#endif
 #ifndef FB_NODES_PER_ITER
 #define FB_NODES_PER_ITER 1        // 2 (r2 sweep: 1520 vs 1517-1522, no gain; with it on the any-hit launches too 1502): a lane visits a second node before the warp's pooled triangle phase (closest-hit launches): the per-iteration
                                    // bookkeeping (scan, pair list, ray shuffles, hit delivery, refill vote) is paid once per two node visits and the
@@ -684,10 +687,14 @@ __global__ void __launch_bounds__(128, FB_SHADE_MIN_BLOCKS) k_shade(DeviceScene 
 #endif
 
 			// ---- EyeVertex::setup (src/bpt_utils.h:585-642) ----
-			V3 unused; float s, t;
-			setup_geometry<false>(sc, tri, hit.z, hit.w, g, unused, s, t);
+			float s, t; uint32 material_id;
+#if FB_TRI_SHADE_RECORD
+			setup_hit_geometry(sc, tri, hit.z, hit.w, g, s, t, material_id);
+#else
+			{ V3 unused; setup_geometry<false>(sc, tri, hit.z, hit.w, g, unused, s, t); material_id = (uint32)__ldg(sc.material_indices + tri); }
+#endif
 			position = ray_o + hit.x * ray_d;
-			const MeshMaterial* m = sc.materials + __ldg(sc.material_indices + tri);
+			const MeshMaterial* m = sc.materials + material_id;
 			const float4* m4 = reinterpret_cast<const float4*>(m);
 			const float4 mp = __ldg(m4 + 6);                      // roughness, ior, opacity, flags
 			kd = V3(__ldg(m4 + 0)) * texture_rgb(sc, s, t, load_texref(m, 8));

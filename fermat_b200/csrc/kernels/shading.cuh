@@ -72,6 +72,31 @@ FB_D void setup_geometry(const DeviceScene& sc, uint32 tri, float u, float v, Fr
 	else { s = u; t = v; }
 }
 
+// The same frame and texture coordinates for a HIT vertex, from the per-triangle shading record (DeviceScene::tri_shade): one 32-B gather
+// instead of the index -> vertices chain; identical arithmetic on identical values (the record copies the packed normals and uvs), so the
+// result is the one setup_geometry<false> returns, bit for bit. Also returns the triangle's material id.
+FB_D void setup_hit_geometry(const DeviceScene& sc, uint32 tri, float u, float v, Frame& g, float& s, float& t, uint32& material_id)
+{
+	const uint4 r0 = __ldg(sc.tri_shade + 2u * tri), r1 = __ldg(sc.tri_shade + 2u * tri + 1u);
+	const float w = 1.0f - u - v;
+	const V3 n0 = unpack_normal(r0.x), n1 = unpack_normal(r0.y), n2 = unpack_normal(r0.z);
+	const V3 N = normalize(n2 * w + n0 * u + n1 * v);
+	g.normal_s = N;
+	g.tangent = orthogonal(N);
+	g.binormal = cross(N, g.tangent);
+	if (sc.texture_indices_comp)
+	{
+		const int tx = (int)r0.w, ty = (int)r1.x, tz = (int)r1.y;
+		const V2 t0 = tx >= 0 ? decompress_tex(sc, tx) : V2(1.0f, 0.0f);
+		const V2 t1 = ty >= 0 ? decompress_tex(sc, ty) : V2(0.0f, 1.0f);
+		const V2 t2 = tz >= 0 ? decompress_tex(sc, tz) : V2(0.0f, 0.0f);
+		s = t2.x * w + t0.x * u + t1.x * v;
+		t = t2.y * w + t0.y * u + t1.y * v;
+	}
+	else { s = u; t = v; }
+	material_id = r1.z;
+}
+
 // bilinear_texture_lookup at LOD 0 with wrap (src/texture_view.h:171-202); default value (1,1,1,1)
 // (the filtered fetch is kept out of line: it is called from five places and inlining five copies of its
 // fmodf/bilinear code bloats the shade kernel past the instruction cache)

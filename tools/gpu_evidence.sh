@@ -6,6 +6,8 @@
 # Copy what is to be judged into profiles/ (tools/ncu_summary.py condenses the .ncu-rep: see profiles/README.md).
 # Keep ncu --set full captures to a dozen launches: 72 launches with sources exceed gpurun's 64 MiB return limit.
 TAG=${1:-rXX}
+# (round 2: the sweeps of tools/sweep.py run first when SWEEP is set)
+[ -n "$SWEEP" ] && python tools/sweep.py $TAG $SWEEP
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm --format=csv > gpurun_out/${TAG}_gpu.txt
 timeout 600 python -m pytest tests -x -q -m gpu > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "pytest exit $?" | tee -a gpurun_out/${TAG}_pytest_gpu.log
