@@ -156,7 +156,8 @@ def run_reference(args):
     import fermat_b200 as fb
     import oracle
     scene, name = workload(args)
-    res = frame_size(args, 1)
+    # the same config as the GPU arm at this N: under torchrun the frame is the weak-scaling frame of `world` ranks (1600 sqrt(N) x 900 sqrt(N))
+    res = frame_size(args, max(int(os.environ.get("WORLD_SIZE", "1")), 1))
     sc = fb.Scene(["-i", scene, "-r", str(res[0]), str(res[1]), "-bounces", str(BOUNCES)])
     P = res[0] * res[1]
     fbuf = oracle.new_framebuffer(sc.view)
@@ -181,7 +182,8 @@ def run_reference(args):
     sample = "each step = one oracle pass over every %d-th pixel of %dx%d (%d pixels)" % (stride, res[0], res[1], pixels.size)
     emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "Msamples/s", "n_gpus": 0, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "scene bathroom2 of the reference's models/ (snapshot scenes/_cache/bathroom2.fbs), the reference's default sampler seeds; no synthetic rays",
         "config": {"workload": "%s -pt %dx%d, %d bounces" % (name, res[0], res[1], BOUNCES), "note": "CPU restatement of the reference algorithm (the reference needs OptiX 6 / Win32 and cannot run)"},
         "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
