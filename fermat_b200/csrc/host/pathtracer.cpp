@@ -11,7 +11,7 @@ using namespace fb;
 // fermat_b200/__init__.py mirrors this struct (PASS_COUNTERS_DTYPE) for fb200_diag_pass_counters
 static_assert(sizeof(PassCounters) == 20480, "PassCounters layout changed: update PASS_COUNTERS_DTYPE in fermat_b200/__init__.py");
 
-PathTracer::PathTracer() : m_tiles_x(0), m_owned_pixels(0), m_passes(0), m_device_ms(0.0), m_ev0(NULL), m_ev1(NULL), m_ev_start(NULL), m_overlap(1), m_trace_ctas(0), m_psf(false), m_events(false), m_profiling(false)
+PathTracer::PathTracer() : m_tiles_x(0), m_owned_pixels(0), m_passes(0), m_device_ms(0.0), m_ev0(NULL), m_ev1(NULL), m_ev_start(NULL), m_overlap(1), m_trace_ctas(0), m_shade_split(0), m_psf(false), m_events(false), m_profiling(false)
 {
 	memset(&m_psf_view, 0, sizeof(m_psf_view));
 	for (int i = 0; i < 4; ++i) { m_class_ms[i] = 0.0; m_class_launches[i] = 0; }
@@ -31,6 +31,8 @@ PathTracer::~PathTracer()
 		if (f->ev_shaded) cudaEventDestroy(f->ev_shaded);
 		if (f->ev_shadowed) cudaEventDestroy(f->ev_shadowed);
 		if (f->ev_done) cudaEventDestroy(f->ev_done);
+		if (f->ev_traced) cudaEventDestroy(f->ev_traced);
+		if (f->ev_path) cudaEventDestroy(f->ev_path);
 		delete f;
 	}
 	for (size_t i = 0; i < m_spans.size(); ++i) { cudaEventDestroy(m_spans[i].a); cudaEventDestroy(m_spans[i].b); }
@@ -99,6 +101,9 @@ void PathTracer::init(int argc, char** argv, RenderingContext& renderer)
 	if (n_sub < 1) n_sub = 1;
 	env = getenv("FB200_OVERLAP");
 	m_overlap = env ? atoi(env) : 1;
+	// shade as two kernels on the sub-frame's two streams (k_shade<.., SHADE_LIGHT> / <.., SHADE_PATH>, pt_kernels.cu); not for -psfpt
+	env = getenv("FB200_SHADE_SPLIT");
+	m_shade_split = (env ? atoi(env) : 0) && !m_psf;
 	env = getenv("FB200_TRACE_CTAS");
 	// each persistent trace launch takes this many CTA slots per SM, so that the kernels of two streams are co-resident
 	// (sweep on bathroom2, Msamples/s: 1 sub-frame 1040; 2 sub-frames x 4 CTAs 1045, x 2 CTAs 1110; 4 x 1 1129; 6 x 2 878)
@@ -115,7 +120,7 @@ void PathTracer::init(int argc, char** argv, RenderingContext& renderer)
 		Arena arena(dry_run ? NULL : m_memory_pool.ptr);
 		for (uint32 k = 0; k < n_sub; ++k)
 		{
-			if (dry_run) { m_sub[k] = new SubFrame(); m_sub[k]->stream = m_sub[k]->side_stream = NULL; m_sub[k]->ev_shaded = m_sub[k]->ev_shadowed = m_sub[k]->ev_done = NULL; memset(m_sub[k]->queue, 0, sizeof(m_sub[k]->queue)); memset(&m_sub[k]->shadow, 0, sizeof(m_sub[k]->shadow)); memset(&m_sub[k]->shadow_dl, 0, sizeof(m_sub[k]->shadow_dl)); }
+			if (dry_run) { m_sub[k] = new SubFrame(); m_sub[k]->stream = m_sub[k]->side_stream = NULL; m_sub[k]->ev_shaded = m_sub[k]->ev_shadowed = m_sub[k]->ev_done = m_sub[k]->ev_traced = m_sub[k]->ev_path = NULL; memset(m_sub[k]->queue, 0, sizeof(m_sub[k]->queue)); memset(&m_sub[k]->shadow, 0, sizeof(m_sub[k]->shadow)); memset(&m_sub[k]->shadow_dl, 0, sizeof(m_sub[k]->shadow_dl)); }
 			SubFrame& f = *m_sub[k];
 			f.n_tiles = (uint32)sub_tiles[k].size();
 			f.capacity = (uint64_t)f.n_tiles * 32u * 32u;
@@ -151,6 +156,8 @@ void PathTracer::init(int argc, char** argv, RenderingContext& renderer)
 		cuda_check(cudaEventCreateWithFlags(&f.ev_shaded, cudaEventDisableTiming), "event");
 		cuda_check(cudaEventCreateWithFlags(&f.ev_shadowed, cudaEventDisableTiming), "event");
 		cuda_check(cudaEventCreateWithFlags(&f.ev_done, cudaEventDisableTiming), "event");
+		cuda_check(cudaEventCreateWithFlags(&f.ev_traced, cudaEventDisableTiming), "event");
+		cuda_check(cudaEventCreateWithFlags(&f.ev_path, cudaEventDisableTiming), "event");
 	}
 
 	{
@@ -325,7 +332,33 @@ void PathTracer::render_subframe(SubFrame& f, const PassParams& pass, const std:
 	uint32 n_launches = 0;
 	const PsfView* psf = m_psf ? &m_psf_view : NULL;
 	const bool dirlights = sc.n_dir_lights != 0;
-	for (uint32 bounce = 0; bounce < L; ++bounce)
+	for (uint32 bounce = 0; bounce < L && overlap && m_shade_split; ++bounce)
+	{
+		// Split shade (FB200_SHADE_SPLIT). Main stream: [accumulate(b-1) done] PATH(b) -> closest trace(b+1). Side stream: [closest trace(b) done]
+		// LIGHT(b) -> shadow trace(b) -> [PATH(b) done] accumulate(b). Per-pixel frame-buffer order is the unsplit one: emissive(b) (PATH) before
+		// next-event(b) (accumulate) before emissive(b+1).
+		const PathQueue& in = f.queue[bounce & 1];
+		const PathQueue& out = f.queue[(bounce + 1) & 1];
+		float seq6[6];
+		for (int i = 0; i < 6; ++i) seq6[i] = seq[(bounce + 1) * 6 + i];
+		if (bounce == 0) { cuda_check(launch_trace_closest(sc, lc, in, ctr, 0, stream), "trace"); renderer.kernel_launches += 1; }
+		cuda_check(cudaEventRecord(f.ev_traced, stream), "event record");
+		cuda_check(cudaStreamWaitEvent(f.side_stream, f.ev_traced, 0), "wait");
+		cuda_check(launch_shade(sc, lc, pp, in, out, f.shadow, f.shadow_dl, fbv, ctr, tot, bounce, seq6, (uint32)f.capacity, f.side_stream, NULL, 1), "shade (light)");
+		if (dirlights) { cuda_check(launch_trace_shadow(sc, lc, f.shadow_dl, fbv, ctr, tot, bounce, pp.frame_weight, f.side_stream, 1, &n_launches, NULL, 1), "trace_shadow"); renderer.kernel_launches += n_launches; }
+		cuda_check(launch_trace_shadow(sc, lc, f.shadow, fbv, ctr, tot, bounce, pp.frame_weight, f.side_stream, 0, &n_launches, NULL, 1), "trace_shadow");
+		renderer.kernel_launches += n_launches + 2;
+		if (bounce > 0) cuda_check(cudaStreamWaitEvent(stream, f.ev_shadowed, 0), "wait");              // accumulate(b-1) before the emissive adds of PATH(b)
+		cuda_check(launch_shade(sc, lc, pp, in, out, f.shadow, f.shadow_dl, fbv, ctr, tot, bounce, seq6, (uint32)f.capacity, stream, NULL, 2), "shade (path)");
+		cuda_check(cudaEventRecord(f.ev_path, stream), "event record");
+		if (bounce + 1 < L) { cuda_check(launch_trace_closest(sc, lc, out, ctr, bounce + 1, stream), "trace"); renderer.kernel_launches += 1; }
+		cuda_check(cudaStreamWaitEvent(f.side_stream, f.ev_path, 0), "wait");
+		if (dirlights) { cuda_check(launch_trace_shadow(sc, lc, f.shadow_dl, fbv, ctr, tot, bounce, pp.frame_weight, f.side_stream, 1, &n_launches, NULL, 2), "accumulate"); renderer.kernel_launches += n_launches; }
+		cuda_check(launch_trace_shadow(sc, lc, f.shadow, fbv, ctr, tot, bounce, pp.frame_weight, f.side_stream, 0, &n_launches, NULL, 2), "accumulate");
+		renderer.kernel_launches += n_launches;
+		cuda_check(cudaEventRecord(f.ev_shadowed, f.side_stream), "event record");
+	}
+	for (uint32 bounce = 0; bounce < L && !(overlap && m_shade_split); ++bounce)
 	{
 		span.bounce = bounce;
 		const PathQueue& in = f.queue[bounce & 1];

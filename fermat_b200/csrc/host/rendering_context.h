@@ -229,6 +229,7 @@ private:
 		fb::ShadowQueue  shadow_dl;               // scenes with DirectionalLights: the queue of their shadow rays (traced and accumulated before the next-event queue)
 		cudaStream_t     stream, side_stream;     // stream == NULL: the context's stream
 		cudaEvent_t      ev_shaded, ev_shadowed, ev_done;
+		cudaEvent_t      ev_traced, ev_path;      // FB200_SHADE_SPLIT: closest-hit trace of this bounce done / the path half of its shade done
 	};
 	std::vector<SubFrame*> m_sub;
 	fb::DeviceBuffer m_totals;
@@ -238,6 +239,7 @@ private:
 	cudaEvent_t      m_ev0, m_ev1, m_ev_start;
 	int              m_overlap;               // 0: one stream per sub-frame; else the shadow trace of bounce b runs beside the closest-hit trace of bounce b+1
 	int              m_trace_ctas;            // CTAs per SM of each persistent trace launch
+	int              m_shade_split;           // FB200_SHADE_SPLIT: shade as two kernels (light sampling / path extension) on the two streams of a sub-frame
 	// `-psfpt` (path-space filtering, src/renderers/psfpt_impl.h): the same loop with PSFPTVertexProcessor's policies, a hash of cache
 	// cells that lives across passes, and a splat of the references at the end of the pass
 	bool             m_psf;

@@ -631,11 +631,20 @@ struct ShadeArgs
 // (r01 profile: 22 % of the stall samples were "no instruction" with the 157 KB monolith).
 // PSF: PSFPTVertexProcessor's policies (src/psfpt_vertex_processor.h) instead of PTVertexProcessor's - the `-psfpt` renderer on the same
 // loop; every difference is behind `if (PSF)`, so the `-pt` instantiations are the kernels they were.
-template <bool DIRLIGHT, bool PSF = false>
-__global__ void __launch_bounds__(128, FB_SHADE_MIN_BLOCKS) k_shade(DeviceScene sc, ShadeArgs a)
+// PARTS: which phases this instantiation runs. SHADE_ALL = the whole vertex (one launch per bounce). With FB200_SHADE_SPLIT the host launches
+// SHADE_LIGHT (vertex set-up + directional lights + next-event estimation -> shadow queues) and SHADE_PATH (vertex set-up + G-buffer / albedo
+// + emissive hit + scattering -> next-bounce queue) as two kernels on two streams: each repeats the set-up but holds one Bsdf evaluation
+// less, and the closest-hit trace of bounce b+1 waits for SHADE_PATH only while the shadow trace of bounce b waits for SHADE_LIGHT only.
+enum ShadeParts { SHADE_LIGHT = 1, SHADE_PATH = 2, SHADE_ALL = 3 };
+#ifndef FB_SHADE_PART_BLOCKS
+#define FB_SHADE_PART_BLOCKS 8         // CTAs of 128 threads per SM of the two part kernels (64 registers)
+#endif
+
+template <bool DIRLIGHT, bool PSF = false, int PARTS = SHADE_ALL>
+__global__ void __launch_bounds__(128, PARTS == SHADE_ALL ? FB_SHADE_MIN_BLOCKS : FB_SHADE_PART_BLOCKS) k_shade(DeviceScene sc, ShadeArgs a)
 {
 	const uint32 n = a.ctr->in_size[a.bounce];
-	if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&a.tot->shade_events, (unsigned long long)n);
+	if ((PARTS & SHADE_PATH) && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&a.tot->shade_events, (unsigned long long)n);
 	const PTOptions& o = sc.options;
 	const uint32 bounce = a.bounce;
 	uint32* shadow_counter = &a.ctr->shadow_size[bounce];
@@ -738,7 +747,7 @@ __global__ void __launch_bounds__(128, FB_SHADE_MIN_BLOCKS) k_shade(DeviceScene 
 				vinfo = psf_pack(slot, 0u, new_entry ? 1u : 0u);
 			}
 
-			if (bounce == 0)
+			if ((PARTS & SHADE_PATH) && bounce == 0)
 			{
 				// G-buffer (pathtracer_core.h:802-806; GBufferView::pack_geometry, src/framebuffer.h:84-90)
 				if (a.fb.gb_geo)
@@ -774,7 +783,7 @@ __global__ void __launch_bounds__(128, FB_SHADE_MIN_BLOCKS) k_shade(DeviceScene 
 		}
 
 		// ---- directional lights (pathtracer_core.h:870-988) ----
-		if (DIRLIGHT && a.do_dirlight)
+		if ((PARTS & SHADE_LIGHT) && DIRLIGHT && a.do_dirlight)
 		{
 			bool dl_on = false;
 			float4 dl_o, dl_d, dl_wd, dl_wg;
@@ -820,7 +829,7 @@ __global__ void __launch_bounds__(128, FB_SHADE_MIN_BLOCKS) k_shade(DeviceScene 
 		}
 
 		// ---- next-event estimation (pathtracer_core.h:991-1106) ----
-		if (a.do_nee)
+		if ((PARTS & SHADE_LIGHT) && a.do_nee)
 		{
 			bool nee_on = false;
 			float4 nee_o, nee_d, nee_wd, nee_wg;
@@ -886,7 +895,7 @@ __global__ void __launch_bounds__(128, FB_SHADE_MIN_BLOCKS) k_shade(DeviceScene 
 		}
 
 		// ---- emissive hit with MIS against NEE at the previous vertex (pathtracer_core.h:1109-1154) ----
-		if (a.do_emissive && valid)
+		if ((PARTS & SHADE_PATH) && a.do_emissive && valid)
 		{
 			float light_pdf;
 			if (sc.use_vpls) light_pdf = fmaxf(fabsf(ke.x), fmaxf(fabsf(ke.y), fabsf(ke.z))) / sc.vpl_norm;
@@ -917,7 +926,7 @@ __global__ void __launch_bounds__(128, FB_SHADE_MIN_BLOCKS) k_shade(DeviceScene 
 		}
 
 		// ---- scattering with implicit Russian roulette (pathtracer_core.h:1157-1247) ----
-		if (a.do_scatter)
+		if ((PARTS & SHADE_PATH) && a.do_scatter)
 		{
 			bool scat_on = false;
 			float4 sc_o, sc_d, sc_w; uint32 sc_info = 0;
@@ -1098,8 +1107,9 @@ cudaError_t launch_trace_closest(const DeviceScene& sc, const LaunchConfig& lc, 
 bool kernels_split_accumulate() { return FB_SPLIT_ACCUMULATE != 0; }
 
 cudaError_t launch_trace_shadow(const DeviceScene& sc, const LaunchConfig& lc, const ShadowQueue& sq, const FrameBufferView& fb, PassCounters* ctr, PassTotals* tot,
-								uint32 bounce, float frame_weight, cudaStream_t s, int which, uint32* launches, const PsfView* psf)
+								uint32 bounce, float frame_weight, cudaStream_t s, int which, uint32* launches, const PsfView* psf, int stages)
 {
+	// stages: 1 = the trace only, 2 = the accumulation pass only, 3 = both (the two can be separated by an event: FB200_SHADE_SPLIT)
 	// which = 0: the next-event queue; 1: the directional-light queue (its own counters: the two are accumulated one after the other)
 	TraceArgs a; memset(&a, 0, sizeof(a));
 	a.ray_o = sq.ray_o; a.ray_d = sq.ray_d; a.stride = 1;
@@ -1107,9 +1117,14 @@ cudaError_t launch_trace_shadow(const DeviceScene& sc, const LaunchConfig& lc, c
 	a.w_d = sq.w_d; a.w_g = sq.w_g; a.fb = fb; a.frame_weight = frame_weight; a.bounce = bounce; a.event_counter = &tot->shadow_events;
 	a.occluded = sq.occluded;
 	a.stat_max = ctr->stat_max[1][bounce]; a.stat_sum = ctr->stat_sum[1][bounce];
-	if (launches) *launches = 1;
-	k_trace<TRACE_QUEUE_SHADOW><<<lc.sm_count * lc.trace_ctas_per_sm, lc.trace_threads, staged_smem(sc), s>>>(sc, a);
+	if (launches) *launches = 0;
+	if (stages & 1)
+	{
+		k_trace<TRACE_QUEUE_SHADOW><<<lc.sm_count * lc.trace_ctas_per_sm, lc.trace_threads, staged_smem(sc), s>>>(sc, a);
+		if (launches) *launches += 1;
+	}
 #if FB_SPLIT_ACCUMULATE
+	if (stages & 2)
 	{
 		AccumArgs ac; memset(&ac, 0, sizeof(ac));
 		ac.n_ptr = a.n_ptr; ac.occluded = sq.occluded; ac.w_d = sq.w_d; ac.w_g = sq.w_g; ac.vinfo = sq.vinfo; ac.fb = fb; ac.frame_weight = frame_weight; ac.bounce = bounce;
@@ -1151,7 +1166,7 @@ cudaError_t launch_clamp_frame(const FrameBufferView& fb, const PixelSet& ps, fl
 }
 
 cudaError_t launch_shade(const DeviceScene& sc, const LaunchConfig& lc, const PassParams& pp, const PathQueue& in, const PathQueue& out, const ShadowQueue& sq, const ShadowQueue& sq_dl,
-						 const FrameBufferView& fb, PassCounters* ctr, PassTotals* tot, uint32 bounce, const float seq6[6], uint32 capacity, cudaStream_t s, const PsfView* psf)
+						 const FrameBufferView& fb, PassCounters* ctr, PassTotals* tot, uint32 bounce, const float seq6[6], uint32 capacity, cudaStream_t s, const PsfView* psf, int parts)
 {
 	ShadeArgs a;
 	memset(&a.psf, 0, sizeof(a.psf));
@@ -1172,12 +1187,22 @@ cudaError_t launch_shade(const DeviceScene& sc, const LaunchConfig& lc, const Pa
 	if (blocks == 0) blocks = 1;
 	if (psf)
 	{
-		if (sc.n_dir_lights) return cudaErrorNotSupported;
+		if (sc.n_dir_lights || parts != SHADE_ALL) return cudaErrorNotSupported;
 		a.psf = *psf;
 		k_shade<false, true><<<blocks, threads, 0, s>>>(sc, a);
 	}
-	else if (sc.n_dir_lights) k_shade<true><<<blocks, threads, 0, s>>>(sc, a);
-	else k_shade<false><<<blocks, threads, 0, s>>>(sc, a);
+	else if (sc.n_dir_lights)
+	{
+		if (parts == SHADE_LIGHT) k_shade<true, false, SHADE_LIGHT><<<blocks, threads, 0, s>>>(sc, a);
+		else if (parts == SHADE_PATH) k_shade<true, false, SHADE_PATH><<<blocks, threads, 0, s>>>(sc, a);
+		else k_shade<true><<<blocks, threads, 0, s>>>(sc, a);
+	}
+	else
+	{
+		if (parts == SHADE_LIGHT) k_shade<false, false, SHADE_LIGHT><<<blocks, threads, 0, s>>>(sc, a);
+		else if (parts == SHADE_PATH) k_shade<false, false, SHADE_PATH><<<blocks, threads, 0, s>>>(sc, a);
+		else k_shade<false><<<blocks, threads, 0, s>>>(sc, a);
+	}
 	return cudaGetLastError();
 }
 
