@@ -191,21 +191,41 @@ M4 mul(const M4& A, const M4& B)
 	}
 	return R;
 }
+// Inverse of a 4x4 matrix in float by the adjugate, with the expansion order of cugar::invert(Matrix<T,4,4>) (contrib/cugar/linalg/
+// matrix_inline.h:292-361): the camera of a .pbrt scene is the inverse of the current transform applied to the origin and the axes
+// (src/mesh/pbrt_importer.cpp:164-173), and its bits decide every primary ray - tests/test_importers.py compares them with the reference's
+// own importer. (Round 1 inverted in double by Gauss-Jordan: the same camera to 1e-7, not to the bit.)
 bool invert(const M4& M, M4& inv)
 {
-	double a[4][8];
-	for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { a[i][j] = M.m[i * 4 + j]; a[i][j + 4] = i == j; }
-	for (int c = 0; c < 4; ++c)
+	const float* a = M.m;
+	auto A = [&](int r, int c) { return a[4 * r + c]; };
+	// 2x2 determinants of rows p, q over the column pairs (2,3) (1,3) (1,2) (0,3) (0,2) (0,1)
+	auto det2 = [&](int p, int q, float t[6])
 	{
-		int p = c;
-		for (int r = c + 1; r < 4; ++r) if (fabs(a[r][c]) > fabs(a[p][c])) p = r;
-		if (fabs(a[p][c]) < 1e-30) return false;
-		if (p != c) for (int j = 0; j < 8; ++j) std::swap(a[p][j], a[c][j]);
-		const double d = a[c][c];
-		for (int j = 0; j < 8; ++j) a[c][j] /= d;
-		for (int r = 0; r < 4; ++r) if (r != c) { const double fct = a[r][c]; for (int j = 0; j < 8; ++j) a[r][j] -= fct * a[c][j]; }
-	}
-	for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) inv.m[i * 4 + j] = (float)a[i][j + 4];
+		t[0] = A(p, 2) * A(q, 3) - A(p, 3) * A(q, 2); t[1] = A(p, 1) * A(q, 3) - A(p, 3) * A(q, 1); t[2] = A(p, 1) * A(q, 2) - A(p, 2) * A(q, 1);
+		t[3] = A(p, 0) * A(q, 3) - A(p, 3) * A(q, 0); t[4] = A(p, 0) * A(q, 2) - A(p, 2) * A(q, 0); t[5] = A(p, 0) * A(q, 1) - A(p, 1) * A(q, 0);
+	};
+	// the four 3x3 minors that share those determinants, expanded along row R
+	auto cof = [&](int R, const float t[6], float c[4])
+	{
+		c[0] = A(R, 1) * t[0] - A(R, 2) * t[1] + A(R, 3) * t[2];
+		c[1] = A(R, 0) * t[0] - A(R, 2) * t[3] + A(R, 3) * t[4];
+		c[2] = A(R, 0) * t[1] - A(R, 1) * t[3] + A(R, 3) * t[5];
+		c[3] = A(R, 0) * t[2] - A(R, 1) * t[4] + A(R, 2) * t[5];
+	};
+	float t[6], c[4], r[16];
+	const float sgn[4] = { 1.0f, -1.0f, 1.0f, -1.0f };
+	det2(2, 3, t);
+	cof(1, t, c); for (int k = 0; k < 4; ++k) r[4 * k + 0] = sgn[k] * c[k];
+	cof(0, t, c); for (int k = 0; k < 4; ++k) r[4 * k + 1] = -sgn[k] * c[k];
+	det2(1, 3, t);
+	cof(0, t, c); for (int k = 0; k < 4; ++k) r[4 * k + 2] = sgn[k] * c[k];
+	det2(1, 2, t);
+	cof(0, t, c); for (int k = 0; k < 4; ++k) r[4 * k + 3] = -sgn[k] * c[k];
+	float d = A(0, 0) * r[0] + A(0, 1) * r[4] + A(0, 2) * r[8] + A(0, 3) * r[12];
+	if (d == 0.0f) return false;
+	d = 1.0f / d;
+	for (int i = 0; i < 16; ++i) inv.m[i] = r[i] * d;
 	return true;
 }
 V3 ptrans(const M4& M, V3 v) { return V3(M.m[0] * v.x + M.m[1] * v.y + M.m[2] * v.z + M.m[3], M.m[4] * v.x + M.m[5] * v.y + M.m[6] * v.z + M.m[7], M.m[8] * v.x + M.m[9] * v.y + M.m[10] * v.z + M.m[11]); }
@@ -346,13 +366,13 @@ struct Importer
 		auto is_float = [](const Param& p) { return p.type == "float" && !p.floats.empty(); };
 		if (type == "matte")
 		{
-			m.diffuse = f4(V3(0.5f));
+			m.diffuse = float4{ 0.5f, 0.5f, 0.5f, 0.5f };               // cugar::Vector4f(0.5f): all four components (pbrt_importer.cpp:658)
 			for (const Param& p : ps) { if (p.name == "Kd" && is_rgb(p)) m.diffuse = f4(rgb(p)); else if (p.name == "Kd" && is_tex(p)) tex(p, m.diffuse_map); }
 		}
 		else if (type == "substrate")
 		{
 			float ur = 0.1f, vr = 0.1f;
-			m.diffuse = f4(V3(0.5f)); m.specular = f4(V3(0.5f));
+			m.diffuse = float4{ 0.5f, 0.5f, 0.5f, 0.5f }; m.specular = float4{ 0.5f, 0.5f, 0.5f, 0.5f };      // (:687-688)
 			for (const Param& p : ps)
 			{
 				if (p.name == "Kd" && is_rgb(p)) m.diffuse = f4(rgb(p)); else if (p.name == "Kd" && is_tex(p)) tex(p, m.diffuse_map);
@@ -367,7 +387,7 @@ struct Importer
 		else if (type == "glass")
 		{
 			float ur = 0.00001f, vr = 0.00001f;
-			m.opacity = 0.02f; m.specular = f4(V3(1.0f));
+			m.opacity = 0.02f; m.specular = float4{ 1.0f, 1.0f, 1.0f, 1.0f };                               // (:757-758)
 			for (const Param& p : ps)
 			{
 				if (p.name == "Kt" && is_rgb(p)) m.opacity = (p.floats[0] + p.floats[1] + p.floats[2]) / 3.0f;
@@ -504,6 +524,9 @@ struct Importer
 			Mesh other; make_sphere(other, 1.0e6f, true);
 			MeshMaterial m; memset(&m, 0, sizeof(m));
 			m.ambient_map = m.diffuse_map = m.diffuse_trans_map = m.specular_map = m.emissive_map = m.bump_map = no_texture();
+			// MeshMaterial::zero_material (src/mesh/MeshView.h:76-90): all colours 0, roughness 0, ior 1, OPACITY 1 (round 1 left it 0: paths
+			// that hit the environment sphere went on through it as glossy transmission instead of ending there - found by tests/test_importers.py)
+			m.opacity = 1.0f;
 			m.emissive = float4{ 1, 1, 1, 1 }; m.emissive_map.texture = tex; m.roughness = 1.0f; m.index_of_refraction = 0.0f;
 			materials.push_back(m); material_names.push_back("");
 			merge_with_material(other, (int)materials.size() - 1);

@@ -757,8 +757,11 @@ void compress_tex(Mesh& mesh)
 	float2 lo = { 1.0e30f, 1.0e30f }, hi = { -1.0e30f, -1.0e30f };
 	for (size_t i = 0; i < mesh.texture_data.size(); ++i)
 	{
-		lo.x = fminf(lo.x, mesh.texture_data[i].x); lo.y = fminf(lo.y, mesh.texture_data[i].y);
-		hi.x = fmaxf(hi.x, mesh.texture_data[i].x); hi.y = fmaxf(hi.y, mesh.texture_data[i].y);
+		// cugar::min / max are `a < b ? a : b` / `a > b ? a : b` (contrib/cugar/basic/numbers.h:536-540): among equal values (+0 / -0) the LAST
+		// one inserted wins, which fminf / fmaxf do not promise (tests/test_importers.py: CornellBox-Glossy's bias is +0, not -0)
+		const float2 t = mesh.texture_data[i];
+		lo.x = lo.x < t.x ? lo.x : t.x; lo.y = lo.y < t.y ? lo.y : t.y;
+		hi.x = hi.x > t.x ? hi.x : t.x; hi.y = hi.y > t.y ? hi.y : t.y;
 	}
 	mesh.tex_bias = lo;
 	mesh.tex_scale = float2{ hi.x - lo.x, hi.y - lo.y };

@@ -415,3 +415,43 @@ class RefPt:
         out = np.empty((rec.shape[0], 16), np.float32)
         self.vp.ref_vertex_processor(_fptr(rec), _fptr(out), C.c_uint(rec.shape[0]))
         return out
+
+
+class RefLoader:
+    """The REFERENCE's own scene loaders and mesh pre-processing compiled on this host (oracle/_ref/libref_loader.so: src/mesh/{MeshBase,glm,
+    MeshLoader,MeshStorage,fermat_loader,pbrt_importer,pbrt_parser}.cpp + rply, run in RenderingContextImpl::init's order, src/renderer.cu:700-744)."""
+
+    @staticmethod
+    def load():
+        L = _ref_so("libref_loader.so")
+        return RefLoader(L) if L is not None else None
+
+    def __init__(self, L):
+        self.L = L
+        L.ref_load_scene.restype = C.c_void_p; L.ref_load_scene.argtypes = [C.c_char_p]
+        L.ref_scene_array.restype = C.c_void_p; L.ref_scene_array.argtypes = [C.c_void_p, C.c_int]
+        L.ref_scene_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float)]
+        L.ref_free_scene.argtypes = [C.c_void_p]
+
+    def scene(self, path):
+        """dict of the pre-processed arrays the reference's RenderingContext would hold after loading `path`"""
+        h = self.L.ref_load_scene(str(path).encode())
+        if not h:
+            raise RuntimeError("the reference's loader failed on %s" % path)
+        cnt = (C.c_int * 6)(); f = (C.c_float * 19)()
+        self.L.ref_scene_info(h, cnt, f)
+        nt, nv, nm, ntex, ndl, cam = list(cnt)
+
+        def arr(which, dtype, shape):
+            p = self.L.ref_scene_array(h, which)
+            if not p or not int(np.prod(shape)):
+                return None
+            n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n,)).view(dtype).reshape(shape).copy()
+        f = np.array(list(f), np.float32)
+        out = dict(num_triangles=nt, num_vertices=nv, num_materials=nm, num_textures=ntex, has_camera=bool(cam),
+                   tex_bias=f[0:2], tex_scale=f[2:4], exposure=f[4], gamma=f[5], eye=f[6:9], aim=f[9:12], up=f[12:15], dx=f[15:18], fov=f[18],
+                   vertex_indices=arr(0, np.int32, (nt, 4)), vertex_data=arr(1, np.float32, (nv, 4)), texture_indices_comp=arr(2, np.int32, (nt, 4)),
+                   material_indices=arr(3, np.int32, (nt,)), materials=arr(4, np.uint32, (nm, 52)), dir_lights=arr(5, np.float32, (ndl, 6)))
+        self.L.ref_free_scene(h)
+        return out

@@ -458,7 +458,117 @@ namespace cugar { inline size_t min(const size_t a, const size_t b) { return a <
 namespace cugar {
 inline Vector2f operator-(const Vector2f a, const float b) { return Vector2f(a.x - b, a.y - b); }   // src/camera.h:182
 inline Vector3f operator-(const float a, const Vector3f b) { return Vector3f(a - b.x, a - b.y, a - b.z); }
+inline Vector3f operator-(const Vector3f a, const float b) { return Vector3f(a.x - b, a.y - b, a.z - b); }                   // src/mesh/pbrt_importer.cpp:61
+inline Vector3f operator+(const Vector3f a, const float b) { return Vector3f(a.x + b, a.y + b, a.z + b); }                   // :63, :68
 }
 #define random fermat_random                                                                       // src/tiled_sampling.h:44 vs glibc's random()
 EOF
+cat > $OVF/optixu/optixu_math_namespace.h <<'EOF'
+#pragma once
+#include <optixu/optixu_matrix.h>
+namespace optix { typedef ::float3 float3; typedef ::float2 float2; typedef ::float4 float4; }
+EOF
+cat > $OVF/optixu/optixu_aabb_namespace.h <<'EOF'
+#pragma once
+// stub of optix::Aabb for src/mesh/MeshBase.cpp (bounding box of the vertex array); the OptiX SDK is absent
+#include <optixu/optixu_math_namespace.h>
+#include <float.h>
+namespace optix {
+struct Aabb
+{
+	float3 m_min, m_max;
+	Aabb() { m_min = make_float3(FLT_MAX, FLT_MAX, FLT_MAX); m_max = make_float3(-FLT_MAX, -FLT_MAX, -FLT_MAX); }
+	void include(const float3& p)
+	{
+		m_min.x = p.x < m_min.x ? p.x : m_min.x; m_min.y = p.y < m_min.y ? p.y : m_min.y; m_min.z = p.z < m_min.z ? p.z : m_min.z;
+		m_max.x = p.x > m_max.x ? p.x : m_max.x; m_max.y = p.y > m_max.y ? p.y : m_max.y; m_max.z = p.z > m_max.z ? p.z : m_max.z;
+	}
+};
+}
+EOF
 echo "built $OVF (syntax-check overlay for code written against the reference's renderer.h)"
+
+# ---- the reference's own SCENE LOADERS and mesh pre-processing: src/mesh/{MeshBase,glm,MeshLoader,MeshStorage,fermat_loader,
+# pbrt_importer,pbrt_parser}.cpp + rply + src/files.cpp compile on the host through overlay_full (plain C++ once the OptiX math headers
+# are stubbed). ref_load_scene follows RenderingContextImpl::init's dispatch and pre-processing order (src/renderer.cu:700-744):
+# load -> compress_normals -> compress_tex -> unify_vertex_attributes -> apply_material_flags. Pins the product's importers
+# (host/scene.cpp, host/pbrt_loader.cpp) array for array: tests/test_importers.py.
+cat > $OUT/ref_loader_shim.cpp <<'EOF'
+#include <mesh/MeshStorage.h>
+#include <mesh/fermat_loader.h>
+#include <mesh/pbrt_importer.h>
+#include <mesh/pbrt_parser.h>
+#include <camera.h>
+#include <lights.h>
+#include <string.h>
+#include <string>
+#include <vector>
+struct RefLoaded
+{
+	MeshStorage mesh; Camera camera; std::vector<DirectionalLight> dir_lights; float exposure, gamma; bool has_camera;
+};
+extern "C" void* ref_load_scene(const char* filename)
+{
+	RefLoaded* r = new RefLoaded(); r->exposure = 1.0f; r->gamma = 2.2f; r->has_camera = false;
+	try
+	{
+		std::vector<std::string> scene_dirs; scene_dirs.push_back(""); 
+		{ std::string f(filename); const size_t p = f.find_last_of("/\\"); scene_dirs.push_back(p == std::string::npos ? std::string("") : f.substr(0, p + 1)); }
+		std::vector<std::string> dirs = scene_dirs;
+		std::vector<Camera> cameras;
+		const size_t n = strlen(filename);
+		if (n > 3 && strcmp(filename + n - 3, ".fa") == 0) load_scene(filename, r->mesh, cameras, r->dir_lights, dirs, scene_dirs);
+		else if (n > 5 && strcmp(filename + n - 5, ".pbrt") == 0)
+		{
+			pbrt::FermatImporter importer(filename, &r->mesh, &r->camera, &r->dir_lights, &scene_dirs);
+			pbrt::import(filename, &importer);
+			importer.finish();
+			r->exposure = importer.m_film.exposure; r->gamma = importer.m_film.gamma; r->has_camera = true;
+		}
+		else loadModel(filename, r->mesh);
+		if (cameras.size()) { r->camera = cameras[0]; r->has_camera = true; }
+		r->mesh.compress_normals();
+		r->mesh.compress_tex();
+		unify_vertex_attributes(r->mesh);
+		apply_material_flags(r->mesh);
+	}
+	catch (...) { delete r; return NULL; }
+	return r;
+}
+extern "C" void ref_free_scene(void* h) { delete static_cast<RefLoaded*>(h); }
+// counts: triangles, vertices, materials, textures, dir lights, has_camera; f: tex_bias(2) tex_scale(2) exposure gamma eye(3) aim(3) up(3) dx(3) fov
+extern "C" void ref_scene_info(void* h, int* counts, float* f)
+{
+	RefLoaded* r = static_cast<RefLoaded*>(h);
+	const MeshView v = r->mesh.view();
+	counts[0] = v.num_triangles; counts[1] = v.num_vertices; counts[2] = v.num_materials; counts[3] = r->mesh.getNumTextures(); counts[4] = (int)r->dir_lights.size(); counts[5] = r->has_camera ? 1 : 0;
+	f[0] = v.tex_bias.x; f[1] = v.tex_bias.y; f[2] = v.tex_scale.x; f[3] = v.tex_scale.y; f[4] = r->exposure; f[5] = r->gamma;
+	const Camera& c = r->camera;
+	f[6] = c.eye.x; f[7] = c.eye.y; f[8] = c.eye.z; f[9] = c.aim.x; f[10] = c.aim.y; f[11] = c.aim.z; f[12] = c.up.x; f[13] = c.up.y; f[14] = c.up.z;
+	f[15] = c.dx.x; f[16] = c.dx.y; f[17] = c.dx.z; f[18] = c.fov;
+}
+// 0 vertex_indices (int4 / triangle), 1 vertex_data (float4 / vertex), 2 texture_indices_comp (int4 / triangle, may be NULL), 3 material_indices,
+// 4 materials (208 B each), 5 directional lights (dir xyz, colour rgb)
+extern "C" const void* ref_scene_array(void* h, int which)
+{
+	RefLoaded* r = static_cast<RefLoaded*>(h);
+	const MeshView v = r->mesh.view();
+	static std::vector<float> dl;
+	switch (which)
+	{
+	case 0: return v.vertex_indices; case 1: return v.vertex_data; case 2: return v.texture_indices_comp; case 3: return v.material_indices; case 4: return v.materials;
+	case 5: dl.clear(); for (size_t i = 0; i < r->dir_lights.size(); ++i) { const DirectionalLight& l = r->dir_lights[i]; const float f[6] = { l.dir.x, l.dir.y, l.dir.z, l.color.x, l.color.y, l.color.z }; dl.insert(dl.end(), f, f + 6); } return dl.data();
+	}
+	return NULL;
+}
+extern "C" const char* ref_scene_texture_name(void* h, int i) { return static_cast<RefLoaded*>(h)->mesh.m_textures[i].c_str(); }
+EOF
+LFLAGS="-O2 -std=c++14 -fPIC -w -fpermissive -ffp-contract=off -include $OVF/adapter_prefix.h -DFERMAT_API_EXTERN= -DFERMAT_API= -DSUTILAPI= -DSUTILCLASSAPI= -DTHRUST_DEVICE_SYSTEM=THRUST_DEVICE_SYSTEM_CPP -I$OVF -I$REF/src -I$REF/src/mesh -I$REF/contrib -I/usr/local/cuda/include"
+mkdir -p $OUT/obj
+gcc -O2 -fPIC -w -c $REF/src/mesh/rply-1.01/rply.c -o $OUT/obj/rply.o
+for f in mesh/MeshBase mesh/glm mesh/MeshLoader mesh/MeshStorage mesh/fermat_loader mesh/pbrt_importer mesh/pbrt_parser files; do
+  $CXX $LFLAGS -c $REF/src/$f.cpp -o $OUT/obj/$(basename $f).o &
+done
+wait
+$CXX $LFLAGS -shared -o $OUT/libref_loader.so $OUT/ref_loader_shim.cpp $OUT/obj/*.o -L/usr/local/cuda/lib64 -lcudart_static -ldl -lrt -lpthread
+echo "built $OUT/libref_loader.so"
