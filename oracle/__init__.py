@@ -455,3 +455,35 @@ class RefLoader:
                    material_indices=arr(3, np.int32, (nt,)), materials=arr(4, np.uint32, (nm, 52)), dir_lights=arr(5, np.float32, (ndl, 6)))
         self.L.ref_free_scene(h)
         return out
+
+
+class RefSah:
+    """The REFERENCE's own full-sweep SAH builder (contrib/cugar/bvh/bvh_sah_builder.h) and cost function (bvh_inline.h:184-205) compiled on this
+    host (oracle/_ref/libref_sah.so): the quality yardstick of SURVEY row 8f-1 for the product's trees."""
+
+    @staticmethod
+    def load():
+        L = _ref_so("libref_sah.so")
+        return RefSah(L) if L is not None else None
+
+    def __init__(self, L):
+        self.L = L
+        L.ref_sah_build.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_double)]
+        L.ref_sah_cost_of.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_double)]
+
+    @staticmethod
+    def _out(o):
+        return {"cugar_cost": o[0], "area_cost": o[1], "nodes": int(o[2]), "leaves": int(o[3]), "max_depth": int(o[4])}
+
+    def build(self, boxes, max_leaf=3):
+        """boxes: (n, 6) float32 (min, max) -> costs and counts of the tree the reference's builder makes of them"""
+        boxes = np.ascontiguousarray(boxes, np.float32)
+        o = (C.c_double * 5)()
+        self.L.ref_sah_build(boxes.ctypes.data, len(boxes), max_leaf, o)
+        return self._out(o)
+
+    def cost_of(self, nodes_ptr, n_nodes):
+        """the reference's compute_sah_cost on a tree of n_nodes Bvh_node_3d records at nodes_ptr"""
+        o = (C.c_double * 5)()
+        self.L.ref_sah_cost_of(nodes_ptr, n_nodes, o)
+        return self._out(o)

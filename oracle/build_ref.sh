@@ -200,6 +200,75 @@ $CXX -O2 -std=c++14 -fPIC -shared -w -fpermissive -ffp-contract=off \
     -o $OUT/libref_psf.so $OUT/ref_psf_shim.cpp
 echo "built $OUT/libref_psf.so"
 
+# ---- the reference's own full-sweep SAH builder (contrib/cugar/bvh/bvh_sah_builder.h, host C++) as the QUALITY oracle of SURVEY row
+# 8f-1: builds over triangle boxes, reports cugar's own compute_sah_cost (bvh_inline.h:184-205) and the plain sum-of-areas cost the
+# product prints; ref_sah_cost_of evaluates cugar's cost function on a tree handed in as Bvh_node_3d records (the product's Bvh2).
+# Overlay: the header was left behind by a change of Bvh_node's constructors (nothing in the reference instantiates it): the two
+# constructor calls get the kLeaf / kInternal tags of bvh_node.h:55-65, the older `namespace deprecated` twin is cut, and max_element (only reached
+# above m_single_axis_threshold = 64 M primitives) a definition. The split search itself is compiled as it lies.
+mkdir -p $OV/cugar/bvh
+sed -E -e '/^namespace deprecated \{/,/^\} \/\/ namespace deprecated/d' $REF/contrib/cugar/bvh/bvh_sah_builder.h > $OV/cugar/bvh/bvh_sah_builder.h
+sed -E -e '/^namespace deprecated \{/,/^\} \/\/ namespace deprecated/d' -e 's/bvh_node_type\( node\.m_begin, node\.m_end \)/bvh_node_type( Bvh_node::kLeaf, node.m_begin, node.m_end )/' \
+       -e 's/bvh_node_type\( left_node_index \)/bvh_node_type( Bvh_node::kInternal, left_node_index )/' \
+       $REF/contrib/cugar/bvh/bvh_sah_builder_inline.h > $OV/cugar/bvh/bvh_sah_builder_inline.h
+cat > $OUT/ref_sah_shim.cpp <<'EOF'
+#include <vector>
+#include <algorithm>
+#include <cugar/basic/types.h>
+#include <cugar/basic/numbers.h>
+#include <cugar/linalg/vector.h>
+#include <cugar/linalg/bbox.h>
+#include <cugar/bvh/bvh.h>
+namespace cugar { inline int max_element(const Vector3f& v) { return v[0] >= v[1] ? (v[0] >= v[2] ? 0 : 2) : (v[1] >= v[2] ? 1 : 2); } }
+#include <cugar/bvh/bvh_sah_builder.h>
+static double sum_cost(const cugar::Bvh<3>& bvh)
+{
+	const double root = cugar::area(bvh.m_bboxes[0]);
+	double c = 0.0;
+	for (size_t i = 0; i < bvh.m_nodes.size(); ++i)
+		c += double(cugar::area(bvh.m_bboxes[i])) * (bvh.m_nodes[i].is_leaf() ? double(bvh.m_nodes[i].get_leaf_size()) : 1.0);
+	return c / root;
+}
+// boxes: n x 6 floats (min, max). out[0] = cugar::compute_sah_cost, out[1] = sum-of-areas cost, out[2] = nodes, out[3] = leaves, out[4] = max depth
+extern "C" int ref_sah_build(const float* boxes, unsigned n, unsigned max_leaf, double* out)
+{
+	std::vector<cugar::Bbox3f> bb(n);
+	for (unsigned i = 0; i < n; ++i)
+		bb[i] = cugar::Bbox3f(cugar::Vector3f(boxes[6 * i], boxes[6 * i + 1], boxes[6 * i + 2]), cugar::Vector3f(boxes[6 * i + 3], boxes[6 * i + 4], boxes[6 * i + 5]));
+	cugar::Bvh<3> bvh;
+	cugar::Bvh_sah_builder builder;
+	builder.set_max_leaf_size(max_leaf);
+	cugar::Bvh_sah_builder::Stats stats;
+	builder.build(bb.begin(), bb.end(), &bvh, &stats);
+	unsigned leaves = 0;
+	for (size_t i = 0; i < bvh.m_nodes.size(); ++i) leaves += bvh.m_nodes[i].is_leaf() ? 1u : 0u;
+	out[0] = cugar::compute_sah_cost(bvh); out[1] = sum_cost(bvh); out[2] = double(bvh.m_nodes.size()); out[3] = double(leaves); out[4] = double(stats.m_max_depth);
+	return 0;
+}
+// nodes: n Bvh_node_3d records (32 B: two node words, then the box; bvh_node.h:79-137); out as above (out[4] unused)
+extern "C" int ref_sah_cost_of(const unsigned* nodes, unsigned n, double* out)
+{
+	cugar::Bvh<3> bvh;
+	bvh.m_nodes.resize(n); bvh.m_bboxes.resize(n);
+	unsigned leaves = 0;
+	for (unsigned i = 0; i < n; ++i)
+	{
+		const cugar::Bvh_node_3d& nd = reinterpret_cast<const cugar::Bvh_node_3d*>(nodes)[i];
+		bvh.m_bboxes[i] = nd.bbox;
+		if (nd.is_leaf()) { bvh.m_nodes[i] = cugar::Bvh_node(cugar::Bvh_node::kLeaf, nd.get_leaf_begin(), nd.get_leaf_begin() + nd.get_leaf_size()); ++leaves; }
+		else bvh.m_nodes[i] = cugar::Bvh_node(cugar::Bvh_node::kInternal, nd.get_child_index(), nd.get_range_size());
+	}
+	out[0] = cugar::compute_sah_cost(bvh); out[1] = sum_cost(bvh); out[2] = double(n); out[3] = double(leaves); out[4] = 0.0;
+	return 0;
+}
+EOF
+$CXX -O2 -std=c++14 -fPIC -shared -w -fpermissive -ffp-contract=off \
+    -include $OV/ref_prefix.h \
+    -DFERMAT_API_EXTERN= -DTHRUST_DEVICE_SYSTEM=THRUST_DEVICE_SYSTEM_CPP \
+    -I$OV -I$REF/src -I$REF/contrib -I/usr/local/cuda/include \
+    -o $OUT/libref_sah.so $OUT/ref_sah_shim.cpp
+echo "built $OUT/libref_sah.so"
+
 # ---- more of the `-pt` path pinned to the reference's own code (round 2): the multi-jittered sampler tables (src/tiled_sampling.h),
 # MIS (src/mis_utils.h), vertex set-up (src/mesh_utils.h setup_differential_geometry), the mesh light (src/lights.h MeshLight::
 # sample_impl / map_impl, src/edf.h) and the PT vertex processor's channel routing + add_in (src/pathtracer_vertex_processor.h,

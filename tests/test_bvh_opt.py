@@ -180,3 +180,31 @@ def test_shadow_order_follows_the_probe_unless_forced(fb, monkeypatch):
     order, probe = sc.shadow_order()
     assert order == (1 if probe[1] < 0.95 * probe[0] else 0)
     sc.close()
+
+
+@pytest.mark.parametrize("scene,slack", [("cornellbox_glossy", 1.0), ("water_caustic", 1.0), ("bathroom2", 1.0)])
+def test_tree_quality_against_the_reference_sah_builder(fb, scene, slack):
+    """SURVEY row 8f-1 names contrib/cugar/bvh/bvh_sah_builder.h as the quality oracle: the reference's own (full-sweep) SAH builder, compiled on
+    this host by oracle/build_ref.sh, builds a tree over the same triangle boxes with the same leaf size; the product's tree (binned SAH +
+    insertion-based optimisation) must not cost more, by the reference's own cost function and by the plain sum of areas."""
+    import oracle as orc
+    ref = orc.RefSah.load()
+    if ref is None:
+        pytest.skip("oracle/_ref/libref_sah.so is built where /root/reference exists")
+    path = os.path.join(CACHE, scene + ".fbs")
+    if not os.path.exists(path):
+        pytest.skip("scene snapshot not built")
+    sc = fb.Scene(["-i", path, "-r", "64", "64"])
+    v = sc.view
+    n_tri = int(v.num_triangles)
+    vi = np.ctypeslib.as_array(v.vertex_indices, (n_tri, 4))
+    vd = np.ctypeslib.as_array(v.vertex_data, (int(v.num_vertices), 4))
+    p = vd[vi[:, :3].reshape(-1), :3].reshape(n_tri, 3, 3)
+    boxes = np.concatenate([p.min(axis=1), p.max(axis=1)], axis=1).astype(np.float32)
+    theirs = ref.build(boxes, 3)
+    ours = ref.cost_of(v.bvh_nodes, int(v.n_bvh_nodes))
+    print("\n%s: reference Bvh_sah_builder cost %.3f (sum of areas %.3f, %d nodes, depth %d); product %.3f (%.3f, %d nodes)" % (
+        scene, theirs["cugar_cost"], theirs["area_cost"], theirs["nodes"], theirs["max_depth"], ours["cugar_cost"], ours["area_cost"], ours["nodes"]))
+    assert abs(ours["area_cost"] - sc.bvh_stats()["sah_cost"]) < 1e-3 * ours["area_cost"]      # the product's own figure is the same quantity
+    assert ours["cugar_cost"] <= theirs["cugar_cost"] * slack
+    assert ours["area_cost"] <= theirs["area_cost"] * slack
