@@ -92,6 +92,10 @@ def lib():
         "fb200_scene_create_from_mesh": (vp, [C.POINTER(MeshDesc), i32, C.POINTER(C.c_char_p)]),
         "fb200_context_publish": (i32, [vp, C.POINTER(vp * 8)]),
         "fb200_context_update_scene": (i32, [vp, pf]),
+        "fb200_context_rl_state": (i32, [vp, C.POINTER(u64 * 20)]),
+        "fb200_context_rl_clear": (i32, [vp]),
+        "fb200_context_rl_update": (i32, [vp, i32]),
+        "fb200_context_rl_locate": (i32, [vp, C.POINTER(u32), pf, u32, C.POINTER(u32)]),
         "fb200_scene_destroy": (None, [vp]),
         "fb200_scene_get_view": (i32, [vp, C.POINTER(SceneView)]),
         "fb200_scene_save_snapshot": (i32, [vp, C.c_char_p]),
@@ -461,6 +465,39 @@ class RenderingContext(_Handle):
         assert v.size == 4 * self.scene.view.num_vertices
         self._chk(lib().fb200_context_update_scene(self._h, _fptr(v)))
         lib().fb200_scene_get_view(self.scene._h, C.byref(self.scene.view))
+
+    # ---- `-nee-alg rl`: the reinforcement-learning light sampler's state (include/fermat_b200.h fb200_context_rl_state)
+    def rl_state(self):
+        """zero-copy CUDA tensor views of the sampler's arrays + its sizes (contexts created with `-nee-alg rl`)"""
+        import torch
+        o = (C.c_uint64 * 20)()
+        self._chk(lib().fb200_context_rl_state(self._h, C.byref(o)))
+        cells, C0, n_vtls, n_nodes, n_loc = int(o[0]), int(o[1]), int(o[2]), int(o[3]), int(o[18])
+        dev = "cuda:%d" % self.device
+
+        def t(ptr, shape, typestr):
+            return torch.as_tensor(_CudaArray(ptr, shape, typestr), device=dev)
+        return {
+            "cells": cells, "init_cluster_count": C0, "n_vtls": n_vtls, "n_tree_nodes": n_nodes,
+            "keys": t(o[4], (cells,), "<i8"), "occupied": t(o[5], (cells,), "<i4"), "n_occupied": t(o[6], (1,), "<i4"),
+            "pdfs": t(o[7], (cells, C0), "<f4"), "cdfs": t(o[8], (cells, C0), "<f4"), "cluster_counts": t(o[9], (cells,), "<i4"),
+            "cluster_nodes": t(o[10], (cells, C0), "<i4"), "cluster_ends": t(o[11], (cells, C0), "<i4"),
+            "vtls": t(o[12], (n_vtls, 8), "<f4"), "tree_nodes": t(o[13], (n_nodes, 8), "<i4"), "tree_parents": t(o[14], (n_nodes,), "<i4"),
+            "tree_ranges": t(o[15], (n_nodes, 2), "<i4"), "locate_roots": t(o[16], (int(self.scene.view.num_triangles),), "<i4"),
+            "locate_nodes": t(o[17], (n_loc,), "<i4"),
+        }
+
+    def rl_clear(self):
+        self._chk(lib().fb200_context_rl_clear(self._h))
+
+    def rl_update(self, adaptive=True):
+        self._chk(lib().fb200_context_rl_update(self._h, 1 if adaptive else 0))
+
+    def rl_locate(self, prims, uv):
+        prims = np.ascontiguousarray(prims, np.uint32); uv = np.ascontiguousarray(uv, np.float32)
+        out = np.zeros(len(prims), np.uint32)
+        self._chk(lib().fb200_context_rl_locate(self._h, prims.ctypes.data_as(C.POINTER(C.c_uint32)), _fptr(uv), len(prims), out.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return out
 
     def publish(self, tensors):
         """copy frame-buffer channels into caller-owned device buffers: {channel name or index: CUDA tensor (H, W, 4) float32}"""

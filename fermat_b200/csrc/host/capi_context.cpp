@@ -254,6 +254,34 @@ int fb200_context_update_scene(fb200_context* c, const float* vertex_data)
 	return guarded([&] { c->rc.update_geometry(vertex_data); });
 }
 
+static PathTracer* rl_renderer(fb200_context* c)
+{
+	PathTracer* pt = dynamic_cast<PathTracer*>(c->rc.renderer());
+	if (!pt || !pt->rl_enabled()) throw std::runtime_error("the context was not created with -nee-alg rl");
+	return pt;
+}
+int fb200_context_rl_state(fb200_context* c, uint64_t out[20])
+{
+	return guarded([&] {
+		PathTracer* pt = rl_renderer(c);
+		const fb::RlView& v = pt->rl_view();
+		const fb::MeshVTLs& m = pt->vtls();
+		const uint64_t vals[20] = { (uint64_t)v.mask + 1u, v.init_cluster_count, v.n_vtls, (uint64_t)m.bvh_nodes.size(),
+			(uint64_t)v.keys, (uint64_t)v.occupied, (uint64_t)v.n_occupied, (uint64_t)v.pdfs, (uint64_t)v.cdfs, (uint64_t)v.cluster_counts, (uint64_t)v.cluster_nodes, (uint64_t)v.cluster_ends,
+			(uint64_t)v.vtls, (uint64_t)pt->rl_tree(0), (uint64_t)pt->rl_tree(1), (uint64_t)pt->rl_tree(2), (uint64_t)v.locate_roots, (uint64_t)v.locate_nodes, (uint64_t)m.locate_nodes.size(), 0 };
+		for (int i = 0; i < 20; ++i) out[i] = vals[i];
+	});
+}
+int fb200_context_rl_clear(fb200_context* c) { return guarded([&] { rl_renderer(c)->rl_clear(c->rc); }); }
+int fb200_context_rl_update(fb200_context* c, int adaptive) { return guarded([&] { rl_renderer(c)->rl_update(c->rc, adaptive != 0); }); }
+int fb200_context_rl_locate(fb200_context* c, const uint32_t* prims, const float* uv, uint32_t n, uint32_t* vtl_out)
+{
+	return guarded([&] {
+		const fb::MeshVTLs& m = rl_renderer(c)->vtls();
+		for (uint32_t i = 0; i < n; ++i) vtl_out[i] = m.locate(prims[i], uv[2 * i], uv[2 * i + 1]);
+	});
+}
+
 int fb200_context_publish(fb200_context* c, float* const device_channels[8])
 {
 	return guarded([&] {

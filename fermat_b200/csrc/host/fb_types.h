@@ -71,6 +71,15 @@ struct VPL                           // reference src/lights.h:59-76 (16 B)
 };
 static_assert(sizeof(VPL) == 16, "VPL must stay 16 B");
 
+// Virtual Triangular Light (reference src/vtl.h:43-113, 32 B): a sub-triangle of mesh triangle `prim_id`, corners as barycentrics of it
+struct VTL
+{
+	uint32 prim_id;
+	float  area;
+	float2 uv0, uv1, uv2;
+};
+static_assert(sizeof(VTL) == 32, "VTL must stay 32 B");
+
 struct DirectionalLight              // reference src/lights.h:256-295 (payload only)
 {
 	float3 dir;
@@ -126,7 +135,7 @@ struct PTOptions
 	uint32 direct_lighting, direct_lighting_nee, direct_lighting_bsdf;
 	uint32 indirect_lighting_nee, indirect_lighting_bsdf;
 	uint32 visible_lights, diffuse_scattering, glossy_scattering, indirect_glossy, rr;
-	uint32 nee_type;                 // 0 mesh, 1 vpl (default), 2 rl (unsupported here)
+	uint32 nee_type;                 // 0 mesh, 1 vpl (default), 2 rl
 };
 
 // ---- our own layouts -----------------------------------------------------------------------

@@ -3,6 +3,7 @@
 // (src/pathtracer_kernels.h:309-391), restated for a device-resident schedule: the whole pass is enqueued
 // on one stream, queue sizes stay on the device, nothing is read back.
 #include "rendering_context.h"
+#include "../kernels/rl_kernels.h"
 #include <string.h>
 #include <stdlib.h>
 
@@ -11,9 +12,10 @@ using namespace fb;
 // fermat_b200/__init__.py mirrors this struct (PASS_COUNTERS_DTYPE) for fb200_diag_pass_counters
 static_assert(sizeof(PassCounters) == 20480, "PassCounters layout changed: update PASS_COUNTERS_DTYPE in fermat_b200/__init__.py");
 
-PathTracer::PathTracer() : m_tiles_x(0), m_owned_pixels(0), m_passes(0), m_device_ms(0.0), m_ev0(NULL), m_ev1(NULL), m_ev_start(NULL), m_overlap(1), m_trace_ctas(0), m_shade_split(0), m_psf(false), m_events(false), m_profiling(false)
+PathTracer::PathTracer() : m_tiles_x(0), m_owned_pixels(0), m_passes(0), m_device_ms(0.0), m_ev0(NULL), m_ev1(NULL), m_ev_start(NULL), m_overlap(1), m_trace_ctas(0), m_shade_split(0), m_psf(false), m_rl(false), m_events(false), m_profiling(false)
 {
 	memset(&m_psf_view, 0, sizeof(m_psf_view));
+	memset(&m_rl_view, 0, sizeof(m_rl_view));
 	for (int i = 0; i < 4; ++i) { m_class_ms[i] = 0.0; m_class_launches[i] = 0; }
 	memset(m_bounce_ms, 0, sizeof(m_bounce_ms));
 	pt_options_defaults(m_options);
@@ -80,14 +82,17 @@ void PathTracer::init(int argc, char** argv, RenderingContext& renderer)
 	m_options = s.options;
 	const uint2 res = renderer.res();
 
-	fprintf(stderr, "  %s settings:\n    path-length     : %u\n    nee algorithm   : %s\n", m_psf ? "PSFPT" : "PT", m_options.max_path_length, m_options.nee_type == 1 ? "vpl" : "mesh");
+	fprintf(stderr, "  %s settings:\n    path-length     : %u\n    nee algorithm   : %s\n", m_psf ? "PSFPT" : "PT", m_options.max_path_length, m_options.nee_type == 2 ? "rl" : m_options.nee_type == 1 ? "vpl" : "mesh");
 	if (m_psf)
 	{
 		const fb200_psf_options& po = s.psf;
 		fprintf(stderr, "    filter width    : %f\n    filter depth    : %u\n    filter min-dist : %f\n    firefly filter  : %f\n", po.psf_width, po.psf_depth, po.psf_min_dist, po.firefly_filter);
 		if (!kernels_split_accumulate()) throw std::runtime_error("-psfpt needs kernels built with FB_SPLIT_ACCUMULATE");
 		if (!s.scene.dir_lights.empty()) throw std::runtime_error("-psfpt: directional lights are not supported");
+		if (m_options.nee_type == 2) throw std::runtime_error("-psfpt -nee-alg rl: not supported");
 	}
+	m_rl = m_options.nee_type == 2;
+	if (m_rl && !kernels_split_accumulate()) throw std::runtime_error("-nee-alg rl needs kernels built with FB_SPLIT_ACCUMULATE");
 
 	// tile shard of this process: tile T = ty*tiles_x + tx belongs to rank (T + ty) % shard_count
 	std::vector<uint32> tiles;
@@ -96,14 +101,15 @@ void PathTracer::init(int argc, char** argv, RenderingContext& renderer)
 	// sub-frames: the owned tiles dealt round-robin (FB200_SUBFRAMES, default 2; at least 64 tiles each)
 	// (`-psfpt`: one sub-frame - the references are splat once every path of the pass has fed its cell)
 	const char* env = getenv("FB200_SUBFRAMES");
-	uint32 n_sub = m_psf ? 1u : (env ? (uint32)atoi(env) : 2u);
+	// (`-nee-alg rl`: one sub-frame too - the sampler's cells are updated between passes, behind every path of the last one)
+	uint32 n_sub = (m_psf || m_rl) ? 1u : (env ? (uint32)atoi(env) : 2u);
 	while (n_sub > 1 && tiles.size() / n_sub < 64) n_sub--;
 	if (n_sub < 1) n_sub = 1;
 	env = getenv("FB200_OVERLAP");
 	m_overlap = env ? atoi(env) : 1;
 	// shade as two kernels on the sub-frame's two streams (k_shade<.., SHADE_LIGHT> / <.., SHADE_PATH>, pt_kernels.cu); not for -psfpt
 	env = getenv("FB200_SHADE_SPLIT");
-	m_shade_split = (env ? atoi(env) : 0) && !m_psf;
+	m_shade_split = (env ? atoi(env) : 0) && !m_psf && !m_rl;
 	env = getenv("FB200_TRACE_CTAS");
 	// each persistent trace launch takes this many CTA slots per SM, so that the kernels of two streams are co-resident
 	// (sweep on bathroom2, Msamples/s: 1 sub-frame 1040; 2 sub-frames x 4 CTAs 1045, x 2 CTAs 1110; 4 x 1 1129; 6 x 2 878)
@@ -124,7 +130,7 @@ void PathTracer::init(int argc, char** argv, RenderingContext& renderer)
 			SubFrame& f = *m_sub[k];
 			f.n_tiles = (uint32)sub_tiles[k].size();
 			f.capacity = (uint64_t)f.n_tiles * 32u * 32u;
-			carve(arena, f.capacity, f.capacity, f.queue, f.shadow, m_psf);
+			carve(arena, f.capacity, f.capacity, f.queue, f.shadow, m_psf || m_rl);
 			if (dirlights)
 			{
 				ShadowQueue& d = f.shadow_dl;
@@ -183,11 +189,78 @@ void PathTracer::init(int argc, char** argv, RenderingContext& renderer)
 		m_psf_view.bbox_hi[0] = bb.hi.x; m_psf_view.bbox_hi[1] = bb.hi.y; m_psf_view.bbox_hi[2] = bb.hi.z;
 		fprintf(stderr, "  allocating filter cache: %.1f MB (%llu cells)\n", float(n * 24) / (1024 * 1024), (unsigned long long)n);
 	}
+	if (m_rl) init_rl(renderer);
 	m_totals.alloc(sizeof(PassTotals));
 	cuda_check(cudaMemsetAsync(m_totals.ptr, 0, sizeof(PassTotals), renderer.raw_stream()), "memset totals");
 	cuda_check(cudaEventCreate(&m_ev0), "event"); cuda_check(cudaEventCreate(&m_ev1), "event");
 	cuda_check(cudaEventCreateWithFlags(&m_ev_start, cudaEventDisableTiming), "event");
 	renderer.synchronize();      // the uploads above read host vectors that go out of scope here
+}
+
+// PathTracer::init's RL branch (src/renderers/pathtracer_impl.h:168-177): the VTLs (as many as pixels), their cluster tree, the cells
+void PathTracer::init_rl(RenderingContext& renderer)
+{
+	fb200_scene& s = *renderer.scene();
+	const uint2 res = renderer.res();
+	fprintf(stderr, "  creating mesh VTLs... started\n");
+	m_vtls.init(res.x * res.y, s.scene,
+		[&renderer](const std::vector<float4>& pts, const float bbox[6], std::vector<Bvh2Node>& nodes, std::vector<uint32>& index) { renderer.build_lbvh_points(pts, bbox, nodes, index); }, 0u);
+	const uint32 C = (uint32)m_vtls.clusters.size();
+	fprintf(stderr, "  creating mesh VTLs... done (%u VTLs, %u clusters)\n", (uint32)m_vtls.vtls.size(), C);
+	if (m_vtls.vtls.empty() || C == 0) throw std::runtime_error("-nee-alg rl: the scene has no emissive surface to build VTLs on");
+	if (C > FB_RL_MAX_CLUSTERS) throw std::runtime_error("-nee-alg rl: more initial clusters than the kernels hold");
+
+	cudaStream_t st = renderer.stream();
+	m_rl_vtls.upload(m_vtls.vtls.data(), m_vtls.vtls.size() * sizeof(VTL), st);
+	m_rl_locate_roots.upload(m_vtls.locate_roots.data(), m_vtls.locate_roots.size() * 4, st);
+	m_rl_locate_nodes.upload(m_vtls.locate_nodes.data(), m_vtls.locate_nodes.size() * 4, st);
+	m_rl_tree_nodes.upload(m_vtls.bvh_nodes.data(), m_vtls.bvh_nodes.size() * sizeof(Bvh2Node), st);
+	m_rl_tree_parents.upload(m_vtls.bvh_parents.data(), m_vtls.bvh_parents.size() * 4, st);
+	m_rl_tree_ranges.upload(m_vtls.bvh_ranges.data(), m_vtls.bvh_ranges.size() * sizeof(uint2), st);
+	m_rl_init_nodes.upload(m_vtls.clusters.data(), C * 4, st);
+	m_rl_init_offsets.upload(m_vtls.cluster_offsets.data(), (C + 1) * 4, st);
+	// the CDF of a fresh cell: update_cdfs_kernel (src/clustered_rl.cu:69-94) over C values of 0.01
+	std::vector<float> cdf(C);
+	{
+		std::vector<float> scan(C);
+		float sum = 0.0f;
+		for (uint32 i = 0; i < C; ++i) { sum += 0.01f; scan[i] = sum; }
+		for (uint32 i = 0; i < C; ++i) cdf[i] = (scan[i] / sum) * (1.0f - 0.75f) + float(i + 1) * 0.75f / float(C);
+	}
+	m_rl_init_cdf.upload(cdf.data(), C * 4, st);
+
+	// VTL_RL_HASH_SIZE cells (src/pathtracer_core.h:472: 512 K; FB200_RL_HASH_BITS overrides, 10..23)
+	const char* env = getenv("FB200_RL_HASH_BITS");
+	const int bits = env ? atoi(env) : 19;
+	if (bits < 10 || bits > 23) throw std::runtime_error("FB200_RL_HASH_BITS out of range (10..23)");
+	const size_t n = size_t(1) << bits;
+	m_rl_keys.alloc(n * 8); m_rl_occupied.alloc(n * 4); m_rl_n_occupied.alloc(4);
+	m_rl_values.alloc(n * C * 2 * 4); m_rl_counts.alloc(n * 4); m_rl_cluster_nodes.alloc(n * C * 4); m_rl_cluster_ends.alloc(n * C * 4);
+	RlView& v = m_rl_view;
+	v.keys = m_rl_keys.as<unsigned long long>(); v.occupied = m_rl_occupied.as<uint32>(); v.n_occupied = m_rl_n_occupied.as<uint32>(); v.mask = (uint32)(n - 1);
+	v.pdfs = m_rl_values.as<float>(); v.cdfs = m_rl_values.as<float>() + n * C;
+	v.cluster_counts = m_rl_counts.as<uint32>(); v.cluster_nodes = m_rl_cluster_nodes.as<uint32>(); v.cluster_ends = m_rl_cluster_ends.as<uint32>();
+	v.init_cluster_count = C;
+	v.vtls = m_rl_vtls.as<VTL>(); v.n_vtls = (uint32)m_vtls.vtls.size();
+	v.locate_roots = m_rl_locate_roots.as<uint32>(); v.locate_nodes = m_rl_locate_nodes.as<uint32>();
+	const Bbox3& bb = s.scene.bbox;
+	v.bbox_lo[0] = bb.lo.x; v.bbox_lo[1] = bb.lo.y; v.bbox_lo[2] = bb.lo.z; v.bbox_hi[0] = bb.hi.x; v.bbox_hi[1] = bb.hi.y; v.bbox_hi[2] = bb.hi.z;
+	fprintf(stderr, "  initializing VTLs RL... done (%.1f MB)\n", float(n * 8 + n * 4 + n * C * 16 + n * 4) / (1024 * 1024));
+	rl_clear(renderer);
+}
+
+void PathTracer::rl_clear(RenderingContext& renderer)
+{
+	if (!m_rl) throw std::runtime_error("the renderer was not created with -nee-alg rl");
+	cuda_check(launch_rl_clear(m_rl_view, m_rl_init_nodes.as<uint32>(), m_rl_init_offsets.as<uint32>(), m_rl_init_cdf.as<float>(), renderer.launch_config().sm_count, renderer.stream()), "rl clear");
+	renderer.kernel_launches++;
+}
+
+void PathTracer::rl_update(RenderingContext& renderer, bool adaptive)
+{
+	if (!m_rl) throw std::runtime_error("the renderer was not created with -nee-alg rl");
+	cuda_check(launch_rl_update(m_rl_view, m_rl_tree_nodes.as<Bvh2Node>(), m_rl_tree_parents.as<uint32>(), m_rl_tree_ranges.as<uint2>(), adaptive, renderer.launch_config().sm_count, renderer.stream()), "rl update");
+	renderer.kernel_launches++;
 }
 
 void PathTracer::update_scene(RenderingContext& renderer)
@@ -255,6 +328,14 @@ void PathTracer::render(const uint32_t instance, RenderingContext& renderer)
 		const float tn = tanf(c.fov / 2);
 		pp.cam_w_len = sqrtf(pp.W[0] * pp.W[0] + pp.W[1] * pp.W[1] + pp.W[2] * pp.W[2]);
 		pp.cam_sq_pixel_focal = (float(renderer.res().x * renderer.res().y) / 4.0f) / (tn * tn);
+	}
+	if (m_rl)
+	{
+		// PathTracer::update_vtls_rl (src/renderers/pathtracer_impl.h:180-192): the cells are dropped every 32 passes, otherwise every cell's
+		// cut takes one split / collapse step and its CDF is rebuilt from what the last pass learned. On the context's stream, which joins
+		// the sub-frame's first (stream()), and which the sub-frame's pass is then ordered behind (take_touched below).
+		m_rl_view.instance = instance;
+		if ((instance % 32) == 0) rl_clear(renderer); else rl_update(renderer, true);
 	}
 	if (m_psf)
 	{
@@ -331,6 +412,7 @@ void PathTracer::render_subframe(SubFrame& f, const PassParams& pass, const std:
 	const uint32 L = m_options.max_path_length;
 	uint32 n_launches = 0;
 	const PsfView* psf = m_psf ? &m_psf_view : NULL;
+	const RlView* rl = m_rl ? &m_rl_view : NULL;
 	const bool dirlights = sc.n_dir_lights != 0;
 	for (uint32 bounce = 0; bounce < L && overlap && m_shade_split; ++bounce)
 	{
@@ -374,13 +456,13 @@ void PathTracer::render_subframe(SubFrame& f, const PassParams& pass, const std:
 		for (int i = 0; i < 6; ++i) seq6[i] = seq[(bounce + 1) * 6 + i];
 		if (overlap && bounce > 0) cuda_check(cudaStreamWaitEvent(stream, f.ev_shadowed, 0), "wait");   // shadow(b-1) before shade(b)
 		begin(2);
-		cuda_check(launch_shade(sc, lc, pp, in, out, f.shadow, f.shadow_dl, fbv, ctr, tot, bounce, seq6, (uint32)f.capacity, stream, psf), "shade");
+		cuda_check(launch_shade(sc, lc, pp, in, out, f.shadow, f.shadow_dl, fbv, ctr, tot, bounce, seq6, (uint32)f.capacity, stream, psf, 3, rl), "shade");
 		end();
 		if (!overlap)
 		{
 			begin(3);
 			if (dirlights) { cuda_check(launch_trace_shadow(sc, lc, f.shadow_dl, fbv, ctr, tot, bounce, pp.frame_weight, stream, 1, &n_launches, psf), "trace_shadow"); renderer.kernel_launches += n_launches; }
-			cuda_check(launch_trace_shadow(sc, lc, f.shadow, fbv, ctr, tot, bounce, pp.frame_weight, stream, 0, &n_launches, psf), "trace_shadow");
+			cuda_check(launch_trace_shadow(sc, lc, f.shadow, fbv, ctr, tot, bounce, pp.frame_weight, stream, 0, &n_launches, psf, 3, rl), "trace_shadow");
 			end();
 			renderer.kernel_launches += n_launches;
 		}
@@ -389,7 +471,7 @@ void PathTracer::render_subframe(SubFrame& f, const PassParams& pass, const std:
 			cuda_check(cudaEventRecord(f.ev_shaded, stream), "event record");
 			cuda_check(cudaStreamWaitEvent(f.side_stream, f.ev_shaded, 0), "wait");
 			if (dirlights) { cuda_check(launch_trace_shadow(sc, lc, f.shadow_dl, fbv, ctr, tot, bounce, pp.frame_weight, f.side_stream, 1, &n_launches, psf), "trace_shadow"); renderer.kernel_launches += n_launches; }
-			cuda_check(launch_trace_shadow(sc, lc, f.shadow, fbv, ctr, tot, bounce, pp.frame_weight, f.side_stream, 0, &n_launches, psf), "trace_shadow");
+			cuda_check(launch_trace_shadow(sc, lc, f.shadow, fbv, ctr, tot, bounce, pp.frame_weight, f.side_stream, 0, &n_launches, psf, 3, rl), "trace_shadow");
 			renderer.kernel_launches += n_launches;
 			cuda_check(cudaEventRecord(f.ev_shadowed, f.side_stream), "event record");
 			if (bounce + 1 < L)

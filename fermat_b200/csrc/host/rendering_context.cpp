@@ -514,6 +514,32 @@ void RenderingContext::diag_unpack(uint32_t rank, uint32_t count, const std::vec
 	cuda_check(cudaStreamSynchronize(m_copy_stream), "diag_unpack");
 }
 
+void RenderingContext::build_lbvh_points(const std::vector<float4>& points, const float bbox[6], std::vector<Bvh2Node>& nodes, std::vector<uint32_t>& index)
+{
+	// every point becomes a degenerate triangle (i, i, i): its box and the centre the builder codes are the point itself
+	const uint32 n = (uint32)points.size();
+	if (n == 0 || n >= (1u << 27)) throw std::runtime_error("build_lbvh_points: unsupported point count");
+	std::vector<int4> tris(n);
+	for (uint32 i = 0; i < n; ++i) tris[i] = int4{ (int)i, (int)i, (int)i, 0 };
+	DeviceBuffer d_tris, d_points, work, d_bvh2, d_index, d_count;
+	d_tris.upload(tris.data(), (size_t)n * sizeof(int4), m_stream);
+	d_points.upload(points.data(), (size_t)n * sizeof(float4), m_stream);
+	work.alloc(lbvh_workspace_bytes(n));
+	d_bvh2.alloc(2 * (size_t)n * sizeof(Bvh2Node));
+	d_index.alloc((size_t)n * sizeof(uint32));
+	d_count.alloc(8);
+	cuda_check(launch_lbvh_build(d_tris.as<int4>(), d_points.as<float4>(), n, bbox, 1u, work.ptr, work.bytes, d_bvh2.as<Bvh2Node>(), d_index.as<uint32>(), NULL,
+		d_count.as<uint32>(), m_lc.sm_count, m_stream), "lbvh build (points)");
+	kernel_launches += 4 + 2 * LBVH_MAX_LEVELS + 8;
+	uint32 count[2] = { 0, 0 };
+	cuda_check(cudaMemcpyAsync(count, d_count.ptr, 8, cudaMemcpyDeviceToHost, m_stream), "D2H");
+	cuda_check(cudaStreamSynchronize(m_stream), "lbvh build (points)");
+	if (count[0] != count[1]) throw std::runtime_error("build_lbvh_points: the radix tree is deeper than LBVH_MAX_LEVELS");
+	nodes.resize(count[1]); index.resize(n);
+	cuda_check(cudaMemcpy(nodes.data(), d_bvh2.ptr, (size_t)count[1] * sizeof(Bvh2Node), cudaMemcpyDeviceToHost), "D2H");
+	cuda_check(cudaMemcpy(index.data(), d_index.ptr, (size_t)n * sizeof(uint32), cudaMemcpyDeviceToHost), "D2H");
+}
+
 uint32_t RenderingContext::build_lbvh(uint32_t max_leaf_size, bool adopt, std::vector<Bvh2Node>* nodes_out, std::vector<uint32_t>* index_out,
 									  std::vector<uint64_t>* codes_out, float* device_ms)
 {

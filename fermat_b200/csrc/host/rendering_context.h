@@ -6,6 +6,7 @@
 #include "renderer_interface.h"
 #include "comm.h"
 #include "pt_scene.h"
+#include "mesh_vtls.h"
 #include "../kernels/device_scene.h"
 #include "../kernels/pt_kernels.h"
 #include "../kernels/lbvh_kernels.h"
@@ -130,6 +131,8 @@ struct RenderingContext
 	// then leaves the current tree in place.
 	uint32_t                build_lbvh(uint32_t max_leaf_size, bool adopt, std::vector<fb::Bvh2Node>* nodes, std::vector<uint32_t>* index,
 									   std::vector<uint64_t>* codes, float* device_ms);
+	// the same builder over a point set (one point per leaf): the cluster tree of the VTLs (host/mesh_vtls.h). `bbox` is the Morton frame.
+	void                    build_lbvh_points(const std::vector<float4>& points, const float bbox[6], std::vector<fb::Bvh2Node>& nodes, std::vector<uint32_t>& index);
 	// RenderingContext::filter (src/renderer.cu:1099-1160): FILTERED_C = DIRECT_C + albedo-modulated EAW-filtered
 	// DIFFUSE_C and SPECULAR_C (7 a-trous iterations, variance-guided). Needs the G-buffer of the pass just rendered.
 	void                    filter(const uint32_t instance);
@@ -245,6 +248,23 @@ private:
 	bool             m_psf;
 	fb::DeviceBuffer m_psf_keys, m_psf_values;
 	fb::PsfView      m_psf_view;
+	// `-nee-alg rl` (src/renderers/pathtracer_impl.h:168-192): the VTLs, their cluster tree and the learning sampler's cells (kernels/rl_kernels.cu)
+	bool             m_rl;
+	fb::MeshVTLs     m_vtls;
+	fb::DeviceBuffer m_rl_vtls, m_rl_locate_roots, m_rl_locate_nodes, m_rl_tree_nodes, m_rl_tree_parents, m_rl_tree_ranges;
+	fb::DeviceBuffer m_rl_init_nodes, m_rl_init_offsets, m_rl_init_cdf;
+	fb::DeviceBuffer m_rl_keys, m_rl_occupied, m_rl_n_occupied, m_rl_values, m_rl_counts, m_rl_cluster_nodes, m_rl_cluster_ends;
+	fb::RlView       m_rl_view;
+	void             init_rl(RenderingContext& renderer);
+public:
+	// AdaptiveClusteredRLStorage::clear / update on the context's stream (PathTracer::update_vtls_rl does one of them per pass); for tests
+	bool             rl_enabled() const { return m_rl; }
+	void             rl_clear(RenderingContext& renderer);
+	void             rl_update(RenderingContext& renderer, bool adaptive);
+	const fb::RlView& rl_view() const { return m_rl_view; }
+	const fb::MeshVTLs& vtls() const { return m_vtls; }
+	const void*      rl_tree(int which) const { return which == 0 ? m_rl_tree_nodes.ptr : which == 1 ? m_rl_tree_parents.ptr : m_rl_tree_ranges.ptr; }
+private:
 	void             render_subframe(SubFrame& f, const fb::PassParams& pp, const std::vector<float>& seq, RenderingContext& renderer, cudaStream_t stream, bool overlap);
 	bool             m_events;
 	bool             m_profiling;

@@ -58,8 +58,8 @@ struct PathQueue
 	float4* hit;        // t, as_float(triId), u, v   (written by the closest-hit kernel)
 	float4* weight;     // path weight rgb, p_prev
 	uint32* pixel;      // PixelInfo bits: pixel:27 comp:4 diffuse:1 (src/pathtracer_core.h:527-542)
-	// `-psfpt` only (NULL otherwise): the ray cone {radius so far, solid-angle pdf of the direction} and the vertex processor's
-	// per-path word (PTRayQueue::cones, pixels.y: src/pathtracer_queues.h:44-53)
+	// `-psfpt` and `-nee-alg rl` only (NULL otherwise): the ray cone {radius so far, solid-angle pdf of the direction} and the vertex
+	// processor's per-path word (PTRayQueue::cones, pixels.y: src/pathtracer_queues.h:44-53) / the RL cell of the previous vertex (pixels.z)
 	float2* cone;
 	uint32* vinfo;
 };
@@ -71,7 +71,7 @@ struct ShadowQueue
 	float4* w_d;        // diffuse NEE weight rgb, .w = as_float(PixelInfo bits)
 	float4* w_g;        // glossy NEE weight rgb
 	unsigned char* occluded;   // outcome of the shadow trace, read by the accumulation kernel (FB_SPLIT_ACCUMULATE)
-	uint32* vinfo;             // `-psfpt` only: the vertex_info of the vertex the shadow ray leaves (src/pathtracer_core.h:1098)
+	uint32* vinfo;             // `-psfpt`: the vertex_info of the vertex the shadow ray leaves (src/pathtracer_core.h:1098); `-nee-alg rl`: its cell and cluster (rl_pack)
 };
 
 // State of the path-space filter (`-psfpt`, src/renderers/psfpt_impl.h:101-113): the hash of cache cells, their values, and the queue
@@ -86,6 +86,34 @@ struct PsfView
 	float4* ref_w_d; float4* ref_w_g; uint2* ref_pixels;   // [bounce * ref_capacity + i]
 	uint32  ref_capacity;
 	uint32  psf_depth; float psf_width, psf_max_prob, firefly_filter;
+	float   bbox_lo[3], bbox_hi[3];
+	uint32  instance;
+};
+
+// State of the reinforcement-learning next-event sampler (`-nee-alg rl`: src/direct_lighting_rl.h over AdaptiveClusteredRLView,
+// src/clustered_rl.h:124-156, and VTLMeshView, src/vtl_mesh_view.h). A shading cell (spatial hash of position and normal) owns a cut
+// through the VTL cluster tree and one learned value per cluster; light samples are drawn from the cell's CDF over its clusters and
+// every shadow ray feeds its outcome back. As with PsfView, a cell's slot IS its position in the open-addressing table (the reference
+// compacts slots through a second table and spins until the inserting thread has published it); `occupied` lists the positions in use
+// for the per-pass update kernel.
+#define FB_RL_MAX_CLUSTERS 256u
+#define FB_RL_NO_SLOT      0xFFFFFFFFu     // no next-event estimation at that vertex (DirectLightingRL::INVALID_SLOT)
+#define FB_RL_UNIFORM_SLOT 0xFFFFFFFEu     // the table was full: VTLs drawn uniformly
+#define FB_RL_NO_SAMPLE    0xFFFFFFFFu     // DirectLightingRL::INVALID_SAMPLE
+struct RlView
+{
+	unsigned long long* keys;       // ~0 = empty; mask + 1 entries
+	uint32* occupied;               // table positions in insertion order
+	uint32* n_occupied;
+	uint32  mask;
+	float*  pdfs;                   // [slot * init_cluster_count + cluster]: the learned values (AdaptiveClusteredRLView::pdfs)
+	float*  cdfs;                   // the sampling CDFs, rebuilt from the values once per pass
+	uint32* cluster_counts;         // [slot]
+	uint32* cluster_nodes;          // [slot * init_cluster_count + cluster]: nodes of the cut
+	uint32* cluster_ends;           // one past the last VTL of each cluster
+	uint32  init_cluster_count;
+	const VTL* vtls; uint32 n_vtls;
+	const uint32* locate_roots; const uint32* locate_nodes;     // point location: host/mesh_vtls.h
 	float   bbox_lo[3], bbox_hi[3];
 	uint32  instance;
 };

@@ -15,6 +15,7 @@
 #include "pt_kernels.h"
 #include "traversal.cuh"
 #include "shading.cuh"
+#include "rl_sampler.cuh"
 
 namespace fb {
 
@@ -532,6 +533,7 @@ struct AccumArgs
 	const float4* w_d; const float4* w_g; const uint32* vinfo;
 	FrameBufferView fb; float frame_weight; uint32 bounce;
 	PsfView psf;
+	RlView rl;                       // RL instantiation only
 };
 
 // PSFPTVertexProcessor::accumulate_nee (src/psfpt_vertex_processor.h:374-438) for one unoccluded shadow ray. The queue carries the
@@ -570,12 +572,26 @@ FB_D void accumulate_unoccluded_psf(const AccumArgs& a, const uint32 ray_idx)
 	}
 }
 
-template <bool PSF>
+// RL: every shadow ray, occluded or not, reports to the cell and cluster it was drawn from (DirectLightingRL::update through solve_occlusion,
+// src/pathtracer_core.h:723-724, src/direct_lighting_rl.h:171-185): the value learned is the largest component of the sample's weight, 0 when occluded
+template <bool PSF, bool RL = false>
 __global__ void __launch_bounds__(256) k_accumulate_unoccluded(AccumArgs a)
 {
 	const uint32 n = *a.n_ptr;
 	for (uint32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-		if (a.occluded[i] == 0) { if (PSF) accumulate_unoccluded_psf(a, i); else accumulate_unoccluded(a, i); }
+	{
+		const bool occluded = a.occluded[i] != 0;
+		if (RL)
+		{
+			const uint32 word = a.vinfo[i];
+			if (word != FB_RL_NO_SAMPLE)
+			{
+				const V3 w = V3(ld_stream(a.w_d + i)) + V3(ld_stream(a.w_g + i));
+				rl_update(a.rl, rl_packed_slot(word), rl_packed_cluster(word), occluded ? 0.0f : max_comp(w));
+			}
+		}
+		if (!occluded) { if (PSF) accumulate_unoccluded_psf(a, i); else accumulate_unoccluded(a, i); }
+	}
 }
 
 // psf_blending_kernel (src/renderers/psfpt_impl.h:101-131) over the reference-queue segment of one bounce: a pixel owns at most one
@@ -624,6 +640,7 @@ struct ShadeArgs
 	uint32 bounce; float frame_weight; float seq[6];
 	uint32 do_nee, do_emissive, do_scatter, do_dirlight;
 	PsfView psf;                     // PSF instantiation only
+	RlView rl;                       // RL instantiation only
 };
 
 // DIRLIGHT: scenes with DirectionalLights (rare) get their own instantiation; keeping that block — a second inlined
@@ -635,12 +652,13 @@ struct ShadeArgs
 // SHADE_LIGHT (vertex set-up + directional lights + next-event estimation -> shadow queues) and SHADE_PATH (vertex set-up + G-buffer / albedo
 // + emissive hit + scattering -> next-bounce queue) as two kernels on two streams: each repeats the set-up but holds one Bsdf evaluation
 // less, and the closest-hit trace of bounce b+1 waits for SHADE_PATH only while the shadow trace of bounce b waits for SHADE_LIGHT only.
+// RL: next-event samples come from DirectLightingRL (src/direct_lighting_rl.h) instead of DirectLightingMesh: `-nee-alg rl`, rl_sampler.cuh.
 enum ShadeParts { SHADE_LIGHT = 1, SHADE_PATH = 2, SHADE_ALL = 3 };
 #ifndef FB_SHADE_PART_BLOCKS
 #define FB_SHADE_PART_BLOCKS 8         // CTAs of 128 threads per SM of the two part kernels (64 registers)
 #endif
 
-template <bool DIRLIGHT, bool PSF = false, int PARTS = SHADE_ALL>
+template <bool DIRLIGHT, bool PSF = false, int PARTS = SHADE_ALL, bool RL = false>
 __global__ void __launch_bounds__(128, PARTS == SHADE_ALL ? FB_SHADE_MIN_BLOCKS : FB_SHADE_PART_BLOCKS) k_shade(DeviceScene sc, ShadeArgs a)
 {
 	const uint32 n = a.ctr->in_size[a.bounce];
@@ -665,6 +683,8 @@ __global__ void __launch_bounds__(128, PARTS == SHADE_ALL ? FB_SHADE_MIN_BLOCKS 
 		// PSF: this vertex's / the scattered path's CacheInfo, the scattered ray's cone, the reference this vertex appends
 		uint32 vinfo = FB_PSF_INVALID, prev_vinfo = FB_PSF_INVALID; bool new_entry = false; float cone_radius = 0.0f;
 		bool ref_on = false; float4 ref_wd, ref_wg; uint32 ref_cache = FB_PSF_INVALID;
+		// RL: the light sampler's cell of this vertex and of the previous one
+		uint32 nee_slot = FB_RL_NO_SLOT, prev_nee_slot = FB_RL_NO_SLOT;
 
 		float4 hit = make_float4(-1.0f, 0.0f, 0.0f, 0.0f);
 		if (valid) { hit = ld_stream(a.in.hit + idx); valid = (hit.x > 0.0f) && (__float_as_int(hit.y) >= 0); }
@@ -745,6 +765,16 @@ __global__ void __launch_bounds__(128, PARTS == SHADE_ALL ? FB_SHADE_MIN_BLOCKS 
 					}
 				}
 				vinfo = psf_pack(slot, 0u, new_entry ? 1u : 0u);
+			}
+			// ---- DirectLightingRL::preprocess_vertex (src/direct_lighting_rl.h:69-113, called at src/pathtracer_core.h:816-834) ----
+			if (RL)
+			{
+				const float2 cone = a.in.cone[idx];
+				prev_nee_slot = a.in.vinfo[idx];
+				const float prev_G_prime = fabsf(dot(in, g.normal_s)) / (hit.x * hit.x);
+				const float area_prob = 1.0f / sqrtf(cone.y * prev_G_prime);
+				cone_radius = cone.x + area_prob;
+				if (a.do_nee) nee_slot = rl_preprocess_vertex(a.rl, sc.res_x, sc.res_y, position, in, g, pixel, bounce, (info >> 31) != 0u, cone_radius);
 			}
 
 			if ((PARTS & SHADE_PATH) && bounce == 0)
@@ -833,10 +863,27 @@ __global__ void __launch_bounds__(128, PARTS == SHADE_ALL ? FB_SHADE_MIN_BLOCKS 
 		{
 			bool nee_on = false;
 			float4 nee_o, nee_d, nee_wd, nee_wg;
+			uint32 nee_word = FB_RL_NO_SAMPLE;
 			if (valid)
 			{
 				uint32 prim; float lu, lv;
-				if (sc.use_vpls)
+				float rl_light_pdf = 0.0f;
+				if (RL)
+				{
+					// DirectLightingRL::sample (src/direct_lighting_rl.h:117-150): a VTL by the cell's clustered CDF, then a point of it
+					// (VTLMeshView::sample, src/vtl_mesh_view.h:52-76; like the reference, (z0, z1) is not folded into the triangle)
+					float sel_pdf; uint32 vtl_idx;
+					if (nee_slot < FB_RL_UNIFORM_SLOT) { uint32 cluster; vtl_idx = rl_sample(a.rl, nee_slot, z[2], &sel_pdf, &cluster); nee_word = rl_pack(nee_slot, cluster); }
+					else { vtl_idx = cg_quantize(z[2], a.rl.n_vtls); sel_pdf = 1.0f / float(a.rl.n_vtls); }
+					const float4* vp = reinterpret_cast<const float4*>(a.rl.vtls + vtl_idx);
+					const float4 v0 = __ldg(vp), v1 = __ldg(vp + 1);       // {prim, area, uv0}, {uv1, uv2}
+					prim = __float_as_uint(v0.x);
+					const float wz = 1.0f - z[0] - z[1];
+					lu = v1.z * wz + v0.z * z[0] + v1.x * z[1];
+					lv = v1.w * wz + v0.w * z[0] + v1.y * z[1];
+					rl_light_pdf = (1.0f / v0.y) * sel_pdf;
+				}
+				else if (sc.use_vpls)
 				{
 					const uint32 l = min((uint32)(z[2] * float(sc.n_vpls)), sc.n_vpls - 1);
 					const float4 vpl = __ldg(reinterpret_cast<const float4*>(sc.vpls) + l);
@@ -855,6 +902,7 @@ __global__ void __launch_bounds__(128, PARTS == SHADE_ALL ? FB_SHADE_MIN_BLOCKS 
 				setup_geometry<true>(sc, prim, lu, lv, lg, lpos, ls, lt);
 				float light_pdf; V3 edf;
 				light_map(sc, prim, ls, lt, light_pdf, edf);
+				if (RL) light_pdf = rl_light_pdf;
 
 				V3 out = lpos - position;
 				const float d2 = fmaxf(1.0e-8f, square_length(out));
@@ -892,13 +940,23 @@ __global__ void __launch_bounds__(128, PARTS == SHADE_ALL ? FB_SHADE_MIN_BLOCKS 
 			const uint32 slot = warp_append_slot(shadow_counter, nee_on);
 			if (nee_on) { st_stream(a.sq.ray_o + slot, nee_o); st_stream(a.sq.ray_d + slot, nee_d); st_stream(a.sq.w_d + slot, nee_wd); st_stream(a.sq.w_g + slot, nee_wg); }
 			if (PSF && nee_on) a.sq.vinfo[slot] = vinfo;
+			if (RL && nee_on) a.sq.vinfo[slot] = nee_word;
 		}
 
 		// ---- emissive hit with MIS against NEE at the previous vertex (pathtracer_core.h:1109-1154) ----
 		if ((PARTS & SHADE_PATH) && a.do_emissive && valid)
 		{
 			float light_pdf;
-			if (sc.use_vpls) light_pdf = fmaxf(fabsf(ke.x), fmaxf(fabsf(ke.y), fabsf(ke.z))) / sc.vpl_norm;
+			if (RL)
+			{
+				// DirectLightingRL::map (src/direct_lighting_rl.h:154-167): the VTL under the hit point, times the probability that the
+				// previous vertex's cell picks it
+				const uint32 vtl_idx = vtl_locate(a.rl, tri, hit.z, hit.w);
+				light_pdf = vtl_idx != 0xFFFFFFFFu ? 1.0f / __ldg(&a.rl.vtls[vtl_idx].area) : 0.0f;
+				if (prev_nee_slot != FB_RL_NO_SLOT && vtl_idx != 0xFFFFFFFFu)
+					light_pdf *= prev_nee_slot == FB_RL_UNIFORM_SLOT ? 1.0f / float(a.rl.n_vtls) : rl_pdf(a.rl, prev_nee_slot, vtl_idx);
+			}
+			else if (sc.use_vpls) light_pdf = fmaxf(fabsf(ke.x), fmaxf(fabsf(ke.y), fabsf(ke.z))) / sc.vpl_norm;
 			else light_pdf = (__ldg(sc.mesh_cdf + tri) - (tri ? __ldg(sc.mesh_cdf + tri - 1) : 0.0f)) * __ldg(sc.mesh_inv_area + tri);
 			const V3 f_L = dot(g.normal_s, in) > 0.0f ? ke : V3(0.0f);
 			const float d2 = fmaxf(1.0e-10f, hit_t * hit_t);
@@ -943,6 +1001,7 @@ __global__ void __launch_bounds__(128, PARTS == SHADE_ALL ? FB_SHADE_MIN_BLOCKS 
 					if (new_entry && (out_comp & kDiffuseMask)) ow = gg / psf_floor4(kd);
 					sc_cone = make_float2(cone_radius, fmaxf(p, 32.0f));
 				}
+				if (RL) sc_cone = make_float2(cone_radius, fmaxf(p, 32.0f));
 				if (out_comp != kAbsorption && p != 0.0f && max_comp(ow) > 0.0f && is_finite(ow))
 				{
 					scat_on = true;
@@ -956,6 +1015,7 @@ __global__ void __launch_bounds__(128, PARTS == SHADE_ALL ? FB_SHADE_MIN_BLOCKS 
 			const uint32 slot = warp_append_slot(scatter_counter, scat_on);
 			if (scat_on) { st_stream(a.out.ray_o + slot, sc_o); st_stream(a.out.ray_d + slot, sc_d); st_stream(a.out.weight + slot, sc_w); st_stream(a.out.pixel + slot, sc_info); }
 			if (PSF && scat_on) { a.out.cone[slot] = sc_cone; a.out.vinfo[slot] = sc_vinfo; }
+			if (RL && scat_on) { a.out.cone[slot] = sc_cone; a.out.vinfo[slot] = nee_slot; }      // src/pathtracer_core.h:1222-1240
 		}
 		if (PSF)
 		{
@@ -1107,7 +1167,7 @@ cudaError_t launch_trace_closest(const DeviceScene& sc, const LaunchConfig& lc, 
 bool kernels_split_accumulate() { return FB_SPLIT_ACCUMULATE != 0; }
 
 cudaError_t launch_trace_shadow(const DeviceScene& sc, const LaunchConfig& lc, const ShadowQueue& sq, const FrameBufferView& fb, PassCounters* ctr, PassTotals* tot,
-								uint32 bounce, float frame_weight, cudaStream_t s, int which, uint32* launches, const PsfView* psf, int stages)
+								uint32 bounce, float frame_weight, cudaStream_t s, int which, uint32* launches, const PsfView* psf, int stages, const RlView* rl)
 {
 	// stages: 1 = the trace only, 2 = the accumulation pass only, 3 = both (the two can be separated by an event: FB200_SHADE_SPLIT)
 	// which = 0: the next-event queue; 1: the directional-light queue (its own counters: the two are accumulated one after the other)
@@ -1129,11 +1189,12 @@ cudaError_t launch_trace_shadow(const DeviceScene& sc, const LaunchConfig& lc, c
 		AccumArgs ac; memset(&ac, 0, sizeof(ac));
 		ac.n_ptr = a.n_ptr; ac.occluded = sq.occluded; ac.w_d = sq.w_d; ac.w_g = sq.w_g; ac.vinfo = sq.vinfo; ac.fb = fb; ac.frame_weight = frame_weight; ac.bounce = bounce;
 		if (psf) { ac.psf = *psf; k_accumulate_unoccluded<true><<<lc.sm_count * 4, 256, 0, s>>>(ac); }
+		else if (rl && which == 0) { ac.rl = *rl; k_accumulate_unoccluded<false, true><<<lc.sm_count * 4, 256, 0, s>>>(ac); }
 		else k_accumulate_unoccluded<false><<<lc.sm_count * 4, 256, 0, s>>>(ac);
 		if (launches) *launches += 1;
 	}
 #else
-	if (psf) return cudaErrorNotSupported;       // (the filtered renderer needs the accumulation pass)
+	if (psf || rl) return cudaErrorNotSupported;       // (the filtered renderer and the RL sampler need the accumulation pass)
 #endif
 	return cudaGetLastError();
 }
@@ -1166,10 +1227,11 @@ cudaError_t launch_clamp_frame(const FrameBufferView& fb, const PixelSet& ps, fl
 }
 
 cudaError_t launch_shade(const DeviceScene& sc, const LaunchConfig& lc, const PassParams& pp, const PathQueue& in, const PathQueue& out, const ShadowQueue& sq, const ShadowQueue& sq_dl,
-						 const FrameBufferView& fb, PassCounters* ctr, PassTotals* tot, uint32 bounce, const float seq6[6], uint32 capacity, cudaStream_t s, const PsfView* psf, int parts)
+						 const FrameBufferView& fb, PassCounters* ctr, PassTotals* tot, uint32 bounce, const float seq6[6], uint32 capacity, cudaStream_t s, const PsfView* psf, int parts, const RlView* rl)
 {
 	ShadeArgs a;
 	memset(&a.psf, 0, sizeof(a.psf));
+	memset(&a.rl, 0, sizeof(a.rl));
 	a.in = in; a.out = out; a.sq = sq; a.sq_dl = sq_dl; a.fb = fb; a.ctr = ctr; a.tot = tot; a.bounce = bounce; a.frame_weight = pp.frame_weight;
 	for (int i = 0; i < 6; ++i) a.seq[i] = seq6[i];
 	// compute_per_bounce_options (pathtracer_core.h:594-620)
@@ -1190,6 +1252,13 @@ cudaError_t launch_shade(const DeviceScene& sc, const LaunchConfig& lc, const Pa
 		if (sc.n_dir_lights || parts != SHADE_ALL) return cudaErrorNotSupported;
 		a.psf = *psf;
 		k_shade<false, true><<<blocks, threads, 0, s>>>(sc, a);
+	}
+	else if (rl)
+	{
+		if (parts != SHADE_ALL) return cudaErrorNotSupported;
+		a.rl = *rl;
+		if (sc.n_dir_lights) k_shade<true, false, SHADE_ALL, true><<<blocks, threads, 0, s>>>(sc, a);
+		else k_shade<false, false, SHADE_ALL, true><<<blocks, threads, 0, s>>>(sc, a);
 	}
 	else if (sc.n_dir_lights)
 	{

@@ -52,11 +52,13 @@ cudaError_t launch_trace_closest(const DeviceScene& sc, const LaunchConfig& lc, 
 cudaError_t launch_shade(const DeviceScene& sc, const LaunchConfig& lc, const PassParams& pp, const PathQueue& in, const PathQueue& out, const ShadowQueue& sq, const ShadowQueue& sq_dl,
 						 const FrameBufferView& fb, PassCounters* ctr, PassTotals* tot, uint32 bounce, const float seq6[6], uint32 capacity, cudaStream_t s,
 						 const PsfView* psf = NULL,       // psf != NULL: the `-psfpt` vertex processor
-						 int parts = 3);                  // 3 = the whole vertex; 1 = set-up + light sampling only (-> shadow queues), 2 = set-up + emissive + scattering only (-> next queue)
+						 int parts = 3,                   // 3 = the whole vertex; 1 = set-up + light sampling only (-> shadow queues), 2 = set-up + emissive + scattering only (-> next queue)
+						 const RlView* rl = NULL);        // rl != NULL: next-event samples from the reinforcement-learning sampler (`-nee-alg rl`)
 // shadow trace + solve_occlusion of one shadow queue of bounce `bounce`: which = 0 the next-event queue (`sq`), 1 the directional-light queue
 cudaError_t launch_trace_shadow(const DeviceScene& sc, const LaunchConfig& lc, const ShadowQueue& sq, const FrameBufferView& fb, PassCounters* ctr, PassTotals* tot,
 								uint32 bounce, float frame_weight, cudaStream_t s, int which = 0, uint32* launches = NULL, const PsfView* psf = NULL,
-								int stages = 3);     // 1 = the trace only, 2 = the accumulation pass only, 3 = both
+								int stages = 3,      // 1 = the trace only, 2 = the accumulation pass only, 3 = both
+								const RlView* rl = NULL);   // rl != NULL (next-event queue): every shadow ray's outcome is fed back to the sampler
 // `-psfpt`: splat the references of one bounce (psf_blending, src/renderers/psfpt_impl.h:101-143); RenderingContext::clamp_frame (src/renderer.cu:421-427)
 cudaError_t launch_psf_blend(const LaunchConfig& lc, const PsfView& psf, const FrameBufferView& fb, const PassCounters* ctr, uint32 bounce, float frame_weight, cudaStream_t s);
 cudaError_t launch_clamp_frame(const FrameBufferView& fb, const PixelSet& ps, float max_value, cudaStream_t s);

@@ -264,6 +264,18 @@ int fb200_context_select_renderer(fb200_context*, uint32_t id);
  * recomputes what depends on geometry on the host (bounding box, triangle CDF, VPLs), uploads, and the renderer rebuilds the scene BVH
  * ON THE DEVICE (CUGAR-format LBVH + 8-wide collapse; no host tree build). Topology, materials and textures are unchanged. Blocking. */
 int fb200_context_update_scene(fb200_context*, const float* vertex_data);
+/* `-nee-alg rl` (src/direct_lighting_rl.h, src/clustered_rl.h AdaptiveClusteredRLStorage, src/mesh_lights.h MeshVTLStorage): the state of
+ * the reinforcement-learning light sampler of a context created with that option, for inspection and tests. out[0..19] =
+ * {cells in the table, initial cluster count, VTL count, cluster-tree nodes, DEVICE pointers: keys (u64 per cell), occupied (u32), n_occupied (u32),
+ *  pdfs (f32, cells x clusters), cdfs (same), cluster_counts (u32 per cell), cluster_nodes (u32, cells x clusters), cluster_ends (same),
+ *  vtls (32 B each: src/vtl.h), tree nodes (Bvh_node_3d), tree parents (u32), tree ranges (2 x u32), locate_roots (u32 per triangle), locate_nodes (u32),
+ *  locate node count, 0}. fb200_context_rl_clear = AdaptiveClusteredRLStorage::clear, fb200_context_rl_update = ::update(adaptive):
+ * what PathTracer::render runs before a pass (src/renderers/pathtracer_impl.h:180-192), enqueued on the context's stream.
+ * fb200_context_rl_locate: VTLMeshView::map's lookup on the host - the VTL of triangle prim that holds (u, v), 0xFFFFFFFF if none. */
+int fb200_context_rl_state(fb200_context*, uint64_t out[20]);
+int fb200_context_rl_clear(fb200_context*);
+int fb200_context_rl_update(fb200_context*, int adaptive);
+int fb200_context_rl_locate(fb200_context*, const uint32_t* prims, const float* uv, uint32_t n, uint32_t* vtl_out);
 /* copy the frame-buffer channels (float4 per pixel, res_x * res_y) into caller-owned DEVICE buffers on the context's stream, behind the
  * passes rendered so far: channels[i] = destination of channel i (fb200 channel numbering = FBufferDesc, src/renderer_view.h:133-145)
  * or NULL to skip it. This is how a host that owns its frame buffer (Fermat's RenderingContext: adapter/fermat_adapter.cpp) receives

@@ -487,3 +487,81 @@ class RefSah:
         o = (C.c_double * 5)()
         self.L.ref_sah_cost_of(nodes_ptr, n_nodes, o)
         return self._out(o)
+
+
+class RlState:
+    """The `-nee-alg rl` sampler restated on the CPU (oracle_rl.h): the VTLs with their cluster tree and initial cut (MeshVTLStorage::init with
+    `n_target` VTLs) and the learning sampler's cells across passes (AdaptiveClusteredRLStorage)."""
+
+    VTL_DTYPE = np.dtype([("prim_id", "<u4"), ("area", "<f4"), ("uv0", "<f4", 2), ("uv1", "<f4", 2), ("uv2", "<f4", 2)])
+
+    def __init__(self, view, n_target):
+        L = lib()
+        L.oracle_rl_create.restype = C.c_void_p
+        L.oracle_rl_create.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_int)]
+        L.oracle_rl_destroy.argtypes = [C.c_void_p]
+        L.oracle_rl_sizes.argtypes = [C.c_void_p, C.POINTER(C.c_uint64 * 4)]
+        L.oracle_rl_array.restype = C.c_void_p
+        L.oracle_rl_array.argtypes = [C.c_void_p, C.c_int]
+        L.oracle_rl_locate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+        L.oracle_rl_step.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.oracle_rl_sample.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_render_pass_rl.restype = C.c_int
+        L.oracle_render_pass_rl.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_float), C.c_void_p, C.c_int, C.POINTER(OracleStats)]
+        err = C.c_int(0)
+        self.view = view
+        self._h = L.oracle_rl_create(C.addressof(view), int(n_target), C.byref(err))
+        if not self._h:
+            raise RuntimeError({-1: "the scene has no emitter", -2: "textured emitters are not restated in the oracle"}.get(err.value, "oracle_rl_create failed"))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().oracle_rl_destroy(self._h)
+            self._h = None
+
+    def sizes(self):
+        o = (C.c_uint64 * 4)()
+        lib().oracle_rl_sizes(self._h, C.byref(o))
+        return {"vtls": int(o[0]), "tree_nodes": int(o[1]), "clusters": int(o[2]), "cells": int(o[3])}
+
+    def _arr(self, which, dtype, shape):
+        p = lib().oracle_rl_array(self._h, which)
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n,)).view(dtype).reshape(shape).copy()
+
+    def arrays(self):
+        z = self.sizes()
+        return {"vtls": self._arr(0, self.VTL_DTYPE, (z["vtls"],)), "tree_nodes": self._arr(1, "<u4", (z["tree_nodes"], 2)),
+                "tree_ranges": self._arr(2, "<u4", (z["tree_nodes"], 2)), "tree_parents": self._arr(3, "<u4", (z["tree_nodes"],)),
+                "clusters": self._arr(4, "<u4", (z["clusters"],)), "cluster_offsets": self._arr(5, "<u4", (z["clusters"] + 1,))}
+
+    def locate(self, prims, uv):
+        prims = np.ascontiguousarray(prims, np.uint32); uv = np.ascontiguousarray(uv, np.float32)
+        out = np.zeros(len(prims), np.uint32)
+        lib().oracle_rl_locate(self._h, prims.ctypes.data, uv.ctypes.data, len(prims), out.ctypes.data)
+        return out
+
+    def step(self, counts, nodes, ends, pdfs, adaptive=True):
+        """AdaptiveClusteredRLStorage::update on rows of C entries: returns (counts, nodes, ends, pdfs, cdfs) after one split / collapse step + CDF rebuild"""
+        counts = np.array(counts, np.uint32); nodes = np.array(nodes, np.uint32); ends = np.array(ends, np.uint32); pdfs = np.array(pdfs, np.float32)
+        n, Cn = nodes.shape
+        cdfs = np.zeros((n, Cn), np.float32)
+        lib().oracle_rl_step(self._h, n, Cn, counts.ctypes.data, nodes.ctypes.data, ends.ctypes.data, pdfs.ctypes.data, cdfs.ctypes.data, 1 if adaptive else 0)
+        return counts, nodes, ends, pdfs, cdfs
+
+    @staticmethod
+    def sample(count, ends, cdfs, z):
+        """AdaptiveClusteredRLView::sample / ::pdf on one cell: (index, pdf, cluster, pdf(index)) per z"""
+        ends = np.ascontiguousarray(ends, np.uint32); cdfs = np.ascontiguousarray(cdfs, np.float32); z = np.ascontiguousarray(z, np.float32)
+        lib().oracle_rl_sample.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        n = len(z)
+        index = np.zeros(n, np.uint32); pdf = np.zeros(n, np.float32); cluster = np.zeros(n, np.uint32); pdf2 = np.zeros(n, np.float32)
+        lib().oracle_rl_sample(len(ends), int(count), ends.ctypes.data, cdfs.ctypes.data, z.ctypes.data, n, index.ctypes.data, pdf.ctypes.data, cluster.ctypes.data, pdf2.ctypes.data)
+        return index, pdf, cluster, pdf2
+
+    def render_pass(self, instance, fb, threads=0):
+        """PathTracer::render with the RL sampler: update_vtls_rl, then one progressive pass into `fb` (in place), whole frame"""
+        st = OracleStats()
+        rc = lib().oracle_render_pass_rl(C.addressof(self.view), int(instance), _fptr(fb), self._h, int(threads), C.byref(st))
+        assert rc == 0
+        return st

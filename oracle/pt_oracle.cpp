@@ -33,6 +33,8 @@
 #include "oracle_bsdf.h"
 #include <vector>
 #include <unordered_map>
+#include <queue>
+#include <deque>
 #include <algorithm>
 #include <stdio.h>
 #ifdef _OPENMP
@@ -481,8 +483,10 @@ static inline vec3 psf_clamp_sample(vec3 v, float ff) { return finite3(v) ? vec3
 static inline vec3 psf_floor4(vec3 c) { return vec3(fmaxf(c.x, 1.0e-4f), fmaxf(c.y, 1.0e-4f), fmaxf(c.z, 1.0e-4f)); }   // modulate / demodulate, src/filters.h:57-72
 
 // one path, all bounces; psf != NULL: the PSFPTVertexProcessor policies instead of PTVertexProcessor's
+#include "oracle_rl.h"
+
 static void trace_path(const SceneRef& sc, const Sampler& smp, FB& fb, uint32_t px, uint32_t py, float frame_weight, vec3 U, vec3 V, vec3 W, PassStats& st, bool count_trav,
-					   PsfState* psf = NULL, uint32_t instance = 0)
+					   PsfState* psf = NULL, uint32_t instance = 0, RlState* rl = NULL)
 {
 	const fb200_scene_view* s = sc.s;
 	const fb200_pt_options& o = s->options;
@@ -509,7 +513,8 @@ static void trace_path(const SceneRef& sc, const Sampler& smp, FB& fb, uint32_t 
 	const fb200_psf_options& po = s->psf;
 	float cone_x = 0.0f, cone_y = 0.0f;
 	uint32_t prev_vinfo = PSF_INVALID;
-	if (psf)
+	uint32_t prev_nee_slot = RL_INVALID;      // DirectLightingRL: the cell of the previous vertex (PTRayQueue::pixels.z)
+	if (psf || rl)
 	{
 		// camera_direction_pdf (src/camera.h:232-252) with square_pixel_focal_length (:122-128)
 		const float W_len = sqrtf(dot(W, W));
@@ -607,6 +612,28 @@ static void trace_path(const SceneRef& sc, const Sampler& smp, FB& fb, uint32_t 
 			}
 			vinfo = psf_pack(slot, 0, new_entry ? 1u : 0u);
 		}
+		// DirectLightingRL::preprocess_vertex (src/direct_lighting_rl.h:69-113; cone radius: src/pathtracer_core.h:816-819)
+		uint32_t nee_slot = RL_INVALID;
+		if (rl)
+		{
+			const float prev_G_prime = fabsf(dot(in, g.normal_s)) / (hit.t * hit.t);
+			const float area_prob = 1.0f / sqrtf(cone_y * prev_G_prime);
+			cone_radius = cone_x + area_prob;
+			if (do_nee)
+			{
+				const float cone_scale = 32.0f;
+				const float filter_scale = diffuse_flag ? 0.2f : 1.5f;
+				const uint32_t base_dim = (diffuse_flag ? 0u : instance) * 6u;
+				const uint32_t random_set = cg_hash(pixel + s->res_x * s->res_y * bounce);
+				float jitter[6];
+				for (uint32_t i = 0; i < 6; ++i) jitter[i] = randfloat(base_dim + i, random_set);
+				const vec3 lo(s->bbox_min[0], s->bbox_min[1], s->bbox_min[2]), hi(s->bbox_max[0], s->bbox_max[1], s->bbox_max[2]);
+				const float bbox_delta = max_comp(hi - lo);
+				const vec3 Ns = dot(in, g.normal_s) > 0.0f ? g.normal_s : -g.normal_s;
+				const uint64_t key = spatial_hash(g.position, Ns, g.tangent, g.binormal, lo, hi, jitter, fminf(cone_radius * cone_scale, bbox_delta * 0.05f), filter_scale);
+				nee_slot = rl_find_slot(*rl, key);
+			}
+		}
 
 		float z[6];
 		for (uint32_t i = 0; i < 6; ++i) z[i] = smp.sample_2d(px, py, (bounce + 1) * 6 + i);
@@ -647,14 +674,30 @@ static void trace_path(const SceneRef& sc, const Sampler& smp, FB& fb, uint32_t 
 		}
 
 		// next-event estimation (pathtracer_core.h:991-1106)
+		uint32_t nee_cluster = RL_INVALID;
 		if (do_nee)
 		{
 			uint32_t prim; float lu, lv;
-			sample_light_vertex(s, n_vpls, z, &prim, &lu, &lv);
+			float rl_light_pdf = 0.0f;
+			if (rl)
+			{
+				// DirectLightingRL::sample (src/direct_lighting_rl.h:117-150) -> VTLMeshView::sample (src/vtl_mesh_view.h:52-76); (z0, z1) is
+				// not folded into the triangle there
+				float sel_pdf;
+				const uint32_t vtl_idx = rl_sample(*rl, nee_slot, z[2], &sel_pdf, &nee_cluster);
+				const RlVTL& vtl = rl->vtls[vtl_idx];
+				prim = vtl.prim_id;
+				const float wz = 1.0f - z[0] - z[1];
+				lu = vtl.uv2[0] * wz + vtl.uv0[0] * z[0] + vtl.uv1[0] * z[1];
+				lv = vtl.uv2[1] * wz + vtl.uv0[1] * z[0] + vtl.uv1[1] * z[1];
+				rl_light_pdf = (1.0f / vtl.area) * sel_pdf;
+			}
+			else sample_light_vertex(s, n_vpls, z, &prim, &lu, &lv);
 			Geom lg;
 			setup_differential_geometry(sc, prim, lu, lv, &lg);
 			float light_pdf; vec3 edf;
 			light_map(sc, use_vpls, prim, lg, &light_pdf, &edf);
+			if (rl) light_pdf = rl_light_pdf;
 
 			vec3 out = lg.position - g.position;
 			const float d2 = fmaxf(1.0e-8f, square_length(out));
@@ -694,6 +737,13 @@ static void trace_path(const SceneRef& sc, const Sampler& smp, FB& fb, uint32_t 
 		{
 			float light_pdf; vec3 edf;
 			light_map(sc, use_vpls, (uint32_t)hit.tri, g, &light_pdf, &edf);
+			if (rl)
+			{
+				// DirectLightingRL::map (src/direct_lighting_rl.h:154-167) -> VTLMeshView::map (src/vtl_mesh_view.h:83-112)
+				const uint32_t vtl_idx = rl_locate(*rl, (uint32_t)hit.tri, hit.u, hit.v);
+				light_pdf = vtl_idx != RL_INVALID ? 1.0f / rl->vtls[vtl_idx].area : 0.0f;
+				if (prev_nee_slot != RL_INVALID && vtl_idx != RL_INVALID) light_pdf *= rl_pdf(*rl, prev_nee_slot, vtl_idx);
+			}
 			const vec3 f_L = dot(g.normal_s, in) > 0.0f ? edf : vec3(0.0f);
 			const float d2 = fmaxf(1.0e-10f, hit.t * hit.t);
 			const float G_partial = fabsf(dot(in, g.normal_s)) / d2;
@@ -745,6 +795,8 @@ static void trace_path(const SceneRef& sc, const Sampler& smp, FB& fb, uint32_t 
 			{
 				st.shadow_events++;
 				const bool occluded = trace_any(sc, pend[k].r, count_trav ? &st.trav_shadow : NULL);
+				// DirectLightingRL::update through solve_occlusion (src/pathtracer_core.h:723-724, src/direct_lighting_rl.h:171-185)
+				if (rl && k == 1 && nee_cluster != RL_INVALID) rl_update(*rl, nee_slot, nee_cluster, occluded ? 0.0f : max_comp(pend[k].w_d + pend[k].w_g));
 				if (!occluded && psf)
 				{
 					// PSFPTVertexProcessor::accumulate_nee (src/psfpt_vertex_processor.h:374-438). The shadow queue carries the vertex_info
@@ -788,6 +840,7 @@ static void trace_path(const SceneRef& sc, const Sampler& smp, FB& fb, uint32_t 
 		ray = next; w = next_w; p_prev = next_p;
 		cone_x = cone_radius; cone_y = fmaxf(next_p, 32.0f);      // Bekaert's footprint, src/pathtracer_core.h:1222-1227
 		prev_vinfo = next_vinfo;
+		prev_nee_slot = nee_slot;
 		diffuse_flag = diffuse_flag || (next_comp & cDiffuseMask);
 		comp = next_comp & 0xFu;      // PixelInfo::comp is a 4-bit field (pathtracer_core.h:527-542)
 		(void)diffuse_flag;
@@ -819,8 +872,8 @@ struct oracle_stats { uint64_t shade_events, shadow_events, nodes_visited, tris_
 // explicit list `pixels` (n_pixels entries) when it is not NULL. fb: 8 channels x res_x*res_y x float4.
 // Runs rescale_frame (multiply_frame, src/renderer.cu:292-311,413-416) on the touched pixels first and
 // update_variances (:333-362) afterwards, as RenderingContext::render / PathTracer::render do.
-int oracle_render_pass(const fb200_scene_view* s, uint32_t instance, float* fbdata, const uint32_t* pixels, uint64_t n_pixels,
-					   int n_threads, int count_traversal, oracle_stats* out)
+static int render_pass_impl(const fb200_scene_view* s, uint32_t instance, float* fbdata, const uint32_t* pixels, uint64_t n_pixels,
+					   int n_threads, int count_traversal, oracle_stats* out, RlState* rl)
 {
 	SceneRef sc = { s, s->vertex_indices, s->vertex_data, reinterpret_cast<const NodePOD*>(s->bvh_nodes) };
 	const size_t P = (size_t)s->res_x * s->res_y;
@@ -852,7 +905,7 @@ int oracle_render_pass(const fb200_scene_view* s, uint32_t instance, float* fbda
 			const int scaled[6] = { DIFFUSE_C, DIFFUSE_A, SPECULAR_C, SPECULAR_A, DIRECT_C, COMPOSITED_C };
 			for (int c = 0; c < 6; ++c) for (int i = 0; i < 4; ++i) fb.px(scaled[c], p)[i] *= scale;
 
-			trace_path(sc, smp, fb, p % s->res_x, p / s->res_x, frame_weight, U, V, W, st, count_traversal != 0);
+			trace_path(sc, smp, fb, p % s->res_x, p / s->res_x, frame_weight, U, V, W, st, count_traversal != 0, NULL, instance, rl);
 
 			// update_variances_kernel
 			const float nl[4] = {
@@ -876,6 +929,82 @@ int oracle_render_pass(const fb200_scene_view* s, uint32_t instance, float* fbda
 	}
 	if (out) *out = total;
 	return 0;
+}
+
+int oracle_render_pass(const fb200_scene_view* s, uint32_t instance, float* fbdata, const uint32_t* pixels, uint64_t n_pixels,
+					   int n_threads, int count_traversal, oracle_stats* out)
+{
+	return render_pass_impl(s, instance, fbdata, pixels, n_pixels, n_threads, count_traversal, out, NULL);
+}
+
+// ---- `-nee-alg rl` (oracle_rl.h) ----
+// MeshVTLStorage::init with n_target VTLs + an empty AdaptiveClusteredRLStorage. err: 0, -1 no emitters, -2 textured emitter (unsupported here)
+void* oracle_rl_create(const fb200_scene_view* s, uint32_t n_target, int* err)
+{
+	SceneRef sc = { s, s->vertex_indices, s->vertex_data, reinterpret_cast<const NodePOD*>(s->bvh_nodes) };
+	RlState* st = new RlState();
+	const int e = rl_build(sc, n_target, *st);
+	if (err) *err = e;
+	if (e != 0) { delete st; return NULL; }
+	return st;
+}
+void oracle_rl_destroy(void* st) { delete static_cast<RlState*>(st); }
+// sizes: {VTLs, tree nodes, initial clusters, cells}
+void oracle_rl_sizes(const void* state, uint64_t out[4])
+{
+	const RlState* st = static_cast<const RlState*>(state);
+	out[0] = st->vtls.size(); out[1] = st->tree_parents.size(); out[2] = st->clusters.size(); out[3] = st->cells.size();
+}
+// which: 0 VTLs (32 B each), 1 tree node words (2 per node), 2 tree ranges (2 per node), 3 tree parents, 4 clusters, 5 cluster offsets
+const void* oracle_rl_array(const void* state, int which)
+{
+	const RlState* st = static_cast<const RlState*>(state);
+	switch (which)
+	{
+	case 0: return st->vtls.data();
+	case 1: return st->tree_nodes.data();
+	case 2: return st->tree_ranges.data();
+	case 3: return st->tree_parents.data();
+	case 4: return st->clusters.data();
+	case 5: return st->cluster_offsets.data();
+	}
+	return NULL;
+}
+void oracle_rl_locate(const void* state, const uint32_t* prims, const float* uv, uint32_t n, uint32_t* out)
+{
+	const RlState* st = static_cast<const RlState*>(state);
+	for (uint32_t i = 0; i < n; ++i) out[i] = rl_locate(*st, prims[i], uv[2 * i], uv[2 * i + 1]);
+}
+// AdaptiveClusteredRLStorage::update on caller-provided cells: n_cells rows of C entries (counts[n_cells] in / out; nodes, ends, pdfs in / out; cdfs out)
+void oracle_rl_step(const void* state, uint32_t n_cells, uint32_t C, uint32_t* counts, uint32_t* nodes, uint32_t* ends, float* pdfs, float* cdfs, int adaptive)
+{
+	const RlState* st = static_cast<const RlState*>(state);
+	for (uint32_t k = 0; k < n_cells; ++k)
+	{
+		RlCell c; c.count = counts[k];
+		c.nodes.assign(nodes + (size_t)k * C, nodes + (size_t)(k + 1) * C); c.ends.assign(ends + (size_t)k * C, ends + (size_t)(k + 1) * C);
+		c.pdfs.assign(pdfs + (size_t)k * C, pdfs + (size_t)(k + 1) * C); c.cdfs.assign(C, 0.0f);
+		if (adaptive) rl_split_and_collapse(*st, c);
+		rl_update_cdf(c);
+		counts[k] = c.count;
+		std::copy(c.nodes.begin(), c.nodes.end(), nodes + (size_t)k * C); std::copy(c.ends.begin(), c.ends.end(), ends + (size_t)k * C);
+		std::copy(c.pdfs.begin(), c.pdfs.end(), pdfs + (size_t)k * C); std::copy(c.cdfs.begin(), c.cdfs.end(), cdfs + (size_t)k * C);
+	}
+}
+// sample / pdf of a caller-provided cell: the arithmetic of AdaptiveClusteredRLView::sample and ::pdf on rows of C entries
+void oracle_rl_sample(uint32_t C, uint32_t count, const uint32_t* ends, const float* cdfs, const float* z, uint32_t n, uint32_t* index, float* pdf, uint32_t* cluster, float* pdf_of_index)
+{
+	RlState st;
+	RlCell c; c.count = count; c.ends.assign(ends, ends + C); c.cdfs.assign(cdfs, cdfs + C); c.nodes.assign(C, 0u); c.pdfs.assign(C, 0.0f);
+	st.cells.push_back(c);
+	for (uint32_t i = 0; i < n; ++i) { index[i] = rl_sample(st, 0, z[i], pdf + i, cluster + i); pdf_of_index[i] = rl_pdf(st, 0, index[i]); }
+}
+// PathTracer::render with the RL sampler (src/renderers/pathtracer_impl.h:239-266): update_vtls_rl, then the pass
+int oracle_render_pass_rl(const fb200_scene_view* s, uint32_t instance, float* fbdata, void* state, int n_threads, oracle_stats* out)
+{
+	RlState* st = static_cast<RlState*>(state);
+	rl_begin_pass(*st, instance);
+	return render_pass_impl(s, instance, fbdata, NULL, 0, n_threads, 0, out, st);
 }
 
 // the restated spatial hash on records {P, N, T, B, bbox_lo, bbox_hi (3 floats each), samples[6], cone_radius, filter_radius} = 26 floats
