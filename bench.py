@@ -266,7 +266,7 @@ def run_ours(args):
     def make_context(res):
         """scene (replicated) + context of this rank's tile shard; for N > 1 the ranks join the product's NCCL communicator"""
         # --psfpt: the path-space filtering renderer on the same workload (not the headline metric: BASELINE.json names -pt)
-        sc = fb.Scene(["-i", scene, "-r", str(res[0]), str(res[1]), "-bounces", str(BOUNCES), "-shard", str(rank), str(world)] + (["-psfpt"] if args.psfpt else []))
+        sc = fb.Scene(["-i", scene, "-r", str(res[0]), str(res[1]), "-bounces", str(BOUNCES), "-shard", str(rank), str(world)] + (["-psfpt"] if args.psfpt else []) + (["-nee-alg", args.nee_alg] if args.nee_alg else []))
         rc = fb.RenderingContext(sc, local)
         if world > 1:
             ids = [fb.comm_unique_id() if rank == 0 else None]
@@ -389,7 +389,7 @@ def run_ours(args):
 
     # ---------------- BASELINE.json configs[4] as named: bathroom2 3840x2160 FIXED, tile-sharded over the N GPUs ----------------
     strong = None
-    if not args.no_strong and not args.psfpt and not args.res and name == "bathroom2":
+    if not args.no_strong and not args.psfpt and not args.nee_alg and not args.res and name == "bathroom2":
         strong = strong_c5(args, make_context, make_step, sync_all, rank, world, local)
 
     if rank != 0:
@@ -400,7 +400,7 @@ def run_ours(args):
     # ---------------- CPU baseline (rank 0, N = 1 only) and roofline ----------------
     base, trav = (None, None)
     trav_file = os.path.join(ROOT, "profiles", "trav_counts_%s.json" % name.split()[0])
-    if world == 1 and not args.no_cpu_baseline and not args.psfpt:
+    if world == 1 and not args.no_cpu_baseline and not args.psfpt and not args.nee_alg:
         base, trav = cpu_baseline(scene, res)
     if trav is None and os.path.exists(trav_file):
         trav = json.load(open(trav_file))
@@ -442,7 +442,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "scene bathroom2 of the reference's models/ (snapshot scenes/_cache/bathroom2.fbs), the reference's default sampler seeds; no synthetic rays",
-        "config": {"workload": "%s %s %dx%d, %d bounces" % (name, "-psfpt" if args.psfpt else "-pt", res[0], res[1], BOUNCES),
+        "config": {"workload": "%s %s%s %dx%d, %d bounces" % (name, "-psfpt" if args.psfpt else "-pt", (" -nee-alg " + args.nee_alg) if args.nee_alg else "", res[0], res[1], BOUNCES),
                    "passes": "default seeds, instances %d..%d" % (args.warmup, args.warmup + args.steps - 1),
                    "parallelism": "tile-sharded x%d, one NCCL collective per pass: gather of every rank's packed COMPOSITED tiles on rank 0 (fb200_context_gather_image)" % world if world > 1 else "single GPU",
                    "l2": "working set per pass (queues + 8-channel frame buffer, > 400 MB) exceeds the 126 MB L2",
@@ -495,6 +495,7 @@ def main():
     ap.add_argument("--res", type=int, nargs=2, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong_c5 block (bathroom2 3840x2160 fixed, tile-sharded over the N GPUs)")
+    ap.add_argument("--nee-alg", dest="nee_alg", default=None, choices=["mesh", "vpl", "rl"], help="next-event sampler other than the default vpl (GPU arm only, N=1; not the headline metric)")
     ap.add_argument("--psfpt", action="store_true", help="measure the -psfpt renderer instead of -pt (GPU arm only; implies --no-cpu-baseline)")
     args = ap.parse_args()
     if args.warmup < 3:
