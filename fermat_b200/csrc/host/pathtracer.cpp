@@ -101,8 +101,9 @@ void PathTracer::init(int argc, char** argv, RenderingContext& renderer)
 	// sub-frames: the owned tiles dealt round-robin (FB200_SUBFRAMES, default 2; at least 64 tiles each)
 	// (`-psfpt`: one sub-frame - the references are splat once every path of the pass has fed its cell)
 	const char* env = getenv("FB200_SUBFRAMES");
-	// (`-nee-alg rl`: one sub-frame too - the sampler's cells are updated between passes, behind every path of the last one)
-	uint32 n_sub = (m_psf || m_rl) ? 1u : (env ? (uint32)atoi(env) : 2u);
+	// (`-nee-alg rl` keeps its sub-frames: they share the sampler's cells, and the update between two passes runs on the context's stream, which
+	// joins every sub-frame of the last pass first and which the next pass is ordered behind)
+	uint32 n_sub = m_psf ? 1u : (env ? (uint32)atoi(env) : 2u);
 	while (n_sub > 1 && tiles.size() / n_sub < 64) n_sub--;
 	if (n_sub < 1) n_sub = 1;
 	env = getenv("FB200_OVERLAP");
