@@ -555,12 +555,20 @@ struct Importer
 			else if (tok == "Rotate")
 			{
 				float v[4]; floats(4, v);
-				const float a = v[0] * 3.14159265358979323846f / 180.0f; const V3 ax = normalize(V3(v[1], v[2], v[3]));
-				const float c = cosf(a), s = sinf(a), t = 1 - c;
-				M4 R = M4::identity();
-				R.m[0] = t * ax.x * ax.x + c; R.m[1] = t * ax.x * ax.y - s * ax.z; R.m[2] = t * ax.x * ax.z + s * ax.y;
-				R.m[4] = t * ax.x * ax.y + s * ax.z; R.m[5] = t * ax.y * ax.y + c; R.m[6] = t * ax.y * ax.z - s * ax.x;
-				R.m[8] = t * ax.x * ax.z - s * ax.y; R.m[9] = t * ax.y * ax.z + s * ax.x; R.m[10] = t * ax.z * ax.z + c;
+				// cugar::rotation_around_axis as Fermat's importer gets it (src/mesh/pbrt_importer.cpp:125-128, contrib/cugar/linalg/matrix_inline.h:683-700):
+				// the axis is taken as given (not normalised) and the rotation about Z is conjugated as B Rz B^T with the basis vectors in the ROWS
+				// of B - not the rotation pbrt means unless the basis happens to be symmetric. Scenes written for Fermat see this matrix, so do we.
+				const float a = v[0] * 3.14159265358979323846f / 180.0f; const V3 ax(v[1], v[2], v[3]);
+				V3 tg;
+				if (ax.x * ax.x < ax.y * ax.y) tg = (ax.x * ax.x < ax.z * ax.z) ? V3(0.0f, -ax.z, ax.y) : V3(-ax.y, ax.x, 0.0f);
+				else tg = (ax.y * ax.y < ax.z * ax.z) ? V3(ax.z, 0.0f, -ax.x) : V3(-ax.y, ax.x, 0.0f);
+				const V3 bn = cross(ax, tg);
+				M4 B = M4::identity(), Bt = M4::identity(), Rz = M4::identity();
+				const float bv[3][3] = { { tg.x, tg.y, tg.z }, { bn.x, bn.y, bn.z }, { ax.x, ax.y, ax.z } };
+				for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { B.m[r * 4 + c] = bv[r][c]; Bt.m[c * 4 + r] = bv[r][c]; }
+				const float sn = sinf(a), cs = cosf(a);
+				Rz.m[0] = cs; Rz.m[5] = cs; Rz.m[4] = sn; Rz.m[1] = -sn;
+				const M4 R = mul(mul(B, Rz), Bt);
 				xf.back() = mul(R, xf.back());
 			}
 			else if (tok == "LookAt")

@@ -51,6 +51,60 @@ def dirlight_fa(tmp_path_factory):
     return str(p)
 
 
+def generated_pbrt(tmp_path_factory):
+    """every directive, shape, light and material parameter the reference's importer reads (src/mesh/pbrt_importer.cpp:117-360, 367-615, 643-862), once"""
+    p = tmp_path_factory.mktemp("pbrt") / "gen.pbrt"
+    ply = os.path.join(REF_MODELS, "material-testball", "models", "Mesh000.ply")
+    p.write_text("""
+LookAt 0.5 1.25 4.0  0.1 0.4 0.0  0 1 0
+Film "image" "integer xresolution" [ 64 ] "integer yresolution" [ 48 ] "float exposure" [ 1.5 ] "float gamma" [ 2.0 ]
+Camera "perspective" "float fov" [ 37.5 ]
+WorldBegin
+  LightSource "distant" "rgb L" [ 1.5 1.25 0.75 ] "point from" [ 1 4 2 ] "point to" [ 0 0 0.5 ]
+  AttributeBegin
+    Material "matte" "rgb Kd" [ 0.6 0.5 0.25 ]
+    Translate 0 -0.5 0
+    Scale 4 1 4
+    Shape "trianglemesh" "integer indices" [ 0 1 2 0 2 3 ] "point P" [ -1 0 -1  -1 0 1  1 0 1  1 0 -1 ]
+  AttributeEnd
+  AttributeBegin
+    AreaLightSource "diffuse" "rgb L" [ 17 12 4 ]
+    Material "matte" "rgb Kd" [ 0.1 0.2 0.3 ]
+    Translate 0 2.5 0
+    Rotate 180 1 0 0
+    Shape "trianglemesh" "integer indices" [ 0 1 2 0 2 3 ] "point P" [ -0.25 0 -0.25  -0.25 0 0.25  0.25 0 0.25  0.25 0 -0.25 ]
+      "normal N" [ 0 1 0  0 1 0  0 1 0  0 1 0 ] "float uv" [ 0 0  0 1  1 1  1 0 ]
+  AttributeEnd
+  AttributeBegin
+    Material "substrate" "rgb Kd" [ 0.25 0.125 0.0625 ] "rgb Ks" [ 0.0625 0.07 0.08 ] "rgb Kr" [ 0.04 0.05 0.06 ] "float uroughness" [ 0.2 ] "float vroughness" [ 0.1 ] "float eta" [ 1.4 ]
+    Translate -1.25 0 0
+    Rotate 35 0 1 0
+    Shape "disk" "float radius" [ 0.5 ]
+  AttributeEnd
+  AttributeBegin
+    Material "glass" "rgb Kt" [ 0.9 0.95 1.0 ] "rgb Kr" [ 0.07 0.06 0.05 ] "float index" [ 1.33 ] "float uroughness" [ 0.02 ] "float vroughness" [ 0.03 ] "rgb coat" [ 0.01 0.02 0.03 ]
+    TransformBegin
+      Translate 1.25 0.25 0.5
+      Scale 0.4 0.4 0.4
+      Shape "plymesh" "string filename" [ "%s" ]
+    TransformEnd
+  AttributeEnd
+  MakeNamedMaterial "M1" "string type" [ "metal" ] "rgb eta" [ 0.2 0.9 1.1 ] "rgb k" [ 3.9 2.4 2.1 ] "float roughness" [ 0.15 ]
+  MakeNamedMaterial "M2" "string type" [ "metal" ] "rgb eta" [ 1.2 0.9 0.6 ] "rgb k" [ 7.0 6.0 5.0 ] "float uroughness" [ 0.05 ] "float vroughness" [ 0.3 ] "rgb Kr" [ 0.5 0.6 0.7 ]
+  NamedMaterial "M1"
+  TransformBegin
+    Transform [ 0.5 0 0 0  0 0.5 0 0  0 0 0.5 0  0.2 0.3 -1.0 1 ]
+    Shape "trianglemesh" "integer indices" [ 0 1 2 ] "point P" [ 0 0 0  1 0 0  0 1 0 ]
+  TransformEnd
+  NamedMaterial "M2"
+  Identity
+  Translate 0 0 -2
+  Shape "trianglemesh" "integer indices" [ 0 2 1 ] "point P" [ 0 0 0  1 0 0  0 1 0 ] "float uv" [ 0 0  1 0  0 1 ]
+WorldEnd
+""" % ply)
+    return str(p)
+
+
 SCENES = {
     "cornellbox_jp": lambda t: os.path.join(REF_MODELS, "CornellBox", "CornellBox-JP.obj"),
     "cornellbox_glossy": lambda t: os.path.join(REF_MODELS, "CornellBox", "CornellBox-Glossy.obj"),
@@ -58,6 +112,7 @@ SCENES = {
     "material_testball_pbrt": lambda t: os.path.join(REF_MODELS, "material-testball", "scene.pbrt"),
     "fa_transforms_and_directional_lights": dirlight_fa,
     "bathroom2_fa": bathroom_fa,
+    "pbrt_every_directive": generated_pbrt,
 }
 
 
