@@ -51,6 +51,93 @@ def dirlight_fa(tmp_path_factory):
     return str(p)
 
 
+def generated_fa_obj_mtl(tmp_path_factory):
+    """every command of the .fa grammar (src/mesh/fermat_loader.cpp:85-330) and every statement of the MTL / OBJ readers
+    (src/mesh/MeshBase.cpp:492-712, 721-1500), once: nested Begin / End, Transform, RotateX / Y / Z, LoadMesh / LoadScene, LoadMaterials +
+    SetMaterial, quads and polygons, negative indices, all four face index forms, groups, several materials"""
+    d = tmp_path_factory.mktemp("gen_fa")
+    (d / "all.mtl").write_text("""# every statement the reader knows
+newmtl first
+Ka 0.01 0.02 0.03
+Kd 0.5 0.25 0.125
+Ks 0.04 0.05 0.06
+Ke 0 0 0
+Kr 0.1 0.2 0.3
+Ns 50
+Ni 1.45
+d 0.75
+illum 2
+newmtl glassy
+Kd 0.0 0.0 0.0
+Ks 0.9 0.9 0.9
+Td 0.7 0.8 0.9
+Tr 0.5
+Ns 400
+Ni 1.33
+reflectivity 0.25 0.25 0.5
+emissive 0 0 0
+flags 3
+newmtl lamp
+Kd 0.2 0.2 0.2
+Ke 10 8 6
+Ns 1
+""")
+    (d / "extra.mtl").write_text("newmtl override\nKd 0.9 0.1 0.1\nKs 0.02 0.02 0.02\nNs 25\n")
+    (d / "a.obj").write_text("""mtllib all.mtl
+v -1 0 -1
+v -1 0 1
+v 1 0 1
+v 1 0 -1
+v 0 1.5 0
+vn 0 1 0
+vn 0.70710678 0.70710678 0
+vn -0.70710678 0.70710678 0
+vt 0 0
+vt 0 1
+vt 1 1
+vt 1 0
+vt 0.5 0.5
+g floor
+usemtl first
+f 1/1/1 2/2/1 3/3/1 4/4/1
+g sides
+usemtl glassy
+f 1//2 2//2 5//2
+f -4/3 -3/4 -1/5
+s 1
+f 3 4 5
+g lamp
+usemtl lamp
+f 4/4/3 1/1/3 5/5/3
+""")
+    (d / "b.obj").write_text("""v 0 0 0
+v 0.5 0 0
+v 0.5 0.5 0
+v 0 0.5 0
+v 0.25 0.75 0
+f 1 2 3 4 5
+""")
+    p = d / "gen.fa"
+    p.write_text("""Camera persp eye 0.5 1.25 4 aim 0.1 0.4 0 up 0 1 0 fov 0.9
+Begin
+ Transform 1 0 0 0.25  0 1 0 0  0 0 1 -0.5  0 0 0 1
+ RotateX 20
+ Begin
+  RotateZ -35
+  Scale 0.5 2 1.25
+  LoadMesh a.obj
+ End
+ RotateY 60
+ LoadMaterials extra.mtl
+ SetMaterial override
+ Translate 0 1 0
+ LoadScene b.obj
+End
+DirectionalLight dir 0.1 -1 0.2 color 1 2 3
+""")
+    return str(p)
+
+
 def generated_pbrt(tmp_path_factory):
     """every directive, shape, light and material parameter the reference's importer reads (src/mesh/pbrt_importer.cpp:117-360, 367-615, 643-862), once"""
     p = tmp_path_factory.mktemp("pbrt") / "gen.pbrt"
@@ -113,6 +200,7 @@ SCENES = {
     "fa_transforms_and_directional_lights": dirlight_fa,
     "bathroom2_fa": bathroom_fa,
     "pbrt_every_directive": generated_pbrt,
+    "fa_obj_mtl_every_statement": generated_fa_obj_mtl,
 }
 
 
