@@ -133,9 +133,11 @@ void load_ply(const std::string& filename, Mesh& mesh)
 						std::vector<int> idx(cnt);
 						for (int k = 0; k < cnt; ++k) idx[k] = (int)read_value(pr.type);
 						if (pr.name != "vertex_indices" && pr.name != "vertex_index") continue;
-						for (int k = 2; k < cnt; ++k)
+						// one triangle per face, made of its first three indices: "num_verts is disregarded; we assume only triangles are given"
+						// (plyFaceLoadDataCB, src/mesh/MeshBase.cpp:307-345) - a quad loses its second half in Fermat, so it does here
+						if (cnt >= 3)
 						{
-							const int4 t = { idx[0], idx[k - 1], idx[k], 0 };
+							const int4 t = { idx[0], idx[1], idx[2], 0 };
 							mesh.vertex_indices.push_back(t);
 							if (has_n) mesh.normal_indices.push_back(t);
 							if (has_t) mesh.texture_indices.push_back(t);

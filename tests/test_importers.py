@@ -138,6 +138,59 @@ DirectionalLight dir 0.1 -1 0.2 color 1 2 3
     return str(p)
 
 
+def generated_ply(tmp_path_factory):
+    """PLY through the pbrt importer's plymesh (src/mesh/MeshBase.cpp:1440-1540 over rply): ascii, binary little- and big-endian; with and without
+    normals; (u, v) and (s, t) texture coordinates; extra properties to skip; triangles and quads; uchar and int list counts"""
+    import struct
+    d = tmp_path_factory.mktemp("gen_ply")
+    P = [(-1, 0, -1), (-1, 0.25, 1), (1, 0, 1), (1, 0.5, -1), (0, 1.5, 0)]
+    N = [(0, 1, 0), (0.6, 0.8, 0), (0, 0.8, 0.6), (-0.6, 0.8, 0), (0, 0, 1)]
+    T = [(0, 0), (0, 1), (1, 1), (1, 0), (0.5, 0.5)]
+    tri = [(0, 1, 2), (0, 2, 3), (3, 4, 0)]
+    (d / "ascii.ply").write_text("ply\nformat ascii 1.0\ncomment made for the test\nelement vertex 5\nproperty float x\nproperty float y\nproperty float z\n"
+                                 "property float nx\nproperty float ny\nproperty float nz\nproperty float u\nproperty float v\nproperty uchar red\n"
+                                 "element face 3\nproperty list uchar int vertex_indices\nend_header\n" +
+                                 "".join("%g %g %g %g %g %g %g %g %d\n" % (P[i] + N[i] + T[i] + (17 * i,)) for i in range(5)) +
+                                 "".join("3 %d %d %d\n" % t for t in tri))
+    with open(d / "le.ply", "wb") as f:
+        f.write(b"ply\nformat binary_little_endian 1.0\nelement vertex 5\nproperty float x\nproperty float y\nproperty float z\nproperty float s\nproperty float t\n"
+                b"element face 2\nproperty list uchar int vertex_indices\nend_header\n")
+        for i in range(5):
+            f.write(struct.pack("<5f", *(P[i] + T[i])))
+        f.write(struct.pack("<B4i", 4, 0, 1, 2, 3))            # a quad
+        f.write(struct.pack("<B3i", 3, 3, 4, 0))
+    with open(d / "be.ply", "wb") as f:
+        f.write(b"ply\nformat binary_big_endian 1.0\nelement vertex 5\nproperty float x\nproperty float y\nproperty float z\nproperty float nx\nproperty float ny\nproperty float nz\n"
+                b"element face 3\nproperty list int uint vertex_indices\nend_header\n")
+        for i in range(5):
+            f.write(struct.pack(">6f", *(P[i] + N[i])))
+        for t in tri:
+            f.write(struct.pack(">i3I", 3, *t))
+    p = d / "ply.pbrt"
+    p.write_text("""
+LookAt 0 2 5  0 0.5 0  0 1 0
+Camera "perspective" "float fov" [ 40 ]
+WorldBegin
+  AttributeBegin
+    AreaLightSource "diffuse" "rgb L" [ 5 5 5 ]
+    Material "matte" "rgb Kd" [ 0.5 0.5 0.5 ]
+    Shape "plymesh" "string filename" [ "ascii.ply" ]
+  AttributeEnd
+  Material "substrate" "rgb Kd" [ 0.3 0.2 0.1 ] "rgb Ks" [ 0.05 0.05 0.05 ] "float uroughness" [ 0.1 ] "float vroughness" [ 0.1 ]
+  TransformBegin
+    Translate 2.5 0 0
+    Shape "plymesh" "string filename" [ "le.ply" ]
+  TransformEnd
+  Material "metal" "rgb eta" [ 0.2 0.9 1.1 ] "rgb k" [ 3.9 2.4 2.1 ] "float roughness" [ 0.2 ]
+  TransformBegin
+    Translate -2.5 0 0
+    Shape "plymesh" "string filename" [ "be.ply" ]
+  TransformEnd
+WorldEnd
+""")
+    return str(p)
+
+
 def generated_pbrt(tmp_path_factory):
     """every directive, shape, light and material parameter the reference's importer reads (src/mesh/pbrt_importer.cpp:117-360, 367-615, 643-862), once"""
     p = tmp_path_factory.mktemp("pbrt") / "gen.pbrt"
@@ -201,6 +254,7 @@ SCENES = {
     "bathroom2_fa": bathroom_fa,
     "pbrt_every_directive": generated_pbrt,
     "fa_obj_mtl_every_statement": generated_fa_obj_mtl,
+    "ply_formats": generated_ply,
 }
 
 
@@ -239,7 +293,7 @@ def test_importer_equals_the_references_own(fb, ref_loader, tmp_path_factory, na
         textured = (mats[:, [28, 32, 36, 40, 44, 48]] != 0xFFFFFFFF).any(axis=1)[mi]
         same = (tic[:, :3] == want["texture_indices_comp"][:, :3]).all(axis=1)
         assert same[textured].all()
-        if name in ("bathroom2_fa", "material_testball_pbrt"):
+        if name in ("bathroom2_fa", "material_testball_pbrt", "ply_formats"):
             assert same.all()
         assert np.array_equal(np.array(v.tex_bias[:], np.float32).view(np.uint32), want["tex_bias"].view(np.uint32))
         assert np.array_equal(np.array(v.tex_scale[:], np.float32).view(np.uint32), want["tex_scale"].view(np.uint32))
