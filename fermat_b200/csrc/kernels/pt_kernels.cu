@@ -152,7 +152,9 @@ __global__ void __launch_bounds__(256) k_generate_primary(DeviceScene sc, PassPa
 #define FB_REFILL_LANES 1          // idle lanes of a warp that trigger a refill from the ray queue
 #endif
 #ifndef FB_STAGE_KB
-#define FB_STAGE_KB 8              // KB of top-of-tree nodes each trace CTA stages in shared memory (sweep: 0 638, 8 630, 16 626, 55 599 Msamples/s)
+#define FB_STAGE_KB 1              // KB of top-of-tree nodes each trace CTA stages in shared memory with one TMA bulk copy: the root and the two levels under it
+                                   // (12 nodes), which every ray reads. More costs L1: r2 sweep on bathroom2, Msamples/s: 0 KB 1611-1618, 1 KB 1607-1614, 2 KB 1581, 4 KB 1585,
+                                   // 8 KB 1569 (profiles/r2s_sweep.txt; r1 sweep: 0 638, 8 630, 16 626, 55 599)
 #endif
 #ifndef FB_TRI_LOOP
 #define FB_TRI_LOOP 1
@@ -1081,6 +1083,20 @@ cudaError_t configure_kernels(LaunchConfig& lc, int device)
 	e = cudaFuncSetAttribute(k_trace<TRACE_RAYS_CLOSEST>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem + stack_smem); if (e) return e;
 	e = cudaFuncSetAttribute(k_trace<TRACE_RAYS_SHADOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem + stack_smem); if (e) return e;
 	lc.staged_bytes = (uint32)max_smem - 16u;
+	// FB200_CARVEOUT_TRACE / FB200_CARVEOUT_SHADE (experiments): preferred shared-memory share of the SM's 228 KB in percent (the rest is L1);
+	// unset = the driver's choice from the launch's shared-memory size
+	if (const char* env = getenv("FB200_CARVEOUT_TRACE"))
+	{
+		const int pct = atoi(env);
+		cudaFuncSetAttribute(k_trace<TRACE_QUEUE_CLOSEST>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+		cudaFuncSetAttribute(k_trace<TRACE_QUEUE_SHADOW>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+	}
+	if (const char* env = getenv("FB200_CARVEOUT_SHADE"))
+	{
+		const int pct = atoi(env);
+		cudaFuncSetAttribute(k_shade<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+		cudaFuncSetAttribute(k_accumulate_unoccluded<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+	}
 	return cudaSuccess;
 }
 

@@ -91,6 +91,33 @@ struct TravRay
 struct TravHit { float t; int tri; float bu, bv; };
 
 // load the 5 x 16 B of node `idx` from the staged shared-memory copy or from global memory
+// Cache hints of the tree loads (experiments, profiles/r2q_sweep.txt): FB_TRI_LOAD_HINT 1 = triangles do not allocate in L1 (a triangle is rarely
+// read twice by one SM, a node is), 2 = L1 evict-first; FB_NODE_LOAD_HINT 1 = nodes are the last to leave L1
+#ifndef FB_TRI_LOAD_HINT
+#define FB_TRI_LOAD_HINT 0
+#endif
+#ifndef FB_NODE_LOAD_HINT
+#define FB_NODE_LOAD_HINT 0
+#endif
+FB_D float4 ld_tri4(const float4* p)
+{
+#if FB_TRI_LOAD_HINT == 1
+	float4 v; asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p)); return v;
+#elif FB_TRI_LOAD_HINT == 2
+	float4 v; asm volatile("ld.global.nc.L1::evict_first.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p)); return v;
+#else
+	return __ldg(p);
+#endif
+}
+FB_D float4 ld_node4(const float4* p)
+{
+#if FB_NODE_LOAD_HINT == 1
+	float4 v; asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p)); return v;
+#else
+	return __ldg(p);
+#endif
+}
+
 FB_D void load_node(const WideNode* __restrict__ nodes, const float4* __restrict__ smem_nodes, uint32 staged, uint32 idx,
 					float4& n0, float4& n1, float4& n2, float4& n3, float4& n4)
 {
@@ -102,7 +129,7 @@ FB_D void load_node(const WideNode* __restrict__ nodes, const float4* __restrict
 	else
 	{
 		const float4* p = reinterpret_cast<const float4*>(nodes) + (size_t)idx * 5u;
-		n0 = __ldg(p); n1 = __ldg(p + 1); n2 = __ldg(p + 2); n3 = __ldg(p + 3); n4 = __ldg(p + 4);
+		n0 = ld_node4(p); n1 = ld_node4(p + 1); n2 = ld_node4(p + 2); n3 = ld_node4(p + 3); n4 = ld_node4(p + 4);
 	}
 }
 
@@ -313,7 +340,7 @@ struct Traversal
 		const uint32 k = bfind(tgroup.y);
 		tgroup.y &= ~(1u << k);
 		const float4* tp = reinterpret_cast<const float4*>(sc.tris) + (size_t)(tgroup.x + k) * 3u;
-		const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+		const float4 a = ld_tri4(tp), b = ld_tri4(tp + 1), c = ld_tri4(tp + 2);
 		if (ANY_HIT && (mask & __float_as_uint(b.w))) return false;
 
 		// Moller-Trumbore, unfused, same operation order as oracle/pt_oracle.cpp intersect_tri()
@@ -426,7 +453,7 @@ struct Traversal
 				}
 				const float4 a = ring[0], b = ring[1], c = ring[2];
 #else
-				const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+				const float4 a = ld_tri4(tp), b = ld_tri4(tp + 1), c = ld_tri4(tp + 2);
 #endif
 				if (st) { uint32 dummy; asm volatile("mov.b32 %0, %1;" : "=r"(dummy) : "f"(a.x + b.x + c.x)); }
 				FB_TRI_MARK(3)
