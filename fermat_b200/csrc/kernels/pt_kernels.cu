@@ -74,6 +74,9 @@ __global__ void __launch_bounds__(256) k_update_variances(FrameBufferView fb, Pi
 // ------------------------------------------------------------------------------------------------
 // primary rays
 // ------------------------------------------------------------------------------------------------
+#ifndef FB_PRIMARY_BLOCK_W
+#define FB_PRIMARY_BLOCK_W 32        // pixels of a tile row one warp of k_generate_primary starts (32 = one row of the tile; 8 = an 8x4 block)
+#endif
 __global__ void __launch_bounds__(256) k_generate_primary(DeviceScene sc, PassParams pp, PathQueue q, PassCounters* ctr, float seq0, float seq1, FrameBufferView fb)
 {
 	const uint32 j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -83,8 +86,17 @@ __global__ void __launch_bounds__(256) k_generate_primary(DeviceScene sc, PassPa
 	if (valid)
 	{
 		const uint32 tile = __ldg(pp.tile_list + tile_slot);
-		px = (tile % pp.tiles_x) * FB_TILE + (j & (FB_TILE - 1));
-		py = (tile / pp.tiles_x) * FB_TILE + ((j / FB_TILE) & (FB_TILE - 1));
+#if FB_PRIMARY_BLOCK_W == 32
+		const uint32 tx = j & (FB_TILE - 1), ty = (j / FB_TILE) & (FB_TILE - 1);
+#else
+		// a warp's 32 pixels are a FB_PRIMARY_BLOCK_W x (32 / W) block of the tile instead of one row of it: a tighter bundle of primary rays
+		// (and of whatever they hit: the queues keep this order through the compactions). Which thread starts which pixel changes nothing per pixel.
+		const uint32 k = j & (FB_TILE * FB_TILE - 1), w = k >> 5, l = k & 31u;
+		const uint32 blocks_x = FB_TILE / FB_PRIMARY_BLOCK_W, bh = 32u / FB_PRIMARY_BLOCK_W;
+		const uint32 tx = (w % blocks_x) * FB_PRIMARY_BLOCK_W + (l % FB_PRIMARY_BLOCK_W), ty = (w / blocks_x) * bh + (l / FB_PRIMARY_BLOCK_W);
+#endif
+		px = (tile % pp.tiles_x) * FB_TILE + tx;
+		py = (tile / pp.tiles_x) * FB_TILE + ty;
 		valid = px < sc.res_x && py < sc.res_y;
 	}
 	const uint32 slot = warp_append_slot(&ctr->in_size[0], valid);
