@@ -96,6 +96,8 @@ def lib():
         "fb200_context_rl_clear": (i32, [vp]),
         "fb200_context_rl_update": (i32, [vp, i32]),
         "fb200_context_rl_locate": (i32, [vp, C.POINTER(u32), pf, u32, C.POINTER(u32)]),
+        "fb200_diag_rl_sample": (i32, [vp, C.POINTER(u32), pf, u32, C.POINTER(u32), pf, C.POINTER(u32), pf]),
+        "fb200_diag_rl_locate": (i32, [vp, C.POINTER(u32), pf, u32, C.POINTER(u32)]),
         "fb200_scene_destroy": (None, [vp]),
         "fb200_scene_get_view": (i32, [vp, C.POINTER(SceneView)]),
         "fb200_scene_save_snapshot": (i32, [vp, C.c_char_p]),
@@ -497,6 +499,21 @@ class RenderingContext(_Handle):
         prims = np.ascontiguousarray(prims, np.uint32); uv = np.ascontiguousarray(uv, np.float32)
         out = np.zeros(len(prims), np.uint32)
         self._chk(lib().fb200_context_rl_locate(self._h, prims.ctypes.data_as(C.POINTER(C.c_uint32)), _fptr(uv), len(prims), out.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return out
+
+    def rl_sample_probe(self, cells, z):
+        """the device's AdaptiveClusteredRLView::sample / ::pdf on (cell, z) pairs: (index, pdf, cluster, pdf(cell, index))"""
+        cells = np.ascontiguousarray(cells, np.uint32); z = np.ascontiguousarray(z, np.float32)
+        n = len(cells)
+        index = np.zeros(n, np.uint32); pdf = np.zeros(n, np.float32); cluster = np.zeros(n, np.uint32); pdf2 = np.zeros(n, np.float32)
+        up = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint32))
+        self._chk(lib().fb200_diag_rl_sample(self._h, up(cells), _fptr(z), n, up(index), _fptr(pdf), up(cluster), _fptr(pdf2)))
+        return index, pdf, cluster, pdf2
+
+    def rl_locate_device(self, prims, uv):
+        prims = np.ascontiguousarray(prims, np.uint32); uv = np.ascontiguousarray(uv, np.float32)
+        out = np.zeros(len(prims), np.uint32)
+        self._chk(lib().fb200_diag_rl_locate(self._h, prims.ctypes.data_as(C.POINTER(C.c_uint32)), _fptr(uv), len(prims), out.ctypes.data_as(C.POINTER(C.c_uint32))))
         return out
 
     def publish(self, tensors):

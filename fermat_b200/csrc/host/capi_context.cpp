@@ -1,5 +1,6 @@
 // capi_context.cpp — device half of the C ABI declared in include/fermat_b200.h
 #include "rendering_context.h"
+#include "../kernels/rl_kernels.h"
 #include <string.h>
 
 namespace fb { void set_last_error(const std::string& e); }
@@ -279,6 +280,35 @@ int fb200_context_rl_locate(fb200_context* c, const uint32_t* prims, const float
 	return guarded([&] {
 		const fb::MeshVTLs& m = rl_renderer(c)->vtls();
 		for (uint32_t i = 0; i < n; ++i) vtl_out[i] = m.locate(prims[i], uv[2 * i], uv[2 * i + 1]);
+	});
+}
+
+int fb200_diag_rl_sample(fb200_context* c, const uint32_t* cells, const float* z, uint32_t n, uint32_t* index, float* pdf, uint32_t* cluster, float* pdf_of_index)
+{
+	return guarded([&] {
+		PathTracer* pt = rl_renderer(c);
+		cudaStream_t st = c->rc.stream();
+		fb::DeviceBuffer d_cells, d_z, d_out;
+		d_cells.upload(cells, (size_t)n * 4, st); d_z.upload(z, (size_t)n * 4, st); d_out.alloc((size_t)n * 16 + 16);
+		uint32_t* o = d_out.as<uint32_t>();
+		fb::cuda_check(fb::launch_rl_probe_sample(pt->rl_view(), d_cells.as<uint32_t>(), d_z.as<float>(), n, o, reinterpret_cast<float*>(o + n), o + 2 * (size_t)n, reinterpret_cast<float*>(o + 3 * (size_t)n), st), "rl probe");
+		fb::cuda_check(cudaMemcpyAsync(index, o, (size_t)n * 4, cudaMemcpyDeviceToHost, st), "D2H");
+		fb::cuda_check(cudaMemcpyAsync(pdf, o + n, (size_t)n * 4, cudaMemcpyDeviceToHost, st), "D2H");
+		fb::cuda_check(cudaMemcpyAsync(cluster, o + 2 * (size_t)n, (size_t)n * 4, cudaMemcpyDeviceToHost, st), "D2H");
+		fb::cuda_check(cudaMemcpyAsync(pdf_of_index, o + 3 * (size_t)n, (size_t)n * 4, cudaMemcpyDeviceToHost, st), "D2H");
+		c->rc.synchronize();
+	});
+}
+int fb200_diag_rl_locate(fb200_context* c, const uint32_t* prims, const float* uv, uint32_t n, uint32_t* vtl_out)
+{
+	return guarded([&] {
+		PathTracer* pt = rl_renderer(c);
+		cudaStream_t st = c->rc.stream();
+		fb::DeviceBuffer d_prims, d_uv, d_out;
+		d_prims.upload(prims, (size_t)n * 4, st); d_uv.upload(uv, (size_t)n * 8, st); d_out.alloc((size_t)n * 4 + 16);
+		fb::cuda_check(fb::launch_rl_probe_locate(pt->rl_view(), d_prims.as<uint32_t>(), d_uv.as<float2>(), n, d_out.as<uint32_t>(), st), "rl probe");
+		fb::cuda_check(cudaMemcpyAsync(vtl_out, d_out.ptr, (size_t)n * 4, cudaMemcpyDeviceToHost, st), "D2H");
+		c->rc.synchronize();
 	});
 }
 

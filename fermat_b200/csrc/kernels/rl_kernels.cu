@@ -171,6 +171,31 @@ __global__ void __launch_bounds__(32 * RL_WARPS_PER_CTA) k_rl_update(RlView v, R
 	}
 }
 
+// parity probes: the device functions of rl_sampler.cuh on caller-chosen inputs (tests/test_rl_nee.py)
+__global__ void k_rl_probe_sample(RlView v, const uint32* __restrict__ slots, const float* __restrict__ z, uint32 n, uint32* index, float* pdf, uint32* cluster, float* pdf_of_index)
+{
+	const uint32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	float p; uint32 c;
+	const uint32 idx = rl_sample(v, slots[i], z[i], &p, &c);
+	index[i] = idx; pdf[i] = p; cluster[i] = c; pdf_of_index[i] = rl_pdf(v, slots[i], idx);
+}
+__global__ void k_rl_probe_locate(RlView v, const uint32* __restrict__ prims, const float2* __restrict__ uv, uint32 n, uint32* out)
+{
+	const uint32 i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) out[i] = vtl_locate(v, prims[i], uv[i].x, uv[i].y);
+}
+cudaError_t launch_rl_probe_sample(const RlView& v, const uint32* slots, const float* z, uint32 n, uint32* index, float* pdf, uint32* cluster, float* pdf_of_index, cudaStream_t s)
+{
+	if (n) k_rl_probe_sample<<<(n + 127) / 128, 128, 0, s>>>(v, slots, z, n, index, pdf, cluster, pdf_of_index);
+	return cudaGetLastError();
+}
+cudaError_t launch_rl_probe_locate(const RlView& v, const uint32* prims, const float2* uv, uint32 n, uint32* out, cudaStream_t s)
+{
+	if (n) k_rl_probe_locate<<<(n + 127) / 128, 128, 0, s>>>(v, prims, uv, n, out);
+	return cudaGetLastError();
+}
+
 cudaError_t launch_rl_clear(const RlView& v, const uint32* init_nodes, const uint32* init_offsets, const float* init_cdf, int sm_count, cudaStream_t s)
 {
 	if (v.init_cluster_count == 0 || v.init_cluster_count > FB_RL_MAX_CLUSTERS) return cudaErrorInvalidValue;

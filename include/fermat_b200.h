@@ -276,6 +276,10 @@ int fb200_context_rl_state(fb200_context*, uint64_t out[20]);
 int fb200_context_rl_clear(fb200_context*);
 int fb200_context_rl_update(fb200_context*, int adaptive);
 int fb200_context_rl_locate(fb200_context*, const uint32_t* prims, const float* uv, uint32_t n, uint32_t* vtl_out);
+/* parity probes of the DEVICE functions (kernels/rl_sampler.cuh) on host arrays: AdaptiveClusteredRLView::sample and ::pdf (src/clustered_rl_inline.h:123-177)
+ * for n (cell, z) pairs -> VTL index, its pdf, the cluster, and pdf(cell, index); VTLMeshView::map's lookup for n (triangle, u, v) -> VTL index */
+int fb200_diag_rl_sample(fb200_context*, const uint32_t* cells, const float* z, uint32_t n, uint32_t* index, float* pdf, uint32_t* cluster, float* pdf_of_index);
+int fb200_diag_rl_locate(fb200_context*, const uint32_t* prims, const float* uv, uint32_t n, uint32_t* vtl_out);
 /* copy the frame-buffer channels (float4 per pixel, res_x * res_y) into caller-owned DEVICE buffers on the context's stream, behind the
  * passes rendered so far: channels[i] = destination of channel i (fb200 channel numbering = FBufferDesc, src/renderer_view.h:133-145)
  * or NULL to skip it. This is how a host that owns its frame buffer (Fermat's RenderingContext: adapter/fermat_adapter.cpp) receives

@@ -357,3 +357,46 @@ def test_rl_on_bathroom2(fb, oracle):
     assert np.isfinite(g).all()
     assert abs(g[..., :3].mean() - o[..., :3].mean()) < 0.05 * o[..., :3].mean()
     rc.close(); sc.close()
+
+
+@pytest.mark.gpu
+def test_device_sampler_arithmetic_matches_the_oracle(fb, oracle, monkeypatch):
+    """rl_sample / rl_pdf / vtl_locate as the kernels run them (kernels/rl_sampler.cuh, through fb200_diag_rl_*) on cells whose cuts and values a few
+    rendered passes shaped: index, pdf, cluster and pdf(cell, index) bit for bit against AdaptiveClusteredRLView::sample / ::pdf restated on the
+    CPU over the same arrays; point location identical to the host's and equal to the restatement's except on shared edges."""
+    monkeypatch.setenv("FB200_RL_HASH_BITS", "14")
+    sc, rc = _context(fb, cornell_args(64, 4, ["-nee-alg", "rl"]))
+    rc.clear()
+    for i in range(6):
+        rc.render(i)
+    rc.rl_update(True)                                         # CDFs from what pass 5 learned
+    rc.synchronize()
+    s = rc.rl_state()
+    n_occ = int(s["n_occupied"].cpu()[0])
+    assert n_occ > 200
+    rng = np.random.default_rng(13)
+    cells = s["occupied"][:n_occ].cpu().numpy().view(np.uint32)[rng.choice(n_occ, 64, replace=False)]
+    counts = s["cluster_counts"].cpu().numpy().view(np.uint32)
+    idx = cells.astype(np.int64)
+    ends = s["cluster_ends"][idx].cpu().numpy().view(np.uint32); cdfs = s["cdfs"][idx].cpu().numpy()
+    z = np.concatenate([rng.random(500).astype(np.float32), np.array([0.0, 1.0, np.float32(1.0) - np.float32(2 ** -24)], np.float32)])
+    learned = 0
+    for k, cell in enumerate(cells):
+        got = rc.rl_sample_probe(np.full(len(z), cell, np.uint32), z)
+        want = oracle.RlState.sample(int(counts[cell]), ends[k], cdfs[k], z)
+        for g, w in zip(got, want):
+            assert np.array_equal(g.view(np.uint32), w.view(np.uint32)), (k, cell)
+        learned += int(np.unique(got[1]).size > 1)
+    assert learned > 32                                        # most cells no longer sample uniformly
+    # point location on the device = on the host, bit for bit (same descent), ~ the restatement's grid + inside test
+    st = oracle.RlState(sc.view, 64 * 64)
+    em = np.unique(st.arrays()["vtls"]["prim_id"])
+    n = 20000
+    prim = rng.choice(em, n).astype(np.uint32)
+    uv = rng.random((n, 2)).astype(np.float32)
+    flip = uv.sum(axis=1) > 1
+    uv[flip] = 1 - uv[flip]
+    dev, host, ref = rc.rl_locate_device(prim, uv), rc.rl_locate(prim, uv), st.locate(prim, uv)
+    assert np.array_equal(dev, host)
+    assert (dev != ref).mean() < 2e-3
+    rc.close(); sc.close()
