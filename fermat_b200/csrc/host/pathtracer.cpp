@@ -59,15 +59,18 @@ struct Arena
 		return p;
 	}
 };
-void carve(Arena& a, size_t cap, size_t shadow_cap, PathQueue q[2], ShadowQueue& sq, bool psf)
+void carve(Arena& a, size_t cap, size_t shadow_cap, PathQueue q[2], ShadowQueue& sq, bool psf, bool rl)
 {
 	for (int i = 0; i < 2; ++i)
 	{
 		q[i].ray_o = a.alloc<float4>(cap); q[i].ray_d = a.alloc<float4>(cap); q[i].hit = a.alloc<float4>(cap);
 		q[i].weight = a.alloc<float4>(cap); q[i].pixel = a.alloc<uint32>(cap);
-		if (psf) { q[i].cone = a.alloc<float2>(cap); q[i].vinfo = a.alloc<uint32>(cap); }
+		if (psf || rl) q[i].cone = a.alloc<float2>(cap);
+		if (psf) q[i].vinfo = a.alloc<uint32>(cap);
+		if (rl) q[i].nee = a.alloc<uint32>(cap);
 	}
 	if (psf) sq.vinfo = a.alloc<uint32>(shadow_cap);
+	if (rl) sq.nee = a.alloc<uint32>(shadow_cap);
 	sq.ray_o = a.alloc<float4>(shadow_cap); sq.ray_d = a.alloc<float4>(shadow_cap);
 	sq.w_d = a.alloc<float4>(shadow_cap); sq.w_g = a.alloc<float4>(shadow_cap);
 	sq.occluded = a.alloc<unsigned char>(shadow_cap);
@@ -89,7 +92,6 @@ void PathTracer::init(int argc, char** argv, RenderingContext& renderer)
 		fprintf(stderr, "    filter width    : %f\n    filter depth    : %u\n    filter min-dist : %f\n    firefly filter  : %f\n", po.psf_width, po.psf_depth, po.psf_min_dist, po.firefly_filter);
 		if (!kernels_split_accumulate()) throw std::runtime_error("-psfpt needs kernels built with FB_SPLIT_ACCUMULATE");
 		if (!s.scene.dir_lights.empty()) throw std::runtime_error("-psfpt: directional lights are not supported");
-		if (m_options.nee_type == 2) throw std::runtime_error("-psfpt -nee-alg rl: not supported");
 	}
 	m_rl = m_options.nee_type == 2;
 	if (m_rl && !kernels_split_accumulate()) throw std::runtime_error("-nee-alg rl needs kernels built with FB_SPLIT_ACCUMULATE");
@@ -131,7 +133,7 @@ void PathTracer::init(int argc, char** argv, RenderingContext& renderer)
 			SubFrame& f = *m_sub[k];
 			f.n_tiles = (uint32)sub_tiles[k].size();
 			f.capacity = (uint64_t)f.n_tiles * 32u * 32u;
-			carve(arena, f.capacity, f.capacity, f.queue, f.shadow, m_psf || m_rl);
+			carve(arena, f.capacity, f.capacity, f.queue, f.shadow, m_psf, m_rl);
 			if (dirlights)
 			{
 				ShadowQueue& d = f.shadow_dl;

@@ -219,7 +219,6 @@ void scene_init(fb200_scene& s, int argc, const char* const* argv, const fb200_m
 	if (s.psf.psf_temporal_reuse == 0) s.psf.psf_temporal_reuse = 1;
 	if (s.psf.log_hash_size < 10 || s.psf.log_hash_size > 28) throw std::runtime_error("-psf-hash-bits out of range (10..28)");
 	if (s.options.max_path_length == 0 || s.options.max_path_length > 62) throw std::runtime_error("unsupported path length");
-	if (s.options.nee_type == 2 && s.shard_count > 1) throw std::runtime_error("-nee-alg rl with -shard: every shard would learn its own sampler; not supported");
 
 	if (mesh) scene_from_mesh_desc(*mesh, s.scene, overwrite_camera);
 	else load_scene(filename, s.scene, overwrite_camera);

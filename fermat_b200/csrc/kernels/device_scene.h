@@ -62,6 +62,7 @@ struct PathQueue
 	// processor's per-path word (PTRayQueue::cones, pixels.y: src/pathtracer_queues.h:44-53) / the RL cell of the previous vertex (pixels.z)
 	float2* cone;
 	uint32* vinfo;
+	uint32* nee;        // `-nee-alg rl` only: the light sampler's cell of the previous vertex (PTRayQueue::pixels.z)
 };
 
 struct ShadowQueue
@@ -71,7 +72,8 @@ struct ShadowQueue
 	float4* w_d;        // diffuse NEE weight rgb, .w = as_float(PixelInfo bits)
 	float4* w_g;        // glossy NEE weight rgb
 	unsigned char* occluded;   // outcome of the shadow trace, read by the accumulation kernel (FB_SPLIT_ACCUMULATE)
-	uint32* vinfo;             // `-psfpt`: the vertex_info of the vertex the shadow ray leaves (src/pathtracer_core.h:1098); `-nee-alg rl`: its cell and cluster (rl_pack)
+	uint32* vinfo;             // `-psfpt`: the vertex_info of the vertex the shadow ray leaves (src/pathtracer_core.h:1098)
+	uint32* nee;               // `-nee-alg rl`: the cell and the cluster the light sample was drawn from (rl_pack; PTRayQueue::pixels.z / .w)
 };
 
 // State of the path-space filter (`-psfpt`, src/renderers/psfpt_impl.h:101-113): the hash of cache cells, their values, and the queue

@@ -144,7 +144,8 @@ __global__ void __launch_bounds__(256) k_generate_primary(DeviceScene sc, PassPa
 			}
 		}
 		q.cone[slot] = make_float2(0.0f, out_p);
-		q.vinfo[slot] = FB_PSF_INVALID;
+		if (q.vinfo) q.vinfo[slot] = FB_PSF_INVALID;
+		if (q.nee) q.nee[slot] = FB_RL_NO_SLOT;
 	}
 }
 
@@ -544,7 +545,7 @@ __global__ void __launch_bounds__(FB_TRACE_THREADS, FB_TRACE_MIN_BLOCKS) k_trace
 struct AccumArgs
 {
 	const uint32* n_ptr; const unsigned char* occluded;
-	const float4* w_d; const float4* w_g; const uint32* vinfo;
+	const float4* w_d; const float4* w_g; const uint32* vinfo; const uint32* nee;
 	FrameBufferView fb; float frame_weight; uint32 bounce;
 	PsfView psf;
 	RlView rl;                       // RL instantiation only
@@ -597,7 +598,7 @@ __global__ void __launch_bounds__(256) k_accumulate_unoccluded(AccumArgs a)
 		const bool occluded = a.occluded[i] != 0;
 		if (RL)
 		{
-			const uint32 word = a.vinfo[i];
+			const uint32 word = a.nee[i];
 			if (word != FB_RL_NO_SAMPLE)
 			{
 				const V3 w = V3(ld_stream(a.w_d + i)) + V3(ld_stream(a.w_g + i));
@@ -783,11 +784,14 @@ __global__ void __launch_bounds__(128, PARTS == SHADE_ALL ? FB_SHADE_MIN_BLOCKS 
 			// ---- DirectLightingRL::preprocess_vertex (src/direct_lighting_rl.h:69-113, called at src/pathtracer_core.h:816-834) ----
 			if (RL)
 			{
-				const float2 cone = a.in.cone[idx];
-				prev_nee_slot = a.in.vinfo[idx];
-				const float prev_G_prime = fabsf(dot(in, g.normal_s)) / (hit.x * hit.x);
-				const float area_prob = 1.0f / sqrtf(cone.y * prev_G_prime);
-				cone_radius = cone.x + area_prob;
+				prev_nee_slot = a.in.nee[idx];
+				if (!PSF)          // (the filtered renderer has just computed the same radius)
+				{
+					const float2 cone = a.in.cone[idx];
+					const float prev_G_prime = fabsf(dot(in, g.normal_s)) / (hit.x * hit.x);
+					const float area_prob = 1.0f / sqrtf(cone.y * prev_G_prime);
+					cone_radius = cone.x + area_prob;
+				}
 				if (a.do_nee) nee_slot = rl_preprocess_vertex(a.rl, sc.res_x, sc.res_y, position, in, g, pixel, bounce, (info >> 31) != 0u, cone_radius);
 			}
 
@@ -954,7 +958,7 @@ __global__ void __launch_bounds__(128, PARTS == SHADE_ALL ? FB_SHADE_MIN_BLOCKS 
 			const uint32 slot = warp_append_slot(shadow_counter, nee_on);
 			if (nee_on) { st_stream(a.sq.ray_o + slot, nee_o); st_stream(a.sq.ray_d + slot, nee_d); st_stream(a.sq.w_d + slot, nee_wd); st_stream(a.sq.w_g + slot, nee_wg); }
 			if (PSF && nee_on) a.sq.vinfo[slot] = vinfo;
-			if (RL && nee_on) a.sq.vinfo[slot] = nee_word;
+			if (RL && nee_on) a.sq.nee[slot] = nee_word;
 		}
 
 		// ---- emissive hit with MIS against NEE at the previous vertex (pathtracer_core.h:1109-1154) ----
@@ -1029,7 +1033,7 @@ __global__ void __launch_bounds__(128, PARTS == SHADE_ALL ? FB_SHADE_MIN_BLOCKS 
 			const uint32 slot = warp_append_slot(scatter_counter, scat_on);
 			if (scat_on) { st_stream(a.out.ray_o + slot, sc_o); st_stream(a.out.ray_d + slot, sc_d); st_stream(a.out.weight + slot, sc_w); st_stream(a.out.pixel + slot, sc_info); }
 			if (PSF && scat_on) { a.out.cone[slot] = sc_cone; a.out.vinfo[slot] = sc_vinfo; }
-			if (RL && scat_on) { a.out.cone[slot] = sc_cone; a.out.vinfo[slot] = nee_slot; }      // src/pathtracer_core.h:1222-1240
+			if (RL && scat_on) { a.out.cone[slot] = sc_cone; a.out.nee[slot] = nee_slot; }      // src/pathtracer_core.h:1222-1240
 		}
 		if (PSF)
 		{
@@ -1215,8 +1219,9 @@ cudaError_t launch_trace_shadow(const DeviceScene& sc, const LaunchConfig& lc, c
 	if (stages & 2)
 	{
 		AccumArgs ac; memset(&ac, 0, sizeof(ac));
-		ac.n_ptr = a.n_ptr; ac.occluded = sq.occluded; ac.w_d = sq.w_d; ac.w_g = sq.w_g; ac.vinfo = sq.vinfo; ac.fb = fb; ac.frame_weight = frame_weight; ac.bounce = bounce;
-		if (psf) { ac.psf = *psf; k_accumulate_unoccluded<true><<<lc.sm_count * 4, 256, 0, s>>>(ac); }
+		ac.n_ptr = a.n_ptr; ac.occluded = sq.occluded; ac.w_d = sq.w_d; ac.w_g = sq.w_g; ac.vinfo = sq.vinfo; ac.nee = sq.nee; ac.fb = fb; ac.frame_weight = frame_weight; ac.bounce = bounce;
+		if (psf && rl && which == 0) { ac.psf = *psf; ac.rl = *rl; k_accumulate_unoccluded<true, true><<<lc.sm_count * 4, 256, 0, s>>>(ac); }
+		else if (psf) { ac.psf = *psf; k_accumulate_unoccluded<true><<<lc.sm_count * 4, 256, 0, s>>>(ac); }
 		else if (rl && which == 0) { ac.rl = *rl; k_accumulate_unoccluded<false, true><<<lc.sm_count * 4, 256, 0, s>>>(ac); }
 		else k_accumulate_unoccluded<false><<<lc.sm_count * 4, 256, 0, s>>>(ac);
 		if (launches) *launches += 1;
@@ -1279,7 +1284,8 @@ cudaError_t launch_shade(const DeviceScene& sc, const LaunchConfig& lc, const Pa
 	{
 		if (sc.n_dir_lights || parts != SHADE_ALL) return cudaErrorNotSupported;
 		a.psf = *psf;
-		k_shade<false, true><<<blocks, threads, 0, s>>>(sc, a);
+		if (rl) { a.rl = *rl; k_shade<false, true, SHADE_ALL, true><<<blocks, threads, 0, s>>>(sc, a); }
+		else k_shade<false, true><<<blocks, threads, 0, s>>>(sc, a);
 	}
 	else if (rl)
 	{

@@ -559,6 +559,16 @@ class RlState:
         lib().oracle_rl_sample(len(ends), int(count), ends.ctypes.data, cdfs.ctypes.data, z.ctypes.data, n, index.ctypes.data, pdf.ctypes.data, cluster.ctypes.data, pdf2.ctypes.data)
         return index, pdf, cluster, pdf2
 
+    def render_pass_psf(self, instance, fb, psf_state, threads=0):
+        """PSFPT::render with the RL sampler (`-psfpt -nee-alg rl`): one filtered pass into `fb` (in place), whole frame"""
+        L = lib()
+        L.oracle_render_pass_psf_rl.restype = C.c_int
+        L.oracle_render_pass_psf_rl.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_float), C.c_void_p, C.c_void_p, C.c_int, C.POINTER(OracleStats)]
+        st = OracleStats()
+        rc = L.oracle_render_pass_psf_rl(C.addressof(self.view), int(instance), _fptr(fb), psf_state._h, self._h, int(threads), C.byref(st))
+        assert rc == 0
+        return st
+
     def render_pass(self, instance, fb, threads=0):
         """PathTracer::render with the RL sampler: update_vtls_rl, then one progressive pass into `fb` (in place), whole frame"""
         st = OracleStats()

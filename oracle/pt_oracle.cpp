@@ -1028,7 +1028,7 @@ uint64_t oracle_psf_cells(const void* st) { return static_cast<const PsfState*>(
 
 // PSFPT::render (src/renderers/psfpt_impl.h:256-265): rescale_frame, the path tracing loop with PSFPTVertexProcessor, psf_blending of
 // the references (:101-143), update_variances, clamp_frame(100). Whole frame only.
-int oracle_render_pass_psf(const fb200_scene_view* s, uint32_t instance, float* fbdata, void* state, int n_threads, oracle_stats* out)
+static int render_pass_psf_impl(const fb200_scene_view* s, uint32_t instance, float* fbdata, void* state, int n_threads, oracle_stats* out, RlState* rl)
 {
 	if (s->n_dir_lights) return -1;              // (directional lights are not carried into the filtered renderer)
 	PsfState* psf = static_cast<PsfState*>(state);
@@ -1060,7 +1060,7 @@ int oracle_render_pass_psf(const fb200_scene_view* s, uint32_t instance, float* 
 			lum[3] = max_comp(vec3(fb.px(COMPOSITED_C, p)[0], fb.px(COMPOSITED_C, p)[1], fb.px(COMPOSITED_C, p)[2]));
 			const int scaled[6] = { DIFFUSE_C, DIFFUSE_A, SPECULAR_C, SPECULAR_A, DIRECT_C, COMPOSITED_C };
 			for (int c = 0; c < 6; ++c) for (int i = 0; i < 4; ++i) fb.px(scaled[c], p)[i] *= scale;
-			trace_path(sc, smp, fb, p % s->res_x, p / s->res_x, frame_weight, U, V, W, st, false, psf, instance);
+			trace_path(sc, smp, fb, p % s->res_x, p / s->res_x, frame_weight, U, V, W, st, false, psf, instance, rl);
 		}
 		#pragma omp critical
 		{
@@ -1105,6 +1105,18 @@ int oracle_render_pass_psf(const fb200_scene_view* s, uint32_t instance, float* 
 	}
 	if (out) *out = total;
 	return 0;
+}
+
+int oracle_render_pass_psf(const fb200_scene_view* s, uint32_t instance, float* fbdata, void* state, int n_threads, oracle_stats* out)
+{
+	return render_pass_psf_impl(s, instance, fbdata, state, n_threads, out, NULL);
+}
+// PSFPT::render with the RL light sampler (src/renderers/psfpt_impl.h:343-383): update_vtls_rl, then the filtered pass
+int oracle_render_pass_psf_rl(const fb200_scene_view* s, uint32_t instance, float* fbdata, void* psf_state, void* rl_state, int n_threads, oracle_stats* out)
+{
+	RlState* rl = static_cast<RlState*>(rl_state);
+	rl_begin_pass(*rl, instance);
+	return render_pass_psf_impl(s, instance, fbdata, psf_state, n_threads, out, rl);
 }
 
 // closest hit for n rays {o.xyz, tmin, d.xyz, tmax} -> hits {t, as_float(tri), u, v}

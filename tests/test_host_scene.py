@@ -158,7 +158,7 @@ def test_bad_arguments_fail_loudly(fb):
     with pytest.raises(RuntimeError):
         fb.Scene(cornell_args(8, 1, ["-shard", "2", "2"]))
     with pytest.raises(RuntimeError):
-        fb.Scene(cornell_args(64, 1, ["-nee-alg", "rl", "-shard", "0", "2"]))      # every shard would learn a sampler of its own
+        fb.Scene(cornell_args(8, 1, ["-bounces", "200"]))                          # PassCounters holds 64 bounces
 
 
 def test_no_cpu_fallback_without_gpu(fb, cornell_scene):

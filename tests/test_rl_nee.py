@@ -29,8 +29,11 @@ def test_option_is_parsed_and_guarded(fb):
     sc = fb.Scene(cornell_args(32, 2, ["-nee-alg", "rl"]))
     assert sc.view.options.nee_type == 2                       # NEE_ALGORITHM_RL, src/renderers/pathtracer.h:162-164
     sc.close()
-    with pytest.raises(RuntimeError):
-        fb.Scene(cornell_args(64, 2, ["-nee-alg", "rl", "-shard", "0", "2"]))
+    # with -psfpt (src/renderers/psfpt_impl.h:343-383) and with tile shards (every shard learns the sampler of its own pixels)
+    for extra in (["-psfpt"], ["-shard", "0", "2"]):
+        sc = fb.Scene(cornell_args(64, 2, ["-nee-alg", "rl"] + extra))
+        assert sc.view.options.nee_type == 2
+        sc.close()
 
 
 def test_vtls_tile_the_emitters_and_the_cut_partitions_them(fb, oracle):
@@ -400,3 +403,53 @@ def test_device_sampler_arithmetic_matches_the_oracle(fb, oracle, monkeypatch):
     assert np.array_equal(dev, host)
     assert (dev != ref).mean() < 2e-3
     rc.close(); sc.close()
+
+
+@pytest.mark.gpu
+def test_psfpt_with_the_rl_sampler_matches_the_oracle(fb, oracle):
+    """`-psfpt -nee-alg rl` (PSFPT::render's RL branch, src/renderers/psfpt_impl.h:343-383): the filtered renderer's vertex processor and the
+    learning light sampler on the same kernels. Pass 0 per pixel (nothing learned, same cells on both sides), a few passes statistically."""
+    args = cornell_args(64, 4, ["-psfpt", "-nee-alg", "rl", "-psf-hash-bits", "18"])
+    sc, rc = _context(fb, args)
+    rc.clear(); rc.render(0)
+    g0 = rc.download("COMPOSITED_C")
+    ost = oracle.RlState(sc.view, 64 * 64); ps = oracle.PsfState()
+    w0 = oracle.new_framebuffer(sc.view)
+    ev0 = ost.render_pass_psf(0, w0, ps).shade_events
+    bad = np.abs(g0[..., :3] - w0[5][..., :3]).max(axis=2) > 1e-3 * (1 + w0[5][..., :3].max(axis=2))
+    assert bad.mean() < 1e-2, "pixels that differ at pass 0: %d" % bad.sum()
+    assert rel_l2(g0, w0[5]) < 5e-3
+    N = 24
+    rc.clear()
+    for i in range(N):
+        rc.render(i)
+    g = rc.download("COMPOSITED_C")
+    st = rc.stats()
+    ost = oracle.RlState(sc.view, 64 * 64); ps = oracle.PsfState()
+    want = oracle.new_framebuffer(sc.view)
+    events = 0
+    for i in range(N):
+        events += ost.render_pass_psf(i, want, ps).shade_events
+    assert np.isfinite(g).all()
+    assert abs(g[..., :3].mean() - want[5][..., :3].mean()) < 0.015 * want[5][..., :3].mean()
+    assert rel_l2(g, want[5]) < 0.08
+    rc.close(); sc.close()
+
+
+@pytest.mark.gpu
+def test_rl_with_tile_shards(fb):
+    """Every shard learns the sampler of its own pixels: the shard renders its tiles only, and what it renders is the estimate the unsharded
+    context makes of those pixels, to the noise of two runs."""
+    N = 24
+    sc, rc, full, _ = _gpu_passes(fb, cornell_args(96, 4, ["-nee-alg", "rl"]), N)
+    sc2, rc2, part, _ = _gpu_passes(fb, cornell_args(96, 4, ["-nee-alg", "rl", "-shard", "1", "2"]), N)
+    owned = np.zeros(96 * 96, bool)
+    owned[sc2.owned_pixels()] = True
+    owned = owned.reshape(96, 96)
+    a, b = full["COMPOSITED_C"][..., :3], part["COMPOSITED_C"][..., :3]
+    assert (b[~owned] == 0).all() and owned.sum() > 0 and (~owned).sum() > 0
+    assert abs(b[owned].mean() - a[owned].mean()) < 0.03 * a[owned].mean()
+    for x in (rc, rc2):
+        x.close()
+    for x in (sc, sc2):
+        x.close()
