@@ -33,8 +33,14 @@ FB_D uint32 rl_find_slot(const RlView& v, unsigned long long key)
 	uint32 h = (uint32)h64 & v.mask;
 	for (uint32 probe = 0; probe < 4096u; ++probe)
 	{
-		const unsigned long long old = atomicCAS(v.keys + h, ~0ull, key);
-		if (old == ~0ull) { v.occupied[atomicAdd(v.n_occupied, 1u)] = h; return h; }
+		// cells live for 32 passes and a warp's vertices mostly share one: look before the compare-and-swap, which is needed only to claim an
+		// empty position (a key, once written, never changes until the table is cleared between passes)
+		unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(v.keys + h);
+		if (old == ~0ull)
+		{
+			old = atomicCAS(v.keys + h, ~0ull, key);
+			if (old == ~0ull) { v.occupied[atomicAdd(v.n_occupied, 1u)] = h; return h; }
+		}
 		if (old == key) return h;
 		h = (h + 1u) & v.mask;
 	}
