@@ -1277,7 +1277,10 @@ cudaError_t launch_shade(const DeviceScene& sc, const LaunchConfig& lc, const Pa
 	a.do_dirlight = (bounce + 2 <= o.max_path_length) && (bounce > 0 || o.direct_lighting) && sc.n_dir_lights;
 	const uint32 threads = 128;
 	uint32 blocks = (capacity + threads - 1) / threads;
-	const uint32 max_blocks = (uint32)lc.sm_count * 16u;
+	// grid of the grid-stride shade kernels in CTAs per SM (6 are resident; FB200_SHADE_BLOCKS_PER_SM overrides). r2 sweep, shade us per launch /
+	// Msamples/s of the pass: 6 84.2 / 1581, 12 83.3 / 1589, 16 80.1 / 1605, 24 77.2 / 1621, 48 77.1 / 1610 (profiles/r2y_sweep.txt)
+	static const uint32 blocks_per_sm = [] { const char* e = getenv("FB200_SHADE_BLOCKS_PER_SM"); const int v = e ? atoi(e) : 24; return (uint32)(v > 0 ? v : 24); }();
+	const uint32 max_blocks = (uint32)lc.sm_count * blocks_per_sm;
 	if (blocks > max_blocks) blocks = max_blocks;
 	if (blocks == 0) blocks = 1;
 	if (psf)
