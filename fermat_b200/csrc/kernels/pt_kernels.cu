@@ -1219,11 +1219,13 @@ cudaError_t launch_trace_shadow(const DeviceScene& sc, const LaunchConfig& lc, c
 	if (stages & 2)
 	{
 		AccumArgs ac; memset(&ac, 0, sizeof(ac));
+		// grid of the grid-stride accumulation pass in CTAs of 256 threads per SM (FB200_ACC_BLOCKS_PER_SM overrides)
+		static const int acc_blocks = [] { const char* e = getenv("FB200_ACC_BLOCKS_PER_SM"); const int v = e ? atoi(e) : 8; return v > 0 ? v : 8; }();   // r2z sweep: 2 1598, 4 1619, 8 1623, 16 1621 Msamples/s
 		ac.n_ptr = a.n_ptr; ac.occluded = sq.occluded; ac.w_d = sq.w_d; ac.w_g = sq.w_g; ac.vinfo = sq.vinfo; ac.nee = sq.nee; ac.fb = fb; ac.frame_weight = frame_weight; ac.bounce = bounce;
-		if (psf && rl && which == 0) { ac.psf = *psf; ac.rl = *rl; k_accumulate_unoccluded<true, true><<<lc.sm_count * 4, 256, 0, s>>>(ac); }
-		else if (psf) { ac.psf = *psf; k_accumulate_unoccluded<true><<<lc.sm_count * 4, 256, 0, s>>>(ac); }
-		else if (rl && which == 0) { ac.rl = *rl; k_accumulate_unoccluded<false, true><<<lc.sm_count * 4, 256, 0, s>>>(ac); }
-		else k_accumulate_unoccluded<false><<<lc.sm_count * 4, 256, 0, s>>>(ac);
+		if (psf && rl && which == 0) { ac.psf = *psf; ac.rl = *rl; k_accumulate_unoccluded<true, true><<<lc.sm_count * acc_blocks, 256, 0, s>>>(ac); }
+		else if (psf) { ac.psf = *psf; k_accumulate_unoccluded<true><<<lc.sm_count * acc_blocks, 256, 0, s>>>(ac); }
+		else if (rl && which == 0) { ac.rl = *rl; k_accumulate_unoccluded<false, true><<<lc.sm_count * acc_blocks, 256, 0, s>>>(ac); }
+		else k_accumulate_unoccluded<false><<<lc.sm_count * acc_blocks, 256, 0, s>>>(ac);
 		if (launches) *launches += 1;
 	}
 #else
