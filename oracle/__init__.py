@@ -433,6 +433,14 @@ class RefLoader:
         L.ref_scene_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float)]
         L.ref_free_scene.argtypes = [C.c_void_p]
 
+    def camera(self, cam, aspect, res, dirs):
+        """src/camera.h compiled on the host: (U, V, W as 9 floats, camera_direction_pdf of each direction) for cam = eye, aim, up, fov"""
+        cam = np.ascontiguousarray(cam, np.float32); dirs = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+        self.L.ref_camera.argtypes = [C.c_void_p, C.c_float, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+        frame = np.zeros(9, np.float32); pdf = np.zeros(len(dirs), np.float32)
+        self.L.ref_camera(cam.ctypes.data, C.c_float(float(aspect)), int(res[0]), int(res[1]), frame.ctypes.data, dirs.ctypes.data, len(dirs), pdf.ctypes.data)
+        return frame, pdf
+
     def scene(self, path):
         """dict of the pre-processed arrays the reference's RenderingContext would hold after loading `path`"""
         h = self.L.ref_load_scene(str(path).encode())
@@ -575,3 +583,13 @@ class RlState:
         rc = lib().oracle_render_pass_rl(C.addressof(self.view), int(instance), _fptr(fb), self._h, int(threads), C.byref(st))
         assert rc == 0
         return st
+
+
+def probe_camera(view, dirs):
+    """the oracle's camera_frame of `view` (U, V, W as 9 floats) and its primary cone pdf of each direction"""
+    L = lib()
+    L.oracle_probe_camera.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    dirs = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+    frame = np.zeros(9, np.float32); pdf = np.zeros(len(dirs), np.float32)
+    L.oracle_probe_camera(C.addressof(view), frame.ctypes.data, dirs.ctypes.data, len(dirs), pdf.ctypes.data)
+    return frame, pdf

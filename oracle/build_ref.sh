@@ -631,6 +631,19 @@ extern "C" const void* ref_scene_array(void* h, int which)
 	return NULL;
 }
 extern "C" const char* ref_scene_texture_name(void* h, int i) { return static_cast<RefLoaded*>(h)->mesh.m_textures[i].c_str(); }
+// src/camera.h on the host: camera_frame (:142-173) and camera_direction_pdf (:232-252) with Camera::square_pixel_focal_length (:122-128).
+// cam = eye, aim, up (3 each), fov; out = U, V, W (3 each); pdf of n directions d[3n]
+extern "C" void ref_camera(const float* cam, float aspect, unsigned res_x, unsigned res_y, float* out, const float* d, unsigned n, float* pdf)
+{
+	Camera c;
+	c.eye = make_float3(cam[0], cam[1], cam[2]); c.aim = make_float3(cam[3], cam[4], cam[5]); c.up = make_float3(cam[6], cam[7], cam[8]); c.fov = cam[9];
+	cugar::Vector3f U, V, W;
+	camera_frame(c, aspect, U, V, W);
+	for (int i = 0; i < 3; ++i) { out[i] = U[i]; out[3 + i] = V[i]; out[6 + i] = W[i]; }
+	const float W_len = cugar::length(W);
+	const float sq = c.square_pixel_focal_length(res_x, res_y);
+	for (unsigned i = 0; i < n; ++i) pdf[i] = camera_direction_pdf(U, V, W, W_len, sq, cugar::Vector3f(d[3 * i], d[3 * i + 1], d[3 * i + 2]), false);
+}
 EOF
 LFLAGS="-O2 -std=c++14 -fPIC -w -fpermissive -ffp-contract=off -include $OVF/adapter_prefix.h -DFERMAT_API_EXTERN= -DFERMAT_API= -DSUTILAPI= -DSUTILCLASSAPI= -DTHRUST_DEVICE_SYSTEM=THRUST_DEVICE_SYSTEM_CPP -I$OVF -I$REF/src -I$REF/src/mesh -I$REF/contrib -I/usr/local/cuda/include"
 mkdir -p $OUT/obj

@@ -483,6 +483,25 @@ static inline vec3 psf_clamp_sample(vec3 v, float ff) { return finite3(v) ? vec3
 static inline vec3 psf_floor4(vec3 c) { return vec3(fmaxf(c.x, 1.0e-4f), fmaxf(c.y, 1.0e-4f), fmaxf(c.z, 1.0e-4f)); }   // modulate / demodulate, src/filters.h:57-72
 
 // one path, all bounces; psf != NULL: the PSFPTVertexProcessor policies instead of PTVertexProcessor's
+// the pdf of a primary ray's direction, the .y of the primary ray cone (src/pathtracer_kernels.h:153-159): camera_direction_pdf
+// (src/camera.h:232-252) with Camera::square_pixel_focal_length (:122-128)
+static float primary_cone_pdf(const fb200_scene_view* s, vec3 U, vec3 V, vec3 W, vec3 d)
+{
+	const float W_len = sqrtf(dot(W, W));
+	const float tn = tanf(s->fov / 2);
+	const float sq_focal = (float(s->res_x * s->res_y) / 4.0f) / (tn * tn);
+	const float t = dot(d, W) / (W_len * W_len);
+	if (t < 0.0f) return 0.0f;
+	const vec3 I = d / t - W;
+	const float Ix = dot(I, U) / square_length(U), Iy = dot(I, V) / square_length(V);
+	if (Ix >= -1.0f && Ix <= 1.0f && Iy >= -1.0f && Iy <= 1.0f)
+	{
+		const float cos_theta = dot(d, W) / W_len;
+		return sq_focal / (cos_theta * cos_theta * cos_theta);
+	}
+	return 0.0f;
+}
+
 #include "oracle_rl.h"
 
 static void trace_path(const SceneRef& sc, const Sampler& smp, FB& fb, uint32_t px, uint32_t py, float frame_weight, vec3 U, vec3 V, vec3 W, PassStats& st, bool count_trav,
@@ -516,21 +535,7 @@ static void trace_path(const SceneRef& sc, const Sampler& smp, FB& fb, uint32_t 
 	uint32_t prev_nee_slot = RL_INVALID;      // DirectLightingRL: the cell of the previous vertex (PTRayQueue::pixels.z)
 	if (psf || rl)
 	{
-		// camera_direction_pdf (src/camera.h:232-252) with square_pixel_focal_length (:122-128)
-		const float W_len = sqrtf(dot(W, W));
-		const float tn = tanf(s->fov / 2);
-		const float sq_focal = (float(s->res_x * s->res_y) / 4.0f) / (tn * tn);
-		const float t = dot(ray.d, W) / (W_len * W_len);
-		if (t >= 0.0f)
-		{
-			const vec3 I = ray.d / t - W;
-			const float Ix = dot(I, U) / square_length(U), Iy = dot(I, V) / square_length(V);
-			if (Ix >= -1.0f && Ix <= 1.0f && Iy >= -1.0f && Iy <= 1.0f)
-			{
-				const float cos_theta = dot(ray.d, W) / W_len;
-				cone_y = sq_focal / (cos_theta * cos_theta * cos_theta);
-			}
-		}
+		cone_y = primary_cone_pdf(s, U, V, W, ray.d);
 	}
 
 	for (uint32_t bounce = 0; bounce < o.max_path_length; ++bounce)
@@ -1236,6 +1241,13 @@ int oracle_probe_light(const fb200_scene_view* s, const float* Z, int use_vpls, 
 	return 0;
 }
 float oracle_probe_power_heuristic(float p1, float p2) { return power_heuristic(p1, p2); }
+// camera_frame of the view -> out[0..8] = U, V, W; the primary cone pdf of n directions d[3n] -> pdf[n]
+void oracle_probe_camera(const fb200_scene_view* s, float* out, const float* d, uint32_t n, float* pdf)
+{
+	vec3 U, V, W; camera_frame(s, U, V, W);
+	out[0] = U.x; out[1] = U.y; out[2] = U.z; out[3] = V.x; out[4] = V.y; out[5] = V.z; out[6] = W.x; out[7] = W.y; out[8] = W.z;
+	for (uint32_t i = 0; i < n; ++i) pdf[i] = primary_cone_pdf(s, U, V, W, vec3(d[3 * i], d[3 * i + 1], d[3 * i + 2]));
+}
 // rec (26 floats): kind (0 accumulate_emissive, 1 accumulate_nee, 2 compute_nee_weights), in_bounce, frame_weight, comp, a(3), b(3),
 // COMPOSITED(4) DIRECT(4) DIFFUSE(4) SPECULAR(4) of one pixel -> out (16 floats): the four channels afterwards (kind 2: w_d, w_g)
 int oracle_probe_vertex_processor(const float* rec, float* out, uint32_t n)

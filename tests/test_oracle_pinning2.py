@@ -130,3 +130,29 @@ def test_vpl_table_against_an_independent_restatement(fb, scene, res):
     assert np.float32(v.vpl_norm).view(np.uint32) == want["norm"].view(np.uint32)
     assert len(np.unique(bits(got[:, 0]))) >= 2                                   # (several emitting triangles were drawn)
     sc.close()
+
+
+def test_camera_frame_and_primary_cone_pdf(fb, oracle):
+    """src/camera.h: camera_frame (:142-173) and camera_direction_pdf with square_pixel_focal_length (:122-128, :232-252) - the reference's own
+    header compiled on the host (oracle/_ref/libref_loader.so ref_camera; golden vectors tests/golden/camera_golden.npz made by
+    tools/make_golden_camera.py) against the oracle's camera_frame and primary cone pdf, bit for bit: golden everywhere, live where _ref exists."""
+    import ctypes
+    g = np.load(os.path.join(GOLDEN, "camera_golden.npz"))
+    sc = fb.Scene(["-i", os.path.join(GOLDEN, "cornellbox_jp.fbs"), "-r", "64", "64", "-bounces", "2"])
+    live = oracle.RefLoader.load()
+    for k in range(len(g["cams"])):
+        cam, res = g["cams"][k], g["res"][k]
+        v = type(sc.view)()               # (a copy: the scene's own view is left alone)
+        ctypes.memmove(ctypes.addressof(v), ctypes.addressof(sc.view), ctypes.sizeof(v))
+        for i in range(3):
+            v.eye[i], v.aim[i], v.up[i] = float(cam[i]), float(cam[3 + i]), float(cam[6 + i])
+        v.fov = float(cam[9]); v.res_x, v.res_y = int(res[0]), int(res[1])
+        v.aspect = float(np.float32(res[0]) / np.float32(res[1]))
+        frame, pdf = oracle.probe_camera(v, g["dirs"][k])
+        assert np.array_equal(frame.view(np.uint32), g["uvw"][k].view(np.uint32)), k
+        assert np.array_equal(pdf.view(np.uint32), g["pdf"][k].view(np.uint32)), k
+        if live is not None:
+            f2, p2 = live.camera(cam, v.aspect, res, g["dirs"][k])
+            assert np.array_equal(f2.view(np.uint32), frame.view(np.uint32)) and np.array_equal(p2.view(np.uint32), pdf.view(np.uint32))
+    assert (g["pdf"] > 0).sum() > 300 and (g["pdf"] == 0).sum() > 100          # directions inside and outside the image
+    sc.close()
