@@ -593,3 +593,46 @@ def probe_camera(view, dirs):
     frame = np.zeros(9, np.float32); pdf = np.zeros(len(dirs), np.float32)
     L.oracle_probe_camera(C.addressof(view), frame.ctypes.data, dirs.ctypes.data, len(dirs), pdf.ctypes.data)
     return frame, pdf
+
+
+# FilterOp bits: this package's (oracle/post_oracle.cpp OP_*) -> the reference's (src/filters.h:39-50)
+_EAW_OP_TO_REF = {1: 0x10, 2: 0x1, 4: 0x2, 8: 0x4, 16: 0x8}
+
+
+def eaw_step(dst, mad, op, w_img, w_min, img, geo, var, params, step_size):
+    """one a-trous step of the restated EAW filter (post_oracle.cpp eaw_step): planes (H, W, 4), var (H, W) or None, params = phi_normal,
+    phi_position, phi_color, E, U, V, W (15 floats); returns the new dst"""
+    L = lib()
+    L.oracle_eaw_step.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint32]
+    dst = np.array(dst, np.float32); img = np.ascontiguousarray(img, np.float32); geo = np.ascontiguousarray(geo, np.float32)
+    w_img = None if w_img is None else np.ascontiguousarray(w_img, np.float32)
+    var = None if var is None else np.ascontiguousarray(var, np.float32)
+    params = np.ascontiguousarray(params, np.float32)
+    h, w = img.shape[:2]
+    L.oracle_eaw_step(dst.ctypes.data, 1 if mad else 0, int(op), None if w_img is None else w_img.ctypes.data, C.c_float(w_min), img.ctypes.data, geo.ctypes.data,
+                      None if var is None else var.ctypes.data, params.ctypes.data, w, h, int(step_size))
+    return dst
+
+
+class RefEaw:
+    """The REFERENCE's own EAW kernels (src/eaw.cu EAW_kernel / EAW_mad_kernel) run on this host, one call per pixel (oracle/_ref/libref_eaw.so)."""
+
+    @staticmethod
+    def load():
+        L = _ref_so("libref_eaw.so")
+        return RefEaw(L) if L is not None else None
+
+    def __init__(self, L):
+        self.L = L
+        L.ref_eaw_step.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
+
+    def step(self, dst, mad, op, w_img, w_min, img, geo, var, params, step_size):
+        dst = np.array(dst, np.float32); img = np.ascontiguousarray(img, np.float32); geo = np.ascontiguousarray(geo, np.float32)
+        w_img = None if w_img is None else np.ascontiguousarray(w_img, np.float32)
+        var = None if var is None else np.ascontiguousarray(var, np.float32)
+        params = np.ascontiguousarray(params, np.float32)
+        h, w = img.shape[:2]
+        ref_op = sum(v for k, v in _EAW_OP_TO_REF.items() if op & k)
+        self.L.ref_eaw_step(dst.ctypes.data, 1 if mad else 0, ref_op, None if w_img is None else w_img.ctypes.data, C.c_float(w_min), img.ctypes.data, geo.ctypes.data,
+                            None if var is None else var.ctypes.data, params.ctypes.data, w, h, int(step_size))
+        return dst

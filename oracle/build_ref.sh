@@ -654,3 +654,41 @@ done
 wait
 $CXX $LFLAGS -shared -o $OUT/libref_loader.so $OUT/ref_loader_shim.cpp $OUT/obj/*.o -L/usr/local/cuda/lib64 -lcudart_static -ldl -lrt -lpthread
 echo "built $OUT/libref_loader.so"
+
+# ---- the reference's own EAW denoiser kernels (src/eaw.cu:34-251: norm_diff, EAW_kernel, EAW_mad_kernel) run on the host, one "thread" per
+# pixel: the kernels' text is cut from the file where it lies (the host wrappers behind it launch with <<< >>>), `__global__` is defined away
+# and threadIdx / blockIdx / blockDim are variables of the shim. Pins oracle/post_oracle.cpp eaw_step.
+sed -e 's/"framebuffer.h"/<framebuffer.h>/' $REF/src/filters.h > $OUT/filters_overlay.h                              # (framebuffer.h: the overlay's copy)
+sed -e 's/"framebuffer.h"/<framebuffer.h>/' -e 's/"filters.h"/"filters_overlay.h"/' $REF/src/eaw.h > $OUT/eaw_overlay.h
+sed -n '1,251p' $REF/src/eaw.cu | sed 's/"eaw.h"/"eaw_overlay.h"/' > $OUT/eaw_kernels_cut.h
+cat > $OUT/ref_eaw_shim.cpp <<'EOF'
+struct RefIdx { unsigned x, y, z; };
+static thread_local RefIdx threadIdx = { 0, 0, 0 }, blockIdx = { 0, 0, 0 };
+static const RefIdx blockDim = { 1, 1, 1 };
+#define __global__
+#include "eaw_kernels_cut.h"
+// params: phi_normal, phi_position, phi_color, E, U, V, W (15 floats). mad == 0: EAW_kernel; else EAW_mad_kernel with the reference's FilterOp bits
+extern "C" void ref_eaw_step(float* dst, int mad, unsigned op, const float* w_img, float w_min, const float* img, const float* geo, const float* var,
+							 const float* params, unsigned rx, unsigned ry, unsigned step_size)
+{
+	FBufferChannelView d, im, w;
+	d.c_ptr = (float4*)dst; d.res_x = rx; d.res_y = ry;
+	im.c_ptr = (float4*)img; im.res_x = rx; im.res_y = ry;
+	w.c_ptr = (float4*)w_img; w.res_x = rx; w.res_y = ry;
+	GBufferView gb; memset(&gb, 0, sizeof(gb));
+	gb.m_geo = (float4*)geo; gb.res_x = rx; gb.res_y = ry;
+	EAWParams p;
+	p.phi_normal = params[0]; p.phi_position = params[1]; p.phi_color = params[2];
+	p.E = cugar::Vector3f(params[3], params[4], params[5]); p.U = cugar::Vector3f(params[6], params[7], params[8]);
+	p.V = cugar::Vector3f(params[9], params[10], params[11]); p.W = cugar::Vector3f(params[12], params[13], params[14]);
+	for (unsigned y = 0; y < ry; ++y)
+		for (unsigned x = 0; x < rx; ++x)
+		{
+			blockIdx.x = x; blockIdx.y = y;
+			if (mad) EAW_mad_kernel(d, op, w, w_min, im, gb, var, p, step_size);
+			else EAW_kernel(d, im, gb, var, p, step_size);
+		}
+}
+EOF
+$CXX $LFLAGS -I$OUT -shared -o $OUT/libref_eaw.so $OUT/ref_eaw_shim.cpp -L/usr/local/cuda/lib64 -lcudart_static -ldl -lrt -lpthread
+echo "built $OUT/libref_eaw.so"

@@ -129,6 +129,17 @@ inline F4 tonemap(F4 c, float exposure, float gamma)
 
 extern "C" {
 
+// one a-trous step on caller-provided planes (tests/test_post.py against the reference's own kernels): params = phi_normal, phi_position,
+// phi_color, E, U, V, W; op in this file's OP_* bits
+void oracle_eaw_step(float* dst, int mad, int op, const float* w_img, float w_min, const float* img, const float* geo, const float* var,
+					 const float* params, int rx, int ry, uint32_t step_size)
+{
+	Params p;
+	p.phi_normal = params[0]; p.phi_position = params[1]; p.phi_color = params[2];
+	p.E = F3{ params[3], params[4], params[5] }; p.U = F3{ params[6], params[7], params[8] }; p.V = F3{ params[9], params[10], params[11] }; p.W = F3{ params[12], params[13], params[14] };
+	eaw_step(reinterpret_cast<F4*>(dst), mad != 0, op, reinterpret_cast<const F4*>(w_img), w_min, reinterpret_cast<const F4*>(img), reinterpret_cast<const F4*>(geo), var, p, rx, ry, step_size);
+}
+
 void oracle_filter_variance(const float* img4, int rx, int ry, uint32_t FW, float* var)
 {
 	const F4* img = reinterpret_cast<const F4*>(img4);

@@ -170,3 +170,39 @@ def test_device_to_rgba_matches_the_restatement(fb, oracle, tmp_path):
     fb.write_tga(tmp_path / "cornell.tga", rc.to_rgba(0))
     assert os.path.getsize(tmp_path / "cornell.tga") == 18 + 80 * 80 * 3
     rc.close(); sc.close()
+
+
+def eaw_cases():
+    """inputs of the EAW pinning test (also read by tools/make_golden_eaw.py): random colours over a creased surface with a band of misses, every
+    FilterOp combination RenderingContext::filter uses (src/renderer.cu:1099-1160) plus the plain kernel, step sizes 1..16, with and without variance"""
+    cases = []
+    for k, (mad, op, step, use_var) in enumerate([(False, 0, 1, True), (False, 0, 4, False), (True, 4, 1, True), (True, 8 | 1, 16, True), (True, 2, 2, False),
+                                                  (True, 16 | 1, 8, True), (True, 0, 1, True)]):
+        fb, geo, cam = _synthetic(h=20, w=28, seed=100 + k)
+        rng = np.random.default_rng(200 + k)
+        geo = geo.copy()
+        geo[5:7, 3:20] = MISS                                           # a band of misses
+        geo[..., :3] += (0.01 * rng.random(geo[..., :3].shape)).astype(np.float32)
+        img = (fb[0] + fb[4]).astype(np.float32)
+        w_img = fb[1].copy(); w_img[2, 2] = 0.0                         # one weight below w_min
+        var = (0.05 * rng.random(img.shape[:2])).astype(np.float32) if use_var else None
+        params = np.concatenate([[2.0, 1.0, (k * k + 1) / 10000.0], cam]).astype(np.float32)
+        dst = rng.random(img.shape).astype(np.float32)                 # read in add mode
+        cases.append(dict(dst=dst, mad=mad, op=op, w_img=w_img if mad else None, w_min=1.0e-4, img=img, geo=geo, var=var, params=params, step_size=step))
+    return cases
+
+
+def test_eaw_step_is_the_references_kernel(oracle):
+    """post_oracle.cpp eaw_step against the reference's own EAW_kernel / EAW_mad_kernel (src/eaw.cu:34-251) run on the host one pixel at a time
+    (oracle/build_ref.sh -> libref_eaw.so): bit for bit - golden hashes everywhere (tests/golden/eaw_golden.npz, tools/make_golden_eaw.py), live where _ref exists."""
+    import hashlib
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "eaw_golden.npz"))
+    live = oracle.RefEaw.load()
+    for k, case in enumerate(eaw_cases()):
+        got = oracle.eaw_step(**case)
+        assert np.array_equal(got.reshape(-1)[::37].view(np.uint32), g["stride_%d" % k].view(np.uint32)), k
+        assert np.array_equal(np.frombuffer(hashlib.sha256(got.tobytes()).digest(), np.uint8), g["sha_%d" % k]), k
+        if live is not None:
+            assert np.array_equal(live.step(**case).view(np.uint32), got.view(np.uint32)), k
+        assert not np.array_equal(got, case["dst"])
