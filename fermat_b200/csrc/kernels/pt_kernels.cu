@@ -812,10 +812,14 @@ __global__ void __launch_bounds__(128, PARTS == SHADE_ALL ? FB_SHADE_MIN_BLOCKS 
 					a.fb.gb_depth[pixel] = hit.x;
 				}
 				// surface albedos (pathtracer_core.h:809-811)
+				// (all four components: EyeVertex::setup multiplies the float4 colours by the float4 texel, src/bpt_utils.h:617-620; the fourth is 0
+				// for materials read from .mtl files, 0.5 for the Vector4f(0.5f) defaults of the pbrt importer)
+				const float kd_w = __ldg(m4 + 0).w * texture_alpha(sc, s, t, load_texref(m, 8));
+				const float ks_w = __ldg(m4 + 3).w * texture_alpha(sc, s, t, load_texref(m, 10));
 				float4 da = a.fb.channels[FB_DIFFUSE_A][pixel], sa = a.fb.channels[FB_SPECULAR_A][pixel];
-				da.x += kd.x * a.frame_weight; da.y += kd.y * a.frame_weight; da.z += kd.z * a.frame_weight; da.w += 0.0f * a.frame_weight;
+				da.x += kd.x * a.frame_weight; da.y += kd.y * a.frame_weight; da.z += kd.z * a.frame_weight; da.w += kd_w * a.frame_weight;
 				sa.x += (ks.x + 1.0f) * 0.5f * a.frame_weight; sa.y += (ks.y + 1.0f) * 0.5f * a.frame_weight;
-				sa.z += (ks.z + 1.0f) * 0.5f * a.frame_weight; sa.w += (0.0f + 1.0f) * 0.5f * a.frame_weight;
+				sa.z += (ks.z + 1.0f) * 0.5f * a.frame_weight; sa.w += (ks_w + 1.0f) * 0.5f * a.frame_weight;
 				a.fb.channels[FB_DIFFUSE_A][pixel] = da; a.fb.channels[FB_SPECULAR_A][pixel] = sa;
 			}
 

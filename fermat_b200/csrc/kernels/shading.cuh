@@ -125,6 +125,22 @@ static __device__ __noinline__ V3 texture_fetch_bilinear(const TextureView tex, 
 			  (q0.z * (1 - u) + q1.z * u) * (1 - v) + (q2.z * (1 - u) + q3.z * u) * v);
 }
 
+// the fourth component of the same lookup (the albedo channels of bounce 0 carry it: EyeVertex::setup multiplies float4 by float4)
+static __device__ __noinline__ float texture_alpha(const DeviceScene& sc, float s, float t, const TextureReference ref)
+{
+	if (ref.texture == 0xFFFFFFFFu || ref.texture >= sc.num_textures) return 1.0f;
+	const TextureView tex = sc.textures[ref.texture];
+	if (tex.texels == NULL) return 1.0f;
+	s *= ref.scaling.x; t *= ref.scaling.y;
+	s = mod1(s, 1.0f); t = mod1(t, 1.0f);
+	const uint32 x = min((uint32)(s * tex.res_x), tex.res_x - 1), y = min((uint32)(t * tex.res_y), tex.res_y - 1);
+	const uint32 xx = (x + 1) % tex.res_x, yy = (y + 1) % tex.res_y;
+	const float q0 = __ldg(&tex.texels[(size_t)y * tex.res_x + x].w), q1 = __ldg(&tex.texels[(size_t)y * tex.res_x + xx].w);
+	const float q2 = __ldg(&tex.texels[(size_t)yy * tex.res_x + x].w), q3 = __ldg(&tex.texels[(size_t)yy * tex.res_x + xx].w);
+	const float u = mod1(s * tex.res_x, 1.0f), v = mod1(t * tex.res_y, 1.0f);
+	return (q0 * (1 - u) + q1 * u) * (1 - v) + (q2 * (1 - u) + q3 * u) * v;
+}
+
 FB_D TextureReference load_texref(const MeshMaterial* m, int which)   // which: byte offset / 16 of the reference inside MeshMaterial
 {
 	const float4 r = __ldg(reinterpret_cast<const float4*>(m) + which);

@@ -636,3 +636,88 @@ class RefEaw:
         self.L.ref_eaw_step(dst.ctypes.data, 1 if mad else 0, ref_op, None if w_img is None else w_img.ctypes.data, C.c_float(w_min), img.ctypes.data, geo.ctypes.data,
                             None if var is None else var.ctypes.data, params.ctypes.data, w, h, int(step_size))
         return dst
+
+
+class _RefFrame(C.Structure):       # struct RefFrame of oracle/_ref/ref_shade_shim.cpp
+    _fields_ = [("cam", C.c_float * 10), ("res_x", C.c_uint32), ("res_y", C.c_uint32), ("aspect", C.c_float),
+                ("n_dir_lights", C.c_uint32), ("dir_lights", C.c_void_p), ("glossy_reflectance", C.c_void_p),
+                ("n_dims", C.c_uint32), ("tile", C.c_uint32), ("shifts", C.c_void_p), ("options", C.c_uint32 * 12), ("instance", C.c_uint32), ("bounce", C.c_uint32)]
+
+
+def probe_shade_vertex(view, instance, bounce, records):
+    """the oracle's shade_vertex_restated on (n, 24) vertex records -> (n, 80) (layout: oracle_probe_shade_vertex in pt_oracle.cpp)"""
+    L = lib()
+    L.oracle_probe_shade_vertex.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32]
+    rec = np.ascontiguousarray(records, np.float32).reshape(-1, 24)
+    out = np.zeros((len(rec), 80), np.float32)
+    L.oracle_probe_shade_vertex(C.addressof(view), int(instance), int(bounce), rec.ctypes.data, out.ctypes.data, len(rec))
+    return out
+
+
+class RefShade:
+    """The REFERENCE's own shade_vertex (src/pathtracer_core.h:752-1254) with its EyeVertex, Bsdf, MeshLight, DirectLightingMesh and PTVertexProcessor,
+    compiled for this host (oracle/_ref/libref_shade.so) and run one vertex at a time behind a context that records the rays the vertex emits."""
+
+    @staticmethod
+    def load():
+        L, P = _ref_so("libref_shade.so"), RefPt.load()
+        return RefShade(L, P) if L is not None and P is not None else None
+
+    def __init__(self, L, pt):
+        self.L, self.pt = L, pt
+        L.ref_shade_vertex.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+
+    def shade_vertex(self, view, instance, bounce, records):
+        s = self.pt._scene(view)
+        f = _RefFrame()
+        for i in range(3):
+            f.cam[i], f.cam[3 + i], f.cam[6 + i] = view.eye[i], view.aim[i], view.up[i]
+        f.cam[9] = view.fov
+        f.res_x, f.res_y, f.aspect = view.res_x, view.res_y, view.aspect
+        f.n_dir_lights = view.n_dir_lights; f.dir_lights = C.cast(view.dir_lights, C.c_void_p)
+        f.glossy_reflectance = C.cast(view.glossy_reflectance, C.c_void_p)
+        f.n_dims, f.tile, f.shifts = view.n_dimensions, view.tile_size, C.cast(view.shifts, C.c_void_p)
+        o = view.options
+        for k, name in enumerate(("max_path_length", "direct_lighting", "direct_lighting_nee", "direct_lighting_bsdf", "indirect_lighting_nee", "indirect_lighting_bsdf",
+                                  "visible_lights", "diffuse_scattering", "glossy_scattering", "indirect_glossy", "rr", "nee_type")):
+            f.options[k] = int(getattr(o, name))
+        f.instance, f.bounce = int(instance), int(bounce)
+        rec = np.ascontiguousarray(records, np.float32).reshape(-1, 24)
+        out = np.zeros((len(rec), 80), np.float32)
+        self.L.ref_shade_vertex(C.byref(s), C.byref(f), rec.ctypes.data, out.ctypes.data, len(rec))
+        return out
+
+
+def vertex_records(view, n, seed, bounce):
+    """(m, 24) vertex records for the shade-vertex probes: camera rays through random pixels, followed `bounce` times along random directions"""
+    rng = np.random.default_rng(seed)
+    frame, _ = probe_camera(view, np.zeros((0, 3), np.float32))
+    U, V, W = frame[0:3], frame[3:6], frame[6:9]
+    px = rng.integers(0, view.res_x, n).astype(np.uint32); py = rng.integers(0, view.res_y, n).astype(np.uint32)
+    xy = np.stack([(px + rng.random(n)) / view.res_x * 2 - 1, (py + rng.random(n)) / view.res_y * 2 - 1], 1).astype(np.float32)
+    rays = np.zeros((n, 8), np.float32)
+    rays[:, 0:3] = np.array(view.eye[:], np.float32); rays[:, 4:7] = xy[:, :1] * U + xy[:, 1:] * V + W; rays[:, 3] = 0.0; rays[:, 7] = 1e34
+    for b in range(bounce + 1):
+        hits, _, _ = trace(view, rays)
+        ok = hits[:, 0] > 0
+        rays, hits, px, py = rays[ok], hits[ok], px[ok], py[ok]
+        if b == bounce:
+            break
+        pos = rays[:, 0:3] + hits[:, 0:1] * rays[:, 4:7]
+        d = rng.normal(size=(len(rays), 3)).astype(np.float32); d /= np.linalg.norm(d, axis=1, keepdims=True)
+        nxt = np.zeros((len(rays), 8), np.float32)
+        nxt[:, 0:3] = pos; nxt[:, 4:7] = d; nxt[:, 3] = 1e-3; nxt[:, 7] = 1e8
+        rays = nxt
+    m = len(rays)
+    rec = np.zeros((m, 24), np.float32)
+    comp = rng.integers(0, 16, m).astype(np.uint32) if bounce else np.zeros(m, np.uint32)
+    diff = rng.integers(0, 2, m).astype(np.uint32) if bounce else np.zeros(m, np.uint32)
+    info = (px + py * np.uint32(view.res_x)) | (comp << 27) | (diff << 31)
+    rec[:, 0] = info.view(np.float32); rec[:, 1] = px.view(np.float32); rec[:, 2] = py.view(np.float32)
+    rec[:, 3:6] = rays[:, 0:3]; rec[:, 6] = np.float32(rays[0, 3]) if m else 0; rec[:, 7:10] = rays[:, 4:7]; rec[:, 10] = rays[:, 7]
+    rec[:, 11:15] = hits
+    rec[:, 15:18] = (rng.random((m, 3)) * 2).astype(np.float32) if bounce else 1.0
+    rec[:, 18] = (rng.random(m) * 5).astype(np.float32) if bounce else 1.0
+    rec[:, 19] = np.uint32(0xFFFFFFFF).view(np.float32); rec[:, 20] = np.uint32(0xFFFFFFFF).view(np.float32)
+    rec[:, 21] = (rng.random(m) * 0.01).astype(np.float32); rec[:, 22] = (32 + rng.random(m) * 1000).astype(np.float32)
+    return rec

@@ -692,3 +692,207 @@ extern "C" void ref_eaw_step(float* dst, int mad, unsigned op, const float* w_im
 EOF
 $CXX $LFLAGS -I$OUT -shared -o $OUT/libref_eaw.so $OUT/ref_eaw_shim.cpp -L/usr/local/cuda/lib64 -lcudart_static -ldl -lrt -lpthread
 echo "built $OUT/libref_eaw.so"
+
+# ---- the reference's own shade_vertex (src/pathtracer_core.h:752-1254: the glue of the hot path - vertex set-up, directional lights, next-event
+# estimation, emissive hits with MIS, scattering, frame-buffer writes) with its own EyeVertex, Bsdf, MeshLight, DirectLightingMesh and
+# PTVertexProcessor, compiled for the host and run one vertex at a time: the header is device code, so the CUDA built-ins it names become
+# host stand-ins (dev_emul.h), two vector operators optixu would supply are defined, and the headers that quote-include buffers.h /
+# framebuffer.h get overlay copies that include the overlay's. The context is the shim's: trace_ray / trace_shadow_ray record what the vertex
+# emits instead of appending to queues. Pins oracle/pt_oracle.cpp shade_vertex_restated (tests/test_shade_vertex_pinning.py).
+OVS=$OUT/overlay_shade
+rm -rf $OVS; mkdir -p $OVS/cugar/basic/cuda
+sed 's/"buffers.h"/<buffers.h>/' $REF/src/hashmap.h > $OVS/hashmap.h
+sed 's/"framebuffer.h"/<framebuffer.h>/' $REF/src/filters.h > $OVS/filters.h
+sed -e 's/"framebuffer.h"/<framebuffer.h>/' -e 's/"filters.h"/<filters.h>/' $REF/src/eaw.h > $OVS/eaw.h
+# (BlockHashSet / BlockHashMap: CTA-wide containers with an MSVC-only base-class initialiser, used by clustered_rl.cu only)
+sed -e '/^struct BlockHashSet/,/^};/d' -e '/^struct BlockHashMap/,/^};/d' $REF/contrib/cugar/basic/cuda/hash.h | sed -e 's/^template <typename KeyT, typename HashT, uint32 CTA_SIZE, uint32 TABLE_SIZE, KeyT INVALID_KEY = 0xFFFFFFFF>$//' > $OVS/cugar/basic/cuda/hash.h
+cat > $OVS/dev_emul.h <<'EOF'
+// host stand-ins for the CUDA built-ins the path tracing headers name (one "thread" at a time)
+#pragma once
+#include <stdint.h>
+#include <string.h>
+#include <math.h>
+struct RefIdx3 { unsigned x, y, z; };
+static thread_local RefIdx3 threadIdx = { 0, 0, 0 }, blockIdx = { 0, 0, 0 };
+static const RefIdx3 blockDim = { 1, 1, 1 }, gridDim = { 1, 1, 1 };
+static const int warpSize = 32;
+inline void __syncthreads() {}
+inline void __threadfence() {}
+inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
+inline unsigned __activemask() { return 1u; }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __ffs(int v) { return __builtin_ffs(v); }
+template <typename T> inline T __shfl_sync(unsigned, T v, int, int = 32) { return v; }
+template <typename T> inline T __ldg(const T* p) { return *p; }
+inline unsigned atomicAdd(unsigned* p, unsigned v) { const unsigned o = *p; *p = o + v; return o; }
+inline int atomicAdd(int* p, int v) { const int o = *p; *p = o + v; return o; }
+inline float atomicAdd(float* p, float v) { const float o = *p; *p = o + v; return o; }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }
+inline unsigned atomicCAS(unsigned* p, unsigned c, unsigned v) { const unsigned o = *p; if (o == c) *p = v; return o; }
+inline unsigned long long atomicCAS(unsigned long long* p, unsigned long long c, unsigned long long v) { const unsigned long long o = *p; if (o == c) *p = v; return o; }
+inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+inline int __float_as_int(float f) { int u; memcpy(&u, &f, 4); return u; }
+inline float __int_as_float(int u) { float f; memcpy(&f, &u, 4); return f; }
+inline long long clock64() { return 0; }
+inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+EOF
+cat > $OUT/ref_shade_shim.cpp <<'EOF'
+#include "dev_emul.h"
+#include <vector>
+#include <vector_types.h>
+#include <cugar/linalg/vector.h>
+inline float4& operator*=(float4& a, const cugar::Vector4f& b) { a.x *= b.x; a.y *= b.y; a.z *= b.z; a.w *= b.w; return a; }
+inline float4& operator+=(float4& a, const cugar::Vector4f& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; return a; }
+inline float2 operator*(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+inline float2 operator-(float2 a, float s) { return make_float2(a.x - s, a.y - s); }
+#include <pathtracer_core.h>
+#include <pathtracer_vertex_processor.h>
+
+struct RefScene     // as in ref_pt_shim.cpp (filled by oracle/__init__.py from fb200_scene_view)
+{
+	int num_vertices, num_triangles, num_materials, num_textures;
+	int* vertex_indices; float* vertex_data; int* texture_indices_comp; int* material_indices; MeshMaterial* materials;
+	float tex_bias[2], tex_scale[2];
+	float** texels; unsigned* tex_res;
+	unsigned n_prims; float* mesh_cdf; float* mesh_inv_area; unsigned n_vpls; VPL* vpls; float vpl_norm;
+};
+struct RefFrame     // what a pass adds to the scene
+{
+	float cam[10];                      // eye, aim, up, fov
+	unsigned res_x, res_y; float aspect;
+	unsigned n_dir_lights; const float* dir_lights;       // {dir, color} x n
+	const float* glossy_reflectance;
+	unsigned n_dims, tile; const float* shifts;           // [dim][tile * tile]
+	unsigned options[12];               // PTOptions: max_path_length, direct_lighting, direct_lighting_nee, direct_lighting_bsdf, indirect_lighting_nee,
+	                                    // indirect_lighting_bsdf, visible_lights, diffuse_scattering, glossy_scattering, indirect_glossy, rr, nee_type
+	unsigned instance, bounce;
+};
+static MeshView mesh_view(const RefScene& s)
+{
+	MeshView m; memset(&m, 0, sizeof(m));
+	m.num_vertices = s.num_vertices; m.num_triangles = s.num_triangles; m.num_materials = s.num_materials;
+	m.vertex_stride = 4; m.normal_stride = 3; m.texture_stride = 2;
+	m.tex_bias = make_float2(s.tex_bias[0], s.tex_bias[1]); m.tex_scale = make_float2(s.tex_scale[0], s.tex_scale[1]);
+	m.vertex_indices = s.vertex_indices; m.vertex_data = s.vertex_data; m.texture_indices_comp = s.texture_indices_comp;
+	m.material_indices = s.material_indices; m.materials = s.materials;
+	return m;
+}
+struct ShadowRec { PixelInfo pixel; MaskedRay ray; cugar::Vector3f w, w_d, w_g; uint32 vinfo, nee_slot, nee_sample; };
+struct CaptureContext : PTContextBase<PTOptions>
+{
+	DirectLightingMesh dl;
+	bool scatter_on; PixelInfo sc_pixel; MaskedRay sc_ray; cugar::Vector4f sc_w; cugar::Vector2f sc_cone; uint32 sc_vinfo, sc_nee;
+	std::vector<ShadowRec> shadows;
+	template <typename VP>
+	void trace_ray(VP&, RenderingContextView&, const PixelInfo pixel, const MaskedRay ray, const cugar::Vector4f weight,
+				   const cugar::Vector2f cone = cugar::Vector2f(0), const uint32 vertex_info = uint32(-1), const uint32 nee_slot = uint32(-1))
+	{
+		scatter_on = true; sc_pixel = pixel; sc_ray = ray; sc_w = weight; sc_cone = cone; sc_vinfo = vertex_info; sc_nee = nee_slot;
+	}
+	template <typename VP>
+	void trace_shadow_ray(VP&, RenderingContextView&, const PixelInfo pixel, const MaskedRay ray, const cugar::Vector3f weight, const cugar::Vector3f weight_d,
+						  const cugar::Vector3f weight_g, const uint32 vertex_info = uint32(-1), const uint32 nee_slot = uint32(-1), const uint32 nee_sample = uint32(-1))
+	{
+		ShadowRec r; r.pixel = pixel; r.ray = ray; r.w = weight; r.w_d = weight_d; r.w_g = weight_g; r.vinfo = vertex_info; r.nee_slot = nee_slot; r.nee_sample = nee_sample;
+		shadows.push_back(r);
+	}
+};
+static inline float bits(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+static inline unsigned ubits(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+static void put_ray(float* o, const MaskedRay& r) { o[0] = r.origin.x; o[1] = r.origin.y; o[2] = r.origin.z; o[3] = bits(r.mask); o[4] = r.dir.x; o[5] = r.dir.y; o[6] = r.dir.z; o[7] = r.tmax; }
+
+// in: 24 floats per vertex {PixelInfo bits, pixel x, pixel y (as uint bits), ray origin xyz, mask bits, dir xyz, tmax, hit t, triId bits, u, v, w xyzw,
+// prev_vertex_info bits, prev_nee bits, cone xy, 0}; out: 80 floats per vertex (layout: oracle_probe_shade_vertex in oracle/pt_oracle.cpp)
+extern "C" int ref_shade_vertex(const RefScene* s, const RefFrame* f, const float* in, float* out, unsigned n)
+{
+	std::vector<TextureView> levels(s->num_textures ? s->num_textures : 1); std::vector<MipMapView> maps(s->num_textures ? s->num_textures : 1);
+	for (int t = 0; t < s->num_textures; ++t)
+	{
+		levels[t].c = reinterpret_cast<float4*>(s->texels[t]); levels[t].res_x = s->tex_res[2 * t]; levels[t].res_y = s->tex_res[2 * t + 1];
+		maps[t].levels = &levels[t]; maps[t].n_levels = s->texels[t] ? 1u : 0u; maps[t].res_x = levels[t].res_x; maps[t].res_y = levels[t].res_y;
+	}
+	const MeshView mesh = mesh_view(*s);
+	const MeshLight mesh_light(s->n_prims, s->mesh_cdf, s->mesh_inv_area, mesh, maps.data(), 0u, NULL, s->vpls, s->vpl_norm);
+	const MeshLight mesh_vpls(s->n_prims, s->mesh_cdf, s->mesh_inv_area, mesh, maps.data(), s->n_vpls, NULL, s->vpls, s->vpl_norm);
+	std::vector<DirectionalLight> dls(f->n_dir_lights ? f->n_dir_lights : 1);
+	for (unsigned i = 0; i < f->n_dir_lights; ++i)
+	{
+		dls[i].dir = cugar::Vector3f(f->dir_lights[6 * i], f->dir_lights[6 * i + 1], f->dir_lights[6 * i + 2]);
+		dls[i].color = cugar::Vector3f(f->dir_lights[6 * i + 3], f->dir_lights[6 * i + 4], f->dir_lights[6 * i + 5]);
+	}
+	Camera cam;
+	cam.eye = make_float3(f->cam[0], f->cam[1], f->cam[2]); cam.aim = make_float3(f->cam[3], f->cam[4], f->cam[5]); cam.up = make_float3(f->cam[6], f->cam[7], f->cam[8]); cam.fov = f->cam[9];
+	// a frame buffer of the frame's size, zeroed: a vertex touches one pixel, which is read back and cleared
+	const size_t P = (size_t)f->res_x * f->res_y;
+	std::vector<float4> planes(P * FBufferDesc::NUM_CHANNELS, make_float4(0, 0, 0, 0));
+	std::vector<FBufferChannelView> channels(FBufferDesc::NUM_CHANNELS);
+	for (unsigned c = 0; c < (unsigned)FBufferDesc::NUM_CHANNELS; ++c) { channels[c].c_ptr = planes.data() + c * P; channels[c].res_x = f->res_x; channels[c].res_y = f->res_y; }
+	std::vector<float4> gb_geo(P), gb_uv(P); std::vector<uint32> gb_tri(P); std::vector<float> gb_depth(P);
+	FBufferView fbv; memset(&fbv, 0, sizeof(fbv));
+	fbv.channels = channels.data(); fbv.n_channels = FBufferDesc::NUM_CHANNELS;
+	fbv.gbuffer.m_geo = gb_geo.data(); fbv.gbuffer.m_uv = gb_uv.data(); fbv.gbuffer.m_tri = gb_tri.data(); fbv.gbuffer.m_depth = gb_depth.data();
+	fbv.gbuffer.res_x = f->res_x; fbv.gbuffer.res_y = f->res_y;
+	RenderingContextView renderer(cam, f->n_dir_lights, dls.data(), mesh, mesh_light, mesh_vpls, maps.data(), 0u, NULL, NULL, NULL, f->glossy_reflectance,
+								  f->res_x, f->res_y, f->aspect, 1.0f, 2.2f, 1.0f, kShaded, fbv, f->instance);
+	// TiledSequence::set_instance (src/tiled_sequence.cu:100-110): samples[d][i] = fmodf(randfloat(d, instance + 1) + shifts[d][i], 1)
+	const size_t S = (size_t)f->tile * f->tile;
+	std::vector<float> samples((size_t)f->n_dims * S);
+	for (unsigned d = 0; d < f->n_dims; ++d)
+	{
+		const float seq = cugar::randfloat(d, f->instance + 1);
+		for (size_t i = 0; i < S; ++i) samples[d * S + i] = fmodf(seq + f->shifts[d * S + i], 1.0f);
+	}
+	CaptureContext context;
+	PTOptions& o = context.options;
+	o.max_path_length = f->options[0]; o.direct_lighting = f->options[1]; o.direct_lighting_nee = f->options[2]; o.direct_lighting_bsdf = f->options[3];
+	o.indirect_lighting_nee = f->options[4]; o.indirect_lighting_bsdf = f->options[5]; o.visible_lights = f->options[6]; o.diffuse_scattering = f->options[7];
+	o.glossy_scattering = f->options[8]; o.indirect_glossy = f->options[9]; o.rr = f->options[10]; o.nee_type = f->options[11];
+	context.sequence.n_dimensions = f->n_dims; context.sequence.tile_size = f->tile; context.sequence.samples = samples.data(); context.sequence.shifts = f->shifts;
+	context.frame_weight = 1.0f / float(f->instance + 1);
+	context.in_bounce = f->bounce;
+	context.bbox = cugar::Bbox3f();
+	context.device_timers = NULL;
+	context.dl = DirectLightingMesh(f->options[11] == NEE_ALGORITHM_VPL && s->n_vpls ? mesh_vpls : mesh_light);
+	compute_per_bounce_options(context, renderer);
+	PTVertexProcessor vertex_processor;
+	const int fb_channels[6] = { FBufferDesc::DIFFUSE_C, FBufferDesc::DIFFUSE_A, FBufferDesc::SPECULAR_C, FBufferDesc::SPECULAR_A, FBufferDesc::DIRECT_C, FBufferDesc::COMPOSITED_C };
+	for (unsigned i = 0; i < n; ++i)
+	{
+		const float* r = in + 24 * (size_t)i; float* q = out + 80 * (size_t)i;
+		memset(q, 0, 80 * sizeof(float));
+		const PixelInfo pixel_info(ubits(r[0]));
+		const uint2 pixel = make_uint2(ubits(r[1]), ubits(r[2]));
+		MaskedRay ray; ray.origin = make_float3(r[3], r[4], r[5]); ray.mask = ubits(r[6]); ray.dir = make_float3(r[7], r[8], r[9]); ray.tmax = r[10];
+		Hit hit; hit.t = r[11]; hit.triId = (int)ubits(r[12]); hit.u = r[13]; hit.v = r[14];
+		context.scatter_on = false; context.shadows.clear();
+		const bool cont = shade_vertex(context, vertex_processor, renderer, f->bounce, pixel_info, pixel, ray, hit, cugar::Vector4f(r[15], r[16], r[17], r[18]),
+									   ubits(r[19]), ubits(r[20]), cugar::Vector2f(r[21], r[22]));
+		q[0] = cont ? 1.0f : 0.0f;
+		if (context.scatter_on)
+		{
+			q[1] = 1.0f; q[2] = bits(uint32(context.sc_pixel)); put_ray(q + 3, context.sc_ray);
+			q[11] = context.sc_w.x; q[12] = context.sc_w.y; q[13] = context.sc_w.z; q[14] = context.sc_w.w; q[15] = context.sc_cone.x; q[16] = context.sc_cone.y;
+		}
+		for (size_t k = 0; k < context.shadows.size() && k < 2; ++k)
+		{
+			float* h = q + 17 + 19 * k; const ShadowRec& sr = context.shadows[k];
+			h[0] = 1.0f; h[1] = bits(uint32(sr.pixel)); put_ray(h + 2, sr.ray);
+			h[10] = sr.w.x; h[11] = sr.w.y; h[12] = sr.w.z; h[13] = sr.w_d.x; h[14] = sr.w_d.y; h[15] = sr.w_d.z; h[16] = sr.w_g.x; h[17] = sr.w_g.y; h[18] = sr.w_g.z;
+		}
+		const uint32 p = pixel_info.pixel;
+		for (int c = 0; c < 6; ++c)
+		{
+			float4& v = planes[(size_t)fb_channels[c] * P + p];
+			q[55 + 4 * c] = v.x; q[56 + 4 * c] = v.y; q[57 + 4 * c] = v.z; q[58 + 4 * c] = v.w;
+			v = make_float4(0, 0, 0, 0);
+		}
+		q[79] = float(context.shadows.size());
+	}
+	return 0;
+}
+EOF
+$CXX -O2 -std=c++14 -fPIC -w -fpermissive -ffp-contract=off -include $OVF/adapter_prefix.h -DFERMAT_API_EXTERN= -DFERMAT_API= -DSUTILAPI= -DSUTILCLASSAPI= \
+    -DTHRUST_DEVICE_SYSTEM=THRUST_DEVICE_SYSTEM_CPP -I$OVS -I$OVF -I$REF/src -I$REF/src/mesh -I$REF/src/renderers -I$REF/contrib -I/usr/local/cuda/include \
+    -shared -o $OUT/libref_shade.so $OUT/ref_shade_shim.cpp -L/usr/local/cuda/lib64 -lcudart_static -ldl -lrt -lpthread
+echo "built $OUT/libref_shade.so"

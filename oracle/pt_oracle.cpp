@@ -504,6 +504,288 @@ static float primary_cone_pdf(const fb200_scene_view* s, vec3 U, vec3 V, vec3 W,
 
 #include "oracle_rl.h"
 
+// One vertex of a path: what shade_vertex (src/pathtracer_core.h:752-1254) does between the closest hit and the queues - vertex set-up, G-buffer and
+// albedo writes, the light samplers' and the vertex processor's preprocess steps, directional lights, next-event estimation, the emissive hit
+// with MIS, scattering. The shadow rays it emits come back in `pend` (directional light, then next-event: queue order), the scattered ray in
+// `next`; tracing them and solve_occlusion are the caller's (trace_path below; oracle_probe_shade_vertex runs it on caller-chosen vertices
+// beside the reference's own shade_vertex compiled for the host, oracle/_ref/libref_shade.so).
+struct PendingShadow { bool on; Ray r; vec3 w_d, w_g; };
+struct VertexIO
+{
+	// in
+	uint32_t bounce, px, py, comp; bool diffuse_flag; Ray ray; Hit hit; vec3 w; float p_prev, cone_x, cone_y; uint32_t prev_vinfo, prev_nee_slot;
+	bool do_nee, do_emissive, do_scatter;
+	bool want_cone;        // compute the ray cone although neither -psfpt nor the RL sampler reads it (the reference always does)
+	// out
+	PendingShadow pend[2]; bool cont; Ray next; vec3 next_w; float next_p; uint32_t next_comp, next_vinfo, vinfo; float cone_radius; uint32_t nee_slot, nee_cluster;
+};
+static void shade_vertex_restated(const SceneRef& sc, const Sampler& smp, FB& fb, float frame_weight, VertexIO& io, PsfState* psf, uint32_t instance, RlState* rl)
+{
+	const fb200_scene_view* s = sc.s;
+	const fb200_pt_options& o = s->options;
+	const fb200_psf_options& po = s->psf;
+	const uint32_t bounce = io.bounce, px = io.px, py = io.py, pixel = px + py * s->res_x, comp = io.comp;
+	const bool diffuse_flag = io.diffuse_flag, do_nee = io.do_nee, do_emissive = io.do_emissive, do_scatter = io.do_scatter;
+	const Ray& ray = io.ray; const Hit& hit = io.hit; const vec3 w = io.w;
+	const float p_prev = io.p_prev, cone_x = io.cone_x, cone_y = io.cone_y;
+	const uint32_t prev_vinfo = io.prev_vinfo, prev_nee_slot = io.prev_nee_slot;
+	const bool have_vpls = s->n_vpls > 0;
+	const bool use_vpls = o.nee_type == 1 && have_vpls;
+	const uint32_t n_vpls = use_vpls ? s->n_vpls : 0;
+	(void)have_vpls; (void)prev_nee_slot; (void)po;
+
+	// EyeVertex::setup
+	Geom g;
+	setup_differential_geometry(sc, (uint32_t)hit.tri, hit.u, hit.v, &g);
+	g.position = ray.o + hit.t * ray.d;
+	const Material mat = fetch_material(sc, (uint32_t)hit.tri, g, true);
+	const vec3 in = -normalize(ray.d);
+	const Bsdf bsdf(mat, s->glossy_reflectance);
+
+	if (bounce == 0 && g_gbuffer.geo)
+	{
+		// G-buffer (pathtracer_core.h:802-806; pack_geometry src/framebuffer.h:84-90; uniform_sphere_to_square
+		// contrib/cugar/spherical/mappings_inline.h:174-185; pack_vector contrib/cugar/linalg/vector_inl.h:454-462)
+		const vec3 N = g.normal_s;
+		float phi;
+		if (fabsf(N.z) >= 1.0f - 1.0e-5f) phi = 0.0f;
+		else { phi = atan2f(N.y, N.x); phi = phi < 0.0f ? phi + 2.0f * PI_F : phi; }
+		const float sqx = phi / (2.0f * PI_F), sqy = (N.z + 1.0f) * 0.5f;
+		const uint32_t qx = (uint32_t)std::max(std::min((int32_t)(sqx * 32767.0f), 32766), 0), qy = (uint32_t)std::max(std::min((int32_t)(sqy * 32767.0f), 32766), 0);
+		float* geo = g_gbuffer.geo + 4 * (size_t)pixel; float* uv = g_gbuffer.uv + 4 * (size_t)pixel;
+		geo[0] = g.position.x; geo[1] = g.position.y; geo[2] = g.position.z; geo[3] = u2f(qx | (qy << 15));
+		uv[0] = hit.u; uv[1] = hit.v; uv[2] = g.st[0]; uv[3] = g.st[1];
+		g_gbuffer.tri[pixel] = (uint32_t)hit.tri;
+		g_gbuffer.depth[pixel] = hit.t;
+	}
+	if (bounce == 0)
+	{
+		// albedo channels
+		// (all four components: EyeVertex::setup multiplies the float4 colours by the float4 texel, src/bpt_utils.h:617-620; the fourth is 0 for
+		// materials read from .mtl files, 0.5 for the Vector4f(0.5f) defaults of the pbrt importer)
+		const MeshMaterialPOD& mp = reinterpret_cast<const MeshMaterialPOD*>(s->materials)[s->material_indices[hit.tri]];
+		const float kd_w = mp.diffuse[3] * bilinear_texture_lookup(s, g.st[0], g.st[1], mp.diffuse_map).w;
+		const float ks_w = mp.specular[3] * bilinear_texture_lookup(s, g.st[0], g.st[1], mp.specular_map).w;
+		float* da = fb.px(DIFFUSE_A, pixel); float* sa = fb.px(SPECULAR_A, pixel);
+		da[0] += mat.diffuse.x * frame_weight; da[1] += mat.diffuse.y * frame_weight; da[2] += mat.diffuse.z * frame_weight; da[3] += kd_w * frame_weight;
+		sa[0] += (mat.specular.x + 1.0f) * 0.5f * frame_weight; sa[1] += (mat.specular.y + 1.0f) * 0.5f * frame_weight;
+		sa[2] += (mat.specular.z + 1.0f) * 0.5f * frame_weight; sa[3] += (ks_w + 1.0f) * 0.5f * frame_weight;
+	}
+
+	// PSFPTVertexProcessor::preprocess_vertex (src/psfpt_vertex_processor.h:123-199), cone radius as in shade_vertex (src/pathtracer_core.h:816-819)
+	const uint32_t info = pixel | (comp << 27) | ((diffuse_flag ? 1u : 0u) << 31);      // PixelInfo of the incoming path
+	uint32_t vinfo = PSF_INVALID; bool new_entry = false; float cone_radius = 0.0f;
+	if (psf)
+	{
+		const float prev_G_prime = fabsf(dot(in, g.normal_s)) / (hit.t * hit.t);
+		const float area_prob = 1.0f / sqrtf(cone_y * prev_G_prime);      // cugar::rsqrtf; stated as an exact division on both sides
+		cone_radius = cone_x + area_prob;
+		uint32_t slot = psf_slot(prev_vinfo);
+		if (slot == PSF_INVALID_SLOT && bounce >= po.psf_depth && p_prev < po.psf_max_prob)
+		{
+			const uint32_t pixel_hash = pixel + instance * s->res_x * s->res_y;
+			float jitter[6];
+			for (uint32_t i = 0; i < 6; ++i) jitter[i] = randfloat(i, pixel_hash);
+			const float filter_scale = bounce == 0 ? 2.0f : 1.0f;
+			const vec3 Ns = dot(in, g.normal_s) > 0.0f ? g.normal_s : -g.normal_s;
+			const uint64_t key = spatial_hash(g.position, Ns, g.tangent, g.binormal, vec3(s->bbox_min[0], s->bbox_min[1], s->bbox_min[2]),
+											  vec3(s->bbox_max[0], s->bbox_max[1], s->bbox_max[2]), jitter, cone_radius * po.psf_width, filter_scale);
+			const vec3 w_mod = w * psf_floor4(mat.diffuse);
+			PsfRef ref;
+			ref.pixel_info = info;
+			ref.w_d = (comp & cDiffuseMask) ? w_mod : vec3(0.0f);
+			ref.w_g = ((comp & cGlossyMask) && bounce) ? w_mod : vec3(0.0f);
+			psf->acquire();
+			slot = psf->insert(key);
+			psf->values[4 * (size_t)slot + 3] += 1.0f;
+			ref.cache = psf_pack(slot, PSF_ALL_COMPS, 0);
+			psf->refs[bounce < 64 ? bounce : 63].push_back(ref);
+			psf->release();
+			new_entry = true;
+		}
+		vinfo = psf_pack(slot, 0, new_entry ? 1u : 0u);
+	}
+	// DirectLightingRL::preprocess_vertex (src/direct_lighting_rl.h:69-113; cone radius: src/pathtracer_core.h:816-819)
+	uint32_t nee_slot = RL_INVALID;
+	if (rl || io.want_cone)
+	{
+		const float prev_G_prime = fabsf(dot(in, g.normal_s)) / (hit.t * hit.t);
+		const float area_prob = 1.0f / sqrtf(cone_y * prev_G_prime);
+		cone_radius = cone_x + area_prob;
+		if (rl && do_nee)
+		{
+			const float cone_scale = 32.0f;
+			const float filter_scale = diffuse_flag ? 0.2f : 1.5f;
+			const uint32_t base_dim = (diffuse_flag ? 0u : instance) * 6u;
+			const uint32_t random_set = cg_hash(pixel + s->res_x * s->res_y * bounce);
+			float jitter[6];
+			for (uint32_t i = 0; i < 6; ++i) jitter[i] = randfloat(base_dim + i, random_set);
+			const vec3 lo(s->bbox_min[0], s->bbox_min[1], s->bbox_min[2]), hi(s->bbox_max[0], s->bbox_max[1], s->bbox_max[2]);
+			const float bbox_delta = max_comp(hi - lo);
+			const vec3 Ns = dot(in, g.normal_s) > 0.0f ? g.normal_s : -g.normal_s;
+			const uint64_t key = spatial_hash(g.position, Ns, g.tangent, g.binormal, lo, hi, jitter, fminf(cone_radius * cone_scale, bbox_delta * 0.05f), filter_scale);
+			nee_slot = rl_find_slot(*rl, key);
+		}
+	}
+
+	float z[6];
+	for (uint32_t i = 0; i < 6; ++i) z[i] = smp.sample_2d(px, py, (bounce + 1) * 6 + i);
+
+	PendingShadow* pend = io.pend;
+	pend[0].on = pend[1].on = false;
+
+	// directional lights (pathtracer_core.h:870-988)
+	if ((bounce + 2 <= o.max_path_length) && (bounce > 0 || o.direct_lighting) && s->n_dir_lights)
+	{
+		const uint32_t li = (uint32_t)std::max(std::min((int32_t)(z[2] * float(s->n_dir_lights)), (int32_t)(s->n_dir_lights - 1)), 0);
+		const vec3 ldir(s->dir_lights[6 * li], s->dir_lights[6 * li + 1], s->dir_lights[6 * li + 2]);
+		const vec3 lcol(s->dir_lights[6 * li + 3], s->dir_lights[6 * li + 4], s->dir_lights[6 * li + 5]);
+		const float FAR = 1.0e8f;
+		const vec3 lpos = g.position - ldir * FAR;
+		float light_pdf = 1.0f;
+		light_pdf /= s->n_dir_lights;
+		vec3 out = lpos - g.position;
+		const float d2 = fmaxf(1.0e-8f, square_length(out));
+		out *= 1.0f / sqrtf(d2);
+		vec3 f[4]; float p[4];
+		bsdf.f_and_p(g, in, out, f, p);
+		const vec3 edf = FAR * FAR * lcol;
+		const vec3 f_L = (dot(ldir, -out) > 0.0f ? edf : vec3(0.0f)) / light_pdf;
+		const float G = fabsf(dot(out, g.normal_s) * dot(out, ldir)) / d2;
+		const vec3 fd = o.diffuse_scattering ? f[kDR] + f[kDT] : vec3(0.0f), fg = o.glossy_scattering ? f[kGR] + f[kGT] : vec3(0.0f);
+		const vec3 fl = f_L * G * 1.0f;
+		const vec3 w_d = (bounce == 0 ? fd : fd + fg) * w * fl, w_g = (bounce == 0 ? fg : fd + fg) * w * fl;
+		const vec3 ow = w_d + w_g;
+		if (max_comp(ow) > 0.0f && finite3(ow))
+		{
+			pend[0].on = true;
+			pend[0].r.o = g.position - ray.d * 1.0e-3f;
+			pend[0].r.d = lpos - pend[0].r.o;
+			pend[0].r.mask = 0x1u; pend[0].r.tmax = 0.9999f; pend[0].r.tmin = 0.0f;
+			pend[0].w_d = w_d; pend[0].w_g = w_g;
+		}
+	}
+
+	// next-event estimation (pathtracer_core.h:991-1106)
+	uint32_t nee_cluster = RL_INVALID;
+	if (do_nee)
+	{
+		uint32_t prim; float lu, lv;
+		float rl_light_pdf = 0.0f;
+		if (rl)
+		{
+			// DirectLightingRL::sample (src/direct_lighting_rl.h:117-150) -> VTLMeshView::sample (src/vtl_mesh_view.h:52-76); (z0, z1) is
+			// not folded into the triangle there
+			float sel_pdf;
+			const uint32_t vtl_idx = rl_sample(*rl, nee_slot, z[2], &sel_pdf, &nee_cluster);
+			const RlVTL& vtl = rl->vtls[vtl_idx];
+			prim = vtl.prim_id;
+			const float wz = 1.0f - z[0] - z[1];
+			lu = vtl.uv2[0] * wz + vtl.uv0[0] * z[0] + vtl.uv1[0] * z[1];
+			lv = vtl.uv2[1] * wz + vtl.uv0[1] * z[0] + vtl.uv1[1] * z[1];
+			rl_light_pdf = (1.0f / vtl.area) * sel_pdf;
+		}
+		else sample_light_vertex(s, n_vpls, z, &prim, &lu, &lv);
+		Geom lg;
+		setup_differential_geometry(sc, prim, lu, lv, &lg);
+		float light_pdf; vec3 edf;
+		light_map(sc, use_vpls, prim, lg, &light_pdf, &edf);
+		if (rl) light_pdf = rl_light_pdf;
+
+		vec3 out = lg.position - g.position;
+		const float d2 = fmaxf(1.0e-8f, square_length(out));
+		out *= 1.0f / sqrtf(d2);
+		vec3 f[4]; float p[4];
+		bsdf.f_and_p(g, in, out, f, p);
+		vec3 f_s(0.0f); float p_s = 0.0f;
+		if (o.diffuse_scattering) { f_s += f[kDR] + f[kDT]; p_s += p[kDR] + p[kDT]; }
+		if (o.glossy_scattering) { f_s += f[kGR] + f[kGT]; p_s += p[kGR] + p[kGT]; }
+		const vec3 f_L = (dot(lg.normal_s, -out) > 0.0f ? edf : vec3(0.0f)) / light_pdf;
+		const float G = fabsf(dot(out, g.normal_s) * dot(out, lg.normal_s)) / d2;
+		const float p1 = light_pdf, p2 = p_s * G;
+		const float mis_w = ((bounce == 0 && o.direct_lighting_bsdf) || (bounce > 0 && o.indirect_lighting_bsdf)) ? power_heuristic(p1, p2) : 1.0f;
+		const vec3 fd = o.diffuse_scattering ? f[kDR] + f[kDT] : vec3(0.0f), fg = o.glossy_scattering ? f[kGR] + f[kGT] : vec3(0.0f);
+		const vec3 fl = f_L * G * mis_w;
+		vec3 w_d, w_g;
+		pt_compute_nee_weights(bounce, fd, fg, w, fl, &w_d, &w_g);
+		if (psf)
+		{
+			// PSFPTVertexProcessor::compute_nee_weights (src/psfpt_vertex_processor.h:204-268)
+			if (new_entry) { w_d = (fd / psf_floor4(mat.diffuse)) * fl; w_g = fg * w * fl; }
+			else { w_d = fd * w * fl; w_g = fg * w * fl; }
+		}
+		const vec3 ow = w_d + w_g;
+		if (max_comp(ow) > 0.0f && finite3(ow))
+		{
+			pend[1].on = true;
+			pend[1].r.o = g.position - ray.d * 1.0e-4f;
+			pend[1].r.d = lg.position - pend[1].r.o;
+			pend[1].r.mask = 0x2u; pend[1].r.tmax = 0.9999f; pend[1].r.tmin = 0.0f;
+			pend[1].w_d = w_d; pend[1].w_g = w_g;
+		}
+	}
+
+	// emissive hit (pathtracer_core.h:1109-1154)
+	if (do_emissive)
+	{
+		float light_pdf; vec3 edf;
+		light_map(sc, use_vpls, (uint32_t)hit.tri, g, &light_pdf, &edf);
+		if (rl)
+		{
+			// DirectLightingRL::map (src/direct_lighting_rl.h:154-167) -> VTLMeshView::map (src/vtl_mesh_view.h:83-112)
+			const uint32_t vtl_idx = rl_locate(*rl, (uint32_t)hit.tri, hit.u, hit.v);
+			light_pdf = vtl_idx != RL_INVALID ? 1.0f / rl->vtls[vtl_idx].area : 0.0f;
+			if (prev_nee_slot != RL_INVALID && vtl_idx != RL_INVALID) light_pdf *= rl_pdf(*rl, prev_nee_slot, vtl_idx);
+		}
+		const vec3 f_L = dot(g.normal_s, in) > 0.0f ? edf : vec3(0.0f);
+		const float d2 = fmaxf(1.0e-10f, hit.t * hit.t);
+		const float G_partial = fabsf(dot(in, g.normal_s)) / d2;
+		const float p1 = pdf_product(G_partial, p_prev), p2 = light_pdf;
+		const float mis_w = ((bounce == 1 && o.direct_lighting_nee) || (bounce > 1 && o.indirect_lighting_nee)) ? power_heuristic(p1, p2) : 1.0f;
+		const vec3 ow = w * f_L * mis_w;
+		if (max_comp(ow) > 0.0f && finite3(ow))
+		{
+			// PTVertexProcessor::accumulate_emissive, or PSFPTVertexProcessor's (src/psfpt_vertex_processor.h:326-369): clamped, and into
+			// the cache cell once the path feeds one
+			const vec3 cw = psf ? psf_clamp_sample(ow, po.firefly_filter) : ow;
+			if (!psf || psf_slot(prev_vinfo) == PSF_INVALID_SLOT) pt_accumulate_emissive(fb, bounce, comp, pixel, cw, frame_weight);
+			else
+			{
+				psf->acquire();
+				float* v = &psf->values[4 * (size_t)psf_slot(prev_vinfo)];
+				v[0] += cw.x; v[1] += cw.y; v[2] += cw.z;
+				psf->release();
+			}
+		}
+	}
+
+	// scattering (pathtracer_core.h:1157-1247)
+	bool cont = false;
+	Ray next; vec3 next_w(0.0f); float next_p = 0.0f; uint32_t next_comp = 0, next_vinfo = PSF_INVALID;
+	if (do_scatter)
+	{
+		// NOTE: component masks other than "all" are out of scope of the oracle
+		uint32_t out_comp; vec3 out, gg; float p, p_proj;
+		bsdf.sample(g, z + 3, in, out_comp, out, p, p_proj, gg);
+		vec3 ow = gg * w;
+		if (psf)
+		{
+			// PSFPTVertexProcessor::compute_scattering_weights (src/psfpt_vertex_processor.h:273-321)
+			next_vinfo = (psf_slot(prev_vinfo) == PSF_INVALID_SLOT && (out_comp & cGlossyMask)) ? prev_vinfo : psf_pack(psf_slot(vinfo), PSF_ALL_COMPS, 0);
+			if (new_entry && (out_comp & cDiffuseMask)) ow = gg / psf_floor4(mat.diffuse);
+		}
+		if (out_comp != cAbsorption && p != 0.0f && max_comp(ow) > 0.0f && finite3(ow))
+		{
+			cont = true;
+			next.o = g.position; next.d = out; next.tmin = 1.0e-3f; next.tmax = 1.0e8f; next.mask = 0;
+			next_w = ow; next_p = p; next_comp = out_comp;
+		}
+	}
+
+	io.cont = cont; io.next = next; io.next_w = next_w; io.next_p = next_p; io.next_comp = next_comp; io.next_vinfo = next_vinfo;
+	io.vinfo = vinfo; io.cone_radius = cone_radius; io.nee_slot = nee_slot; io.nee_cluster = nee_cluster;
+}
+
 static void trace_path(const SceneRef& sc, const Sampler& smp, FB& fb, uint32_t px, uint32_t py, float frame_weight, vec3 U, vec3 V, vec3 W, PassStats& st, bool count_trav,
 					   PsfState* psf = NULL, uint32_t instance = 0, RlState* rl = NULL)
 {
@@ -513,8 +795,6 @@ static void trace_path(const SceneRef& sc, const Sampler& smp, FB& fb, uint32_t 
 	// PathTracer::init falls back to the plain mesh sampler when there are no VPLs (pathtracer_impl.h:165-166);
 	// do_nee is gated on the VPL count whichever sampler is active (pathtracer_core.h:601-602)
 	const bool have_vpls = s->n_vpls > 0;
-	const bool use_vpls = o.nee_type == 1 && have_vpls;
-	const uint32_t n_vpls = use_vpls ? s->n_vpls : 0;
 
 	// primary ray (pathtracer_core.h:633-656)
 	Ray ray;
@@ -551,248 +831,14 @@ static void trace_path(const SceneRef& sc, const Sampler& smp, FB& fb, uint32_t 
 		const Hit hit = trace_closest(sc, ray, ts);
 		if (!(hit.t > 0.0f && hit.tri >= 0)) return;       // environment: nothing (pathtracer_core.h:1249-1252)
 
-		// EyeVertex::setup
-		Geom g;
-		setup_differential_geometry(sc, (uint32_t)hit.tri, hit.u, hit.v, &g);
-		g.position = ray.o + hit.t * ray.d;
-		const Material mat = fetch_material(sc, (uint32_t)hit.tri, g, true);
-		const vec3 in = -normalize(ray.d);
-		const Bsdf bsdf(mat, s->glossy_reflectance);
-
-		if (bounce == 0 && g_gbuffer.geo)
-		{
-			// G-buffer (pathtracer_core.h:802-806; pack_geometry src/framebuffer.h:84-90; uniform_sphere_to_square
-			// contrib/cugar/spherical/mappings_inline.h:174-185; pack_vector contrib/cugar/linalg/vector_inl.h:454-462)
-			const vec3 N = g.normal_s;
-			float phi;
-			if (fabsf(N.z) >= 1.0f - 1.0e-5f) phi = 0.0f;
-			else { phi = atan2f(N.y, N.x); phi = phi < 0.0f ? phi + 2.0f * PI_F : phi; }
-			const float sqx = phi / (2.0f * PI_F), sqy = (N.z + 1.0f) * 0.5f;
-			const uint32_t qx = (uint32_t)std::max(std::min((int32_t)(sqx * 32767.0f), 32766), 0), qy = (uint32_t)std::max(std::min((int32_t)(sqy * 32767.0f), 32766), 0);
-			float* geo = g_gbuffer.geo + 4 * (size_t)pixel; float* uv = g_gbuffer.uv + 4 * (size_t)pixel;
-			geo[0] = g.position.x; geo[1] = g.position.y; geo[2] = g.position.z; geo[3] = u2f(qx | (qy << 15));
-			uv[0] = hit.u; uv[1] = hit.v; uv[2] = g.st[0]; uv[3] = g.st[1];
-			g_gbuffer.tri[pixel] = (uint32_t)hit.tri;
-			g_gbuffer.depth[pixel] = hit.t;
-		}
-		if (bounce == 0)
-		{
-			// albedo channels
-			float* da = fb.px(DIFFUSE_A, pixel); float* sa = fb.px(SPECULAR_A, pixel);
-			da[0] += mat.diffuse.x * frame_weight; da[1] += mat.diffuse.y * frame_weight; da[2] += mat.diffuse.z * frame_weight; da[3] += 0.0f * frame_weight;
-			sa[0] += (mat.specular.x + 1.0f) * 0.5f * frame_weight; sa[1] += (mat.specular.y + 1.0f) * 0.5f * frame_weight;
-			sa[2] += (mat.specular.z + 1.0f) * 0.5f * frame_weight; sa[3] += (0.0f + 1.0f) * 0.5f * frame_weight;
-		}
-
-		// PSFPTVertexProcessor::preprocess_vertex (src/psfpt_vertex_processor.h:123-199), cone radius as in shade_vertex (src/pathtracer_core.h:816-819)
-		const uint32_t info = pixel | (comp << 27) | ((diffuse_flag ? 1u : 0u) << 31);      // PixelInfo of the incoming path
-		uint32_t vinfo = PSF_INVALID; bool new_entry = false; float cone_radius = 0.0f;
-		if (psf)
-		{
-			const float prev_G_prime = fabsf(dot(in, g.normal_s)) / (hit.t * hit.t);
-			const float area_prob = 1.0f / sqrtf(cone_y * prev_G_prime);      // cugar::rsqrtf; stated as an exact division on both sides
-			cone_radius = cone_x + area_prob;
-			uint32_t slot = psf_slot(prev_vinfo);
-			if (slot == PSF_INVALID_SLOT && bounce >= po.psf_depth && p_prev < po.psf_max_prob)
-			{
-				const uint32_t pixel_hash = pixel + instance * s->res_x * s->res_y;
-				float jitter[6];
-				for (uint32_t i = 0; i < 6; ++i) jitter[i] = randfloat(i, pixel_hash);
-				const float filter_scale = bounce == 0 ? 2.0f : 1.0f;
-				const vec3 Ns = dot(in, g.normal_s) > 0.0f ? g.normal_s : -g.normal_s;
-				const uint64_t key = spatial_hash(g.position, Ns, g.tangent, g.binormal, vec3(s->bbox_min[0], s->bbox_min[1], s->bbox_min[2]),
-												  vec3(s->bbox_max[0], s->bbox_max[1], s->bbox_max[2]), jitter, cone_radius * po.psf_width, filter_scale);
-				const vec3 w_mod = w * psf_floor4(mat.diffuse);
-				PsfRef ref;
-				ref.pixel_info = info;
-				ref.w_d = (comp & cDiffuseMask) ? w_mod : vec3(0.0f);
-				ref.w_g = ((comp & cGlossyMask) && bounce) ? w_mod : vec3(0.0f);
-				psf->acquire();
-				slot = psf->insert(key);
-				psf->values[4 * (size_t)slot + 3] += 1.0f;
-				ref.cache = psf_pack(slot, PSF_ALL_COMPS, 0);
-				psf->refs[bounce < 64 ? bounce : 63].push_back(ref);
-				psf->release();
-				new_entry = true;
-			}
-			vinfo = psf_pack(slot, 0, new_entry ? 1u : 0u);
-		}
-		// DirectLightingRL::preprocess_vertex (src/direct_lighting_rl.h:69-113; cone radius: src/pathtracer_core.h:816-819)
-		uint32_t nee_slot = RL_INVALID;
-		if (rl)
-		{
-			const float prev_G_prime = fabsf(dot(in, g.normal_s)) / (hit.t * hit.t);
-			const float area_prob = 1.0f / sqrtf(cone_y * prev_G_prime);
-			cone_radius = cone_x + area_prob;
-			if (do_nee)
-			{
-				const float cone_scale = 32.0f;
-				const float filter_scale = diffuse_flag ? 0.2f : 1.5f;
-				const uint32_t base_dim = (diffuse_flag ? 0u : instance) * 6u;
-				const uint32_t random_set = cg_hash(pixel + s->res_x * s->res_y * bounce);
-				float jitter[6];
-				for (uint32_t i = 0; i < 6; ++i) jitter[i] = randfloat(base_dim + i, random_set);
-				const vec3 lo(s->bbox_min[0], s->bbox_min[1], s->bbox_min[2]), hi(s->bbox_max[0], s->bbox_max[1], s->bbox_max[2]);
-				const float bbox_delta = max_comp(hi - lo);
-				const vec3 Ns = dot(in, g.normal_s) > 0.0f ? g.normal_s : -g.normal_s;
-				const uint64_t key = spatial_hash(g.position, Ns, g.tangent, g.binormal, lo, hi, jitter, fminf(cone_radius * cone_scale, bbox_delta * 0.05f), filter_scale);
-				nee_slot = rl_find_slot(*rl, key);
-			}
-		}
-
-		float z[6];
-		for (uint32_t i = 0; i < 6; ++i) z[i] = smp.sample_2d(px, py, (bounce + 1) * 6 + i);
-
-		struct Pending { bool on; Ray r; vec3 w_d, w_g; } pend[2];
-		pend[0].on = pend[1].on = false;
-
-		// directional lights (pathtracer_core.h:870-988)
-		if ((bounce + 2 <= o.max_path_length) && (bounce > 0 || o.direct_lighting) && s->n_dir_lights)
-		{
-			const uint32_t li = (uint32_t)std::max(std::min((int32_t)(z[2] * float(s->n_dir_lights)), (int32_t)(s->n_dir_lights - 1)), 0);
-			const vec3 ldir(s->dir_lights[6 * li], s->dir_lights[6 * li + 1], s->dir_lights[6 * li + 2]);
-			const vec3 lcol(s->dir_lights[6 * li + 3], s->dir_lights[6 * li + 4], s->dir_lights[6 * li + 5]);
-			const float FAR = 1.0e8f;
-			const vec3 lpos = g.position - ldir * FAR;
-			float light_pdf = 1.0f;
-			light_pdf /= s->n_dir_lights;
-			vec3 out = lpos - g.position;
-			const float d2 = fmaxf(1.0e-8f, square_length(out));
-			out *= 1.0f / sqrtf(d2);
-			vec3 f[4]; float p[4];
-			bsdf.f_and_p(g, in, out, f, p);
-			const vec3 edf = FAR * FAR * lcol;
-			const vec3 f_L = (dot(ldir, -out) > 0.0f ? edf : vec3(0.0f)) / light_pdf;
-			const float G = fabsf(dot(out, g.normal_s) * dot(out, ldir)) / d2;
-			const vec3 fd = o.diffuse_scattering ? f[kDR] + f[kDT] : vec3(0.0f), fg = o.glossy_scattering ? f[kGR] + f[kGT] : vec3(0.0f);
-			const vec3 fl = f_L * G * 1.0f;
-			const vec3 w_d = (bounce == 0 ? fd : fd + fg) * w * fl, w_g = (bounce == 0 ? fg : fd + fg) * w * fl;
-			const vec3 ow = w_d + w_g;
-			if (max_comp(ow) > 0.0f && finite3(ow))
-			{
-				pend[0].on = true;
-				pend[0].r.o = g.position - ray.d * 1.0e-3f;
-				pend[0].r.d = lpos - pend[0].r.o;
-				pend[0].r.mask = 0x1u; pend[0].r.tmax = 0.9999f; pend[0].r.tmin = 0.0f;
-				pend[0].w_d = w_d; pend[0].w_g = w_g;
-			}
-		}
-
-		// next-event estimation (pathtracer_core.h:991-1106)
-		uint32_t nee_cluster = RL_INVALID;
-		if (do_nee)
-		{
-			uint32_t prim; float lu, lv;
-			float rl_light_pdf = 0.0f;
-			if (rl)
-			{
-				// DirectLightingRL::sample (src/direct_lighting_rl.h:117-150) -> VTLMeshView::sample (src/vtl_mesh_view.h:52-76); (z0, z1) is
-				// not folded into the triangle there
-				float sel_pdf;
-				const uint32_t vtl_idx = rl_sample(*rl, nee_slot, z[2], &sel_pdf, &nee_cluster);
-				const RlVTL& vtl = rl->vtls[vtl_idx];
-				prim = vtl.prim_id;
-				const float wz = 1.0f - z[0] - z[1];
-				lu = vtl.uv2[0] * wz + vtl.uv0[0] * z[0] + vtl.uv1[0] * z[1];
-				lv = vtl.uv2[1] * wz + vtl.uv0[1] * z[0] + vtl.uv1[1] * z[1];
-				rl_light_pdf = (1.0f / vtl.area) * sel_pdf;
-			}
-			else sample_light_vertex(s, n_vpls, z, &prim, &lu, &lv);
-			Geom lg;
-			setup_differential_geometry(sc, prim, lu, lv, &lg);
-			float light_pdf; vec3 edf;
-			light_map(sc, use_vpls, prim, lg, &light_pdf, &edf);
-			if (rl) light_pdf = rl_light_pdf;
-
-			vec3 out = lg.position - g.position;
-			const float d2 = fmaxf(1.0e-8f, square_length(out));
-			out *= 1.0f / sqrtf(d2);
-			vec3 f[4]; float p[4];
-			bsdf.f_and_p(g, in, out, f, p);
-			vec3 f_s(0.0f); float p_s = 0.0f;
-			if (o.diffuse_scattering) { f_s += f[kDR] + f[kDT]; p_s += p[kDR] + p[kDT]; }
-			if (o.glossy_scattering) { f_s += f[kGR] + f[kGT]; p_s += p[kGR] + p[kGT]; }
-			const vec3 f_L = (dot(lg.normal_s, -out) > 0.0f ? edf : vec3(0.0f)) / light_pdf;
-			const float G = fabsf(dot(out, g.normal_s) * dot(out, lg.normal_s)) / d2;
-			const float p1 = light_pdf, p2 = p_s * G;
-			const float mis_w = ((bounce == 0 && o.direct_lighting_bsdf) || (bounce > 0 && o.indirect_lighting_bsdf)) ? power_heuristic(p1, p2) : 1.0f;
-			const vec3 fd = o.diffuse_scattering ? f[kDR] + f[kDT] : vec3(0.0f), fg = o.glossy_scattering ? f[kGR] + f[kGT] : vec3(0.0f);
-			const vec3 fl = f_L * G * mis_w;
-			vec3 w_d, w_g;
-			pt_compute_nee_weights(bounce, fd, fg, w, fl, &w_d, &w_g);
-			if (psf)
-			{
-				// PSFPTVertexProcessor::compute_nee_weights (src/psfpt_vertex_processor.h:204-268)
-				if (new_entry) { w_d = (fd / psf_floor4(mat.diffuse)) * fl; w_g = fg * w * fl; }
-				else { w_d = fd * w * fl; w_g = fg * w * fl; }
-			}
-			const vec3 ow = w_d + w_g;
-			if (max_comp(ow) > 0.0f && finite3(ow))
-			{
-				pend[1].on = true;
-				pend[1].r.o = g.position - ray.d * 1.0e-4f;
-				pend[1].r.d = lg.position - pend[1].r.o;
-				pend[1].r.mask = 0x2u; pend[1].r.tmax = 0.9999f; pend[1].r.tmin = 0.0f;
-				pend[1].w_d = w_d; pend[1].w_g = w_g;
-			}
-		}
-
-		// emissive hit (pathtracer_core.h:1109-1154)
-		if (do_emissive)
-		{
-			float light_pdf; vec3 edf;
-			light_map(sc, use_vpls, (uint32_t)hit.tri, g, &light_pdf, &edf);
-			if (rl)
-			{
-				// DirectLightingRL::map (src/direct_lighting_rl.h:154-167) -> VTLMeshView::map (src/vtl_mesh_view.h:83-112)
-				const uint32_t vtl_idx = rl_locate(*rl, (uint32_t)hit.tri, hit.u, hit.v);
-				light_pdf = vtl_idx != RL_INVALID ? 1.0f / rl->vtls[vtl_idx].area : 0.0f;
-				if (prev_nee_slot != RL_INVALID && vtl_idx != RL_INVALID) light_pdf *= rl_pdf(*rl, prev_nee_slot, vtl_idx);
-			}
-			const vec3 f_L = dot(g.normal_s, in) > 0.0f ? edf : vec3(0.0f);
-			const float d2 = fmaxf(1.0e-10f, hit.t * hit.t);
-			const float G_partial = fabsf(dot(in, g.normal_s)) / d2;
-			const float p1 = pdf_product(G_partial, p_prev), p2 = light_pdf;
-			const float mis_w = ((bounce == 1 && o.direct_lighting_nee) || (bounce > 1 && o.indirect_lighting_nee)) ? power_heuristic(p1, p2) : 1.0f;
-			const vec3 ow = w * f_L * mis_w;
-			if (max_comp(ow) > 0.0f && finite3(ow))
-			{
-				// PTVertexProcessor::accumulate_emissive, or PSFPTVertexProcessor's (src/psfpt_vertex_processor.h:326-369): clamped, and into
-				// the cache cell once the path feeds one
-				const vec3 cw = psf ? psf_clamp_sample(ow, po.firefly_filter) : ow;
-				if (!psf || psf_slot(prev_vinfo) == PSF_INVALID_SLOT) pt_accumulate_emissive(fb, bounce, comp, pixel, cw, frame_weight);
-				else
-				{
-					psf->acquire();
-					float* v = &psf->values[4 * (size_t)psf_slot(prev_vinfo)];
-					v[0] += cw.x; v[1] += cw.y; v[2] += cw.z;
-					psf->release();
-				}
-			}
-		}
-
-		// scattering (pathtracer_core.h:1157-1247)
-		bool cont = false;
-		Ray next; vec3 next_w(0.0f); float next_p = 0.0f; uint32_t next_comp = 0, next_vinfo = PSF_INVALID;
-		if (do_scatter)
-		{
-			// NOTE: component masks other than "all" are out of scope of the oracle
-			uint32_t out_comp; vec3 out, gg; float p, p_proj;
-			bsdf.sample(g, z + 3, in, out_comp, out, p, p_proj, gg);
-			vec3 ow = gg * w;
-			if (psf)
-			{
-				// PSFPTVertexProcessor::compute_scattering_weights (src/psfpt_vertex_processor.h:273-321)
-				next_vinfo = (psf_slot(prev_vinfo) == PSF_INVALID_SLOT && (out_comp & cGlossyMask)) ? prev_vinfo : psf_pack(psf_slot(vinfo), PSF_ALL_COMPS, 0);
-				if (new_entry && (out_comp & cDiffuseMask)) ow = gg / psf_floor4(mat.diffuse);
-			}
-			if (out_comp != cAbsorption && p != 0.0f && max_comp(ow) > 0.0f && finite3(ow))
-			{
-				cont = true;
-				next.o = g.position; next.d = out; next.tmin = 1.0e-3f; next.tmax = 1.0e8f; next.mask = 0;
-				next_w = ow; next_p = p; next_comp = out_comp;
-			}
-		}
+		VertexIO io;
+		io.bounce = bounce; io.px = px; io.py = py; io.comp = comp; io.diffuse_flag = diffuse_flag; io.ray = ray; io.hit = hit; io.w = w; io.p_prev = p_prev;
+		io.cone_x = cone_x; io.cone_y = cone_y; io.prev_vinfo = prev_vinfo; io.prev_nee_slot = prev_nee_slot;
+		io.do_nee = do_nee; io.do_emissive = do_emissive; io.do_scatter = do_scatter; io.want_cone = false;
+		shade_vertex_restated(sc, smp, fb, frame_weight, io, psf, instance, rl);
+		const PendingShadow* pend = io.pend;
+		const uint32_t vinfo = io.vinfo, nee_slot = io.nee_slot, nee_cluster = io.nee_cluster, next_comp = io.next_comp, next_vinfo = io.next_vinfo;
+		const bool cont = io.cont; const Ray next = io.next; const vec3 next_w = io.next_w; const float next_p = io.next_p, cone_radius = io.cone_radius;
 
 		// solve_occlusion for this wave's shadow rays (dir-light first, then NEE: queue order)
 		for (int k = 0; k < 2; ++k)
@@ -1241,6 +1287,70 @@ int oracle_probe_light(const fb200_scene_view* s, const float* Z, int use_vpls, 
 	return 0;
 }
 float oracle_probe_power_heuristic(float p1, float p2) { return power_heuristic(p1, p2); }
+// shade_vertex_restated on caller-chosen vertices, beside the reference's own shade_vertex (oracle/_ref/libref_shade.so ref_shade_vertex, same records).
+// in: 24 floats per vertex {PixelInfo bits, pixel x, pixel y (uint bits), ray origin xyz, mask bits, dir xyz, tmax, hit t, triId bits, u, v, w xyzw,
+// prev_vertex_info bits, prev_nee bits, cone xy, 0}. out: 80 floats per vertex: [0] path continues; scattered ray [1] on, [2] PixelInfo bits, [3..10] origin,
+// mask bits, dir, tmax, [11..14] weight + pdf, [15..16] cone; shadow rays in emission order at [17] and [36]: on, PixelInfo bits, ray (8), w (3), w_d (3), w_g (3);
+// [55..78] what the vertex added to DIFFUSE_C, DIFFUSE_A, SPECULAR_C, SPECULAR_A, DIRECT_C, COMPOSITED_C of its pixel; [79] shadow rays emitted.
+int oracle_probe_shade_vertex(const fb200_scene_view* s, uint32_t instance, uint32_t bounce, const float* in, float* out, uint32_t n)
+{
+	SceneRef sc = { s, s->vertex_indices, s->vertex_data, reinterpret_cast<const NodePOD*>(s->bvh_nodes) };
+	const fb200_pt_options& o = s->options;
+	const size_t P = (size_t)s->res_x * s->res_y;
+	std::vector<float> planes(8 * P * 4, 0.0f);
+	FB fb = { planes.data(), P };
+	Sampler smp(s, instance);
+	const float frame_weight = 1.0f / float(instance + 1);
+	const bool have_vpls = s->n_vpls > 0;
+	const bool do_nee = have_vpls && (bounce + 2 <= o.max_path_length) &&
+		((bounce == 0 && o.direct_lighting_nee && o.direct_lighting) || (bounce > 0 && o.indirect_lighting_nee));
+	const bool do_emissive = (bounce == 0 && o.visible_lights) || (bounce == 1 && o.direct_lighting_bsdf && o.direct_lighting) || (bounce > 1 && o.indirect_lighting_bsdf);
+	const uint32_t max_path_vertices = o.max_path_length + (((o.max_path_length == 2 && o.direct_lighting_bsdf) || (o.max_path_length > 2 && o.indirect_lighting_bsdf)) ? 1 : 0);
+	const bool do_scatter = bounce + 2 < max_path_vertices;
+	const int chan[6] = { DIFFUSE_C, DIFFUSE_A, SPECULAR_C, SPECULAR_A, DIRECT_C, COMPOSITED_C };
+	for (uint32_t i = 0; i < n; ++i)
+	{
+		const float* r = in + 24 * (size_t)i; float* q = out + 80 * (size_t)i;
+		memset(q, 0, 80 * sizeof(float));
+		const uint32_t info = f2u(r[0]);
+		VertexIO io;
+		io.bounce = bounce; io.px = f2u(r[1]); io.py = f2u(r[2]); io.comp = (info >> 27) & 0xFu; io.diffuse_flag = (info >> 31) != 0u;
+		io.ray.o = vec3(r[3], r[4], r[5]); io.ray.tmin = 0.0f; io.ray.mask = f2u(r[6]); io.ray.d = vec3(r[7], r[8], r[9]); io.ray.tmax = r[10];
+		io.hit.t = r[11]; io.hit.tri = (int)f2u(r[12]); io.hit.u = r[13]; io.hit.v = r[14];
+		io.w = vec3(r[15], r[16], r[17]); io.p_prev = r[18];
+		io.prev_vinfo = f2u(r[19]); io.prev_nee_slot = f2u(r[20]); io.cone_x = r[21]; io.cone_y = r[22];
+		io.do_nee = do_nee; io.do_emissive = do_emissive; io.do_scatter = do_scatter; io.want_cone = true;
+		if (!(io.hit.t > 0.0f && io.hit.tri >= 0)) continue;          // (shade_vertex returns false on a miss and touches nothing)
+		shade_vertex_restated(sc, smp, fb, frame_weight, io, NULL, instance, NULL);
+		q[0] = io.cont ? 1.0f : 0.0f;
+		const uint32_t pixel = io.px + io.py * s->res_x;
+		auto put_ray = [](float* d, const Ray& ray, uint32_t mask_bits) { d[0] = ray.o.x; d[1] = ray.o.y; d[2] = ray.o.z; d[3] = u2f(mask_bits); d[4] = ray.d.x; d[5] = ray.d.y; d[6] = ray.d.z; d[7] = ray.tmax; };
+		if (io.cont)
+		{
+			const uint32_t diffuse = (io.diffuse_flag || (io.next_comp & cDiffuseMask)) ? 1u : 0u;
+			q[1] = 1.0f; q[2] = u2f(pixel | ((io.next_comp & 0xFu) << 27) | (diffuse << 31));
+			put_ray(q + 3, io.next, f2u(io.next.tmin));                // (the scattered ray keeps its tmin in the mask word, src/pathtracer_core.h:1219)
+			q[11] = io.next_w.x; q[12] = io.next_w.y; q[13] = io.next_w.z; q[14] = io.next_p; q[15] = io.cone_radius; q[16] = fmaxf(io.next_p, 32.0f);
+		}
+		uint32_t k = 0;
+		for (int j = 0; j < 2; ++j)
+			if (io.pend[j].on)
+			{
+				float* h = q + 17 + 19 * k; const PendingShadow& ps = io.pend[j];
+				h[0] = 1.0f; h[1] = u2f(info); put_ray(h + 2, ps.r, ps.r.mask);
+				const vec3 wsum = ps.w_d + ps.w_g;
+				h[10] = wsum.x; h[11] = wsum.y; h[12] = wsum.z; h[13] = ps.w_d.x; h[14] = ps.w_d.y; h[15] = ps.w_d.z; h[16] = ps.w_g.x; h[17] = ps.w_g.y; h[18] = ps.w_g.z;
+				++k;
+			}
+		q[79] = float(k);
+		for (int c = 0; c < 6; ++c)
+		{
+			float* v = fb.px(chan[c], pixel);
+			for (int a = 0; a < 4; ++a) { q[55 + 4 * c + a] = v[a]; v[a] = 0.0f; }
+		}
+	}
+	return 0;
+}
 // camera_frame of the view -> out[0..8] = U, V, W; the primary cone pdf of n directions d[3n] -> pdf[n]
 void oracle_probe_camera(const fb200_scene_view* s, float* out, const float* d, uint32_t n, float* pdf)
 {

@@ -1,0 +1,41 @@
+#!/usr/bin/env python
+"""Golden vectors of the REFERENCE's own shade_vertex (src/pathtracer_core.h:752-1254) compiled for this host (oracle/build_ref.sh ->
+oracle/_ref/libref_shade.so): for the two scene fixtures that travel with the repository (tests/golden/cornellbox_jp.fbs with the VPL sampler,
+cornellbox_dirlight.fbs with the mesh sampler and two directional lights) and bounces 0..3, a SHA-256 and strided samples of the 80 floats the
+vertex produces per record (scattered ray, shadow rays, frame-buffer deltas). The records themselves are regenerated from a seed
+(oracle.vertex_records). Writes tests/golden/shade_vertex_golden.npz; tests/test_shade_vertex_pinning.py checks the oracle against it everywhere and
+against the live reference code where oracle/_ref exists. Needs /root/reference at build time only."""
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import fermat_b200 as fb
+    import oracle
+    from test_shade_vertex_pinning import GOLDEN_CASES, INSTANCE, N_RECORDS
+    R = oracle.RefShade.load()
+    if R is None:
+        raise SystemExit("oracle/_ref/libref_shade.so missing: run oracle/build_ref.sh where /root/reference exists")
+    out = {}
+    for name, args in GOLDEN_CASES.items():
+        sc = fb.Scene(args)
+        for bounce in range(4):
+            rec = oracle.vertex_records(sc.view, N_RECORDS, 1000 + bounce, bounce)
+            ref = R.shade_vertex(sc.view, INSTANCE, bounce, rec)
+            out["%s_b%d_sha" % (name, bounce)] = np.frombuffer(hashlib.sha256(ref.tobytes()).digest(), np.uint8)
+            out["%s_b%d_stride" % (name, bounce)] = ref.reshape(-1)[::53].copy()
+            out["%s_b%d_n" % (name, bounce)] = np.array([len(rec), int(ref[:, 0].sum()), int(ref[:, 79].sum())])
+        sc.close()
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "shade_vertex_golden.npz"), **out)
+    print("wrote shade_vertex_golden.npz:", {k: v.tolist() for k, v in out.items() if k.endswith("_n")})
+
+
+if __name__ == "__main__":
+    main()
