@@ -577,6 +577,31 @@ class RlState:
         assert rc == 0
         return st
 
+    def cell(self, slot):
+        """(count, nodes, ends, pdfs, cdfs) of one cell"""
+        L = lib()
+        L.oracle_rl_cell.restype = C.c_int
+        L.oracle_rl_cell.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        Cn = self.sizes()["clusters"]
+        count = np.zeros(1, np.uint32); nodes = np.zeros(Cn, np.uint32); ends = np.zeros(Cn, np.uint32); pdfs = np.zeros(Cn, np.float32); cdfs = np.zeros(Cn, np.float32)
+        if L.oracle_rl_cell(self._h, int(slot), count.ctypes.data, nodes.ctypes.data, ends.ctypes.data, pdfs.ctypes.data, cdfs.ctypes.data) != 0:
+            raise IndexError(slot)
+        return int(count[0]), nodes, ends, pdfs, cdfs
+
+    def update_cells(self):
+        """AdaptiveClusteredRLStorage::update on every cell (split / collapse + CDF)"""
+        lib().oracle_rl_update_cells.argtypes = [C.c_void_p]
+        lib().oracle_rl_update_cells(self._h)
+
+    def probe_shade_vertex(self, instance, bounce, records, occluded):
+        """shade_vertex_restated with this sampler on (n, 24) records: ((n, 80) outputs, (n, 6) cell / cluster words)"""
+        L = lib()
+        L.oracle_probe_shade_vertex_rl.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+        rec = np.ascontiguousarray(records, np.float32).reshape(-1, 24); occ = np.ascontiguousarray(occluded, np.uint8)
+        out = np.zeros((len(rec), 80), np.float32); words = np.zeros((len(rec), 6), np.uint32)
+        L.oracle_probe_shade_vertex_rl(C.addressof(self.view), self._h, int(instance), int(bounce), rec.ctypes.data, out.ctypes.data, words.ctypes.data, occ.ctypes.data, len(rec))
+        return out, words
+
     def render_pass(self, instance, fb, threads=0):
         """PathTracer::render with the RL sampler: update_vtls_rl, then one progressive pass into `fb` (in place), whole frame"""
         st = OracleStats()
@@ -666,6 +691,65 @@ class RefShade:
     def __init__(self, L, pt):
         self.L, self.pt = L, pt
         L.ref_shade_vertex.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+
+    def _frame(self, view, instance, bounce):
+        f = _RefFrame()
+        for i in range(3):
+            f.cam[i], f.cam[3 + i], f.cam[6 + i] = view.eye[i], view.aim[i], view.up[i]
+        f.cam[9] = view.fov
+        f.res_x, f.res_y, f.aspect = view.res_x, view.res_y, view.aspect
+        f.n_dir_lights = view.n_dir_lights; f.dir_lights = C.cast(view.dir_lights, C.c_void_p)
+        f.glossy_reflectance = C.cast(view.glossy_reflectance, C.c_void_p)
+        f.n_dims, f.tile, f.shifts = view.n_dimensions, view.tile_size, C.cast(view.shifts, C.c_void_p)
+        o = view.options
+        for k, name in enumerate(("max_path_length", "direct_lighting", "direct_lighting_nee", "direct_lighting_bsdf", "indirect_lighting_nee", "indirect_lighting_bsdf",
+                                  "visible_lights", "diffuse_scattering", "glossy_scattering", "indirect_glossy", "rr", "nee_type")):
+            f.options[k] = int(getattr(o, name))
+        f.instance, f.bounce = int(instance), int(bounce)
+        return f
+
+    def rl_create(self, vtls, hash_size, init_ends, init_cdf):
+        """the reference's VTLMeshView (UV-BVH built by src/uv_bvh.cu) + an AdaptiveClusteredRLView over host arrays, every cell in its initial state"""
+        L = self.L
+        L.ref_rl_create.restype = C.c_void_p
+        L.ref_rl_create.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.ref_rl_destroy.argtypes = [C.c_void_p]; L.ref_rl_cells.restype = C.c_uint32; L.ref_rl_cells.argtypes = [C.c_void_p]
+        L.ref_rl_set_cell.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_rl_get_pdfs.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        L.ref_rl_locate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+        L.ref_shade_vertex_rl.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+        vtls = np.ascontiguousarray(vtls); init_ends = np.ascontiguousarray(init_ends, np.uint32); init_cdf = np.ascontiguousarray(init_cdf, np.float32)
+        return L.ref_rl_create(vtls.ctypes.data, len(vtls), int(hash_size), len(init_ends), init_ends.ctypes.data, init_cdf.ctypes.data)
+
+    def rl_destroy(self, h):
+        self.L.ref_rl_destroy(h)
+
+    def rl_cells(self, h):
+        return int(self.L.ref_rl_cells(h))
+
+    def rl_set_cell(self, h, slot, count, ends, pdfs, cdfs):
+        ends = np.ascontiguousarray(ends, np.uint32); pdfs = np.ascontiguousarray(pdfs, np.float32); cdfs = np.ascontiguousarray(cdfs, np.float32)
+        self.L.ref_rl_set_cell(h, int(slot), int(count), ends.ctypes.data, pdfs.ctypes.data, cdfs.ctypes.data)
+
+    def rl_pdfs(self, h, slot, n_clusters):
+        out = np.zeros(n_clusters, np.float32)
+        self.L.ref_rl_get_pdfs(h, int(slot), out.ctypes.data)
+        return out
+
+    def rl_locate(self, h, prims, uv):
+        prims = np.ascontiguousarray(prims, np.uint32); uv = np.ascontiguousarray(uv, np.float32)
+        out = np.zeros(len(prims), np.uint32)
+        self.L.ref_rl_locate(h, prims.ctypes.data, uv.ctypes.data, len(prims), out.ctypes.data)
+        return out
+
+    def shade_vertex_rl(self, view, h, instance, bounce, records, occluded):
+        s = self.pt._scene(view)
+        f = self._frame(view, instance, bounce)
+        bbox = np.array(list(view.bbox_min[:]) + list(view.bbox_max[:]), np.float32)
+        rec = np.ascontiguousarray(records, np.float32).reshape(-1, 24); occ = np.ascontiguousarray(occluded, np.uint8)
+        out = np.zeros((len(rec), 80), np.float32); words = np.zeros((len(rec), 6), np.uint32)
+        self.L.ref_shade_vertex_rl(C.byref(s), C.byref(f), h, bbox.ctypes.data, rec.ctypes.data, out.ctypes.data, words.ctypes.data, occ.ctypes.data, len(rec))
+        return out, words
 
     def shade_vertex(self, view, instance, bounce, records):
         s = self.pt._scene(view)

@@ -1292,7 +1292,35 @@ float oracle_probe_power_heuristic(float p1, float p2) { return power_heuristic(
 // prev_vertex_info bits, prev_nee bits, cone xy, 0}. out: 80 floats per vertex: [0] path continues; scattered ray [1] on, [2] PixelInfo bits, [3..10] origin,
 // mask bits, dir, tmax, [11..14] weight + pdf, [15..16] cone; shadow rays in emission order at [17] and [36]: on, PixelInfo bits, ray (8), w (3), w_d (3), w_g (3);
 // [55..78] what the vertex added to DIFFUSE_C, DIFFUSE_A, SPECULAR_C, SPECULAR_A, DIRECT_C, COMPOSITED_C of its pixel; [79] shadow rays emitted.
+static int probe_shade_vertex_impl(const fb200_scene_view* s, uint32_t instance, uint32_t bounce, const float* in, float* out, uint32_t n, RlState* rl, uint32_t* rl_out, const uint8_t* occluded);
 int oracle_probe_shade_vertex(const fb200_scene_view* s, uint32_t instance, uint32_t bounce, const float* in, float* out, uint32_t n)
+{
+	return probe_shade_vertex_impl(s, instance, bounce, in, out, n, NULL, NULL, NULL);
+}
+// the same with the RL light sampler (state: oracle_rl_create): rl_out = 6 words per vertex {cell carried by the scattered ray, [cell, cluster] of the shadow rays
+// in emission order, 0xFFFFFFFF where none}; occluded = one byte per vertex, what DirectLightingRL::update is told about the vertex's next-event ray
+int oracle_probe_shade_vertex_rl(const fb200_scene_view* s, void* state, uint32_t instance, uint32_t bounce, const float* in, float* out, uint32_t* rl_out, const uint8_t* occluded, uint32_t n)
+{
+	return probe_shade_vertex_impl(s, instance, bounce, in, out, n, static_cast<RlState*>(state), rl_out, occluded);
+}
+// one cell of the sampler: count, then nodes / ends / pdfs / cdfs (C entries each); returns 0, -1 if there is no such cell
+int oracle_rl_cell(const void* state, uint32_t slot, uint32_t* count, uint32_t* nodes, uint32_t* ends, float* pdfs, float* cdfs)
+{
+	const RlState* st = static_cast<const RlState*>(state);
+	if (slot >= st->cells.size()) return -1;
+	const RlCell& c = st->cells[slot];
+	*count = c.count;
+	std::copy(c.nodes.begin(), c.nodes.end(), nodes); std::copy(c.ends.begin(), c.ends.end(), ends);
+	std::copy(c.pdfs.begin(), c.pdfs.end(), pdfs); std::copy(c.cdfs.begin(), c.cdfs.end(), cdfs);
+	return 0;
+}
+// AdaptiveClusteredRLStorage::update on the state's cells (what oracle_render_pass_rl does before a pass that does not clear)
+void oracle_rl_update_cells(void* state)
+{
+	RlState* st = static_cast<RlState*>(state);
+	for (size_t k = 0; k < st->cells.size(); ++k) { rl_split_and_collapse(*st, st->cells[k]); rl_update_cdf(st->cells[k]); }
+}
+static int probe_shade_vertex_impl(const fb200_scene_view* s, uint32_t instance, uint32_t bounce, const float* in, float* out, uint32_t n, RlState* rl, uint32_t* rl_out, const uint8_t* occluded)
 {
 	SceneRef sc = { s, s->vertex_indices, s->vertex_data, reinterpret_cast<const NodePOD*>(s->bvh_nodes) };
 	const fb200_pt_options& o = s->options;
@@ -1320,8 +1348,9 @@ int oracle_probe_shade_vertex(const fb200_scene_view* s, uint32_t instance, uint
 		io.w = vec3(r[15], r[16], r[17]); io.p_prev = r[18];
 		io.prev_vinfo = f2u(r[19]); io.prev_nee_slot = f2u(r[20]); io.cone_x = r[21]; io.cone_y = r[22];
 		io.do_nee = do_nee; io.do_emissive = do_emissive; io.do_scatter = do_scatter; io.want_cone = true;
+		if (rl_out) for (int k = 0; k < 6; ++k) rl_out[6 * (size_t)i + k] = 0xFFFFFFFFu;
 		if (!(io.hit.t > 0.0f && io.hit.tri >= 0)) continue;          // (shade_vertex returns false on a miss and touches nothing)
-		shade_vertex_restated(sc, smp, fb, frame_weight, io, NULL, instance, NULL);
+		shade_vertex_restated(sc, smp, fb, frame_weight, io, NULL, instance, rl);
 		q[0] = io.cont ? 1.0f : 0.0f;
 		const uint32_t pixel = io.px + io.py * s->res_x;
 		auto put_ray = [](float* d, const Ray& ray, uint32_t mask_bits) { d[0] = ray.o.x; d[1] = ray.o.y; d[2] = ray.o.z; d[3] = u2f(mask_bits); d[4] = ray.d.x; d[5] = ray.d.y; d[6] = ray.d.z; d[7] = ray.tmax; };
@@ -1330,6 +1359,7 @@ int oracle_probe_shade_vertex(const fb200_scene_view* s, uint32_t instance, uint
 			const uint32_t diffuse = (io.diffuse_flag || (io.next_comp & cDiffuseMask)) ? 1u : 0u;
 			q[1] = 1.0f; q[2] = u2f(pixel | ((io.next_comp & 0xFu) << 27) | (diffuse << 31));
 			put_ray(q + 3, io.next, f2u(io.next.tmin));                // (the scattered ray keeps its tmin in the mask word, src/pathtracer_core.h:1219)
+			if (rl_out) rl_out[6 * (size_t)i] = io.nee_slot;
 			q[11] = io.next_w.x; q[12] = io.next_w.y; q[13] = io.next_w.z; q[14] = io.next_p; q[15] = io.cone_radius; q[16] = fmaxf(io.next_p, 32.0f);
 		}
 		uint32_t k = 0;
@@ -1340,6 +1370,11 @@ int oracle_probe_shade_vertex(const fb200_scene_view* s, uint32_t instance, uint
 				h[0] = 1.0f; h[1] = u2f(info); put_ray(h + 2, ps.r, ps.r.mask);
 				const vec3 wsum = ps.w_d + ps.w_g;
 				h[10] = wsum.x; h[11] = wsum.y; h[12] = wsum.z; h[13] = ps.w_d.x; h[14] = ps.w_d.y; h[15] = ps.w_d.z; h[16] = ps.w_g.x; h[17] = ps.w_g.y; h[18] = ps.w_g.z;
+				if (rl && j == 1)
+				{
+					rl_out[6 * (size_t)i + 1 + 2 * k] = io.nee_slot; rl_out[6 * (size_t)i + 2 + 2 * k] = io.nee_cluster;
+					if (io.nee_cluster != RL_INVALID) rl_update(*rl, io.nee_slot, io.nee_cluster, occluded[i] ? 0.0f : max_comp(wsum));
+				}
 				++k;
 			}
 		q[79] = float(k);

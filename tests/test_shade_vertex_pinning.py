@@ -80,3 +80,91 @@ def test_shade_vertex_is_the_references_own(fb, oracle, libm_trig, name):
         total += len(rec)
     assert total > 1000
     sc.close()
+
+
+# ---- the same with the reference's own DirectLightingRL (`-nee-alg rl`)
+RL_ARGS = ["-i", os.path.join(GOLDEN, "cornellbox_jp.fbs"), "-r", "48", "48", "-bounces", "4", "-nee-alg", "rl"]
+RL_ROUNDS = (0, 1, 2, 1)         # bounce of each round; between rounds every cell takes one split / collapse step and gets a new CDF
+
+
+def rl_rounds(oracle, sc, st, step):
+    """drive `step(round, bounce, records, occluded) -> (outputs, words)` through RL_ROUNDS on seeded vertices, updating the restatement's cells in between"""
+    rng = np.random.default_rng(3)
+    results = []
+    for rnd, bounce in enumerate(RL_ROUNDS):
+        rec = oracle.vertex_records(sc.view, 3000, 40 + rnd, bounce)
+        if bounce:                                                       # a cell of the previous vertex, for DirectLightingRL::map
+            rec[:, 20] = rng.integers(0, max(st.sizes()["cells"], 1), len(rec)).astype(np.uint32).view(np.float32)
+        occ = (rng.random(len(rec)) < 0.4).astype(np.uint8)
+        results.append(step(rnd, bounce, rec, occ))
+        st.update_cells()
+    return results
+
+
+def test_rl_vertex_against_golden_vectors_of_the_references_own(fb, oracle, libm_trig):
+    g = np.load(os.path.join(GOLDEN, "shade_vertex_golden.npz"))
+    sc = fb.Scene(RL_ARGS)
+    st = oracle.RlState(sc.view, 48 * 48)
+    res = rl_rounds(oracle, sc, st, lambda rnd, bounce, rec, occ: st.probe_shade_vertex(rnd, bounce, rec, occ))
+    for rnd, (out, words) in enumerate(res):
+        assert np.array_equal(np.frombuffer(hashlib.sha256(out.tobytes() + words.tobytes()).digest(), np.uint8), g["rl_round%d_sha" % rnd]), rnd
+        assert np.array_equal(out.reshape(-1)[::53].view(np.uint32), g["rl_round%d_stride" % rnd].view(np.uint32)), rnd
+    assert st.sizes()["cells"] == int(g["rl_cells"])
+    sc.close()
+
+
+def test_rl_vertex_is_the_references_own(fb, oracle, libm_trig):
+    """DirectLightingRL (src/direct_lighting_rl.h) over AdaptiveClusteredRLView (src/clustered_rl_inline.h: find_slot, sample, pdf, update), VTLMeshView
+    (src/vtl_mesh_view.h: sample, map) and the VTL UV-BVH built and searched by the reference's own code (src/uv_bvh.cu, uv_bvh_view.h), inside the
+    reference's own shade_vertex on the host - against oracle_rl.h inside shade_vertex_restated, over four rounds of vertices with the cells' cuts and
+    CDFs updated in between (by the restatement: the reference's update is a pair of CUDA kernels; its result is copied into the reference's arrays):
+    vertex outputs, cell and cluster of every light sample, the number of cells and every learned value bit for bit; point location identical."""
+    R = oracle.RefShade.load()
+    if R is None:
+        pytest.skip("oracle/_ref/libref_shade.so is built where /root/reference exists")
+    sc = fb.Scene(RL_ARGS)
+    st = oracle.RlState(sc.view, 48 * 48)
+    a = st.arrays()
+    C = len(a["clusters"])
+    fresh = oracle.RlState(sc.view, 48 * 48)
+    r0 = oracle.vertex_records(sc.view, 50, 1, 0)
+    fresh.probe_shade_vertex(0, 0, r0, np.zeros(len(r0), np.uint8))
+    h = R.rl_create(a["vtls"], 1 << 16, a["cluster_offsets"][1:], fresh.cell(0)[4])
+
+    def step(rnd, bounce, rec, occ):
+        o1, w1 = st.probe_shade_vertex(rnd, bounce, rec, occ)
+        o2, w2 = R.shade_vertex_rl(sc.view, h, rnd, bounce, rec, occ)
+        assert np.array_equal(o1.view(np.uint32), o2.view(np.uint32)), rnd
+        assert np.array_equal(w1, w2), rnd
+        n_cells = st.sizes()["cells"]
+        assert n_cells == R.rl_cells(h)
+        for s in range(n_cells):
+            assert np.array_equal(st.cell(s)[3].view(np.uint32), R.rl_pdfs(h, s, C).view(np.uint32)), (rnd, s)
+        return o1, w1
+
+    def step_and_sync(rnd, bounce, rec, occ):
+        r = step(rnd, bounce, rec, occ)
+        return r
+
+    rng = np.random.default_rng(3)
+    for rnd, bounce in enumerate(RL_ROUNDS):
+        rec = oracle.vertex_records(sc.view, 3000, 40 + rnd, bounce)
+        if bounce:
+            rec[:, 20] = rng.integers(0, max(st.sizes()["cells"], 1), len(rec)).astype(np.uint32).view(np.float32)
+        occ = (rng.random(len(rec)) < 0.4).astype(np.uint8)
+        o, w = step_and_sync(rnd, bounce, rec, occ)
+        assert (w[:, 2] != 0xFFFFFFFF).sum() > 100                     # light samples were drawn through cells
+        st.update_cells()
+        for s in range(st.sizes()["cells"]):
+            cnt, nodes, ends, pdfs, cdfs = st.cell(s)
+            R.rl_set_cell(h, s, cnt, ends, pdfs, cdfs)
+    assert st.sizes()["cells"] > 1000
+    em = np.unique(a["vtls"]["prim_id"])
+    n = 20000
+    prim = rng.choice(em, n).astype(np.uint32)
+    uv = rng.random((n, 2)).astype(np.float32)
+    flip = uv.sum(axis=1) > 1
+    uv[flip] = 1 - uv[flip]
+    assert np.array_equal(st.locate(prim, uv), R.rl_locate(h, prim, uv))
+    R.rl_destroy(h)
+    sc.close()
