@@ -96,6 +96,25 @@ class PsfState:
     __del__ = close
 
 
+def probe_shade_vertex_psf(view, state, instance, bounce, records, occluded):
+    """shade_vertex_restated with the filtered renderer's vertex processor on (n, 24) records: ((n, 80) outputs, (n, 4) words, (n, 8) reference weights)"""
+    L = lib()
+    L.oracle_probe_shade_vertex_psf.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+    rec = np.ascontiguousarray(records, np.float32).reshape(-1, 24); occ = np.ascontiguousarray(occluded, np.uint8)
+    out = np.zeros((len(rec), 80), np.float32); words = np.zeros((len(rec), 4), np.uint32); ref_w = np.zeros((len(rec), 8), np.float32)
+    L.oracle_probe_shade_vertex_psf(C.addressof(view), state._h, int(instance), int(bounce), rec.ctypes.data, out.ctypes.data, words.ctypes.data, ref_w.ctypes.data, occ.ctypes.data, len(rec))
+    return out, words, ref_w
+
+
+def psf_values(state, n):
+    """the first n cells of the filter cache: (n, 4) = rgb sum, sample count"""
+    L = lib()
+    L.oracle_psf_values.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    out = np.zeros((n, 4), np.float32)
+    L.oracle_psf_values(state._h, out.ctypes.data, int(n))
+    return out
+
+
 def render_pass_psf(view, instance, fb, state, threads=0):
     """One progressive pass of the path-space filtering path tracer (PSFPT::render) into `fb` (in place), whole frame."""
     st = OracleStats()
@@ -750,6 +769,36 @@ class RefShade:
         out = np.zeros((len(rec), 80), np.float32); words = np.zeros((len(rec), 6), np.uint32)
         self.L.ref_shade_vertex_rl(C.byref(s), C.byref(f), h, bbox.ctypes.data, rec.ctypes.data, out.ctypes.data, words.ctypes.data, occ.ctypes.data, len(rec))
         return out, words
+
+    def psf_create(self, hash_size=1 << 16):
+        L = self.L
+        L.ref_psf_create.restype = C.c_void_p; L.ref_psf_create.argtypes = [C.c_uint32]
+        L.ref_psf_destroy.argtypes = [C.c_void_p]; L.ref_psf_cells.restype = C.c_uint32; L.ref_psf_cells.argtypes = [C.c_void_p]
+        L.ref_psf_values.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        L.ref_shade_vertex_psf.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+        return L.ref_psf_create(int(hash_size))
+
+    def psf_destroy(self, h):
+        self.L.ref_psf_destroy(h)
+
+    def psf_cells(self, h):
+        return int(self.L.ref_psf_cells(h))
+
+    def psf_values(self, h, n):
+        out = np.zeros((n, 4), np.float32)
+        self.L.ref_psf_values(h, out.ctypes.data, int(n))
+        return out
+
+    def shade_vertex_psf(self, view, h, instance, bounce, records, occluded):
+        s = self.pt._scene(view)
+        f = self._frame(view, instance, bounce)
+        bbox = np.array(list(view.bbox_min[:]) + list(view.bbox_max[:]), np.float32)
+        p = view.psf
+        opts = np.array([p.psf_depth, p.psf_width, p.psf_max_prob, p.firefly_filter], np.float32)
+        rec = np.ascontiguousarray(records, np.float32).reshape(-1, 24); occ = np.ascontiguousarray(occluded, np.uint8)
+        out = np.zeros((len(rec), 80), np.float32); words = np.zeros((len(rec), 4), np.uint32); ref_w = np.zeros((len(rec), 8), np.float32)
+        self.L.ref_shade_vertex_psf(C.byref(s), C.byref(f), h, bbox.ctypes.data, opts.ctypes.data, rec.ctypes.data, out.ctypes.data, words.ctypes.data, ref_w.ctypes.data, occ.ctypes.data, len(rec))
+        return out, words, ref_w
 
     def shade_vertex(self, view, instance, bounce, records):
         s = self.pt._scene(view)

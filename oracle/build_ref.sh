@@ -1056,6 +1056,162 @@ extern "C" int ref_shade_vertex_rl(const RefScene* s, const RefFrame* f, void* r
 	}
 	return 0;
 }
+// ---- the same vertex with the reference's own PSFPTVertexProcessor (src/psfpt_vertex_processor.h: preprocess_vertex with the jittered spatial hash and the
+// cache insertion, compute_nee_weights, compute_scattering_weights, accumulate_emissive, accumulate_nee) behind a PSFPT context whose hash map and cell
+// values are host arrays and whose reference queue records what is appended
+#include <psfpt.h>
+#include <psfpt_vertex_processor.h>
+struct RefPsfRec { uint32 pixel, cache; float4 w_d, w_g; };
+struct RefPsfQueue
+{
+	std::vector<RefPsfRec>* recs;
+	void warp_append(const PixelInfo pixel, const PSFPTVertexProcessor::CacheInfo cache_slot, const float4 weight_d, const float4 weight_g)
+	{
+		RefPsfRec r; r.pixel = pixel.packed; r.cache = cache_slot.packed; r.w_d = weight_d; r.w_g = weight_g;
+		recs->push_back(r);
+	}
+};
+struct RefPsf
+{
+	uint32 hash_size;
+	std::vector<uint64> keys, unique; std::vector<uint32> slots; uint32 count;
+	std::vector<float4> values;
+	std::vector<RefPsfRec> refs;
+};
+extern "C" void* ref_psf_create(unsigned hash_size)
+{
+	RefPsf* r = new RefPsf();
+	r->hash_size = hash_size;
+	r->keys.assign(hash_size, 0xFFFFFFFFFFFFFFFFllu); r->unique.assign(hash_size, 0); r->slots.assign(hash_size, 0xFFFFFFFFu); r->count = 0;
+	r->values.assign(hash_size, make_float4(0, 0, 0, 0));
+	return r;
+}
+extern "C" void ref_psf_destroy(void* h) { delete static_cast<RefPsf*>(h); }
+extern "C" unsigned ref_psf_cells(void* h) { return static_cast<RefPsf*>(h)->count; }
+extern "C" void ref_psf_values(void* h, float* out, unsigned n) { memcpy(out, static_cast<RefPsf*>(h)->values.data(), (size_t)n * 16); }
+struct CaptureContextPSF : PTContextBase<PSFPTOptions>
+{
+	typedef cugar::cuda::SyncFreeHashMap<uint64, uint32, 0xFFFFFFFFFFFFFFFFllu> HashMap;
+	RefPsfQueue ref_queue;
+	HashMap psf_hashmap;
+	float4* psf_values;
+	DirectLightingMesh dl;
+	bool scatter_on; PixelInfo sc_pixel; MaskedRay sc_ray; cugar::Vector4f sc_w; cugar::Vector2f sc_cone; uint32 sc_vinfo, sc_nee;
+	std::vector<ShadowRec> shadows;
+	template <typename VP>
+	void trace_ray(VP&, RenderingContextView&, const PixelInfo pixel, const MaskedRay ray, const cugar::Vector4f weight,
+				   const cugar::Vector2f cone = cugar::Vector2f(0), const uint32 vertex_info = uint32(-1), const uint32 nee_slot = uint32(-1))
+	{
+		scatter_on = true; sc_pixel = pixel; sc_ray = ray; sc_w = weight; sc_cone = cone; sc_vinfo = vertex_info; sc_nee = nee_slot;
+	}
+	template <typename VP>
+	void trace_shadow_ray(VP&, RenderingContextView&, const PixelInfo pixel, const MaskedRay ray, const cugar::Vector3f weight, const cugar::Vector3f weight_d,
+						  const cugar::Vector3f weight_g, const uint32 vertex_info = uint32(-1), const uint32 nee_slot = uint32(-1), const uint32 nee_sample = uint32(-1))
+	{
+		ShadowRec r; r.pixel = pixel; r.ray = ray; r.w = weight; r.w_d = weight_d; r.w_g = weight_g; r.vinfo = vertex_info; r.nee_slot = nee_slot; r.nee_sample = nee_sample;
+		shadows.push_back(r);
+	}
+};
+// as ref_shade_vertex; psf_opts = psf_depth, psf_width, psf_max_prob, firefly_filter; words = 4 per vertex {vertex_info of the scattered ray, of the shadow ray,
+// cache word of the reference appended (0xFFFFFFFF: none), 0}; ref_w = 8 floats per vertex (the reference's two weights); occluded: one byte per vertex - an
+// unoccluded next-event ray goes through PSFPTVertexProcessor::accumulate_nee (solve_occlusion, src/pathtracer_core.h:705-738) before the pixel is read back
+extern "C" int ref_shade_vertex_psf(const RefScene* s, const RefFrame* f, void* psf_handle, const float* bbox, const float* psf_opts, const float* in, float* out,
+									unsigned* words, float* ref_w, const unsigned char* occluded, unsigned n)
+{
+	RefPsf* psf = static_cast<RefPsf*>(psf_handle);
+	std::vector<TextureView> levels(s->num_textures ? s->num_textures : 1); std::vector<MipMapView> maps(s->num_textures ? s->num_textures : 1);
+	for (int t = 0; t < s->num_textures; ++t)
+	{
+		levels[t].c = reinterpret_cast<float4*>(s->texels[t]); levels[t].res_x = s->tex_res[2 * t]; levels[t].res_y = s->tex_res[2 * t + 1];
+		maps[t].levels = &levels[t]; maps[t].n_levels = s->texels[t] ? 1u : 0u; maps[t].res_x = levels[t].res_x; maps[t].res_y = levels[t].res_y;
+	}
+	const MeshView mesh = mesh_view(*s);
+	const MeshLight mesh_light(s->n_prims, s->mesh_cdf, s->mesh_inv_area, mesh, maps.data(), 0u, NULL, s->vpls, s->vpl_norm);
+	const MeshLight mesh_vpls(s->n_prims, s->mesh_cdf, s->mesh_inv_area, mesh, maps.data(), s->n_vpls, NULL, s->vpls, s->vpl_norm);
+	std::vector<DirectionalLight> dls(1);
+	Camera cam;
+	cam.eye = make_float3(f->cam[0], f->cam[1], f->cam[2]); cam.aim = make_float3(f->cam[3], f->cam[4], f->cam[5]); cam.up = make_float3(f->cam[6], f->cam[7], f->cam[8]); cam.fov = f->cam[9];
+	const size_t P = (size_t)f->res_x * f->res_y;
+	std::vector<float4> planes(P * FBufferDesc::NUM_CHANNELS, make_float4(0, 0, 0, 0));
+	std::vector<FBufferChannelView> channels(FBufferDesc::NUM_CHANNELS);
+	for (unsigned c = 0; c < (unsigned)FBufferDesc::NUM_CHANNELS; ++c) { channels[c].c_ptr = planes.data() + c * P; channels[c].res_x = f->res_x; channels[c].res_y = f->res_y; }
+	std::vector<float4> gb_geo(P), gb_uv(P); std::vector<uint32> gb_tri(P); std::vector<float> gb_depth(P);
+	FBufferView fbv; memset(&fbv, 0, sizeof(fbv));
+	fbv.channels = channels.data(); fbv.n_channels = FBufferDesc::NUM_CHANNELS;
+	fbv.gbuffer.m_geo = gb_geo.data(); fbv.gbuffer.m_uv = gb_uv.data(); fbv.gbuffer.m_tri = gb_tri.data(); fbv.gbuffer.m_depth = gb_depth.data();
+	fbv.gbuffer.res_x = f->res_x; fbv.gbuffer.res_y = f->res_y;
+	RenderingContextView renderer(cam, 0u, dls.data(), mesh, mesh_light, mesh_vpls, maps.data(), 0u, NULL, NULL, NULL, f->glossy_reflectance,
+								  f->res_x, f->res_y, f->aspect, 1.0f, 2.2f, 1.0f, kShaded, fbv, f->instance);
+	const size_t S = (size_t)f->tile * f->tile;
+	std::vector<float> samples((size_t)f->n_dims * S);
+	for (unsigned d = 0; d < f->n_dims; ++d)
+	{
+		const float seq = cugar::randfloat(d, f->instance + 1);
+		for (size_t i = 0; i < S; ++i) samples[d * S + i] = fmodf(seq + f->shifts[d * S + i], 1.0f);
+	}
+	CaptureContextPSF context;
+	PSFPTOptions& o = context.options;
+	o.max_path_length = f->options[0]; o.direct_lighting = f->options[1]; o.direct_lighting_nee = f->options[2]; o.direct_lighting_bsdf = f->options[3];
+	o.indirect_lighting_nee = f->options[4]; o.indirect_lighting_bsdf = f->options[5]; o.visible_lights = f->options[6]; o.diffuse_scattering = f->options[7];
+	o.glossy_scattering = f->options[8]; o.indirect_glossy = f->options[9]; o.rr = f->options[10]; o.nee_type = f->options[11];
+	o.psf_depth = (uint32)psf_opts[0]; o.psf_width = psf_opts[1]; o.psf_max_prob = psf_opts[2]; o.firefly_filter = psf_opts[3];
+	context.sequence.n_dimensions = f->n_dims; context.sequence.tile_size = f->tile; context.sequence.samples = samples.data(); context.sequence.shifts = f->shifts;
+	context.frame_weight = 1.0f / float(f->instance + 1);
+	context.in_bounce = f->bounce;
+	context.bbox = cugar::Bbox3f(cugar::Vector3f(bbox[0], bbox[1], bbox[2]), cugar::Vector3f(bbox[3], bbox[4], bbox[5]));
+	context.device_timers = NULL;
+	context.dl = DirectLightingMesh(f->options[11] == NEE_ALGORITHM_VPL && s->n_vpls ? mesh_vpls : mesh_light);
+	context.psf_hashmap = CaptureContextPSF::HashMap(psf->hash_size, psf->keys.data(), psf->unique.data(), psf->slots.data(), &psf->count);
+	context.psf_values = psf->values.data();
+	context.ref_queue.recs = &psf->refs;
+	compute_per_bounce_options(context, renderer);
+	PSFPTVertexProcessor vertex_processor(psf_opts[3]);
+	const int fb_channels[6] = { FBufferDesc::DIFFUSE_C, FBufferDesc::DIFFUSE_A, FBufferDesc::SPECULAR_C, FBufferDesc::SPECULAR_A, FBufferDesc::DIRECT_C, FBufferDesc::COMPOSITED_C };
+	for (unsigned i = 0; i < n; ++i)
+	{
+		const float* r = in + 24 * (size_t)i; float* q = out + 80 * (size_t)i; unsigned* w = words + 4 * (size_t)i; float* rw = ref_w + 8 * (size_t)i;
+		memset(q, 0, 80 * sizeof(float)); memset(rw, 0, 8 * sizeof(float));
+		w[0] = w[1] = w[2] = 0xFFFFFFFFu; w[3] = 0u;
+		const PixelInfo pixel_info(ubits(r[0]));
+		const uint2 pixel = make_uint2(ubits(r[1]), ubits(r[2]));
+		MaskedRay ray; ray.origin = make_float3(r[3], r[4], r[5]); ray.mask = ubits(r[6]); ray.dir = make_float3(r[7], r[8], r[9]); ray.tmax = r[10];
+		Hit hit; hit.t = r[11]; hit.triId = (int)ubits(r[12]); hit.u = r[13]; hit.v = r[14];
+		context.scatter_on = false; context.shadows.clear();
+		const size_t refs_before = psf->refs.size();
+		const bool cont = shade_vertex(context, vertex_processor, renderer, f->bounce, pixel_info, pixel, ray, hit, cugar::Vector4f(r[15], r[16], r[17], r[18]),
+									   ubits(r[19]), ubits(r[20]), cugar::Vector2f(r[21], r[22]));
+		q[0] = cont ? 1.0f : 0.0f;
+		if (context.scatter_on)
+		{
+			q[1] = 1.0f; q[2] = bits(uint32(context.sc_pixel)); put_ray(q + 3, context.sc_ray);
+			q[11] = context.sc_w.x; q[12] = context.sc_w.y; q[13] = context.sc_w.z; q[14] = context.sc_w.w; q[15] = context.sc_cone.x; q[16] = context.sc_cone.y;
+			w[0] = context.sc_vinfo;
+		}
+		for (size_t k = 0; k < context.shadows.size() && k < 2; ++k)
+		{
+			float* h = q + 17 + 19 * k; const ShadowRec& sr = context.shadows[k];
+			h[0] = 1.0f; h[1] = bits(uint32(sr.pixel)); put_ray(h + 2, sr.ray);
+			h[10] = sr.w.x; h[11] = sr.w.y; h[12] = sr.w.z; h[13] = sr.w_d.x; h[14] = sr.w_d.y; h[15] = sr.w_d.z; h[16] = sr.w_g.x; h[17] = sr.w_g.y; h[18] = sr.w_g.z;
+			w[1] = sr.vinfo;
+			solve_occlusion(context, vertex_processor, renderer, occluded[i] != 0, sr.pixel, sr.w, sr.w_d, sr.w_g, sr.vinfo, sr.nee_slot, sr.nee_sample);
+		}
+		if (psf->refs.size() > refs_before)
+		{
+			const RefPsfRec& rr = psf->refs.back();
+			w[2] = rr.cache;
+			rw[0] = rr.w_d.x; rw[1] = rr.w_d.y; rw[2] = rr.w_d.z; rw[3] = rr.w_d.w; rw[4] = rr.w_g.x; rw[5] = rr.w_g.y; rw[6] = rr.w_g.z; rw[7] = rr.w_g.w;
+		}
+		const uint32 p = pixel_info.pixel;
+		for (int c = 0; c < 6; ++c)
+		{
+			float4& v = planes[(size_t)fb_channels[c] * P + p];
+			q[55 + 4 * c] = v.x; q[56 + 4 * c] = v.y; q[57 + 4 * c] = v.z; q[58 + 4 * c] = v.w;
+			v = make_float4(0, 0, 0, 0);
+		}
+		q[79] = float(context.shadows.size());
+	}
+	return 0;
+}
 EOF
 $CXX -O2 -std=c++14 -fPIC -w -fpermissive -ffp-contract=off -include $OVF/adapter_prefix.h -DFERMAT_API_EXTERN= -DFERMAT_API= -DSUTILAPI= -DSUTILCLASSAPI= \
     -DTHRUST_DEVICE_SYSTEM=THRUST_DEVICE_SYSTEM_CPP -I$OVS -I$OVF -I$REF/src -I$REF/src/mesh -I$REF/src/renderers -I$REF/contrib -I/usr/local/cuda/include \

@@ -786,6 +786,43 @@ static void shade_vertex_restated(const SceneRef& sc, const Sampler& smp, FB& fb
 	io.vinfo = vinfo; io.cone_radius = cone_radius; io.nee_slot = nee_slot; io.nee_cluster = nee_cluster;
 }
 
+// PSFPTVertexProcessor::accumulate_nee (src/psfpt_vertex_processor.h:374-438) for one unoccluded shadow ray. The shadow queue carries the vertex_info
+// preprocess_vertex returned (comp = 0: src/pathtracer_core.h:1098 passes vertex_info, not out_vertex_info), so the DIFFUSE_COMP branch below is
+// never taken in the reference either; it is restated for completeness.
+static void psf_accumulate_nee(FB& fb, PsfState& psf_state, const fb200_psf_options& po, uint32_t bounce, uint32_t comp, uint32_t pixel, uint32_t vinfo, vec3 wd, vec3 wg, float frame_weight)
+{
+	PsfState* psf = &psf_state;
+	const float ff = po.firefly_filter;
+	if (psf_slot(vinfo) != PSF_INVALID_SLOT)
+	{
+		const bool diffuse_only = psf_comp(vinfo) == PSF_DIFFUSE_COMP;
+		const vec3 cw = diffuse_only ? wd : wd + wg;
+		psf->acquire();
+		float* v = &psf->values[4 * (size_t)psf_slot(vinfo)];
+		v[0] += cw.x; v[1] += cw.y; v[2] += cw.z;
+		psf->release();
+		if (diffuse_only)
+		{
+			fb.add_in(false, COMPOSITED_C, pixel, psf_clamp_sample(wg, ff), frame_weight);
+			fb.add_in(true, (bounce == 0 || (comp & cGlossyMask)) ? SPECULAR_C : DIFFUSE_C, pixel, psf_clamp_sample(wg, ff), frame_weight);
+		}
+	}
+	else
+	{
+		fb.add_in(false, COMPOSITED_C, pixel, psf_clamp_sample(wd + wg, ff), frame_weight);
+		if (bounce == 0)
+		{
+			fb.add_in(true, DIFFUSE_C, pixel, psf_clamp_sample(wd, ff), frame_weight);
+			fb.add_in(true, SPECULAR_C, pixel, psf_clamp_sample(wg, ff), frame_weight);
+		}
+		else
+		{
+			if (comp & cDiffuseMask) fb.add_in(true, DIFFUSE_C, pixel, psf_clamp_sample(wd + wg, ff), frame_weight);
+			if (comp & cGlossyMask)  fb.add_in(true, SPECULAR_C, pixel, psf_clamp_sample(wd + wg, ff), frame_weight);
+		}
+	}
+}
+
 static void trace_path(const SceneRef& sc, const Sampler& smp, FB& fb, uint32_t px, uint32_t py, float frame_weight, vec3 U, vec3 V, vec3 W, PassStats& st, bool count_trav,
 					   PsfState* psf = NULL, uint32_t instance = 0, RlState* rl = NULL)
 {
@@ -848,42 +885,7 @@ static void trace_path(const SceneRef& sc, const Sampler& smp, FB& fb, uint32_t 
 				const bool occluded = trace_any(sc, pend[k].r, count_trav ? &st.trav_shadow : NULL);
 				// DirectLightingRL::update through solve_occlusion (src/pathtracer_core.h:723-724, src/direct_lighting_rl.h:171-185)
 				if (rl && k == 1 && nee_cluster != RL_INVALID) rl_update(*rl, nee_slot, nee_cluster, occluded ? 0.0f : max_comp(pend[k].w_d + pend[k].w_g));
-				if (!occluded && psf)
-				{
-					// PSFPTVertexProcessor::accumulate_nee (src/psfpt_vertex_processor.h:374-438). The shadow queue carries the vertex_info
-					// preprocess_vertex returned (comp = 0: src/pathtracer_core.h:1098 passes vertex_info, not out_vertex_info), so the
-					// DIFFUSE_COMP branch below is never taken in the reference either; it is restated for completeness.
-					const float ff = po.firefly_filter;
-					const vec3 wd = pend[k].w_d, wg = pend[k].w_g;
-					if (psf_slot(vinfo) != PSF_INVALID_SLOT)
-					{
-						const bool diffuse_only = psf_comp(vinfo) == PSF_DIFFUSE_COMP;
-						const vec3 cw = diffuse_only ? wd : wd + wg;
-						psf->acquire();
-						float* v = &psf->values[4 * (size_t)psf_slot(vinfo)];
-						v[0] += cw.x; v[1] += cw.y; v[2] += cw.z;
-						psf->release();
-						if (diffuse_only)
-						{
-							fb.add_in(false, COMPOSITED_C, pixel, psf_clamp_sample(wg, ff), frame_weight);
-							fb.add_in(true, (bounce == 0 || (comp & cGlossyMask)) ? SPECULAR_C : DIFFUSE_C, pixel, psf_clamp_sample(wg, ff), frame_weight);
-						}
-					}
-					else
-					{
-						fb.add_in(false, COMPOSITED_C, pixel, psf_clamp_sample(wd + wg, ff), frame_weight);
-						if (bounce == 0)
-						{
-							fb.add_in(true, DIFFUSE_C, pixel, psf_clamp_sample(wd, ff), frame_weight);
-							fb.add_in(true, SPECULAR_C, pixel, psf_clamp_sample(wg, ff), frame_weight);
-						}
-						else
-						{
-							if (comp & cDiffuseMask) fb.add_in(true, DIFFUSE_C, pixel, psf_clamp_sample(wd + wg, ff), frame_weight);
-							if (comp & cGlossyMask)  fb.add_in(true, SPECULAR_C, pixel, psf_clamp_sample(wd + wg, ff), frame_weight);
-						}
-					}
-				}
+				if (!occluded && psf) psf_accumulate_nee(fb, *psf, po, bounce, comp, pixel, vinfo, pend[k].w_d, pend[k].w_g, frame_weight);
 				else if (!occluded) pt_accumulate_nee(fb, bounce, comp, pixel, pend[k].w_d, pend[k].w_g, frame_weight);
 			}
 
@@ -1292,7 +1294,8 @@ float oracle_probe_power_heuristic(float p1, float p2) { return power_heuristic(
 // prev_vertex_info bits, prev_nee bits, cone xy, 0}. out: 80 floats per vertex: [0] path continues; scattered ray [1] on, [2] PixelInfo bits, [3..10] origin,
 // mask bits, dir, tmax, [11..14] weight + pdf, [15..16] cone; shadow rays in emission order at [17] and [36]: on, PixelInfo bits, ray (8), w (3), w_d (3), w_g (3);
 // [55..78] what the vertex added to DIFFUSE_C, DIFFUSE_A, SPECULAR_C, SPECULAR_A, DIRECT_C, COMPOSITED_C of its pixel; [79] shadow rays emitted.
-static int probe_shade_vertex_impl(const fb200_scene_view* s, uint32_t instance, uint32_t bounce, const float* in, float* out, uint32_t n, RlState* rl, uint32_t* rl_out, const uint8_t* occluded);
+static int probe_shade_vertex_impl(const fb200_scene_view* s, uint32_t instance, uint32_t bounce, const float* in, float* out, uint32_t n, RlState* rl, uint32_t* rl_out, const uint8_t* occluded,
+								   PsfState* psf = NULL, uint32_t* psf_words = NULL, float* psf_ref_w = NULL);
 int oracle_probe_shade_vertex(const fb200_scene_view* s, uint32_t instance, uint32_t bounce, const float* in, float* out, uint32_t n)
 {
 	return probe_shade_vertex_impl(s, instance, bounce, in, out, n, NULL, NULL, NULL);
@@ -1302,6 +1305,20 @@ int oracle_probe_shade_vertex(const fb200_scene_view* s, uint32_t instance, uint
 int oracle_probe_shade_vertex_rl(const fb200_scene_view* s, void* state, uint32_t instance, uint32_t bounce, const float* in, float* out, uint32_t* rl_out, const uint8_t* occluded, uint32_t n)
 {
 	return probe_shade_vertex_impl(s, instance, bounce, in, out, n, static_cast<RlState*>(state), rl_out, occluded);
+}
+// the same with the filtered renderer's vertex processor (state: oracle_psf_create): words = 4 per vertex {vertex_info of the scattered ray, of the next-event
+// shadow ray, cache word of the reference this vertex appended (0xFFFFFFFF: none), 0}, ref_w = that reference's two weights (8 floats); an unoccluded next-event
+// ray goes through accumulate_nee before the pixel is read back
+int oracle_probe_shade_vertex_psf(const fb200_scene_view* s, void* state, uint32_t instance, uint32_t bounce, const float* in, float* out, uint32_t* words, float* ref_w,
+								  const uint8_t* occluded, uint32_t n)
+{
+	return probe_shade_vertex_impl(s, instance, bounce, in, out, n, NULL, NULL, occluded, static_cast<PsfState*>(state), words, ref_w);
+}
+// the first n cells' values (float4 each: rgb sum, sample count), in slot order
+void oracle_psf_values(const void* state, float* out, uint32_t n)
+{
+	const PsfState* st = static_cast<const PsfState*>(state);
+	for (size_t i = 0; i < (size_t)4 * n; ++i) out[i] = i < st->values.size() ? st->values[i] : 0.0f;
 }
 // one cell of the sampler: count, then nodes / ends / pdfs / cdfs (C entries each); returns 0, -1 if there is no such cell
 int oracle_rl_cell(const void* state, uint32_t slot, uint32_t* count, uint32_t* nodes, uint32_t* ends, float* pdfs, float* cdfs)
@@ -1320,7 +1337,8 @@ void oracle_rl_update_cells(void* state)
 	RlState* st = static_cast<RlState*>(state);
 	for (size_t k = 0; k < st->cells.size(); ++k) { rl_split_and_collapse(*st, st->cells[k]); rl_update_cdf(st->cells[k]); }
 }
-static int probe_shade_vertex_impl(const fb200_scene_view* s, uint32_t instance, uint32_t bounce, const float* in, float* out, uint32_t n, RlState* rl, uint32_t* rl_out, const uint8_t* occluded)
+static int probe_shade_vertex_impl(const fb200_scene_view* s, uint32_t instance, uint32_t bounce, const float* in, float* out, uint32_t n, RlState* rl, uint32_t* rl_out, const uint8_t* occluded,
+								   PsfState* psf, uint32_t* psf_words, float* psf_ref_w)
 {
 	SceneRef sc = { s, s->vertex_indices, s->vertex_data, reinterpret_cast<const NodePOD*>(s->bvh_nodes) };
 	const fb200_pt_options& o = s->options;
@@ -1349,8 +1367,10 @@ static int probe_shade_vertex_impl(const fb200_scene_view* s, uint32_t instance,
 		io.prev_vinfo = f2u(r[19]); io.prev_nee_slot = f2u(r[20]); io.cone_x = r[21]; io.cone_y = r[22];
 		io.do_nee = do_nee; io.do_emissive = do_emissive; io.do_scatter = do_scatter; io.want_cone = true;
 		if (rl_out) for (int k = 0; k < 6; ++k) rl_out[6 * (size_t)i + k] = 0xFFFFFFFFu;
+		if (psf_words) { psf_words[4 * (size_t)i] = psf_words[4 * (size_t)i + 1] = psf_words[4 * (size_t)i + 2] = 0xFFFFFFFFu; psf_words[4 * (size_t)i + 3] = 0u; memset(psf_ref_w + 8 * (size_t)i, 0, 32); }
+		const size_t refs_before = psf ? psf->refs[bounce < 64 ? bounce : 63].size() : 0;
 		if (!(io.hit.t > 0.0f && io.hit.tri >= 0)) continue;          // (shade_vertex returns false on a miss and touches nothing)
-		shade_vertex_restated(sc, smp, fb, frame_weight, io, NULL, instance, rl);
+		shade_vertex_restated(sc, smp, fb, frame_weight, io, psf, instance, rl);
 		q[0] = io.cont ? 1.0f : 0.0f;
 		const uint32_t pixel = io.px + io.py * s->res_x;
 		auto put_ray = [](float* d, const Ray& ray, uint32_t mask_bits) { d[0] = ray.o.x; d[1] = ray.o.y; d[2] = ray.o.z; d[3] = u2f(mask_bits); d[4] = ray.d.x; d[5] = ray.d.y; d[6] = ray.d.z; d[7] = ray.tmax; };
@@ -1360,6 +1380,7 @@ static int probe_shade_vertex_impl(const fb200_scene_view* s, uint32_t instance,
 			q[1] = 1.0f; q[2] = u2f(pixel | ((io.next_comp & 0xFu) << 27) | (diffuse << 31));
 			put_ray(q + 3, io.next, f2u(io.next.tmin));                // (the scattered ray keeps its tmin in the mask word, src/pathtracer_core.h:1219)
 			if (rl_out) rl_out[6 * (size_t)i] = io.nee_slot;
+			if (psf_words) psf_words[4 * (size_t)i] = io.next_vinfo;
 			q[11] = io.next_w.x; q[12] = io.next_w.y; q[13] = io.next_w.z; q[14] = io.next_p; q[15] = io.cone_radius; q[16] = fmaxf(io.next_p, 32.0f);
 		}
 		uint32_t k = 0;
@@ -1370,6 +1391,11 @@ static int probe_shade_vertex_impl(const fb200_scene_view* s, uint32_t instance,
 				h[0] = 1.0f; h[1] = u2f(info); put_ray(h + 2, ps.r, ps.r.mask);
 				const vec3 wsum = ps.w_d + ps.w_g;
 				h[10] = wsum.x; h[11] = wsum.y; h[12] = wsum.z; h[13] = ps.w_d.x; h[14] = ps.w_d.y; h[15] = ps.w_d.z; h[16] = ps.w_g.x; h[17] = ps.w_g.y; h[18] = ps.w_g.z;
+				if (psf && j == 1)
+				{
+					psf_words[4 * (size_t)i + 1] = io.vinfo;
+					if (!occluded[i]) psf_accumulate_nee(fb, *psf, s->psf, bounce, io.comp, pixel, io.vinfo, ps.w_d, ps.w_g, frame_weight);
+				}
 				if (rl && j == 1)
 				{
 					rl_out[6 * (size_t)i + 1 + 2 * k] = io.nee_slot; rl_out[6 * (size_t)i + 2 + 2 * k] = io.nee_cluster;
@@ -1378,6 +1404,13 @@ static int probe_shade_vertex_impl(const fb200_scene_view* s, uint32_t instance,
 				++k;
 			}
 		q[79] = float(k);
+		if (psf && psf->refs[bounce < 64 ? bounce : 63].size() > refs_before)
+		{
+			const PsfRef& rr = psf->refs[bounce < 64 ? bounce : 63].back();
+			psf_words[4 * (size_t)i + 2] = rr.cache;
+			float* rw = psf_ref_w + 8 * (size_t)i;
+			rw[0] = rr.w_d.x; rw[1] = rr.w_d.y; rw[2] = rr.w_d.z; rw[4] = rr.w_g.x; rw[5] = rr.w_g.y; rw[6] = rr.w_g.z;
+		}
 		for (int c = 0; c < 6; ++c)
 		{
 			float* v = fb.px(chan[c], pixel);

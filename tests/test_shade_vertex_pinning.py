@@ -168,3 +168,64 @@ def test_rl_vertex_is_the_references_own(fb, oracle, libm_trig):
     assert np.array_equal(st.locate(prim, uv), R.rl_locate(h, prim, uv))
     R.rl_destroy(h)
     sc.close()
+
+
+# ---- the same with the reference's own PSFPTVertexProcessor (`-psfpt`)
+PSF_ARGS = ["-i", os.path.join(GOLDEN, "cornellbox_jp.fbs"), "-r", "48", "48", "-bounces", "4", "-psfpt", "-psf-hash-bits", "16"]
+PSF_ROUNDS = (0, 1, 2, 1, 3)
+
+
+def psf_round_inputs(oracle, sc, n_cells, rng, rnd, bounce):
+    rec = oracle.vertex_records(sc.view, 3000, 60 + rnd, bounce)
+    if bounce:
+        # half of the paths already feed a cell (prev_vertex_info = CacheInfo(slot, ALL_COMPS, 0)), the others none; p_prev on both sides of psf_max_prob
+        fed = rng.random(len(rec)) < 0.5
+        slot = rng.integers(0, max(n_cells, 1), len(rec)).astype(np.uint32) | np.uint32(3 << 29)
+        prev = np.where(fed & (n_cells > 0), slot, np.uint32(0xFFFFFFFF)).astype(np.uint32)
+        rec[:, 19] = prev.view(np.float32)
+        rec[:, 18] = (rng.random(len(rec)) * 64).astype(np.float32)
+    occ = (rng.random(len(rec)) < 0.4).astype(np.uint8)
+    return rec, occ
+
+
+def test_psf_vertex_against_golden_vectors_of_the_references_own(fb, oracle, libm_trig):
+    g = np.load(os.path.join(GOLDEN, "shade_vertex_golden.npz"))
+    sc = fb.Scene(PSF_ARGS)
+    st = oracle.PsfState()
+    rng = np.random.default_rng(5)
+    for rnd, bounce in enumerate(PSF_ROUNDS):
+        rec, occ = psf_round_inputs(oracle, sc, st.cells(), rng, rnd, bounce)
+        out, words, ref_w = oracle.probe_shade_vertex_psf(sc.view, st, rnd, bounce, rec, occ)
+        values = oracle.psf_values(st, st.cells())
+        sha = hashlib.sha256(out.tobytes() + words.tobytes() + ref_w.tobytes() + values.tobytes()).digest()
+        assert np.array_equal(np.frombuffer(sha, np.uint8), g["psf_round%d_sha" % rnd]), rnd
+    assert st.cells() == int(g["psf_cells"]) and st.cells() > 500
+    st.close(); sc.close()
+
+
+def test_psf_vertex_is_the_references_own(fb, oracle, libm_trig):
+    """PSFPTVertexProcessor (src/psfpt_vertex_processor.h: preprocess_vertex with the jittered spatial hash and the cache insertion, compute_nee_weights,
+    compute_scattering_weights, accumulate_emissive, accumulate_nee through solve_occlusion) inside the reference's own shade_vertex on the host, its hash map
+    and cell values on host arrays, against the restated policies inside shade_vertex_restated: vertex outputs, the CacheInfo words travelling with the
+    scattered and shadow rays, every reference appended with its two weights, the number of cells and every cell's value, bit for bit over five rounds."""
+    R = oracle.RefShade.load()
+    if R is None:
+        pytest.skip("oracle/_ref/libref_shade.so is built where /root/reference exists")
+    sc = fb.Scene(PSF_ARGS)
+    st = oracle.PsfState()
+    h = R.psf_create(1 << 16)
+    rng = np.random.default_rng(5)
+    refs = 0
+    for rnd, bounce in enumerate(PSF_ROUNDS):
+        rec, occ = psf_round_inputs(oracle, sc, st.cells(), rng, rnd, bounce)
+        o1, w1, r1 = oracle.probe_shade_vertex_psf(sc.view, st, rnd, bounce, rec, occ)
+        o2, w2, r2 = R.shade_vertex_psf(sc.view, h, rnd, bounce, rec, occ)
+        assert np.array_equal(o1.view(np.uint32), o2.view(np.uint32)), rnd
+        assert np.array_equal(w1, w2) and np.array_equal(r1.view(np.uint32), r2.view(np.uint32)), rnd
+        n = st.cells()
+        assert n == R.psf_cells(h)
+        assert np.array_equal(oracle.psf_values(st, n).view(np.uint32), R.psf_values(h, n).view(np.uint32)), rnd
+        refs += int((w1[:, 2] != 0xFFFFFFFF).sum())
+    assert refs > 1000 and st.cells() > 500
+    R.psf_destroy(h)
+    st.close(); sc.close()

@@ -67,6 +67,20 @@ def main():
     out["rl_cells"] = np.array(R.rl_cells(h))
     R.rl_destroy(h)
     sc.close()
+    # `-psfpt`: the reference's PSFPTVertexProcessor inside its shade_vertex over five rounds (tests/test_shade_vertex_pinning.py psf_round_inputs)
+    from test_shade_vertex_pinning import PSF_ARGS, PSF_ROUNDS, psf_round_inputs
+    sc = fb.Scene(PSF_ARGS)
+    pst = oracle.PsfState()
+    ph = R.psf_create(1 << 16)
+    rng = np.random.default_rng(5)
+    for rnd, bounce in enumerate(PSF_ROUNDS):
+        rec, occ = psf_round_inputs(oracle, sc, pst.cells(), rng, rnd, bounce)
+        oracle.probe_shade_vertex_psf(sc.view, pst, rnd, bounce, rec, occ)          # (keeps the restatement's cell count in step: the inputs of the next round read it)
+        o, w, rw = R.shade_vertex_psf(sc.view, ph, rnd, bounce, rec, occ)
+        values = R.psf_values(ph, R.psf_cells(ph))
+        out["psf_round%d_sha" % rnd] = np.frombuffer(hashlib.sha256(o.tobytes() + w.tobytes() + rw.tobytes() + values.tobytes()).digest(), np.uint8)
+    out["psf_cells"] = np.array(R.psf_cells(ph))
+    R.psf_destroy(ph); pst.close(); sc.close()
     oracle.set_trig_mode(1)
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "shade_vertex_golden.npz"), **out)
     print("wrote shade_vertex_golden.npz:", {k: v.tolist() for k, v in out.items() if k.endswith("_n")})
