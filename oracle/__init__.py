@@ -854,3 +854,37 @@ def vertex_records(view, n, seed, bounce):
     rec[:, 19] = np.uint32(0xFFFFFFFF).view(np.float32); rec[:, 20] = np.uint32(0xFFFFFFFF).view(np.float32)
     rec[:, 21] = (rng.random(m) * 0.01).astype(np.float32); rec[:, 22] = (32 + rng.random(m) * 1000).astype(np.float32)
     return rec
+
+
+class RefVpl:
+    """The REFERENCE's own VPL generator (MeshLightsStorageImpl::init, src/mesh_lights.cu:163-389) compiled on this host (oracle/_ref/libref_vpl.so)."""
+
+    @staticmethod
+    def load():
+        L = _ref_so("libref_vpl.so")
+        return RefVpl(L) if L is not None else None
+
+    def __init__(self, L):
+        self.L = L
+        L.ref_vpl_init.restype = C.c_int
+
+    def init(self, view, n_vpls):
+        """(mesh_cdf, mesh_inv_area, vpls as (n, 4) = prim_id bits, u, v, E in the product's layout, vpl_cdf, norm) for the scene of `view`; untextured emitters only
+        (the mip-mapped estimate of textured ones reads the uncompressed texture coordinates and the mip chain, which the view does not carry)"""
+        nt, ntex = int(view.num_triangles), int(view.num_textures)
+        levels = (C.c_uint32 * max(ntex, 1))(); res = (C.c_uint32 * max(2 * ntex, 2))(); texels = (C.c_void_p * max(ntex, 1))()
+        k = 0
+        for t in range(ntex):
+            if view.textures[t].texels:
+                levels[t] = 1; res[2 * k], res[2 * k + 1] = view.textures[t].res_x, view.textures[t].res_y; texels[k] = C.cast(view.textures[t].texels, C.c_void_p); k += 1
+            else:
+                levels[t] = 0
+        cdf = np.zeros(nt, np.float32); inv = np.zeros(nt, np.float32); vpls = np.zeros((n_vpls, 4), np.float32); vcdf = np.zeros(n_vpls, np.float32); norm = C.c_float(0)
+        n = self.L.ref_vpl_init(C.c_uint32(n_vpls), C.c_int(view.num_vertices), C.c_int(nt), C.c_int(view.num_materials), view.vertex_indices, view.vertex_data,
+                                None, None, view.texture_indices_comp, view.material_indices, C.c_void_p(view.materials), view.tex_bias, view.tex_scale,
+                                C.c_int(ntex), levels, res, texels, cdf.ctypes.data_as(C.c_void_p), inv.ctypes.data_as(C.c_void_p), vpls.ctypes.data_as(C.c_void_p),
+                                vcdf.ctypes.data_as(C.c_void_p), C.byref(norm))
+        assert n == n_vpls
+        ours = np.zeros((n_vpls, 4), np.float32)
+        ours[:, 0], ours[:, 1], ours[:, 2], ours[:, 3] = vpls[:, 2], vpls[:, 0], vpls[:, 1], vpls[:, 3]
+        return cdf, inv, ours, vcdf, np.float32(norm.value)

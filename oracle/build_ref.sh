@@ -1217,3 +1217,78 @@ $CXX -O2 -std=c++14 -fPIC -w -fpermissive -ffp-contract=off -include $OVF/adapte
     -DTHRUST_DEVICE_SYSTEM=THRUST_DEVICE_SYSTEM_CPP -I$OVS -I$OVF -I$REF/src -I$REF/src/mesh -I$REF/src/renderers -I$REF/contrib -I/usr/local/cuda/include \
     -shared -o $OUT/libref_shade.so $OUT/ref_shade_shim.cpp -x c++ $REF/src/uv_bvh.cu -x none $REF/contrib/cugar/basic/atomics.cpp -L/usr/local/cuda/lib64 -lcudart_static -ldl -lrt -lpthread
 echo "built $OUT/libref_shade.so"
+
+# ---- the reference's own VPL generator (MeshLightsStorageImpl::init, src/mesh_lights.cu:163-389: emission-weighted triangle CDF with the mip-mapped estimate for
+# textured emitters, the stratified LFSR draw of the VPLs, the normalisation, the CDF resample) - host code inside a CUDA translation unit whose tail builds an LBVH
+# on the device. The text of the function up to its last host statement is cut from the file where it lies and compiled as a member of a stand-in struct that
+# holds the members it assigns. Pins the product's VPL table (row a19) against the reference's own code (tests/test_oracle_pinning2.py).
+{
+  sed -n '163,389p' $REF/src/mesh_lights.cu
+  echo '}'
+} > $OUT/vpl_init_cut.h
+cat > $OUT/ref_vpl_shim.cpp <<'EOF'
+#include <vector>
+#include <queue>
+#include <math.h>
+#include <vector_types.h>
+#include <cugar/linalg/vector.h>
+#include <cugar/linalg/bbox.h>
+#include <cugar/basic/vector.h>
+#include <cugar/basic/algorithms.h>
+#include <cugar/sampling/lfsr.h>
+#include <mesh/MeshStorage.h>
+#include <mesh_utils.h>
+#include <texture_view.h>
+#include <lights.h>
+struct MeshLightsStorageImpl        // the members the cut text assigns (src/mesh_lights_impl.h:40-80), on the host
+{
+	cugar::vector<cugar::host_tag, float> mesh_cdf, mesh_inv_area, vpl_cdf;
+	cugar::vector<cugar::host_tag, VPL> vpls;
+	MeshView mesh; const MipMapView* textures;
+	float normalization_coeff;
+	MeshLightsStorageImpl() : normalization_coeff(0.0f) {}
+	void init(const uint32 n_vpls, MeshView h_mesh, MeshView d_mesh, const MipMapView* h_textures, const MipMapView* d_textures, const uint32 instance = 0);
+};
+#include "vpl_init_cut.h"
+// arrays in MeshView's layouts; mips: per texture the number of levels, then per level (res_x, res_y) in `mip_res` and the texel pointers in `mip_texels`
+extern "C" int ref_vpl_init(unsigned n_vpls, int num_vertices, int num_triangles, int num_materials, const int* vertex_indices, const float* vertex_data,
+							const int* texture_indices, const float* texture_data, const int* texture_indices_comp, const int* material_indices, const void* materials,
+							const float* tex_bias, const float* tex_scale, int num_textures, const unsigned* mip_levels, const unsigned* mip_res, float** mip_texels,
+							float* mesh_cdf_out, float* mesh_inv_area_out, float* vpls_out, float* vpl_cdf_out, float* norm_out)
+{
+	MeshView m; memset(&m, 0, sizeof(m));
+	m.num_vertices = num_vertices; m.num_triangles = num_triangles; m.num_materials = num_materials;
+	m.vertex_stride = 4; m.normal_stride = 3; m.texture_stride = 2;
+	m.tex_bias = make_float2(tex_bias[0], tex_bias[1]); m.tex_scale = make_float2(tex_scale[0], tex_scale[1]);
+	m.vertex_indices = const_cast<int*>(vertex_indices); m.vertex_data = const_cast<float*>(vertex_data);
+	m.texture_indices = const_cast<int*>(texture_indices); m.texture_data = const_cast<float*>(texture_data);
+	m.texture_indices_comp = const_cast<int*>(texture_indices_comp);
+	m.material_indices = const_cast<int*>(material_indices); m.materials = (MeshMaterial*)materials;
+	std::vector<std::vector<TextureView> > levels(num_textures ? num_textures : 1); std::vector<MipMapView> maps(num_textures ? num_textures : 1);
+	size_t k = 0;
+	for (int t = 0; t < num_textures; ++t)
+	{
+		levels[t].resize(mip_levels[t] ? mip_levels[t] : 1);
+		for (unsigned l = 0; l < mip_levels[t]; ++l, ++k)
+		{
+			levels[t][l].c = reinterpret_cast<float4*>(mip_texels[k]); levels[t][l].res_x = mip_res[2 * k]; levels[t][l].res_y = mip_res[2 * k + 1];
+		}
+		maps[t].levels = levels[t].data(); maps[t].n_levels = mip_levels[t];
+		maps[t].res_x = mip_levels[t] ? levels[t][0].res_x : 0; maps[t].res_y = mip_levels[t] ? levels[t][0].res_y : 0;
+	}
+	MeshLightsStorageImpl impl;
+	impl.init(n_vpls, m, m, maps.data(), maps.data(), 0u);
+	for (int i = 0; i < num_triangles; ++i) { mesh_cdf_out[i] = impl.mesh_cdf[i]; mesh_inv_area_out[i] = impl.mesh_inv_area[i]; }
+	const size_t nv = impl.vpls.size();
+	for (size_t i = 0; i < nv; ++i)
+	{
+		const VPL v = impl.vpls[i];
+		vpls_out[4 * i] = v.uv.x; vpls_out[4 * i + 1] = v.uv.y; unsigned p = v.prim_id; memcpy(&vpls_out[4 * i + 2], &p, 4); vpls_out[4 * i + 3] = v.E;
+		vpl_cdf_out[i] = impl.vpl_cdf[i];
+	}
+	*norm_out = impl.normalization_coeff;
+	return (int)nv;
+}
+EOF
+$CXX $LFLAGS -I$OUT -shared -o $OUT/libref_vpl.so $OUT/ref_vpl_shim.cpp -L/usr/local/cuda/lib64 -lcudart_static -ldl -lrt -lpthread
+echo "built $OUT/libref_vpl.so"

@@ -156,3 +156,47 @@ def test_camera_frame_and_primary_cone_pdf(fb, oracle):
             assert np.array_equal(f2.view(np.uint32), frame.view(np.uint32)) and np.array_equal(p2.view(np.uint32), pdf.view(np.uint32))
     assert (g["pdf"] > 0).sum() > 300 and (g["pdf"] == 0).sum() > 100          # directions inside and outside the image
     sc.close()
+
+
+def _product_vpl_tables(view):
+    import ctypes as C
+    n = int(view.n_vpls)
+    vpls = np.ctypeslib.as_array(C.cast(view.vpls, C.POINTER(C.c_float)), shape=(n, 4))
+    cdf = np.ctypeslib.as_array(view.mesh_cdf, shape=(int(view.n_prims),)); inv = np.ctypeslib.as_array(view.mesh_inv_area, shape=(int(view.n_prims),))
+    return cdf, inv, vpls
+
+
+def test_vpl_table_is_the_references_own_generators(fb, oracle):
+    """a19 against the reference's OWN code: MeshLightsStorageImpl::init (src/mesh_lights.cu:163-389) is host code inside a CUDA translation unit;
+    oracle/build_ref.sh cuts the function's text up to its last host statement and compiles it as a member of a stand-in struct (libref_vpl.so). The
+    PRODUCT's triangle CDF, inverse areas, VPL table and normalisation coefficient (host/mesh_lights.cpp) are compared with its output bit for bit:
+    golden hashes everywhere (tests/golden/vpl_golden.npz, tools/make_golden_vpl.py), the live generator on four scenes where oracle/_ref exists."""
+    import hashlib
+    g = np.load(os.path.join(GOLDEN, "vpl_golden.npz"))
+    for res in (64, 96):
+        sc = fb.Scene(["-i", os.path.join(GOLDEN, "cornellbox_jp.fbs"), "-r", str(res), str(res), "-bounces", "4"])
+        cdf, inv, vpls = _product_vpl_tables(sc.view)
+        sha = hashlib.sha256(cdf.tobytes() + inv.tobytes() + vpls.tobytes()).digest()
+        assert np.array_equal(np.frombuffer(sha, np.uint8), g["sha_view_%d" % res])
+        assert np.float32(sc.view.vpl_norm) == g["norm_%d" % res]
+        sc.close()
+    live = oracle.RefVpl.load()
+    if live is None:
+        pytest.skip("oracle/_ref/libref_vpl.so is built where /root/reference exists")
+    scenes = [["-i", os.path.join(GOLDEN, "cornellbox_jp.fbs"), "-r", "64", "64"], ["-i", os.path.join(GOLDEN, "cornellbox_jp.fbs"), "-r", "96", "96"]]
+    for name, res in (("cornellbox_glossy", (80, 60)), ("bathroom2", (160, 90)), ("water_caustic", (160, 90))):
+        p = os.path.join(CACHE, name + ".fbs")
+        if fb.scene_available(p):
+            scenes.append(["-i", p, "-r", str(res[0]), str(res[1])])
+    for args in scenes:
+        sc = fb.Scene(args)
+        n = int(sc.view.n_vpls)
+        rcdf, rinv, rvpls, rvcdf, rnorm = live.init(sc.view, n)
+        cdf, inv, vpls = _product_vpl_tables(sc.view)
+        assert np.array_equal(vpls.view(np.uint32), rvpls.view(np.uint32)), args
+        assert np.array_equal(cdf.view(np.uint32), rcdf.view(np.uint32)) and np.array_equal(inv.view(np.uint32), rinv.view(np.uint32)), args
+        assert np.float32(sc.view.vpl_norm) == rnorm
+        if args[1].endswith("cornellbox_jp.fbs"):
+            sha = hashlib.sha256(rcdf.tobytes() + rinv.tobytes() + rvpls.tobytes() + rvcdf.tobytes()).digest()
+            assert np.array_equal(np.frombuffer(sha, np.uint8), g["sha_%s" % args[3]])
+        sc.close()
