@@ -560,7 +560,9 @@ class RlState:
         z = self.sizes()
         return {"vtls": self._arr(0, self.VTL_DTYPE, (z["vtls"],)), "tree_nodes": self._arr(1, "<u4", (z["tree_nodes"], 2)),
                 "tree_ranges": self._arr(2, "<u4", (z["tree_nodes"], 2)), "tree_parents": self._arr(3, "<u4", (z["tree_nodes"],)),
-                "clusters": self._arr(4, "<u4", (z["clusters"],)), "cluster_offsets": self._arr(5, "<u4", (z["clusters"] + 1,))}
+                "clusters": self._arr(4, "<u4", (z["clusters"],)), "cluster_offsets": self._arr(5, "<u4", (z["clusters"] + 1,)),
+                "popped": self._arr(6, self.VTL_DTYPE, (z["vtls"],)), "popped_centroids": self._arr(7, "<f4", (z["vtls"], 3)),
+                "centroid_box": self._arr(8, "<f4", (6,))}
 
     def locate(self, prims, uv):
         prims = np.ascontiguousarray(prims, np.uint32); uv = np.ascontiguousarray(uv, np.float32)
@@ -888,3 +890,37 @@ class RefVpl:
         ours = np.zeros((n_vpls, 4), np.float32)
         ours[:, 0], ours[:, 1], ours[:, 2], ours[:, 3] = vpls[:, 2], vpls[:, 0], vpls[:, 1], vpls[:, 3]
         return cdf, inv, ours, vcdf, np.float32(norm.value)
+
+
+class RefVtl:
+    """The reference's own VTL generator and initial cut (MeshVTLStorageImpl::init, src/mesh_lights.cu:542-721 and 769-810) compiled on this host
+    (oracle/build_ref.sh -> oracle/_ref/libref_vtl.so): the host code either side of the device LBVH build of that function."""
+
+    def __init__(self, path):
+        self._lib = C.CDLL(path)
+        self._lib.ref_vtl_init.restype = C.c_int
+        self._lib.ref_vtl_init.argtypes = [C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_uint] + [C.c_void_p] * 3
+        self._lib.ref_vtl_initial_cut.restype = C.c_int
+        self._lib.ref_vtl_initial_cut.argtypes = [C.c_uint, C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p]
+
+    @classmethod
+    def load(cls):
+        p = os.path.join(_HERE, "_ref", "libref_vtl.so")
+        return cls(p) if os.path.exists(p) else None
+
+    def init(self, view, n_target, instance=0):
+        """(vtls in pop order [RlState.VTL_DTYPE], centroids (n, 3), centroid box (6,)) of an untextured scene view"""
+        cap = 4 * int(n_target) + 4 * int(view.num_triangles) + 16
+        vt = np.zeros(cap, RlState.VTL_DTYPE); ctr = np.zeros((cap, 3), np.float32); bb = np.zeros(6, np.float32)
+        n = self._lib.ref_vtl_init(int(n_target), int(instance), int(view.num_vertices), int(view.num_triangles), int(view.num_materials),
+                                   C.cast(view.vertex_indices, C.c_void_p), C.cast(view.vertex_data, C.c_void_p), C.cast(view.material_indices, C.c_void_p),
+                                   C.cast(view.materials, C.c_void_p), cap, vt.ctypes.data, ctr.ctypes.data, bb.ctypes.data)
+        if n < 0:
+            raise RuntimeError("ref_vtl_init: %d VTLs do not fit" % -n)
+        return vt[:n].copy(), ctr[:n].copy(), bb
+
+    def initial_cut(self, tree_nodes, tree_ranges, target=256):
+        nodes = np.ascontiguousarray(tree_nodes, np.uint32); rg = np.ascontiguousarray(tree_ranges, np.uint32)
+        cl = np.zeros(len(nodes) + 1, np.uint32); off = np.zeros(len(nodes) + 1, np.uint32)
+        n = self._lib.ref_vtl_initial_cut(len(nodes), nodes.ctypes.data, rg.ctypes.data, int(target), cl.ctypes.data, off.ctypes.data)
+        return cl[:n].copy(), off[:n].copy()

@@ -1292,3 +1292,96 @@ extern "C" int ref_vpl_init(unsigned n_vpls, int num_vertices, int num_triangles
 EOF
 $CXX $LFLAGS -I$OUT -shared -o $OUT/libref_vpl.so $OUT/ref_vpl_shim.cpp -L/usr/local/cuda/lib64 -lcudart_static -ldl -lrt -lpthread
 echo "built $OUT/libref_vpl.so"
+
+# ---- the reference's own VTL generator (MeshVTLStorageImpl::init, src/mesh_lights.cu:542-721: the energy-prioritised 4-way midpoint subdivision of the emissive
+# triangles, the centroids and their box in pop order) and its initial cut of the cluster tree (src/mesh_lights.cu:769-810, a priority queue by range size), host
+# code around the device LBVH build of the same function. Both texts are cut where they lie; the first ends before the device build, the second runs on a tree
+# handed in as Bvh_node_3d / uint2 arrays. Pins oracle_rl.h's rl_build (tests/test_shade_vertex_pinning.py); the LBVH itself (Morton codes, radix tree) is pinned
+# by tests/test_oracle_pinning.py against the scene BVH builder's golden vectors and is shared with it.
+{
+  sed -n '542,721p' $REF/src/mesh_lights.cu
+  echo '	ref_vtl_out_centroids = h_centroids; ref_vtl_out_bbox = bbox;'
+  echo '}'
+} > $OUT/vtl_init_cut.h
+{
+  sed -n '120,127p' $REF/src/mesh_lights.cu
+  echo 'static void ref_initial_cut(const cugar::vector<cugar::host_tag, cugar::Bvh_node_3d>& h_bvh_nodes, const cugar::vector<cugar::host_tag, uint2>& h_bvh_ranges,'
+  echo '	const uint32 target_clusters, cugar::vector<cugar::host_tag, uint32>& h_clusters, cugar::vector<cugar::host_tag, uint32>& h_cluster_offsets)'
+  echo '{'
+  sed -n '769,810p' $REF/src/mesh_lights.cu | sed -e '/cugar::vector<cugar::host_tag, uint32> h_clusters;/d' -e '/cugar::vector<cugar::host_tag, uint32> h_cluster_offsets;/d'
+  echo '}'
+} > $OUT/vtl_cut_cut.h
+cat > $OUT/ref_vtl_shim.cpp <<'EOF'
+#include <vector>
+#include <queue>
+#include <algorithm>
+#include <math.h>
+#include <stdio.h>
+#include <vector_types.h>
+#include <cugar/linalg/vector.h>
+#include <cugar/linalg/bbox.h>
+#include <cugar/basic/vector.h>
+#include <cugar/basic/numbers.h>
+#include <cugar/basic/algorithms.h>
+#include <cugar/sampling/lfsr.h>
+#include <cugar/bvh/bvh_node.h>
+#include <mesh/MeshStorage.h>
+#include <mesh_utils.h>
+#include <texture_view.h>
+#include <lights.h>
+#include <vtl.h>
+static cugar::vector<cugar::host_tag, float4> ref_vtl_out_centroids;
+static cugar::Bbox3f ref_vtl_out_bbox;
+struct MeshVTLStorageImpl           // the members the cut text assigns (src/mesh_lights_impl.h:80-118), on the host
+{
+	cugar::vector<cugar::host_tag, VTL> vtls;
+	MeshView mesh; const MipMapView* textures;
+	float normalization_coeff;
+	void init(const uint32 n_target_vtls, MeshView h_mesh, MeshView d_mesh, const MipMapView* h_textures, const MipMapView* d_textures, const uint32 instance = 0);
+};
+#include "vtl_init_cut.h"
+#include "vtl_cut_cut.h"
+// VTLs in pop order (8 words each: prim_id, area, uv0, uv1, uv2), their centroids (xyz) and the centroids' box; untextured emitters (no mip chain is handed in)
+extern "C" int ref_vtl_init(unsigned n_target, unsigned instance, int num_vertices, int num_triangles, int num_materials, const int* vertex_indices, const float* vertex_data,
+							const int* material_indices, const void* materials, unsigned max_out, float* vtls_out, float* centroids_out, float* bbox_out)
+{
+	MeshView m; memset(&m, 0, sizeof(m));
+	m.num_vertices = num_vertices; m.num_triangles = num_triangles; m.num_materials = num_materials;
+	m.vertex_stride = 4; m.normal_stride = 3; m.texture_stride = 2;
+	m.vertex_indices = const_cast<int*>(vertex_indices); m.vertex_data = const_cast<float*>(vertex_data);
+	m.material_indices = const_cast<int*>(material_indices); m.materials = (MeshMaterial*)materials;
+	MipMapView none; memset(&none, 0, sizeof(none));
+	MeshVTLStorageImpl impl;
+	impl.init(n_target, m, m, &none, &none, instance);
+	const size_t n = impl.vtls.size();
+	if (n > max_out) return -(int)n;
+	for (size_t i = 0; i < n; ++i)
+	{
+		const VTL v = impl.vtls[i];
+		memcpy(vtls_out + 8 * i, &v, 32);
+		centroids_out[3 * i] = ref_vtl_out_centroids[i].x; centroids_out[3 * i + 1] = ref_vtl_out_centroids[i].y; centroids_out[3 * i + 2] = ref_vtl_out_centroids[i].z;
+	}
+	for (int a = 0; a < 3; ++a) { bbox_out[a] = ref_vtl_out_bbox[0][a]; bbox_out[3 + a] = ref_vtl_out_bbox[1][a]; }
+	return (int)n;
+}
+// the initial cut of a tree given as Bintree words (2 per node) + ranges (2 per node): clusters and their first VTLs, sorted by the latter as the reference's
+// radix sort leaves them (src/mesh_lights.cu:822-827: keys are distinct, the ranges of a cut being disjoint)
+extern "C" int ref_vtl_initial_cut(unsigned n_nodes, const unsigned* node_words, const unsigned* ranges, unsigned target, unsigned* clusters_out, unsigned* offsets_out)
+{
+	cugar::vector<cugar::host_tag, cugar::Bvh_node_3d> nodes(n_nodes); cugar::vector<cugar::host_tag, uint2> rg(n_nodes);
+	for (unsigned i = 0; i < n_nodes; ++i)
+	{
+		nodes[i] = cugar::Bvh_node_3d(make_float4(cugar::binary_cast<float>(node_words[2 * i]), cugar::binary_cast<float>(node_words[2 * i + 1]), 0, 0), make_float4(0, 0, 0, 0));
+		rg[i] = make_uint2(ranges[2 * i], ranges[2 * i + 1]);
+	}
+	cugar::vector<cugar::host_tag, uint32> cl, off;
+	ref_initial_cut(nodes, rg, target, cl, off);
+	std::vector<std::pair<unsigned, unsigned> > s(cl.size());
+	for (size_t i = 0; i < cl.size(); ++i) s[i] = std::make_pair((unsigned)off[i], (unsigned)cl[i]);
+	std::stable_sort(s.begin(), s.end(), [](const std::pair<unsigned, unsigned>& a, const std::pair<unsigned, unsigned>& b) { return a.first < b.first; });
+	for (size_t i = 0; i < s.size(); ++i) { offsets_out[i] = s[i].first; clusters_out[i] = s[i].second; }
+	return (int)s.size();
+}
+EOF
+$CXX $LFLAGS -I$OUT -shared -o $OUT/libref_vtl.so $OUT/ref_vtl_shim.cpp -L/usr/local/cuda/lib64 -lcudart_static -ldl -lrt -lpthread
+echo "built $OUT/libref_vtl.so"

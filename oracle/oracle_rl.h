@@ -39,6 +39,9 @@ struct RlState
 	std::vector<uint32_t> tree_ranges;         // 2 per node
 	std::vector<uint32_t> tree_parents;
 	std::vector<uint32_t> clusters, cluster_offsets;
+	std::vector<RlVTL> popped;                 // the VTLs as the subdivision queue hands them out, before the tree's order (pinning probes)
+	std::vector<float> popped_centroids;       // xyz, same order
+	float centroid_box[6];
 	// point location: per emissive triangle a G x G grid over (u, v) of candidate VTL lists
 	static const uint32_t G = 64;
 	std::unordered_map<uint32_t, uint32_t> grid_of_prim;
@@ -170,6 +173,7 @@ static int rl_build(const SceneRef& sc, uint32_t n_target, RlState& st)
 	st.tree_nodes.resize(2 * (size_t)n_nodes); st.tree_ranges.resize(2 * (size_t)n_nodes); st.tree_parents.resize((size_t)n_nodes);
 	st.tree_parents[0] = RL_INVALID;
 	st.vtls.resize(n);
+	st.popped = popped; st.popped_centroids = ctr; for (int a = 0; a < 6; ++a) st.centroid_box[a] = bb[a];
 	for (uint32_t i = 0; i < n; ++i) st.vtls[i] = popped[order[i]];          // thrust::gather by the tree's index (src/mesh_lights.cu:734-741)
 
 	// the initial cut (src/mesh_lights.cu:747-791)

@@ -1020,6 +1020,9 @@ const void* oracle_rl_array(const void* state, int which)
 	case 3: return st->tree_parents.data();
 	case 4: return st->clusters.data();
 	case 5: return st->cluster_offsets.data();
+	case 6: return st->popped.data();
+	case 7: return st->popped_centroids.data();
+	case 8: return st->centroid_box;
 	}
 	return NULL;
 }

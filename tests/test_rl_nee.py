@@ -79,6 +79,44 @@ def test_vtls_tile_the_emitters_and_the_cut_partitions_them(fb, oracle):
     sc.close()
 
 
+def test_vtl_generation_and_initial_cut_are_the_references_own(fb, oracle):
+    """MeshVTLStorageImpl::init's host code either side of its device LBVH build (src/mesh_lights.cu:542-721: the energy-prioritised subdivision, the centroids
+    and their box in pop order; :769-810: the initial cut of the cluster tree), cut from the file where it lies and compiled on the host
+    (oracle/build_ref.sh -> libref_vtl.so), against oracle_rl.h's rl_build bit for bit: golden hashes everywhere (tests/golden/vtl_golden.npz,
+    tools/make_golden_vtl.py), the live code on four scenes where oracle/_ref exists. The tree between the two halves is the LBVH (Morton-60 codes + radix
+    tree) tests/test_oracle_pinning.py holds to golden vectors; test_vtl_tables_match_the_oracle then compares the PRODUCT's tables with the oracle's on the GPU."""
+    import hashlib
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "vtl_golden.npz"))
+    sc = fb.Scene(cornell_args(64, 3))
+    for n_target in (300, 2000):
+        a = oracle.RlState(sc.view, n_target).arrays()
+        assert len(a["popped"]) == int(g["n_%d" % n_target])
+        sha = hashlib.sha256(a["popped"].tobytes() + a["popped_centroids"].tobytes() + a["centroid_box"].tobytes()).digest()
+        assert np.array_equal(np.frombuffer(sha, np.uint8), g["sha_gen_%d" % n_target])
+        sha = hashlib.sha256(a["clusters"].tobytes() + a["cluster_offsets"][:-1].tobytes()).digest()
+        assert np.array_equal(np.frombuffer(sha, np.uint8), g["sha_cut_%d" % n_target])
+        assert sorted(map(bytes, a["popped"].view(np.uint8).reshape(-1, 32))) == sorted(map(bytes, a["vtls"].view(np.uint8).reshape(-1, 32)))   # the tree's order permutes them
+    sc.close()
+    live = oracle.RefVtl.load()
+    if live is None:
+        pytest.skip("oracle/_ref/libref_vtl.so is built where /root/reference exists")
+    cases = [(cornell_args(64, 3), 300), (cornell_args(64, 3), 2000)]
+    for name, n_target in (("cornellbox_glossy", 4000), ("bathroom2", 8000), ("water_caustic", 3000)):
+        p = os.path.join(CACHE, name + ".fbs")
+        if fb.scene_available(p):
+            cases.append((["-i", p, "-r", "64", "64"], n_target))
+    for args, n_target in cases:
+        sc = fb.Scene(args)
+        a = oracle.RlState(sc.view, n_target).arrays()
+        vt, ctr, bb = live.init(sc.view, n_target)
+        assert np.array_equal(vt.view(np.uint32), a["popped"].view(np.uint32)), args
+        assert np.array_equal(ctr.view(np.uint32), a["popped_centroids"].view(np.uint32)) and np.array_equal(bb, a["centroid_box"]), args
+        cl, off = live.initial_cut(a["tree_nodes"], a["tree_ranges"])
+        assert np.array_equal(cl, a["clusters"]) and np.array_equal(off, a["cluster_offsets"][:-1]), args
+        sc.close()
+
+
 def test_sampler_arithmetic_of_one_cell(oracle):
     """AdaptiveClusteredRLView::sample / ::pdf: the pdf returned with a sample is the pdf of that index, indices stay inside their cluster,
     and the histogram of many samples follows the CDF."""
