@@ -924,3 +924,55 @@ class RefVtl:
         cl = np.zeros(len(nodes) + 1, np.uint32); off = np.zeros(len(nodes) + 1, np.uint32)
         n = self._lib.ref_vtl_initial_cut(len(nodes), nodes.ctypes.data, rg.ctypes.data, int(target), cl.ctypes.data, off.ctypes.data)
         return cl[:n].copy(), off[:n].copy()
+
+
+def frame_op(op, fb, f=0.0, u=0):
+    """the restated frame kernels on (8, P, 4) planes in place: op 0 multiply_frame(f), 1 update_variances(u), 2 clamp_frame(f)"""
+    L = lib()
+    L.oracle_frame_op.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_float, C.c_uint32]
+    L.oracle_frame_op.restype = None
+    assert fb.dtype == np.float32 and fb.flags.c_contiguous and fb.shape[0] == 8 and fb.shape[-1] == 4
+    L.oracle_frame_op(int(op), fb.ctypes.data, fb.size // 32, float(f), int(u))
+    return fb
+
+
+def psf_blend(fb, words, w_d, w_g, cells, firefly_filter, frame_weight):
+    """the restated psf_blending on (8, P, 4) planes in place: words (n, 2) uint32 {PixelInfo, CacheInfo}, weights (n, 4), cells (m, 4)"""
+    L = lib()
+    L.oracle_psf_blend.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32] + [C.c_void_p] * 4 + [C.c_float, C.c_float]
+    L.oracle_psf_blend.restype = None
+    words = np.ascontiguousarray(words, np.uint32); w_d = np.ascontiguousarray(w_d, np.float32); w_g = np.ascontiguousarray(w_g, np.float32)
+    cells = np.ascontiguousarray(cells, np.float32)
+    L.oracle_psf_blend(fb.ctypes.data, fb.size // 32, len(words), words.ctypes.data, w_d.ctypes.data, w_g.ctypes.data, cells.ctypes.data, float(firefly_filter), float(frame_weight))
+    return fb
+
+
+class RefFrameKernels:
+    """The reference's own multiply_frame / update_variances / clamp_frame kernels (src/renderer.cu:292-362) and psf_blending_kernel
+    (src/renderers/psfpt_impl.h:111-152) run on the host one thread at a time (oracle/build_ref.sh -> oracle/_ref/libref_frame.so)."""
+
+    def __init__(self, path):
+        self._lib = C.CDLL(path)
+        self._lib.ref_frame_op.argtypes = [C.c_int, C.c_void_p, C.c_uint, C.c_uint, C.c_float, C.c_uint]
+        self._lib.ref_frame_op.restype = None
+        self._lib.ref_psf_blend.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_uint] + [C.c_void_p] * 4 + [C.c_float, C.c_float]
+        self._lib.ref_psf_blend.restype = None
+        order = (C.c_int * 8)()
+        n = self._lib.ref_frame_channels(order)
+        assert n == 8 and list(order) == list(range(8)), "the oracle's channel planes follow FBufferDesc's order"
+
+    @classmethod
+    def load(cls):
+        p = os.path.join(_HERE, "_ref", "libref_frame.so")
+        return cls(p) if os.path.exists(p) else None
+
+    def frame_op(self, op, fb, res, f=0.0, u=0):
+        self._lib.ref_frame_op(int(op), fb.ctypes.data, int(res[0]), int(res[1]), float(f), int(u))
+        return fb
+
+    def psf_blend(self, fb, res, words, w_d, w_g, cells, firefly_filter, frame_weight):
+        words = np.ascontiguousarray(words, np.uint32); w_d = np.ascontiguousarray(w_d, np.float32); w_g = np.ascontiguousarray(w_g, np.float32)
+        cells = np.ascontiguousarray(cells, np.float32)
+        self._lib.ref_psf_blend(fb.ctypes.data, int(res[0]), int(res[1]), len(words), words.ctypes.data, w_d.ctypes.data, w_g.ctypes.data, cells.ctypes.data,
+                                float(firefly_filter), float(frame_weight))
+        return fb

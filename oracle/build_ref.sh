@@ -1218,6 +1218,92 @@ $CXX -O2 -std=c++14 -fPIC -w -fpermissive -ffp-contract=off -include $OVF/adapte
     -shared -o $OUT/libref_shade.so $OUT/ref_shade_shim.cpp -x c++ $REF/src/uv_bvh.cu -x none $REF/contrib/cugar/basic/atomics.cpp -L/usr/local/cuda/lib64 -lcudart_static -ldl -lrt -lpthread
 echo "built $OUT/libref_shade.so"
 
+# ---- the reference's own frame kernels (src/renderer.cu: multiply_frame_kernel :292-312, clamp_frame_kernel :314-331, update_variances_kernel :333-362) and the
+# filtered renderer's psf_blending_kernel (src/renderers/psfpt_impl.h:111-152) run on the host one thread at a time: the kernels' text is cut from the files
+# where they lie (renderer.cu pulls in every renderer and OptiX; psfpt_impl.h the device queues), `__global__` is defined away, threadIdx / blockIdx / blockDim are
+# the shim's. The blending kernel's body gets a signature with the context as a template parameter (its own is PSFPTContext<T>, whose base holds the device
+# queues); the shim's context carries the members the body names. Pins pt_oracle.cpp's FB::multiply_pixel / update_variance_pixel / clamp_pixel / psf_blend.
+{
+  echo '#define __global__'
+  sed -n '292,312p' $REF/src/renderer.cu
+  sed -n '314,331p' $REF/src/renderer.cu
+  sed -n '333,362p' $REF/src/renderer.cu
+  echo 'template <typename TContext>'
+  echo 'void psf_blending_kernel(const uint32 in_queue_size, TContext context, RenderingContextView renderer, const float frame_weight)'
+  sed -n '113,152p' $REF/src/renderers/psfpt_impl.h
+} > $OUT/frame_kernels_cut.h
+cat > $OUT/ref_frame_shim.cpp <<'EOF'
+#include "dev_emul.h"
+#include <vector>
+#include <vector_types.h>
+#include <cugar/linalg/vector.h>
+inline float4& operator*=(float4& a, const cugar::Vector4f& b) { a.x *= b.x; a.y *= b.y; a.z *= b.z; a.w *= b.w; return a; }
+inline float4& operator+=(float4& a, const cugar::Vector4f& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; return a; }
+inline float4& operator*=(float4& a, const float b) { a.x *= b; a.y *= b; a.z *= b; a.w *= b; return a; }
+inline float2 operator*(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+inline float2 operator-(float2 a, float s) { return make_float2(a.x - s, a.y - s); }
+#include <pathtracer_core.h>
+#include <psfpt.h>
+#include <psfpt_vertex_processor.h>
+// update_variances_kernel multiplies and divides a Vector4f by a uint32: nvcc converts the integer to float (the one viable overload there); gcc also sees the
+// Matrix overloads and calls it ambiguous, so the conversion is spelled out
+inline cugar::Vector4f operator*(const unsigned a, const cugar::Vector4f& b) { return float(a) * b; }
+inline cugar::Vector4f operator/(const cugar::Vector4f& a, const unsigned b) { return a / float(b); }
+#undef FERMAT_ASSERT
+#define FERMAT_ASSERT(x)
+#include "frame_kernels_cut.h"
+struct FrameOnly        // a RenderingContextView whose frame buffer is the caller's planes (FBufferDesc order, P float4 each)
+{
+	std::vector<FBufferChannelView> channels; FBufferView fbv; RenderingContextView view;
+	FrameOnly(float* fbdata, unsigned res_x, unsigned res_y, unsigned instance) : channels(FBufferDesc::NUM_CHANNELS)
+	{
+		const size_t P = (size_t)res_x * res_y;
+		for (unsigned c = 0; c < (unsigned)FBufferDesc::NUM_CHANNELS; ++c) { channels[c].c_ptr = reinterpret_cast<float4*>(fbdata) + c * P; channels[c].res_x = res_x; channels[c].res_y = res_y; }
+		memset(&fbv, 0, sizeof(fbv)); fbv.channels = channels.data(); fbv.n_channels = FBufferDesc::NUM_CHANNELS;
+		memset(&view, 0, sizeof(view)); view.res_x = res_x; view.res_y = res_y; view.fb = fbv; view.instance = instance;
+	}
+};
+extern "C" int ref_frame_channels(int* order)      // the reference's channel ids in the order the oracle's planes use
+{
+	order[0] = FBufferDesc::DIFFUSE_C; order[1] = FBufferDesc::DIFFUSE_A; order[2] = FBufferDesc::SPECULAR_C; order[3] = FBufferDesc::SPECULAR_A;
+	order[4] = FBufferDesc::DIRECT_C; order[5] = FBufferDesc::COMPOSITED_C; order[6] = FBufferDesc::FILTERED_C; order[7] = FBufferDesc::LUMINANCE;
+	return FBufferDesc::NUM_CHANNELS;
+}
+// op 0 = multiply_frame_kernel(f), 1 = update_variances_kernel(u), 2 = clamp_frame_kernel(f), over every pixel
+extern "C" void ref_frame_op(int op, float* fbdata, unsigned res_x, unsigned res_y, float f, unsigned u)
+{
+	FrameOnly fr(fbdata, res_x, res_y, 0u);
+	for (unsigned p = 0; p < res_x * res_y; ++p)
+	{
+		blockIdx.x = p; threadIdx.x = 0;
+		if (op == 0) multiply_frame_kernel(fr.view, f);
+		else if (op == 1) update_variances_kernel(fr.view, u);
+		else clamp_frame_kernel(fr.view, f);
+	}
+	blockIdx.x = 0;
+}
+struct BlendContext { struct { float4* weights_d; float4* weights_g; uint2* pixels; } ref_queue; float4* psf_values; PSFPTOptions options; };
+// psf_blending_kernel over n references in order; words = 2 per reference {PixelInfo, CacheInfo}
+extern "C" void ref_psf_blend(float* fbdata, unsigned res_x, unsigned res_y, unsigned n, const unsigned* words, const float* w_d, const float* w_g, const float* cells,
+							  float firefly_filter, float frame_weight)
+{
+	FrameOnly fr(fbdata, res_x, res_y, 0u);
+	BlendContext context;
+	context.ref_queue.weights_d = (float4*)w_d; context.ref_queue.weights_g = (float4*)w_g; context.ref_queue.pixels = (uint2*)words;
+	context.psf_values = (float4*)cells; context.options.firefly_filter = firefly_filter;
+	for (unsigned i = 0; i < n; ++i)
+	{
+		blockIdx.x = i; threadIdx.x = 0;
+		psf_blending_kernel(n, context, fr.view, frame_weight);
+	}
+	blockIdx.x = 0;
+}
+EOF
+$CXX -O2 -std=c++14 -fPIC -w -fpermissive -ffp-contract=off -include $OVF/adapter_prefix.h -DFERMAT_API_EXTERN= -DFERMAT_API= -DSUTILAPI= -DSUTILCLASSAPI= \
+    -DTHRUST_DEVICE_SYSTEM=THRUST_DEVICE_SYSTEM_CPP -I$OVS -I$OVF -I$OUT -I$REF/src -I$REF/src/mesh -I$REF/src/renderers -I$REF/contrib -I/usr/local/cuda/include \
+    -shared -o $OUT/libref_frame.so $OUT/ref_frame_shim.cpp -x none $REF/contrib/cugar/basic/atomics.cpp -L/usr/local/cuda/lib64 -lcudart_static -ldl -lrt -lpthread
+echo "built $OUT/libref_frame.so"
+
 # ---- the reference's own VPL generator (MeshLightsStorageImpl::init, src/mesh_lights.cu:163-389: emission-weighted triangle CDF with the mip-mapped estimate for
 # textured emitters, the stratified LFSR draw of the VPLs, the normalisation, the CDF resample) - host code inside a CUDA translation unit whose tail builds an LBVH
 # on the device. The text of the function up to its last host statement is cut from the file where it lies and compiled as a member of a stand-in struct that

@@ -320,6 +320,44 @@ struct FB
 		m[0] += f.x * inv_n; m[1] += f.y * inv_n; m[2] += f.z * inv_n;
 		if (var) { const float ld = max_comp(delta); m[3] += ld * ld * inv_n; }
 	}
+	float lum_of(int ch, uint32_t p) { const float* m = px(ch, p); return max_comp(vec3(m[0], m[1], m[2])); }
+	// multiply_frame_kernel (src/renderer.cu:292-311): save the luminances, then scale the six accumulated channels
+	void multiply_pixel(uint32_t p, float scale)
+	{
+		float* lum = px(7, p);
+		lum[0] = lum_of(4, p); lum[1] = lum_of(0, p); lum[2] = lum_of(2, p); lum[3] = lum_of(5, p);
+		const int scaled[6] = { 0, 1, 2, 3, 4, 5 };
+		for (int c = 0; c < 6; ++c) for (int i = 0; i < 4; ++i) px(scaled[c], p)[i] *= scale;
+	}
+	// update_variances_kernel (src/renderer.cu:333-362)
+	void update_variance_pixel(uint32_t p, uint32_t n)
+	{
+		const float* lum = px(7, p);
+		const float nl[4] = { lum_of(4, p), lum_of(0, p), lum_of(2, p), lum_of(5, p) };
+		const int vch[4] = { 4, 0, 2, 5 };
+		for (int c = 0; c < 4; ++c)
+		{
+			const float d1 = n * (nl[c] - lum[c]), d2 = (n - 1) * (nl[c] - lum[c]);
+			px(vch[c], p)[3] += (d1 * d2) / (n * n);
+		}
+	}
+	// clamp_frame_kernel (src/renderer.cu:314-331): all four components of the four colour channels
+	void clamp_pixel(uint32_t p, float max_value)
+	{
+		const int vch[4] = { 4, 0, 2, 5 };
+		for (int c = 0; c < 4; ++c) for (int i = 0; i < 4; ++i) px(vch[c], p)[i] = fminf(px(vch[c], p)[i], max_value);
+	}
+	// psf_blending_kernel's body for one valid reference (src/renderers/psfpt_impl.h:127-150): the cell's mean times the reference's weights
+	void psf_blend(uint32_t pixel_info, const float* cell, vec3 w_d, vec3 w_g, float firefly_filter, float frame_weight)
+	{
+		const uint32_t pixel = pixel_info & 0x07FFFFFFu, rcomp = (pixel_info >> 27) & 0xFu;
+		const vec3 c(cell[0] / cell[3], cell[1] / cell[3], cell[2] / cell[3]);
+		const vec3 w = ((rcomp & cDiffuseMask) ? w_d : vec3(0.0f)) + ((rcomp & cGlossyMask) ? w_g : vec3(0.0f));
+		const vec3 cw = c * w;
+		add_in(false, 5, pixel, vec3(fminf(cw.x, firefly_filter), fminf(cw.y, firefly_filter), fminf(cw.z, firefly_filter)), frame_weight);
+		if (rcomp & cDiffuseMask) add_in(true, 0, pixel, c * w_d, frame_weight);
+		if (rcomp & cGlossyMask)  add_in(true, 2, pixel, c * w_g, frame_weight);
+	}
 };
 
 static inline float power_heuristic(float p1, float p2)
@@ -950,28 +988,12 @@ static int render_pass_impl(const fb200_scene_view* s, uint32_t instance, float*
 		{
 			const uint32_t p = pixels ? pixels[k] : (uint32_t)k;
 			// multiply_frame_kernel
-			float* lum = fb.px(LUMINANCE, p);
-			lum[0] = max_comp(vec3(fb.px(DIRECT_C, p)[0], fb.px(DIRECT_C, p)[1], fb.px(DIRECT_C, p)[2]));
-			lum[1] = max_comp(vec3(fb.px(DIFFUSE_C, p)[0], fb.px(DIFFUSE_C, p)[1], fb.px(DIFFUSE_C, p)[2]));
-			lum[2] = max_comp(vec3(fb.px(SPECULAR_C, p)[0], fb.px(SPECULAR_C, p)[1], fb.px(SPECULAR_C, p)[2]));
-			lum[3] = max_comp(vec3(fb.px(COMPOSITED_C, p)[0], fb.px(COMPOSITED_C, p)[1], fb.px(COMPOSITED_C, p)[2]));
-			const int scaled[6] = { DIFFUSE_C, DIFFUSE_A, SPECULAR_C, SPECULAR_A, DIRECT_C, COMPOSITED_C };
-			for (int c = 0; c < 6; ++c) for (int i = 0; i < 4; ++i) fb.px(scaled[c], p)[i] *= scale;
+			fb.multiply_pixel(p, scale);
 
 			trace_path(sc, smp, fb, p % s->res_x, p / s->res_x, frame_weight, U, V, W, st, count_traversal != 0, NULL, instance, rl);
 
 			// update_variances_kernel
-			const float nl[4] = {
-				max_comp(vec3(fb.px(DIRECT_C, p)[0], fb.px(DIRECT_C, p)[1], fb.px(DIRECT_C, p)[2])),
-				max_comp(vec3(fb.px(DIFFUSE_C, p)[0], fb.px(DIFFUSE_C, p)[1], fb.px(DIFFUSE_C, p)[2])),
-				max_comp(vec3(fb.px(SPECULAR_C, p)[0], fb.px(SPECULAR_C, p)[1], fb.px(SPECULAR_C, p)[2])),
-				max_comp(vec3(fb.px(COMPOSITED_C, p)[0], fb.px(COMPOSITED_C, p)[1], fb.px(COMPOSITED_C, p)[2])) };
-			const int vch[4] = { DIRECT_C, DIFFUSE_C, SPECULAR_C, COMPOSITED_C };
-			for (int c = 0; c < 4; ++c)
-			{
-				const float d1 = n * (nl[c] - lum[c]), d2 = (n - 1) * (nl[c] - lum[c]);
-				fb.px(vch[c], p)[3] += (d1 * d2) / (n * n);
-			}
+			fb.update_variance_pixel(p, n);
 		}
 		#pragma omp critical
 		{
@@ -1109,13 +1131,7 @@ static int render_pass_psf_impl(const fb200_scene_view* s, uint32_t instance, fl
 		for (long long k = 0; k < (long long)P; ++k)
 		{
 			const uint32_t p = (uint32_t)k;
-			float* lum = fb.px(LUMINANCE, p);
-			lum[0] = max_comp(vec3(fb.px(DIRECT_C, p)[0], fb.px(DIRECT_C, p)[1], fb.px(DIRECT_C, p)[2]));
-			lum[1] = max_comp(vec3(fb.px(DIFFUSE_C, p)[0], fb.px(DIFFUSE_C, p)[1], fb.px(DIFFUSE_C, p)[2]));
-			lum[2] = max_comp(vec3(fb.px(SPECULAR_C, p)[0], fb.px(SPECULAR_C, p)[1], fb.px(SPECULAR_C, p)[2]));
-			lum[3] = max_comp(vec3(fb.px(COMPOSITED_C, p)[0], fb.px(COMPOSITED_C, p)[1], fb.px(COMPOSITED_C, p)[2]));
-			const int scaled[6] = { DIFFUSE_C, DIFFUSE_A, SPECULAR_C, SPECULAR_A, DIRECT_C, COMPOSITED_C };
-			for (int c = 0; c < 6; ++c) for (int i = 0; i < 4; ++i) fb.px(scaled[c], p)[i] *= scale;
+			fb.multiply_pixel(p, scale);
 			trace_path(sc, smp, fb, p % s->res_x, p / s->res_x, frame_weight, U, V, W, st, false, psf, instance, rl);
 		}
 		#pragma omp critical
@@ -1131,33 +1147,13 @@ static int render_pass_psf_impl(const fb200_scene_view* s, uint32_t instance, fl
 			const PsfRef& r = psf->refs[b][i];
 			const uint32_t slot = psf_slot(r.cache);
 			if (slot == PSF_INVALID_SLOT) continue;
-			const uint32_t pixel = r.pixel_info & 0x07FFFFFFu, rcomp = (r.pixel_info >> 27) & 0xFu;
-			const float* cv = &psf->values[4 * (size_t)slot];
-			const vec3 c(cv[0] / cv[3], cv[1] / cv[3], cv[2] / cv[3]);
-			const vec3 w = ((rcomp & cDiffuseMask) ? r.w_d : vec3(0.0f)) + ((rcomp & cGlossyMask) ? r.w_g : vec3(0.0f));
-			const vec3 cw = c * w, ff(s->psf.firefly_filter);
-			fb.add_in(false, COMPOSITED_C, pixel, vec3(fminf(cw.x, ff.x), fminf(cw.y, ff.y), fminf(cw.z, ff.z)), frame_weight);
-			if (rcomp & cDiffuseMask) fb.add_in(true, DIFFUSE_C, pixel, c * r.w_d, frame_weight);
-			if (rcomp & cGlossyMask)  fb.add_in(true, SPECULAR_C, pixel, c * r.w_g, frame_weight);
+			fb.psf_blend(r.pixel_info, &psf->values[4 * (size_t)slot], r.w_d, r.w_g, s->psf.firefly_filter, frame_weight);
 		}
 	#pragma omp parallel for schedule(static)
 	for (long long k = 0; k < (long long)P; ++k)
 	{
-		const uint32_t p = (uint32_t)k;
-		const float* lum = fb.px(LUMINANCE, p);
-		const float nl[4] = {
-			max_comp(vec3(fb.px(DIRECT_C, p)[0], fb.px(DIRECT_C, p)[1], fb.px(DIRECT_C, p)[2])),
-			max_comp(vec3(fb.px(DIFFUSE_C, p)[0], fb.px(DIFFUSE_C, p)[1], fb.px(DIFFUSE_C, p)[2])),
-			max_comp(vec3(fb.px(SPECULAR_C, p)[0], fb.px(SPECULAR_C, p)[1], fb.px(SPECULAR_C, p)[2])),
-			max_comp(vec3(fb.px(COMPOSITED_C, p)[0], fb.px(COMPOSITED_C, p)[1], fb.px(COMPOSITED_C, p)[2])) };
-		const int vch[4] = { DIRECT_C, DIFFUSE_C, SPECULAR_C, COMPOSITED_C };
-		for (int c = 0; c < 4; ++c)
-		{
-			const float d1 = n * (nl[c] - lum[c]), d2 = (n - 1) * (nl[c] - lum[c]);
-			fb.px(vch[c], p)[3] += (d1 * d2) / (n * n);
-		}
-		// clamp_frame_kernel (src/renderer.cu:314-331): all four components of the four colour channels
-		for (int c = 0; c < 4; ++c) for (int i = 0; i < 4; ++i) fb.px(vch[c], p)[i] = fminf(fb.px(vch[c], p)[i], 100.0f);
+		fb.update_variance_pixel((uint32_t)k, n);
+		fb.clamp_pixel((uint32_t)k, 100.0f);
 	}
 	if (out) *out = total;
 	return 0;
@@ -1316,6 +1312,28 @@ int oracle_probe_shade_vertex_psf(const fb200_scene_view* s, void* state, uint32
 								  const uint8_t* occluded, uint32_t n)
 {
 	return probe_shade_vertex_impl(s, instance, bounce, in, out, n, NULL, NULL, occluded, static_cast<PsfState*>(state), words, ref_w);
+}
+// the frame kernels on a whole frame (fbdata: 8 channel planes of P float4): op 0 = multiply_frame(f), 1 = update_variances(u), 2 = clamp_frame(f)
+void oracle_frame_op(int op, float* fbdata, uint64_t P, float f, uint32_t u)
+{
+	FB fb = { fbdata, (size_t)P };
+	for (uint64_t p = 0; p < P; ++p)
+	{
+		if (op == 0) fb.multiply_pixel((uint32_t)p, f);
+		else if (op == 1) fb.update_variance_pixel((uint32_t)p, u);
+		else fb.clamp_pixel((uint32_t)p, f);
+	}
+}
+// psf_blending over n references in order: words = 2 per reference {PixelInfo, CacheInfo}; cells = the float4 cell values the cache words index
+void oracle_psf_blend(float* fbdata, uint64_t P, uint32_t n, const uint32_t* words, const float* w_d, const float* w_g, const float* cells, float firefly_filter, float frame_weight)
+{
+	FB fb = { fbdata, (size_t)P };
+	for (uint32_t i = 0; i < n; ++i)
+	{
+		const uint32_t slot = psf_slot(words[2 * i + 1]);
+		if (slot == PSF_INVALID_SLOT) continue;
+		fb.psf_blend(words[2 * i], cells + 4 * (size_t)slot, vec3(w_d[4 * i], w_d[4 * i + 1], w_d[4 * i + 2]), vec3(w_g[4 * i], w_g[4 * i + 1], w_g[4 * i + 2]), firefly_filter, frame_weight);
+	}
 }
 // the first n cells' values (float4 each: rgb sum, sample count), in slot order
 void oracle_psf_values(const void* state, float* out, uint32_t n)

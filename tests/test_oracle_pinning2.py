@@ -200,3 +200,26 @@ def test_vpl_table_is_the_references_own_generators(fb, oracle):
             sha = hashlib.sha256(rcdf.tobytes() + rinv.tobytes() + rvpls.tobytes() + rvcdf.tobytes()).digest()
             assert np.array_equal(np.frombuffer(sha, np.uint8), g["sha_%s" % args[3]])
         sc.close()
+
+
+def test_frame_kernels_and_psf_blending_are_the_references_own(oracle):
+    """multiply_frame / update_variances / clamp_frame (src/renderer.cu:292-362) and psf_blending_kernel (src/renderers/psfpt_impl.h:111-152): the kernels' own
+    text run on the host one thread at a time (oracle/build_ref.sh -> libref_frame.so) against the units the oracle's passes are made of
+    (pt_oracle.cpp FB::multiply_pixel / update_variance_pixel / clamp_pixel / psf_blend), bit for bit: golden hashes everywhere
+    (tests/golden/frame_golden.npz, tools/make_golden_frame.py), the live kernels where oracle/_ref exists."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_frame", os.path.join(os.path.dirname(GOLDEN), "..", "tools", "make_golden_frame.py"))
+    mk = importlib.util.module_from_spec(spec); spec.loader.exec_module(mk)
+    g = np.load(os.path.join(GOLDEN, "frame_golden.npz"))
+    fb, ops, blend = mk.frame_cases()
+    assert np.array_equal(mk.sha(fb, *blend[:4]), g["sha_inputs"]), "the seeded inputs differ from the ones the golden file was made from"
+    live = oracle.RefFrameKernels.load()
+    for i, (op, f, u) in enumerate(ops):
+        a = oracle.frame_op(op, fb.copy(), f, u)
+        assert np.array_equal(mk.sha(a), g["sha_op_%d" % i]), (op, f, u)
+        if live is not None:
+            assert np.array_equal(a.view(np.uint32), live.frame_op(op, fb.copy(), mk.RES, f, u).view(np.uint32)), (op, f, u)
+    a = oracle.psf_blend(fb.copy(), *blend)
+    assert not np.array_equal(a, fb) and np.array_equal(mk.sha(a), g["sha_blend"])
+    if live is not None:
+        assert np.array_equal(a.view(np.uint32), live.psf_blend(fb.copy(), mk.RES, *blend).view(np.uint32))
