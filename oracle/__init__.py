@@ -970,6 +970,25 @@ class RefFrameKernels:
         self._lib.ref_frame_op(int(op), fb.ctypes.data, int(res[0]), int(res[1]), float(f), int(u))
         return fb
 
+    def to_rgba(self, fb, geo, uv, res, mode, exposure, gamma):
+        """to_rgba_kernel (src/renderer.cu:83-282) on (8, P, 4) planes + the G-buffer's geo / uv planes (P, 4) -> (P, 4) uint8"""
+        self._lib.ref_to_rgba.argtypes = [C.c_void_p] * 3 + [C.c_uint] * 3 + [C.c_float, C.c_float, C.c_void_p]
+        self._lib.ref_to_rgba.restype = None
+        fb = np.ascontiguousarray(fb, np.float32); geo = np.ascontiguousarray(geo, np.float32); uv = np.ascontiguousarray(uv, np.float32)
+        out = np.zeros((int(res[0]) * int(res[1]), 4), np.uint8)
+        self._lib.ref_to_rgba(fb.ctypes.data, geo.ctypes.data, uv.ctypes.data, int(res[0]), int(res[1]), int(mode), float(exposure), float(gamma), out.ctypes.data)
+        return out
+
+    def filter_variance(self, img, fw):
+        """filter_variance_kernel (src/renderer.cu:366-390) on an (H, W, 4) plane -> (H, W)"""
+        self._lib.ref_filter_variance.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_uint, C.c_void_p]
+        self._lib.ref_filter_variance.restype = None
+        img = np.ascontiguousarray(img, np.float32)
+        h, w = img.shape[:2]
+        var = np.zeros((h, w), np.float32)
+        self._lib.ref_filter_variance(img.ctypes.data, w, h, int(fw), var.ctypes.data)
+        return var
+
     def psf_blend(self, fb, res, words, w_d, w_g, cells, firefly_filter, frame_weight):
         words = np.ascontiguousarray(words, np.uint32); w_d = np.ascontiguousarray(w_d, np.float32); w_g = np.ascontiguousarray(w_g, np.float32)
         cells = np.ascontiguousarray(cells, np.float32)

@@ -1218,7 +1218,8 @@ $CXX -O2 -std=c++14 -fPIC -w -fpermissive -ffp-contract=off -include $OVF/adapte
     -shared -o $OUT/libref_shade.so $OUT/ref_shade_shim.cpp -x c++ $REF/src/uv_bvh.cu -x none $REF/contrib/cugar/basic/atomics.cpp -L/usr/local/cuda/lib64 -lcudart_static -ldl -lrt -lpthread
 echo "built $OUT/libref_shade.so"
 
-# ---- the reference's own frame kernels (src/renderer.cu: multiply_frame_kernel :292-312, clamp_frame_kernel :314-331, update_variances_kernel :333-362) and the
+# ---- the reference's own frame kernels (src/renderer.cu: multiply_frame_kernel :292-312, clamp_frame_kernel :314-331, update_variances_kernel :333-362,
+# to_rgba_kernel :83-282, filter_variance_kernel :366-390) and the
 # filtered renderer's psf_blending_kernel (src/renderers/psfpt_impl.h:111-152) run on the host one thread at a time: the kernels' text is cut from the files
 # where they lie (renderer.cu pulls in every renderer and OptiX; psfpt_impl.h the device queues), `__global__` is defined away, threadIdx / blockIdx / blockDim are
 # the shim's. The blending kernel's body gets a signature with the context as a template parameter (its own is PSFPTContext<T>, whose base holds the device
@@ -1228,6 +1229,8 @@ echo "built $OUT/libref_shade.so"
   sed -n '292,312p' $REF/src/renderer.cu
   sed -n '314,331p' $REF/src/renderer.cu
   sed -n '333,362p' $REF/src/renderer.cu
+  sed -n '83,282p' $REF/src/renderer.cu
+  sed -n '366,390p' $REF/src/renderer.cu
   echo 'template <typename TContext>'
   echo 'void psf_blending_kernel(const uint32 in_queue_size, TContext context, RenderingContextView renderer, const float frame_weight)'
   sed -n '113,152p' $REF/src/renderers/psfpt_impl.h
@@ -1281,6 +1284,24 @@ extern "C" void ref_frame_op(int op, float* fbdata, unsigned res_x, unsigned res
 		else clamp_frame_kernel(fr.view, f);
 	}
 	blockIdx.x = 0;
+}
+// to_rgba_kernel over every pixel (every ShadingMode but kCharts, which needs the mesh groups); geo / uv: the G-buffer planes (P float4 each)
+extern "C" void ref_to_rgba(float* fbdata, float* geo, float* uv, unsigned res_x, unsigned res_y, unsigned mode, float exposure, float gamma, unsigned char* rgba)
+{
+	FrameOnly fr(fbdata, res_x, res_y, 0u);
+	fr.view.fb.gbuffer.m_geo = reinterpret_cast<float4*>(geo); fr.view.fb.gbuffer.m_uv = reinterpret_cast<float4*>(uv);
+	fr.view.fb.gbuffer.res_x = res_x; fr.view.fb.gbuffer.res_y = res_y;
+	fr.view.shading_mode = (ShadingMode)mode; fr.view.exposure = exposure; fr.view.gamma = gamma;
+	for (unsigned p = 0; p < res_x * res_y; ++p) { blockIdx.x = p; threadIdx.x = 0; to_rgba_kernel(fr.view, rgba); }
+	blockIdx.x = 0;
+}
+// filter_variance_kernel over every pixel of one channel plane
+extern "C" void ref_filter_variance(float* img, unsigned res_x, unsigned res_y, unsigned FW, float* var)
+{
+	FBufferChannelView ch; ch.c_ptr = reinterpret_cast<float4*>(img); ch.res_x = res_x; ch.res_y = res_y;
+	for (unsigned y = 0; y < res_y; ++y)
+		for (unsigned x = 0; x < res_x; ++x) { blockIdx.x = x; blockIdx.y = y; threadIdx.x = threadIdx.y = 0; filter_variance_kernel(ch, var, FW); }
+	blockIdx.x = blockIdx.y = 0;
 }
 struct BlendContext { struct { float4* weights_d; float4* weights_g; uint2* pixels; } ref_queue; float4* psf_values; PSFPTOptions options; };
 // psf_blending_kernel over n references in order; words = 2 per reference {PixelInfo, CacheInfo}

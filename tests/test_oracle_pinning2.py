@@ -223,3 +223,18 @@ def test_frame_kernels_and_psf_blending_are_the_references_own(oracle):
     assert not np.array_equal(a, fb) and np.array_equal(mk.sha(a), g["sha_blend"])
     if live is not None:
         assert np.array_equal(a.view(np.uint32), live.psf_blend(fb.copy(), mk.RES, *blend).view(np.uint32))
+    # to_rgba_kernel (src/renderer.cu:83-282) and filter_variance_kernel (:366-390): post_oracle.cpp's restatements. powf is libm's on both sides here; the
+    # product's device powf is compared with the restatement to +-1 code in tests/test_post.py
+    geo, uv = mk.gbuffer_planes()
+    assert np.array_equal(mk.sha(geo, uv), g["sha_gbuffer"])
+    H, W = mk.RES[1], mk.RES[0]
+    for mode in mk.RGBA_MODES:
+        a = oracle.to_rgba(fb.reshape(8, H, W, 4), geo.reshape(H, W, 4), uv.reshape(H, W, 4), mode, 1.5, 2.2).reshape(-1, 4)
+        assert np.array_equal(mk.sha(a), g["sha_rgba_%d" % mode]), mode
+        if live is not None:
+            assert np.array_equal(a, live.to_rgba(fb, geo, uv, mk.RES, mode, 1.5, 2.2)), mode
+    for fw in (1, 2, 3):
+        a = oracle.filter_variance(fb[3].reshape(H, W, 4), fw)
+        assert np.array_equal(mk.sha(a), g["sha_var_%d" % fw]), fw
+        if live is not None:
+            assert np.array_equal(a.view(np.uint32), live.filter_variance(fb[3].reshape(H, W, 4), fw).view(np.uint32)), fw

@@ -31,6 +31,22 @@ def frame_cases():
     return fb, ops, (words, w_d, w_g, cells, 2.0, 0.25)
 
 
+RGBA_MODES = (0, 1, 4, 5, 6, 7, 8, 9, 10, 11, 12)          # every ShadingMode but kUVStretch (not in the kernel) and kCharts (needs the mesh groups)
+
+
+def gbuffer_planes():
+    """the G-buffer's geo plane (word 0 = the packed normal GBufferView::unpack_normal reads, the rest unused by to_rgba) and its uv plane"""
+    rng = np.random.default_rng(9)
+    P = RES[0] * RES[1]
+    n = rng.normal(size=(P, 3)).astype(np.float32); n /= np.linalg.norm(n, axis=1, keepdims=True).astype(np.float32)
+    geo = np.zeros((P, 4), np.float32)
+    # unit normals as floats in words 0..2 plus, every 11th pixel, a random 30-bit pattern in word 0: unpack_normal is exercised on arbitrary words
+    geo[:, 0] = n[:, 0]; geo[:, 1] = n[:, 1]; geo[:, 2] = n[:, 2]; geo[:, 3] = rng.random(P, dtype=np.float32) * np.float32(10)
+    geo.view(np.uint32)[::11, 0] = rng.integers(0, 2 ** 32, len(geo[::11]), dtype=np.uint64).astype(np.uint32) & np.uint32(0x3FFFFFFF)
+    uv = rng.random((P, 4), dtype=np.float32) * np.float32(1.2)
+    return geo, uv
+
+
 def sha(*arrays):
     return np.frombuffer(hashlib.sha256(b"".join(np.ascontiguousarray(a).tobytes() for a in arrays)).digest(), np.uint8)
 
@@ -45,6 +61,12 @@ def main():
     for i, (op, f, u) in enumerate(ops):
         out["sha_op_%d" % i] = sha(R.frame_op(op, fb.copy(), RES, f, u))
     out["sha_blend"] = sha(R.psf_blend(fb.copy(), RES, *blend))
+    geo, uv = gbuffer_planes()
+    out["sha_gbuffer"] = sha(geo, uv)
+    for mode in RGBA_MODES:
+        out["sha_rgba_%d" % mode] = sha(R.to_rgba(fb, geo, uv, RES, mode, 1.5, 2.2))
+    for fw in (1, 2, 3):
+        out["sha_var_%d" % fw] = sha(R.filter_variance(fb[3].reshape(RES[1], RES[0], 4), fw))
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "frame_golden.npz"), **out)
     print("wrote frame_golden.npz (%d entries)" % len(out))
 
