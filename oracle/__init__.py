@@ -729,6 +729,16 @@ class RefShade:
         f.instance, f.bounce = int(instance), int(bounce)
         return f
 
+    def primary_rays(self, view, instance):
+        """generate_primary_rays_kernel's own text over every pixel (src/pathtracer_kernels.h:133-163): (P, 20) floats {ray (8), weight (4), queue words (4),
+        cone (2), 0, 0} and the queue size it wrote"""
+        self.L.ref_primary_rays.restype = C.c_uint32
+        self.L.ref_primary_rays.argtypes = [C.c_void_p, C.c_void_p]
+        f = self._frame(view, instance, 0)
+        out = np.zeros((int(view.res_x) * int(view.res_y), 20), np.float32)
+        n = self.L.ref_primary_rays(C.addressof(f), out.ctypes.data)
+        return out, int(n)
+
     def rl_create(self, vtls, hash_size, init_ends, init_cdf):
         """the reference's VTLMeshView (UV-BVH built by src/uv_bvh.cu) + an AdaptiveClusteredRLView over host arrays, every cell in its initial state"""
         L = self.L
@@ -995,3 +1005,13 @@ class RefFrameKernels:
         self._lib.ref_psf_blend(fb.ctypes.data, int(res[0]), int(res[1]), len(words), words.ctypes.data, w_d.ctypes.data, w_g.ctypes.data, cells.ctypes.data,
                                 float(firefly_filter), float(frame_weight))
         return fb
+
+
+def probe_primary_rays(view, instance):
+    """the restated primary rays of a pass: (P, 10) floats {origin, mask bits, dir, tmax, 0, cone pdf}"""
+    L = lib()
+    L.oracle_probe_primary_rays.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+    L.oracle_probe_primary_rays.restype = None
+    out = np.zeros((int(view.res_x) * int(view.res_y), 10), np.float32)
+    L.oracle_probe_primary_rays(C.addressof(view), int(instance), out.ctypes.data)
+    return out

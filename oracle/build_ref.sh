@@ -737,6 +737,7 @@ inline float __int_as_float(int u) { float f; memcpy(&f, &u, 4); return f; }
 inline long long clock64() { return 0; }
 inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 EOF
+sed -n '133,163p' $REF/src/pathtracer_kernels.h > $OUT/primary_kernel_cut.h      # generate_primary_rays_kernel's text (ref_primary_rays below)
 cat > $OUT/ref_shade_shim.cpp <<'EOF'
 #include "dev_emul.h"
 #include <vector>
@@ -1211,6 +1212,52 @@ extern "C" int ref_shade_vertex_psf(const RefScene* s, const RefFrame* f, void* 
 		q[79] = float(context.shadows.size());
 	}
 	return 0;
+}
+// ---- generate_primary_rays_kernel (src/pathtracer_kernels.h:133-163) from its own text (primary_kernel_cut.h: `__global__` defined away, the shim's
+// threadIdx / blockIdx), over a context whose input queue is four host arrays: per pixel the ray, the filter weight, the queue words and the ray cone
+#define __global__
+#include "primary_kernel_cut.h"
+#undef __global__
+struct PrimaryQueue { MaskedRay* rays; float4* weights; uint4* pixels; float2* cones; uint32* size; };
+struct PrimaryContext : PTContextBase<PTOptions> { PrimaryQueue in_queue; };
+// out: 20 floats per pixel of the frame {ray origin, mask bits, dir, tmax, weight (4), queue words (4, bits), cone (2), 0, 0}; returns the queue size the kernel wrote
+extern "C" unsigned ref_primary_rays(const RefFrame* f, float* out)
+{
+	Camera cam;
+	cam.eye = make_float3(f->cam[0], f->cam[1], f->cam[2]); cam.aim = make_float3(f->cam[3], f->cam[4], f->cam[5]); cam.up = make_float3(f->cam[6], f->cam[7], f->cam[8]); cam.fov = f->cam[9];
+	RenderingContextView renderer; memset(&renderer, 0, sizeof(renderer));
+	renderer.camera = cam; renderer.res_x = f->res_x; renderer.res_y = f->res_y; renderer.aspect = f->aspect; renderer.instance = f->instance;
+	const size_t P = (size_t)f->res_x * f->res_y, S = (size_t)f->tile * f->tile;
+	std::vector<float> samples((size_t)f->n_dims * S);
+	for (unsigned d = 0; d < f->n_dims; ++d)
+	{
+		const float seq = cugar::randfloat(d, f->instance + 1);
+		for (size_t i = 0; i < S; ++i) samples[d * S + i] = fmodf(seq + f->shifts[d * S + i], 1.0f);
+	}
+	PrimaryContext context;
+	context.sequence.n_dimensions = f->n_dims; context.sequence.tile_size = f->tile; context.sequence.samples = samples.data(); context.sequence.shifts = f->shifts;
+	std::vector<MaskedRay> rays(P); std::vector<float4> weights(P); std::vector<uint4> pixels(P); std::vector<float2> cones(P); uint32 size = 0;
+	context.in_queue.rays = rays.data(); context.in_queue.weights = weights.data(); context.in_queue.pixels = pixels.data(); context.in_queue.cones = cones.data(); context.in_queue.size = &size;
+	// generate_primary_rays (src/pathtracer_kernels.h:170-181)
+	cugar::Vector3f U, V, W;
+	camera_frame(renderer.camera, renderer.aspect, U, V, W);
+	const float square_pixel_focal_length = renderer.camera.square_pixel_focal_length(renderer.res_x, renderer.res_y);
+	for (unsigned y = 0; y < f->res_y; ++y)
+		for (unsigned x = 0; x < f->res_x; ++x)
+		{
+			blockIdx.x = x; blockIdx.y = y; threadIdx.x = threadIdx.y = 0;
+			generate_primary_rays_kernel(context, renderer, U, V, W, length(W), square_pixel_focal_length);
+		}
+	blockIdx.x = blockIdx.y = 0;
+	for (size_t i = 0; i < P; ++i)
+	{
+		float* q = out + 20 * i;
+		put_ray(q, rays[i]);
+		q[8] = weights[i].x; q[9] = weights[i].y; q[10] = weights[i].z; q[11] = weights[i].w;
+		q[12] = bits(pixels[i].x); q[13] = bits(pixels[i].y); q[14] = bits(pixels[i].z); q[15] = bits(pixels[i].w);
+		q[16] = cones[i].x; q[17] = cones[i].y; q[18] = q[19] = 0.0f;
+	}
+	return size;
 }
 EOF
 $CXX -O2 -std=c++14 -fPIC -w -fpermissive -ffp-contract=off -include $OVF/adapter_prefix.h -DFERMAT_API_EXTERN= -DFERMAT_API= -DSUTILAPI= -DSUTILCLASSAPI= \

@@ -367,6 +367,18 @@ static inline float power_heuristic(float p1, float p2)
 }
 static inline float pdf_product(float p1, float p2) { return std::isfinite(p1) && std::isfinite(p2) ? p1 * p2 : INFINITY; }
 
+// generate_primary_ray (src/pathtracer_core.h:633-656): the pixel's first two sample dimensions jitter the position inside the pixel
+static inline Ray primary_ray(const fb200_scene_view* s, const Sampler& smp, uint32_t px, uint32_t py, vec3 U, vec3 V, vec3 W)
+{
+	Ray ray;
+	const float u = smp.sample_2d(px, py, 0), v = smp.sample_2d(px, py, 1);
+	const float dx = (px + u) / float(s->res_x) * 2.f - 1.f, dy = (py + v) / float(s->res_y) * 2.f - 1.f;
+	ray.o = vec3(s->eye[0], s->eye[1], s->eye[2]);
+	ray.d = dx * U + dy * V + W;
+	ray.tmin = 0.0f; ray.tmax = 1e34f; ray.mask = 0;
+	return ray;
+}
+
 struct GBufferOut { float* geo; float* uv; uint32_t* tri; float* depth; };
 static GBufferOut g_gbuffer = { NULL, NULL, NULL, NULL };     // optional outputs, set by oracle_set_gbuffer
 
@@ -871,15 +883,7 @@ static void trace_path(const SceneRef& sc, const Sampler& smp, FB& fb, uint32_t 
 	// do_nee is gated on the VPL count whichever sampler is active (pathtracer_core.h:601-602)
 	const bool have_vpls = s->n_vpls > 0;
 
-	// primary ray (pathtracer_core.h:633-656)
-	Ray ray;
-	{
-		const float u = smp.sample_2d(px, py, 0), v = smp.sample_2d(px, py, 1);
-		const float dx = (px + u) / float(s->res_x) * 2.f - 1.f, dy = (py + v) / float(s->res_y) * 2.f - 1.f;
-		ray.o = vec3(s->eye[0], s->eye[1], s->eye[2]);
-		ray.d = dx * U + dy * V + W;
-		ray.tmin = 0.0f; ray.tmax = 1e34f; ray.mask = 0;
-	}
+	Ray ray = primary_ray(s, smp, px, py, U, V, W);
 	vec3 w(1.0f); float p_prev = 1.0f;
 	uint32_t comp = 0; bool diffuse_flag = false;
 	TravStats* ts = count_trav ? &st.trav : NULL;
@@ -1446,6 +1450,21 @@ void oracle_probe_camera(const fb200_scene_view* s, float* out, const float* d, 
 	vec3 U, V, W; camera_frame(s, U, V, W);
 	out[0] = U.x; out[1] = U.y; out[2] = U.z; out[3] = V.x; out[4] = V.y; out[5] = V.z; out[6] = W.x; out[7] = W.y; out[8] = W.z;
 	for (uint32_t i = 0; i < n; ++i) pdf[i] = primary_cone_pdf(s, U, V, W, vec3(d[3 * i], d[3 * i + 1], d[3 * i + 2]));
+}
+// every pixel's primary ray as the pass generates it + the cone pdf generate_primary_rays_kernel stores (src/pathtracer_kernels.h:133-163):
+// 10 floats per pixel {origin, mask bits, dir, tmax, 0, pdf}
+void oracle_probe_primary_rays(const fb200_scene_view* s, uint32_t instance, float* out)
+{
+	vec3 U, V, W; camera_frame(s, U, V, W);
+	Sampler smp(s, instance);
+	for (uint32_t py = 0; py < s->res_y; ++py)
+		for (uint32_t px = 0; px < s->res_x; ++px)
+		{
+			const Ray r = primary_ray(s, smp, px, py, U, V, W);
+			float* q = out + 10 * ((size_t)px + (size_t)py * s->res_x);
+			q[0] = r.o.x; q[1] = r.o.y; q[2] = r.o.z; memcpy(&q[3], &r.mask, 4); q[4] = r.d.x; q[5] = r.d.y; q[6] = r.d.z; q[7] = r.tmax;
+			q[8] = 0.0f; q[9] = primary_cone_pdf(s, U, V, W, r.d);
+		}
 }
 // rec (26 floats): kind (0 accumulate_emissive, 1 accumulate_nee, 2 compute_nee_weights), in_bounce, frame_weight, comp, a(3), b(3),
 // COMPOSITED(4) DIRECT(4) DIFFUSE(4) SPECULAR(4) of one pixel -> out (16 floats): the four channels afterwards (kind 2: w_d, w_g)

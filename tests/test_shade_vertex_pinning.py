@@ -229,3 +229,36 @@ def test_psf_vertex_is_the_references_own(fb, oracle, libm_trig):
     assert refs > 1000 and st.cells() > 500
     R.psf_destroy(h)
     st.close(); sc.close()
+
+
+def test_primary_rays_are_the_references_own_kernels(fb, oracle):
+    """generate_primary_rays_kernel (src/pathtracer_kernels.h:133-163: generate_primary_ray with the pixel's first two sample dimensions, camera_direction_pdf into
+    the ray cone, the queue words and the unit filter weight) from its own text, run on the host over every pixel, against the oracle's primary_ray +
+    primary_cone_pdf bit for bit: golden hashes everywhere (tests/golden/primary_golden.npz, tools/make_golden_primary.py), the live kernel on two scenes and
+    three passes where oracle/_ref exists."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_primary", os.path.join(os.path.dirname(GOLDEN), "..", "tools", "make_golden_primary.py"))
+    mk = importlib.util.module_from_spec(spec); spec.loader.exec_module(mk)
+    g = np.load(os.path.join(GOLDEN, "primary_golden.npz"))
+    sc = fb.Scene(["-i", os.path.join(GOLDEN, "cornellbox_jp.fbs"), "-r", "64", "48"])
+    for inst in mk.PASSES:
+        a = oracle.probe_primary_rays(sc.view, inst)
+        assert np.array_equal(mk.sha(a[:, :8], a[:, 9]), g["sha_%d" % inst]), inst
+    sc.close()
+    live = oracle.RefShade.load()
+    if live is None:
+        pytest.skip("oracle/_ref/libref_shade.so is built where /root/reference exists")
+    cases = [["-i", os.path.join(GOLDEN, "cornellbox_jp.fbs"), "-r", "64", "48"]]
+    p = os.path.join(CACHE, "bathroom2.fbs")
+    if fb.scene_available(p):
+        cases.append(["-i", p, "-r", "160", "90"])
+    for args in cases:
+        sc = fb.Scene(args)
+        for inst in mk.PASSES:
+            a = oracle.probe_primary_rays(sc.view, inst); b, n = live.primary_rays(sc.view, inst)
+            assert n == len(b) == len(a)
+            assert np.array_equal(a[:, :8].view(np.uint32), b[:, :8].view(np.uint32)) and np.array_equal(a[:, 9].view(np.uint32), b[:, 17].view(np.uint32)), (args, inst)
+            # what else the kernel writes per pixel: unit weight, {pixel, no vertex info, no light cell, -1}, cone radius 0
+            assert np.all(b[:, 8:12] == 1) and np.array_equal(b[:, 12].view(np.uint32), np.arange(len(b), dtype=np.uint32))
+            assert np.all(b[:, 13:16].view(np.uint32) == 0xFFFFFFFF) and np.all(b[:, 16] == 0)
+        sc.close()
