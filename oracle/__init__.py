@@ -1015,3 +1015,30 @@ def probe_primary_rays(view, instance):
     out = np.zeros((int(view.res_x) * int(view.res_y), 10), np.float32)
     L.oracle_probe_primary_rays(C.addressof(view), int(instance), out.ctypes.data)
     return out
+
+
+class RefRlStep:
+    """The reference's own per-pass sampler update (split_and_collapse_kernel + the adaptive update_cdfs_kernel, src/clustered_rl.cu:68-95, 245-493) run on the
+    host by a lock-step CTA emulator (oracle/build_ref.sh -> oracle/_ref/libref_rlstep.so)."""
+
+    def __init__(self, path):
+        self._lib = C.CDLL(path)
+        self._lib.ref_rl_step.restype = C.c_int
+        self._lib.ref_rl_step.argtypes = [C.c_uint] + [C.c_void_p] * 3 + [C.c_uint, C.c_uint] + [C.c_void_p] * 5 + [C.c_int]
+
+    @classmethod
+    def load(cls):
+        p = os.path.join(_HERE, "_ref", "libref_rlstep.so")
+        return cls(p) if os.path.exists(p) else None
+
+    def step(self, tree_nodes, tree_ranges, tree_parents, counts, nodes, ends, pdfs, adaptive=True):
+        """AdaptiveClusteredRLStorage::update on rows of C entries: (counts, nodes, ends, pdfs, cdfs) afterwards"""
+        tn = np.ascontiguousarray(tree_nodes, np.uint32); tr = np.ascontiguousarray(tree_ranges, np.uint32); tp = np.ascontiguousarray(tree_parents, np.uint32)
+        counts = np.array(counts, np.uint32); nodes = np.array(nodes, np.uint32); ends = np.array(ends, np.uint32); pdfs = np.array(pdfs, np.float32)
+        n, Cn = nodes.shape
+        cdfs = np.zeros((n, Cn), np.float32)
+        rc = self._lib.ref_rl_step(len(tp), tn.ctypes.data, tr.ctypes.data, tp.ctypes.data, n, Cn, counts.ctypes.data, nodes.ctypes.data, ends.ctypes.data,
+                                   pdfs.ctypes.data, cdfs.ctypes.data, 1 if adaptive else 0)
+        if rc:
+            raise RuntimeError("ref_rl_step: unsupported cluster count %d" % Cn)
+        return counts, nodes, ends, pdfs, cdfs

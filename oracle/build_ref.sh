@@ -1539,3 +1539,184 @@ extern "C" int ref_vtl_initial_cut(unsigned n_nodes, const unsigned* node_words,
 EOF
 $CXX $LFLAGS -I$OUT -shared -o $OUT/libref_vtl.so $OUT/ref_vtl_shim.cpp -L/usr/local/cuda/lib64 -lcudart_static -ldl -lrt -lpthread
 echo "built $OUT/libref_vtl.so"
+
+# ---- the reference's own per-pass sampler update (AdaptiveClusteredRLStorage::update, src/clustered_rl.cu:568-588): split_and_collapse_kernel over
+# cta_split_and_collapse (:245-493) and the adaptive update_cdfs_kernel (:68-95), CTA-wide kernels with shared memory, barriers, cub block reductions / scans and
+# cugar's block hash map. Their text is cut from the file where it lies and run on the host by a lock-step CTA emulator: one fibre (ucontext) per thread,
+# __syncthreads() hands control back to a scheduler that resumes every thread of the CTA in thread order until all have reached the barrier; __shared__ is static
+# storage (one CTA runs at a time). cub::BlockReduce / BlockScan are stand-ins with the same interface over that barrier (a float scan adds left to right - cub's
+# own order on the device is a tree, so the CDFs are pinned to the restatement's order, not to the GPU's rounding); cugar's BlockHashMap is the reference's own with
+# the two-phase-lookup spelling g++ wants (this-> / a named base). Where the kernel leaves a race to the hardware - several threads with the same minimal parent or
+# maximal cluster power writing one shared word - the emulator's thread order picks the last, so tests use cells without such ties.
+# Pins oracle_rl.h rl_split_and_collapse / rl_update_cdf (tests/test_rl_nee.py).
+OVC=$OUT/overlay_cta
+rm -rf $OVC; mkdir -p $OVC/cugar/basic/cuda
+sed -e '/^struct BlockHashSet/,/^};/d' $REF/contrib/cugar/basic/cuda/hash.h | sed -e '0,/^template <typename KeyT, typename HashT, uint32 CTA_SIZE, uint32 TABLE_SIZE, KeyT INVALID_KEY = 0xFFFFFFFF>$/{//d}' \
+    -e 's/BlockHashMap(TempStorage& _storage) : HashMap( TABLE_SIZE/BlockHashMap(TempStorage\& _storage) : HashMap<KeyT,HashT,INVALID_KEY>( TABLE_SIZE/' \
+    -e 's/^            hash\[ CTA_SIZE \* i + threadIdx.x \] = INVALID_KEY;/            this->hash[ CTA_SIZE * i + threadIdx.x ] = INVALID_KEY;/' \
+    -e 's/^            \*count = 0;/            *this->count = 0;/' > $OVC/cugar/basic/cuda/hash.h
+cat > $OVC/cta_emul.h <<'EOF'
+// a lock-step CTA on the host: one fibre per thread, barriers hand control to the scheduler (see oracle/build_ref.sh)
+#pragma once
+#include <ucontext.h>
+#include <stdint.h>
+#include <string.h>
+#include <math.h>
+#include <vector>
+struct RefIdx3 { unsigned x, y, z; };
+static RefIdx3 threadIdx = { 0, 0, 0 }, blockIdx = { 0, 0, 0 }, blockDim = { 1, 1, 1 }, gridDim = { 1, 1, 1 };
+struct CtaEmul
+{
+	ucontext_t main_ctx; std::vector<ucontext_t> ctx; std::vector<char> stacks; std::vector<char> done; unsigned cur;
+	void (*body)(void*); void* arg;
+};
+static CtaEmul g_cta;
+static void cta_trampoline() { g_cta.body(g_cta.arg); g_cta.done[g_cta.cur] = 1; swapcontext(&g_cta.ctx[g_cta.cur], &g_cta.main_ctx); }
+inline void __syncthreads() { swapcontext(&g_cta.ctx[g_cta.cur], &g_cta.main_ctx); }
+inline void __threadfence() {}
+// run body(arg) as n threads of one CTA
+static void cta_run(unsigned n, void (*body)(void*), void* arg)
+{
+	const size_t STACK = 128 * 1024;
+	g_cta.ctx.resize(n); g_cta.stacks.resize((size_t)n * STACK); g_cta.done.assign(n, 0); g_cta.body = body; g_cta.arg = arg;
+	blockDim.x = n;
+	for (unsigned t = 0; t < n; ++t)
+	{
+		getcontext(&g_cta.ctx[t]);
+		g_cta.ctx[t].uc_stack.ss_sp = g_cta.stacks.data() + (size_t)t * STACK; g_cta.ctx[t].uc_stack.ss_size = STACK; g_cta.ctx[t].uc_link = &g_cta.main_ctx;
+		makecontext(&g_cta.ctx[t], cta_trampoline, 0);
+	}
+	for (bool any = true; any;)
+	{
+		any = false;
+		for (unsigned t = 0; t < n; ++t)
+			if (!g_cta.done[t]) { g_cta.cur = t; threadIdx.x = t; swapcontext(&g_cta.main_ctx, &g_cta.ctx[t]); any = true; }
+	}
+	threadIdx.x = 0;
+}
+inline unsigned atomicAdd(unsigned* p, unsigned v) { const unsigned o = *p; *p = o + v; return o; }
+inline int atomicAdd(int* p, int v) { const int o = *p; *p = o + v; return o; }
+inline float atomicAdd(float* p, float v) { const float o = *p; *p = o + v; return o; }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; *p = o + v; return o; }
+inline unsigned atomicCAS(unsigned* p, unsigned c, unsigned v) { const unsigned o = *p; if (o == c) *p = v; return o; }
+inline unsigned long long atomicCAS(unsigned long long* p, unsigned long long c, unsigned long long v) { const unsigned long long o = *p; if (o == c) *p = v; return o; }
+template <typename T> inline T __ldg(const T* p) { return *p; }
+inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __ffs(int v) { return __builtin_ffs(v); }
+EOF
+cat > $OVC/cub_standin.h <<'EOF'
+// stand-ins for the two cub block primitives clustered_rl.cu uses, over the emulator's barrier
+#pragma once
+namespace cub_emul {
+struct Min { template <typename T> T operator()(const T& a, const T& b) const { return b < a ? b : a; } };
+struct Max { template <typename T> T operator()(const T& a, const T& b) const { return a < b ? b : a; } };
+template <typename T, int DIM>
+struct BlockReduce
+{
+	struct TempStorage { T v[DIM]; };
+	TempStorage& s;
+	BlockReduce(TempStorage& t) : s(t) {}
+	// the result is valid in thread 0 only, as in cub
+	template <typename Op> T Reduce(T x, Op op, int num_valid)
+	{
+		__syncthreads();
+		s.v[threadIdx.x] = x;
+		__syncthreads();
+		T r = s.v[0];
+		if (threadIdx.x == 0) for (int i = 1; i < num_valid; ++i) r = op(r, s.v[i]);
+		__syncthreads();
+		return r;
+	}
+};
+template <typename T, int DIM>
+struct BlockScan
+{
+	struct TempStorage { T v[DIM]; };
+	TempStorage& s;
+	BlockScan(TempStorage& t) : s(t) {}
+	void InclusiveSum(T in, T& out, T& aggregate)
+	{
+		__syncthreads();
+		s.v[threadIdx.x] = in;
+		__syncthreads();
+		T acc = s.v[0], mine = s.v[0];
+		for (int i = 1; i < DIM; ++i) { acc = acc + s.v[i]; if (i == (int)threadIdx.x) mine = acc; }
+		__syncthreads();
+		out = mine; aggregate = acc;
+	}
+	void ExclusiveSum(T in, T& out, T& aggregate)
+	{
+		__syncthreads();
+		s.v[threadIdx.x] = in;
+		__syncthreads();
+		T acc = T(0), mine = T(0);
+		for (int i = 0; i < DIM; ++i) { if (i == (int)threadIdx.x) mine = acc; acc = acc + s.v[i]; }
+		__syncthreads();
+		out = mine; aggregate = acc;
+	}
+};
+}
+EOF
+{
+  sed -n '68,95p' $REF/src/clustered_rl.cu
+  sed -n '245,493p' $REF/src/clustered_rl.cu
+} > $OUT/rl_step_cut.h
+cat > $OUT/ref_rlstep_shim.cpp <<'EOF'
+#include "cta_emul.h"
+#include <vector_types.h>
+#include <cugar/basic/types.h>
+#include <cugar/basic/numbers.h>
+#include <cugar/basic/atomics.h>
+#include <cugar/basic/cuda/pointers.h>
+#include <cugar/basic/cuda/hash.h>
+#include <cugar/bvh/bvh_node.h>
+#include "cub_standin.h"
+using cugar::uint32;
+#define cub cub_emul
+#define BIAS 0.75f
+#define __global__
+#define __device__
+#define __shared__ static
+#include "rl_step_cut.h"
+#undef __shared__
+struct StepArgs { SplitKernelParams split; uint32 n_entries, C; const uint32* counts; float* values; float* cdfs; };
+template <uint32 DIM> static void split_body(void* a) { split_and_collapse_kernel<DIM>(static_cast<StepArgs*>(a)->split); }
+template <uint32 DIM> static void cdf_body(void* a) { StepArgs* s = static_cast<StepArgs*>(a); update_cdfs_kernel<DIM>(s->n_entries, s->C, s->counts, s->values, s->cdfs, false); }
+// AdaptiveClusteredRLStorage::update on rows of C entries (in place) over a cluster tree given as Bintree words (2 per node), ranges (2 per node) and parents
+extern "C" int ref_rl_step(unsigned n_nodes, const unsigned* node_words, const unsigned* ranges, const unsigned* parents, unsigned n_cells, unsigned C,
+						   unsigned* counts, unsigned* nodes, unsigned* ends, float* pdfs, float* cdfs, int adaptive)
+{
+	std::vector<cugar::Bvh_node_3d> bn(n_nodes); std::vector<uint2> rg(n_nodes);
+	for (unsigned i = 0; i < n_nodes; ++i)
+	{
+		bn[i] = cugar::Bvh_node_3d(make_float4(cugar::binary_cast<float>(node_words[2 * i]), cugar::binary_cast<float>(node_words[2 * i + 1]), 0, 0), make_float4(0, 0, 0, 0));
+		rg[i] = make_uint2(ranges[2 * i], ranges[2 * i + 1]);
+	}
+	StepArgs a;
+	a.split.n_entries = n_cells; a.split.init_cluster_count = C; a.split.cluster_counts = counts; a.split.cluster_indices = nodes; a.split.cluster_ends = ends;
+	a.split.cluster_powers = pdfs; a.split.bvh_nodes = bn.data(); a.split.bvh_ranges = rg.data(); a.split.bvh_parents = parents;
+	a.n_entries = n_cells; a.C = C; a.counts = counts; a.values = pdfs; a.cdfs = cdfs;
+	// the launch dispatch of split_and_collapse / update_cdfs (src/clustered_rl.cu:495-520, 115-130): the block is the next of 128 / 256 / 512 / 1024 holding C
+	const unsigned dim = C <= 128 ? 128 : C <= 256 ? 256 : C <= 512 ? 512 : C <= 1024 ? 1024 : 0;
+	if (!dim) return -1;
+	for (unsigned k = 0; k < n_cells; ++k)
+	{
+		blockIdx.x = k;
+		if (adaptive)
+		{
+			if (dim == 128) cta_run(128, split_body<128>, &a); else if (dim == 256) cta_run(256, split_body<256>, &a);
+			else if (dim == 512) cta_run(512, split_body<512>, &a); else cta_run(1024, split_body<1024>, &a);
+		}
+		if (dim == 128) cta_run(128, cdf_body<128>, &a); else if (dim == 256) cta_run(256, cdf_body<256>, &a);
+		else if (dim == 512) cta_run(512, cdf_body<512>, &a); else cta_run(1024, cdf_body<1024>, &a);
+	}
+	blockIdx.x = 0;
+	return 0;
+}
+EOF
+$CXX -O1 -std=c++14 -fPIC -w -fpermissive -ffp-contract=off -include $OVF/adapter_prefix.h -DFERMAT_API_EXTERN= -DFERMAT_API= -DTHRUST_DEVICE_SYSTEM=THRUST_DEVICE_SYSTEM_CPP \
+    -I$OVC -I$OVF -I$OUT -I$REF/src -I$REF/contrib -I/usr/local/cuda/include \
+    -shared -o $OUT/libref_rlstep.so $OUT/ref_rlstep_shim.cpp -x none $REF/contrib/cugar/basic/atomics.cpp -L/usr/local/cuda/lib64 -lcudart_static -ldl -lrt -lpthread
+echo "built $OUT/libref_rlstep.so"

@@ -117,6 +117,34 @@ def test_vtl_generation_and_initial_cut_are_the_references_own(fb, oracle):
         sc.close()
 
 
+def test_split_collapse_and_cdfs_are_the_references_own_kernels(fb, oracle):
+    """AdaptiveClusteredRLStorage::update (src/clustered_rl.cu:568-588): split_and_collapse_kernel over cta_split_and_collapse (:245-493: the block hash map of
+    parents, the shared-memory sums up the ancestor chains, the block min / max, the scan that compacts the new cut in place) and the adaptive update_cdfs_kernel
+    (:68-95) - CTA-wide kernels - from their own text, run on the host by a lock-step CTA emulator (one fibre per thread, barriers hand control to a
+    scheduler; oracle/build_ref.sh -> libref_rlstep.so), against oracle_rl.h's rl_split_and_collapse / rl_update_cdf: cut sizes, nodes, ends, powers and CDFs
+    bit for bit over six rounds, adaptive and not. Golden hashes everywhere (tests/golden/rlstep_golden.npz, tools/make_golden_rlstep.py), the live kernels where
+    oracle/_ref exists. The cells carry no two equal parent or cluster powers (the kernel leaves such ties to the hardware's write order)."""
+    import importlib.util
+    from conftest import GOLDEN
+    spec = importlib.util.spec_from_file_location("make_golden_rlstep", os.path.join(os.path.dirname(GOLDEN), "..", "tools", "make_golden_rlstep.py"))
+    mk = importlib.util.module_from_spec(spec); spec.loader.exec_module(mk)
+    g = np.load(os.path.join(GOLDEN, "rlstep_golden.npz"))
+    sc, st, a = mk.tree(fb, oracle)
+    live = oracle.RefRlStep.load()
+    for adaptive in (True, False):
+        hs = mk.run(lambda c, n, e, p, ad: st.step(c, n, e, p, ad), a, adaptive)
+        for it, h in enumerate(hs):
+            assert np.array_equal(h, g["sha_%d_%d" % (int(adaptive), it)]), (adaptive, it)
+        if live is not None:
+            hl = mk.run(lambda c, n, e, p, ad: live.step(a["tree_nodes"], a["tree_ranges"], a["tree_parents"], c, n, e, p, ad), a, adaptive)
+            assert all(np.array_equal(x, y) for x, y in zip(hs, hl)), adaptive
+    # the rounds did move the cuts
+    c, n, e, p, factors = mk.step_cases(a)
+    c2, n2, e2, p2, cdf = st.step(c, n, e, p, True)
+    assert sum(not np.array_equal(n2[k], n[k]) for k in range(1, len(n))) >= len(n) - 2 and np.array_equal(n2[0], n[0])
+    sc.close()
+
+
 def test_sampler_arithmetic_of_one_cell(oracle):
     """AdaptiveClusteredRLView::sample / ::pdf: the pdf returned with a sample is the pdf of that index, indices stay inside their cluster,
     and the histogram of many samples follows the CDF."""
