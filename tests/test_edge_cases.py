@@ -1,0 +1,129 @@
+"""Edge cases of the hot path, through the C ABI against the CPU oracle (needs a B200: pytest -m gpu; the scene-building halves also run on the CPU).
+
+What the reference handles silently and a drop-in must too: a scene without emitters (MeshLightsStorageImpl::init warns and leaves zero VPLs,
+src/mesh_lights.cu:246-250; next-event estimation is then gated off, src/pathtracer_core.h:601-602), a camera that sees nothing (every primary ray misses:
+the queues of bounce 1 are empty), frames smaller than a warp / a tile and with sides that are no multiple of anything (ragged last blocks, partial sampler
+tiles), a path length of one (no scattering, no next-event estimation past the first vertex) and of one pixel. Scenes are derived from the fixture through
+fb200_scene_create_from_mesh, the entry the source-level adapter uses."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import cornell_args, rel_l2
+
+CHANNELS = ("COMPOSITED_C", "DIRECT_C", "DIFFUSE_C", "SPECULAR_C", "DIFFUSE_A", "SPECULAR_A")
+
+
+def _derived_scene(fb, args, no_emitters=False, look_away=False):
+    """the fixture's mesh with its emitters switched off and / or its camera turned around; returns (scene, keep-alive)"""
+    base = fb.Scene(cornell_args(32, 1))
+    d = base.mesh_desc()
+    keep = [base]
+    if no_emitters:
+        mats = np.ctypeslib.as_array(C.cast(d.materials, C.POINTER(C.c_float)), shape=(int(d.num_materials), 52)).copy()
+        assert mats[:, 16:19].max() > 0
+        mats[:, 16:20] = 0                      # MeshMaterial::emissive (src/mesh/MeshView.h)
+        d.materials = mats.ctypes.data
+        keep.append(mats)
+    if look_away:
+        eye, aim = np.array(list(d.eye)), np.array(list(d.aim))
+        for i in range(3):
+            d.aim[i] = float(2 * eye[i] - aim[i])
+    return fb.Scene(args, mesh=d), keep
+
+
+def _compare(fb, oracle, sc, passes):
+    rc = fb.RenderingContext(sc)
+    fbuf = oracle.new_framebuffer(sc.view)
+    shade = 0
+    for i in range(passes):
+        rc.render(i)
+        shade += oracle.render_pass(sc.view, i, fbuf).shade_events
+    out = {}
+    for name in CHANNELS:
+        g, o = rc.download(name), fbuf[fb.FB_CHANNELS[name]]
+        assert np.isfinite(g).all(), name
+        assert g.shape == o.shape
+        assert float(np.abs(g.astype(np.float64) - o.astype(np.float64)).max()) <= 1e-5 * max(1.0, float(np.abs(o).max())), name
+        out[name] = g
+    assert rc.stats()["shade_events"] == shade
+    rc.close()
+    return out, shade
+
+
+def test_edge_scenes_build_and_the_oracle_renders_them(fb, oracle):
+    """CPU half: the derived scenes exist, carry what the reference would (zero VPLs, a zero normalisation), and the oracle renders them"""
+    sc, keep = _derived_scene(fb, ["-r", "37", "23", "-bounces", "3"], no_emitters=True)
+    assert sc.view.n_vpls == 0 and sc.view.vpl_norm == 0.0
+    f = oracle.new_framebuffer(sc.view)
+    st = oracle.render_pass(sc.view, 0, f)
+    assert st.shade_events > 37 * 23 and not f[5].any() and f[1].max() > 0       # no light anywhere, albedo still written
+    sc.close()
+    sc, keep = _derived_scene(fb, ["-r", "40", "24", "-bounces", "3"], look_away=True)
+    f = oracle.new_framebuffer(sc.view)
+    oracle.render_pass(sc.view, 0, f)
+    assert not f[:6].any()
+    sc.close()
+    with pytest.raises(RuntimeError, match="resolution"):
+        fb.Scene(cornell_args(32, 1)[:2] + ["-r", "0", "16"])
+
+
+@pytest.mark.gpu
+def test_scene_without_emitters(fb, oracle):
+    sc, keep = _derived_scene(fb, ["-r", "37", "23", "-bounces", "3"], no_emitters=True)
+    out, shade = _compare(fb, oracle, sc, 3)
+    assert not out["COMPOSITED_C"][..., :3].any() and out["DIFFUSE_A"].max() > 0 and shade > 3 * 37 * 23
+    sc.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nee_alg", ["vpl", "mesh"])
+def test_camera_that_sees_nothing(fb, oracle, nee_alg):
+    sc, keep = _derived_scene(fb, ["-r", "40", "24", "-bounces", "3", "-nee-alg", nee_alg], look_away=True)
+    out, shade = _compare(fb, oracle, sc, 2)
+    assert all(not out[name].any() for name in CHANNELS)
+    sc.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("res,bounces", [((1, 1), 3), ((3, 2), 0), ((67, 41), 0), ((67, 41), 3), ((129, 5), 2), ((5, 131), 2)])
+def test_ragged_and_tiny_frames(fb, oracle, res, bounces):
+    """frames below a warp, below a sampler tile, with sides that divide nothing; bounces 0 = a path length of one (emission of the first vertex only)"""
+    sc = fb.Scene(cornell_args(32, 1)[:2] + ["-r", str(res[0]), str(res[1]), "-bounces", str(bounces)])
+    out, shade = _compare(fb, oracle, sc, 4)
+    assert shade >= 4 * res[0] * res[1] or bounces == 0
+    if res[0] * res[1] > 1000:
+        fbuf = oracle.new_framebuffer(sc.view)
+        for i in range(4):
+            oracle.render_pass(sc.view, i, fbuf)
+        assert rel_l2(out["COMPOSITED_C"], fbuf[5]) < 1e-5
+    sc.close()
+
+
+@pytest.mark.gpu
+def test_ragged_frames_with_the_filtered_renderer_and_shards(fb, oracle):
+    """the same ragged frame through -psfpt (whole-frame passes) and split over three tile shards whose sum is the frame"""
+    args = cornell_args(32, 1)[:2] + ["-r", "67", "41", "-bounces", "2"]
+    sc = fb.Scene(args)
+    rc = fb.RenderingContext(sc)
+    for i in range(2):
+        rc.render(i)
+    full = rc.download("COMPOSITED_C")
+    rc.close(); sc.close()
+    total = np.zeros_like(full)
+    for r in range(3):
+        s2 = fb.Scene(args + ["-shard", str(r), "3"])
+        r2 = fb.RenderingContext(s2)
+        for i in range(2):
+            r2.render(i)
+        total += r2.download("COMPOSITED_C")
+        r2.close(); s2.close()
+    assert np.array_equal(total, full)
+    sp = fb.Scene(args + ["-psfpt"])
+    rp = fb.RenderingContext(sp)
+    for i in range(2):
+        rp.render(i)
+    g = rp.download("COMPOSITED_C")
+    assert np.isfinite(g).all() and g[..., :3].max() <= 100.0 and g[..., :3].mean() > 0
+    rp.close(); sp.close()
