@@ -127,3 +127,42 @@ def test_ragged_frames_with_the_filtered_renderer_and_shards(fb, oracle):
     g = rp.download("COMPOSITED_C")
     assert np.isfinite(g).all() and g[..., :3].max() <= 100.0 and g[..., :3].mean() > 0
     rp.close(); sp.close()
+
+
+@pytest.mark.gpu
+def test_rl_sampler_without_emitters_falls_back_like_the_reference(fb, oracle):
+    """PathTracer::init "disables smart algorithms if there are no emissive surfaces" (src/renderers/pathtracer_impl.h:163-165): `-nee-alg rl` on a scene
+    without emitters runs with the plain mesh sampler - no VTLs, no cells - and renders what the oracle does (albedo, no light)"""
+    sc, keep = _derived_scene(fb, ["-r", "24", "16", "-bounces", "2", "-nee-alg", "rl"], no_emitters=True)
+    out, shade = _compare(fb, oracle, sc, 2)
+    assert not out["COMPOSITED_C"][..., :3].any() and out["DIFFUSE_A"].max() > 0
+    rc = fb.RenderingContext(sc)
+    with pytest.raises(RuntimeError):
+        rc.rl_state()                           # there is no sampler state to look at
+    rc.close(); sc.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("res", [(1, 1), (13, 7)])
+def test_rl_sampler_with_fewer_vtls_than_clusters(fb, oracle, monkeypatch, res):
+    """`-nee-alg rl` asks for as many VTLs as pixels: a 1x1 frame leaves one VTL per emissive triangle and a cut of two clusters, 13x7 a cut of 92 - both
+    below the 256 the cells are sized for. Tables equal to the restatement's, the first pass (nothing learned yet) equal per pixel, later passes run."""
+    monkeypatch.setenv("FB200_RL_HASH_BITS", "10")
+    sc = fb.Scene(cornell_args(32, 1)[:2] + ["-r", str(res[0]), str(res[1]), "-bounces", "2", "-nee-alg", "rl"])
+    rc = fb.RenderingContext(sc)
+    st = oracle.RlState(sc.view, res[0] * res[1])
+    a = st.arrays()
+    s = rc.rl_state()
+    assert s["n_vtls"] == len(a["vtls"]) and s["init_cluster_count"] == len(a["clusters"]) < 256
+    assert np.array_equal(s["vtls"].cpu().numpy().view(np.uint32), a["vtls"].view(np.uint32).reshape(-1, 8))
+    rc.render(0)
+    want = oracle.new_framebuffer(sc.view)
+    events = st.render_pass(0, want).shade_events
+    g = rc.download("COMPOSITED_C")
+    assert rc.stats()["shade_events"] == events
+    assert float(np.abs(g[..., :3] - want[5][..., :3]).max()) <= 1e-4 * (1 + float(want[5][..., :3].max()))
+    for i in range(1, 40):                       # crosses the clear at pass 32 (pathtracer_impl.h:239-266)
+        rc.render(i)
+    g = rc.download("COMPOSITED_C")
+    assert np.isfinite(g).all() and g[..., :3].mean() > 0
+    rc.close(); sc.close()
