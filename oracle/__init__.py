@@ -1042,3 +1042,17 @@ class RefRlStep:
         if rc:
             raise RuntimeError("ref_rl_step: unsupported cluster count %d" % Cn)
         return counts, nodes, ends, pdfs, cdfs
+
+
+def ref_write_tga(path, rgba):
+    """the reference's own cugar::write_tga (contrib/cugar/image/tga.cpp, compiled as is: oracle/_ref/libref_tga.so) on an (H, W, 4) uint8 image;
+    returns False where oracle/_ref was not built"""
+    p = os.path.join(_HERE, "_ref", "libref_tga.so")
+    if not os.path.exists(p):
+        return False
+    L = C.CDLL(p)
+    L.ref_write_tga.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p]
+    rgba = np.ascontiguousarray(rgba, np.uint8)
+    if L.ref_write_tga(str(path).encode(), rgba.shape[1], rgba.shape[0], rgba.ctypes.data) != 0:
+        raise RuntimeError("ref_write_tga failed")
+    return True

@@ -1720,3 +1720,16 @@ $CXX -O1 -std=c++14 -fPIC -w -fpermissive -ffp-contract=off -include $OVF/adapte
     -I$OVC -I$OVF -I$OUT -I$REF/src -I$REF/contrib -I/usr/local/cuda/include \
     -shared -o $OUT/libref_rlstep.so $OUT/ref_rlstep_shim.cpp -x none $REF/contrib/cugar/basic/atomics.cpp -L/usr/local/cuda/lib64 -lcudart_static -ldl -lrt -lpthread
 echo "built $OUT/libref_rlstep.so"
+
+# ---- the reference's own TGA writer (contrib/cugar/image/tga.cpp: write_tga, what main.cu:184 saves a frame with), compiled as is. Pins the product's
+# fb200_write_tga byte for byte (tests/test_post.py).
+cat > $OUT/ref_tga_shim.cpp <<'EOF'
+#include <cugar/image/tga.h>
+extern "C" int ref_write_tga(const char* filename, int width, int height, const unsigned char* rgba)
+{
+	return cugar::write_tga(filename, width, height, rgba, cugar::TGAPixels::RGBA) ? 0 : -1;
+}
+EOF
+mkdir -p $OUT/overlay_tga; : > $OUT/overlay_tga/windows.h          # tga.cpp includes <windows.h> and uses nothing of it
+$CXX $LFLAGS -I$OUT/overlay_tga -shared -o $OUT/libref_tga.so $OUT/ref_tga_shim.cpp $REF/contrib/cugar/image/tga.cpp
+echo "built $OUT/libref_tga.so"

@@ -109,6 +109,24 @@ def test_write_tga_layout(fb, tmp_path):
         fb.write_tga(tmp_path / "no_such_dir" / "x.tga", img)
 
 
+def test_write_tga_is_the_references_own_writer(fb, oracle, tmp_path):
+    """fb200_write_tga against cugar::write_tga(TGAPixels::RGBA) itself (contrib/cugar/image/tga.cpp compiled as is, oracle/build_ref.sh -> libref_tga.so):
+    the files are the same bytes, for odd sizes and every byte value; a golden SHA-256 of the reference's file keeps the check where oracle/_ref is absent"""
+    import hashlib
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (37, 53, 4), dtype=np.uint8)
+    img[0, :, :] = np.arange(53, dtype=np.uint8)[:, None] * 4
+    fb.write_tga(tmp_path / "ours.tga", img)
+    ours = (tmp_path / "ours.tga").read_bytes()
+    assert hashlib.sha256(ours).hexdigest() == "7e14e3af3547db4d4419a4b21544193f2c4c4903e9e0bfdf129acfe8e5110674"
+    if oracle.ref_write_tga(tmp_path / "ref.tga", img):
+        assert (tmp_path / "ref.tga").read_bytes() == ours
+    one = np.array([[[9, 8, 7, 6]]], np.uint8)
+    fb.write_tga(tmp_path / "one.tga", one)
+    if oracle.ref_write_tga(tmp_path / "one_ref.tga", one):
+        assert (tmp_path / "one_ref.tga").read_bytes() == (tmp_path / "one.tga").read_bytes()
+
+
 # ---------------------------------------------------------------------------------------------------------
 # device
 # ---------------------------------------------------------------------------------------------------------
