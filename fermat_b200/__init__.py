@@ -141,6 +141,8 @@ def lib():
         "fb200_context_to_rgba": (i32, [vp, u32, vp]),
         "fb200_context_rgba_device_ptr": (vp, [vp]),
         "fb200_scene_get_tonemap": (i32, [vp, pf, pf]),
+        "fb200_scene_texture_coordinates": (i32, [vp, C.POINTER(C.POINTER(C.c_int32)), C.POINTER(pf), C.POINTER(u32)]),
+        "fb200_scene_texture_level": (i32, [vp, u32, u32, C.POINTER(pf), C.POINTER(u32), C.POINTER(u32)]),
         "fb200_write_tga": (i32, [C.c_char_p, u32, u32, vp]),
         "fb200_context_build_lbvh": (C.c_int64, [vp, u32, i32, vp, u64, C.POINTER(u32), C.POINTER(u64), pf]),
         "fb200_trace": (i32, [vp, pf, pf, u32]),
@@ -285,6 +287,18 @@ class Scene(_Handle):
         lib().fb200_scene_get_tonemap(self._h, C.byref(e), C.byref(g))
         return e.value, g.value
 
+    def texture_levels(self, texture):
+        """the mip chain of one texture as the host holds it: list of (H, W, 4) float32 arrays, level 0 first (empty for a texture that failed to load)"""
+        out = []
+        while True:
+            p, w, h = C.POINTER(C.c_float)(), C.c_uint32(), C.c_uint32()
+            rc = lib().fb200_scene_texture_level(self._h, int(texture), len(out), C.byref(p), C.byref(w), C.byref(h))
+            if rc < 0:
+                raise RuntimeError(lib().fb200_last_error().decode())
+            if rc > 0:
+                return out
+            out.append(np.ctypeslib.as_array(p, shape=(h.value, w.value, 4)).copy())
+
     def mesh_desc(self):
         """this scene's pre-processed arrays as a MeshDesc (pointers into this scene's memory: keep it alive while the descriptor is used)"""
         v = self.view
@@ -292,6 +306,10 @@ class Scene(_Handle):
         d.num_triangles, d.num_vertices, d.num_materials, d.num_textures = v.num_triangles, v.num_vertices, v.num_materials, v.num_textures
         d.vertex_indices, d.vertex_data, d.texture_indices_comp, d.material_indices = v.vertex_indices, v.vertex_data, v.texture_indices_comp, v.material_indices
         d.materials, d.textures = v.materials, v.textures
+        ti, td, nc = C.POINTER(C.c_int32)(), C.POINTER(C.c_float)(), C.c_uint32()
+        if lib().fb200_scene_texture_coordinates(self._h, C.byref(ti), C.byref(td), C.byref(nc)) != 0:
+            raise RuntimeError(_err())
+        d.texture_indices, d.texture_data, d.num_texture_coordinates = ti, td, nc.value
         for i in range(2):
             d.tex_bias[i], d.tex_scale[i] = v.tex_bias[i], v.tex_scale[i]
         for i in range(3):

@@ -83,6 +83,26 @@ int fb200_scene_get_tonemap(const fb200_scene* s, float* exposure, float* gamma)
 	return 0;
 }
 
+int fb200_scene_texture_level(const fb200_scene* s, uint32_t texture, uint32_t level, const float** texels, uint32_t* res_x, uint32_t* res_y)
+{
+	if (!s || !texels || !res_x || !res_y) { fb::set_last_error("null argument"); return -1; }
+	if (texture >= s->scene.textures.size()) { fb::set_last_error("fb200_scene_texture_level: no such texture"); return -1; }
+	const fb::TextureImage& t = s->scene.textures[texture];
+	if (level >= t.levels.size()) return 1;
+	*texels = reinterpret_cast<const float*>(t.levels[level].data()); *res_x = t.res_x[level]; *res_y = t.res_y[level];
+	return 0;
+}
+
+int fb200_scene_texture_coordinates(const fb200_scene* s, const int32_t** indices, const float** data, uint32_t* num_coordinates)
+{
+	if (!s || !indices || !data || !num_coordinates) { fb::set_last_error("null argument"); return -1; }
+	const fb::Mesh& m = s->scene.mesh;
+	*indices = m.texture_indices.empty() ? NULL : reinterpret_cast<const int32_t*>(m.texture_indices.data());
+	*data = m.texture_data.empty() ? NULL : reinterpret_cast<const float*>(m.texture_data.data());
+	*num_coordinates = (uint32_t)m.texture_data.size();
+	return 0;
+}
+
 int fb200_write_tga(const char* filename, uint32_t width, uint32_t height, const uint8_t* rgba)
 {
 	if (!filename || !rgba || width > 65535u || height > 65535u) { fb::set_last_error("fb200_write_tga: bad argument"); return -1; }

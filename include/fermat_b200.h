@@ -182,6 +182,15 @@ int      fb200_diag_wide_trace_shadow(const fb200_scene*, const float* rays, uin
 /* film exposure and gamma of the scene (RenderingContext's m_exposure / m_gamma, src/renderer.cu:715-717; 1 and 2.2
  * unless a pbrt film sets them) */
 int fb200_scene_get_tonemap(const fb200_scene*, float* exposure, float* gamma);
+/* One level of a texture's mip chain as the host holds it: MipMapStorage<HOST_BUFFER>::levels[level] (src/texture.h:117-120, built by
+ * MipMapStorage::set -> generate_mips / downsample, :151-262, from the .tga / .pfm texels of src/renderer.cu:803-862). The VPL generator's
+ * estimate of a textured emitter reads it (src/mesh_lights.cu:205-250). Returns 0, 1 when the chain has no such level (a texture that could not be
+ * loaded has none: n_levels == 0), -1 on a bad argument. The pointer lives as long as the scene. */
+/* The uncompressed texture coordinates the host keeps beside the fp16 ones of the view (MeshView::texture_indices / texture_data,
+ * src/mesh/MeshView.h:131-137): int4 per triangle (-1 = none) and float2 per coordinate; NULL / 0 when the mesh has none. The VPL generator's
+ * textured branch reads them (src/mesh_lights.cu:193-197); fb200_mesh_desc takes them back in. Pointers live as long as the scene. */
+int fb200_scene_texture_coordinates(const fb200_scene*, const int32_t** indices, const float** data, uint32_t* num_coordinates);
+int fb200_scene_texture_level(const fb200_scene*, uint32_t texture, uint32_t level, const float** texels, uint32_t* res_x, uint32_t* res_y);
 /* cugar::write_tga with TGAPixels::RGBA (contrib/cugar/image/tga.cpp:133-185): 24-bit uncompressed BGR, rows in buffer
  * order. Returns 0 on success. */
 int fb200_write_tga(const char* filename, uint32_t width, uint32_t height, const uint8_t* rgba);

@@ -880,20 +880,37 @@ class RefVpl:
         self.L = L
         L.ref_vpl_init.restype = C.c_int
 
-    def init(self, view, n_vpls):
-        """(mesh_cdf, mesh_inv_area, vpls as (n, 4) = prim_id bits, u, v, E in the product's layout, vpl_cdf, norm) for the scene of `view`; untextured emitters only
-        (the mip-mapped estimate of textured ones reads the uncompressed texture coordinates and the mip chain, which the view does not carry)"""
+    def init(self, view, n_vpls, scene=None):
+        """(mesh_cdf, mesh_inv_area, vpls as (n, 4) = prim_id bits, u, v, E in the product's layout, vpl_cdf, norm) for the scene of `view`. The mip-mapped
+        estimate of TEXTURED emitters reads the uncompressed texture coordinates and the whole mip chain, which the view does not carry: pass the product's
+        `scene` (fermat_b200.Scene) to hand them over (mesh_desc() + texture_levels()); without it only LOD 0 is given and emitters must be untextured"""
         nt, ntex = int(view.num_triangles), int(view.num_textures)
-        levels = (C.c_uint32 * max(ntex, 1))(); res = (C.c_uint32 * max(2 * ntex, 2))(); texels = (C.c_void_p * max(ntex, 1))()
-        k = 0
-        for t in range(ntex):
-            if view.textures[t].texels:
-                levels[t] = 1; res[2 * k], res[2 * k + 1] = view.textures[t].res_x, view.textures[t].res_y; texels[k] = C.cast(view.textures[t].texels, C.c_void_p); k += 1
-            else:
-                levels[t] = 0
+        keep = []
+        tex_idx = tex_data = None
+        if scene is not None:
+            d = scene.mesh_desc()
+            keep.append(d)
+            tex_idx, tex_data = d.texture_indices, d.texture_data
+            chains = [scene.texture_levels(t) for t in range(ntex)]
+            n_lv = sum(len(c) for c in chains)
+            levels = (C.c_uint32 * max(ntex, 1))(); res = (C.c_uint32 * max(2 * n_lv, 2))(); texels = (C.c_void_p * max(n_lv, 1))()
+            k = 0
+            for t, chain in enumerate(chains):
+                levels[t] = len(chain)
+                for lv in chain:
+                    lv = np.ascontiguousarray(lv, np.float32); keep.append(lv)
+                    res[2 * k], res[2 * k + 1] = lv.shape[1], lv.shape[0]; texels[k] = lv.ctypes.data; k += 1
+        else:
+            levels = (C.c_uint32 * max(ntex, 1))(); res = (C.c_uint32 * max(2 * ntex, 2))(); texels = (C.c_void_p * max(ntex, 1))()
+            k = 0
+            for t in range(ntex):
+                if view.textures[t].texels:
+                    levels[t] = 1; res[2 * k], res[2 * k + 1] = view.textures[t].res_x, view.textures[t].res_y; texels[k] = C.cast(view.textures[t].texels, C.c_void_p); k += 1
+                else:
+                    levels[t] = 0
         cdf = np.zeros(nt, np.float32); inv = np.zeros(nt, np.float32); vpls = np.zeros((n_vpls, 4), np.float32); vcdf = np.zeros(n_vpls, np.float32); norm = C.c_float(0)
         n = self.L.ref_vpl_init(C.c_uint32(n_vpls), C.c_int(view.num_vertices), C.c_int(nt), C.c_int(view.num_materials), view.vertex_indices, view.vertex_data,
-                                None, None, view.texture_indices_comp, view.material_indices, C.c_void_p(view.materials), view.tex_bias, view.tex_scale,
+                                tex_idx, tex_data, view.texture_indices_comp, view.material_indices, C.c_void_p(view.materials), view.tex_bias, view.tex_scale,
                                 C.c_int(ntex), levels, res, texels, cdf.ctypes.data_as(C.c_void_p), inv.ctypes.data_as(C.c_void_p), vpls.ctypes.data_as(C.c_void_p),
                                 vcdf.ctypes.data_as(C.c_void_p), C.byref(norm))
         assert n == n_vpls
@@ -1056,3 +1073,28 @@ def ref_write_tga(path, rgba):
     if L.ref_write_tga(str(path).encode(), rgba.shape[1], rgba.shape[0], rgba.ctypes.data) != 0:
         raise RuntimeError("ref_write_tga failed")
     return True
+
+
+class RefTexture:
+    """The reference's own texture loading (the .tga / .pfm branch of RenderingContextImpl::init, src/renderer.cu:804-867, over contrib/cugar/image and
+    MipMapStorage<HOST_BUFFER>::set, src/texture.h) compiled on this host (oracle/build_ref.sh -> oracle/_ref/libref_tex.so)."""
+
+    def __init__(self, path):
+        self._lib = C.CDLL(path)
+        self._lib.ref_texture_load.argtypes = [C.c_char_p]; self._lib.ref_texture_load.restype = C.c_int
+        self._lib.ref_texture_level.argtypes = [C.c_int, C.POINTER(C.c_uint), C.POINTER(C.c_uint)]; self._lib.ref_texture_level.restype = C.POINTER(C.c_float)
+
+    @classmethod
+    def load(cls):
+        p = os.path.join(_HERE, "_ref", "libref_tex.so")
+        return cls(p) if os.path.exists(p) else None
+
+    def levels(self, filename):
+        """the mip chain of a texture file: list of (H, W, 4) float32 arrays, level 0 first (empty: the reference could not load it)"""
+        n = self._lib.ref_texture_load(str(filename).encode())
+        out = []
+        for l in range(n):
+            w, h = C.c_uint(), C.c_uint()
+            p = self._lib.ref_texture_level(l, C.byref(w), C.byref(h))
+            out.append(np.ctypeslib.as_array(p, shape=(h.value, w.value, 4)).copy())
+        return out

@@ -1733,3 +1733,43 @@ EOF
 mkdir -p $OUT/overlay_tga; : > $OUT/overlay_tga/windows.h          # tga.cpp includes <windows.h> and uses nothing of it
 $CXX $LFLAGS -I$OUT/overlay_tga -shared -o $OUT/libref_tga.so $OUT/ref_tga_shim.cpp $REF/contrib/cugar/image/tga.cpp
 echo "built $OUT/libref_tga.so"
+
+# ---- the reference's own texture loading: the .tga / .pfm branch of RenderingContextImpl::init (src/renderer.cu:804-867, cut where it lies: load_tga / load_pfm
+# of contrib/cugar/image, the conversion to float4, MipMapStorage<HOST_BUFFER>::set -> generate_mips / downsample of src/texture.h). Pins the product's load_tga /
+# load_pfm / build_mip_chain (host/scene.cpp) level by level (tests/test_importers.py) and feeds the VPL generator's textured branch (libref_vpl.so).
+sed -n '804,867p' $REF/src/renderer.cu > $OUT/texture_load_cut.h
+cat > $OUT/ref_tex_shim.cpp <<'EOF'
+#include <stdio.h>
+#include <string.h>
+#include <vector>
+#include <texture.h>
+#include <cugar/image/tga.h>
+#include <cugar/image/pfm.h>
+struct NoDevice { template <typename T> NoDevice& operator=(const T&) { return *this; } };       // stands in for the device copy the block makes
+static MipMapStorage<HOST_BUFFER>* load_one(char* texture_name)
+{
+	std::vector<MipMapStorage<HOST_BUFFER>*> m_textures_h(1, new MipMapStorage<HOST_BUFFER>());
+	NoDevice nd; std::vector<NoDevice*> m_textures_d(1, &nd);
+	const uint32 i = 0;
+#include "texture_load_cut.h"
+	return m_textures_h[0];
+}
+static MipMapStorage<HOST_BUFFER>* g_tex = NULL;
+// loads a file; returns the number of levels (0: not loaded). ref_texture_level then hands out each level (float4 texels, res)
+extern "C" int ref_texture_load(const char* filename)
+{
+	char name[2048]; strncpy(name, filename, 2047); name[2047] = 0;
+	delete g_tex;
+	g_tex = load_one(name);
+	return (int)g_tex->level_count();
+}
+extern "C" const float* ref_texture_level(int level, unsigned* res_x, unsigned* res_y)
+{
+	const TextureView v = g_tex->levels[level]->view();
+	*res_x = v.res_x; *res_y = v.res_y;
+	return reinterpret_cast<const float*>(v.c);
+}
+EOF
+mkdir -p $OUT/overlay_tga; : > $OUT/overlay_tga/windows.h
+$CXX $LFLAGS -I$OUT -I$OUT/overlay_tga -shared -o $OUT/libref_tex.so $OUT/ref_tex_shim.cpp $REF/contrib/cugar/image/tga.cpp $REF/contrib/cugar/image/pfm.cpp -L/usr/local/cuda/lib64 -lcudart_static -ldl -lrt -lpthread
+echo "built $OUT/libref_tex.so"

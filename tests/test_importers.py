@@ -305,3 +305,141 @@ def test_importer_equals_the_references_own(fb, ref_loader, tmp_path_factory, na
     if v.n_dir_lights:
         assert np.array_equal(np.ctypeslib.as_array(v.dir_lights, shape=(int(v.n_dir_lights), 6)).view(np.uint32), want["dir_lights"].view(np.uint32))
     sc.close()
+
+
+def ctypes_string(ptr, n):
+    import ctypes
+    return ctypes.string_at(ptr, n)
+
+
+def _write_tga(path, img, ident=b""):
+    """an uncompressed true-colour TGA of an (H, W, 3 or 4) uint8 RGB(A) image (rows in file order = array order)"""
+    h, w, c = img.shape
+    hdr = bytes([len(ident), 0, 2, 0, 0, 0, 0, 0, 0, 0, 0, 0, w & 255, w >> 8, h & 255, h >> 8, 8 * c, 0])
+    bgr = img[..., [2, 1, 0] + ([3] if c == 4 else [])]
+    with open(path, "wb") as f:
+        f.write(hdr + ident + np.ascontiguousarray(bgr).tobytes())
+
+
+def _write_pfm(path, img, little=True):
+    h, w, _ = img.shape
+    with open(path, "wb") as f:
+        f.write(("PF\n%d %d\n%s\n" % (w, h, "-1.0" if little else "1.0")).encode())
+        f.write(np.ascontiguousarray(img, "<f4" if little else ">f4").tobytes())
+
+
+@pytest.fixture(scope="module")
+def textured_obj(tmp_path_factory):
+    """a quad lit by a TEXTURED emitter (map_Ke on a .pfm), with .tga maps of both depths and sizes that halve unevenly; plus a texture that is not there
+    and one in a format the loader does not know"""
+    d = tmp_path_factory.mktemp("textured")
+    rng = np.random.default_rng(11)
+    (d / "textures").mkdir()
+    _write_tga(d / "textures" / "kd24.tga", rng.integers(0, 256, (6, 13, 3), dtype=np.uint8))
+    _write_tga(d / "textures" / "ks32.tga", rng.integers(0, 256, (8, 8, 4), dtype=np.uint8), ident=b"made by a test")
+    _write_pfm(d / "textures" / "ke.pfm", (rng.random((20, 36, 3), dtype=np.float32) * 3).astype(np.float32))
+    _write_pfm(d / "textures" / "kd_be.pfm", rng.random((5, 10, 3), dtype=np.float32), little=False)
+    (d / "textures" / "bad.png").write_bytes(b"not an image")
+    (d / "t.mtl").write_text("""newmtl floor
+Kd 0.6 0.6 0.6
+map_Kd textures/kd24.tga
+map_Ks textures/ks32.tga
+newmtl lamp
+Kd 0.1 0.1 0.1
+Ke 5 4 3
+map_Ke textures/ke.pfm
+newmtl wall
+Kd 0.5 0.5 0.5
+map_Kd textures/kd_be.pfm
+newmtl broken
+Kd 0.5 0.5 0.5
+map_Kd textures/missing.tga
+map_Ks textures/bad.png
+""")
+    (d / "t.obj").write_text("""mtllib t.mtl
+v -2 0 -2
+v 2 0 -2
+v 2 0 2
+v -2 0 2
+v -1 3 -1
+v 1 3 -1
+v 1 3 1
+v -1 3 1
+v -2 0 -2
+v -2 4 -2
+v 2 4 -2
+v 2 0 -2.5
+vt 0 0
+vt 1 0
+vt 1 1
+vt 0 1
+vt 0.1 0.2
+vt 2.7 0.3
+vt 2.9 1.8
+vt 0.2 1.6
+vn 0 1 0
+vn 0 -1 0
+usemtl floor
+f 1/1/1 2/2/1 3/3/1
+f 1/1/1 3/3/1 4/4/1
+usemtl lamp
+f 5/5/2 7/7/2 6/6/2
+f 5/5/2 8/8/2 7/7/2
+usemtl wall
+f 9/1 10/4 11/3
+usemtl broken
+f 9/1 11/3 12/2
+""")
+    return str(d / "t.obj")
+
+
+def test_texture_files_and_mip_chains_equal_the_references_own(fb, oracle, textured_obj):
+    """The .tga / .pfm branch of RenderingContextImpl::init (src/renderer.cu:804-867: cugar::load_tga / load_pfm, texels to float4, MipMapStorage::set ->
+    generate_mips / downsample, src/texture.h:151-262) cut from the file and compiled on the host (oracle/build_ref.sh -> libref_tex.so) against the product's
+    load_tga / load_pfm / build_mip_chain (host/scene.cpp) read back through fb200_scene_texture_level: every level of every texture bit for bit - 24- and
+    32-bit TGA with an ident field, little- and big-endian PFM, sizes that halve unevenly (13x6 -> 6x3 -> 3x1), a missing file and an unknown format (no levels on
+    either side). Then the VPL generator's TEXTURED branch (src/mesh_lights.cu:188-245: the lod from the triangle's footprint, ten LFSR samples of that level)
+    through the reference's own generator (libref_vpl.so) fed with those chains: the product's CDF, inverse areas, VPLs and normalisation equal it bit for bit."""
+    import hashlib
+    sc = fb.Scene(["-i", textured_obj, "-r", "40", "30"])
+    v = sc.view
+    names = ["kd24.tga", "ks32.tga", "ke.pfm", "kd_be.pfm", "missing.tga", "bad.png"]
+    assert int(v.num_textures) == len(names)
+    # golden arm (the hashes are of the REFERENCE's outputs on these seeded files, taken where the live arm below passed)
+    h = hashlib.sha256()
+    for t in range(len(names)):
+        for lv in sc.texture_levels(t):
+            h.update(np.ascontiguousarray(lv).tobytes())
+    h.update(np.ctypeslib.as_array(v.mesh_cdf, shape=(int(v.n_prims),)).tobytes())
+    h.update(ctypes_string(v.vpls, 16 * int(v.n_vpls)))
+    assert h.hexdigest() == "43c29419afa7b254b367917e18ec915b025dcc187d3537d7ec1f7aa4ee5206a1"
+    live = oracle.RefTexture.load()
+    if live is None:
+        sc.close()
+        pytest.skip("oracle/_ref/libref_tex.so is built where /root/reference exists")
+    shapes = []
+    for t, name in enumerate(names):
+        ours = sc.texture_levels(t)
+        ref = live.levels(os.path.join(os.path.dirname(textured_obj), "textures", name))
+        assert len(ours) == len(ref), name
+        for a, b in zip(ours, ref):
+            assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32)), name
+        shapes.append([a.shape[:2] for a in ours])
+    assert shapes[0] == [(6, 13), (3, 6), (1, 3)] and shapes[1] == [(8, 8), (4, 4), (2, 2), (1, 1)] and shapes[4] == [] and shapes[5] == []
+    assert len(shapes[2]) == 5 and shapes[3] == [(5, 10), (2, 5), (1, 2)]
+    gen = oracle.RefVpl.load()
+    n = int(v.n_vpls)
+    rcdf, rinv, rvpls, rvcdf, rnorm = gen.init(v, n, scene=sc)
+    import ctypes as C
+    vpls = np.ctypeslib.as_array(C.cast(v.vpls, C.POINTER(C.c_float)), shape=(n, 4))
+    cdf = np.ctypeslib.as_array(v.mesh_cdf, shape=(int(v.n_prims),)); inv = np.ctypeslib.as_array(v.mesh_inv_area, shape=(int(v.n_prims),))
+    assert np.array_equal(cdf.view(np.uint32), rcdf.view(np.uint32)) and np.array_equal(inv.view(np.uint32), rinv.view(np.uint32))
+    assert np.array_equal(vpls.view(np.uint32), rvpls.view(np.uint32)) and np.float32(v.vpl_norm) == rnorm
+    # the emitter really went through the textured branch: its material names the .pfm (texture 2, five levels) and the plain estimate Ke x area differs
+    mats = np.ctypeslib.as_array(C.cast(v.materials, C.POINTER(C.c_float)), shape=(int(v.num_materials), 52))
+    lamp = [m for m in range(int(v.num_materials)) if mats[m, 16:19].max() > 0]
+    assert len(lamp) == 1 and len(sc.texture_levels(2)) == 5
+    tri = [i for i in range(int(v.num_triangles)) if np.ctypeslib.as_array(v.material_indices, shape=(int(v.num_triangles),))[i] == lamp[0]]
+    steps = np.diff(np.concatenate([[0.0], cdf.astype(np.float64)]))[tri]
+    assert len(tri) == 2 and steps.min() > 0 and abs(steps[0] - steps[1]) > 1e-6      # a textured emitter's two triangles do not weigh the same
+    sc.close()
