@@ -442,4 +442,12 @@ def test_texture_files_and_mip_chains_equal_the_references_own(fb, oracle, textu
     tri = [i for i in range(int(v.num_triangles)) if np.ctypeslib.as_array(v.material_indices, shape=(int(v.num_triangles),))[i] == lamp[0]]
     steps = np.diff(np.concatenate([[0.0], cdf.astype(np.float64)]))[tri]
     assert len(tri) == 2 and steps.min() > 0 and abs(steps[0] - steps[1]) > 1e-6      # a textured emitter's two triangles do not weigh the same
+    # the same scene through a snapshot and through fb200_scene_create_from_mesh: chains, coordinates and therefore the VPL table survive both
+    want = C.string_at(v.vpls, 16 * n)
+    snap = os.path.join(os.path.dirname(textured_obj), "t.fbs")
+    sc.save_snapshot(snap)
+    for other in (fb.Scene(["-i", snap, "-r", "40", "30"]), fb.Scene(["-r", "40", "30"], mesh=sc.mesh_desc())):
+        assert C.string_at(other.view.vpls, 16 * int(other.view.n_vpls)) == want and other.view.vpl_norm == v.vpl_norm
+        assert [len(other.texture_levels(t)) for t in range(len(names))] == [len(x) for x in shapes]
+        other.close()
     sc.close()
