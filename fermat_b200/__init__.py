@@ -141,6 +141,7 @@ def lib():
         "fb200_context_to_rgba": (i32, [vp, u32, vp]),
         "fb200_context_rgba_device_ptr": (vp, [vp]),
         "fb200_scene_get_tonemap": (i32, [vp, pf, pf]),
+        "fb200_diag_vtls_generate": (i32, [vp, u32, u32, pf, u32, C.POINTER(u32)]),
         "fb200_scene_texture_coordinates": (i32, [vp, C.POINTER(C.POINTER(C.c_int32)), C.POINTER(pf), C.POINTER(u32)]),
         "fb200_scene_texture_level": (i32, [vp, u32, u32, C.POINTER(pf), C.POINTER(u32), C.POINTER(u32)]),
         "fb200_write_tga": (i32, [C.c_char_p, u32, u32, vp]),
@@ -286,6 +287,16 @@ class Scene(_Handle):
         e, g = C.c_float(), C.c_float()
         lib().fb200_scene_get_tonemap(self._h, C.byref(e), C.byref(g))
         return e.value, g.value
+
+    def generate_vtls(self, n_target, instance=0):
+        """host-only diagnostic: the VTLs `-nee-alg rl` builds for n_target, in the subdivision queue's pop order: (n, 8) float32 words"""
+        n = C.c_uint32()
+        if lib().fb200_diag_vtls_generate(self._h, int(n_target), int(instance), None, 0, C.byref(n)) != 0:
+            raise RuntimeError(_err())
+        out = np.zeros((n.value, 8), np.float32)
+        if n.value and lib().fb200_diag_vtls_generate(self._h, int(n_target), int(instance), _fptr(out), n.value, C.byref(n)) != 0:
+            raise RuntimeError(_err())
+        return out
 
     def texture_levels(self, texture):
         """the mip chain of one texture as the host holds it: list of (H, W, 4) float32 arrays, level 0 first (empty for a texture that failed to load)"""

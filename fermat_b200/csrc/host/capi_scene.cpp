@@ -1,9 +1,11 @@
 // capi_scene.cpp — host-only half of the C ABI declared in include/fermat_b200.h
 #include "pt_scene.h"
+#include "mesh_vtls.h"
 #include <stdexcept>
 #include <string>
 #include <vector>
 #include <stdio.h>
+#include <string.h>
 
 namespace fb {
 static thread_local std::string g_last_error;
@@ -101,6 +103,49 @@ int fb200_scene_texture_coordinates(const fb200_scene* s, const int32_t** indice
 	*data = m.texture_data.empty() ? NULL : reinterpret_cast<const float*>(m.texture_data.data());
 	*num_coordinates = (uint32_t)m.texture_data.size();
 	return 0;
+}
+
+int fb200_diag_vtls_generate(const fb200_scene* s, uint32_t n_target, uint32_t instance, float* vtls_out, uint32_t max_out, uint32_t* n_out)
+{
+	if (!s || !n_out) { fb::set_last_error("null argument"); return -1; }
+	try
+	{
+		// the host half of MeshVTLs::init with a stand-in for the device LBVH: a balanced tree over the points in the order they come (the
+		// queue's pop order), children behind their parents - so the VTLs keep that order and can be compared with the reference's generator
+		fb::MeshVTLs m;
+		m.init(n_target, s->scene, [](const std::vector<float4>& pts, const float*, std::vector<fb::Bvh2Node>& nodes, std::vector<fb::uint32>& index)
+		{
+			const fb::uint32 n = (fb::uint32)pts.size();
+			index.resize(n);
+			for (fb::uint32 i = 0; i < n; ++i) index[i] = i;
+			struct Span { fb::uint32 lo, hi; };
+			std::vector<Span> spans(1, Span{ 0u, n });
+			nodes.assign(1, fb::Bvh2Node());
+			for (size_t k = 0; k < spans.size(); ++k)
+			{
+				const Span sp = spans[k];
+				fb::Bvh2Node nd; memset(&nd, 0, sizeof(nd));
+				nd.range_size = sp.hi - sp.lo;
+				if (sp.hi - sp.lo == 1) nd.packed_info = sp.lo << 2;
+				else
+				{
+					const fb::uint32 mid = (sp.lo + sp.hi) / 2, c0 = (fb::uint32)spans.size();
+					nd.packed_info = (c0 << 2) | 3u;
+					spans.push_back(Span{ sp.lo, mid }); spans.push_back(Span{ mid, sp.hi });
+					nodes.resize(spans.size());
+				}
+				nodes[k] = nd;
+			}
+		}, instance);
+		*n_out = (uint32_t)m.vtls.size();
+		if (vtls_out)
+		{
+			if (m.vtls.size() > max_out) { fb::set_last_error("fb200_diag_vtls_generate: output too small"); return -1; }
+			memcpy(vtls_out, m.vtls.data(), m.vtls.size() * sizeof(fb::VTL));
+		}
+		return 0;
+	}
+	catch (const std::exception& e) { fb::set_last_error(e.what()); return -1; }
 }
 
 int fb200_write_tga(const char* filename, uint32_t width, uint32_t height, const uint8_t* rgba)

@@ -186,6 +186,11 @@ int fb200_scene_get_tonemap(const fb200_scene*, float* exposure, float* gamma);
  * MipMapStorage::set -> generate_mips / downsample, :151-262, from the .tga / .pfm texels of src/renderer.cu:803-862). The VPL generator's
  * estimate of a textured emitter reads it (src/mesh_lights.cu:205-250). Returns 0, 1 when the chain has no such level (a texture that could not be
  * loaded has none: n_levels == 0), -1 on a bad argument. The pointer lives as long as the scene. */
+/* Diagnostic, host only (no device): the Virtual Triangular Lights `-nee-alg rl` would build for n_target (MeshVTLStorageImpl::init,
+ * src/mesh_lights.cu:632-721: energy-prioritised 4-way subdivision of the emissive triangles, textured emitters estimated from the mip chain),
+ * in the order the subdivision queue hands them out, i.e. before the cluster tree reorders them. 8 words per VTL (src/vtl.h: prim_id, area,
+ * uv0, uv1, uv2). vtls_out may be NULL to ask for the count. */
+int fb200_diag_vtls_generate(const fb200_scene*, uint32_t n_target, uint32_t instance, float* vtls_out, uint32_t max_out, uint32_t* n_out);
 /* The uncompressed texture coordinates the host keeps beside the fp16 ones of the view (MeshView::texture_indices / texture_data,
  * src/mesh/MeshView.h:131-137): int4 per triangle (-1 = none) and float2 per coordinate; NULL / 0 when the mesh has none. The VPL generator's
  * textured branch reads them (src/mesh_lights.cu:193-197); fb200_mesh_desc takes them back in. Pointers live as long as the scene. */

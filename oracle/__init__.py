@@ -926,7 +926,7 @@ class RefVtl:
     def __init__(self, path):
         self._lib = C.CDLL(path)
         self._lib.ref_vtl_init.restype = C.c_int
-        self._lib.ref_vtl_init.argtypes = [C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_uint] + [C.c_void_p] * 3
+        self._lib.ref_vtl_init.argtypes = [C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_uint] + [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 3
         self._lib.ref_vtl_initial_cut.restype = C.c_int
         self._lib.ref_vtl_initial_cut.argtypes = [C.c_uint, C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p]
 
@@ -935,13 +935,30 @@ class RefVtl:
         p = os.path.join(_HERE, "_ref", "libref_vtl.so")
         return cls(p) if os.path.exists(p) else None
 
-    def init(self, view, n_target, instance=0):
-        """(vtls in pop order [RlState.VTL_DTYPE], centroids (n, 3), centroid box (6,)) of an untextured scene view"""
+    def init(self, view, n_target, instance=0, scene=None):
+        """(vtls in pop order [RlState.VTL_DTYPE], centroids (n, 3), centroid box (6,)). Textured emitters need the product's `scene` (fermat_b200.Scene): its
+        uncompressed texture coordinates and mip chains are handed to the generator (as RefVpl.init does)"""
         cap = 4 * int(n_target) + 4 * int(view.num_triangles) + 16
         vt = np.zeros(cap, RlState.VTL_DTYPE); ctr = np.zeros((cap, 3), np.float32); bb = np.zeros(6, np.float32)
+        keep = []; ntex = 0; tex_idx = tex_data = levels = res = texels = None
+        if scene is not None:
+            d = scene.mesh_desc(); keep.append(d)
+            ntex = int(view.num_textures)
+            tex_idx, tex_data = C.cast(d.texture_indices, C.c_void_p), C.cast(d.texture_data, C.c_void_p)
+            chains = [scene.texture_levels(t) for t in range(ntex)]
+            n_lv = sum(len(c) for c in chains)
+            levels = (C.c_uint32 * max(ntex, 1))(); res = (C.c_uint32 * max(2 * n_lv, 2))(); texels = (C.c_void_p * max(n_lv, 1))()
+            k = 0
+            for t, chain in enumerate(chains):
+                levels[t] = len(chain)
+                for lv in chain:
+                    lv = np.ascontiguousarray(lv, np.float32); keep.append(lv)
+                    res[2 * k], res[2 * k + 1] = lv.shape[1], lv.shape[0]; texels[k] = lv.ctypes.data; k += 1
         n = self._lib.ref_vtl_init(int(n_target), int(instance), int(view.num_vertices), int(view.num_triangles), int(view.num_materials),
                                    C.cast(view.vertex_indices, C.c_void_p), C.cast(view.vertex_data, C.c_void_p), C.cast(view.material_indices, C.c_void_p),
-                                   C.cast(view.materials, C.c_void_p), cap, vt.ctypes.data, ctr.ctypes.data, bb.ctypes.data)
+                                   C.cast(view.materials, C.c_void_p), cap, vt.ctypes.data, ctr.ctypes.data, bb.ctypes.data,
+                                   tex_idx, tex_data, ntex, C.cast(levels, C.c_void_p) if levels is not None else None,
+                                   C.cast(res, C.c_void_p) if res is not None else None, C.cast(texels, C.c_void_p) if texels is not None else None)
         if n < 0:
             raise RuntimeError("ref_vtl_init: %d VTLs do not fit" % -n)
         return vt[:n].copy(), ctr[:n].copy(), bb

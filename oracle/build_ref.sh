@@ -1495,18 +1495,33 @@ struct MeshVTLStorageImpl           // the members the cut text assigns (src/mes
 };
 #include "vtl_init_cut.h"
 #include "vtl_cut_cut.h"
-// VTLs in pop order (8 words each: prim_id, area, uv0, uv1, uv2), their centroids (xyz) and the centroids' box; untextured emitters (no mip chain is handed in)
+// VTLs in pop order (8 words each: prim_id, area, uv0, uv1, uv2), their centroids (xyz) and the centroids' box
 extern "C" int ref_vtl_init(unsigned n_target, unsigned instance, int num_vertices, int num_triangles, int num_materials, const int* vertex_indices, const float* vertex_data,
-							const int* material_indices, const void* materials, unsigned max_out, float* vtls_out, float* centroids_out, float* bbox_out)
+							const int* material_indices, const void* materials, unsigned max_out, float* vtls_out, float* centroids_out, float* bbox_out,
+							const int* texture_indices, const float* texture_data, int num_textures, const unsigned* mip_levels, const unsigned* mip_res, float** mip_texels)
 {
 	MeshView m; memset(&m, 0, sizeof(m));
 	m.num_vertices = num_vertices; m.num_triangles = num_triangles; m.num_materials = num_materials;
 	m.vertex_stride = 4; m.normal_stride = 3; m.texture_stride = 2;
 	m.vertex_indices = const_cast<int*>(vertex_indices); m.vertex_data = const_cast<float*>(vertex_data);
+	m.texture_indices = const_cast<int*>(texture_indices); m.texture_data = const_cast<float*>(texture_data);
 	m.material_indices = const_cast<int*>(material_indices); m.materials = (MeshMaterial*)materials;
-	MipMapView none; memset(&none, 0, sizeof(none));
+	// mips as in ref_vpl_init: per texture the number of levels, then per level (res_x, res_y) and the texel pointer; none = every emitter untextured
+	std::vector<std::vector<TextureView> > levels(num_textures ? num_textures : 1); std::vector<MipMapView> maps(num_textures ? num_textures : 1);
+	memset(maps.data(), 0, maps.size() * sizeof(MipMapView));
+	size_t k = 0;
+	for (int t = 0; t < num_textures; ++t)
+	{
+		levels[t].resize(mip_levels[t] ? mip_levels[t] : 1);
+		for (unsigned l = 0; l < mip_levels[t]; ++l, ++k)
+		{
+			levels[t][l].c = reinterpret_cast<float4*>(mip_texels[k]); levels[t][l].res_x = mip_res[2 * k]; levels[t][l].res_y = mip_res[2 * k + 1];
+		}
+		maps[t].levels = levels[t].data(); maps[t].n_levels = mip_levels[t];
+		maps[t].res_x = mip_levels[t] ? levels[t][0].res_x : 0; maps[t].res_y = mip_levels[t] ? levels[t][0].res_y : 0;
+	}
 	MeshVTLStorageImpl impl;
-	impl.init(n_target, m, m, &none, &none, instance);
+	impl.init(n_target, m, m, maps.data(), maps.data(), instance);
 	const size_t n = impl.vtls.size();
 	if (n > max_out) return -(int)n;
 	for (size_t i = 0; i < n; ++i)

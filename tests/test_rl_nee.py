@@ -145,6 +145,33 @@ def test_split_collapse_and_cdfs_are_the_references_own_kernels(fb, oracle):
     sc.close()
 
 
+def test_product_vtl_generation_is_the_references_own(fb, oracle, tmp_path):
+    """The PRODUCT's host half of MeshVTLs::init (host/mesh_vtls.cpp, read through the host-only fb200_diag_vtls_generate: the subdivision queue's pop order,
+    a stand-in tree instead of the device LBVH) against the reference's own generator compiled on the host (libref_vtl.so) directly, bit for bit - on the
+    fixture, the benchmark scenes where their snapshots exist, and a scene whose emitter is TEXTURED (compute_E's mip-mapped branch, src/mesh_lights.cu:568-616:
+    lod from the VTL's texture-space footprint, ten LFSR samples of that level), which the oracle does not restate. Golden hashes keep the check where oracle/_ref is absent."""
+    import hashlib
+    from conftest import GOLDEN, write_textured_scene
+    obj = write_textured_scene(tmp_path)
+    cases = [("cornell_300", cornell_args(64, 3), 300), ("cornell_2000", cornell_args(64, 3), 2000), ("textured_64", ["-i", obj, "-r", "16", "16"], 64), ("textured_1500", ["-i", obj, "-r", "16", "16"], 1500)]
+    golden = {"cornell_300": "474ed2f7fa72110a98ece0386e13096a4c1120d66920a2028c43fb85657e9984", "cornell_2000": "678d609918396eb296e0a3058d4fbdc2cfa0bb5d08b3b28d98eca99ca29654de", "textured_64": "e72f746d0397cce8c597cb81903f1c9645f680fa86a4fd5908deb36334f7dc5f", "textured_1500": "4f7326ea1f90a85dc08815386ed55ebfcf7b15f09a2d47f6709a786f6e91af8b"}
+    for name in ("cornellbox_glossy", "bathroom2", "water_caustic"):
+        p = os.path.join(CACHE, name + ".fbs")
+        if fb.scene_available(p):
+            cases.append((name, ["-i", p, "-r", "64", "64"], 3000))
+    live = oracle.RefVtl.load()
+    for name, args, n_target in cases:
+        sc = fb.Scene(args)
+        ours = sc.generate_vtls(n_target)
+        assert len(ours) >= n_target
+        if name in golden:
+            assert hashlib.sha256(ours.tobytes()).hexdigest() == golden[name], name
+        if live is not None:
+            vt, ctr, bb = live.init(sc.view, n_target, scene=sc)
+            assert np.array_equal(ours.view(np.uint32), vt.view(np.uint32).reshape(-1, 8)), name
+        sc.close()
+
+
 def test_sampler_arithmetic_of_one_cell(oracle):
     """AdaptiveClusteredRLView::sample / ::pdf: the pdf returned with a sample is the pdf of that index, indices stay inside their cluster,
     and the histogram of many samples follows the CDF."""
