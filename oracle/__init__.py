@@ -773,6 +773,26 @@ class RefShade:
         self.L.ref_rl_locate(h, prims.ctypes.data, uv.ctypes.data, len(prims), out.ctypes.data)
         return out
 
+    def render_pass(self, view, instance, fb, frame_kernels=None):
+        """THE REFERENCE'S OWN PASS on the host (ref_render_pass: path_trace_loop with its dispatchers and kernels, src/pathtracer_kernels.h:128-391, over the
+        reference's queues, shade_vertex, solve_occlusion and PTVertexProcessor) accumulated into fb (8, H, W, 4), as oracle.render_pass does. The two ray queries
+        (OptiX in the reference) are the oracle's traversal. With `frame_kernels` (RefFrameKernels) the reference's own rescale_frame before and
+        update_variances after run too (RenderingContextImpl::render, src/renderer.cu:1040-1046 + PathTracer::render's last line); returns shade_events"""
+        L = self.L
+        L.ref_render_pass.restype = C.c_uint64
+        L.ref_render_pass.argtypes = [C.c_void_p] * 6
+        s = self.pt._scene(view)
+        f = self._frame(view, instance, 0)
+        assert fb.dtype == np.float32 and fb.flags.c_contiguous and fb.shape[0] == 8
+        res = (int(view.res_x), int(view.res_y))
+        if frame_kernels is not None:
+            frame_kernels.frame_op(0, fb, res, f=float(np.float32(instance) / np.float32(instance + 1)))
+        O = lib()
+        n = L.ref_render_pass(C.addressof(s), C.addressof(f), fb.ctypes.data, C.addressof(view), C.cast(O.oracle_trace, C.c_void_p), C.cast(O.oracle_trace_shadow, C.c_void_p))
+        if frame_kernels is not None:
+            frame_kernels.frame_op(1, fb, res, u=instance + 1)
+        return int(n)
+
     def shade_vertex_rl(self, view, h, instance, bounce, records, occluded):
         s = self.pt._scene(view)
         f = self._frame(view, instance, bounce)

@@ -737,6 +737,14 @@ inline float __int_as_float(int u) { float f; memcpy(&f, &u, 4); return f; }
 inline long long clock64() { return 0; }
 inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 EOF
+# pathtracer_kernels.h up to the end of path_trace_loop for the host (ref_render_pass below): the renderer / rt includes dropped (the shim declares the two members
+# the loop uses), the three kernel launches rewritten as REF_LAUNCH(grid, block, kernel(args))
+# cugar's warp_atomics.h: warp_increment only (what PTRayQueue::warp_append calls); the rest of the file is built on the reference's vendored cub, which is device code
+{ sed -n '1,91p' $REF/contrib/cugar/basic/cuda/warp_atomics.h | sed -e '/#include <cub\/cub.cuh>/d'; echo '} // namespace cuda'; echo '} // namespace cugar'; } > $OVS/cugar/basic/cuda/warp_atomics.h
+sed -n '1,391p' $REF/src/pathtracer_kernels.h | sed -e '/#include <rt.h>/d' -e 's/#pragma once//' \
+    -e 's/generate_primary_rays_kernel << < gridSize, blockSize >> > (\(.*\));/REF_LAUNCH(gridSize, blockSize, generate_primary_rays_kernel(\1));/' \
+    -e 's/shade_hits_kernel<blockSize \/ 32><<< gridSize, blockSize >>>( \(.*\) );/REF_LAUNCH(gridSize, blockSize, (shade_hits_kernel<blockSize \/ 32>(\1)));/' \
+    -e 's/solve_occlusion_kernel<<< gridSize, blockSize >>>( \(.*\) );/REF_LAUNCH(gridSize, blockSize, solve_occlusion_kernel(\1));/' > $OVS/pathtracer_kernels_host.h
 sed -n '133,163p' $REF/src/pathtracer_kernels.h > $OUT/primary_kernel_cut.h      # generate_primary_rays_kernel's text (ref_primary_rays below)
 cat > $OUT/ref_shade_shim.cpp <<'EOF'
 #include "dev_emul.h"
@@ -1216,7 +1224,9 @@ extern "C" int ref_shade_vertex_psf(const RefScene* s, const RefFrame* f, void* 
 // ---- generate_primary_rays_kernel (src/pathtracer_kernels.h:133-163) from its own text (primary_kernel_cut.h: `__global__` defined away, the shim's
 // threadIdx / blockIdx), over a context whose input queue is four host arrays: per pixel the ray, the filter weight, the queue words and the ray cone
 #define __global__
+namespace primary_only {      // (the whole header, with this kernel again, is included further down for ref_render_pass)
 #include "primary_kernel_cut.h"
+}
 #undef __global__
 struct PrimaryQueue { MaskedRay* rays; float4* weights; uint4* pixels; float2* cones; uint32* size; };
 struct PrimaryContext : PTContextBase<PTOptions> { PrimaryQueue in_queue; };
@@ -1246,7 +1256,7 @@ extern "C" unsigned ref_primary_rays(const RefFrame* f, float* out)
 		for (unsigned x = 0; x < f->res_x; ++x)
 		{
 			blockIdx.x = x; blockIdx.y = y; threadIdx.x = threadIdx.y = 0;
-			generate_primary_rays_kernel(context, renderer, U, V, W, length(W), square_pixel_focal_length);
+			primary_only::generate_primary_rays_kernel(context, renderer, U, V, W, length(W), square_pixel_focal_length);
 		}
 	blockIdx.x = blockIdx.y = 0;
 	for (size_t i = 0; i < P; ++i)
@@ -1258,6 +1268,118 @@ extern "C" unsigned ref_primary_rays(const RefFrame* f, float* out)
 		q[16] = cones[i].x; q[17] = cones[i].y; q[18] = q[19] = 0.0f;
 	}
 	return size;
+}
+// ---- the reference's own PASS on the host: path_trace_loop (src/pathtracer_kernels.h:309-391) with its dispatchers and kernels (generate_primary_rays, shade_hits,
+// solve_occlusion: the whole header up to the loop's end, pathtracer_kernels_host.h: the three `<<< >>>` launches rewritten as REF_LAUNCH, which runs the kernel
+// once per thread on the host) over the reference's own PTRayQueue / PTContextQueues / shade_vertex / solve_occlusion / PTVertexProcessor. What is NOT the
+// reference's: the two ray queries (closed-source OptiX in the reference: RTContext::trace / trace_shadow are handed in by the caller - the oracle's traversal), the
+// device-to-host copies of the queue sizes (memcpy) and the RenderingContext, of which the loop uses get_rt_context() only.
+struct RTContext
+{
+	typedef int (*closest_fn)(const void*, const float*, float*, unsigned, unsigned long long*, unsigned long long*);
+	typedef int (*shadow_fn)(const void*, const float*, unsigned char*, unsigned);
+	const void* view; closest_fn closest; shadow_fn shadow;
+	void trace(const uint32 count, const Ray* rays, Hit* hits) { closest(view, reinterpret_cast<const float*>(rays), reinterpret_cast<float*>(hits), count, NULL, NULL); }
+	void trace_shadow(const uint32 count, const MaskedRay* rays, Hit* hits)
+	{
+		std::vector<unsigned char> occ(count);
+		shadow(view, reinterpret_cast<const float*>(rays), occ.data(), count);
+		for (uint32 i = 0; i < count; ++i) { hits[i].t = occ[i] ? 1.0f : -1.0f; hits[i].triId = occ[i] ? 0 : -1; hits[i].u = hits[i].v = 0.0f; }
+	}
+};
+static RTContext* g_host_rt = NULL;
+RTContext* RenderingContext::get_rt_context() const { return g_host_rt; }      // the one member of RenderingContext the loop uses (src/renderer.h:208)
+inline int __match_all_sync(unsigned, unsigned long long, int* pred) { *pred = 1; return 1; }
+#define REF_LAUNCH(g, b, call) do { const dim3 _g(g), _b(b); for (unsigned _y = 0; _y < _g.y * _b.y; ++_y) for (unsigned _x = 0; _x < _g.x * _b.x; ++_x) \
+	{ blockIdx.x = _x; blockIdx.y = _y; threadIdx.x = threadIdx.y = 0; call; } blockIdx.x = blockIdx.y = 0; } while (0)
+#define __global__
+#define __launch_bounds__(...)
+#undef CUDA_CHECK
+#define CUDA_CHECK(x)
+#undef FERMAT_CUDA_TIME
+#define FERMAT_CUDA_TIME(x)
+#define cudaMemcpy(d, s, n, k) memcpy(d, s, n)
+#define cudaMemset(d, v, n) memset(d, v, n)
+#include "pathtracer_kernels_host.h"
+#undef cudaMemcpy
+#undef cudaMemset
+#undef __global__
+template <typename TDirectLightingSampler>
+struct HostPathTracingContext : PTContextBase<PTOptions>, PTContextQueues { TDirectLightingSampler dl; };     // PathTracingContext, src/renderers/pathtracer_impl.h:60-64
+struct HostQueue
+{
+	std::vector<MaskedRay> rays; std::vector<Hit> hits; std::vector<float4> weights, weights_d, weights_g; std::vector<uint4> pixels; std::vector<float2> cones; uint32 size;
+	PTRayQueue view(size_t n, bool shadow)      // alloc_queues (src/pathtracer_kernels.h:90-126): the shadow queue holds two entries per pixel and the split weights, no cones
+	{
+		rays.resize(n); hits.resize(n); weights.resize(n); pixels.resize(n); size = 0;
+		PTRayQueue q;
+		q.rays = rays.data(); q.hits = hits.data(); q.weights = weights.data(); q.pixels = pixels.data(); q.size = &size;
+		if (shadow) { weights_d.resize(n); weights_g.resize(n); q.weights_d = weights_d.data(); q.weights_g = weights_g.data(); q.cones = NULL; }
+		else { cones.resize(n); q.cones = cones.data(); q.weights_d = NULL; q.weights_g = NULL; }
+		return q;
+	}
+};
+// PathTracer::render's mesh-sampler branch (src/renderers/pathtracer_impl.h:271-292) between rescale_frame and update_variances: fbdata = the frame's 8 channel planes
+// (P float4 each, FBufferDesc order), accumulated into; returns the loop's shade_events
+extern "C" unsigned long long ref_render_pass(const RefScene* s, const RefFrame* f, float* fbdata, const void* view, void* closest, void* shadow)
+{
+	std::vector<TextureView> levels(s->num_textures ? s->num_textures : 1); std::vector<MipMapView> maps(s->num_textures ? s->num_textures : 1);
+	for (int t = 0; t < s->num_textures; ++t)
+	{
+		levels[t].c = reinterpret_cast<float4*>(s->texels[t]); levels[t].res_x = s->tex_res[2 * t]; levels[t].res_y = s->tex_res[2 * t + 1];
+		maps[t].levels = &levels[t]; maps[t].n_levels = s->texels[t] ? 1u : 0u; maps[t].res_x = levels[t].res_x; maps[t].res_y = levels[t].res_y;
+	}
+	const MeshView mesh = mesh_view(*s);
+	const MeshLight mesh_light(s->n_prims, s->mesh_cdf, s->mesh_inv_area, mesh, maps.data(), 0u, NULL, s->vpls, s->vpl_norm);
+	const MeshLight mesh_vpls(s->n_prims, s->mesh_cdf, s->mesh_inv_area, mesh, maps.data(), s->n_vpls, NULL, s->vpls, s->vpl_norm);
+	std::vector<DirectionalLight> dls(f->n_dir_lights ? f->n_dir_lights : 1);
+	for (unsigned i = 0; i < f->n_dir_lights; ++i)
+	{
+		dls[i].dir = cugar::Vector3f(f->dir_lights[6 * i], f->dir_lights[6 * i + 1], f->dir_lights[6 * i + 2]);
+		dls[i].color = cugar::Vector3f(f->dir_lights[6 * i + 3], f->dir_lights[6 * i + 4], f->dir_lights[6 * i + 5]);
+	}
+	Camera cam;
+	cam.eye = make_float3(f->cam[0], f->cam[1], f->cam[2]); cam.aim = make_float3(f->cam[3], f->cam[4], f->cam[5]); cam.up = make_float3(f->cam[6], f->cam[7], f->cam[8]); cam.fov = f->cam[9];
+	const size_t P = (size_t)f->res_x * f->res_y;
+	std::vector<FBufferChannelView> channels(FBufferDesc::NUM_CHANNELS);
+	for (unsigned c = 0; c < (unsigned)FBufferDesc::NUM_CHANNELS; ++c) { channels[c].c_ptr = reinterpret_cast<float4*>(fbdata) + c * P; channels[c].res_x = f->res_x; channels[c].res_y = f->res_y; }
+	std::vector<float4> gb_geo(P), gb_uv(P); std::vector<uint32> gb_tri(P); std::vector<float> gb_depth(P);
+	FBufferView fbv; memset(&fbv, 0, sizeof(fbv));
+	fbv.channels = channels.data(); fbv.n_channels = FBufferDesc::NUM_CHANNELS;
+	fbv.gbuffer.m_geo = gb_geo.data(); fbv.gbuffer.m_uv = gb_uv.data(); fbv.gbuffer.m_tri = gb_tri.data(); fbv.gbuffer.m_depth = gb_depth.data();
+	fbv.gbuffer.res_x = f->res_x; fbv.gbuffer.res_y = f->res_y;
+	RenderingContextView renderer_view(cam, f->n_dir_lights, dls.data(), mesh, mesh_light, mesh_vpls, maps.data(), 0u, NULL, NULL, NULL, f->glossy_reflectance,
+									   f->res_x, f->res_y, f->aspect, 1.0f, 2.2f, 1.0f, kShaded, fbv, f->instance);
+	const size_t S = (size_t)f->tile * f->tile;
+	std::vector<float> samples((size_t)f->n_dims * S);
+	for (unsigned d = 0; d < f->n_dims; ++d)
+	{
+		const float seq = cugar::randfloat(d, f->instance + 1);
+		for (size_t i = 0; i < S; ++i) samples[d * S + i] = fmodf(seq + f->shifts[d * S + i], 1.0f);
+	}
+	HostQueue in_q, scatter_q, shadow_q;
+	uint64 device_timers[16];
+	HostPathTracingContext<DirectLightingMesh> context;
+	PTOptions& o = context.options;
+	o.max_path_length = f->options[0]; o.direct_lighting = f->options[1]; o.direct_lighting_nee = f->options[2]; o.direct_lighting_bsdf = f->options[3];
+	o.indirect_lighting_nee = f->options[4]; o.indirect_lighting_bsdf = f->options[5]; o.visible_lights = f->options[6]; o.diffuse_scattering = f->options[7];
+	o.glossy_scattering = f->options[8]; o.indirect_glossy = f->options[9]; o.rr = f->options[10]; o.nee_type = f->options[11];
+	context.in_bounce = 0;
+	context.in_queue = in_q.view(P, false); context.scatter_queue = scatter_q.view(P, false); context.shadow_queue = shadow_q.view(2 * P, true);
+	context.sequence.n_dimensions = f->n_dims; context.sequence.tile_size = f->tile; context.sequence.samples = samples.data(); context.sequence.shifts = f->shifts;
+	context.frame_weight = 1.0f / float(renderer_view.instance + 1);
+	context.device_timers = device_timers;
+	context.bbox = cugar::Bbox3f();
+	// PathTracer::init falls back to the plain mesh sampler when there are no VPLs (src/renderers/pathtracer_impl.h:163-165)
+	context.dl = DirectLightingMesh(f->options[11] == NEE_ALGORITHM_VPL && s->n_vpls ? renderer_view.mesh_vpls : renderer_view.mesh_light);
+	PTVertexProcessor vertex_processor;
+	RTContext rt; rt.view = view; rt.closest = (RTContext::closest_fn)closest; rt.shadow = (RTContext::shadow_fn)shadow;
+	g_host_rt = &rt;
+	alignas(16) static char renderer_mem[4096];          // never constructed: the loop only calls get_rt_context() on it
+	RenderingContext& renderer = *reinterpret_cast<RenderingContext*>(renderer_mem);
+	PTLoopStats stats;
+	path_trace_loop(context, vertex_processor, renderer, renderer_view, stats);
+	return stats.shade_events;
 }
 EOF
 $CXX -O2 -std=c++14 -fPIC -w -fpermissive -ffp-contract=off -include $OVF/adapter_prefix.h -DFERMAT_API_EXTERN= -DFERMAT_API= -DSUTILAPI= -DSUTILCLASSAPI= \

@@ -262,3 +262,37 @@ def test_primary_rays_are_the_references_own_kernels(fb, oracle):
             assert np.all(b[:, 8:12] == 1) and np.array_equal(b[:, 12].view(np.uint32), np.arange(len(b), dtype=np.uint32))
             assert np.all(b[:, 13:16].view(np.uint32) == 0xFFFFFFFF) and np.all(b[:, 16] == 0)
         sc.close()
+
+
+def test_whole_pass_is_the_references_own(fb, oracle, libm_trig):
+    """THE REFERENCE'S OWN PASS against the oracle's, frame for frame: path_trace_loop (src/pathtracer_kernels.h:309-391) with its dispatchers and kernels
+    (generate_primary_rays, shade_hits, solve_occlusion: the header itself, its three `<<< >>>` launches run once per thread on the host), over the reference's
+    own PTRayQueue / PTContextQueues / shade_vertex / solve_occlusion / PTVertexProcessor, between the reference's own rescale_frame and update_variances
+    kernels - everything of PathTracer::render but the two ray queries, which are closed-source OptiX in the reference and the oracle's traversal here. All eight
+    frame-buffer channels after every pass and the loop's shade_events equal oracle.render_pass bit for bit: VPL and mesh samplers, directional lights (two
+    shadow-queue entries per vertex), a path length of two on a ragged frame; golden hashes everywhere (tests/golden/pass_golden.npz, tools/make_golden_pass.py),
+    the live pass on the fixtures and on the four benchmark scenes where oracle/_ref and the snapshots exist. The oracle runs with libm's sinf / cosf here, as
+    the reference does on a host; what the GPU parity tests compare against is the same oracle with the fixed-sequence sincos it shares with the kernels."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_pass", os.path.join(os.path.dirname(GOLDEN), "..", "tools", "make_golden_pass.py"))
+    mk = importlib.util.module_from_spec(spec); spec.loader.exec_module(mk)
+    g = np.load(os.path.join(GOLDEN, "pass_golden.npz"))
+    live = oracle.RefShade.load(); kernels = oracle.RefFrameKernels.load()
+    cases = dict(mk.CASES)
+    if live is not None and kernels is not None:
+        for name, res, bounces in (("bathroom2", (160, 90), 8), ("water_caustic", (96, 96), 8), ("cornellbox_glossy", (80, 60), 6), ("material_testball", (80, 60), 5)):
+            p = os.path.join(CACHE, name + ".fbs")
+            if fb.scene_available(p):
+                cases[name] = ["-i", p, "-r", str(res[0]), str(res[1]), "-bounces", str(bounces)]
+    for name, args in cases.items():
+        sc = fb.Scene(args)
+        a = oracle.new_framebuffer(sc.view); b = oracle.new_framebuffer(sc.view)
+        for i in range(mk.PASSES if name in mk.CASES else 2):
+            ev = oracle.render_pass(sc.view, i, a).shade_events
+            if name in mk.CASES:
+                assert np.array_equal(mk.sha(a), g["%s_sha_%d" % (name, i)]) and ev == int(g["%s_events_%d" % (name, i)]), (name, i)
+            if live is not None and kernels is not None:
+                assert live.render_pass(sc.view, i, b, kernels) == ev, (name, i)
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (name, i)
+        assert a[5][..., :3].mean() > 0
+        sc.close()
