@@ -136,7 +136,7 @@ def cpu_baseline(scene, res, threads=0, target_s=12.0, count_traversal=True):
         passes += 1
         dt = time.perf_counter() - t
     cores = threads if threads > 0 else oracle.num_threads()
-    out = {"value": events / dt * 1e-6, "unit": "Msamples/s", "cores": cores, "kind": "port",
+    out = {"value": events / dt * 1e-6, "unit": "Msamples/s", "cores": cores, "kind": "port", "pinned": "the port's frames equal the reference's own pass (path_trace_loop + its kernels run on the host, oracle/_ref) bit for bit: tests/test_shade_vertex_pinning.py::test_whole_pass_is_the_references_own",
            "sample": "oracle (scalar C++ restatement, OpenMP over pixels), %d passes over every %d-th pixel of %dx%d (%d pixels, %d samples, %.1f s)" % (
                passes, stride, res[0], res[1], pixels.size, events, dt)}
     trav = None
@@ -185,7 +185,7 @@ def run_reference(args):
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "scene bathroom2 of the reference's models/ (snapshot scenes/_cache/bathroom2.fbs), the reference's default sampler seeds; no synthetic rays",
         "config": {"workload": "%s -pt %dx%d, %d bounces" % (name, res[0], res[1], BOUNCES), "note": "CPU restatement of the reference algorithm (the reference needs OptiX 6 / Win32 and cannot run)"},
-        "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample, "pinned": "the port's frames equal the reference's own pass (path_trace_loop + its kernels run on the host, oracle/_ref) bit for bit: tests/test_shade_vertex_pinning.py::test_whole_pass_is_the_references_own"},
         "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
