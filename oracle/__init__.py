@@ -793,6 +793,25 @@ class RefShade:
             frame_kernels.frame_op(1, fb, res, u=instance + 1)
         return int(n)
 
+    def render_pass_rl(self, view, instance, fb, h, frame_kernels=None):
+        """as render_pass with the reference's own DirectLightingRL over the sampler state `h` (rl_create): PathTracer::render's RL branch for one pass; the
+        per-pass update of the sampler (update_vtls_rl) is the caller's"""
+        L = self.L
+        L.ref_render_pass_rl.restype = C.c_uint64
+        L.ref_render_pass_rl.argtypes = [C.c_void_p] * 8
+        s = self.pt._scene(view)
+        f = self._frame(view, instance, 0)
+        bbox = np.array(list(view.bbox_min[:]) + list(view.bbox_max[:]), np.float32)
+        res = (int(view.res_x), int(view.res_y))
+        if frame_kernels is not None:
+            frame_kernels.frame_op(0, fb, res, f=float(np.float32(instance) / np.float32(instance + 1)))
+        O = lib()
+        n = L.ref_render_pass_rl(C.addressof(s), C.addressof(f), fb.ctypes.data, C.addressof(view), C.cast(O.oracle_trace, C.c_void_p), C.cast(O.oracle_trace_shadow, C.c_void_p),
+                                 h, bbox.ctypes.data)
+        if frame_kernels is not None:
+            frame_kernels.frame_op(1, fb, res, u=instance + 1)
+        return int(n)
+
     def shade_vertex_rl(self, view, h, instance, bounce, records, occluded):
         s = self.pt._scene(view)
         f = self._frame(view, instance, bounce)

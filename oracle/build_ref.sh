@@ -1319,9 +1319,10 @@ struct HostQueue
 		return q;
 	}
 };
-// PathTracer::render's mesh-sampler branch (src/renderers/pathtracer_impl.h:271-292) between rescale_frame and update_variances: fbdata = the frame's 8 channel planes
-// (P float4 each, FBufferDesc order), accumulated into; returns the loop's shade_events
-extern "C" unsigned long long ref_render_pass(const RefScene* s, const RefFrame* f, float* fbdata, const void* view, void* closest, void* shadow)
+// PathTracer::render between rescale_frame and update_variances (src/renderers/pathtracer_impl.h:252-292; the sampler is the caller's): fbdata = the frame's 8 channel
+// planes (P float4 each, FBufferDesc order), accumulated into; returns the loop's shade_events
+template <typename TDirectLightingSampler, typename TMakeSampler>
+static unsigned long long render_pass_host(const RefScene* s, const RefFrame* f, float* fbdata, const void* view, void* closest, void* shadow, const float* bbox, TMakeSampler make_sampler)
 {
 	std::vector<TextureView> levels(s->num_textures ? s->num_textures : 1); std::vector<MipMapView> maps(s->num_textures ? s->num_textures : 1);
 	for (int t = 0; t < s->num_textures; ++t)
@@ -1359,7 +1360,7 @@ extern "C" unsigned long long ref_render_pass(const RefScene* s, const RefFrame*
 	}
 	HostQueue in_q, scatter_q, shadow_q;
 	uint64 device_timers[16];
-	HostPathTracingContext<DirectLightingMesh> context;
+	HostPathTracingContext<TDirectLightingSampler> context;
 	PTOptions& o = context.options;
 	o.max_path_length = f->options[0]; o.direct_lighting = f->options[1]; o.direct_lighting_nee = f->options[2]; o.direct_lighting_bsdf = f->options[3];
 	o.indirect_lighting_nee = f->options[4]; o.indirect_lighting_bsdf = f->options[5]; o.visible_lights = f->options[6]; o.diffuse_scattering = f->options[7];
@@ -1369,9 +1370,8 @@ extern "C" unsigned long long ref_render_pass(const RefScene* s, const RefFrame*
 	context.sequence.n_dimensions = f->n_dims; context.sequence.tile_size = f->tile; context.sequence.samples = samples.data(); context.sequence.shifts = f->shifts;
 	context.frame_weight = 1.0f / float(renderer_view.instance + 1);
 	context.device_timers = device_timers;
-	context.bbox = cugar::Bbox3f();
-	// PathTracer::init falls back to the plain mesh sampler when there are no VPLs (src/renderers/pathtracer_impl.h:163-165)
-	context.dl = DirectLightingMesh(f->options[11] == NEE_ALGORITHM_VPL && s->n_vpls ? renderer_view.mesh_vpls : renderer_view.mesh_light);
+	context.bbox = bbox ? cugar::Bbox3f(cugar::Vector3f(bbox[0], bbox[1], bbox[2]), cugar::Vector3f(bbox[3], bbox[4], bbox[5])) : cugar::Bbox3f();
+	context.dl = make_sampler(renderer_view, mesh, maps.data());
 	PTVertexProcessor vertex_processor;
 	RTContext rt; rt.view = view; rt.closest = (RTContext::closest_fn)closest; rt.shadow = (RTContext::shadow_fn)shadow;
 	g_host_rt = &rt;
@@ -1380,6 +1380,28 @@ extern "C" unsigned long long ref_render_pass(const RefScene* s, const RefFrame*
 	PTLoopStats stats;
 	path_trace_loop(context, vertex_processor, renderer, renderer_view, stats);
 	return stats.shade_events;
+}
+extern "C" unsigned long long ref_render_pass(const RefScene* s, const RefFrame* f, float* fbdata, const void* view, void* closest, void* shadow)
+{
+	const bool vpl = f->options[11] == NEE_ALGORITHM_VPL && s->n_vpls;      // PathTracer::init falls back to the plain mesh sampler when there are no VPLs (pathtracer_impl.h:163-165)
+	return render_pass_host<DirectLightingMesh>(s, f, fbdata, view, closest, shadow, NULL,
+		[vpl](const RenderingContextView& rv, const MeshView&, const MipMapView*) { return DirectLightingMesh(vpl ? rv.mesh_vpls : rv.mesh_light); });
+}
+// PathTracer::render's RL branch (src/renderers/pathtracer_impl.h:252-270) for one pass over the sampler state of `rl_handle` (ref_rl_create): DirectLightingRL over
+// AdaptiveClusteredRLView + VTLMeshView as in ref_shade_vertex_rl; update_vtls_rl (the per-pass clear / split-collapse / CDF update) is the caller's
+extern "C" unsigned long long ref_render_pass_rl(const RefScene* s, const RefFrame* f, float* fbdata, const void* view, void* closest, void* shadow, void* rl_handle, const float* bbox)
+{
+	RefRl* rl = static_cast<RefRl*>(rl_handle);
+	return render_pass_host<DirectLightingRL>(s, f, fbdata, view, closest, shadow, bbox,
+		[rl](const RenderingContextView&, const MeshView& mesh, const MipMapView* maps)
+		{
+			AdaptiveClusteredRLView rv;
+			rv.hash_size = rl->hash_size;
+			rv.hashmap = AdaptiveClusteredRLView::HashMap(rl->hash_size, rl->keys.data(), rl->unique.data(), rl->slots.data(), &rl->count);
+			rv.init_cluster_count = rl->C; rv.cluster_counts = rl->cluster_counts.data(); rv.cluster_ends = rl->cluster_ends.data();
+			rv.pdfs = rl->values.data(); rv.cdfs = rl->values.data() + (size_t)rl->hash_size * rl->C;
+			return DirectLightingRL(rv, VTLMeshView((uint32)rl->vtls.size(), &rl->vtls[0], rl->uvbvh.view(), mesh, maps));
+		});
 }
 EOF
 $CXX -O2 -std=c++14 -fPIC -w -fpermissive -ffp-contract=off -include $OVF/adapter_prefix.h -DFERMAT_API_EXTERN= -DFERMAT_API= -DSUTILAPI= -DSUTILCLASSAPI= \

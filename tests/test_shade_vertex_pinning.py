@@ -296,3 +296,46 @@ def test_whole_pass_is_the_references_own(fb, oracle, libm_trig):
                 assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (name, i)
         assert a[5][..., :3].mean() > 0
         sc.close()
+
+
+def test_whole_rl_pass_is_the_references_own(fb, oracle, libm_trig):
+    """PathTracer::render's RL branch on the host: the same loop, kernels and queues with the reference's own DirectLightingRL over AdaptiveClusteredRLView +
+    VTLMeshView + the UV-BVH (ref_render_pass_rl), against RlState.render_pass for the first pass (every cell fresh; what is learned afterwards depends on the
+    order shadow rays report in - bounce-major in the wavefront, path-major in the restatement - so later passes are compared per vertex, test_rl_vertex_*):
+    all eight channels, the shade events and the number of cells bit for bit on the fixture. On bathroom2 the hit barycentrics (which pass through fp16) land
+    exactly on VTL edges now and then; which of the two VTLs `map` names is then the search order's choice (the reference's UV-BVH, the restatement's candidate
+    list, the product's subdivision descent), and the MIS weight of that emissive hit follows the cluster it names: a handful of pixels of the two channels an
+    emissive hit at bounce >= 1 feeds may differ, nothing else."""
+    import hashlib
+    live = oracle.RefShade.load(); kernels = oracle.RefFrameKernels.load()
+    cases = [("cornell", ["-i", os.path.join(GOLDEN, "cornellbox_jp.fbs"), "-r", "48", "48", "-bounces", "3", "-nee-alg", "rl"], 48 * 48)]
+    p = os.path.join(CACHE, "bathroom2.fbs")
+    if live is not None and fb.scene_available(p):
+        cases.append(("bathroom2", ["-i", p, "-r", "96", "54", "-bounces", "4", "-nee-alg", "rl"], 96 * 54))
+    for name, args, n_target in cases:
+        sc = fb.Scene(args)
+        st = oracle.RlState(sc.view, n_target)
+        a = oracle.new_framebuffer(sc.view)
+        ev = st.render_pass(0, a, threads=1).shade_events
+        if name == "cornell":      # golden arm: the hash of the REFERENCE's frame, taken where the live arm below passed
+            assert hashlib.sha256(a.tobytes()).hexdigest() == "9d8f0fcfd961384087d03af6f5609e4bbc10f955db9358196fd7bf45aa925184" and ev == 5438
+        if live is None or kernels is None:
+            sc.close()
+            continue
+        arr = st.arrays()
+        fresh = oracle.RlState(sc.view, n_target)
+        r0 = oracle.vertex_records(sc.view, 50, 1, 0)
+        fresh.probe_shade_vertex(0, 0, r0, np.zeros(len(r0), np.uint8))
+        h = live.rl_create(arr["vtls"], 1 << 16, arr["cluster_offsets"][1:], fresh.cell(0)[4])
+        b = oracle.new_framebuffer(sc.view)
+        assert live.render_pass_rl(sc.view, 0, b, h, kernels) == ev
+        assert live.rl_cells(h) == st.sizes()["cells"]
+        if name == "cornell":
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+        else:
+            for c in (1, 2, 3, 4, 6, 7):
+                assert np.array_equal(a[c].view(np.uint32), b[c].view(np.uint32)), c
+            differing = (a[5] != b[5]).any(axis=2)
+            assert differing.mean() < 2e-3 and np.array_equal(differing, (a[0] != b[0]).any(axis=2))
+        live.rl_destroy(h)
+        sc.close()
