@@ -793,6 +793,31 @@ class RefShade:
             frame_kernels.frame_op(1, fb, res, u=instance + 1)
         return int(n)
 
+    def render_pass_psf(self, view, instance, fb, h, frame_kernels):
+        """PSFPT::render on the host (src/renderers/psfpt_impl.h:287-299): the reference's own rescale_frame, render_pass (the loop with PSFPTVertexProcessor over
+        the cache state `h` from psf_create, cleared every psf_temporal_reuse passes, then psf_blending), update_variances and clamp_frame(100).
+        Returns (shade_events, references blended)"""
+        L = self.L
+        L.ref_render_pass_psf.restype = C.c_uint64
+        L.ref_render_pass_psf.argtypes = [C.c_void_p] * 10
+        L.ref_psf_clear.argtypes = [C.c_void_p]
+        s = self.pt._scene(view)
+        f = self._frame(view, instance, 0)
+        bbox = np.array(list(view.bbox_min[:]) + list(view.bbox_max[:]), np.float32)
+        p = view.psf
+        opts = np.array([p.psf_depth, p.psf_width, p.psf_max_prob, p.firefly_filter], np.float32)
+        res = (int(view.res_x), int(view.res_y))
+        frame_kernels.frame_op(0, fb, res, f=float(np.float32(instance) / np.float32(instance + 1)))
+        if instance % max(int(p.psf_temporal_reuse), 1) == 0:
+            L.ref_psf_clear(h)
+        O = lib()
+        n_refs = C.c_uint32()
+        n = L.ref_render_pass_psf(C.addressof(s), C.addressof(f), fb.ctypes.data, C.addressof(view), C.cast(O.oracle_trace, C.c_void_p), C.cast(O.oracle_trace_shadow, C.c_void_p),
+                                  h, bbox.ctypes.data, opts.ctypes.data, C.addressof(n_refs))
+        frame_kernels.frame_op(1, fb, res, u=instance + 1)
+        frame_kernels.frame_op(2, fb, res, f=100.0)
+        return int(n), int(n_refs.value)
+
     def render_pass_rl(self, view, instance, fb, h, frame_kernels=None):
         """as render_pass with the reference's own DirectLightingRL over the sampler state `h` (rl_create): PathTracer::render's RL branch for one pass; the
         per-pass update of the sampler (update_vtls_rl) is the caller's"""

@@ -745,6 +745,7 @@ sed -n '1,391p' $REF/src/pathtracer_kernels.h | sed -e '/#include <rt.h>/d' -e '
     -e 's/generate_primary_rays_kernel << < gridSize, blockSize >> > (\(.*\));/REF_LAUNCH(gridSize, blockSize, generate_primary_rays_kernel(\1));/' \
     -e 's/shade_hits_kernel<blockSize \/ 32><<< gridSize, blockSize >>>( \(.*\) );/REF_LAUNCH(gridSize, blockSize, (shade_hits_kernel<blockSize \/ 32>(\1)));/' \
     -e 's/solve_occlusion_kernel<<< gridSize, blockSize >>>( \(.*\) );/REF_LAUNCH(gridSize, blockSize, solve_occlusion_kernel(\1));/' > $OVS/pathtracer_kernels_host.h
+sed -n '113,152p' $REF/src/renderers/psfpt_impl.h > $OUT/psf_blend_cut.h                  # psf_blending_kernel's body (ref_render_pass_psf below)
 sed -n '133,163p' $REF/src/pathtracer_kernels.h > $OUT/primary_kernel_cut.h      # generate_primary_rays_kernel's text (ref_primary_rays below)
 cat > $OUT/ref_shade_shim.cpp <<'EOF'
 #include "dev_emul.h"
@@ -1402,6 +1403,100 @@ extern "C" unsigned long long ref_render_pass_rl(const RefScene* s, const RefFra
 			rv.pdfs = rl->values.data(); rv.cdfs = rl->values.data() + (size_t)rl->hash_size * rl->C;
 			return DirectLightingRL(rv, VTLMeshView((uint32)rl->vtls.size(), &rl->vtls[0], rl->uvbvh.view(), mesh, maps));
 		});
+}
+// ---- PSFPT::render_pass's mesh-sampler branch on the host (src/renderers/psfpt_impl.h:390-436): the same path_trace_loop with the reference's own
+// PSFPTVertexProcessor over a context shaped like PSFPTContext (the queues of the loop + the reference queue, the cache's hash map and cell values on the host
+// arrays of `psf_handle`), then psf_blending_kernel (its own text, psf_blend_cut.h) over the references the pass appended, in queue order
+namespace psf_pass {
+#define __global__
+template <typename TContext>
+void psf_blending_kernel(const uint32 in_queue_size, TContext context, RenderingContextView renderer, const float frame_weight)
+#include "psf_blend_cut.h"
+#undef __global__
+}
+template <typename TDirectLightingSampler>
+struct HostPSFPTContext : PTContextBase<PSFPTOptions>, PTContextQueues
+{
+	typedef cugar::cuda::SyncFreeHashMap<uint64, uint32, 0xFFFFFFFFFFFFFFFFllu> HashMap;
+	RefPsfQueue ref_queue; HashMap psf_hashmap; float4* psf_values; TDirectLightingSampler dl;
+};
+struct BlendQueueView { float4* weights_d; float4* weights_g; uint2* pixels; };
+struct BlendContextView { BlendQueueView ref_queue; float4* psf_values; PSFPTOptions options; };
+// the cache is cleared when instance % psf_temporal_reuse == 0 (src/renderers/psfpt_impl.h:376-377: the hash only; a new cell's value is zeroed on insertion)
+extern "C" void ref_psf_clear(void* h)
+{
+	RefPsf* r = static_cast<RefPsf*>(h);
+	std::fill(r->keys.begin(), r->keys.end(), 0xFFFFFFFFFFFFFFFFllu); std::fill(r->slots.begin(), r->slots.end(), 0xFFFFFFFFu); r->count = 0;
+}
+// psf_opts = psf_depth, psf_width, psf_max_prob, firefly_filter; returns the loop's shade_events, *n_refs = the references blended
+extern "C" unsigned long long ref_render_pass_psf(const RefScene* s, const RefFrame* f, float* fbdata, const void* view, void* closest, void* shadow, void* psf_handle,
+												  const float* bbox, const float* psf_opts, unsigned* n_refs)
+{
+	RefPsf* psf = static_cast<RefPsf*>(psf_handle);
+	std::vector<TextureView> levels(s->num_textures ? s->num_textures : 1); std::vector<MipMapView> maps(s->num_textures ? s->num_textures : 1);
+	for (int t = 0; t < s->num_textures; ++t)
+	{
+		levels[t].c = reinterpret_cast<float4*>(s->texels[t]); levels[t].res_x = s->tex_res[2 * t]; levels[t].res_y = s->tex_res[2 * t + 1];
+		maps[t].levels = &levels[t]; maps[t].n_levels = s->texels[t] ? 1u : 0u; maps[t].res_x = levels[t].res_x; maps[t].res_y = levels[t].res_y;
+	}
+	const MeshView mesh = mesh_view(*s);
+	const MeshLight mesh_light(s->n_prims, s->mesh_cdf, s->mesh_inv_area, mesh, maps.data(), 0u, NULL, s->vpls, s->vpl_norm);
+	const MeshLight mesh_vpls(s->n_prims, s->mesh_cdf, s->mesh_inv_area, mesh, maps.data(), s->n_vpls, NULL, s->vpls, s->vpl_norm);
+	std::vector<DirectionalLight> dls(1);
+	Camera cam;
+	cam.eye = make_float3(f->cam[0], f->cam[1], f->cam[2]); cam.aim = make_float3(f->cam[3], f->cam[4], f->cam[5]); cam.up = make_float3(f->cam[6], f->cam[7], f->cam[8]); cam.fov = f->cam[9];
+	const size_t P = (size_t)f->res_x * f->res_y;
+	std::vector<FBufferChannelView> channels(FBufferDesc::NUM_CHANNELS);
+	for (unsigned c = 0; c < (unsigned)FBufferDesc::NUM_CHANNELS; ++c) { channels[c].c_ptr = reinterpret_cast<float4*>(fbdata) + c * P; channels[c].res_x = f->res_x; channels[c].res_y = f->res_y; }
+	std::vector<float4> gb_geo(P), gb_uv(P); std::vector<uint32> gb_tri(P); std::vector<float> gb_depth(P);
+	FBufferView fbv; memset(&fbv, 0, sizeof(fbv));
+	fbv.channels = channels.data(); fbv.n_channels = FBufferDesc::NUM_CHANNELS;
+	fbv.gbuffer.m_geo = gb_geo.data(); fbv.gbuffer.m_uv = gb_uv.data(); fbv.gbuffer.m_tri = gb_tri.data(); fbv.gbuffer.m_depth = gb_depth.data();
+	fbv.gbuffer.res_x = f->res_x; fbv.gbuffer.res_y = f->res_y;
+	RenderingContextView renderer_view(cam, 0u, dls.data(), mesh, mesh_light, mesh_vpls, maps.data(), 0u, NULL, NULL, NULL, f->glossy_reflectance,
+									   f->res_x, f->res_y, f->aspect, 1.0f, 2.2f, 1.0f, kShaded, fbv, f->instance);
+	const size_t S = (size_t)f->tile * f->tile;
+	std::vector<float> samples((size_t)f->n_dims * S);
+	for (unsigned d = 0; d < f->n_dims; ++d)
+	{
+		const float seq = cugar::randfloat(d, f->instance + 1);
+		for (size_t i = 0; i < S; ++i) samples[d * S + i] = fmodf(seq + f->shifts[d * S + i], 1.0f);
+	}
+	HostQueue in_q, scatter_q, shadow_q;
+	uint64 device_timers[16];
+	HostPSFPTContext<DirectLightingMesh> context;
+	PSFPTOptions& o = context.options;
+	o.max_path_length = f->options[0]; o.direct_lighting = f->options[1]; o.direct_lighting_nee = f->options[2]; o.direct_lighting_bsdf = f->options[3];
+	o.indirect_lighting_nee = f->options[4]; o.indirect_lighting_bsdf = f->options[5]; o.visible_lights = f->options[6]; o.diffuse_scattering = f->options[7];
+	o.glossy_scattering = f->options[8]; o.indirect_glossy = f->options[9]; o.rr = f->options[10]; o.nee_type = f->options[11];
+	o.psf_depth = (uint32)psf_opts[0]; o.psf_width = psf_opts[1]; o.psf_max_prob = psf_opts[2]; o.firefly_filter = psf_opts[3];
+	context.in_bounce = 0;
+	context.in_queue = in_q.view(P, false); context.scatter_queue = scatter_q.view(P, false); context.shadow_queue = shadow_q.view(2 * P, true);
+	context.sequence.n_dimensions = f->n_dims; context.sequence.tile_size = f->tile; context.sequence.samples = samples.data(); context.sequence.shifts = f->shifts;
+	context.frame_weight = 1.0f / float(renderer_view.instance + 1);
+	context.device_timers = device_timers;
+	context.bbox = cugar::Bbox3f(cugar::Vector3f(bbox[0], bbox[1], bbox[2]), cugar::Vector3f(bbox[3], bbox[4], bbox[5]));
+	context.dl = DirectLightingMesh(f->options[11] == NEE_ALGORITHM_VPL && s->n_vpls ? renderer_view.mesh_vpls : renderer_view.mesh_light);
+	context.psf_hashmap = HostPSFPTContext<DirectLightingMesh>::HashMap(psf->hash_size, psf->keys.data(), psf->unique.data(), psf->slots.data(), &psf->count);
+	context.psf_values = psf->values.data();
+	psf->refs.clear();                                    // "reset the reference queue size"
+	context.ref_queue.recs = &psf->refs;
+	PSFPTVertexProcessor vertex_processor(psf_opts[3]);
+	RTContext rt; rt.view = view; rt.closest = (RTContext::closest_fn)closest; rt.shadow = (RTContext::shadow_fn)shadow;
+	g_host_rt = &rt;
+	alignas(16) static char renderer_mem[4096];
+	RenderingContext& renderer = *reinterpret_cast<RenderingContext*>(renderer_mem);
+	PTLoopStats stats;
+	path_trace_loop(context, vertex_processor, renderer, renderer_view, stats);
+	// psf_blending (src/renderers/psfpt_impl.h:156-165) over the queue the pass filled
+	const size_t n = psf->refs.size();
+	std::vector<float4> w_d(n ? n : 1), w_g(n ? n : 1); std::vector<uint2> px(n ? n : 1);
+	for (size_t i = 0; i < n; ++i) { w_d[i] = psf->refs[i].w_d; w_g[i] = psf->refs[i].w_g; px[i] = make_uint2(psf->refs[i].pixel, psf->refs[i].cache); }
+	BlendContextView bc; bc.ref_queue.weights_d = w_d.data(); bc.ref_queue.weights_g = w_g.data(); bc.ref_queue.pixels = px.data(); bc.psf_values = psf->values.data(); bc.options = context.options;
+	for (size_t i = 0; i < n; ++i) { blockIdx.x = (unsigned)i; threadIdx.x = 0; psf_pass::psf_blending_kernel((uint32)n, bc, renderer_view, 1.0f / float(renderer_view.instance + 1)); }
+	blockIdx.x = 0;
+	*n_refs = (unsigned)n;
+	return stats.shade_events;
 }
 EOF
 $CXX -O2 -std=c++14 -fPIC -w -fpermissive -ffp-contract=off -include $OVF/adapter_prefix.h -DFERMAT_API_EXTERN= -DFERMAT_API= -DSUTILAPI= -DSUTILCLASSAPI= \

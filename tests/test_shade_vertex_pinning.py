@@ -339,3 +339,34 @@ def test_whole_rl_pass_is_the_references_own(fb, oracle, libm_trig):
             assert differing.mean() < 2e-3 and np.array_equal(differing, (a[0] != b[0]).any(axis=2))
         live.rl_destroy(h)
         sc.close()
+
+
+def test_whole_psf_pass_is_the_references_own(fb, oracle, libm_trig):
+    """PSFPT::render on the host (src/renderers/psfpt_impl.h:287-436): the reference's own rescale_frame, the same path_trace_loop with PSFPTVertexProcessor over
+    the cache (hash map + cell values on host arrays, cleared every psf_temporal_reuse passes), psf_blending_kernel over the reference queue the pass filled,
+    update_variances and clamp_frame(100) - against oracle.render_pass_psf over three passes. Shade events, the number of cells and the channels no cache sum
+    feeds (DIRECT_C, both albedos) are equal bit for bit; the cache sums are float atomics in the reference - their order is the hardware's there, queue order in
+    this host run, path order in the restatement - so the channels blended from them agree to the rounding of those sums (1e-5 relative, per-pixel L2 < 1e-6)."""
+    live = oracle.RefShade.load(); kernels = oracle.RefFrameKernels.load()
+    if live is None or kernels is None:
+        pytest.skip("oracle/_ref/libref_shade.so / libref_frame.so are built where /root/reference exists")
+    cases = [["-i", os.path.join(GOLDEN, "cornellbox_jp.fbs"), "-r", "48", "48", "-bounces", "3", "-psfpt"]]
+    p = os.path.join(CACHE, "bathroom2.fbs")
+    if fb.scene_available(p):
+        cases.append(["-i", p, "-r", "96", "54", "-bounces", "4", "-psfpt"])
+    for args in cases:
+        sc = fb.Scene(args)
+        st = oracle.PsfState(); h = live.psf_create(1 << 18)
+        a = oracle.new_framebuffer(sc.view); b = oracle.new_framebuffer(sc.view)
+        for i in range(3):
+            ev = oracle.render_pass_psf(sc.view, i, a, st, threads=1).shade_events
+            ev_ref, n_refs = live.render_pass_psf(sc.view, i, b, h, kernels)
+            assert ev_ref == ev and live.psf_cells(h) == st.cells() and n_refs > 0, (args, i)
+            for c in (1, 3, 4):
+                assert np.array_equal(a[c][..., :3].view(np.uint32), b[c][..., :3].view(np.uint32)), (args, i, c)
+            assert np.allclose(a, b, rtol=1e-5, atol=1e-6)
+            d = a[5][..., :3].astype(np.float64) - b[5][..., :3].astype(np.float64)
+            assert np.sqrt((d ** 2).mean()) / a[5][..., :3].mean() < 1e-6
+        assert a[5][..., :3].max() <= 100.0 and b[5][..., :3].max() <= 100.0
+        live.psf_destroy(h); st.close()
+        sc.close()
