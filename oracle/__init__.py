@@ -1129,6 +1129,21 @@ class RefRlStep:
         p = os.path.join(_HERE, "_ref", "libref_rlstep.so")
         return cls(p) if os.path.exists(p) else None
 
+    def fresh_cells(self, n_cells, init_nodes, init_offsets):
+        """AdaptiveClusteredRLStorage::clear's kernels (init_clusters + update_cdfs(init)) on n_cells rows: (counts, nodes, ends, pdfs, cdfs)"""
+        self._lib.ref_rl_fresh_cells.restype = C.c_int
+        self._lib.ref_rl_fresh_cells.argtypes = [C.c_uint, C.c_uint] + [C.c_void_p] * 7
+        ni = np.ascontiguousarray(init_nodes, np.uint32); no = np.ascontiguousarray(init_offsets, np.uint32)
+        Cn = len(ni)
+        assert len(no) == Cn + 1
+        # update_cdfs_kernel(init) stores 0.01 from every thread of its block, also those past the row (the reference's table has hash_size rows behind it): pad
+        rows = n_cells + 1024 // Cn + 2
+        counts = np.zeros(rows, np.uint32); nodes = np.zeros((rows, Cn), np.uint32); ends = np.zeros((rows, Cn), np.uint32)
+        pdfs = np.zeros((rows, Cn), np.float32); cdfs = np.zeros((rows, Cn), np.float32)
+        if self._lib.ref_rl_fresh_cells(n_cells, Cn, ni.ctypes.data, no.ctypes.data, counts.ctypes.data, nodes.ctypes.data, ends.ctypes.data, pdfs.ctypes.data, cdfs.ctypes.data):
+            raise RuntimeError("ref_rl_fresh_cells: unsupported cluster count %d" % Cn)
+        return counts[:n_cells].copy(), nodes[:n_cells].copy(), ends[:n_cells].copy(), pdfs[:n_cells].copy(), cdfs[:n_cells].copy()
+
     def step(self, tree_nodes, tree_ranges, tree_parents, counts, nodes, ends, pdfs, adaptive=True):
         """AdaptiveClusteredRLStorage::update on rows of C entries: (counts, nodes, ends, pdfs, cdfs) afterwards"""
         tn = np.ascontiguousarray(tree_nodes, np.uint32); tr = np.ascontiguousarray(tree_ranges, np.uint32); tp = np.ascontiguousarray(tree_parents, np.uint32)

@@ -1915,6 +1915,7 @@ struct BlockScan
 EOF
 {
   sed -n '68,95p' $REF/src/clustered_rl.cu
+  sed -n '132,155p' $REF/src/clustered_rl.cu          # init_clusters_kernel (ref_rl_fresh_cells below)
   sed -n '245,493p' $REF/src/clustered_rl.cu
 } > $OUT/rl_step_cut.h
 cat > $OUT/ref_rlstep_shim.cpp <<'EOF'
@@ -1938,6 +1939,30 @@ using cugar::uint32;
 struct StepArgs { SplitKernelParams split; uint32 n_entries, C; const uint32* counts; float* values; float* cdfs; };
 template <uint32 DIM> static void split_body(void* a) { split_and_collapse_kernel<DIM>(static_cast<StepArgs*>(a)->split); }
 template <uint32 DIM> static void cdf_body(void* a) { StepArgs* s = static_cast<StepArgs*>(a); update_cdfs_kernel<DIM>(s->n_entries, s->C, s->counts, s->values, s->cdfs, false); }
+template <uint32 DIM> static void cdf_init_body(void* a) { StepArgs* s = static_cast<StepArgs*>(a); update_cdfs_kernel<DIM>(s->n_entries, s->C, s->counts, s->values, s->cdfs, true); }
+struct InitArgs { uint32 n_entries, C; const uint32* init_nodes; const uint32* init_offsets; uint32* counts; uint32* nodes; uint32* ends; };
+static void init_body(void* a) { InitArgs* s = static_cast<InitArgs*>(a); init_clusters_kernel(s->n_entries, s->C, s->init_nodes, s->init_offsets, s->counts, s->nodes, s->ends); }
+// AdaptiveClusteredRLStorage::clear (src/clustered_rl.cu:590-598) without the hash: init_clusters (the initial cut into every cell, block = the next power of two
+// holding C, :157-171) and update_cdfs(init = true) (every value 0.01, then the CDF) on rows of C entries
+extern "C" int ref_rl_fresh_cells(unsigned n_cells, unsigned C, const unsigned* init_nodes, const unsigned* init_offsets, unsigned* counts, unsigned* nodes, unsigned* ends,
+								  float* pdfs, float* cdfs)
+{
+	const unsigned dim = C <= 128 ? 128 : C <= 256 ? 256 : C <= 512 ? 512 : C <= 1024 ? 1024 : 0;
+	if (!dim) return -1;
+	unsigned pow2 = 1; while (pow2 < C) pow2 <<= 1;
+	InitArgs ia; ia.n_entries = n_cells; ia.C = C; ia.init_nodes = init_nodes; ia.init_offsets = init_offsets; ia.counts = counts; ia.nodes = nodes; ia.ends = ends;
+	StepArgs a; memset(&a, 0, sizeof(a));
+	a.n_entries = n_cells; a.C = C; a.counts = counts; a.values = pdfs; a.cdfs = cdfs;
+	for (unsigned k = 0; k < n_cells; ++k)
+	{
+		blockIdx.x = k;
+		cta_run(pow2, init_body, &ia);
+		if (dim == 128) cta_run(128, cdf_init_body<128>, &a); else if (dim == 256) cta_run(256, cdf_init_body<256>, &a);
+		else if (dim == 512) cta_run(512, cdf_init_body<512>, &a); else cta_run(1024, cdf_init_body<1024>, &a);
+	}
+	blockIdx.x = 0;
+	return 0;
+}
 // AdaptiveClusteredRLStorage::update on rows of C entries (in place) over a cluster tree given as Bintree words (2 per node), ranges (2 per node) and parents
 extern "C" int ref_rl_step(unsigned n_nodes, const unsigned* node_words, const unsigned* ranges, const unsigned* parents, unsigned n_cells, unsigned C,
 						   unsigned* counts, unsigned* nodes, unsigned* ends, float* pdfs, float* cdfs, int adaptive)

@@ -138,6 +138,19 @@ def test_split_collapse_and_cdfs_are_the_references_own_kernels(fb, oracle):
         if live is not None:
             hl = mk.run(lambda c, n, e, p, ad: live.step(a["tree_nodes"], a["tree_ranges"], a["tree_parents"], c, n, e, p, ad), a, adaptive)
             assert all(np.array_equal(x, y) for x, y in zip(hs, hl)), adaptive
+    # a fresh cell: AdaptiveClusteredRLStorage::clear's kernels (init_clusters_kernel + update_cdfs_kernel(init), src/clustered_rl.cu:68-95, 132-171) against the
+    # cell the restatement creates on first touch - also for a cut below the smallest block (83 clusters in a block of 128)
+    if live is not None:
+        for res in (48, 9):
+            s2 = fb.Scene(["-i", os.path.join(GOLDEN, "cornellbox_jp.fbs"), "-r", str(res), str(res), "-bounces", "2", "-nee-alg", "rl"])
+            st2 = oracle.RlState(s2.view, res * res); a2 = st2.arrays()
+            Cn = len(a2["clusters"])
+            counts, nodes, ends, pdfs, cdfs = live.fresh_cells(3, a2["clusters"], a2["cluster_offsets"])
+            c1, n1, e1, p1, cdf1 = st2.step(np.full(1, Cn, np.uint32), a2["clusters"][None, :], a2["cluster_offsets"][None, 1:], np.full((1, Cn), 0.01, np.float32), False)
+            for k in range(3):
+                assert counts[k] == Cn and np.array_equal(nodes[k], a2["clusters"]) and np.array_equal(ends[k], a2["cluster_offsets"][1:])
+                assert np.all(pdfs[k] == np.float32(0.01)) and np.array_equal(cdfs[k].view(np.uint32), cdf1[0].view(np.uint32))
+            s2.close()
     # the rounds did move the cuts
     c, n, e, p, factors = mk.step_cases(a)
     c2, n2, e2, p2, cdf = st.step(c, n, e, p, True)
