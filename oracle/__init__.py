@@ -672,6 +672,19 @@ class RefEaw:
         self.L = L
         L.ref_eaw_step.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
 
+    def filter(self, fb, geo, view, instance):
+        """RenderingContextImpl::filter (src/renderer.cu:1099-1160: FILTERED_C = DIRECT_C, then per diffuse / specular channel filter_variance(2) and seven EAW
+        iterations, demodulated by the albedo on the way in, modulated and added on the way out) from its own text over the reference's own EAW dispatchers, on
+        an (8, H, W, 4) frame buffer in place; returns channel 6"""
+        self.L.ref_filter.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_float, C.c_uint32]
+        self.L.ref_filter.restype = None
+        assert fb.dtype == np.float32 and fb.flags["C_CONTIGUOUS"] and fb.shape[0] == 8
+        geo = np.ascontiguousarray(geo, np.float32)
+        cam = np.array(list(view.eye[:]) + list(view.aim[:]) + list(view.up[:]) + [view.fov], np.float32)
+        h, w = fb.shape[1:3]
+        self.L.ref_filter(fb.ctypes.data, geo.ctypes.data, w, h, cam.ctypes.data, C.c_float(view.aspect), int(instance))
+        return fb[6]
+
     def step(self, dst, mad, op, w_img, w_min, img, geo, var, params, step_size):
         dst = np.array(dst, np.float32); img = np.ascontiguousarray(img, np.float32); geo = np.ascontiguousarray(geo, np.float32)
         w_img = None if w_img is None else np.ascontiguousarray(w_img, np.float32)

@@ -661,6 +661,14 @@ echo "built $OUT/libref_loader.so"
 sed -e 's/"framebuffer.h"/<framebuffer.h>/' $REF/src/filters.h > $OUT/filters_overlay.h                              # (framebuffer.h: the overlay's copy)
 sed -e 's/"framebuffer.h"/<framebuffer.h>/' -e 's/"filters.h"/"filters_overlay.h"/' $REF/src/eaw.h > $OUT/eaw_overlay.h
 sed -n '1,251p' $REF/src/eaw.cu | sed 's/"eaw.h"/"eaw_overlay.h"/' > $OUT/eaw_kernels_cut.h
+# RenderingContext::filter on the host (ref_filter below): the EAW dispatchers (src/eaw.cu:252-368) and filter_variance (src/renderer.cu:366-399) with their
+# launches rewritten as REF_LAUNCH, and the body of RenderingContextImpl::filter (src/renderer.cu:1101-1160, the branch that is compiled in)
+{
+  sed -n '252,368p' $REF/src/eaw.cu | sed -e 's/EAW_kernel << < gridSize, blockSize >> > (\(.*\));/REF_LAUNCH(gridSize, blockSize, EAW_kernel(\1));/' \
+      -e 's/EAW_mad_kernel<< < gridSize, blockSize >> > (\(.*\));/REF_LAUNCH(gridSize, blockSize, EAW_mad_kernel(\1));/'
+  sed -n '366,399p' $REF/src/renderer.cu | sed -e 's/filter_variance_kernel << < gridSize, blockSize >> > (\(.*\));/REF_LAUNCH(gridSize, blockSize, filter_variance_kernel(\1));/'
+} > $OUT/eaw_host_cut.h
+sed -n '1101,1160p' $REF/src/renderer.cu | sed -e '/^#if 1$/d' > $OUT/filter_body_cut.h
 cat > $OUT/ref_eaw_shim.cpp <<'EOF'
 struct RefIdx { unsigned x, y, z; };
 static thread_local RefIdx threadIdx = { 0, 0, 0 }, blockIdx = { 0, 0, 0 };
@@ -688,6 +696,47 @@ extern "C" void ref_eaw_step(float* dst, int mad, unsigned op, const float* w_im
 			if (mad) EAW_mad_kernel(d, op, w, w_min, im, gb, var, p, step_size);
 			else EAW_kernel(d, im, gb, var, p, step_size);
 		}
+}
+// ---- RenderingContextImpl::filter (src/renderer.cu:1099-1160) on the host: its body over stand-ins for the members it names (the frame buffer's channel storage
+// with view() and the channel-to-channel copy, the two ping-pong channels, the variance buffer, camera and aspect), through the reference's own EAW dispatchers
+// and filter_variance (their launches run the kernel once per thread)
+#include <camera.h>
+#include <renderer_view.h>      // FBufferDesc
+#include <vector>
+#include <string.h>
+#define REF_LAUNCH(g, b, call) do { const dim3 _g(g), _b(b); for (unsigned _y = 0; _y < _g.y * _b.y; ++_y) for (unsigned _x = 0; _x < _g.x * _b.x; ++_x) \
+	{ blockIdx.x = _x; blockIdx.y = _y; threadIdx.x = threadIdx.y = 0; call; } blockIdx.x = blockIdx.y = 0; } while (0)
+#undef CUDA_CHECK
+#define CUDA_CHECK(x)
+#include "eaw_host_cut.h"
+struct ChannelStore
+{
+	FBufferChannelView v;
+	FBufferChannelView view() { return v; }
+	ChannelStore& operator=(const ChannelStore& o) { memcpy(v.c_ptr, o.v.c_ptr, sizeof(float4) * (size_t)v.res_x * v.res_y); return *this; }
+};
+struct GBufferStore { GBufferView v; GBufferView view() { return v; } };
+struct FrameStore { ChannelStore channels[FBufferDesc::NUM_CHANNELS]; GBufferStore gbuffer; };
+struct VarStore { float* p; float* ptr() { return p; } };
+static void filter_host(FrameStore& m_fb, ChannelStore* m_fb_temp, VarStore& m_var, const Camera& m_camera, const float m_aspect, const uint32 instance)
+{
+#include "filter_body_cut.h"
+}
+// fbdata: 8 channel planes (FBufferDesc order) of rx * ry float4, FILTERED_C written; geo: the G-buffer's geometry plane; cam: eye, aim, up, fov
+extern "C" void ref_filter(float* fbdata, const float* geo, unsigned rx, unsigned ry, const float* cam, float aspect, unsigned instance)
+{
+	const size_t P = (size_t)rx * ry;
+	FrameStore fb;
+	for (unsigned c = 0; c < (unsigned)FBufferDesc::NUM_CHANNELS; ++c) { fb.channels[c].v.c_ptr = (float4*)fbdata + c * P; fb.channels[c].v.res_x = rx; fb.channels[c].v.res_y = ry; }
+	memset(&fb.gbuffer.v, 0, sizeof(fb.gbuffer.v));
+	fb.gbuffer.v.m_geo = (float4*)geo; fb.gbuffer.v.res_x = rx; fb.gbuffer.v.res_y = ry;
+	std::vector<float4> t0(P), t1(P); std::vector<float> var(P);
+	ChannelStore temp[2];
+	temp[0].v.c_ptr = t0.data(); temp[0].v.res_x = rx; temp[0].v.res_y = ry; temp[1].v.c_ptr = t1.data(); temp[1].v.res_x = rx; temp[1].v.res_y = ry;
+	VarStore vs; vs.p = var.data();
+	Camera camera;
+	camera.eye = make_float3(cam[0], cam[1], cam[2]); camera.aim = make_float3(cam[3], cam[4], cam[5]); camera.up = make_float3(cam[6], cam[7], cam[8]); camera.fov = cam[9];
+	filter_host(fb, temp, vs, camera, aspect, instance);
 }
 EOF
 $CXX $LFLAGS -I$OUT -shared -o $OUT/libref_eaw.so $OUT/ref_eaw_shim.cpp -L/usr/local/cuda/lib64 -lcudart_static -ldl -lrt -lpthread

@@ -127,6 +127,36 @@ def test_write_tga_is_the_references_own_writer(fb, oracle, tmp_path):
         assert (tmp_path / "one_ref.tga").read_bytes() == (tmp_path / "one.tga").read_bytes()
 
 
+def test_filter_is_the_references_own(fb, oracle):
+    """RenderingContextImpl::filter (src/renderer.cu:1099-1160) from its own text - FILTERED_C = DIRECT_C, then per diffuse / specular channel filter_variance(2)
+    and the seven-iteration EAW dispatcher of src/eaw.cu:321-368 (demodulate by the albedo on the way in, plain a-trous steps through the ping-pong buffers,
+    modulate and add on the way out) over the reference's own kernels, every launch run once per thread on the host (oracle/build_ref.sh -> libref_eaw.so
+    ref_filter) - against post_oracle.cpp's oracle_filter on rendered frames with their G-buffers: FILTERED_C bit for bit, the other channels untouched.
+    A golden hash of the reference's output keeps the check where oracle/_ref is absent."""
+    import hashlib
+    live = oracle.RefEaw.load()
+    cases = [("cornell", cornell_args(48, 3), 4)]
+    p = os.path.join(CACHE, "bathroom2.fbs")
+    if live is not None and fb.scene_available(p):
+        cases.append(("bathroom2", ["-i", p, "-r", "96", "54", "-bounces", "4"], 3))
+    for name, args, n in cases:
+        sc = fb.Scene(args)
+        f = oracle.new_framebuffer(sc.view)
+        for i in range(n):
+            st, gb = oracle.render_pass_with_gbuffer(sc.view, i, f)
+        geo = gb["geo"] if isinstance(gb, dict) else gb[0]
+        a = oracle.eaw_filter(f.copy(), geo, oracle.camera_frame(sc.view), n - 1)
+        assert np.isfinite(a).all() and a[..., :3].mean() > 0
+        if name == "cornell":
+            assert hashlib.sha256(a.tobytes()).hexdigest() == "4c1171c99ac3e3feec0532e077cb363685924b875bbb9c2de08f063ce71428a9"
+        if live is not None:
+            g2 = f.copy()
+            b = live.filter(g2, geo, sc.view, n - 1)
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), name
+            assert np.array_equal(np.delete(g2, 6, 0), np.delete(f, 6, 0))
+        sc.close()
+
+
 # ---------------------------------------------------------------------------------------------------------
 # device
 # ---------------------------------------------------------------------------------------------------------
