@@ -36,6 +36,9 @@ def test_scene_view_of_cornellbox(cornell_scene):
     bits = vd[:, 3].view(np.uint32)
     n = np.stack([(bits & 1023), (bits >> 10) & 1023, (bits >> 20) & 1023], 1).astype(np.float32) / 1023 * 2 - 1
     assert np.allclose(np.linalg.norm(n, axis=1), 1.0, atol=5e-3)
+    # the scene box the spatial hashes of -psfpt and -nee-alg rl quantise in: RenderingContextImpl::compute_bbox (src/renderer.cu:1086-1096), the box of
+    # every unified vertex
+    assert np.array_equal(vd[:, :3].min(0), np.array(v.bbox_min[:], np.float32)) and np.array_equal(vd[:, :3].max(0), np.array(v.bbox_max[:], np.float32))
 
 
 def test_vpls_lie_on_emitters(cornell_scene):
