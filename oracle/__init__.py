@@ -786,11 +786,12 @@ class RefShade:
         self.L.ref_rl_locate(h, prims.ctypes.data, uv.ctypes.data, len(prims), out.ctypes.data)
         return out
 
-    def render_pass(self, view, instance, fb, frame_kernels=None):
+    def render_pass(self, view, instance, fb, frame_kernels=None, gbuffer=None):
         """THE REFERENCE'S OWN PASS on the host (ref_render_pass: path_trace_loop with its dispatchers and kernels, src/pathtracer_kernels.h:128-391, over the
         reference's queues, shade_vertex, solve_occlusion and PTVertexProcessor) accumulated into fb (8, H, W, 4), as oracle.render_pass does. The two ray queries
         (OptiX in the reference) are the oracle's traversal. With `frame_kernels` (RefFrameKernels) the reference's own rescale_frame before and
-        update_variances after run too (RenderingContextImpl::render, src/renderer.cu:1040-1046 + PathTracer::render's last line); returns shade_events"""
+        update_variances after run too (RenderingContextImpl::render, src/renderer.cu:1040-1046 + PathTracer::render's last line); `gbuffer` = {geo (H, W, 4) f32,
+        uv (H, W, 4) f32, tri (H, W) u32, depth (H, W) f32} receives the G-buffer the pass writes over a 0xFF clear; returns shade_events"""
         L = self.L
         L.ref_render_pass.restype = C.c_uint64
         L.ref_render_pass.argtypes = [C.c_void_p] * 6
@@ -801,7 +802,13 @@ class RefShade:
         if frame_kernels is not None:
             frame_kernels.frame_op(0, fb, res, f=float(np.float32(instance) / np.float32(instance + 1)))
         O = lib()
-        n = L.ref_render_pass(C.addressof(s), C.addressof(f), fb.ctypes.data, C.addressof(view), C.cast(O.oracle_trace, C.c_void_p), C.cast(O.oracle_trace_shadow, C.c_void_p))
+        L.ref_set_gbuffer_out.argtypes = [C.c_void_p] * 4
+        if gbuffer is not None:
+            L.ref_set_gbuffer_out(gbuffer["geo"].ctypes.data, gbuffer["uv"].ctypes.data, gbuffer["tri"].ctypes.data, gbuffer["depth"].ctypes.data)
+        try:
+            n = L.ref_render_pass(C.addressof(s), C.addressof(f), fb.ctypes.data, C.addressof(view), C.cast(O.oracle_trace, C.c_void_p), C.cast(O.oracle_trace_shadow, C.c_void_p))
+        finally:
+            L.ref_set_gbuffer_out(None, None, None, None)
         if frame_kernels is not None:
             frame_kernels.frame_op(1, fb, res, u=instance + 1)
         return int(n)

@@ -1371,6 +1371,9 @@ struct HostQueue
 };
 // PathTracer::render between rescale_frame and update_variances (src/renderers/pathtracer_impl.h:252-292; the sampler is the caller's): fbdata = the frame's 8 channel
 // planes (P float4 each, FBufferDesc order), accumulated into; returns the loop's shade_events
+// optional outputs of the next pass: the G-buffer the first bounce writes (src/pathtracer_core.h:802-812), cleared to 0xFF bytes first as GBufferStorage::clear does
+static float* g_gb_geo_out = NULL; static float* g_gb_uv_out = NULL; static unsigned* g_gb_tri_out = NULL; static float* g_gb_depth_out = NULL;
+extern "C" void ref_set_gbuffer_out(float* geo, float* uv, unsigned* tri, float* depth) { g_gb_geo_out = geo; g_gb_uv_out = uv; g_gb_tri_out = tri; g_gb_depth_out = depth; }
 template <typename TDirectLightingSampler, typename TMakeSampler>
 static unsigned long long render_pass_host(const RefScene* s, const RefFrame* f, float* fbdata, const void* view, void* closest, void* shadow, const float* bbox, TMakeSampler make_sampler)
 {
@@ -1395,6 +1398,7 @@ static unsigned long long render_pass_host(const RefScene* s, const RefFrame* f,
 	std::vector<FBufferChannelView> channels(FBufferDesc::NUM_CHANNELS);
 	for (unsigned c = 0; c < (unsigned)FBufferDesc::NUM_CHANNELS; ++c) { channels[c].c_ptr = reinterpret_cast<float4*>(fbdata) + c * P; channels[c].res_x = f->res_x; channels[c].res_y = f->res_y; }
 	std::vector<float4> gb_geo(P), gb_uv(P); std::vector<uint32> gb_tri(P); std::vector<float> gb_depth(P);
+	memset(gb_geo.data(), 0xFF, P * 16); memset(gb_uv.data(), 0xFF, P * 16); memset(gb_tri.data(), 0xFF, P * 4); memset(gb_depth.data(), 0xFF, P * 4);
 	FBufferView fbv; memset(&fbv, 0, sizeof(fbv));
 	fbv.channels = channels.data(); fbv.n_channels = FBufferDesc::NUM_CHANNELS;
 	fbv.gbuffer.m_geo = gb_geo.data(); fbv.gbuffer.m_uv = gb_uv.data(); fbv.gbuffer.m_tri = gb_tri.data(); fbv.gbuffer.m_depth = gb_depth.data();
@@ -1429,6 +1433,7 @@ static unsigned long long render_pass_host(const RefScene* s, const RefFrame* f,
 	RenderingContext& renderer = *reinterpret_cast<RenderingContext*>(renderer_mem);
 	PTLoopStats stats;
 	path_trace_loop(context, vertex_processor, renderer, renderer_view, stats);
+	if (g_gb_geo_out) { memcpy(g_gb_geo_out, gb_geo.data(), P * 16); memcpy(g_gb_uv_out, gb_uv.data(), P * 16); memcpy(g_gb_tri_out, gb_tri.data(), P * 4); memcpy(g_gb_depth_out, gb_depth.data(), P * 4); }
 	return stats.shade_events;
 }
 extern "C" unsigned long long ref_render_pass(const RefScene* s, const RefFrame* f, float* fbdata, const void* view, void* closest, void* shadow)

@@ -294,6 +294,14 @@ def test_whole_pass_is_the_references_own(fb, oracle, libm_trig):
             if live is not None and kernels is not None:
                 assert live.render_pass(sc.view, i, b, kernels) == ev, (name, i)
                 assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (name, i)
+        if live is not None and kernels is not None:
+            # the G-buffer the first bounce writes (packed position + normal, hit and texture coordinates, triangle, depth; 0xFF where no primary ray hit)
+            h, w = int(sc.view.res_y), int(sc.view.res_x)
+            st, ga = oracle.render_pass_with_gbuffer(sc.view, 0, oracle.new_framebuffer(sc.view))
+            gb = {"geo": np.zeros((h, w, 4), np.float32), "uv": np.zeros((h, w, 4), np.float32), "tri": np.zeros((h, w), np.uint32), "depth": np.zeros((h, w), np.float32)}
+            live.render_pass(sc.view, 0, oracle.new_framebuffer(sc.view), kernels, gbuffer=gb)
+            for k in ga:
+                assert np.array_equal(ga[k].view(np.uint32), gb[k].view(np.uint32)), (name, k)
         assert a[5][..., :3].mean() > 0
         sc.close()
 
