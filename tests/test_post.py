@@ -157,6 +157,38 @@ def test_filter_is_the_references_own(fb, oracle):
         sc.close()
 
 
+def test_image_file_of_the_references_own_pipeline(fb, oracle, tmp_path):
+    """the capstone of the host-side pins: what `fermat -pt -o out.tga` computes, stage by stage from the reference's OWN code on the host - four passes of
+    path_trace_loop between rescale_frame and update_variances (libref_shade / libref_frame), RenderingContext::filter (libref_eaw), to_rgba_kernel in both the
+    shaded and the filtered mode (libref_frame), cugar::write_tga (libref_tga) - against the restated pipeline ending in the PRODUCT's TGA writer: the two files
+    are the same bytes. (Ray queries: the oracle's traversal on both sides; trigonometry: libm on both sides.)"""
+    live = oracle.RefShade.load(); kernels = oracle.RefFrameKernels.load(); eaw = oracle.RefEaw.load()
+    if live is None or kernels is None or eaw is None:
+        pytest.skip("oracle/_ref is built where /root/reference exists")
+    oracle.set_trig_mode(0)
+    try:
+        sc = fb.Scene(cornell_args(48, 3))
+        h, w = int(sc.view.res_y), int(sc.view.res_x)
+        a = oracle.new_framebuffer(sc.view); b = oracle.new_framebuffer(sc.view)
+        gb = {"geo": np.zeros((h, w, 4), np.float32), "uv": np.zeros((h, w, 4), np.float32), "tri": np.zeros((h, w), np.uint32), "depth": np.zeros((h, w), np.float32)}
+        for i in range(4):
+            st, ga = oracle.render_pass_with_gbuffer(sc.view, i, a)
+            live.render_pass(sc.view, i, b, kernels, gbuffer=gb)
+        oracle.eaw_filter(a, ga["geo"], oracle.camera_frame(sc.view), 3)
+        eaw.filter(b, gb["geo"], sc.view, 3)
+        exposure, gamma = sc.tonemap()
+        for mode, tag in ((0, "shaded"), (10, "filtered")):
+            ours = oracle.to_rgba(a, ga["geo"], ga["uv"], mode, exposure, gamma)
+            ref = kernels.to_rgba(b.reshape(8, h * w, 4), gb["geo"].reshape(-1, 4), gb["uv"].reshape(-1, 4), (w, h), mode, exposure, gamma).reshape(h, w, 4)
+            fb.write_tga(tmp_path / ("ours_%s.tga" % tag), ours)
+            assert oracle.ref_write_tga(tmp_path / ("ref_%s.tga" % tag), ref)
+            x, y = (tmp_path / ("ours_%s.tga" % tag)).read_bytes(), (tmp_path / ("ref_%s.tga" % tag)).read_bytes()
+            assert x == y and len(x) == 18 + 3 * h * w and len(set(x[18:])) > 50
+        sc.close()
+    finally:
+        oracle.set_trig_mode(1)
+
+
 # ---------------------------------------------------------------------------------------------------------
 # device
 # ---------------------------------------------------------------------------------------------------------
